@@ -1,0 +1,285 @@
+"""ctypes mirror of include/arts_b200.h (the C ABI) and the flat host containers.
+
+The containers are the flattened forms a reference-side shim produces from
+``AbsorptionBands`` (src/core/lbl/lbl_data.h:31-68,196-300), ``ArrayOfAtmPoint``
+(src/core/atm/atm_field.h:67-82) and ``ArrayOfPropagationPathPoint``
+(src/core/path/path_point.h:14-35); see INTEGRATION.md for the C++ side.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# ---- constants mirrored from the header ------------------------------------
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3, 4
+SPECIES_BATH = -1
+VAR_G0, VAR_D0, VAR_DV, VAR_Y, VAR_G, NVAR = 0, 1, 2, 3, 4, 5
+TM_ABSENT, TM_T0, TM_T1, TM_T2, TM_T3, TM_T4, TM_T5, TM_AER, TM_DPL, TM_POLY = -1, 0, 1, 2, 3, 4, 5, 6, 7, 8
+LINESHAPE_VP_LTE, LINESHAPE_OTHER = 0, 1
+CUTOFF_NONE, CUTOFF_BYLINE = 0, 1
+RTE_CONSTANT, RTE_LINSRC, RTE_LINPROP = 0, 1, 2
+TARGET_T, TARGET_VMR = 0, 1
+FLAG_K_ZERO_INIT, FLAG_TRAN_EXACT, FLAG_RETURN_K = 1, 2, 4
+
+RTE_OPTIONS = {"constant": RTE_CONSTANT, "linsrc": RTE_LINSRC, "lintau": RTE_LINSRC, "linprop": RTE_LINPROP}
+
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class CatalogDesc(C.Structure):
+    _fields_ = [
+        ("n_species", C.c_int32),
+        ("n_isot", C.c_int32),
+        ("n_bands", C.c_int32),
+        ("n_lines", C.c_int64),
+        ("n_ls", C.c_int64),
+        ("isot_species", _i32p),
+        ("isot_mass", _dp),
+        ("band_isot", _i32p),
+        ("band_lineshape", _i32p),
+        ("band_cutoff_type", _i32p),
+        ("band_cutoff_value", _dp),
+        ("band_offset", _i64p),
+        ("f0", _dp),
+        ("a", _dp),
+        ("e0", _dp),
+        ("gu", _dp),
+        ("gl", _dp),
+        ("T0", _dp),
+        ("z_on", _u8p),
+        ("z_gu", _dp),
+        ("z_gl", _dp),
+        ("two_Ju", _i32p),
+        ("two_Jl", _i32p),
+        ("ls_offset", _i64p),
+        ("ls_species", _i32p),
+        ("ls_type", _i32p),
+        ("ls_X", _dp),
+    ]
+
+
+class AtmPathDesc(C.Structure):
+    _fields_ = [
+        ("np", C.c_int32),
+        ("T", _dp),
+        ("P", _dp),
+        ("vmr", _dp),
+        ("isorat", _dp),
+        ("Q", _dp),
+        ("dQdT", _dp),
+        ("mag", _dp),
+        ("los", _dp),
+    ]
+
+
+class Target(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("species", C.c_int32)]
+
+
+def _arr(x, dtype, shape=None):
+    a = np.ascontiguousarray(x, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def ptr(a: np.ndarray | None, ctype):
+    if a is None:
+        return C.cast(None, C.POINTER(ctype))
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def dptr(a):
+    return ptr(a, C.c_double)
+
+
+@dataclass
+class HostCatalog:
+    """AbsorptionBands flattened to SoA (what ab200_catalog_create consumes).
+
+    Lines are stored band-contiguous and, inside a band, sorted by ``f0`` like
+    the reference requires for ``band_data::active_lines`` (lbl_data.cpp:61-68).
+    """
+
+    n_species: int
+    isot_species: np.ndarray
+    isot_mass: np.ndarray
+    band_isot: np.ndarray
+    band_offset: np.ndarray
+    f0: np.ndarray
+    a: np.ndarray
+    e0: np.ndarray
+    gu: np.ndarray
+    gl: np.ndarray
+    T0: np.ndarray
+    ls_offset: np.ndarray
+    ls_species: np.ndarray
+    ls_type: np.ndarray  # [n_ls, NVAR]
+    ls_X: np.ndarray  # [n_ls, NVAR, 4]
+    band_lineshape: np.ndarray | None = None
+    band_cutoff_type: np.ndarray | None = None
+    band_cutoff_value: np.ndarray | None = None
+    z_on: np.ndarray | None = None
+    z_gu: np.ndarray | None = None
+    z_gl: np.ndarray | None = None
+    two_Ju: np.ndarray | None = None
+    two_Jl: np.ndarray | None = None
+    _keep: list = field(default_factory=list, repr=False)
+
+    def __post_init__(self):
+        nb = len(self.band_isot)
+        nl = len(self.f0)
+        self.isot_species = _arr(self.isot_species, np.int32)
+        self.isot_mass = _arr(self.isot_mass, np.float64)
+        self.band_isot = _arr(self.band_isot, np.int32)
+        self.band_offset = _arr(self.band_offset, np.int64)
+        for name in ("f0", "a", "e0", "gu", "gl", "T0"):
+            setattr(self, name, _arr(getattr(self, name), np.float64))
+        self.ls_offset = _arr(self.ls_offset, np.int64)
+        self.ls_species = _arr(self.ls_species, np.int32)
+        nls = len(self.ls_species)
+        self.ls_type = _arr(self.ls_type, np.int32, (nls, NVAR))
+        self.ls_X = _arr(self.ls_X, np.float64, (nls, NVAR, 4))
+        self.band_lineshape = _arr(np.zeros(nb) if self.band_lineshape is None else self.band_lineshape, np.int32)
+        self.band_cutoff_type = _arr(np.zeros(nb) if self.band_cutoff_type is None else self.band_cutoff_type, np.int32)
+        self.band_cutoff_value = _arr(
+            np.full(nb, np.inf) if self.band_cutoff_value is None else self.band_cutoff_value, np.float64
+        )
+        self.z_on = _arr(np.zeros(nl) if self.z_on is None else self.z_on, np.uint8)
+        self.z_gu = _arr(np.zeros(nl) if self.z_gu is None else self.z_gu, np.float64)
+        self.z_gl = _arr(np.zeros(nl) if self.z_gl is None else self.z_gl, np.float64)
+        self.two_Ju = _arr(np.zeros(nl) if self.two_Ju is None else self.two_Ju, np.int32)
+        self.two_Jl = _arr(np.zeros(nl) if self.two_Jl is None else self.two_Jl, np.int32)
+        assert self.band_offset.shape == (nb + 1,) and self.band_offset[-1] == nl
+        assert self.ls_offset.shape == (nl + 1,) and self.ls_offset[-1] == nls
+
+    @property
+    def n_lines(self) -> int:
+        return int(len(self.f0))
+
+    @property
+    def n_isot(self) -> int:
+        return int(len(self.isot_species))
+
+    @property
+    def n_bands(self) -> int:
+        return int(len(self.band_isot))
+
+    def desc(self) -> CatalogDesc:
+        d = CatalogDesc()
+        d.n_species = self.n_species
+        d.n_isot = self.n_isot
+        d.n_bands = self.n_bands
+        d.n_lines = self.n_lines
+        d.n_ls = len(self.ls_species)
+        d.isot_species = ptr(self.isot_species, C.c_int32)
+        d.isot_mass = dptr(self.isot_mass)
+        d.band_isot = ptr(self.band_isot, C.c_int32)
+        d.band_lineshape = ptr(self.band_lineshape, C.c_int32)
+        d.band_cutoff_type = ptr(self.band_cutoff_type, C.c_int32)
+        d.band_cutoff_value = dptr(self.band_cutoff_value)
+        d.band_offset = ptr(self.band_offset, C.c_int64)
+        for name in ("f0", "a", "e0", "gu", "gl", "T0", "z_gu", "z_gl"):
+            setattr(d, name, dptr(getattr(self, name)))
+        d.z_on = ptr(self.z_on, C.c_uint8)
+        d.two_Ju = ptr(self.two_Ju, C.c_int32)
+        d.two_Jl = ptr(self.two_Jl, C.c_int32)
+        d.ls_offset = ptr(self.ls_offset, C.c_int64)
+        d.ls_species = ptr(self.ls_species, C.c_int32)
+        d.ls_type = ptr(self.ls_type, C.c_int32)
+        d.ls_X = dptr(self.ls_X)
+        return d
+
+
+@dataclass
+class AtmPath:
+    """ArrayOfAtmPoint + the los of ArrayOfPropagationPathPoint, flattened per level."""
+
+    T: np.ndarray
+    P: np.ndarray
+    vmr: np.ndarray  # [np, n_species]
+    isorat: np.ndarray  # [np, n_isot]
+    Q: np.ndarray  # [np, n_isot]
+    dQdT: np.ndarray | None = None
+    mag: np.ndarray | None = None  # [np, 3]
+    los: np.ndarray | None = None  # [np, 2]
+
+    def __post_init__(self):
+        self.T = _arr(self.T, np.float64)
+        n = len(self.T)
+        self.P = _arr(self.P, np.float64)
+        self.vmr = _arr(self.vmr, np.float64).reshape(n, -1)
+        self.isorat = _arr(self.isorat, np.float64).reshape(n, -1)
+        self.Q = _arr(self.Q, np.float64).reshape(n, -1)
+        if self.dQdT is not None:
+            self.dQdT = _arr(self.dQdT, np.float64).reshape(n, -1)
+        if self.mag is not None:
+            self.mag = _arr(self.mag, np.float64).reshape(n, 3)
+        if self.los is not None:
+            self.los = _arr(self.los, np.float64).reshape(n, 2)
+
+    @property
+    def np_(self) -> int:
+        return int(len(self.T))
+
+    def level(self, ip: int) -> "AtmPath":
+        s = slice(ip, ip + 1)
+        return AtmPath(
+            self.T[s], self.P[s], self.vmr[s], self.isorat[s], self.Q[s],
+            None if self.dQdT is None else self.dQdT[s],
+            None if self.mag is None else self.mag[s],
+            None if self.los is None else self.los[s],
+        )
+
+    def desc(self) -> AtmPathDesc:
+        d = AtmPathDesc()
+        d.np = self.np_
+        d.T = dptr(self.T)
+        d.P = dptr(self.P)
+        d.vmr = dptr(self.vmr)
+        d.isorat = dptr(self.isorat)
+        d.Q = dptr(self.Q)
+        d.dQdT = dptr(self.dQdT)
+        d.mag = dptr(self.mag)
+        d.los = dptr(self.los)
+        return d
+
+
+def make_targets(targets) -> tuple[C.Array | None, int]:
+    """targets: iterable of ("T",) / ("VMR", species_id) or (kind, species) ints."""
+    lst = []
+    for t in targets or ():
+        if isinstance(t, str):
+            t = (t,)
+        kind = t[0]
+        if kind in ("T", "t"):
+            lst.append((TARGET_T, 0))
+        elif kind in ("VMR", "vmr"):
+            lst.append((TARGET_VMR, int(t[1])))
+        else:
+            lst.append((int(kind), int(t[1]) if len(t) > 1 else 0))
+    if not lst:
+        return None, 0
+    arr = (Target * len(lst))()
+    for i, (k, s) in enumerate(lst):
+        arr[i].kind = k
+        arr[i].species = s
+    return arr, len(lst)
+
+
+# argument lists shared by the CUDA library (ab200_*) and the oracle (orc_*)
+SIG_PROPMAT_LEVELS_CORE = [
+    C.c_int64, _dp, C.c_int64, C.POINTER(AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(Target),
+]
+SIG_TRAMAT = [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, C.c_uint32, _dp, _dp, _dp, _dp, _dp]
+SIG_SRCVEC = [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, C.c_int64, _dp, C.c_int32, _dp, _dp]
+SIG_RTE = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+SIG_CLEARSKY_CORE = [
+    C.c_int64, _dp, C.c_int64, C.POINTER(AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(Target), _dp,
+    C.c_int32, C.c_int32, _dp, C.c_uint32, _dp, _dp, _dp,
+]

@@ -1,0 +1,555 @@
+// api.cu — the C ABI of include/arts_b200.h: error plumbing, the device-resident path
+// workspace and the host-buffer entry points the ARTS workspace-method shims call.
+//
+// Host orchestration only; the arithmetic is in lbl.cu (stage 1) and stokes.cu (stage 2).
+// No CPU fallback anywhere: a missing device or a failing CUDA call is an error return.
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "catalog.hpp"
+#include "lbl.hpp"
+#include "stokes.hpp"
+
+namespace ab200 {
+
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+
+int set_error(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")";
+  cudaGetLastError();  // clear the sticky-less error state
+  return AB200_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+static constexpr size_t PREP_BUDGET_BYTES = size_t(8) << 30;  // line records kept resident per batch of levels
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) return 0;
+  AB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return 0;
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+struct ab200_path {
+  const ab200_catalog* cat = nullptr;
+  int64_t nf = 0, k_pitch = 0;
+  int32_t np = 0, nq = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  // inputs
+  double* d_f = nullptr;      // [np][nf] capacity
+  double* d_small = nullptr;  // packed small per-level arrays, see upload()
+  double *d_T = nullptr, *d_P = nullptr, *d_H = nullptr, *d_vmr = nullptr, *d_isorat = nullptr, *d_Q = nullptr,
+         *d_npm = nullptr, *d_frange = nullptr, *d_r = nullptr;
+  double* h_small = nullptr;  // pinned staging of the same
+  size_t small_doubles = 0;
+  double* d_Ibkg = nullptr;
+  SegmentDev* d_segs = nullptr;  // [2][nsegments] capacity; mode-0 list then mode-1 list
+  SegmentDev* h_segs = nullptr;
+  int32_t nsegs[2] = {0, 0};
+  // workspace
+  double* d_prep = nullptr;
+  double* d_summary = nullptr;
+  int32_t levels_per_batch = 0;
+  int* d_flags = nullptr;
+  // outputs
+  double* d_K = nullptr;  // [np][k_pitch][7]
+  double* d_I = nullptr;  // [nf][4]
+
+  int64_t f_stride = 0;
+  int32_t rte_option = AB200_RTE_LINSRC, no_neg = 1;
+  uint32_t flags = 0;
+  bool uploaded = false, k_preloaded = false;
+
+  ~ab200_path() {
+    cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary);
+    cudaFree(d_flags); cudaFree(d_K); cudaFree(d_I);
+    if (h_small) cudaFreeHost(h_small);
+    if (h_segs) cudaFreeHost(h_segs);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+};
+
+extern "C" {
+
+const char* ab200_last_error(void) { return g_err.c_str(); }
+
+int ab200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t ab200_launch_count(int reset) {
+  const int64_t n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// path workspace
+// ---------------------------------------------------------------------------
+int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab200_path** out) {
+  if (!cat || !out) return set_error(AB200_ERR_INVALID, "ab200_path_create: null argument");
+  *out = nullptr;
+  if (nf < 0 || np < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_path_create: negative size");
+  if (nq > 0)
+    return set_error(AB200_ERR_UNSUPPORTED,
+                     "Jacobian targets (nq > 0) are not on the GPU path in this build (no CPU fallback)");
+  std::unique_ptr<ab200_path> p(new ab200_path());
+  p->cat = cat;
+  p->nf = nf;
+  p->np = np;
+  p->nq = nq;
+  p->k_pitch = (nf + 127) / 128 * 128;
+  AB_CUDA(cudaSetDevice(cat->device));
+  AB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  p->own_stream = true;
+
+  const size_t snp = static_cast<size_t>(np);
+  AB_TRY(dev_alloc(&p->d_f, snp * nf));
+  // packed small arrays: T, P, H [np] | vmr [np][ns] | isorat, Q [np][ni] | npm [np][4][7] | frange [np][2] | r [np]
+  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1);
+  AB_TRY(dev_alloc(&p->d_small, p->small_doubles));
+  if (p->small_doubles) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_small), p->small_doubles * sizeof(double)));
+  double* q = p->d_small;
+  p->d_T = q; q += snp;
+  p->d_P = q; q += snp;
+  p->d_H = q; q += snp;
+  p->d_vmr = q; q += snp * cat->n_species;
+  p->d_isorat = q; q += snp * cat->n_isot;
+  p->d_Q = q; q += snp * cat->n_isot;
+  p->d_npm = q; q += snp * 28;
+  p->d_frange = q; q += snp * 2;
+  p->d_r = q;
+  AB_TRY(dev_alloc(&p->d_Ibkg, static_cast<size_t>(nf) * 4));
+  AB_TRY(dev_alloc(&p->d_I, static_cast<size_t>(nf) * 4));
+  AB_TRY(dev_alloc(&p->d_K, snp * p->k_pitch * 7));
+  const size_t nseg = cat->segments.size();
+  AB_TRY(dev_alloc(&p->d_segs, 2 * nseg));
+  if (nseg) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_segs), 2 * nseg * sizeof(SegmentDev)));
+  AB_TRY(dev_alloc(&p->d_flags, 1));
+  AB_CUDA(cudaMemset(p->d_flags, 0, sizeof(int)));
+
+  const size_t per_level = static_cast<size_t>(cat->ntiles) * tile_doubles() * sizeof(double);
+  int lpb = np;
+  if (per_level > 0) lpb = static_cast<int>(std::max<size_t>(1, std::min<size_t>(snp, PREP_BUDGET_BYTES / per_level)));
+  p->levels_per_batch = std::max(lpb, 1);
+  AB_TRY(dev_alloc(&p->d_prep, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * tile_doubles()));
+  AB_TRY(dev_alloc(&p->d_summary, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * SUMMARY_DOUBLES));
+  *out = p.release();
+  return AB200_OK;
+}
+
+void ab200_path_destroy(ab200_path* p) { delete p; }
+
+int ab200_path_set_stream(ab200_path* p, void* stream) {
+  if (!p) return set_error(AB200_ERR_INVALID, "ab200_path_set_stream: null path");
+  if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+  p->stream = static_cast<cudaStream_t>(stream);
+  p->own_stream = false;
+  return AB200_OK;
+}
+
+int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, const ab200_atm_path* atm,
+                      int32_t select_species, int32_t no_negative_absorption, const ab200_target* targets,
+                      const double* r, int32_t hse_derivative, int32_t rte_option, const double* I_bkg,
+                      uint32_t flags) {
+  (void)targets;
+  (void)hse_derivative;
+  if (!p || !f || !atm) return set_error(AB200_ERR_INVALID, "ab200_path_upload: null argument");
+  const ab200_catalog* cat = p->cat;
+  const int np = p->np;
+  if (atm->np != np)
+    return set_error(AB200_ERR_INVALID, "atm path has " + std::to_string(atm->np) + " levels, workspace " + std::to_string(np));
+  if (f_level_stride != 0 && f_level_stride != p->nf)
+    return set_error(AB200_ERR_INVALID, "f_level_stride must be 0 (shared grid) or nf (one grid per level)");
+  if (rte_option == AB200_RTE_LINPROP)
+    return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path (no CPU fallback)");
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC)
+    return set_error(AB200_ERR_INVALID, "unknown rte_option");
+  if (select_species != AB200_SPECIES_BATH && (select_species < 0 || select_species >= cat->n_species))
+    return set_error(AB200_ERR_INVALID, "select_species out of range");
+  if (!atm->T || !atm->P || !atm->vmr || !atm->isorat || !atm->Q)
+    return set_error(AB200_ERR_INVALID, "atm path: T, P, vmr, isorat and Q are required");
+  AB_CUDA(cudaSetDevice(cat->device));
+
+  const size_t snp = static_cast<size_t>(np);
+  double* h = p->h_small;
+  double *hT = h, *hP = hT + snp, *hH = hP + snp, *hv = hH + snp, *hi = hv + snp * cat->n_species,
+         *hQ = hi + snp * cat->n_isot, *hn = hQ + snp * cat->n_isot, *hfr = hn + snp * 28, *hr = hfr + snp * 2;
+  for (int ip = 0; ip < np; ip++) {
+    if (!(atm->T[ip] > 0) || !(atm->P[ip] >= 0))
+      return set_error(AB200_ERR_INVALID, "level " + std::to_string(ip) + ": temperature must be > 0 and pressure >= 0");
+    hT[ip] = atm->T[ip];
+    hP[ip] = atm->P[ip];
+    double mag[3] = {0, 0, 0}, los[2] = {0, 0};
+    if (atm->mag) std::copy(atm->mag + 3 * ip, atm->mag + 3 * ip + 3, mag);
+    if (atm->los) std::copy(atm->los + 2 * ip, atm->los + 2 * ip + 2, los);
+    hH[ip] = std::hypot(mag[0], mag[1], mag[2]);
+    for (int pol = 0; pol < 4; pol++) norm_view(pol, mag, los, hn + (static_cast<size_t>(ip) * 4 + pol) * 7);
+    const double* fl = f + ip * f_level_stride;
+    hfr[2 * ip]     = p->nf ? fl[0] : 0.0;
+    hfr[2 * ip + 1] = p->nf ? fl[p->nf - 1] : 0.0;
+    hr[ip] = (r && ip < np - 1) ? r[ip] : 0.0;
+    for (int s = 0; s < cat->n_species; s++) {
+      const double v = atm->vmr[static_cast<size_t>(ip) * cat->n_species + s];
+      if (!(v >= 0)) return set_error(AB200_ERR_INVALID, "level " + std::to_string(ip) + ": negative or NaN VMR");
+      hv[static_cast<size_t>(ip) * cat->n_species + s] = v;
+    }
+    for (int i = 0; i < cat->n_isot; i++) {
+      const double ir = atm->isorat[static_cast<size_t>(ip) * cat->n_isot + i];
+      const double Q  = atm->Q[static_cast<size_t>(ip) * cat->n_isot + i];
+      if (!(ir >= 0) || !(Q > 0))
+        return set_error(AB200_ERR_INVALID,
+                         "level " + std::to_string(ip) + ": isotopologue ratio must be >= 0 and partition function > 0");
+      hi[static_cast<size_t>(ip) * cat->n_isot + i] = ir;
+      hQ[static_cast<size_t>(ip) * cat->n_isot + i] = Q;
+    }
+  }
+  if (p->small_doubles)
+    AB_CUDA(cudaMemcpyAsync(p->d_small, h, p->small_doubles * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  const size_t nfl = static_cast<size_t>(p->nf) * (f_level_stride ? np : 1);
+  if (nfl) AB_CUDA(cudaMemcpyAsync(p->d_f, f, nfl * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  if (I_bkg && p->nf)
+    AB_CUDA(cudaMemcpyAsync(p->d_Ibkg, I_bkg, static_cast<size_t>(p->nf) * 4 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+
+  // segments selected by species (lbl_lineshape.cpp:191), split by kernel
+  const size_t nseg = cat->segments.size();
+  p->nsegs[0] = p->nsegs[1] = 0;
+  for (const Segment& s : cat->segments) {
+    if (!(select_species == AB200_SPECIES_BATH || select_species == s.species)) continue;
+    SegmentDev d{s.tile_begin, s.tile_end, s.cutoff, s.pol, s.has_cutoff};
+    p->h_segs[s.mode * nseg + p->nsegs[s.mode]++] = d;
+  }
+  if (nseg) AB_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, 2 * nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice, p->stream));
+
+  p->f_stride   = f_level_stride;
+  p->rte_option = rte_option;
+  p->no_neg     = no_negative_absorption;
+  p->flags      = flags;
+  p->uploaded   = true;
+  p->k_preloaded = false;
+  return AB200_OK;
+}
+
+int ab200_path_run_propmat(ab200_path* p) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_propmat: path not uploaded");
+  const ab200_catalog* cat = p->cat;
+  AB_CUDA(cudaSetDevice(cat->device));
+  const size_t kbytes = static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double);
+  if (!p->k_preloaded && kbytes) AB_CUDA(cudaMemsetAsync(p->d_K, 0, kbytes, p->stream));
+  if (cat->ntiles == 0 || p->nf == 0) return AB200_OK;
+  const size_t nseg = cat->segments.size();
+  for (int lev0 = 0; lev0 < p->np; lev0 += p->levels_per_batch) {
+    const int nlev = std::min(p->levels_per_batch, p->np - lev0);
+    PrepareParams pp{};
+    pp.f0 = cat->d_f0; pp.a = cat->d_a; pp.e0 = cat->d_e0; pp.gu = cat->d_gu; pp.T0 = cat->d_T0;
+    pp.line_isot = cat->d_line_isot; pp.ls_offset = cat->d_ls_offset; pp.ls_species = cat->d_ls_species;
+    pp.ls_type = cat->d_ls_type; pp.ls_X = cat->d_ls_X; pp.isot_species = cat->d_isot_species;
+    pp.isot_mass = cat->d_isot_mass; pp.sub_parent = cat->d_sub_parent; pp.sub_Sz = cat->d_sub_Sz;
+    pp.sub_dzc = cat->d_sub_dzc; pp.tile_cutoff = cat->d_tile_cutoff;
+    pp.n_species = cat->n_species; pp.n_isot = cat->n_isot; pp.ntiles = cat->ntiles;
+    pp.T = p->d_T + lev0; pp.P = p->d_P + lev0; pp.H = p->d_H + lev0;
+    pp.vmr = p->d_vmr + static_cast<size_t>(lev0) * cat->n_species;
+    pp.isorat = p->d_isorat + static_cast<size_t>(lev0) * cat->n_isot;
+    pp.Q = p->d_Q + static_cast<size_t>(lev0) * cat->n_isot;
+    pp.frange = p->d_frange + 2 * static_cast<size_t>(lev0);
+    pp.prep = p->d_prep; pp.summary = p->d_summary; pp.flags = p->d_flags;
+    AB_TRY(launch_prepare(pp, nlev, p->stream));
+
+    SumParams sp{};
+    sp.f = p->d_f + static_cast<size_t>(lev0) * p->f_stride;
+    sp.f_stride = p->f_stride; sp.nf = p->nf; sp.k_pitch = p->k_pitch;
+    sp.T = p->d_T + lev0; sp.P = p->d_P + lev0;
+    sp.npm = p->d_npm + static_cast<size_t>(lev0) * 28;
+    sp.prep = p->d_prep; sp.summary = p->d_summary; sp.tile_count = cat->d_tile_count; sp.ntiles = cat->ntiles;
+    sp.no_negative_absorption = p->no_neg;
+    sp.K = p->d_K + static_cast<size_t>(lev0) * p->k_pitch * 7;
+    for (int mode = 0; mode < 2; mode++) {
+      sp.segs = p->d_segs + mode * nseg;
+      sp.nsegs = p->nsegs[mode];
+      AB_TRY(launch_sum(sp, nlev, mode, p->stream));
+    }
+  }
+  return AB200_OK;
+}
+
+int ab200_path_run_stokes(ab200_path* p) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_stokes: path not uploaded");
+  if (p->np < 1) return set_error(AB200_ERR_INVALID, "ab200_path_run_stokes: empty path");
+  AB_CUDA(cudaSetDevice(p->cat->device));
+  StokesParams sp{};
+  sp.np = p->np; sp.nf = p->nf; sp.K = p->d_K; sp.k_pitch = p->k_pitch; sp.f = p->d_f; sp.f_stride = p->f_stride;
+  sp.T = p->d_T; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
+  sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
+  return launch_stokes_chain(sp, p->stream);
+}
+
+static int check_flags(ab200_path* p) {
+  int h = 0;
+  AB_CUDA(cudaMemcpyAsync(&h, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  AB_CUDA(cudaStreamSynchronize(p->stream));
+  if (h) {
+    cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->stream);
+    if (h & 2) return set_error(AB200_ERR_INVALID, "non-finite line-shape parameter (f0', 1/GD, G0 or strength) at some level");
+    return set_error(AB200_ERR_UNSUPPORTED, "negative pressure broadening (G0 < 0) is outside the GPU path");
+  }
+  return AB200_OK;
+}
+
+int ab200_path_sync(ab200_path* p) {
+  if (!p) return set_error(AB200_ERR_INVALID, "ab200_path_sync: null path");
+  return check_flags(p);
+}
+
+int ab200_path_download(ab200_path* p, double* I, double* dI, double* K, double* dK) {
+  if (!p) return set_error(AB200_ERR_INVALID, "ab200_path_download: null path");
+  if (dI || dK) return set_error(AB200_ERR_UNSUPPORTED, "Jacobian outputs are not on the GPU path in this build");
+  if (I && p->nf)
+    AB_CUDA(cudaMemcpyAsync(I, p->d_I, static_cast<size_t>(p->nf) * 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (K && p->nf && p->np)
+    AB_CUDA(cudaMemcpy2DAsync(K, static_cast<size_t>(p->nf) * 56, p->d_K, static_cast<size_t>(p->k_pitch) * 56,
+                              static_cast<size_t>(p->nf) * 56, p->np, cudaMemcpyDeviceToHost, p->stream));
+  return check_flags(p);
+}
+
+void* ab200_path_device_ptr(ab200_path* p, int which) {
+  if (!p) return nullptr;
+  switch (which) {
+    case 0: return p->d_I;
+    case 1: return p->d_K;
+    default: return nullptr;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points (what the WSM shims call)
+// ---------------------------------------------------------------------------
+namespace {
+std::atomic<uint64_t> g_serial{0};
+struct PathCache {
+  ab200_path* path = nullptr;
+  const ab200_catalog* cat = nullptr;
+  int64_t nf = -1, ntiles = -1;
+  int32_t np = -1, nq = -1;
+};
+thread_local PathCache t_cache;
+
+// one cached workspace per host thread: the shims are called repeatedly with the same
+// shapes (once per (pos, los) under measurement_vecFromSensor, src/m_rad.cc:321-343)
+int cached_path(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab200_path** out) {
+  PathCache& c = t_cache;
+  if (c.path && c.cat == cat && c.nf == nf && c.np == np && c.nq == nq && c.ntiles == cat->ntiles) {
+    *out = c.path;
+    return AB200_OK;
+  }
+  if (c.path) {
+    ab200_path_destroy(c.path);
+    c.path = nullptr;
+  }
+  AB_TRY(ab200_path_create(cat, nf, np, nq, out));
+  c = PathCache{*out, cat, nf, cat->ntiles, np, nq};
+  return AB200_OK;
+}
+}  // namespace
+
+// drop the calling thread's cached workspace (call before destroying a catalog it was built on)
+int ab200_release_thread_cache(void) {
+  if (t_cache.path) ab200_path_destroy(t_cache.path);
+  t_cache = PathCache{};
+  return AB200_OK;
+}
+
+int ab200_propmat_levels(const ab200_catalog* cat, int64_t nf, const double* f, int64_t f_level_stride,
+                         const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
+                         int32_t nq, const ab200_target* targets, uint32_t flags, double* K, double* dK) {
+  if (!cat || !atm || !f || !K) return set_error(AB200_ERR_INVALID, "ab200_propmat_levels: null argument");
+  if (nq > 0 && !dK) return set_error(AB200_ERR_INVALID, "ab200_propmat_levels: dK is null with nq > 0");
+  ab200_path* p = nullptr;
+  AB_TRY(cached_path(cat, nf, atm->np, nq, &p));
+  AB_TRY(ab200_path_upload(p, f, f_level_stride, atm, select_species, no_negative_absorption, targets, nullptr, 0,
+                           AB200_RTE_LINSRC, nullptr, flags));
+  if (!(flags & AB200_FLAG_K_ZERO_INIT) && nf && atm->np) {  // += into the caller's values
+    AB_CUDA(cudaMemcpy2DAsync(p->d_K, static_cast<size_t>(p->k_pitch) * 56, K, static_cast<size_t>(nf) * 56,
+                              static_cast<size_t>(nf) * 56, atm->np, cudaMemcpyHostToDevice, p->stream));
+    p->k_preloaded = true;
+  }
+  AB_TRY(ab200_path_run_propmat(p));
+  return ab200_path_download(p, nullptr, nullptr, K, nullptr);
+}
+
+int ab200_clearsky_emission(const ab200_catalog* cat, int64_t nf, const double* f, int64_t f_level_stride,
+                            const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
+                            int32_t nq, const ab200_target* targets, const double* r, int32_t hse_derivative,
+                            int32_t rte_option, const double* I_bkg, uint32_t flags, double* I, double* dI,
+                            double* K_out) {
+  if (!cat || !atm || !f || !I || !I_bkg) return set_error(AB200_ERR_INVALID, "ab200_clearsky_emission: null argument");
+  if (atm->np > 1 && !r) return set_error(AB200_ERR_INVALID, "ab200_clearsky_emission: r is null");
+  if (nq > 0 && !dI) return set_error(AB200_ERR_INVALID, "ab200_clearsky_emission: dI is null with nq > 0");
+  ab200_path* p = nullptr;
+  AB_TRY(cached_path(cat, nf, atm->np, nq, &p));
+  AB_TRY(ab200_path_upload(p, f, f_level_stride, atm, select_species, no_negative_absorption, targets, r,
+                           hse_derivative, rte_option, I_bkg, flags));
+  AB_TRY(ab200_path_run_propmat(p));
+  AB_TRY(ab200_path_run_stokes(p));
+  return ab200_path_download(p, I, nullptr, (flags & AB200_FLAG_RETURN_K) ? K_out : nullptr, nullptr);
+}
+
+// --- un-fused compatibility entry points -----------------------------------------
+namespace {
+struct DevBuf {
+  double* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  int alloc(size_t n) { return dev_alloc(&p, n); }
+};
+}  // namespace
+
+int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double* dK, const double* r,
+                 const double* dr, int32_t rte_option, uint32_t flags, double* T, double* L, double* P, double* dT,
+                 double* dL) {
+  (void)dK; (void)dr; (void)dT; (void)dL;
+  if (nq > 0) return set_error(AB200_ERR_UNSUPPORTED, "ab200_tramat: Jacobian targets are not on the GPU path in this build");
+  if (rte_option == AB200_RTE_LINPROP) return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path");
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC) return set_error(AB200_ERR_INVALID, "unknown rte_option");
+  if (np < 0 || nf < 0) return set_error(AB200_ERR_INVALID, "ab200_tramat: negative size");
+  if (np == 0 || nf == 0) return AB200_OK;
+  const bool linsrc = rte_option == AB200_RTE_LINSRC;
+  if (!K || !T || !P || (np > 1 && !r) || (linsrc && !L)) return set_error(AB200_ERR_INVALID, "ab200_tramat: null argument");
+  const size_t nk = static_cast<size_t>(np) * nf * 7, nm = static_cast<size_t>(np) * nf * 16;
+  DevBuf dK_, dr_, dT_, dL_, dP_;
+  AB_TRY(dK_.alloc(nk)); AB_TRY(dr_.alloc(std::max(np - 1, 1))); AB_TRY(dT_.alloc(nm)); AB_TRY(dP_.alloc(nm));
+  if (linsrc) AB_TRY(dL_.alloc(nm));
+  AB_CUDA(cudaMemcpy(dK_.p, K, nk * sizeof(double), cudaMemcpyHostToDevice));
+  if (np > 1) AB_CUDA(cudaMemcpy(dr_.p, r, (np - 1) * sizeof(double), cudaMemcpyHostToDevice));
+  AB_TRY(launch_tramat(np, nf, dK_.p, dr_.p, linsrc, (flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0, dT_.p, dL_.p, dP_.p, 0));
+  AB_CUDA(cudaMemcpy(T, dT_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
+  AB_CUDA(cudaMemcpy(P, dP_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (linsrc) AB_CUDA(cudaMemcpy(L, dL_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+int ab200_srcvec(int32_t np, int64_t nf, int32_t nq, const double* K, const double* f, int64_t f_level_stride,
+                 const double* T_level, int32_t it, double* J, double* dJ) {
+  if (np < 0 || nf < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_srcvec: negative size");
+  if (np == 0 || nf == 0) return AB200_OK;
+  if (!K || !f || !T_level || !J || (nq > 0 && !dJ)) return set_error(AB200_ERR_INVALID, "ab200_srcvec: null argument");
+  if (f_level_stride != 0 && f_level_stride != nf) return set_error(AB200_ERR_INVALID, "f_level_stride must be 0 or nf");
+  const size_t nk = static_cast<size_t>(np) * nf * 7, nj = static_cast<size_t>(np) * nf * 4;
+  const size_t nfl = static_cast<size_t>(nf) * (f_level_stride ? np : 1);
+  DevBuf dK_, df_, dT_, dJ_, ddJ_;
+  AB_TRY(dK_.alloc(nk)); AB_TRY(df_.alloc(nfl)); AB_TRY(dT_.alloc(np)); AB_TRY(dJ_.alloc(nj)); AB_TRY(ddJ_.alloc(nj * nq));
+  AB_CUDA(cudaMemcpy(dK_.p, K, nk * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(df_.p, f, nfl * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(dT_.p, T_level, np * sizeof(double), cudaMemcpyHostToDevice));
+  AB_TRY(launch_srcvec(np, nf, nq, dK_.p, df_.p, f_level_stride, dT_.p, it, dJ_.p, ddJ_.p, 0));
+  AB_CUDA(cudaMemcpy(J, dJ_.p, nj * sizeof(double), cudaMemcpyDeviceToHost));
+  if (nq) AB_CUDA(cudaMemcpy(dJ, ddJ_.p, nj * nq * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+int ab200_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, const double* T, const double* L,
+                       const double* P, const double* dT, const double* dL, const double* J, const double* dJ,
+                       const double* I_bkg, double* I, double* dI) {
+  (void)P; (void)dT; (void)dL; (void)dJ; (void)dI;
+  if (nq > 0) return set_error(AB200_ERR_UNSUPPORTED, "ab200_rte_emission: Jacobian targets are not on the GPU path in this build");
+  if (rte_option == AB200_RTE_LINPROP) return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path");
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC) return set_error(AB200_ERR_INVALID, "unknown rte_option");
+  if (np < 0 || nf < 0) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: negative size");
+  if (nf == 0) return AB200_OK;
+  const bool linsrc = rte_option == AB200_RTE_LINSRC;
+  if (!T || !J || !I_bkg || !I || (linsrc && !L)) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: null argument");
+  const size_t nm = static_cast<size_t>(np) * nf * 16, nj = static_cast<size_t>(np) * nf * 4;
+  DevBuf dT_, dL_, dJ_, dB_, dI_;
+  AB_TRY(dT_.alloc(nm)); AB_TRY(dJ_.alloc(nj)); AB_TRY(dB_.alloc(nf * 4)); AB_TRY(dI_.alloc(nf * 4));
+  if (linsrc) AB_TRY(dL_.alloc(nm));
+  AB_CUDA(cudaMemcpy(dT_.p, T, nm * sizeof(double), cudaMemcpyHostToDevice));
+  if (linsrc) AB_CUDA(cudaMemcpy(dL_.p, L, nm * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(dJ_.p, J, nj * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(dB_.p, I_bkg, nf * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  AB_TRY(launch_rte_emission(linsrc, np, nf, dT_.p, dL_.p, dJ_.p, dB_.p, dI_.p, 0));
+  AB_CUDA(cudaMemcpy(I, dI_.p, nf * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+int ab200_planck_tb(int64_t nf, const double* f, double* I) {
+  if (nf < 0) return set_error(AB200_ERR_INVALID, "ab200_planck_tb: negative size");
+  if (nf == 0) return AB200_OK;
+  if (!f || !I) return set_error(AB200_ERR_INVALID, "ab200_planck_tb: null argument");
+  DevBuf df_, dI_;
+  AB_TRY(df_.alloc(nf)); AB_TRY(dI_.alloc(nf * 4));
+  AB_CUDA(cudaMemcpy(df_.p, f, nf * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(dI_.p, I, nf * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  AB_TRY(launch_planck_tb(nf, df_.p, dI_.p, 0));
+  AB_CUDA(cudaMemcpy(I, dI_.p, nf * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------
+int ab200_measure_dfma_peak(int iters, double* tflops, double* ms) {
+  if (!tflops || !ms || iters <= 0) return set_error(AB200_ERR_INVALID, "ab200_measure_dfma_peak: bad argument");
+  int dev = 0, sms = 0;
+  AB_CUDA(cudaGetDevice(&dev));
+  AB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8;
+  DevBuf out;
+  AB_TRY(out.alloc(1));
+  cudaEvent_t e0, e1;
+  AB_CUDA(cudaEventCreate(&e0));
+  AB_CUDA(cudaEventCreate(&e1));
+  AB_TRY(launch_dfma_peak(iters / 4 + 1, blocks, out.p, 0));  // warm-up
+  AB_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    AB_CUDA(cudaEventRecord(e0, 0));
+    AB_TRY(launch_dfma_peak(iters, blocks, out.p, 0));
+    AB_CUDA(cudaEventRecord(e1, 0));
+    AB_CUDA(cudaEventSynchronize(e1));
+    float t = 0;
+    AB_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    best = std::min(best, t);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double fma = double(blocks) * 256.0 * double(iters) * 64.0;  // 8 chains x 8 unrolled
+  *ms     = best;
+  *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
+  return AB200_OK;
+}
+
+int ab200_faddeeva_w(int64_t n, const double* zr, const double* zi, double* wr, double* wi) {
+  if (n < 0) return set_error(AB200_ERR_INVALID, "ab200_faddeeva_w: negative size");
+  if (n == 0) return AB200_OK;
+  if (!zr || !zi || !wr || !wi) return set_error(AB200_ERR_INVALID, "ab200_faddeeva_w: null argument");
+  DevBuf a, b, c, d;
+  AB_TRY(a.alloc(n)); AB_TRY(b.alloc(n)); AB_TRY(c.alloc(n)); AB_TRY(d.alloc(n));
+  AB_CUDA(cudaMemcpy(a.p, zr, n * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(b.p, zi, n * sizeof(double), cudaMemcpyHostToDevice));
+  AB_TRY(launch_faddeeva(n, a.p, b.p, c.p, d.p, 0));
+  AB_CUDA(cudaMemcpy(wr, c.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  AB_CUDA(cudaMemcpy(wi, d.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// common.cuh — shared device/host helpers of the arts_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/arts_b200.h"
+
+namespace ab200 {
+
+// ---- constants: same expressions as src/core/util/arts_constants.h:57-254 ----
+namespace cst {
+constexpr double pi          = 3.14159265358979323846264338327950288;
+constexpr double inv_sqrt_pi = 0.564189583547756286948079451560772586;
+constexpr double c           = 299792458;
+constexpr double h           = 6.62607015e-34;
+constexpr double k           = 1.380649e-23;
+constexpr double NA          = 6.02214076e23;
+constexpr double e           = 1.602176634e-19;
+constexpr double alpha       = 7.2973525693e-3;
+constexpr double R_inf       = 10973731.568160;
+constexpr double inv_two_pi  = (1.0 / pi) / 2;
+constexpr double h_bar       = h * inv_two_pi;
+constexpr double m_e         = 2 * h * R_inf / (c * (alpha * alpha));
+constexpr double bohr_magneton = e * h_bar / (2 * m_e);
+constexpr double R           = k * NA;
+constexpr double doppler_broadening_const_squared = 2000 * R / (c * c);
+}  // namespace cst
+
+// ---- geometry of the line catalog on the device ---------------------------
+constexpr int TL        = 256;  // (sub-)lines per tile; tiles never straddle a segment
+constexpr int REC_GROUP = 4;    // doubles per record group (one LDS.128 pair)
+constexpr int N_GROUPS  = 4;    // groups per line record -> 16 doubles = 128 B per (level, line)
+constexpr int REC_DOUBLES = REC_GROUP * N_GROUPS;
+// record layout of one tile (for one level): [group][line][4]
+//   group 0: f0', c1 = g^2 + h, c2 = 4 g^2, A1 = Si*g          (far wing, real part)
+//   group 1: igd, y, s_re, E1(y)                                (near evaluation, real strength)
+//   group 2: c3 = g^2 - h, A2 = Sr, A3 = -Sr*g, A4 = Si         (far wing, complex part)
+//   group 3: s_im, cut_re, cut_im, unused                       (line mixing, cutoff value)
+// with g = G0 [Hz], h = GD^2/2, S = i*s*GD/sqrt(pi) = Sr + i Si, (igd, y, s) the reference's
+// single_shape (lbl_lineshape_voigt_lte.h:20-33).  The real-only kernel streams group 0 for
+// far tiles and groups 0-1 for near tiles; the complex kernel groups 0+2 or all four.
+constexpr size_t tile_doubles() { return size_t(TL) * REC_DOUBLES; }
+
+// tile summary written by the prepare kernel: f0'min, f0'max, min igd, min y
+constexpr int SUMMARY_DOUBLES = 4;
+
+// far-wing boundary of the reference's Faddeeva: x + |y| > 4000 -> nu <= 2 closed form
+// (3rdparty/Faddeeva/Faddeeva.cc:707-725)
+constexpr double FAR_LIMIT = 4000.0;
+
+enum Pol : int { POL_NO = 0, POL_PI = 1, POL_SM = 2, POL_SP = 3 };
+
+// ---- error plumbing ---------------------------------------------------------
+int set_error(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define AB_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) return ::ab200::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define AB_TRY(expr)        \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+// ---- small device helpers -----------------------------------------------------
+#ifdef __CUDACC__
+// 1/d to ~1 ulp: MUFU.RCP64H seed (2^-20) + one cubic Newton step (error^3 = 2^-60).
+// Valid for normal, finite, non-zero d (the callers' denominators are sums of squares > 0).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double e = __fma_rn(-d, r, 1.0);
+  const double t = __fma_rn(e, e, e);
+  return __fma_rn(r, t, r);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) ----------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+#endif
+
+}  // namespace ab200

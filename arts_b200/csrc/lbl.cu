@@ -1,0 +1,572 @@
+// lbl.cu — stage 1 of the hot path: line-by-line Voigt propagation matrix.
+//
+//   K1  lbl_prepare_kernel   per (sub-line, level) shape parameters
+//       replaces single_shape_builder / line_strength_calc / band_shape_helper
+//       (reference src/core/lbl/lbl_lineshape_voigt_lte.cpp:22-36,145-204,394-429) and the
+//       line-shape model mixing (lbl_lineshape_model.cpp:14-35,70-90; lbl_temperature_model.h:62-314)
+//   K2  lbl_sum_real_kernel / lbl_sum_cplx_kernel   sum over lines of s*w(z) per frequency
+//       replaces band_shape::operator() and ComputeData::core_calc (:431-436, :591-608, :959-981)
+//   K3  the epilogue of K2: scl(f) = -N f expm1(-hf/kT) c^2/8pi, per-(band,pol) clamp and
+//       Propmat accumulation (:944-953, :1688-1692, lbl_zeeman.h:432-440)
+//
+// Data flow: K1 writes one 128-byte record per (level, sub-line) in tiles of TL = 256 lines
+// (layout in common.cuh).  K2 runs one CTA per (512-frequency block, level); it streams the
+// level's line tiles through shared memory with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier, 3 stages), every thread keeps 4 frequencies in registers and applies each line
+// (an LDS.128 broadcast) to them.  Tiles whose every (line, frequency) pair lies in the
+// reference's far-wing region run a branch-free 11-instruction FP64 body; other tiles take
+// the per-pair path with the same far-wing arithmetic bit for bit, so the result does not
+// depend on how frequencies are tiled or sharded across GPUs.  Line sums are formed per
+// tile from zero and added to the segment sum in tile order (a function of the catalog
+// only).  The kernel is FP64-pipe bound; bytes are negligible (8 KB of line data per 131072
+// evaluations).
+#include <cfloat>
+
+#include "catalog.hpp"
+#include "faddeeva.cuh"
+#include "lbl.hpp"
+
+namespace ab200 {
+
+// ---------------------------------------------------------------------------
+// temperature models, lbl_temperature_model.h:62-283 (values only; d/dT in lbl_jac.cu)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double tm_value(int type, const double* __restrict__ x, double T0, double T) {
+  switch (type) {
+    case AB200_TM_T0: return x[0];
+    case AB200_TM_T1: return x[0] * pow(T0 / T, x[1]);
+    case AB200_TM_T2: return x[0] * pow(T0 / T, x[1]) * (1 + x[2] * log(T / T0));
+    case AB200_TM_T3: return x[0] + x[1] * (T - T0);
+    case AB200_TM_T4: return (x[0] + x[1] * (T0 / T - 1)) * pow(T0 / T, x[2]);
+    case AB200_TM_T5: return x[0] * pow(T0 / T, 0.25 + 1.5 * x[1]);
+    case AB200_TM_AER:
+      if (T < 250.0) return x[0] + (T - 200.0) * (x[1] - x[0]) / (250.0 - 200.0);
+      if (T > 296.0) return x[2] + (T - 296.0) * (x[3] - x[2]) / (340.0 - 296.0);
+      return x[1] + (T - 250.0) * (x[2] - x[1]) / (296.0 - 250.0);
+    case AB200_TM_DPL: return x[0] * pow(T0 / T, x[1]) + x[2] * pow(T0 / T, x[3]);
+    case AB200_TM_POLY: return x[0] + T * (x[1] + T * (x[2] + T * x[3]));
+    default: return 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
+  const int64_t tile = blockIdx.x;
+  const int lev      = blockIdx.y;
+  const int lane     = threadIdx.x;
+  const int64_t slot = tile * TL + lane;
+  const int64_t par  = p.sub_parent[slot];
+
+  const double T = p.T[lev], P = p.P[lev];
+  double f0s = 0.0, igd = 0.0, y = 0.0, s_re = 0.0, s_im = 0.0, G0 = 0.0, GD = 1.0;
+  bool real_line = par >= 0;
+  if (real_line) {
+    const int isot = p.line_isot[par];
+    const int spec = p.isot_species[isot];
+    const double T0 = p.T0[par];
+    // model::{G0,D0,DV,Y,G}(atm): VMR-weighted mixture, Bath = remainder
+    double res[AB200_NVAR], bth[AB200_NVAR];
+    double vmr_sum = 0.0;
+    bool has_bath  = false;
+#pragma unroll
+    for (int v = 0; v < AB200_NVAR; v++) res[v] = bth[v] = 0.0;
+    for (int64_t i = p.ls_offset[par]; i < p.ls_offset[par + 1]; i++) {
+      const int sp = p.ls_species[i];
+      const double vm = sp == AB200_SPECIES_BATH ? 0.0 : p.vmr[int64_t(lev) * p.n_species + sp];
+      if (sp == AB200_SPECIES_BATH) has_bath = true; else vmr_sum += vm;
+#pragma unroll
+      for (int v = 0; v < AB200_NVAR; v++) {
+        const int type = p.ls_type[i * AB200_NVAR + v];
+        double val = 0.0;
+        if (type != AB200_TM_ABSENT) {
+          const double ps = (v == AB200_VAR_G || v == AB200_VAR_DV) ? P * P : P;  // lbl_lineshape_model.cpp:27-35
+          val = ps * tm_value(type, p.ls_X + (i * AB200_NVAR + v) * 4, T0, T);
+        }
+        if (sp == AB200_SPECIES_BATH) bth[v] = val; else res[v] += vm * val;
+      }
+    }
+    double X[AB200_NVAR];
+#pragma unroll
+    for (int v = 0; v < AB200_NVAR; v++) X[v] = has_bath ? res[v] + (1.0 - vmr_sum) * bth[v] : res[v] / vmr_sum;
+    G0 = X[AB200_VAR_G0];
+
+    const double f0_cat = p.f0[par];
+    const double f0c    = f0_cat + X[AB200_VAR_D0] + X[AB200_VAR_DV];  // line_center_calc :145-147
+    const double gd_part = sqrt(cst::doppler_broadening_const_squared * T / p.isot_mass[isot]);
+    GD  = gd_part * f0c;
+    f0s = f0c + p.H[lev] * p.sub_dzc[slot];  // as_zeeman :190
+    igd = 1.0 / GD;                          // engine A: unsplit centre :191,199
+    y   = G0 * igd;
+    // line::s, lbl_data.h:66-68 ; line_strength_calc :22-36
+    const double s0 = p.a[par] * p.gu[par] * exp(-p.e0[par] / (cst::k * T)) /
+                      (f0_cat * f0_cat * f0_cat * p.Q[int64_t(lev) * p.n_isot + isot]);
+    const double pre = cst::inv_sqrt_pi * igd * p.isorat[int64_t(lev) * p.n_isot + isot] *
+                       p.vmr[int64_t(lev) * p.n_species + spec];
+    const double Sz = p.sub_Sz[slot];
+    s_re = Sz * (pre * (1.0 + X[AB200_VAR_G]) * s0);
+    s_im = Sz * (pre * (-X[AB200_VAR_Y]) * s0);
+
+    // ByLine cutoff: band_data::active_lines on the catalog f0 (lbl_data.cpp:61-68, :407-412)
+    const double cut = p.tile_cutoff[tile];
+    if (cut < DBL_MAX) {
+      const double fmin = p.frange[2 * lev], fmax = p.frange[2 * lev + 1];
+      if (!(f0_cat >= fmin - cut && f0_cat <= fmax + cut)) real_line = false;
+    }
+    if (y < 0.0) atomicOr(p.flags, 1);
+    if (!isfinite(f0s) || !isfinite(igd) || !isfinite(y) || !isfinite(s_re) || !isfinite(s_im)) atomicOr(p.flags, 2);
+  }
+
+  double rec[REC_DOUBLES];
+  if (real_line) {
+    const double g  = G0;
+    const double h  = 0.5 * GD * GD;
+    const double g2 = g * g;
+    const double Si = s_re * GD * cst::inv_sqrt_pi;   // S = i*s*GD/sqrt(pi)
+    const double Sr = -s_im * GD * cst::inv_sqrt_pi;
+    rec[0] = f0s; rec[1] = g2 + h; rec[2] = 4.0 * g2; rec[3] = Si * g;
+    rec[4] = igd; rec[5] = y; rec[6] = s_re; rec[7] = (y <= 7.0 && y >= 0.0) ? series_E1(y) : 0.0;
+    rec[8] = g2 - h; rec[9] = Sr; rec[10] = -Sr * g; rec[11] = Si;
+    rec[12] = s_im; rec[13] = 0.0; rec[14] = 0.0; rec[15] = 0.0;
+    const double cut = p.tile_cutoff[tile];
+    if (cut < DBL_MAX) {
+      // band_shape::operator()(cut): ls(ls.f0 + cutoff) = s * w(igd*cutoff + i y), :610-616
+      double wr, wi;
+      faddeeva_w(igd * ((f0s + cut) - f0s), y, wr, wi);
+      rec[13] = s_re * wr - s_im * wi;
+      rec[14] = s_re * wi + s_im * wr;
+    }
+  } else {
+    // padding / inactive: contributes exactly +0 in the far loops, skipped in the near loops
+#pragma unroll
+    for (int i = 0; i < REC_DOUBLES; i++) rec[i] = 0.0;
+    rec[0] = (par >= 0) ? DBL_MAX : 0.0;  // inactive cutoff line: outside every window
+    rec[1] = -1.0;                        // D2 = (q+1)^2 > 0
+    rec[8] = -1.0;
+  }
+  double* out = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
+#pragma unroll
+  for (int g = 0; g < N_GROUPS; g++) {
+    double2* o = reinterpret_cast<double2*>(out + (int64_t(g) * TL + lane) * REC_GROUP);
+    o[0] = make_double2(rec[4 * g + 0], rec[4 * g + 1]);
+    o[1] = make_double2(rec[4 * g + 2], rec[4 * g + 3]);
+  }
+
+  // tile summary: min/max f0', min igd, min y over contributing lines
+  double v_min = real_line ? f0s : DBL_MAX, v_max = real_line ? f0s : -DBL_MAX;
+  double v_igd = real_line ? igd : DBL_MAX, v_y = real_line ? y : DBL_MAX;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v_min = fmin(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+    v_max = fmax(v_max, __shfl_xor_sync(0xffffffffu, v_max, o));
+    v_igd = fmin(v_igd, __shfl_xor_sync(0xffffffffu, v_igd, o));
+    v_y   = fmin(v_y, __shfl_xor_sync(0xffffffffu, v_y, o));
+  }
+  __shared__ double red[TL / 32][4];
+  if ((lane & 31) == 0) {
+    red[lane >> 5][0] = v_min; red[lane >> 5][1] = v_max; red[lane >> 5][2] = v_igd; red[lane >> 5][3] = v_y;
+  }
+  __syncthreads();
+  if (lane == 0) {
+    for (int w = 1; w < TL / 32; w++) {
+      v_min = fmin(v_min, red[w][0]); v_max = fmax(v_max, red[w][1]);
+      v_igd = fmin(v_igd, red[w][2]); v_y = fmin(v_y, red[w][3]);
+    }
+    double* s = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
+    s[0] = v_min; s[1] = v_max; s[2] = v_igd; s[3] = v_y;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2 / K3
+// ---------------------------------------------------------------------------
+constexpr int SUM_NT    = 128;   // threads per CTA
+constexpr int SUM_R     = 4;     // frequencies per thread
+constexpr int F_TILE    = SUM_NT * SUM_R;
+constexpr int CHUNK     = 4096;  // tiles classified per pass
+constexpr uint8_t CLS_SKIP = 0, CLS_FAR = 1, CLS_NEAR = 2;
+
+// classification of one (frequency block, line tile) pair, conservative w.r.t. the per-pair
+// tests of the near loops (1e-9 relative margin covers every rounding in them)
+__device__ __forceinline__ uint8_t classify_tile(const double* __restrict__ s, double fblk_min, double fblk_max,
+                                                 double cutoff) {
+  const double f0min = s[0], f0max = s[1];
+  if (f0min > f0max) return CLS_SKIP;  // no contributing line
+  const double dist = fmax(0.0, fmax(fblk_min - f0max, f0min - fblk_max));
+  if (dist > cutoff * (1.0 + 1e-9)) return CLS_SKIP;
+  if (cutoff < DBL_MAX) return CLS_NEAR;  // windows need the per-pair predicate
+  return (s[2] * dist + s[3] > FAR_LIMIT * (1.0 + 1e-9)) ? CLS_FAR : CLS_NEAR;
+}
+
+// scl(f), ComputeData ctor lbl_lineshape_voigt_lte.cpp:944-953
+__device__ __forceinline__ double line_scale(double f, double T, double P) {
+  constexpr double c = cst::c * cst::c / (8 * cst::pi);
+  const double N     = P / (cst::k * T);  // number_density, physics_funcs.h:54
+  const double r     = (cst::h * f) / (cst::k * T);
+  return -N * f * expm1(-r) * c;
+}
+
+template <int STAGES, int STAGE_DOUBLES>
+struct TilePipe {
+  uint64_t* full;    // [STAGES]
+  double* buf;       // [STAGES][STAGE_DOUBLES]
+  uint32_t it = 0;   // tiles consumed so far (stage/phase bookkeeping)
+  __device__ __forceinline__ double* stage(uint32_t i) const { return buf + size_t(i % STAGES) * STAGE_DOUBLES; }
+};
+
+// --------------------------- real-only kernel (mode 0) ----------------------
+// Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
+__global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
+  constexpr int STAGES = 3;
+  constexpr int STAGE_DOUBLES = 2 * TL * REC_GROUP;  // groups 0 and 1
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sbuf      = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);
+  uint8_t* cls      = reinterpret_cast<uint8_t*>(full + STAGES);
+
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t fblk = int64_t(blockIdx.x) * F_TILE;
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+
+  double f[SUM_R];
+#pragma unroll
+  for (int r = 0; r < SUM_R; r++) {
+    const int64_t i = fblk + r * SUM_NT + tid;
+    f[r] = fg[i < p.nf ? i : p.nf - 1];
+  }
+  const double fblk_min = fg[fblk];
+  const double fblk_max = fg[(fblk + F_TILE - 1 < p.nf) ? fblk + F_TILE - 1 : p.nf - 1];
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
+  uint32_t it = 0;
+
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    double accS[SUM_R];
+#pragma unroll
+    for (int r = 0; r < SUM_R; r++) accS[r] = 0.0;
+
+    for (int64_t c0 = seg.tile_begin; c0 < seg.tile_end; c0 += CHUNK) {
+      const int n = int(min(int64_t(CHUNK), seg.tile_end - c0));
+      for (int t = tid; t < n; t += SUM_NT)
+        cls[t] = classify_tile(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, DBL_MAX);
+      __syncthreads();
+
+      auto issue = [&](int t) {
+        const uint32_t st   = (it + t) % STAGES;
+        const uint32_t bytes = (cls[t] == CLS_FAR ? 1 : 2) * TL * REC_GROUP * sizeof(double);
+        mbar_expect_tx(&full[st], bytes);
+        tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + t) * tile_doubles(), bytes, &full[st]);
+      };
+      if (tid == 0)
+        for (int t = 0; t < STAGES - 1 && t < n; t++) issue(t);
+
+      for (int t = 0; t < n; t++) {
+        if (tid == 0 && t + STAGES - 1 < n) issue(t + STAGES - 1);
+        const uint32_t st = (it + t) % STAGES;
+        mbar_wait(&full[st], ((it + t) / STAGES) & 1);
+        const double2* __restrict__ rec = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);
+        const int count = p.tile_count[c0 + t];
+        double acc[SUM_R];
+#pragma unroll
+        for (int r = 0; r < SUM_R; r++) acc[r] = 0.0;
+        if (cls[t] == CLS_FAR) {
+#pragma unroll 4
+          for (int l = 0; l < count; l++) {
+            const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', c1 | c2, A1
+#pragma unroll
+            for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y);
+          }
+        } else {
+          const double2* __restrict__ rec1 = rec + 2 * TL;
+          for (int l = 0; l < count; l++) {
+            const double2 a = rec[2 * l], b = rec[2 * l + 1];
+            const double2 c = rec1[2 * l], d = rec1[2 * l + 1];  // igd, y | s_re, E1
+#pragma unroll
+            for (int r = 0; r < SUM_R; r++) {
+              const double u  = __dsub_rn(f[r], a.x);
+              const double ax = __dmul_rn(fabs(u), c.x);
+              if (__dadd_rn(ax, c.y) > FAR_LIMIT) {
+                acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y);
+              } else {
+                double wr, wi;
+                w_near(c.x * u, c.y, d.y, wr, wi);
+                acc[r] = __fma_rn(d.x, wr, acc[r]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < SUM_R; r++) accS[r] = __dadd_rn(accS[r], acc[r]);
+        __syncthreads();
+      }
+      it += n;
+    }
+
+    // K3: scale, clamp, accumulate A (npm = (1,0,...,0) for pol = no)
+    const double T = p.T[lev], P = p.P[lev];
+#pragma unroll
+    for (int r = 0; r < SUM_R; r++) {
+      const int64_t i = fblk + r * SUM_NT + tid;
+      if (i < p.nf) {
+        const double F = line_scale(f[r], T, P) * accS[r];
+        if (!(p.no_negative_absorption && F < 0.0)) {
+          double* k = p.K + (int64_t(lev) * p.k_pitch + i) * 7;
+          k[0] += F;
+        }
+      }
+    }
+  }
+}
+
+// --------------------------- complex kernel (mode 1) -------------------------
+// Segments: one (band, pol) each; line mixing, Zeeman sub-lines, ByLine cutoff; 7 components.
+constexpr int CPLX_R = 2;
+constexpr int CPLX_NT = 256;
+constexpr int CPLX_F_TILE = CPLX_NT * CPLX_R;
+
+__global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
+  constexpr int STAGES = 2;
+  constexpr int STAGE_DOUBLES = N_GROUPS * TL * REC_GROUP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sbuf   = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);
+  uint8_t* cls   = reinterpret_cast<uint8_t*>(full + STAGES);
+  __shared__ int n_active;
+  uint16_t* act  = reinterpret_cast<uint16_t*>(cls + CHUNK);  // compacted tile list of the chunk
+
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t fblk = int64_t(blockIdx.x) * CPLX_F_TILE;
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+
+  double f[CPLX_R];
+#pragma unroll
+  for (int r = 0; r < CPLX_R; r++) {
+    const int64_t i = fblk + r * CPLX_NT + tid;
+    f[r] = fg[i < p.nf ? i : p.nf - 1];
+  }
+  const double fblk_min = fg[fblk];
+  const double fblk_max = fg[(fblk + CPLX_F_TILE - 1 < p.nf) ? fblk + CPLX_F_TILE - 1 : p.nf - 1];
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
+  uint32_t it = 0;
+
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    const double cutoff  = seg.has_cutoff ? seg.cutoff : DBL_MAX;
+    double accS_re[CPLX_R], accS_im[CPLX_R];
+#pragma unroll
+    for (int r = 0; r < CPLX_R; r++) accS_re[r] = accS_im[r] = 0.0;
+
+    for (int64_t c0 = seg.tile_begin; c0 < seg.tile_end; c0 += CHUNK) {
+      const int nall = int(min(int64_t(CHUNK), seg.tile_end - c0));
+      for (int t = tid; t < nall; t += CPLX_NT)
+        cls[t] = classify_tile(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, cutoff);
+      __syncthreads();
+      if (tid == 0) {  // compact the non-skipped tiles, keeping catalog order
+        int n = 0;
+        for (int t = 0; t < nall; t++)
+          if (cls[t] != CLS_SKIP) act[n++] = uint16_t(t);
+        n_active = n;
+      }
+      __syncthreads();
+      const int n = n_active;
+
+      auto issue = [&](int j) {
+        const int t       = act[j];
+        const uint32_t st = (it + j) % STAGES;
+        double* dst       = sbuf + size_t(st) * STAGE_DOUBLES;
+        const double* src = prep + (c0 + t) * tile_doubles();
+        constexpr uint32_t GB = TL * REC_GROUP * sizeof(double);
+        if (cls[t] == CLS_FAR) {  // groups 0 and 2
+          mbar_expect_tx(&full[st], 2 * GB);
+          tma_load_1d(dst, src, GB, &full[st]);
+          tma_load_1d(dst + 2 * TL * REC_GROUP, src + 2 * TL * REC_GROUP, GB, &full[st]);
+        } else {
+          mbar_expect_tx(&full[st], 4 * GB);
+          tma_load_1d(dst, src, 4 * GB, &full[st]);
+        }
+      };
+      if (tid == 0)
+        for (int j = 0; j < STAGES - 1 && j < n; j++) issue(j);
+
+      for (int j = 0; j < n; j++) {
+        if (tid == 0 && j + STAGES - 1 < n) issue(j + STAGES - 1);
+        const int t       = act[j];
+        const uint32_t st = (it + j) % STAGES;
+        mbar_wait(&full[st], ((it + j) / STAGES) & 1);
+        const double2* __restrict__ g0 = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);
+        const double2* __restrict__ g1 = g0 + 2 * TL;
+        const double2* __restrict__ g2 = g0 + 4 * TL;
+        const double2* __restrict__ g3 = g0 + 6 * TL;
+        const int count = p.tile_count[c0 + t];
+        double are[CPLX_R], aim[CPLX_R];
+#pragma unroll
+        for (int r = 0; r < CPLX_R; r++) are[r] = aim[r] = 0.0;
+        if (cls[t] == CLS_FAR) {
+#pragma unroll 2
+          for (int l = 0; l < count; l++) {
+            const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', c1 | c2, A1
+            const double2 c = g2[2 * l], d = g2[2 * l + 1];  // c3, A2 | A3, A4
+#pragma unroll
+            for (int r = 0; r < CPLX_R; r++)
+              far_accumulate_cplx(are[r], aim[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, c.x, c.y, d.x, d.y);
+          }
+        } else {
+          for (int l = 0; l < count; l++) {
+            const double2 a = g0[2 * l], b = g0[2 * l + 1];
+            const double2 e = g1[2 * l], g = g1[2 * l + 1];  // igd, y | s_re, E1
+            const double2 c = g2[2 * l], d = g2[2 * l + 1];
+            const double2 h = g3[2 * l], k = g3[2 * l + 1];  // s_im, cut_re | cut_im, -
+#pragma unroll
+            for (int r = 0; r < CPLX_R; r++) {
+              if (seg.has_cutoff) {
+                // frequency_spans: lower_bound(f - cutoff) .. upper_bound(f + cutoff),
+                // lbl_lineshape_voigt_lte.h:123-133
+                if (!(a.x >= f[r] - cutoff && a.x <= f[r] + cutoff)) continue;
+              }
+              const double u  = __dsub_rn(f[r], a.x);
+              const double ax = __dmul_rn(fabs(u), e.x);
+              if (__dadd_rn(ax, e.y) > FAR_LIMIT) {
+                far_accumulate_cplx(are[r], aim[r], u, a.y, b.x, b.y, c.x, c.y, d.x, d.y);
+              } else {
+                double wr, wi;
+                w_near(e.x * u, e.y, g.y, wr, wi);
+                are[r] = __fma_rn(g.x, wr, __fma_rn(-h.x, wi, are[r]));
+                aim[r] = __fma_rn(g.x, wi, __fma_rn(h.x, wr, aim[r]));
+              }
+              if (seg.has_cutoff) {  // ls(f) - ls(f0' + cutoff), :591-608
+                are[r] -= h.y;
+                aim[r] -= k.x;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < CPLX_R; r++) {
+          accS_re[r] = __dadd_rn(accS_re[r], are[r]);
+          accS_im[r] = __dadd_rn(accS_im[r], aim[r]);
+        }
+        __syncthreads();
+      }
+      it += n;
+      __syncthreads();
+    }
+
+    // K3: scale, clamp per (band, pol), accumulate the 7 components with npm(pol)
+    const double T = p.T[lev], P = p.P[lev];
+    const double* __restrict__ npm = p.npm + (int64_t(lev) * 4 + seg.pol) * 7;
+    const bool all_zero = npm[0] == 0 && npm[1] == 0 && npm[2] == 0 && npm[3] == 0 && npm[4] == 0 && npm[5] == 0 &&
+                          npm[6] == 0;  // early return of calculate(), :1663
+#pragma unroll
+    for (int r = 0; r < CPLX_R; r++) {
+      const int64_t i = fblk + r * CPLX_NT + tid;
+      if (i < p.nf && !all_zero) {
+        const double scl = line_scale(f[r], T, P);
+        const double Fre = scl * accS_re[r], Fim = scl * accS_im[r];
+        if (!(p.no_negative_absorption && Fre < 0.0)) {
+          double* k = p.K + (int64_t(lev) * p.k_pitch + i) * 7;
+          k[0] += npm[0] * Fre; k[1] += npm[1] * Fre; k[2] += npm[2] * Fre; k[3] += npm[3] * Fre;
+          k[4] += npm[4] * Fim; k[5] += npm[5] * Fim; k[6] += npm[6] * Fim;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+size_t lbl_real_smem_bytes() { return size_t(3) * 2 * TL * REC_GROUP * sizeof(double) + 3 * sizeof(uint64_t) + CHUNK; }
+size_t lbl_cplx_smem_bytes() {
+  return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + CHUNK * sizeof(uint16_t);
+}
+
+int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream) {
+  if (p.ntiles == 0 || nlev == 0) return 0;
+  dim3 grid(static_cast<unsigned>(p.ntiles), static_cast<unsigned>(nlev));
+  lbl_prepare_kernel<<<grid, TL, 0, stream>>>(p);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream) {
+  if (p.nsegs == 0 || nlev == 0 || p.nf == 0) return 0;
+  static bool attr_set[2] = {false, false};
+  if (mode == 0) {
+    const size_t smem = lbl_real_smem_bytes();
+    if (!attr_set[0]) {
+      AB_CUDA(cudaFuncSetAttribute(lbl_sum_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      attr_set[0] = true;
+    }
+    dim3 grid(static_cast<unsigned>((p.nf + F_TILE - 1) / F_TILE), static_cast<unsigned>(nlev));
+    lbl_sum_real_kernel<<<grid, SUM_NT, smem, stream>>>(p);
+  } else {
+    const size_t smem = lbl_cplx_smem_bytes();
+    if (!attr_set[1]) {
+      AB_CUDA(cudaFuncSetAttribute(lbl_sum_cplx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      attr_set[1] = true;
+    }
+    dim3 grid(static_cast<unsigned>((p.nf + CPLX_F_TILE - 1) / CPLX_F_TILE), static_cast<unsigned>(nlev));
+    lbl_sum_cplx_kernel<<<grid, CPLX_NT, smem, stream>>>(p);
+  }
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// stand-alone w(z) evaluator (tests) and DFMA peak probe (roofline denominator)
+// ---------------------------------------------------------------------------
+__global__ void faddeeva_kernel(int64_t n, const double* zr, const double* zi, double* wr, double* wi) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) faddeeva_w(zr[i], zi[i], wr[i], wi[i]);
+}
+
+int launch_faddeeva(int64_t n, const double* zr, const double* zi, double* wr, double* wi, cudaStream_t stream) {
+  if (n == 0) return 0;
+  faddeeva_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(n, zr, zi, wr, wi);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* out) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+      a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) out[0] = s;  // keep the chain alive without a store in practice
+}
+
+int launch_dfma_peak(int iters, int blocks, double* d_out, cudaStream_t stream) {
+  dfma_peak_kernel<<<blocks, 256, 0, stream>>>(iters, d_out);
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ab200

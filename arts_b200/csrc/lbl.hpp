@@ -1,0 +1,54 @@
+// lbl.hpp — kernel parameter blocks and launchers of stage 1 (lbl.cu).
+#pragma once
+
+#include "catalog.hpp"
+
+namespace ab200 {
+
+struct PrepareParams {
+  // catalog (device)
+  const double *f0, *a, *e0, *gu, *T0;
+  const int32_t* line_isot;
+  const int64_t* ls_offset;
+  const int32_t* ls_species;
+  const int32_t* ls_type;
+  const double* ls_X;
+  const int32_t* isot_species;
+  const double* isot_mass;
+  const int64_t* sub_parent;
+  const double *sub_Sz, *sub_dzc;
+  const double* tile_cutoff;
+  int32_t n_species, n_isot;
+  int64_t ntiles;
+  // levels of this batch (device, already offset to the first level of the batch)
+  const double *T, *P, *vmr, *isorat, *Q, *H;
+  const double* frange;  // [nlev][2] first / last frequency of the level's grid
+  // outputs
+  double* prep;     // [nlev][ntiles][N_GROUPS][TL][4]
+  double* summary;  // [nlev][ntiles][4]
+  int* flags;       // bit 0: negative G0, bit 1: non-finite shape parameter
+};
+
+struct SumParams {
+  const double* f;   // [nlev][nf] (f_stride = nf) or [nf] (f_stride = 0), offset to the batch
+  int64_t f_stride;
+  int64_t nf;
+  const double *T, *P;  // [nlev]
+  const double* npm;    // [nlev][4][7] zeeman::norm_view per polarisation
+  const double* prep;
+  const double* summary;
+  const int32_t* tile_count;
+  int64_t ntiles;
+  const SegmentDev* segs;  // segments selected for this launch (device)
+  int32_t nsegs;
+  int32_t no_negative_absorption;
+  double* K;  // [nlev][k_pitch][7], offset to the batch
+  int64_t k_pitch;
+};
+
+int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream);
+int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream);
+int launch_faddeeva(int64_t n, const double* zr, const double* zi, double* wr, double* wi, cudaStream_t stream);
+int launch_dfma_peak(int iters, int blocks, double* d_out, cudaStream_t stream);
+
+}  // namespace ab200

@@ -1,0 +1,32 @@
+// stokes.hpp — kernel parameter block and launchers of stage 2 (stokes.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace ab200 {
+
+struct StokesParams {
+  int32_t np;
+  int64_t nf;
+  const double* K;     // [np][k_pitch][7]; k_pitch % 128 == 0 so every 128-frequency row block is a full TMA box
+  int64_t k_pitch;
+  const double* f;     // [np][nf] or [nf]
+  int64_t f_stride;
+  const double* T;     // [np] level temperatures
+  const double* r;     // [np-1] layer lengths
+  const double* I_bkg; // [nf][4]
+  double* I;           // [nf][4]
+  int32_t rte_option;
+  int32_t tran_exact;
+};
+
+int launch_stokes_chain(const StokesParams& p, cudaStream_t stream);
+int launch_planck_tb(int64_t nf, const double* f, double* I, cudaStream_t stream);
+int launch_tramat(int np, int64_t nf, const double* K, const double* r, int linsrc, int exact, double* T, double* L,
+                  double* P, cudaStream_t stream);
+int launch_srcvec(int np, int64_t nf, int nq, const double* K, const double* f, int64_t f_stride, const double* Tlev,
+                  int it, double* J, double* dJ, cudaStream_t stream);
+int launch_rte_emission(int linsrc, int np, int64_t nf, const double* T, const double* L, const double* J,
+                        const double* I_bkg, double* I, cudaStream_t stream);
+
+}  // namespace ab200

@@ -1,0 +1,297 @@
+"""Host-side mirror of the reference's workspace methods on the clear-sky spectral path.
+
+Same names, argument meaning and error behaviour as the ARTS WSMs, on the flattened
+containers of ``arts_b200._abi`` and numpy arrays with the reference's storage layouts:
+
+=====================================  ===========================================
+reference WSM (file:line)              here
+=====================================  ===========================================
+spectral_propmatAddLines               :func:`spectral_propmatAddLines`
+  (src/m_lbl.cc:242-300)
+spectral_propmat_pathFromPath          :func:`spectral_propmat_pathFromPath`
+  (src/m_propmat.cc:5-65)
+spectral_tramat_pathFromPath           :func:`spectral_tramat_pathFromPath`
+  (src/m_tramat.cc:3-27)
+spectral_rad_srcvec_pathFromPropmat    :func:`spectral_rad_srcvec_pathFromPropmat`
+  (src/m_srcvec.cc:8-31)
+spectral_radStepByStepEmission         :func:`spectral_radStepByStepEmission`
+  (src/m_spectral_radiance.cc:18-46)
+spectral_radClearskyEmission           :func:`spectral_radClearskyEmission` (fused)
+  (src/workspace_meta_methods.cpp:166-181)
+spectral_radApplyUnit... (PlanckBT)    :func:`spectral_radApplyPlanckTb`
+=====================================  ===========================================
+
+Everything calls the CUDA library through the C ABI (``include/arts_b200.h``); nothing
+here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi as abi
+from ._abi import AtmPath, HostCatalog, dptr, make_targets
+from ._lib import Ab200Error, check, lib  # noqa: F401
+
+
+def device_count() -> int:
+    return int(lib().ab200_device_count())
+
+
+class Catalog:
+    """Device-resident ``AbsorptionBands`` (ab200_catalog); immutable, shareable."""
+
+    def __init__(self, host: HostCatalog):
+        self.host = host
+        self._h = C.c_void_p()
+        d = host.desc()
+        check(lib().ab200_catalog_create(C.byref(d), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def counts(self):
+        out = (C.c_int64 * 4)()
+        check(lib().ab200_catalog_counts(self._h, out))
+        return list(out)
+
+    def close(self):
+        if self._h:
+            lib().ab200_release_thread_cache()
+            lib().ab200_catalog_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_catalog(abs_bands) -> Catalog:
+    return abs_bands if isinstance(abs_bands, Catalog) else Catalog(abs_bands)
+
+
+def _f_arg(f, np_):
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    if f.ndim == 1:
+        return f, 0, f.shape[0]
+    if f.shape[0] != np_:
+        raise ValueError(f"Not same size: freq_grid_path {f.shape[0]} element(s), atm_path {np_} element(s)")
+    return f, f.shape[1], f.shape[1]
+
+
+def _rte(option) -> int:
+    if isinstance(option, str):
+        if option not in abi.RTE_OPTIONS:
+            raise ValueError(f"Bad TransmittanceOption: {option}")
+        return abi.RTE_OPTIONS[option]
+    return int(option)
+
+
+# ---------------------------------------------------------------------------
+def spectral_propmatAddLines(spectral_propmat, spectral_propmat_jac, freq_grid, jac_targets, select_species,
+                             abs_bands, atm_point: AtmPath, no_negative_absorption=1):
+    """``spectral_propmat[nf,7] += lines`` at one atmospheric point (src/m_lbl.cc:242-300)."""
+    if atm_point.np_ != 1:
+        raise ValueError("spectral_propmatAddLines takes a single AtmPoint")
+    K = spectral_propmat.reshape(1, *spectral_propmat.shape)
+    dK = None if spectral_propmat_jac is None else spectral_propmat_jac.reshape(1, *spectral_propmat_jac.shape)
+    spectral_propmat_pathFromPath(abs_bands, freq_grid, atm_point, jac_targets=jac_targets,
+                                  select_species=select_species, no_negative_absorption=no_negative_absorption,
+                                  out=K, out_jac=dK, accumulate=True)
+    return spectral_propmat
+
+
+def spectral_propmat_pathFromPath(abs_bands, freq_grid_path, atm_path: AtmPath, jac_targets=(),
+                                  select_species=abi.SPECIES_BATH, no_negative_absorption=1, out=None, out_jac=None,
+                                  accumulate=False):
+    """All levels of ``spectral_propmat_path`` with the lines-only agenda (src/m_propmat.cc:5-65).
+
+    Returns ``(K[np,nf,7], dK[np,nq,nf,7])``.
+    """
+    cat = _as_catalog(abs_bands)
+    f, stride, nf = _f_arg(freq_grid_path, atm_path.np_)
+    tg, nq = make_targets(jac_targets)
+    np_ = atm_path.np_
+    K = np.zeros((np_, nf, 7)) if out is None else out
+    dK = (np.zeros((np_, nq, nf, 7)) if out_jac is None else out_jac) if nq else None
+    if K.shape != (np_, nf, 7) or not K.flags.c_contiguous or K.dtype != np.float64:
+        raise ValueError("spectral_propmat must be a C-contiguous float64 [np, nf, 7] array")
+    flags = 0 if accumulate else abi.FLAG_K_ZERO_INIT
+    a = atm_path.desc()
+    check(lib().ab200_propmat_levels(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
+                                     int(no_negative_absorption), nq, tg, flags, dptr(K), dptr(dK)))
+    return K, dK
+
+
+@dataclass
+class TransmittanceMatrix:
+    """rtepack::TransmittanceMatrix (rtepack_transmission.h:10-25): T, L, P [nf,np,4,4], dT, dL [2,nf,np,nq,4,4]."""
+
+    option: str
+    T: np.ndarray
+    L: np.ndarray | None
+    P: np.ndarray
+    dT: np.ndarray
+    dL: np.ndarray | None
+
+
+def spectral_tramat_pathFromPath(spectral_propmat_path, spectral_propmat_jac_path, r, atm_T, rte_option="linsrc",
+                                 hse_derivative=0, it=-1, flags=0) -> TransmittanceMatrix:
+    """src/m_tramat.cc:3-27; ``r`` = distance(ray_path) [np-1]; ``it`` = position of the T target."""
+    K = np.ascontiguousarray(spectral_propmat_path, dtype=np.float64)
+    np_, nf, _ = K.shape
+    dK = spectral_propmat_jac_path
+    nq = 0 if dK is None else dK.shape[1]
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    if r.shape != (max(np_ - 1, 0),):
+        raise ValueError(f"dr and r must have compatible sizes. r: {r.shape}, np-1: {np_ - 1}, nq: {nq}")
+    dr = np.zeros((2, max(np_ - 1, 0), nq))
+    if hse_derivative and it >= 0:  # m_tramat.cc:18-24
+        atm_T = np.asarray(atm_T, dtype=np.float64)
+        dr[0, :, it] = r / (2.0 * atm_T[:-1])
+        dr[1, :, it] = r / (2.0 * atm_T[1:])
+    opt = _rte(rte_option)
+    T = np.empty((nf, np_, 4, 4))
+    P = np.empty((nf, np_, 4, 4))
+    L = np.empty((nf, np_, 4, 4)) if opt != abi.RTE_CONSTANT else None
+    dT = np.empty((2, nf, np_, nq, 4, 4))
+    dL = np.empty((2, nf, np_, nq, 4, 4)) if opt != abi.RTE_CONSTANT else None
+    check(lib().ab200_tramat(np_, nf, nq, dptr(K), dptr(None if nq == 0 else np.ascontiguousarray(dK)), dptr(r),
+                             dptr(dr), opt, flags, dptr(T), dptr(L), dptr(P), dptr(dT), dptr(dL)))
+    name = rte_option if isinstance(rte_option, str) else {0: "constant", 1: "linsrc", 2: "linprop"}[opt]
+    return TransmittanceMatrix(name, T, L, P, dT, dL)
+
+
+def spectral_rad_srcvec_pathFromPropmat(spectral_propmat_path, freq_grid_path, atm_T, it=-1, nq=0):
+    """src/m_srcvec.cc:8-31 in LTE: returns ``(J[nf,np,4], dJ[nf,np,nq,4])``."""
+    K = np.ascontiguousarray(spectral_propmat_path, dtype=np.float64)
+    np_, nf, _ = K.shape
+    f, stride, nf2 = _f_arg(freq_grid_path, np_)
+    if nf2 != nf:
+        raise ValueError("All forward parameters must have same shape")
+    T = np.ascontiguousarray(atm_T, dtype=np.float64)
+    J = np.empty((nf, np_, 4))
+    dJ = np.empty((nf, np_, nq, 4))
+    check(lib().ab200_srcvec(np_, nf, nq, dptr(K), dptr(f), stride, dptr(T), it, dptr(J), dptr(dJ)))
+    return J, dJ
+
+
+def spectral_radStepByStepEmission(spectral_tramat: TransmittanceMatrix, J, dJ, spectral_rad_bkg):
+    """src/m_spectral_radiance.cc:18-46: returns ``(spectral_rad[nf,4], spectral_rad_jac_path[nf,np,nq,4])``."""
+    T = spectral_tramat.T
+    nf, np_ = T.shape[:2]
+    nq = dJ.shape[2] if dJ is not None else 0
+    bkg = np.ascontiguousarray(spectral_rad_bkg, dtype=np.float64)
+    if bkg.shape[0] != nf:
+        raise ValueError(f"Bad background radiance size: spectral_rad_bkg: {bkg.shape[0]}, expected: {nf}")
+    I = np.empty((nf, 4))
+    dI = np.zeros((nf, np_, nq, 4))
+    check(lib().ab200_rte_emission(_rte(spectral_tramat.option), np_, nf, nq, dptr(T), dptr(spectral_tramat.L),
+                                   dptr(spectral_tramat.P), dptr(spectral_tramat.dT), dptr(spectral_tramat.dL),
+                                   dptr(np.ascontiguousarray(J)), dptr(dJ), dptr(bkg), dptr(I), dptr(dI)))
+    return I, dI
+
+
+def spectral_radClearskyEmission(abs_bands, freq_grid_path, atm_path: AtmPath, r, spectral_rad_bkg,
+                                 rte_option="linsrc", jac_targets=(), select_species=abi.SPECIES_BATH,
+                                 no_negative_absorption=1, hse_derivative=0, flags=0, return_propmat=False):
+    """The fused path: propagation matrix -> transmission -> source -> recursion on the device.
+
+    Returns ``(spectral_rad[nf,4], spectral_rad_jac_path | None[, spectral_propmat_path])``.
+    """
+    cat = _as_catalog(abs_bands)
+    np_ = atm_path.np_
+    f, stride, nf = _f_arg(freq_grid_path, np_)
+    tg, nq = make_targets(jac_targets)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    bkg = np.ascontiguousarray(spectral_rad_bkg, dtype=np.float64)
+    if bkg.shape != (nf, 4):
+        raise ValueError(f"Bad background radiance size: spectral_rad_bkg: {bkg.shape[0]}, expected: {nf}")
+    if r.shape != (max(np_ - 1, 0),):
+        raise ValueError(f"r must have np-1 = {np_ - 1} elements, has {r.shape}")
+    I = np.empty((nf, 4))
+    dI = np.empty((nf, np_, nq, 4)) if nq else None
+    K = np.empty((np_, nf, 7)) if return_propmat else None
+    if return_propmat:
+        flags |= abi.FLAG_RETURN_K
+    a = atm_path.desc()
+    check(lib().ab200_clearsky_emission(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
+                                        int(no_negative_absorption), nq, tg, dptr(r), int(hse_derivative),
+                                        _rte(rte_option), dptr(bkg), flags, dptr(I), dptr(dI), dptr(K)))
+    return (I, dI, K) if return_propmat else (I, dI)
+
+
+def spectral_radApplyPlanckTb(spectral_rad, freq_grid):
+    """PlanckBT unit conversion (spectral_radiance_transform_operator.cc:46-87), returns a new array."""
+    f = np.ascontiguousarray(freq_grid, dtype=np.float64)
+    out = np.array(spectral_rad, dtype=np.float64, order="C", copy=True)
+    check(lib().ab200_planck_tb(len(f), dptr(f), dptr(out)))
+    return out
+
+
+def faddeeva_w(z):
+    """Device w(z) (tests)."""
+    z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
+    zr, zi = np.ascontiguousarray(z.real), np.ascontiguousarray(z.imag)
+    wr, wi = np.empty_like(zr), np.empty_like(zr)
+    check(lib().ab200_faddeeva_w(len(zr), dptr(zr), dptr(zi), dptr(wr), dptr(wi)))
+    return wr + 1j * wi
+
+
+def measure_dfma_peak(iters=20000):
+    t, ms = C.c_double(), C.c_double()
+    check(lib().ab200_measure_dfma_peak(int(iters), C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
+class Path:
+    """Device-resident workspace of one propagation path (ab200_path): upload once, run, download."""
+
+    def __init__(self, cat: Catalog, nf: int, np_: int, nq: int = 0, stream=None):
+        self.cat, self.nf, self.np_, self.nq = cat, int(nf), int(np_), int(nq)
+        self._h = C.c_void_p()
+        check(lib().ab200_path_create(cat.handle, self.nf, self.np_, self.nq, C.byref(self._h)))
+        if stream is not None:
+            check(lib().ab200_path_set_stream(self._h, C.c_void_p(int(stream))))
+
+    def upload(self, f, atm: AtmPath, r, I_bkg, rte_option="linsrc", targets=(), select_species=abi.SPECIES_BATH,
+               no_negative_absorption=1, hse_derivative=0, flags=0):
+        f, stride, nf = _f_arg(f, atm.np_)
+        assert nf == self.nf and atm.np_ == self.np_
+        tg, _ = make_targets(targets)
+        self._keep = (f, atm, np.ascontiguousarray(r, dtype=np.float64), np.ascontiguousarray(I_bkg, dtype=np.float64))
+        a = atm.desc()
+        check(lib().ab200_path_upload(self._h, dptr(f), stride, C.byref(a), int(select_species),
+                                      int(no_negative_absorption), tg, dptr(self._keep[2]), int(hse_derivative),
+                                      _rte(rte_option), dptr(self._keep[3]), flags))
+
+    def run_propmat(self):
+        check(lib().ab200_path_run_propmat(self._h))
+
+    def run_stokes(self):
+        check(lib().ab200_path_run_stokes(self._h))
+
+    def sync(self):
+        check(lib().ab200_path_sync(self._h))
+
+    def download(self, I=None, K=None):
+        check(lib().ab200_path_download(self._h, dptr(I), dptr(None), dptr(K), dptr(None)))
+
+    def device_ptr(self, which: int) -> int:
+        return int(lib().ab200_path_device_ptr(self._h, which) or 0)
+
+    def close(self):
+        if self._h:
+            lib().ab200_path_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

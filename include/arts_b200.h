@@ -1,0 +1,233 @@
+/* arts_b200.h — C ABI of the B200-native clear-sky spectral hot path for ARTS.
+ *
+ * This is the drop-in boundary: the bodies of the ARTS workspace methods
+ *   spectral_propmatAddLines             (reference src/m_lbl.cc:242-300)
+ *   spectral_propmat_pathFromPath        (reference src/m_propmat.cc:5-65)
+ *   spectral_tramat_pathFromPath         (reference src/m_tramat.cc:3-27)
+ *   spectral_rad_srcvec_pathFromPropmat  (reference src/m_srcvec.cc:8-31)
+ *   spectral_radStepByStepEmission       (reference src/m_spectral_radiance.cc:18-46)
+ * become shims that flatten their C++ arguments into the plain arrays below
+ * and call these functions.  No torch / C++ types cross
+ * the boundary.  Every function returns 0 on success; on failure it returns a
+ * non-zero AB200_ERR_* code and ab200_last_error() holds the message (thread
+ * local).  There is NO CPU fallback: without a usable CUDA device every
+ * compute entry point fails with AB200_ERR_CUDA.
+ *
+ * All floating point data are IEEE double ("Numeric", reference
+ * src/core/util/configtypes.h:7-13).  Layouts of Propmat / Stokvec / Muelmat
+ * arrays are the reference's own storage layouts (row-major contiguous,
+ * src/core/matpack/matpack_mdspan_data_t.h:38-47):
+ *   Propmat  = 7 doubles [A,B,C,D,U,V,W]   (rtepack_propagation_matrix.h:12-30)
+ *   Stokvec  = 4 doubles [I,Q,U,V]
+ *   Muelmat  = 16 doubles, row-major 4x4
+ */
+#ifndef ARTS_B200_H
+#define ARTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------ */
+#define AB200_OK 0
+#define AB200_ERR_INVALID 1     /* bad argument or shape (the shim's ARTS_USER_ERROR) */
+#define AB200_ERR_UNSUPPORTED 2 /* input outside the path (non VP_LTE band, linprop, ...) */
+#define AB200_ERR_CUDA 3        /* CUDA runtime failure / no device */
+#define AB200_ERR_NOMEM 4
+
+/* ---- enums mirrored from the reference -------------------------------- */
+/* SpeciesEnum::Bath: "all other species" broadener, and "all species" as
+ * select_species (lbl_lineshape.cpp:191). */
+#define AB200_SPECIES_BATH (-1)
+
+/* LineShapeModelVariable subset used by the Voigt LTE engine
+ * (lbl_lineshape_voigt_lte.cpp:22-36,145-204). */
+enum { AB200_VAR_G0 = 0, AB200_VAR_D0 = 1, AB200_VAR_DV = 2, AB200_VAR_Y = 3, AB200_VAR_G = 4, AB200_NVAR = 5 };
+
+/* LineShapeModelType (lbl_temperature_model.h:18-34); POLY limited to 4 coefficients. */
+enum {
+  AB200_TM_ABSENT = -1,
+  AB200_TM_T0 = 0,
+  AB200_TM_T1 = 1,
+  AB200_TM_T2 = 2,
+  AB200_TM_T3 = 3,
+  AB200_TM_T4 = 4,
+  AB200_TM_T5 = 5,
+  AB200_TM_AER = 6,
+  AB200_TM_DPL = 7,
+  AB200_TM_POLY = 8
+};
+
+/* LineByLineLineshape: only VP_LTE is on the path. */
+enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1 };
+/* LineByLineCutoffType (lbl_data.h:178-194). */
+enum { AB200_CUTOFF_NONE = 0, AB200_CUTOFF_BYLINE = 1 };
+/* TransmittanceOption (arts_options.cc:953-1030); linsrc is the default rte_option. */
+enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 /* unsupported */ };
+/* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR). */
+enum { AB200_TARGET_T = 0, AB200_TARGET_VMR = 1 };
+
+/* flags (bit mask) */
+#define AB200_FLAG_K_ZERO_INIT 1u /* caller's K/dK are known to be zero: skip their H2D (+= still holds) */
+#define AB200_FLAG_TRAN_EXACT 2u  /* use the exact Cayley-Hamilton eigen pair instead of the reference's \
+                                     literal rtepack_transmission.cc:64-70 arithmetic */
+#define AB200_FLAG_RETURN_K 4u    /* clearsky_emission: also copy K back to the host */
+
+/* ---- catalog: AbsorptionBands flattened (lbl_data.h:31-68,196-300) ----- */
+typedef struct ab200_catalog_desc {
+  int32_t n_species; /* size of the vmr vector per level; species ids are 0..n_species-1 */
+  int32_t n_isot;    /* isotopologues referenced by bands */
+  int32_t n_bands;
+  int64_t n_lines;
+  int64_t n_ls; /* total number of (line, broadener) entries */
+
+  const int32_t *isot_species; /* [n_isot] species id of each isotopologue */
+  const double *isot_mass;     /* [n_isot] g/mol (SpeciesIsotope::mass) */
+
+  const int32_t *band_isot;         /* [n_bands] */
+  const int32_t *band_lineshape;    /* [n_bands] AB200_LINESHAPE_* */
+  const int32_t *band_cutoff_type;  /* [n_bands] AB200_CUTOFF_* */
+  const double *band_cutoff_value;  /* [n_bands] Hz */
+  const int64_t *band_offset;       /* [n_bands+1] lines of band b are [band_offset[b], band_offset[b+1]) */
+
+  const double *f0, *a, *e0, *gu, *gl; /* [n_lines] lbl::line members */
+  const double *T0;                    /* [n_lines] line_shape::model::T0 */
+
+  const uint8_t *z_on;   /* [n_lines] zeeman::model::on */
+  const double *z_gu;    /* [n_lines] zeeman g upper */
+  const double *z_gl;    /* [n_lines] zeeman g lower */
+  const int32_t *two_Ju; /* [n_lines] 2*J upper (Rational) */
+  const int32_t *two_Jl; /* [n_lines] 2*J lower */
+
+  const int64_t *ls_offset;  /* [n_lines+1] broadeners of line l are [ls_offset[l], ls_offset[l+1]) */
+  const int32_t *ls_species; /* [n_ls] species id or AB200_SPECIES_BATH */
+  const int32_t *ls_type;    /* [n_ls][AB200_NVAR] AB200_TM_* (ABSENT if the variable is not in the map) */
+  const double *ls_X;        /* [n_ls][AB200_NVAR][4] X0..X3 */
+} ab200_catalog_desc;
+
+/* ---- ArrayOfAtmPoint + ArrayOfPropagationPathPoint flattened ------------ */
+typedef struct ab200_atm_path {
+  int32_t np;
+  const double *T;      /* [np] K */
+  const double *P;      /* [np] Pa */
+  const double *vmr;    /* [np][n_species] */
+  const double *isorat; /* [np][n_isot] isotopologue ratios atm[spec] */
+  const double *Q;      /* [np][n_isot] PartitionFunctions::Q(T, isot) */
+  const double *dQdT;   /* [np][n_isot] PartitionFunctions::dQdT(T, isot); may be NULL if no T target */
+  const double *mag;    /* [np][3] magnetic field u,v,w [T]; may be NULL (=0) */
+  const double *los;    /* [np][2] zenith, azimuth [deg] (PropagationPathPoint::los); may be NULL (=0) */
+} ab200_atm_path;
+
+typedef struct ab200_target {
+  int32_t kind;    /* AB200_TARGET_* */
+  int32_t species; /* for AB200_TARGET_VMR */
+} ab200_target;
+
+typedef struct ab200_catalog ab200_catalog; /* opaque, immutable after create, shareable across threads */
+typedef struct ab200_path ab200_path;       /* opaque device-resident path workspace */
+
+/* message of the last failure on the calling thread */
+const char *ab200_last_error(void);
+
+/* number of usable CUDA devices (0 -> every compute call fails) */
+int ab200_device_count(void);
+
+/* Copies the description to the current CUDA device as SoA + pre-expanded
+ * Zeeman sub-lines (lbl_zeeman.cpp:261-309, lbl_zeeman.h:342-352).
+ * Replaces: the AoS-of-maps walk in band_shape_helper (lbl_lineshape_voigt_lte.cpp:394-429). */
+int ab200_catalog_create(const ab200_catalog_desc *desc, ab200_catalog **out);
+void ab200_catalog_destroy(ab200_catalog *cat);
+/* number of (sub-)lines after Zeeman expansion, per polarisation no,pi,sm,sp */
+int ab200_catalog_counts(const ab200_catalog *cat, int64_t counts[4]);
+
+/* spectral_propmatAddLines (np == 1) and spectral_propmat_pathFromPath with
+ * the lines-only agenda (all levels in one call).
+ *   f:  [np][nf] when f_level_stride == nf (freq_grid_path), or [nf] shared when 0
+ *   K:  [np][nf][7]  accumulated (+=) like lbl_lineshape_voigt_lte.cpp:1688-1692
+ *   dK: [np][nq][nf][7] accumulated (+=) (PropmatMatrix [nq,nf] per level); NULL if nq == 0
+ * all host pointers. */
+int ab200_propmat_levels(const ab200_catalog *cat, int64_t nf, const double *f, int64_t f_level_stride,
+                         const ab200_atm_path *atm, int32_t select_species, int32_t no_negative_absorption,
+                         int32_t nq, const ab200_target *targets, uint32_t flags, double *K, double *dK);
+
+/* spectral_tramat_pathFromPath -> TransmittanceMatrix::init (rtepack_transmission.cc:1254-1328).
+ *   K [np][nf][7], dK [np][nq][nf][7], r [np-1], dr [2][np-1][nq]
+ *   T,L,P [nf][np][16] (index 0 = identity), dT,dL [2][nf][np][nq][16]; L/dL may be NULL for constant. */
+int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double *K, const double *dK, const double *r,
+                 const double *dr, int32_t rte_option, uint32_t flags, double *T, double *L, double *P,
+                 double *dT, double *dL);
+
+/* spectral_rad_srcvec_pathFromPropmat -> SourceVector::init (rtepack_source.cc:52-105), LTE (S_nlte = 0).
+ *   f [np][nf] or [nf] (stride 0), T_level [np], it = index of the T target or -1
+ *   J [nf][np][4], dJ [nf][np][nq][4] */
+int ab200_srcvec(int32_t np, int64_t nf, int32_t nq, const double *K, const double *f, int64_t f_level_stride,
+                 const double *T_level, int32_t it, double *J, double *dJ);
+
+/* spectral_radStepByStepEmission -> rte_emission (rtepack_rtestep.cc:265-404).
+ *   I_bkg [nf][4]; I [nf][4]; dI [nf][np][nq][4] */
+int ab200_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, const double *T, const double *L,
+                       const double *P, const double *dT, const double *dL, const double *J, const double *dJ,
+                       const double *I_bkg, double *I, double *dI);
+
+/* The fused fast path: the canonical sequence of spectral_radClearskyEmission
+ * (workspace_meta_methods.cpp:166-181) from the propagation matrix to the
+ * radiance.  K, T, Lambda, J never leave the device / registers.
+ *   r [np-1] layer lengths, hse_derivative as in m_tramat.cc:18-24
+ *   I [nf][4], dI [nf][np][nq][4] (NULL if nq==0), K_out [np][nf][7] only with AB200_FLAG_RETURN_K */
+int ab200_clearsky_emission(const ab200_catalog *cat, int64_t nf, const double *f, int64_t f_level_stride,
+                            const ab200_atm_path *atm, int32_t select_species, int32_t no_negative_absorption,
+                            int32_t nq, const ab200_target *targets, const double *r, int32_t hse_derivative,
+                            int32_t rte_option, const double *I_bkg, uint32_t flags, double *I, double *dI,
+                            double *K_out);
+
+/* spectral_radApplyUnitFromSpectralRadiance with PlanckBT
+ * (spectral_radiance_transform_operator.cc:46-87): in place on I [nf][4]. */
+int ab200_planck_tb(int64_t nf, const double *f, double *I);
+
+/* ---- device-resident path workspace (what clearsky_emission is built on) --- */
+/* stream: a cudaStream_t (as void*) the caller wants the kernels on, or NULL for the library's own. */
+int ab200_path_create(const ab200_catalog *cat, int64_t nf, int32_t np, int32_t nq, ab200_path **out);
+void ab200_path_destroy(ab200_path *p);
+int ab200_path_set_stream(ab200_path *p, void *stream);
+/* H2D of one path's inputs (asynchronous on the path's stream, through pinned staging). */
+int ab200_path_upload(ab200_path *p, const double *f, int64_t f_level_stride, const ab200_atm_path *atm,
+                      int32_t select_species, int32_t no_negative_absorption, const ab200_target *targets,
+                      const double *r, int32_t hse_derivative, int32_t rte_option, const double *I_bkg,
+                      uint32_t flags);
+/* launches K1 (prepare) + K2/K3 (line sum) into the resident K, asynchronously */
+int ab200_path_run_propmat(ab200_path *p);
+/* launches the fused K4-K7 Stokes chain on the resident K, asynchronously */
+int ab200_path_run_stokes(ab200_path *p);
+/* D2H of the results (synchronises the stream). Any pointer may be NULL. */
+int ab200_path_download(ab200_path *p, double *I, double *dI, double *K, double *dK);
+int ab200_path_sync(ab200_path *p);
+/* raw device pointers (for NCCL gathers by the caller): which = 0: I [nf][4], 1: K [np][nf][7], 2: dI, 3: dK */
+void *ab200_path_device_ptr(ab200_path *p, int which);
+/* kernels launched by the library on this thread since the last call (bench.py's gpu_launches) */
+int64_t ab200_launch_count(int reset);
+
+/* The host-buffer entry points keep one device workspace per calling host thread (the shims are
+ * called repeatedly with identical shapes, src/m_rad.cc:321-343).  Drops the calling thread's. */
+int ab200_release_thread_cache(void);
+
+/* Host-only helpers of the Zeeman pre-expansion (no GPU needed; used by tests and shims):
+ * sub-line strengths / splitting coefficients [Hz/T] of one line and polarisation
+ * (pol: 0 no, 1 pi, 2 sigma-, 3 sigma+; lbl_zeeman.cpp:261-309, lbl_zeeman.h:342-352); returns the
+ * number of sub-lines.  norm_view: the 7-vector of lbl_zeeman.cpp:413-455. */
+int ab200_zeeman_components(int on, double gu, double gl, int two_Ju, int two_Jl, int pol, int64_t cap,
+                            double *strength, double *splitting);
+int ab200_norm_view(int pol, const double *mag, const double *los, double *npm);
+
+/* ---- measurement helpers ------------------------------------------------ */
+/* Dependency-free DFMA loop on all SMs; returns achieved FP64 TFLOP/s (2 flop per DFMA) and the
+ * kernel time.  MEASURED_PEAKS.json has no FP64 number. */
+int ab200_measure_dfma_peak(int iters, double *tflops, double *ms);
+/* Register-resident w(z) for tests: evaluates the device Faddeeva at n points (host arrays). */
+int ab200_faddeeva_w(int64_t n, const double *zr, const double *zi, double *wr, double *wi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTS_B200_H */

@@ -1,0 +1,1438 @@
+// oracle/oracle.cpp — CPU restatement of the reference's clear-sky spectral hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product (arts_b200/, include/) may
+// link, import or execute this file; it is used by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs
+// as the checker and the CPU baseline.
+//
+// What it restates (all paths relative to /root/reference):
+//   stage 1  src/core/lbl/lbl_lineshape_voigt_lte.cpp  (engine A, the one behind
+//            spectral_propmatAddLines, src/m_lbl.cc:242-300)
+//            src/core/lbl/lbl_lineshape_model.cpp, lbl_temperature_model.h,
+//            lbl_data.h, lbl_zeeman.{h,cpp}, lbl_lineshape.cpp:168-208
+//   stage 2  src/core/rtepack/rtepack_transmission.cc, rtepack_source.cc,
+//            rtepack_rtestep.cc, rtepack_multitype.h, rtepack_propagation_matrix.h
+//   scalars  src/core/physics/physics_funcs.{h,cc}, src/core/util/arts_constants.h,
+//            src/core/operators/spectral_radiance_transform_operator.cc
+// Each function cites the lines it follows.  Faddeeva::w is NOT restated: the
+// reference's own 3rdparty/Faddeeva/Faddeeva.cc is compiled where it lies and
+// linked in (oracle/Makefile), so the dominant arithmetic of the path is the
+// reference's object code.
+//
+// Parity pins (tests/test_oracle_*.py): Faddeeva 57-point KAT
+// (Faddeeva.cc:4041-4195), the catalog-free fixture
+// tests/core/linsrc/test_linsrc_convergence.py, exp(-K) against scipy expm
+// (src/tests/test_rtepack.cc:12-33).  Full-pipeline goldens of the reference need
+// external catalogs (arts-cat-data) and are unpinned here: see DESIGN.md.
+//
+// The flattened inputs are the C-ABI structs of include/arts_b200.h, so tests
+// feed byte-identical inputs to this oracle and to the CUDA library.
+
+#include <omp.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numbers>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../include/arts_b200.h"
+
+namespace Faddeeva {
+// reference 3rdparty/Faddeeva/Faddeeva.hh:36
+extern std::complex<double> w(std::complex<double> z, double relerr);
+}  // namespace Faddeeva
+
+namespace {
+using Numeric = double;
+using Complex = std::complex<double>;
+using Index   = std::int64_t;
+
+thread_local std::string g_err;
+
+// ---------------------------------------------------------------------------
+// Constants: src/core/util/arts_constants.h:57-254 (same expressions, so the
+// doubles are bit-identical)
+// ---------------------------------------------------------------------------
+namespace Constant {
+constexpr Numeric pi          = std::numbers::pi;
+constexpr Numeric inv_pi      = std::numbers::inv_pi;
+constexpr Numeric two_pi      = 2 * pi;
+constexpr Numeric inv_two_pi  = inv_pi / 2;
+constexpr Numeric inv_sqrt_pi = std::numbers::inv_sqrtpi;
+constexpr Numeric c           = 299792458;
+constexpr Numeric h           = 6.62607015e-34;
+constexpr Numeric h_bar       = h * inv_two_pi;
+constexpr Numeric e           = 1.602176634e-19;
+constexpr Numeric k           = 1.380649e-23;
+constexpr Numeric NA          = 6.02214076e23;
+constexpr Numeric alpha       = 7.2973525693e-3;
+constexpr Numeric R_inf       = 10973731.568160;
+constexpr Numeric m_e         = 2 * h * R_inf / (c * (alpha * alpha));
+constexpr Numeric bohr_magneton = e * h_bar / (2 * m_e);
+constexpr Numeric R           = k * NA;
+constexpr Numeric doppler_broadening_const_squared = 2'000 * R / (c * c);
+}  // namespace Constant
+
+constexpr Numeric pow2(Numeric x) { return x * x; }
+constexpr Numeric pow3(Numeric x) { return x * x * x; }
+constexpr Numeric pow4(Numeric x) { return pow2(pow2(x)); }
+inline Numeric deg2rad(Numeric x) { return x * (Constant::pi / 180); }
+
+// ---------------------------------------------------------------------------
+// physics: src/core/physics/physics_funcs.cc:153-158,192-197,254-263 and
+// physics_funcs.h:54-72
+// ---------------------------------------------------------------------------
+Numeric planck(Numeric f, Numeric t) {
+  constexpr Numeric a = 2 * Constant::h / pow2(Constant::c);
+  constexpr Numeric b = Constant::h / Constant::k;
+  return a * pow3(f) / std::expm1((b * f) / t);
+}
+
+Numeric dplanck_dt(Numeric f, Numeric t) {
+  constexpr Numeric a        = 2 * Constant::h / pow2(Constant::c);
+  constexpr Numeric b        = Constant::h / Constant::k;
+  const Numeric inv_exp_t_m1 = 1.0 / std::expm1(b * f / t);
+  return a * b * pow4(f) * inv_exp_t_m1 * (1 + inv_exp_t_m1) / pow2(t);
+}
+
+Numeric invplanck(Numeric i, Numeric f) {
+  constexpr Numeric a = Constant::h / Constant::k;
+  constexpr Numeric b = 2 * Constant::h / (Constant::c * Constant::c);
+  return (a * f) / std::log1p((b * f * f * f) / i);
+}
+
+constexpr Numeric number_density(Numeric p, Numeric t) { return p / (Constant::k * t); }
+constexpr Numeric dnumber_density_dt(Numeric p, Numeric t) { return -p / (Constant::k * pow2(t)); }
+
+// ---------------------------------------------------------------------------
+// Temperature models: src/core/lbl/lbl_temperature_model.h:62-314
+// ---------------------------------------------------------------------------
+Numeric tm_value(int type, const double* x, Numeric T0, Numeric T) {
+  switch (type) {
+    case AB200_TM_T0: return x[0];
+    case AB200_TM_T1: return x[0] * std::pow(T0 / T, x[1]);
+    case AB200_TM_T2: return x[0] * std::pow(T0 / T, x[1]) * (1 + x[2] * std::log(T / T0));
+    case AB200_TM_T3: return x[0] + x[1] * (T - T0);
+    case AB200_TM_T4: return (x[0] + x[1] * (T0 / T - 1)) * std::pow(T0 / T, x[2]);
+    case AB200_TM_T5: return x[0] * std::pow(T0 / T, 0.25 + 1.5 * x[1]);
+    case AB200_TM_AER:
+      if (T < 250.0) return x[0] + (T - 200.0) * (x[1] - x[0]) / (250.0 - 200.0);
+      if (T > 296.0) return x[2] + (T - 296.0) * (x[3] - x[2]) / (340.0 - 296.0);
+      return x[1] + (T - 250.0) * (x[2] - x[1]) / (296.0 - 250.0);
+    case AB200_TM_DPL: return x[0] * std::pow(T0 / T, x[1]) + x[2] * std::pow(T0 / T, x[3]);
+    case AB200_TM_POLY: {
+      Numeric poly_fac = 1.0, poly_sum = 0.0;
+      for (int i = 0; i < 4; i++) {
+        poly_sum += x[i] * poly_fac;
+        poly_fac *= T;
+      }
+      return poly_sum;
+    }
+  }
+  return std::numeric_limits<Numeric>::quiet_NaN();
+}
+
+// d/dT of the above: lbl_temperature_model.h:81-283 (d*_dT members)
+Numeric tm_dT(int type, const double* x, Numeric T0, Numeric T) {
+  switch (type) {
+    case AB200_TM_T0: return 0;
+    case AB200_TM_T1: return -x[0] * x[1] * std::pow(T0 / T, x[1]) / T;
+    case AB200_TM_T2:
+      return -x[0] * x[1] * std::pow(T0 / T, x[1]) * (x[2] * std::log(T / T0) + 1.) / T +
+             x[0] * x[2] * std::pow(T0 / T, x[1]) / T;
+    case AB200_TM_T3: return x[1];
+    case AB200_TM_T4:
+      return -x[2] * std::pow(T0 / T, x[2]) * (x[0] + x[1] * (T0 / T - 1.)) / T -
+             T0 * x[1] * std::pow(T0 / T, x[2]) / (T * T);
+    case AB200_TM_T5: return -x[0] * std::pow(T0 / T, 1.5 * x[1] + 0.25) * (1.5 * x[1] + 0.25) / T;
+    case AB200_TM_AER:
+      if (T < 250.0) return (x[1] - x[0]) / (250.0 - 200.0);
+      if (T > 296.0) return (x[3] - x[2]) / (340.0 - 296.0);
+      return (x[2] - x[1]) / (296.0 - 250.0);
+    case AB200_TM_DPL:
+      return -x[0] * x[1] * std::pow(T0 / T, x[1]) / T + -x[2] * x[3] * std::pow(T0 / T, x[3]) / T;
+    case AB200_TM_POLY: {
+      Numeric poly_fac = 1.0, poly_sum = 0.0;
+      for (int i = 1; i < 4; ++i) {
+        poly_sum += static_cast<Numeric>(i) * x[i] * poly_fac;
+        poly_fac *= T;
+      }
+      return poly_sum;
+    }
+  }
+  return std::numeric_limits<Numeric>::quiet_NaN();
+}
+
+// ---------------------------------------------------------------------------
+// Atmosphere point view
+// ---------------------------------------------------------------------------
+struct AtmPt {
+  Numeric T, P;
+  const double* vmr;     // [n_species]
+  const double* isorat;  // [n_isot]
+  const double* Q;
+  const double* dQdT;
+  Numeric mag[3];
+  Numeric los[2];
+  Numeric vmr_of(int s) const { return s < 0 ? 0.0 : vmr[s]; }
+};
+
+AtmPt atm_at(const ab200_catalog_desc& d, const ab200_atm_path& a, int ip) {
+  AtmPt p{};
+  p.T      = a.T[ip];
+  p.P      = a.P[ip];
+  p.vmr    = a.vmr + static_cast<Index>(ip) * d.n_species;
+  p.isorat = a.isorat + static_cast<Index>(ip) * d.n_isot;
+  p.Q      = a.Q + static_cast<Index>(ip) * d.n_isot;
+  p.dQdT   = a.dQdT ? a.dQdT + static_cast<Index>(ip) * d.n_isot : nullptr;
+  for (int i = 0; i < 3; i++) p.mag[i] = a.mag ? a.mag[3 * ip + i] : 0.0;
+  for (int i = 0; i < 2; i++) p.los[i] = a.los ? a.los[2 * ip + i] : 0.0;
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// Line-shape model: src/core/lbl/lbl_lineshape_model.cpp:14-35 (pressure
+// scaling), :70-113 (mixing + dVMR), :127-148 (dT).
+// ---------------------------------------------------------------------------
+struct LineView {
+  const ab200_catalog_desc& d;
+  Index l;
+  Numeric a() const { return d.a[l]; }
+  Numeric f0() const { return d.f0[l]; }
+  Numeric e0() const { return d.e0[l]; }
+  Numeric gu() const { return d.gu[l]; }
+  Numeric T0() const { return d.T0[l]; }
+
+  static Numeric pscale(int var, Numeric P) {
+    return (var == AB200_VAR_G || var == AB200_VAR_DV) ? P * P : P;
+  }
+
+  // species_model::VAR(T0,T,P): lbl_lineshape_model.cpp:14-35
+  Numeric single(Index ils, int var, Numeric T, Numeric P, bool dT) const {
+    const int type = d.ls_type[ils * AB200_NVAR + var];
+    if (type == AB200_TM_ABSENT) return 0.0;
+    const double* x = d.ls_X + (ils * AB200_NVAR + var) * 4;
+    return pscale(var, P) * (dT ? tm_dT(type, x, T0(), T) : tm_value(type, x, T0(), T));
+  }
+
+  // model::VAR(atm) and model::dVAR_dT(atm): lbl_lineshape_model.cpp:70-90,127-148
+  Numeric mix(int var, const AtmPt& atm, bool dT = false) const {
+    Numeric vmr = 0.0, res = 0.0, bth = std::numeric_limits<Numeric>::quiet_NaN();
+    for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++) {
+      const Numeric this_res = single(i, var, atm.T, atm.P, dT);
+      if (d.ls_species[i] != AB200_SPECIES_BATH) {
+        const Numeric this_vmr  = atm.vmr_of(d.ls_species[i]);
+        vmr                    += this_vmr;
+        res                    += this_vmr * this_res;
+      } else {
+        bth = this_res;
+      }
+    }
+    if (not std::isnan(bth)) return res + (1.0 - vmr) * bth;
+    return res / vmr;
+  }
+
+  // model::dVAR_dVMR(atm, species): lbl_lineshape_model.cpp:92-113
+  Numeric dmix_dVMR(int var, const AtmPt& atm, int species) const {
+    Index ptr = -1, bth = -1;
+    for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++) {
+      if (d.ls_species[i] == species) ptr = i;
+      if (d.ls_species[i] == AB200_SPECIES_BATH) bth = i;
+    }
+    if (ptr < 0) return 0.0;
+    const Numeric x = single(ptr, var, atm.T, atm.P, false);
+    if (species == AB200_SPECIES_BATH) return -x;
+    if (bth >= 0) return x - single(bth, var, atm.T, atm.P, false);
+    Numeric t = 0.0;
+    for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++) t += atm.vmr_of(d.ls_species[i]);
+    return (t - x) / t * t;  // sic, lbl_lineshape_model.cpp:112
+  }
+
+  // line::s(T,Q): lbl_data.h:66-68
+  Numeric s(Numeric T, Numeric Q) const {
+    return a() * gu() * std::exp(-e0() / (Constant::k * T)) / (pow3(f0()) * Q);
+  }
+  // line::ds_dT: lbl_data.h:138-142
+  Numeric ds_dT(Numeric T, Numeric Q, Numeric dQ_dT) const {
+    return a() * gu() * (e0() * Q - Constant::k * pow2(T) * dQ_dT) * std::exp(-e0() / (Constant::k * T)) /
+           (pow3(f0()) * Constant::k * pow2(T) * pow2(Q));
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Zeeman: src/core/lbl/lbl_zeeman.h:18-160,342-352 and lbl_zeeman.cpp:261-309,
+// :321-455.  wigner3j(Jl,1,Ju,ml,dm,-mu) is the reference's 3rdparty/wigner
+// call (lbl_zeeman.cpp:276); here it is the Racah formula in long double, all
+// arguments doubled integers.
+// ---------------------------------------------------------------------------
+long double lfact(int n) { return std::lgamma(static_cast<long double>(n) + 1.0L); }
+
+Numeric wigner3j_2(int tj1, int tj2, int tj3, int tm1, int tm2, int tm3) {
+  if (tm1 + tm2 + tm3 != 0) return 0;
+  if (std::abs(tm1) > tj1 || std::abs(tm2) > tj2 || std::abs(tm3) > tj3) return 0;
+  if (tj3 > tj1 + tj2 || tj3 < std::abs(tj1 - tj2)) return 0;
+  if ((tj1 + tj2 + tj3) % 2) return 0;
+  if ((tj1 + tm1) % 2 || (tj2 + tm2) % 2 || (tj3 + tm3) % 2) return 0;
+  auto h = [](int x) { return x / 2; };
+  const long double ldelta = lfact(h(tj1 + tj2 - tj3)) + lfact(h(tj1 - tj2 + tj3)) + lfact(h(-tj1 + tj2 + tj3)) -
+                             lfact(h(tj1 + tj2 + tj3) + 1);
+  const long double lpre = 0.5L * (ldelta + lfact(h(tj1 + tm1)) + lfact(h(tj1 - tm1)) + lfact(h(tj2 + tm2)) +
+                                   lfact(h(tj2 - tm2)) + lfact(h(tj3 + tm3)) + lfact(h(tj3 - tm3)));
+  const int kmin = std::max({0, h(tj2 - tj3 - tm1), h(tj1 - tj3 + tm2)});
+  const int kmax = std::min({h(tj1 + tj2 - tj3), h(tj1 - tm1), h(tj2 + tm2)});
+  long double sum = 0;
+  for (int k = kmin; k <= kmax; k++) {
+    const long double lden = lfact(k) + lfact(h(tj1 + tj2 - tj3) - k) + lfact(h(tj1 - tm1) - k) +
+                             lfact(h(tj2 + tm2) - k) + lfact(h(tj3 - tj2 + tm1) + k) +
+                             lfact(h(tj3 - tj1 - tm2) + k);
+    sum += ((k % 2) ? -1.0L : 1.0L) * std::exp(lpre - lden);
+  }
+  const int ph = h(tj1 - tj2 - tm3);
+  return static_cast<Numeric>(((ph % 2) ? -1.0L : 1.0L) * sum);
+}
+
+enum Pol { POL_NO = 0, POL_PI = 1, POL_SM = 2, POL_SP = 3 };
+
+int zeeman_dM(Pol p) { return p == POL_SM ? -1 : (p == POL_SP ? 1 : 0); }                    // lbl_zeeman.h:18-26
+Numeric polarization_factor(Pol p) { return p == POL_PI ? 1.5 : (p == POL_NO ? 1.0 : .75); }  // :154-162
+
+struct ZeemanView {
+  bool on;
+  Numeric gu, gl;
+  int tJu, tJl;
+
+  // model::size, lbl_zeeman.cpp:298-309 with zeeman::size lbl_zeeman.h:92-96
+  Index size(Pol p) const {
+    if (on) return p == POL_NO ? 0 : tJl + 1;
+    return p == POL_NO ? 1 : 0;
+  }
+  // 2*Ml, 2*Mu: lbl_zeeman.h:112-136
+  int tMl(Pol, Index n) const { return -tJl + 2 * static_cast<int>(n); }
+  int tMu(Pol p, Index n) const { return tMl(p, n) + 2 * zeeman_dM(p); }
+
+  // model::Strength, lbl_zeeman.cpp:261-277
+  Numeric Strength(Pol p, Index n) const {
+    if (p == POL_NO) return 1.0;
+    const int ml = tMl(p, n), mu = tMu(p, n);
+    if (std::abs(ml) > tJl or std::abs(mu) > tJu) return 0.0;
+    const Numeric C = polarization_factor(p);
+    return C * pow2(wigner3j_2(tJl, 2, tJu, ml, 2 * zeeman_dM(p), -mu));
+  }
+  // model::Splitting, lbl_zeeman.h:342-352
+  Numeric Splitting(Pol p, Index n) const {
+    constexpr Numeric C = Constant::bohr_magneton / Constant::h;
+    if (p == POL_NO) return 0.0;
+    return C * (0.5 * tMu(p, n) * gu - 0.5 * tMl(p, n) * gl);
+  }
+};
+
+// zeeman::norm_view, lbl_zeeman.cpp:321-331,413-455
+void norm_view(Pol p, const Numeric mag[3], const Numeric los[2], Numeric npm[7]) {
+  const Numeric u = mag[0], v = mag[1], w = mag[2];
+  const Numeric sa = std::sin(deg2rad(los[1])), ca = std::cos(deg2rad(los[1]));
+  const Numeric sz = std::sin(deg2rad(los[0])), cz = std::cos(deg2rad(los[0]));
+  const Numeric H    = std::hypot(u, v, w);
+  const Numeric uct  = sz * sa * u + sz * ca * v + cz * w;
+  const Numeric duct = u * sa * cz + v * ca * cz - w * sz;
+  const Numeric theta = H == 0 ? 0 : std::acos(uct / H);
+  const Numeric eta   = -std::atan2(ca * u - sa * v, -duct);
+  const Numeric CT    = std::cos(theta);
+  const Numeric ST2   = pow2(std::sin(theta));
+  const Numeric Q     = ST2 * std::cos(2 * eta);
+  const Numeric U     = ST2 * std::sin(2 * eta);
+  const Numeric pi_[7] = {ST2, -Q, U, 0, 0, U, Q};
+  const Numeric sm_[7] = {2 - ST2, Q, -U, 2 * CT, -2 * CT, -U, -Q};
+  const Numeric sp_[7] = {2 - ST2, Q, -U, -2 * CT, 2 * CT, -U, -Q};
+  const Numeric no_[7] = {1, 0, 0, 0, 0, 0, 0};
+  const Numeric* src = p == POL_PI ? pi_ : p == POL_SM ? sm_ : p == POL_SP ? sp_ : no_;
+  for (int i = 0; i < 7; i++) npm[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------
+// single_shape: src/core/lbl/lbl_lineshape_voigt_lte.h:20-56 and
+// lbl_lineshape_voigt_lte.cpp:22-36,145-204,239-268
+// ---------------------------------------------------------------------------
+struct single_shape {
+  Numeric f0{}, inv_gd{}, z_imag{};
+  Complex s{};
+  Complex z(Numeric f) const { return Complex{inv_gd * (f - f0), z_imag}; }
+  static Complex F(Complex z_) { return Faddeeva::w(z_, 0); }
+  Complex operator()(Numeric f) const { return s * F(z(f)); }
+  // forward finite difference, lbl_lineshape_voigt_lte.cpp:250-268
+  static Complex dF(Complex z_, Complex F_) {
+    const Complex dz{std::max(1e-4 * std::abs(z_.real()), 1e-4), std::max(1e-4 * std::abs(z_.imag()), 1e-4)};
+    const Complex F_2 = Faddeeva::w(z_ + dz, 0);
+    return (F_2 - F_) / dz;
+  }
+  // single_shape::dT / dVMR, lbl_lineshape_voigt_lte.cpp:310-323
+  Complex dX(Complex ds, Complex dz, Numeric dz_fac, Numeric f) const {
+    const Complex z_ = z(f);
+    const Complex F_ = F(z_);
+    const Complex dF_ = dF(z_, F_);
+    return ds * F_ + s * (dz + dz_fac * z_) * dF_;
+  }
+};
+
+struct line_pos {
+  Index line;
+  Index iz;
+};
+
+// line_strength_calc, lbl_lineshape_voigt_lte.cpp:22-36
+Complex line_strength_calc(Numeric inv_gd, int isot, int spec, const LineView& ln, const AtmPt& atm) {
+  const auto s    = ln.s(atm.T, atm.Q[isot]);
+  const Numeric G = ln.mix(AB200_VAR_G, atm);
+  const Numeric Y = ln.mix(AB200_VAR_Y, atm);
+  const Complex lm{1 + G, -Y};
+  const Numeric r = atm.isorat[isot];
+  const Numeric x = atm.vmr_of(spec);
+  return Constant::inv_sqrt_pi * inv_gd * r * x * lm * s;
+}
+
+// dline_strength_calc_dVMR, lbl_lineshape_voigt_lte.cpp:86-114
+Complex dline_strength_calc_dVMR(Numeric inv_gd, Numeric f0, int isot, int spec, int target_spec,
+                                 const LineView& ln, const AtmPt& atm) {
+  const auto s      = ln.s(atm.T, atm.Q[isot]);
+  const Numeric G   = ln.mix(AB200_VAR_G, atm);
+  const Numeric Y   = ln.mix(AB200_VAR_Y, atm);
+  const Numeric dG  = ln.dmix_dVMR(AB200_VAR_G, atm, target_spec);
+  const Numeric dY  = ln.dmix_dVMR(AB200_VAR_Y, atm, target_spec);
+  const Numeric dD0 = ln.dmix_dVMR(AB200_VAR_D0, atm, target_spec);
+  const Numeric dDV = ln.dmix_dVMR(AB200_VAR_DV, atm, target_spec);
+  const Numeric df0 = dD0 + dDV;
+  const Complex lm{1 + G, -Y};
+  const Complex dlm = {dG, -dY};
+  const Numeric r   = atm.isorat[isot];
+  const Numeric x   = atm.vmr_of(spec);
+  if (target_spec == spec) {
+    return -Constant::inv_sqrt_pi * inv_gd * r * s * (x * (df0 / f0) * lm - (x * dlm + lm));
+  }
+  return -Constant::inv_sqrt_pi * inv_gd * r * s * x * ((df0 / f0) * lm - dlm);
+}
+
+// dline_strength_calc_dT, lbl_lineshape_voigt_lte.cpp:116-143
+Complex dline_strength_calc_dT(Numeric inv_gd, Numeric f0, int isot, int spec, const LineView& ln,
+                               const AtmPt& atm) {
+  const Numeric T   = atm.T;
+  const auto s      = ln.s(T, atm.Q[isot]);
+  const auto ds     = ln.ds_dT(T, atm.Q[isot], atm.dQdT ? atm.dQdT[isot] : 0.0);
+  const Numeric G   = ln.mix(AB200_VAR_G, atm);
+  const Numeric Y   = ln.mix(AB200_VAR_Y, atm);
+  const Numeric dG  = ln.mix(AB200_VAR_G, atm, true);
+  const Numeric dY  = ln.mix(AB200_VAR_Y, atm, true);
+  const Numeric dD0 = ln.mix(AB200_VAR_D0, atm, true);
+  const Numeric dDV = ln.mix(AB200_VAR_DV, atm, true);
+  const Numeric df0 = dD0 + dDV;
+  const Complex lm{1 + G, -Y};
+  const Complex dlm = {dG, -dY};
+  const Numeric r   = atm.isorat[isot];
+  const Numeric x   = atm.vmr_of(spec);
+  return Constant::inv_sqrt_pi * inv_gd * r * x *
+         (2 * T * (dlm * s + lm * ds) * f0 - 2 * T * df0 * lm * s - f0 * lm * s) / (2 * T * f0);
+}
+
+// line_center_calc, :145-147
+Numeric line_center_calc(const LineView& ln, const AtmPt& atm) {
+  return ln.f0() + ln.mix(AB200_VAR_D0, atm) + ln.mix(AB200_VAR_DV, atm);
+}
+
+// band_shape_helper + lines_push_back + zeeman_push_back + single_shape_builder,
+// lbl_lineshape_voigt_lte.cpp:165-204,338-429.  ByLine uses band_data::active_lines
+// (lbl_data.cpp:61-68) on the catalog f0 (lines of a band are sorted by f0).
+void band_shape_helper(std::vector<single_shape>& lines, std::vector<line_pos>& pos,
+                       const ab200_catalog_desc& d, int ib, const AtmPt& atm, Numeric fmin, Numeric fmax,
+                       Pol pol) {
+  lines.resize(0);
+  pos.resize(0);
+  const int isot = d.band_isot[ib];
+  const int spec = d.isot_species[isot];
+  Index lo = d.band_offset[ib], hi = d.band_offset[ib + 1];
+  if (d.band_cutoff_type[ib] == AB200_CUTOFF_BYLINE) {
+    const Numeric c = d.band_cutoff_value[ib];
+    const double* b = d.f0 + lo;
+    const double* e = d.f0 + hi;
+    const double* low = std::lower_bound(b, e, fmin - c);
+    const double* upp = std::upper_bound(low, e, fmax + c);
+    hi = lo + (upp - b);
+    lo = lo + (low - b);
+  }
+  const Numeric H = std::hypot(atm.mag[0], atm.mag[1], atm.mag[2]);
+  for (Index il = lo; il < hi; il++) {
+    const LineView ln{d, il};
+    const ZeemanView z{d.z_on[il] != 0, d.z_gu[il], d.z_gl[il], d.two_Ju[il], d.two_Jl[il]};
+    if (not((z.on and pol != POL_NO) or (not z.on and pol == POL_NO))) continue;
+    // single_shape_builder ctor :177-186
+    const Numeric f0             = line_center_calc(ln, atm);
+    const Numeric scaled_gd_part = std::sqrt(Constant::doppler_broadening_const_squared * atm.T / d.isot_mass[isot]);
+    const Numeric G0             = ln.mix(AB200_VAR_G0, atm);
+    if (pol == POL_NO) {
+      single_shape s;  // operator single_shape() :198-204
+      s.f0     = f0;
+      s.inv_gd = 1.0 / (scaled_gd_part * f0);
+      s.z_imag = G0 * s.inv_gd;
+      s.s      = line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+      lines.push_back(s);
+      pos.push_back({il, std::numeric_limits<Index>::max()});
+    } else {
+      const Index nz = z.size(pol);
+      for (Index iz = 0; iz < nz; iz++) {
+        single_shape s;  // as_zeeman :188-196 (inv_gd uses the unsplit centre)
+        s.f0     = f0 + H * z.Splitting(pol, iz);
+        s.inv_gd = 1.0 / (scaled_gd_part * f0);
+        s.z_imag = G0 * s.inv_gd;
+        s.s      = z.Strength(pol, iz) * line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+        if (s.s == 0.0) continue;  // pop_back :354-357
+        lines.push_back(s);
+        pos.push_back({il, iz});
+      }
+    }
+  }
+  // stdr::sort(zip(lines,pos)) by f0 :426-428
+  std::vector<Index> order(lines.size());
+  std::iota(order.begin(), order.end(), Index{0});
+  std::sort(order.begin(), order.end(), [&](Index a, Index b) { return lines[a].f0 < lines[b].f0; });
+  std::vector<single_shape> l2(lines.size());
+  std::vector<line_pos> p2(pos.size());
+  for (size_t i = 0; i < order.size(); i++) {
+    l2[i] = lines[order[i]];
+    p2[i] = pos[order[i]];
+  }
+  lines.swap(l2);
+  pos.swap(p2);
+}
+
+// find_offset_and_count_of_frequency_range, lbl_lineshape_voigt_lte.h:123-133
+std::pair<Index, Index> freq_range(const std::vector<single_shape>& lines, Numeric f, Numeric cutoff) {
+  if (cutoff < std::numeric_limits<Numeric>::infinity()) {
+    auto low = std::lower_bound(lines.begin(), lines.end(), f - cutoff,
+                                [](const single_shape& l, Numeric v) { return l.f0 < v; });
+    auto upp = std::upper_bound(lines.begin(), lines.end(), f + cutoff,
+                                [](Numeric v, const single_shape& l) { return v < l.f0; });
+    return {low - lines.begin(), upp - low};
+  }
+  return {0, static_cast<Index>(lines.size())};
+}
+
+// zeeman::scale, lbl_zeeman.h:432-440
+inline void add_scaled(double* pm, const Numeric npm[7], Complex F) {
+  pm[0] += npm[0] * F.real();
+  pm[1] += npm[1] * F.real();
+  pm[2] += npm[2] * F.real();
+  pm[3] += npm[3] * F.real();
+  pm[4] += npm[4] * F.imag();
+  pm[5] += npm[5] * F.imag();
+  pm[6] += npm[6] * F.imag();
+}
+
+// voigt::lte::calculate for one (band, pol) over one frequency range,
+// lbl_lineshape_voigt_lte.cpp:1652-1725 with ComputeData ctor :936-956,
+// core_calc :959-981, dt_core_calc :984-1033, dVMR_core_calc :1153-1189 and
+// compute_derivative :1463-1561.
+void calculate_band(double* pm, double* dpm, Index nf_total, const double* f_grid, Index f_lo, Index f_n,
+                    const ab200_catalog_desc& d, int ib, const AtmPt& atm, Pol pol, int nq,
+                    const ab200_target* targets, bool no_negative_absorption, std::vector<single_shape>& lines,
+                    std::vector<line_pos>& pos) {
+  Numeric npm[7];
+  norm_view(pol, atm.mag, atm.los, npm);
+  if (std::all_of(npm, npm + 7, [](Numeric n) { return n == 0; })) return;
+  if (f_n == 0) return;
+  const double* fg = f_grid + f_lo;
+  const int isot   = d.band_isot[ib];
+  const int spec   = d.isot_species[isot];
+
+  band_shape_helper(lines, pos, d, ib, atm, fg[0], fg[f_n - 1], pol);
+  if (lines.empty()) return;
+  const bool has_cut   = d.band_cutoff_type[ib] != AB200_CUTOFF_NONE;
+  const Numeric cutoff = has_cut ? d.band_cutoff_value[ib] : std::numeric_limits<Numeric>::infinity();
+  const size_t nl      = lines.size();
+
+  // ComputeData ctor: scl :944-953
+  std::vector<Numeric> scl(f_n);
+  {
+    const Numeric N = number_density(atm.P, atm.T), T = atm.T;
+    for (Index i = 0; i < f_n; i++) {
+      constexpr Numeric c = Constant::c * Constant::c / (8 * Constant::pi);
+      const Numeric r     = (Constant::h * fg[i]) / (Constant::k * T);
+      scl[i]              = -N * fg[i] * std::expm1(-r) * c;
+    }
+  }
+
+  // core_calc :959-981 (+ band_shape::operator() :431-436, :591-608)
+  std::vector<Complex> shape(f_n), cut(nl);
+  if (has_cut) {
+    for (size_t i = 0; i < nl; i++) cut[i] = lines[i](lines[i].f0 + cutoff);
+    for (Index i = 0; i < f_n; i++) {
+      const auto [start, count] = freq_range(lines, fg[i], cutoff);
+      Complex out{};
+      for (Index j = start; j < start + count; j++) out += lines[j](fg[i]) - cut[j];
+      shape[i] = out;
+    }
+  } else {
+    for (Index i = 0; i < f_n; i++) {
+      Complex out{};
+      for (size_t j = 0; j < nl; j++) out += lines[j](fg[i]);
+      shape[i] = out;
+    }
+  }
+
+  // :1688-1692
+  for (Index i = 0; i < f_n; i++) {
+    const auto F = scl[i] * shape[i];
+    if (no_negative_absorption and F.real() < 0) continue;
+    add_scaled(pm + (f_lo + i) * 7, npm, F);
+  }
+
+  // Jacobian targets :1694-1708
+  std::vector<Complex> ds(nl), dz(nl), dcut(nl), dshape(f_n);
+  std::vector<Numeric> dz_fac(nl), dscl(f_n);
+  for (int iq = 0; iq < nq; iq++) {
+    double* dp = dpm + (static_cast<Index>(iq) * nf_total + f_lo) * 7;
+    const Numeric T = atm.T;
+    bool is_T = targets[iq].kind == AB200_TARGET_T;
+    if (is_T) {
+      // dt_core_calc :984-1033
+      const Numeric N = number_density(atm.P, T), dN = dnumber_density_dt(atm.P, T);
+      for (Index i = 0; i < f_n; i++) {
+        constexpr Numeric c = Constant::c * Constant::c / (8 * Constant::pi);
+        const Numeric r     = (Constant::h * fg[i]) / (Constant::k * T);
+        dscl[i]             = -fg[i] * (N * r * std::exp(-r) / T + dN * std::expm1(-r)) * c;
+      }
+      for (size_t i = 0; i < nl; i++) {
+        const LineView ln{d, pos[i].line};
+        const ZeemanView z{d.z_on[ln.l] != 0, d.z_gu[ln.l], d.z_gl[ln.l], d.two_Ju[ln.l], d.two_Jl[ln.l]};
+        const Numeric inv_gd = lines[i].inv_gd;
+        const Numeric f0     = lines[i].f0;
+        const Numeric dD0 = ln.mix(AB200_VAR_D0, atm, true), dDV = ln.mix(AB200_VAR_DV, atm, true);
+        dz_fac[i] = (-2 * T * dD0 - 2 * T * dDV - f0) / (2 * T * f0);
+        ds[i]     = z.Strength(pol, pos[i].iz) * dline_strength_calc_dT(inv_gd, f0, isot, spec, ln, atm);
+        dz[i]     = inv_gd * Complex{-(dD0 + dDV), ln.mix(AB200_VAR_G0, atm, true)};
+      }
+    } else {
+      // dVMR_core_calc :1153-1189
+      const int tspec = targets[iq].species;
+      for (size_t i = 0; i < nl; i++) {
+        const LineView ln{d, pos[i].line};
+        const ZeemanView z{d.z_on[ln.l] != 0, d.z_gu[ln.l], d.z_gl[ln.l], d.two_Ju[ln.l], d.two_Jl[ln.l]};
+        const Numeric inv_gd = lines[i].inv_gd;
+        const Numeric f0     = lines[i].f0;
+        const Numeric dD0 = ln.dmix_dVMR(AB200_VAR_D0, atm, tspec), dDV = ln.dmix_dVMR(AB200_VAR_DV, atm, tspec);
+        dz_fac[i] = -(dD0 + dDV) / f0;
+        ds[i]     = z.Strength(pol, pos[i].iz) * dline_strength_calc_dVMR(inv_gd, f0, isot, spec, tspec, ln, atm);
+        dz[i]     = inv_gd * Complex{-(dD0 + dDV), ln.dmix_dVMR(AB200_VAR_G0, atm, tspec)};
+      }
+    }
+    // band_shape::dT / dVMR with and without cutoff :475-507, :655-720
+    if (has_cut) {
+      for (size_t i = 0; i < nl; i++) dcut[i] = lines[i].dX(ds[i], dz[i], dz_fac[i], lines[i].f0 + cutoff);
+      for (Index i = 0; i < f_n; i++) {
+        const auto [start, count] = freq_range(lines, fg[i], cutoff);
+        Complex out{};
+        for (Index j = start; j < start + count; j++) out += lines[j].dX(ds[j], dz[j], dz_fac[j], fg[i]) - dcut[j];
+        dshape[i] = out;
+      }
+    } else {
+      for (Index i = 0; i < f_n; i++) {
+        Complex out{};
+        for (size_t j = 0; j < nl; j++) out += lines[j].dX(ds[j], dz[j], dz_fac[j], fg[i]);
+        dshape[i] = out;
+      }
+    }
+    // compute_derivative :1474-1481 (T) and :1553-1560 (VMR)
+    for (Index i = 0; i < f_n; i++) {
+      const Complex dF = is_T ? dscl[i] * shape[i] + scl[i] * dshape[i] : scl[i] * dshape[i];
+      add_scaled(dp + i * 7, npm, dF);
+    }
+  }
+}
+
+// lbl::calculate, src/core/lbl/lbl_lineshape.cpp:75-209 (VP_LTE bands only):
+// pol=no over all selected bands, then pi, sm, sp.
+void lbl_calculate(double* pm, double* dpm, Index nf, const double* f_grid, Index f_lo, Index f_n,
+                   const ab200_catalog_desc& d, const AtmPt& atm, int select_species, int nq,
+                   const ab200_target* targets, bool no_negative_absorption) {
+  std::vector<single_shape> lines;
+  std::vector<line_pos> pos;
+  for (Pol pol : {POL_NO, POL_PI, POL_SM, POL_SP}) {
+    for (int ib = 0; ib < d.n_bands; ib++) {
+      const int spec = d.isot_species[d.band_isot[ib]];
+      if (select_species == spec or select_species == AB200_SPECIES_BATH) {
+        calculate_band(pm, dpm, nf, f_grid, f_lo, f_n, d, ib, atm, pol, nq, targets, no_negative_absorption,
+                       lines, pos);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// rtepack value types
+// ---------------------------------------------------------------------------
+struct propmat {
+  Numeric v[7];
+  Numeric A() const { return v[0]; }
+  Numeric B() const { return v[1]; }
+  Numeric C() const { return v[2]; }
+  Numeric D() const { return v[3]; }
+  Numeric U() const { return v[4]; }
+  Numeric V() const { return v[5]; }
+  Numeric W() const { return v[6]; }
+  // rtepack_propagation_matrix.h:41-49
+  bool is_rotational() const { return A() == 0.0 and B() == 0.0 and C() == 0.0 and D() == 0.0; }
+  bool is_polarized() const { return B() != 0 or C() != 0 or D() != 0 or U() != 0 or V() != 0 or W() != 0; }
+};
+inline propmat load_pm(const double* p) {
+  propmat k;
+  std::memcpy(k.v, p, sizeof(k.v));
+  return k;
+}
+
+struct stokvec {
+  Numeric v[4]{0, 0, 0, 0};
+};
+inline stokvec operator+(stokvec a, const stokvec& b) {
+  for (int i = 0; i < 4; i++) a.v[i] += b.v[i];
+  return a;
+}
+inline stokvec operator-(stokvec a, const stokvec& b) {
+  for (int i = 0; i < 4; i++) a.v[i] -= b.v[i];
+  return a;
+}
+inline stokvec operator-(stokvec a) {
+  for (int i = 0; i < 4; i++) a.v[i] = -a.v[i];
+  return a;
+}
+// rtepack_stokes_vector.h:120 (std::midpoint per element)
+inline stokvec avg(const stokvec& a, const stokvec& b) {
+  stokvec o;
+  for (int i = 0; i < 4; i++) o.v[i] = std::midpoint(a.v[i], b.v[i]);
+  return o;
+}
+
+struct muelmat {
+  Numeric m[16];
+  muelmat() { id(1.0); }
+  muelmat(Numeric d) { id(d); }  // diagonal ctor, rtepack_mueller_matrix.h
+  void id(Numeric d) {
+    for (auto& x : m) x = 0;
+    m[0] = m[5] = m[10] = m[15] = d;
+  }
+  static muelmat zero() { return muelmat(0.0); }
+};
+inline muelmat make_mm(std::initializer_list<Numeric> l) {
+  muelmat o;
+  std::copy(l.begin(), l.end(), o.m);
+  return o;
+}
+inline muelmat operator*(const muelmat& a, const muelmat& b) {  // rtepack_mueller_matrix.h:101-150
+  muelmat o = muelmat::zero();
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      o.m[4 * i + j] = a.m[4 * i + 0] * b.m[0 + j] + a.m[4 * i + 1] * b.m[4 + j] + a.m[4 * i + 2] * b.m[8 + j] +
+                       a.m[4 * i + 3] * b.m[12 + j];
+  return o;
+}
+inline muelmat operator*(muelmat a, Numeric s) {
+  for (auto& x : a.m) x *= s;
+  return a;
+}
+inline muelmat operator*(Numeric s, muelmat a) { return a * s; }
+inline muelmat operator+(muelmat a, const muelmat& b) {
+  for (int i = 0; i < 16; i++) a.m[i] += b.m[i];
+  return a;
+}
+// rtepack_multitype.h:58-68
+inline stokvec operator*(const muelmat& a, const stokvec& b) {
+  const Numeric* m = a.m;
+  const Numeric s1 = b.v[0], s2 = b.v[1], s3 = b.v[2], s4 = b.v[3];
+  stokvec o;
+  o.v[0] = m[0] * s1 + m[1] * s2 + m[2] * s3 + m[3] * s4;
+  o.v[1] = m[4] * s1 + m[5] * s2 + m[6] * s3 + m[7] * s4;
+  o.v[2] = m[9] * s2 + m[10] * s3 + m[11] * s4 + m[8] * s1;
+  o.v[3] = m[12] * s1 + m[13] * s2 + m[14] * s3 + m[15] * s4;
+  return o;
+}
+
+// ---------------------------------------------------------------------------
+// rtepack::tran — src/core/rtepack/rtepack_transmission.cc:20-150 (ctor and
+// operator()), :207-275 (linsrc), :277-447 (linsrc_deriv), :558-674 (deriv).
+// `exact` selects the mathematically exact eigen pair x^2=(S-B)/2, y^2=(S+B)/2
+// instead of the reference's literal lines :67-70 (x2 = sqrt(t1), x = sqrt(x2)),
+// see DESIGN.md "reference quirks".  Default (exact=false) is the reference.
+// ---------------------------------------------------------------------------
+constexpr Numeric too_small = 1e-4;
+
+struct tran {
+  Numeric a, exp_a;
+  Numeric b, c, d, u, v, w;
+  Numeric b2, c2, d2, u2, v2, w2;
+  Numeric B, C, S;
+  Numeric x2, y2, x, y, cy, sy, cx, sx;
+  Numeric ix, iy, inv_x2y2;
+  Numeric C0, C1, C2, C3;
+  bool polarized, x_zero, y_zero, both_zero, either_zero;
+
+  tran(const propmat& k1, const propmat& k2, const Numeric r, bool exact)
+      : a{-0.5 * r * (k1.A() + k2.A())}, exp_a{std::exp(a)}, polarized(k1.is_polarized() or k2.is_polarized()) {
+    if (not polarized) return;
+    b = -0.5 * r * (k1.B() + k2.B());
+    c = -0.5 * r * (k1.C() + k2.C());
+    d = -0.5 * r * (k1.D() + k2.D());
+    u = -0.5 * r * (k1.U() + k2.U());
+    v = -0.5 * r * (k1.V() + k2.V());
+    w = -0.5 * r * (k1.W() + k2.W());
+    b2 = b * b;
+    c2 = c * c;
+    d2 = d * d;
+    u2 = u * u;
+    v2 = v * v;
+    w2 = w * w;
+    B  = u2 + v2 + w2 - b2 - c2 - d2;
+    C  = -pow2(d * u - c * v + b * w);
+    const Numeric disc = B * B - 4 * C;
+    S                  = std::sqrt(std::max<Numeric>(0.0, disc));
+    const Numeric t1   = 0.5 * (S - B);
+    const Numeric t2   = 0.5 * (S + B);
+    if (exact) {
+      x2 = std::max<Numeric>(0.0, t1);
+      y2 = std::max<Numeric>(0.0, t2);
+    } else {
+      x2 = std::sqrt(std::max<Numeric>(0.0, t1));  // :67
+      y2 = std::sqrt(std::max<Numeric>(0.0, t2));  // :68
+    }
+    x  = std::sqrt(x2);
+    y  = std::sqrt(y2);
+    cy = std::cos(y);
+    sy = std::sin(y);
+    cx = std::cosh(x);
+    sx = std::sinh(x);
+    x_zero      = x < too_small;
+    y_zero      = y < too_small;
+    both_zero   = y_zero and x_zero;
+    either_zero = y_zero or x_zero;
+    ix          = x_zero ? 0.0 : 1.0 / x;
+    iy          = y_zero ? 0.0 : 1.0 / y;
+    inv_x2y2    = both_zero ? 1.0 : 1.0 / (x2 + y2);
+    C0          = either_zero ? 1.0 : (cy * x2 + cx * y2) * inv_x2y2;
+    C1          = either_zero ? 1.0 : (sy * x2 * iy + sx * y2 * ix) * inv_x2y2;
+    C2          = both_zero ? 0.5 : (cx - cy) * inv_x2y2;
+    C3          = both_zero ? 1.0 / 6.0 : ((x_zero ? 1.0 : sx * ix) - (y_zero ? 1.0 : sy * iy)) * inv_x2y2;
+    polarized   = std::isfinite(C0) and std::isfinite(C1) and std::isfinite(C2) and std::isfinite(C3);
+  }
+
+  muelmat operator()() const {  // :118-150
+    if (not polarized) return muelmat(exp_a);
+    const Numeric C2b = C2 * (c * u + d * v);
+    const Numeric C2c = C2 * (b * u - d * w);
+    const Numeric C2d = C2 * (b * v + c * w);
+    const Numeric C2u = C2 * (b * c - v * w);
+    const Numeric C2v = C2 * (b * d + u * w);
+    const Numeric C2w = C2 * (c * d - u * v);
+    const Numeric C3b = C3 * (b * (B - w2) + w * (c * v - d * u));
+    const Numeric C3c = C3 * (c * (v2 - B) - v * (d * u + b * w));
+    const Numeric C3d = C3 * (d * (u2 - B) - u * (c * v - b * w));
+    const Numeric C3u = C3 * (d * (c * v - b * w) - u * (B + d2));
+    const Numeric C3v = C3 * (c * (d * u + b * w) - v * (B + c2));
+    const Numeric C3w = C3 * (b * (c * v - d * u) - w * (B + b2));
+    const Numeric M00 = C0 + C2 * (b2 + c2 + d2);
+    const Numeric M11 = C0 + C2 * (b2 - u2 - v2);
+    const Numeric M22 = C0 + C2 * (c2 - u2 - w2);
+    const Numeric M33 = C0 + C2 * (d2 - v2 - w2);
+    return exp_a * make_mm({M00, C1 * b - C2b - C3b, C1 * c + C2c + C3c, C1 * d + C2d + C3d,
+                            C1 * b + C2b - C3b, M11, C1 * u + C2u + C3u, C1 * v + C2v + C3v,
+                            C1 * c - C2c + C3c, -C1 * u + C2u - C3u, M22, C1 * w + C2w + C3w,
+                            C1 * d - C2d + C3d, -C1 * v + C2v - C3v, -C1 * w + C2w - C3w, M33});
+  }
+
+  static Numeric func_F(Numeric z) { return std::abs(z) < 1e-8 ? 1.0 + z * 0.5 + z * z / 6.0 : std::expm1(z) / z; }
+  static Numeric func_Fp(Numeric z) {
+    if (std::abs(z) < too_small) return 0.5 + z / 3.0 + z * z / 8.0;
+    const Numeric ez = std::exp(z);
+    return (ez * (z - 1.0) + 1.0) / (z * z);
+  }
+  static Numeric func_Fpp(Numeric z) {
+    if (std::abs(z) < too_small) return 1.0 / 3.0 + z / 4.0 + z * z / 10.0;
+    const Numeric ez = std::exp(z);
+    return (ez * (z * z - 2.0 * z + 2.0) - 2.0) / (z * z * z);
+  }
+  static Numeric func_F3p(Numeric z) {
+    if (std::abs(z) < too_small) return 0.25 + z * 0.2;
+    const Numeric ez = std::exp(z);
+    const Numeric z2 = z * z;
+    const Numeric z3 = z2 * z;
+    return (ez * (z3 - 3.0 * z2 + 6.0 * z - 6.0) + 6.0) / (z3 * z);
+  }
+  static Numeric func_F4p(Numeric z) {
+    if (std::abs(z) < too_small) return 0.2 + z / 6.0;
+    const Numeric ez = std::exp(z);
+    const Numeric z2 = z * z;
+    const Numeric z3 = z2 * z;
+    const Numeric z4 = z2 * z2;
+    const Numeric z5 = z4 * z;
+    return (ez * (z4 - 4.0 * z3 + 12.0 * z2 - 24.0 * z + 24.0) - 24.0) / z5;
+  }
+
+  muelmat S_mat() const { return make_mm({0, b, c, d, b, 0, u, v, c, -u, 0, w, d, -v, -w, 0}); }
+
+  muelmat linsrc() const {  // :207-275
+    if (not polarized) return muelmat(func_F(a));
+    Numeric l0, l1, l2, l3;
+    if (both_zero) {
+      l0 = func_F(a);
+      l1 = func_Fp(a);
+      if (std::abs(a) < too_small) {
+        l2 = 1.0 / 6.0 + a / 12.0;
+        l3 = 1.0 / 24.0 + a / 60.0;
+      } else {
+        const Numeric ez = std::exp(a);
+        const Numeric a2 = a * a;
+        const Numeric a3 = a2 * a;
+        l2               = 0.5 * (ez * (a2 - 2.0 * a + 2.0) - 2.0) / a3;
+        l3               = (ez * (a3 - 3.0 * a2 + 6.0 * a - 6.0) + 6.0) / (6.0 * a2 * a2);
+      }
+    } else {
+      Numeric Pp, Pm_div_x;
+      if (x_zero) {
+        Pp       = func_F(a);
+        Pm_div_x = func_Fp(a);
+      } else {
+        const Numeric f1 = func_F(a + x);
+        const Numeric f2 = func_F(a - x);
+        Pp               = 0.5 * (f1 + f2);
+        Pm_div_x         = 0.5 * (f1 - f2) / x;
+      }
+      Numeric Qp, q_im;
+      if (y_zero) {
+        Qp   = func_F(a);
+        q_im = func_Fp(a);
+      } else {
+        const Numeric denom       = a * a + y * y;
+        const Numeric ea_cy_m1    = exp_a * cy - 1.0;
+        const Numeric ea_sy       = exp_a * sy;
+        Qp                        = (a * ea_cy_m1 + y * ea_sy) / denom;
+        const Numeric sin_y_div_y = (std::abs(y) < 1e-6) ? 1.0 - y * y / 6.0 : std::sin(y) / y;
+        q_im                      = (a * exp_a * sin_y_div_y - ea_cy_m1) / denom;
+      }
+      l2 = (Pp - Qp) * inv_x2y2;
+      l0 = Pp - l2 * x2;
+      l3 = (Pm_div_x - q_im) * inv_x2y2;
+      l1 = Pm_div_x - l3 * x2;
+    }
+    const muelmat Sm  = S_mat();
+    const muelmat S2m = Sm * Sm;
+    const muelmat S3m = Sm * S2m;
+    return muelmat(l0) + Sm * l1 + S2m * l2 + S3m * l3;
+  }
+
+  muelmat deriv(const muelmat& t, const propmat& k1, const propmat& k2, const propmat& dk, const Numeric r,
+                const Numeric dr) const {  // :558-674
+    const Numeric da = -0.5 * (r * dk.A() + dr * (k1.A() + k2.A()));
+    if (not polarized) return muelmat(da * exp_a);
+    const Numeric db  = -0.5 * (r * dk.B() + dr * (k1.B() + k2.B()));
+    const Numeric dc  = -0.5 * (r * dk.C() + dr * (k1.C() + k2.C()));
+    const Numeric dd  = -0.5 * (r * dk.D() + dr * (k1.D() + k2.D()));
+    const Numeric du  = -0.5 * (r * dk.U() + dr * (k1.U() + k2.U()));
+    const Numeric dv  = -0.5 * (r * dk.V() + dr * (k1.V() + k2.V()));
+    const Numeric dw  = -0.5 * (r * dk.W() + dr * (k1.W() + k2.W()));
+    const Numeric db2 = 2 * db * b;
+    const Numeric dc2 = 2 * dc * c;
+    const Numeric dd2 = 2 * dd * d;
+    const Numeric du2 = 2 * du * u;
+    const Numeric dv2 = 2 * dv * v;
+    const Numeric dw2 = 2 * dw * w;
+    const Numeric dB  = du2 + dv2 + dw2 - db2 - dc2 - dd2;
+    const Numeric dC  = -2 * (d * u - c * v + b * w) * (dd * u + d * du - dc * v - c * dv + db * w + b * dw);
+    const Numeric dS  = (B * dB - 2 * dC) / S;
+    const Numeric dx2 = 0.25 * (dS - dB) / x2;
+    const Numeric dy2 = 0.25 * (dS + dB) / y2;
+    const Numeric dx  = 0.5 * dx2 / x;
+    const Numeric dy  = 0.5 * dy2 / y;
+    const Numeric dcy = -sy * dy;
+    const Numeric dsy = cy * dy;
+    const Numeric dcx = sx * dx;
+    const Numeric dsx = cx * dx;
+    const Numeric dix = -dx * ix * ix;
+    const Numeric diy = -dy * iy * iy;
+    const Numeric dx2dy2 = dx2 + dy2;
+    const Numeric dC0 =
+        either_zero ? 0.0 : (dcy * x2 + cy * dx2 + dcx * y2 + cx * dy2 - C0 * dx2dy2) * inv_x2y2;
+    const Numeric dC1 = either_zero ? 0.0
+                                    : (dsy * x2 * iy + sy * dx2 * iy + sy * x2 * diy + dsx * y2 * ix +
+                                       sx * dy2 * ix + sx * y2 * dix - C1 * dx2dy2) *
+                                          inv_x2y2;
+    const Numeric dC2 =
+        both_zero ? 0.0 : ((x_zero ? 0.0 : (dcx - C2 * dx2)) - (y_zero ? 0.0 : (dcy + C2 * dy2))) * inv_x2y2;
+    const Numeric dC3 = both_zero ? 0.0
+                                  : ((x_zero ? 0.0 : (dsx * ix + sx * dix - C3 * dx2)) -
+                                     (y_zero ? 0.0 : (dsy * iy + sy * diy + C3 * dy2))) *
+                                        inv_x2y2;
+    const Numeric dC2b = dC2 * (c * u + d * v) + C2 * (dc * u + c * du + dd * v + d * dv);
+    const Numeric dC2c = dC2 * (b * u - d * w) + C2 * (db * u + b * du - dd * w - d * dw);
+    const Numeric dC2d = dC2 * (b * v + c * w) + C2 * (db * v + b * dv + dc * w + c * dw);
+    const Numeric dC2u = dC2 * (b * c - v * w) + C2 * (db * c + b * dc - dv * w - v * dw);
+    const Numeric dC2v = dC2 * (b * d + u * w) + C2 * (db * d + b * dd + du * w + u * dw);
+    const Numeric dC2w = dC2 * (c * d - u * v) + C2 * (dc * d + c * dd - du * v - u * dv);
+    const Numeric dC3b = dC3 * (b * (B - w2) + w * (c * v - d * u)) +
+                         C3 * (db * (B - w2) + b * (dB - dw2) + dw * (c * v - d * u) +
+                               w * (dc * v + c * dv - dd * u - d * du));
+    const Numeric dC3c = dC3 * (c * (v2 - B) - v * (d * u + b * w)) +
+                         C3 * (dc * (v2 - B) + c * (dv2 - dB) - dv * (d * u + b * w) -
+                               v * (dd * u + d * du + db * w + b * dw));
+    const Numeric dC3d = dC3 * (d * (u2 - B) - u * (c * v - b * w)) +
+                         C3 * (dd * (u2 - B) + d * (du2 - dB) - du * (c * v - b * w) -
+                               u * (dc * v + c * dv - db * w - b * dw));
+    const Numeric dC3u = dC3 * (d * (c * v - b * w) - u * (B + d2)) +
+                         C3 * (dd * (c * v - b * w) + d * (dc * v + c * dv - db * w - b * dw) - du * (B + d2) -
+                               u * (dB + dd2));
+    const Numeric dC3v = dC3 * (c * (d * u + b * w) - v * (B + c2)) +
+                         C3 * (dc * (d * u + b * w) + c * (dd * u + d * du + db * w + b * dw) - dv * (B + c2) -
+                               v * (dB + dc2));
+    const Numeric dC3w = dC3 * (b * (c * v - d * u) - w * (B + b2)) +
+                         C3 * (db * (c * v - d * u) + b * (dc * v + c * dv - dd * u - d * du) - dw * (B + b2) -
+                               w * (dB + db2));
+    const Numeric dM00 = dC0 + dC2 * (b2 + c2 + d2) + C2 * (db2 + dc2 + dd2);
+    const Numeric dM11 = dC0 + dC2 * (b2 - u2 - v2) + C2 * (db2 - du2 - dv2);
+    const Numeric dM22 = dC0 + dC2 * (c2 - u2 - w2) + C2 * (dc2 - du2 - dw2);
+    const Numeric dM33 = dC0 + dC2 * (d2 - v2 - w2) + C2 * (dd2 - dv2 - dw2);
+    return da * t +
+           exp_a * make_mm({dM00, dC1 * b + C1 * db - dC2b - dC3b, dC1 * c + C1 * dc + dC2c + dC3c,
+                            dC1 * d + C1 * dd + dC2d + dC3d, dC1 * b + C1 * db + dC2b - dC3b, dM11,
+                            dC1 * u + C1 * du + dC2u + dC3u, dC1 * v + C1 * dv + dC2v + dC3v,
+                            dC1 * c + C1 * dc - dC2c + dC3c, -dC1 * u - C1 * du + dC2u - dC3u, dM22,
+                            dC1 * w + C1 * dw + dC2w + dC3w, dC1 * d + C1 * dd - dC2d + dC3d,
+                            -dC1 * v - C1 * dv + dC2v - dC3v, -dC1 * w - C1 * dw + dC2w - dC3w, dM33});
+  }
+
+  muelmat linsrc_deriv(const propmat& dk, const Numeric r, const Numeric dr) const {  // :277-447
+    const Numeric inv_r = (std::abs(r) > 1e-20) ? 1.0 / r : 0.0;
+    const Numeric dr_r  = dr * inv_r;
+    const Numeric da    = dr_r * a - 0.5 * r * dk.A();
+    if (not polarized) return muelmat(func_Fp(a) * da);
+    const Numeric db  = dr_r * b - 0.5 * r * dk.B();
+    const Numeric dc  = dr_r * c - 0.5 * r * dk.C();
+    const Numeric dd  = dr_r * d - 0.5 * r * dk.D();
+    const Numeric du  = dr_r * u - 0.5 * r * dk.U();
+    const Numeric dv  = dr_r * v - 0.5 * r * dk.V();
+    const Numeric dw  = dr_r * w - 0.5 * r * dk.W();
+    const Numeric db2 = 2.0 * db * b;
+    const Numeric dc2 = 2.0 * dc * c;
+    const Numeric dd2 = 2.0 * dd * d;
+    const Numeric du2 = 2.0 * du * u;
+    const Numeric dv2 = 2.0 * dv * v;
+    const Numeric dw2 = 2.0 * dw * w;
+    const Numeric dB  = du2 + dv2 + dw2 - db2 - dc2 - dd2;
+    const Numeric dC  = -2.0 * (d * u - c * v + b * w) * (dd * u + d * du - dc * v - c * dv + db * w + b * dw);
+    const Numeric dS_val = (S > 1e-9) ? (B * dB - 2.0 * dC) / S : 0.0;
+    const Numeric dx2    = (x2 > 1e-9) ? 0.25 * (dS_val - dB) / x2 : 0.0;
+    const Numeric dy2    = (y2 > 1e-9) ? 0.25 * (dS_val + dB) / y2 : 0.0;
+    const Numeric dx     = (x > 1e-9) ? 0.5 * dx2 / x : 0.0;
+    const Numeric dy     = (y > 1e-9) ? 0.5 * dy2 / y : 0.0;
+    Numeric l1, l2, l3;
+    Numeric dl0, dl1, dl2, dl3;
+    if (both_zero) {
+      const Numeric fpa  = func_Fp(a);
+      const Numeric fppa = func_Fpp(a);
+      dl0                = fpa * da;
+      l1                 = fpa;
+      dl1                = fppa * da;
+      if (std::abs(a) < too_small) {
+        l2  = 1.0 / 6.0 + a / 12.0;
+        dl2 = da / 12.0;
+        l3  = 1.0 / 24.0 + a / 60.0;
+        dl3 = da / 60.0;
+      } else {
+        const Numeric f3pa = func_F3p(a);
+        const Numeric f4pa = func_F4p(a);
+        l2                 = 0.5 * fppa;
+        dl2                = 0.5 * f3pa * da;
+        l3                 = f3pa / 6.0;
+        dl3                = f4pa / 6.0 * da;
+      }
+    } else {
+      Numeric Pp = 0.0, Pm_div_x = 0.0, Qp = 0.0, q_im = 0.0;
+      Numeric dPp = 0.0, dPm_div_x = 0.0, dQp = 0.0, dq_im = 0.0;
+      if (x_zero) {
+        Pp        = func_F(a);
+        dPp       = func_Fp(a) * da + 0.5 * func_Fpp(a) * dx2;
+        Pm_div_x  = func_Fp(a);
+        dPm_div_x = func_Fpp(a) * da + (func_F3p(a) / 6.0) * dx2;
+      } else {
+        const Numeric f_apx   = func_F(a + x);
+        const Numeric f_amx   = func_F(a - x);
+        const Numeric fp_apx  = func_Fp(a + x);
+        const Numeric fp_amx  = func_Fp(a - x);
+        Pp                    = 0.5 * (f_apx + f_amx);
+        const Numeric sum_fp  = fp_apx + fp_amx;
+        const Numeric diff_fp = fp_apx - fp_amx;
+        dPp                   = 0.5 * sum_fp * da + 0.5 * diff_fp * dx;
+        Pm_div_x              = 0.5 * (f_apx - f_amx) / x;
+        const Numeric dPm_da  = 0.5 * diff_fp / x;
+        Numeric dPm_dx;
+        if (x < 1e-3) {
+          dPm_dx = func_F3p(a) * x / 3.0;
+        } else {
+          const Numeric diff_f = f_apx - f_amx;
+          dPm_dx               = (x * sum_fp - diff_f) / (2.0 * x * x);
+        }
+        dPm_div_x = dPm_da * da + dPm_dx * dx;
+      }
+      if (y_zero) {
+        Qp    = func_F(a);
+        dQp   = func_Fp(a) * da - 0.5 * func_Fpp(a) * dy2;
+        q_im  = func_Fp(a);
+        dq_im = func_Fpp(a) * da - (func_F3p(a) / 6.0) * dy2;
+      } else {
+        const Numeric denom       = a * a + y * y;
+        const Numeric ea_cy_m1    = exp_a * cy - 1.0;
+        const Numeric ea_sy       = exp_a * sy;
+        Qp                        = (a * ea_cy_m1 + y * ea_sy) / denom;
+        const Numeric sin_y_div_y = (std::abs(y) < 1e-6) ? 1.0 - y * y / 6.0 : std::sin(y) / y;
+        q_im                      = (a * exp_a * sin_y_div_y - ea_cy_m1) / denom;
+        const Numeric ImF         = (a * exp_a * sy - y * ea_cy_m1) / denom;
+        const Numeric A_val       = exp_a * ((a - 1.0) * cy - y * sy) + 1.0;
+        const Numeric B_val       = exp_a * ((a - 1.0) * sy + y * cy);
+        const Numeric C_val       = a * a - y * y;
+        const Numeric D_val       = 2.0 * a * y;
+        const Numeric denom2      = C_val * C_val + D_val * D_val;
+        const Numeric Fp_re       = (A_val * C_val + B_val * D_val) / denom2;
+        const Numeric Fp_im       = (B_val * C_val - A_val * D_val) / denom2;
+        dQp                       = Fp_re * da - Fp_im * dy;
+        const Numeric dImF        = Fp_im * da + Fp_re * dy;
+        dq_im                     = (y * dImF - ImF * dy) / (y * y);
+      }
+      const Numeric inv  = inv_x2y2;
+      const Numeric dinv = -inv * inv * (dx2 + dy2);
+      l2                 = (Pp - Qp) * inv;
+      dl2                = (dPp - dQp) * inv + (Pp - Qp) * dinv;
+      dl0                = dPp - dl2 * x2 - l2 * dx2;
+      l3                 = (Pm_div_x - q_im) * inv;
+      dl3                = (dPm_div_x - dq_im) * inv + (Pm_div_x - q_im) * dinv;
+      l1                 = Pm_div_x - l3 * x2;
+      dl1                = dPm_div_x - dl3 * x2 - l3 * dx2;
+    }
+    const muelmat Sm   = S_mat();
+    const muelmat dSm  = make_mm({0, db, dc, dd, db, 0, du, dv, dc, -du, 0, dw, dd, -dv, -dw, 0});
+    const muelmat S2m  = Sm * Sm;
+    const muelmat dS2m = dSm * Sm + Sm * dSm;
+    const muelmat S3m  = Sm * S2m;
+    const muelmat dS3m = dSm * S2m + Sm * dS2m;
+    return muelmat(dl0) + Sm * dl1 + dSm * l1 + S2m * dl2 + dS2m * l2 + S3m * dl3 + dS3m * l3;
+  }
+};
+
+void store(double* p, const muelmat& m) { std::memcpy(p, m.m, 16 * sizeof(double)); }
+muelmat load_mm(const double* p) {
+  muelmat m;
+  std::memcpy(m.m, p, 16 * sizeof(double));
+  return m;
+}
+stokvec load_sv(const double* p) {
+  stokvec s;
+  std::memcpy(s.v, p, 4 * sizeof(double));
+  return s;
+}
+void store(double* p, const stokvec& s) { std::memcpy(p, s.v, 4 * sizeof(double)); }
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+}  // namespace
+
+// ===========================================================================
+// exported oracle entry points (same argument meaning as include/arts_b200.h)
+// ===========================================================================
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+int orc_num_threads(void) { return omp_get_max_threads(); }
+
+// Faddeeva::w of the reference, vectorised (lbl_lineshape_voigt_lte.cpp:239)
+int orc_faddeeva_w(int64_t n, const double* zr, const double* zi, double* wr, double* wi) {
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; i++) {
+    const Complex w = Faddeeva::w(Complex{zr[i], zi[i]}, 0);
+    wr[i]           = w.real();
+    wi[i]           = w.imag();
+  }
+  return 0;
+}
+
+int orc_wigner3j(int tj1, int tj2, int tj3, int tm1, int tm2, int tm3, double* out) {
+  *out = wigner3j_2(tj1, tj2, tj3, tm1, tm2, tm3);
+  return 0;
+}
+
+// zeeman sub-line table for one line and polarisation (tests compare the library's expansion)
+int orc_zeeman_components(int on, double gu, double gl, int tJu, int tJl, int pol, int64_t cap, double* strength,
+                          double* splitting) {
+  const ZeemanView z{on != 0, gu, gl, tJu, tJl};
+  const Index n = z.size(static_cast<Pol>(pol));
+  for (Index i = 0; i < n and i < cap; i++) {
+    strength[i]  = z.Strength(static_cast<Pol>(pol), i);
+    splitting[i] = z.Splitting(static_cast<Pol>(pol), i);
+  }
+  return static_cast<int>(n);
+}
+
+int orc_norm_view(int pol, const double* mag, const double* los, double* npm) {
+  norm_view(static_cast<Pol>(pol), mag, los, npm);
+  return 0;
+}
+
+// spectral_propmatAddLines / spectral_propmat_pathFromPath with the lines-only
+// agenda.  Parallelised like the reference: over levels (m_propmat.cc:42) when
+// there are at least as many levels as threads, else over contiguous frequency
+// chunks per level (m_lbl.cc:273-295 with omp_offset_count,
+// matpack_mdspan_algorithm.cc:4-18).  The result does not depend on the choice.
+int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f, int64_t f_level_stride,
+                       const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
+                       int32_t nq, const ab200_target* targets, double* K, double* dK) {
+  if (!d || !atm || !f || !K) return fail(AB200_ERR_INVALID, "null argument");
+  for (int ib = 0; ib < d->n_bands; ib++)
+    if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE) return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE bands");
+  if (nq > 0 && !dK) return fail(AB200_ERR_INVALID, "dK is null with nq > 0");
+  const int np       = atm->np;
+  const int nthreads = omp_get_max_threads();
+  if (np >= nthreads || nf < nthreads) {
+#pragma omp parallel for schedule(dynamic)
+    for (int ip = 0; ip < np; ip++) {
+      const AtmPt a = atm_at(*d, *atm, ip);
+      lbl_calculate(K + static_cast<Index>(ip) * nf * 7, nq ? dK + static_cast<Index>(ip) * nq * nf * 7 : nullptr,
+                    nf, f + ip * f_level_stride, 0, nf, *d, a, select_species, nq, targets,
+                    no_negative_absorption != 0);
+    }
+  } else {
+    for (int ip = 0; ip < np; ip++) {
+      const AtmPt a = atm_at(*d, *atm, ip);
+      // omp_offset_count: dn = nf / n, last chunk takes the remainder
+      const Index n  = nthreads;
+      const Index dn = nf / n;
+#pragma omp parallel for
+      for (Index i = 0; i < n; i++) {
+        const Index lo = i * dn;
+        const Index cn = (i == n - 1) ? nf - lo : dn;
+        lbl_calculate(K + static_cast<Index>(ip) * nf * 7,
+                      nq ? dK + static_cast<Index>(ip) * nq * nf * 7 : nullptr, nf, f + ip * f_level_stride, lo,
+                      cn, *d, a, select_species, nq, targets, no_negative_absorption != 0);
+      }
+    }
+  }
+  return 0;
+}
+
+// TransmittanceMatrix::init, rtepack_transmission.cc:1254-1328 with constant
+// :1114-1149 and linsrc :1151-1193.
+int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double* dK, const double* r,
+               const double* dr, int32_t rte_option, uint32_t flags, double* T, double* L, double* P, double* dT,
+               double* dL) {
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC)
+    return fail(AB200_ERR_UNSUPPORTED, "rte_option must be constant or linsrc");
+  const bool exact  = flags & AB200_FLAG_TRAN_EXACT;
+  const bool linsrc = rte_option == AB200_RTE_LINSRC;
+  const muelmat id;
+  const muelmat zero = muelmat::zero();
+  // :1300-1314 identity / zero init
+#pragma omp parallel for
+  for (Index iv = 0; iv < nf; iv++) {
+    for (int i = 0; i < np; i++) {
+      store(T + (iv * np + i) * 16, id);
+      if (linsrc && L) store(L + (iv * np + i) * 16, id);
+      for (int t = 0; t < 2; t++)
+        for (int j = 0; j < nq; j++) {
+          store(dT + (((static_cast<Index>(t) * nf + iv) * np + i) * nq + j) * 16, zero);
+          if (linsrc && dL) store(dL + (((static_cast<Index>(t) * nf + iv) * np + i) * nq + j) * 16, zero);
+        }
+    }
+  }
+  auto dK_at = [&](int i, int j, Index iv) { return load_pm(dK + ((static_cast<Index>(i) * nq + j) * nf + iv) * 7); };
+  auto dXi   = [&](double* base, int t, Index iv, int i, int j) {
+    return base + (((static_cast<Index>(t) * nf + iv) * np + i) * nq + j) * 16;
+  };
+#pragma omp parallel for collapse(2)
+  for (int i = 1; i < np; i++) {
+    for (Index iv = 0; iv < nf; ++iv) {
+      const propmat k1 = load_pm(K + (static_cast<Index>(i - 1) * nf + iv) * 7);
+      const propmat k2 = load_pm(K + (static_cast<Index>(i) * nf + iv) * 7);
+      const tran ts{k1, k2, r[i - 1], exact};
+      const muelmat Tm = ts();
+      store(T + (iv * np + i) * 16, Tm);
+      if (linsrc) store(L + (iv * np + i) * 16, ts.linsrc());
+      for (int j = 0; j < nq; j++) {
+        const Numeric dr0 = dr[(0 * (np - 1) + (i - 1)) * nq + j];
+        const Numeric dr1 = dr[(1 * (np - 1) + (i - 1)) * nq + j];
+        store(dXi(dT, 0, iv, i - 1, j), ts.deriv(Tm, k1, k2, dK_at(i - 1, j, iv), r[i - 1], dr0));
+        store(dXi(dT, 1, iv, i, j), ts.deriv(Tm, k1, k2, dK_at(i, j, iv), r[i - 1], dr1));
+        if (linsrc) {
+          store(dXi(dL, 0, iv, i - 1, j), ts.linsrc_deriv(dK_at(i - 1, j, iv), r[i - 1], dr0));
+          store(dXi(dL, 1, iv, i, j), ts.linsrc_deriv(dK_at(i, j, iv), r[i - 1], dr1));
+        }
+      }
+    }
+  }
+  // :1322-1327 cumulative transmission
+#pragma omp parallel for
+  for (Index i = 0; i < nf; i++) {
+    muelmat acc;
+    store(P + (i * np + 0) * 16, acc);
+    for (int j = 1; j < np; j++) {
+      acc = acc * load_mm(T + (i * np + j) * 16);
+      store(P + (i * np + j) * 16, acc);
+    }
+  }
+  return 0;
+}
+
+// SourceVector::init (spectral), rtepack_source.cc:52-105, in LTE (nlte = 0, dnlte = 0):
+// J = B(f,T) (+ K^-1 * 0), dJ[k] = [it==k ? dB/dT : 0, 0,0,0] - K^-1 (dK * 0 - 0).
+int orc_srcvec(int32_t np, int64_t nf, int32_t nq, const double* K, const double* f, int64_t f_level_stride,
+               const double* T_level, int32_t it, double* J, double* dJ) {
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < np; i++) {
+    for (Index j = 0; j < nf; j++) {
+      const propmat k = load_pm(K + (static_cast<Index>(i) * nf + j) * 7);
+      stokvec Jv;
+      const bool rot = k.is_rotational();
+      if (not rot) Jv.v[0] = planck(f[i * f_level_stride + j], T_level[i]);
+      store(J + (j * np + i) * 4, Jv);
+      for (int q = 0; q < nq; q++) {
+        stokvec d;
+        if (not rot and it == q) d.v[0] = dplanck_dt(f[i * f_level_stride + j], T_level[i]);
+        store(dJ + ((j * np + i) * nq + q) * 4, d);
+      }
+    }
+  }
+  return 0;
+}
+
+// rte_emission, rtepack_rtestep.cc:265-404 (+ the background copy and zero
+// init of m_spectral_radiance.cc:36-40)
+int orc_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, const double* T, const double* L,
+                     const double* P, const double* dT, const double* dL, const double* J, const double* dJ,
+                     const double* I_bkg, double* I, double* dI) {
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC)
+    return fail(AB200_ERR_UNSUPPORTED, "rte_option must be constant or linsrc");
+  auto dXi = [&](const double* base, int t, Index iv, int i, int j) {
+    return load_mm(base + (((static_cast<Index>(t) * nf + iv) * np + i) * nq + j) * 16);
+  };
+#pragma omp parallel for
+  for (Index iv = 0; iv < nf; iv++) {
+    stokvec Iv = load_sv(I_bkg + iv * 4);
+    std::vector<stokvec> dIv(static_cast<size_t>(np) * nq);
+    auto Jv  = [&](int i) { return load_sv(J + (iv * np + i) * 4); };
+    auto dJv = [&](int i, int q) { return load_sv(dJ + ((iv * np + i) * nq + q) * 4); };
+    for (int i = np - 2; i >= 0; i--) {
+      const muelmat Tm = load_mm(T + (iv * np + i + 1) * 16);
+      if (rte_option == AB200_RTE_CONSTANT) {  // :287-309
+        const stokvec Jm = avg(Jv(i), Jv(i + 1));
+        Iv               = Iv - Jm;
+        if (nq) {
+          const muelmat Pm = load_mm(P + (iv * np + i) * 16);
+          for (int iq = 0; iq < nq; iq++) {
+            const stokvec dJ0 = dJv(i, iq), dJ1 = dJv(i + 1, iq);
+            dIv[i * nq + iq]       = dIv[i * nq + iq] + Pm * (dXi(dT, 0, iv, i, iq) * Iv + avg(dJ0, -(Tm * dJ0)));
+            dIv[(i + 1) * nq + iq] = dIv[(i + 1) * nq + iq] + Pm * (dXi(dT, 1, iv, i + 1, iq) * Iv + avg(dJ1, -(Tm * dJ1)));
+          }
+        }
+        Iv = Tm * Iv + Jm;
+      } else {  // linevo :341-370
+        const muelmat Lm    = load_mm(L + (iv * np + i + 1) * 16);
+        const stokvec J0    = Jv(i + 1);
+        const stokvec J1    = Jv(i);
+        const stokvec ImJ0  = Iv - J0;
+        const stokvec J0mJ1 = J0 - J1;
+        if (nq) {
+          const muelmat Pm = load_mm(P + (iv * np + i) * 16);
+          for (int iq = 0; iq < nq; iq++) {
+            const stokvec dJ0 = dJv(i, iq), dJ1 = dJv(i + 1, iq);
+            dIv[i * nq + iq] = dIv[i * nq + iq] + Pm * (dJ1 - Lm * dJ0 + dXi(dT, 0, iv, i, iq) * ImJ0 +
+                                                        dXi(dL, 0, iv, i, iq) * J0mJ1);
+            dIv[(i + 1) * nq + iq] =
+                dIv[(i + 1) * nq + iq] + Pm * (dXi(dT, 1, iv, i + 1, iq) * ImJ0 + dXi(dL, 1, iv, i + 1, iq) * J0mJ1 +
+                                               Lm * dJ1 - Tm * dJ0);
+          }
+        }
+        Iv = Tm * ImJ0 + Lm * J0mJ1 + J1;
+      }
+    }
+    store(I + iv * 4, Iv);
+    for (int i = 0; i < np; i++)
+      for (int q = 0; q < nq; q++) store(dI + ((iv * np + i) * nq + q) * 4, dIv[i * nq + q]);
+  }
+  return 0;
+}
+
+// The canonical sequence of spectral_radClearskyEmission
+// (workspace_meta_methods.cpp:166-181) from spectral_propmat_pathFromPath on,
+// un-fused exactly like the reference (T, L, P, dT, dL, J, dJ materialised).
+int orc_clearsky_emission(const ab200_catalog_desc* d, int64_t nf, const double* f, int64_t f_level_stride,
+                          const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
+                          int32_t nq, const ab200_target* targets, const double* r, int32_t hse_derivative,
+                          int32_t rte_option, const double* I_bkg, uint32_t flags, double* I, double* dI,
+                          double* K_out) {
+  const int np = atm->np;
+  std::vector<double> K(static_cast<size_t>(np) * nf * 7, 0.0), dK(static_cast<size_t>(np) * nq * nf * 7, 0.0);
+  int rc = orc_propmat_levels(d, nf, f, f_level_stride, atm, select_species, no_negative_absorption, nq, targets,
+                              K.data(), dK.data());
+  if (rc) return rc;
+  // m_tramat.cc:14-24
+  int it = -1;
+  for (int q = 0; q < nq; q++)
+    if (targets[q].kind == AB200_TARGET_T) it = q;
+  std::vector<double> dr(static_cast<size_t>(2) * (np - 1) * nq, 0.0);
+  if (hse_derivative and it >= 0) {
+    for (int ip = 0; ip < np - 1; ip++) {
+      dr[(0 * (np - 1) + ip) * nq + it] = r[ip] / (2.0 * atm->T[ip]);
+      dr[(1 * (np - 1) + ip) * nq + it] = r[ip] / (2.0 * atm->T[ip + 1]);
+    }
+  }
+  const size_t nm = static_cast<size_t>(nf) * np * 16;
+  std::vector<double> T(nm), L(nm), P(nm), dT(2 * nm * nq), dL(2 * nm * nq);
+  rc = orc_tramat(np, nf, nq, K.data(), dK.data(), r, dr.data(), rte_option, flags, T.data(), L.data(), P.data(),
+                  dT.data(), dL.data());
+  if (rc) return rc;
+  std::vector<double> J(static_cast<size_t>(nf) * np * 4), dJ(static_cast<size_t>(nf) * np * nq * 4);
+  rc = orc_srcvec(np, nf, nq, K.data(), f, f_level_stride, atm->T, it, J.data(), dJ.data());
+  if (rc) return rc;
+  rc = orc_rte_emission(rte_option, np, nf, nq, T.data(), L.data(), P.data(), dT.data(), dL.data(), J.data(),
+                        dJ.data(), I_bkg, I, dI);
+  if (rc) return rc;
+  if (K_out) std::memcpy(K_out, K.data(), K.size() * sizeof(double));
+  return 0;
+}
+
+// spectral_planck_op, spectral_radiance_transform_operator.cc:46-87 (forward part)
+int orc_planck_tb(int64_t nf, const double* f, double* I) {
+  for (int64_t j = 0; j < nf; j++) {
+    double* v        = I + 4 * j;
+    const Numeric fj = f[j];
+    const Numeric n0 = invplanck(v[0], fj);
+    const Numeric n1 = invplanck(0.5 * (v[0] + v[1]), fj) - invplanck(0.5 * (v[0] - v[1]), fj);
+    const Numeric n2 = invplanck(0.5 * (v[0] + v[2]), fj) - invplanck(0.5 * (v[0] - v[2]), fj);
+    const Numeric n3 = invplanck(0.5 * (v[0] + v[3]), fj) - invplanck(0.5 * (v[0] - v[3]), fj);
+    v[0] = n0;
+    v[1] = n1;
+    v[2] = n2;
+    v[3] = n3;
+  }
+  return 0;
+}
+
+int orc_planck(int64_t n, const double* f, double T, double* B) {
+  for (int64_t i = 0; i < n; i++) B[i] = planck(f[i], T);
+  return 0;
+}
+
+// rtepack::tran for single inputs (tests: exp(-K r) against scipy expm, src/tests/test_rtepack.cc:12-33)
+int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, double* T, double* L) {
+  const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};
+  store(T, ts());
+  if (L) store(L, ts.linsrc());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+"""GPU parity of stage 1 (spectral_propmatAddLines / spectral_propmat_pathFromPath) through the C ABI
+against the CPU oracle (engine A of the reference, src/core/lbl/lbl_lineshape_voigt_lte.cpp:1652-1725)."""
+import numpy as np
+import pytest
+
+from arts_b200 import _abi as abi
+from arts_b200 import synth
+from tests.conftest import assert_propmat_close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c1_full_config(wsm, orc):
+    """BASELINE config 1: 1 species, 1k Voigt lines, 1e4 frequencies, 1 level; <= 1e-9 relative."""
+    c = synth.case_c1()
+    Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K = np.zeros((c.nf, 7))
+    wsm.spectral_propmatAddLines(K, None, c.f, (), abi.SPECIES_BATH, c.cat, c.atm)
+    assert_propmat_close(K[None], Kref)
+    assert (K[:, 0] > 0).all() and not K[:, 1:].any()
+
+
+def test_addlines_accumulates(wsm, orc):
+    """+= semantics of lbl_lineshape_voigt_lte.cpp:1691 on the caller's array."""
+    c = synth.case_c1(nl=100, nf=777)
+    Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K = np.full((c.nf, 7), 0.25)
+    wsm.spectral_propmatAddLines(K, None, c.f, (), abi.SPECIES_BATH, c.cat, c.atm)
+    assert_propmat_close((K - 0.25)[None], Kref, rtol=1e-9, atol_scale=1e-9)
+    assert np.array_equal(K[:, 1:], np.full((c.nf, 6), 0.25))
+
+
+@pytest.mark.parametrize("nf,nl,np_", [(1, 2, 1), (257, 64, 6), (513, 600, 3), (1025, 38, 2)])
+def test_ragged_sizes(wsm, orc, nf, nl, np_):
+    c = synth.tiny_case(nl=nl, nf=nf, np_=np_)
+    Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    assert_propmat_close(K, Kref)
+
+
+def test_select_species_and_sum(wsm, orc):
+    c = synth.tiny_case(nl=200, nf=400, np_=4)
+    cat = wsm.Catalog(c.cat)
+    Kall, _ = wsm.spectral_propmat_pathFromPath(cat, c.f, c.atm)
+    parts = []
+    for s in range(c.cat.n_species):
+        Ks, _ = wsm.spectral_propmat_pathFromPath(cat, c.f, c.atm, select_species=s)
+        Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm, select_species=s)
+        assert_propmat_close(Ks, Kref)
+        parts.append(Ks)
+    assert_propmat_close(sum(parts), Kall, rtol=1e-13)
+    cat.close()
+
+
+def test_per_level_frequency_grids(wsm, orc):
+    """freq_grid_path: one (wind-shifted) grid per level (src/m_ppvar.cc:47-77)."""
+    c = synth.tiny_case(nl=100, nf=300, np_=5)
+    f2 = c.f[None, :] * (1 + 1e-6 * np.arange(c.np_)[:, None])
+    Kref, _ = orc.propmat_levels(c.cat, f2, c.atm)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, f2, c.atm)
+    assert_propmat_close(K, Kref)
+
+
+@pytest.mark.parametrize("cutoff", [0.3e9, 2e9, 750e9])
+def test_byline_cutoff(wsm, orc, cutoff):
+    """LineByLineCutoffType::ByLine (lbl_lineshape_voigt_lte.cpp:591-616, lbl_data.cpp:61-68)."""
+    c = synth.case_c1(nl=300, nf=1500, cutoff=cutoff)
+    Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm, no_negative_absorption=0)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, no_negative_absorption=0)
+    assert_propmat_close(K, Kref, atol_scale=1e-11)
+    Kref1, _ = orc.propmat_levels(c.cat, c.f, c.atm, no_negative_absorption=1)
+    K1, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, no_negative_absorption=1)
+    assert_propmat_close(K1, Kref1, atol_scale=1e-11)
+
+
+@pytest.mark.parametrize("los", [(180.0, 0.0), (120.0, 30.0)])
+def test_zeeman_polarised(wsm, orc, los):
+    """BASELINE config 3 (reduced nf): full 7-component Propmat with Zeeman sub-lines and line mixing."""
+    c = synth.case_c3(nf=38 * 40, np_=7, los=los)
+    Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    cat = wsm.Catalog(c.cat)
+    assert sum(cat.counts()[1:]) == 4446 and cat.counts()[0] == 0
+    K, _ = wsm.spectral_propmat_pathFromPath(cat, c.f, c.atm)
+    assert_propmat_close(K, Kref)
+    assert np.abs(K[..., 1:]).max() > 0
+    cat.close()
+
+
+def test_line_mixing_clamp(wsm, orc):
+    """Per-band negative clamp (lbl_lineshape_voigt_lte.cpp:1688-1692) with strong line mixing."""
+    c = synth.case_c1(nl=40, nf=900)
+    c.cat.ls_type[:, abi.VAR_Y] = abi.TM_T1
+    rng = np.random.default_rng(5)
+    c.cat.ls_X[:, abi.VAR_Y, 0] = rng.uniform(-3e-3, 3e-3, len(c.cat.ls_species))
+    c.cat.ls_X[:, abi.VAR_Y, 1] = 0.8
+    c.cat.ls_type[:, abi.VAR_G] = abi.TM_T1
+    c.cat.ls_X[:, abi.VAR_G, 0] = rng.uniform(-1e-9, 1e-9, len(c.cat.ls_species))
+    c.cat.ls_X[:, abi.VAR_G, 1] = 0.5
+    for clamp in (0, 1):
+        Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm, no_negative_absorption=clamp)
+        K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, no_negative_absorption=clamp)
+        assert_propmat_close(K, Kref, atol_scale=1e-11)
+    Kref0, _ = orc.propmat_levels(c.cat, c.f, c.atm, no_negative_absorption=0)
+    assert (Kref0[..., 0] < 0).any(), "fixture must exercise the clamp"
+
+
+def test_temperature_models(wsm, orc):
+    """Every LineShapeModelType (lbl_temperature_model.h:62-283) through the prepare kernel."""
+    c = synth.case_c1(nl=90, nf=400)
+    n = len(c.cat.ls_species)
+    rng = np.random.default_rng(7)
+    types = [abi.TM_T0, abi.TM_T1, abi.TM_T2, abi.TM_T3, abi.TM_T4, abi.TM_T5, abi.TM_AER, abi.TM_DPL, abi.TM_POLY]
+    t = np.array(types)[np.arange(n) % len(types)]
+    c.cat.ls_type[:, abi.VAR_G0] = t
+    X = c.cat.ls_X[:, abi.VAR_G0]
+    X[:, 0] = rng.uniform(1e4, 3e4, n)
+    X[:, 1] = rng.uniform(0.5, 1.0, n)
+    X[:, 2] = rng.uniform(0.0, 0.3, n)
+    X[:, 3] = rng.uniform(0.0, 1.0, n)
+    aer = t == abi.TM_AER
+    X[aer, 1:] = X[aer, :1] * rng.uniform(0.8, 1.2, (aer.sum(), 3))
+    poly = t == abi.TM_POLY
+    X[poly, 1] = 10.0
+    X[poly, 2] = 1e-2
+    X[poly, 3] = 1e-5
+    t3 = t == abi.TM_T3
+    X[t3, 1] = 20.0
+    dpl = t == abi.TM_DPL
+    X[dpl, 2] = X[dpl, 0] * 0.1
+    for T in (230.0, 260.0, 300.0):
+        c.atm.T[:] = T
+        Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+        K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+        assert_propmat_close(K, Kref)
+
+
+def test_errors_are_loud(wsm):
+    c = synth.tiny_case()
+    c.cat.band_lineshape[0] = abi.LINESHAPE_OTHER
+    with pytest.raises(wsm.Ab200Error) as e:
+        wsm.Catalog(c.cat)
+    assert e.value.code == abi.ERR_UNSUPPORTED and "VP_LTE" in str(e.value)
+    c = synth.tiny_case()
+    with pytest.raises(wsm.Ab200Error) as e:
+        wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, select_species=99)
+    assert e.value.code == abi.ERR_INVALID
+    with pytest.raises(wsm.Ab200Error) as e:
+        wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option="linprop")
+    assert e.value.code == abi.ERR_UNSUPPORTED
+    with pytest.raises(ValueError):
+        wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg[:-1])

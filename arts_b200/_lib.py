@@ -59,6 +59,7 @@ def lib():
         _vp, _dp, C.c_int64, C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.POINTER(abi.Target), _dp, C.c_int32,
         C.c_int32, _dp, C.c_uint32,
     ]
+    L.ab200_path_set_grid_bounds.argtypes = [_vp, _dp]
     L.ab200_path_run_propmat.argtypes = [_vp]
     L.ab200_path_run_stokes.argtypes = [_vp]
     L.ab200_path_download.argtypes = [_vp, _dp, _dp, _dp, _dp]

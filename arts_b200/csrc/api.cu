@@ -72,6 +72,7 @@ struct ab200_path {
   double* d_K = nullptr;  // [np][k_pitch][7]
   double* d_I = nullptr;  // [nf][4]
 
+  std::vector<double> grid_bounds;  // [np][2] bounds of the whole (unsharded) grid, empty = use the uploaded grid's
   int64_t f_stride = 0;
   int32_t rte_option = AB200_RTE_LINSRC, no_neg = 1;
   uint32_t flags = 0;
@@ -170,6 +171,19 @@ int ab200_path_set_stream(ab200_path* p, void* stream) {
   return AB200_OK;
 }
 
+int ab200_path_set_grid_bounds(ab200_path* p, const double* bounds) {
+  if (!p) return set_error(AB200_ERR_INVALID, "ab200_path_set_grid_bounds: null path");
+  if (!bounds) {
+    p->grid_bounds.clear();
+    return AB200_OK;
+  }
+  for (int ip = 0; ip < p->np; ip++)
+    if (!(bounds[2 * ip] <= bounds[2 * ip + 1]))
+      return set_error(AB200_ERR_INVALID, "ab200_path_set_grid_bounds: bounds must be ascending and finite");
+  p->grid_bounds.assign(bounds, bounds + 2 * static_cast<size_t>(p->np));
+  return AB200_OK;
+}
+
 int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, const ab200_atm_path* atm,
                       int32_t select_species, int32_t no_negative_absorption, const ab200_target* targets,
                       const double* r, int32_t hse_derivative, int32_t rte_option, const double* I_bkg,
@@ -208,8 +222,13 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
     hH[ip] = std::hypot(mag[0], mag[1], mag[2]);
     for (int pol = 0; pol < 4; pol++) norm_view(pol, mag, los, hn + (static_cast<size_t>(ip) * 4 + pol) * 7);
     const double* fl = f + ip * f_level_stride;
-    hfr[2 * ip]     = p->nf ? fl[0] : 0.0;
-    hfr[2 * ip + 1] = p->nf ? fl[p->nf - 1] : 0.0;
+    if (!p->grid_bounds.empty()) {
+      hfr[2 * ip]     = p->grid_bounds[2 * ip];
+      hfr[2 * ip + 1] = p->grid_bounds[2 * ip + 1];
+    } else {
+      hfr[2 * ip]     = p->nf ? fl[0] : 0.0;
+      hfr[2 * ip + 1] = p->nf ? fl[p->nf - 1] : 0.0;
+    }
     hr[ip] = (r && ip < np - 1) ? r[ip] : 0.0;
     for (int s = 0; s < cat->n_species; s++) {
       const double v = atm->vmr[static_cast<size_t>(ip) * cat->n_species + s];

@@ -110,6 +110,22 @@ __device__ __forceinline__ void w_series(double x, double y, double E1, double& 
     sr += vm;
     si = __fma_rn(tm, vm, si);
   }
+  if (x < 1e-2) {
+    // n0 == 0 here: the +k / -k terms of the odd sum cancel down to O(x), which the running
+    // products p^k, p^-k cannot resolve (Im w -> 0 linearly at the line centre; the
+    // reference's Taylor branch, Faddeeva.cc:811-842).  Pair them analytically:
+    // g0 (p^k - p^-k) = 2 g0 sinh(2 a x k), |2 a x k| <= 0.125 -> 5-term odd series (2e-17).
+    si = 0.0;
+#pragma unroll 1
+    for (int k = 1; k <= fad::W; ++k) {
+      const double t  = fad::A * k;
+      const double u  = 2.0 * t * x;
+      const double u2 = u * u;
+      const double sh =
+          u * __fma_rn(u2, __fma_rn(u2, __fma_rn(u2, __fma_rn(u2, 1.0 / 362880.0, 1.0 / 5040.0), 1.0 / 120.0), 1.0 / 6.0), 1.0);
+      si = __fma_rn(t * fad::T[k], 2.0 * g0 * sh * fast_rcp(__fma_rn(t, t, y2)), si);
+    }
+  }
   wr = __fma_rn(0.5 * fad::CC * y, sr, re);
   wi = __fma_rn(0.5 * fad::CC, si, im);
 }

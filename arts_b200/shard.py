@@ -1,0 +1,94 @@
+"""Frequency sharding of the clear-sky path across the GPUs of one box.
+
+The path is independent per frequency end to end (line sum per f, RTE chain per f), so the
+ascending ``freq_grid`` is cut into contiguous blocks — the same split the reference uses for
+its OpenMP frequency chunks, ``matpack::omp_offset_count``
+(src/core/matpack/matpack_mdspan_algorithm.cc:4-18, called from src/m_lbl.cc:273) — one block
+per rank, catalog and atmosphere replicated.  There is no data-path collective in the compute;
+the only exchange is the gather of ``spectral_rad`` [nf, 4] (and nothing else) at the end.
+
+``torch.distributed`` is the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU
+tests); the arrays being gathered are the library's own device buffers, wrapped zero-copy.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def frequency_ranges(nf: int, n: int) -> list[tuple[int, int]]:
+    """``[(offset, nelem)] * n`` exactly as matpack::omp_offset_count(nf, n): ``nf // n`` elements
+    per block, the remainder to the last block."""
+    if n < 1:
+        raise ValueError("need at least one shard")
+    if n == 1:
+        return [(0, nf)]
+    dn = nf // n
+    out = [(i * dn, dn) for i in range(n - 1)]
+    out.append(((n - 1) * dn, nf - (n - 1) * dn))
+    return out
+
+
+def max_block(nf: int, n: int) -> int:
+    return max(c for _, c in frequency_ranges(nf, n))
+
+
+class DeviceArray:
+    """Zero-copy view of a library-owned device buffer for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+            "strides": None,
+        }
+
+
+def as_torch(ptr: int, shape, device):
+    import torch
+
+    return torch.as_tensor(DeviceArray(ptr, shape), device=device)
+
+
+def gather_spectral_rad(local, nf: int, group=None, dst: int | None = None):
+    """Gathers the per-rank blocks ``local`` [nelem_rank, 4] (torch tensor on the rank's device, or
+    CPU tensor with gloo) into the full ``spectral_rad`` [nf, 4].
+
+    Blocks are padded to the largest block so that one ``all_gather_into_tensor`` (NCCL
+    AllGather over NVLink/NVSwitch) moves everything; with ``dst`` set only that rank assembles
+    and returns the result (others return None).  The value at frequency j never depends on
+    the number of ranks: blocks are copied, not reduced.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    ranges = frequency_ranges(nf, world)
+    off, cnt = ranges[rank]
+    if tuple(local.shape) != (cnt, 4):
+        raise ValueError(f"rank {rank}: local block has shape {tuple(local.shape)}, expected {(cnt, 4)}")
+    blk = max(c for _, c in ranges)
+    send = local
+    if cnt != blk:
+        send = torch.zeros((blk, 4), dtype=local.dtype, device=local.device)
+        send[:cnt] = local
+    recv = torch.empty((world * blk, 4), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if dst is not None and rank != dst:
+        return None
+    if all(c == blk for _, c in ranges):
+        return recv[:nf]
+    out = torch.empty((nf, 4), dtype=local.dtype, device=local.device)
+    for r, (o, c) in enumerate(ranges):
+        out[o:o + c] = recv[r * blk:r * blk + c]
+    return out
+
+
+def shard_case(case, rank: int, world: int):
+    """The frequency shard of a synthetic ``Case`` for one rank (catalog / atmosphere shared)."""
+    import copy
+
+    off, cnt = frequency_ranges(case.nf, world)[rank]
+    c = copy.copy(case)
+    c.f = np.ascontiguousarray(case.f[off:off + cnt])
+    c.I_bkg = np.ascontiguousarray(case.I_bkg[off:off + cnt])
+    return c, off, cnt

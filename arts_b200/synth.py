@@ -282,8 +282,9 @@ def tiny_case(nl=64, nf=257, np_=6, seed=11, zeeman=False, cutoff=None, rte_opti
         c3.name = "tiny-zeeman"
         c3.targets = tuple(targets)
         return c3
-    cat = _multi_species_catalog(rng, 2, nl // 2, 2, 100e9, 130e9, [31.99, 18.01], [1.0, 30.0], decades=1.0,
-                                 cutoff=cutoff)
+    per_species = max(nl // 2, 1)
+    cat = _multi_species_catalog(rng, 2, per_species, 2 if per_species % 2 == 0 else 1, 100e9, 130e9, [31.99, 18.01],
+                                 [1.0, 30.0], decades=1.0, cutoff=cutoff)
     atm, r = _nadir_atmosphere(np_, 2, [1e-2, 0.21], z_top_km=40.0)
     f = np.linspace(100e9, 130e9, nf)
     I_bkg = np.zeros((nf, 4))

@@ -270,6 +270,11 @@ class Path:
                                       int(no_negative_absorption), tg, dptr(self._keep[2]), int(hse_derivative),
                                       _rte(rte_option), dptr(self._keep[3]), flags))
 
+    def set_grid_bounds(self, bounds):
+        """``bounds`` [np,2]: first / last frequency of the whole (unsharded) grid per level, or None."""
+        b = None if bounds is None else np.ascontiguousarray(np.broadcast_to(np.asarray(bounds, float), (self.np_, 2)))
+        check(lib().ab200_path_set_grid_bounds(self._h, dptr(b)))
+
     def run_propmat(self):
         check(lib().ab200_path_run_propmat(self._h))
 

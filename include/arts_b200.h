@@ -196,6 +196,12 @@ int ab200_path_upload(ab200_path *p, const double *f, int64_t f_level_stride, co
                       int32_t select_species, int32_t no_negative_absorption, const ab200_target *targets,
                       const double *r, int32_t hse_derivative, int32_t rte_option, const double *I_bkg,
                       uint32_t flags);
+/* Frequency sharding: the ByLine line selection band_data::active_lines (lbl_data.cpp:61-68) uses the first
+ * and last frequency of the grid of the call (lbl_lineshape_voigt_lte.cpp:1672-1680).  A rank that uploads
+ * only its shard of the grid passes the bounds of the WHOLE grid here (before ab200_path_upload) so that the
+ * result is bit-identical for every shard count.  bounds: [np][2] = {f_first, f_last} per level, or NULL to
+ * go back to the bounds of the uploaded grid. */
+int ab200_path_set_grid_bounds(ab200_path *p, const double *bounds);
 /* launches K1 (prepare) + K2/K3 (line sum) into the resident K, asynchronously */
 int ab200_path_run_propmat(ab200_path *p);
 /* launches the fused K4-K7 Stokes chain on the resident K, asynchronously */

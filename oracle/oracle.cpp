@@ -546,7 +546,14 @@ void calculate_band(double* pm, double* dpm, Index nf_total, const double* f_gri
   const int isot   = d.band_isot[ib];
   const int spec   = d.isot_species[isot];
 
-  band_shape_helper(lines, pos, d, ib, atm, fg[0], fg[f_n - 1], pol);
+  // fmin/fmax of band_data::active_lines (:1672-1680): the reference takes them from the
+  // frequency range of the call.  Its chunked stand-alone branch (m_lbl.cc:273-295) therefore
+  // selects a slightly different line set per OpenMP chunk when a pressure shift moves a line
+  // across the cutoff window of a chunk-edge frequency (thread-count dependent, DESIGN.md
+  // quirk 7).  The parity target is the unchunked call (m_lbl.cc:256-271, the branch every
+  // path-level caller takes, m_propmat.cc:42): the bounds are those of the whole grid of the
+  // call even when this oracle splits the grid over threads.
+  band_shape_helper(lines, pos, d, ib, atm, f_grid[0], f_grid[nf_total - 1], pol);
   if (lines.empty()) return;
   const bool has_cut   = d.band_cutoff_type[ib] != AB200_CUTOFF_NONE;
   const Numeric cutoff = has_cut ? d.band_cutoff_value[ib] : std::numeric_limits<Numeric>::infinity();

@@ -79,7 +79,7 @@ def test_zeeman_polarised(wsm, orc, los):
     c = synth.case_c3(nf=38 * 40, np_=7, los=los)
     Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm)
     cat = wsm.Catalog(c.cat)
-    assert sum(cat.counts()[1:]) == 4446 and cat.counts()[0] == 0
+    assert sum(cat.counts()[1:]) == 4332 and cat.counts()[0] == 0  # 4446 components, 114 with zero strength popped (:354-357)
     K, _ = wsm.spectral_propmat_pathFromPath(cat, c.f, c.atm)
     assert_propmat_close(K, Kref)
     assert np.abs(K[..., 1:]).max() > 0

@@ -1,0 +1,198 @@
+"""Pins of the CPU oracle against the reference's own golden vectors and fixtures (no GPU).
+
+The oracle (oracle/oracle.cpp + the reference's own Faddeeva.cc object) is the parity
+authority of the GPU tests, so it is itself checked here against everything the reference's
+test suite offers for this path without external data:
+
+* the 57-point w(z) known-answer test, 3rdparty/Faddeeva/Faddeeva.cc:4041-4195, threshold
+  1e-13 (:4222)  -> tests/golden/faddeeva_kat.json
+* exp(-K) of rtepack::tran against a Pade matrix exponential on the random K of
+  src/tests/test_rtepack.cc:12-33 (here scipy.linalg.expm)
+* the catalog-free fixture tests/core/linsrc/test_linsrc_convergence.py (orderings :95-96,
+  :181-182) and its brightness temperatures recorded in tests/golden/linsrc_convergence.json
+* closed forms: Planck / inverse Planck round trip, the scalar transmission limits.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+import scipy.special
+
+from arts_b200 import _abi as abi
+from arts_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _relerr(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def test_faddeeva_kat_57_points(orc):
+    d = json.load(open(os.path.join(GOLD, "faddeeva_kat.json")))
+    z = np.array([complex(float(a), float(b)) for a, b in d["z"]])
+    w = np.array([complex(float(a), float(b)) for a, b in d["w"]])
+    assert len(z) == 57
+    got = orc.faddeeva_w(z)
+    # the reference's criterion (Faddeeva.cc:4205-4222): relative error of each part, with
+    # inf/nan/zero handled like its relerr()
+    for g, r in zip(got, w):
+        for a, b in ((g.real, r.real), (g.imag, r.imag)):
+            if np.isnan(b):
+                assert np.isnan(a)
+            elif np.isinf(b):
+                assert a == b
+            elif b == 0:
+                assert abs(a) <= 1e-13
+            else:
+                assert abs(a - b) / abs(b) <= d["threshold"], (g, r)
+
+
+def test_faddeeva_is_scipy_wofz(orc):
+    """scipy.special.wofz is the same MIT Faddeeva package: the reference object code must agree with it."""
+    rng = np.random.default_rng(0)
+    z = rng.uniform(-40, 40, 20000) + 1j * 10 ** rng.uniform(-12, 2, 20000)
+    got, ref = orc.faddeeva_w(z), scipy.special.wofz(z)
+    assert _relerr(got, ref).max() <= 4e-16 * 64
+
+
+def _propmat_matrix(k):
+    a, b, c, d, u, v, w = k
+    return np.array([[a, b, c, d], [b, a, u, v], [c, -u, a, w], [d, -v, -w, a]])
+
+
+def test_tran_vs_expm_random_K(orc):
+    """src/tests/test_rtepack.cc:12-33: K = [U(0,0.01), U(-0.01,0.01) x 6], T = tran(K, K, 1)() vs expm(-K).
+
+    The reference's literal eigenvalue arithmetic (rtepack_transmission.cc:67-70 takes the square root
+    twice) deviates from the true exponential at O(|K r|^2); the variant behind
+    AB200_FLAG_TRAN_EXACT uses the true eigenvalue squares and agrees with expm down to the reference's
+    own ``too_small = 1e-4`` series cut (:20,77-111).  Both are pinned so the GPU can be compared with
+    either; the literal one is the parity target (it IS the reference's CPU path)."""
+    rng = np.random.default_rng(7)
+    worst_lit, worst_ex = 0.0, 0.0
+    for _ in range(100):
+        k = np.concatenate([rng.uniform(0, 0.01, 1), rng.uniform(-0.01, 0.01, 6)])
+        ref = scipy.linalg.expm(-_propmat_matrix(k))
+        T_lit, _ = orc.tran(k, k, 1.0, 0)
+        T_ex, _ = orc.tran(k, k, 1.0, abi.FLAG_TRAN_EXACT)
+        worst_lit = max(worst_lit, np.abs(T_lit - ref).max())
+        worst_ex = max(worst_ex, np.abs(T_ex - ref).max())
+    assert worst_ex <= 2e-11, worst_ex
+    assert 1e-7 < worst_lit <= 2e-5, worst_lit  # the quirk is real and of this size at |K r| ~ 1e-2
+
+
+def test_tran_exact_vs_expm_large_K(orc):
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        k = np.concatenate([rng.uniform(0.5, 2, 1), rng.uniform(-1, 1, 6)])
+        r = rng.uniform(0.1, 3.0)
+        ref = scipy.linalg.expm(-r * _propmat_matrix(k))
+        T_ex, _ = orc.tran(k, k, r, abi.FLAG_TRAN_EXACT)
+        np.testing.assert_allclose(T_ex, ref, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
+
+
+def test_linsrc_lambda_is_the_source_integral(orc):
+    """Lambda of tran::linsrc (rtepack_transmission.cc:207-275) against quadrature of its defining
+    integral  int_0^1 exp(-K r s) ds  ... checked through the identity  Lambda * (-K r) = T - 1."""
+    rng = np.random.default_rng(9)
+    for _ in range(30):
+        k = np.concatenate([rng.uniform(0.5, 2, 1), rng.uniform(-0.4, 0.4, 6)])
+        r = rng.uniform(0.1, 2.0)
+        T, L = orc.tran(k, k, r, abi.FLAG_TRAN_EXACT)
+        M = -r * _propmat_matrix(k)
+        np.testing.assert_allclose(L @ M, T - np.eye(4), rtol=1e-10, atol=1e-12)
+
+
+def _linsrc_fixture(orc, varying):
+    """Inputs exactly as tests/core/linsrc/test_linsrc_convergence.py:24-92 / :110-178."""
+    f = np.array([100e9])
+    out = {"constant": [], "linsrc": []}
+    N, scl = 2**12, 1.0
+    while N >= 2:
+        k = np.linspace(1e-2, 1e-4, N) if varying else np.full(N, 1e-2)
+        K = np.zeros((N, 1, 7))
+        K[:, 0, 0] = k
+        Tlev = np.linspace(200.0, 300.0, N)
+        r = np.full(N - 1, scl)
+        bkg = np.zeros((1, 4))
+        bkg[0, 0] = orc.planck(f, 100.0)[0]
+        for opt in ("linsrc", "constant"):
+            Tr, Lr, Pr, dTr, dLr = orc.tramat(K, None, r, None, opt)
+            Jr, dJr = orc.srcvec(K, f, Tlev)
+            Ir, _ = orc.rte_emission(opt, Tr, Lr, Pr, dTr, dLr, Jr, dJr, bkg)
+            out[opt].append(float(orc.planck_tb(f, Ir)[0, 0]))
+        N //= 2
+        scl *= 2
+    return out
+
+
+@pytest.mark.parametrize("varying", [False, True])
+def test_linsrc_convergence_fixture(orc, varying):
+    out = _linsrc_fixture(orc, varying)
+    lin, linsrc = np.array(out["constant"]), np.array(out["linsrc"])
+    # the reference's assertion (:95-96, :181-182)
+    assert np.all(lin / lin[0] >= linsrc / linsrc[0])
+    # recorded brightness temperatures (made by tests/golden/make_oracle_goldens.py from this oracle;
+    # they pin the oracle against drift and are what the GPU test compares with on the box)
+    gold = json.load(open(os.path.join(GOLD, "linsrc_convergence.json")))["varying" if varying else "constant_k"]
+    np.testing.assert_allclose(lin, gold["constant"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(linsrc, gold["linsrc"], rtol=0, atol=1e-9)
+    # physics of the fixture: the finest grid is converged to < 1 mK between the two options
+    assert abs(lin[0] - linsrc[0]) < 1e-3
+
+
+def test_planck_roundtrip_and_tb_operator(orc):
+    f = np.linspace(1e9, 3e13, 500)
+    for T in (2.735, 100.0, 288.0):
+        B = orc.planck(f, T)
+        a, b = 2 * synth.H / synth.C0**2, synth.H / synth.KB
+        np.testing.assert_allclose(B, a * f**3 / np.expm1(b * f / T), rtol=1e-15)
+        I = np.zeros((len(f), 4))
+        I[:, 0] = B
+        I[:, 1] = 0.1 * B
+        tb = orc.planck_tb(f, I)
+        np.testing.assert_allclose(tb[:, 0], T, rtol=1e-12)
+        # spectral_radiance_transform_operator.cc:67-84: Q -> Tb((I+Q)/2) - Tb((I-Q)/2)
+        inv = lambda x: (b * f) / np.log1p(a * f**3 / x)
+        np.testing.assert_allclose(tb[:, 1], inv(0.55 * B) - inv(0.45 * B), rtol=1e-12)
+        assert np.all(tb[:, 2:] == 0)
+
+
+def test_propmat_single_line_against_direct_formula(orc):
+    """One Voigt line, no shift: K.A = scl(f) * Re[s * wofz(z)] written out from SURVEY Appendix A."""
+    c = synth.case_c1(nl=1, nf=501)
+    cat = c.cat
+    K, _ = orc.propmat_levels(cat, c.f, c.atm)
+    T, P = c.atm.T[0], c.atm.P[0]
+    kB, h, c0 = synth.KB, synth.H, synth.C0
+    # two broadeners: self (vmr) + bath (1 - vmr); T1 model X0 (T0/T)^X1, G0 and D0 scale with P
+    vmr = c.atm.vmr[0, 0]
+    X = cat.ls_X
+    t1 = lambda i, v: X[i, v, 0] * (296.0 / T) ** X[i, v, 1]
+    G0 = P * (vmr * t1(0, abi.VAR_G0) + (1 - vmr) * t1(1, abi.VAR_G0))
+    D0 = P * (vmr * t1(0, abi.VAR_D0) + (1 - vmr) * t1(1, abi.VAR_D0))
+    f0 = cat.f0[0]
+    R = kB * 6.02214076e23
+    gd = np.sqrt(2000 * R / c0**2 * T / 31.9898) * (f0 + D0)
+    s0 = cat.a[0] * cat.gu[0] * np.exp(-cat.e0[0] / (kB * T)) / (f0**3 * c.atm.Q[0, 0])
+    s = (1 / np.sqrt(np.pi)) / gd * 0.995 * vmr * s0
+    z = (c.f - (f0 + D0)) / gd + 1j * G0 / gd
+    scl = -(P / (kB * T)) * c.f * np.expm1(-h * c.f / (kB * T)) * c0**2 / (8 * np.pi)
+    ref = scl * s * scipy.special.wofz(z).real
+    np.testing.assert_allclose(K[0, :, 0], ref, rtol=2e-13)
+    assert np.all(K[0, :, 1:] == 0)
+
+
+def test_propmat_is_linear_in_lines_and_thread_count_invariant(orc):
+    """Sum over two disjoint catalogs equals the joint catalog (different species -> separate bands),
+    and the per-frequency result does not depend on the OpenMP chunking (m_lbl.cc:273-295)."""
+    c = synth.tiny_case(nl=64, nf=300, np_=3)
+    Kall, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K0, _ = orc.propmat_levels(c.cat, c.f, c.atm, select_species=0)
+    K1, _ = orc.propmat_levels(c.cat, c.f, c.atm, select_species=1)
+    np.testing.assert_allclose(K0 + K1, Kall, rtol=1e-14)
+    Ka, _ = orc.propmat_levels(c.cat, c.f[:137], c.atm)
+    assert np.array_equal(Ka, Kall[:, :137])

@@ -39,6 +39,11 @@ def lib():
     L = C.CDLL(SO_PATH)
     L.ab200_last_error.restype = C.c_char_p
     L.ab200_device_count.restype = C.c_int
+    L.ab200_set_device.argtypes = [C.c_int]
+    L.ab200_set_thread_stream.argtypes = [_vp]
+    L.ab200_path_set_timing.argtypes = [_vp, C.c_int]
+    L.ab200_path_get_timings.argtypes = [_vp, _dp, C.POINTER(C.c_int64)]
+    L.ab200_path_region_histogram.argtypes = [_vp, C.c_int64, C.c_uint64, _dp]
     L.ab200_launch_count.restype = C.c_int64
     L.ab200_launch_count.argtypes = [C.c_int]
     L.ab200_catalog_create.argtypes = [C.POINTER(abi.CatalogDesc), C.POINTER(_vp)]

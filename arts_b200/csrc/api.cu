@@ -72,6 +72,13 @@ struct ab200_path {
   double* d_K = nullptr;  // [np][k_pitch][7]
   double* d_I = nullptr;  // [nf][4]
 
+  // per-kernel timing (ab200_path_set_timing)
+  bool timing = false;
+  struct Pending { int cls; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> free_events;
+  double t_ms[4] = {0, 0, 0, 0};
+  int64_t t_n[4] = {0, 0, 0, 0};
   std::vector<double> grid_bounds;  // [np][2] bounds of the whole (unsharded) grid, empty = use the uploaded grid's
   int64_t f_stride = 0;
   int32_t rte_option = AB200_RTE_LINSRC, no_neg = 1;
@@ -83,6 +90,8 @@ struct ab200_path {
     cudaFree(d_flags); cudaFree(d_K); cudaFree(d_I);
     if (h_small) cudaFreeHost(h_small);
     if (h_segs) cudaFreeHost(h_segs);
+    for (auto& q : pending) { cudaEventDestroy(q.e0); cudaEventDestroy(q.e1); }
+    for (auto e : free_events) cudaEventDestroy(e);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -98,6 +107,11 @@ int ab200_device_count(void) {
     return 0;
   }
   return n;
+}
+
+int ab200_set_device(int device) {
+  AB_CUDA(cudaSetDevice(device));
+  return AB200_OK;
 }
 
 int64_t ab200_launch_count(int reset) {
@@ -271,6 +285,59 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   return AB200_OK;
 }
 
+namespace {
+// RAII-free scoped timer: records an event pair around one launch when timing is on
+struct LaunchTimer {
+  ab200_path* p;
+  int cls;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  LaunchTimer(ab200_path* p_, int cls_) : p(p_), cls(cls_) {
+    if (!p->timing) return;
+    auto get = [&]() {
+      cudaEvent_t e = nullptr;
+      if (!p->free_events.empty()) { e = p->free_events.back(); p->free_events.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    e0 = get();
+    e1 = get();
+    cudaEventRecord(e0, p->stream);
+  }
+  void stop() {
+    if (!e0) return;
+    cudaEventRecord(e1, p->stream);
+    p->pending.push_back({cls, e0, e1});
+    e0 = nullptr;
+  }
+};
+
+void fill_params(const ab200_path* p, int lev0, PrepareParams& pp, SumParams& sp) {
+  const ab200_catalog* cat = p->cat;
+  pp = PrepareParams{};
+  pp.f0 = cat->d_f0; pp.a = cat->d_a; pp.e0 = cat->d_e0; pp.gu = cat->d_gu; pp.T0 = cat->d_T0;
+  pp.line_isot = cat->d_line_isot; pp.ls_offset = cat->d_ls_offset; pp.ls_species = cat->d_ls_species;
+  pp.ls_type = cat->d_ls_type; pp.ls_X = cat->d_ls_X; pp.isot_species = cat->d_isot_species;
+  pp.isot_mass = cat->d_isot_mass; pp.sub_parent = cat->d_sub_parent; pp.sub_Sz = cat->d_sub_Sz;
+  pp.sub_dzc = cat->d_sub_dzc; pp.tile_cutoff = cat->d_tile_cutoff;
+  pp.n_species = cat->n_species; pp.n_isot = cat->n_isot; pp.ntiles = cat->ntiles;
+  pp.T = p->d_T + lev0; pp.P = p->d_P + lev0; pp.H = p->d_H + lev0;
+  pp.vmr = p->d_vmr + static_cast<size_t>(lev0) * cat->n_species;
+  pp.isorat = p->d_isorat + static_cast<size_t>(lev0) * cat->n_isot;
+  pp.Q = p->d_Q + static_cast<size_t>(lev0) * cat->n_isot;
+  pp.frange = p->d_frange + 2 * static_cast<size_t>(lev0);
+  pp.prep = p->d_prep; pp.summary = p->d_summary; pp.flags = p->d_flags;
+
+  sp = SumParams{};
+  sp.f = p->d_f + static_cast<size_t>(lev0) * p->f_stride;
+  sp.f_stride = p->f_stride; sp.nf = p->nf; sp.k_pitch = p->k_pitch;
+  sp.T = p->d_T + lev0; sp.P = p->d_P + lev0;
+  sp.npm = p->d_npm + static_cast<size_t>(lev0) * 28;
+  sp.prep = p->d_prep; sp.summary = p->d_summary; sp.tile_count = cat->d_tile_count; sp.ntiles = cat->ntiles;
+  sp.no_negative_absorption = p->no_neg;
+  sp.K = p->d_K + static_cast<size_t>(lev0) * p->k_pitch * 7;
+}
+}  // namespace
+
 int ab200_path_run_propmat(ab200_path* p) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_propmat: path not uploaded");
   const ab200_catalog* cat = p->cat;
@@ -281,35 +348,81 @@ int ab200_path_run_propmat(ab200_path* p) {
   const size_t nseg = cat->segments.size();
   for (int lev0 = 0; lev0 < p->np; lev0 += p->levels_per_batch) {
     const int nlev = std::min(p->levels_per_batch, p->np - lev0);
-    PrepareParams pp{};
-    pp.f0 = cat->d_f0; pp.a = cat->d_a; pp.e0 = cat->d_e0; pp.gu = cat->d_gu; pp.T0 = cat->d_T0;
-    pp.line_isot = cat->d_line_isot; pp.ls_offset = cat->d_ls_offset; pp.ls_species = cat->d_ls_species;
-    pp.ls_type = cat->d_ls_type; pp.ls_X = cat->d_ls_X; pp.isot_species = cat->d_isot_species;
-    pp.isot_mass = cat->d_isot_mass; pp.sub_parent = cat->d_sub_parent; pp.sub_Sz = cat->d_sub_Sz;
-    pp.sub_dzc = cat->d_sub_dzc; pp.tile_cutoff = cat->d_tile_cutoff;
-    pp.n_species = cat->n_species; pp.n_isot = cat->n_isot; pp.ntiles = cat->ntiles;
-    pp.T = p->d_T + lev0; pp.P = p->d_P + lev0; pp.H = p->d_H + lev0;
-    pp.vmr = p->d_vmr + static_cast<size_t>(lev0) * cat->n_species;
-    pp.isorat = p->d_isorat + static_cast<size_t>(lev0) * cat->n_isot;
-    pp.Q = p->d_Q + static_cast<size_t>(lev0) * cat->n_isot;
-    pp.frange = p->d_frange + 2 * static_cast<size_t>(lev0);
-    pp.prep = p->d_prep; pp.summary = p->d_summary; pp.flags = p->d_flags;
-    AB_TRY(launch_prepare(pp, nlev, p->stream));
-
-    SumParams sp{};
-    sp.f = p->d_f + static_cast<size_t>(lev0) * p->f_stride;
-    sp.f_stride = p->f_stride; sp.nf = p->nf; sp.k_pitch = p->k_pitch;
-    sp.T = p->d_T + lev0; sp.P = p->d_P + lev0;
-    sp.npm = p->d_npm + static_cast<size_t>(lev0) * 28;
-    sp.prep = p->d_prep; sp.summary = p->d_summary; sp.tile_count = cat->d_tile_count; sp.ntiles = cat->ntiles;
-    sp.no_negative_absorption = p->no_neg;
-    sp.K = p->d_K + static_cast<size_t>(lev0) * p->k_pitch * 7;
+    PrepareParams pp;
+    SumParams sp;
+    fill_params(p, lev0, pp, sp);
+    {
+      LaunchTimer t(p, 0);
+      AB_TRY(launch_prepare(pp, nlev, p->stream));
+      t.stop();
+    }
     for (int mode = 0; mode < 2; mode++) {
       sp.segs = p->d_segs + mode * nseg;
       sp.nsegs = p->nsegs[mode];
+      if (sp.nsegs == 0) continue;
+      LaunchTimer t(p, 1 + mode);
       AB_TRY(launch_sum(sp, nlev, mode, p->stream));
+      t.stop();
     }
   }
+  return AB200_OK;
+}
+
+int ab200_path_set_timing(ab200_path* p, int on) {
+  if (!p) return set_error(AB200_ERR_INVALID, "ab200_path_set_timing: null path");
+  p->timing = on != 0;
+  return AB200_OK;
+}
+
+int ab200_path_get_timings(ab200_path* p, double ms[4], int64_t launches[4]) {
+  if (!p || !ms || !launches) return set_error(AB200_ERR_INVALID, "ab200_path_get_timings: null argument");
+  AB_CUDA(cudaSetDevice(p->cat->device));
+  AB_CUDA(cudaStreamSynchronize(p->stream));
+  for (auto& q : p->pending) {
+    float t = 0.f;
+    AB_CUDA(cudaEventElapsedTime(&t, q.e0, q.e1));
+    p->t_ms[q.cls] += t;
+    p->t_n[q.cls] += 1;
+    p->free_events.push_back(q.e0);
+    p->free_events.push_back(q.e1);
+  }
+  p->pending.clear();
+  for (int i = 0; i < 4; i++) {
+    ms[i] = p->t_ms[i];
+    launches[i] = p->t_n[i];
+    p->t_ms[i] = 0;
+    p->t_n[i] = 0;
+  }
+  return AB200_OK;
+}
+
+int ab200_path_region_histogram(ab200_path* p, int64_t samples_per_level, uint64_t seed, double out[8]) {
+  if (!p || !out) return set_error(AB200_ERR_INVALID, "ab200_path_region_histogram: null argument");
+  if (!p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_region_histogram: path not uploaded");
+  for (int i = 0; i < 8; i++) out[i] = 0.0;
+  const ab200_catalog* cat = p->cat;
+  if (cat->ntiles == 0 || p->nf == 0 || p->np == 0) return AB200_OK;
+  AB_CUDA(cudaSetDevice(cat->device));
+  double* d_out = nullptr;
+  AB_TRY(dev_alloc(&d_out, 8));
+  cudaError_t e = cudaMemsetAsync(d_out, 0, 8 * sizeof(double), p->stream);
+  int rc = 0;
+  const size_t nseg = cat->segments.size();
+  for (int lev0 = 0; lev0 < p->np && !rc && e == cudaSuccess; lev0 += p->levels_per_batch) {
+    const int nlev = std::min(p->levels_per_batch, p->np - lev0);
+    PrepareParams pp;
+    SumParams sp;
+    fill_params(p, lev0, pp, sp);
+    sp.segs  = p->d_segs + nseg;  // the mode-1 list carries the cutoff windows
+    sp.nsegs = p->nsegs[1];
+    rc = launch_prepare(pp, nlev, p->stream);
+    if (!rc) rc = launch_region_histogram(sp, nlev, samples_per_level, seed + 7919ull * lev0, d_out, p->stream);
+  }
+  if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 8 * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+  if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  cudaFree(d_out);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "ab200_path_region_histogram", __FILE__, __LINE__);
   return AB200_OK;
 }
 
@@ -321,7 +434,10 @@ int ab200_path_run_stokes(ab200_path* p) {
   sp.np = p->np; sp.nf = p->nf; sp.K = p->d_K; sp.k_pitch = p->k_pitch; sp.f = p->d_f; sp.f_stride = p->f_stride;
   sp.T = p->d_T; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
   sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
-  return launch_stokes_chain(sp, p->stream);
+  LaunchTimer t(p, 3);
+  AB_TRY(launch_stokes_chain(sp, p->stream));
+  t.stop();
+  return AB200_OK;
 }
 
 static int check_flags(ab200_path* p) {
@@ -373,6 +489,8 @@ struct PathCache {
   int32_t np = -1, nq = -1;
 };
 thread_local PathCache t_cache;
+thread_local bool t_stream_set = false;
+thread_local void* t_stream = nullptr;
 
 // one cached workspace per host thread: the shims are called repeatedly with the same
 // shapes (once per (pos, los) under measurement_vecFromSensor, src/m_rad.cc:321-343)
@@ -380,6 +498,7 @@ int cached_path(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab
   PathCache& c = t_cache;
   if (c.path && c.cat == cat && c.nf == nf && c.np == np && c.nq == nq && c.ntiles == cat->ntiles) {
     *out = c.path;
+    if (t_stream_set && c.path->stream != static_cast<cudaStream_t>(t_stream)) AB_TRY(ab200_path_set_stream(c.path, t_stream));
     return AB200_OK;
   }
   if (c.path) {
@@ -388,9 +507,20 @@ int cached_path(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab
   }
   AB_TRY(ab200_path_create(cat, nf, np, nq, out));
   c = PathCache{*out, cat, nf, cat->ntiles, np, nq};
+  if (t_stream_set) AB_TRY(ab200_path_set_stream(*out, t_stream));
   return AB200_OK;
 }
 }  // namespace
+
+int ab200_set_thread_stream(void* stream) {
+  t_stream_set = stream != nullptr;
+  t_stream     = stream;
+  if (!t_stream_set && t_cache.path && !t_cache.path->own_stream) {  // back to a private stream
+    ab200_path_destroy(t_cache.path);
+    t_cache = PathCache{};
+  }
+  return AB200_OK;
+}
 
 // drop the calling thread's cached workspace (call before destroying a catalog it was built on)
 int ab200_release_thread_cache(void) {

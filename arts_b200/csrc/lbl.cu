@@ -20,6 +20,7 @@
 // tile from zero and added to the segment sum in tile order (a function of the catalog
 // only).  The kernel is FP64-pipe bound; bytes are negligible (8 KB of line data per 131072
 // evaluations).
+#include <algorithm>
 #include <cfloat>
 
 #include "catalog.hpp"
@@ -545,6 +546,66 @@ int launch_faddeeva(int64_t n, const double* zr, const double* zi, double* wr, d
   if (n == 0) return 0;
   faddeeva_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(n, zr, zi, wr, wi);
   count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// region histogram (roofline weights; not on the product path)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void region_histogram_kernel(SumParams p, int64_t samples_per_level, uint64_t seed, double* out) {
+  __shared__ unsigned long long h[8];
+  if (threadIdx.x < 8) h[threadIdx.x] = 0ull;
+  __syncthreads();
+  const int lev = blockIdx.y;
+  const double* __restrict__ fg   = p.f + int64_t(lev) * p.f_stride;
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < samples_per_level;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const uint64_t r1 = mix64(seed + 0x10001ull * uint64_t(lev) + 2 * uint64_t(i));
+    const uint64_t r2 = mix64(r1 + 1);
+    const int64_t slot = int64_t(r1 % uint64_t(p.ntiles * TL));
+    const int64_t tile = slot / TL;
+    const int l        = int(slot % TL);
+    if (l >= p.tile_count[tile]) continue;  // padding slot: redraw is not needed for a uniform sample of real lines
+    const double* g0 = prep + tile * tile_doubles() + (int64_t(0) * TL + l) * REC_GROUP;
+    const double* g1 = prep + tile * tile_doubles() + (int64_t(1) * TL + l) * REC_GROUP;
+    const double f0s = g0[0], igd = g1[0], y = g1[1];
+    const double f = fg[int64_t(r2 % uint64_t(p.nf))];
+    atomicAdd(&h[7], 1ull);
+    // segment of the tile (cutoff window): linear scan, nsegs is small
+    double cutoff = DBL_MAX;
+    for (int is = 0; is < p.nsegs; is++)
+      if (tile >= p.segs[is].tile_begin && tile < p.segs[is].tile_end && p.segs[is].has_cutoff) cutoff = p.segs[is].cutoff;
+    if (g0[1] == -1.0 || !(f0s >= f - cutoff && f0s <= f + cutoff)) {
+      atomicAdd(&h[6], 1ull);
+      continue;
+    }
+    const double x = fabs(igd * (f - f0s));
+    if (x + y > 1e7) atomicAdd(&h[0], 1ull);
+    else if (x + y > FAR_LIMIT) atomicAdd(&h[1], 1ull);
+    else if (cf_region(x, y)) {
+      atomicAdd(&h[2], 1ull);
+      atomicAdd(&h[5], (unsigned long long)floor(3.9 + 11.398 / (0.08254 * x + 0.1421 * y + 0.2023)));
+    } else if (x < 10.0) atomicAdd(&h[3], 1ull);
+    else atomicAdd(&h[4], 1ull);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && h[threadIdx.x]) atomicAdd(&out[threadIdx.x], double(h[threadIdx.x]));
+}
+
+int launch_region_histogram(const SumParams& p, int nlev, int64_t samples_per_level, uint64_t seed, double* d_out,
+                            cudaStream_t stream) {
+  if (p.ntiles == 0 || p.nf == 0 || nlev == 0 || samples_per_level <= 0) return 0;
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>(296, (samples_per_level + 255) / 256)), static_cast<unsigned>(nlev));
+  region_histogram_kernel<<<grid, 256, 0, stream>>>(p, samples_per_level, seed, d_out);
   AB_CUDA(cudaGetLastError());
   return 0;
 }

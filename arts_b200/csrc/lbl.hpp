@@ -48,6 +48,9 @@ struct SumParams {
 
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream);
 int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream);
+// region histogram of the evaluations of one batch of levels (measurement helper, see arts_b200.h)
+int launch_region_histogram(const SumParams& p, int nlev, int64_t samples_per_level, uint64_t seed, double* d_out,
+                            cudaStream_t stream);
 int launch_faddeeva(int64_t n, const double* zr, const double* zi, double* wr, double* wi, cudaStream_t stream);
 int launch_dfma_peak(int iters, int blocks, double* d_out, cudaStream_t stream);
 

@@ -40,6 +40,15 @@ def device_count() -> int:
     return int(lib().ab200_device_count())
 
 
+def set_device(device: int):
+    check(lib().ab200_set_device(int(device)))
+
+
+def set_thread_stream(stream):
+    """cudaStream_t (int) for this thread's host-buffer entry points, or None for the library's own."""
+    check(lib().ab200_set_thread_stream(C.c_void_p(int(stream)) if stream else C.c_void_p()))
+
+
 class Catalog:
     """Device-resident ``AbsorptionBands`` (ab200_catalog); immutable, shareable."""
 
@@ -274,6 +283,22 @@ class Path:
         """``bounds`` [np,2]: first / last frequency of the whole (unsharded) grid per level, or None."""
         b = None if bounds is None else np.ascontiguousarray(np.broadcast_to(np.asarray(bounds, float), (self.np_, 2)))
         check(lib().ab200_path_set_grid_bounds(self._h, dptr(b)))
+
+    def set_timing(self, on=True):
+        check(lib().ab200_path_set_timing(self._h, int(bool(on))))
+
+    def timings(self):
+        """{kernel class: (ms, launches)} since the last call; synchronises the path's stream."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        check(lib().ab200_path_get_timings(self._h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(("prepare", "sum_real", "sum_cplx", "stokes"))}
+
+    def region_histogram(self, samples_per_level=200_000, seed=1):
+        """Sampled histogram of the reference's Faddeeva regions over this path's evaluations (see header)."""
+        out = (C.c_double * 8)()
+        check(lib().ab200_path_region_histogram(self._h, int(samples_per_level), int(seed), out))
+        return np.array(out[:])
 
     def run_propmat(self):
         check(lib().ab200_path_run_propmat(self._h))

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the clear-sky spectral hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: BASELINE.json configs[1] ("C2"): 5 species, 1e5 synthetic Voigt lines, 100-level nadir
+path, 1e5 frequencies PER GPU (weak scaling: the N-GPU run uses an N x 1e5-point grid over the
+same 1-1000 GHz span, cut into contiguous shards like the reference's OpenMP frequency chunks),
+linsrc Stokes chain, spectral_rad gathered over NCCL.  One "step" = one pass of the hot path over
+that input: line prepare (K1) + line sum (K2/K3) + fused Stokes chain (K4-K6) + gather.
+
+Printed (rank 0, one JSON line): `value` = line*freq*level evaluations per second of the whole job
+with inputs resident in HBM, timed with CUDA events, max over ranks; `e2e` = the same metric
+through the reference-facing C-ABI call with HOST buffers (H2D and D2H inside the timed region);
+`roofline` for the dominant kernel (FP64-pipe bound line sum: algorithmic FLOPs of SURVEY.md 8(d)
+over the event-timed kernel duration, against the DFMA peak measured in this run);
+`roofline_stokes` (HBM bound); `cpu_baseline` = the CPU oracle (a port of the reference's path
+linked with the reference's own Faddeeva.cc) on this box's host cores on a bounded sample.
+
+`--impl reference` times that CPU implementation alone, on the same config and metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "line*freq*level evals/s"
+UNIT = "evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rte", default="linsrc", choices=["linsrc", "constant"])
+    # workload size knobs (defaults = BASELINE configs[1]); smaller values are for quick checks only
+    ap.add_argument("--lines-per-species", type=int, default=20_000)
+    ap.add_argument("--nf-per-gpu", type=int, default=100_000)
+    ap.add_argument("--levels", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, world):
+    from arts_b200 import synth
+
+    nf = args.nf_per_gpu * world
+    case = synth.case_c2(lines_per_species=args.lines_per_species, nf=nf, np_=args.levels, rte_option=args.rte)
+    name = (f"C2 (BASELINE configs[1]): 5 species x {args.lines_per_species} Voigt lines, {args.levels}-level nadir path, "
+            f"{args.nf_per_gpu} frequencies per GPU over 1-1000 GHz, {args.rte} Stokes chain")
+    return case, name
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 7]
+        os.unlink(self.f.name)
+        sm, reasons, smax, pw = [], set(), None, []
+        for r in rows:
+            r = [x.strip() for x in r]
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+# --------------------------------------------------------------------------- CPU arm
+def oracle_sample(case, idx, rte):
+    """Runs the CPU oracle on the frequency subset ``idx`` of ``case``; returns seconds."""
+    from tests import oracle_lib as orc
+
+    f = np.ascontiguousarray(case.f[idx])
+    bkg = np.ascontiguousarray(case.I_bkg[idx])
+    t0 = time.perf_counter()
+    orc.clearsky_emission(case.cat, f, case.atm, case.r, bkg, rte_option=rte)
+    return time.perf_counter() - t0
+
+
+def calibrate_sample(case, rte, target_s):
+    """Strided (grid-representative) frequency sample sized so that one oracle pass takes ~target_s."""
+    from tests import oracle_lib as orc
+
+    nthreads = orc.num_threads()
+    n0 = max(nthreads, 16)
+    idx = np.linspace(0, case.nf - 1, n0).astype(np.int64)
+    oracle_sample(case, idx[: max(nthreads // 2, 2)], rte)  # page in
+    t = oracle_sample(case, idx, rte)
+    n = int(min(case.nf, max(n0, n0 * target_s / max(t, 1e-6))))
+    return np.unique(np.linspace(0, case.nf - 1, n).astype(np.int64)), nthreads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port + the reference's Faddeeva object) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    case, name = workload(args, 1)
+    idx, cores = calibrate_sample(case, args.rte, args.cpu_seconds)
+    for _ in range(args.warmup):
+        oracle_sample(case, idx[: max(len(idx) // 8, 1)], args.rte)
+    ts = [oracle_sample(case, idx, args.rte) for _ in range(args.steps)]
+    evals = float(case.n_lines) * len(idx) * case.np_
+    value = evals * len(ts) / sum(ts)
+    sample = f"{len(idx)} of {case.nf} frequencies (uniform stride) x all {case.n_lines} lines x {case.np_} levels per step"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "oracle/oracle.cpp (restatement of the reference's lbl + rtepack path) linked with the "
+                                 "reference's own 3rdparty/Faddeeva/Faddeeva.cc object; the reference itself needs "
+                                 "GCC >= 14 and external data and cannot be built here (DESIGN.md)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage2": {"metric": "freq*level Stokes steps/s", "note": "included in the step; < 0.1% of CPU time"},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from arts_b200 import roofline, shard, wsm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available() or wsm.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device — arts_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    wsm.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    case, name = workload(args, world)
+    mine, off, cnt = shard.shard_case(case, rank, world)
+    nl, np_, nf_total = case.n_lines, case.np_, case.nf
+
+    stream = torch.cuda.current_stream()
+    cat = wsm.Catalog(case.cat)
+    path = wsm.Path(cat, cnt, np_, 0, stream=stream.cuda_stream)
+    path.set_grid_bounds(np.tile([case.f[0], case.f[-1]], (np_, 1)))
+    path.upload(mine.f, mine.atm, mine.r, mine.I_bkg, rte_option=args.rte)
+    I_local = shard.as_torch(path.device_ptr(0), (cnt, 4), dev)
+
+    dfma_tflops, _ = wsm.measure_dfma_peak(20000)
+    hist = path.region_histogram(200_000, seed=1)
+    fl_eval, region_frac = roofline.flops_per_eval(hist)
+
+    def step():
+        path.run_propmat()
+        path.run_stokes()
+        if world > 1:
+            return shard.gather_spectral_rad(I_local, nf_total)
+        return I_local
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wsm.lib().ab200_launch_count(1)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    path.timings()  # drop warm-up records
+    path.set_timing(True)
+    wsm.lib().ab200_launch_count(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = int(wsm.lib().ab200_launch_count(0))
+    kt = path.timings()
+    path.set_timing(False)
+    checksum = float(out[:, 0].sum().item())
+
+    evals_per_step = float(nl) * nf_total * np_
+    value = evals_per_step * args.steps / (ms * 1e-3)
+
+    # dominant kernel: the real-only line sum (mode 0); algorithmic FLOPs / event-timed duration
+    k_ms, k_n = kt["sum_real"]
+    k_ms_per = k_ms / max(k_n, 1)
+    flops_per_launch = fl_eval * float(nl) * cnt * np_ / max(k_n / args.steps, 1)
+    achieved_tf = flops_per_launch / (k_ms_per * 1e-3) / 1e12 if k_ms_per > 0 else 0.0
+    s_ms, s_n = kt["stokes"]
+    s_ms_per = s_ms / max(s_n, 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    st_bytes = roofline.stokes_bytes_per_step(np_) * cnt * np_
+    st_gbs = st_bytes / (s_ms_per * 1e-3) / 1e9 if s_ms_per > 0 else 0.0
+
+    # e2e: the reference-facing C-ABI call with host (pinned) buffers, H2D + D2H inside the timed region
+    f_h = torch.from_numpy(mine.f).pin_memory().numpy()
+    b_h = torch.from_numpy(mine.I_bkg).pin_memory().numpy()
+    wsm.set_thread_stream(stream.cuda_stream)
+    wsm.spectral_radClearskyEmission(cat, f_h, mine.atm, mine.r, b_h, rte_option=args.rte)  # builds the thread workspace
+    barrier()
+    n_e2e = max(2, min(args.steps, 3))
+    e0.record()
+    for _ in range(n_e2e):
+        I_host, _ = wsm.spectral_radClearskyEmission(cat, f_h, mine.atm, mine.r, b_h, rte_option=args.rte)
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = evals_per_step * n_e2e / (float(ms_e2e.item()) * 1e-3)
+    h2d = int(f_h.nbytes + b_h.nbytes + 8 * np_ * (3 + 3 * case.cat.n_species + 28 + 3))
+    d2h = int(I_host.nbytes)
+    e2e_matches = bool(np.array_equal(I_host, I_local.cpu().numpy()))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "lines": nl, "levels": np_, "nf_total": nf_total, "nf_per_gpu": cnt,
+                   "sharding": "contiguous frequency blocks (matpack::omp_offset_count), catalog replicated, "
+                               "one NCCL all-gather of spectral_rad" if world > 1 else "single GPU",
+                   "l2": "inputs exceed L2: per step the kernels stream %.2f GB of line records and %.2f GB of K "
+                         "(L2 = 126 MB), no flush needed" % (cat.host.n_lines * 128.0 * np_ / 1e9, cnt * np_ * 56.0 / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "call": "ab200_clearsky_emission (host buffers, pinned)", "equals_resident_result": e2e_matches},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "kernel": "lbl_sum_real_kernel", "achieved": achieved_tf, "peak": dfma_tflops,
+                     "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None, "traffic": None,
+                     "peak_source": "DFMA loop measured in this run (ab200_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 figure",
+                     "algorithmic_flop_per_eval": fl_eval, "regions": region_frac, "kernel_ms": k_ms_per,
+                     "kernel_share_of_step": k_ms / ms if ms else None},
+        "roofline_stokes": {"bound": "hbm", "kernel": "stokes_chain_kernel", "achieved": st_gbs, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": None, "kernel_ms": s_ms_per,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+        "stage2": {"metric": "freq*level Stokes steps/s", "value": float(cnt) * np_ * world / (s_ms_per * 1e-3) if s_ms_per else None,
+                   "unit": "steps/s"},
+        "kernel_ms": {k: v[0] / max(v[1], 1) for k, v in kt.items()},
+        "checksum_I": checksum,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        idx, cores = calibrate_sample(case, args.rte, args.cpu_seconds)
+        t = oracle_sample(case, idx, args.rte)
+        line["cpu_baseline"] = {
+            "value": float(nl) * len(idx) * np_ / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(idx)} of {nf_total} frequencies (uniform stride) x all {nl} lines x {np_} levels, {t:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line))
+    path.close()
+    cat.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: note: W < 3 warm-up steps — number not valid for reporting", file=sys.stderr)
+    sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))
+
+
+if __name__ == "__main__":
+    main()

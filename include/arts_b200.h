@@ -133,6 +133,9 @@ const char *ab200_last_error(void);
 
 /* number of usable CUDA devices (0 -> every compute call fails) */
 int ab200_device_count(void);
+/* Makes `device` current for the calling host thread (one process per GPU: call once with LOCAL_RANK).
+ * Catalogs and path workspaces are created on the device that is current at the time. */
+int ab200_set_device(int device);
 
 /* Copies the description to the current CUDA device as SoA + pre-expanded
  * Zeeman sub-lines (lbl_zeeman.cpp:261-309, lbl_zeeman.h:342-352).
@@ -214,6 +217,9 @@ void *ab200_path_device_ptr(ab200_path *p, int which);
 /* kernels launched by the library on this thread since the last call (bench.py's gpu_launches) */
 int64_t ab200_launch_count(int reset);
 
+/* Stream the calling thread's host-buffer entry points (propmat_levels, clearsky_emission) run on:
+ * a cudaStream_t as void*, or NULL for a private non-blocking stream (the default). */
+int ab200_set_thread_stream(void *stream);
 /* The host-buffer entry points keep one device workspace per calling host thread (the shims are
  * called repeatedly with identical shapes, src/m_rad.cc:321-343).  Drops the calling thread's. */
 int ab200_release_thread_cache(void);
@@ -227,6 +233,20 @@ int ab200_zeeman_components(int on, double gu, double gl, int two_Ju, int two_Jl
 int ab200_norm_view(int pol, const double *mag, const double *los, double *npm);
 
 /* ---- measurement helpers ------------------------------------------------ */
+/* Per-kernel device timing of a path workspace with CUDA events on the path's stream (never under a
+ * profiler).  on != 0 starts recording every launch of run_propmat / run_stokes; ab200_path_get_timings
+ * synchronises the stream and returns, per kernel class, the accumulated milliseconds and launch counts
+ * since the last call: class 0 = line prepare (K1), 1 = real line sum (K2/K3, mode 0), 2 = complex line sum
+ * (mode 1), 3 = fused Stokes chain (K4-K6). */
+int ab200_path_set_timing(ab200_path *p, int on);
+int ab200_path_get_timings(ab200_path *p, double ms[4], int64_t launches[4]);
+/* Histogram of the reference's Faddeeva regions (3rdparty/Faddeeva/Faddeeva.cc:689-741,786,890) over a
+ * uniform random sample of the path's (line, frequency, level) evaluations — the weights of the
+ * algorithmic FLOP count of SURVEY.md 8(d).  out[0..4] = samples in R1 (x+y > 1e7), R2 (> 4000), R3
+ * (continued fraction), R4 (series, x < 10), R5 (x >= 10, tiny y); out[5] = sum of the continued-fraction
+ * term count nu over the R3 samples; out[6] = samples outside a ByLine cutoff window (not evaluated by the
+ * reference); out[7] = samples drawn.  Needs an uploaded path. */
+int ab200_path_region_histogram(ab200_path *p, int64_t samples_per_level, uint64_t seed, double out[8]);
 /* Dependency-free DFMA loop on all SMs; returns achieved FP64 TFLOP/s (2 flop per DFMA) and the
  * kernel time.  MEASURED_PEAKS.json has no FP64 number. */
 int ab200_measure_dfma_peak(int iters, double *tflops, double *ms);

@@ -169,33 +169,41 @@ __device__ __forceinline__ void w_near(double x, double y, double E1, double& wr
 
 // ---- far wing in line space --------------------------------------------------
 // s*w(z) with z = igd*(u + i g), |z| large:  s*w = S*zeta/(zeta^2 - h), zeta = u + i g,
-// S = i*s*GD/sqrt(pi), h = GD^2/2, GD = 1/igd (algebraically Faddeeva.cc:721-725).
-//   Re(s w) = [A1 (q + c1) + A2 u (q + c3)] / D2,   Im(s w) = [A3 (q + c1) + A4 u (q + c3)] / D2
-//   q = u^2, D2 = (q - c1)^2 + c2 q, c1 = g^2 + h, c3 = g^2 - h, c2 = 4 g^2,
-//   A1 = Si g, A2 = Sr, A3 = -Sr g, A4 = Si.
-// Explicit rounding intrinsics: the compiler may not re-associate or contract these, so
-// the fast tile loop and the per-pair path of the general loop produce identical bits —
-// this is what makes the result independent of the frequency tiling / sharding.
-__device__ __forceinline__ double far_accumulate_re(double acc, double u, double c1, double c2, double A1) {
-  const double q  = __dmul_rn(u, u);
-  const double n  = __dadd_rn(q, c1);
-  const double d  = __dsub_rn(q, c1);
-  const double D2 = __fma_rn(d, d, __dmul_rn(c2, q));
-  const double t  = __dmul_rn(n, fast_rcp(D2));
-  return __fma_rn(A1, t, acc);
+// S = i*s*GD/sqrt(pi), h = GD^2/2, GD = 1/igd (algebraically Faddeeva.cc:721-725).  With q = u^2:
+//   D2      = (q - c1)^2 + 4 g^2 q = q (q + b) + c0,   c1 = g^2 + h, c3 = g^2 - h, b = 2 c3, c0 = c1^2
+//   Re(s w) = [(A1 q + B1) + u (A2 q + B2)] / D2,      A1 = Si g, B1 = A1 c1, A2 = Sr,  B2 = A2 c3
+//   Im(s w) = [(A3 q + B3) + u (A4 q + B4)] / D2,      A3 = -Sr g, B3 = A3 c1, A4 = Si, B4 = A4 c3
+// (no cancellation in the far region: either q >> h, or g^2 >> h so that b > 0).
+// The real part costs 8 FP64-pipe instructions per (line, frequency): DADD u, DMUL q, DADD q+b,
+// DFMA D2, MUFU.RCP64H + 2 DFMA (one Newton step: 2^-40 ~ 9e-13 relative, three orders inside the
+// 1e-9 parity bound for sums of same-sign terms), DFMA numerator, DFMA accumulate.
+// Explicit rounding intrinsics: the compiler may not re-associate or contract these, so the fast tile
+// loop and the per-pair path of the general loop produce identical bits — this is what makes the
+// result independent of the frequency tiling / sharding.
+__device__ __forceinline__ double far_rcp(double D2) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(D2));
+  const double e = __fma_rn(-D2, r, 1.0);
+  return __fma_rn(r, e, r);
+}
+// cubic step for the complex path (dispersive parts change sign: keep ~1e-16 per term)
+__device__ __forceinline__ double far_D2(double q, double b, double c0) { return __fma_rn(q, __dadd_rn(q, b), c0); }
+
+__device__ __forceinline__ double far_accumulate_re(double acc, double u, double b, double c0, double A1, double B1) {
+  const double q = __dmul_rn(u, u);
+  const double r = far_rcp(far_D2(q, b, c0));
+  return __fma_rn(__fma_rn(A1, q, B1), r, acc);
 }
 
-__device__ __forceinline__ void far_accumulate_cplx(double& acc_re, double& acc_im, double u, double c1, double c2,
-                                                    double A1, double c3, double A2, double A3, double A4) {
+__device__ __forceinline__ void far_accumulate_cplx(double& acc_re, double& acc_im, double u, double b, double c0,
+                                                    double A1, double B1, double A2, double B2, double A3, double B3,
+                                                    double A4, double B4) {
   const double q  = __dmul_rn(u, u);
-  const double n  = __dadd_rn(q, c1);
-  const double d  = __dsub_rn(q, c1);
-  const double D2 = __fma_rn(d, d, __dmul_rn(c2, q));
-  const double rc = fast_rcp(D2);
-  const double t1 = __dmul_rn(n, rc);
-  const double t2 = __dmul_rn(__dmul_rn(u, __dadd_rn(q, c3)), rc);
-  acc_re          = __fma_rn(A1, t1, __fma_rn(A2, t2, acc_re));
-  acc_im          = __fma_rn(A3, t1, __fma_rn(A4, t2, acc_im));
+  const double r  = fast_rcp(far_D2(q, b, c0));
+  const double nr = __fma_rn(u, __fma_rn(A2, q, B2), __fma_rn(A1, q, B1));
+  const double ni = __fma_rn(u, __fma_rn(A4, q, B4), __fma_rn(A3, q, B3));
+  acc_re          = __fma_rn(nr, r, acc_re);
+  acc_im          = __fma_rn(ni, r, acc_im);
 }
 
 // Stand-alone w(z) for arbitrary finite z (tests, ab200_faddeeva_w); y < 0 through the

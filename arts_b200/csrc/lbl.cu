@@ -120,31 +120,34 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
   }
 
   double rec[REC_DOUBLES];
+#pragma unroll
+  for (int i = 0; i < REC_DOUBLES; i++) rec[i] = 0.0;
   if (real_line) {
     const double g  = G0;
     const double h  = 0.5 * GD * GD;
     const double g2 = g * g;
+    const double c1 = g2 + h, c3 = g2 - h;
     const double Si = s_re * GD * cst::inv_sqrt_pi;   // S = i*s*GD/sqrt(pi)
     const double Sr = -s_im * GD * cst::inv_sqrt_pi;
-    rec[0] = f0s; rec[1] = g2 + h; rec[2] = 4.0 * g2; rec[3] = Si * g;
-    rec[4] = igd; rec[5] = y; rec[6] = s_re; rec[7] = (y <= 7.0 && y >= 0.0) ? series_E1(y) : 0.0;
-    rec[8] = g2 - h; rec[9] = Sr; rec[10] = -Sr * g; rec[11] = Si;
-    rec[12] = s_im; rec[13] = 0.0; rec[14] = 0.0; rec[15] = 0.0;
+    const double A1 = Si * g, A2 = Sr, A3 = -Sr * g, A4 = Si;
+    rec[0] = f0s; rec[1] = 2.0 * c3; rec[2] = c1 * c1; rec[3] = A1;
+    rec[4] = A1 * c1; rec[5] = igd; rec[6] = y; rec[7] = s_re;
+    rec[8] = (y <= 7.0 && y >= 0.0) ? series_E1(y) : 0.0; rec[9] = s_im;
+    rec[12] = A2; rec[13] = A2 * c3; rec[14] = A3; rec[15] = A3 * c1;
+    rec[16] = A4; rec[17] = A4 * c3;
     const double cut = p.tile_cutoff[tile];
     if (cut < DBL_MAX) {
       // band_shape::operator()(cut): ls(ls.f0 + cutoff) = s * w(igd*cutoff + i y), :610-616
       double wr, wi;
       faddeeva_w(igd * ((f0s + cut) - f0s), y, wr, wi);
-      rec[13] = s_re * wr - s_im * wi;
-      rec[14] = s_re * wi + s_im * wr;
+      rec[10] = s_re * wr - s_im * wi;
+      rec[11] = s_re * wi + s_im * wr;
     }
   } else {
-    // padding / inactive: contributes exactly +0 in the far loops, skipped in the near loops
-#pragma unroll
-    for (int i = 0; i < REC_DOUBLES; i++) rec[i] = 0.0;
+    // padding / inactive: contributes exactly +0 in the far loops (numerators 0, D2 = q^2 + 1 > 0),
+    // skipped in the near loops
     rec[0] = (par >= 0) ? DBL_MAX : 0.0;  // inactive cutoff line: outside every window
-    rec[1] = -1.0;                        // D2 = (q+1)^2 > 0
-    rec[8] = -1.0;
+    rec[2] = 1.0;
   }
   double* out = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
 #pragma unroll
@@ -186,6 +189,7 @@ constexpr int SUM_NT    = 128;   // threads per CTA
 constexpr int SUM_R     = 4;     // frequencies per thread
 constexpr int F_TILE    = SUM_NT * SUM_R;
 constexpr int CHUNK     = 4096;  // tiles classified per pass
+constexpr int REAL_STAGES = 2;   // 2 x 24 KB of line records per CTA: 4 CTAs per SM stay resident
 constexpr uint8_t CLS_SKIP = 0, CLS_FAR = 1, CLS_NEAR = 2;
 
 // classification of one (frequency block, line tile) pair, conservative w.r.t. the per-pair
@@ -208,19 +212,11 @@ __device__ __forceinline__ double line_scale(double f, double T, double P) {
   return -N * f * expm1(-r) * c;
 }
 
-template <int STAGES, int STAGE_DOUBLES>
-struct TilePipe {
-  uint64_t* full;    // [STAGES]
-  double* buf;       // [STAGES][STAGE_DOUBLES]
-  uint32_t it = 0;   // tiles consumed so far (stage/phase bookkeeping)
-  __device__ __forceinline__ double* stage(uint32_t i) const { return buf + size_t(i % STAGES) * STAGE_DOUBLES; }
-};
-
 // --------------------------- real-only kernel (mode 0) ----------------------
 // Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
 __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
-  constexpr int STAGES = 3;
-  constexpr int STAGE_DOUBLES = 2 * TL * REC_GROUP;  // groups 0 and 1
+  constexpr int STAGES = REAL_STAGES;
+  constexpr int STAGE_DOUBLES = 3 * TL * REC_GROUP;  // groups 0, 1 (far) and 2 (near)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
   uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);
@@ -264,7 +260,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
 
       auto issue = [&](int t) {
         const uint32_t st   = (it + t) % STAGES;
-        const uint32_t bytes = (cls[t] == CLS_FAR ? 1 : 2) * TL * REC_GROUP * sizeof(double);
+        const uint32_t bytes = (cls[t] == CLS_FAR ? 2 : 3) * TL * REC_GROUP * sizeof(double);
         mbar_expect_tx(&full[st], bytes);
         tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + t) * tile_doubles(), bytes, &full[st]);
       };
@@ -280,28 +276,31 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
         double acc[SUM_R];
 #pragma unroll
         for (int r = 0; r < SUM_R; r++) acc[r] = 0.0;
+        const double2* __restrict__ rec1 = rec + 2 * TL;
         if (cls[t] == CLS_FAR) {
 #pragma unroll 4
           for (int l = 0; l < count; l++) {
-            const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', c1 | c2, A1
+            const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', b | c0, A1
+            const double B1 = reinterpret_cast<const double*>(rec1 + 2 * l)[0];
 #pragma unroll
-            for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y);
+            for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1);
           }
         } else {
-          const double2* __restrict__ rec1 = rec + 2 * TL;
+          const double2* __restrict__ rec2 = rec + 4 * TL;
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];
-            const double2 c = rec1[2 * l], d = rec1[2 * l + 1];  // igd, y | s_re, E1
+            const double2 c = rec1[2 * l], d = rec1[2 * l + 1];  // B1, igd | y, s_re
+            const double E1 = reinterpret_cast<const double*>(rec2 + 2 * l)[0];
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) {
               const double u  = __dsub_rn(f[r], a.x);
-              const double ax = __dmul_rn(fabs(u), c.x);
-              if (__dadd_rn(ax, c.y) > FAR_LIMIT) {
-                acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y);
+              const double ax = __dmul_rn(fabs(u), c.y);
+              if (__dadd_rn(ax, d.x) > FAR_LIMIT) {
+                acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y, c.x);
               } else {
                 double wr, wi;
-                w_near(c.x * u, c.y, d.y, wr, wi);
-                acc[r] = __fma_rn(d.x, wr, acc[r]);
+                w_near(c.y * u, d.x, E1, wr, wi);
+                acc[r] = __fma_rn(d.y, wr, acc[r]);
               }
             }
           }
@@ -396,13 +395,13 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
         double* dst       = sbuf + size_t(st) * STAGE_DOUBLES;
         const double* src = prep + (c0 + t) * tile_doubles();
         constexpr uint32_t GB = TL * REC_GROUP * sizeof(double);
-        if (cls[t] == CLS_FAR) {  // groups 0 and 2
-          mbar_expect_tx(&full[st], 2 * GB);
-          tma_load_1d(dst, src, GB, &full[st]);
-          tma_load_1d(dst + 2 * TL * REC_GROUP, src + 2 * TL * REC_GROUP, GB, &full[st]);
-        } else {
+        if (cls[t] == CLS_FAR) {  // groups 0-1 and 3-4
           mbar_expect_tx(&full[st], 4 * GB);
-          tma_load_1d(dst, src, 4 * GB, &full[st]);
+          tma_load_1d(dst, src, 2 * GB, &full[st]);
+          tma_load_1d(dst + 3 * TL * REC_GROUP, src + 3 * TL * REC_GROUP, 2 * GB, &full[st]);
+        } else {
+          mbar_expect_tx(&full[st], 5 * GB);
+          tma_load_1d(dst, src, 5 * GB, &full[st]);
         }
       };
       if (tid == 0)
@@ -417,6 +416,7 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
         const double2* __restrict__ g1 = g0 + 2 * TL;
         const double2* __restrict__ g2 = g0 + 4 * TL;
         const double2* __restrict__ g3 = g0 + 6 * TL;
+        const double2* __restrict__ g4 = g0 + 8 * TL;
         const int count = p.tile_count[c0 + t];
         double are[CPLX_R], aim[CPLX_R];
 #pragma unroll
@@ -424,18 +424,21 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
         if (cls[t] == CLS_FAR) {
 #pragma unroll 2
           for (int l = 0; l < count; l++) {
-            const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', c1 | c2, A1
-            const double2 c = g2[2 * l], d = g2[2 * l + 1];  // c3, A2 | A3, A4
+            const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', b | c0, A1
+            const double B1 = reinterpret_cast<const double*>(g1 + 2 * l)[0];
+            const double2 c = g3[2 * l], d = g3[2 * l + 1];  // A2, B2 | A3, B3
+            const double2 e = g4[2 * l];                     // A4, B4
 #pragma unroll
             for (int r = 0; r < CPLX_R; r++)
-              far_accumulate_cplx(are[r], aim[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, c.x, c.y, d.x, d.y);
+              far_accumulate_cplx(are[r], aim[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1, c.x, c.y, d.x, d.y, e.x, e.y);
           }
         } else {
           for (int l = 0; l < count; l++) {
             const double2 a = g0[2 * l], b = g0[2 * l + 1];
-            const double2 e = g1[2 * l], g = g1[2 * l + 1];  // igd, y | s_re, E1
-            const double2 c = g2[2 * l], d = g2[2 * l + 1];
-            const double2 h = g3[2 * l], k = g3[2 * l + 1];  // s_im, cut_re | cut_im, -
+            const double2 m = g1[2 * l], n = g1[2 * l + 1];  // B1, igd | y, s_re
+            const double2 h = g2[2 * l], k = g2[2 * l + 1];  // E1, s_im | cut_re, cut_im
+            const double2 c = g3[2 * l], d = g3[2 * l + 1];
+            const double2 e = g4[2 * l];
 #pragma unroll
             for (int r = 0; r < CPLX_R; r++) {
               if (seg.has_cutoff) {
@@ -444,18 +447,18 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
                 if (!(a.x >= f[r] - cutoff && a.x <= f[r] + cutoff)) continue;
               }
               const double u  = __dsub_rn(f[r], a.x);
-              const double ax = __dmul_rn(fabs(u), e.x);
-              if (__dadd_rn(ax, e.y) > FAR_LIMIT) {
-                far_accumulate_cplx(are[r], aim[r], u, a.y, b.x, b.y, c.x, c.y, d.x, d.y);
+              const double ax = __dmul_rn(fabs(u), m.y);
+              if (__dadd_rn(ax, n.x) > FAR_LIMIT) {
+                far_accumulate_cplx(are[r], aim[r], u, a.y, b.x, b.y, m.x, c.x, c.y, d.x, d.y, e.x, e.y);
               } else {
                 double wr, wi;
-                w_near(e.x * u, e.y, g.y, wr, wi);
-                are[r] = __fma_rn(g.x, wr, __fma_rn(-h.x, wi, are[r]));
-                aim[r] = __fma_rn(g.x, wi, __fma_rn(h.x, wr, aim[r]));
+                w_near(m.y * u, n.x, h.x, wr, wi);
+                are[r] = __fma_rn(n.y, wr, __fma_rn(-h.y, wi, are[r]));
+                aim[r] = __fma_rn(n.y, wi, __fma_rn(h.y, wr, aim[r]));
               }
               if (seg.has_cutoff) {  // ls(f) - ls(f0' + cutoff), :591-608
-                are[r] -= h.y;
-                aim[r] -= k.x;
+                are[r] -= k.x;
+                aim[r] -= k.y;
               }
             }
           }
@@ -495,7 +498,9 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
-size_t lbl_real_smem_bytes() { return size_t(3) * 2 * TL * REC_GROUP * sizeof(double) + 3 * sizeof(uint64_t) + CHUNK; }
+size_t lbl_real_smem_bytes() {
+  return size_t(REAL_STAGES) * 3 * TL * REC_GROUP * sizeof(double) + REAL_STAGES * sizeof(uint64_t) + CHUNK;
+}
 size_t lbl_cplx_smem_bytes() {
   return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + CHUNK * sizeof(uint16_t);
 }
@@ -577,14 +582,14 @@ __global__ void region_histogram_kernel(SumParams p, int64_t samples_per_level, 
     if (l >= p.tile_count[tile]) continue;  // padding slot: redraw is not needed for a uniform sample of real lines
     const double* g0 = prep + tile * tile_doubles() + (int64_t(0) * TL + l) * REC_GROUP;
     const double* g1 = prep + tile * tile_doubles() + (int64_t(1) * TL + l) * REC_GROUP;
-    const double f0s = g0[0], igd = g1[0], y = g1[1];
+    const double f0s = g0[0], igd = g1[1], y = g1[2];
     const double f = fg[int64_t(r2 % uint64_t(p.nf))];
     atomicAdd(&h[7], 1ull);
     // segment of the tile (cutoff window): linear scan, nsegs is small
     double cutoff = DBL_MAX;
     for (int is = 0; is < p.nsegs; is++)
       if (tile >= p.segs[is].tile_begin && tile < p.segs[is].tile_end && p.segs[is].has_cutoff) cutoff = p.segs[is].cutoff;
-    if (g0[1] == -1.0 || !(f0s >= f - cutoff && f0s <= f + cutoff)) {
+    if (igd == 0.0 || !(f0s >= f - cutoff && f0s <= f + cutoff)) {
       atomicAdd(&h[6], 1ull);
       continue;
     }

@@ -32,17 +32,16 @@ constexpr double doppler_broadening_const_squared = 2000 * R / (c * c);
 // ---- geometry of the line catalog on the device ---------------------------
 constexpr int TL        = 256;  // (sub-)lines per tile; tiles never straddle a segment
 constexpr int REC_GROUP = 4;    // doubles per record group (one LDS.128 pair)
-constexpr int N_GROUPS  = 5;    // groups per line record -> 20 doubles = 160 B per (level, line)
+constexpr int N_GROUPS  = 4;    // groups per line record -> 16 doubles = 128 B per (level, line)
 constexpr int REC_DOUBLES = REC_GROUP * N_GROUPS;
 // record layout of one tile (for one level): [group][line][4]
-//   group 0: f0', b = 2(g^2 - h), c0 = (g^2 + h)^2, A1 = Si*g     (far wing, real part)
-//   group 1: B1 = A1 (g^2 + h), igd, y, s_re                      (far wing real | near evaluation)
-//   group 2: E1(y), s_im, cut_re, cut_im                          (near evaluation, line mixing, cutoff value)
-//   group 3: A2 = Sr, B2 = A2 (g^2 - h), A3 = -Sr*g, B3 = A3 (g^2 + h)   (far wing, complex part)
-//   group 4: A4 = Si, B4 = A4 (g^2 - h), unused, unused
+//   group 0: f0', c3 = g^2 - h, kappa = 4 g^2 h, A1 = Si*g          (far wing, real part)
+//   group 1: B1 = 2 h A1, igd, y, s_re                              (far wing real | near evaluation)
+//   group 2: E1(y), s_im, cut_re, cut_im                            (near evaluation, line mixing, cutoff value)
+//   group 3: A2 = Sr, A3 = -Sr*g, B3 = 2 h A3, A4 = Si              (far wing, complex part)
 // with g = G0 [Hz], h = GD^2/2, S = i*s*GD/sqrt(pi) = Sr + i Si, (igd, y, s) the reference's
 // single_shape (lbl_lineshape_voigt_lte.h:20-33).  The real-only kernel streams groups 0-1 for
-// far tiles and 0-2 for near tiles; the complex kernel groups 0-1 + 3-4 or all five.
+// far tiles and 0-2 for near tiles; the complex kernel groups 0-1 + 3 or all four.
 constexpr size_t tile_doubles() { return size_t(TL) * REC_DOUBLES; }
 
 // tile summary written by the prepare kernel: f0'min, f0'max, min igd, min y

@@ -7,7 +7,7 @@
 // converged:
 //   * far wing  (|x|+y > 4000, the reference's nu<=2 region :707-725): closed form
 //     evaluated in *line space* (Hz) with per-line constants prepared once per level,
-//     11 FP64 instructions per (line, frequency) for the real part, one MUFU reciprocal.
+//     7 FP64 instructions per (line, frequency) for the real part, one MUFU reciprocal.
 //   * continued fraction (the reference's region :695-700 with its nu(z) fit :729) with
 //     the same number of terms, reciprocal by MUFU + one cubic Newton step.
 //   * core (everything else): the Zaghloul-Ali sampling sum (ACM TOMS 916, the method
@@ -169,14 +169,15 @@ __device__ __forceinline__ void w_near(double x, double y, double E1, double& wr
 
 // ---- far wing in line space --------------------------------------------------
 // s*w(z) with z = igd*(u + i g), |z| large:  s*w = S*zeta/(zeta^2 - h), zeta = u + i g,
-// S = i*s*GD/sqrt(pi), h = GD^2/2, GD = 1/igd (algebraically Faddeeva.cc:721-725).  With q = u^2:
-//   D2      = (q - c1)^2 + 4 g^2 q = q (q + b) + c0,   c1 = g^2 + h, c3 = g^2 - h, b = 2 c3, c0 = c1^2
-//   Re(s w) = [(A1 q + B1) + u (A2 q + B2)] / D2,      A1 = Si g, B1 = A1 c1, A2 = Sr,  B2 = A2 c3
-//   Im(s w) = [(A3 q + B3) + u (A4 q + B4)] / D2,      A3 = -Sr g, B3 = A3 c1, A4 = Si, B4 = A4 c3
-// (no cancellation in the far region: either q >> h, or g^2 >> h so that b > 0).
-// The real part costs 8 FP64-pipe instructions per (line, frequency): DADD u, DMUL q, DADD q+b,
-// DFMA D2, MUFU.RCP64H + 2 DFMA (one Newton step: 2^-40 ~ 9e-13 relative, three orders inside the
-// 1e-9 parity bound for sums of same-sign terms), DFMA numerator, DFMA accumulate.
+// S = i*s*GD/sqrt(pi), h = GD^2/2, GD = 1/igd (algebraically Faddeeva.cc:721-725).  With
+// Q = u^2 + c3, c3 = g^2 - h (= |zeta|^2 - h, no cancellation in the far region |z| > 2000):
+//   D2      = |zeta^2 - h|^2 = Q^2 + kappa,            kappa = 4 g^2 h >= 0
+//   Re(s w) = [(A1 Q + B1) + (u A2) Q] / D2,           A1 = Si g,  B1 = 2 h A1, A2 = Sr
+//   Im(s w) = [(A3 Q + B3) + (u A4) Q] / D2,           A3 = -Sr g, B3 = 2 h A3, A4 = Si
+// The real part costs 7 FP64-pipe instructions per (line, frequency): DADD u, DFMA Q, DFMA D2,
+// MUFU.RCP64H + 2 DFMA (one Newton step: 2^-40 ~ 9e-13 relative, three orders inside the 1e-9
+// parity bound for sums of same-sign terms), DFMA numerator, DFMA accumulate — against the 28
+// algorithmic flop of the reference's closed form.
 // Explicit rounding intrinsics: the compiler may not re-associate or contract these, so the fast tile
 // loop and the per-pair path of the general loop produce identical bits — this is what makes the
 // result independent of the frequency tiling / sharding.
@@ -186,22 +187,20 @@ __device__ __forceinline__ double far_rcp(double D2) {
   const double e = __fma_rn(-D2, r, 1.0);
   return __fma_rn(r, e, r);
 }
-// cubic step for the complex path (dispersive parts change sign: keep ~1e-16 per term)
-__device__ __forceinline__ double far_D2(double q, double b, double c0) { return __fma_rn(q, __dadd_rn(q, b), c0); }
 
-__device__ __forceinline__ double far_accumulate_re(double acc, double u, double b, double c0, double A1, double B1) {
-  const double q = __dmul_rn(u, u);
-  const double r = far_rcp(far_D2(q, b, c0));
-  return __fma_rn(__fma_rn(A1, q, B1), r, acc);
+__device__ __forceinline__ double far_accumulate_re(double acc, double u, double c3, double kappa, double A1, double B1) {
+  const double Q = __fma_rn(u, u, c3);
+  const double r = far_rcp(__fma_rn(Q, Q, kappa));
+  return __fma_rn(__fma_rn(A1, Q, B1), r, acc);
 }
 
-__device__ __forceinline__ void far_accumulate_cplx(double& acc_re, double& acc_im, double u, double b, double c0,
-                                                    double A1, double B1, double A2, double B2, double A3, double B3,
-                                                    double A4, double B4) {
-  const double q  = __dmul_rn(u, u);
-  const double r  = fast_rcp(far_D2(q, b, c0));
-  const double nr = __fma_rn(u, __fma_rn(A2, q, B2), __fma_rn(A1, q, B1));
-  const double ni = __fma_rn(u, __fma_rn(A4, q, B4), __fma_rn(A3, q, B3));
+// complex part: cubic reciprocal step (the dispersive parts change sign, keep ~1e-16 per term)
+__device__ __forceinline__ void far_accumulate_cplx(double& acc_re, double& acc_im, double u, double c3, double kappa,
+                                                    double A1, double B1, double A2, double A3, double B3, double A4) {
+  const double Q  = __fma_rn(u, u, c3);
+  const double r  = fast_rcp(__fma_rn(Q, Q, kappa));
+  const double nr = __fma_rn(__dmul_rn(u, A2), Q, __fma_rn(A1, Q, B1));
+  const double ni = __fma_rn(__dmul_rn(u, A4), Q, __fma_rn(A3, Q, B3));
   acc_re          = __fma_rn(nr, r, acc_re);
   acc_im          = __fma_rn(ni, r, acc_im);
 }

@@ -126,15 +126,13 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
     const double g  = G0;
     const double h  = 0.5 * GD * GD;
     const double g2 = g * g;
-    const double c1 = g2 + h, c3 = g2 - h;
     const double Si = s_re * GD * cst::inv_sqrt_pi;   // S = i*s*GD/sqrt(pi)
     const double Sr = -s_im * GD * cst::inv_sqrt_pi;
-    const double A1 = Si * g, A2 = Sr, A3 = -Sr * g, A4 = Si;
-    rec[0] = f0s; rec[1] = 2.0 * c3; rec[2] = c1 * c1; rec[3] = A1;
-    rec[4] = A1 * c1; rec[5] = igd; rec[6] = y; rec[7] = s_re;
+    const double A1 = Si * g, A3 = -Sr * g;
+    rec[0] = f0s; rec[1] = g2 - h; rec[2] = 4.0 * g2 * h; rec[3] = A1;
+    rec[4] = 2.0 * h * A1; rec[5] = igd; rec[6] = y; rec[7] = s_re;
     rec[8] = (y <= 7.0 && y >= 0.0) ? series_E1(y) : 0.0; rec[9] = s_im;
-    rec[12] = A2; rec[13] = A2 * c3; rec[14] = A3; rec[15] = A3 * c1;
-    rec[16] = A4; rec[17] = A4 * c3;
+    rec[12] = Sr; rec[13] = A3; rec[14] = 2.0 * h * A3; rec[15] = Si;
     const double cut = p.tile_cutoff[tile];
     if (cut < DBL_MAX) {
       // band_shape::operator()(cut): ls(ls.f0 + cutoff) = s * w(igd*cutoff + i y), :610-616
@@ -144,7 +142,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
       rec[11] = s_re * wi + s_im * wr;
     }
   } else {
-    // padding / inactive: contributes exactly +0 in the far loops (numerators 0, D2 = q^2 + 1 > 0),
+    // padding / inactive: contributes exactly +0 in the far loops (numerators 0, D2 = Q^2 + 1 > 0),
     // skipped in the near loops
     rec[0] = (par >= 0) ? DBL_MAX : 0.0;  // inactive cutoff line: outside every window
     rec[2] = 1.0;
@@ -212,6 +210,19 @@ __device__ __forceinline__ double line_scale(double f, double T, double P) {
   return -N * f * expm1(-r) * c;
 }
 
+// per-line refinement of a NEAR (tile, block) pair: 1 if every frequency of the block is in the
+// far region of line l (same conservative margin as classify_tile), else 0.  CTA-uniform.
+template <int NT>
+__device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const double2* __restrict__ g0,
+                                           const double2* __restrict__ g1, int count, double fblk_min, double fblk_max,
+                                           bool all_slow) {
+  for (int l = threadIdx.x; l < count; l += NT) {
+    const double f0s = g0[2 * l].x, igd = g1[2 * l].y, y = g1[2 * l + 1].x;
+    const double dist = fmax(0.0, fmax(fblk_min - f0s, f0s - fblk_max));
+    flag[l] = (!all_slow && igd * dist + y > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
+  }
+}
+
 // --------------------------- real-only kernel (mode 0) ----------------------
 // Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
 __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
   uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);
   uint8_t* cls      = reinterpret_cast<uint8_t*>(full + STAGES);
+  uint8_t* lflag    = cls + CHUNK;  // [TL]
 
   const int tid = threadIdx.x;
   const int lev = blockIdx.y;
@@ -271,25 +283,33 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
         if (tid == 0 && t + STAGES - 1 < n) issue(t + STAGES - 1);
         const uint32_t st = (it + t) % STAGES;
         mbar_wait(&full[st], ((it + t) / STAGES) & 1);
-        const double2* __restrict__ rec = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);
+        const double2* __restrict__ rec  = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);
+        const double2* __restrict__ rec1 = rec + 2 * TL;
         const int count = p.tile_count[c0 + t];
         double acc[SUM_R];
 #pragma unroll
         for (int r = 0; r < SUM_R; r++) acc[r] = 0.0;
-        const double2* __restrict__ rec1 = rec + 2 * TL;
         if (cls[t] == CLS_FAR) {
 #pragma unroll 4
           for (int l = 0; l < count; l++) {
-            const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', b | c0, A1
+            const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', c3 | kappa, A1
             const double B1 = reinterpret_cast<const double*>(rec1 + 2 * l)[0];
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1);
           }
-        } else {
+        } else if (cls[t] == CLS_NEAR) {
           const double2* __restrict__ rec2 = rec + 4 * TL;
+          flag_lines<SUM_NT>(lflag, rec, rec1, count, fblk_min, fblk_max, false);
+          __syncthreads();
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];
-            const double2 c = rec1[2 * l], d = rec1[2 * l + 1];  // B1, igd | y, s_re
+            const double2 c = rec1[2 * l];  // B1, igd
+            if (lflag[l]) {
+#pragma unroll
+              for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, c.x);
+              continue;
+            }
+            const double2 d = rec1[2 * l + 1];  // y, s_re
             const double E1 = reinterpret_cast<const double*>(rec2 + 2 * l)[0];
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) {
@@ -341,8 +361,9 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
   double* sbuf   = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);
   uint8_t* cls   = reinterpret_cast<uint8_t*>(full + STAGES);
+  uint8_t* lflag = cls + CHUNK;                                          // [TL]
+  uint16_t* act  = reinterpret_cast<uint16_t*>(lflag + TL);              // compacted tile list of the chunk
   __shared__ int n_active;
-  uint16_t* act  = reinterpret_cast<uint16_t*>(cls + CHUNK);  // compacted tile list of the chunk
 
   const int tid = threadIdx.x;
   const int lev = blockIdx.y;
@@ -395,13 +416,13 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
         double* dst       = sbuf + size_t(st) * STAGE_DOUBLES;
         const double* src = prep + (c0 + t) * tile_doubles();
         constexpr uint32_t GB = TL * REC_GROUP * sizeof(double);
-        if (cls[t] == CLS_FAR) {  // groups 0-1 and 3-4
-          mbar_expect_tx(&full[st], 4 * GB);
+        if (cls[t] == CLS_FAR) {  // groups 0-1 and 3
+          mbar_expect_tx(&full[st], 3 * GB);
           tma_load_1d(dst, src, 2 * GB, &full[st]);
-          tma_load_1d(dst + 3 * TL * REC_GROUP, src + 3 * TL * REC_GROUP, 2 * GB, &full[st]);
+          tma_load_1d(dst + 3 * TL * REC_GROUP, src + 3 * TL * REC_GROUP, GB, &full[st]);
         } else {
-          mbar_expect_tx(&full[st], 5 * GB);
-          tma_load_1d(dst, src, 5 * GB, &full[st]);
+          mbar_expect_tx(&full[st], 4 * GB);
+          tma_load_1d(dst, src, 4 * GB, &full[st]);
         }
       };
       if (tid == 0)
@@ -416,7 +437,6 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
         const double2* __restrict__ g1 = g0 + 2 * TL;
         const double2* __restrict__ g2 = g0 + 4 * TL;
         const double2* __restrict__ g3 = g0 + 6 * TL;
-        const double2* __restrict__ g4 = g0 + 8 * TL;
         const int count = p.tile_count[c0 + t];
         double are[CPLX_R], aim[CPLX_R];
 #pragma unroll
@@ -424,21 +444,28 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
         if (cls[t] == CLS_FAR) {
 #pragma unroll 2
           for (int l = 0; l < count; l++) {
-            const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', b | c0, A1
+            const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', c3 | kappa, A1
             const double B1 = reinterpret_cast<const double*>(g1 + 2 * l)[0];
-            const double2 c = g3[2 * l], d = g3[2 * l + 1];  // A2, B2 | A3, B3
-            const double2 e = g4[2 * l];                     // A4, B4
+            const double2 c = g3[2 * l], d = g3[2 * l + 1];  // A2, A3 | B3, A4
 #pragma unroll
             for (int r = 0; r < CPLX_R; r++)
-              far_accumulate_cplx(are[r], aim[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1, c.x, c.y, d.x, d.y, e.x, e.y);
+              far_accumulate_cplx(are[r], aim[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1, c.x, c.y, d.x, d.y);
           }
         } else {
+          flag_lines<CPLX_NT>(lflag, g0, g1, count, fblk_min, fblk_max, seg.has_cutoff != 0);
+          __syncthreads();
           for (int l = 0; l < count; l++) {
             const double2 a = g0[2 * l], b = g0[2 * l + 1];
-            const double2 m = g1[2 * l], n = g1[2 * l + 1];  // B1, igd | y, s_re
-            const double2 h = g2[2 * l], k = g2[2 * l + 1];  // E1, s_im | cut_re, cut_im
+            const double2 m = g1[2 * l];                     // B1, igd
             const double2 c = g3[2 * l], d = g3[2 * l + 1];
-            const double2 e = g4[2 * l];
+            if (lflag[l]) {
+#pragma unroll
+              for (int r = 0; r < CPLX_R; r++)
+                far_accumulate_cplx(are[r], aim[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, m.x, c.x, c.y, d.x, d.y);
+              continue;
+            }
+            const double2 n2 = g1[2 * l + 1];                // y, s_re
+            const double2 h = g2[2 * l], k = g2[2 * l + 1];  // E1, s_im | cut_re, cut_im
 #pragma unroll
             for (int r = 0; r < CPLX_R; r++) {
               if (seg.has_cutoff) {
@@ -448,13 +475,13 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
               }
               const double u  = __dsub_rn(f[r], a.x);
               const double ax = __dmul_rn(fabs(u), m.y);
-              if (__dadd_rn(ax, n.x) > FAR_LIMIT) {
-                far_accumulate_cplx(are[r], aim[r], u, a.y, b.x, b.y, m.x, c.x, c.y, d.x, d.y, e.x, e.y);
+              if (__dadd_rn(ax, n2.x) > FAR_LIMIT) {
+                far_accumulate_cplx(are[r], aim[r], u, a.y, b.x, b.y, m.x, c.x, c.y, d.x, d.y);
               } else {
                 double wr, wi;
-                w_near(m.y * u, n.x, h.x, wr, wi);
-                are[r] = __fma_rn(n.y, wr, __fma_rn(-h.y, wi, are[r]));
-                aim[r] = __fma_rn(n.y, wi, __fma_rn(h.y, wr, aim[r]));
+                w_near(m.y * u, n2.x, h.x, wr, wi);
+                are[r] = __fma_rn(n2.y, wr, __fma_rn(-h.y, wi, are[r]));
+                aim[r] = __fma_rn(n2.y, wi, __fma_rn(h.y, wr, aim[r]));
               }
               if (seg.has_cutoff) {  // ls(f) - ls(f0' + cutoff), :591-608
                 are[r] -= k.x;
@@ -499,10 +526,10 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
 // host launchers
 // ---------------------------------------------------------------------------
 size_t lbl_real_smem_bytes() {
-  return size_t(REAL_STAGES) * 3 * TL * REC_GROUP * sizeof(double) + REAL_STAGES * sizeof(uint64_t) + CHUNK;
+  return size_t(REAL_STAGES) * 3 * TL * REC_GROUP * sizeof(double) + REAL_STAGES * sizeof(uint64_t) + CHUNK + TL;
 }
 size_t lbl_cplx_smem_bytes() {
-  return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + CHUNK * sizeof(uint16_t);
+  return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + TL + CHUNK * sizeof(uint16_t);
 }
 
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream) {

@@ -165,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "stage2": {"metric": "freq*level Stokes steps/s", "note": "included in the step; < 0.1% of CPU time"},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -315,7 +315,7 @@ def run_b200(args):
             "value": float(nl) * len(idx) * np_ / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{len(idx)} of {nf_total} frequencies (uniform stride) x all {nl} lines x {np_} levels, {t:.1f} s"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     path.close()
     cat.close()
     if world > 1:
@@ -323,8 +323,22 @@ def run_b200(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was
+    routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # native libraries (e.g. "NCCL version ..." banners) write to fd 1: keep stdout to the JSON line
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: W < 3 warm-up steps — number not valid for reporting", file=sys.stderr)
     sys.exit(run_reference(args) if args.impl == "reference" else run_b200(args))

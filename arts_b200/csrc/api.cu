@@ -71,6 +71,16 @@ struct ab200_path {
   // outputs
   double* d_K = nullptr;  // [np][k_pitch][7]
   double* d_I = nullptr;  // [nf][4]
+  // Jacobian targets (nq > 0)
+  double* d_dK = nullptr;    // [np][nq][k_pitch][7]
+  double* d_dI = nullptr;    // [nf][np][nq][4]
+  double* d_Ilev = nullptr;  // [np][nf][4] radiance arriving at each level
+  double* d_jac = nullptr;   // [levels_per_batch][ntiles][nq][2][TL][4]
+  double* d_jcom = nullptr;  // [levels_per_batch][ntiles][TL]
+  double *d_dQdT = nullptr, *d_dr = nullptr;
+  int32_t tg_kind[AB200_MAX_TARGETS] = {0}, tg_species[AB200_MAX_TARGETS] = {0};
+  int32_t it = -1;  // position of the temperature target
+  bool dk_preloaded = false;
 
   // per-kernel timing (ab200_path_set_timing)
   bool timing = false;
@@ -88,6 +98,7 @@ struct ab200_path {
   ~ab200_path() {
     cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary);
     cudaFree(d_flags); cudaFree(d_K); cudaFree(d_I);
+    cudaFree(d_dK); cudaFree(d_dI); cudaFree(d_Ilev); cudaFree(d_jac); cudaFree(d_jcom);
     if (h_small) cudaFreeHost(h_small);
     if (h_segs) cudaFreeHost(h_segs);
     for (auto& q : pending) { cudaEventDestroy(q.e0); cudaEventDestroy(q.e1); }
@@ -127,9 +138,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   if (!cat || !out) return set_error(AB200_ERR_INVALID, "ab200_path_create: null argument");
   *out = nullptr;
   if (nf < 0 || np < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_path_create: negative size");
-  if (nq > 0)
-    return set_error(AB200_ERR_UNSUPPORTED,
-                     "Jacobian targets (nq > 0) are not on the GPU path in this build (no CPU fallback)");
+  if (nq > AB200_MAX_TARGETS)
+    return set_error(AB200_ERR_UNSUPPORTED, "at most " + std::to_string(AB200_MAX_TARGETS) + " Jacobian targets per call");
   std::unique_ptr<ab200_path> p(new ab200_path());
   p->cat = cat;
   p->nf = nf;
@@ -143,7 +153,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   const size_t snp = static_cast<size_t>(np);
   AB_TRY(dev_alloc(&p->d_f, snp * nf));
   // packed small arrays: T, P, H [np] | vmr [np][ns] | isorat, Q [np][ni] | npm [np][4][7] | frange [np][2] | r [np]
-  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1);
+  //                      | dQdT [np][ni] | dr [2][np][nq]
+  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq));
   AB_TRY(dev_alloc(&p->d_small, p->small_doubles));
   if (p->small_doubles) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_small), p->small_doubles * sizeof(double)));
   double* q = p->d_small;
@@ -155,7 +166,9 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->d_Q = q; q += snp * cat->n_isot;
   p->d_npm = q; q += snp * 28;
   p->d_frange = q; q += snp * 2;
-  p->d_r = q;
+  p->d_r = q; q += snp;
+  p->d_dQdT = q; q += snp * cat->n_isot;
+  p->d_dr = q;
   AB_TRY(dev_alloc(&p->d_Ibkg, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_I, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_K, snp * p->k_pitch * 7));
@@ -165,12 +178,19 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   AB_TRY(dev_alloc(&p->d_flags, 1));
   AB_CUDA(cudaMemset(p->d_flags, 0, sizeof(int)));
 
-  const size_t per_level = static_cast<size_t>(cat->ntiles) * tile_doubles() * sizeof(double);
+  const size_t per_level = static_cast<size_t>(cat->ntiles) * (tile_doubles() + static_cast<size_t>(nq) * 2 * TL * 4 + (nq ? TL : 0)) * sizeof(double);
   int lpb = np;
   if (per_level > 0) lpb = static_cast<int>(std::max<size_t>(1, std::min<size_t>(snp, PREP_BUDGET_BYTES / per_level)));
   p->levels_per_batch = std::max(lpb, 1);
   AB_TRY(dev_alloc(&p->d_prep, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * tile_doubles()));
   AB_TRY(dev_alloc(&p->d_summary, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * SUMMARY_DOUBLES));
+  if (nq > 0) {
+    AB_TRY(dev_alloc(&p->d_jac, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * nq * 2 * TL * 4));
+    AB_TRY(dev_alloc(&p->d_jcom, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * TL));
+    AB_TRY(dev_alloc(&p->d_dK, snp * nq * p->k_pitch * 7));
+    AB_TRY(dev_alloc(&p->d_dI, static_cast<size_t>(nf) * snp * nq * 4));
+    AB_TRY(dev_alloc(&p->d_Ilev, snp * nf * 4));
+  }
   *out = p.release();
   return AB200_OK;
 }
@@ -202,8 +222,6 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
                       int32_t select_species, int32_t no_negative_absorption, const ab200_target* targets,
                       const double* r, int32_t hse_derivative, int32_t rte_option, const double* I_bkg,
                       uint32_t flags) {
-  (void)targets;
-  (void)hse_derivative;
   if (!p || !f || !atm) return set_error(AB200_ERR_INVALID, "ab200_path_upload: null argument");
   const ab200_catalog* cat = p->cat;
   const int np = p->np;
@@ -220,11 +238,33 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   if (!atm->T || !atm->P || !atm->vmr || !atm->isorat || !atm->Q)
     return set_error(AB200_ERR_INVALID, "atm path: T, P, vmr, isorat and Q are required");
   AB_CUDA(cudaSetDevice(cat->device));
+  p->it = -1;
+  if (p->nq > 0) {
+    if (!targets) return set_error(AB200_ERR_INVALID, "ab200_path_upload: targets is null with nq > 0");
+    if (flags & AB200_FLAG_TRAN_EXACT)
+      return set_error(AB200_ERR_UNSUPPORTED, "AB200_FLAG_TRAN_EXACT has no Jacobian (the reference differentiates its literal form)");
+    for (int q = 0; q < p->nq; q++) {
+      p->tg_kind[q]    = targets[q].kind;
+      p->tg_species[q] = targets[q].species;
+      if (targets[q].kind == AB200_TARGET_T) {
+        if (!atm->dQdT) return set_error(AB200_ERR_INVALID, "atm path: dQdT is required with a temperature target");
+        if (p->it < 0) p->it = q;
+      } else if (targets[q].kind == AB200_TARGET_VMR) {
+        if (targets[q].species < 0 || targets[q].species >= cat->n_species)
+          return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": species out of range");
+      } else {
+        return set_error(AB200_ERR_UNSUPPORTED, "Jacobian target " + std::to_string(q) +
+                                                    ": only temperature and species VMR targets are on the GPU path");
+      }
+    }
+  }
 
   const size_t snp = static_cast<size_t>(np);
   double* h = p->h_small;
   double *hT = h, *hP = hT + snp, *hH = hP + snp, *hv = hH + snp, *hi = hv + snp * cat->n_species,
-         *hQ = hi + snp * cat->n_isot, *hn = hQ + snp * cat->n_isot, *hfr = hn + snp * 28, *hr = hfr + snp * 2;
+         *hQ = hi + snp * cat->n_isot, *hn = hQ + snp * cat->n_isot, *hfr = hn + snp * 28, *hr = hfr + snp * 2,
+         *hdQ = hr + snp, *hdr = hdQ + snp * cat->n_isot;
+  std::fill(hdr, hdr + 2 * snp * p->nq, 0.0);
   for (int ip = 0; ip < np; ip++) {
     if (!(atm->T[ip] > 0) || !(atm->P[ip] >= 0))
       return set_error(AB200_ERR_INVALID, "level " + std::to_string(ip) + ": temperature must be > 0 and pressure >= 0");
@@ -257,6 +297,12 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
                          "level " + std::to_string(ip) + ": isotopologue ratio must be >= 0 and partition function > 0");
       hi[static_cast<size_t>(ip) * cat->n_isot + i] = ir;
       hQ[static_cast<size_t>(ip) * cat->n_isot + i] = Q;
+      hdQ[static_cast<size_t>(ip) * cat->n_isot + i] = atm->dQdT ? atm->dQdT[static_cast<size_t>(ip) * cat->n_isot + i] : 0.0;
+    }
+    // hydrostatic path-length derivative, m_tramat.cc:18-24: dr [2][np-1][nq]
+    if (hse_derivative && p->it >= 0 && r && ip < np - 1) {
+      hdr[static_cast<size_t>(ip) * p->nq + p->it]            = r[ip] / (2.0 * atm->T[ip]);
+      hdr[(snp - 1 + ip) * p->nq + p->it]                     = r[ip] / (2.0 * atm->T[ip + 1]);
     }
   }
   if (p->small_doubles)
@@ -282,6 +328,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   p->flags      = flags;
   p->uploaded   = true;
   p->k_preloaded = false;
+  p->dk_preloaded = false;
   return AB200_OK;
 }
 
@@ -344,6 +391,7 @@ int ab200_path_run_propmat(ab200_path* p) {
   AB_CUDA(cudaSetDevice(cat->device));
   const size_t kbytes = static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double);
   if (!p->k_preloaded && kbytes) AB_CUDA(cudaMemsetAsync(p->d_K, 0, kbytes, p->stream));
+  if (p->nq > 0 && !p->dk_preloaded && kbytes) AB_CUDA(cudaMemsetAsync(p->d_dK, 0, kbytes * p->nq, p->stream));
   if (cat->ntiles == 0 || p->nf == 0) return AB200_OK;
   const size_t nseg = cat->segments.size();
   for (int lev0 = 0; lev0 < p->np; lev0 += p->levels_per_batch) {
@@ -363,6 +411,28 @@ int ab200_path_run_propmat(ab200_path* p) {
       LaunchTimer t(p, 1 + mode);
       AB_TRY(launch_sum(sp, nlev, mode, p->stream));
       t.stop();
+    }
+    if (p->nq > 0) {
+      JacPrepParams jp{};
+      JacSumParams js{};
+      jp.nq = js.nq = p->nq;
+      for (int q = 0; q < p->nq; q++) {
+        jp.kind[q] = js.kind[q] = p->tg_kind[q];
+        jp.species[q] = p->tg_species[q];
+      }
+      jp.dQdT = p->d_dQdT + static_cast<size_t>(lev0) * cat->n_isot;
+      jp.jac = p->d_jac;
+      jp.jcom = p->d_jcom;
+      js.jac = p->d_jac;
+      js.jcom = p->d_jcom;
+      js.dK = p->d_dK + static_cast<size_t>(lev0) * p->nq * p->k_pitch * 7;
+      AB_TRY(launch_prepare_jac(pp, jp, nlev, p->stream));
+      for (int mode = 0; mode < 2; mode++) {
+        sp.segs = p->d_segs + mode * nseg;
+        sp.nsegs = p->nsegs[mode];
+        if (sp.nsegs == 0) continue;
+        AB_TRY(launch_sum_jac(sp, js, nlev, p->stream));
+      }
     }
   }
   return AB200_OK;
@@ -434,9 +504,19 @@ int ab200_path_run_stokes(ab200_path* p) {
   sp.np = p->np; sp.nf = p->nf; sp.K = p->d_K; sp.k_pitch = p->k_pitch; sp.f = p->d_f; sp.f_stride = p->f_stride;
   sp.T = p->d_T; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
   sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
-  LaunchTimer t(p, 3);
-  AB_TRY(launch_stokes_chain(sp, p->stream));
-  t.stop();
+  sp.I_lev = p->nq > 0 ? p->d_Ilev : nullptr;
+  {
+    LaunchTimer t(p, 3);
+    AB_TRY(launch_stokes_chain(sp, p->stream));
+    t.stop();
+  }
+  if (p->nq > 0) {
+    StokesJacParams jp{};
+    jp.np = p->np; jp.nq = p->nq; jp.nf = p->nf; jp.K = p->d_K; jp.dK = p->d_dK; jp.k_pitch = p->k_pitch;
+    jp.f = p->d_f; jp.f_stride = p->f_stride; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
+    jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option;
+    AB_TRY(launch_stokes_jac(jp, p->stream));
+  }
   return AB200_OK;
 }
 
@@ -459,7 +539,14 @@ int ab200_path_sync(ab200_path* p) {
 
 int ab200_path_download(ab200_path* p, double* I, double* dI, double* K, double* dK) {
   if (!p) return set_error(AB200_ERR_INVALID, "ab200_path_download: null path");
-  if (dI || dK) return set_error(AB200_ERR_UNSUPPORTED, "Jacobian outputs are not on the GPU path in this build");
+  if ((dI || dK) && p->nq == 0) return set_error(AB200_ERR_INVALID, "ab200_path_download: the path has no Jacobian targets");
+  if (dI && p->nf && p->np)
+    AB_CUDA(cudaMemcpyAsync(dI, p->d_dI, static_cast<size_t>(p->nf) * p->np * p->nq * 4 * sizeof(double), cudaMemcpyDeviceToHost,
+                            p->stream));
+  if (dK && p->nf && p->np)
+    AB_CUDA(cudaMemcpy2DAsync(dK, static_cast<size_t>(p->nf) * 56, p->d_dK, static_cast<size_t>(p->k_pitch) * 56,
+                              static_cast<size_t>(p->nf) * 56, static_cast<size_t>(p->np) * p->nq, cudaMemcpyDeviceToHost,
+                              p->stream));
   if (I && p->nf)
     AB_CUDA(cudaMemcpyAsync(I, p->d_I, static_cast<size_t>(p->nf) * 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   if (K && p->nf && p->np)
@@ -473,6 +560,8 @@ void* ab200_path_device_ptr(ab200_path* p, int which) {
   switch (which) {
     case 0: return p->d_I;
     case 1: return p->d_K;
+    case 2: return p->d_dI;
+    case 3: return p->d_dK;
     default: return nullptr;
   }
 }
@@ -542,9 +631,15 @@ int ab200_propmat_levels(const ab200_catalog* cat, int64_t nf, const double* f, 
     AB_CUDA(cudaMemcpy2DAsync(p->d_K, static_cast<size_t>(p->k_pitch) * 56, K, static_cast<size_t>(nf) * 56,
                               static_cast<size_t>(nf) * 56, atm->np, cudaMemcpyHostToDevice, p->stream));
     p->k_preloaded = true;
+    if (nq > 0) {
+      AB_CUDA(cudaMemcpy2DAsync(p->d_dK, static_cast<size_t>(p->k_pitch) * 56, dK, static_cast<size_t>(nf) * 56,
+                                static_cast<size_t>(nf) * 56, static_cast<size_t>(atm->np) * nq, cudaMemcpyHostToDevice,
+                                p->stream));
+      p->dk_preloaded = true;
+    }
   }
   AB_TRY(ab200_path_run_propmat(p));
-  return ab200_path_download(p, nullptr, nullptr, K, nullptr);
+  return ab200_path_download(p, nullptr, nullptr, K, nq > 0 ? dK : nullptr);
 }
 
 int ab200_clearsky_emission(const ab200_catalog* cat, int64_t nf, const double* f, int64_t f_level_stride,
@@ -561,7 +656,7 @@ int ab200_clearsky_emission(const ab200_catalog* cat, int64_t nf, const double* 
                            hse_derivative, rte_option, I_bkg, flags));
   AB_TRY(ab200_path_run_propmat(p));
   AB_TRY(ab200_path_run_stokes(p));
-  return ab200_path_download(p, I, nullptr, (flags & AB200_FLAG_RETURN_K) ? K_out : nullptr, nullptr);
+  return ab200_path_download(p, I, nq > 0 ? dI : nullptr, (flags & AB200_FLAG_RETURN_K) ? K_out : nullptr, nullptr);
 }
 
 // --- un-fused compatibility entry points -----------------------------------------
@@ -576,16 +671,18 @@ struct DevBuf {
 int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double* dK, const double* r,
                  const double* dr, int32_t rte_option, uint32_t flags, double* T, double* L, double* P, double* dT,
                  double* dL) {
-  (void)dK; (void)dr; (void)dT; (void)dL;
-  if (nq > 0) return set_error(AB200_ERR_UNSUPPORTED, "ab200_tramat: Jacobian targets are not on the GPU path in this build");
   if (rte_option == AB200_RTE_LINPROP) return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path");
   if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC) return set_error(AB200_ERR_INVALID, "unknown rte_option");
-  if (np < 0 || nf < 0) return set_error(AB200_ERR_INVALID, "ab200_tramat: negative size");
+  if (np < 0 || nf < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_tramat: negative size");
   if (np == 0 || nf == 0) return AB200_OK;
   const bool linsrc = rte_option == AB200_RTE_LINSRC;
   if (!K || !T || !P || (np > 1 && !r) || (linsrc && !L)) return set_error(AB200_ERR_INVALID, "ab200_tramat: null argument");
+  if (nq > 0 && (!dK || !dT || (np > 1 && !dr) || (linsrc && !dL)))
+    return set_error(AB200_ERR_INVALID, "ab200_tramat: null Jacobian argument with nq > 0");
+  if (nq > 0 && (flags & AB200_FLAG_TRAN_EXACT))
+    return set_error(AB200_ERR_UNSUPPORTED, "AB200_FLAG_TRAN_EXACT has no Jacobian (the reference differentiates its literal form)");
   const size_t nk = static_cast<size_t>(np) * nf * 7, nm = static_cast<size_t>(np) * nf * 16;
-  DevBuf dK_, dr_, dT_, dL_, dP_;
+  DevBuf dK_, dr_, dT_, dL_, dP_, ddK_, ddr_, ddT_, ddL_;
   AB_TRY(dK_.alloc(nk)); AB_TRY(dr_.alloc(std::max(np - 1, 1))); AB_TRY(dT_.alloc(nm)); AB_TRY(dP_.alloc(nm));
   if (linsrc) AB_TRY(dL_.alloc(nm));
   AB_CUDA(cudaMemcpy(dK_.p, K, nk * sizeof(double), cudaMemcpyHostToDevice));
@@ -594,6 +691,18 @@ int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const doub
   AB_CUDA(cudaMemcpy(T, dT_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
   AB_CUDA(cudaMemcpy(P, dP_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
   if (linsrc) AB_CUDA(cudaMemcpy(L, dL_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (nq > 0) {
+    const size_t nd = 2 * nm * nq;
+    AB_TRY(ddK_.alloc(nk * nq)); AB_TRY(ddr_.alloc(2 * static_cast<size_t>(std::max(np - 1, 1)) * nq)); AB_TRY(ddT_.alloc(nd));
+    if (linsrc) AB_TRY(ddL_.alloc(nd));
+    AB_CUDA(cudaMemcpy(ddK_.p, dK, nk * nq * sizeof(double), cudaMemcpyHostToDevice));
+    if (np > 1) AB_CUDA(cudaMemcpy(ddr_.p, dr, 2 * static_cast<size_t>(np - 1) * nq * sizeof(double), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemset(ddT_.p, 0, nd * sizeof(double)));  // dT = muelmat::constant(0), rtepack_transmission.cc:1300-1314
+    if (linsrc) AB_CUDA(cudaMemset(ddL_.p, 0, nd * sizeof(double)));
+    AB_TRY(launch_tramat_jac(np, nf, nq, dK_.p, ddK_.p, dr_.p, ddr_.p, linsrc, ddT_.p, ddL_.p, 0));
+    AB_CUDA(cudaMemcpy(dT, ddT_.p, nd * sizeof(double), cudaMemcpyDeviceToHost));
+    if (linsrc) AB_CUDA(cudaMemcpy(dL, ddL_.p, nd * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   return AB200_OK;
 }
 
@@ -619,23 +728,37 @@ int ab200_srcvec(int32_t np, int64_t nf, int32_t nq, const double* K, const doub
 int ab200_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, const double* T, const double* L,
                        const double* P, const double* dT, const double* dL, const double* J, const double* dJ,
                        const double* I_bkg, double* I, double* dI) {
-  (void)P; (void)dT; (void)dL; (void)dJ; (void)dI;
-  if (nq > 0) return set_error(AB200_ERR_UNSUPPORTED, "ab200_rte_emission: Jacobian targets are not on the GPU path in this build");
   if (rte_option == AB200_RTE_LINPROP) return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path");
   if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC) return set_error(AB200_ERR_INVALID, "unknown rte_option");
-  if (np < 0 || nf < 0) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: negative size");
+  if (np < 0 || nf < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: negative size");
   if (nf == 0) return AB200_OK;
   const bool linsrc = rte_option == AB200_RTE_LINSRC;
   if (!T || !J || !I_bkg || !I || (linsrc && !L)) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: null argument");
+  if (nq > 0 && (!P || !dT || !dJ || !dI || (linsrc && !dL)))
+    return set_error(AB200_ERR_INVALID, "ab200_rte_emission: null Jacobian argument with nq > 0");
   const size_t nm = static_cast<size_t>(np) * nf * 16, nj = static_cast<size_t>(np) * nf * 4;
-  DevBuf dT_, dL_, dJ_, dB_, dI_;
+  DevBuf dT_, dL_, dJ_, dB_, dI_, dP_, ddT_, ddL_, ddJ_, ddI_;
   AB_TRY(dT_.alloc(nm)); AB_TRY(dJ_.alloc(nj)); AB_TRY(dB_.alloc(nf * 4)); AB_TRY(dI_.alloc(nf * 4));
   if (linsrc) AB_TRY(dL_.alloc(nm));
   AB_CUDA(cudaMemcpy(dT_.p, T, nm * sizeof(double), cudaMemcpyHostToDevice));
   if (linsrc) AB_CUDA(cudaMemcpy(dL_.p, L, nm * sizeof(double), cudaMemcpyHostToDevice));
   AB_CUDA(cudaMemcpy(dJ_.p, J, nj * sizeof(double), cudaMemcpyHostToDevice));
   AB_CUDA(cudaMemcpy(dB_.p, I_bkg, nf * 4 * sizeof(double), cudaMemcpyHostToDevice));
-  AB_TRY(launch_rte_emission(linsrc, np, nf, dT_.p, dL_.p, dJ_.p, dB_.p, dI_.p, 0));
+  if (nq == 0) {
+    AB_TRY(launch_rte_emission(linsrc, np, nf, dT_.p, dL_.p, dJ_.p, dB_.p, dI_.p, 0));
+  } else {
+    const size_t nd = 2 * nm * nq;
+    AB_TRY(dP_.alloc(nm)); AB_TRY(ddT_.alloc(nd)); AB_TRY(ddJ_.alloc(nj * nq)); AB_TRY(ddI_.alloc(nj * nq));
+    if (linsrc) AB_TRY(ddL_.alloc(nd));
+    AB_CUDA(cudaMemcpy(dP_.p, P, nm * sizeof(double), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemcpy(ddT_.p, dT, nd * sizeof(double), cudaMemcpyHostToDevice));
+    if (linsrc) AB_CUDA(cudaMemcpy(ddL_.p, dL, nd * sizeof(double), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemcpy(ddJ_.p, dJ, nj * nq * sizeof(double), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemset(ddI_.p, 0, nj * nq * sizeof(double)));  // spectral_rad_jac_path = 0, m_spectral_radiance.cc:36-40
+    AB_TRY(launch_rte_emission_jac(linsrc, np, nf, nq, dT_.p, dL_.p, dP_.p, ddT_.p, ddL_.p, dJ_.p, ddJ_.p, dB_.p, dI_.p,
+                                   ddI_.p, 0));
+    AB_CUDA(cudaMemcpy(dI, ddI_.p, nj * nq * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   AB_CUDA(cudaMemcpy(I, dI_.p, nf * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   return AB200_OK;
 }

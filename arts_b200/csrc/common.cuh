@@ -51,6 +51,8 @@ constexpr int SUMMARY_DOUBLES = 4;
 // (3rdparty/Faddeeva/Faddeeva.cc:707-725)
 constexpr double FAR_LIMIT = 4000.0;
 
+constexpr int AB200_MAX_TARGETS = 8;  // Jacobian targets per call (temperature + species VMRs)
+
 enum Pol : int { POL_NO = 0, POL_PI = 1, POL_SM = 2, POL_SP = 3 };
 
 // ---- error plumbing ---------------------------------------------------------

@@ -26,29 +26,9 @@
 #include "catalog.hpp"
 #include "faddeeva.cuh"
 #include "lbl.hpp"
+#include "lbl_model.cuh"
 
 namespace ab200 {
-
-// ---------------------------------------------------------------------------
-// temperature models, lbl_temperature_model.h:62-283 (values only; d/dT in lbl_jac.cu)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double tm_value(int type, const double* __restrict__ x, double T0, double T) {
-  switch (type) {
-    case AB200_TM_T0: return x[0];
-    case AB200_TM_T1: return x[0] * pow(T0 / T, x[1]);
-    case AB200_TM_T2: return x[0] * pow(T0 / T, x[1]) * (1 + x[2] * log(T / T0));
-    case AB200_TM_T3: return x[0] + x[1] * (T - T0);
-    case AB200_TM_T4: return (x[0] + x[1] * (T0 / T - 1)) * pow(T0 / T, x[2]);
-    case AB200_TM_T5: return x[0] * pow(T0 / T, 0.25 + 1.5 * x[1]);
-    case AB200_TM_AER:
-      if (T < 250.0) return x[0] + (T - 200.0) * (x[1] - x[0]) / (250.0 - 200.0);
-      if (T > 296.0) return x[2] + (T - 296.0) * (x[3] - x[2]) / (340.0 - 296.0);
-      return x[1] + (T - 250.0) * (x[2] - x[1]) / (296.0 - 250.0);
-    case AB200_TM_DPL: return x[0] * pow(T0 / T, x[1]) + x[2] * pow(T0 / T, x[3]);
-    case AB200_TM_POLY: return x[0] + T * (x[1] + T * (x[2] + T * x[3]));
-    default: return 0.0;
-  }
-}
 
 // ---------------------------------------------------------------------------
 // K1

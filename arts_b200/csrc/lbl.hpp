@@ -46,7 +46,26 @@ struct SumParams {
   int64_t k_pitch;
 };
 
+// Jacobian targets (lbl_jac.cu)
+struct JacPrepParams {
+  int32_t nq;
+  int32_t kind[AB200_MAX_TARGETS];     // AB200_TARGET_*
+  int32_t species[AB200_MAX_TARGETS];  // for VMR targets
+  const double* dQdT;                  // [nlev][n_isot], offset to the batch
+  double* jac;                         // [nlev][ntiles][nq][2][TL][4]
+  double* jcom;                        // [nlev][ntiles][TL]
+};
+struct JacSumParams {
+  int32_t nq, q0;
+  int32_t kind[AB200_MAX_TARGETS];
+  const double* jac;
+  const double* jcom;
+  double* dK;  // [nlev][nq][k_pitch][7], offset to the batch
+};
+
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream);
+int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev, cudaStream_t stream);
+int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream);
 int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream);
 // region histogram of the evaluations of one batch of levels (measurement helper, see arts_b200.h)
 int launch_region_histogram(const SumParams& p, int nlev, int64_t samples_per_level, uint64_t seed, double* d_out,

@@ -1,0 +1,315 @@
+// lbl_jac.cu — Jacobian part of stage 1 (nq > 0): d(propagation matrix)/d(temperature | VMR).
+//
+//   lbl_prepare_jac_kernel   per (sub-line, level, target): ds, dz, dz_fac (+ the cutoff value of dX)
+//       replaces ComputeData::dt_core_calc / dVMR_core_calc
+//       (reference src/core/lbl/lbl_lineshape_voigt_lte.cpp:984-1033, :1153-1189) with
+//       dline_strength_calc_dT :116-143, dline_strength_calc_dVMR :86-114, line::ds_dT lbl_data.h:138-142
+//       and the model derivatives lbl_lineshape_model.cpp:92-148
+//   lbl_sum_jac_kernel       sum over lines of dX = ds F + s (dz + dz_fac z) dF per frequency and target
+//       replaces band_shape::dT / dVMR (:475-507, :655-720) and compute_derivative (:1463-1561)
+//
+// The reference differentiates w(z) by a FORWARD FINITE DIFFERENCE (single_shape::dF, :250-268:
+// dz = max(1e-4 |.|, 1e-4) per component, one extra w per pair); parity means reproducing that, not
+// the analytic -2 z w + 2i/sqrt(pi).  Both w(z) and w(z + dz) go through the same
+// region map as the reference (far closed forms, continued fraction, series).
+#include <algorithm>
+#include <cfloat>
+
+#include "catalog.hpp"
+#include "faddeeva.cuh"
+#include "lbl.hpp"
+#include "lbl_model.cuh"
+
+namespace ab200 {
+
+struct cplx {
+  double re, im;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ cplx cscale(double s, cplx a) { return {s * a.re, s * a.im}; }
+__device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
+  const double d = 1.0 / (b.re * b.re + b.im * b.im);
+  return {(a.re * b.re + a.im * b.im) * d, (a.im * b.re - a.re * b.im) * d};
+}
+
+// w(x + i y) for any finite x, y >= 0, with the reference's region map (Faddeeva.cc:689-741):
+// nu == 1 (x+y > 1e7, :708-720), nu == 2 (:721-725), continued fraction, series.  E1 = series_E1(y).
+__device__ __forceinline__ cplx w_any(double x, double y, double E1) {
+  const double ax = fabs(x);
+  double wr, wi;
+  if (ax + y > 1e7) {
+    if (ax > y) {
+      const double yax   = y / ax;
+      const double denom = fad::ISPI / (ax + yax * y);
+      wr = denom * yax;
+      wi = denom;
+    } else {
+      const double xya   = ax / y;
+      const double denom = fad::ISPI / (xya * ax + y);
+      wr = denom;
+      wi = denom * xya;
+    }
+  } else if (ax + y > FAR_LIMIT) {
+    // nu == 2 in the reference's own operand order: dr = x^2 - y^2 - 1/2, di = 2 x y
+    const double dr = ax * ax - y * y - 0.5, di = 2 * ax * y;
+    const double denom = fad::ISPI / (dr * dr + di * di);
+    wr = denom * (ax * di - y * dr);
+    wi = denom * (ax * dr + y * di);
+  } else if (cf_region(ax, y)) {
+    w_cf(ax, y, wr, wi);
+  } else {
+    w_series(ax, y, E1, wr, wi);
+  }
+  return {wr, x < 0.0 ? -wi : wi};
+}
+
+// single_shape::all(f): z, F = w(z), dF by the forward finite difference of :250-268
+__device__ __forceinline__ void z_F_dF(double x, double y, double E1, double E1p, cplx& z, cplx& F, cplx& dF) {
+  z = {x, y};
+  F = w_any(x, y, E1);
+  const cplx dz{fmax(1e-4 * fabs(x), 1e-4), fmax(1e-4 * fabs(y), 1e-4)};
+  const cplx F2 = w_any(x + dz.re, y + dz.im, E1p);
+  dF = cdiv(csub(F2, F), dz);
+}
+
+// single_shape::dT / dVMR, :310-323
+__device__ __forceinline__ cplx dX(cplx s, cplx ds, cplx dzq, double dz_fac, cplx z, cplx F, cplx dF) {
+  const cplx t = cadd(dzq, cscale(dz_fac, z));
+  return cadd(cmul(ds, F), cmul(cmul(s, t), dF));
+}
+
+// ---------------------------------------------------------------------------
+// per (sub-line, level, target) derivative records
+//   jac  [lev][tile][q][2][TL][4] : (ds_re, ds_im, dz_re, dz_im) | (dz_fac, dcut_re, dcut_im, 0)
+//   jcom [lev][tile][TL]          : E1(y + dy), the series constant of the displaced point
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, JacPrepParams jp) {
+  const int64_t tile = blockIdx.x;
+  const int lev      = blockIdx.y;
+  const int lane     = threadIdx.x;
+  const int64_t slot = tile * TL + lane;
+  const int64_t par  = p.sub_parent[slot];
+  const double* rec  = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
+  const double f0s   = rec[(0 * TL + lane) * REC_GROUP + 0];
+  const double igd   = rec[(1 * TL + lane) * REC_GROUP + 1];
+  const double y     = rec[(1 * TL + lane) * REC_GROUP + 2];
+  const double s_re  = rec[(1 * TL + lane) * REC_GROUP + 3];
+  const double E1    = rec[(2 * TL + lane) * REC_GROUP + 0];
+  const double s_im  = rec[(2 * TL + lane) * REC_GROUP + 1];
+  const bool live    = par >= 0 && igd != 0.0;  // padding and inactive cutoff lines have igd == 0
+
+  const double yp  = y + fmax(1e-4 * fabs(y), 1e-4);
+  const double E1p = (live && yp <= 7.0) ? series_E1(yp) : 0.0;
+  jp.jcom[(int64_t(lev) * p.ntiles + tile) * TL + lane] = E1p;
+
+  const double T = p.T[lev], P = p.P[lev];
+  const double cut = p.tile_cutoff[tile];
+  for (int q = 0; q < jp.nq; q++) {
+    double o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+      const int isot = p.line_isot[par];
+      const int spec = p.isot_species[isot];
+      LineModel lm{p.ls_offset, p.ls_species, p.ls_type, p.ls_X, par, p.T0[par], T, P, p.vmr + int64_t(lev) * p.n_species};
+      const double G = lm.mix(AB200_VAR_G, false), Y = lm.mix(AB200_VAR_Y, false);
+      const double f0c = p.f0[par];
+      const double Q   = p.Q[int64_t(lev) * p.n_isot + isot];
+      const double ex  = exp(-p.e0[par] / (cst::k * T));
+      const double sl  = p.a[par] * p.gu[par] * ex / (f0c * f0c * f0c * Q);  // line::s, lbl_data.h:66-68
+      const double r   = p.isorat[int64_t(lev) * p.n_isot + isot];
+      const double x   = p.vmr[int64_t(lev) * p.n_species + spec];
+      const double Sz  = p.sub_Sz[slot];
+      const cplx lmc{1 + G, -Y};
+      double dD0, dDV, dG0, dG, dY;
+      cplx ds;
+      double dz_fac;
+      if (jp.kind[q] == AB200_TARGET_T) {
+        dD0 = lm.mix(AB200_VAR_D0, true); dDV = lm.mix(AB200_VAR_DV, true); dG0 = lm.mix(AB200_VAR_G0, true);
+        dG  = lm.mix(AB200_VAR_G, true);  dY  = lm.mix(AB200_VAR_Y, true);
+        const double dQ  = jp.dQdT[int64_t(lev) * p.n_isot + isot];
+        const double dsl = p.a[par] * p.gu[par] * (p.e0[par] * Q - cst::k * (T * T) * dQ) * ex /
+                           (f0c * f0c * f0c * cst::k * (T * T) * (Q * Q));  // line::ds_dT, lbl_data.h:138-142
+        const double df0 = dD0 + dDV;
+        const cplx dlm{dG, -dY};
+        // dline_strength_calc_dT, :116-143
+        const cplx num = csub(csub(cscale(2 * T * f0s, cadd(cscale(sl, dlm), cscale(dsl, lmc))), cscale(2 * T * df0 * sl, lmc)),
+                              cscale(f0s * sl, lmc));
+        ds     = cscale(Sz * (cst::inv_sqrt_pi * igd * r * x) / (2 * T * f0s), num);
+        dz_fac = (-2 * T * dD0 - 2 * T * dDV - f0s) / (2 * T * f0s);  // :1013-1015
+      } else {
+        const int ts = jp.species[q];
+        dD0 = lm.dmix_dvmr(AB200_VAR_D0, ts); dDV = lm.dmix_dvmr(AB200_VAR_DV, ts); dG0 = lm.dmix_dvmr(AB200_VAR_G0, ts);
+        dG  = lm.dmix_dvmr(AB200_VAR_G, ts);  dY  = lm.dmix_dvmr(AB200_VAR_Y, ts);
+        const double df0 = dD0 + dDV;
+        const cplx dlm{dG, -dY};
+        // dline_strength_calc_dVMR, :86-114
+        const double pre = -cst::inv_sqrt_pi * igd * r * sl;
+        if (ts == spec) {
+          ds = cscale(Sz * pre, csub(cscale(x * (df0 / f0s), lmc), cadd(cscale(x, dlm), lmc)));
+        } else {
+          ds = cscale(Sz * pre * x, csub(cscale(df0 / f0s, lmc), dlm));
+        }
+        dz_fac = -(dD0 + dDV) / f0s;  // :1176
+      }
+      const cplx dzq{igd * -(dD0 + dDV), igd * dG0};
+      o[0] = ds.re; o[1] = ds.im; o[2] = dzq.re; o[3] = dzq.im; o[4] = dz_fac;
+      if (cut < DBL_MAX) {  // band_shape::dT(dcut, ...) at f0' + cutoff, :475-486
+        cplx z, F, dF;
+        z_F_dF(igd * ((f0s + cut) - f0s), y, E1, E1p, z, F, dF);
+        const cplx dc = dX({s_re, s_im}, ds, dzq, dz_fac, z, F, dF);
+        o[5] = dc.re; o[6] = dc.im;
+      }
+    }
+    double* out = jp.jac + ((int64_t(lev) * p.ntiles + tile) * jp.nq + q) * (2 * TL * 4);
+    double2* o0 = reinterpret_cast<double2*>(out + (0 * TL + lane) * 4);
+    double2* o1 = reinterpret_cast<double2*>(out + (1 * TL + lane) * 4);
+    o0[0] = make_double2(o[0], o[1]); o0[1] = make_double2(o[2], o[3]);
+    o1[0] = make_double2(o[4], o[5]); o1[1] = make_double2(o[6], o[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// line sum with derivatives
+// ---------------------------------------------------------------------------
+constexpr int JAC_NT = 128;
+constexpr int JAC_R  = 2;
+constexpr int JAC_F_TILE = JAC_NT * JAC_R;
+constexpr int JAC_Q  = 4;  // targets per pass
+
+// dscl(f) of dt_core_calc, :990-1000
+__device__ __forceinline__ double line_scale_dT(double f, double T, double P) {
+  constexpr double c = cst::c * cst::c / (8 * cst::pi);
+  const double N  = P / (cst::k * T);
+  const double dN = -P / (cst::k * (T * T));
+  const double r  = (cst::h * f) / (cst::k * T);
+  return -f * (N * r * exp(-r) / T + dN * expm1(-r)) * c;
+}
+__device__ __forceinline__ double line_scale_v(double f, double T, double P) {
+  constexpr double c = cst::c * cst::c / (8 * cst::pi);
+  const double N     = P / (cst::k * T);
+  const double r     = (cst::h * f) / (cst::k * T);
+  return -N * f * expm1(-r) * c;
+}
+
+__global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSumParams jp) {
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t fblk = int64_t(blockIdx.x) * JAC_F_TILE;
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  double f[JAC_R];
+#pragma unroll
+  for (int r = 0; r < JAC_R; r++) {
+    const int64_t i = fblk + r * JAC_NT + tid;
+    f[r] = fg[i < p.nf ? i : p.nf - 1];
+  }
+  const double fblk_min = fg[fblk];
+  const double fblk_max = fg[(fblk + JAC_F_TILE - 1 < p.nf) ? fblk + JAC_F_TILE - 1 : p.nf - 1];
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
+  const double* __restrict__ jcom = jp.jcom + int64_t(lev) * p.ntiles * TL;
+  const int nqp = min(JAC_Q, jp.nq - jp.q0);
+  const double T = p.T[lev], P = p.P[lev];
+
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    const double cutoff  = seg.has_cutoff ? seg.cutoff : DBL_MAX;
+    cplx shape[JAC_R], acc[JAC_Q][JAC_R];
+#pragma unroll
+    for (int r = 0; r < JAC_R; r++) {
+      shape[r] = {0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < JAC_Q; q++) acc[q][r] = {0.0, 0.0};
+    }
+    for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
+      const double* __restrict__ s4 = summ + t * SUMMARY_DOUBLES;
+      if (s4[0] > s4[1]) continue;  // no contributing line
+      if (fmax(0.0, fmax(fblk_min - s4[1], s4[0] - fblk_max)) > cutoff * (1.0 + 1e-9)) continue;
+      const double2* __restrict__ g0 = reinterpret_cast<const double2*>(prep + t * tile_doubles());
+      const double2* __restrict__ g1 = g0 + 2 * TL;
+      const double2* __restrict__ g2 = g0 + 4 * TL;
+      const double* __restrict__ jt  = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
+      const int count = p.tile_count[t];
+      for (int l = 0; l < count; l++) {
+        const double2 a = __ldg(g0 + 2 * l);                           // f0', c3
+        const double2 m = __ldg(g1 + 2 * l), n2 = __ldg(g1 + 2 * l + 1);  // B1, igd | y, s_re
+        const double2 h = __ldg(g2 + 2 * l), k = __ldg(g2 + 2 * l + 1);   // E1, s_im | cut_re, cut_im
+        if (m.y == 0.0) continue;                                     // inactive cutoff line
+        const double E1p = __ldg(jcom + t * TL + l);
+        const cplx s{n2.y, h.y};
+        cplx ds[JAC_Q], dzq[JAC_Q], dcut[JAC_Q];
+        double dzf[JAC_Q];
+#pragma unroll
+        for (int q = 0; q < JAC_Q; q++) {
+          if (q < nqp) {
+            const double2* __restrict__ j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+            const double2* __restrict__ j1 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (1 * TL + l) * 4);
+            const double2 u0 = __ldg(j0), u1 = __ldg(j0 + 1), u2 = __ldg(j1), u3 = __ldg(j1 + 1);
+            ds[q] = {u0.x, u0.y}; dzq[q] = {u1.x, u1.y}; dzf[q] = u2.x; dcut[q] = {u2.y, u3.x};
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < JAC_R; r++) {
+          if (seg.has_cutoff && !(a.x >= f[r] - cutoff && a.x <= f[r] + cutoff)) continue;
+          cplx z, F, dF;
+          z_F_dF(m.y * (f[r] - a.x), n2.x, h.x, E1p, z, F, dF);
+          cplx sh = cmul(s, F);
+          if (seg.has_cutoff) sh = csub(sh, {k.x, k.y});
+          shape[r] = cadd(shape[r], sh);
+#pragma unroll
+          for (int q = 0; q < JAC_Q; q++) {
+            if (q < nqp) {
+              cplx d = dX(s, ds[q], dzq[q], dzf[q], z, F, dF);
+              if (seg.has_cutoff) d = csub(d, dcut[q]);
+              acc[q][r] = cadd(acc[q][r], d);
+            }
+          }
+        }
+      }
+    }
+    // compute_derivative :1474-1481 (T) and :1553-1560 (VMR): dpm += npm (.) (dscl shape + scl dshape)
+    const double* __restrict__ npm = p.npm + (int64_t(lev) * 4 + seg.pol) * 7;
+    const bool all_zero = npm[0] == 0 && npm[1] == 0 && npm[2] == 0 && npm[3] == 0 && npm[4] == 0 && npm[5] == 0 &&
+                          npm[6] == 0;
+    if (all_zero) continue;
+#pragma unroll
+    for (int r = 0; r < JAC_R; r++) {
+      const int64_t i = fblk + r * JAC_NT + tid;
+      if (i >= p.nf) continue;
+      const double scl = line_scale_v(f[r], T, P);
+#pragma unroll
+      for (int q = 0; q < JAC_Q; q++) {
+        if (q < nqp) {
+          cplx d = cscale(scl, acc[q][r]);
+          if (jp.kind[jp.q0 + q] == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
+          double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
+          o[0] += npm[0] * d.re; o[1] += npm[1] * d.re; o[2] += npm[2] * d.re; o[3] += npm[3] * d.re;
+          o[4] += npm[4] * d.im; o[5] += npm[5] * d.im; o[6] += npm[6] * d.im;
+        }
+      }
+    }
+  }
+}
+
+int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev, cudaStream_t stream) {
+  if (p.ntiles == 0 || nlev == 0 || jp.nq == 0) return 0;
+  dim3 grid(static_cast<unsigned>(p.ntiles), static_cast<unsigned>(nlev));
+  lbl_prepare_jac_kernel<<<grid, TL, 0, stream>>>(p, jp);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream) {
+  if (p.nsegs == 0 || nlev == 0 || p.nf == 0 || jp.nq == 0) return 0;
+  dim3 grid(static_cast<unsigned>((p.nf + JAC_F_TILE - 1) / JAC_F_TILE), static_cast<unsigned>(nlev));
+  for (int q0 = 0; q0 < jp.nq; q0 += JAC_Q) {
+    jp.q0 = q0;
+    lbl_sum_jac_kernel<<<grid, JAC_NT, 0, stream>>>(p, jp);
+    count_launch();
+    AB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace ab200

@@ -247,6 +247,212 @@ struct Tran {
     m[0] += l0; m[5] += l0; m[10] += l0; m[15] += l0;
   }
 
+  // d/dq of operator()(), rtepack_transmission.cc:558-674: t = T of this layer, dk = dK/dq of ONE end
+  // level, dr = d r / dq (hydrostatic term).  Literal (quirk 6) arithmetic only.
+  __device__ __forceinline__ void deriv(const double* __restrict__ t, const Propmat& k1, const Propmat& k2, const Propmat& dk,
+                                        double r, double dr, double* __restrict__ m) const {
+    const double da = -0.5 * (r * dk.A + dr * (k1.A + k2.A));
+    if (!polarized) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) m[i] = 0.0;
+      m[0] = m[5] = m[10] = m[15] = da * exp_a;
+      return;
+    }
+    const double db  = -0.5 * (r * dk.B + dr * (k1.B + k2.B));
+    const double dc  = -0.5 * (r * dk.C + dr * (k1.C + k2.C));
+    const double dd  = -0.5 * (r * dk.D + dr * (k1.D + k2.D));
+    const double du  = -0.5 * (r * dk.U + dr * (k1.U + k2.U));
+    const double dv  = -0.5 * (r * dk.V + dr * (k1.V + k2.V));
+    const double dw  = -0.5 * (r * dk.W + dr * (k1.W + k2.W));
+    const double db2 = 2 * db * b, dc2 = 2 * dc * c, dd2 = 2 * dd * d, du2 = 2 * du * u, dv2 = 2 * dv * v, dw2 = 2 * dw * w;
+    const double dB  = du2 + dv2 + dw2 - db2 - dc2 - dd2;
+    const double dC  = -2 * (d * u - c * v + b * w) * (dd * u + d * du - dc * v - c * dv + db * w + b * dw);
+    const double dS  = (B * dB - 2 * dC) / S;
+    const double dx2 = 0.25 * (dS - dB) / x2;
+    const double dy2 = 0.25 * (dS + dB) / y2;
+    const double dx  = 0.5 * dx2 / x;
+    const double dy  = 0.5 * dy2 / y;
+    const double dcy = -sy * dy, dsy = cy * dy, dcx = sx * dx, dsx = cx * dx;
+    const double dix = -dx * ix * ix, diy = -dy * iy * iy;
+    const double dx2dy2 = dx2 + dy2;
+    const double dC0 = either_zero ? 0.0 : (dcy * x2 + cy * dx2 + dcx * y2 + cx * dy2 - C0 * dx2dy2) * inv_x2y2;
+    const double dC1 = either_zero ? 0.0
+                                   : (dsy * x2 * iy + sy * dx2 * iy + sy * x2 * diy + dsx * y2 * ix + sx * dy2 * ix +
+                                      sx * y2 * dix - C1 * dx2dy2) *
+                                         inv_x2y2;
+    const double dC2 = both_zero ? 0.0 : ((x_zero ? 0.0 : (dcx - C2 * dx2)) - (y_zero ? 0.0 : (dcy + C2 * dy2))) * inv_x2y2;
+    const double dC3 = both_zero ? 0.0
+                                 : ((x_zero ? 0.0 : (dsx * ix + sx * dix - C3 * dx2)) -
+                                    (y_zero ? 0.0 : (dsy * iy + sy * diy + C3 * dy2))) *
+                                       inv_x2y2;
+    const double dC2b = dC2 * (c * u + d * v) + C2 * (dc * u + c * du + dd * v + d * dv);
+    const double dC2c = dC2 * (b * u - d * w) + C2 * (db * u + b * du - dd * w - d * dw);
+    const double dC2d = dC2 * (b * v + c * w) + C2 * (db * v + b * dv + dc * w + c * dw);
+    const double dC2u = dC2 * (b * c - v * w) + C2 * (db * c + b * dc - dv * w - v * dw);
+    const double dC2v = dC2 * (b * d + u * w) + C2 * (db * d + b * dd + du * w + u * dw);
+    const double dC2w = dC2 * (c * d - u * v) + C2 * (dc * d + c * dd - du * v - u * dv);
+    const double dC3b = dC3 * (b * (B - w2) + w * (c * v - d * u)) +
+                        C3 * (db * (B - w2) + b * (dB - dw2) + dw * (c * v - d * u) + w * (dc * v + c * dv - dd * u - d * du));
+    const double dC3c = dC3 * (c * (v2 - B) - v * (d * u + b * w)) +
+                        C3 * (dc * (v2 - B) + c * (dv2 - dB) - dv * (d * u + b * w) - v * (dd * u + d * du + db * w + b * dw));
+    const double dC3d = dC3 * (d * (u2 - B) - u * (c * v - b * w)) +
+                        C3 * (dd * (u2 - B) + d * (du2 - dB) - du * (c * v - b * w) - u * (dc * v + c * dv - db * w - b * dw));
+    const double dC3u = dC3 * (d * (c * v - b * w) - u * (B + d2)) +
+                        C3 * (dd * (c * v - b * w) + d * (dc * v + c * dv - db * w - b * dw) - du * (B + d2) - u * (dB + dd2));
+    const double dC3v = dC3 * (c * (d * u + b * w) - v * (B + c2)) +
+                        C3 * (dc * (d * u + b * w) + c * (dd * u + d * du + db * w + b * dw) - dv * (B + c2) - v * (dB + dc2));
+    const double dC3w = dC3 * (b * (c * v - d * u) - w * (B + b2)) +
+                        C3 * (db * (c * v - d * u) + b * (dc * v + c * dv - dd * u - d * du) - dw * (B + b2) - w * (dB + db2));
+    const double dM00 = dC0 + dC2 * (b2 + c2 + d2) + C2 * (db2 + dc2 + dd2);
+    const double dM11 = dC0 + dC2 * (b2 - u2 - v2) + C2 * (db2 - du2 - dv2);
+    const double dM22 = dC0 + dC2 * (c2 - u2 - w2) + C2 * (dc2 - du2 - dw2);
+    const double dM33 = dC0 + dC2 * (d2 - v2 - w2) + C2 * (dd2 - dv2 - dw2);
+    const double e[16] = {dM00,
+                          dC1 * b + C1 * db - dC2b - dC3b,
+                          dC1 * c + C1 * dc + dC2c + dC3c,
+                          dC1 * d + C1 * dd + dC2d + dC3d,
+                          dC1 * b + C1 * db + dC2b - dC3b,
+                          dM11,
+                          dC1 * u + C1 * du + dC2u + dC3u,
+                          dC1 * v + C1 * dv + dC2v + dC3v,
+                          dC1 * c + C1 * dc - dC2c + dC3c,
+                          -dC1 * u - C1 * du + dC2u - dC3u,
+                          dM22,
+                          dC1 * w + C1 * dw + dC2w + dC3w,
+                          dC1 * d + C1 * dd - dC2d + dC3d,
+                          -dC1 * v - C1 * dv + dC2v - dC3v,
+                          -dC1 * w - C1 * dw + dC2w - dC3w,
+                          dM33};
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = da * t[i] + exp_a * e[i];
+  }
+
+  // d/dq of linsrc(), rtepack_transmission.cc:277-447
+  __device__ __forceinline__ void linsrc_deriv(const Propmat& dk, double r, double dr, double* __restrict__ m) const {
+    const double inv_r = (fabs(r) > 1e-20) ? 1.0 / r : 0.0;
+    const double dr_r  = dr * inv_r;
+    const double da    = dr_r * a - 0.5 * r * dk.A;
+    if (!polarized) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) m[i] = 0.0;
+      m[0] = m[5] = m[10] = m[15] = func_Fp(a) * da;
+      return;
+    }
+    const double db  = dr_r * b - 0.5 * r * dk.B;
+    const double dc  = dr_r * c - 0.5 * r * dk.C;
+    const double dd  = dr_r * d - 0.5 * r * dk.D;
+    const double du  = dr_r * u - 0.5 * r * dk.U;
+    const double dv  = dr_r * v - 0.5 * r * dk.V;
+    const double dw  = dr_r * w - 0.5 * r * dk.W;
+    const double db2 = 2.0 * db * b, dc2 = 2.0 * dc * c, dd2 = 2.0 * dd * d, du2 = 2.0 * du * u, dv2 = 2.0 * dv * v,
+                 dw2 = 2.0 * dw * w;
+    const double dB  = du2 + dv2 + dw2 - db2 - dc2 - dd2;
+    const double dC  = -2.0 * (d * u - c * v + b * w) * (dd * u + d * du - dc * v - c * dv + db * w + b * dw);
+    const double dS_val = (S > 1e-9) ? (B * dB - 2.0 * dC) / S : 0.0;
+    const double dx2    = (x2 > 1e-9) ? 0.25 * (dS_val - dB) / x2 : 0.0;
+    const double dy2    = (y2 > 1e-9) ? 0.25 * (dS_val + dB) / y2 : 0.0;
+    const double dx     = (x > 1e-9) ? 0.5 * dx2 / x : 0.0;
+    const double dy     = (y > 1e-9) ? 0.5 * dy2 / y : 0.0;
+    double l1, l2, l3, dl0, dl1, dl2, dl3;
+    if (both_zero) {
+      const double fpa  = func_Fp(a);
+      const double fppa = func_Fpp(a);
+      dl0 = fpa * da;
+      l1  = fpa;
+      dl1 = fppa * da;
+      if (fabs(a) < too_small) {
+        l2  = 1.0 / 6.0 + a / 12.0;
+        dl2 = da / 12.0;
+        l3  = 1.0 / 24.0 + a / 60.0;
+        dl3 = da / 60.0;
+      } else {
+        const double f3pa = func_F3p(a);
+        const double f4pa = func_F4p(a);
+        l2  = 0.5 * fppa;
+        dl2 = 0.5 * f3pa * da;
+        l3  = f3pa / 6.0;
+        dl3 = f4pa / 6.0 * da;
+      }
+    } else {
+      double Pp = 0.0, Pm_div_x = 0.0, Qp = 0.0, q_im = 0.0, dPp = 0.0, dPm_div_x = 0.0, dQp = 0.0, dq_im = 0.0;
+      if (x_zero) {
+        Pp        = func_F(a);
+        dPp       = func_Fp(a) * da + 0.5 * func_Fpp(a) * dx2;
+        Pm_div_x  = func_Fp(a);
+        dPm_div_x = func_Fpp(a) * da + (func_F3p(a) / 6.0) * dx2;
+      } else {
+        const double f_apx = func_F(a + x), f_amx = func_F(a - x);
+        const double fp_apx = func_Fp(a + x), fp_amx = func_Fp(a - x);
+        Pp                   = 0.5 * (f_apx + f_amx);
+        const double sum_fp  = fp_apx + fp_amx;
+        const double diff_fp = fp_apx - fp_amx;
+        dPp                  = 0.5 * sum_fp * da + 0.5 * diff_fp * dx;
+        Pm_div_x             = 0.5 * (f_apx - f_amx) / x;
+        const double dPm_da  = 0.5 * diff_fp / x;
+        double dPm_dx;
+        if (x < 1e-3) {
+          dPm_dx = func_F3p(a) * x / 3.0;
+        } else {
+          const double diff_f = f_apx - f_amx;
+          dPm_dx              = (x * sum_fp - diff_f) / (2.0 * x * x);
+        }
+        dPm_div_x = dPm_da * da + dPm_dx * dx;
+      }
+      if (y_zero) {
+        Qp    = func_F(a);
+        dQp   = func_Fp(a) * da - 0.5 * func_Fpp(a) * dy2;
+        q_im  = func_Fp(a);
+        dq_im = func_Fpp(a) * da - (func_F3p(a) / 6.0) * dy2;
+      } else {
+        const double denom       = a * a + y * y;
+        const double ea_cy_m1    = exp_a * cy - 1.0;
+        const double ea_sy       = exp_a * sy;
+        Qp                       = (a * ea_cy_m1 + y * ea_sy) / denom;
+        const double sin_y_div_y = (fabs(y) < 1e-6) ? 1.0 - y * y / 6.0 : sy / y;
+        q_im                     = (a * exp_a * sin_y_div_y - ea_cy_m1) / denom;
+        const double ImF         = (a * exp_a * sy - y * ea_cy_m1) / denom;
+        const double A_val       = exp_a * ((a - 1.0) * cy - y * sy) + 1.0;
+        const double B_val       = exp_a * ((a - 1.0) * sy + y * cy);
+        const double C_val       = a * a - y * y;
+        const double D_val       = 2.0 * a * y;
+        const double denom2      = C_val * C_val + D_val * D_val;
+        const double Fp_re       = (A_val * C_val + B_val * D_val) / denom2;
+        const double Fp_im       = (B_val * C_val - A_val * D_val) / denom2;
+        dQp                      = Fp_re * da - Fp_im * dy;
+        const double dImF        = Fp_im * da + Fp_re * dy;
+        dq_im                    = (y * dImF - ImF * dy) / (y * y);
+      }
+      const double inv  = inv_x2y2;
+      const double dinv = -inv * inv * (dx2 + dy2);
+      l2  = (Pp - Qp) * inv;
+      dl2 = (dPp - dQp) * inv + (Pp - Qp) * dinv;
+      dl0 = dPp - dl2 * x2 - l2 * dx2;
+      l3  = (Pm_div_x - q_im) * inv;
+      dl3 = (dPm_div_x - dq_im) * inv + (Pm_div_x - q_im) * dinv;
+      l1  = Pm_div_x - l3 * x2;
+      dl1 = dPm_div_x - dl3 * x2 - l3 * dx2;
+    }
+    double s[16], ds[16], s2[16], ds2[16], s3[16], ds3[16], t1[16], t2[16];
+    S_mat(s);
+    ds[0] = 0;   ds[1] = db;   ds[2] = dc;   ds[3] = dd;
+    ds[4] = db;  ds[5] = 0;    ds[6] = du;   ds[7] = dv;
+    ds[8] = dc;  ds[9] = -du;  ds[10] = 0;   ds[11] = dw;
+    ds[12] = dd; ds[13] = -dv; ds[14] = -dw; ds[15] = 0;
+    mat_mul(s, s, s2);
+    mat_mul(ds, s, t1);
+    mat_mul(s, ds, t2);
+#pragma unroll
+    for (int i = 0; i < 16; i++) ds2[i] = t1[i] + t2[i];
+    mat_mul(s, s2, s3);
+    mat_mul(ds, s2, t1);
+    mat_mul(s, ds2, t2);
+#pragma unroll
+    for (int i = 0; i < 16; i++) ds3[i] = t1[i] + t2[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = s[i] * dl1 + ds[i] * l1 + s2[i] * dl2 + ds2[i] * l2 + s3[i] * dl3 + ds3[i] * l3;
+    m[0] += dl0; m[5] += dl0; m[10] += dl0; m[15] += dl0;
+  }
+
   // Lambda * (j,0,0,0)^T: first column of Lambda times j — all the LTE recursion needs,
   // because the LTE source vector has only an I component (rtepack_source.cc:88-95).
   __device__ __forceinline__ void L_col0(double j, double* __restrict__ o) const {

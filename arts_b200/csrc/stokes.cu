@@ -120,7 +120,14 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
     const Propmat k = load_propmat(&sK[st][tid * 7]);
     const double f  = p.f[int64_t(lev) * p.f_stride + ivc];
     const double j  = source_I(k, f, p.T[lev]);
-    if (n > 0) rte_step<LINSRC>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0);
+    if (n > 0) {
+      if (p.I_lev && active) {  // radiance arriving at level lev+1 (Jacobian pass B)
+        double2* o = reinterpret_cast<double2*>(p.I_lev + (int64_t(lev + 1) * p.nf + iv) * 4);
+        o[0] = make_double2(I[0], I[1]);
+        o[1] = make_double2(I[2], I[3]);
+      }
+      rte_step<LINSRC>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0);
+    }
     k_next = k;
     j_next = j;
     __syncthreads();  // everyone has read stage st before it is refilled

@@ -16,11 +16,36 @@ struct StokesParams {
   const double* r;     // [np-1] layer lengths
   const double* I_bkg; // [nf][4]
   double* I;           // [nf][4]
+  double* I_lev;       // optional [np][nf][4]: radiance arriving at every level (for the Jacobian pass), or nullptr
   int32_t rte_option;
   int32_t tran_exact;
 };
 
+// fused Jacobian pass B (stokes_jac.cu)
+struct StokesJacParams {
+  int32_t np, nq;
+  int64_t nf;
+  const double* K;      // [np][k_pitch][7]
+  const double* dK;     // [np][nq][k_pitch][7]
+  int64_t k_pitch;
+  const double* f;      // [np][nf] or [nf]
+  int64_t f_stride;
+  const double* T;      // [np]
+  const double* r;      // [np-1]
+  const double* dr;     // [2][np-1][nq]
+  const double* I_lev;  // [np][nf][4] radiance arriving at each level (pass A)
+  double* dI;           // [nf][np][nq][4]
+  int32_t it;           // index of the temperature target or -1
+  int32_t rte_option;
+};
+
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream);
+int launch_stokes_jac(const StokesJacParams& p, cudaStream_t stream);
+int launch_tramat_jac(int np, int64_t nf, int nq, const double* K, const double* dK, const double* r, const double* dr,
+                      int linsrc, double* dT, double* dL, cudaStream_t stream);
+int launch_rte_emission_jac(int linsrc, int np, int64_t nf, int nq, const double* T, const double* L, const double* P,
+                            const double* dT, const double* dL, const double* J, const double* dJ, const double* I_bkg,
+                            double* I, double* dI, cudaStream_t stream);
 int launch_planck_tb(int64_t nf, const double* f, double* I, cudaStream_t stream);
 int launch_tramat(int np, int64_t nf, const double* K, const double* r, int linsrc, int exact, double* T, double* L,
                   double* P, cudaStream_t stream);

@@ -170,8 +170,13 @@ def spectral_tramat_pathFromPath(spectral_propmat_path, spectral_propmat_jac_pat
     L = np.empty((nf, np_, 4, 4)) if opt != abi.RTE_CONSTANT else None
     dT = np.empty((2, nf, np_, nq, 4, 4))
     dL = np.empty((2, nf, np_, nq, 4, 4)) if opt != abi.RTE_CONSTANT else None
-    check(lib().ab200_tramat(np_, nf, nq, dptr(K), dptr(None if nq == 0 else np.ascontiguousarray(dK)), dptr(r),
-                             dptr(dr), opt, flags, dptr(T), dptr(L), dptr(P), dptr(dT), dptr(dL)))
+    dKc = None if nq == 0 else np.ascontiguousarray(dK, dtype=np.float64)
+    if nq:
+        dT[...] = 0.0  # the library fills only the entries the reference writes (rest: muelmat::constant(0))
+        if dL is not None:
+            dL[...] = 0.0
+    check(lib().ab200_tramat(np_, nf, nq, dptr(K), dptr(dKc), dptr(r), dptr(dr), opt, flags, dptr(T), dptr(L), dptr(P),
+                             dptr(dT), dptr(dL)))
     name = rte_option if isinstance(rte_option, str) else {0: "constant", 1: "linsrc", 2: "linprop"}[opt]
     return TransmittanceMatrix(name, T, L, P, dT, dL)
 
@@ -200,9 +205,11 @@ def spectral_radStepByStepEmission(spectral_tramat: TransmittanceMatrix, J, dJ, 
         raise ValueError(f"Bad background radiance size: spectral_rad_bkg: {bkg.shape[0]}, expected: {nf}")
     I = np.empty((nf, 4))
     dI = np.zeros((nf, np_, nq, 4))
+    Jc = np.ascontiguousarray(J, dtype=np.float64)
+    dJc = None if dJ is None else np.ascontiguousarray(dJ, dtype=np.float64)
     check(lib().ab200_rte_emission(_rte(spectral_tramat.option), np_, nf, nq, dptr(T), dptr(spectral_tramat.L),
                                    dptr(spectral_tramat.P), dptr(spectral_tramat.dT), dptr(spectral_tramat.dL),
-                                   dptr(np.ascontiguousarray(J)), dptr(dJ), dptr(bkg), dptr(I), dptr(dI)))
+                                   dptr(Jc), dptr(dJc), dptr(bkg), dptr(I), dptr(dI)))
     return I, dI
 
 
@@ -309,8 +316,8 @@ class Path:
     def sync(self):
         check(lib().ab200_path_sync(self._h))
 
-    def download(self, I=None, K=None):
-        check(lib().ab200_path_download(self._h, dptr(I), dptr(None), dptr(K), dptr(None)))
+    def download(self, I=None, K=None, dI=None, dK=None):
+        check(lib().ab200_path_download(self._h, dptr(I), dptr(dI), dptr(K), dptr(dK)))
 
     def device_ptr(self, which: int) -> int:
         return int(lib().ab200_path_device_ptr(self._h, which) or 0)

@@ -196,3 +196,53 @@ def test_propmat_is_linear_in_lines_and_thread_count_invariant(orc):
     np.testing.assert_allclose(K0 + K1, Kall, rtol=1e-14)
     Ka, _ = orc.propmat_levels(c.cat, c.f[:137], c.atm)
     assert np.array_equal(Ka, Kall[:, :137])
+
+
+# ---------------------------------------------------------------------------
+# Jacobian rows: the reference pins them against perturbations (tests/core/jac/full_arts_emission.py:79,
+# 2 % tolerance; tests/core/zeeman/propmat_jac.py:61, rtol 1e-3).  Same idea on synthetic inputs.
+# ---------------------------------------------------------------------------
+def _perturbed(c, level, dT=0.0, species=None, dvmr=0.0):
+    import copy
+
+    atm = copy.deepcopy(c.atm)
+    atm.T[level] += dT
+    atm.Q[level] = atm.Q[level] * (atm.T[level] / c.atm.T[level])  # synthetic Q(T) is linear in T
+    if species is not None:
+        atm.vmr[level, species] += dvmr
+    return atm
+
+
+def test_oracle_propmat_jacobian_vs_perturbation(orc):
+    c = synth.tiny_case(nl=40, nf=120, np_=2)
+    tg = (("T",), ("VMR", 1))
+    _, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    lev = 1
+    h = 1e-3
+    Kp, _ = orc.propmat_levels(c.cat, c.f, _perturbed(c, lev, dT=+h))
+    Km, _ = orc.propmat_levels(c.cat, c.f, _perturbed(c, lev, dT=-h))
+    fd = (Kp[lev, :, 0] - Km[lev, :, 0]) / (2 * h)
+    np.testing.assert_allclose(dK[lev, 0, :, 0], fd, rtol=1e-3)
+    v = c.atm.vmr[lev, 1]
+    Kp, _ = orc.propmat_levels(c.cat, c.f, _perturbed(c, lev, species=1, dvmr=+1e-4 * v))
+    Km, _ = orc.propmat_levels(c.cat, c.f, _perturbed(c, lev, species=1, dvmr=-1e-4 * v))
+    fd = (Kp[lev, :, 0] - Km[lev, :, 0]) / (2e-4 * v)
+    np.testing.assert_allclose(dK[lev, 1, :, 0], fd, rtol=1e-3)
+
+
+@pytest.mark.parametrize("option", ["constant", "linsrc"])
+def test_oracle_radiance_jacobian_vs_perturbation(orc, option):
+    c = synth.tiny_case(nl=40, nf=60, np_=6, rte_option=option)
+    tg = (("T",), ("VMR", 1))
+    I, dI = orc.clearsky_emission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option=option, targets=tg, hse_derivative=0)
+    for lev in (0, 3, 5):
+        h = 1e-2
+        Ip, _ = orc.clearsky_emission(c.cat, c.f, _perturbed(c, lev, dT=+h), c.r, c.I_bkg, rte_option=option)
+        Im, _ = orc.clearsky_emission(c.cat, c.f, _perturbed(c, lev, dT=-h), c.r, c.I_bkg, rte_option=option)
+        fd = (Ip[:, 0] - Im[:, 0]) / (2 * h)
+        np.testing.assert_allclose(dI[:, lev, 0, 0], fd, rtol=2e-2, atol=1e-3 * np.abs(dI[:, :, 0, 0]).max())
+        v = c.atm.vmr[lev, 1]
+        Ip, _ = orc.clearsky_emission(c.cat, c.f, _perturbed(c, lev, species=1, dvmr=+1e-3 * v), c.r, c.I_bkg, rte_option=option)
+        Im, _ = orc.clearsky_emission(c.cat, c.f, _perturbed(c, lev, species=1, dvmr=-1e-3 * v), c.r, c.I_bkg, rte_option=option)
+        fd = (Ip[:, 0] - Im[:, 0]) / (2e-3 * v)
+        np.testing.assert_allclose(dI[:, lev, 1, 0], fd, rtol=2e-2, atol=1e-3 * np.abs(dI[:, :, 1, 0]).max())

@@ -77,7 +77,7 @@ struct ab200_path {
   double* d_Ilev = nullptr;  // [np][nf][4] radiance arriving at each level
   double* d_jac = nullptr;   // [levels_per_batch][ntiles][nq][2][TL][4]
   double* d_jcom = nullptr;  // [levels_per_batch][ntiles][TL]
-  double *d_dQdT = nullptr, *d_dr = nullptr;
+  double *d_dQdT = nullptr, *d_dr = nullptr, *d_invT = nullptr;
   int32_t tg_kind[AB200_MAX_TARGETS] = {0}, tg_species[AB200_MAX_TARGETS] = {0};
   int32_t it = -1;  // position of the temperature target
   bool dk_preloaded = false;
@@ -153,8 +153,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   const size_t snp = static_cast<size_t>(np);
   AB_TRY(dev_alloc(&p->d_f, snp * nf));
   // packed small arrays: T, P, H [np] | vmr [np][ns] | isorat, Q [np][ni] | npm [np][4][7] | frange [np][2] | r [np]
-  //                      | dQdT [np][ni] | dr [2][np][nq]
-  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq));
+  //                      | dQdT [np][ni] | dr [2][np][nq] | 1/T [np]
+  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq) + 1);
   AB_TRY(dev_alloc(&p->d_small, p->small_doubles));
   if (p->small_doubles) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_small), p->small_doubles * sizeof(double)));
   double* q = p->d_small;
@@ -168,7 +168,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->d_frange = q; q += snp * 2;
   p->d_r = q; q += snp;
   p->d_dQdT = q; q += snp * cat->n_isot;
-  p->d_dr = q;
+  p->d_dr = q; q += 2 * snp * nq;
+  p->d_invT = q;
   AB_TRY(dev_alloc(&p->d_Ibkg, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_I, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_K, snp * p->k_pitch * 7));
@@ -263,13 +264,14 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   double* h = p->h_small;
   double *hT = h, *hP = hT + snp, *hH = hP + snp, *hv = hH + snp, *hi = hv + snp * cat->n_species,
          *hQ = hi + snp * cat->n_isot, *hn = hQ + snp * cat->n_isot, *hfr = hn + snp * 28, *hr = hfr + snp * 2,
-         *hdQ = hr + snp, *hdr = hdQ + snp * cat->n_isot;
+         *hdQ = hr + snp, *hdr = hdQ + snp * cat->n_isot, *hiT = hdr + 2 * snp * p->nq;
   std::fill(hdr, hdr + 2 * snp * p->nq, 0.0);
   for (int ip = 0; ip < np; ip++) {
     if (!(atm->T[ip] > 0) || !(atm->P[ip] >= 0))
       return set_error(AB200_ERR_INVALID, "level " + std::to_string(ip) + ": temperature must be > 0 and pressure >= 0");
     hT[ip] = atm->T[ip];
     hP[ip] = atm->P[ip];
+    hiT[ip] = 1.0 / atm->T[ip];
     double mag[3] = {0, 0, 0}, los[2] = {0, 0};
     if (atm->mag) std::copy(atm->mag + 3 * ip, atm->mag + 3 * ip + 3, mag);
     if (atm->los) std::copy(atm->los + 2 * ip, atm->los + 2 * ip + 2, los);
@@ -502,9 +504,10 @@ int ab200_path_run_stokes(ab200_path* p) {
   AB_CUDA(cudaSetDevice(p->cat->device));
   StokesParams sp{};
   sp.np = p->np; sp.nf = p->nf; sp.K = p->d_K; sp.k_pitch = p->k_pitch; sp.f = p->d_f; sp.f_stride = p->f_stride;
-  sp.T = p->d_T; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
+  sp.T = p->d_T; sp.invT = p->d_invT; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
   sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
   sp.I_lev = p->nq > 0 ? p->d_Ilev : nullptr;
+  sp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded) ? 1 : 0;  // only mode-0 (real, pol = no) segments wrote K
   {
     LaunchTimer t(p, 3);
     AB_TRY(launch_stokes_chain(sp, p->stream));

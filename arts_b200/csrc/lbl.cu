@@ -22,6 +22,7 @@
 // evaluations).
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "catalog.hpp"
 #include "faddeeva.cuh"
@@ -205,14 +206,16 @@ __device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const dou
 
 // --------------------------- real-only kernel (mode 0) ----------------------
 // Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
+template <bool DECOUPLED>
 __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
   constexpr int STAGES = REAL_STAGES;
   constexpr int STAGE_DOUBLES = 3 * TL * REC_GROUP;  // groups 0, 1 (far) and 2 (near)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);
-  uint8_t* cls      = reinterpret_cast<uint8_t*>(full + STAGES);
-  uint8_t* lflag    = cls + CHUNK;  // [TL]
+  uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);  // TMA -> consumers
+  uint64_t* empty   = full + STAGES;                                               // consumers -> producer
+  uint8_t* cls      = reinterpret_cast<uint8_t*>(empty + STAGES);
+  uint8_t* lflag    = cls + CHUNK;  // [STAGES][TL]
 
   const int tid = threadIdx.x;
   const int lev = blockIdx.y;
@@ -229,14 +232,17 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
   const double fblk_max = fg[(fblk + F_TILE - 1 < p.nf) ? fblk + F_TILE - 1 : p.nf - 1];
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], SUM_NT / 32);
+    }
     mbar_fence_init();
   }
   __syncthreads();
 
   const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
-  uint32_t it = 0;
+  uint32_t it = 0;  // tiles consumed so far by this CTA (ring position)
 
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
@@ -246,12 +252,17 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
 
     for (int64_t c0 = seg.tile_begin; c0 < seg.tile_end; c0 += CHUNK) {
       const int n = int(min(int64_t(CHUNK), seg.tile_end - c0));
+      __syncthreads();  // every warp is done with the previous chunk's classes
       for (int t = tid; t < n; t += SUM_NT)
         cls[t] = classify_tile(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, DBL_MAX);
       __syncthreads();
 
+      // The warps of the CTA are decoupled: a stage is refilled when all four warps have released it
+      // (empty barrier), not at a CTA-wide barrier, so a warp may run up to one tile ahead.
       auto issue = [&](int t) {
-        const uint32_t st   = (it + t) % STAGES;
+        const uint32_t g  = it + t;
+        const uint32_t st = g % STAGES;
+        if (DECOUPLED && g >= STAGES) mbar_wait(&empty[st], ((g / STAGES) - 1) & 1);
         const uint32_t bytes = (cls[t] == CLS_FAR ? 2 : 3) * TL * REC_GROUP * sizeof(double);
         mbar_expect_tx(&full[st], bytes);
         tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + t) * tile_doubles(), bytes, &full[st]);
@@ -279,12 +290,13 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
           }
         } else if (cls[t] == CLS_NEAR) {
           const double2* __restrict__ rec2 = rec + 4 * TL;
-          flag_lines<SUM_NT>(lflag, rec, rec1, count, fblk_min, fblk_max, false);
-          __syncthreads();
+          uint8_t* __restrict__ lf = lflag + st * TL;
+          flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false);
+          __syncthreads();  // near tiles (rare) are processed in step by the whole CTA
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];
             const double2 c = rec1[2 * l];  // B1, igd
-            if (lflag[l]) {
+            if (lf[l]) {
 #pragma unroll
               for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, c.x);
               continue;
@@ -307,7 +319,12 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
         }
 #pragma unroll
         for (int r = 0; r < SUM_R; r++) accS[r] = __dadd_rn(accS[r], acc[r]);
-        __syncthreads();
+        if (DECOUPLED) {
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&empty[st]);  // this warp has released stage st
+        } else {
+          __syncthreads();
+        }
       }
       it += n;
     }
@@ -506,7 +523,7 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
 // host launchers
 // ---------------------------------------------------------------------------
 size_t lbl_real_smem_bytes() {
-  return size_t(REAL_STAGES) * 3 * TL * REC_GROUP * sizeof(double) + REAL_STAGES * sizeof(uint64_t) + CHUNK + TL;
+  return size_t(REAL_STAGES) * 3 * TL * REC_GROUP * sizeof(double) + 2 * REAL_STAGES * sizeof(uint64_t) + CHUNK + REAL_STAGES * TL;
 }
 size_t lbl_cplx_smem_bytes() {
   return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + TL + CHUNK * sizeof(uint16_t);
@@ -527,11 +544,14 @@ int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream) {
   if (mode == 0) {
     const size_t smem = lbl_real_smem_bytes();
     if (!attr_set[0]) {
-      AB_CUDA(cudaFuncSetAttribute(lbl_sum_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      AB_CUDA(cudaFuncSetAttribute(lbl_sum_real_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      AB_CUDA(cudaFuncSetAttribute(lbl_sum_real_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       attr_set[0] = true;
     }
     dim3 grid(static_cast<unsigned>((p.nf + F_TILE - 1) / F_TILE), static_cast<unsigned>(nlev));
-    lbl_sum_real_kernel<<<grid, SUM_NT, smem, stream>>>(p);
+    static const bool decoupled = [] { const char* e = getenv("AB200_SUM_DECOUPLED"); return e ? atoi(e) != 0 : false; }();  // measured on B200: the CTA-wide barrier per tile is 5 % faster (profiles/r1_ab_decoupled.txt)
+    if (decoupled) lbl_sum_real_kernel<true><<<grid, SUM_NT, smem, stream>>>(p);
+    else lbl_sum_real_kernel<false><<<grid, SUM_NT, smem, stream>>>(p);
   } else {
     const size_t smem = lbl_cplx_smem_bytes();
     if (!attr_set[1]) {

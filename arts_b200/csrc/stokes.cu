@@ -22,21 +22,29 @@
 namespace ab200 {
 using namespace rte;
 
-constexpr int ST_NT     = 128;
-constexpr int ST_STAGES = 4;
+constexpr int ST_NT     = 128;  // 4 warps, each an independent pipeline over 32 frequencies
+constexpr int ST_STAGES = 5;    // 5 x 1792 B per warp in flight; 35 KB per CTA -> 6 CTAs per SM
 
 // source of one level: J = B(f,T) e_I, or 0 if K is purely rotational (rtepack_source.cc:88-95, LTE)
 __device__ __forceinline__ double source_I(const Propmat& k, double f, double T) {
   return k.is_rotational() ? 0.0 : planck(f, T);
 }
 
-// one step of the recursion over layer (i, i+1): k0 = K_i (sensor side), k1 = K_{i+1}
-template <bool LINSRC>
+// one step of the recursion over layer (i, i+1): k0 = K_i (sensor side), k1 = K_{i+1}.
+// SCALAR: the caller guarantees that both levels are unpolarised (only A != 0), so the polarised
+// branch is compiled out; the arithmetic of the branch taken is identical in both instantiations.
+template <bool LINSRC, bool SCALAR>
 __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& k0, const Propmat& k1, double j0 /*J_i*/,
                                          double j1 /*J_{i+1}*/, double r, bool exact) {
   Tran t;
-  t.init(k0, k1, r, exact);
-  if (!t.polarized) {
+  if (SCALAR) {
+    t.a         = -0.5 * r * (k0.A + k1.A);
+    t.exp_a     = exp(t.a);
+    t.polarized = false;
+  } else {
+    t.init(k0, k1, r, exact);
+  }
+  if (SCALAR || !t.polarized) {
     if (LINSRC) {  // linevo :341-370 with scalar T, Lambda
       const double lam = func_F(t.a);
       const double dj  = j1 - j0;
@@ -76,32 +84,65 @@ __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& 
   }
 }
 
+// Scalar fast path of the FUSED chain (only A != 0 on the whole path): same formulas as rte_step's
+// unpolarised branch with the transcendental count cut to two per step — exp(a) and F(a) = expm1(a)/a
+// share one expm1, the two divisions become MUFU reciprocals + Newton (fast_rcp, ~1 ulp), and
+// hf/kT uses the per-level 1/T.  Differences from the literal form are a few ulp (parity: 1e-9 on I).
 template <bool LINSRC>
-__global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
-  __shared__ __align__(128) double sK[ST_STAGES][ST_NT * 7];
-  __shared__ uint64_t full[ST_STAGES];
-  const int tid      = threadIdx.x;
-  const int64_t iv0  = int64_t(blockIdx.x) * ST_NT;
-  const int64_t iv   = iv0 + tid;
-  const bool active  = iv < p.nf;
-  const int np       = p.np;
-  constexpr uint32_t ROW_BYTES = ST_NT * 7 * sizeof(double);
+__device__ __forceinline__ void rte_step_scalar(double* __restrict__ I, double A0, double A1, double j0, double j1, double r) {
+  const double a = -0.5 * r * (A0 + A1);
+  double ea;
+  if (LINSRC) {
+    const double em  = expm1(a);
+    ea               = em + 1.0;
+    const double lam = fabs(a) < 1e-8 ? 1.0 + a * 0.5 + a * a / 6.0 : em * fast_rcp(a);
+    I[0] = ea * (I[0] - j1) + lam * (j1 - j0) + j0;
+  } else {
+    ea              = exp(a);
+    const double jm = (j0 + j1) * 0.5;
+    I[0] = ea * (I[0] - jm) + jm;
+  }
+  I[1] = ea * I[1];
+  I[2] = ea * I[2];
+  I[3] = ea * I[3];
+}
+// B(f,T) = (2h/c^2) f^3 / expm1(h f / k T) with af3 = (2h/c^2) f^3 and invT = 1/T
+__device__ __forceinline__ double planck_fast(double f, double af3, double invT) {
+  constexpr double b = cst::h / cst::k;
+  const double x = (b * f) * invT;
+  return x > 700.0 ? 0.0 : af3 * fast_rcp(expm1(x));
+}
 
-  if (tid == 0) {
-    for (int s = 0; s < ST_STAGES; s++) mbar_init(&full[s], 1);
+// Every warp owns 32 consecutive frequencies and its own ring of ST_STAGES shared-memory stages;
+// lane 0 refills a stage with one 1792-byte TMA bulk copy (the K rows of 32 frequencies at one
+// level) as soon as the warp has moved that stage into registers.  No CTA-wide barrier in the loop.
+template <bool LINSRC, bool SCALAR>
+__global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
+  __shared__ __align__(128) double sK[ST_NT / 32][ST_STAGES][32 * 7];
+  __shared__ uint64_t full[ST_NT / 32][ST_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t iv0 = int64_t(blockIdx.x) * ST_NT + warp * 32;
+  if (iv0 >= p.nf) return;  // whole warp idle
+  const int64_t iv  = iv0 + lane;
+  const bool active = iv < p.nf;
+  const int np      = p.np;
+  constexpr uint32_t ROW_BYTES = 32 * 7 * sizeof(double);
+
+  if (lane == 0) {
+    for (int s = 0; s < ST_STAGES; s++) mbar_init(&full[warp][s], 1);
     mbar_fence_init();
   }
-  __syncthreads();
+  __syncwarp();
 
   // levels are consumed from np-1 (background side) down to 0; step n reads level np-1-n
   auto issue = [&](int n) {
     const int lev     = np - 1 - n;
     const uint32_t st = n % ST_STAGES;
-    mbar_expect_tx(&full[st], ROW_BYTES);
-    tma_load_1d(&sK[st][0], p.K + (int64_t(lev) * p.k_pitch + iv0) * 7, ROW_BYTES, &full[st]);
+    mbar_expect_tx(&full[warp][st], ROW_BYTES);
+    tma_load_1d(&sK[warp][st][0], p.K + (int64_t(lev) * p.k_pitch + iv0) * 7, ROW_BYTES, &full[warp][st]);
   };
-  if (tid == 0)
-    for (int n = 0; n < ST_STAGES - 1 && n < np; n++) issue(n);
+  if (lane == 0)
+    for (int n = 0; n < ST_STAGES && n < np; n++) issue(n);
 
   double I[4] = {0, 0, 0, 0};
   if (active) {
@@ -110,27 +151,37 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
     I[0] = b0.x; I[1] = b0.y; I[2] = b1.x; I[3] = b1.y;
   }
   const int64_t ivc = active ? iv : p.nf - 1;
+  const bool shared_grid = p.f_stride == 0;
+  double f = p.f[ivc];
+  constexpr double planck_a = 2 * cst::h / (cst::c * cst::c);
+  double af3 = planck_a * (f * f * f);
   Propmat k_next{};
   double j_next = 0.0;
   for (int n = 0; n < np; n++) {
-    if (tid == 0 && n + ST_STAGES - 1 < np) issue(n + ST_STAGES - 1);
     const int lev     = np - 1 - n;
     const uint32_t st = n % ST_STAGES;
-    mbar_wait(&full[st], (n / ST_STAGES) & 1);
-    const Propmat k = load_propmat(&sK[st][tid * 7]);
-    const double f  = p.f[int64_t(lev) * p.f_stride + ivc];
-    const double j  = source_I(k, f, p.T[lev]);
+    mbar_wait(&full[warp][st], (n / ST_STAGES) & 1);
+    Propmat k{};
+    if (SCALAR) k.A = sK[warp][st][lane * 7];
+    else k = load_propmat(&sK[warp][st][lane * 7]);
+    __syncwarp();  // every lane has moved its row out of stage st
+    if (lane == 0 && n + ST_STAGES < np) issue(n + ST_STAGES);
+    if (!shared_grid) {
+      f   = p.f[int64_t(lev) * p.f_stride + ivc];
+      af3 = planck_a * (f * f * f);
+    }
+    const double j = SCALAR ? (k.A == 0.0 ? 0.0 : planck_fast(f, af3, p.invT[lev])) : source_I(k, f, p.T[lev]);
     if (n > 0) {
       if (p.I_lev && active) {  // radiance arriving at level lev+1 (Jacobian pass B)
         double2* o = reinterpret_cast<double2*>(p.I_lev + (int64_t(lev + 1) * p.nf + iv) * 4);
         o[0] = make_double2(I[0], I[1]);
         o[1] = make_double2(I[2], I[3]);
       }
-      rte_step<LINSRC>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0);
+      if (SCALAR) rte_step_scalar<LINSRC>(I, k.A, k_next.A, j, j_next, p.r[lev]);
+      else rte_step<LINSRC, false>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0);
     }
     k_next = k;
     j_next = j;
-    __syncthreads();  // everyone has read stage st before it is refilled
   }
   if (active) {
     double2* o = reinterpret_cast<double2*>(p.I + iv * 4);
@@ -142,10 +193,14 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream) {
   if (p.nf == 0) return 0;
   const unsigned grid = static_cast<unsigned>((p.nf + ST_NT - 1) / ST_NT);
-  if (p.rte_option == AB200_RTE_LINSRC)
-    stokes_chain_kernel<true><<<grid, ST_NT, 0, stream>>>(p);
-  else
-    stokes_chain_kernel<false><<<grid, ST_NT, 0, stream>>>(p);
+  const bool lin = p.rte_option == AB200_RTE_LINSRC;
+  if (p.scalar) {
+    if (lin) stokes_chain_kernel<true, true><<<grid, ST_NT, 0, stream>>>(p);
+    else stokes_chain_kernel<false, true><<<grid, ST_NT, 0, stream>>>(p);
+  } else {
+    if (lin) stokes_chain_kernel<true, false><<<grid, ST_NT, 0, stream>>>(p);
+    else stokes_chain_kernel<false, false><<<grid, ST_NT, 0, stream>>>(p);
+  }
   count_launch();
   AB_CUDA(cudaGetLastError());
   return 0;

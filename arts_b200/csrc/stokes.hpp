@@ -13,12 +13,14 @@ struct StokesParams {
   const double* f;     // [np][nf] or [nf]
   int64_t f_stride;
   const double* T;     // [np] level temperatures
+  const double* invT;  // [np] 1 / T
   const double* r;     // [np-1] layer lengths
   const double* I_bkg; // [nf][4]
   double* I;           // [nf][4]
   double* I_lev;       // optional [np][nf][4]: radiance arriving at every level (for the Jacobian pass), or nullptr
   int32_t rte_option;
   int32_t tran_exact;
+  int32_t scalar;      // K is known to have only A != 0 (no polarised segment was summed): scalar fast path
 };
 
 // fused Jacobian pass B (stokes_jac.cu)

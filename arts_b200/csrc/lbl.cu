@@ -164,9 +164,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
 // ---------------------------------------------------------------------------
 // K2 / K3
 // ---------------------------------------------------------------------------
-constexpr int SUM_NT    = 128;   // threads per CTA
-constexpr int SUM_R     = 4;     // frequencies per thread
-constexpr int F_TILE    = SUM_NT * SUM_R;
+// default geometry of the real line sum: 128 threads x 4 frequencies per thread = 512-frequency blocks
 constexpr int CHUNK     = 4096;  // tiles classified per pass
 constexpr int REAL_STAGES = 2;   // 2 x 24 KB of line records per CTA: 4 CTAs per SM stay resident
 constexpr uint8_t CLS_SKIP = 0, CLS_FAR = 1, CLS_NEAR = 2;
@@ -206,8 +204,9 @@ __device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const dou
 
 // --------------------------- real-only kernel (mode 0) ----------------------
 // Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
-template <bool DECOUPLED>
+template <bool DECOUPLED, int SUM_R, int SUM_NT, int UNROLL>
 __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
+  constexpr int F_TILE = SUM_NT * SUM_R;
   constexpr int STAGES = REAL_STAGES;
   constexpr int STAGE_DOUBLES = 3 * TL * REC_GROUP;  // groups 0, 1 (far) and 2 (near)
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
 #pragma unroll
         for (int r = 0; r < SUM_R; r++) acc[r] = 0.0;
         if (cls[t] == CLS_FAR) {
-#pragma unroll 4
+#pragma unroll UNROLL
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', c3 | kappa, A1
             const double B1 = reinterpret_cast<const double*>(rec1 + 2 * l)[0];
@@ -543,15 +542,29 @@ int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream) {
   static bool attr_set[2] = {false, false};
   if (mode == 0) {
     const size_t smem = lbl_real_smem_bytes();
-    if (!attr_set[0]) {
-      AB_CUDA(cudaFuncSetAttribute(lbl_sum_real_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      AB_CUDA(cudaFuncSetAttribute(lbl_sum_real_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      attr_set[0] = true;
+    // geometry variants (R frequencies per thread, threads per CTA, line unroll); 0 is the tuned default
+    static const int variant = [] { const char* e = getenv("AB200_SUM_VARIANT"); return e ? atoi(e) : 0; }();
+    auto go = [&](auto kernel, int nt, int r) -> int {
+      static bool attr = false;
+      if (!attr) {
+        AB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr = true;
+      }
+      dim3 grid(static_cast<unsigned>((p.nf + nt * r - 1) / (nt * r)), static_cast<unsigned>(nlev));
+      kernel<<<grid, nt, smem, stream>>>(p);
+      return 0;
+    };
+    switch (variant) {
+      case 1: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 8>, 128, 4)); break;
+      case 2: AB_TRY(go(lbl_sum_real_kernel<false, 8, 64, 4>, 64, 8)); break;
+      case 3: AB_TRY(go(lbl_sum_real_kernel<false, 2, 256, 4>, 256, 2)); break;
+      case 4: AB_TRY(go(lbl_sum_real_kernel<false, 4, 256, 4>, 256, 4)); break;
+      case 5: AB_TRY(go(lbl_sum_real_kernel<false, 6, 128, 4>, 128, 6)); break;
+      case 6: AB_TRY(go(lbl_sum_real_kernel<true, 4, 128, 4>, 128, 4)); break;
+      case 7: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 2>, 128, 4)); break;
+      case 8: AB_TRY(go(lbl_sum_real_kernel<false, 8, 128, 2>, 128, 8)); break;
+      default: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 4>, 128, 4)); break;
     }
-    dim3 grid(static_cast<unsigned>((p.nf + F_TILE - 1) / F_TILE), static_cast<unsigned>(nlev));
-    static const bool decoupled = [] { const char* e = getenv("AB200_SUM_DECOUPLED"); return e ? atoi(e) != 0 : false; }();  // measured on B200: the CTA-wide barrier per tile is 5 % faster (profiles/r1_ab_decoupled.txt)
-    if (decoupled) lbl_sum_real_kernel<true><<<grid, SUM_NT, smem, stream>>>(p);
-    else lbl_sum_real_kernel<false><<<grid, SUM_NT, smem, stream>>>(p);
   } else {
     const size_t smem = lbl_cplx_smem_bytes();
     if (!attr_set[1]) {

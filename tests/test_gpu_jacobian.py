@@ -179,3 +179,32 @@ def test_jacobian_errors_are_loud(wsm):
     with pytest.raises(Ab200Error) as e:
         wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=((5, 0),))
     assert e.value.code == abi.ERR_UNSUPPORTED
+
+
+def test_reentrant_from_host_threads(wsm, orc):
+    """The shims are called concurrently from OpenMP worker threads (src/m_rad.cc:321-343): every entry point
+    must be re-entrant with one device workspace per host thread and a shared immutable catalog."""
+    import threading
+
+    cases = [synth.case_c5_single(n_lines=200, nf=300 + 37 * i, np_=10 + i) for i in range(4)]
+    cat = wsm.Catalog(cases[0].cat)  # same catalog for all paths
+    tg = (("T",), ("VMR", 0))
+    out, err = [None] * len(cases), []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                c = cases[i]
+                out[i] = wsm.spectral_radClearskyEmission(cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=tg)
+            wsm.lib().ab200_release_thread_cache()
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not err, err
+    for i, c in enumerate(cases):
+        I, dI = wsm.spectral_radClearskyEmission(cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=tg)
+        assert np.array_equal(out[i][0], I) and np.array_equal(out[i][1], dI)
+    cat.close()

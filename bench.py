@@ -258,6 +258,13 @@ def run_b200(args):
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = {}
+    try:  # per-launch DRAM bytes from the committed ncu capture of this shape (profiles/traffic.json), else null
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj["shape"] == {"lines": nl, "nf_per_gpu": cnt, "levels": np_}:
+            traffic = tj
+    except (OSError, KeyError, ValueError):
+        pass
     st_bytes = roofline.stokes_bytes_per_step(np_) * cnt * np_
     st_gbs = st_bytes / (s_ms_per * 1e-3) / 1e9 if s_ms_per > 0 else 0.0
 
@@ -295,12 +302,13 @@ def run_b200(args):
                 "steps": n_e2e, "call": "ab200_clearsky_emission (host buffers, pinned)", "equals_resident_result": e2e_matches},
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "kernel": "lbl_sum_real_kernel", "achieved": achieved_tf, "peak": dfma_tflops,
-                     "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None, "traffic": traffic.get("lbl_sum_real_kernel"),
                      "peak_source": "DFMA loop measured in this run (ab200_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 figure",
                      "algorithmic_flop_per_eval": fl_eval, "regions": region_frac, "kernel_ms": k_ms_per,
                      "kernel_share_of_step": k_ms / ms if ms else None},
         "roofline_stokes": {"bound": "hbm", "kernel": "stokes_chain_kernel", "achieved": st_gbs, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": None, "kernel_ms": s_ms_per,
+                            "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": traffic.get("stokes_chain_kernel"),
+                            "algorithmic_bytes": st_bytes, "kernel_ms": s_ms_per,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
         "stage2": {"metric": "freq*level Stokes steps/s", "value": float(cnt) * np_ * world / (s_ms_per * 1e-3) if s_ms_per else None,
                    "unit": "steps/s"},

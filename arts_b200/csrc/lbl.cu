@@ -266,11 +266,15 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
         mbar_expect_tx(&full[st], bytes);
         tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + t) * tile_doubles(), bytes, &full[st]);
       };
+      // prefetch distance: with the CTA barrier a stage is free as soon as the previous tile is done
+      // (STAGES - 1 tiles in flight); decoupled warps keep one stage of slack so that the producer
+      // never waits for a straggler
+      constexpr int AHEAD = (DECOUPLED && STAGES > 2) ? STAGES - 2 : STAGES - 1;
       if (tid == 0)
-        for (int t = 0; t < STAGES - 1 && t < n; t++) issue(t);
+        for (int t = 0; t < AHEAD && t < n; t++) issue(t);
 
       for (int t = 0; t < n; t++) {
-        if (tid == 0 && t + STAGES - 1 < n) issue(t + STAGES - 1);
+        if (tid == 0 && t + AHEAD < n) issue(t + AHEAD);
         const uint32_t st = (it + t) % STAGES;
         mbar_wait(&full[st], ((it + t) / STAGES) & 1);
         const double2* __restrict__ rec  = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);

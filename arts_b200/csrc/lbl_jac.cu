@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
 constexpr int JAC_NT = 128;
 constexpr int JAC_R  = 2;
 constexpr int JAC_F_TILE = JAC_NT * JAC_R;
-constexpr int JAC_Q  = 4;  // targets per pass
+constexpr int JAC_Q  = 4;   // targets per pass
+constexpr int JAC_BASE_FIELDS = 9;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im
+constexpr int JAC_Q_FIELDS    = 7;  // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im
 
 // dscl(f) of dt_core_calc, :990-1000
 __device__ __forceinline__ double line_scale_dT(double f, double T, double P) {
@@ -192,7 +194,33 @@ __device__ __forceinline__ double line_scale_v(double f, double T, double P) {
   return -N * f * expm1(-r) * c;
 }
 
+// nu == 2 closed form of the reference (Faddeeva.cc:721-725) for x = |Re z| >= 0, y >= 0; branch free
+__device__ __forceinline__ cplx w_far2(double ax, double y) {
+  const double dr = ax * ax - y * y - 0.5, di = 2 * ax * y;
+  const double denom = fad::ISPI * fast_rcp(dr * dr + di * di);
+  return {denom * (ax * di - y * dr), denom * (ax * dr + y * di)};
+}
+// z, F, dF for a pair that is far together with its displaced point (tile / line level guarantee)
+__device__ __forceinline__ void z_F_dF_far(double x, double y, cplx& z, cplx& F, cplx& dF) {
+  z = {x, y};
+  const double ax = fabs(x);
+  F = w_far2(ax, y);
+  const cplx dz{fmax(1e-4 * ax, 1e-4), fmax(1e-4 * y, 1e-4)};
+  const double x2 = x + dz.re;
+  cplx F2 = w_far2(fabs(x2), y + dz.im);
+  if (x < 0.0) F.im = -F.im;
+  if (x2 < 0.0) F2.im = -F2.im;
+  const double d = fast_rcp(dz.re * dz.re + dz.im * dz.im);
+  const cplx n = csub(F2, F);
+  dF = {(n.re * dz.re + n.im * dz.im) * d, (n.im * dz.re - n.re * dz.im) * d};
+}
+
+template <int NQ>
 __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSumParams jp) {
+  extern __shared__ __align__(16) double sm[];  // [JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS][TL]
+  __shared__ int tile_far;
+  double* const sb = sm;
+  double* const sq = sm + JAC_BASE_FIELDS * TL;
   const int tid = threadIdx.x;
   const int lev = blockIdx.y;
   const int64_t fblk = int64_t(blockIdx.x) * JAC_F_TILE;
@@ -208,61 +236,72 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
   const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
   const double* __restrict__ jcom = jp.jcom + int64_t(lev) * p.ntiles * TL;
-  const int nqp = min(JAC_Q, jp.nq - jp.q0);
   const double T = p.T[lev], P = p.P[lev];
 
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
     const double cutoff  = seg.has_cutoff ? seg.cutoff : DBL_MAX;
-    cplx shape[JAC_R], acc[JAC_Q][JAC_R];
+    cplx shape[JAC_R], acc[NQ][JAC_R];
 #pragma unroll
     for (int r = 0; r < JAC_R; r++) {
       shape[r] = {0.0, 0.0};
 #pragma unroll
-      for (int q = 0; q < JAC_Q; q++) acc[q][r] = {0.0, 0.0};
+      for (int q = 0; q < NQ; q++) acc[q][r] = {0.0, 0.0};
     }
     for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
       const double* __restrict__ s4 = summ + t * SUMMARY_DOUBLES;
-      if (s4[0] > s4[1]) continue;  // no contributing line
-      if (fmax(0.0, fmax(fblk_min - s4[1], s4[0] - fblk_max)) > cutoff * (1.0 + 1e-9)) continue;
-      const double2* __restrict__ g0 = reinterpret_cast<const double2*>(prep + t * tile_doubles());
-      const double2* __restrict__ g1 = g0 + 2 * TL;
-      const double2* __restrict__ g2 = g0 + 4 * TL;
-      const double* __restrict__ jt  = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
+      if (s4[0] > s4[1]) continue;  // no contributing line (CTA uniform)
+      const double dist = fmax(0.0, fmax(fblk_min - s4[1], s4[0] - fblk_max));
+      if (dist > cutoff * (1.0 + 1e-9)) continue;
       const int count = p.tile_count[t];
-      for (int l = 0; l < count; l++) {
-        const double2 a = __ldg(g0 + 2 * l);                           // f0', c3
-        const double2 m = __ldg(g1 + 2 * l), n2 = __ldg(g1 + 2 * l + 1);  // B1, igd | y, s_re
-        const double2 h = __ldg(g2 + 2 * l), k = __ldg(g2 + 2 * l + 1);   // E1, s_im | cut_re, cut_im
-        if (m.y == 0.0) continue;                                     // inactive cutoff line
-        const double E1p = __ldg(jcom + t * TL + l);
-        const cplx s{n2.y, h.y};
-        cplx ds[JAC_Q], dzq[JAC_Q], dcut[JAC_Q];
-        double dzf[JAC_Q];
+      __syncthreads();  // previous tile fully consumed
+      // stage the tile: the records of K1 + the derivative records of this pass, SoA in shared memory
+      for (int l = tid; l < count; l += JAC_NT) {
+        const double* g = prep + t * tile_doubles();
+        const double2 a = *reinterpret_cast<const double2*>(g + (0 * TL + l) * REC_GROUP);
+        const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);
+        const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);
+        const double2 h = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP);
+        const double2 k = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP + 2);
+        sb[0 * TL + l] = a.x; sb[1 * TL + l] = m.y; sb[2 * TL + l] = n.x; sb[3 * TL + l] = n.y; sb[4 * TL + l] = h.y;
+        sb[5 * TL + l] = h.x; sb[6 * TL + l] = jcom[t * TL + l]; sb[7 * TL + l] = k.x; sb[8 * TL + l] = k.y;
+        const double* jt = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
 #pragma unroll
-        for (int q = 0; q < JAC_Q; q++) {
-          if (q < nqp) {
-            const double2* __restrict__ j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
-            const double2* __restrict__ j1 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (1 * TL + l) * 4);
-            const double2 u0 = __ldg(j0), u1 = __ldg(j0 + 1), u2 = __ldg(j1), u3 = __ldg(j1 + 1);
-            ds[q] = {u0.x, u0.y}; dzq[q] = {u1.x, u1.y}; dzf[q] = u2.x; dcut[q] = {u2.y, u3.x};
-          }
+        for (int q = 0; q < NQ; q++) {
+          const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+          const double2* j1 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (1 * TL + l) * 4);
+          const double2 u0 = j0[0], u1 = j0[1], u2 = j1[0], u3 = j1[1];
+          double* o = sq + q * JAC_Q_FIELDS * TL;
+          o[0 * TL + l] = u0.x; o[1 * TL + l] = u0.y; o[2 * TL + l] = u1.x; o[3 * TL + l] = u1.y;
+          o[4 * TL + l] = u2.x; o[5 * TL + l] = u2.y; o[6 * TL + l] = u3.x;
         }
+      }
+      // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|)
+      if (tid == 0) tile_far = (!seg.has_cutoff && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
+      __syncthreads();
+      const bool far = tile_far != 0;
+      for (int l = 0; l < count; l++) {
+        const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l], y = sb[2 * TL + l];
+        if (igd == 0.0) continue;  // inactive cutoff line
+        const cplx s{sb[3 * TL + l], sb[4 * TL + l]};
 #pragma unroll
         for (int r = 0; r < JAC_R; r++) {
-          if (seg.has_cutoff && !(a.x >= f[r] - cutoff && a.x <= f[r] + cutoff)) continue;
+          if (seg.has_cutoff && !(f0s >= f[r] - cutoff && f0s <= f[r] + cutoff)) continue;
           cplx z, F, dF;
-          z_F_dF(m.y * (f[r] - a.x), n2.x, h.x, E1p, z, F, dF);
+          if (far) z_F_dF_far(igd * (f[r] - f0s), y, z, F, dF);
+          else z_F_dF(igd * (f[r] - f0s), y, sb[5 * TL + l], sb[6 * TL + l], z, F, dF);
           cplx sh = cmul(s, F);
-          if (seg.has_cutoff) sh = csub(sh, {k.x, k.y});
+          if (seg.has_cutoff) sh = csub(sh, {sb[7 * TL + l], sb[8 * TL + l]});
           shape[r] = cadd(shape[r], sh);
+          const cplx sdF = cmul(s, dF);
 #pragma unroll
-          for (int q = 0; q < JAC_Q; q++) {
-            if (q < nqp) {
-              cplx d = dX(s, ds[q], dzq[q], dzf[q], z, F, dF);
-              if (seg.has_cutoff) d = csub(d, dcut[q]);
-              acc[q][r] = cadd(acc[q][r], d);
-            }
+          for (int q = 0; q < NQ; q++) {
+            const double* o = sq + q * JAC_Q_FIELDS * TL;
+            const cplx ds{o[0 * TL + l], o[1 * TL + l]}, dzq{o[2 * TL + l], o[3 * TL + l]};
+            const cplx tq = cadd(dzq, cscale(o[4 * TL + l], z));
+            cplx d = cadd(cmul(ds, F), cmul(tq, sdF));  // dX, :310-323
+            if (seg.has_cutoff) d = csub(d, {o[5 * TL + l], o[6 * TL + l]});
+            acc[q][r] = cadd(acc[q][r], d);
           }
         }
       }
@@ -278,14 +317,12 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
       if (i >= p.nf) continue;
       const double scl = line_scale_v(f[r], T, P);
 #pragma unroll
-      for (int q = 0; q < JAC_Q; q++) {
-        if (q < nqp) {
-          cplx d = cscale(scl, acc[q][r]);
-          if (jp.kind[jp.q0 + q] == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
-          double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
-          o[0] += npm[0] * d.re; o[1] += npm[1] * d.re; o[2] += npm[2] * d.re; o[3] += npm[3] * d.re;
-          o[4] += npm[4] * d.im; o[5] += npm[5] * d.im; o[6] += npm[6] * d.im;
-        }
+      for (int q = 0; q < NQ; q++) {
+        cplx d = cscale(scl, acc[q][r]);
+        if (jp.kind[jp.q0 + q] == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
+        double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
+        o[0] += npm[0] * d.re; o[1] += npm[1] * d.re; o[2] += npm[2] * d.re; o[3] += npm[3] * d.re;
+        o[4] += npm[4] * d.im; o[5] += npm[5] * d.im; o[6] += npm[6] * d.im;
       }
     }
   }
@@ -300,14 +337,31 @@ int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev
   return 0;
 }
 
+template <int NQ>
+static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
+  const size_t smem = size_t(JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS) * TL * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr = true;
+  }
+  lbl_sum_jac_kernel<NQ><<<grid, JAC_NT, smem, stream>>>(p, jp);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream) {
   if (p.nsegs == 0 || nlev == 0 || p.nf == 0 || jp.nq == 0) return 0;
   dim3 grid(static_cast<unsigned>((p.nf + JAC_F_TILE - 1) / JAC_F_TILE), static_cast<unsigned>(nlev));
   for (int q0 = 0; q0 < jp.nq; q0 += JAC_Q) {
     jp.q0 = q0;
-    lbl_sum_jac_kernel<<<grid, JAC_NT, 0, stream>>>(p, jp);
-    count_launch();
-    AB_CUDA(cudaGetLastError());
+    switch (std::min(JAC_Q, jp.nq - q0)) {
+      case 1: AB_TRY(launch_sum_jac_n<1>(p, jp, grid, stream)); break;
+      case 2: AB_TRY(launch_sum_jac_n<2>(p, jp, grid, stream)); break;
+      case 3: AB_TRY(launch_sum_jac_n<3>(p, jp, grid, stream)); break;
+      default: AB_TRY(launch_sum_jac_n<4>(p, jp, grid, stream)); break;
+    }
   }
   return 0;
 }

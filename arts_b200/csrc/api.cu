@@ -392,7 +392,10 @@ int ab200_path_run_propmat(ab200_path* p) {
   const ab200_catalog* cat = p->cat;
   AB_CUDA(cudaSetDevice(cat->device));
   const size_t kbytes = static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double);
-  if (!p->k_preloaded && kbytes) AB_CUDA(cudaMemsetAsync(p->d_K, 0, kbytes, p->stream));
+  // With mode-0 (real) segments selected the real line sum writes whole K records itself (vector stores);
+  // only without them, or when the caller's K is accumulated into, K is zeroed / kept and updated in place.
+  const bool store_full = !p->k_preloaded && p->nsegs[0] > 0 && cat->ntiles > 0 && p->nf > 0;
+  if (!p->k_preloaded && !store_full && kbytes) AB_CUDA(cudaMemsetAsync(p->d_K, 0, kbytes, p->stream));
   if (p->nq > 0 && !p->dk_preloaded && kbytes) AB_CUDA(cudaMemsetAsync(p->d_dK, 0, kbytes * p->nq, p->stream));
   if (cat->ntiles == 0 || p->nf == 0) return AB200_OK;
   const size_t nseg = cat->segments.size();
@@ -406,6 +409,7 @@ int ab200_path_run_propmat(ab200_path* p) {
       AB_TRY(launch_prepare(pp, nlev, p->stream));
       t.stop();
     }
+    sp.k_store_full = store_full ? 1 : 0;
     for (int mode = 0; mode < 2; mode++) {
       sp.segs = p->d_segs + mode * nseg;
       sp.nsegs = p->nsegs[mode];

@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
   constexpr int F_TILE = SUM_NT * SUM_R;
   constexpr int STAGES = REAL_STAGES;
   constexpr int STAGE_DOUBLES = 3 * TL * REC_GROUP;  // groups 0, 1 (far) and 2 (near)
+  static_assert(F_TILE * 7 <= STAGES * STAGE_DOUBLES, "the K store staging reuses the line-record ring");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
   uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);  // TMA -> consumers
@@ -242,6 +243,9 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
   const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
   uint32_t it = 0;  // tiles consumed so far by this CTA (ring position)
+  double kacc[SUM_R];  // sum over the segments of the clamped, scaled line sums: one K update per frequency
+#pragma unroll
+  for (int r = 0; r < SUM_R; r++) kacc[r] = 0.0;
 
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
@@ -332,18 +336,36 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
       it += n;
     }
 
-    // K3: scale, clamp, accumulate A (npm = (1,0,...,0) for pol = no)
+    // K3: scale, clamp per segment (npm = (1,0,...,0) for pol = no), :944-953, :1688-1692
     const double T = p.T[lev], P = p.P[lev];
 #pragma unroll
     for (int r = 0; r < SUM_R; r++) {
+      const double F = line_scale(f[r], T, P) * accS[r];
+      if (!(p.no_negative_absorption && F < 0.0)) kacc[r] += F;
+    }
+  }
+
+  if (p.k_store_full) {
+    // vectorised store of whole Propmat records: stage the block's [F_TILE][7] doubles in shared memory
+    // (the line-record ring is free now) and write them as coalesced 16-byte vectors
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SUM_R; r++) {
+      double* o = sbuf + size_t(r * SUM_NT + tid) * 7;
+      o[0] = kacc[r];
+#pragma unroll
+      for (int c = 1; c < 7; c++) o[c] = 0.0;
+    }
+    __syncthreads();
+    const int64_t rows = min(int64_t(F_TILE), p.k_pitch - fblk);  // k_pitch is a multiple of 128 >= nf
+    double2* __restrict__ dst = reinterpret_cast<double2*>(p.K + (int64_t(lev) * p.k_pitch + fblk) * 7);
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(sbuf);
+    for (int64_t v = tid; v < rows * 7 / 2; v += SUM_NT) dst[v] = src[v];
+  } else {
+#pragma unroll
+    for (int r = 0; r < SUM_R; r++) {
       const int64_t i = fblk + r * SUM_NT + tid;
-      if (i < p.nf) {
-        const double F = line_scale(f[r], T, P) * accS[r];
-        if (!(p.no_negative_absorption && F < 0.0)) {
-          double* k = p.K + (int64_t(lev) * p.k_pitch + i) * 7;
-          k[0] += F;
-        }
-      }
+      if (i < p.nf) p.K[(int64_t(lev) * p.k_pitch + i) * 7] += kacc[r];
     }
   }
 }
@@ -559,15 +581,13 @@ int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream) {
       return 0;
     };
     switch (variant) {
-      case 1: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 8>, 128, 4)); break;
+      case 1: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 4>, 128, 4)); break;
       case 2: AB_TRY(go(lbl_sum_real_kernel<false, 8, 64, 4>, 64, 8)); break;
       case 3: AB_TRY(go(lbl_sum_real_kernel<false, 2, 256, 4>, 256, 2)); break;
-      case 4: AB_TRY(go(lbl_sum_real_kernel<false, 4, 256, 4>, 256, 4)); break;
       case 5: AB_TRY(go(lbl_sum_real_kernel<false, 6, 128, 4>, 128, 6)); break;
       case 6: AB_TRY(go(lbl_sum_real_kernel<true, 4, 128, 4>, 128, 4)); break;
       case 7: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 2>, 128, 4)); break;
-      case 8: AB_TRY(go(lbl_sum_real_kernel<false, 8, 128, 2>, 128, 8)); break;
-      default: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 4>, 128, 4)); break;
+      default: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 8>, 128, 4)); break;  // measured best (profiles/r1_ab_decoupled.txt)
     }
   } else {
     const size_t smem = lbl_cplx_smem_bytes();

@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1);
           }
-        } else if (cls[t] == CLS_NEAR) {
+        } else if (cls[t] == CLS_NEAR && !p.debug_skip_near) {
           const double2* __restrict__ rec2 = rec + 4 * TL;
           uint8_t* __restrict__ lf = lflag + st * TL;
           flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false);
@@ -563,8 +563,11 @@ int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream) {
   return 0;
 }
 
-int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream) {
-  if (p.nsegs == 0 || nlev == 0 || p.nf == 0) return 0;
+int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
+  if (p_in.nsegs == 0 || nlev == 0 || p_in.nf == 0) return 0;
+  SumParams p = p_in;
+  static const int skip_near = [] { const char* e = getenv("AB200_DEBUG_SKIP_NEAR"); return e ? atoi(e) : 0; }();
+  p.debug_skip_near = skip_near;
   static bool attr_set[2] = {false, false};
   if (mode == 0) {
     const size_t smem = lbl_real_smem_bytes();

@@ -44,6 +44,7 @@ struct SumParams {
   int32_t no_negative_absorption;
   double* K;  // [nlev][k_pitch][7], offset to the batch
   int64_t k_pitch;
+  int32_t debug_skip_near;  // measurement only (AB200_DEBUG_SKIP_NEAR=1): near tiles contribute nothing
   int32_t k_store_full;  // real kernel: K is not initialised; write whole records {A,0,0,0,0,0,0} with vector stores
 };
 

@@ -52,12 +52,22 @@ def parse_args():
     ap.add_argument("--levels", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
+                    help="c2 = BASELINE configs[1] (default, weak scaling); c4 = configs[3]: 1e6 lines x 1e6 frequencies x 100 "
+                         "levels, the frequency grid of FIXED total size sharded over the GPUs (strong scaling)")
+    ap.add_argument("--c4-lines", type=int, default=1_000_000)
+    ap.add_argument("--c4-nf", type=int, default=1_000_000)
     return ap.parse_args()
 
 
 def workload(args, world):
     from arts_b200 import synth
 
+    if args.workload == "c4":
+        case = synth.case_c4(n_lines=args.c4_lines, nf=args.c4_nf, np_=args.levels)
+        case.rte_option = args.rte
+        return case, (f"C4 (BASELINE configs[3]): {args.c4_lines} lines x {args.c4_nf} frequencies (1-100 THz, total, sharded over "
+                      f"the GPUs) x {args.levels} levels, no cutoff, {args.rte} Stokes chain")
     nf = args.nf_per_gpu * world
     case = synth.case_c2(lines_per_species=args.lines_per_species, nf=nf, np_=args.levels, rte_option=args.rte)
     name = (f"C2 (BASELINE configs[1]): 5 species x {args.lines_per_species} Voigt lines, {args.levels}-level nadir path, "
@@ -290,7 +300,7 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "lines": nl, "levels": np_, "nf_total": nf_total, "nf_per_gpu": cnt,
                    "sharding": "contiguous frequency blocks (matpack::omp_offset_count), catalog replicated, "

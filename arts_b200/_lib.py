@@ -11,7 +11,7 @@ import os
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libarts_b200.so")
+SO_PATH = os.path.join(_HERE, os.environ.get("AB200_LIB", "libarts_b200.so"))  # AB200_LIB: experimental builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "arts_b200.h")
 
 _dp = C.POINTER(C.c_double)
@@ -73,6 +73,7 @@ def lib():
     L.ab200_path_device_ptr.restype = _vp
     L.ab200_release_thread_cache.argtypes = []
     L.ab200_measure_dfma_peak.argtypes = [C.c_int, _dp, _dp]
+    L.ab200_measure_dfma_mix.argtypes = [C.c_int, _dp, _dp]
     L.ab200_faddeeva_w.argtypes = [C.c_int64, _dp, _dp, _dp, _dp]
     L.ab200_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, _dp, _dp]
     L.ab200_norm_view.argtypes = [C.c_int, _dp, _dp, _dp]

@@ -786,7 +786,7 @@ int ab200_planck_tb(int64_t nf, const double* f, double* I) {
 // ---------------------------------------------------------------------------
 // measurement helpers
 // ---------------------------------------------------------------------------
-int ab200_measure_dfma_peak(int iters, double* tflops, double* ms) {
+static int measure_fp64(int iters, bool mix, double* tflops, double* ms) {
   if (!tflops || !ms || iters <= 0) return set_error(AB200_ERR_INVALID, "ab200_measure_dfma_peak: bad argument");
   int dev = 0, sms = 0;
   AB_CUDA(cudaGetDevice(&dev));
@@ -797,12 +797,13 @@ int ab200_measure_dfma_peak(int iters, double* tflops, double* ms) {
   cudaEvent_t e0, e1;
   AB_CUDA(cudaEventCreate(&e0));
   AB_CUDA(cudaEventCreate(&e1));
-  AB_TRY(launch_dfma_peak(iters / 4 + 1, blocks, out.p, 0));  // warm-up
+  const int sign = mix ? -1 : 1;
+  AB_TRY(launch_dfma_peak(sign * (iters / 4 + 1), blocks, out.p, 0));  // warm-up
   AB_CUDA(cudaDeviceSynchronize());
   float best = 1e30f;
   for (int rep = 0; rep < 3; rep++) {
     AB_CUDA(cudaEventRecord(e0, 0));
-    AB_TRY(launch_dfma_peak(iters, blocks, out.p, 0));
+    AB_TRY(launch_dfma_peak(sign * iters, blocks, out.p, 0));
     AB_CUDA(cudaEventRecord(e1, 0));
     AB_CUDA(cudaEventSynchronize(e1));
     float t = 0;
@@ -811,11 +812,15 @@ int ab200_measure_dfma_peak(int iters, double* tflops, double* ms) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  const double fma = double(blocks) * 256.0 * double(iters) * 64.0;  // 8 chains x 8 unrolled
+  // plain: 8 chains x 8 unrolled DFMA per iteration; mix: 8 chains x 7 DFMA (+ 1 MUFU.RCP64H each)
+  const double fma = double(blocks) * 256.0 * double(iters) * (mix ? 56.0 : 64.0);
   *ms     = best;
   *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
   return AB200_OK;
 }
+
+int ab200_measure_dfma_peak(int iters, double* tflops, double* ms) { return measure_fp64(iters, false, tflops, ms); }
+int ab200_measure_dfma_mix(int iters, double* tflops, double* ms) { return measure_fp64(iters, true, tflops, ms); }
 
 int ab200_faddeeva_w(int64_t n, const double* zr, const double* zi, double* wr, double* wi) {
   if (n < 0) return set_error(AB200_ERR_INVALID, "ab200_faddeeva_w: negative size");

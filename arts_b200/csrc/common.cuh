@@ -30,7 +30,10 @@ constexpr double doppler_broadening_const_squared = 2000 * R / (c * c);
 }  // namespace cst
 
 // ---- geometry of the line catalog on the device ---------------------------
-constexpr int TL        = 256;  // (sub-)lines per tile; tiles never straddle a segment
+#ifndef AB200_TL
+#define AB200_TL 256
+#endif
+constexpr int TL        = AB200_TL;  // (sub-)lines per tile; tiles never straddle a segment
 constexpr int REC_GROUP = 4;    // doubles per record group (one LDS.128 pair)
 constexpr int N_GROUPS  = 4;    // groups per line record -> 16 doubles = 128 B per (level, line)
 constexpr int REC_DOUBLES = REC_GROUP * N_GROUPS;

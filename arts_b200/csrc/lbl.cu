@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
 // ---------------------------------------------------------------------------
 // default geometry of the real line sum: 128 threads x 4 frequencies per thread = 512-frequency blocks
 constexpr int CHUNK     = 4096;  // tiles classified per pass
-constexpr int REAL_STAGES = 2;   // 2 x 24 KB of line records per CTA: 4 CTAs per SM stay resident
+constexpr int REAL_STAGES = 2;   // 2 x 16 KB of line records per CTA
+// shared-memory ring of the real kernel; also the staging area of its vectorised K store (512 x 7 doubles)
+constexpr int REAL_RING_DOUBLES = (REAL_STAGES * 2 * TL * REC_GROUP > 512 * 7) ? REAL_STAGES * 2 * TL * REC_GROUP : 512 * 7;
 constexpr uint8_t CLS_SKIP = 0, CLS_FAR = 1, CLS_NEAR = 2;
 
 // classification of one (frequency block, line tile) pair, conservative w.r.t. the per-pair
@@ -204,15 +206,20 @@ __device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const dou
 
 // --------------------------- real-only kernel (mode 0) ----------------------
 // Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
+// 6 CTAs (24 warps) per SM: 80 registers, 36 KB of shared memory.  Measured on B200 (profiles/r1_ab_decoupled.txt):
+// the far loop is latency bound at 16 warps unless ptxas happens to interleave lines well; 24 warps is robust.
+#ifndef AB200_SUM_MINB
+#define AB200_SUM_MINB 6
+#endif
 template <bool DECOUPLED, int SUM_R, int SUM_NT, int UNROLL>
-__global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
+__global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(SumParams p) {
   constexpr int F_TILE = SUM_NT * SUM_R;
   constexpr int STAGES = REAL_STAGES;
-  constexpr int STAGE_DOUBLES = 3 * TL * REC_GROUP;  // groups 0, 1 (far) and 2 (near)
-  static_assert(F_TILE * 7 <= STAGES * STAGE_DOUBLES, "the K store staging reuses the line-record ring");
+  constexpr int STAGE_DOUBLES = 2 * TL * REC_GROUP;  // groups 0 and 1; E1 (group 2) of the rare series pairs comes from L2
+  static_assert(F_TILE * 7 <= REAL_RING_DOUBLES, "the K store staging reuses the line-record ring");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + STAGES * STAGE_DOUBLES);  // TMA -> consumers
+  uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + REAL_RING_DOUBLES);  // TMA -> consumers
   uint64_t* empty   = full + STAGES;                                               // consumers -> producer
   uint8_t* cls      = reinterpret_cast<uint8_t*>(empty + STAGES);
   uint8_t* lflag    = cls + CHUNK;  // [STAGES][TL]
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
         const uint32_t g  = it + t;
         const uint32_t st = g % STAGES;
         if (DECOUPLED && g >= STAGES) mbar_wait(&empty[st], ((g / STAGES) - 1) & 1);
-        const uint32_t bytes = (cls[t] == CLS_FAR ? 2 : 3) * TL * REC_GROUP * sizeof(double);
+        constexpr uint32_t bytes = 2 * TL * REC_GROUP * sizeof(double);
         mbar_expect_tx(&full[st], bytes);
         tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + t) * tile_doubles(), bytes, &full[st]);
       };
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
             for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1);
           }
         } else if (cls[t] == CLS_NEAR && !p.debug_skip_near) {
-          const double2* __restrict__ rec2 = rec + 4 * TL;
+          const double* __restrict__ g2 = prep + (c0 + t) * tile_doubles() + size_t(2) * TL * REC_GROUP;  // E1 at [l][0]
           uint8_t* __restrict__ lf = lflag + st * TL;
           flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false);
           __syncthreads();  // near tiles (rare) are processed in step by the whole CTA
@@ -309,7 +316,6 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
               continue;
             }
             const double2 d = rec1[2 * l + 1];  // y, s_re
-            const double E1 = reinterpret_cast<const double*>(rec2 + 2 * l)[0];
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) {
               const double u  = __dsub_rn(f[r], a.x);
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(SUM_NT) lbl_sum_real_kernel(SumParams p) {
                 acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y, c.x);
               } else {
                 double wr, wi;
-                w_near(c.y * u, d.x, E1, wr, wi);
+                w_near(c.y * u, d.x, __ldg(g2 + l * REC_GROUP), wr, wi);
                 acc[r] = __fma_rn(d.y, wr, acc[r]);
               }
             }
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
 // host launchers
 // ---------------------------------------------------------------------------
 size_t lbl_real_smem_bytes() {
-  return size_t(REAL_STAGES) * 3 * TL * REC_GROUP * sizeof(double) + 2 * REAL_STAGES * sizeof(uint64_t) + CHUNK + REAL_STAGES * TL;
+  return size_t(REAL_RING_DOUBLES) * sizeof(double) + 2 * REAL_STAGES * sizeof(uint64_t) + CHUNK + REAL_STAGES * TL;
 }
 size_t lbl_cplx_smem_bytes() {
   return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + TL + CHUNK * sizeof(uint16_t);
@@ -587,7 +593,6 @@ int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
       case 1: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 4>, 128, 4)); break;
       case 2: AB_TRY(go(lbl_sum_real_kernel<false, 8, 64, 4>, 64, 8)); break;
       case 3: AB_TRY(go(lbl_sum_real_kernel<false, 2, 256, 4>, 256, 2)); break;
-      case 5: AB_TRY(go(lbl_sum_real_kernel<false, 6, 128, 4>, 128, 6)); break;
       case 6: AB_TRY(go(lbl_sum_real_kernel<true, 4, 128, 4>, 128, 4)); break;
       case 7: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 2>, 128, 4)); break;
       default: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 8>, 128, 4)); break;  // measured best (profiles/r1_ab_decoupled.txt)
@@ -696,7 +701,35 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* out) 
   if (s == 123.456) out[0] = s;  // keep the chain alive without a store in practice
 }
 
+// the far-wing instruction mix: 7 DFMA-class instructions + 1 MUFU.RCP64H per evaluation, 8 independent
+// chains per thread.  Measures what the FP64 pipe sustains next to the reciprocal seeds (the kernel's ceiling).
+__global__ void __launch_bounds__(256) dfma_mix_kernel(int iters, double* out) {
+  double a[8];
+#pragma unroll
+  for (int u = 0; u < 8; u++) a[u] = 1.0 + threadIdx.x * 1e-9 + u;
+  const double m = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      double x = a[u], r;
+      x = __fma_rn(x, m, c); x = __fma_rn(x, m, c); x = __fma_rn(x, m, c); x = __fma_rn(x, m, c);
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+      x = __fma_rn(r, m, x); x = __fma_rn(x, m, c); x = __fma_rn(x, m, c);
+      a[u] = x;
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int u = 0; u < 8; u++) s += a[u];
+  if (s == 123.456) out[0] = s;
+}
+
 int launch_dfma_peak(int iters, int blocks, double* d_out, cudaStream_t stream) {
+  if (iters < 0) {  // mix mode
+    dfma_mix_kernel<<<blocks, 256, 0, stream>>>(-iters, d_out);
+    AB_CUDA(cudaGetLastError());
+    return 0;
+  }
   dfma_peak_kernel<<<blocks, 256, 0, stream>>>(iters, d_out);
   AB_CUDA(cudaGetLastError());
   return 0;

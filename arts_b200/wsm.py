@@ -265,6 +265,12 @@ def measure_dfma_peak(iters=20000):
     return t.value, ms.value
 
 
+def measure_dfma_mix(iters=20000):
+    t, ms = C.c_double(), C.c_double()
+    check(lib().ab200_measure_dfma_mix(int(iters), C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
 class Path:
     """Device-resident workspace of one propagation path (ab200_path): upload once, run, download."""
 

@@ -250,6 +250,9 @@ int ab200_path_region_histogram(ab200_path *p, int64_t samples_per_level, uint64
 /* Dependency-free DFMA loop on all SMs; returns achieved FP64 TFLOP/s (2 flop per DFMA) and the
  * kernel time.  MEASURED_PEAKS.json has no FP64 number. */
 int ab200_measure_dfma_peak(int iters, double *tflops, double *ms);
+/* Same loop with the far-wing instruction mix: 7 DFMA + 1 MUFU.RCP64H (reciprocal seed) per chain step; returns
+ * the DFMA TFLOP/s the FP64 pipe sustains next to the reciprocal seeds (the practical ceiling of the line sum). */
+int ab200_measure_dfma_mix(int iters, double *tflops, double *ms);
 /* Register-resident w(z) for tests: evaluates the device Faddeeva at n points (host arrays). */
 int ab200_faddeeva_w(int64_t n, const double *zr, const double *zi, double *wr, double *wi);
 

@@ -74,6 +74,7 @@ class AtmPathDesc(C.Structure):
         ("dQdT", _dp),
         ("mag", _dp),
         ("los", _dp),
+        ("wind", _dp),
     ]
 
 
@@ -208,6 +209,7 @@ class AtmPath:
     dQdT: np.ndarray | None = None
     mag: np.ndarray | None = None  # [np, 3]
     los: np.ndarray | None = None  # [np, 2]
+    wind: np.ndarray | None = None  # [np, 3] u, v, w [m/s]
 
     def __post_init__(self):
         self.T = _arr(self.T, np.float64)
@@ -222,6 +224,8 @@ class AtmPath:
             self.mag = _arr(self.mag, np.float64).reshape(n, 3)
         if self.los is not None:
             self.los = _arr(self.los, np.float64).reshape(n, 2)
+        if self.wind is not None:
+            self.wind = _arr(self.wind, np.float64).reshape(n, 3)
 
     @property
     def np_(self) -> int:
@@ -234,6 +238,7 @@ class AtmPath:
             None if self.dQdT is None else self.dQdT[s],
             None if self.mag is None else self.mag[s],
             None if self.los is None else self.los[s],
+            None if self.wind is None else self.wind[s],
         )
 
     def desc(self) -> AtmPathDesc:
@@ -247,6 +252,7 @@ class AtmPath:
         d.dQdT = dptr(self.dQdT)
         d.mag = dptr(self.mag)
         d.los = dptr(self.los)
+        d.wind = dptr(self.wind)
         return d
 
 

@@ -77,7 +77,7 @@ struct ab200_path {
   double* d_Ilev = nullptr;  // [np][nf][4] radiance arriving at each level
   double* d_jac = nullptr;   // [levels_per_batch][ntiles][nq][2][TL][4]
   double* d_jcom = nullptr;  // [levels_per_batch][ntiles][TL]
-  double *d_dQdT = nullptr, *d_dr = nullptr, *d_invT = nullptr;
+  double *d_dQdT = nullptr, *d_dr = nullptr, *d_invT = nullptr, *d_ffac = nullptr;
   int32_t tg_kind[AB200_MAX_TARGETS] = {0}, tg_species[AB200_MAX_TARGETS] = {0};
   int32_t it = -1;  // position of the temperature target
   bool dk_preloaded = false;
@@ -153,8 +153,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   const size_t snp = static_cast<size_t>(np);
   AB_TRY(dev_alloc(&p->d_f, snp * nf));
   // packed small arrays: T, P, H [np] | vmr [np][ns] | isorat, Q [np][ni] | npm [np][4][7] | frange [np][2] | r [np]
-  //                      | dQdT [np][ni] | dr [2][np][nq] | 1/T [np]
-  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq) + 1);
+  //                      | dQdT [np][ni] | dr [2][np][nq] | 1/T [np] | wind factor [np]
+  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq) + 2);
   AB_TRY(dev_alloc(&p->d_small, p->small_doubles));
   if (p->small_doubles) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_small), p->small_doubles * sizeof(double)));
   double* q = p->d_small;
@@ -169,7 +169,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->d_r = q; q += snp;
   p->d_dQdT = q; q += snp * cat->n_isot;
   p->d_dr = q; q += 2 * snp * nq;
-  p->d_invT = q;
+  p->d_invT = q; q += snp;
+  p->d_ffac = q;
   AB_TRY(dev_alloc(&p->d_Ibkg, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_I, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_K, snp * p->k_pitch * 7));
@@ -264,7 +265,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   double* h = p->h_small;
   double *hT = h, *hP = hT + snp, *hH = hP + snp, *hv = hH + snp, *hi = hv + snp * cat->n_species,
          *hQ = hi + snp * cat->n_isot, *hn = hQ + snp * cat->n_isot, *hfr = hn + snp * 28, *hr = hfr + snp * 2,
-         *hdQ = hr + snp, *hdr = hdQ + snp * cat->n_isot, *hiT = hdr + 2 * snp * p->nq;
+         *hdQ = hr + snp, *hdr = hdQ + snp * cat->n_isot, *hiT = hdr + 2 * snp * p->nq, *hff = hiT + snp;
   std::fill(hdr, hdr + 2 * snp * p->nq, 0.0);
   for (int ip = 0; ip < np; ip++) {
     if (!(atm->T[ip] > 0) || !(atm->P[ip] >= 0))
@@ -276,14 +277,18 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
     if (atm->mag) std::copy(atm->mag + 3 * ip, atm->mag + 3 * ip + 3, mag);
     if (atm->los) std::copy(atm->los + 2 * ip, atm->los + 2 * ip + 2, los);
     hH[ip] = std::hypot(mag[0], mag[1], mag[2]);
+    double fac = 1.0;
+    if (atm->wind && !wind_factor(atm->wind + 3 * ip, los, &fac))
+      return set_error(AB200_ERR_INVALID, "level " + std::to_string(ip) + ": Negative frequency scaling factor (wind_shift)");
+    hff[ip] = fac;
     for (int pol = 0; pol < 4; pol++) norm_view(pol, mag, los, hn + (static_cast<size_t>(ip) * 4 + pol) * 7);
     const double* fl = f + ip * f_level_stride;
     if (!p->grid_bounds.empty()) {
-      hfr[2 * ip]     = p->grid_bounds[2 * ip];
-      hfr[2 * ip + 1] = p->grid_bounds[2 * ip + 1];
+      hfr[2 * ip]     = fac * p->grid_bounds[2 * ip];
+      hfr[2 * ip + 1] = fac * p->grid_bounds[2 * ip + 1];
     } else {
-      hfr[2 * ip]     = p->nf ? fl[0] : 0.0;
-      hfr[2 * ip + 1] = p->nf ? fl[p->nf - 1] : 0.0;
+      hfr[2 * ip]     = p->nf ? fac * fl[0] : 0.0;
+      hfr[2 * ip + 1] = p->nf ? fac * fl[p->nf - 1] : 0.0;
     }
     hr[ip] = (r && ip < np - 1) ? r[ip] : 0.0;
     for (int s = 0; s < cat->n_species; s++) {
@@ -379,6 +384,7 @@ void fill_params(const ab200_path* p, int lev0, PrepareParams& pp, SumParams& sp
   sp = SumParams{};
   sp.f = p->d_f + static_cast<size_t>(lev0) * p->f_stride;
   sp.f_stride = p->f_stride; sp.nf = p->nf; sp.k_pitch = p->k_pitch;
+  sp.ffac = p->d_ffac + lev0;
   sp.T = p->d_T + lev0; sp.P = p->d_P + lev0;
   sp.npm = p->d_npm + static_cast<size_t>(lev0) * 28;
   sp.prep = p->d_prep; sp.summary = p->d_summary; sp.tile_count = cat->d_tile_count; sp.ntiles = cat->ntiles;
@@ -508,7 +514,7 @@ int ab200_path_run_stokes(ab200_path* p) {
   AB_CUDA(cudaSetDevice(p->cat->device));
   StokesParams sp{};
   sp.np = p->np; sp.nf = p->nf; sp.K = p->d_K; sp.k_pitch = p->k_pitch; sp.f = p->d_f; sp.f_stride = p->f_stride;
-  sp.T = p->d_T; sp.invT = p->d_invT; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
+  sp.T = p->d_T; sp.invT = p->d_invT; sp.ffac = p->d_ffac; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
   sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
   sp.I_lev = p->nq > 0 ? p->d_Ilev : nullptr;
   sp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded) ? 1 : 0;  // only mode-0 (real, pol = no) segments wrote K
@@ -520,7 +526,7 @@ int ab200_path_run_stokes(ab200_path* p) {
   if (p->nq > 0) {
     StokesJacParams jp{};
     jp.np = p->np; jp.nq = p->nq; jp.nf = p->nf; jp.K = p->d_K; jp.dK = p->d_dK; jp.k_pitch = p->k_pitch;
-    jp.f = p->d_f; jp.f_stride = p->f_stride; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
+    jp.f = p->d_f; jp.f_stride = p->f_stride; jp.ffac = p->d_ffac; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
     jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option;
     AB_TRY(launch_stokes_jac(jp, p->stream));
   }

@@ -86,6 +86,24 @@ void norm_view(int pol, const double mag[3], const double los[2], double npm[7])
   }
 }
 
+bool wind_factor(const double wind[3], const double los[2], double* fac_out) {
+  const double deg = cst::pi / 180;
+  const double u = wind[0], v = wind[1], w = wind[2];
+  double za = 180 - los[0], aa = los[1] + 180;  // path::mirror
+  if (aa > 180) aa -= 360;
+  const double f2   = (u * u + v * v) + w * w;
+  const double f    = std::sqrt(f2);
+  const double za_f = f == w ? 0.0 : std::acos(w / f);
+  const double aa_f = std::atan2(u, v);
+  const double za_p = za * deg, aa_p = aa * deg;
+  const double dp   = std::cos(za_f) * std::cos(za_p) + std::sin(za_f) * std::sin(za_p) * std::cos(aa_f - aa_p);
+  double fac        = 1.0 - (f * dp) / cst::c;
+  if (fac <= 0) return false;
+  if (std::isnan(fac)) fac = 1.0;  // "Zero shift if nan"
+  *fac_out = fac;
+  return true;
+}
+
 template <typename T>
 static int upload(T** dst, const T* src, size_t n) {
   *dst = nullptr;

@@ -228,15 +228,16 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
   const int lev = blockIdx.y;
   const int64_t fblk = int64_t(blockIdx.x) * F_TILE;
   const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double ffac = p.ffac[lev];  // freq_grid_pathFromPath on the fly (1.0 without wind: f * 1 == f exactly)
 
   double f[SUM_R];
 #pragma unroll
   for (int r = 0; r < SUM_R; r++) {
     const int64_t i = fblk + r * SUM_NT + tid;
-    f[r] = fg[i < p.nf ? i : p.nf - 1];
+    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
   }
-  const double fblk_min = fg[fblk];
-  const double fblk_max = fg[(fblk + F_TILE - 1 < p.nf) ? fblk + F_TILE - 1 : p.nf - 1];
+  const double fblk_min = ffac * fg[fblk];
+  const double fblk_max = ffac * fg[(fblk + F_TILE - 1 < p.nf) ? fblk + F_TILE - 1 : p.nf - 1];
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -397,15 +398,16 @@ __global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
   const int lev = blockIdx.y;
   const int64_t fblk = int64_t(blockIdx.x) * CPLX_F_TILE;
   const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double ffac = p.ffac[lev];  // freq_grid_pathFromPath on the fly (1.0 without wind: f * 1 == f exactly)
 
   double f[CPLX_R];
 #pragma unroll
   for (int r = 0; r < CPLX_R; r++) {
     const int64_t i = fblk + r * CPLX_NT + tid;
-    f[r] = fg[i < p.nf ? i : p.nf - 1];
+    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
   }
-  const double fblk_min = fg[fblk];
-  const double fblk_max = fg[(fblk + CPLX_F_TILE - 1 < p.nf) ? fblk + CPLX_F_TILE - 1 : p.nf - 1];
+  const double fblk_min = ffac * fg[fblk];
+  const double fblk_max = ffac * fg[(fblk + CPLX_F_TILE - 1 < p.nf) ? fblk + CPLX_F_TILE - 1 : p.nf - 1];
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
@@ -655,7 +657,7 @@ __global__ void region_histogram_kernel(SumParams p, int64_t samples_per_level, 
     const double* g0 = prep + tile * tile_doubles() + (int64_t(0) * TL + l) * REC_GROUP;
     const double* g1 = prep + tile * tile_doubles() + (int64_t(1) * TL + l) * REC_GROUP;
     const double f0s = g0[0], igd = g1[1], y = g1[2];
-    const double f = fg[int64_t(r2 % uint64_t(p.nf))];
+    const double f = p.ffac[lev] * fg[int64_t(r2 % uint64_t(p.nf))];
     atomicAdd(&h[7], 1ull);
     // segment of the tile (cutoff window): linear scan, nsegs is small
     double cutoff = DBL_MAX;

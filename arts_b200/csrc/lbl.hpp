@@ -33,6 +33,7 @@ struct SumParams {
   const double* f;   // [nlev][nf] (f_stride = nf) or [nf] (f_stride = 0), offset to the batch
   int64_t f_stride;
   int64_t nf;
+  const double* ffac;   // [nlev] wind-shift factor of each level's grid (1 without wind)
   const double *T, *P;  // [nlev]
   const double* npm;    // [nlev][4][7] zeeman::norm_view per polarisation
   const double* prep;

@@ -225,14 +225,15 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
   const int lev = blockIdx.y;
   const int64_t fblk = int64_t(blockIdx.x) * JAC_F_TILE;
   const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double ffac = p.ffac[lev];
   double f[JAC_R];
 #pragma unroll
   for (int r = 0; r < JAC_R; r++) {
     const int64_t i = fblk + r * JAC_NT + tid;
-    f[r] = fg[i < p.nf ? i : p.nf - 1];
+    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
   }
-  const double fblk_min = fg[fblk];
-  const double fblk_max = fg[(fblk + JAC_F_TILE - 1 < p.nf) ? fblk + JAC_F_TILE - 1 : p.nf - 1];
+  const double fblk_min = ffac * fg[fblk];
+  const double fblk_max = ffac * fg[(fblk + JAC_F_TILE - 1 < p.nf) ? fblk + JAC_F_TILE - 1 : p.nf - 1];
   const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
   const double* __restrict__ jcom = jp.jcom + int64_t(lev) * p.ntiles * TL;

@@ -151,10 +151,11 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
     I[0] = b0.x; I[1] = b0.y; I[2] = b1.x; I[3] = b1.y;
   }
   const int64_t ivc = active ? iv : p.nf - 1;
-  const bool shared_grid = p.f_stride == 0;
-  double f = p.f[ivc];
+  const double f_raw = p.f[ivc];
+  double f = f_raw;
   constexpr double planck_a = 2 * cst::h / (cst::c * cst::c);
   double af3 = planck_a * (f * f * f);
+  double ffac_prev = 1.0;  // shared grid: recompute f and f^3 only when the level's wind factor changes
   Propmat k_next{};
   double j_next = 0.0;
   for (int n = 0; n < np; n++) {
@@ -166,9 +167,11 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
     else k = load_propmat(&sK[warp][st][lane * 7]);
     __syncwarp();  // every lane has moved its row out of stage st
     if (lane == 0 && n + ST_STAGES < np) issue(n + ST_STAGES);
-    if (!shared_grid) {
-      f   = p.f[int64_t(lev) * p.f_stride + ivc];
-      af3 = planck_a * (f * f * f);
+    const double ffac = p.ffac[lev];
+    if (p.f_stride != 0 || ffac != ffac_prev) {
+      f         = ffac * (p.f_stride != 0 ? p.f[int64_t(lev) * p.f_stride + ivc] : f_raw);
+      af3       = planck_a * (f * f * f);
+      ffac_prev = ffac;
     }
     const double j = SCALAR ? (k.A == 0.0 ? 0.0 : planck_fast(f, af3, p.invT[lev])) : source_I(k, f, p.T[lev]);
     if (n > 0) {

@@ -12,6 +12,7 @@ struct StokesParams {
   int64_t k_pitch;
   const double* f;     // [np][nf] or [nf]
   int64_t f_stride;
+  const double* ffac;  // [np] wind-shift factor of each level's grid (1 without wind)
   const double* T;     // [np] level temperatures
   const double* invT;  // [np] 1 / T
   const double* r;     // [np-1] layer lengths
@@ -32,6 +33,7 @@ struct StokesJacParams {
   int64_t k_pitch;
   const double* f;      // [np][nf] or [nf]
   int64_t f_stride;
+  const double* ffac;   // [np]
   const double* T;      // [np]
   const double* r;      // [np-1]
   const double* dr;     // [2][np-1][nq]

@@ -218,11 +218,11 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
   for (int q = 0; q < AB200_MAX_TARGETS; q++) carry[q][0] = carry[q][1] = carry[q][2] = carry[q][3] = 0.0;
 
   Propmat k0 = load_propmat(p.K + (int64_t(0) * p.k_pitch + iv) * 7);
-  double f0  = p.f[iv];
+  double f0  = p.ffac[0] * p.f[iv];
   double j0  = k0.is_rotational() ? 0.0 : planck(f0, p.T[0]);
   for (int i = 0; i + 1 < np; i++) {
     const Propmat k1 = load_propmat(p.K + (int64_t(i + 1) * p.k_pitch + iv) * 7);
-    const double f1  = p.f[int64_t(i + 1) * p.f_stride + iv];
+    const double f1  = p.ffac[i + 1] * p.f[int64_t(i + 1) * p.f_stride + iv];
     const double j1  = k1.is_rotational() ? 0.0 : planck(f1, p.T[i + 1]);
     const double ri  = p.r[i];
     Tran t;

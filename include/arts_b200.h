@@ -118,6 +118,10 @@ typedef struct ab200_atm_path {
   const double *dQdT;   /* [np][n_isot] PartitionFunctions::dQdT(T, isot); may be NULL if no T target */
   const double *mag;    /* [np][3] magnetic field u,v,w [T]; may be NULL (=0) */
   const double *los;    /* [np][2] zenith, azimuth [deg] (PropagationPathPoint::los); may be NULL (=0) */
+  const double *wind;   /* [np][3] wind u,v,w [m/s] (AtmPoint::wind); may be NULL (=0).  With winds the library applies
+                           freq_grid_pathFromPath (src/m_ppvar.cc:47-77, wind_shift src/m_frequency_grid.cc:4-84) on the
+                           device: level ip sees fac[ip] * f with fac = 1 - |wind| cos(angle(wind, mirrored los)) / c,
+                           so the caller passes ONE grid instead of np shifted copies */
 } ab200_atm_path;
 
 typedef struct ab200_target {

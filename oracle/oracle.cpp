@@ -180,6 +180,7 @@ struct AtmPt {
   const double* dQdT;
   Numeric mag[3];
   Numeric los[2];
+  Numeric wind[3];
   Numeric vmr_of(int s) const { return s < 0 ? 0.0 : vmr[s]; }
 };
 
@@ -193,7 +194,36 @@ AtmPt atm_at(const ab200_catalog_desc& d, const ab200_atm_path& a, int ip) {
   p.dQdT   = a.dQdT ? a.dQdT + static_cast<Index>(ip) * d.n_isot : nullptr;
   for (int i = 0; i < 3; i++) p.mag[i] = a.mag ? a.mag[3 * ip + i] : 0.0;
   for (int i = 0; i < 2; i++) p.los[i] = a.los ? a.los[2 * ip + i] : 0.0;
+  for (int i = 0; i < 3; i++) p.wind[i] = a.wind ? a.wind[3 * ip + i] : 0.0;
   return p;
+}
+
+// wind_shift, src/m_frequency_grid.cc:4-55 (the frequency scaling factor only; the wind Jacobian
+// is outside the path) with path::mirror, src/core/path/path_point.cpp:33-39.
+// Returns false for a non-positive factor (the reference throws).
+bool wind_factor(const AtmPt& atm, Numeric& fac) {
+  constexpr Numeric c = Constant::c;
+  const Numeric u = atm.wind[0], v = atm.wind[1], w = atm.wind[2];
+  Numeric za = 180 - atm.los[0], aa = atm.los[1] + 180;
+  if (aa > 180) aa -= 360;
+  const Numeric u2v2 = u * u + v * v;
+  const Numeric w2   = w * w;
+  const Numeric f2   = u2v2 + w2;
+  const Numeric f    = std::sqrt(f2);
+  const Numeric za_f = f == w ? 0.0 : std::acos(w / f);
+  const Numeric aa_f = std::atan2(u, v);
+  const Numeric za_p = deg2rad(za);
+  const Numeric aa_p = deg2rad(aa);
+  const Numeric czaf = std::cos(za_f);
+  const Numeric szaf = std::sin(za_f);
+  const Numeric czap = std::cos(za_p);
+  const Numeric szap = std::sin(za_p);
+  const Numeric caa  = std::cos(aa_f - aa_p);
+  const Numeric dp   = czaf * czap + szaf * szap * caa;
+  fac                = 1.0 - (f * dp) / c;
+  if (fac <= 0) return false;
+  if (std::isnan(fac)) fac = 1.0;  // "Zero shift if nan" :40-44
+  return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -1153,6 +1183,31 @@ int fail(int code, const std::string& msg) {
 // ===========================================================================
 // exported oracle entry points (same argument meaning as include/arts_b200.h)
 // ===========================================================================
+// freq_grid_pathFromPath (src/m_ppvar.cc:47-77) for a whole path: with winds, [np][nf] shifted grids
+// fac[ip] * freq_grid replace the caller's grid
+struct PathGrid {
+  std::vector<double> buf;
+  const double* f;
+  int64_t stride;
+};
+int path_grid(const ab200_catalog_desc& d, const ab200_atm_path& atm, int64_t nf, const double* f, int64_t stride,
+              PathGrid& out) {
+  if (!atm.wind) {
+    out.f      = f;
+    out.stride = stride;
+    return 0;
+  }
+  out.buf.resize(static_cast<size_t>(atm.np) * nf);
+  for (int ip = 0; ip < atm.np; ip++) {
+    Numeric fac;
+    if (not wind_factor(atm_at(d, atm, ip), fac)) return fail(AB200_ERR_INVALID, "Negative frequency scaling factor");
+    for (int64_t i = 0; i < nf; i++) out.buf[static_cast<size_t>(ip) * nf + i] = fac * f[ip * stride + i];
+  }
+  out.f      = out.buf.data();
+  out.stride = nf;
+  return 0;
+}
+
 extern "C" {
 
 const char* orc_last_error(void) { return g_err.c_str(); }
@@ -1196,10 +1251,14 @@ int orc_norm_view(int pol, const double* mag, const double* los, double* npm) {
 // there are at least as many levels as threads, else over contiguous frequency
 // chunks per level (m_lbl.cc:273-295 with omp_offset_count,
 // matpack_mdspan_algorithm.cc:4-18).  The result does not depend on the choice.
-int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f, int64_t f_level_stride,
+int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f_in, int64_t f_level_stride_in,
                        const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
                        int32_t nq, const ab200_target* targets, double* K, double* dK) {
-  if (!d || !atm || !f || !K) return fail(AB200_ERR_INVALID, "null argument");
+  if (!d || !atm || !f_in || !K) return fail(AB200_ERR_INVALID, "null argument");
+  PathGrid pg;
+  if (int rc = path_grid(*d, *atm, nf, f_in, f_level_stride_in, pg)) return rc;
+  const double* f              = pg.f;
+  const int64_t f_level_stride = pg.stride;
   for (int ib = 0; ib < d->n_bands; ib++)
     if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE) return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE bands");
   if (nq > 0 && !dK) return fail(AB200_ERR_INVALID, "dK is null with nq > 0");
@@ -1383,7 +1442,13 @@ int orc_clearsky_emission(const ab200_catalog_desc* d, int64_t nf, const double*
                           double* K_out) {
   const int np = atm->np;
   std::vector<double> K(static_cast<size_t>(np) * nf * 7, 0.0), dK(static_cast<size_t>(np) * nq * nf * 7, 0.0);
-  int rc = orc_propmat_levels(d, nf, f, f_level_stride, atm, select_species, no_negative_absorption, nq, targets,
+  PathGrid pg;
+  if (int rcg = path_grid(*d, *atm, nf, f, f_level_stride, pg)) return rcg;
+  ab200_atm_path atm_nw = *atm;  // the grids below are already shifted
+  atm_nw.wind           = nullptr;
+  f                     = pg.f;
+  f_level_stride        = pg.stride;
+  int rc = orc_propmat_levels(d, nf, f, f_level_stride, &atm_nw, select_species, no_negative_absorption, nq, targets,
                               K.data(), dK.data());
   if (rc) return rc;
   // m_tramat.cc:14-24

@@ -246,3 +246,26 @@ def test_oracle_radiance_jacobian_vs_perturbation(orc, option):
         Im, _ = orc.clearsky_emission(c.cat, c.f, _perturbed(c, lev, species=1, dvmr=-1e-3 * v), c.r, c.I_bkg, rte_option=option)
         fd = (Ip[:, 0] - Im[:, 0]) / (2e-3 * v)
         np.testing.assert_allclose(dI[:, lev, 1, 0], fd, rtol=2e-2, atol=1e-3 * np.abs(dI[:, :, 1, 0]).max())
+
+
+def test_oracle_wind_shift_factor(orc):
+    """wind_shift (src/m_frequency_grid.cc:4-55): fac = 1 - wind . n / c with n the propagation direction
+    (path::mirror of the sensor-style los); checked through its effect on a single narrow line."""
+    import copy
+
+    c = synth.case_c1(nl=1, nf=4001)
+    c.f = np.linspace(c.cat.f0[0] - 2e6, c.cat.f0[0] + 2e6, c.nf)  # resolve the Doppler core
+    c.atm.P[:] = 10.0
+    K0, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    atm = copy.deepcopy(c.atm)
+    atm.los = np.array([[180.0, 0.0]])  # nadir-looking sensor: photons travel straight up
+    atm.wind = np.array([[0.0, 0.0, 300.0]])  # updraft along the propagation direction
+    K1, _ = orc.propmat_levels(c.cat, c.f, atm)
+    fac = 1 - 300.0 / synth.C0
+    # level sees fac * f: the line peak moves to f0' / fac
+    df = c.f[1] - c.f[0]
+    shift = (np.argmax(K1[0, :, 0]) - np.argmax(K0[0, :, 0])) * df
+    assert abs(shift - c.cat.f0[0] * (1 / fac - 1)) <= 1.5 * df
+    atm.wind = np.array([[300.0, -200.0, 0.0]])  # horizontal wind, vertical path: no shift at all
+    K2, _ = orc.propmat_levels(c.cat, c.f, atm)
+    np.testing.assert_allclose(K2, K0, rtol=1e-9)

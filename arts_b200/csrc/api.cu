@@ -231,9 +231,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
     return set_error(AB200_ERR_INVALID, "atm path has " + std::to_string(atm->np) + " levels, workspace " + std::to_string(np));
   if (f_level_stride != 0 && f_level_stride != p->nf)
     return set_error(AB200_ERR_INVALID, "f_level_stride must be 0 (shared grid) or nf (one grid per level)");
-  if (rte_option == AB200_RTE_LINPROP)
-    return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path (no CPU fallback)");
-  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC)
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC && rte_option != AB200_RTE_LINPROP)
     return set_error(AB200_ERR_INVALID, "unknown rte_option");
   if (select_species != AB200_SPECIES_BATH && (select_species < 0 || select_species >= cat->n_species))
     return set_error(AB200_ERR_INVALID, "select_species out of range");
@@ -517,6 +515,7 @@ int ab200_path_run_stokes(ab200_path* p) {
   sp.T = p->d_T; sp.invT = p->d_invT; sp.ffac = p->d_ffac; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
   sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
   sp.I_lev = p->nq > 0 ? p->d_Ilev : nullptr;
+  sp.flags = p->d_flags;
   sp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded) ? 1 : 0;  // only mode-0 (real, pol = no) segments wrote K
   {
     LaunchTimer t(p, 3);
@@ -527,7 +526,7 @@ int ab200_path_run_stokes(ab200_path* p) {
     StokesJacParams jp{};
     jp.np = p->np; jp.nq = p->nq; jp.nf = p->nf; jp.K = p->d_K; jp.dK = p->d_dK; jp.k_pitch = p->k_pitch;
     jp.f = p->d_f; jp.f_stride = p->f_stride; jp.ffac = p->d_ffac; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
-    jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option;
+    jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option; jp.flags = p->d_flags;
     AB_TRY(launch_stokes_jac(jp, p->stream));
   }
   return AB200_OK;
@@ -540,6 +539,10 @@ static int check_flags(ab200_path* p) {
   if (h) {
     cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->stream);
     if (h & 2) return set_error(AB200_ERR_INVALID, "non-finite line-shape parameter (f0', 1/GD, G0 or strength) at some level");
+    if (h & 4)
+      return set_error(AB200_ERR_UNSUPPORTED,
+                       "rte_option linprop with a polarised propagation matrix and a positive absorption gradient is outside "
+                       "the GPU path (rtepack_transmission.cc:467-474; no CPU fallback)");
     return set_error(AB200_ERR_UNSUPPORTED, "negative pressure broadening (G0 < 0) is outside the GPU path");
   }
   return AB200_OK;
@@ -684,11 +687,12 @@ struct DevBuf {
 int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double* dK, const double* r,
                  const double* dr, int32_t rte_option, uint32_t flags, double* T, double* L, double* P, double* dT,
                  double* dL) {
-  if (rte_option == AB200_RTE_LINPROP) return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path");
-  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC) return set_error(AB200_ERR_INVALID, "unknown rte_option");
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC && rte_option != AB200_RTE_LINPROP)
+    return set_error(AB200_ERR_INVALID, "unknown rte_option");
   if (np < 0 || nf < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_tramat: negative size");
   if (np == 0 || nf == 0) return AB200_OK;
-  const bool linsrc = rte_option == AB200_RTE_LINSRC;
+  const bool linprop = rte_option == AB200_RTE_LINPROP;
+  const bool linsrc  = rte_option == AB200_RTE_LINSRC || linprop;  // L, dL exist for both
   if (!K || !T || !P || (np > 1 && !r) || (linsrc && !L)) return set_error(AB200_ERR_INVALID, "ab200_tramat: null argument");
   if (nq > 0 && (!dK || !dT || (np > 1 && !dr) || (linsrc && !dL)))
     return set_error(AB200_ERR_INVALID, "ab200_tramat: null Jacobian argument with nq > 0");
@@ -700,7 +704,18 @@ int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const doub
   if (linsrc) AB_TRY(dL_.alloc(nm));
   AB_CUDA(cudaMemcpy(dK_.p, K, nk * sizeof(double), cudaMemcpyHostToDevice));
   if (np > 1) AB_CUDA(cudaMemcpy(dr_.p, r, (np - 1) * sizeof(double), cudaMemcpyHostToDevice));
-  AB_TRY(launch_tramat(np, nf, dK_.p, dr_.p, linsrc, (flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0, dT_.p, dL_.p, dP_.p, 0));
+  int* d_flag = nullptr;
+  AB_TRY(dev_alloc(&d_flag, 1));
+  struct FlagGuard { int* p; ~FlagGuard() { cudaFree(p); } } flag_guard{d_flag};
+  AB_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
+  AB_TRY(launch_tramat(np, nf, dK_.p, dr_.p, linsrc, (flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0, dT_.p, dL_.p, dP_.p, linprop,
+                       d_flag, 0));
+  int h_flag = 0;
+  AB_CUDA(cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h_flag & 4)
+    return set_error(AB200_ERR_UNSUPPORTED,
+                     "rte_option linprop with a polarised propagation matrix and a positive absorption gradient is outside the "
+                     "GPU path (rtepack_transmission.cc:467-474; no CPU fallback)");
   AB_CUDA(cudaMemcpy(T, dT_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
   AB_CUDA(cudaMemcpy(P, dP_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
   if (linsrc) AB_CUDA(cudaMemcpy(L, dL_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
@@ -712,7 +727,7 @@ int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const doub
     if (np > 1) AB_CUDA(cudaMemcpy(ddr_.p, dr, 2 * static_cast<size_t>(np - 1) * nq * sizeof(double), cudaMemcpyHostToDevice));
     AB_CUDA(cudaMemset(ddT_.p, 0, nd * sizeof(double)));  // dT = muelmat::constant(0), rtepack_transmission.cc:1300-1314
     if (linsrc) AB_CUDA(cudaMemset(ddL_.p, 0, nd * sizeof(double)));
-    AB_TRY(launch_tramat_jac(np, nf, nq, dK_.p, ddK_.p, dr_.p, ddr_.p, linsrc, ddT_.p, ddL_.p, 0));
+    AB_TRY(launch_tramat_jac(np, nf, nq, dK_.p, ddK_.p, dr_.p, ddr_.p, linsrc, ddT_.p, ddL_.p, linprop, 0));
     AB_CUDA(cudaMemcpy(dT, ddT_.p, nd * sizeof(double), cudaMemcpyDeviceToHost));
     if (linsrc) AB_CUDA(cudaMemcpy(dL, ddL_.p, nd * sizeof(double), cudaMemcpyDeviceToHost));
   }
@@ -741,11 +756,11 @@ int ab200_srcvec(int32_t np, int64_t nf, int32_t nq, const double* K, const doub
 int ab200_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, const double* T, const double* L,
                        const double* P, const double* dT, const double* dL, const double* J, const double* dJ,
                        const double* I_bkg, double* I, double* dI) {
-  if (rte_option == AB200_RTE_LINPROP) return set_error(AB200_ERR_UNSUPPORTED, "rte_option linprop is outside the GPU path");
-  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC) return set_error(AB200_ERR_INVALID, "unknown rte_option");
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC && rte_option != AB200_RTE_LINPROP)
+    return set_error(AB200_ERR_INVALID, "unknown rte_option");
   if (np < 0 || nf < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: negative size");
   if (nf == 0) return AB200_OK;
-  const bool linsrc = rte_option == AB200_RTE_LINSRC;
+  const bool linsrc = rte_option != AB200_RTE_CONSTANT;  // linsrc and linprop share linevo (rtepack_rtestep.cc:392-401)
   if (!T || !J || !I_bkg || !I || (linsrc && !L)) return set_error(AB200_ERR_INVALID, "ab200_rte_emission: null argument");
   if (nq > 0 && (!P || !dT || !dJ || !dI || (linsrc && !dL)))
     return set_error(AB200_ERR_INVALID, "ab200_rte_emission: null Jacobian argument with nq > 0");

@@ -7,6 +7,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "faddeeva.cuh"
 
 namespace ab200 {
 namespace rte {
@@ -74,6 +75,56 @@ __device__ __forceinline__ double func_F4p(double z) {  // :305-313
   const double z4 = z2 * z2;
   const double z5 = z4 * z;
   return (ez * (z4 - 4.0 * z3 + 12.0 * z2 - 24.0 * z + 24.0) - 24.0) / z5;
+}
+
+// Faddeeva::Dawson(x) for real x (reference 3rdparty/Faddeeva, used by tran::linsrc_linprop
+// rtepack_transmission.cc:453): D(x) = sqrt(pi)/2 Im w(x + 0i), odd; through the register-resident w(z).
+__device__ __forceinline__ double dawson(double x) {
+  const double ax = fabs(x);
+  double wr, wi;
+  if (ax > FAR_LIMIT) w_far_z(ax, 0.0, wr, wi);
+  else if (cf_region(ax, 0.0)) w_cf(ax, 0.0, wr, wi);
+  else w_series(ax, 0.0, 1.0 /* E1(0) = erfcx(0) */, wr, wi);
+  const double d = 0.886226925452758013649083741671 * wi;  // sqrt(pi)/2
+  return x < 0.0 ? -d : d;
+}
+
+// rte_option = linprop (tran::linsrc_linprop, rtepack_transmission.cc:449-475): which branch a layer takes.
+//   0: gradient below 1e-8 -> the linsrc operator (:456-457)   1: unpolarised Dawson form (:459-465)
+//   2: polarised (complex matrix sqrt / dawson, :467-474) -> outside the GPU path, reported as an error
+__device__ __forceinline__ int linprop_case(double k1A, double k2A, double r, bool polarized) {
+  const double alpha2 = (k2A - k1A) / (2.0 * r);
+  if (alpha2 < 1e-8) return 0;
+  return polarized ? 2 : 1;
+}
+__device__ __forceinline__ double linprop_lambda(double k1A, double k2A, double r, double t00) {
+  const double alpha = sqrt((k2A - k1A) / (2.0 * r));
+  const double u0    = k1A / (2.0 * alpha);
+  const double u1    = k2A / (2.0 * alpha);
+  return (dawson(u1) - t00 * dawson(u0)) / (r * alpha);
+}
+// tran::linsrc_linprop_deriv, unpolarised closed form :493-541
+__device__ __forceinline__ double linprop_lambda_deriv(double k1a, double k2a, double dk, double t00, double dt00, double r,
+                                                       double dr, bool k1_deriv) {
+  const double denom = 2.0 * r;
+  const double alpha = sqrt(fmax(0.0, (k2a - k1a) / denom));
+  const double u0 = k1a / (2.0 * alpha), u1 = k2a / (2.0 * alpha);
+  const double D0 = dawson(u0), D1 = dawson(u1);
+  const double dD0 = 1.0 - 2.0 * u0 * D0, dD1 = 1.0 - 2.0 * u1 * D1;
+  double d_alpha, d_u0, d_u1;
+  if (k1_deriv) {
+    d_alpha = -0.5 * dk / (denom * alpha);
+    d_u0    = (dk * 2.0 * alpha - k1a * 2.0 * d_alpha) / (4.0 * alpha * alpha);
+    d_u1    = -k2a * d_alpha / (2.0 * alpha * alpha);
+  } else {
+    d_alpha = 0.5 * dk / (denom * alpha);
+    d_u0    = -k1a * d_alpha / (2.0 * alpha * alpha);
+    d_u1    = (dk * 2.0 * alpha - k2a * 2.0 * d_alpha) / (4.0 * alpha * alpha);
+  }
+  const double d_num       = dD1 * d_u1 - dt00 * D0 - t00 * dD0 * d_u0 - t00 * D0 * d_u0;  // sic, :531-532
+  const double denom_val   = r * alpha;
+  const double d_denom_val = dr * alpha + r * d_alpha;
+  return (d_num * denom_val - (D1 - t00 * D0) * d_denom_val) / (denom_val * denom_val);
 }
 
 // 4x4 row-major helpers

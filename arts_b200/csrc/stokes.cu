@@ -35,7 +35,7 @@ __device__ __forceinline__ double source_I(const Propmat& k, double f, double T)
 // branch is compiled out; the arithmetic of the branch taken is identical in both instantiations.
 template <bool LINSRC, bool SCALAR>
 __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& k0, const Propmat& k1, double j0 /*J_i*/,
-                                         double j1 /*J_{i+1}*/, double r, bool exact) {
+                                         double j1 /*J_{i+1}*/, double r, bool exact, bool linprop, int* __restrict__ flags) {
   Tran t;
   if (SCALAR) {
     t.a         = -0.5 * r * (k0.A + k1.A);
@@ -46,7 +46,8 @@ __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& 
   }
   if (SCALAR || !t.polarized) {
     if (LINSRC) {  // linevo :341-370 with scalar T, Lambda
-      const double lam = func_F(t.a);
+      const double lam = (linprop && linprop_case(k0.A, k1.A, r, false) == 1) ? linprop_lambda(k0.A, k1.A, r, t.exp_a)
+                                                                               : func_F(t.a);
       const double dj  = j1 - j0;
       I[0] = t.exp_a * (I[0] - j1) + lam * dj + j0;
       I[1] = t.exp_a * I[1];
@@ -63,6 +64,7 @@ __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& 
   }
   double Tm[16];
   t.T(Tm);
+  if (LINSRC && linprop && linprop_case(k0.A, k1.A, r, true) == 2) atomicOr(flags, 4);  // polarised linprop
   if (LINSRC) {
     const double v[4] = {I[0] - j1, I[1], I[2], I[3]};  // I - J_{i+1}
     double o[4], l[4];
@@ -89,13 +91,16 @@ __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& 
 // share one expm1, the two divisions become MUFU reciprocals + Newton (fast_rcp, ~1 ulp), and
 // hf/kT uses the per-level 1/T.  Differences from the literal form are a few ulp (parity: 1e-9 on I).
 template <bool LINSRC>
-__device__ __forceinline__ void rte_step_scalar(double* __restrict__ I, double A0, double A1, double j0, double j1, double r) {
+__device__ __forceinline__ void rte_step_scalar(double* __restrict__ I, double A0, double A1, double j0, double j1, double r,
+                                                bool linprop) {
   const double a = -0.5 * r * (A0 + A1);
   double ea;
   if (LINSRC) {
     const double em  = expm1(a);
     ea               = em + 1.0;
-    const double lam = fabs(a) < 1e-8 ? 1.0 + a * 0.5 + a * a / 6.0 : em * fast_rcp(a);
+    double lam;
+    if (linprop && linprop_case(A0, A1, r, false) == 1) lam = linprop_lambda(A0, A1, r, ea);
+    else lam = fabs(a) < 1e-8 ? 1.0 + a * 0.5 + a * a / 6.0 : em * fast_rcp(a);
     I[0] = ea * (I[0] - j1) + lam * (j1 - j0) + j0;
   } else {
     ea              = exp(a);
@@ -180,8 +185,8 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
         o[0] = make_double2(I[0], I[1]);
         o[1] = make_double2(I[2], I[3]);
       }
-      if (SCALAR) rte_step_scalar<LINSRC>(I, k.A, k_next.A, j, j_next, p.r[lev]);
-      else rte_step<LINSRC, false>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0);
+      if (SCALAR) rte_step_scalar<LINSRC>(I, k.A, k_next.A, j, j_next, p.r[lev], p.rte_option == AB200_RTE_LINPROP);
+      else rte_step<LINSRC, false>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0, p.rte_option == AB200_RTE_LINPROP, p.flags);
     }
     k_next = k;
     j_next = j;
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream) {
   if (p.nf == 0) return 0;
   const unsigned grid = static_cast<unsigned>((p.nf + ST_NT - 1) / ST_NT);
-  const bool lin = p.rte_option == AB200_RTE_LINSRC;
+  const bool lin = p.rte_option != AB200_RTE_CONSTANT;  // linsrc and linprop share the linevo recursion
   if (p.scalar) {
     if (lin) stokes_chain_kernel<true, true><<<grid, ST_NT, 0, stream>>>(p);
     else stokes_chain_kernel<false, true><<<grid, ST_NT, 0, stream>>>(p);
@@ -248,7 +253,7 @@ __device__ __forceinline__ void diag16(double* __restrict__ m, double d) {
 // TransmittanceMatrix::init forward part: T, L [nf][np][16], index 0 = identity (:1300-1314),
 // one thread per (frequency, level); constant :1114-1131, linsrc :1151-1169
 __global__ void tramat_kernel(int np, int64_t nf, const double* __restrict__ K, const double* __restrict__ r, int linsrc,
-                              int exact, double* __restrict__ T, double* __restrict__ L) {
+                              int exact, double* __restrict__ T, double* __restrict__ L, int linprop, int* __restrict__ flags) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= nf * np) return;
   const int64_t iv = idx / np;
@@ -267,7 +272,11 @@ __global__ void tramat_kernel(int np, int64_t nf, const double* __restrict__ K, 
   if (t.polarized) t.T(m); else diag16(m, t.exp_a);
   store16(T + idx * 16, m);
   if (linsrc) {
-    if (t.polarized) t.L(m); else diag16(m, func_F(t.a));
+    const int lc = linprop ? linprop_case(k1.A, k2.A, r[i - 1], t.polarized) : 0;
+    if (lc == 2) atomicOr(flags, 4);
+    if (lc == 1) diag16(m, linprop_lambda(k1.A, k2.A, r[i - 1], t.exp_a));
+    else if (t.polarized) t.L(m);
+    else diag16(m, func_F(t.a));
     store16(L + idx * 16, m);
   }
 }
@@ -349,10 +358,10 @@ __global__ void rte_emission_kernel(int linsrc, int np, int64_t nf, const double
 }
 
 int launch_tramat(int np, int64_t nf, const double* K, const double* r, int linsrc, int exact, double* T, double* L,
-                  double* P, cudaStream_t stream) {
+                  double* P, int linprop, int* flags, cudaStream_t stream) {
   if (nf == 0 || np == 0) return 0;
   const int64_t n = nf * np;
-  tramat_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(np, nf, K, r, linsrc, exact, T, L);
+  tramat_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(np, nf, K, r, linsrc, exact, T, L, linprop, flags);
   count_launch();
   AB_CUDA(cudaGetLastError());
   cumtran_kernel<<<static_cast<unsigned>((nf + 127) / 128), 128, 0, stream>>>(np, nf, T, P);

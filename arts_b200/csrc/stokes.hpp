@@ -21,6 +21,7 @@ struct StokesParams {
   double* I_lev;       // optional [np][nf][4]: radiance arriving at every level (for the Jacobian pass), or nullptr
   int32_t rte_option;
   int32_t tran_exact;
+  int* flags;          // device error flags (bit 2: polarised layer with rte_option linprop)
   int32_t scalar;      // K is known to have only A != 0 (no polarised segment was summed): scalar fast path
 };
 
@@ -41,18 +42,19 @@ struct StokesJacParams {
   double* dI;           // [nf][np][nq][4]
   int32_t it;           // index of the temperature target or -1
   int32_t rte_option;
+  int* flags;
 };
 
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream);
 int launch_stokes_jac(const StokesJacParams& p, cudaStream_t stream);
 int launch_tramat_jac(int np, int64_t nf, int nq, const double* K, const double* dK, const double* r, const double* dr,
-                      int linsrc, double* dT, double* dL, cudaStream_t stream);
+                      int linsrc, double* dT, double* dL, int linprop, cudaStream_t stream);
 int launch_rte_emission_jac(int linsrc, int np, int64_t nf, int nq, const double* T, const double* L, const double* P,
                             const double* dT, const double* dL, const double* J, const double* dJ, const double* I_bkg,
                             double* I, double* dI, cudaStream_t stream);
 int launch_planck_tb(int64_t nf, const double* f, double* I, cudaStream_t stream);
 int launch_tramat(int np, int64_t nf, const double* K, const double* r, int linsrc, int exact, double* T, double* L,
-                  double* P, cudaStream_t stream);
+                  double* P, int linprop, int* flags, cudaStream_t stream);
 int launch_srcvec(int np, int64_t nf, int nq, const double* K, const double* f, int64_t f_stride, const double* Tlev,
                   int it, double* J, double* dJ, cudaStream_t stream);
 int launch_rte_emission(int linsrc, int np, int64_t nf, const double* T, const double* L, const double* J,

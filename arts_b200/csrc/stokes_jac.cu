@@ -72,7 +72,7 @@ __device__ __forceinline__ void layer_terms(const double* __restrict__ T, const 
 // ---------------------------------------------------------------------------
 __global__ void tramat_jac_kernel(int np, int64_t nf, int nq, const double* __restrict__ K, const double* __restrict__ dK,
                                   const double* __restrict__ r, const double* __restrict__ dr, int linsrc,
-                                  double* __restrict__ dT, double* __restrict__ dL) {
+                                  double* __restrict__ dT, double* __restrict__ dL, int linprop) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= nf * (np - 1)) return;
   const int64_t iv = idx / (np - 1);
@@ -93,18 +93,24 @@ __global__ void tramat_jac_kernel(int np, int64_t nf, int nq, const double* __re
     double* o0 = dT + ((iv * np + (i - 1)) * nq + j) * 16;
     double* o1 = dT + half + ((iv * np + i) * nq + j) * 16;
     t.deriv(Tm, k1, k2, dk0, ri, dr0, m);
+    const double dt00_0 = m[0];
 #pragma unroll
     for (int e = 0; e < 16; e++) o0[e] = m[e];
     t.deriv(Tm, k1, k2, dk1, ri, dr1, m);
+    const double dt00_1 = m[0];
 #pragma unroll
     for (int e = 0; e < 16; e++) o1[e] = m[e];
     if (linsrc) {
       double* l0 = dL + ((iv * np + (i - 1)) * nq + j) * 16;
       double* l1 = dL + half + ((iv * np + i) * nq + j) * 16;
-      t.linsrc_deriv(dk0, ri, dr0, m);
+      // linprop (TransmittanceMatrix::linprop :1225-1247) passes dr1 to BOTH derivative calls (:1238, sic)
+      const int lc = linprop ? linprop_case(k1.A, k2.A, ri, t.polarized) : 0;
+      if (lc == 1) diag_of(m, linprop_lambda_deriv(k1.A, k2.A, dk0.A, Tm[0], dt00_0, ri, dr1, true));
+      else t.linsrc_deriv(dk0, ri, linprop ? dr1 : dr0, m);
 #pragma unroll
       for (int e = 0; e < 16; e++) l0[e] = m[e];
-      t.linsrc_deriv(dk1, ri, dr1, m);
+      if (lc == 1) diag_of(m, linprop_lambda_deriv(k1.A, k2.A, dk1.A, Tm[0], dt00_1, ri, dr1, false));
+      else t.linsrc_deriv(dk1, ri, dr1, m);
 #pragma unroll
       for (int e = 0; e < 16; e++) l1[e] = m[e];
     }
@@ -112,10 +118,10 @@ __global__ void tramat_jac_kernel(int np, int64_t nf, int nq, const double* __re
 }
 
 int launch_tramat_jac(int np, int64_t nf, int nq, const double* K, const double* dK, const double* r, const double* dr,
-                      int linsrc, double* dT, double* dL, cudaStream_t stream) {
+                      int linsrc, double* dT, double* dL, int linprop, cudaStream_t stream) {
   if (nf == 0 || np < 2 || nq == 0) return 0;
   const int64_t n = nf * (np - 1);
-  tramat_jac_kernel<<<static_cast<unsigned>((n + 63) / 64), 64, 0, stream>>>(np, nf, nq, K, dK, r, dr, linsrc, dT, dL);
+  tramat_jac_kernel<<<static_cast<unsigned>((n + 63) / 64), 64, 0, stream>>>(np, nf, nq, K, dK, r, dr, linsrc, dT, dL, linprop);
   count_launch();
   AB_CUDA(cudaGetLastError());
   return 0;
@@ -229,7 +235,13 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
     t.init(k0, k1, ri, false);
     double Tm[16], Lm[16];
     if (t.polarized) t.T(Tm); else diag_of(Tm, t.exp_a);
-    if (LINSRC) { if (t.polarized) t.L(Lm); else diag_of(Lm, func_F(t.a)); }
+    const int lc = (LINSRC && p.rte_option == AB200_RTE_LINPROP) ? linprop_case(k0.A, k1.A, ri, t.polarized) : 0;
+    if (lc == 2) atomicOr(p.flags, 4);
+    if (LINSRC) {
+      if (lc == 1) diag_of(Lm, linprop_lambda(k0.A, k1.A, ri, t.exp_a));
+      else if (t.polarized) t.L(Lm);
+      else diag_of(Lm, func_F(t.a));
+    }
     // radiance arriving at level i+1
     const double* Il = p.I_lev + (int64_t(i + 1) * p.nf + iv) * 4;
     double v[4], jd[4] = {0, 0, 0, 0};
@@ -251,8 +263,14 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
       t.deriv(Tm, k0, k1, dk0, ri, dr0, dT0);
       t.deriv(Tm, k0, k1, dk1, ri, dr1, dT1);
       if (LINSRC) {
-        t.linsrc_deriv(dk0, ri, dr0, dL0);
-        t.linsrc_deriv(dk1, ri, dr1, dL1);
+        const bool lp = p.rte_option == AB200_RTE_LINPROP;  // dr1 in both calls for linprop (:1238, sic)
+        if (lc == 1) {
+          diag_of(dL0, linprop_lambda_deriv(k0.A, k1.A, dk0.A, Tm[0], dT0[0], ri, dr1, true));
+          diag_of(dL1, linprop_lambda_deriv(k0.A, k1.A, dk1.A, Tm[0], dT1[0], ri, dr1, false));
+        } else {
+          t.linsrc_deriv(dk0, ri, lp ? dr1 : dr0, dL0);
+          t.linsrc_deriv(dk1, ri, dr1, dL1);
+        }
       }
       double c0[4], c1[4], o[4];
       layer_terms<LINSRC>(Tm, Lm, dT0, dT1, dL0, dL1, v, jd, dj0, dj1, c0, c1);
@@ -284,7 +302,7 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
 int launch_stokes_jac(const StokesJacParams& p, cudaStream_t stream) {
   if (p.nf == 0 || p.nq == 0 || p.np == 0) return 0;
   const unsigned grid = static_cast<unsigned>((p.nf + 63) / 64);
-  if (p.rte_option == AB200_RTE_LINSRC)
+  if (p.rte_option != AB200_RTE_CONSTANT)
     stokes_jac_kernel<true><<<grid, 64, 0, stream>>>(p);
   else
     stokes_jac_kernel<false><<<grid, 64, 0, stream>>>(p);

@@ -65,7 +65,7 @@ enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1 };
 /* LineByLineCutoffType (lbl_data.h:178-194). */
 enum { AB200_CUTOFF_NONE = 0, AB200_CUTOFF_BYLINE = 1 };
 /* TransmittanceOption (arts_options.cc:953-1030); linsrc is the default rte_option. */
-enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 /* unsupported */ };
+enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 /* unpolarised layers only, else AB200_ERR_UNSUPPORTED */ };
 /* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR). */
 enum { AB200_TARGET_T = 0, AB200_TARGET_VMR = 1 };
 

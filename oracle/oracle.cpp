@@ -46,6 +46,8 @@
 namespace Faddeeva {
 // reference 3rdparty/Faddeeva/Faddeeva.hh:36
 extern std::complex<double> w(std::complex<double> z, double relerr);
+// reference 3rdparty/Faddeeva/Faddeeva.hh:56 (used by tran::linsrc_linprop, rtepack_transmission.cc:453)
+extern double Dawson(double x);
 }  // namespace Faddeeva
 
 namespace {
@@ -1159,6 +1161,57 @@ struct tran {
     const muelmat dS3m = dSm * S2m + Sm * dS2m;
     return muelmat(dl0) + Sm * dl1 + dSm * l1 + S2m * dl2 + dS2m * l2 + S3m * dl3 + dS3m * l3;
   }
+
+  // tran::linsrc_linprop, :449-475.  Only the unpolarised branch is restated (the polarised one needs the
+  // complex matrix sqrt / inverse / dawson of :872-1002, outside the path: DESIGN.md section 7); `ok` reports it.
+  muelmat linsrc_linprop(const muelmat& t, const propmat& k1, const propmat& k2, const Numeric r, bool& ok) const {
+    ok = true;
+    const Numeric alpha2A = (k2.A() - k1.A()) / (2.0 * r);
+    if (alpha2A < 1e-8) return linsrc();  // "Ignore when the gradient is negative"
+    if (polarized) {
+      ok = false;
+      return muelmat::zero();
+    }
+    const Numeric alpha = std::sqrt(alpha2A);
+    const Numeric u0    = k1.A() / (2.0 * alpha);
+    const Numeric u1    = k2.A() / (2.0 * alpha);
+    return muelmat((Faddeeva::Dawson(u1) - t.m[0] * Faddeeva::Dawson(u0)) / (r * alpha));
+  }
+
+  // tran::linsrc_linprop_deriv, :477-556 (unpolarised closed form; the polarised branch is a perturbation
+  // of the unsupported polarised linsrc_linprop)
+  muelmat linsrc_linprop_deriv(const muelmat& t, const propmat& k1, const propmat& k2, const propmat& dk_in,
+                               const muelmat& dt, const Numeric r, const Numeric dr, bool k1_deriv, bool& ok) const {
+    ok = true;
+    const Numeric alpha2A = (k2.A() - k1.A()) / (2.0 * r);
+    if (alpha2A < 1e-8) return linsrc_deriv(dk_in, r, dr);
+    if (polarized) {
+      ok = false;
+      return muelmat::zero();
+    }
+    const Numeric k1a = k1.A(), k2a = k2.A(), dk = dk_in.A();
+    const Numeric delta_k = k2a - k1a;
+    const Numeric denom   = 2.0 * r;
+    const Numeric alpha   = std::sqrt(std::max(0.0, delta_k / denom));
+    const Numeric u0 = k1a / (2.0 * alpha), u1 = k2a / (2.0 * alpha);
+    const Numeric D0 = Faddeeva::Dawson(u0), D1 = Faddeeva::Dawson(u1);
+    const Numeric dD0 = 1.0 - 2.0 * u0 * D0, dD1 = 1.0 - 2.0 * u1 * D1;
+    const Numeric t00 = t.m[0], dt00 = dt.m[0];
+    Numeric d_alpha, d_u0, d_u1;
+    if (k1_deriv) {
+      d_alpha = -0.5 * dk / (denom * alpha);
+      d_u0    = (dk * 2.0 * alpha - k1a * 2.0 * d_alpha) / (4.0 * alpha * alpha);
+      d_u1    = -k2a * d_alpha / (2.0 * alpha * alpha);
+    } else {
+      d_alpha = 0.5 * dk / (denom * alpha);
+      d_u0    = -k1a * d_alpha / (2.0 * alpha * alpha);
+      d_u1    = (dk * 2.0 * alpha - k2a * 2.0 * d_alpha) / (4.0 * alpha * alpha);
+    }
+    const Numeric d_num       = dD1 * d_u1 - dt00 * D0 - t00 * dD0 * d_u0 - t00 * D0 * d_u0;  // sic, :531-532
+    const Numeric denom_val   = r * alpha;
+    const Numeric d_denom_val = dr * alpha + r * d_alpha;
+    return muelmat((d_num * denom_val - (D1 - t00 * D0) * d_denom_val) / (denom_val * denom_val));
+  }
 };
 
 void store(double* p, const muelmat& m) { std::memcpy(p, m.m, 16 * sizeof(double)); }
@@ -1296,10 +1349,12 @@ int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f_
 int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double* dK, const double* r,
                const double* dr, int32_t rte_option, uint32_t flags, double* T, double* L, double* P, double* dT,
                double* dL) {
-  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC)
-    return fail(AB200_ERR_UNSUPPORTED, "rte_option must be constant or linsrc");
-  const bool exact  = flags & AB200_FLAG_TRAN_EXACT;
-  const bool linsrc = rte_option == AB200_RTE_LINSRC;
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC && rte_option != AB200_RTE_LINPROP)
+    return fail(AB200_ERR_INVALID, "unknown rte_option");
+  const bool exact   = flags & AB200_FLAG_TRAN_EXACT;
+  const bool linprop = rte_option == AB200_RTE_LINPROP;
+  const bool linsrc  = rte_option == AB200_RTE_LINSRC || linprop;  // L, dL exist for both (:1300-1306)
+  bool all_ok        = true;
   const muelmat id;
   const muelmat zero = muelmat::zero();
   // :1300-1314 identity / zero init
@@ -1327,13 +1382,26 @@ int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double
       const tran ts{k1, k2, r[i - 1], exact};
       const muelmat Tm = ts();
       store(T + (iv * np + i) * 16, Tm);
-      if (linsrc) store(L + (iv * np + i) * 16, ts.linsrc());
+      bool ok = true;
+      if (linprop) store(L + (iv * np + i) * 16, ts.linsrc_linprop(Tm, k1, k2, r[i - 1], ok));
+      else if (linsrc) store(L + (iv * np + i) * 16, ts.linsrc());
+      if (not ok) {
+#pragma omp atomic write
+        all_ok = false;
+      }
       for (int j = 0; j < nq; j++) {
         const Numeric dr0 = dr[(0 * (np - 1) + (i - 1)) * nq + j];
         const Numeric dr1 = dr[(1 * (np - 1) + (i - 1)) * nq + j];
-        store(dXi(dT, 0, iv, i - 1, j), ts.deriv(Tm, k1, k2, dK_at(i - 1, j, iv), r[i - 1], dr0));
-        store(dXi(dT, 1, iv, i, j), ts.deriv(Tm, k1, k2, dK_at(i, j, iv), r[i - 1], dr1));
-        if (linsrc) {
+        const muelmat dT0m = ts.deriv(Tm, k1, k2, dK_at(i - 1, j, iv), r[i - 1], dr0);
+        const muelmat dT1m = ts.deriv(Tm, k1, k2, dK_at(i, j, iv), r[i - 1], dr1);
+        store(dXi(dT, 0, iv, i - 1, j), dT0m);
+        store(dXi(dT, 1, iv, i, j), dT1m);
+        if (linprop) {  // TransmittanceMatrix::linprop :1225-1247; note dr1 in BOTH calls (:1238)
+          bool ok2 = true;
+          store(dXi(dL, 0, iv, i - 1, j),
+                ts.linsrc_linprop_deriv(Tm, k1, k2, dK_at(i - 1, j, iv), dT0m, r[i - 1], dr1, true, ok2));
+          store(dXi(dL, 1, iv, i, j), ts.linsrc_linprop_deriv(Tm, k1, k2, dK_at(i, j, iv), dT1m, r[i - 1], dr1, false, ok2));
+        } else if (linsrc) {
           store(dXi(dL, 0, iv, i - 1, j), ts.linsrc_deriv(dK_at(i - 1, j, iv), r[i - 1], dr0));
           store(dXi(dL, 1, iv, i, j), ts.linsrc_deriv(dK_at(i, j, iv), r[i - 1], dr1));
         }
@@ -1350,6 +1418,8 @@ int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double
       store(P + (i * np + j) * 16, acc);
     }
   }
+  if (not all_ok)
+    return fail(AB200_ERR_UNSUPPORTED, "linprop with a polarised propagation matrix is outside the restated path");
   return 0;
 }
 
@@ -1380,8 +1450,9 @@ int orc_srcvec(int32_t np, int64_t nf, int32_t nq, const double* K, const double
 int orc_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, const double* T, const double* L,
                      const double* P, const double* dT, const double* dL, const double* J, const double* dJ,
                      const double* I_bkg, double* I, double* dI) {
-  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC)
-    return fail(AB200_ERR_UNSUPPORTED, "rte_option must be constant or linsrc");
+  if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC && rte_option != AB200_RTE_LINPROP)
+    return fail(AB200_ERR_INVALID, "unknown rte_option");
+  if (rte_option == AB200_RTE_LINPROP) rte_option = AB200_RTE_LINSRC;  // rte_emission: linsrc and linprop share linevo (:392-401)
   auto dXi = [&](const double* base, int t, Index iv, int i, int j) {
     return load_mm(base + (((static_cast<Index>(t) * nf + iv) * np + i) * nq + j) * 16);
   };

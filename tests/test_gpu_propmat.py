@@ -145,7 +145,7 @@ def test_errors_are_loud(wsm):
         wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, select_species=99)
     assert e.value.code == abi.ERR_INVALID
     with pytest.raises(wsm.Ab200Error) as e:
-        wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option="linprop")
-    assert e.value.code == abi.ERR_UNSUPPORTED
+        wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option=7)
+    assert e.value.code == abi.ERR_INVALID
     with pytest.raises(ValueError):
         wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg[:-1])

@@ -109,7 +109,7 @@ def test_linsrc_lambda_is_the_source_integral(orc):
 def _linsrc_fixture(orc, varying):
     """Inputs exactly as tests/core/linsrc/test_linsrc_convergence.py:24-92 / :110-178."""
     f = np.array([100e9])
-    out = {"constant": [], "linsrc": []}
+    out = {"constant": [], "linsrc": [], "linprop": []}
     N, scl = 2**12, 1.0
     while N >= 2:
         k = np.linspace(1e-2, 1e-4, N) if varying else np.full(N, 1e-2)
@@ -119,7 +119,7 @@ def _linsrc_fixture(orc, varying):
         r = np.full(N - 1, scl)
         bkg = np.zeros((1, 4))
         bkg[0, 0] = orc.planck(f, 100.0)[0]
-        for opt in ("linsrc", "constant"):
+        for opt in ("linsrc", "constant", "linprop"):
             Tr, Lr, Pr, dTr, dLr = orc.tramat(K, None, r, None, opt)
             Jr, dJr = orc.srcvec(K, f, Tlev)
             Ir, _ = orc.rte_emission(opt, Tr, Lr, Pr, dTr, dLr, Jr, dJr, bkg)
@@ -132,14 +132,16 @@ def _linsrc_fixture(orc, varying):
 @pytest.mark.parametrize("varying", [False, True])
 def test_linsrc_convergence_fixture(orc, varying):
     out = _linsrc_fixture(orc, varying)
-    lin, linsrc = np.array(out["constant"]), np.array(out["linsrc"])
-    # the reference's assertion (:95-96, :181-182)
+    lin, linsrc, linprop = np.array(out["constant"]), np.array(out["linsrc"]), np.array(out["linprop"])
+    # the reference's assertions (:95-96, :181-182, :269-270)
     assert np.all(lin / lin[0] >= linsrc / linsrc[0])
+    assert np.all(lin / lin[0] >= linprop / linprop[0])
     # recorded brightness temperatures (made by tests/golden/make_oracle_goldens.py from this oracle;
     # they pin the oracle against drift and are what the GPU test compares with on the box)
     gold = json.load(open(os.path.join(GOLD, "linsrc_convergence.json")))["varying" if varying else "constant_k"]
     np.testing.assert_allclose(lin, gold["constant"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(linsrc, gold["linsrc"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(linprop, gold["linprop"], rtol=0, atol=1e-9)
     # physics of the fixture: the finest grid is converged to < 1 mK between the two options
     assert abs(lin[0] - linsrc[0]) < 1e-3
 

@@ -82,6 +82,7 @@ def test_unfused_linprop_scalar_with_jacobians(wsm, orc):
 @pytest.mark.parametrize("targets", [(), (("T",), ("VMR", 3))])
 def test_fused_linprop_scalar(wsm, orc, targets):
     c = synth.case_c2(lines_per_species=300, nf=900, np_=25, bands_per_species=3, rte_option="linprop")
+    c.cat.a[:] *= 100.0  # strong enough that 16 % of the layers have a gradient above the 1e-8 threshold (:456)
     Ir, dIr = orc.clearsky_emission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option="linprop", targets=targets, hse_derivative=1)
     I, dI = wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option="linprop", jac_targets=targets,
                                              hse_derivative=1)

@@ -174,13 +174,13 @@ constexpr uint8_t CLS_SKIP = 0, CLS_FAR = 1, CLS_NEAR = 2;
 // classification of one (frequency block, line tile) pair, conservative w.r.t. the per-pair
 // tests of the near loops (1e-9 relative margin covers every rounding in them)
 __device__ __forceinline__ uint8_t classify_tile(const double* __restrict__ s, double fblk_min, double fblk_max,
-                                                 double cutoff) {
+                                                 double cutoff, double far_limit = FAR_LIMIT) {
   const double f0min = s[0], f0max = s[1];
   if (f0min > f0max) return CLS_SKIP;  // no contributing line
   const double dist = fmax(0.0, fmax(fblk_min - f0max, f0min - fblk_max));
   if (dist > cutoff * (1.0 + 1e-9)) return CLS_SKIP;
   if (cutoff < DBL_MAX) return CLS_NEAR;  // windows need the per-pair predicate
-  return (s[2] * dist + s[3] > FAR_LIMIT * (1.0 + 1e-9)) ? CLS_FAR : CLS_NEAR;
+  return (s[2] * dist + s[3] > far_limit * (1.0 + 1e-9)) ? CLS_FAR : CLS_NEAR;
 }
 
 // scl(f), ComputeData ctor lbl_lineshape_voigt_lte.cpp:944-953
@@ -196,11 +196,11 @@ __device__ __forceinline__ double line_scale(double f, double T, double P) {
 template <int NT>
 __device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const double2* __restrict__ g0,
                                            const double2* __restrict__ g1, int count, double fblk_min, double fblk_max,
-                                           bool all_slow) {
+                                           bool all_slow, double far_limit = FAR_LIMIT) {
   for (int l = threadIdx.x; l < count; l += NT) {
     const double f0s = g0[2 * l].x, igd = g1[2 * l].y, y = g1[2 * l + 1].x;
     const double dist = fmax(0.0, fmax(fblk_min - f0s, f0s - fblk_max));
-    flag[l] = (!all_slow && igd * dist + y > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
+    flag[l] = (!all_slow && igd * dist + y > far_limit * (1.0 + 1e-9)) ? 1 : 0;
   }
 }
 
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
       const int n = int(min(int64_t(CHUNK), seg.tile_end - c0));
       __syncthreads();  // every warp is done with the previous chunk's classes
       for (int t = tid; t < n; t += SUM_NT)
-        cls[t] = classify_tile(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, DBL_MAX);
+        cls[t] = classify_tile(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, DBL_MAX, FAR_LIMIT_REAL_SUM);
       __syncthreads();
 
       // The warps of the CTA are decoupled: a stage is refilled when all four warps have released it
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
         } else if (cls[t] == CLS_NEAR && !p.debug_skip_near) {
           const double* __restrict__ g2 = prep + (c0 + t) * tile_doubles() + size_t(2) * TL * REC_GROUP;  // E1 at [l][0]
           uint8_t* __restrict__ lf = lflag + st * TL;
-          flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false);
+          flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false, FAR_LIMIT_REAL_SUM);
           __syncthreads();  // near tiles (rare) are processed in step by the whole CTA
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
             for (int r = 0; r < SUM_R; r++) {
               const double u  = __dsub_rn(f[r], a.x);
               const double ax = __dmul_rn(fabs(u), c.y);
-              if (__dadd_rn(ax, d.x) > FAR_LIMIT) {
+              if (__dadd_rn(ax, d.x) > FAR_LIMIT_REAL_SUM) {
                 acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y, c.x);
               } else {
                 double wr, wi;

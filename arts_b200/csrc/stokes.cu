@@ -33,9 +33,11 @@ __device__ __forceinline__ double source_I(const Propmat& k, double f, double T)
 // one step of the recursion over layer (i, i+1): k0 = K_i (sensor side), k1 = K_{i+1}.
 // SCALAR: the caller guarantees that both levels are unpolarised (only A != 0), so the polarised
 // branch is compiled out; the arithmetic of the branch taken is identical in both instantiations.
-template <bool LINSRC, bool SCALAR>
+template <int OPT /* AB200_RTE_* */, bool SCALAR>
 __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& k0, const Propmat& k1, double j0 /*J_i*/,
-                                         double j1 /*J_{i+1}*/, double r, bool exact, bool linprop, int* __restrict__ flags) {
+                                         double j1 /*J_{i+1}*/, double r, bool exact, int* __restrict__ flags) {
+  constexpr bool LINSRC  = OPT != AB200_RTE_CONSTANT;  // linsrc and linprop share the linevo recursion
+  constexpr bool linprop = OPT == AB200_RTE_LINPROP;
   Tran t;
   if (SCALAR) {
     t.a         = -0.5 * r * (k0.A + k1.A);
@@ -90,9 +92,10 @@ __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& 
 // unpolarised branch with the transcendental count cut to two per step — exp(a) and F(a) = expm1(a)/a
 // share one expm1, the two divisions become MUFU reciprocals + Newton (fast_rcp, ~1 ulp), and
 // hf/kT uses the per-level 1/T.  Differences from the literal form are a few ulp (parity: 1e-9 on I).
-template <bool LINSRC>
-__device__ __forceinline__ void rte_step_scalar(double* __restrict__ I, double A0, double A1, double j0, double j1, double r,
-                                                bool linprop) {
+template <int OPT>
+__device__ __forceinline__ void rte_step_scalar(double* __restrict__ I, double A0, double A1, double j0, double j1, double r) {
+  constexpr bool LINSRC  = OPT != AB200_RTE_CONSTANT;
+  constexpr bool linprop = OPT == AB200_RTE_LINPROP;
   const double a = -0.5 * r * (A0 + A1);
   double ea;
   if (LINSRC) {
@@ -121,7 +124,7 @@ __device__ __forceinline__ double planck_fast(double f, double af3, double invT)
 // Every warp owns 32 consecutive frequencies and its own ring of ST_STAGES shared-memory stages;
 // lane 0 refills a stage with one 1792-byte TMA bulk copy (the K rows of 32 frequencies at one
 // level) as soon as the warp has moved that stage into registers.  No CTA-wide barrier in the loop.
-template <bool LINSRC, bool SCALAR>
+template <int OPT, bool SCALAR>
 __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
   __shared__ __align__(128) double sK[ST_NT / 32][ST_STAGES][32 * 7];
   __shared__ uint64_t full[ST_NT / 32][ST_STAGES];
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
         o[0] = make_double2(I[0], I[1]);
         o[1] = make_double2(I[2], I[3]);
       }
-      if (SCALAR) rte_step_scalar<LINSRC>(I, k.A, k_next.A, j, j_next, p.r[lev], p.rte_option == AB200_RTE_LINPROP);
-      else rte_step<LINSRC, false>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0, p.rte_option == AB200_RTE_LINPROP, p.flags);
+      if (SCALAR) rte_step_scalar<OPT>(I, k.A, k_next.A, j, j_next, p.r[lev]);
+      else rte_step<OPT, false>(I, k, k_next, j, j_next, p.r[lev], p.tran_exact != 0, p.flags);
     }
     k_next = k;
     j_next = j;
@@ -201,13 +204,14 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream) {
   if (p.nf == 0) return 0;
   const unsigned grid = static_cast<unsigned>((p.nf + ST_NT - 1) / ST_NT);
-  const bool lin = p.rte_option != AB200_RTE_CONSTANT;  // linsrc and linprop share the linevo recursion
-  if (p.scalar) {
-    if (lin) stokes_chain_kernel<true, true><<<grid, ST_NT, 0, stream>>>(p);
-    else stokes_chain_kernel<false, true><<<grid, ST_NT, 0, stream>>>(p);
-  } else {
-    if (lin) stokes_chain_kernel<true, false><<<grid, ST_NT, 0, stream>>>(p);
-    else stokes_chain_kernel<false, false><<<grid, ST_NT, 0, stream>>>(p);
+  auto go = [&](auto kernel) { kernel<<<grid, ST_NT, 0, stream>>>(p); };
+  switch (p.rte_option * 2 + (p.scalar ? 1 : 0)) {
+    case AB200_RTE_CONSTANT * 2 + 0: go(stokes_chain_kernel<AB200_RTE_CONSTANT, false>); break;
+    case AB200_RTE_CONSTANT * 2 + 1: go(stokes_chain_kernel<AB200_RTE_CONSTANT, true>); break;
+    case AB200_RTE_LINSRC * 2 + 0: go(stokes_chain_kernel<AB200_RTE_LINSRC, false>); break;
+    case AB200_RTE_LINSRC * 2 + 1: go(stokes_chain_kernel<AB200_RTE_LINSRC, true>); break;
+    case AB200_RTE_LINPROP * 2 + 0: go(stokes_chain_kernel<AB200_RTE_LINPROP, false>); break;
+    default: go(stokes_chain_kernel<AB200_RTE_LINPROP, true>); break;
   }
   count_launch();
   AB_CUDA(cudaGetLastError());

@@ -149,3 +149,19 @@ def test_errors_are_loud(wsm):
     assert e.value.code == abi.ERR_INVALID
     with pytest.raises(ValueError):
         wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg[:-1])
+
+
+def test_mid_wing_closed_form_accuracy(wsm, orc):
+    """The real line sum uses the far-wing closed form from |x|+y > 1000 (FAR_LIMIT_REAL_SUM) where the reference
+    still runs its continued fraction: the difference is 1/(2 z^4) <= 5e-13 relative, far inside the 1e-9 bound."""
+    c = synth.case_c1(nl=1, nf=4000)
+    c.atm.P[:] = 5.0  # nearly pure Doppler line: y << 1, x = (f - f0') / G_D
+    f0 = c.cat.f0[0]
+    gd = np.sqrt(2000 * 1.380649e-23 * 6.02214076e23 / 299792458.0**2 * 250.0 / 31.9898) * f0
+    x = np.linspace(300.0, 9000.0, c.nf)
+    c.f = f0 + x * gd
+    Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    rel = np.abs(K[0, :, 0] - Kr[0, :, 0]) / Kr[0, :, 0]
+    assert rel.max() <= 2e-12, (rel.max(), x[np.argmax(rel)])
+    assert rel[(x > 1000) & (x < 4000)].max() > 1e-15  # the closed form is really in use there

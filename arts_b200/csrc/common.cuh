@@ -54,7 +54,8 @@ constexpr int SUMMARY_DOUBLES = 4;
 // (3rdparty/Faddeeva/Faddeeva.cc:707-725)
 constexpr double FAR_LIMIT = 4000.0;
 // The closed form i z / (sqrt(pi) (z^2 - 1/2)) the reference uses above 4000 differs from w(z) by
-// 1/(2 z^4) relative, i.e. <= 5e-13 for |z| >= 1000 (the accuracy Faddeeva.cc itself claims is ~1e-13).
+// 1/(2 z^4) relative (real part for y << x: 2.5/x^4), i.e. <= 2.5e-12 for |z| >= 1000 — measured 2.7e-12 at
+// x = 1024 in tests/test_gpu_propmat.py::test_mid_wing_closed_form_accuracy.
 // The real line sum (same-sign terms, no cancellation) therefore uses it from |x|+y > 1000: four times
 // fewer pairs in the expensive continued-fraction branch, parity bound 1e-9 untouched.
 constexpr double FAR_LIMIT_REAL_SUM = 1000.0;

@@ -441,6 +441,7 @@ int ab200_path_run_propmat(ab200_path* p) {
         sp.segs = p->d_segs + mode * nseg;
         sp.nsegs = p->nsegs[mode];
         if (sp.nsegs == 0) continue;
+        js.real_lines = mode == 0 ? 1 : 0;
         AB_TRY(launch_sum_jac(sp, js, nlev, p->stream));
       }
     }

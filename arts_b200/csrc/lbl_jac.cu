@@ -176,8 +176,8 @@ constexpr int JAC_NT = 128;
 constexpr int JAC_R  = 2;
 constexpr int JAC_F_TILE = JAC_NT * JAC_R;
 constexpr int JAC_Q  = 4;   // targets per pass
-constexpr int JAC_BASE_FIELDS = 9;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im
-constexpr int JAC_Q_FIELDS    = 7;  // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im
+constexpr int JAC_BASE_FIELDS = 14;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im | y2, y^2+1/2, y2^2+1/2, y y2-1/2, s_re/sqrt(pi)
+constexpr int JAC_Q_FIELDS    = 8;   // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im | dz_im + dz_fac y
 
 // dscl(f) of dt_core_calc, :990-1000
 __device__ __forceinline__ double line_scale_dT(double f, double T, double P) {
@@ -266,6 +266,11 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
         const double2 k = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP + 2);
         sb[0 * TL + l] = a.x; sb[1 * TL + l] = m.y; sb[2 * TL + l] = n.x; sb[3 * TL + l] = n.y; sb[4 * TL + l] = h.y;
         sb[5 * TL + l] = h.x; sb[6 * TL + l] = jcom[t * TL + l]; sb[7 * TL + l] = k.x; sb[8 * TL + l] = k.y;
+        {  // constants of the closed-form far path (real lines): displaced y, the y-only parts of D1, D2 and z z2 + 1/2
+          const double y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
+          sb[9 * TL + l] = y2; sb[10 * TL + l] = y * y + 0.5; sb[11 * TL + l] = y2 * y2 + 0.5; sb[12 * TL + l] = y * y2 - 0.5;
+          sb[13 * TL + l] = n.y * cst::inv_sqrt_pi;
+        }
         const double* jt = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
@@ -275,12 +280,50 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
           double* o = sq + q * JAC_Q_FIELDS * TL;
           o[0 * TL + l] = u0.x; o[1 * TL + l] = u0.y; o[2 * TL + l] = u1.x; o[3 * TL + l] = u1.y;
           o[4 * TL + l] = u2.x; o[5 * TL + l] = u2.y; o[6 * TL + l] = u3.x;
+          o[7 * TL + l] = u1.y + u2.x * n.x;  // Im(dz + dz_fac z) does not depend on the frequency
         }
       }
       // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|)
       if (tid == 0) tile_far = (!seg.has_cutoff && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
       __syncthreads();
       const bool far = tile_far != 0;
+      if (far && jp.real_lines) {
+        // Closed-form far path for real lines (mode-0 segments: s, ds real; only Re dX is used since npm = (1,0,...)).
+        // With c = i/sqrt(pi), D1 = z^2 - 1/2, D2 = (z+dz)^2 - 1/2, P = D1 D2:
+        //   F = c z / D1 = c z D2 conj(P) / |P|^2,      dF = (F(z+dz) - F(z)) / dz = -c (z (z+dz) + 1/2) conj(P) / |P|^2
+        // i.e. the reference's forward difference (:250-268) evaluated without the subtraction: ONE reciprocal per pair.
+#pragma unroll 2
+        for (int l = 0; l < count; l++) {
+          const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
+          if (igd == 0.0) continue;
+          const double y = sb[2 * TL + l], y2 = sb[9 * TL + l], cy1 = sb[10 * TL + l], cy2 = sb[11 * TL + l],
+                       yy = sb[12 * TL + l], sp = sb[13 * TL + l], sre = sb[3 * TL + l];
+#pragma unroll
+          for (int r = 0; r < JAC_R; r++) {
+            const double x  = igd * (f[r] - f0s);
+            const double x2 = x + fmax(1e-4 * fabs(x), 1e-4);
+            const double A = __fma_rn(x, x, -cy1), B = 2.0 * y * x;
+            const double A2 = __fma_rn(x2, x2, -cy2), B2 = 2.0 * y2 * x2;
+            const double Pr = A * A2 - B * B2, Pi = A * B2 + B * A2;
+            const double Mr = __fma_rn(x, x2, -yy), Mi = x * y2 + y * x2;
+            const double n  = far_rcp(Pr * Pr + Pi * Pi);
+            const double dFr = (Mi * Pr - Mr * Pi) * n;    // sqrt(pi) Re dF
+            const double dFi = -(Mr * Pr + Mi * Pi) * n;   // sqrt(pi) Im dF
+            const double Wr = x * A2 - y * B2, Wi = x * B2 + y * A2;
+            const double Fr = (Wr * Pi - Wi * Pr) * n;     // sqrt(pi) Re F
+            shape[r].re = __fma_rn(sp, Fr, shape[r].re);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              const double* o = sq + q * JAC_Q_FIELDS * TL;
+              const double tr = __fma_rn(o[4 * TL + l], x, o[2 * TL + l]);
+              const double g  = tr * dFr - o[7 * TL + l] * dFi;
+              acc[q][r].re += (o[0 * TL + l] * cst::inv_sqrt_pi) * Fr + sp * g;
+            }
+          }
+          (void)sre;
+        }
+        continue;
+      }
       for (int l = 0; l < count; l++) {
         const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l], y = sb[2 * TL + l];
         if (igd == 0.0) continue;  // inactive cutoff line

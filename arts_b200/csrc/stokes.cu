@@ -173,8 +173,18 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
     Propmat k{};
     if (SCALAR) k.A = sK[warp][st][lane * 7];
     else k = load_propmat(&sK[warp][st][lane * 7]);
-    __syncwarp();  // every lane has moved its row out of stage st
-    if (lane == 0 && n + ST_STAGES < np) issue(n + ST_STAGES);
+    // Stage st may only be refilled once every lane's shared-memory loads have RETURNED: a warp barrier orders
+    // instruction issue, not the completion of LDS, and a TMA write overtaking a queued LDS was observed on B200
+    // (a few wrong lanes per 1e7 steps).  The ballot consumes the loaded registers of all lanes (scoreboard wait),
+    // and the proxy fence orders those generic-proxy reads before the async-proxy write.
+    int bits = __double2hiint(k.A);
+    if (!SCALAR) bits |= __double2hiint(k.B) | __double2hiint(k.C) | __double2hiint(k.D) | __double2hiint(k.U) |
+                         __double2hiint(k.V) | __double2hiint(k.W);
+    const unsigned landed = __ballot_sync(0xffffffffu, bits != 0x7ff00001);
+    if (lane == 0 && landed != 0u && n + ST_STAGES < np) {
+      fence_proxy_async_smem();
+      issue(n + ST_STAGES);
+    }
     const double ffac = p.ffac[lev];
     if (p.f_stride != 0 || ffac != ffac_prev) {
       f         = ffac * (p.f_stride != 0 ? p.f[int64_t(lev) * p.f_stride + ivc] : f_raw);

@@ -56,3 +56,40 @@ def test_config4_frequency_shard(wsm, orc):
     c = synth.case_c4(f_slice=(500_000, 565_536))
     assert c.cat.n_lines == 1_000_000 and c.nf == 65_536 and c.np_ == 100
     _check(wsm, orc, c, n_sample=24)
+
+
+def test_repeated_steps_are_bit_identical(wsm):
+    """Run-to-run determinism at the bench shape (1e7 Stokes steps per pass): the TMA ring of the chain kernel once
+    refilled a stage before every lane's shared-memory load had returned (a few wrong lanes per pass, found with
+    tools/det_check.py); repeated passes must give the same bits."""
+    c = synth.case_c2()
+    cat = wsm.Catalog(c.cat)
+    path = wsm.Path(cat, c.nf, c.np_)
+    ref = None
+    for option in ("linsrc", "constant"):
+        path.upload(c.f, c.atm, c.r, c.I_bkg, rte_option=option)
+        path.run_propmat()
+        outs = []
+        for _ in range(4):
+            path.run_stokes()
+            I = np.empty((c.nf, 4))
+            path.download(I=I)
+            outs.append(I)
+        for I in outs[1:]:
+            assert np.array_equal(I, outs[0]), option
+    c3 = synth.case_c3()
+    cat3 = wsm.Catalog(c3.cat)
+    p3 = wsm.Path(cat3, c3.nf, c3.np_)
+    p3.upload(c3.f, c3.atm, c3.r, c3.I_bkg)
+    p3.run_propmat()
+    outs = []
+    for _ in range(3):
+        p3.run_stokes()
+        I = np.empty((c3.nf, 4))
+        p3.download(I=I)
+        outs.append(I)
+    assert np.array_equal(outs[1], outs[0]) and np.array_equal(outs[2], outs[0])
+    for p in (path, p3):
+        p.close()
+    cat.close()
+    cat3.close()

@@ -93,6 +93,7 @@ struct ab200_path {
   int64_t f_stride = 0;
   int32_t rte_option = AB200_RTE_LINSRC, no_neg = 1;
   uint32_t flags = 0;
+  cudaEvent_t ev_staged = nullptr;  // the pinned staging blocks may be refilled once this has completed
   bool uploaded = false, k_preloaded = false;
 
   ~ab200_path() {
@@ -101,6 +102,7 @@ struct ab200_path {
     cudaFree(d_dK); cudaFree(d_dI); cudaFree(d_Ilev); cudaFree(d_jac); cudaFree(d_jcom);
     if (h_small) cudaFreeHost(h_small);
     if (h_segs) cudaFreeHost(h_segs);
+    if (ev_staged) cudaEventDestroy(ev_staged);
     for (auto& q : pending) { cudaEventDestroy(q.e0); cudaEventDestroy(q.e1); }
     for (auto e : free_events) cudaEventDestroy(e);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -238,6 +240,9 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   if (!atm->T || !atm->P || !atm->vmr || !atm->isorat || !atm->Q)
     return set_error(AB200_ERR_INVALID, "atm path: T, P, vmr, isorat and Q are required");
   AB_CUDA(cudaSetDevice(cat->device));
+  // the previous upload's asynchronous copies out of the pinned staging blocks must have run before they are refilled
+  if (p->ev_staged) AB_CUDA(cudaEventSynchronize(p->ev_staged));
+  else AB_CUDA(cudaEventCreateWithFlags(&p->ev_staged, cudaEventDisableTiming));
   p->it = -1;
   if (p->nq > 0) {
     if (!targets) return set_error(AB200_ERR_INVALID, "ab200_path_upload: targets is null with nq > 0");
@@ -327,6 +332,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   }
   if (nseg) AB_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, 2 * nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice, p->stream));
 
+  AB_CUDA(cudaEventRecord(p->ev_staged, p->stream));
   p->f_stride   = f_level_stride;
   p->rte_option = rte_option;
   p->no_neg     = no_negative_absorption;

@@ -198,7 +198,9 @@ int ab200_planck_tb(int64_t nf, const double *f, double *I);
 int ab200_path_create(const ab200_catalog *cat, int64_t nf, int32_t np, int32_t nq, ab200_path **out);
 void ab200_path_destroy(ab200_path *p);
 int ab200_path_set_stream(ab200_path *p, void *stream);
-/* H2D of one path's inputs (asynchronous on the path's stream, through pinned staging). */
+/* H2D of one path's inputs (asynchronous on the path's stream; small arrays go through pinned staging owned by the
+ * workspace, f and I_bkg are copied straight from the caller's buffers, which must stay unchanged until the next
+ * ab200_path_sync / ab200_path_download if they are pinned). */
 int ab200_path_upload(ab200_path *p, const double *f, int64_t f_level_stride, const ab200_atm_path *atm,
                       int32_t select_species, int32_t no_negative_absorption, const ab200_target *targets,
                       const double *r, int32_t hse_derivative, int32_t rte_option, const double *I_bkg,

@@ -212,6 +212,7 @@ def run_b200(args):
     I_local = shard.as_torch(path.device_ptr(0), (cnt, 4), dev)
 
     dfma_tflops, _ = wsm.measure_dfma_peak(20000)
+    dfma_mix_tflops, _ = wsm.measure_dfma_mix(20000)
     hist = path.region_histogram(200_000, seed=1)
     fl_eval, region_frac = roofline.flops_per_eval(hist)
 
@@ -315,6 +316,12 @@ def run_b200(args):
                      "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None, "traffic": traffic.get("lbl_sum_real_kernel"),
                      "peak_source": "DFMA loop measured in this run (ab200_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 figure",
                      "algorithmic_flop_per_eval": fl_eval, "regions": region_frac, "kernel_ms": k_ms_per,
+                     "executed": {"fp64_instr_per_far_eval": 7,
+                                  "dfma_equiv_tflops": 14.0 * float(nl) * cnt * np_ / max(k_n / args.steps, 1) / (k_ms_per * 1e-3) / 1e12 if k_ms_per > 0 else None,
+                                  "peak_with_rcp_mix_tflops": dfma_mix_tflops,
+                                  "note": "frac > 1 because the reference's closed form costs 28 algorithmic FLOP per far-wing "
+                                          "evaluation and the kernel needs 7 FP64-pipe instructions (14 FLOP slots) + 1 MUFU; "
+                                          "dfma_equiv / peak is the FP64-pipe utilisation (ncu: profiles/r1d_lbl_sum_real.ncu.txt)"},
                      "kernel_share_of_step": k_ms / ms if ms else None},
         "roofline_stokes": {"bound": "hbm", "kernel": "stokes_chain_kernel", "achieved": st_gbs, "peak": hbm_peak,
                             "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": traffic.get("stokes_chain_kernel"),

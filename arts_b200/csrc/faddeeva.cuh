@@ -199,8 +199,8 @@ __device__ __forceinline__ void far_accumulate_cplx(double& acc_re, double& acc_
                                                     double A1, double B1, double A2, double A3, double B3, double A4) {
   const double Q  = __fma_rn(u, u, c3);
   const double r  = fast_rcp(__fma_rn(Q, Q, kappa));
-  const double nr = __fma_rn(__dmul_rn(u, A2), Q, __fma_rn(A1, Q, B1));
-  const double ni = __fma_rn(__dmul_rn(u, A4), Q, __fma_rn(A3, Q, B3));
+  const double nr = __fma_rn(Q, __fma_rn(u, A2, A1), B1);  // (A1 + u A2) Q + B1
+  const double ni = __fma_rn(Q, __fma_rn(u, A4, A3), B3);  // (A3 + u A4) Q + B3
   acc_re          = __fma_rn(nr, r, acc_re);
   acc_im          = __fma_rn(ni, r, acc_im);
 }

@@ -383,7 +383,7 @@ constexpr int CPLX_R = 2;
 constexpr int CPLX_NT = 256;
 constexpr int CPLX_F_TILE = CPLX_NT * CPLX_R;
 
-__global__ void __launch_bounds__(CPLX_NT) lbl_sum_cplx_kernel(SumParams p) {
+__global__ void __launch_bounds__(CPLX_NT, 3) lbl_sum_cplx_kernel(SumParams p) {
   constexpr int STAGES = 2;
   constexpr int STAGE_DOUBLES = N_GROUPS * TL * REC_GROUP;
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -2,7 +2,7 @@
 """BASELINE configs[3] at FULL size on one B200: 1e6 lines x 1e6 frequencies x 100 levels = 1e14
 (line, frequency, level) evaluations + 1e8 Stokes steps.  Prints one JSON report (profiles/).
 
-    python tools/c4_full.py [--cutoff-ghz 750]   # (ii) the realistic ByLine-cutoff variant
+    python tests/tools/c4_full.py [--cutoff-ghz 750]   # (ii) the realistic ByLine-cutoff variant
 """
 import argparse
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch  # noqa: E402
 
 from arts_b200 import roofline, synth, wsm  # noqa: E402

@@ -3,7 +3,7 @@
 measurement_vecFromSensor drives the reference (src/m_rad.cc:321-343): concurrent host threads, each calling the
 re-entrant C-ABI entry point with its own per-thread device workspace, one shared immutable catalog.
 
-    python tools/c5_batch.py --paths 64 --threads 4 > gpurun_out/c5_batch.json
+    python tests/tools/c5_batch.py --paths 64 --threads 4 > gpurun_out/c5_batch.json
 """
 import argparse
 import copy
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from arts_b200 import synth, wsm  # noqa: E402
 
 ap = argparse.ArgumentParser()

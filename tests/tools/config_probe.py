@@ -2,7 +2,7 @@
 """Device-timed throughput of the BASELINE configs that are not the bench workload (C1, C3, C5 one path),
 with a parity spot check against the CPU oracle on a frequency sample.  One JSON object on stdout.
 
-    python tools/config_probe.py > gpurun_out/configs.json
+    python tests/tools/config_probe.py > gpurun_out/configs.json
 """
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch  # noqa: E402
 
 from arts_b200 import roofline, synth, wsm  # noqa: E402

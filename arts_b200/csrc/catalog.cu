@@ -122,7 +122,7 @@ ab200_catalog::~ab200_catalog() {
   cudaFree(d_ls_offset); cudaFree(d_ls_species); cudaFree(d_ls_type); cudaFree(d_ls_X);
   cudaFree(d_isot_species); cudaFree(d_isot_mass);
   cudaFree(d_sub_parent); cudaFree(d_sub_Sz); cudaFree(d_sub_dzc);
-  cudaFree(d_tile_count); cudaFree(d_tile_cutoff);
+  cudaFree(d_tile_count); cudaFree(d_sub_cut); cudaFree(d_tile_mode);
 }
 
 extern "C" int ab200_zeeman_components(int on, double gu, double gl, int two_Ju, int two_Jl, int pol, int64_t cap,
@@ -196,7 +196,6 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   std::vector<int32_t> line_isot(d->n_lines);
   std::vector<char> band_simple(d->n_bands, 1);
   for (int b = 0; b < d->n_bands; b++) {
-    if (d->band_cutoff_type[b] != AB200_CUTOFF_NONE) band_simple[b] = 0;
     for (int64_t l = d->band_offset[b]; l < d->band_offset[b + 1]; l++) {
       line_isot[l] = d->band_isot[b];
       if (d->z_on[l] || !(d->a[l] >= 0) || !(d->gu[l] >= 0)) band_simple[b] = 0;
@@ -208,7 +207,13 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   }
 
   std::vector<int64_t> sub_parent;
-  std::vector<double> sub_Sz, sub_dzc, tile_cutoff;
+  std::vector<double> sub_Sz, sub_dzc, sub_cut;
+  std::vector<uint8_t> tile_mode;
+  constexpr double INF = std::numeric_limits<double>::infinity();
+  auto line_cutoff = [&](int64_t l) {  // ByLine cutoff of the band line l belongs to
+    const int64_t b = std::upper_bound(d->band_offset, d->band_offset + d->n_bands + 1, l) - d->band_offset - 1;
+    return d->band_cutoff_type[b] == AB200_CUTOFF_BYLINE ? d->band_cutoff_value[b] : INF;
+  };
   auto close_segment = [&](Segment seg, std::vector<int64_t>& par, std::vector<double>& sz, std::vector<double>& dz) {
     if (par.empty()) return;
     // sort by catalog f0 (sub-lines of one parent stay adjacent: stable)
@@ -221,16 +226,18 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
     for (int64_t t = 0; t < nt; t++) {
       const int64_t lo = t * TL, hi = std::min<int64_t>(seg.nsub, lo + TL);
       cat->tile_count.push_back(static_cast<int32_t>(hi - lo));
-      tile_cutoff.push_back(seg.cutoff);
+      tile_mode.push_back(static_cast<uint8_t>(seg.mode));
       for (int64_t i = lo; i < lo + TL; i++) {
         if (i < hi) {
           sub_parent.push_back(par[order[i]]);
           sub_Sz.push_back(sz[order[i]]);
           sub_dzc.push_back(dz[order[i]]);
+          sub_cut.push_back(line_cutoff(par[order[i]]));
         } else {
           sub_parent.push_back(-1);
           sub_Sz.push_back(0.0);
           sub_dzc.push_back(0.0);
+          sub_cut.push_back(INF);
         }
       }
     }
@@ -257,7 +264,13 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
     }
     Segment seg{};
     seg.band = -1; seg.isot = -1; seg.species = s; seg.pol = POL_NO; seg.mode = 0; seg.has_cutoff = 0;
-    seg.cutoff = std::numeric_limits<double>::infinity();
+    seg.cutoff = 0.0;  // largest cutoff of the merged lines (+inf as soon as one line has none): tile skipping only
+    for (int64_t l : par) {
+      const double c = line_cutoff(l);
+      seg.cutoff = std::max(seg.cutoff, c);
+      if (c < INF) seg.has_cutoff = 1;  // at least one line carries a window
+    }
+    if (par.empty()) seg.cutoff = INF;
     close_segment(seg, par, sz, dz);
   }
   // (2) every other band: one segment per polarisation, in the reference's order
@@ -303,7 +316,8 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   rc = rc ? rc : upload(&cat->d_sub_Sz, sub_Sz.data(), sub_Sz.size());
   rc = rc ? rc : upload(&cat->d_sub_dzc, sub_dzc.data(), sub_dzc.size());
   rc = rc ? rc : upload(&cat->d_tile_count, cat->tile_count.data(), cat->tile_count.size());
-  rc = rc ? rc : upload(&cat->d_tile_cutoff, tile_cutoff.data(), tile_cutoff.size());
+  rc = rc ? rc : upload(&cat->d_sub_cut, sub_cut.data(), sub_cut.size());
+  rc = rc ? rc : upload(&cat->d_tile_mode, tile_mode.data(), tile_mode.size());
   if (rc) {
     delete cat;
     return rc;

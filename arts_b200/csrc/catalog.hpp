@@ -12,9 +12,10 @@ namespace ab200 {
 
 // A segment is the unit the reference clamps and scales on: one (band, polarisation)
 // pair (voigt::lte::calculate, lbl_lineshape_voigt_lte.cpp:1652-1692).  Bands whose lines
-// have no line mixing, no Zeeman effect and no cutoff have a non-negative real sum, so
+// have no line mixing and no Zeeman effect have a non-negative real sum — with a ByLine
+// cutoff too, because every term ls(f) - ls(f0' + cutoff) is >= 0 inside its window — so
 // the clamp can never trigger; all such bands of one species are merged into a single
-// segment (mode 0) whose lines are sorted by f0.
+// segment (mode 0) whose lines are sorted by f0 and carry their own cutoff.
 struct Segment {
   int32_t band;     // band index, or -1 for a merged segment
   int32_t isot;     // isotopologue of the band (-1 if merged over several)
@@ -65,7 +66,8 @@ struct ab200_catalog {
   double* d_sub_dzc = nullptr;      // zeeman::model::Splitting [Hz/T]
   // per tile
   int32_t* d_tile_count = nullptr;
-  double* d_tile_cutoff = nullptr;  // cutoff of the tile's segment (+inf if none)
+  double* d_sub_cut = nullptr;      // per slot: ByLine cutoff of the line's band [Hz] (+inf if none / padding)
+  uint8_t* d_tile_mode = nullptr;   // per tile: mode of its segment (0 real, 1 complex)
 
   ~ab200_catalog();
 };

@@ -40,15 +40,17 @@ constexpr int REC_DOUBLES = REC_GROUP * N_GROUPS;
 // record layout of one tile (for one level): [group][line][4]
 //   group 0: f0', c3 = g^2 - h, kappa = 4 g^2 h, A1 = Si*g          (far wing, real part)
 //   group 1: B1 = 2 h A1, igd, y, s_re                              (far wing real | near evaluation)
-//   group 2: E1(y), s_im, cut_re, cut_im                            (near evaluation, line mixing, cutoff value)
+//   group 2: E1(y), s_im, cut_re, cut_im                            (near evaluation, line mixing, cutoff value;
+//            in real merged segments (mode 0) s_im == 0 and the slot holds the line's cutoff [Hz] instead)
 //   group 3: A2 = Sr, A3 = -Sr*g, B3 = 2 h A3, A4 = Si              (far wing, complex part)
 // with g = G0 [Hz], h = GD^2/2, S = i*s*GD/sqrt(pi) = Sr + i Si, (igd, y, s) the reference's
 // single_shape (lbl_lineshape_voigt_lte.h:20-33).  The real-only kernel streams groups 0-1 for
 // far tiles and 0-2 for near tiles; the complex kernel groups 0-1 + 3 or all four.
 constexpr size_t tile_doubles() { return size_t(TL) * REC_DOUBLES; }
 
-// tile summary written by the prepare kernel: f0'min, f0'max, min igd, min y
-constexpr int SUMMARY_DOUBLES = 4;
+// tile summary written by the prepare kernel: f0'min, f0'max, min igd, min y | min cutoff, max cutoff,
+// sum of the cutoff values ls(f0' + cutoff) (real part), unused — over the contributing lines of the tile
+constexpr int SUMMARY_DOUBLES = 8;
 
 // far-wing boundary of the reference's Faddeeva: x + |y| > 4000 -> nu <= 2 closed form
 // (3rdparty/Faddeeva/Faddeeva.cc:707-725)

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
     s_im = Sz * (pre * (-X[AB200_VAR_Y]) * s0);
 
     // ByLine cutoff: band_data::active_lines on the catalog f0 (lbl_data.cpp:61-68, :407-412)
-    const double cut = p.tile_cutoff[tile];
+    const double cut = p.sub_cut[slot];
     if (cut < DBL_MAX) {
       const double fmin = p.frange[2 * lev], fmax = p.frange[2 * lev + 1];
       if (!(f0_cat >= fmin - cut && f0_cat <= fmax + cut)) real_line = false;
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
   double rec[REC_DOUBLES];
 #pragma unroll
   for (int i = 0; i < REC_DOUBLES; i++) rec[i] = 0.0;
+  double v_cut = 0.0, v_cutval = 0.0;
   if (real_line) {
     const double g  = G0;
     const double h  = 0.5 * GD * GD;
@@ -114,14 +115,24 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
     rec[4] = 2.0 * h * A1; rec[5] = igd; rec[6] = y; rec[7] = s_re;
     rec[8] = (y <= 7.0 && y >= 0.0) ? series_E1(y) : 0.0; rec[9] = s_im;
     rec[12] = Sr; rec[13] = A3; rec[14] = 2.0 * h * A3; rec[15] = Si;
-    const double cut = p.tile_cutoff[tile];
+    const double cut = p.sub_cut[slot];
     if (cut < DBL_MAX) {
       // band_shape::operator()(cut): ls(ls.f0 + cutoff) = s * w(igd*cutoff + i y), :610-616
-      double wr, wi;
-      faddeeva_w(igd * ((f0s + cut) - f0s), y, wr, wi);
-      rec[10] = s_re * wr - s_im * wi;
-      rec[11] = s_re * wi + s_im * wr;
+      const double uc = (f0s + cut) - f0s;
+      if (p.tile_mode[tile] == 0 && igd * uc + y > FAR_LIMIT_REAL_SUM) {
+        // real kernel: the window edge lies in the far region, where ls(f) comes from the closed form; the same
+        // form for the cutoff value makes ls(f) - ls(f0' + cutoff) vanish exactly at the edge and keeps the
+        // RELATIVE error of the difference at 3 * 2.5 / x_cut^4 (the closed form's error is smooth, ~x^-6)
+        rec[10] = far_accumulate_re(0.0, uc, rec[1], rec[2], rec[3], rec[4]);
+      } else {
+        double wr, wi;
+        faddeeva_w(igd * uc, y, wr, wi);
+        rec[10] = s_re * wr - s_im * wi;
+        rec[11] = s_re * wi + s_im * wr;
+      }
     }
+    if (p.tile_mode[tile] == 0) rec[9] = cut;  // real merged segment: s_im == 0, the slot carries the line's cutoff
+    v_cut = cut; v_cutval = rec[10];
   } else {
     // padding / inactive: contributes exactly +0 in the far loops (numerators 0, D2 = Q^2 + 1 > 0),
     // skipped in the near loops
@@ -136,28 +147,40 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
     o[1] = make_double2(rec[4 * g + 2], rec[4 * g + 3]);
   }
 
-  // tile summary: min/max f0', min igd, min y over contributing lines
+  // tile summary over contributing lines: min/max f0', min igd, min y; min/max cutoff, sum of the cutoff values
+  // (summed in line order, like the per-pair loop of the real kernel does: bit-identical when every line is in window)
   double v_min = real_line ? f0s : DBL_MAX, v_max = real_line ? f0s : -DBL_MAX;
   double v_igd = real_line ? igd : DBL_MAX, v_y = real_line ? y : DBL_MAX;
+  double v_cmin = real_line ? fmin(v_cut, DBL_MAX) : DBL_MAX, v_cmax = real_line ? fmin(v_cut, DBL_MAX) : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    v_min = fmin(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
-    v_max = fmax(v_max, __shfl_xor_sync(0xffffffffu, v_max, o));
-    v_igd = fmin(v_igd, __shfl_xor_sync(0xffffffffu, v_igd, o));
-    v_y   = fmin(v_y, __shfl_xor_sync(0xffffffffu, v_y, o));
+    v_min  = fmin(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+    v_max  = fmax(v_max, __shfl_xor_sync(0xffffffffu, v_max, o));
+    v_igd  = fmin(v_igd, __shfl_xor_sync(0xffffffffu, v_igd, o));
+    v_y    = fmin(v_y, __shfl_xor_sync(0xffffffffu, v_y, o));
+    v_cmin = fmin(v_cmin, __shfl_xor_sync(0xffffffffu, v_cmin, o));
+    v_cmax = fmax(v_cmax, __shfl_xor_sync(0xffffffffu, v_cmax, o));
   }
-  __shared__ double red[TL / 32][4];
+  __shared__ double red[TL / 32][6];
+  __shared__ double cutvals[TL];
+  cutvals[lane] = v_cutval;
   if ((lane & 31) == 0) {
-    red[lane >> 5][0] = v_min; red[lane >> 5][1] = v_max; red[lane >> 5][2] = v_igd; red[lane >> 5][3] = v_y;
+    double* r = red[lane >> 5];
+    r[0] = v_min; r[1] = v_max; r[2] = v_igd; r[3] = v_y; r[4] = v_cmin; r[5] = v_cmax;
   }
   __syncthreads();
   if (lane == 0) {
     for (int w = 1; w < TL / 32; w++) {
       v_min = fmin(v_min, red[w][0]); v_max = fmax(v_max, red[w][1]);
       v_igd = fmin(v_igd, red[w][2]); v_y = fmin(v_y, red[w][3]);
+      v_cmin = fmin(v_cmin, red[w][4]); v_cmax = fmax(v_cmax, red[w][5]);
     }
+    v_cutval = 0.0;
+    if (v_cmin < DBL_MAX)
+      for (int l = 0; l < TL; l++) v_cutval += cutvals[l];
     double* s = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
     s[0] = v_min; s[1] = v_max; s[2] = v_igd; s[3] = v_y;
+    s[4] = v_cmin; s[5] = v_cmax; s[6] = v_cutval; s[7] = 0.0;
   }
 }
 
@@ -166,6 +189,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
 // ---------------------------------------------------------------------------
 // default geometry of the real line sum: 128 threads x 4 frequencies per thread = 512-frequency blocks
 constexpr int CHUNK     = 4096;  // tiles classified per pass
+constexpr int REAL_CHUNK = 2048; // real kernel: 2-byte list entries, same 4 KB of shared memory
 constexpr int REAL_STAGES = 2;   // 2 x 16 KB of line records per CTA
 // shared-memory ring of the real kernel; also the staging area of its vectorised K store (512 x 7 doubles)
 constexpr int REAL_RING_DOUBLES = (REAL_STAGES * 2 * TL * REC_GROUP > 512 * 7) ? REAL_STAGES * 2 * TL * REC_GROUP : 512 * 7;
@@ -180,6 +204,23 @@ __device__ __forceinline__ uint8_t classify_tile(const double* __restrict__ s, d
   const double dist = fmax(0.0, fmax(fblk_min - f0max, f0min - fblk_max));
   if (dist > cutoff * (1.0 + 1e-9)) return CLS_SKIP;
   if (cutoff < DBL_MAX) return CLS_NEAR;  // windows need the per-pair predicate
+  return (s[2] * dist + s[3] > far_limit * (1.0 + 1e-9)) ? CLS_FAR : CLS_NEAR;
+}
+
+// Real merged segments: every line has its own cutoff window (or none: cutoff = +inf -> DBL_MAX in the summary).
+//   SKIP    no pair of (block, tile) is inside a window
+//   FAR/NEAR every pair is inside its line's window ("full-in": the fast loops apply and the cutoff values are
+//           subtracted once per frequency as the tile's sum)
+//   PART    windows cut through the pair set: per-pair predicate
+constexpr uint8_t CLS_PART = 3;
+__device__ __forceinline__ uint8_t classify_tile_real(const double* __restrict__ s, double fblk_min, double fblk_max,
+                                                      double far_limit) {
+  const double f0min = s[0], f0max = s[1];
+  if (f0min > f0max) return CLS_SKIP;
+  const double dist = fmax(0.0, fmax(fblk_min - f0max, f0min - fblk_max));
+  if (dist > s[5] * (1.0 + 1e-9)) return CLS_SKIP;
+  const double dmax = fmax(fblk_max - f0min, f0max - fblk_min);  // >= |f - f0'| of every pair
+  if (dmax > s[4] * (1.0 - 1e-9)) return CLS_PART;
   return (s[2] * dist + s[3] > far_limit * (1.0 + 1e-9)) ? CLS_FAR : CLS_NEAR;
 }
 
@@ -205,7 +246,7 @@ __device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const dou
 }
 
 // --------------------------- real-only kernel (mode 0) ----------------------
-// Segments: merged bands without line mixing / Zeeman / cutoff; output: Propmat.A only.
+// Segments: merged bands without line mixing / Zeeman (ByLine cutoffs allowed, per line); output: Propmat.A only.
 // 6 CTAs (24 warps) per SM: 80 registers, 36 KB of shared memory.  Measured on B200 (profiles/r1_ab_decoupled.txt):
 // the far loop is latency bound at 16 warps unless ptxas happens to interleave lines well; 24 warps is robust.
 #ifndef AB200_SUM_MINB
@@ -221,8 +262,9 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
   uint64_t* full    = reinterpret_cast<uint64_t*>(sbuf + REAL_RING_DOUBLES);  // TMA -> consumers
   uint64_t* empty   = full + STAGES;                                               // consumers -> producer
-  uint8_t* cls      = reinterpret_cast<uint8_t*>(empty + STAGES);
-  uint8_t* lflag    = cls + CHUNK;  // [STAGES][TL]
+  uint16_t* act     = reinterpret_cast<uint16_t*>(empty + STAGES);  // [REAL_CHUNK] class, then compacted tile | class << 14
+  uint8_t* lflag    = reinterpret_cast<uint8_t*>(act + REAL_CHUNK);  // [STAGES][TL]
+  __shared__ int n_active;
 
   const int tid = threadIdx.x;
   const int lev = blockIdx.y;
@@ -257,16 +299,33 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
 
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
+    // far-wing closed form beyond x + y = 1000: relative error 2.5 / x^4 of a term (2.5e-12).  With cutoffs the
+    // cutoff value of a far window edge comes from the same form (prepare kernel), so the difference is as accurate
+    constexpr double far_limit = FAR_LIMIT_REAL_SUM;
     double accS[SUM_R];
 #pragma unroll
     for (int r = 0; r < SUM_R; r++) accS[r] = 0.0;
 
-    for (int64_t c0 = seg.tile_begin; c0 < seg.tile_end; c0 += CHUNK) {
-      const int n = int(min(int64_t(CHUNK), seg.tile_end - c0));
-      __syncthreads();  // every warp is done with the previous chunk's classes
-      for (int t = tid; t < n; t += SUM_NT)
-        cls[t] = classify_tile(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, DBL_MAX, FAR_LIMIT_REAL_SUM);
+    for (int64_t c0 = seg.tile_begin; c0 < seg.tile_end; c0 += REAL_CHUNK) {
+      const int nall = int(min(int64_t(REAL_CHUNK), seg.tile_end - c0));
+      __syncthreads();  // every warp is done with the previous chunk's list
+      for (int t = tid; t < nall; t += SUM_NT)
+        act[t] = classify_tile_real(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, far_limit);
       __syncthreads();
+      if (tid < 32) {  // warp 0 compacts the non-skipped tiles in place (j <= t), keeping catalog order
+        int n = 0;
+        for (int t0 = 0; t0 < nall; t0 += 32) {
+          const int t = t0 + tid;
+          const uint16_t c = t < nall ? act[t] : uint16_t(CLS_SKIP);
+          const unsigned m = __ballot_sync(0xffffffffu, c != CLS_SKIP);
+          if (c != CLS_SKIP) act[n + __popc(m & ((1u << tid) - 1u))] = uint16_t(t | (c << 14));
+          n += __popc(m);
+          __syncwarp();
+        }
+        if (tid == 0) n_active = n;
+      }
+      __syncthreads();
+      const int n = n_active;
 
       // The warps of the CTA are decoupled: a stage is refilled when all four warps have released it
       // (empty barrier), not at a CTA-wide barrier, so a warp may run up to one tile ahead.
@@ -276,7 +335,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
         if (DECOUPLED && g >= STAGES) mbar_wait(&empty[st], ((g / STAGES) - 1) & 1);
         constexpr uint32_t bytes = 2 * TL * REC_GROUP * sizeof(double);
         mbar_expect_tx(&full[st], bytes);
-        tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + t) * tile_doubles(), bytes, &full[st]);
+        tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + (act[t] & 0x3fff)) * tile_doubles(), bytes, &full[st]);
       };
       // prefetch distance: with the CTA barrier a stage is free as soon as the previous tile is done
       // (STAGES - 1 tiles in flight); decoupled warps keep one stage of slack so that the producer
@@ -291,11 +350,16 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
         mbar_wait(&full[st], ((it + t) / STAGES) & 1);
         const double2* __restrict__ rec  = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);
         const double2* __restrict__ rec1 = rec + 2 * TL;
-        const int count = p.tile_count[c0 + t];
+        const int tile_cls = act[t] >> 14;
+        const int64_t tile = c0 + (act[t] & 0x3fff);
+        const int count = p.tile_count[tile];
         double acc[SUM_R];
 #pragma unroll
         for (int r = 0; r < SUM_R; r++) acc[r] = 0.0;
-        if (cls[t] == CLS_FAR) {
+        // cutoff values of the tile's lines, summed in line order apart from the terms: the result of a frequency
+        // does not depend on the class its block gave the tile (frequency-shard invariance stays bit-exact)
+        double cut_sum = seg.has_cutoff ? summ[tile * SUMMARY_DOUBLES + 6] : 0.0;
+        if (tile_cls == CLS_FAR) {
 #pragma unroll UNROLL
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];  // f0', c3 | kappa, A1
@@ -303,25 +367,36 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1);
           }
-        } else if (cls[t] == CLS_NEAR && !p.debug_skip_near) {
-          const double* __restrict__ g2 = prep + (c0 + t) * tile_doubles() + size_t(2) * TL * REC_GROUP;  // E1 at [l][0]
+        } else if (!p.debug_skip_near) {
+          // group 2 of the tile from L2: E1 at [l][0], the line's cutoff at [l][1], its cutoff value at [l][2]
+          const double* __restrict__ g2 = prep + tile * tile_doubles() + size_t(2) * TL * REC_GROUP;
+          const bool part = tile_cls == CLS_PART;
+          double cutp[SUM_R];
+#pragma unroll
+          for (int r = 0; r < SUM_R; r++) cutp[r] = 0.0;
           uint8_t* __restrict__ lf = lflag + st * TL;
-          flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false, FAR_LIMIT_REAL_SUM);
+          flag_lines<SUM_NT>(lf, rec, rec1, count, fblk_min, fblk_max, false, far_limit);
           __syncthreads();  // near tiles (rare) are processed in step by the whole CTA
           for (int l = 0; l < count; l++) {
             const double2 a = rec[2 * l], b = rec[2 * l + 1];
             const double2 c = rec1[2 * l];  // B1, igd
-            if (lf[l]) {
+            if (c.y == 0.0) continue;       // inactive line of a cutoff band
+            if (lf[l] && !part) {
 #pragma unroll
               for (int r = 0; r < SUM_R; r++) acc[r] = far_accumulate_re(acc[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, c.x);
               continue;
             }
             const double2 d = rec1[2 * l + 1];  // y, s_re
+            const double lcut = part ? __ldg(g2 + l * REC_GROUP + 1) : DBL_MAX;
+            const double lval = part ? __ldg(g2 + l * REC_GROUP + 2) : 0.0;
 #pragma unroll
             for (int r = 0; r < SUM_R; r++) {
+              // frequency_spans: lower_bound(f - cutoff) .. upper_bound(f + cutoff), lbl_lineshape_voigt_lte.h:123-133
+              if (part && !(a.x >= f[r] - lcut && a.x <= f[r] + lcut)) continue;
+              cutp[r] += lval;  // ls(f) - ls(f0' + cutoff), :591-608
               const double u  = __dsub_rn(f[r], a.x);
               const double ax = __dmul_rn(fabs(u), c.y);
-              if (__dadd_rn(ax, d.x) > FAR_LIMIT_REAL_SUM) {
+              if (__dadd_rn(ax, d.x) > far_limit) {
                 acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y, c.x);
               } else {
                 double wr, wi;
@@ -330,9 +405,15 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
               }
             }
           }
-        }
+          if (part) {
 #pragma unroll
-        for (int r = 0; r < SUM_R; r++) accS[r] = __dadd_rn(accS[r], acc[r]);
+            for (int r = 0; r < SUM_R; r++) acc[r] -= cutp[r];
+            cut_sum = 0.0;
+          }
+        }
+        // every pair of a FAR / NEAR tile is inside its window: the cutoff values of all its lines at once
+#pragma unroll
+        for (int r = 0; r < SUM_R; r++) accS[r] = __dadd_rn(accS[r], __dsub_rn(acc[r], cut_sum));
         if (DECOUPLED) {
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty[st]);  // this warp has released stage st
@@ -556,7 +637,8 @@ __global__ void __launch_bounds__(CPLX_NT, 3) lbl_sum_cplx_kernel(SumParams p) {
 // host launchers
 // ---------------------------------------------------------------------------
 size_t lbl_real_smem_bytes() {
-  return size_t(REAL_RING_DOUBLES) * sizeof(double) + 2 * REAL_STAGES * sizeof(uint64_t) + CHUNK + REAL_STAGES * TL;
+  return size_t(REAL_RING_DOUBLES) * sizeof(double) + 2 * REAL_STAGES * sizeof(uint64_t) + REAL_CHUNK * sizeof(uint16_t) +
+         REAL_STAGES * TL;
 }
 size_t lbl_cplx_smem_bytes() {
   return size_t(2) * N_GROUPS * TL * REC_GROUP * sizeof(double) + 2 * sizeof(uint64_t) + CHUNK + TL + CHUNK * sizeof(uint16_t);
@@ -663,6 +745,7 @@ __global__ void region_histogram_kernel(SumParams p, int64_t samples_per_level, 
     double cutoff = DBL_MAX;
     for (int is = 0; is < p.nsegs; is++)
       if (tile >= p.segs[is].tile_begin && tile < p.segs[is].tile_end && p.segs[is].has_cutoff) cutoff = p.segs[is].cutoff;
+    if (p.tile_mode[tile] == 0) cutoff = prep[tile * tile_doubles() + (int64_t(2) * TL + l) * REC_GROUP + 1];
     if (igd == 0.0 || !(f0s >= f - cutoff && f0s <= f + cutoff)) {
       atomicAdd(&h[6], 1ull);
       continue;

@@ -17,7 +17,8 @@ struct PrepareParams {
   const double* isot_mass;
   const int64_t* sub_parent;
   const double *sub_Sz, *sub_dzc;
-  const double* tile_cutoff;
+  const double* sub_cut;     // [slot] ByLine cutoff [Hz], +inf if none
+  const uint8_t* tile_mode;  // [tile] 0: real merged segment (record slot 9 holds the line's cutoff), 1: complex
   int32_t n_species, n_isot;
   int64_t ntiles;
   // levels of this batch (device, already offset to the first level of the batch)
@@ -39,6 +40,7 @@ struct SumParams {
   const double* prep;
   const double* summary;
   const int32_t* tile_count;
+  const uint8_t* tile_mode;
   int64_t ntiles;
   const SegmentDev* segs;  // segments selected for this launch (device)
   int32_t nsegs;

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
   const double y     = rec[(1 * TL + lane) * REC_GROUP + 2];
   const double s_re  = rec[(1 * TL + lane) * REC_GROUP + 3];
   const double E1    = rec[(2 * TL + lane) * REC_GROUP + 0];
-  const double s_im  = rec[(2 * TL + lane) * REC_GROUP + 1];
+  // real merged segments keep the line's cutoff in the s_im slot (s_im == 0 there)
+  const double s_im  = p.tile_mode[tile] == 0 ? 0.0 : rec[(2 * TL + lane) * REC_GROUP + 1];
   const bool live    = par >= 0 && igd != 0.0;  // padding and inactive cutoff lines have igd == 0
 
   const double yp  = y + fmax(1e-4 * fabs(y), 1e-4);
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
   jp.jcom[(int64_t(lev) * p.ntiles + tile) * TL + lane] = E1p;
 
   const double T = p.T[lev], P = p.P[lev];
-  const double cut = p.tile_cutoff[tile];
+  const double cut = p.sub_cut[slot];
   for (int q = 0; q < jp.nq; q++) {
     double o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
@@ -253,7 +254,10 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
       const double* __restrict__ s4 = summ + t * SUMMARY_DOUBLES;
       if (s4[0] > s4[1]) continue;  // no contributing line (CTA uniform)
       const double dist = fmax(0.0, fmax(fblk_min - s4[1], s4[0] - fblk_max));
-      if (dist > cutoff * (1.0 + 1e-9)) continue;
+      // real merged segments: per-line cutoffs (s4[4], s4[5] = min, max over the tile; DBL_MAX without)
+      const double tile_cut    = jp.real_lines ? s4[5] : cutoff;
+      const bool tile_has_cut  = jp.real_lines ? s4[4] < DBL_MAX : seg.has_cutoff != 0;
+      if (dist > tile_cut * (1.0 + 1e-9)) continue;
       const int count = p.tile_count[t];
       __syncthreads();  // previous tile fully consumed
       // stage the tile: the records of K1 + the derivative records of this pass, SoA in shared memory
@@ -264,8 +268,10 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
         const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);
         const double2 h = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP);
         const double2 k = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP + 2);
-        sb[0 * TL + l] = a.x; sb[1 * TL + l] = m.y; sb[2 * TL + l] = n.x; sb[3 * TL + l] = n.y; sb[4 * TL + l] = h.y;
-        sb[5 * TL + l] = h.x; sb[6 * TL + l] = jcom[t * TL + l]; sb[7 * TL + l] = k.x; sb[8 * TL + l] = k.y;
+        sb[0 * TL + l] = a.x; sb[1 * TL + l] = m.y; sb[2 * TL + l] = n.x; sb[3 * TL + l] = n.y;
+        sb[4 * TL + l] = jp.real_lines ? 0.0 : h.y;  // s_im
+        sb[5 * TL + l] = h.x; sb[6 * TL + l] = jcom[t * TL + l]; sb[7 * TL + l] = k.x;
+        sb[8 * TL + l] = jp.real_lines ? h.y : k.y;  // cut_im | real lines: the line's cutoff [Hz]
         {  // constants of the closed-form far path (real lines): displaced y, the y-only parts of D1, D2 and z z2 + 1/2
           const double y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
           sb[9 * TL + l] = y2; sb[10 * TL + l] = y * y + 0.5; sb[11 * TL + l] = y2 * y2 + 0.5; sb[12 * TL + l] = y * y2 - 0.5;
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
         }
       }
       // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|)
-      if (tid == 0) tile_far = (!seg.has_cutoff && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
+      if (tid == 0) tile_far = (!tile_has_cut && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
       __syncthreads();
       const bool far = tile_far != 0;
       if (far && jp.real_lines) {
@@ -328,14 +334,17 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
         const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l], y = sb[2 * TL + l];
         if (igd == 0.0) continue;  // inactive cutoff line
         const cplx s{sb[3 * TL + l], sb[4 * TL + l]};
+        const double lcut = jp.real_lines ? sb[8 * TL + l] : cutoff;
+        const bool lhas   = lcut < DBL_MAX;
+        const cplx cutval{sb[7 * TL + l], jp.real_lines ? 0.0 : sb[8 * TL + l]};
 #pragma unroll
         for (int r = 0; r < JAC_R; r++) {
-          if (seg.has_cutoff && !(f0s >= f[r] - cutoff && f0s <= f[r] + cutoff)) continue;
+          if (lhas && !(f0s >= f[r] - lcut && f0s <= f[r] + lcut)) continue;
           cplx z, F, dF;
           if (far) z_F_dF_far(igd * (f[r] - f0s), y, z, F, dF);
           else z_F_dF(igd * (f[r] - f0s), y, sb[5 * TL + l], sb[6 * TL + l], z, F, dF);
           cplx sh = cmul(s, F);
-          if (seg.has_cutoff) sh = csub(sh, {sb[7 * TL + l], sb[8 * TL + l]});
+          if (lhas) sh = csub(sh, cutval);
           shape[r] = cadd(shape[r], sh);
           const cplx sdF = cmul(s, dF);
 #pragma unroll
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
             const cplx ds{o[0 * TL + l], o[1 * TL + l]}, dzq{o[2 * TL + l], o[3 * TL + l]};
             const cplx tq = cadd(dzq, cscale(o[4 * TL + l], z));
             cplx d = cadd(cmul(ds, F), cmul(tq, sdF));  // dX, :310-323
-            if (seg.has_cutoff) d = csub(d, {o[5 * TL + l], o[6 * TL + l]});
+            if (lhas) d = csub(d, {o[5 * TL + l], o[6 * TL + l]});
             acc[q][r] = cadd(acc[q][r], d);
           }
         }

@@ -73,6 +73,41 @@ def test_byline_cutoff(wsm, orc, cutoff):
     assert_propmat_close(K1, Kref1, atol_scale=1e-11)
 
 
+@pytest.mark.parametrize("cutoffs", [(3e9,), (1.5e9, None, 6e9), (0.2e9, 40e9)])
+def test_byline_cutoff_many_tiles(wsm, orc, cutoffs):
+    """Real bands with ByLine cutoffs are merged per species and summed by the real kernel with one window per line:
+    enough lines and frequencies that (block, tile) pairs outside every window, inside every window and cut by
+    window edges all occur, with bands of different cutoffs (and none) interleaved in one species."""
+    nb = len(cutoffs)
+    per_band = 4000
+    rng = np.random.default_rng(11)
+    c = synth.case_c1(nl=nb * per_band, nf=6000, seed=3)
+    for b in range(nb):  # each band sorted by f0 (lbl_data.cpp:61-68), bands interleaved in frequency
+        c.cat.f0[b * per_band:(b + 1) * per_band] = np.sort(rng.uniform(100e9, 130e9, per_band))
+    c.cat.band_isot = np.zeros(nb, np.int32)
+    c.cat.band_lineshape = np.zeros(nb, np.int32)
+    c.cat.band_offset = np.arange(nb + 1, dtype=np.int64) * per_band
+    c.cat.band_cutoff_type = np.array([abi.CUTOFF_NONE if v is None else abi.CUTOFF_BYLINE for v in cutoffs], np.int32)
+    c.cat.band_cutoff_value = np.array([np.inf if v is None else v for v in cutoffs])
+    cat = wsm.Catalog(c.cat)
+    assert cat.counts()[0] == nb * per_band, "all bands must land in the merged real segment"
+    for clamp in (0, 1):
+        Kref, _ = orc.propmat_levels(c.cat, c.f, c.atm, no_negative_absorption=clamp)
+        K, _ = wsm.spectral_propmat_pathFromPath(cat, c.f, c.atm, no_negative_absorption=clamp)
+        assert_propmat_close(K, Kref, atol_scale=1e-11)
+    # a sub-grid sees other window bounds of active_lines but the same values (shard invariance with cutoffs)
+    fs = c.f[1000:2500]
+    path = wsm.Path(cat, len(fs), 1)
+    path.set_grid_bounds([c.f[0], c.f[-1]])  # before upload: active_lines sees the whole grid
+    path.upload(fs, c.atm, np.zeros(0), np.zeros((len(fs), 4)), no_negative_absorption=1)
+    path.run_propmat()
+    Ks = np.empty((1, len(fs), 7))
+    path.download(K=Ks)
+    assert np.array_equal(Ks, K[:, 1000:2500])
+    path.close()
+    cat.close()
+
+
 @pytest.mark.parametrize("los", [(180.0, 0.0), (120.0, 30.0)])
 def test_zeeman_polarised(wsm, orc, los):
     """BASELINE config 3 (reduced nf): full 7-component Propmat with Zeeman sub-lines and line mixing."""

@@ -82,6 +82,32 @@ class Target(C.Structure):
     _fields_ = [("kind", C.c_int32), ("species", C.c_int32)]
 
 
+class ObserverDesc(C.Structure):
+    """ab200_observer (include/arts_b200.h)."""
+
+    _fields_ = [
+        ("bkg_kind", C.c_int32),
+        ("bkg_T", C.c_double),
+        ("nx", C.c_int32),
+        ("map_offset", C.POINTER(C.c_int64)),
+        ("map_x", C.POINTER(C.c_int32)),
+        ("map_w", _dp),
+        ("n_bkg", C.c_int32),
+        ("bkg_x", C.POINTER(C.c_int32)),
+        ("bkg_w", _dp),
+        ("unit", C.c_int32),
+        ("n_real", C.c_double),
+        ("n_channels", C.c_int32),
+        ("w_offset", C.POINTER(C.c_int64)),
+        ("w_freq", C.POINTER(C.c_int64)),
+        ("w_stokes", _dp),
+    ]
+
+
+UNITS = {"unit": 0, "RJBT": 1, "PlanckBT": 2, "W_m2_m_sr": 3, "W_m2_m1_sr": 4}
+BKG_UPLOADED, BKG_PLANCK = 0, 1
+
+
 def _arr(x, dtype, shape=None):
     a = np.ascontiguousarray(x, dtype=dtype)
     if shape is not None:
@@ -253,6 +279,63 @@ class AtmPath:
         d.mag = dptr(self.mag)
         d.los = dptr(self.los)
         d.wind = dptr(self.wind)
+        return d
+
+
+@dataclass
+class Observer:
+    """The host glue around one path, flattened (ab200_observer): background, the path-point -> state-vector map of
+    ``spectral_rad_jacAddPathPropagation`` (src/m_rad.cc:62-127), the unit of ``spectral_rad_transform_operator`` and
+    this path's rows of the sensor's sparse weight matrices (``SensorObsel::sumup``, src/core/sensor/obsel.cpp:246-279).
+
+    ``path_map[ip][t]`` is a list of ``(x index, weight)``; ``bkg_rows`` a list of ``(x index, weight)`` for the
+    surface-temperature target; ``channels[c]`` a list of ``(frequency index, (wI, wQ, wU, wV))``.
+    """
+
+    nx: int
+    path_map: list | None = None
+    bkg_T: float | None = None  # None: the uploaded I_bkg
+    bkg_rows: list = field(default_factory=list)
+    unit: str = "unit"
+    n_real: float = 1.0
+    channels: list = field(default_factory=list)
+
+    def desc(self, np_: int, nq: int) -> ObserverDesc:
+        off, xs, ws = [0], [], []
+        for ip in range(np_):
+            for t in range(nq):
+                for (x, w) in (self.path_map[ip][t] if self.path_map else ()):
+                    xs.append(int(x)); ws.append(float(w))
+                off.append(len(xs))
+        self._map_offset = np.asarray(off, np.int64)
+        self._map_x = np.asarray(xs, np.int32)
+        self._map_w = np.asarray(ws, np.float64)
+        self._bkg_x = np.asarray([r[0] for r in self.bkg_rows], np.int32)
+        self._bkg_w = np.asarray([r[1] for r in self.bkg_rows], np.float64)
+        woff, wf, wst = [0], [], []
+        for ch in self.channels:
+            for (j, w4) in ch:
+                wf.append(int(j)); wst.append([float(v) for v in w4])
+            woff.append(len(wf))
+        self._w_offset = np.asarray(woff, np.int64)
+        self._w_freq = np.asarray(wf, np.int64)
+        self._w_stokes = np.asarray(wst, np.float64).reshape(-1, 4)
+        d = ObserverDesc()
+        d.bkg_kind = BKG_UPLOADED if self.bkg_T is None else BKG_PLANCK
+        d.bkg_T = 0.0 if self.bkg_T is None else float(self.bkg_T)
+        d.nx = int(self.nx)
+        d.map_offset = ptr(self._map_offset, C.c_int64)
+        d.map_x = ptr(self._map_x, C.c_int32)
+        d.map_w = dptr(self._map_w)
+        d.n_bkg = len(self._bkg_x)
+        d.bkg_x = ptr(self._bkg_x, C.c_int32)
+        d.bkg_w = dptr(self._bkg_w)
+        d.unit = UNITS[self.unit]
+        d.n_real = float(self.n_real)
+        d.n_channels = len(self.channels)
+        d.w_offset = ptr(self._w_offset, C.c_int64)
+        d.w_freq = ptr(self._w_freq, C.c_int64)
+        d.w_stokes = dptr(self._w_stokes)
         return d
 
 

@@ -69,6 +69,8 @@ def lib():
     L.ab200_path_run_stokes.argtypes = [_vp]
     L.ab200_path_download.argtypes = [_vp, _dp, _dp, _dp, _dp]
     L.ab200_path_sync.argtypes = [_vp]
+    L.ab200_path_run_observer.argtypes = [_vp, C.POINTER(abi.ObserverDesc)]
+    L.ab200_path_download_observer.argtypes = [_vp, _dp, _dp, _dp, _dp]
     L.ab200_path_device_ptr.argtypes = [_vp, C.c_int]
     L.ab200_path_device_ptr.restype = _vp
     L.ab200_release_thread_cache.argtypes = []

@@ -96,6 +96,24 @@ struct ab200_path {
   cudaEvent_t ev_staged = nullptr;  // the pinned staging blocks may be refilled once this has completed
   bool uploaded = false, k_preloaded = false;
 
+  // observer epilogue (ab200_path_run_observer)
+  struct DevBuf {  // grow-only device array
+    void* p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n) {
+      if (n <= bytes) return 0;
+      cudaFree(p);
+      p = nullptr; bytes = 0;
+      if (cudaMalloc(&p, n) != cudaSuccess) { cudaGetLastError(); return 1; }
+      bytes = n;
+      return 0;
+    }
+    ~DevBuf() { cudaFree(p); }
+  };
+  DevBuf o_Jx, o_y, o_Jy, o_map_offset, o_map_x, o_map_w, o_bkg_x, o_bkg_w, o_w_offset, o_w_freq, o_w_stokes;
+  int32_t o_nx = 0, o_nch = 0;
+  bool o_ran = false, o_has_jx = false;
+
   ~ab200_path() {
     cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary);
     cudaFree(d_flags); cudaFree(d_K); cudaFree(d_I);
@@ -513,7 +531,9 @@ int ab200_path_region_histogram(ab200_path* p, int64_t samples_per_level, uint64
   return AB200_OK;
 }
 
-int ab200_path_run_stokes(ab200_path* p) {
+static int check_flags(ab200_path* p);
+
+static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_stokes: path not uploaded");
   if (p->np < 1) return set_error(AB200_ERR_INVALID, "ab200_path_run_stokes: empty path");
   AB_CUDA(cudaSetDevice(p->cat->device));
@@ -529,14 +549,133 @@ int ab200_path_run_stokes(ab200_path* p) {
     AB_TRY(launch_stokes_chain(sp, p->stream));
     t.stop();
   }
-  if (p->nq > 0) {
+  if (p->nq > 0 || (obs && obs->n_bkg > 0)) {
     StokesJacParams jp{};
     jp.np = p->np; jp.nq = p->nq; jp.nf = p->nf; jp.K = p->d_K; jp.dK = p->d_dK; jp.k_pitch = p->k_pitch;
     jp.f = p->d_f; jp.f_stride = p->f_stride; jp.ffac = p->d_ffac; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
     jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option; jp.flags = p->d_flags;
+    if (obs) {  // x-space accumulation inside the pass; the per-level dI is not written
+      jp.dI = nullptr;
+      jp.Jx = static_cast<double*>(p->o_Jx.p);
+      jp.map_offset = static_cast<const int64_t*>(p->o_map_offset.p);
+      jp.map_x = static_cast<const int32_t*>(p->o_map_x.p);
+      jp.map_w = static_cast<const double*>(p->o_map_w.p);
+      jp.n_bkg = obs->bkg_kind == AB200_BKG_PLANCK ? obs->n_bkg : 0;
+      jp.bkg_x = static_cast<const int32_t*>(p->o_bkg_x.p);
+      jp.bkg_w = static_cast<const double*>(p->o_bkg_w.p);
+      jp.bkg_T = obs->bkg_T;
+    }
     AB_TRY(launch_stokes_jac(jp, p->stream));
   }
   return AB200_OK;
+}
+
+int ab200_path_run_stokes(ab200_path* p) { return run_stokes_impl(p, nullptr); }
+
+int ab200_path_run_observer(ab200_path* p, const ab200_observer* o) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: path not uploaded");
+  if (!o) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: null observer");
+  if (p->np < 1) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: empty path");
+  if (p->f_stride != 0)
+    return set_error(AB200_ERR_UNSUPPORTED,
+                     "ab200_path_run_observer needs the sensor's frequency grid: upload one grid (f_level_stride = 0) and "
+                     "pass the wind in ab200_atm_path instead of per-level grids");
+  if (o->unit < AB200_UNIT_UNIT || o->unit > AB200_UNIT_W_M2_M1_SR)
+    return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: unknown spectral radiance unit");
+  if (o->bkg_kind != AB200_BKG_UPLOADED && o->bkg_kind != AB200_BKG_PLANCK)
+    return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: unknown background kind");
+  if (o->bkg_kind == AB200_BKG_PLANCK && !(o->bkg_T > 0))
+    return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: the background temperature must be positive");
+  if (o->nx < 0 || o->n_bkg < 0 || o->n_channels < 0) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: negative size");
+  const int32_t n_bkg = o->bkg_kind == AB200_BKG_PLANCK ? o->n_bkg : 0;
+  const int64_t rows = int64_t(p->np) * p->nq;
+  const bool has_jx = o->nx > 0 && (p->nq > 0 || n_bkg > 0);
+  if (p->nq > 0 && o->nx > 0 && (!o->map_offset || o->map_offset[0] != 0))
+    return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: map_offset must start at 0");
+  const int64_t nmap = (p->nq > 0 && o->nx > 0) ? o->map_offset[rows] : 0;
+  // Mismatched input sizes of spectral_rad_jacAddPathPropagation (m_rad.cc:77-99): every x index inside [0, nx)
+  for (int64_t r = 0; r < (nmap ? rows : 0); r++)
+    if (o->map_offset[r + 1] < o->map_offset[r]) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: map_offset must ascend");
+  for (int64_t e = 0; e < nmap; e++)
+    if (o->map_x[e] < 0 || o->map_x[e] >= o->nx)
+      return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: path map entry " + std::to_string(e) + " is outside the state vector");
+  for (int32_t b = 0; b < n_bkg; b++)
+    if (o->bkg_x[b] < 0 || o->bkg_x[b] >= o->nx)
+      return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: background row " + std::to_string(b) + " is outside the state vector");
+  const int64_t nnz = o->n_channels ? o->w_offset[o->n_channels] : 0;
+  if (o->n_channels && o->w_offset[0] != 0) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: w_offset must start at 0");
+  for (int32_t c = 0; c < o->n_channels; c++)
+    if (o->w_offset[c + 1] < o->w_offset[c]) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: w_offset must ascend");
+  for (int64_t e = 0; e < nnz; e++)
+    if (o->w_freq[e] < 0 || o->w_freq[e] >= p->nf)
+      return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: sensor weight " + std::to_string(e) + " is outside the frequency grid");
+  AB_CUDA(cudaSetDevice(p->cat->device));
+
+  auto put = [&](ab200_path::DevBuf& b, const void* src, size_t bytes) -> int {
+    if (bytes == 0) return 0;
+    if (b.reserve(bytes)) return set_error(AB200_ERR_NOMEM, "ab200_path_run_observer: out of device memory");
+    AB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, p->stream));  // pageable source: staged before return
+    return 0;
+  };
+  if (nmap) {
+    AB_TRY(put(p->o_map_offset, o->map_offset, (rows + 1) * sizeof(int64_t)));
+    AB_TRY(put(p->o_map_x, o->map_x, nmap * sizeof(int32_t)));
+    AB_TRY(put(p->o_map_w, o->map_w, nmap * sizeof(double)));
+  } else if (p->nq > 0 && has_jx) {  // no entries: an all-zero offset table
+    std::vector<int64_t> zero(rows + 1, 0);
+    AB_TRY(put(p->o_map_offset, zero.data(), zero.size() * sizeof(int64_t)));
+    AB_CUDA(cudaStreamSynchronize(p->stream));
+  }
+  AB_TRY(put(p->o_bkg_x, o->bkg_x, n_bkg * sizeof(int32_t)));
+  AB_TRY(put(p->o_bkg_w, o->bkg_w, n_bkg * sizeof(double)));
+  AB_TRY(put(p->o_w_offset, o->w_offset, o->n_channels ? (o->n_channels + 1) * sizeof(int64_t) : 0));
+  AB_TRY(put(p->o_w_freq, o->w_freq, nnz * sizeof(int64_t)));
+  AB_TRY(put(p->o_w_stokes, o->w_stokes, nnz * 4 * sizeof(double)));
+  if (has_jx) {
+    const size_t bytes = static_cast<size_t>(o->nx) * p->nf * 4 * sizeof(double);
+    if (p->o_Jx.reserve(bytes)) return set_error(AB200_ERR_NOMEM, "ab200_path_run_observer: out of device memory for spectral_rad_jac");
+    AB_CUDA(cudaMemsetAsync(p->o_Jx.p, 0, bytes, p->stream));  // spectral_rad_jacEmpty, m_rad.cc:14-23
+  }
+  if (o->n_channels) {
+    if (p->o_y.reserve(o->n_channels * sizeof(double)) ||
+        p->o_Jy.reserve(std::max<size_t>(1, static_cast<size_t>(o->n_channels) * o->nx) * sizeof(double)))
+      return set_error(AB200_ERR_NOMEM, "ab200_path_run_observer: out of device memory");
+  }
+  if (o->bkg_kind == AB200_BKG_PLANCK) AB_TRY(launch_background_planck(p->nf, p->d_f, o->bkg_T, p->d_Ibkg, p->stream));
+
+  ab200_observer oo = *o;
+  if (!has_jx) oo.n_bkg = 0;
+  if (has_jx) {
+    AB_TRY(run_stokes_impl(p, &oo));
+  } else {
+    AB_TRY(run_stokes_impl(p, nullptr));
+  }
+  double* Jx = has_jx ? static_cast<double*>(p->o_Jx.p) : nullptr;
+  AB_TRY(launch_unit_transform(p->nf, o->nx, p->d_f, o->unit, o->n_real, p->d_I, Jx, p->stream));
+  AB_TRY(launch_sensor_sumup(p->nf, o->nx, o->n_channels, static_cast<const int64_t*>(p->o_w_offset.p),
+                             static_cast<const int64_t*>(p->o_w_freq.p), static_cast<const double*>(p->o_w_stokes.p), p->d_I,
+                             Jx, static_cast<double*>(p->o_y.p), static_cast<double*>(p->o_Jy.p), p->stream));
+  p->o_nx = o->nx; p->o_nch = o->n_channels; p->o_ran = true; p->o_has_jx = has_jx;
+  return AB200_OK;
+}
+
+int ab200_path_download_observer(ab200_path* p, double* I, double* Jx, double* y, double* Jy) {
+  if (!p || !p->o_ran) return set_error(AB200_ERR_INVALID, "ab200_path_download_observer: ab200_path_run_observer has not run");
+  if (I && p->nf)
+    AB_CUDA(cudaMemcpyAsync(I, p->d_I, static_cast<size_t>(p->nf) * 4 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  const size_t jx_bytes = static_cast<size_t>(p->o_nx) * p->nf * 4 * sizeof(double);
+  if (Jx && jx_bytes) {
+    if (p->o_has_jx) AB_CUDA(cudaMemcpyAsync(Jx, p->o_Jx.p, jx_bytes, cudaMemcpyDeviceToHost, p->stream));
+    else std::memset(Jx, 0, jx_bytes);  // no target reaches the state vector: spectral_rad_jacEmpty
+  }
+  if (y && p->o_nch)
+    AB_CUDA(cudaMemcpyAsync(y, p->o_y.p, p->o_nch * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (Jy && p->o_nch && p->o_nx) {
+    const size_t bytes = static_cast<size_t>(p->o_nch) * p->o_nx * sizeof(double);
+    if (p->o_has_jx) AB_CUDA(cudaMemcpyAsync(Jy, p->o_Jy.p, bytes, cudaMemcpyDeviceToHost, p->stream));
+    else std::memset(Jy, 0, bytes);
+  }
+  return check_flags(p);
 }
 
 static int check_flags(ab200_path* p) {

@@ -39,7 +39,17 @@ struct StokesJacParams {
   const double* r;      // [np-1]
   const double* dr;     // [2][np-1][nq]
   const double* I_lev;  // [np][nf][4] radiance arriving at each level (pass A)
-  double* dI;           // [nf][np][nq][4]
+  double* dI;           // [nf][np][nq][4], or nullptr when only the x-space Jacobian is wanted
+  // observer epilogue (x-space accumulation inside the pass, spectral_rad_jacAddPathPropagation m_rad.cc:62-127 and
+  // spectral_rad_jacFromBackground :26-60): Jx [nx][nf][4] zero on entry, or nullptr
+  double* Jx;
+  const int64_t* map_offset;  // [np*nq + 1] CSR over (level, target)
+  const int32_t* map_x;
+  const double* map_w;
+  int32_t n_bkg;              // surface-temperature rows: Jx[bkg_x][f] += P[f][np-1] (bkg_w dB/dT(f, bkg_T), 0, 0, 0)
+  const int32_t* bkg_x;
+  const double* bkg_w;
+  double bkg_T;
   int32_t it;           // index of the temperature target or -1
   int32_t rte_option;
   int* flags;
@@ -53,6 +63,14 @@ int launch_rte_emission_jac(int linsrc, int np, int64_t nf, int nq, const double
                             const double* dT, const double* dL, const double* J, const double* dJ, const double* I_bkg,
                             double* I, double* dI, cudaStream_t stream);
 int launch_planck_tb(int64_t nf, const double* f, double* I, cudaStream_t stream);
+
+// observer epilogue (observer.cu)
+int launch_background_planck(int64_t nf, const double* f, double T, double* I_bkg, cudaStream_t stream);
+int launch_unit_transform(int64_t nf, int32_t nx, const double* f, int32_t unit, double n_real, double* I, double* Jx,
+                          cudaStream_t stream);
+int launch_sensor_sumup(int64_t nf, int32_t nx, int32_t n_channels, const int64_t* w_offset, const int64_t* w_freq,
+                        const double* w_stokes, const double* I, const double* Jx, double* y, double* Jy,
+                        cudaStream_t stream);
 int launch_tramat(int np, int64_t nf, const double* K, const double* r, int linsrc, int exact, double* T, double* L,
                   double* P, int linprop, int* flags, cudaStream_t stream);
 int launch_srcvec(int np, int64_t nf, int nq, const double* K, const double* f, int64_t f_stride, const double* Tlev,

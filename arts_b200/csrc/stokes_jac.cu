@@ -210,6 +210,27 @@ int launch_rte_emission_jac(int linsrc, int np, int64_t nf, int nq, const double
 //   I_lev [np][nf][4]: radiance arriving at level i from behind (written by stokes_chain_kernel, pass A)
 //   dK    [np][nq][k_pitch... ] see StokesJacParams
 // ---------------------------------------------------------------------------
+// one finished element of spectral_rad_jac_path [nf][np][nq]: stored, and / or mapped to the state vector with the
+// flat interpolation weights of path point i (m_rad.cc:107-125; the thread owns column iv of Jx: no atomics)
+__device__ __forceinline__ void emit(const StokesJacParams& p, int64_t iv, int i, int q, double d0, double d1, double d2,
+                                     double d3) {
+  if (p.dI) {
+    double* d = p.dI + ((iv * p.np + i) * p.nq + q) * 4;
+    d[0] = d0; d[1] = d1; d[2] = d2; d[3] = d3;
+  }
+  if (p.Jx) {
+    const int64_t row = int64_t(i) * p.nq + q;
+    for (int64_t e = p.map_offset[row]; e < p.map_offset[row + 1]; e++) {
+      const double w = p.map_w[e];
+      if (w == 0.0) continue;
+      double2* x = reinterpret_cast<double2*>(p.Jx + (int64_t(p.map_x[e]) * p.nf + iv) * 4);
+      double2 a = x[0], b = x[1];
+      a.x = __fma_rn(w, d0, a.x); a.y = __fma_rn(w, d1, a.y); b.x = __fma_rn(w, d2, b.x); b.y = __fma_rn(w, d3, b.y);
+      x[0] = a; x[1] = b;
+    }
+  }
+}
+
 template <bool LINSRC>
 __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
   const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -243,14 +264,16 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
       else diag_of(Lm, func_F(t.a));
     }
     // radiance arriving at level i+1
-    const double* Il = p.I_lev + (int64_t(i + 1) * p.nf + iv) * 4;
-    double v[4], jd[4] = {0, 0, 0, 0};
-    if (LINSRC) {  // J0 = J[i+1], J1 = J[i] in the reference's naming
-      v[0] = Il[0] - j1; v[1] = Il[1]; v[2] = Il[2]; v[3] = Il[3];
-      jd[0] = j1 - j0;
-    } else {
-      const double jm = (j0 + j1) * 0.5;
-      v[0] = Il[0] - jm; v[1] = Il[1]; v[2] = Il[2]; v[3] = Il[3];
+    double v[4] = {0, 0, 0, 0}, jd[4] = {0, 0, 0, 0};
+    if (nq > 0) {
+      const double* Il = p.I_lev + (int64_t(i + 1) * p.nf + iv) * 4;
+      if (LINSRC) {  // J0 = J[i+1], J1 = J[i] in the reference's naming
+        v[0] = Il[0] - j1; v[1] = Il[1]; v[2] = Il[2]; v[3] = Il[3];
+        jd[0] = j1 - j0;
+      } else {
+        const double jm = (j0 + j1) * 0.5;
+        v[0] = Il[0] - jm; v[1] = Il[1]; v[2] = Il[2]; v[3] = Il[3];
+      }
     }
     for (int q = 0; q < nq; q++) {
       const Propmat dk0 = load_propmat(p.dK + ((int64_t(i) * nq + q) * p.k_pitch + iv) * 7);
@@ -275,8 +298,7 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
       double c0[4], c1[4], o[4];
       layer_terms<LINSRC>(Tm, Lm, dT0, dT1, dL0, dL1, v, jd, dj0, dj1, c0, c1);
       mv(Pm, c0, o);
-      double* d0 = p.dI + ((iv * np + i) * nq + q) * 4;
-      d0[0] = carry[q][0] + o[0]; d0[1] = carry[q][1] + o[1]; d0[2] = carry[q][2] + o[2]; d0[3] = carry[q][3] + o[3];
+      emit(p, iv, i, q, carry[q][0] + o[0], carry[q][1] + o[1], carry[q][2] + o[2], carry[q][3] + o[3]);
       mv(Pm, c1, o);
       carry[q][0] = o[0]; carry[q][1] = o[1]; carry[q][2] = o[2]; carry[q][3] = o[3];
     }
@@ -293,14 +315,22 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
     }
     k0 = k1; f0 = f1; j0 = j1;
   }
-  for (int q = 0; q < nq; q++) {  // last level only receives the dI1 term
-    double* d0 = p.dI + ((iv * np + (np - 1)) * nq + q) * 4;
-    d0[0] = carry[q][0]; d0[1] = carry[q][1]; d0[2] = carry[q][2]; d0[3] = carry[q][3];
+  for (int q = 0; q < nq; q++)  // last level only receives the dI1 term
+    emit(p, iv, np - 1, q, carry[q][0], carry[q][1], carry[q][2], carry[q][3]);
+  if (p.Jx && p.n_bkg > 0) {
+    // spectral_rad_jacFromBackground (m_rad.cc:26-60) of spectral_radSurfaceBlackbody's Jacobian (m_background.cc:126-140):
+    // P_{np-1} (w dB/dT, 0, 0, 0), with the sensor's frequency grid
+    const double dB = dplanck_dt(p.f[iv], p.bkg_T);
+    for (int b = 0; b < p.n_bkg; b++) {
+      const double s = p.bkg_w[b] * dB;
+      double* x = p.Jx + (int64_t(p.bkg_x[b]) * p.nf + iv) * 4;
+      x[0] += Pm[0] * s; x[1] += Pm[4] * s; x[2] += Pm[8] * s; x[3] += Pm[12] * s;
+    }
   }
 }
 
 int launch_stokes_jac(const StokesJacParams& p, cudaStream_t stream) {
-  if (p.nf == 0 || p.nq == 0 || p.np == 0) return 0;
+  if (p.nf == 0 || p.np == 0 || (p.nq == 0 && !(p.Jx && p.n_bkg > 0))) return 0;
   const unsigned grid = static_cast<unsigned>((p.nf + 63) / 64);
   if (p.rte_option != AB200_RTE_CONSTANT)
     stokes_jac_kernel<true><<<grid, 64, 0, stream>>>(p);

@@ -286,7 +286,8 @@ class Path:
         f, stride, nf = _f_arg(f, atm.np_)
         assert nf == self.nf and atm.np_ == self.np_
         tg, _ = make_targets(targets)
-        self._keep = (f, atm, np.ascontiguousarray(r, dtype=np.float64), np.ascontiguousarray(I_bkg, dtype=np.float64))
+        self._keep = (f, atm, np.ascontiguousarray(r, dtype=np.float64),
+                      None if I_bkg is None else np.ascontiguousarray(I_bkg, dtype=np.float64))
         a = atm.desc()
         check(lib().ab200_path_upload(self._h, dptr(f), stride, C.byref(a), int(select_species),
                                       int(no_negative_absorption), tg, dptr(self._keep[2]), int(hse_derivative),
@@ -324,6 +325,26 @@ class Path:
 
     def download(self, I=None, K=None, dI=None, dK=None):
         check(lib().ab200_path_download(self._h, dptr(I), dptr(dI), dptr(K), dptr(dK)))
+
+    def run_observer(self, obs: abi.Observer):
+        """Stokes chain + the host glue of ``spectral_rad_observer_agenda`` / ``measurement_vecFromSensor`` on the
+        device: background from a temperature (src/m_background.cc:55-141), ``spectral_rad_jacFromBackground`` and
+        ``spectral_rad_jacAddPathPropagation`` (src/m_rad.cc:26-127) inside the Jacobian pass,
+        ``spectral_rad_transform_operator`` and ``SensorObsel::sumup`` (src/core/sensor/obsel.cpp:246-279)."""
+        self._obs = obs
+        d = obs.desc(self.np_, self.nq)
+        check(lib().ab200_path_run_observer(self._h, C.byref(d)))
+
+    def download_observer(self, want_jx=True):
+        """Returns ``(spectral_rad [nf,4], spectral_rad_jac [nx,nf,4] or None, y [nch], Jy [nch,nx])``."""
+        obs = self._obs
+        I = np.empty((self.nf, 4))
+        Jx = np.empty((obs.nx, self.nf, 4)) if want_jx and obs.nx else None
+        nch = len(obs.channels)
+        y = np.empty(nch) if nch else None
+        Jy = np.empty((nch, obs.nx)) if nch and obs.nx else None
+        check(lib().ab200_path_download_observer(self._h, dptr(I), dptr(Jx), dptr(y), dptr(Jy)))
+        return I, Jx, y, Jy
 
     def device_ptr(self, which: int) -> int:
         return int(lib().ab200_path_device_ptr(self._h, which) or 0)

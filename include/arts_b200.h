@@ -223,6 +223,56 @@ void *ab200_path_device_ptr(ab200_path *p, int which);
 /* kernels launched by the library on this thread since the last call (bench.py's gpu_launches) */
 int64_t ab200_launch_count(int reset);
 
+/* ---- observer epilogue on the device (the callers' glue around the path) --------------------
+ * What spectral_rad_observer_agenda / measurement_vecFromSensor do on the host after the RTE, applied to the
+ * resident results of one path so that only the state-space Jacobian or the sensor channels cross PCIe:
+ *   1. background radiance from a temperature: spectral_radSurfaceBlackbody / spectral_radUniformCosmicBackground
+ *      (src/m_background.cc:55-71,113-141), with the surface-temperature rows of spectral_rad_bkg_jac;
+ *   2. spectral_rad_jacFromBackground (src/m_rad.cc:26-60): Jx[i][f] = P[f][np-1] * bkg_jac[i][f];
+ *   3. spectral_rad_jacAddPathPropagation (src/m_rad.cc:62-127): Jx[i][f] = fma(w, dI[f][ip][t], Jx[i][f]) with the
+ *      field's flat interpolation weights of every path point (computed by the shim: AtmField::flat_weight);
+ *   4. spectral_rad_transform_operator (spectral_radiance_transform_operator.cc:8-122) on I and Jx;
+ *   5. SensorObsel::sumup (src/core/sensor/obsel.cpp:246-279) of this path's poslos row: y[c] and Jy[c][i].
+ * The x-space accumulation runs inside the fused Jacobian pass (the per-level dI is never written). */
+#define AB200_UNIT_UNIT 0       /* spectral_unit_op :8-19 */
+#define AB200_UNIT_RJBT 1       /* spectral_rjbt_op :21-44 */
+#define AB200_UNIT_PLANCKBT 2   /* spectral_planck_op :46-87 */
+#define AB200_UNIT_W_M2_M_SR 3  /* spectral_W_m2_m_sr_op :89-112 */
+#define AB200_UNIT_W_M2_M1_SR 4 /* spectral_W_m2_m1_sr_op :114-122 */
+#define AB200_BKG_UPLOADED 0    /* the I_bkg given to ab200_path_upload, no background Jacobian */
+#define AB200_BKG_PLANCK 1      /* B(f, bkg_T) e_I formed on the device from the sensor's frequency grid */
+
+typedef struct ab200_observer {
+  int32_t bkg_kind; /* AB200_BKG_* */
+  double bkg_T;     /* surface temperature (single_value of SurfaceKey::t) or the cosmic background's */
+  int32_t nx;       /* JacobianTargets::x_size(): rows of spectral_rad_jac */
+  /* step 3: CSR over rows ip * nq + t (level, target): x index (x_start included) and weight of every entry */
+  const int64_t *map_offset; /* [np * nq + 1] */
+  const int32_t *map_x;
+  const double *map_w;
+  /* steps 1-2: x rows of the surface temperature target, flat_weights at the ground point; bkg_jac = w dB/dT */
+  int32_t n_bkg;
+  const int32_t *bkg_x;
+  const double *bkg_w;
+  /* step 4 */
+  int32_t unit;  /* AB200_UNIT_* */
+  double n_real; /* ray_path.front().nreal */
+  /* step 5: CSR over channels of the sparse weight rows with irow == this path's poslos index (sorted by icol) */
+  int32_t n_channels; /* 0: no sensor sum-up */
+  const int64_t *w_offset; /* [n_channels + 1] */
+  const int64_t *w_freq;   /* icol */
+  const double *w_stokes;  /* [nnz][4] */
+} ab200_observer;
+
+/* Runs the Stokes chain (with the observer's background), the fused Jacobian pass with x-space accumulation, the unit
+ * transform and the sensor sum-up on the resident K / dK (after ab200_path_run_propmat), asynchronously.  The index
+ * arrays are copied to the device on the path's stream through pageable memory: they may be freed after the call. */
+int ab200_path_run_observer(ab200_path *p, const ab200_observer *obs);
+/* D2H of the observer results (synchronises).  Any pointer may be NULL.  I [nf][4] transformed spectral_rad;
+ * Jx [nx][nf][4] transformed spectral_rad_jac; y [n_channels] and Jy [n_channels][nx]: this path's contribution,
+ * which the shim adds to measurement_vec / measurement_jac (src/m_rad.cc:346-351). */
+int ab200_path_download_observer(ab200_path *p, double *I, double *Jx, double *y, double *Jy);
+
 /* Stream the calling thread's host-buffer entry points (propmat_levels, clearsky_emission) run on:
  * a cudaStream_t as void*, or NULL for a private non-blocking stream (the default). */
 int ab200_set_thread_stream(void *stream);

@@ -1570,6 +1570,138 @@ int orc_planck(int64_t n, const double* f, double T, double* B) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// observer epilogue: the host glue around the path
+// ---------------------------------------------------------------------------
+// physics_funcs.cc:76-83
+static Numeric dinvplanckdI(Numeric i, Numeric f) {
+  constexpr Numeric a = Constant::h / Constant::k;
+  constexpr Numeric b = 2 * Constant::h / (Constant::c * Constant::c);
+  const Numeric d     = b * f * f * f / i;
+  const Numeric binv  = a * f / std::log1p(d);
+  return binv * binv / (a * f * i * (1 / d + 1));
+}
+// physics_funcs.cc:172-176
+static Numeric invrayjean(Numeric i, Numeric f) {
+  constexpr Numeric a = Constant::c * Constant::c / (2 * Constant::k);
+  return (a * i) / (f * f);
+}
+
+// from_temp, m_background.cc:55-63 (spectral_radSurfaceBlackbody :113-141, spectral_radUniformCosmicBackground :65-72);
+// dB [nf] = dplanck_dt(f, T) of the surface-temperature Jacobian (:131-138)
+int orc_background(int64_t nf, const double* f, double T, double* I_bkg, double* dB) {
+  for (int64_t j = 0; j < nf; j++) {
+    I_bkg[4 * j] = planck(f[j], T);
+    I_bkg[4 * j + 1] = I_bkg[4 * j + 2] = I_bkg[4 * j + 3] = 0.0;
+    if (dB) dB[j] = dplanck_dt(f[j], T);
+  }
+  return 0;
+}
+
+// Steps 2-5 of the observer epilogue on host arrays.
+//   P  [nf][np][16] cumulative transmittance of the path (TransmittanceMatrix::P)
+//   I  [nf][4] in: spectral_rad, out: transformed;  dI [nf][np][nq][4] spectral_rad_jac_path
+//   Jx [nx][nf][4] out;  y [n_channels], Jy [n_channels][nx] out (this path's contribution)
+int orc_observer(int32_t np, int64_t nf, int32_t nq, const double* f, const ab200_observer* o, const double* P,
+                 double* I, const double* dI, double* Jx, double* y, double* Jy) {
+  const Index nx = o->nx;
+  std::vector<double> scratch;
+  if (!Jx) {
+    scratch.assign(static_cast<size_t>(nx) * nf * 4, 0.0);
+    Jx = scratch.data();
+  }
+  auto jx = [&](Index i, Index j) { return Jx + (i * nf + j) * 4; };
+  // spectral_radSurfaceBlackbody's spectral_rad_jac, m_background.cc:126-140
+  for (Index k = 0; k < nx * nf * 4; k++) Jx[k] = 0.0;
+  if (o->bkg_kind == AB200_BKG_PLANCK)
+    for (int b = 0; b < o->n_bkg; b++)
+      for (Index j = 0; j < nf; j++) jx(o->bkg_x[b], j)[0] += o->bkg_w[b] * dplanck_dt(f[j], o->bkg_T);
+  // spectral_rad_jacFromBackground, m_rad.cc:26-60
+  if (nq > 0 || o->n_bkg > 0)
+    for (Index i = 0; i < nx; i++)
+      for (Index j = 0; j < nf; j++) {
+        const stokvec r = load_mm(P + (j * np + (np - 1)) * 16) * load_sv(jx(i, j));
+        std::memcpy(jx(i, j), r.v, sizeof(r.v));
+      }
+  // spectral_rad_jacAddPathPropagation, m_rad.cc:62-127 (targets outermost, then path points, then weights)
+  for (int t = 0; t < nq; t++)
+    for (int ip = 0; ip < np; ip++)
+      for (int64_t e = o->map_offset[ip * nq + t]; e < o->map_offset[ip * nq + t + 1]; e++) {
+        const Numeric w = o->map_w[e];
+        if (w == 0.0) continue;
+        for (Index j = 0; j < nf; j++) {
+          const double* a = dI + ((j * np + ip) * nq + t) * 4;
+          double* b       = jx(o->map_x[e], j);
+          for (int c = 0; c < 4; c++) b[c] = std::fma(w, a[c], b[c]);
+        }
+      }
+  // spectral_rad_transform_operator, spectral_radiance_transform_operator.cc:8-122
+  const Numeric n2 = o->n_real * o->n_real;
+  for (Index j = 0; j < nf; j++) {
+    double* v = I + 4 * j;
+    Numeric dv[4] = {1, 1, 1, 1};
+    switch (o->unit) {
+      case AB200_UNIT_UNIT:
+        if (o->n_real != 1.0) {
+          for (int c = 0; c < 4; c++) { v[c] *= n2; dv[c] = n2; }
+        }
+        break;
+      case AB200_UNIT_RJBT: {
+        const Numeric df = invrayjean(1.0, f[j]);
+        for (int c = 0; c < 4; c++) { v[c] *= df; dv[c] = df; }
+      } break;
+      case AB200_UNIT_PLANCKBT: {
+        const Numeric fj = f[j];
+        dv[0] = dinvplanckdI(v[0], fj);
+        for (int c = 1; c < 4; c++) dv[c] = dinvplanckdI(0.5 * (v[0] + v[c]), fj) - dinvplanckdI(0.5 * (v[0] - v[c]), fj);
+        Numeric n[4];
+        n[0] = invplanck(v[0], fj);
+        for (int c = 1; c < 4; c++) n[c] = invplanck(0.5 * (v[0] + v[c]), fj) - invplanck(0.5 * (v[0] - v[c]), fj);
+        for (int c = 0; c < 4; c++) v[c] = n[c];
+      } break;
+      case AB200_UNIT_W_M2_M_SR: {
+        const Numeric df = (f[j] * (f[j] / Constant::c));
+        for (int c = 0; c < 4; c++) { v[c] *= df * n2; dv[c] = df * n2; }
+      } break;
+      case AB200_UNIT_W_M2_M1_SR:
+        for (int c = 0; c < 4; c++) { v[c] *= n2 * Constant::c; dv[c] = n2 * Constant::c; }
+        break;
+      default: return fail(AB200_ERR_INVALID, "unknown spectral radiance unit");
+    }
+    const bool scale = !(o->unit == AB200_UNIT_UNIT && o->n_real == 1.0);
+    if (scale)
+      for (Index i = 0; i < nx; i++)
+        for (int c = 0; c < 4; c++) jx(i, j)[c] *= dv[c];
+  }
+  // SensorObsel::sumup, obsel.cpp:246-279 (this path's poslos row; entries sorted by icol)
+  for (int ch = 0; ch < o->n_channels; ch++) {
+    Numeric sum = 0.0;
+    for (int64_t e = o->w_offset[ch]; e < o->w_offset[ch + 1]; e++) {
+      const double* a = I + 4 * o->w_freq[e];
+      const double* w = o->w_stokes + 4 * e;
+      sum += a[0] * w[0] + a[1] * w[1] + a[2] * w[2] + a[3] * w[3];  // dot = transform_reduce, matpack_mdspan_helpers_reduce.h:218-222
+    }
+    if (y) y[ch] = sum;
+    if (Jy)
+      for (Index i = 0; i < nx; i++) {
+        Numeric s = 0.0;
+        for (int64_t e = o->w_offset[ch]; e < o->w_offset[ch + 1]; e++) {
+          const double* a = jx(i, o->w_freq[e]);
+          const double* w = o->w_stokes + 4 * e;
+          s += a[0] * w[0] + a[1] * w[1] + a[2] * w[2] + a[3] * w[3];
+        }
+        Jy[static_cast<Index>(ch) * nx + i] = s;
+      }
+  }
+  return 0;
+}
+
+// scalar entry points of the unit conversions (pins against their analytic inverses in tests/test_oracle_pins.py)
+double orc_invplanck(double i, double f) { return invplanck(i, f); }
+double orc_dinvplanckdI(double i, double f) { return dinvplanckdI(i, f); }
+double orc_invrayjean(double i, double f) { return invrayjean(i, f); }
+double orc_dplanck_dt(double f, double t) { return dplanck_dt(f, t); }
+
 // rtepack::tran for single inputs (tests: exp(-K r) against scipy expm, src/tests/test_rtepack.cc:12-33)
 int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, double* T, double* L) {
   const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};

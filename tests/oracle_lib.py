@@ -50,6 +50,11 @@ def lib():
         L.orc_wigner3j.argtypes = [C.c_int] * 6 + [dp]
         L.orc_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp]
         L.orc_norm_view.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_background.argtypes = [C.c_int64, dp, C.c_double, dp, dp]
+        L.orc_observer.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(abi.ObserverDesc), dp, dp, dp, dp, dp, dp]
+        for name in ("orc_invplanck", "orc_dinvplanckdI", "orc_invrayjean", "orc_dplanck_dt"):
+            getattr(L, name).argtypes = [C.c_double, C.c_double]
+            getattr(L, name).restype = C.c_double
         _lib = L
     return _lib
 
@@ -189,3 +194,45 @@ def norm_view(pol, mag, los):
     out = np.empty(7)
     lib().orc_norm_view(pol, dptr(mag), dptr(los), dptr(out))
     return out
+
+
+def background(f, T):
+    """from_temp (src/m_background.cc:55-63): (I_bkg [nf,4], dB/dT [nf])."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    I = np.empty((len(f), 4))
+    dB = np.empty(len(f))
+    _check(lib().orc_background(len(f), dptr(f), float(T), dptr(I), dptr(dB)))
+    return I, dB
+
+
+def observer(f, obs: abi.Observer, P, I, dI):
+    """Steps 2-5 of the observer epilogue: returns (I transformed [nf,4], Jx [nx,nf,4], y [nch], Jy [nch,nx])."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    nf = len(f)
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    np_ = P.shape[1]
+    dI = None if dI is None else np.ascontiguousarray(dI, dtype=np.float64)
+    nq = 0 if dI is None else dI.shape[2]
+    d = obs.desc(np_, nq)
+    Io = np.array(I, dtype=np.float64, order="C", copy=True)
+    Jx = np.zeros((obs.nx, nf, 4))
+    y = np.zeros(d.n_channels)
+    Jy = np.zeros((d.n_channels, obs.nx))
+    _check(lib().orc_observer(np_, nf, nq, dptr(f), C.byref(d), dptr(P), dptr(Io), dptr(dI), dptr(Jx), dptr(y), dptr(Jy)))
+    return Io, Jx, y, Jy
+
+
+def invplanck(i, f):
+    return lib().orc_invplanck(float(i), float(f))
+
+
+def dinvplanckdI(i, f):
+    return lib().orc_dinvplanckdI(float(i), float(f))
+
+
+def invrayjean(i, f):
+    return lib().orc_invrayjean(float(i), float(f))
+
+
+def dplanck_dt(f, t):
+    return lib().orc_dplanck_dt(float(f), float(t))

@@ -271,3 +271,75 @@ def test_oracle_wind_shift_factor(orc):
     atm.wind = np.array([[300.0, -200.0, 0.0]])  # horizontal wind, vertical path: no shift at all
     K2, _ = orc.propmat_levels(c.cat, c.f, atm)
     np.testing.assert_allclose(K2, K0, rtol=1e-9)
+
+
+def test_unit_conversion_functions_against_their_definitions(orc):
+    """invplanck / dinvplanckdI / invrayjean / dplanck_dt of the transform operators and the surface-blackbody
+    Jacobian (physics_funcs.cc:76-83,153-158,172-176,254-263), pinned to closed forms evaluated with mpmath-free
+    numpy in extended precision: B(invplanck(I)) == I, d invplanck/dI by a centred difference, Rayleigh-Jeans law."""
+    h, k, c = 6.62607015e-34, 1.380649e-23, 299792458.0
+    for f in (1e9, 89e9, 183.31e9, 2e12, 30e12):
+        for T in (2.7255, 77.0, 250.0, 310.0):
+            B = float(orc.planck(np.array([f]), T)[0])
+            assert orc.invplanck(B, f) == pytest.approx(T, rel=1e-13)
+            eps = 1e-5 * B
+            fd = (orc.invplanck(B + eps, f) - orc.invplanck(B - eps, f)) / (2 * eps)
+            assert orc.dinvplanckdI(B, f) == pytest.approx(fd, rel=1e-8)
+            assert orc.dinvplanckdI(B, f) * orc.dplanck_dt(f, T) == pytest.approx(1.0, rel=1e-12)
+            dT = 1e-4 * T
+            fdB = (float(orc.planck(np.array([f]), T + dT)[0]) - float(orc.planck(np.array([f]), T - dT)[0])) / (2 * dT)
+            assert orc.dplanck_dt(f, T) == pytest.approx(fdB, rel=1e-6)
+        assert orc.invrayjean(3e-15, f) == pytest.approx(3e-15 * c * c / (2 * k * f * f), rel=1e-15)
+    assert h > 0
+
+
+def test_oracle_observer_epilogue_against_numpy(orc):
+    """orc_observer (m_rad.cc:26-127, spectral_radiance_transform_operator.cc:8-122, obsel.cpp:246-279) against an
+    independent dense numpy formulation on random inputs: Jx = W^T dI + P_bkg (w dB/dT e_I), unit scaling, y = S I."""
+    rng = np.random.default_rng(3)
+    nf, np_, nq, nx = 17, 5, 2, 7
+    f = np.linspace(50e9, 60e9, nf)
+    P = rng.normal(size=(nf, np_, 4, 4)) * 0.3
+    I = np.abs(rng.normal(size=(nf, 4))) * 1e-15
+    I[:, 0] += 3e-15
+    I[:, 1:] *= 0.05
+    dI = rng.normal(size=(nf, np_, nq, 4)) * 1e-17
+    path_map = [[[(int(rng.integers(nx)), float(rng.uniform(0, 1))) for _ in range(int(rng.integers(0, 3)))]
+                 for _ in range(nq)] for _ in range(np_)]
+    channels = [[(int(j), tuple(rng.normal(size=4))) for j in sorted(rng.choice(nf, 5, replace=False))] for _ in range(3)]
+    Tb = 288.0
+    for unit in ("unit", "RJBT", "PlanckBT", "W_m2_m_sr", "W_m2_m1_sr"):
+        obs = abi.Observer(nx=nx, path_map=path_map, bkg_T=Tb, bkg_rows=[(6, 0.7), (2, 0.3)], unit=unit, n_real=1.0003,
+                           channels=channels)
+        Io, Jx, y, Jy = orc.observer(f, obs, P.reshape(nf, np_, 16), I, dI)
+        # dense restatement
+        W = np.zeros((nx, np_, nq))
+        for ip in range(np_):
+            for t in range(nq):
+                for (x, w) in path_map[ip][t]:
+                    W[x, ip, t] += w
+        ref = np.einsum("xpt,fptc->xfc", W, dI)
+        _, dB = orc.background(f, Tb)
+        for (x, w) in obs.bkg_rows:
+            ref[x] += P[:, np_ - 1, :, 0] * (w * dB)[:, None]
+        n2 = 1.0003 ** 2
+        if unit == "PlanckBT":
+            Iref = orc.planck_tb(f, I)
+            d = np.empty((nf, 4))
+            for j in range(nf):
+                d[j, 0] = orc.dinvplanckdI(I[j, 0], f[j])
+                for c in range(1, 4):
+                    d[j, c] = orc.dinvplanckdI(0.5 * (I[j, 0] + I[j, c]), f[j]) - orc.dinvplanckdI(0.5 * (I[j, 0] - I[j, c]), f[j])
+        else:
+            s = {"unit": n2 * np.ones(nf), "RJBT": 299792458.0 ** 2 / (2 * 1.380649e-23 * f * f),
+                 "W_m2_m_sr": f * f / 299792458.0 * n2, "W_m2_m1_sr": n2 * 299792458.0 * np.ones(nf)}[unit]
+            Iref, d = I * s[:, None], np.repeat(s[:, None], 4, 1)
+        ref = ref * d[None]
+        np.testing.assert_allclose(Io, Iref, rtol=1e-13)
+        np.testing.assert_allclose(Jx, ref, rtol=1e-12, atol=1e-14 * np.abs(ref).max())
+        S = np.zeros((3, nf, 4))
+        for ch, ent in enumerate(channels):
+            for (j, w4) in ent:
+                S[ch, j] += w4
+        np.testing.assert_allclose(y, np.einsum("cfs,fs->c", S, Iref), rtol=1e-12, atol=1e-14 * np.abs(Iref).max())
+        np.testing.assert_allclose(Jy, np.einsum("cfs,xfs->cx", S, ref), rtol=1e-11, atol=1e-13 * np.abs(ref).max())

@@ -49,6 +49,7 @@ struct ab200_path {
   const ab200_catalog* cat = nullptr;
   int64_t nf = 0, k_pitch = 0;
   int32_t np = 0, nq = 0;
+  int32_t np_cap = 0;  // levels the workspace was created for; an upload may bring fewer (ragged batches of paths)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
 
@@ -164,6 +165,7 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->cat = cat;
   p->nf = nf;
   p->np = np;
+  p->np_cap = np;
   p->nq = nq;
   p->k_pitch = (nf + 127) / 128 * 128;
   AB_CUDA(cudaSetDevice(cat->device));
@@ -246,9 +248,11 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
                       uint32_t flags) {
   if (!p || !f || !atm) return set_error(AB200_ERR_INVALID, "ab200_path_upload: null argument");
   const ab200_catalog* cat = p->cat;
+  if (atm->np < 0 || atm->np > p->np_cap)
+    return set_error(AB200_ERR_INVALID, "atm path has " + std::to_string(atm->np) + " levels, the workspace was created for " +
+                                            std::to_string(p->np_cap));
+  p->np = atm->np;  // ragged batches: a workspace created for the longest path takes every shorter one
   const int np = p->np;
-  if (atm->np != np)
-    return set_error(AB200_ERR_INVALID, "atm path has " + std::to_string(atm->np) + " levels, workspace " + std::to_string(np));
   if (f_level_stride != 0 && f_level_stride != p->nf)
     return set_error(AB200_ERR_INVALID, "f_level_stride must be 0 (shared grid) or nf (one grid per level)");
   if (rte_option != AB200_RTE_CONSTANT && rte_option != AB200_RTE_LINSRC && rte_option != AB200_RTE_LINPROP)
@@ -283,11 +287,12 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   }
 
   const size_t snp = static_cast<size_t>(np);
+  const size_t scap = static_cast<size_t>(p->np_cap);  // the packed arrays are laid out for the capacity
   double* h = p->h_small;
-  double *hT = h, *hP = hT + snp, *hH = hP + snp, *hv = hH + snp, *hi = hv + snp * cat->n_species,
-         *hQ = hi + snp * cat->n_isot, *hn = hQ + snp * cat->n_isot, *hfr = hn + snp * 28, *hr = hfr + snp * 2,
-         *hdQ = hr + snp, *hdr = hdQ + snp * cat->n_isot, *hiT = hdr + 2 * snp * p->nq, *hff = hiT + snp;
-  std::fill(hdr, hdr + 2 * snp * p->nq, 0.0);
+  double *hT = h, *hP = hT + scap, *hH = hP + scap, *hv = hH + scap, *hi = hv + scap * cat->n_species,
+         *hQ = hi + scap * cat->n_isot, *hn = hQ + scap * cat->n_isot, *hfr = hn + scap * 28, *hr = hfr + scap * 2,
+         *hdQ = hr + scap, *hdr = hdQ + scap * cat->n_isot, *hiT = hdr + 2 * scap * p->nq, *hff = hiT + scap;
+  std::fill(hdr, hdr + 2 * scap * p->nq, 0.0);
   for (int ip = 0; ip < np; ip++) {
     if (!(atm->T[ip] > 0) || !(atm->P[ip] >= 0))
       return set_error(AB200_ERR_INVALID, "level " + std::to_string(ip) + ": temperature must be > 0 and pressure >= 0");

@@ -276,6 +276,7 @@ class Path:
 
     def __init__(self, cat: Catalog, nf: int, np_: int, nq: int = 0, stream=None):
         self.cat, self.nf, self.np_, self.nq = cat, int(nf), int(np_), int(nq)
+        self.np_cap = int(np_)
         self._h = C.c_void_p()
         check(lib().ab200_path_create(cat.handle, self.nf, self.np_, self.nq, C.byref(self._h)))
         if stream is not None:
@@ -284,7 +285,8 @@ class Path:
     def upload(self, f, atm: AtmPath, r, I_bkg, rte_option="linsrc", targets=(), select_species=abi.SPECIES_BATH,
                no_negative_absorption=1, hse_derivative=0, flags=0):
         f, stride, nf = _f_arg(f, atm.np_)
-        assert nf == self.nf and atm.np_ == self.np_
+        assert nf == self.nf and atm.np_ <= self.np_cap, "the workspace takes paths of up to np_cap levels"
+        self.np_ = atm.np_
         tg, _ = make_targets(targets)
         self._keep = (f, atm, np.ascontiguousarray(r, dtype=np.float64),
                       None if I_bkg is None else np.ascontiguousarray(I_bkg, dtype=np.float64))
@@ -359,3 +361,59 @@ class Path:
             self.close()
         except Exception:
             pass
+
+
+def measurement_vecFromSensor(abs_bands, freq_grid, simulations, jac_targets=(), rte_option="linsrc",
+                              no_negative_absorption=1, hse_derivative=0, n_workspaces=2):
+    """``measurement_vecFromSensor`` (src/m_rad.cc:301-362, the ``low_memory`` loop over ``SensorSimulations``) for
+    clear-sky emission observers sharing one frequency grid: every simulation is one propagation path
+    ``(atm_path, r, Observer[, I_bkg])`` (``I_bkg`` only when the observer has no background temperature); its spectral radiance and state-space Jacobian stay on the device and only its
+    contribution to the channels comes back (``measurement_vec[iv] += obsel.sumup(...)``, :346-351).
+
+    Paths may have different numbers of levels.  ``n_workspaces`` device workspaces on their own streams are used
+    round-robin, so one path's transfers overlap the next one's kernels.  Returns ``(y [M], J [M, nx])``.
+    """
+    cat = _as_catalog(abs_bands)
+    f = np.ascontiguousarray(freq_grid, dtype=np.float64)
+    sims = list(simulations)
+    if not sims:
+        return np.zeros(0), np.zeros((0, 0))
+    tg, nq = make_targets(jac_targets)
+    M, nx = len(sims[0][2].channels), sims[0][2].nx
+    np_cap = max(s[0].np_ for s in sims)
+    y, J = np.zeros(M), np.zeros((M, nx))
+    work = [Path(cat, len(f), np_cap, nq) for _ in range(max(1, min(n_workspaces, len(sims))))]
+    busy = [False] * len(work)
+
+    def drain(k):
+        _, _, yk, Jk = work[k].download_observer(want_jx=False)
+        if yk is not None:
+            y[:] += yk
+        if Jk is not None:
+            J[:] += Jk
+        busy[k] = False
+
+    try:
+        for i, sim in enumerate(sims):
+            atm, r, obs = sim[:3]
+            if obs.bkg_T is None and len(sim) < 4:
+                raise ValueError("a simulation without background temperature needs its I_bkg")
+            if len(obs.channels) != M or obs.nx != nx:
+                raise ValueError("every simulation must address the same channels and state vector")
+            k = i % len(work)
+            if busy[k]:
+                drain(k)
+            w = work[k]
+            w.upload(f, atm, r, None if obs.bkg_T is not None else sim[3], rte_option=rte_option,
+                     targets=jac_targets, no_negative_absorption=no_negative_absorption, hse_derivative=hse_derivative)
+            w.run_propmat()
+            w.run_observer(obs)
+            busy[k] = True
+        n = len(sims)
+        for i in range(max(0, n - len(work)), n):  # the rest in the order of the simulations: a fixed summation order
+            if busy[i % len(work)]:
+                drain(i % len(work))
+    finally:
+        for w in work:
+            w.close()
+    return y, J

@@ -157,3 +157,24 @@ def test_observer_rejects_bad_input(wsm):
     path.run_observer(obs)  # still usable afterwards
     path.download_observer()
     path.close(); cat.close()
+
+
+def test_measurement_vec_from_sensor_ragged_batch(wsm, orc):
+    """measurement_vecFromSensor (src/m_rad.cc:301-362): a batch of paths of different lengths, one workspace pair,
+    only the channel contributions leave the device; against the sum of the oracle's per-path results."""
+    rng = np.random.default_rng(8)
+    base = synth.tiny_case(nl=64, nf=200, np_=7, targets=TARGETS)
+    sims, yref, Jref = [], 0.0, 0.0
+    for k, np_ in enumerate((7, 4, 6, 5, 7)):
+        c = synth.tiny_case(nl=64, nf=200, np_=np_, targets=TARGETS)
+        c.atm.T = c.atm.T + 0.7 * k  # different paths see different atmospheres
+        obs = _observer(c, 2, "PlanckBT", rng, bkg_T=280.0 + k)
+        sims.append((c.atm, c.r, obs))
+        _, _, y, Jy = _oracle(orc, c, TARGETS, obs)
+        yref, Jref = yref + y, Jref + Jy
+    y, J = wsm.measurement_vecFromSensor(base.cat, base.f, sims, jac_targets=TARGETS)
+    np.testing.assert_allclose(y, yref, rtol=1e-9)
+    assert np.abs(J - Jref).max() <= 2e-7 * np.abs(Jref).max()
+    # one workspace, same numbers bit for bit (the order of accumulation is the order of the simulations)
+    y1, J1 = wsm.measurement_vecFromSensor(base.cat, base.f, sims, jac_targets=TARGETS, n_workspaces=1)
+    assert np.array_equal(y, y1) and np.array_equal(J, J1)

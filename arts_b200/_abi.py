@@ -21,7 +21,7 @@ LINESHAPE_VP_LTE, LINESHAPE_OTHER = 0, 1
 CUTOFF_NONE, CUTOFF_BYLINE = 0, 1
 RTE_CONSTANT, RTE_LINSRC, RTE_LINPROP = 0, 1, 2
 TARGET_T, TARGET_VMR = 0, 1
-FLAG_K_ZERO_INIT, FLAG_TRAN_EXACT, FLAG_RETURN_K = 1, 2, 4
+FLAG_K_ZERO_INIT, FLAG_TRAN_EXACT, FLAG_RETURN_K, FLAG_NO_EMISSION = 1, 2, 4, 8
 
 RTE_OPTIONS = {"constant": RTE_CONSTANT, "linsrc": RTE_LINSRC, "lintau": RTE_LINSRC, "linprop": RTE_LINPROP}
 
@@ -368,6 +368,7 @@ SIG_PROPMAT_LEVELS_CORE = [
 SIG_TRAMAT = [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp, C.c_int32, C.c_uint32, _dp, _dp, _dp, _dp, _dp]
 SIG_SRCVEC = [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, C.c_int64, _dp, C.c_int32, _dp, _dp]
 SIG_RTE = [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+SIG_TRANSMISSION = [C.c_int32, C.c_int64, C.c_int32, _dp, _dp, _dp, _dp, _dp, _dp]
 SIG_CLEARSKY_CORE = [
     C.c_int64, _dp, C.c_int64, C.POINTER(AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(Target), _dp,
     C.c_int32, C.c_int32, _dp, C.c_uint32, _dp, _dp, _dp,

@@ -54,6 +54,7 @@ def lib():
     L.ab200_tramat.argtypes = abi.SIG_TRAMAT
     L.ab200_srcvec.argtypes = abi.SIG_SRCVEC
     L.ab200_rte_emission.argtypes = abi.SIG_RTE
+    L.ab200_rte_transmission.argtypes = abi.SIG_TRANSMISSION
     L.ab200_clearsky_emission.argtypes = [_vp] + abi.SIG_CLEARSKY_CORE
     L.ab200_planck_tb.argtypes = [C.c_int64, _dp, _dp]
     L.ab200_path_create.argtypes = [_vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(_vp)]

@@ -547,6 +547,7 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
   sp.T = p->d_T; sp.invT = p->d_invT; sp.ffac = p->d_ffac; sp.r = p->d_r; sp.I_bkg = p->d_Ibkg; sp.I = p->d_I; sp.rte_option = p->rte_option;
   sp.tran_exact = (p->flags & AB200_FLAG_TRAN_EXACT) ? 1 : 0;
   sp.I_lev = p->nq > 0 ? p->d_Ilev : nullptr;
+  sp.no_emission = (p->flags & AB200_FLAG_NO_EMISSION) ? 1 : 0;
   sp.flags = p->d_flags;
   sp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded) ? 1 : 0;  // only mode-0 (real, pol = no) segments wrote K
   {
@@ -559,6 +560,7 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
     jp.np = p->np; jp.nq = p->nq; jp.nf = p->nf; jp.K = p->d_K; jp.dK = p->d_dK; jp.k_pitch = p->k_pitch;
     jp.f = p->d_f; jp.f_stride = p->f_stride; jp.ffac = p->d_ffac; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
     jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option; jp.flags = p->d_flags;
+    jp.no_emission = (p->flags & AB200_FLAG_NO_EMISSION) ? 1 : 0;
     if (obs) {  // x-space accumulation inside the pass; the per-level dI is not written
       jp.dI = nullptr;
       jp.Jx = static_cast<double*>(p->o_Jx.p);
@@ -938,6 +940,37 @@ int ab200_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, c
                                    ddI_.p, 0));
     AB_CUDA(cudaMemcpy(dI, ddI_.p, nj * nq * sizeof(double), cudaMemcpyDeviceToHost));
   }
+  AB_CUDA(cudaMemcpy(I, dI_.p, nf * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+int ab200_rte_transmission(int32_t np, int64_t nf, int32_t nq, const double* T, const double* P, const double* dT,
+                           const double* I_bkg, double* I, double* dI) {
+  if (np < 0 || nf < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_rte_transmission: negative size");
+  if (nf == 0) return AB200_OK;
+  if (!P || !I_bkg || !I) return set_error(AB200_ERR_INVALID, "ab200_rte_transmission: null argument");
+  if (nq > 0 && (!T || !dT || !dI)) return set_error(AB200_ERR_INVALID, "ab200_rte_transmission: null Jacobian argument with nq > 0");
+  if (np == 0) return AB200_OK;  // rtepack_rtestep.cc:465
+  const size_t nm = static_cast<size_t>(np) * nf * 16, nj = static_cast<size_t>(np) * nf * 4;
+  DevBuf dP_, dB_, dI_;
+  AB_TRY(dP_.alloc(nm)); AB_TRY(dB_.alloc(nf * 4)); AB_TRY(dI_.alloc(nf * 4));
+  AB_CUDA(cudaMemcpy(dP_.p, P, nm * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(dB_.p, I_bkg, nf * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  if (nq > 0) {
+    // the derivative of the transmitted radiance = the `constant` emission recursion with J = 0, dJ = 0
+    const size_t nd = 2 * nm * nq;
+    DevBuf dT_, ddT_, dJ_, ddJ_, ddI_;
+    AB_TRY(dT_.alloc(nm)); AB_TRY(ddT_.alloc(nd)); AB_TRY(dJ_.alloc(nj)); AB_TRY(ddJ_.alloc(nj * nq)); AB_TRY(ddI_.alloc(nj * nq));
+    AB_CUDA(cudaMemcpy(dT_.p, T, nm * sizeof(double), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemcpy(ddT_.p, dT, nd * sizeof(double), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMemset(dJ_.p, 0, nj * sizeof(double)));
+    AB_CUDA(cudaMemset(ddJ_.p, 0, nj * nq * sizeof(double)));
+    AB_CUDA(cudaMemset(ddI_.p, 0, nj * nq * sizeof(double)));  // dI = 0, rtepack_rtestep.cc:467
+    AB_TRY(launch_rte_emission_jac(false, np, nf, nq, dT_.p, nullptr, dP_.p, ddT_.p, nullptr, dJ_.p, ddJ_.p, dB_.p, dI_.p,
+                                   ddI_.p, 0));
+    AB_CUDA(cudaMemcpy(dI, ddI_.p, nj * nq * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  AB_TRY(launch_transmission_apply(np, nf, dP_.p, dB_.p, dI_.p, 0));  // I = P[np-1] I0, :469-470
   AB_CUDA(cudaMemcpy(I, dI_.p, nf * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   return AB200_OK;
 }

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
       af3       = planck_a * (f * f * f);
       ffac_prev = ffac;
     }
-    const double j = SCALAR ? (k.A == 0.0 ? 0.0 : planck_fast(f, af3, p.invT[lev])) : source_I(k, f, p.T[lev]);
+    const double j = p.no_emission ? 0.0 : SCALAR ? (k.A == 0.0 ? 0.0 : planck_fast(f, af3, p.invT[lev])) : source_I(k, f, p.T[lev]);
     if (n > 0) {
       if (p.I_lev && active) {  // radiance arriving at level lev+1 (Jacobian pass B)
         double2* o = reinterpret_cast<double2*>(p.I_lev + (int64_t(lev + 1) * p.nf + iv) * 4);
@@ -241,6 +241,24 @@ __global__ void planck_tb_kernel(int64_t nf, const double* __restrict__ f, doubl
   v[1] = invplanck(0.5 * (v0 + v1), fj) - invplanck(0.5 * (v0 - v1), fj);
   v[2] = invplanck(0.5 * (v0 + v2), fj) - invplanck(0.5 * (v0 - v2), fj);
   v[3] = invplanck(0.5 * (v0 + v3), fj) - invplanck(0.5 * (v0 - v3), fj);
+}
+
+// rte_transmission forward part, rtepack_rtestep.cc:469-470: I = P[iv][np-1] * I0
+__global__ void transmission_apply_kernel(int np, int64_t nf, const double* __restrict__ P, const double* __restrict__ I_bkg,
+                                          double* __restrict__ I) {
+  const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (iv >= nf) return;
+  double o[4];
+  mat_vec(P + (iv * np + (np - 1)) * 16, I_bkg + iv * 4, o);
+  I[iv * 4 + 0] = o[0]; I[iv * 4 + 1] = o[1]; I[iv * 4 + 2] = o[2]; I[iv * 4 + 3] = o[3];
+}
+
+int launch_transmission_apply(int np, int64_t nf, const double* P, const double* I_bkg, double* I, cudaStream_t stream) {
+  if (nf == 0 || np == 0) return 0;
+  transmission_apply_kernel<<<static_cast<unsigned>((nf + 127) / 128), 128, 0, stream>>>(np, nf, P, I_bkg, I);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_planck_tb(int64_t nf, const double* f, double* I, cudaStream_t stream) {

@@ -23,6 +23,7 @@ struct StokesParams {
   int32_t tran_exact;
   int* flags;          // device error flags (bit 2: polarised layer with rte_option linprop)
   int32_t scalar;      // K is known to have only A != 0 (no polarised segment was summed): scalar fast path
+  int32_t no_emission; // J = 0 at every level: pure transmission (AB200_FLAG_NO_EMISSION)
 };
 
 // fused Jacobian pass B (stokes_jac.cu)
@@ -53,6 +54,7 @@ struct StokesJacParams {
   int32_t it;           // index of the temperature target or -1
   int32_t rte_option;
   int* flags;
+  int32_t no_emission;  // J = 0, dJ = 0 at every level
 };
 
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream);
@@ -63,6 +65,7 @@ int launch_rte_emission_jac(int linsrc, int np, int64_t nf, int nq, const double
                             const double* dT, const double* dL, const double* J, const double* dJ, const double* I_bkg,
                             double* I, double* dI, cudaStream_t stream);
 int launch_planck_tb(int64_t nf, const double* f, double* I, cudaStream_t stream);
+int launch_transmission_apply(int np, int64_t nf, const double* P, const double* I_bkg, double* I, cudaStream_t stream);
 
 // observer epilogue (observer.cu)
 int launch_background_planck(int64_t nf, const double* f, double T, double* I_bkg, cudaStream_t stream);

@@ -246,11 +246,12 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
 
   Propmat k0 = load_propmat(p.K + (int64_t(0) * p.k_pitch + iv) * 7);
   double f0  = p.ffac[0] * p.f[iv];
-  double j0  = k0.is_rotational() ? 0.0 : planck(f0, p.T[0]);
+  const bool emit_src = !p.no_emission;
+  double j0  = (k0.is_rotational() || !emit_src) ? 0.0 : planck(f0, p.T[0]);
   for (int i = 0; i + 1 < np; i++) {
     const Propmat k1 = load_propmat(p.K + (int64_t(i + 1) * p.k_pitch + iv) * 7);
     const double f1  = p.ffac[i + 1] * p.f[int64_t(i + 1) * p.f_stride + iv];
-    const double j1  = k1.is_rotational() ? 0.0 : planck(f1, p.T[i + 1]);
+    const double j1  = (k1.is_rotational() || !emit_src) ? 0.0 : planck(f1, p.T[i + 1]);
     const double ri  = p.r[i];
     Tran t;
     t.init(k0, k1, ri, false);
@@ -280,8 +281,8 @@ __global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
       const Propmat dk1 = load_propmat(p.dK + ((int64_t(i + 1) * nq + q) * p.k_pitch + iv) * 7);
       const double dr0 = p.dr[int64_t(i) * nq + q];
       const double dr1 = p.dr[(int64_t(np - 1) + i) * nq + q];
-      const double dj0[4] = {(q == p.it && !k0.is_rotational()) ? dplanck_dt(f0, p.T[i]) : 0.0, 0.0, 0.0, 0.0};
-      const double dj1[4] = {(q == p.it && !k1.is_rotational()) ? dplanck_dt(f1, p.T[i + 1]) : 0.0, 0.0, 0.0, 0.0};
+      const double dj0[4] = {(q == p.it && emit_src && !k0.is_rotational()) ? dplanck_dt(f0, p.T[i]) : 0.0, 0.0, 0.0, 0.0};
+      const double dj1[4] = {(q == p.it && emit_src && !k1.is_rotational()) ? dplanck_dt(f1, p.T[i + 1]) : 0.0, 0.0, 0.0, 0.0};
       double dT0[16], dT1[16], dL0[16], dL1[16];
       t.deriv(Tm, k0, k1, dk0, ri, dr0, dT0);
       t.deriv(Tm, k0, k1, dk1, ri, dr1, dT1);

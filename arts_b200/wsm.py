@@ -213,6 +213,23 @@ def spectral_radStepByStepEmission(spectral_tramat: TransmittanceMatrix, J, dJ, 
     return I, dI
 
 
+def spectral_radCumulativeTransmission(spectral_tramat: TransmittanceMatrix, spectral_rad_bkg):
+    """src/m_spectral_radiance.cc:49-74 (``rte_transmission``, rtepack_rtestep.cc:456-503): the background radiance
+    seen through the path, ``P[:, np-1] @ spectral_rad_bkg``, and its transmission-only ``spectral_rad_jac_path``."""
+    P = spectral_tramat.P
+    nf, np_ = P.shape[:2]
+    dT = spectral_tramat.dT
+    nq = 0 if dT is None else dT.shape[3]
+    bkg = np.ascontiguousarray(spectral_rad_bkg, dtype=np.float64)
+    if bkg.shape[0] != nf:
+        raise ValueError(f"Bad background radiance size: spectral_rad_bkg: {bkg.shape[0]}, expected: {nf}")
+    I = np.empty((nf, 4))
+    dI = np.zeros((nf, np_, nq, 4))
+    check(lib().ab200_rte_transmission(np_, nf, nq, dptr(spectral_tramat.T), dptr(P), dptr(dT if nq else None), dptr(bkg),
+                                       dptr(I), dptr(dI)))
+    return I, dI
+
+
 def spectral_radClearskyEmission(abs_bands, freq_grid_path, atm_path: AtmPath, r, spectral_rad_bkg,
                                  rte_option="linsrc", jac_targets=(), select_species=abi.SPECIES_BATH,
                                  no_negative_absorption=1, hse_derivative=0, flags=0, return_propmat=False):

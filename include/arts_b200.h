@@ -74,6 +74,7 @@ enum { AB200_TARGET_T = 0, AB200_TARGET_VMR = 1 };
 #define AB200_FLAG_TRAN_EXACT 2u  /* use the exact Cayley-Hamilton eigen pair instead of the reference's \
                                      literal rtepack_transmission.cc:64-70 arithmetic */
 #define AB200_FLAG_RETURN_K 4u    /* clearsky_emission: also copy K back to the host */
+#define AB200_FLAG_NO_EMISSION 8u /* fused path: pure transmission, J = 0 at every level (spectral_radCumulativeTransmission) */
 
 /* ---- catalog: AbsorptionBands flattened (lbl_data.h:31-68,196-300) ----- */
 typedef struct ab200_catalog_desc {
@@ -188,6 +189,15 @@ int ab200_clearsky_emission(const ab200_catalog *cat, int64_t nf, const double *
                             int32_t nq, const ab200_target *targets, const double *r, int32_t hse_derivative,
                             int32_t rte_option, const double *I_bkg, uint32_t flags, double *I, double *dI,
                             double *K_out);
+
+/* spectral_radCumulativeTransmission (src/m_spectral_radiance.cc:49-74 -> rte_transmission,
+ * rtepack_rtestep.cc:456-503): spectral_rad = P[.,np-1] * spectral_rad_bkg and the transmission-only
+ * spectral_rad_jac_path.  T, P [nf][np][16], dT [2][nf][np][nq][16] as produced by ab200_tramat.
+ * The Jacobian is the derivative of the transmitted radiance (the emission recursion with J = 0); the reference's
+ * loop indexes the layer transmittance as Ts[i+1][iv] (frequency and level swapped) and files the dT[1] term one
+ * level early, so for nq > 0 there is no defined reference output to be equal to. */
+int ab200_rte_transmission(int32_t np, int64_t nf, int32_t nq, const double *T, const double *P, const double *dT,
+                           const double *I_bkg, double *I, double *dI);
 
 /* spectral_radApplyUnitFromSpectralRadiance with PlanckBT
  * (spectral_radiance_transform_operator.cc:46-87): in place on I [nf][4]. */

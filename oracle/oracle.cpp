@@ -1503,6 +1503,42 @@ int orc_rte_emission(int32_t rte_option, int32_t np, int64_t nf, int32_t nq, con
   return 0;
 }
 
+// rte_transmission, rtepack_rtestep.cc:456-503 (spectral_radCumulativeTransmission, m_spectral_radiance.cc:49-74).
+// Forward part literal: I = P[iv][N-1] * I0 (:469-470).  Jacobian: the reference's loop (:476-491) reads the layer
+// transmittance as Ts[i + 1][iv] - frequency and level swapped, out of bounds unless nf == np - and adds the
+// dTs[1, iv, i] term to level i - 1 instead of i, so it has no defined output to restate.  What is restated here is
+// its evident intent, the exact product rule of I = T_1 ... T_{N-1} I0 in the reference's own conventions
+// (dT[0][i] = dT_{i+1}/dx_i, dT[1][i] = dT_i/dx_i; suffix product P, prefix Pi):
+//   dI[i] += Pi[i] dT[0][i] (T_{i+2} ... T_{N-1}) I0  +  Pi[i-1] dT[1][i] (T_{i+1} ... T_{N-1}) I0
+// pinned by tests/test_oracle_pins.py against perturbed forward runs and against rte_emission with J = 0.
+int orc_rte_transmission(int32_t np, int64_t nf, int32_t nq, const double* T, const double* P, const double* dT,
+                         const double* I_bkg, double* I, double* dI) {
+  if (np == 0) return 0;
+  auto dXi = [&](int t, Index iv, int i, int j) {
+    return load_mm(dT + (((static_cast<Index>(t) * nf + iv) * np + i) * nq + j) * 16);
+  };
+#pragma omp parallel for
+  for (Index iv = 0; iv < nf; iv++) {
+    const stokvec src = load_sv(I_bkg + iv * 4);
+    store(I + iv * 4, load_mm(P + (iv * np + (np - 1)) * 16) * src);
+    if (nq == 0) continue;
+    std::vector<stokvec> dIv(static_cast<size_t>(np) * nq);
+    muelmat Sfx = 1.0;  // T_{i+2} ... T_{N-1}
+    for (int i = np - 2; i >= 0; i--) {
+      const muelmat R = load_mm(T + (iv * np + i + 1) * 16) * Sfx;  // T_{i+1} ... T_{N-1}
+      const muelmat Pm = load_mm(P + (iv * np + i) * 16);
+      for (int iq = 0; iq < nq; iq++) {
+        dIv[i * nq + iq]       = dIv[i * nq + iq] + Pm * (dXi(0, iv, i, iq) * (Sfx * src));
+        dIv[(i + 1) * nq + iq] = dIv[(i + 1) * nq + iq] + Pm * (dXi(1, iv, i + 1, iq) * (Sfx * src));
+      }
+      Sfx = R;
+    }
+    for (int i = 0; i < np; i++)
+      for (int q = 0; q < nq; q++) store(dI + ((iv * np + i) * nq + q) * 4, dIv[i * nq + q]);
+  }
+  return 0;
+}
+
 // The canonical sequence of spectral_radClearskyEmission
 // (workspace_meta_methods.cpp:166-181) from spectral_propmat_pathFromPath on,
 // un-fused exactly like the reference (T, L, P, dT, dL, J, dJ materialised).

@@ -43,6 +43,7 @@ def lib():
         L.orc_tramat.argtypes = abi.SIG_TRAMAT
         L.orc_srcvec.argtypes = abi.SIG_SRCVEC
         L.orc_rte_emission.argtypes = abi.SIG_RTE
+        L.orc_rte_transmission.argtypes = abi.SIG_TRANSMISSION
         L.orc_clearsky_emission.argtypes = [C.POINTER(abi.CatalogDesc)] + abi.SIG_CLEARSKY_CORE
         L.orc_planck_tb.argtypes = [C.c_int64, dp, dp]
         L.orc_planck.argtypes = [C.c_int64, dp, C.c_double, dp]
@@ -132,6 +133,18 @@ def rte_emission(rte_option, T, L, P, dT, dL, J, dJ, I_bkg):
     dI = np.empty((nf, np_, nq, 4))
     _check(lib().orc_rte_emission(abi.RTE_OPTIONS[rte_option], np_, nf, nq, dptr(T), dptr(L), dptr(P), dptr(dT),
                                   dptr(dL), dptr(J), dptr(dJ), dptr(I_bkg), dptr(I), dptr(dI)))
+    return I, dI
+
+
+def rte_transmission(T, P, dT, I_bkg):
+    """rte_transmission (rtepack_rtestep.cc:456-503): (I [nf,4], dI [nf,np,nq,4])."""
+    nf, np_, _ = P.shape
+    nq = 0 if dT is None else dT.shape[3]
+    I_bkg = np.ascontiguousarray(I_bkg, dtype=np.float64)
+    I = np.empty((nf, 4))
+    dI = np.zeros((nf, np_, nq, 4))
+    _check(lib().orc_rte_transmission(np_, nf, nq, dptr(np.ascontiguousarray(T)), dptr(np.ascontiguousarray(P)),
+                                      dptr(None if dT is None else np.ascontiguousarray(dT)), dptr(I_bkg), dptr(I), dptr(dI)))
     return I, dI
 
 

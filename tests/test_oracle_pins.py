@@ -343,3 +343,30 @@ def test_oracle_observer_epilogue_against_numpy(orc):
                 S[ch, j] += w4
         np.testing.assert_allclose(y, np.einsum("cfs,fs->c", S, Iref), rtol=1e-12, atol=1e-14 * np.abs(Iref).max())
         np.testing.assert_allclose(Jy, np.einsum("cfs,xfs->cx", S, ref), rtol=1e-11, atol=1e-13 * np.abs(ref).max())
+
+
+def test_oracle_transmission_against_emission_with_zero_source_and_perturbation(orc):
+    """rte_transmission (rtepack_rtestep.cc:456-503).  The forward part is literal.  The reference's Jacobian loop reads
+    Ts[i + 1][iv] with frequency and level swapped, so the oracle restates its intent; pinned here two ways: it equals
+    the `constant` emission recursion with J = 0, dJ = 0 (same product rule, independent code), and a perturbed run."""
+    c = synth.tiny_case(nl=40, nf=50, np_=6)
+    tg = (("T",), ("VMR", 1))
+    K, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    T, L, P, dT, dL = orc.tramat(K, dK, c.r, None, "constant")
+    I0 = np.zeros((c.nf, 4)); I0[:, 0] = 1.0; I0[:, 1] = 0.2
+    I, dI = orc.rte_transmission(T, P, dT, I0)
+    np.testing.assert_allclose(I, np.einsum("fij,fj->fi", P[:, -1].reshape(-1, 4, 4), I0), rtol=1e-15)
+    Z, dZ = np.zeros((c.nf, c.np_, 4)), np.zeros((c.nf, c.np_, 2, 4))
+    Ie, dIe = orc.rte_emission("constant", T, L, P, dT, dL, Z, dZ, I0)
+    np.testing.assert_allclose(I, Ie, rtol=1e-13)
+    np.testing.assert_allclose(dI, dIe, rtol=1e-11, atol=1e-15 * np.abs(dIe).max())
+    assert np.abs(dI).max() > 0
+    for lev in (0, 2, 5):
+        v = c.atm.vmr[lev, 1]
+        res = []
+        for sgn in (+1, -1):
+            Kp, _ = orc.propmat_levels(c.cat, c.f, _perturbed(c, lev, species=1, dvmr=sgn * 1e-3 * v))
+            Tp, _, Pp, _, _ = orc.tramat(Kp, None, c.r, None, "constant")
+            res.append(orc.rte_transmission(Tp, Pp, None, I0)[0])
+        fd = (res[0][:, 0] - res[1][:, 0]) / (2e-3 * v)
+        np.testing.assert_allclose(dI[:, lev, 1, 0], fd, rtol=1e-4, atol=1e-6 * np.abs(dI[:, :, 1, 0]).max())

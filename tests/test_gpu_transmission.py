@@ -31,14 +31,15 @@ def test_unfused_transmission(wsm, orc, zeeman, option):
     tm = wsm.TransmittanceMatrix(option, T.reshape(c.nf, c.np_, 4, 4), None, P.reshape(c.nf, c.np_, 4, 4),
                                  dT.reshape(2, c.nf, c.np_, 2, 4, 4), None)
     I, dI = wsm.spectral_radCumulativeTransmission(tm, I0)
-    assert np.array_equal(I, Ir), "I = P[np-1] I0 is one matrix-vector product: bit-exact"
+    # one matrix-vector product per frequency; the device contracts it into FMAs
+    np.testing.assert_allclose(I, Ir, rtol=1e-14, atol=1e-15 * np.abs(Ir).max())
     for q in range(2):
         assert_jac_close(dI[:, :, q], dIr[:, :, q], rtol=1e-12, what=f"transmission dI target {q}")
     assert np.abs(dIr).max() > 0
     # no targets: only the forward part
     tm0 = wsm.TransmittanceMatrix(option, tm.T, None, tm.P, None, None)
     I2, dI2 = wsm.spectral_radCumulativeTransmission(tm0, I0)
-    assert np.array_equal(I2, Ir) and dI2.shape == (c.nf, c.np_, 0, 4)
+    assert np.array_equal(I2, I) and dI2.shape == (c.nf, c.np_, 0, 4)
     with pytest.raises(ValueError, match="Bad background radiance size"):
         wsm.spectral_radCumulativeTransmission(tm, I0[:-1])
 
@@ -46,6 +47,8 @@ def test_unfused_transmission(wsm, orc, zeeman, option):
 @pytest.mark.parametrize("zeeman", [False, True])
 def test_fused_transmission(wsm, orc, zeeman):
     c = synth.tiny_case(nl=64, nf=38 * 5 if zeeman else 300, np_=7, zeeman=zeeman)
+    if not zeeman:
+        c.cat.a *= 0.01  # optical depths of 1..6 instead of 70..650: a transmission worth comparing at 1e-9
     I0 = _sun(c.nf)
     K, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=TARGETS)
     T, L, P, dT, dL = orc.tramat(K, dK, c.r, None, "linsrc")

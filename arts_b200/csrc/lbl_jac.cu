@@ -177,7 +177,7 @@ constexpr int JAC_NT = 128;
 constexpr int JAC_R  = 2;
 constexpr int JAC_F_TILE = JAC_NT * JAC_R;
 constexpr int JAC_Q  = 4;   // targets per pass
-constexpr int JAC_BASE_FIELDS = 14;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im | y2, y^2+1/2, y2^2+1/2, y y2-1/2, s_re/sqrt(pi)
+constexpr int JAC_BASE_FIELDS = 16;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im | y2, y^2+1/2, y2^2+1/2, y y2-1/2, s_re/sqrt(pi), 2y, 2y2
 constexpr int JAC_Q_FIELDS    = 8;   // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im | dz_im + dz_fac y
 
 // dscl(f) of dt_core_calc, :990-1000
@@ -216,10 +216,42 @@ __device__ __forceinline__ void z_F_dF_far(double x, double y, cplx& z, cplx& F,
   dF = {(n.re * dz.re + n.im * dz.im) * d, (n.im * dz.re - n.re * dz.im) * d};
 }
 
+// Closed form of a far pair of a REAL line, shared by all targets.  With c = i/sqrt(pi), D1 = z^2 - 1/2,
+// D2 = (z+dz)^2 - 1/2, P = D1 D2:
+//   F = c z / D1 = c z D2 conj(P) / |P|^2,      dF = (F(z+dz) - F(z)) / dz = -c (z (z+dz) + 1/2) conj(P) / |P|^2
+// i.e. the reference's forward difference (lbl_lineshape_voigt_lte.cpp:250-268) of its nu = 2 form evaluated without the
+// subtraction, ONE reciprocal per pair.  G1 = sqrt(pi) Re F, G2 = sqrt(pi) Re dF, G3 = -sqrt(pi) Im dF, G4 = x G2; a target adds
+//   Re(ds F + (dz + dz_fac z) s dF) = A_q G1 + B_q G2 + C_q G4 + D_q G3 (+ E_q G5, G5 = sqrt(pi) Im F)
+// with A_q = Re ds / sqrt(pi), B_q = sp Re dz, C_q = sp dz_fac, D_q = sp Im(dz + dz_fac z), E_q = -Im ds / sqrt(pi),
+// sp = s / sqrt(pi): 35 FP64 instructions per pair + 4 per target (38 + 5 where some Im ds != 0).
+struct FarLine {  // y-only constants of a line
+  double y, y2, ty, ty2, cy1, cy2, yy;
+  __device__ __forceinline__ void from_y(double y_) {
+    y = y_; y2 = y + fmax(1e-4 * fabs(y), 1e-4); ty = 2.0 * y; ty2 = 2.0 * y2;
+    cy1 = y * y + 0.5; cy2 = y2 * y2 + 0.5; yy = y * y2 - 0.5;
+  }
+};
+template <bool IM>
+__device__ __forceinline__ void far_pair(const FarLine& c, double x, double x2, double& G1, double& G2, double& G3, double& G4,
+                                         double& G5) {
+  const double A  = __fma_rn(x, x, -c.cy1), B = __dmul_rn(c.ty, x);
+  const double A2 = __fma_rn(x2, x2, -c.cy2), B2 = __dmul_rn(c.ty2, x2);
+  const double Pr = __fma_rn(A, A2, -__dmul_rn(B, B2)), Pi = __fma_rn(A, B2, __dmul_rn(B, A2));
+  const double Mr = __fma_rn(x, x2, -c.yy), Mi = __fma_rn(x, c.y2, __dmul_rn(c.y, x2));
+  const double n  = far_rcp(__fma_rn(Pr, Pr, __dmul_rn(Pi, Pi)));
+  const double N2 = __fma_rn(Mi, Pr, -__dmul_rn(Mr, Pi));
+  const double N3 = __fma_rn(Mr, Pr, __dmul_rn(Mi, Pi));
+  const double Wr = __fma_rn(x, A2, -__dmul_rn(c.y, B2)), Wi = __fma_rn(x, B2, __dmul_rn(c.y, A2));
+  const double N1 = __fma_rn(Wr, Pi, -__dmul_rn(Wi, Pr));
+  G1 = __dmul_rn(N1, n); G2 = __dmul_rn(N2, n); G3 = __dmul_rn(N3, n); G4 = __dmul_rn(x, G2);
+  // sqrt(pi) Im F, only where a strength derivative has an imaginary part: the reference's d/dVMR of an ABSENT
+  // Y or G model is the sum of the broadeners' VMRs when the line has no bath broadener (lbl_lineshape_model.cpp:112, sic)
+  G5 = IM ? __dmul_rn(__fma_rn(Wr, Pr, __dmul_rn(Wi, Pi)), n) : 0.0;
+}
+
 template <int NQ>
 __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSumParams jp) {
   extern __shared__ __align__(16) double sm[];  // [JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS][TL]
-  __shared__ int tile_far;
   double* const sb = sm;
   double* const sq = sm + JAC_BASE_FIELDS * TL;
   const int tid = threadIdx.x;
@@ -259,75 +291,97 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
       const bool tile_has_cut  = jp.real_lines ? s4[4] < DBL_MAX : seg.has_cutoff != 0;
       if (dist > tile_cut * (1.0 + 1e-9)) continue;
       const int count = p.tile_count[t];
+      // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|); CTA uniform
+      const bool far = !tile_has_cut && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9);
+      const bool far_closed = far && jp.real_lines;
       __syncthreads();  // previous tile fully consumed
       // stage the tile: the records of K1 + the derivative records of this pass, SoA in shared memory
-      for (int l = tid; l < count; l += JAC_NT) {
-        const double* g = prep + t * tile_doubles();
-        const double2 a = *reinterpret_cast<const double2*>(g + (0 * TL + l) * REC_GROUP);
-        const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);
-        const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);
-        const double2 h = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP);
-        const double2 k = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP + 2);
-        sb[0 * TL + l] = a.x; sb[1 * TL + l] = m.y; sb[2 * TL + l] = n.x; sb[3 * TL + l] = n.y;
-        sb[4 * TL + l] = jp.real_lines ? 0.0 : h.y;  // s_im
-        sb[5 * TL + l] = h.x; sb[6 * TL + l] = jcom[t * TL + l]; sb[7 * TL + l] = k.x;
-        sb[8 * TL + l] = jp.real_lines ? h.y : k.y;  // cut_im | real lines: the line's cutoff [Hz]
-        {  // constants of the closed-form far path (real lines): displaced y, the y-only parts of D1, D2 and z z2 + 1/2
-          const double y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
-          sb[9 * TL + l] = y2; sb[10 * TL + l] = y * y + 0.5; sb[11 * TL + l] = y2 * y2 + 0.5; sb[12 * TL + l] = y * y2 - 0.5;
-          sb[13 * TL + l] = n.y * cst::inv_sqrt_pi;
-        }
-        const double* jt = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
+      const double* g = prep + t * tile_doubles();
+      const double* jt = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
+      bool any_im = false;
+      if (far_closed) {
+        // only what the closed form reads, with the per-line factors folded in (see far_pair)
+        for (int l = tid; l < count; l += JAC_NT) {
+          const double f0s = g[(0 * TL + l) * REC_GROUP];
+          const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
+          const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
+          const double y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4), sp = n.y * cst::inv_sqrt_pi;
+          sb[0 * TL + l] = f0s; sb[1 * TL + l] = m.y; sb[2 * TL + l] = y; sb[9 * TL + l] = y2;
+          sb[10 * TL + l] = y * y + 0.5; sb[11 * TL + l] = y2 * y2 + 0.5; sb[12 * TL + l] = y * y2 - 0.5;
+          sb[13 * TL + l] = sp; sb[14 * TL + l] = 2.0 * y; sb[15 * TL + l] = 2.0 * y2;
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-          const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
-          const double2* j1 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (1 * TL + l) * 4);
-          const double2 u0 = j0[0], u1 = j0[1], u2 = j1[0], u3 = j1[1];
-          double* o = sq + q * JAC_Q_FIELDS * TL;
-          o[0 * TL + l] = u0.x; o[1 * TL + l] = u0.y; o[2 * TL + l] = u1.x; o[3 * TL + l] = u1.y;
-          o[4 * TL + l] = u2.x; o[5 * TL + l] = u2.y; o[6 * TL + l] = u3.x;
-          o[7 * TL + l] = u1.y + u2.x * n.x;  // Im(dz + dz_fac z) does not depend on the frequency
+          for (int q = 0; q < NQ; q++) {
+            const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+            const double2 u0 = j0[0], u1 = j0[1];                      // ds_re, ds_im | dz_re, dz_im
+            const double dz_fac = jt[q * (2 * TL * 4) + (1 * TL + l) * 4];
+            double* o = sq + q * JAC_Q_FIELDS * TL;
+            o[0 * TL + l] = u0.x * cst::inv_sqrt_pi;                   // A_q: Re ds / sqrt(pi)
+            o[1 * TL + l] = -u0.y * cst::inv_sqrt_pi;                  // E_q: -Im ds / sqrt(pi)
+            any_im |= u0.y != 0.0;
+            o[2 * TL + l] = sp * u1.x;                                 // B_q
+            o[4 * TL + l] = sp * dz_fac;                               // C_q
+            o[7 * TL + l] = sp * (u1.y + dz_fac * y);                  // D_q: Im(dz + dz_fac z) does not depend on f
+          }
+        }
+      } else {
+        for (int l = tid; l < count; l += JAC_NT) {
+          const double2 a = *reinterpret_cast<const double2*>(g + (0 * TL + l) * REC_GROUP);
+          const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);
+          const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);
+          const double2 h = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP);
+          const double2 k = *reinterpret_cast<const double2*>(g + (2 * TL + l) * REC_GROUP + 2);
+          sb[0 * TL + l] = a.x; sb[1 * TL + l] = m.y; sb[2 * TL + l] = n.x; sb[3 * TL + l] = n.y;
+          sb[4 * TL + l] = jp.real_lines ? 0.0 : h.y;  // s_im
+          sb[5 * TL + l] = h.x; sb[6 * TL + l] = jcom[t * TL + l]; sb[7 * TL + l] = k.x;
+          sb[8 * TL + l] = jp.real_lines ? h.y : k.y;  // cut_im | real lines: the line's cutoff [Hz]
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+            const double2* j1 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (1 * TL + l) * 4);
+            const double2 u0 = j0[0], u1 = j0[1], u2 = j1[0], u3 = j1[1];
+            double* o = sq + q * JAC_Q_FIELDS * TL;
+            o[0 * TL + l] = u0.x; o[1 * TL + l] = u0.y; o[2 * TL + l] = u1.x; o[3 * TL + l] = u1.y;
+            o[4 * TL + l] = u2.x; o[5 * TL + l] = u2.y; o[6 * TL + l] = u3.x;
+          }
         }
       }
-      // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|)
-      if (tid == 0) tile_far = (!tile_has_cut && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9)) ? 1 : 0;
-      __syncthreads();
-      const bool far = tile_far != 0;
-      if (far && jp.real_lines) {
-        // Closed-form far path for real lines (mode-0 segments: s, ds real; only Re dX is used since npm = (1,0,...)).
-        // With c = i/sqrt(pi), D1 = z^2 - 1/2, D2 = (z+dz)^2 - 1/2, P = D1 D2:
-        //   F = c z / D1 = c z D2 conj(P) / |P|^2,      dF = (F(z+dz) - F(z)) / dz = -c (z (z+dz) + 1/2) conj(P) / |P|^2
-        // i.e. the reference's forward difference (:250-268) evaluated without the subtraction: ONE reciprocal per pair.
+      const bool tile_im = __syncthreads_or(any_im) != 0;
+      if (far_closed) {
+        // closed-form far path for real lines (mode-0 segments: s, ds real; only Re dX is used since npm = (1,0,...))
+        auto far_loop = [&](auto im_tag) {
+          constexpr bool IM = decltype(im_tag)::value;
 #pragma unroll 2
-        for (int l = 0; l < count; l++) {
-          const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
-          if (igd == 0.0) continue;
-          const double y = sb[2 * TL + l], y2 = sb[9 * TL + l], cy1 = sb[10 * TL + l], cy2 = sb[11 * TL + l],
-                       yy = sb[12 * TL + l], sp = sb[13 * TL + l], sre = sb[3 * TL + l];
-#pragma unroll
-          for (int r = 0; r < JAC_R; r++) {
-            const double x  = igd * (f[r] - f0s);
-            const double x2 = x + fmax(1e-4 * fabs(x), 1e-4);
-            const double A = __fma_rn(x, x, -cy1), B = 2.0 * y * x;
-            const double A2 = __fma_rn(x2, x2, -cy2), B2 = 2.0 * y2 * x2;
-            const double Pr = A * A2 - B * B2, Pi = A * B2 + B * A2;
-            const double Mr = __fma_rn(x, x2, -yy), Mi = x * y2 + y * x2;
-            const double n  = far_rcp(Pr * Pr + Pi * Pi);
-            const double dFr = (Mi * Pr - Mr * Pi) * n;    // sqrt(pi) Re dF
-            const double dFi = -(Mr * Pr + Mi * Pi) * n;   // sqrt(pi) Im dF
-            const double Wr = x * A2 - y * B2, Wi = x * B2 + y * A2;
-            const double Fr = (Wr * Pi - Wi * Pr) * n;     // sqrt(pi) Re F
-            shape[r].re = __fma_rn(sp, Fr, shape[r].re);
+          for (int l = 0; l < count; l++) {
+            const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
+            if (__double2hiint(igd) == 0) continue;  // igd == 0: inactive cutoff line (integer test, off the FP64 pipe)
+            const FarLine c{sb[2 * TL + l], sb[9 * TL + l], sb[14 * TL + l], sb[15 * TL + l], sb[10 * TL + l], sb[11 * TL + l],
+                            sb[12 * TL + l]};
+            const double sp = sb[13 * TL + l];
+            double Aq[NQ], Bq[NQ], Cq[NQ], Dq[NQ], Eq[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
               const double* o = sq + q * JAC_Q_FIELDS * TL;
-              const double tr = __fma_rn(o[4 * TL + l], x, o[2 * TL + l]);
-              const double g  = tr * dFr - o[7 * TL + l] * dFi;
-              acc[q][r].re += (o[0 * TL + l] * cst::inv_sqrt_pi) * Fr + sp * g;
+              Aq[q] = o[0 * TL + l]; Bq[q] = o[2 * TL + l]; Cq[q] = o[4 * TL + l]; Dq[q] = o[7 * TL + l];
+              Eq[q] = IM ? o[1 * TL + l] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < JAC_R; r++) {
+              const double x  = __dmul_rn(igd, __dsub_rn(f[r], f0s));
+              const double x2 = __dadd_rn(x, fmax(__dmul_rn(1e-4, fabs(x)), 1e-4));
+              double G1, G2, G3, G4, G5;
+              far_pair<IM>(c, x, x2, G1, G2, G3, G4, G5);
+              shape[r].re = __fma_rn(sp, G1, shape[r].re);
+#pragma unroll
+              for (int q = 0; q < NQ; q++) {
+                double a = __fma_rn(Dq[q], G3, acc[q][r].re);
+                if (IM) a = __fma_rn(Eq[q], G5, a);
+                acc[q][r].re = __fma_rn(Aq[q], G1, __fma_rn(Bq[q], G2, __fma_rn(Cq[q], G4, a)));
+              }
             }
           }
-          (void)sre;
-        }
+        };
+        if (tile_im) far_loop(std::true_type{});
+        else far_loop(std::false_type{});
         continue;
       }
       for (int l = 0; l < count; l++) {
@@ -337,9 +391,40 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
         const double lcut = jp.real_lines ? sb[8 * TL + l] : cutoff;
         const bool lhas   = lcut < DBL_MAX;
         const cplx cutval{sb[7 * TL + l], jp.real_lines ? 0.0 : sb[8 * TL + l]};
+        // real lines: most pairs of a near tile are still far; they take the closed form, per pair
+        FarLine c;
+        double sp = 0.0, Aq[NQ], Bq[NQ], Cq[NQ], Dq[NQ], Eq[NQ];
+        if (jp.real_lines) {
+          c.from_y(y);
+          sp = s.re * cst::inv_sqrt_pi;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const double* o = sq + q * JAC_Q_FIELDS * TL;
+            Aq[q] = o[0 * TL + l] * cst::inv_sqrt_pi; Bq[q] = sp * o[2 * TL + l]; Cq[q] = sp * o[4 * TL + l];
+            Dq[q] = sp * (o[3 * TL + l] + o[4 * TL + l] * y);
+            Eq[q] = -o[1 * TL + l] * cst::inv_sqrt_pi;
+          }
+        }
 #pragma unroll
         for (int r = 0; r < JAC_R; r++) {
           if (lhas && !(f0s >= f[r] - lcut && f0s <= f[r] + lcut)) continue;
+          if (jp.real_lines && jp.pair_far) {
+            const double x  = __dmul_rn(igd, __dsub_rn(f[r], f0s));
+            const double x2 = __dadd_rn(x, fmax(__dmul_rn(1e-4, fabs(x)), 1e-4));
+            if (fmin(fabs(x), fabs(x2)) + y > FAR_LIMIT) {  // the pair and its displaced point are both far
+              double G1, G2, G3, G4, G5;
+              far_pair<true>(c, x, x2, G1, G2, G3, G4, G5);
+              shape[r].re = __fma_rn(sp, G1, shape[r].re);
+              if (lhas) shape[r].re -= cutval.re;
+#pragma unroll
+              for (int q = 0; q < NQ; q++) {
+                acc[q][r].re = __fma_rn(Aq[q], G1, __fma_rn(Bq[q], G2, __fma_rn(Cq[q], G4, __fma_rn(Dq[q], G3,
+                               __fma_rn(Eq[q], G5, acc[q][r].re)))));
+                if (lhas) acc[q][r].re -= sq[(q * JAC_Q_FIELDS + 5) * TL + l];
+              }
+              continue;
+            }
+          }
           cplx z, F, dF;
           if (far) z_F_dF_far(igd * (f[r] - f0s), y, z, F, dF);
           else z_F_dF(igd * (f[r] - f0s), y, sb[5 * TL + l], sb[6 * TL + l], z, F, dF);
@@ -407,6 +492,10 @@ static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 gri
 int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream) {
   if (p.nsegs == 0 || nlev == 0 || p.nf == 0 || jp.nq == 0) return 0;
   dim3 grid(static_cast<unsigned>((p.nf + JAC_F_TILE - 1) / JAC_F_TILE), static_cast<unsigned>(nlev));
+  {
+    const char* e = getenv("AB200_JAC_PAIR_FAR");
+    jp.pair_far = e ? atoi(e) : 1;
+  }
   for (int q0 = 0; q0 < jp.nq; q0 += JAC_Q) {
     jp.q0 = q0;
     switch (std::min(JAC_Q, jp.nq - q0)) {

@@ -208,3 +208,21 @@ def test_reentrant_from_host_threads(wsm, orc):
         I, dI = wsm.spectral_radClearskyEmission(cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=tg)
         assert np.array_equal(out[i][0], I) and np.array_equal(out[i][1], dI)
     cat.close()
+
+
+def test_propmat_jacobian_far_tiles_without_bath_broadener(wsm, orc):
+    """Without a bath broadener the reference's d/dVMR of an ABSENT Y or G model is the sum of the broadeners' VMRs
+    (lbl_lineshape_model.cpp:112), so the strength derivative of a plain Voigt line has an imaginary part and
+    Re(ds F) picks up -Im ds Im F, which dominates in the far wings.  Many lines, so that whole tiles are far from
+    whole frequency blocks and the closed-form tile path is the one that runs."""
+    c = synth.case_c2(lines_per_species=1200, nf=1500, np_=3, bands_per_species=3)
+    bath = c.cat.ls_species == abi.SPECIES_BATH
+    c.cat.ls_species[bath] = 4  # every line: self + species 4, no bath
+    tg = (("VMR", 0), ("VMR", 4), ("T",))
+    Kr, dKr = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    K, dK = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=tg)
+    for q in range(3):
+        # per level: the far wings of the upper levels must not hide behind the line cores of the lowest one
+        for lev in range(c.np_):
+            assert_jac_close(dK[lev, q], dKr[lev, q], what=f"dK target {q} level {lev}")
+    assert np.abs(dKr[:, 0]).max() > 0

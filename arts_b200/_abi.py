@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3, 4
 SPECIES_BATH = -1
 VAR_G0, VAR_D0, VAR_DV, VAR_Y, VAR_G, NVAR = 0, 1, 2, 3, 4, 5
 TM_ABSENT, TM_T0, TM_T1, TM_T2, TM_T3, TM_T4, TM_T5, TM_AER, TM_DPL, TM_POLY = -1, 0, 1, 2, 3, 4, 5, 6, 7, 8
-LINESHAPE_VP_LTE, LINESHAPE_OTHER = 0, 1
+LINESHAPE_VP_LTE, LINESHAPE_OTHER, LINESHAPE_VP_LTE_MIRROR = 0, 1, 2
 CUTOFF_NONE, CUTOFF_BYLINE = 0, 1
 RTE_CONSTANT, RTE_LINSRC, RTE_LINPROP = 0, 1, 2
 TARGET_T, TARGET_VMR = 0, 1

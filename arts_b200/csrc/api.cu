@@ -399,7 +399,7 @@ void fill_params(const ab200_path* p, int lev0, PrepareParams& pp, SumParams& sp
   pp.line_isot = cat->d_line_isot; pp.ls_offset = cat->d_ls_offset; pp.ls_species = cat->d_ls_species;
   pp.ls_type = cat->d_ls_type; pp.ls_X = cat->d_ls_X; pp.isot_species = cat->d_isot_species;
   pp.isot_mass = cat->d_isot_mass; pp.sub_parent = cat->d_sub_parent; pp.sub_Sz = cat->d_sub_Sz;
-  pp.sub_dzc = cat->d_sub_dzc; pp.sub_cut = cat->d_sub_cut; pp.tile_mode = cat->d_tile_mode;
+  pp.sub_dzc = cat->d_sub_dzc; pp.sub_cut = cat->d_sub_cut; pp.tile_mode = cat->d_tile_mode; pp.sub_flags = cat->d_sub_flags;
   pp.n_species = cat->n_species; pp.n_isot = cat->n_isot; pp.ntiles = cat->ntiles;
   pp.T = p->d_T + lev0; pp.P = p->d_P + lev0; pp.H = p->d_H + lev0;
   pp.vmr = p->d_vmr + static_cast<size_t>(lev0) * cat->n_species;

@@ -122,7 +122,7 @@ ab200_catalog::~ab200_catalog() {
   cudaFree(d_ls_offset); cudaFree(d_ls_species); cudaFree(d_ls_type); cudaFree(d_ls_X);
   cudaFree(d_isot_species); cudaFree(d_isot_mass);
   cudaFree(d_sub_parent); cudaFree(d_sub_Sz); cudaFree(d_sub_dzc);
-  cudaFree(d_tile_count); cudaFree(d_sub_cut); cudaFree(d_tile_mode);
+  cudaFree(d_tile_count); cudaFree(d_sub_cut); cudaFree(d_tile_mode); cudaFree(d_sub_flags);
 }
 
 extern "C" int ab200_zeeman_components(int on, double gu, double gl, int two_Ju, int two_Jl, int pol, int64_t cap,
@@ -146,9 +146,13 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   if (d->n_species <= 0 || d->n_isot <= 0 || d->n_bands < 0 || d->n_lines < 0)
     return set_error(AB200_ERR_INVALID, "ab200_catalog_create: negative or zero sizes");
   for (int b = 0; b < d->n_bands; b++) {
-    if (d->band_lineshape[b] != AB200_LINESHAPE_VP_LTE)
-      return set_error(AB200_ERR_UNSUPPORTED,
-                       "band " + std::to_string(b) + ": only the VP_LTE line shape is on the GPU path (no CPU fallback)");
+    if (d->band_lineshape[b] != AB200_LINESHAPE_VP_LTE && d->band_lineshape[b] != AB200_LINESHAPE_VP_LTE_MIRROR)
+      return set_error(AB200_ERR_UNSUPPORTED, "band " + std::to_string(b) +
+                                                  ": only the VP_LTE and VP_LTE_MIRROR line shapes are on the GPU path (no CPU fallback)");
+    if (d->band_lineshape[b] == AB200_LINESHAPE_VP_LTE_MIRROR && d->band_cutoff_type[b] != AB200_CUTOFF_NONE)
+      return set_error(AB200_ERR_UNSUPPORTED, "band " + std::to_string(b) +
+                                                  ": VP_LTE_MIRROR with a cutoff is outside the GPU path (the window of the mirror "
+                                                  "image follows its parent line, lbl_lineshape_voigt_lte_mirrored.cpp:591-608)");
     if (d->band_isot[b] < 0 || d->band_isot[b] >= d->n_isot)
       return set_error(AB200_ERR_INVALID, "band " + std::to_string(b) + ": isotopologue index out of range");
     if (d->band_offset[b + 1] < d->band_offset[b])
@@ -208,18 +212,38 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
 
   std::vector<int64_t> sub_parent;
   std::vector<double> sub_Sz, sub_dzc, sub_cut;
-  std::vector<uint8_t> tile_mode;
+  std::vector<uint8_t> tile_mode, sub_flags;
   constexpr double INF = std::numeric_limits<double>::infinity();
   auto line_cutoff = [&](int64_t l) {  // ByLine cutoff of the band line l belongs to
     const int64_t b = std::upper_bound(d->band_offset, d->band_offset + d->n_bands + 1, l) - d->band_offset - 1;
     return d->band_cutoff_type[b] == AB200_CUTOFF_BYLINE ? d->band_cutoff_value[b] : INF;
   };
+  // VP_LTE_MIRROR (lbl_lineshape_voigt_lte_mirrored.cpp:220): F(f) = w(z(f)) + w(zm(f)), zm = inv_gd (f + f0') + i z_imag.
+  // The mirror image is the same sub-line centred at -f0': every slot of a mirrored band gets a twin slot whose centre
+  // the prepare kernel negates (SUB_TWIN); it sorts to the negative end of a merged segment and is always far.
+  auto band_of = [&](int64_t l) {
+    return std::upper_bound(d->band_offset, d->band_offset + d->n_bands + 1, l) - d->band_offset - 1;
+  };
+  std::vector<uint8_t> fl;  // per entry of the segment under construction: SUB_* flags
+  auto push_mirror_twins = [&](std::vector<int64_t>& par, std::vector<double>& sz, std::vector<double>& dz) {
+    const size_t n = par.size();
+    fl.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+      if (d->band_lineshape[band_of(par[i])] != AB200_LINESHAPE_VP_LTE_MIRROR) continue;
+      fl[i] = SUB_MIRRORED;
+      par.push_back(par[i]); sz.push_back(sz[i]); dz.push_back(dz[i]);
+      fl.push_back(SUB_MIRRORED | SUB_TWIN);
+    }
+  };
   auto close_segment = [&](Segment seg, std::vector<int64_t>& par, std::vector<double>& sz, std::vector<double>& dz) {
     if (par.empty()) return;
-    // sort by catalog f0 (sub-lines of one parent stay adjacent: stable)
+    const int64_t n_real = static_cast<int64_t>(par.size());
+    push_mirror_twins(par, sz, dz);
+    // sort by catalog f0 (sub-lines of one parent stay adjacent: stable); mirror images by -f0
     std::vector<int64_t> order(par.size());
     std::iota(order.begin(), order.end(), int64_t{0});
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return d->f0[par[a]] < d->f0[par[b]]; });
+    auto key = [&](int64_t i) { return (fl[i] & SUB_TWIN) ? -d->f0[par[i]] : d->f0[par[i]]; };
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key(a) < key(b); });
     seg.nsub       = static_cast<int64_t>(par.size());
     seg.tile_begin = cat->ntiles;
     const int64_t nt = (seg.nsub + TL - 1) / TL;
@@ -233,17 +257,19 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
           sub_Sz.push_back(sz[order[i]]);
           sub_dzc.push_back(dz[order[i]]);
           sub_cut.push_back(line_cutoff(par[order[i]]));
+          sub_flags.push_back(fl[order[i]]);
         } else {
           sub_parent.push_back(-1);
           sub_Sz.push_back(0.0);
           sub_dzc.push_back(0.0);
           sub_cut.push_back(INF);
+          sub_flags.push_back(0);
         }
       }
     }
     cat->ntiles += nt;
     seg.tile_end = cat->ntiles;
-    cat->counts[seg.pol] += seg.nsub;
+    cat->counts[seg.pol] += n_real;  // sub-lines of the reference; mirror twins are an implementation detail
     cat->segments.push_back(seg);
     par.clear();
     sz.clear();
@@ -318,6 +344,7 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   rc = rc ? rc : upload(&cat->d_tile_count, cat->tile_count.data(), cat->tile_count.size());
   rc = rc ? rc : upload(&cat->d_sub_cut, sub_cut.data(), sub_cut.size());
   rc = rc ? rc : upload(&cat->d_tile_mode, tile_mode.data(), tile_mode.size());
+  rc = rc ? rc : upload(&cat->d_sub_flags, sub_flags.data(), sub_flags.size());
   if (rc) {
     delete cat;
     return rc;

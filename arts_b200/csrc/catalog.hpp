@@ -16,6 +16,10 @@ namespace ab200 {
 // cutoff too, because every term ls(f) - ls(f0' + cutoff) is >= 0 inside its window — so
 // the clamp can never trigger; all such bands of one species are merged into a single
 // segment (mode 0) whose lines are sorted by f0 and carry their own cutoff.
+// slot flags
+constexpr uint8_t SUB_MIRRORED = 1;  // the slot's band is VP_LTE_MIRROR (its Jacobian uses the frequency-independent zp - zm)
+constexpr uint8_t SUB_TWIN = 2;      // the slot is the mirror image: centre -f0'
+
 struct Segment {
   int32_t band;     // band index, or -1 for a merged segment
   int32_t isot;     // isotopologue of the band (-1 if merged over several)
@@ -68,6 +72,7 @@ struct ab200_catalog {
   int32_t* d_tile_count = nullptr;
   double* d_sub_cut = nullptr;      // per slot: ByLine cutoff of the line's band [Hz] (+inf if none / padding)
   uint8_t* d_tile_mode = nullptr;   // per tile: mode of its segment (0 real, 1 complex)
+  uint8_t* d_sub_flags = nullptr;   // per slot: SUB_* (VP_LTE_MIRROR twins)
 
   ~ab200_catalog();
 };

@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
       const double fmin = p.frange[2 * lev], fmax = p.frange[2 * lev + 1];
       if (!(f0_cat >= fmin - cut && f0_cat <= fmax + cut)) real_line = false;
     }
+    // VP_LTE_MIRROR twin: the same sub-line centred at -f0' (zm = inv_gd (f + f0') + i z_imag,
+    // lbl_lineshape_voigt_lte_mirrored.h:44-46); width and strength come from the real centre above
+    if (p.sub_flags[slot] & SUB_TWIN) f0s = -f0s;
     if (y < 0.0) atomicOr(p.flags, 1);
     if (!isfinite(f0s) || !isfinite(igd) || !isfinite(y) || !isfinite(s_re) || !isfinite(s_im)) atomicOr(p.flags, 2);
   }
@@ -464,7 +467,8 @@ constexpr int CPLX_R = 2;
 constexpr int CPLX_NT = 256;
 constexpr int CPLX_F_TILE = CPLX_NT * CPLX_R;
 
-__global__ void __launch_bounds__(CPLX_NT, 3) lbl_sum_cplx_kernel(SumParams p) {
+template <int MINB, int UNROLL>
+__global__ void __launch_bounds__(CPLX_NT, MINB) lbl_sum_cplx_kernel(SumParams p) {
   constexpr int STAGES = 2;
   constexpr int STAGE_DOUBLES = N_GROUPS * TL * REC_GROUP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(CPLX_NT, 3) lbl_sum_cplx_kernel(SumParams p) {
 #pragma unroll
         for (int r = 0; r < CPLX_R; r++) are[r] = aim[r] = 0.0;
         if (cls[t] == CLS_FAR) {
-#pragma unroll 2
+#pragma unroll UNROLL
           for (int l = 0; l < count; l++) {
             const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', c3 | kappa, A1
             const double B1 = reinterpret_cast<const double*>(g1 + 2 * l)[0];
@@ -683,12 +687,23 @@ int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
     }
   } else {
     const size_t smem = lbl_cplx_smem_bytes();
-    if (!attr_set[1]) {
-      AB_CUDA(cudaFuncSetAttribute(lbl_sum_cplx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      attr_set[1] = true;
-    }
+    static const int variant = [] { const char* e = getenv("AB200_CPLX_VARIANT"); return e ? atoi(e) : 0; }();
     dim3 grid(static_cast<unsigned>((p.nf + CPLX_F_TILE - 1) / CPLX_F_TILE), static_cast<unsigned>(nlev));
-    lbl_sum_cplx_kernel<<<grid, CPLX_NT, smem, stream>>>(p);
+    auto go = [&](auto kernel) -> int {
+      static bool attr = false;
+      if (!attr) {
+        AB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr = true;
+      }
+      kernel<<<grid, CPLX_NT, smem, stream>>>(p);
+      return 0;
+    };
+    switch (variant) {
+      case 1: AB_TRY(go(lbl_sum_cplx_kernel<2, 4>)); break;
+      case 2: AB_TRY(go(lbl_sum_cplx_kernel<2, 8>)); break;
+      case 3: AB_TRY(go(lbl_sum_cplx_kernel<3, 4>)); break;
+      default: AB_TRY(go(lbl_sum_cplx_kernel<3, 2>)); break;
+    }
   }
   count_launch();
   AB_CUDA(cudaGetLastError());

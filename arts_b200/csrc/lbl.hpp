@@ -19,6 +19,7 @@ struct PrepareParams {
   const double *sub_Sz, *sub_dzc;
   const double* sub_cut;     // [slot] ByLine cutoff [Hz], +inf if none
   const uint8_t* tile_mode;  // [tile] 0: real merged segment (record slot 9 holds the line's cutoff), 1: complex
+  const uint8_t* sub_flags;  // [slot] SUB_MIRRORED | SUB_TWIN (catalog.hpp)
   int32_t n_species, n_isot;
   int64_t ntiles;
   // levels of this batch (device, already offset to the first level of the batch)

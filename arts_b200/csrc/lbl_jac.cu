@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
   const int64_t slot = tile * TL + lane;
   const int64_t par  = p.sub_parent[slot];
   const double* rec  = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
-  const double f0s   = rec[(0 * TL + lane) * REC_GROUP + 0];
+  const uint8_t sfl  = p.sub_flags[slot];
+  const double f0rec = rec[(0 * TL + lane) * REC_GROUP + 0];
+  const double f0s   = (sfl & SUB_TWIN) ? -f0rec : f0rec;  // the real centre f0' (a mirror twin's record holds -f0')
   const double igd   = rec[(1 * TL + lane) * REC_GROUP + 1];
   const double y     = rec[(1 * TL + lane) * REC_GROUP + 2];
   const double s_re  = rec[(1 * TL + lane) * REC_GROUP + 3];
@@ -153,7 +155,14 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
         }
         dz_fac = -(dD0 + dDV) / f0s;  // :1176
       }
-      const cplx dzq{igd * -(dD0 + dDV), igd * dG0};
+      cplx dzq{igd * -(dD0 + dDV), igd * dG0};
+      if (sfl & SUB_MIRRORED) {
+        // mirrored dT / dVMR (lbl_lineshape_voigt_lte_mirrored.cpp:305-325): s (dz + dz_fac z_) (dFp + dFm) with
+        // z_ = zp - zm = -2 inv_gd f0', independent of the frequency: fold it into dz and drop the x-proportional part,
+        // for the line and for its twin alike
+        dzq.re += dz_fac * (-2.0 * igd * f0s);
+        dz_fac = 0.0;
+      }
       o[0] = ds.re; o[1] = ds.im; o[2] = dzq.re; o[3] = dzq.im; o[4] = dz_fac;
       if (cut < DBL_MAX) {  // band_shape::dT(dcut, ...) at f0' + cutoff, :475-486
         cplx z, F, dF;

@@ -61,7 +61,9 @@ enum {
 };
 
 /* LineByLineLineshape: only VP_LTE is on the path. */
-enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1 };
+/* LineByLineLineshape: VP_LTE (engine A) and VP_LTE_MIRROR (lbl_lineshape_voigt_lte_mirrored.cpp: every line plus its
+ * mirror image at -f0) are on the path; anything else is AB200_ERR_UNSUPPORTED. */
+enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1, AB200_LINESHAPE_VP_LTE_MIRROR = 2 };
 /* LineByLineCutoffType (lbl_data.h:178-194). */
 enum { AB200_CUTOFF_NONE = 0, AB200_CUTOFF_BYLINE = 1 };
 /* TransmittanceOption (arts_options.cc:953-1030); linsrc is the default rte_option. */

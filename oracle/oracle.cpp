@@ -393,17 +393,29 @@ void norm_view(Pol p, const Numeric mag[3], const Numeric los[2], Numeric npm[7]
 struct single_shape {
   Numeric f0{}, inv_gd{}, z_imag{};
   Complex s{};
+  // VP_LTE_MIRROR (lbl_lineshape_voigt_lte_mirrored.{h,cpp}): the same shape plus its mirror image at -f0,
+  // F(f) = w(z(f)) + w(zm(f)), zm = inv_gd (f + f0) + i z_imag (.h:44-46, .cpp:220)
+  bool mirror{false};
   Complex z(Numeric f) const { return Complex{inv_gd * (f - f0), z_imag}; }
+  Complex zm(Numeric f) const { return Complex{inv_gd * (f + f0), z_imag}; }
   static Complex F(Complex z_) { return Faddeeva::w(z_, 0); }
-  Complex operator()(Numeric f) const { return s * F(z(f)); }
+  Complex operator()(Numeric f) const { return mirror ? s * (F(z(f)) + F(zm(f))) : s * F(z(f)); }
   // forward finite difference, lbl_lineshape_voigt_lte.cpp:250-268
   static Complex dF(Complex z_, Complex F_) {
     const Complex dz{std::max(1e-4 * std::abs(z_.real()), 1e-4), std::max(1e-4 * std::abs(z_.imag()), 1e-4)};
     const Complex F_2 = Faddeeva::w(z_ + dz, 0);
     return (F_2 - F_) / dz;
   }
-  // single_shape::dT / dVMR, lbl_lineshape_voigt_lte.cpp:310-323
+  // single_shape::dT / dVMR, lbl_lineshape_voigt_lte.cpp:310-323; mirrored: lbl_lineshape_voigt_lte_mirrored.cpp:305-325
+  // (z_ = zp - zm, F_ = Fp + Fm, dF_ = dFp + dFm - literal, including the frequency-independent z_)
   Complex dX(Complex ds, Complex dz, Numeric dz_fac, Numeric f) const {
+    if (mirror) {
+      const Complex zp_ = z(f), zm_ = zm(f);
+      const Complex Fp_ = F(zp_), Fm_ = F(zm_);
+      const Complex dFp_ = dF(zp_, Fp_), dFm_ = dF(zm_, Fm_);
+      const Complex z_ = zp_ - zm_;
+      return ds * (Fp_ + Fm_) + s * (dz + dz_fac * z_) * (dFp_ + dFm_);
+    }
     const Complex z_ = z(f);
     const Complex F_ = F(z_);
     const Complex dF_ = dF(z_, F_);
@@ -509,6 +521,7 @@ void band_shape_helper(std::vector<single_shape>& lines, std::vector<line_pos>& 
       s.inv_gd = 1.0 / (scaled_gd_part * f0);
       s.z_imag = G0 * s.inv_gd;
       s.s      = line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+      s.mirror = d.band_lineshape[ib] == AB200_LINESHAPE_VP_LTE_MIRROR;
       lines.push_back(s);
       pos.push_back({il, std::numeric_limits<Index>::max()});
     } else {
@@ -519,6 +532,7 @@ void band_shape_helper(std::vector<single_shape>& lines, std::vector<line_pos>& 
         s.inv_gd = 1.0 / (scaled_gd_part * f0);
         s.z_imag = G0 * s.inv_gd;
         s.s      = z.Strength(pol, iz) * line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+        s.mirror = d.band_lineshape[ib] == AB200_LINESHAPE_VP_LTE_MIRROR;
         if (s.s == 0.0) continue;  // pop_back :354-357
         lines.push_back(s);
         pos.push_back({il, iz});
@@ -1313,7 +1327,8 @@ int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f_
   const double* f              = pg.f;
   const int64_t f_level_stride = pg.stride;
   for (int ib = 0; ib < d->n_bands; ib++)
-    if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE) return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE bands");
+    if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE && d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE_MIRROR)
+      return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE and VP_LTE_MIRROR bands");
   if (nq > 0 && !dK) return fail(AB200_ERR_INVALID, "dK is null with nq > 0");
   const int np       = atm->np;
   const int nthreads = omp_get_max_threads();

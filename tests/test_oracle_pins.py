@@ -370,3 +370,70 @@ def test_oracle_transmission_against_emission_with_zero_source_and_perturbation(
             res.append(orc.rte_transmission(Tp, Pp, None, I0)[0])
         fd = (res[0][:, 0] - res[1][:, 0]) / (2e-3 * v)
         np.testing.assert_allclose(dI[:, lev, 1, 0], fd, rtol=1e-4, atol=1e-6 * np.abs(dI[:, :, 1, 0]).max())
+
+
+def test_mirrored_lineshape_against_direct_formula_and_perturbation(orc):
+    """VP_LTE_MIRROR (lbl_lineshape_voigt_lte_mirrored.cpp:220): F(f) = w(z) + w(zm), zm = inv_gd (f + f0') + i z_imag.
+    One line, against scipy's wofz; the Jacobians (mirrored dT / dVMR, :305-325) against perturbed forward runs."""
+    c = synth.case_c1(nl=1, nf=400)
+    c.cat.f0[0] = 20e9  # low frequency: the mirror image matters
+    c.f = np.linspace(1e9, 60e9, c.nf)
+    c.atm.P[:] = 5e4
+    K0, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    c.cat.band_lineshape[:] = abi.LINESHAPE_VP_LTE_MIRROR
+    tg = (("T",), ("VMR", 0))
+    K, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    # rebuild the single line's shape parameters by hand (engine A's formulas, checked by the VP_LTE pin above)
+    kB, h_, c0 = 1.380649e-23, 6.62607015e-34, 299792458.0
+    T, P, vmr = c.atm.T[0], c.atm.P[0], c.atm.vmr[0, 0]
+    X = c.cat.ls_X
+    g_self = P * X[0, abi.VAR_G0, 0] * (296.0 / T) ** X[0, abi.VAR_G0, 1]
+    g_bath = P * X[1, abi.VAR_G0, 0] * (296.0 / T) ** X[1, abi.VAR_G0, 1]
+    d_self = P * X[0, abi.VAR_D0, 0] * (296.0 / T) ** X[0, abi.VAR_D0, 1]
+    d_bath = P * X[1, abi.VAR_D0, 0] * (296.0 / T) ** X[1, abi.VAR_D0, 1]
+    G0 = vmr * g_self + (1 - vmr) * g_bath
+    f0 = c.cat.f0[0] + vmr * d_self + (1 - vmr) * d_bath
+    gd = np.sqrt(2 * kB * T * 6.02214076e23 / (c.cat.isot_mass[0] * 1e-3) / c0 ** 2) * f0  # sqrt(2 k T N_A / (M c^2)) f0
+    w = scipy.special.wofz((c.f - f0 + 1j * G0) / gd) + scipy.special.wofz((c.f + f0 + 1j * G0) / gd)
+    w0 = scipy.special.wofz((c.f - f0 + 1j * G0) / gd)
+    np.testing.assert_allclose(K[0, :, 0] / K0[0, :, 0], w.real / w0.real, rtol=1e-9)
+    assert (K[0, :, 0] / K0[0, :, 0]).max() > 1.05, "the mirror image must contribute visibly at this frequency"
+    # Jacobian.  The mirrored dX is literal: ds (Fp + Fm) + s (dz + dz_fac (zp - zm)) (dFp + dFm) with the frequency
+    # independent zp - zm (:305-325), which is NOT the derivative of the forward model (DESIGN.md quirk 10), so a
+    # perturbation run cannot pin it.  Instead: the plain engine's dK (pinned above) is linear in the five per-line
+    # numbers (ds, s dz, s dz_fac); fit them from the VP_LTE output with basis functions built from scipy's wofz and
+    # predict the mirrored output with the mirrored basis.
+    c.atm.P[:] = 100.0
+    c.f = np.linspace(c.cat.f0[0] - 40e6, c.cat.f0[0] + 60e6, c.nf)
+    tgv = (("VMR", 0),)
+    c.cat.band_lineshape[:] = abi.LINESHAPE_VP_LTE
+    _, dKa = orc.propmat_levels(c.cat, c.f, c.atm, targets=tgv)
+    c.cat.band_lineshape[:] = abi.LINESHAPE_VP_LTE_MIRROR
+    _, dKm = orc.propmat_levels(c.cat, c.f, c.atm, targets=tgv)
+    P = c.atm.P[0]
+    g_self, g_bath = (P * X[i, abi.VAR_G0, 0] * (296.0 / T) ** X[i, abi.VAR_G0, 1] for i in (0, 1))
+    d_self, d_bath = (P * X[i, abi.VAR_D0, 0] * (296.0 / T) ** X[i, abi.VAR_D0, 1] for i in (0, 1))
+    G0 = vmr * g_self + (1 - vmr) * g_bath
+    f0 = c.cat.f0[0] + vmr * d_self + (1 - vmr) * d_bath
+    gd = np.sqrt(2 * kB * T * 6.02214076e23 / (c.cat.isot_mass[0] * 1e-3) / c0 ** 2) * f0
+
+    def F_dF(z):
+        F = scipy.special.wofz(z)
+        dz = np.maximum(1e-4 * np.abs(z.real), 1e-4) + 1j * np.maximum(1e-4 * np.abs(z.imag), 1e-4)
+        return F, (scipy.special.wofz(z + dz) - F) / dz
+
+    zp, zm = (c.f - f0 + 1j * G0) / gd, (c.f + f0 + 1j * G0) / gd
+    Fp, dFp = F_dF(zp)
+    Fm, dFm = F_dF(zm)
+    scl = -(P / (kB * T)) * c.f * np.expm1(-h_ * c.f / (kB * T)) * c0 ** 2 / (8 * np.pi)
+
+    def basis(F, dF, zfac):
+        return np.stack([F.real, -F.imag, dF.real, -dF.imag, (zfac * dF).real], axis=1)
+
+    coef, res, rank, _ = np.linalg.lstsq(basis(Fp, dFp, zp), dKa[0, 0, :, 0] / scl, rcond=None)
+    assert rank == 5
+    # (the hand-built f0', G0, G_D agree with the oracle's to ~1e-6: that bounds the fit)
+    np.testing.assert_allclose(basis(Fp, dFp, zp) @ coef, dKa[0, 0, :, 0] / scl, rtol=2e-5, atol=1e-7 * np.abs(dKa[0, 0, :, 0] / scl).max())
+    pred = basis(Fp + Fm, dFp + dFm, zp - zm) @ coef
+    np.testing.assert_allclose(dKm[0, 0, :, 0] / scl, pred, rtol=5e-5, atol=1e-6 * np.abs(pred).max())
+    assert np.abs(dKm[0, 0, :, 0] - dKa[0, 0, :, 0]).max() > 1e-3 * np.abs(dKa[0, 0, :, 0]).max(), "the quirk must show"

@@ -82,6 +82,12 @@ class Target(C.Structure):
     _fields_ = [("kind", C.c_int32), ("species", C.c_int32)]
 
 
+class HitranIsotopologue(C.Structure):
+    """ab200_hitran_isotopologue: (HITRAN molecule number, isotopologue character) -> species index and mass."""
+
+    _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double)]
+
+
 class ObserverDesc(C.Structure):
     """ab200_observer (include/arts_b200.h)."""
 

@@ -70,6 +70,14 @@ def lib():
     L.ab200_path_run_stokes.argtypes = [_vp]
     L.ab200_path_download.argtypes = [_vp, _dp, _dp, _dp, _dp]
     L.ab200_path_sync.argtypes = [_vp]
+    L.ab200_hitran_read_par.argtypes = [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.POINTER(abi.HitranIsotopologue),
+                                        C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]
+    L.ab200_hitran_read_par_file.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.HitranIsotopologue),
+                                             C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]
+    L.ab200_hitran_desc.argtypes = [_vp]
+    L.ab200_hitran_desc.restype = C.POINTER(abi.CatalogDesc)
+    L.ab200_hitran_destroy.argtypes = [_vp]
+    L.ab200_hitran_destroy.restype = None
     L.ab200_path_run_observer.argtypes = [_vp, C.POINTER(abi.ObserverDesc)]
     L.ab200_path_download_observer.argtypes = [_vp, _dp, _dp, _dp, _dp]
     L.ab200_path_device_ptr.argtypes = [_vp, C.c_int]

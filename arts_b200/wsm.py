@@ -434,3 +434,51 @@ def measurement_vecFromSensor(abs_bands, freq_grid, simulations, jac_targets=(),
         for w in work:
             w.close()
     return y, J
+
+
+def abs_bandsReadHITRAN(file=None, frequency_range=(-np.inf, np.inf), isotopologues=(), n_species=None, text=None,
+                        file_formatter=("par",), line_strength_option="A", compute_zeeman_parameters=0, n_threads=0):
+    """``abs_bandsReadHITRAN`` (src/m_lbl.cc:302-338) for the plain 160-column ``.par`` format, straight into the SoA
+    catalog: ``isotopologues`` is a list of ``(M, I, species index, mass [g/mol])`` (what ``Hitran::id_from_lookup`` and
+    the isotopologue table give the shim).  Returns a ``HostCatalog`` (one band per isotopologue).
+
+    Records below ``frequency_range[0]`` are skipped and reading stops at the first one above ``frequency_range[1]``
+    (src/core/lbl/lbl_hitran.cpp:146-172).  Quantum-number columns, the ``S`` line-strength option and Zeeman
+    parameters are outside this loader.
+    """
+    if tuple(file_formatter) != ("par",):
+        raise Ab200Error(abi.ERR_UNSUPPORTED if hasattr(abi, "ERR_UNSUPPORTED") else 2,
+                         "only file_formatter = ['par'] is on this path (no quantum-number columns)")
+    if line_strength_option != "A" or compute_zeeman_parameters:
+        raise Ab200Error(2, "only line_strength_option = 'A' without Zeeman parameters is on this path")
+    tab = (abi.HitranIsotopologue * len(isotopologues))()
+    for k, (M, I, sp, mass) in enumerate(isotopologues):
+        tab[k].M, tab[k].I, tab[k].species, tab[k].mass = int(M), str(I).encode()[:1], int(sp), float(mass)
+    ns = int(n_species) if n_species is not None else 1 + max(int(i[2]) for i in isotopologues)
+    h = C.c_void_p()
+    if text is not None:
+        raw = text.encode() if isinstance(text, str) else bytes(text)
+        check(lib().ab200_hitran_read_par(raw, len(raw), float(frequency_range[0]), float(frequency_range[1]), tab,
+                                          len(isotopologues), ns, int(n_threads), C.byref(h)))
+    else:
+        check(lib().ab200_hitran_read_par_file(str(file).encode(), float(frequency_range[0]), float(frequency_range[1]), tab,
+                                               len(isotopologues), ns, int(n_threads), C.byref(h)))
+    try:
+        d = lib().ab200_hitran_desc(h).contents
+        nl, nls, nb, ni = d.n_lines, d.n_ls, d.n_bands, d.n_isot
+
+        def arr(p, n, dtype):
+            return np.ctypeslib.as_array(p, shape=(n,)).astype(dtype, copy=True) if n else np.zeros(0, dtype)
+
+        return HostCatalog(
+            n_species=d.n_species, isot_species=arr(d.isot_species, ni, np.int32), isot_mass=arr(d.isot_mass, ni, np.float64),
+            band_isot=arr(d.band_isot, nb, np.int32), band_offset=arr(d.band_offset, nb + 1, np.int64),
+            f0=arr(d.f0, nl, np.float64), a=arr(d.a, nl, np.float64), e0=arr(d.e0, nl, np.float64),
+            gu=arr(d.gu, nl, np.float64), gl=arr(d.gl, nl, np.float64), T0=arr(d.T0, nl, np.float64),
+            ls_offset=arr(d.ls_offset, nl + 1, np.int64), ls_species=arr(d.ls_species, nls, np.int32),
+            ls_type=arr(d.ls_type, nls * abi.NVAR, np.int32).reshape(nls, abi.NVAR),
+            ls_X=arr(d.ls_X, nls * abi.NVAR * 4, np.float64).reshape(nls, abi.NVAR, 4),
+            band_lineshape=arr(d.band_lineshape, nb, np.int32), band_cutoff_type=arr(d.band_cutoff_type, nb, np.int32),
+            band_cutoff_value=arr(d.band_cutoff_value, nb, np.float64))
+    finally:
+        lib().ab200_hitran_destroy(h)

@@ -235,6 +235,31 @@ void *ab200_path_device_ptr(ab200_path *p, int which);
 /* kernels launched by the library on this thread since the last call (bench.py's gpu_launches) */
 int64_t ab200_launch_count(int reset);
 
+/* ---- catalog ingest: HITRAN .par records straight into the SoA of ab200_catalog_desc -------------
+ * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], line_strength_option = "A",
+ * compute_zeeman_parameters = 0: read_par_line (src/core/lbl/lbl_hitran.cpp:66-89, the 160-column record and its unit
+ * conversions), read_hitran_par (:146-172: records below frequency_range[0] are skipped, reading stops at the first
+ * one above frequency_range[1]) and hitran_record::from (:180-237: T0 = 296 K, G0 = T1(gamma, n) for the line's own
+ * species and for Bath (air), D0 = T0(delta) for both when delta != 0).  Without quantum-number columns the reference
+ * keys its bands by isotopologue: one band per isotopologue, in the order of the table, lines in file order.
+ * The records are parsed by n_threads host threads (0: all cores) without building the reference's AoS of maps. */
+typedef struct ab200_hitran_isotopologue {
+  int32_t M;       /* HITRAN molecule number (columns 1-2) */
+  char I;          /* HITRAN isotopologue character (column 3) */
+  int32_t species; /* the caller's species index of this isotopologue (Hitran::id_from_lookup + SpeciesEnum) */
+  double mass;     /* g/mol */
+} ab200_hitran_isotopologue;
+typedef struct ab200_hitran_catalog ab200_hitran_catalog; /* owns the arrays the description points to */
+int ab200_hitran_read_par(const char *text, int64_t len, double fmin, double fmax,
+                          const ab200_hitran_isotopologue *isotopologues, int32_t n_isot, int32_t n_species,
+                          int32_t n_threads, ab200_hitran_catalog **out);
+int ab200_hitran_read_par_file(const char *filename, double fmin, double fmax,
+                               const ab200_hitran_isotopologue *isotopologues, int32_t n_isot, int32_t n_species,
+                               int32_t n_threads, ab200_hitran_catalog **out);
+/* the description to hand to ab200_catalog_create (valid until ab200_hitran_destroy) */
+const ab200_catalog_desc *ab200_hitran_desc(const ab200_hitran_catalog *cat);
+void ab200_hitran_destroy(ab200_hitran_catalog *cat);
+
 /* ---- observer epilogue on the device (the callers' glue around the path) --------------------
  * What spectral_rad_observer_agenda / measurement_vecFromSensor do on the host after the RTE, applied to the
  * resident results of one path so that only the state-space Jacobian or the sensor channels cross PCIe:

@@ -678,7 +678,15 @@ int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
       kernel<<<grid, nt, smem, stream>>>(p);
       return 0;
     };
-    switch (variant) {
+    // Small problems (config 1: 1e4 frequencies, one level = 20 blocks of 512 on 148 SMs): narrower frequency blocks
+    // fill the machine.  The value at a frequency does not depend on the block it falls in (per-pair arithmetic and the
+    // tile order are the same in every geometry), so the choice is invisible in the results.
+    const int64_t blocks512 = (p.nf + 511) / 512 * nlev;
+    int v = variant;
+    if (v == 0 && blocks512 < 2 * 148) v = ((p.nf + 127) / 128 * nlev < 2 * 148) ? 11 : 10;
+    switch (v) {
+      case 10: AB_TRY(go(lbl_sum_real_kernel<false, 1, 128, 8>, 128, 1)); break;
+      case 11: AB_TRY(go(lbl_sum_real_kernel<false, 1, 64, 8>, 64, 1)); break;
       case 1: AB_TRY(go(lbl_sum_real_kernel<false, 4, 128, 4>, 128, 4)); break;
       case 2: AB_TRY(go(lbl_sum_real_kernel<false, 8, 64, 4>, 64, 8)); break;
       case 3: AB_TRY(go(lbl_sum_real_kernel<false, 2, 256, 4>, 256, 2)); break;

@@ -200,3 +200,22 @@ def test_mid_wing_closed_form_accuracy(wsm, orc):
     rel = np.abs(K[0, :, 0] - Kr[0, :, 0]) / Kr[0, :, 0]
     assert rel.max() <= 4e-12, (rel.max(), x[np.argmax(rel)])
     assert rel[(x > 1000) & (x < 4000)].max() > 1e-15  # the closed form is really in use there
+
+
+def test_small_grid_geometry_is_invisible(wsm):
+    """Small problems run narrower frequency blocks (64 or 128 instead of 512 per CTA).  The value at a frequency must not
+    depend on that: the same frequencies inside a grid large enough for the default geometry give the same bits."""
+    c = synth.case_c1(nl=1000, nf=3000)
+    K_small, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)             # 3000 frequencies: 64-wide blocks
+    K_mid, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f[:40_000 // 16], c.atm)  # 2500: still small
+    big = np.sort(np.concatenate([c.f, np.linspace(99e9, 131e9, 197_001)]))       # 200 001: default geometry
+    K_big, _ = wsm.spectral_propmat_pathFromPath(c.cat, big, c.atm)
+    idx = np.searchsorted(big, c.f)
+    assert np.array_equal(big[idx], c.f)
+    assert np.array_equal(K_big[:, idx], K_small)
+    assert np.array_equal(K_mid, K_small[:, :2500])
+    c2 = synth.case_c1(nl=1000, nf=30_000)                                        # 128-wide blocks
+    K2, _ = wsm.spectral_propmat_pathFromPath(c2.cat, c2.f, c2.atm)
+    big2 = np.sort(np.concatenate([c2.f, np.linspace(99e9, 131e9, 170_001)]))
+    K2b, _ = wsm.spectral_propmat_pathFromPath(c2.cat, big2, c2.atm)
+    assert np.array_equal(K2b[:, np.searchsorted(big2, c2.f)], K2)

@@ -186,8 +186,8 @@ constexpr int JAC_NT = 128;
 constexpr int JAC_R  = 2;
 constexpr int JAC_F_TILE = JAC_NT * JAC_R;
 constexpr int JAC_Q  = 4;   // targets per pass
-constexpr int JAC_BASE_FIELDS = 16;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im | y2, y^2+1/2, y2^2+1/2, y y2-1/2, s_re/sqrt(pi), 2y, 2y2
-constexpr int JAC_Q_FIELDS    = 8;   // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im | dz_im + dz_fac y
+constexpr int JAC_BASE_FIELDS = 10;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im | y2, y^2+1/2, y2^2+1/2, y y2-1/2, s_re/sqrt(pi), 2y, 2y2
+constexpr int JAC_Q_FIELDS    = 7;   // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im | dz_im + dz_fac y
 
 // dscl(f) of dt_core_calc, :990-1000
 __device__ __forceinline__ double line_scale_dT(double f, double T, double P) {
@@ -258,8 +258,9 @@ __device__ __forceinline__ void far_pair(const FarLine& c, double x, double x2, 
   G5 = IM ? __dmul_rn(__fma_rn(Wr, Pr, __dmul_rn(Wi, Pi)), n) : 0.0;
 }
 
+// CTAs per SM the shared-memory footprint allows: (10 + 7 NQ) x 2 KB -> 34 / 48 / 62 / 76 KB
 template <int NQ>
-__global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSumParams jp) {
+__global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_sum_jac_kernel(SumParams p, JacSumParams jp) {
   extern __shared__ __align__(16) double sm[];  // [JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS][TL]
   double* const sb = sm;
   double* const sq = sm + JAC_BASE_FIELDS * TL;
@@ -315,9 +316,10 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
           const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
           const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
           const double y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4), sp = n.y * cst::inv_sqrt_pi;
-          sb[0 * TL + l] = f0s; sb[1 * TL + l] = m.y; sb[2 * TL + l] = y; sb[9 * TL + l] = y2;
-          sb[10 * TL + l] = y * y + 0.5; sb[11 * TL + l] = y2 * y2 + 0.5; sb[12 * TL + l] = y * y2 - 0.5;
-          sb[13 * TL + l] = sp; sb[14 * TL + l] = 2.0 * y; sb[15 * TL + l] = 2.0 * y2;
+          // far layout of the shared slots: 0 f0', 1 igd, 2 y | 3 y2, 4 y^2+1/2, 5 y2^2+1/2, 6 y y2-1/2, 7 sp, 8 2y, 9 2y2
+          sb[0 * TL + l] = f0s; sb[1 * TL + l] = m.y; sb[2 * TL + l] = y; sb[3 * TL + l] = y2;
+          sb[4 * TL + l] = y * y + 0.5; sb[5 * TL + l] = y2 * y2 + 0.5; sb[6 * TL + l] = y * y2 - 0.5;
+          sb[7 * TL + l] = sp; sb[8 * TL + l] = 2.0 * y; sb[9 * TL + l] = 2.0 * y2;
 #pragma unroll
           for (int q = 0; q < NQ; q++) {
             const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
             any_im |= u0.y != 0.0;
             o[2 * TL + l] = sp * u1.x;                                 // B_q
             o[4 * TL + l] = sp * dz_fac;                               // C_q
-            o[7 * TL + l] = sp * (u1.y + dz_fac * y);                  // D_q: Im(dz + dz_fac z) does not depend on f
+            o[3 * TL + l] = sp * (u1.y + dz_fac * y);                  // D_q: Im(dz + dz_fac z) does not depend on f
           }
         }
       } else {
@@ -363,14 +365,14 @@ __global__ void __launch_bounds__(JAC_NT) lbl_sum_jac_kernel(SumParams p, JacSum
           for (int l = 0; l < count; l++) {
             const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
             if (__double2hiint(igd) == 0) continue;  // igd == 0: inactive cutoff line (integer test, off the FP64 pipe)
-            const FarLine c{sb[2 * TL + l], sb[9 * TL + l], sb[14 * TL + l], sb[15 * TL + l], sb[10 * TL + l], sb[11 * TL + l],
-                            sb[12 * TL + l]};
-            const double sp = sb[13 * TL + l];
+            const FarLine c{sb[2 * TL + l], sb[3 * TL + l], sb[8 * TL + l], sb[9 * TL + l], sb[4 * TL + l], sb[5 * TL + l],
+                            sb[6 * TL + l]};
+            const double sp = sb[7 * TL + l];
             double Aq[NQ], Bq[NQ], Cq[NQ], Dq[NQ], Eq[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; q++) {
               const double* o = sq + q * JAC_Q_FIELDS * TL;
-              Aq[q] = o[0 * TL + l]; Bq[q] = o[2 * TL + l]; Cq[q] = o[4 * TL + l]; Dq[q] = o[7 * TL + l];
+              Aq[q] = o[0 * TL + l]; Bq[q] = o[2 * TL + l]; Cq[q] = o[4 * TL + l]; Dq[q] = o[3 * TL + l];
               Eq[q] = IM ? o[1 * TL + l] : 0.0;
             }
 #pragma unroll

@@ -232,7 +232,7 @@ __device__ __forceinline__ void emit(const StokesJacParams& p, int64_t iv, int i
 }
 
 template <bool LINSRC>
-__global__ void __launch_bounds__(64) stokes_jac_kernel(StokesJacParams p) {
+__global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
   const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (iv >= p.nf) return;
   const int np = p.np, nq = p.nq;

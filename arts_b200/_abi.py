@@ -307,6 +307,14 @@ class Observer:
     channels: list = field(default_factory=list)
 
     def desc(self, np_: int, nq: int) -> ObserverDesc:
+        cached = getattr(self, "_desc_cache", None)
+        if cached is not None and cached[0] == (np_, nq, self.nx, self.bkg_T, self.unit, self.n_real):
+            return cached[1]  # the flattening of the Python lists is the expensive part; observers are reused per path
+        d = self._build_desc(np_, nq)
+        self._desc_cache = ((np_, nq, self.nx, self.bkg_T, self.unit, self.n_real), d)
+        return d
+
+    def _build_desc(self, np_: int, nq: int) -> ObserverDesc:
         off, xs, ws = [0], [], []
         for ip in range(np_):
             for t in range(nq):

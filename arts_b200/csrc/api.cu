@@ -561,6 +561,7 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
     jp.f = p->d_f; jp.f_stride = p->f_stride; jp.ffac = p->d_ffac; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
     jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option; jp.flags = p->d_flags;
     jp.no_emission = (p->flags & AB200_FLAG_NO_EMISSION) ? 1 : 0;
+    jp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded && !p->dk_preloaded) ? 1 : 0;
     if (obs) {  // x-space accumulation inside the pass; the per-level dI is not written
       jp.dI = nullptr;
       jp.Jx = static_cast<double*>(p->o_Jx.p);

@@ -55,6 +55,7 @@ struct StokesJacParams {
   int32_t rte_option;
   int* flags;
   int32_t no_emission;  // J = 0, dJ = 0 at every level
+  int32_t scalar;       // K and dK are known to have only A != 0: scalar pass (no 4x4 algebra)
 };
 
 int launch_stokes_chain(const StokesParams& p, cudaStream_t stream);

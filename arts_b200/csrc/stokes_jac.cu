@@ -330,8 +330,99 @@ __global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
   }
 }
 
+// The same pass for an unpolarised path (every K and dK has only A != 0: all segments were real, pol = no): T, Lambda, their
+// derivatives and the running P are scalars, the radiance may still carry Q, U, V from the background.  Same formulas as the
+// unpolarised branches of tran::deriv (:566-569), linsrc_deriv (:289-292), linsrc_linprop_deriv (:493-541) and the
+// recursion (rtepack_rtestep.cc:293-306, :348-367); ~60 registers instead of 255 and no local memory.
+template <int OPT /* AB200_RTE_* */>
+__global__ void __launch_bounds__(128) stokes_jac_scalar_kernel(StokesJacParams p) {
+  constexpr bool LINSRC = OPT != AB200_RTE_CONSTANT;
+  constexpr bool lp     = OPT == AB200_RTE_LINPROP;  // the Dawson-function code only exists in this instantiation
+  const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (iv >= p.nf) return;
+  const int np = p.np, nq = p.nq;
+  const bool emit_src = !p.no_emission;
+  double P = 1.0;
+  double carry[AB200_MAX_TARGETS][4];
+#pragma unroll
+  for (int q = 0; q < AB200_MAX_TARGETS; q++) carry[q][0] = carry[q][1] = carry[q][2] = carry[q][3] = 0.0;
+  double k0 = p.K[(int64_t(0) * p.k_pitch + iv) * 7];
+  double f0 = p.ffac[0] * p.f[iv];
+  double j0 = (k0 == 0.0 || !emit_src) ? 0.0 : planck(f0, p.T[0]);
+  for (int i = 0; i + 1 < np; i++) {
+    const double k1 = p.K[(int64_t(i + 1) * p.k_pitch + iv) * 7];
+    const double f1 = p.ffac[i + 1] * p.f[int64_t(i + 1) * p.f_stride + iv];
+    const double j1 = (k1 == 0.0 || !emit_src) ? 0.0 : planck(f1, p.T[i + 1]);
+    const double ri = p.r[i];
+    const double a  = -0.5 * ri * (k0 + k1);
+    const double T  = exp(a);
+    const int lc    = lp ? linprop_case(k0, k1, ri, false) : 0;
+    const double L  = !LINSRC ? 0.0 : ((lp && lc == 1) ? linprop_lambda(k0, k1, ri, T) : func_F(a));
+    double v[4] = {0, 0, 0, 0}, jd = 0.0;
+    if (nq > 0) {
+      const double2* Il = reinterpret_cast<const double2*>(p.I_lev + (int64_t(i + 1) * p.nf + iv) * 4);
+      const double2 i01 = Il[0], i23 = Il[1];
+      v[0] = i01.x - (LINSRC ? j1 : (j0 + j1) * 0.5); v[1] = i01.y; v[2] = i23.x; v[3] = i23.y;
+      if (LINSRC) jd = j1 - j0;
+    }
+    const double inv_r = (fabs(ri) > 1e-20) ? 1.0 / ri : 0.0;
+    for (int q = 0; q < nq; q++) {
+      const double dk0 = p.dK[((int64_t(i) * nq + q) * p.k_pitch + iv) * 7];
+      const double dk1 = p.dK[((int64_t(i + 1) * nq + q) * p.k_pitch + iv) * 7];
+      const double dr0 = p.dr[int64_t(i) * nq + q];
+      const double dr1 = p.dr[(int64_t(np - 1) + i) * nq + q];
+      const double dj0 = (q == p.it && emit_src && k0 != 0.0) ? dplanck_dt(f0, p.T[i]) : 0.0;
+      const double dj1 = (q == p.it && emit_src && k1 != 0.0) ? dplanck_dt(f1, p.T[i + 1]) : 0.0;
+      const double dT0 = -0.5 * (ri * dk0 + dr0 * (k0 + k1)) * T;
+      const double dT1 = -0.5 * (ri * dk1 + dr1 * (k0 + k1)) * T;
+      double c0[4], c1[4];
+      if (LINSRC) {
+        double dL0, dL1;
+        if (lp && lc == 1) {
+          dL0 = linprop_lambda_deriv(k0, k1, dk0, T, dT0, ri, dr1, true);
+          dL1 = linprop_lambda_deriv(k0, k1, dk1, T, dT1, ri, dr1, false);
+        } else {
+          const double Fp = func_Fp(a);
+          dL0 = Fp * (((lp ? dr1 : dr0) * inv_r) * a - 0.5 * ri * dk0);  // dr1 in both calls for linprop (:1238, sic)
+          dL1 = Fp * ((dr1 * inv_r) * a - 0.5 * ri * dk1);
+        }
+        // dI0 += P (dJ1 - L dJ0 + dT0 ImJ0 + dL0 J0mJ1);  dI1 += P (dT1 ImJ0 + dL1 J0mJ1 + L dJ1 - T dJ0)
+        c0[0] = dj1 - L * dj0 + dT0 * v[0] + dL0 * jd;
+        c1[0] = dT1 * v[0] + dL1 * jd + L * dj1 - T * dj0;
+      } else {
+        c0[0] = dT0 * v[0] + midpoint(dj0, -(T * dj0));
+        c1[0] = dT1 * v[0] + midpoint(dj1, -(T * dj1));
+      }
+#pragma unroll
+      for (int e = 1; e < 4; e++) { c0[e] = dT0 * v[e]; c1[e] = dT1 * v[e]; }
+      emit(p, iv, i, q, carry[q][0] + P * c0[0], carry[q][1] + P * c0[1], carry[q][2] + P * c0[2], carry[q][3] + P * c0[3]);
+#pragma unroll
+      for (int e = 0; e < 4; e++) carry[q][e] = P * c1[e];
+    }
+    P *= T;
+    k0 = k1; f0 = f1; j0 = j1;
+  }
+  for (int q = 0; q < nq; q++) emit(p, iv, np - 1, q, carry[q][0], carry[q][1], carry[q][2], carry[q][3]);
+  if (p.Jx && p.n_bkg > 0) {
+    const double dB = dplanck_dt(p.f[iv], p.bkg_T);
+    for (int b = 0; b < p.n_bkg; b++) p.Jx[(int64_t(p.bkg_x[b]) * p.nf + iv) * 4] += P * (p.bkg_w[b] * dB);
+  }
+}
+
 int launch_stokes_jac(const StokesJacParams& p, cudaStream_t stream) {
   if (p.nf == 0 || p.np == 0 || (p.nq == 0 && !(p.Jx && p.n_bkg > 0))) return 0;
+  if (p.scalar) {
+    const unsigned grid = static_cast<unsigned>((p.nf + 127) / 128);
+    if (p.rte_option == AB200_RTE_LINSRC)
+      stokes_jac_scalar_kernel<AB200_RTE_LINSRC><<<grid, 128, 0, stream>>>(p);
+    else if (p.rte_option == AB200_RTE_LINPROP)
+      stokes_jac_scalar_kernel<AB200_RTE_LINPROP><<<grid, 128, 0, stream>>>(p);
+    else
+      stokes_jac_scalar_kernel<AB200_RTE_CONSTANT><<<grid, 128, 0, stream>>>(p);
+    count_launch();
+    AB_CUDA(cudaGetLastError());
+    return 0;
+  }
   const unsigned grid = static_cast<unsigned>((p.nf + 63) / 64);
   if (p.rte_option != AB200_RTE_CONSTANT)
     stokes_jac_kernel<true><<<grid, 64, 0, stream>>>(p);

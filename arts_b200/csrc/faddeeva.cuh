@@ -211,6 +211,15 @@ __device__ __forceinline__ void far_accumulate_cplx(double& acc_re, double& acc_
   acc_im          = __fma_rn(ni, r, acc_im);
 }
 
+// real part only of the same sum: segments with pol = no scale with npm = (1, 0, ..., 0), their imaginary part is never used
+__device__ __forceinline__ double far_accumulate_cplx_re(double acc_re, double u, double c3, double kappa, double A1, double B1,
+                                                         double A2) {
+  const double Q  = __fma_rn(u, u, c3);
+  const double r  = fast_rcp(__fma_rn(Q, Q, kappa));
+  const double nr = __fma_rn(Q, __fma_rn(u, A2, A1), B1);
+  return __fma_rn(nr, r, acc_re);
+}
+
 // Stand-alone w(z) for arbitrary finite z (tests, ab200_faddeeva_w); y < 0 through the
 // reflection w(z) = 2 exp(-z^2) - w(-z) like Faddeeva.cc:742-748.
 __device__ inline void faddeeva_w(double zr, double zi, double& wr, double& wi) {

@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(CPLX_NT, MINB) lbl_sum_cplx_kernel(SumParams p
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
     const double cutoff  = seg.has_cutoff ? seg.cutoff : DBL_MAX;
+    const bool need_im   = seg.pol != POL_NO;  // npm(no) = (1, 0, 0, 0, 0, 0, 0), lbl_zeeman.cpp:413-455
     double accS_re[CPLX_R], accS_im[CPLX_R];
 #pragma unroll
     for (int r = 0; r < CPLX_R; r++) accS_re[r] = accS_im[r] = 0.0;
@@ -557,7 +558,19 @@ __global__ void __launch_bounds__(CPLX_NT, MINB) lbl_sum_cplx_kernel(SumParams p
         double are[CPLX_R], aim[CPLX_R];
 #pragma unroll
         for (int r = 0; r < CPLX_R; r++) are[r] = aim[r] = 0.0;
-        if (cls[t] == CLS_FAR) {
+        if (cls[t] == CLS_FAR && !need_im) {
+          // pol = no (line mixing without Zeeman splitting): npm = (1, 0, ..., 0), only Re F reaches K.  Same arithmetic
+          // for the real part as below, 9 instead of 12 FP64 instructions per pair.
+#pragma unroll UNROLL
+          for (int l = 0; l < count; l++) {
+            const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', c3 | kappa, A1
+            const double B1 = reinterpret_cast<const double*>(g1 + 2 * l)[0];
+            const double A2 = reinterpret_cast<const double*>(g3 + 2 * l)[0];
+#pragma unroll
+            for (int r = 0; r < CPLX_R; r++)
+              are[r] = far_accumulate_cplx_re(are[r], __dsub_rn(f[r], a.x), a.y, b.x, b.y, B1, A2);
+          }
+        } else if (cls[t] == CLS_FAR) {
 #pragma unroll UNROLL
           for (int l = 0; l < count; l++) {
             const double2 a = g0[2 * l], b = g0[2 * l + 1];  // f0', c3 | kappa, A1

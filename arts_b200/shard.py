@@ -92,3 +92,49 @@ def shard_case(case, rank: int, world: int):
     c.f = np.ascontiguousarray(case.f[off:off + cnt])
     c.I_bkg = np.ascontiguousarray(case.I_bkg[off:off + cnt])
     return c, off, cnt
+
+
+# ---------------------------------------------------------------------------
+# second axis: a batch of propagation paths (BASELINE configs[4]) sharded over the ranks
+# ---------------------------------------------------------------------------
+def path_ranges(n_paths: int, n: int) -> list[tuple[int, int]]:
+    """Contiguous blocks of the simulations of ``measurement_vecFromSensor`` (src/m_rad.cc:321-362), one per rank,
+    the same split as the frequency axis."""
+    return frequency_ranges(n_paths, n)
+
+
+def reduce_measurement(y, J, n_paths: int | None = None, group=None, ordered: bool = False):
+    """Combines the per-rank channel sums ``y`` [M] and ``J`` [M, nx] of a path-sharded batch.
+
+    The reference adds one simulation after the other into ``measurement_vec`` (:346-351).  ``ordered=False``: one
+    all-reduce (NCCL over NVLink / NVSwitch) of the rank sums - the cheapest exchange, the result depends on the number
+    of ranks in the last bits.  ``ordered=True``: ``y`` [n_local, M] and ``J`` [n_local, M, nx] hold the contribution of
+    every path of the rank; blocks are gathered and summed in path order on every rank, so the value is the same for any
+    number of ranks (at the price of moving n_paths * M * (nx + 1) doubles).
+    """
+    import torch
+    import torch.distributed as dist
+
+    if not ordered:
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(J, op=dist.ReduceOp.SUM, group=group)
+        return y, J
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if n_paths is None:
+        raise ValueError("ordered reduction needs the total number of paths")
+    ranges = path_ranges(n_paths, world)
+    off, cnt = ranges[rank]
+    if y.shape[0] != cnt or J.shape[0] != cnt:
+        raise ValueError(f"rank {rank}: {y.shape[0]} path contributions, expected {cnt}")
+    blk = max(c for _, c in ranges)
+    M, nx = J.shape[1], J.shape[2]
+    send = torch.zeros((blk, M, nx + 1), dtype=J.dtype, device=J.device)
+    send[:cnt, :, :nx] = J
+    send[:cnt, :, nx] = y
+    recv = torch.empty((world * blk, M, nx + 1), dtype=J.dtype, device=J.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    tot = torch.zeros((M, nx + 1), dtype=J.dtype, device=J.device)
+    for r, (_, c) in enumerate(ranges):  # path order: rank blocks are contiguous and ascending
+        for i in range(c):
+            tot += recv[r * blk + i]
+    return tot[:, nx].clone(), tot[:, :nx].clone()

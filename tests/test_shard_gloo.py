@@ -72,3 +72,48 @@ def test_gather_rejects_wrong_block_shape():
         assert torch.equal(out, torch.arange(20, dtype=torch.float64).reshape(5, 4))
     finally:
         dist.destroy_process_group()
+
+
+def _path_worker(rank, world, port, n_paths, tmp):
+    """Path-axis sharding (BASELINE configs[4]): every rank runs the observer epilogue of its block of paths with the
+    CPU oracle standing in for the GPU, then the channel sums are combined both ways."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        off, cnt = shard.path_ranges(n_paths, world)[rank]
+        contrib = _path_contributions(n_paths)[off:off + cnt]
+        M, nx = contrib.shape[1], contrib.shape[2] - 1
+        y = torch.from_numpy(np.ascontiguousarray(contrib[:, :, nx]))
+        J = torch.from_numpy(np.ascontiguousarray(contrib[:, :, :nx]))
+        yo, Jo = shard.reduce_measurement(y.clone(), J.clone(), n_paths=n_paths, ordered=True)
+        ys, Js = shard.reduce_measurement(y.sum(0), J.sum(0))
+        np.save(os.path.join(tmp, f"yo_{rank}.npy"), yo.numpy())
+        np.save(os.path.join(tmp, f"Jo_{rank}.npy"), Jo.numpy())
+        np.save(os.path.join(tmp, f"ys_{rank}.npy"), ys.numpy())
+        np.save(os.path.join(tmp, f"Js_{rank}.npy"), Js.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _path_contributions(n_paths, M=4, nx=6):
+    """Deterministic stand-in for the per-path (y, Jy) of ab200_path_download_observer, badly scaled on purpose so
+    that the order of the additions shows in the last bits."""
+    rng = np.random.default_rng(77)
+    return rng.normal(size=(n_paths, M, nx + 1)) * 10.0 ** rng.uniform(-6, 6, size=(n_paths, 1, 1))
+
+
+@pytest.mark.parametrize("world,n_paths", [(2, 7), (3, 10), (2, 1)])
+def test_path_sharded_measurement_reduction(tmp_path, world, n_paths):
+    port = _free_port()
+    mp.spawn(_path_worker, args=(world, port, n_paths, str(tmp_path)), nprocs=world, join=True)
+    contrib = _path_contributions(n_paths)
+    seq = np.zeros(contrib.shape[1:])
+    for i in range(n_paths):  # measurement_vec[iv] += ..., one simulation after the other (src/m_rad.cc:346-351)
+        seq += contrib[i]
+    for r in range(world):
+        yo, Jo = np.load(tmp_path / f"yo_{r}.npy"), np.load(tmp_path / f"Jo_{r}.npy")
+        assert np.array_equal(yo, seq[:, -1]) and np.array_equal(Jo, seq[:, :-1]), "ordered reduction: same bits as one rank"
+        ys, Js = np.load(tmp_path / f"ys_{r}.npy"), np.load(tmp_path / f"Js_{r}.npy")
+        np.testing.assert_allclose(ys, seq[:, -1], rtol=1e-9, atol=1e-9 * np.abs(contrib).max())
+        np.testing.assert_allclose(Js, seq[:, :-1], rtol=1e-9, atol=1e-9 * np.abs(contrib).max())
+    assert shard.path_ranges(10, 3) == [(0, 3), (3, 3), (6, 4)]

@@ -88,6 +88,44 @@ class HitranIsotopologue(C.Structure):
     _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double)]
 
 
+class CiaDatasetDesc(C.Structure):
+    _fields_ = [("nf", C.c_int32), ("nT", C.c_int32), ("f_grid", _dp), ("T_grid", _dp), ("data", _dp)]
+
+
+class CiaRecordDesc(C.Structure):
+    _fields_ = [("species1", C.c_int32), ("species2", C.c_int32), ("n_datasets", C.c_int32),
+                ("datasets", C.POINTER(CiaDatasetDesc))]
+
+
+@dataclass
+class CiaRecord:
+    """CIARecord (src/core/absorption/cia.h): one species pair with its data sets, each a GriddedField2
+    ``(f_grid [nf], T_grid [nT], data [nf, nT])``."""
+
+    species1: int
+    species2: int
+    datasets: list
+
+    def desc(self):
+        self._keep = [(np.ascontiguousarray(f, np.float64), np.ascontiguousarray(T, np.float64), np.ascontiguousarray(d, np.float64))
+                      for (f, T, d) in self.datasets]
+        self._ds = (CiaDatasetDesc * len(self._keep))()
+        for k, (f, T, d) in enumerate(self._keep):
+            assert d.shape == (len(f), len(T))
+            self._ds[k].nf, self._ds[k].nT = len(f), len(T)
+            self._ds[k].f_grid, self._ds[k].T_grid, self._ds[k].data = dptr(f), dptr(T), dptr(d)
+        r = CiaRecordDesc()
+        r.species1, r.species2, r.n_datasets, r.datasets = int(self.species1), int(self.species2), len(self._keep), self._ds
+        return r
+
+
+def cia_records(records):
+    arr = (CiaRecordDesc * len(records))()
+    for k, r in enumerate(records):
+        arr[k] = r.desc()
+    return arr
+
+
 class ObserverDesc(C.Structure):
     """ab200_observer (include/arts_b200.h)."""
 

@@ -13,6 +13,7 @@
 
 #include "catalog.hpp"
 #include "lbl.hpp"
+#include "cia.hpp"
 #include "stokes.hpp"
 
 namespace ab200 {
@@ -92,7 +93,7 @@ struct ab200_path {
   int64_t t_n[4] = {0, 0, 0, 0};
   std::vector<double> grid_bounds;  // [np][2] bounds of the whole (unsharded) grid, empty = use the uploaded grid's
   int64_t f_stride = 0;
-  int32_t rte_option = AB200_RTE_LINSRC, no_neg = 1;
+  int32_t rte_option = AB200_RTE_LINSRC, no_neg = 1, select_species = AB200_SPECIES_BATH;
   uint32_t flags = 0;
   cudaEvent_t ev_staged = nullptr;  // the pinned staging blocks may be refilled once this has completed
   bool uploaded = false, k_preloaded = false;
@@ -359,6 +360,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   p->f_stride   = f_level_stride;
   p->rte_option = rte_option;
   p->no_neg     = no_negative_absorption;
+  p->select_species = select_species;
   p->flags      = flags;
   p->uploaded   = true;
   p->k_preloaded = false;
@@ -580,6 +582,26 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
 
 int ab200_path_run_stokes(ab200_path* p) { return run_stokes_impl(p, nullptr); }
 
+int ab200_path_add_cia(ab200_path* p, const ab200_cia* cia, double T_extrapolfac, int32_t ignore_errors, double dT) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: path not uploaded");
+  if (!cia) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: null CIA data");
+  if (cia_device(cia) != p->cat->device) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: CIA data and path live on different devices");
+  if (p->it >= 0 && !std::isnormal(dT))  // m_cia.cc:89-91
+    return set_error(AB200_ERR_INVALID, "dt must be >0 and not NaN or Inf: " + std::to_string(dT));
+  AB_CUDA(cudaSetDevice(p->cat->device));
+  CiaParams cp{};
+  cp.c = cia_dev(cia);
+  cp.nf = p->nf; cp.f = p->d_f; cp.f_stride = p->f_stride; cp.ffac = p->d_ffac; cp.T = p->d_T; cp.P = p->d_P; cp.vmr = p->d_vmr;
+  cp.n_species = p->cat->n_species; cp.select_species = p->select_species;
+  if (cia_max_species(cia) >= cp.n_species)
+    return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: a CIA record names a species the catalog does not have");
+  cp.K = p->d_K; cp.dK = p->d_dK; cp.k_pitch = p->k_pitch; cp.nq = p->nq; cp.it = p->it;
+  for (int q = 0; q < p->nq; q++) { cp.tg_kind[q] = p->tg_kind[q]; cp.tg_species[q] = p->tg_species[q]; }
+  cp.dt = dT; cp.T_extrapolfac = T_extrapolfac; cp.ignore_errors = ignore_errors; cp.flags = p->d_flags;
+  AB_TRY(launch_cia(cp, p->np, p->stream));
+  return AB200_OK;
+}
+
 int ab200_path_run_observer(ab200_path* p, const ab200_observer* o) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: path not uploaded");
   if (!o) return set_error(AB200_ERR_INVALID, "ab200_path_run_observer: null observer");
@@ -693,6 +715,10 @@ static int check_flags(ab200_path* p) {
   if (h) {
     cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->stream);
     if (h & 2) return set_error(AB200_ERR_INVALID, "non-finite line-shape parameter (f0', 1/GD, G0 or strength) at some level");
+    if (h & 8)
+      return set_error(AB200_ERR_INVALID,
+                       "Problem with CIA species: the temperature of a level is outside the extrapolation range of a data set "
+                       "(check_limit for Temperature, lagrange_interp.h:572-650; pass ignore_errors to get NaN instead)");
     if (h & 4)
       return set_error(AB200_ERR_UNSUPPORTED,
                        "rte_option linprop with a polarised propagation matrix and a positive absorption gradient is outside "

@@ -345,6 +345,10 @@ class Path:
     def download(self, I=None, K=None, dI=None, dK=None):
         check(lib().ab200_path_download(self._h, dptr(I), dptr(dI), dptr(K), dptr(dK)))
 
+    def add_cia(self, cia: "Cia", T_extrapolfac=0.5, ignore_errors=0, dT=0.1):
+        """``spectral_propmatAddCIA`` (src/m_cia.cc:27-178) on the resident K / dK, after ``run_propmat``."""
+        check(lib().ab200_path_add_cia(self._h, cia.handle, float(T_extrapolfac), int(ignore_errors), float(dT)))
+
     def run_observer(self, obs: abi.Observer):
         """Stokes chain + the host glue of ``spectral_rad_observer_agenda`` / ``measurement_vecFromSensor`` on the
         device: background from a temperature (src/m_background.cc:55-141), ``spectral_rad_jacFromBackground`` and
@@ -482,3 +486,47 @@ def abs_bandsReadHITRAN(file=None, frequency_range=(-np.inf, np.inf), isotopolog
             band_cutoff_value=arr(d.band_cutoff_value, nb, np.float64))
     finally:
         lib().ab200_hitran_destroy(h)
+
+
+class Cia:
+    """``abs_cia_data`` on the device (ab200_cia): a list of ``_abi.CiaRecord``."""
+
+    def __init__(self, records):
+        self._records = list(records)
+        arr = abi.cia_records(self._records)
+        self._h = C.c_void_p()
+        check(lib().ab200_cia_create(arr, len(self._records), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().ab200_cia_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def spectral_propmatAddCIA(spectral_propmat, spectral_propmat_jac, freq_grid, jac_targets, select_species, abs_cia_data: Cia,
+                           atm_path: AtmPath, T_extrapolfac=0.5, ignore_errors=0, dT=0.1):
+    """src/m_cia.cc:27-178 for every level of ``atm_path``: ``spectral_propmat`` [np, nf, 7] and ``spectral_propmat_jac``
+    [np, nq, nf, 7] are accumulated in place (``+=``).  ``dT`` is the perturbation of the temperature target."""
+    np_ = atm_path.np_
+    f, stride, nf = _f_arg(freq_grid, np_)
+    tg, nq = make_targets(jac_targets)
+    K = spectral_propmat
+    if K.shape != (np_, nf, 7) or not K.flags.c_contiguous or K.dtype != np.float64:
+        raise ValueError("*f_grid* must match *spectral_propmat*")
+    dK = spectral_propmat_jac
+    if nq and (dK is None or dK.shape != (np_, nq, nf, 7) or not dK.flags.c_contiguous):
+        raise ValueError("*spectral_propmat_jac* must match derived form of *jac_targets*")
+    a = atm_path.desc()
+    check(lib().ab200_cia_levels(abs_cia_data.handle, nf, dptr(f), stride, C.byref(a), atm_path.vmr.shape[1], int(select_species), nq,
+                                 tg, float(dT), float(T_extrapolfac), int(ignore_errors), dptr(K), dptr(dK if nq else None)))
+    return K, dK

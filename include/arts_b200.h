@@ -235,6 +235,37 @@ void *ab200_path_device_ptr(ab200_path *p, int which);
 /* kernels launched by the library on this thread since the last call (bench.py's gpu_launches) */
 int64_t ab200_launch_count(int reset);
 
+/* ---- collision-induced absorption: spectral_propmatAddCIA on the resident K -----------------------
+ * src/m_cia.cc:27-178 with CIARecord::Extract (src/core/absorption/cia.cc:214-226) and cia_interpolation (:76-190):
+ * every dataset of a species pair is a GriddedField2 [frequency, temperature]; third-order Lagrange interpolation in
+ * frequency (extrapolation factor 0.5), order min(3, nT - 1) in temperature (T_extrapolfac), zero outside the dataset's
+ * frequency range, negative overshoots clamped to zero, datasets added;
+ *   K.A += xsec * nd^2 * vmr[species1] * vmr[species2],   nd = P / (k T)
+ * with the reference's temperature Jacobian by perturbation (xsec(T + dT) - xsec(T)) / dT and its VMR Jacobians.
+ * Interpolation: lagrange_interp::make_lags / interp (src/core/matpack/lagrange_interp.h:160-248,300-440,572-650,920-940). */
+typedef struct ab200_cia_dataset {
+  int32_t nf, nT;
+  const double *f_grid; /* [nf] ascending, nf >= 4 */
+  const double *T_grid; /* [nT] ascending */
+  const double *data;   /* [nf][nT] binary absorption cross-section */
+} ab200_cia_dataset;
+typedef struct ab200_cia_record {
+  int32_t species1, species2; /* SpeciesEnumPair, the caller's species indices */
+  int32_t n_datasets;
+  const ab200_cia_dataset *datasets;
+} ab200_cia_record;
+typedef struct ab200_cia ab200_cia; /* device copy, immutable, shareable */
+int ab200_cia_create(const ab200_cia_record *records, int32_t n_records, ab200_cia **out);
+void ab200_cia_destroy(ab200_cia *cia);
+/* Adds the CIA term to the resident K (and to dK of the path's temperature / VMR targets) of an uploaded path, after
+ * ab200_path_run_propmat.  dT: perturbation of the temperature target (JacobianTargets' `d`), ignored without one.
+ * A temperature outside a dataset's extrapolation range is the reference's error unless ignore_errors (then NaN). */
+int ab200_path_add_cia(ab200_path *p, const ab200_cia *cia, double T_extrapolfac, int32_t ignore_errors, double dT);
+/* Host-buffer form (the WSM shim): K [np][nf][7] and dK [np][nq][nf][7] are accumulated (+=) like m_cia.cc:146-177. */
+int ab200_cia_levels(const ab200_cia *cia, int64_t nf, const double *f, int64_t f_level_stride, const ab200_atm_path *atm,
+                     int32_t n_species, int32_t select_species, int32_t nq, const ab200_target *targets, double dT,
+                     double T_extrapolfac, int32_t ignore_errors, double *K, double *dK);
+
 /* ---- catalog ingest: HITRAN .par records straight into the SoA of ab200_catalog_desc -------------
  * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], line_strength_option = "A",
  * compute_zeeman_parameters = 0: read_par_line (src/core/lbl/lbl_hitran.cpp:66-89, the 160-column record and its unit

@@ -1753,6 +1753,138 @@ double orc_dinvplanckdI(double i, double f) { return dinvplanckdI(i, f); }
 double orc_invrayjean(double i, double f) { return invrayjean(i, f); }
 double orc_dplanck_dt(double f, double t) { return dplanck_dt(f, t); }
 
+// ---------------------------------------------------------------------------
+// collision-induced absorption
+// ---------------------------------------------------------------------------
+namespace cia {
+// lagrange_interp::update_pos for the identity transform on an ascending grid (lagrange_interp.h:160-248): the stencil of
+// P = order + 1 points starts at clamp(xp, xf, xe) - Of, xp = the last index whose right neighbour is not below x
+Index start_index(const double* xi, Index n, Index order, Numeric x) {
+  const Index P = order + 1;
+  if (n <= P) return 0;
+  const Index Of = order / 2;
+  const Index xf = Of, xe = n - P / 2 - 1;
+  Index xp = xf;
+  while (xp < xe and xi[xp + 1] < x) ++xp;
+  while (xp > xf and xi[xp] > x) --xp;
+  return std::clamp(xp, xf, xe) - xf;
+}
+// set_weights, lagrange_interp.h:300-440 (non-cyclic branch): the last weight is one minus the others
+void weights(double* w, const double* xi, Index i0, Index order, Numeric x) {
+  for (Index j = 0; j < order; j++) {
+    const Numeric xj = xi[i0 + j];
+    Numeric numer = 1.0, denom = 1.0;
+    for (Index k = 0; k < order; k++) {
+      const Index m = i0 + k + (k >= j);
+      numer *= x - xi[m];
+      denom *= xj - xi[m];
+    }
+    w[j] = numer / denom;
+  }
+  w[order] = 1.0;
+  for (Index j = 0; j < order; j++) w[order] -= w[j];
+}
+// check_limit, lagrange_interp.h:572-650 (ascending, not cyclic): false = outside the extrapolation range
+bool in_limits(const double* xi, Index n, Index order, Numeric limit, Numeric xmin, Numeric xmax) {
+  if (order == 0 or limit <= 0.0) return true;
+  const Numeric hi = xi[n - 1] + limit * (xi[n - 1] - xi[n - 2]);
+  const Numeric lo = xi[0] - limit * (xi[1] - xi[0]);
+  return not(hi < xmax or lo > xmin);
+}
+// cia_interpolation, src/core/absorption/cia.cc:76-190.  Returns false for the exception path (temperature outside the
+// extrapolation range): with `robust` the reference then fills the result with NaN, otherwise it throws.
+bool interpolate(double* result, const double* f, Index nf, Numeric T, const ab200_cia_dataset& ds, Numeric T_extrapolfac) {
+  for (Index i = 0; i < nf; i++) result[i] = 0;
+  Index i_fstart = 0, i_fstop = nf - 1;
+  for (; i_fstart < nf; ++i_fstart)
+    if (f[i_fstart] >= ds.f_grid[0]) break;
+  if (i_fstart == nf) return true;
+  for (; i_fstop >= 0; --i_fstop)
+    if (f[i_fstop] <= ds.f_grid[ds.nf - 1]) break;
+  if (i_fstop == -1) return true;
+  if (i_fstop - i_fstart + 1 < 1) return true;
+  constexpr Index f_order = 3;
+  const Index T_order = std::min<Index>(3, ds.nT - 1);
+  // make_lags: check_limit first (frequencies are inside the grid by construction; the temperature may not be)
+  if (not in_limits(ds.T_grid, ds.nT, T_order, T_extrapolfac, T, T)) return false;
+  double wT[4] = {1, 0, 0, 0};
+  const Index iT = start_index(ds.T_grid, ds.nT, T_order, T);
+  if (T_order > 0) weights(wT, ds.T_grid, iT, T_order, T);
+  for (Index i = i_fstart; i <= i_fstop; i++) {
+    double wf[4];
+    const Index i0 = start_index(ds.f_grid, ds.nf, f_order, f[i]);
+    weights(wf, ds.f_grid, i0, f_order, f[i]);
+    Numeric out = 0;  // interp, lagrange_interp.h:920-940: (field * wf) * wT, frequency index outermost
+    for (Index a = 0; a <= f_order; a++) {
+      if (T_order == 0) {
+        out += ds.data[(i0 + a) * ds.nT + 0] * wf[a];
+      } else {
+        for (Index b = 0; b <= T_order; b++) out += ds.data[(i0 + a) * ds.nT + iT + b] * wf[a] * wT[b];
+      }
+    }
+    result[i] = out < 0 ? 0 : out;  // :181-182
+  }
+  return true;
+}
+}  // namespace cia
+
+// spectral_propmatAddCIA, src/m_cia.cc:27-178, for every level of a path; K [np][nf][7], dK [np][nq][nf][7] are +=.
+int orc_cia_levels(const ab200_cia_record* records, int32_t n_records, int64_t nf, const double* f_in, int64_t f_level_stride,
+                   const ab200_atm_path* atm, int32_t n_species, int32_t select_species, int32_t nq,
+                   const ab200_target* targets, double dt, double T_extrapolfac, int32_t ignore_errors, double* K, double* dK) {
+  const int np = atm->np;
+  int it = -1;
+  for (int q = 0; q < nq; q++)
+    if (targets[q].kind == AB200_TARGET_T and it < 0) it = q;
+  if (it >= 0 and not std::isnormal(dt)) return fail(AB200_ERR_INVALID, "dt must be >0 and not NaN or Inf");
+  std::vector<double> xsec(nf), dxsec(nf), tmp(nf);
+  for (int ip = 0; ip < np; ip++) {
+    const double* f = f_in + ip * f_level_stride;
+    const Numeric T = atm->T[ip], P = atm->P[ip];
+    if (T <= 0) return fail(AB200_ERR_INVALID, "Non-positive temperature");
+    if (P <= 0) return fail(AB200_ERR_INVALID, "Non-positive pressure");
+    const double* vmr = atm->vmr + static_cast<Index>(ip) * n_species;
+    for (int r = 0; r < n_records; r++) {
+      const ab200_cia_record& rec = records[r];
+      if (select_species != AB200_SPECIES_BATH and select_species != rec.species1) continue;
+      const Numeric nd_sec = number_density(P, T) * vmr[rec.species2];
+      // CIARecord::Extract, cia.cc:214-226
+      auto extract = [&](std::vector<double>& res, Numeric temp) -> int {
+        std::fill(res.begin(), res.end(), 0.0);
+        for (int k = 0; k < rec.n_datasets; k++) {
+          const bool ok = cia::interpolate(tmp.data(), f, nf, temp, rec.datasets[k], T_extrapolfac);
+          if (not ok) {
+            if (not ignore_errors) return fail(AB200_ERR_INVALID, "Problem with CIA species: temperature outside the extrapolation range of the data");
+            std::fill(tmp.begin(), tmp.end(), std::numeric_limits<double>::quiet_NaN());
+          }
+          for (Index i = 0; i < nf; i++) res[i] += tmp[i];
+        }
+        return 0;
+      };
+      if (int rc = extract(xsec, T)) return rc;
+      if (it >= 0)
+        if (int rc = extract(dxsec, T + dt)) return rc;
+      const Numeric nd = number_density(P, T), dnd_dt = dnumber_density_dt(P, T);
+      const Numeric dnd_dt_sec = dnumber_density_dt(P, T) * vmr[rec.species2];
+      for (Index iv = 0; iv < nf; iv++) {
+        K[(static_cast<Index>(ip) * nf + iv) * 7] += nd_sec * xsec[iv] * nd * vmr[rec.species1];
+        auto dk = [&](int q) -> double& { return dK[((static_cast<Index>(ip) * nq + q) * nf + iv) * 7]; };
+        if (it >= 0)
+          dk(it) += ((nd_sec * (dxsec[iv] - xsec[iv]) / dt + xsec[iv] * dnd_dt_sec) * nd + xsec[iv] * nd_sec * dnd_dt) *
+                    vmr[rec.species1];
+        // jac_targets.find(species): the first target of that species (:166-175); both lines add the same expression
+        for (int sp : {rec.species1, rec.species2})
+          for (int q = 0; q < nq; q++)
+            if (targets[q].kind == AB200_TARGET_VMR and targets[q].species == sp) {
+              dk(q) += nd_sec * xsec[iv] * nd;
+              break;
+            }
+      }
+    }
+  }
+  return 0;
+}
+
 // rtepack::tran for single inputs (tests: exp(-K r) against scipy expm, src/tests/test_rtepack.cc:12-33)
 int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, double* T, double* L) {
   const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};

@@ -51,6 +51,8 @@ def lib():
         L.orc_wigner3j.argtypes = [C.c_int] * 6 + [dp]
         L.orc_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp]
         L.orc_norm_view.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_cia_levels.argtypes = [C.POINTER(abi.CiaRecordDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
+                                     C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), C.c_double, C.c_double, C.c_int32, dp, dp]
         L.orc_background.argtypes = [C.c_int64, dp, C.c_double, dp, dp]
         L.orc_observer.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(abi.ObserverDesc), dp, dp, dp, dp, dp, dp]
         for name in ("orc_invplanck", "orc_dinvplanckdI", "orc_invrayjean", "orc_dplanck_dt"):
@@ -249,3 +251,17 @@ def invrayjean(i, f):
 
 def dplanck_dt(f, t):
     return lib().orc_dplanck_dt(float(f), float(t))
+
+
+def cia_levels(records, f, atm: AtmPath, select_species=abi.SPECIES_BATH, targets=(), dT=0.1, T_extrapolfac=0.5, ignore_errors=0,
+               K=None, dK=None):
+    """spectral_propmatAddCIA (src/m_cia.cc:27-178) per level; returns (K [np,nf,7], dK [np,nq,nf,7]) accumulated."""
+    f, stride, nf = _f_arg(f, atm.np_)
+    tg, nq = make_targets(targets)
+    K = np.zeros((atm.np_, nf, 7)) if K is None else K
+    dK = np.zeros((atm.np_, nq, nf, 7)) if dK is None else dK
+    arr = abi.cia_records(records)
+    a = atm.desc()
+    _check(lib().orc_cia_levels(arr, len(records), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1], select_species, nq, tg,
+                                float(dT), float(T_extrapolfac), int(ignore_errors), dptr(K), dptr(dK)))
+    return K, dK

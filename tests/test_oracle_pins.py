@@ -437,3 +437,98 @@ def test_mirrored_lineshape_against_direct_formula_and_perturbation(orc):
     pred = basis(Fp + Fm, dFp + dFm, zp - zm) @ coef
     np.testing.assert_allclose(dKm[0, 0, :, 0] / scl, pred, rtol=5e-5, atol=1e-6 * np.abs(pred).max())
     assert np.abs(dKm[0, 0, :, 0] - dKa[0, 0, :, 0]).max() > 1e-3 * np.abs(dKa[0, 0, :, 0]).max(), "the quirk must show"
+
+
+def _cia_fixture(rng, n_species=3):
+    """Two species pairs; one with two data sets (different temperature grids and frequency ranges, as in HITRAN CIA
+    files), one with a single-temperature data set."""
+    def ds(f_lo, f_hi, nf, Ts):
+        f = np.sort(rng.uniform(f_lo, f_hi, nf))
+        f[0], f[-1] = f_lo, f_hi
+        T = np.asarray(Ts, float)
+        base = np.exp(-((f - 0.5 * (f_lo + f_hi)) / (0.2 * (f_hi - f_lo))) ** 2)[:, None] * (1 + 0.3 * np.sin(T / 40.0))[None, :]
+        return f, T, 1e-54 * base * (1 + 0.05 * rng.normal(size=base.shape))
+    return [abi.CiaRecord(0, 1, [ds(2e11, 9e11, 40, [180, 220, 260, 300, 340]), ds(7e11, 2e12, 25, [200, 300])]),
+            abi.CiaRecord(2, 2, [ds(1e11, 6e11, 12, [250.0])])]
+
+
+def test_cia_interpolation_reference_fixture_and_numpy(orc):
+    """cia_interpolation (src/core/absorption/cia.cc:76-190).  (1) The reference's own test set-up (src/tests/test_cia.cc:13-36):
+    a 5 x 3 field that is 1 at (f = 3, T = 200), evaluated at T = 150 on f = 1, 1.5, ..., 5: cubic in f, quadratic in T,
+    against numpy polynomials through the same stencils.  (2) Random tables against an independent scipy/numpy Lagrange
+    evaluation, including the zero outside the data, the clamp of negative overshoots and the sum over data sets."""
+    import numpy.polynomial.polynomial as Pn
+
+    A = np.zeros((5, 3)); A[2, 1] = 1.0
+    rec = [abi.CiaRecord(0, 0, [(np.array([1.0, 2, 3, 4, 5]), np.array([100.0, 200, 300]), A)])]
+    f_out = np.arange(1.0, 9.01, 0.5)
+    atm = abi.AtmPath(T=[150.0], P=[1.380649e-23 * 150.0], vmr=[[1.0]], isorat=[[1.0]], Q=[[1.0]])  # nd = 1, vmr = 1: K.A = xsec
+    K, _ = orc.cia_levels(rec, f_out, atm)
+    wT = np.array([np.prod([(150.0 - tk) / (tj - tk) for tk in (100.0, 200, 300) if tk != tj]) for tj in (100.0, 200, 300)])
+    expect = np.zeros(len(f_out))
+    fg = np.array([1.0, 2, 3, 4, 5])
+    for i, x in enumerate(f_out):
+        if x > 5:
+            continue  # outside the data: zero (:95-118)
+        i0 = 0 if x <= 3 else 1  # lagrange_interp stencil: x in (xi[1], xi[2]] -> 0..3, (xi[2], xi[3]] -> 1..4, clamped
+        st = fg[i0:i0 + 4]
+        wf = np.array([np.prod([(x - xk) / (xj - xk) for xk in st if xk != xj]) for xj in st])
+        expect[i] = max(0.0, float(wf @ A[i0:i0 + 4] @ wT))
+    np.testing.assert_allclose(K[0, :, 0], expect, rtol=1e-13, atol=1e-16)
+    assert expect[4] == pytest.approx(0.75) and expect.max() > 0.7 and (K[0, 9:, 0] == 0).all()
+    assert not K[..., 1:].any()
+
+    rng = np.random.default_rng(12)
+    recs = _cia_fixture(rng)
+    f = np.linspace(0.5e11, 2.2e12, 500)
+    Tl, Pl = np.array([205.0, 251.0, 333.0]), np.array([5e4, 2e4, 9e4])
+    vmr = np.array([[0.78, 0.21, 4e-4]] * 3)
+    atm = abi.AtmPath(T=Tl, P=Pl, vmr=vmr, isorat=np.ones((3, 1)), Q=np.ones((3, 1)))
+    K, _ = orc.cia_levels(recs, f, atm)
+
+    def lag(xg, order, x):  # same stencil rule, weights by the textbook product
+        n, Pn_ = len(xg), order + 1
+        if n <= Pn_:
+            i0 = 0
+        else:
+            m = int(np.searchsorted(xg, x, side="left"))
+            i0 = int(np.clip(m - 1, order // 2, n - Pn_ // 2 - 1)) - order // 2
+        st = xg[i0:i0 + Pn_]
+        return i0, np.array([np.prod([(x - xk) / (xj - xk) for xk in st if xk != xj]) for xj in st])
+
+    kB = 1.380649e-23
+    ref = np.zeros((3, len(f)))
+    for lev in range(3):
+        nd = Pl[lev] / (kB * Tl[lev])
+        for r in recs:
+            xs = np.zeros(len(f))
+            for (fg, Tg, dat) in r.datasets:
+                iT, wT = lag(Tg, min(3, len(Tg) - 1), Tl[lev])
+                for i, x in enumerate(f):
+                    if fg[0] <= x <= fg[-1]:
+                        i0, wf = lag(fg, 3, x)
+                        xs[i] += max(0.0, float(wf @ dat[i0:i0 + 4, iT:iT + len(wT)] @ wT))
+            ref[lev] += xs * nd * nd * vmr[lev, r.species1] * vmr[lev, r.species2]
+    np.testing.assert_allclose(K[..., 0], ref, rtol=1e-11, atol=1e-14 * ref.max())
+    assert ref.max() > 0 and (ref == 0).any()
+    # temperature outside the extrapolation range of the two-temperature set: the reference's exception, or NaN when ignored
+    cold = abi.AtmPath(T=[120.0], P=[5e4], vmr=vmr[:1], isorat=np.ones((1, 1)), Q=np.ones((1, 1)))
+    with pytest.raises(RuntimeError, match="extrapolation range"):
+        orc.cia_levels(recs, f, cold)
+    Kn, _ = orc.cia_levels(recs, f, cold, ignore_errors=1)
+    assert np.isnan(Kn[0, :, 0]).all(), "robust: `result = NAN` for the whole vector of the failing data set (cia.cc:184-189)"
+    # Jacobians: VMR rows are exact derivatives; the temperature row is the reference's perturbation formula
+    tg = (("T",), ("VMR", 0), ("VMR", 1))
+    K2, dK = orc.cia_levels(recs, f, atm, targets=tg, dT=0.1)
+    assert np.array_equal(K2, K)
+    h = 1e-3
+    up = abi.AtmPath(T=Tl, P=Pl, vmr=vmr + h * np.eye(3)[0], isorat=np.ones((3, 1)), Q=np.ones((3, 1)))
+    Kp, _ = orc.cia_levels(recs[:1], f, up)
+    K0, _ = orc.cia_levels(recs[:1], f, atm)
+    _, dK1 = orc.cia_levels(recs[:1], f, atm, targets=tg)
+    np.testing.assert_allclose(dK1[:, 1, :, 0], (Kp - K0)[..., 0] / h, rtol=1e-6, atol=1e-9 * np.abs(dK1[:, 1]).max())
+    # the row of the SECOND species of the pair gets the same expression nd_sec * xsec * nd (m_cia.cc:171-175), which is the
+    # derivative with respect to the first one: literal (DESIGN.md quirk 11), so the two rows are equal
+    assert np.array_equal(dK1[:, 2], dK1[:, 1]) and np.abs(dK1[:, 2]).max() > 0
+    Kt, _ = orc.cia_levels(recs, f, abi.AtmPath(T=Tl + 0.1, P=Pl, vmr=vmr, isorat=np.ones((3, 1)), Q=np.ones((3, 1))))
+    np.testing.assert_allclose(dK[:, 0, :, 0], (Kt - K)[..., 0] / 0.1, rtol=2e-3, atol=2e-3 * np.abs(dK[:, 0]).max())

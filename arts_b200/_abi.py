@@ -88,6 +88,15 @@ class HitranIsotopologue(C.Structure):
     _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double)]
 
 
+class PartfunTable(C.Structure):
+    """ab200_partfun_table: kind 0 interp, 1 coeff, 2 const, 3 static_interp (src/partfun/make_auto_partfuns.cc)."""
+
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("grid", _dp), ("coef", _dp)]
+
+
+PARTFUN_KINDS = {"interp": 0, "coeff": 1, "const": 2, "static_interp": 3}
+
+
 class CiaDatasetDesc(C.Structure):
     _fields_ = [("nf", C.c_int32), ("nT", C.c_int32), ("f_grid", _dp), ("T_grid", _dp), ("data", _dp)]
 

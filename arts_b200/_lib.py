@@ -70,6 +70,7 @@ def lib():
     L.ab200_path_run_stokes.argtypes = [_vp]
     L.ab200_path_download.argtypes = [_vp, _dp, _dp, _dp, _dp]
     L.ab200_path_sync.argtypes = [_vp]
+    L.ab200_partfun_eval.argtypes = [C.POINTER(abi.PartfunTable), C.c_int32, C.c_int32, _dp, _dp, _dp]
     L.ab200_cia_create.argtypes = [C.POINTER(abi.CiaRecordDesc), C.c_int32, C.POINTER(_vp)]
     L.ab200_cia_destroy.argtypes = [_vp]
     L.ab200_cia_destroy.restype = None

@@ -291,6 +291,66 @@ int build(const char* text, int64_t len, double fmin, double fmax, const ab200_h
 
 extern "C" {
 
+// PartitionFunctions::Q / dQdT as generated by src/partfun/make_auto_partfuns.cc:28-153 (literal formulas per table kind)
+int ab200_partfun_eval(const ab200_partfun_table* tables, int32_t n_isot, int32_t np, const double* T, double* Q, double* dQdT) {
+  using ab200::set_error;
+  if (n_isot < 0 || np < 0) return set_error(AB200_ERR_INVALID, "ab200_partfun_eval: negative size");
+  if ((n_isot > 0 && !tables) || (np > 0 && (!T || !Q))) return set_error(AB200_ERR_INVALID, "ab200_partfun_eval: null argument");
+  for (int32_t i = 0; i < n_isot; i++) {
+    const ab200_partfun_table& t = tables[i];
+    const bool gridded = t.kind == AB200_PARTFUN_INTERP || t.kind == AB200_PARTFUN_STATIC_INTERP;
+    if (t.kind < AB200_PARTFUN_INTERP || t.kind > AB200_PARTFUN_STATIC_INTERP)
+      return set_error(AB200_ERR_INVALID, "ab200_partfun_eval: isotopologue " + std::to_string(i) + " has an unknown table kind");
+    if (!t.coef || t.n < 1 || (gridded && (!t.grid || t.n < 2)))
+      return set_error(AB200_ERR_INVALID, "ab200_partfun_eval: isotopologue " + std::to_string(i) + " has an empty table");
+    if (gridded)
+      for (int32_t k = 1; k < t.n; k++)
+        if (!(t.grid[k] > t.grid[k - 1])) return set_error(AB200_ERR_INVALID, "Temperature grid must be increasing");  // :34-37
+  }
+  for (int32_t ip = 0; ip < np; ip++) {
+    const double Tl = T[ip];
+    for (int32_t i = 0; i < n_isot; i++) {
+      const ab200_partfun_table& t = tables[i];
+      double q = 0.0, dq = 0.0;
+      switch (t.kind) {
+        case AB200_PARTFUN_INTERP: {  // :46-61
+          const int64_t i_low = std::lower_bound(t.grid, t.grid + t.n, Tl) - t.grid;
+          const size_t k = std::min<size_t>(static_cast<size_t>(i_low - (i_low > 0)), static_cast<size_t>(t.n - 2));
+          q  = t.coef[k] + (Tl - t.grid[k]) * (t.coef[k + 1] - t.coef[k]) / (t.grid[k + 1] - t.grid[k]);
+          dq = (t.coef[k + 1] - t.coef[k]) / (t.grid[k + 1] - t.grid[k]);
+        } break;
+        case AB200_PARTFUN_COEFF: {  // :77-103
+          double TN = 1.0;
+          q = t.coef[0];
+          for (int32_t k = 1; k < t.n; k++) {
+            TN *= Tl;
+            q += TN * t.coef[k];
+          }
+          dq = t.n > 1 ? t.coef[1] : 0.0;
+          TN = 1.0;
+          for (int32_t k = 2; k < t.n; k++) {
+            TN *= Tl;
+            dq += static_cast<double>(k) * TN * t.coef[k];
+          }
+        } break;
+        case AB200_PARTFUN_CONST: q = t.coef[0]; break;  // :107-115
+        default: {                                     // STATIC_INTERP :117-153
+          const double r_dT = 1.0 / (t.grid[1] - t.grid[0]);
+          const double Tx   = (Tl - t.grid[0]) * r_dT;
+          const size_t iTx  = static_cast<size_t>(Tx);
+          const size_t k    = iTx > static_cast<size_t>(t.n - 2) ? static_cast<size_t>(t.n - 2) : iTx;
+          const double To   = Tx - static_cast<double>(k);
+          q  = t.coef[k] + To * (t.coef[k + 1] - t.coef[k]);
+          dq = (t.coef[k + 1] - t.coef[k]) * r_dT;
+        } break;
+      }
+      Q[static_cast<size_t>(ip) * n_isot + i] = q;
+      if (dQdT) dQdT[static_cast<size_t>(ip) * n_isot + i] = dq;
+    }
+  }
+  return AB200_OK;
+}
+
 int ab200_hitran_read_par(const char* text, int64_t len, double fmin, double fmax, const ab200_hitran_isotopologue* isotopologues,
                           int32_t n_isot, int32_t n_species, int32_t n_threads, ab200_hitran_catalog** out) {
   return ab200::build(text, len, fmin, fmax, isotopologues, n_isot, n_species, n_threads, out);

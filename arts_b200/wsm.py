@@ -530,3 +530,20 @@ def spectral_propmatAddCIA(spectral_propmat, spectral_propmat_jac, freq_grid, ja
     check(lib().ab200_cia_levels(abs_cia_data.handle, nf, dptr(f), stride, C.byref(a), atm_path.vmr.shape[1], int(select_species), nq,
                                  tg, float(dT), float(T_extrapolfac), int(ignore_errors), dptr(K), dptr(dK if nq else None)))
     return K, dK
+
+
+def partition_functions(tables, T):
+    """``PartitionFunctions::Q`` / ``dQdT`` (src/partfun/partfun.h, generated by src/partfun/make_auto_partfuns.cc) for
+    every level: ``tables[i] = (kind, grid | None, coef)`` with kind in interp / coeff / const / static_interp.
+    Returns ``(Q [np, n_isot], dQdT [np, n_isot])`` ready for ``AtmPath``."""
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    keep, arr = [], (abi.PartfunTable * len(tables))()
+    for k, (kind, grid, coef) in enumerate(tables):
+        g = None if grid is None else np.ascontiguousarray(grid, dtype=np.float64)
+        c = np.ascontiguousarray(np.atleast_1d(coef), dtype=np.float64)
+        keep.append((g, c))
+        arr[k].kind, arr[k].n, arr[k].grid, arr[k].coef = abi.PARTFUN_KINDS[kind], len(c), dptr(g), dptr(c)
+    Q = np.empty((len(T), len(tables)))
+    dQ = np.empty((len(T), len(tables)))
+    check(lib().ab200_partfun_eval(arr, len(tables), len(T), dptr(T), dptr(Q), dptr(dQ)))
+    return Q, dQ

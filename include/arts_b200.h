@@ -291,6 +291,27 @@ int ab200_hitran_read_par_file(const char *filename, double fmin, double fmax,
 const ab200_catalog_desc *ab200_hitran_desc(const ab200_hitran_catalog *cat);
 void ab200_hitran_destroy(ab200_hitran_catalog *cat);
 
+/* ---- partition functions: Q(T) and dQ/dT of every isotopologue at every level ---------------------
+ * PartitionFunctions::Q / dQdT (src/partfun/partfun.h) are generated at build time from data tables by
+ * src/partfun/make_auto_partfuns.cc; the four table kinds and their literal formulas:
+ *   INTERP        :28-63   linear interpolation on an increasing grid, i = min(lower_bound(T) - (>0), n - 2)
+ *   COEFF         :65-105  polynomial sum_i Q[i] T^i, derivative sum_i i Q[i] T^(i-1) (running power, same order)
+ *   CONST         :107-115 a constant, derivative 0
+ *   STATIC_INTERP :117-153 equidistant grid: Tx = (T - T0) * (1 / dT), i = min(size_t(Tx), n - 2)
+ * Fills ab200_atm_path.Q and .dQdT from the tables so that the shim need not evaluate them per level. */
+#define AB200_PARTFUN_INTERP 0
+#define AB200_PARTFUN_COEFF 1
+#define AB200_PARTFUN_CONST 2
+#define AB200_PARTFUN_STATIC_INTERP 3
+typedef struct ab200_partfun_table {
+  int32_t kind;       /* AB200_PARTFUN_* */
+  int32_t n;          /* number of grid points (INTERP, STATIC_INTERP) or coefficients (COEFF); 1 for CONST */
+  const double *grid; /* [n] temperatures (INTERP, STATIC_INTERP), else NULL */
+  const double *coef; /* [n] Q values, polynomial coefficients, or the constant */
+} ab200_partfun_table;
+/* Q, dQdT: [np][n_isot] like in ab200_atm_path; dQdT may be NULL. */
+int ab200_partfun_eval(const ab200_partfun_table *tables, int32_t n_isot, int32_t np, const double *T, double *Q, double *dQdT);
+
 /* ---- observer epilogue on the device (the callers' glue around the path) --------------------
  * What spectral_rad_observer_agenda / measurement_vecFromSensor do on the host after the RTE, applied to the
  * resident results of one path so that only the state-space Jacobian or the sensor channels cross PCIe:

@@ -161,3 +161,59 @@ def test_hitran_catalog_through_the_gpu_path(orc):
     for q in range(2):
         assert_jac_close(dK[:, q], dKr[:, q], what=f"HITRAN catalog dK target {q}")
     assert Kr[..., 0].max() > 0
+
+
+def test_partition_function_tables():
+    """PartitionFunctions::Q / dQdT for the four table kinds of src/partfun/make_auto_partfuns.cc:28-153, against a pure-Python
+    restatement of the generated code (bit-exact) and against numpy (interp / polyval) for the meaning."""
+    import bisect
+
+    rng = np.random.default_rng(6)
+    grid = np.sort(rng.uniform(50.0, 600.0, 12))
+    qv = 10.0 * (grid / 296.0) ** 1.5
+    sgrid = np.arange(100.0, 401.0, 25.0)
+    sq = 7.0 * (sgrid / 296.0) ** 1.5
+    poly = np.array([1.5, 0.3, 2e-3, -1e-6])
+    tables = [("interp", grid, qv), ("coeff", None, poly), ("const", None, [42.0]), ("static_interp", sgrid, sq)]
+    T = np.concatenate([rng.uniform(20.0, 700.0, 40), grid[[0, 3, -1]], sgrid[[0, 5, -1]], [99.9, 400.1]])
+    Q, dQ = wsm.partition_functions(tables, T)
+
+    def ref(kind, g, c, t):
+        if kind == "interp":  # :46-61
+            i_low = bisect.bisect_left(list(g), t)
+            i = min(i_low - (i_low > 0), len(c) - 2)
+            return c[i] + (t - g[i]) * (c[i + 1] - c[i]) / (g[i + 1] - g[i]), (c[i + 1] - c[i]) / (g[i + 1] - g[i])
+        if kind == "coeff":  # :77-103
+            res, TN = c[0], 1.0
+            for k in range(1, len(c)):
+                TN *= t
+                res += TN * c[k]
+            d, TN = c[1], 1.0
+            for k in range(2, len(c)):
+                TN *= t
+                d += float(k) * TN * c[k]
+            return res, d
+        if kind == "const":
+            return c[0], 0.0
+        r_dT = 1.0 / (g[1] - g[0])  # :117-153
+        Tx = (t - g[0]) * r_dT
+        iTx = int(Tx) if Tx >= 0 else 2 ** 63  # static_cast<Size> of a negative double: huge, clamped below
+        i = len(c) - 2 if iTx > len(c) - 2 else iTx
+        To = Tx - float(i)
+        return c[i] + To * (c[i + 1] - c[i]), (c[i + 1] - c[i]) * r_dT
+
+    for k, (kind, g, c) in enumerate(tables):
+        for j, t in enumerate(T):
+            if kind == "static_interp" and t < g[0]:
+                continue  # the conversion of a negative double to size_t is undefined behaviour in the generated code
+            q, d = ref(kind, g, np.atleast_1d(np.asarray(c, float)), float(t))
+            assert Q[j, k] == q and dQ[j, k] == d, (kind, t)
+    inside = (T >= grid[0]) & (T <= grid[-1])
+    np.testing.assert_allclose(Q[inside, 0], np.interp(T[inside], grid, qv), rtol=1e-14)
+    np.testing.assert_allclose(Q[:, 1], np.polyval(poly[::-1], T), rtol=1e-13)
+    np.testing.assert_allclose(dQ[:, 1], np.polyval(np.polyder(poly[::-1]), T), rtol=1e-13)
+    ins = (T >= sgrid[0]) & (T <= sgrid[-1])
+    np.testing.assert_allclose(Q[ins, 3], np.interp(T[ins], sgrid, sq), rtol=1e-13)
+    assert (Q[:, 2] == 42.0).all() and not dQ[:, 2].any()
+    with pytest.raises(wsm.Ab200Error, match="Temperature grid must be increasing"):
+        wsm.partition_functions([("interp", grid[::-1], qv)], T)

@@ -1,0 +1,36 @@
+/* The drop-in boundary from plain C: include/arts_b200.h must compile as C99 and the host-only entry points must work
+ * when called the way a cgo / JNI / ctypes stub would call them (no GPU needed for these). */
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "arts_b200.h"
+
+int main(void) {
+  /* the reference's HITRAN fixture record (tests/hitran/single_line.par), `par` columns only */
+  const char *rec =
+      " 11    0.072049 1.875E-30 4.668E-12.09460.391 1922.82890.730.002760          0 1 0          0 1 0  4  2  2        5  "
+      "1  5      534253807294713152     9.0   11.0\n";
+  ab200_hitran_isotopologue tab[1] = {{1, '1', 0, 18.010565}};
+  ab200_hitran_catalog *h = NULL;
+  int rc = ab200_hitran_read_par(rec, (int64_t)strlen(rec), -INFINITY, INFINITY, tab, 1, 1, 1, &h);
+  if (rc != AB200_OK) { printf("read_par failed: %s\n", ab200_last_error()); return 1; }
+  const ab200_catalog_desc *d = ab200_hitran_desc(h);
+  if (d->n_lines != 1 || d->n_bands != 1 || fabs(d->f0[0] - 2.15997e9) > 1e5 || d->gu[0] != 9.0) { printf("bad record\n"); return 2; }
+  ab200_hitran_destroy(h);
+
+  rc = ab200_hitran_read_par("xx\n", 3, -INFINITY, INFINITY, tab, 1, 1, 1, &h);
+  if (rc != AB200_ERR_INVALID || !strstr(ab200_last_error(), "Unexpected end of string")) { printf("error path: %d %s\n", rc, ab200_last_error()); return 3; }
+
+  const double grid[3] = {100.0, 200.0, 300.0}, q[3] = {10.0, 30.0, 60.0}, T[2] = {150.0, 250.0};
+  ab200_partfun_table pt = {AB200_PARTFUN_INTERP, 3, grid, q};
+  double Q[2], dQ[2];
+  rc = ab200_partfun_eval(&pt, 1, 2, T, Q, dQ);
+  if (rc != AB200_OK || Q[0] != 20.0 || Q[1] != 45.0 || dQ[0] != 0.2 || dQ[1] != 0.3) { printf("partfun\n"); return 4; }
+
+  /* compute entry points exist and fail loudly instead of falling back when there is no device or no input */
+  if (ab200_catalog_create(NULL, NULL) != AB200_ERR_INVALID) { printf("null catalog accepted\n"); return 5; }
+  printf("devices visible: %d\n", ab200_device_count());
+  printf("abi smoke ok\n");
+  return 0;
+}

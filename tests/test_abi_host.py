@@ -152,3 +152,24 @@ def test_host_catalog_desc_keeps_arrays_alive_and_typed():
     a = c.atm.desc()
     assert a.np == 2 and a.T[1] == c.atm.T[1]
     assert C.sizeof(abi.Target) == 8
+
+
+def test_header_compiles_as_c99_and_host_entry_points_work_from_c(tmp_path):
+    """The boundary is a C ABI: include/arts_b200.h must be plain C (a cgo / JNI / N-API stub includes it as such), and the
+    host-only entry points (HITRAN ingest, partition functions, error reporting) are exercised from a C program linked
+    against libarts_b200.so (tests/c/abi_smoke.c)."""
+    import os
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "arts_b200")
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", exe, "-L" + lib_dir, "-larts_b200", "-lm", "-Wl,-rpath," + lib_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "abi smoke ok" in r.stdout, r.stdout + r.stderr

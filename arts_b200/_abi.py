@@ -88,6 +88,46 @@ class HitranIsotopologue(C.Structure):
     _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double)]
 
 
+class LookupTableDesc(C.Structure):
+    _fields_ = [("species", C.c_int32), ("nf", C.c_int32), ("np", C.c_int32), ("nt", C.c_int32), ("nw", C.c_int32),
+                ("do_t", C.c_int32), ("do_w", C.c_int32), ("f_grid", _dp), ("log_p_grid", _dp), ("t_pert", _dp), ("w_pert", _dp),
+                ("t_atmref", _dp), ("water_atmref", _dp), ("xsec", _dp)]
+
+
+@dataclass
+class LookupTable:
+    """lookup::table (src/core/lookup/lookup_map.h) of one species: ``xsec`` [nt, nw, np, nf]."""
+
+    species: int
+    f_grid: np.ndarray
+    log_p_grid: np.ndarray
+    t_atmref: np.ndarray
+    xsec: np.ndarray
+    t_pert: np.ndarray | None = None
+    w_pert: np.ndarray | None = None
+    water_atmref: np.ndarray | None = None
+
+    def desc(self):
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        self._k = [c(self.f_grid), c(self.log_p_grid), c(self.t_pert), c(self.w_pert), c(self.t_atmref), c(self.water_atmref),
+                   c(self.xsec)]
+        d = LookupTableDesc()
+        d.species, d.nf, d.np = int(self.species), len(self._k[0]), len(self._k[1])
+        d.do_t, d.do_w = int(self.t_pert is not None), int(self.w_pert is not None)
+        d.nt = len(self._k[2]) if d.do_t else 1
+        d.nw = len(self._k[3]) if d.do_w else 1
+        assert self._k[6].shape == (d.nt, d.nw, d.np, d.nf), (self._k[6].shape, (d.nt, d.nw, d.np, d.nf))
+        d.f_grid, d.log_p_grid, d.t_pert, d.w_pert, d.t_atmref, d.water_atmref, d.xsec = (dptr(a) for a in self._k)
+        return d
+
+
+def lookup_tables(tables):
+    arr = (LookupTableDesc * len(tables))()
+    for k, t in enumerate(tables):
+        arr[k] = t.desc()
+    return arr
+
+
 class PartfunTable(C.Structure):
     """ab200_partfun_table: kind 0 interp, 1 coeff, 2 const, 3 static_interp (src/partfun/make_auto_partfuns.cc)."""
 

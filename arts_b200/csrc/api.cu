@@ -14,6 +14,7 @@
 #include "catalog.hpp"
 #include "lbl.hpp"
 #include "cia.hpp"
+#include "lookup.hpp"
 #include "stokes.hpp"
 
 namespace ab200 {
@@ -582,6 +583,35 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
 
 int ab200_path_run_stokes(ab200_path* p) { return run_stokes_impl(p, nullptr); }
 
+int ab200_path_add_lookup(ab200_path* p, const ab200_lookup* lut, int32_t h2o_species, const double* target_d, int32_t po, int32_t to,
+                          int32_t wo, int32_t fo, double extpolfac, int32_t zero_init) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_add_lookup: path not uploaded");
+  if (!lut) return set_error(AB200_ERR_INVALID, "ab200_path_add_lookup: null lookup data");
+  if (lut_device(lut) != p->cat->device) return set_error(AB200_ERR_INVALID, "ab200_path_add_lookup: lookup data and path live on different devices");
+  if (p->nq > 0 && !target_d) return set_error(AB200_ERR_INVALID, "ab200_path_add_lookup: target_d is null with Jacobian targets");
+  AB_TRY(lut_check_call(lut, p->cat->n_species, h2o_species, p->select_species, po, to, wo, fo));
+  LutParams lp{};
+  for (int q = 0; q < p->nq; q++) {
+    if (!std::isnormal(target_d[q]))
+      return set_error(AB200_ERR_INVALID, "The target " + std::to_string(q) + " is not good, it lacks a perturbation value.");
+    lp.tg_kind[q] = p->tg_kind[q]; lp.tg_species[q] = p->tg_species[q]; lp.tg_d[q] = target_d[q];
+  }
+  AB_CUDA(cudaSetDevice(p->cat->device));
+  if (zero_init) {
+    AB_CUDA(cudaMemsetAsync(p->d_K, 0, static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double), p->stream));
+    if (p->nq > 0)
+      AB_CUDA(cudaMemsetAsync(p->d_dK, 0, static_cast<size_t>(p->np) * p->nq * p->k_pitch * 7 * sizeof(double), p->stream));
+    p->nsegs[1] = 0;  // K holds only A: the scalar Stokes instantiations apply
+  }
+  lp.t = lut_dev(lut);
+  lp.nf = p->nf; lp.f = p->d_f; lp.f_stride = p->f_stride; lp.ffac = p->d_ffac; lp.T = p->d_T; lp.P = p->d_P; lp.vmr = p->d_vmr;
+  lp.n_species = p->cat->n_species; lp.h2o_species = h2o_species; lp.select_species = p->select_species;
+  lp.K = p->d_K; lp.dK = p->d_dK; lp.k_pitch = p->k_pitch; lp.nq = p->nq;
+  lp.no_neg = p->no_neg; lp.po = po; lp.to = to; lp.wo = wo; lp.fo = fo; lp.extpol = extpolfac; lp.flags = p->d_flags;
+  AB_TRY(launch_lookup(lp, p->np, p->stream));
+  return AB200_OK;
+}
+
 int ab200_path_add_cia(ab200_path* p, const ab200_cia* cia, double T_extrapolfac, int32_t ignore_errors, double dT) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: path not uploaded");
   if (!cia) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: null CIA data");
@@ -715,6 +745,10 @@ static int check_flags(ab200_path* p) {
   if (h) {
     cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->stream);
     if (h & 2) return set_error(AB200_ERR_INVALID, "non-finite line-shape parameter (f0', 1/GD, G0 or strength) at some level");
+    if (h & 16)
+      return set_error(AB200_ERR_INVALID,
+                       "Error in check_limit: a frequency, pressure, temperature offset or water ratio is outside the "
+                       "extrapolation limits of a lookup table grid (lagrange_interp.h:572-650)");
     if (h & 8)
       return set_error(AB200_ERR_INVALID,
                        "Problem with CIA species: the temperature of a level is outside the extrapolation range of a data set "

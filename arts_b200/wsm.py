@@ -345,6 +345,15 @@ class Path:
     def download(self, I=None, K=None, dI=None, dK=None):
         check(lib().ab200_path_download(self._h, dptr(I), dptr(dI), dptr(K), dptr(dK)))
 
+    def add_lookup(self, lut: "Lookup", h2o_species=-1, target_d=(), p_interp_order=7, t_interp_order=7, water_interp_order=7,
+                   f_interp_order=7, extpolfac=0.5, zero_init=True):
+        """``spectral_propmatAddLookup`` (src/m_lookup.cc:143-173) on the resident K / dK; with ``zero_init`` instead of the
+        line-by-line term (``spectral_propmat_agendaAuto(use_abs_lookup_data=1)``)."""
+        d = np.ascontiguousarray(target_d, dtype=np.float64)
+        check(lib().ab200_path_add_lookup(self._h, lut.handle, int(h2o_species), dptr(d if len(d) else None), int(p_interp_order),
+                                          int(t_interp_order), int(water_interp_order), int(f_interp_order), float(extpolfac),
+                                          int(bool(zero_init))))
+
     def add_cia(self, cia: "Cia", T_extrapolfac=0.5, ignore_errors=0, dT=0.1):
         """``spectral_propmatAddCIA`` (src/m_cia.cc:27-178) on the resident K / dK, after ``run_propmat``."""
         check(lib().ab200_path_add_cia(self._h, cia.handle, float(T_extrapolfac), int(ignore_errors), float(dT)))
@@ -547,3 +556,80 @@ def partition_functions(tables, T):
     dQ = np.empty((len(T), len(tables)))
     check(lib().ab200_partfun_eval(arr, len(tables), len(T), dptr(T), dptr(Q), dptr(dQ)))
     return Q, dQ
+
+
+class Lookup:
+    """``abs_lookup_data`` on the device (ab200_lookup): a list of ``_abi.LookupTable``."""
+
+    def __init__(self, tables):
+        self._tables = list(tables)
+        arr = abi.lookup_tables(self._tables)
+        self._h = C.c_void_p()
+        check(lib().ab200_lookup_create(arr, len(self._tables), C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().ab200_lookup_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def abs_lookup_dataPrecompute(abs_bands, atm_profile: AtmPath, freq_grid, select_species, temperature_perturbation=None,
+                              water_perturbation=None, h2o_species=None) -> abi.LookupTable:
+    """``abs_lookup_dataPrecompute`` (src/m_lookup.cc:175-197, the ``lookup::table`` constructor src/core/lookup/lookup_map.cpp:22-131)
+    with the line-by-line sum on the GPU: for every temperature offset and water ratio the reference profile is perturbed and
+    ``lbl::calculate`` runs for the selected species with ``no_negative_absorption = true``; all nt * nw * np levels go through
+    ``ab200_propmat_levels`` in one call per (offset, ratio).  ``xsec = K.A / number_density(species)``."""
+    import copy
+
+    cat = _as_catalog(abs_bands)
+    f = np.ascontiguousarray(freq_grid, dtype=np.float64)
+    tp = [0.0] if temperature_perturbation is None else list(temperature_perturbation)
+    wp = [1.0] if water_perturbation is None else list(water_perturbation)
+    if water_perturbation is not None and h2o_species is None:
+        raise ValueError("a water perturbation grid needs the index of H2O in the VMR vector")
+    kB = 1.380649e-23
+    xsec = np.empty((len(tp), len(wp), atm_profile.np_, len(f)))
+    for it, dT in enumerate(tp):
+        for iw, wr in enumerate(wp):
+            atm = copy.deepcopy(atm_profile)
+            atm.T = atm.T + dT
+            if water_perturbation is not None:
+                atm.vmr = atm.vmr.copy()
+                atm.vmr[:, h2o_species] *= wr
+            K, _ = spectral_propmat_pathFromPath(cat, f, atm, select_species=select_species, no_negative_absorption=1)
+            nd = atm.vmr[:, select_species] * atm.P / (kB * atm.T)
+            xsec[it, iw] = K[..., 0] / nd[:, None]
+    return abi.LookupTable(species=int(select_species), f_grid=f, log_p_grid=np.log(atm_profile.P), t_atmref=np.array(atm_profile.T, float),
+                           xsec=xsec, t_pert=None if temperature_perturbation is None else np.asarray(tp, float),
+                           w_pert=None if water_perturbation is None else np.asarray(wp, float),
+                           water_atmref=None if water_perturbation is None else np.array(atm_profile.vmr[:, h2o_species], float))
+
+
+def spectral_propmatAddLookup(spectral_propmat, spectral_propmat_jac, freq_grid, jac_targets, select_species, abs_lookup_data: Lookup,
+                              atm_path: AtmPath, h2o_species=-1, target_d=(), no_negative_absorption=1, p_interp_order=7,
+                              t_interp_order=7, water_interp_order=7, f_interp_order=7, extpolfac=0.5):
+    """src/m_lookup.cc:143-173 for every level of ``atm_path``: ``spectral_propmat`` [np, nf, 7] is accumulated, the rows of
+    ``spectral_propmat_jac`` [np, nq, nf, 7] are assigned (like the reference, :130-135)."""
+    np_ = atm_path.np_
+    f, stride, nf = _f_arg(freq_grid, np_)
+    tg, nq = make_targets(jac_targets)
+    K, dK = spectral_propmat, spectral_propmat_jac
+    if K.shape != (np_, nf, 7) or not K.flags.c_contiguous or K.dtype != np.float64:
+        raise ValueError("spectral_propmat must be a C-contiguous float64 [np, nf, 7] array")
+    d = np.ascontiguousarray(target_d, dtype=np.float64)
+    a = atm_path.desc()
+    check(lib().ab200_lookup_levels(abs_lookup_data.handle, nf, dptr(f), stride, C.byref(a), atm_path.vmr.shape[1], int(h2o_species),
+                                    int(select_species), nq, tg, dptr(d if nq else None), int(no_negative_absorption), int(p_interp_order),
+                                    int(t_interp_order), int(water_interp_order), int(f_interp_order), float(extpolfac), dptr(K),
+                                    dptr(dK if nq else None)))
+    return K, dK

@@ -266,6 +266,44 @@ int ab200_cia_levels(const ab200_cia *cia, int64_t nf, const double *f, int64_t 
                      int32_t n_species, int32_t select_species, int32_t nq, const ab200_target *targets, double dT,
                      double T_extrapolfac, int32_t ignore_errors, double *K, double *dK);
 
+/* ---- absorption lookup tables: spectral_propmatAddLookup on the resident K -----------------------
+ * lookup::table (src/core/lookup/lookup_map.{h,cpp}): per species a cross-section tensor xsec [t_pert][w_pert][p][f]
+ * precomputed with the line-by-line code on a reference profile (table ctor :22-131 = K.A / number density, what
+ * ab200_propmat_levels delivers for the perturbed profiles), extracted by Lagrange interpolation of the given orders
+ * in temperature offset, water ratio, log-pressure (descending grid) and frequency (table::absorption :190-238 with
+ * pressure_/frequency_/water_/temperature_lagrange :133-188), times the species' number density.
+ * _spectral_propmatAddLookup (src/m_lookup.cc:20-141): K.A += absorption where no_negative_absorption == 0 or it is
+ * positive; every Jacobian target by re-extraction at the perturbed point, ASSIGNED to the row (sic, :130-135). */
+typedef struct ab200_lookup_table {
+  int32_t species;           /* the species this table stands for (atm_point.number_density(species)) */
+  int32_t nf, np, nt, nw;    /* nt / nw: size of t_pert / w_pert, or 1 when the table has no such grid (do_t / do_w false) */
+  int32_t do_t, do_w;
+  const double *f_grid;      /* [nf] ascending */
+  const double *log_p_grid;  /* [np] descending */
+  const double *t_pert;      /* [nt] ascending (do_t) */
+  const double *w_pert;      /* [nw] ascending (do_w) */
+  const double *t_atmref;    /* [np] temperature of the reference profile */
+  const double *water_atmref;/* [np] H2O VMR of the reference profile (do_w) */
+  const double *xsec;        /* [nt][nw][np][nf] */
+} ab200_lookup_table;
+typedef struct ab200_lookup ab200_lookup; /* device copy of AbsorptionLookupTables */
+int ab200_lookup_create(const ab200_lookup_table *tables, int32_t n_tables, ab200_lookup **out);
+void ab200_lookup_destroy(ab200_lookup *lut);
+/* Host-buffer form.  h2o_species: index of H2O in the vmr vector (-1 if no table has a water grid).  target_d [nq]: the
+ * perturbation of every Jacobian target (JacobianTargets' `d`).  K [np][nf][7] +=, dK [np][nq][nf][7] rows assigned. */
+int ab200_lookup_levels(const ab200_lookup *lut, int64_t nf, const double *f, int64_t f_level_stride,
+                        const ab200_atm_path *atm, int32_t n_species, int32_t h2o_species, int32_t select_species,
+                        int32_t nq, const ab200_target *targets, const double *target_d, int32_t no_negative_absorption,
+                        int32_t p_interp_order, int32_t t_interp_order, int32_t water_interp_order, int32_t f_interp_order,
+                        double extpolfac, double *K, double *dK);
+
+/* On the resident path: adds the lookup-table absorption to K (and assigns the rows of dK of the path's targets).  With
+ * zero_init the resident K / dK are cleared first - the agenda with use_abs_lookup_data = 1 has no line-by-line term
+ * (src/m_abs.cc:257-266), so ab200_path_run_propmat is simply not called.  no_negative_absorption is the path's. */
+int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_species, const double *target_d,
+                          int32_t p_interp_order, int32_t t_interp_order, int32_t water_interp_order,
+                          int32_t f_interp_order, double extpolfac, int32_t zero_init);
+
 /* ---- catalog ingest: HITRAN .par records straight into the SoA of ab200_catalog_desc -------------
  * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], line_strength_option = "A",
  * compute_zeeman_parameters = 0: read_par_line (src/core/lbl/lbl_hitran.cpp:66-89, the 160-column record and its unit

@@ -1885,6 +1885,153 @@ int orc_cia_levels(const ab200_cia_record* records, int32_t n_records, int64_t n
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// absorption lookup tables
+// ---------------------------------------------------------------------------
+namespace lut {
+constexpr int MAXP = 16;  // stencil points supported (orders up to 15; the defaults are 7)
+struct Lag {
+  Index i0 = 0, order = 0;
+  double w[MAXP];
+};
+// lagrange_interp: check_limit (lagrange_interp.h:572-650), update_pos fixed point (:160-248, both grid orders, nearest
+// neighbour for order 0) and set_weights (:300-440).  Returns false with a message for the reference's exceptions.
+bool make_lag(Lag& l, const double* xi, Index n, Index order, Numeric x, Numeric limit, const char* info, std::string& err) {
+  const bool ascending = n <= 1 or xi[0] < xi[1];
+  if (order >= n) {
+    err = std::string("Error in check_limit for ") + info + ":\nToo few grid points for the given polynomial order";
+    return false;
+  }
+  if (order > 0 and limit > 0.0) {
+    const Numeric hi = ascending ? xi[n - 1] + limit * (xi[n - 1] - xi[n - 2]) : xi[0] + limit * (xi[0] - xi[1]);
+    const Numeric lo = ascending ? xi[0] - limit * (xi[1] - xi[0]) : xi[n - 1] - limit * (xi[n - 2] - xi[n - 1]);
+    if (hi < x or lo > x) {
+      err = std::string("Error in check_limit for ") + info + ":\nExtrapolation limit yields limits to the extrapolation of the grid that are outside the input grid.";
+      return false;
+    }
+  }
+  const Index P = order + 1;
+  l.order = order;
+  if (n <= P) {
+    l.i0 = 0;
+  } else {
+    const Index Of = order / 2, xf = Of, xe = n - P / 2 - 1;
+    Index xp = xf;
+    if (ascending) {
+      while (xp < xe and xi[xp + 1] < x) ++xp;
+      while (xp > xf and xi[xp] > x) --xp;
+    } else {
+      while (xp < xe and xi[xp + 1] > x) ++xp;
+      while (xp > xf and xi[xp] < x) --xp;
+    }
+    if (order == 0) {
+      const Index xn = xp + 1;
+      xp = (xn == n or std::abs(x - xi[xn]) > std::abs(x - xi[xp])) ? xp : xn;
+    }
+    l.i0 = std::clamp(xp, xf, xe) - xf;
+  }
+  for (Index j = 0; j < order; j++) {
+    const Numeric xj = xi[l.i0 + j];
+    Numeric numer = 1.0, denom = 1.0;
+    for (Index k = 0; k < order; k++) {
+      const Index m = l.i0 + k + (k >= j);
+      numer *= x - xi[m];
+      denom *= xj - xi[m];
+    }
+    l.w[j] = numer / denom;
+  }
+  l.w[order] = 1.0;
+  for (Index j = 0; j < order; j++) l.w[order] -= l.w[j];
+  return true;
+}
+Numeric interp1(const double* field, const Lag& l) {
+  Numeric out = 0;
+  for (Index i = 0; i <= l.order; i++) out += field[l.i0 + i] * l.w[i];
+  return out;
+}
+// table::absorption, lookup_map.cpp:190-238
+bool absorption(std::vector<double>& absorb, const ab200_lookup_table& t, const double* f, Index nf, Numeric T, Numeric P,
+                const double* vmr, int h2o, int po, int to, int wo, int fo, Numeric extpol, std::string& err) {
+  Lag plag, tlag, wlag;
+  tlag.w[0] = wlag.w[0] = 1.0;
+  std::vector<Lag> flag(nf);
+  for (Index i = 0; i < nf; i++)
+    if (not make_lag(flag[i], t.f_grid, t.nf, fo, f[i], extpol, "Frequency", err)) return false;
+  if (not make_lag(plag, t.log_p_grid, t.np, po, std::log(P), extpol, "Log-Pressure", err)) return false;
+  if (t.do_w) {  // water_lagrange :161-173
+    const Numeric x = vmr[h2o] / interp1(t.water_atmref, plag);
+    if (not make_lag(wlag, t.w_pert, t.nw, wo, x, extpol, "Water VMR", err)) return false;
+  }
+  if (t.do_t) {  // temperature_lagrange :175-188
+    const Numeric x = T - interp1(t.t_atmref, plag);
+    if (not make_lag(tlag, t.t_pert, t.nt, to, x, extpol, "Temperature", err)) return false;
+  }
+  const Numeric nd = vmr[t.species] * number_density(P, T);  // AtmPoint::number_density(species)
+  for (Index i = 0; i < nf; i++) {
+    // reinterp / interp, lagrange_interp.h:920-940: temperature outermost, then water, pressure, frequency;
+    // every term is ((((field * wt) * ww) * wp) * wf), dimensions the table does not have are left out (:213-231)
+    Numeric out = 0;
+    for (Index a = 0; a <= tlag.order; a++)
+      for (Index b = 0; b <= wlag.order; b++)
+        for (Index c = 0; c <= plag.order; c++)
+          for (Index d = 0; d <= flag[i].order; d++) {
+            Numeric v = t.xsec[(((tlag.i0 + a) * t.nw + wlag.i0 + b) * t.np + plag.i0 + c) * t.nf + flag[i].i0 + d];
+            if (t.do_t) v *= tlag.w[a];
+            if (t.do_w) v *= wlag.w[b];
+            v *= plag.w[c];
+            v *= flag[i].w[d];
+            out += v;
+          }
+    absorb[i] += out * nd;
+  }
+  return true;
+}
+}  // namespace lut
+
+// _spectral_propmatAddLookup, src/m_lookup.cc:20-141, for every level of a path
+int orc_lookup_levels(const ab200_lookup_table* tables, int32_t n_tables, int64_t nf, const double* f_in, int64_t f_level_stride,
+                      const ab200_atm_path* atm, int32_t n_species, int32_t h2o_species, int32_t select_species, int32_t nq,
+                      const ab200_target* targets, const double* target_d, int32_t no_negative_absorption, int32_t po, int32_t to,
+                      int32_t wo, int32_t fo, double extpolfac, double* K, double* dK) {
+  const int np = atm->np;
+  if (std::max({po, to, wo, fo}) >= lut::MAXP) return fail(AB200_ERR_UNSUPPORTED, "interpolation order above 15");
+  std::string err;
+  auto total = [&](std::vector<double>& out, const double* f, Numeric T, Numeric P, const double* vmr) -> int {
+    std::fill(out.begin(), out.end(), 0.0);
+    bool found = false;
+    for (int k = 0; k < n_tables; k++) {
+      if (select_species != AB200_SPECIES_BATH and tables[k].species != select_species) continue;
+      found = true;
+      if (tables[k].nt * tables[k].nw * tables[k].np * tables[k].nf == 0) continue;  // xsec.empty(), :201
+      if (not lut::absorption(out, tables[k], f, nf, T, P, vmr, h2o_species, po, to, wo, fo, extpolfac, err))
+        return fail(AB200_ERR_INVALID, err);
+    }
+    if (select_species != AB200_SPECIES_BATH and not found) return fail(AB200_ERR_INVALID, "no lookup table for the selected species");  // .at()
+    return 0;
+  };
+  std::vector<double> ab(nf), dab(nf), vm(n_species);
+  for (int ip = 0; ip < np; ip++) {
+    const double* f = f_in + ip * f_level_stride;
+    const double* vmr = atm->vmr + static_cast<Index>(ip) * n_species;
+    if (int rc = total(ab, f, atm->T[ip], atm->P[ip], vmr)) return rc;
+    for (Index i = 0; i < nf; i++)
+      if (no_negative_absorption == 0 or ab[i] > 0.0) K[(static_cast<Index>(ip) * nf + i) * 7] += ab[i];
+    for (int q = 0; q < nq; q++) {
+      const Numeric d = target_d[q];
+      if (not std::isnormal(d)) return fail(AB200_ERR_INVALID, "The target is not good, it lacks a perturbation value.");
+      std::copy(vmr, vmr + n_species, vm.begin());
+      Numeric T = atm->T[ip];
+      if (targets[q].kind == AB200_TARGET_T) T += d; else vm[targets[q].species] += d;
+      if (int rc = total(dab, f, T, atm->P[ip], vm.data())) return rc;
+      const Numeric d_inv = 1.0 / d;
+      for (Index i = 0; i < nf; i++)
+        if (no_negative_absorption == 0 or dab[i] > 0.0)
+          dK[((static_cast<Index>(ip) * nq + q) * nf + i) * 7] = (dab[i] - ab[i]) * d_inv;  // '=' (sic), :130-135
+    }
+  }
+  return 0;
+}
+
 // rtepack::tran for single inputs (tests: exp(-K r) against scipy expm, src/tests/test_rtepack.cc:12-33)
 int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, double* T, double* L) {
   const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};

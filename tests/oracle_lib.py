@@ -53,6 +53,9 @@ def lib():
         L.orc_norm_view.argtypes = [C.c_int, dp, dp, dp]
         L.orc_cia_levels.argtypes = [C.POINTER(abi.CiaRecordDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
                                      C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), C.c_double, C.c_double, C.c_int32, dp, dp]
+        L.orc_lookup_levels.argtypes = [C.POINTER(abi.LookupTableDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), dp, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_double, dp, dp]
         L.orc_background.argtypes = [C.c_int64, dp, C.c_double, dp, dp]
         L.orc_observer.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(abi.ObserverDesc), dp, dp, dp, dp, dp, dp]
         for name in ("orc_invplanck", "orc_dinvplanckdI", "orc_invrayjean", "orc_dplanck_dt"):
@@ -264,4 +267,20 @@ def cia_levels(records, f, atm: AtmPath, select_species=abi.SPECIES_BATH, target
     a = atm.desc()
     _check(lib().orc_cia_levels(arr, len(records), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1], select_species, nq, tg,
                                 float(dT), float(T_extrapolfac), int(ignore_errors), dptr(K), dptr(dK)))
+    return K, dK
+
+
+def lookup_levels(tables, f, atm: AtmPath, h2o_species=-1, select_species=abi.SPECIES_BATH, targets=(), target_d=(),
+                  no_negative_absorption=1, orders=(7, 7, 7, 7), extpolfac=0.5, K=None, dK=None):
+    """_spectral_propmatAddLookup (src/m_lookup.cc:20-141) per level; orders = (p, t, water, f)."""
+    f, stride, nf = _f_arg(f, atm.np_)
+    tg, nq = make_targets(targets)
+    K = np.zeros((atm.np_, nf, 7)) if K is None else K
+    dK = np.zeros((atm.np_, nq, nf, 7)) if dK is None else dK
+    arr = abi.lookup_tables(tables)
+    d = np.ascontiguousarray(target_d, dtype=np.float64)
+    a = atm.desc()
+    _check(lib().orc_lookup_levels(arr, len(tables), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1], int(h2o_species), select_species,
+                                   nq, tg, dptr(d), int(no_negative_absorption), *[int(o) for o in orders], float(extpolfac), dptr(K),
+                                   dptr(dK)))
     return K, dK

@@ -532,3 +532,99 @@ def test_cia_interpolation_reference_fixture_and_numpy(orc):
     assert np.array_equal(dK1[:, 2], dK1[:, 1]) and np.abs(dK1[:, 2]).max() > 0
     Kt, _ = orc.cia_levels(recs, f, abi.AtmPath(T=Tl + 0.1, P=Pl, vmr=vmr, isorat=np.ones((3, 1)), Q=np.ones((3, 1))))
     np.testing.assert_allclose(dK[:, 0, :, 0], (Kt - K)[..., 0] / 0.1, rtol=2e-3, atol=2e-3 * np.abs(dK[:, 0]).max())
+
+
+def _lut_fixture(rng, do_t=True, do_w=True, species=0, nf=14, np_=9):
+    f_grid = np.sort(rng.uniform(1e11, 3e11, nf))
+    log_p = (np.linspace(np.log(1e5), np.log(50.0), np_) + rng.uniform(-0.05, 0.05, np_)).copy()  # descending, mildly uneven
+    t_pert = np.array([-30.0, -12.0, 0.0, 10.0, 28.0]) if do_t else None
+    w_pert = np.array([0.2, 0.5, 1.0, 2.0, 4.0, 8.0]) if do_w else None
+    t_ref = np.linspace(290.0, 215.0, np_)
+    w_ref = np.geomspace(2e-2, 1e-5, np_)
+    nt, nw = (5 if do_t else 1), (6 if do_w else 1)
+    xsec = 1e-26 * np.exp(rng.normal(size=(nt, nw, np_, nf)))
+    return abi.LookupTable(species=species, f_grid=f_grid, log_p_grid=log_p, t_atmref=t_ref, xsec=xsec, t_pert=t_pert, w_pert=w_pert,
+                           water_atmref=w_ref if do_w else None)
+
+
+def _np_lag(xg, order, x):
+    """Stencil rule of lagrange_interp (both grid orders, nearest neighbour for order 0) + textbook weights."""
+    xg = np.asarray(xg, float)
+    n, P = len(xg), order + 1
+    asc = n <= 1 or xg[0] < xg[1]
+    if n <= P:
+        i0 = 0
+    else:
+        key = xg if asc else -xg
+        m = int(np.searchsorted(key, x if asc else -x, side="left"))
+        xf, xe = order // 2, n - P // 2 - 1
+        xp = int(np.clip(m - 1, xf, xe))
+        if order == 0 and xp + 1 < n and not abs(x - xg[xp + 1]) > abs(x - xg[xp]):
+            xp = min(xp + 1, xe)
+        i0 = xp - xf
+    st = xg[i0:i0 + P]
+    return i0, np.array([np.prod([(x - xk) / (xj - xk) for xk in st if xk != xj]) for xj in st])
+
+
+@pytest.mark.parametrize("do_t,do_w", [(True, True), (True, False), (False, True), (False, False)])
+def test_lookup_table_extraction_against_numpy(orc, do_t, do_w):
+    """table::absorption (src/core/lookup/lookup_map.cpp:190-238) and _spectral_propmatAddLookup (src/m_lookup.cc:20-141) against an
+    independent numpy evaluation: tensor-product Lagrange interpolation in (temperature offset, water ratio, log p, f)."""
+    rng = np.random.default_rng(31 + 2 * do_t + do_w)
+    tab = _lut_fixture(rng, do_t, do_w, species=1)
+    f = np.sort(rng.uniform(tab.f_grid[0], tab.f_grid[-1], 40))
+    P = np.exp(rng.uniform(tab.log_p_grid[-1], tab.log_p_grid[0], 3))
+    Tref = np.interp(np.log(P), tab.log_p_grid[::-1], tab.t_atmref[::-1])
+    wref = np.interp(np.log(P), tab.log_p_grid[::-1], tab.water_atmref[::-1]) if do_w else np.full(3, 1e-3)
+    atm = abi.AtmPath(T=Tref + np.array([-8.0, 3.0, 15.0]), P=P, vmr=np.stack([wref * np.array([0.6, 1.3, 2.5]), [0.2, 0.21, 0.19]], 1),
+                      isorat=np.ones((3, 1)), Q=np.ones((3, 1)))
+    for orders in ((3, 2, 3, 1), (1, 1, 1, 0), (5, 4, 4, 2)):
+        K, _ = orc.lookup_levels([tab], f, atm, h2o_species=0, orders=orders)
+        ref = np.zeros((3, len(f)))
+        for lev in range(3):
+            ip, wp_ = _np_lag(tab.log_p_grid, orders[0], np.log(P[lev]))
+            it, wt = (0, np.ones(1))
+            iw, ww = (0, np.ones(1))
+            if do_t:
+                it, wt = _np_lag(tab.t_pert, orders[1], atm.T[lev] - float(tab.t_atmref[ip:ip + len(wp_)] @ wp_))
+            if do_w:
+                iw, ww = _np_lag(tab.w_pert, orders[2], atm.vmr[lev, 0] / float(tab.water_atmref[ip:ip + len(wp_)] @ wp_))
+            nd = atm.vmr[lev, 1] * P[lev] / (1.380649e-23 * atm.T[lev])
+            for i, x in enumerate(f):
+                i0, wf = _np_lag(tab.f_grid, orders[3], x)
+                blk = tab.xsec[it:it + len(wt), iw:iw + len(ww), ip:ip + len(wp_), i0:i0 + len(wf)]
+                ref[lev, i] = np.einsum("abcd,a,b,c,d->", blk, wt, ww, wp_, wf) * nd
+        np.testing.assert_allclose(K[..., 0], np.where(ref > 0, ref, 0.0), rtol=1e-10, atol=1e-13 * np.abs(ref).max())
+    # Jacobian rows are ASSIGNED from a re-extraction at the perturbed point (m_lookup.cc:79-136)
+    tg, d = (("T",), ("VMR", 0), ("VMR", 1)), (0.1, 1e-6, 1e-4)
+    dK0 = np.full((3, 3, len(f), 7), 9.0)
+    K, dK = orc.lookup_levels([tab], f, atm, h2o_species=0, targets=tg, target_d=d, orders=(3, 2, 3, 1), no_negative_absorption=0, dK=dK0)
+    for q, (t, dd) in enumerate(zip(tg, d)):
+        pert = abi.AtmPath(T=atm.T + (dd if t[0] == "T" else 0.0), P=P, vmr=atm.vmr + (dd * np.eye(2)[t[1]] if t[0] == "VMR" else 0.0),
+                           isorat=np.ones((3, 1)), Q=np.ones((3, 1)))
+        Kp, _ = orc.lookup_levels([tab], f, pert, h2o_species=0, orders=(3, 2, 3, 1), no_negative_absorption=0)
+        np.testing.assert_allclose(dK[:, q, :, 0], (Kp - K)[..., 0] / dd, rtol=1e-6, atol=1e-9 * np.abs(dK[:, q, :, 0]).max())
+        assert np.array_equal(dK[:, q, :, 1:], np.full_like(dK[:, q, :, 1:], 9.0)), "only A of the row is assigned"
+    # a polynomial table of low degree is reproduced exactly by interpolation of sufficient order
+    tt = tab.t_pert if do_t else np.zeros(1)
+    wv = tab.w_pert if do_w else np.ones(1)
+    poly = lambda t_, w_, lp, ff: (1 + 0.01 * t_) * (1 + 0.3 * w_ - 0.02 * w_ ** 2) * (1 + 0.05 * lp) * (1 + 2e-12 * ff)  # noqa: E731
+    tab2 = abi.LookupTable(species=1, f_grid=tab.f_grid, log_p_grid=tab.log_p_grid, t_atmref=tab.t_atmref, t_pert=tab.t_pert,
+                           w_pert=tab.w_pert, water_atmref=tab.water_atmref,
+                           xsec=poly(tt[:, None, None, None], wv[None, :, None, None], tab.log_p_grid[None, None, :, None],
+                                     tab.f_grid[None, None, None, :]))
+    K, _ = orc.lookup_levels([tab2], f, atm, h2o_species=0, orders=(1, 1, 2, 1))
+    lp = np.log(P)
+    toff = atm.T - np.array([float(tab.t_atmref[i:i + 2] @ w) for i, w in (_np_lag(tab.log_p_grid, 1, x) for x in lp)]) if do_t else np.zeros(3)
+    wrat = atm.vmr[:, 0] / np.array([float(tab.water_atmref[i:i + 2] @ w) for i, w in (_np_lag(tab.log_p_grid, 1, x) for x in lp)]) if do_w else np.ones(3)
+    nd = atm.vmr[:, 1] * P / (1.380649e-23 * atm.T)
+    exact = poly(toff[:, None], wrat[:, None], lp[:, None], f[None, :]) * nd[:, None]
+    np.testing.assert_allclose(K[..., 0], exact, rtol=1e-11)
+    # errors: outside the extrapolation limit; too few points for the order
+    far = abi.AtmPath(T=atm.T, P=P * 1e6, vmr=atm.vmr, isorat=np.ones((3, 1)), Q=np.ones((3, 1)))
+    with pytest.raises(RuntimeError, match="check_limit for Log-Pressure"):
+        orc.lookup_levels([tab], f, far, h2o_species=0, orders=(3, 2, 3, 1))
+    with pytest.raises(RuntimeError, match="Too few grid points"):
+        orc.lookup_levels([tab], f, atm, h2o_species=0, orders=(9, 1, 1, 1))
+    with pytest.raises(RuntimeError, match="no lookup table"):
+        orc.lookup_levels([tab], f, atm, h2o_species=0, select_species=0)

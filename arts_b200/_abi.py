@@ -350,6 +350,18 @@ class AtmPath:
     def np_(self) -> int:
         return int(len(self.T))
 
+    def reversed(self) -> "AtmPath":
+        """The same points in the opposite order (a path runs sensor -> background, a lookup-table profile surface -> top)."""
+        r = lambda a: None if a is None else np.ascontiguousarray(a[::-1])  # noqa: E731
+        return AtmPath(T=r(self.T), P=r(self.P), vmr=r(self.vmr), isorat=r(self.isorat), Q=r(self.Q), dQdT=r(self.dQdT), mag=r(self.mag),
+                       los=r(self.los), wind=r(self.wind))
+
+    def take(self, idx) -> "AtmPath":
+        """The points ``idx`` (any numpy index) as a new path."""
+        r = lambda a: None if a is None else np.ascontiguousarray(a[idx])  # noqa: E731
+        return AtmPath(T=r(self.T), P=r(self.P), vmr=r(self.vmr), isorat=r(self.isorat), Q=r(self.Q), dQdT=r(self.dQdT), mag=r(self.mag),
+                       los=r(self.los), wind=r(self.wind))
+
     def level(self, ip: int) -> "AtmPath":
         s = slice(ip, ip + 1)
         return AtmPath(

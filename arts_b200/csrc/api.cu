@@ -98,6 +98,7 @@ struct ab200_path {
   uint32_t flags = 0;
   cudaEvent_t ev_staged = nullptr;  // the pinned staging blocks may be refilled once this has completed
   bool uploaded = false, k_preloaded = false;
+  bool k_only_A = false;  // K / dK were cleared and filled by a term that only touches A (lookup tables): scalar Stokes path
 
   // observer epilogue (ab200_path_run_observer)
   struct DevBuf {  // grow-only device array
@@ -366,6 +367,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   p->uploaded   = true;
   p->k_preloaded = false;
   p->dk_preloaded = false;
+  p->k_only_A = false;
   return AB200_OK;
 }
 
@@ -427,6 +429,7 @@ int ab200_path_run_propmat(ab200_path* p) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_propmat: path not uploaded");
   const ab200_catalog* cat = p->cat;
   AB_CUDA(cudaSetDevice(cat->device));
+  p->k_only_A = false;
   const size_t kbytes = static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double);
   // With mode-0 (real) segments selected the real line sum writes whole K records itself (vector stores);
   // only without them, or when the caller's K is accumulated into, K is zeroed / kept and updated in place.
@@ -552,7 +555,7 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
   sp.I_lev = p->nq > 0 ? p->d_Ilev : nullptr;
   sp.no_emission = (p->flags & AB200_FLAG_NO_EMISSION) ? 1 : 0;
   sp.flags = p->d_flags;
-  sp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded) ? 1 : 0;  // only mode-0 (real, pol = no) segments wrote K
+  sp.scalar = ((p->nsegs[1] == 0 && !p->k_preloaded) || p->k_only_A) ? 1 : 0;  // only mode-0 (real, pol = no) segments wrote K
   {
     LaunchTimer t(p, 3);
     AB_TRY(launch_stokes_chain(sp, p->stream));
@@ -564,7 +567,7 @@ static int run_stokes_impl(ab200_path* p, const ab200_observer* obs) {
     jp.f = p->d_f; jp.f_stride = p->f_stride; jp.ffac = p->d_ffac; jp.T = p->d_T; jp.r = p->d_r; jp.dr = p->d_dr; jp.I_lev = p->d_Ilev;
     jp.dI = p->d_dI; jp.it = p->it; jp.rte_option = p->rte_option; jp.flags = p->d_flags;
     jp.no_emission = (p->flags & AB200_FLAG_NO_EMISSION) ? 1 : 0;
-    jp.scalar = (p->nsegs[1] == 0 && !p->k_preloaded && !p->dk_preloaded) ? 1 : 0;
+    jp.scalar = ((p->nsegs[1] == 0 && !p->k_preloaded && !p->dk_preloaded) || p->k_only_A) ? 1 : 0;
     if (obs) {  // x-space accumulation inside the pass; the per-level dI is not written
       jp.dI = nullptr;
       jp.Jx = static_cast<double*>(p->o_Jx.p);
@@ -601,7 +604,7 @@ int ab200_path_add_lookup(ab200_path* p, const ab200_lookup* lut, int32_t h2o_sp
     AB_CUDA(cudaMemsetAsync(p->d_K, 0, static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double), p->stream));
     if (p->nq > 0)
       AB_CUDA(cudaMemsetAsync(p->d_dK, 0, static_cast<size_t>(p->np) * p->nq * p->k_pitch * 7 * sizeof(double), p->stream));
-    p->nsegs[1] = 0;  // K holds only A: the scalar Stokes instantiations apply
+    p->k_only_A = true;  // K holds only A: the scalar Stokes instantiations apply
   }
   lp.t = lut_dev(lut);
   lp.nf = p->nf; lp.f = p->d_f; lp.f_stride = p->f_stride; lp.ffac = p->d_ffac; lp.T = p->d_T; lp.P = p->d_P; lp.vmr = p->d_vmr;

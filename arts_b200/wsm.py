@@ -597,6 +597,9 @@ def abs_lookup_dataPrecompute(abs_bands, atm_profile: AtmPath, freq_grid, select
     wp = [1.0] if water_perturbation is None else list(water_perturbation)
     if water_perturbation is not None and h2o_species is None:
         raise ValueError("a water perturbation grid needs the index of H2O in the VMR vector")
+    if atm_profile.np_ > 1 and not (np.diff(atm_profile.P) < 0).all():
+        raise ValueError("the reference profile of a lookup table must have descending pressures (DescendingGrid log_p_grid, "
+                         "src/core/lookup/lookup_map.h)")
     kB = 1.380649e-23
     xsec = np.empty((len(tp), len(wp), atm_profile.np_, len(f)))
     for it, dT in enumerate(tp):

@@ -75,6 +75,8 @@ def lib():
     L.ab200_lookup_destroy.restype = None
     L.ab200_lookup_levels.argtypes = [_vp, C.c_int64, _dp, C.c_int64, C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(abi.Target), _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp, _dp]
+    L.ab200_lookup_precompute.argtypes = [_vp, C.c_int64, _dp, C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int32,
+                                          _dp, C.POINTER(abi.PartfunTable), _dp]
     L.ab200_path_add_lookup.argtypes = [_vp, _vp, C.c_int32, _dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32]
     L.ab200_partfun_eval.argtypes = [C.POINTER(abi.PartfunTable), C.c_int32, C.c_int32, _dp, _dp, _dp]
     L.ab200_cia_create.argtypes = [C.POINTER(abi.CiaRecordDesc), C.c_int32, C.POINTER(_vp)]

@@ -875,6 +875,57 @@ int ab200_propmat_levels(const ab200_catalog* cat, int64_t nf, const double* f, 
   return ab200_path_download(p, nullptr, nullptr, K, nq > 0 ? dK : nullptr);
 }
 
+int ab200_lookup_precompute(const ab200_catalog* cat, int64_t nf, const double* f, const ab200_atm_path* atm_ref, int32_t select_species,
+                            int32_t h2o_species, int32_t nt, const double* t_pert, int32_t nw, const double* w_pert,
+                            const ab200_partfun_table* partfun, double* xsec) {
+  if (!cat || !atm_ref || !xsec || (nf > 0 && !f)) return set_error(AB200_ERR_INVALID, "ab200_lookup_precompute: null argument");
+  if (nf < 0 || nt < 1 || nw < 1 || (t_pert == nullptr && nt != 1) || (w_pert == nullptr && nw != 1))
+    return set_error(AB200_ERR_INVALID, "ab200_lookup_precompute: bad perturbation grid sizes");
+  if (select_species < 0 || select_species >= cat->n_species)
+    return set_error(AB200_ERR_INVALID, "ab200_lookup_precompute: the table needs one species (atm_point.number_density(species))");
+  if (w_pert && (h2o_species < 0 || h2o_species >= cat->n_species))
+    return set_error(AB200_ERR_INVALID, "ab200_lookup_precompute: a water grid needs the index of H2O in the VMR vector");
+  const int np = atm_ref->np;
+  for (int ip = 1; ip < np; ip++)  // DescendingGrid log_p_grid, lookup_map.h
+    if (!(atm_ref->P[ip] < atm_ref->P[ip - 1]))
+      return set_error(AB200_ERR_INVALID, "the reference profile of a lookup table must have descending pressures");
+  if (np == 0 || nf == 0) return AB200_OK;
+  ab200_path* p = nullptr;
+  AB_TRY(cached_path(cat, nf, np, 0, &p));
+  double* d_x = nullptr;
+  AB_TRY(dev_alloc(&d_x, static_cast<size_t>(np) * nf));
+  struct Free { double* q; ~Free() { cudaFree(q); } } guard{d_x};
+  std::vector<double> Tp(np), vp(static_cast<size_t>(np) * cat->n_species), Qp(static_cast<size_t>(np) * cat->n_isot);
+  ab200_atm_path a = *atm_ref;
+  a.T = Tp.data();
+  a.vmr = vp.data();
+  a.dQdT = nullptr;
+  for (int it = 0; it < nt; it++) {
+    for (int ip = 0; ip < np; ip++) Tp[ip] = atm_ref->T[ip] + (t_pert ? t_pert[it] : 0.0);
+    if (partfun) {  // PartitionFunctions::Q at the perturbed temperature, as lbl::calculate does (line_strength_calc :22-36)
+      AB_TRY(ab200_partfun_eval(partfun, cat->n_isot, np, Tp.data(), Qp.data(), nullptr));
+      a.Q = Qp.data();
+    }
+    for (int iw = 0; iw < nw; iw++) {
+      for (int ip = 0; ip < np; ip++) {  // :93-96
+        for (int s = 0; s < cat->n_species; s++) {
+          double v = atm_ref->vmr[static_cast<size_t>(ip) * cat->n_species + s];
+          if (w_pert && s == h2o_species) v *= w_pert[iw];
+          vp[static_cast<size_t>(ip) * cat->n_species + s] = v;
+        }
+      }
+      AB_TRY(ab200_path_upload(p, f, 0, &a, select_species, /*no_negative_absorption=*/1, nullptr, nullptr, 0, AB200_RTE_LINSRC, nullptr,
+                               AB200_FLAG_K_ZERO_INIT));
+      AB_TRY(ab200_path_run_propmat(p));
+      AB_TRY(launch_xsec_from_K(np, nf, p->d_K, p->k_pitch, p->d_T, p->d_P, p->d_vmr, cat->n_species, select_species, d_x, p->stream));
+      AB_CUDA(cudaMemcpyAsync(xsec + (static_cast<size_t>(it) * nw + iw) * np * nf, d_x, static_cast<size_t>(np) * nf * sizeof(double),
+                              cudaMemcpyDeviceToHost, p->stream));
+      AB_TRY(check_flags(p));  // synchronises: Tp / vp and d_x are reused by the next point
+    }
+  }
+  return AB200_OK;
+}
+
 int ab200_clearsky_emission(const ab200_catalog* cat, int64_t nf, const double* f, int64_t f_level_stride,
                             const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
                             int32_t nq, const ab200_target* targets, const double* r, int32_t hse_derivative,

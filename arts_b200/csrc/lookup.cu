@@ -158,6 +158,27 @@ int launch_lookup(const LutParams& p, int nlev, cudaStream_t stream) {
   return 0;
 }
 
+__global__ void xsec_from_K_kernel(int64_t nf, const double* __restrict__ K, int64_t k_pitch, const double* __restrict__ T,
+                                   const double* __restrict__ P, const double* __restrict__ vmr, int n_species, int species,
+                                   double* __restrict__ xsec) {
+  const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (iv >= nf) return;
+  const int lev = blockIdx.y;
+  const double nd     = vmr[int64_t(lev) * n_species + species] * (P[lev] / (cst::k * T[lev]));  // AtmPoint::number_density(species)
+  const double inv_nd = 1.0 / nd;                                                               // lookup_map.cpp:108
+  xsec[int64_t(lev) * nf + iv] = K[(int64_t(lev) * k_pitch + iv) * 7] * inv_nd;
+}
+
+int launch_xsec_from_K(int np, int64_t nf, const double* K, int64_t k_pitch, const double* T, const double* P, const double* vmr,
+                       int n_species, int species, double* xsec, cudaStream_t stream) {
+  if (np == 0 || nf == 0) return 0;
+  dim3 grid(static_cast<unsigned>((nf + 255) / 256), static_cast<unsigned>(np));
+  xsec_from_K_kernel<<<grid, 256, 0, stream>>>(nf, K, k_pitch, T, P, vmr, n_species, species, xsec);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 LutDev lut_dev(const ab200_lookup* l) { return LutDev{l->n_tables, l->d_meta, l->d_off, l->d_pool}; }
 int lut_device(const ab200_lookup* l) { return l->device; }
 

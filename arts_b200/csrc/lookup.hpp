@@ -36,6 +36,9 @@ struct LutParams {
 };
 
 int launch_lookup(const LutParams& p, int nlev, cudaStream_t stream);
+// xsec [np][nf] = K [np][k_pitch][7].A / (vmr[lev][species] P / (k T)): the table constructor's division, lookup_map.cpp:108-111
+int launch_xsec_from_K(int np, int64_t nf, const double* K, int64_t k_pitch, const double* T, const double* P, const double* vmr,
+                       int n_species, int species, double* xsec, cudaStream_t stream);
 LutDev lut_dev(const ab200_lookup* l);
 int lut_device(const ab200_lookup* l);
 // host-side checks of a call against the tables: 0 or an error code with the message set

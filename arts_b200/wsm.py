@@ -584,13 +584,11 @@ class Lookup:
 
 
 def abs_lookup_dataPrecompute(abs_bands, atm_profile: AtmPath, freq_grid, select_species, temperature_perturbation=None,
-                              water_perturbation=None, h2o_species=None) -> abi.LookupTable:
+                              water_perturbation=None, h2o_species=None, partfun_tables=None) -> abi.LookupTable:
     """``abs_lookup_dataPrecompute`` (src/m_lookup.cc:175-197, the ``lookup::table`` constructor src/core/lookup/lookup_map.cpp:22-131)
     with the line-by-line sum on the GPU: for every temperature offset and water ratio the reference profile is perturbed and
     ``lbl::calculate`` runs for the selected species with ``no_negative_absorption = true``; all nt * nw * np levels go through
-    ``ab200_propmat_levels`` in one call per (offset, ratio).  ``xsec = K.A / number_density(species)``."""
-    import copy
-
+    the device in one launch sequence per (offset, ratio) (``ab200_lookup_precompute``).  ``xsec = K.A / number_density(species)``."""
     cat = _as_catalog(abs_bands)
     f = np.ascontiguousarray(freq_grid, dtype=np.float64)
     tp = [0.0] if temperature_perturbation is None else list(temperature_perturbation)
@@ -600,18 +598,21 @@ def abs_lookup_dataPrecompute(abs_bands, atm_profile: AtmPath, freq_grid, select
     if atm_profile.np_ > 1 and not (np.diff(atm_profile.P) < 0).all():
         raise ValueError("the reference profile of a lookup table must have descending pressures (DescendingGrid log_p_grid, "
                          "src/core/lookup/lookup_map.h)")
-    kB = 1.380649e-23
     xsec = np.empty((len(tp), len(wp), atm_profile.np_, len(f)))
-    for it, dT in enumerate(tp):
-        for iw, wr in enumerate(wp):
-            atm = copy.deepcopy(atm_profile)
-            atm.T = atm.T + dT
-            if water_perturbation is not None:
-                atm.vmr = atm.vmr.copy()
-                atm.vmr[:, h2o_species] *= wr
-            K, _ = spectral_propmat_pathFromPath(cat, f, atm, select_species=select_species, no_negative_absorption=1)
-            nd = atm.vmr[:, select_species] * atm.P / (kB * atm.T)
-            xsec[it, iw] = K[..., 0] / nd[:, None]
+    tpa = None if temperature_perturbation is None else np.ascontiguousarray(tp, dtype=np.float64)
+    wpa = None if water_perturbation is None else np.ascontiguousarray(wp, dtype=np.float64)
+    a = atm_profile.desc()
+    pf, keep = None, []
+    if partfun_tables is not None:  # Q at the perturbed temperatures (the reference evaluates it inside lbl::calculate)
+        pf = (abi.PartfunTable * len(partfun_tables))()
+        for k, (kind, grid, coef) in enumerate(partfun_tables):
+            g = None if grid is None else np.ascontiguousarray(grid, dtype=np.float64)
+            cf = np.ascontiguousarray(np.atleast_1d(coef), dtype=np.float64)
+            keep.append((g, cf))
+            pf[k].kind, pf[k].n, pf[k].grid, pf[k].coef = abi.PARTFUN_KINDS[kind], len(cf), dptr(g), dptr(cf)
+    check(lib().ab200_lookup_precompute(cat.handle, len(f), dptr(f), C.byref(a), int(select_species),
+                                        -1 if h2o_species is None else int(h2o_species), len(tp), dptr(tpa), len(wp), dptr(wpa),
+                                        pf, dptr(xsec)))
     return abi.LookupTable(species=int(select_species), f_grid=f, log_p_grid=np.log(atm_profile.P), t_atmref=np.array(atm_profile.T, float),
                            xsec=xsec, t_pert=None if temperature_perturbation is None else np.asarray(tp, float),
                            w_pert=None if water_perturbation is None else np.asarray(wp, float),

@@ -274,6 +274,7 @@ int ab200_cia_levels(const ab200_cia *cia, int64_t nf, const double *f, int64_t 
  * pressure_/frequency_/water_/temperature_lagrange :133-188), times the species' number density.
  * _spectral_propmatAddLookup (src/m_lookup.cc:20-141): K.A += absorption where no_negative_absorption == 0 or it is
  * positive; every Jacobian target by re-extraction at the perturbed point, ASSIGNED to the row (sic, :130-135). */
+struct ab200_partfun_table;
 typedef struct ab200_lookup_table {
   int32_t species;           /* the species this table stands for (atm_point.number_density(species)) */
   int32_t nf, np, nt, nw;    /* nt / nw: size of t_pert / w_pert, or 1 when the table has no such grid (do_t / do_w false) */
@@ -296,6 +297,18 @@ int ab200_lookup_levels(const ab200_lookup *lut, int64_t nf, const double *f, in
                         int32_t nq, const ab200_target *targets, const double *target_d, int32_t no_negative_absorption,
                         int32_t p_interp_order, int32_t t_interp_order, int32_t water_interp_order, int32_t f_interp_order,
                         double extpolfac, double *K, double *dK);
+
+/* abs_lookup_dataPrecompute (src/m_lookup.cc:175-197; the lookup::table constructor src/core/lookup/lookup_map.cpp:22-131) with
+ * the line-by-line sum on the device: for every temperature offset t_pert[it] (NULL: none, nt = 1) and water ratio w_pert[iw]
+ * (NULL: none, nw = 1) the reference profile atm_ref (descending pressure) is perturbed, lbl::calculate runs for select_species
+ * with no_negative_absorption = true, and xsec[it][iw][ip][f] = K.A / atm_point.number_density(select_species).  The division
+ * runs on the device and only the compact A component comes back: 8 B per table element instead of 56. */
+int ab200_lookup_precompute(const ab200_catalog *cat, int64_t nf, const double *f, const ab200_atm_path *atm_ref,
+                            int32_t select_species, int32_t h2o_species, int32_t nt, const double *t_pert, int32_t nw,
+                            const double *w_pert, const struct ab200_partfun_table *partfun, double *xsec);
+/* partfun: [n_isot] partition-function tables (below): the reference evaluates Q at the PERTURBED temperature inside
+ * lbl::calculate, so Q(T + t_pert) is formed here with ab200_partfun_eval.  NULL: atm_ref->Q is used for every offset
+ * (exact only without a temperature grid). */
 
 /* On the resident path: adds the lookup-table absorption to K (and assigns the rows of dK of the path's targets).  With
  * zero_init the resident K / dK are cleared first - the agenda with use_abs_lookup_data = 1 has no line-by-line term

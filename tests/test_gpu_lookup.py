@@ -75,6 +75,17 @@ def test_precomputed_table_reproduces_line_by_line_radiance(wsm, orc):
     K0, _ = orc.propmat_levels(c.cat, c.f, ref_atm, select_species=1)
     nd = ref_atm.vmr[:, 1] * ref_atm.P / (1.380649e-23 * ref_atm.T)
     np.testing.assert_allclose(tables[1].xsec[3, 0], K0[..., 0] / nd[:, None], rtol=1e-9)
+    # with partition-function tables the builder evaluates Q at the perturbed temperature, like lbl::calculate does
+    q_slope = float(ref_atm.Q[0, 0] / ref_atm.T[0])  # the synthetic Q(T) is linear in T
+    pf = [("coeff", None, [0.0, q_slope])] * c.cat.n_species
+    tq = wsm.abs_lookup_dataPrecompute(cat, ref_atm, c.f, 1, temperature_perturbation=t_pert, partfun_tables=pf)
+    cold = copy.deepcopy(ref_atm)
+    cold.T = ref_atm.T + t_pert[0]
+    cold.Q = ref_atm.Q * (cold.T / ref_atm.T)[:, None]
+    Kc, _ = orc.propmat_levels(c.cat, c.f, cold, select_species=1)
+    ndc = cold.vmr[:, 1] * cold.P / (1.380649e-23 * cold.T)
+    np.testing.assert_allclose(tq.xsec[0, 0], Kc[..., 0] / ndc[:, None], rtol=1e-9)
+    assert np.abs(tq.xsec[0, 0] / tables[1].xsec[0, 0] - 1).max() > 0.05, "Q(T) must matter"
     lut = wsm.Lookup(tables)
     worst = 0.0
     for ratio, off in ((0.5, -20.0), (0.5, 10.0), (5.0, 0.0), (5.0, 20.0), (1.0, -10.0)):

@@ -88,6 +88,23 @@ class HitranIsotopologue(C.Structure):
     _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double)]
 
 
+class PredefSpecies(C.Structure):
+    """ab200_predef_species: indices of O2, N2, H2O, CO2, liquidcloud in the VMR vector (-1: absent)."""
+
+    _fields_ = [("o2", C.c_int32), ("n2", C.c_int32), ("h2o", C.c_int32), ("co2", C.c_int32), ("liquidcloud", C.c_int32)]
+
+
+PREDEF_MODELS = {"O2-SelfContStandardType": 0, "N2-SelfContStandardType": 1, "H2O-ForeignContStandardType": 2,
+                 "H2O-SelfContStandardType": 3}
+
+
+def predef_args(models, species):
+    """(int32 array of model ids, PredefSpecies) from tag names and a dict like {"O2": 1, "H2O": 0}."""
+    ids = np.array([PREDEF_MODELS[m] if isinstance(m, str) else int(m) for m in models], dtype=np.int32)
+    sp = PredefSpecies(*(int(species.get(k, -1)) for k in ("O2", "N2", "H2O", "CO2", "liquidcloud")))
+    return ids, sp
+
+
 class LookupTableDesc(C.Structure):
     _fields_ = [("species", C.c_int32), ("nf", C.c_int32), ("np", C.c_int32), ("nt", C.c_int32), ("nw", C.c_int32),
                 ("do_t", C.c_int32), ("do_w", C.c_int32), ("f_grid", _dp), ("log_p_grid", _dp), ("t_pert", _dp), ("w_pert", _dp),

@@ -70,6 +70,9 @@ def lib():
     L.ab200_path_run_stokes.argtypes = [_vp]
     L.ab200_path_download.argtypes = [_vp, _dp, _dp, _dp, _dp]
     L.ab200_path_sync.argtypes = [_vp]
+    L.ab200_predef_levels.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(abi.PredefSpecies), C.c_int64, _dp, C.c_int64,
+                                      C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), _dp, _dp, _dp]
+    L.ab200_path_add_predefined.argtypes = [_vp, C.POINTER(C.c_int32), C.c_int32, C.POINTER(abi.PredefSpecies), _dp]
     L.ab200_lookup_create.argtypes = [C.POINTER(abi.LookupTableDesc), C.c_int32, C.POINTER(_vp)]
     L.ab200_lookup_destroy.argtypes = [_vp]
     L.ab200_lookup_destroy.restype = None

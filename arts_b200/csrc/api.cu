@@ -15,6 +15,7 @@
 #include "lbl.hpp"
 #include "cia.hpp"
 #include "lookup.hpp"
+#include "predef.hpp"
 #include "stokes.hpp"
 
 namespace ab200 {
@@ -613,6 +614,15 @@ int ab200_path_add_lookup(ab200_path* p, const ab200_lookup* lut, int32_t h2o_sp
   lp.no_neg = p->no_neg; lp.po = po; lp.to = to; lp.wo = wo; lp.fo = fo; lp.extpol = extpolfac; lp.flags = p->d_flags;
   AB_TRY(launch_lookup(lp, p->np, p->stream));
   return AB200_OK;
+}
+
+int ab200_path_add_predefined(ab200_path* p, const int32_t* models, int32_t n_models, const ab200_predef_species* species,
+                              const double* target_d) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_add_predefined: path not uploaded");
+  AB_CUDA(cudaSetDevice(p->cat->device));
+  return predef_on_path(models, n_models, species, target_d, p->nf, p->d_f, p->f_stride, p->d_ffac, p->d_T, p->d_P, p->d_vmr,
+                        p->cat->n_species, p->select_species, p->d_K, p->d_dK, p->k_pitch, p->nq, p->tg_kind, p->tg_species, p->np,
+                        p->stream);
 }
 
 int ab200_path_add_cia(ab200_path* p, const ab200_cia* cia, double T_extrapolfac, int32_t ignore_errors, double dT) {

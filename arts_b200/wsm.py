@@ -354,6 +354,13 @@ class Path:
                                           int(t_interp_order), int(water_interp_order), int(f_interp_order), float(extpolfac),
                                           int(bool(zero_init))))
 
+    def add_predefined(self, models, species, target_d=()):
+        """``spectral_propmatAddPredefined`` (src/m_predefined_absorption_models.cc:156-191) on the resident K / dK: ``models`` are
+        tag names ("O2-SelfContStandardType", ...), ``species`` maps "O2" / "N2" / "H2O" / "CO2" / "liquidcloud" to VMR indices."""
+        ids, sp = abi.predef_args(models, species)
+        d = np.ascontiguousarray(target_d, dtype=np.float64)
+        check(lib().ab200_path_add_predefined(self._h, abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), dptr(d if len(d) else None)))
+
     def add_cia(self, cia: "Cia", T_extrapolfac=0.5, ignore_errors=0, dT=0.1):
         """``spectral_propmatAddCIA`` (src/m_cia.cc:27-178) on the resident K / dK, after ``run_propmat``."""
         check(lib().ab200_path_add_cia(self._h, cia.handle, float(T_extrapolfac), int(ignore_errors), float(dT)))
@@ -635,5 +642,24 @@ def spectral_propmatAddLookup(spectral_propmat, spectral_propmat_jac, freq_grid,
     check(lib().ab200_lookup_levels(abs_lookup_data.handle, nf, dptr(f), stride, C.byref(a), atm_path.vmr.shape[1], int(h2o_species),
                                     int(select_species), nq, tg, dptr(d if nq else None), int(no_negative_absorption), int(p_interp_order),
                                     int(t_interp_order), int(water_interp_order), int(f_interp_order), float(extpolfac), dptr(K),
+                                    dptr(dK if nq else None)))
+    return K, dK
+
+
+def spectral_propmatAddPredefined(spectral_propmat, spectral_propmat_jac, abs_predef_data, select_species, jac_targets, freq_grid,
+                                  atm_path: AtmPath, species, target_d=()):
+    """src/m_predefined_absorption_models.cc:156-191 for every level: ``abs_predef_data`` is a list of model tag names,
+    ``species`` maps "O2" / "N2" / "H2O" / "CO2" / "liquidcloud" to VMR indices; K [np, nf, 7] and dK [np, nq, nf, 7] are +=."""
+    np_ = atm_path.np_
+    f, stride, nf = _f_arg(freq_grid, np_)
+    tg, nq = make_targets(jac_targets)
+    ids, sp = abi.predef_args(abs_predef_data, species)
+    K, dK = spectral_propmat, spectral_propmat_jac
+    if K.shape != (np_, nf, 7) or not K.flags.c_contiguous or K.dtype != np.float64:
+        raise ValueError("Mismatch dimensions on internal matrices of xsec and frequency")
+    d = np.ascontiguousarray(target_d, dtype=np.float64)
+    a = atm_path.desc()
+    check(lib().ab200_predef_levels(abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), nf, dptr(f), stride, C.byref(a),
+                                    atm_path.vmr.shape[1], int(select_species), nq, tg, dptr(d if nq else None), dptr(K),
                                     dptr(dK if nq else None)))
     return K, dK

@@ -317,6 +317,27 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
                           int32_t p_interp_order, int32_t t_interp_order, int32_t water_interp_order,
                           int32_t f_interp_order, double extpolfac, int32_t zero_init);
 
+/* ---- predefined continua: spectral_propmatAddPredefined on the resident K -------------------------
+ * src/m_predefined_absorption_models.cc:156-191 -> Absorption::PredefinedModel::compute
+ * (src/core/absorption/predefined_absorption_models.cc:219-317): the model's closed form added to K.A, the temperature row
+ * by perturbation (model(T + d) - model(T)) / d and VMR rows by perturbation for targets of CO2, O2, N2, H2O and
+ * liquidcloud only (:237-241, compute_vmr_deriv :202-216).  Models on the path: the four "StandardType" continua of
+ * src/core/predefined/standard.cc (Rosenkranz 1993 / 1998); every other model name is AB200_ERR_UNSUPPORTED. */
+#define AB200_PREDEF_O2_SELFCONT_STANDARD 0     /* "O2-SelfContStandardType",     Standard::oxygen        standard.cc:51-84 */
+#define AB200_PREDEF_N2_SELFCONT_STANDARD 1     /* "N2-SelfContStandardType",     Standard::nitrogen      :118-138 */
+#define AB200_PREDEF_H2O_FOREIGNCONT_STANDARD 2 /* "H2O-ForeignContStandardType", Standard::water_foreign :166-184 */
+#define AB200_PREDEF_H2O_SELFCONT_STANDARD 3    /* "H2O-SelfContStandardType",    Standard::water_self    :212-226 */
+typedef struct ab200_predef_species { /* indices into the vmr vector, -1 when the atmosphere does not carry the species */
+  int32_t o2, n2, h2o, co2, liquidcloud;
+} ab200_predef_species;
+/* models [n_models]: AB200_PREDEF_*; target_d [nq]: perturbation of every Jacobian target.  K [np][nf][7], dK [np][nq][nf][7] +=. */
+int ab200_predef_levels(const int32_t *models, int32_t n_models, const ab200_predef_species *species, int64_t nf,
+                        const double *f, int64_t f_level_stride, const ab200_atm_path *atm, int32_t n_species,
+                        int32_t select_species, int32_t nq, const ab200_target *targets, const double *target_d,
+                        double *K, double *dK);
+int ab200_path_add_predefined(ab200_path *p, const int32_t *models, int32_t n_models, const ab200_predef_species *species,
+                              const double *target_d);
+
 /* ---- catalog ingest: HITRAN .par records straight into the SoA of ab200_catalog_desc -------------
  * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], line_strength_option = "A",
  * compute_zeeman_parameters = 0: read_par_line (src/core/lbl/lbl_hitran.cpp:66-89, the 160-column record and its unit

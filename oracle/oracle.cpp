@@ -2032,6 +2032,93 @@ int orc_lookup_levels(const ab200_lookup_table* tables, int32_t n_tables, int64_
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// predefined continua: the four "StandardType" models, src/core/predefined/standard.cc
+// ---------------------------------------------------------------------------
+namespace predef {
+struct Pt {
+  Numeric T, P, o2, n2, h2o;
+};
+Numeric model(int m, Numeric f, const Pt& a) {
+  using std::pow;
+  switch (m) {
+    case AB200_PREDEF_O2_SELFCONT_STANDARD: {  // Standard::oxygen :51-84
+      constexpr Numeric C = (1.108e-14 / pow2(3.0e2));
+      const Numeric G0 = 5600.000, G0A = 1.000, G0B = 1.100, XG0d = 0.800, XG0w = 1.000;
+      const Numeric TH    = 3.0e2 / a.T;
+      const Numeric ph2o  = a.P * a.h2o;
+      const Numeric pdry  = a.P - ph2o;
+      const Numeric gamma = G0 * (G0A * pdry * pow(TH, XG0d) + G0B * ph2o * pow(TH, XG0w));
+      return a.o2 * C * a.P * pow2(TH) * (gamma * pow2(f) / (pow2(f) + pow2(gamma)));
+    }
+    case AB200_PREDEF_N2_SELFCONT_STANDARD: {  // Standard::nitrogen :118-138
+      constexpr Numeric C = 1.05e-38, xf = 2.00, xt = 3.55, xp = 2.00;
+      return a.n2 * C * pow(300.00 / a.T, xt) * pow(f, xf) * pow(a.P, xp) * pow(a.n2, xp - 1);
+    }
+    case AB200_PREDEF_H2O_FOREIGNCONT_STANDARD: {  // Standard::water_foreign :166-184
+      constexpr Numeric C = 5.43e-35, x = 0.0;
+      const Numeric pdry  = a.P * (1.000e0 - a.h2o);
+      const Numeric dummy = C * pow(300. / a.T, x + 3) * a.P * pdry;
+      return a.h2o * dummy * pow2(f);
+    }
+    default: {  // Standard::water_self :212-226
+      constexpr Numeric C = 1.796e-33, x = 4.5;
+      const Numeric dummy = C * pow(300. / a.T, x + 3) * pow2(a.P) * a.h2o;
+      return a.h2o * dummy * pow2(f);
+    }
+  }
+}
+int species_of(int m, const ab200_predef_species& s) {  // isot.spec of the model tag
+  return m == AB200_PREDEF_O2_SELFCONT_STANDARD ? s.o2 : m == AB200_PREDEF_N2_SELFCONT_STANDARD ? s.n2 : s.h2o;
+}
+}  // namespace predef
+
+// spectral_propmatAddPredefined (m_predefined_absorption_models.cc:156-191) + PredefinedModel::compute
+// (predefined_absorption_models.cc:219-317) for every level
+int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, int64_t nf, const double* f_in,
+                      int64_t f_level_stride, const ab200_atm_path* atm, int32_t n_species, int32_t select_species, int32_t nq,
+                      const ab200_target* targets, const double* target_d, double* K, double* dK) {
+  const int np = atm->np;
+  auto v = [&](const double* vmr, int idx) { return idx >= 0 ? vmr[idx] : 0.0; };
+  int it = -1;
+  for (int q = 0; q < nq; q++)
+    if (targets[q].kind == AB200_TARGET_T and it < 0) it = q;
+  for (int ip = 0; ip < np; ip++) {
+    const double* f   = f_in + ip * f_level_stride;
+    const double* vmr = atm->vmr + static_cast<Index>(ip) * n_species;
+    const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o)};
+    for (int k = 0; k < n_models; k++) {
+      const int m = models[k];
+      if (m < 0 or m > AB200_PREDEF_H2O_SELFCONT_STANDARD) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;
+      for (Index i = 0; i < nf; i++) {
+        const Numeric pm = predef::model(m, f[i], a);
+        K[(static_cast<Index>(ip) * nf + i) * 7] += pm;
+        auto dk = [&](int q) -> double& { return dK[((static_cast<Index>(ip) * nq + q) * nf + i) * 7]; };
+        if (it >= 0) {  // :256-268
+          predef::Pt b = a;
+          b.T += target_d[it];
+          dk(it) += (predef::model(m, f[i], b) - pm) / target_d[it];
+        }
+        // vmrs_jac :237-241: the first target of CO2, O2, N2, H2O, liquidcloud, in that order
+        for (int idx : {sp->co2, sp->o2, sp->n2, sp->h2o, sp->liquidcloud}) {
+          if (idx < 0) continue;
+          for (int q = 0; q < nq; q++)
+            if (targets[q].kind == AB200_TARGET_VMR and targets[q].species == idx) {
+              predef::Pt b = a;
+              if (idx == sp->o2) b.o2 += target_d[q];
+              if (idx == sp->n2) b.n2 += target_d[q];
+              if (idx == sp->h2o) b.h2o += target_d[q];
+              dk(q) += (predef::model(m, f[i], b) - pm) / target_d[q];
+              break;
+            }
+        }
+      }
+    }
+  }
+  return 0;
+}
+
 // rtepack::tran for single inputs (tests: exp(-K r) against scipy expm, src/tests/test_rtepack.cc:12-33)
 int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, double* T, double* L) {
   const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};

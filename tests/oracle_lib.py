@@ -56,6 +56,8 @@ def lib():
         L.orc_lookup_levels.argtypes = [C.POINTER(abi.LookupTableDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), dp, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_double, dp, dp]
+        L.orc_predef_levels.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(abi.PredefSpecies), C.c_int64, dp, C.c_int64,
+                                        C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), dp, dp, dp]
         L.orc_background.argtypes = [C.c_int64, dp, C.c_double, dp, dp]
         L.orc_observer.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(abi.ObserverDesc), dp, dp, dp, dp, dp, dp]
         for name in ("orc_invplanck", "orc_dinvplanckdI", "orc_invrayjean", "orc_dplanck_dt"):
@@ -283,4 +285,18 @@ def lookup_levels(tables, f, atm: AtmPath, h2o_species=-1, select_species=abi.SP
     _check(lib().orc_lookup_levels(arr, len(tables), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1], int(h2o_species), select_species,
                                    nq, tg, dptr(d), int(no_negative_absorption), *[int(o) for o in orders], float(extpolfac), dptr(K),
                                    dptr(dK)))
+    return K, dK
+
+
+def predef_levels(models, species, f, atm: AtmPath, select_species=abi.SPECIES_BATH, targets=(), target_d=(), K=None, dK=None):
+    """spectral_propmatAddPredefined per level (m_predefined_absorption_models.cc:156-191)."""
+    f, stride, nf = _f_arg(f, atm.np_)
+    tg, nq = make_targets(targets)
+    ids, sp = abi.predef_args(models, species)
+    K = np.zeros((atm.np_, nf, 7)) if K is None else K
+    dK = np.zeros((atm.np_, nq, nf, 7)) if dK is None else dK
+    d = np.ascontiguousarray(target_d, dtype=np.float64)
+    a = atm.desc()
+    _check(lib().orc_predef_levels(abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1],
+                                   select_species, nq, tg, dptr(d), dptr(K), dptr(dK)))
     return K, dK

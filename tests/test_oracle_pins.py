@@ -628,3 +628,47 @@ def test_lookup_table_extraction_against_numpy(orc, do_t, do_w):
         orc.lookup_levels([tab], f, atm, h2o_species=0, orders=(9, 1, 1, 1))
     with pytest.raises(RuntimeError, match="no lookup table"):
         orc.lookup_levels([tab], f, atm, h2o_species=0, select_species=0)
+
+
+def test_standard_continua_against_their_published_forms(orc):
+    """The four "StandardType" continua (src/core/predefined/standard.cc) written out independently in numpy from the formulas
+    of Rosenkranz (1993, 1998): O2 Debye term, N2 collision-induced f^2 T^-3.55, H2O foreign and self f^2 continua."""
+    f = np.linspace(1e9, 1e12, 300)
+    T, P = np.array([288.0, 230.0]), np.array([1.0e5, 2.0e4])
+    vmr = np.array([[0.012, 0.2095, 0.7808], [1e-4, 0.2095, 0.7808]])  # H2O, O2, N2
+    atm = abi.AtmPath(T=T, P=P, vmr=vmr, isorat=np.ones((2, 1)), Q=np.ones((2, 1)))
+    species = {"H2O": 0, "O2": 1, "N2": 2}
+    th = 300.0 / T
+    h2o, o2, n2 = vmr[:, 0], vmr[:, 1], vmr[:, 2]
+    gamma = 5600.0 * ((P - P * h2o) * th ** 0.8 + 1.1 * P * h2o * th)
+    expect = {
+        "O2-SelfContStandardType": (o2 * 1.108e-14 / 9e4 * P * th ** 2)[:, None] * gamma[:, None] * f ** 2 / (f ** 2 + gamma[:, None] ** 2),
+        "N2-SelfContStandardType": (1.05e-38 * th ** 3.55 * P ** 2 * n2 ** 2)[:, None] * f ** 2,
+        "H2O-ForeignContStandardType": (5.43e-35 * th ** 3 * P * (P * (1 - h2o)) * h2o)[:, None] * f ** 2,
+        "H2O-SelfContStandardType": (1.796e-33 * th ** 7.5 * P ** 2 * h2o ** 2)[:, None] * f ** 2,
+    }
+    tot = 0.0
+    for name, ref in expect.items():
+        K, _ = orc.predef_levels([name], species, f, atm)
+        np.testing.assert_allclose(K[..., 0], ref, rtol=1e-13)
+        assert not K[..., 1:].any()
+        tot = tot + ref
+    K, _ = orc.predef_levels(list(expect), species, f, atm)
+    np.testing.assert_allclose(K[..., 0], tot, rtol=1e-13)
+    # a sea-level number everybody knows: the water-vapour continuum near 90 GHz is a few 1e-5 1/m for 1.2 % humidity
+    k90 = float(np.interp(90e9, f, expect["H2O-ForeignContStandardType"][0] + expect["H2O-SelfContStandardType"][0]))
+    assert 1e-5 < k90 < 2e-4
+    # select_species: the species of the model tag; Jacobians by perturbation, only for CO2 / O2 / N2 / H2O / liquidcloud targets
+    Ks, _ = orc.predef_levels(list(expect), species, f, atm, select_species=0)
+    np.testing.assert_allclose(Ks[..., 0], expect["H2O-ForeignContStandardType"] + expect["H2O-SelfContStandardType"], rtol=1e-13)
+    tg, d = (("T",), ("VMR", 0), ("VMR", 2)), (0.1, 1e-6, 1e-4)
+    _, dK = orc.predef_levels(list(expect), species, f, atm, targets=tg, target_d=d)
+    for q, (t, dd) in enumerate(zip(tg, d)):
+        pert = abi.AtmPath(T=T + (dd if t[0] == "T" else 0), P=P, vmr=vmr + (dd * np.eye(3)[t[1]] if t[0] == "VMR" else 0),
+                           isorat=np.ones((2, 1)), Q=np.ones((2, 1)))
+        Kp, _ = orc.predef_levels(list(expect), species, f, pert)
+        np.testing.assert_allclose(dK[:, q, :, 0], (Kp - K)[..., 0] / dd, rtol=1e-5, atol=1e-9 * np.abs(dK[:, q]).max())
+    # a VMR target of a species outside that list is not touched (predefined_absorption_models.cc:237-241)
+    _, dK2 = orc.predef_levels(list(expect), {"H2O": 0, "O2": 1}, f[:5], abi.AtmPath(T=T, P=P, vmr=vmr, isorat=np.ones((2, 1)), Q=np.ones((2, 1))),
+                               targets=(("VMR", 2),), target_d=(1e-4,), select_species=0)
+    assert not dK2.any()

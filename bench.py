@@ -57,6 +57,8 @@ def parse_args():
                          "levels, the frequency grid of FIXED total size sharded over the GPUs (strong scaling)")
     ap.add_argument("--c4-lines", type=int, default=1_000_000)
     ap.add_argument("--c4-nf", type=int, default=1_000_000)
+    ap.add_argument("--c4-cutoff-ghz", type=float, default=0.0,
+                    help="configs[3] variant (ii) of SURVEY 8(d): ByLine cutoff in GHz (0 = none); the metric then counts NOMINAL pairs")
     return ap.parse_args()
 
 
@@ -64,10 +66,12 @@ def workload(args, world):
     from arts_b200 import synth
 
     if args.workload == "c4":
-        case = synth.case_c4(n_lines=args.c4_lines, nf=args.c4_nf, np_=args.levels)
+        cut = args.c4_cutoff_ghz * 1e9 if args.c4_cutoff_ghz > 0 else None
+        case = synth.case_c4(n_lines=args.c4_lines, nf=args.c4_nf, np_=args.levels, cutoff=cut)
         case.rte_option = args.rte
+        cut_txt = "no cutoff" if cut is None else f"ByLine cutoff {args.c4_cutoff_ghz:g} GHz (value counts nominal line x frequency pairs)"
         return case, (f"C4 (BASELINE configs[3]): {args.c4_lines} lines x {args.c4_nf} frequencies (1-100 THz, total, sharded over "
-                      f"the GPUs) x {args.levels} levels, no cutoff, {args.rte} Stokes chain")
+                      f"the GPUs) x {args.levels} levels, {cut_txt}, {args.rte} Stokes chain")
     nf = args.nf_per_gpu * world
     case = synth.case_c2(lines_per_species=args.lines_per_species, nf=nf, np_=args.levels, rte_option=args.rte)
     name = (f"C2 (BASELINE configs[1]): 5 species x {args.lines_per_species} Voigt lines, {args.levels}-level nadir path, "

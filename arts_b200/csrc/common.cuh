@@ -61,6 +61,10 @@ constexpr double FAR_LIMIT = 4000.0;
 // The real line sum (same-sign terms, no cancellation) therefore uses it from |x|+y > 1000: four times
 // fewer pairs in the expensive continued-fraction branch, parity bound 1e-9 untouched.
 constexpr double FAR_LIMIT_REAL_SUM = 1000.0;
+// |x| + y above which the forward line sums evaluate a near pair with the four-term continued fraction in closed form
+// (faddeeva.cuh: w_mid, <= 1.3e-12 relative on both parts, measured against scipy's wofz) instead of the reference's
+// nu(z)-term recurrence.  The Jacobian kernels do not use it: their forward difference amplifies w's error by 1e4.
+constexpr double MID_LIMIT = 48.0;
 
 constexpr int AB200_MAX_TARGETS = 8;  // Jacobian targets per call (temperature + species VMRs)
 

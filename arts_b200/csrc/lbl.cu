@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
                 acc[r] = far_accumulate_re(acc[r], u, a.y, b.x, b.y, c.x);
               } else {
                 double wr, wi;
-                w_near(c.y * u, d.x, __ldg(g2 + l * REC_GROUP), wr, wi);
+                w_near_fast(c.y * u, d.x, __ldg(g2 + l * REC_GROUP), wr, wi);
                 acc[r] = __fma_rn(d.y, wr, acc[r]);
               }
             }
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(CPLX_NT, MINB) lbl_sum_cplx_kernel(SumParams p
                 far_accumulate_cplx(are[r], aim[r], u, a.y, b.x, b.y, m.x, c.x, c.y, d.x, d.y);
               } else {
                 double wr, wi;
-                w_near(m.y * u, n2.x, h.x, wr, wi);
+                w_near_fast(m.y * u, n2.x, h.x, wr, wi);
                 are[r] = __fma_rn(n2.y, wr, __fma_rn(-h.y, wi, are[r]));
                 aim[r] = __fma_rn(n2.y, wi, __fma_rn(h.y, wr, aim[r]));
               }

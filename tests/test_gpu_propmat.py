@@ -202,6 +202,31 @@ def test_mid_wing_closed_form_accuracy(wsm, orc):
     assert rel[(x > 1000) & (x < 4000)].max() > 1e-15  # the closed form is really in use there
 
 
+def test_near_wing_closed_form_accuracy(wsm, orc):
+    """Between |x| + y = 48 (MID_LIMIT) and the far limit the forward line sums evaluate the four-term continued fraction as
+    one rational function instead of the reference's nu(z)-term recurrence: <= 1.3e-12 relative on Re w and Im w; below 48 the
+    reference's own regions run.  One nearly Doppler line (y << x), one pressure-broadened line (y ~ x), and a line-mixing
+    line through the complex kernel (both parts of w)."""
+    for P, ymix in ((5.0, False), (3e4, False), (5.0, True)):
+        c = synth.case_c1(nl=1, nf=3000)
+        c.atm.P[:] = P
+        if ymix:
+            c.cat.ls_type[:, abi.VAR_Y] = abi.TM_T1
+            c.cat.ls_X[:, abi.VAR_Y, 0] = 2e-3 / P
+            c.cat.ls_X[:, abi.VAR_Y, 1] = 0.8
+        f0 = c.cat.f0[0]
+        gd = np.sqrt(2000 * 1.380649e-23 * 6.02214076e23 / 299792458.0**2 * 250.0 / 31.9898) * f0
+        x = np.concatenate([-np.geomspace(900.0, 20.0, 1500), np.geomspace(20.0, 900.0, 1500)])
+        c.f = np.sort(f0 + x * gd)
+        Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm, no_negative_absorption=0)
+        K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, no_negative_absorption=0)
+        rel = np.abs(K[0, :, 0] - Kr[0, :, 0]) / np.abs(Kr[0, :, 0])
+        assert rel.max() <= 5e-12, (P, ymix, rel.max(), c.f[np.argmax(rel)])
+        xs = np.abs(c.f - f0) / gd
+        assert rel[(xs > 60) & (xs < 800)].max() > 1e-15, "the closed form is really in use there"
+        assert rel[xs < 40].max() <= 2e-12  # the reference's own regions, through the ratio-form continued fraction
+
+
 def test_small_grid_geometry_is_invisible(wsm):
     """Small problems run narrower frequency blocks (64 or 128 instead of 512 per CTA).  The value at a frequency must not
     depend on that: the same frequencies inside a grid large enough for the default geometry give the same bits."""

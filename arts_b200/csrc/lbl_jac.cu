@@ -68,8 +68,22 @@ __device__ __forceinline__ cplx w_any(double x, double y, double E1) {
 // single_shape::all(f): z, F = w(z), dF by the forward finite difference of :250-268
 __device__ __forceinline__ void z_F_dF(double x, double y, double E1, double E1p, cplx& z, cplx& F, cplx& dF) {
   z = {x, y};
-  F = w_any(x, y, E1);
   const cplx dz{fmax(1e-4 * fabs(x), 1e-4), fmax(1e-4 * fabs(y), 1e-4)};
+  const double ax = fabs(x);
+  if (ax + y > MID_LIMIT && ax + y <= FAR_LIMIT) {
+    // four-term closed form (faddeeva.cuh w_mid) at both points: its truncation error is a smooth function of z, so
+    // the difference quotient carries it at ~8x its relative size (1e-11 at the limit), not at 1/1e-4.  The branch is
+    // taken on the base point for both evaluations so a pair never mixes two approximations.
+    const double xd = x + dz.re;
+    double wr, wi, vr, vi;
+    w_mid(ax, y, wr, wi);
+    w_mid(fabs(xd), y + dz.im, vr, vi);
+    F = {wr, x < 0.0 ? -wi : wi};
+    const cplx F2{vr, xd < 0.0 ? -vi : vi};
+    dF = cdiv(csub(F2, F), dz);
+    return;
+  }
+  F = w_any(x, y, E1);
   const cplx F2 = w_any(x + dz.re, y + dz.im, E1p);
   dF = cdiv(csub(F2, F), dz);
 }

@@ -86,21 +86,51 @@ void norm_view(int pol, const double mag[3], const double los[2], double npm[7])
   }
 }
 
-bool wind_factor(const double wind[3], const double los[2], double* fac_out) {
+bool wind_factor(const double wind[3], const double los[2], double* fac_out, double* jac_out) {
   const double deg = cst::pi / 180;
   const double u = wind[0], v = wind[1], w = wind[2];
   double za = 180 - los[0], aa = los[1] + 180;  // path::mirror
   if (aa > 180) aa -= 360;
-  const double f2   = (u * u + v * v) + w * w;
+  const double u2v2 = u * u + v * v;
+  const double w2   = w * w;
+  const double f2   = u2v2 + w2;
   const double f    = std::sqrt(f2);
   const double za_f = f == w ? 0.0 : std::acos(w / f);
   const double aa_f = std::atan2(u, v);
   const double za_p = za * deg, aa_p = aa * deg;
-  const double dp   = std::cos(za_f) * std::cos(za_p) + std::sin(za_f) * std::sin(za_p) * std::cos(aa_f - aa_p);
+  const double czaf = std::cos(za_f), szaf = std::sin(za_f), czap = std::cos(za_p), szap = std::sin(za_p);
+  const double caa  = std::cos(aa_f - aa_p);
+  const double dp   = czaf * czap + szaf * szap * caa;
   double fac        = 1.0 - (f * dp) / cst::c;
   if (fac <= 0) return false;
-  if (std::isnan(fac)) fac = 1.0;  // "Zero shift if nan"
+  if (std::isnan(fac)) {  // "Zero shift if nan", :40-44
+    *fac_out = 1.0;
+    if (jac_out) jac_out[0] = jac_out[1] = jac_out[2] = 0.0;
+    return true;
+  }
   *fac_out = fac;
+  if (jac_out) {
+    // freq_wind_shift_jac, :56-82 (with its values at zero wind: df = 1, every other derivative 0)
+    const double scl = f2 * std::sqrt(f2 - w2);
+    const double saa = std::sin(aa_p - aa_f);
+    const double comp[3] = {u, v, w};
+    for (int c = 0; c < 3; c++) {
+      const double df = (f == 0) ? 1.0 : comp[c] / f;
+      double dczaf, dszaf, dcaa;
+      if (c < 2) {
+        dczaf = (f2 == 0) ? 0.0 : (-w * df / f2);
+        dszaf = (f2 == w2) ? 0.0 : (w2 * df / scl);
+        dcaa  = (u2v2 == 0) ? 0.0 : ((c == 0 ? v : -u) * saa / u2v2);
+      } else {
+        dczaf = (f2 == 0) ? 0.0 : (-w * df / f2 + 1.0 / f);
+        dszaf = (scl == 0) ? 0.0 : ((w2 * df - f * w) / scl);
+        dcaa  = 0.0;
+      }
+      const double ddp = c < 2 ? czap * dczaf + szap * caa * dszaf + szap * szaf * dcaa : czap * dczaf + szap * caa * dszaf;
+      jac_out[c] = -(dp * df + f * ddp) / cst::c;
+      jac_out[c] /= fac;
+    }
+  }
   return true;
 }
 

@@ -69,6 +69,7 @@ struct JacSumParams {
   const double* jac;
   const double* jcom;
   double* dK;  // [nlev][nq][k_pitch][7], offset to the batch
+  const double* wind_jac;  // [nlev][3] freq_wind_shift_jac of the batch's levels (wind targets); null = leave d/df
 };
 
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream);

@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
                               cscale(f0s * sl, lmc));
         ds     = cscale(Sz * (cst::inv_sqrt_pi * igd * r * x) / (2 * T * f0s), num);
         dz_fac = (-2 * T * dD0 - 2 * T * dDV - f0s) / (2 * T * f0s);  // :1013-1015
+      } else if (jp.kind[q] >= AB200_TARGET_WIND_U) {
+        // single_shape::df, :275: s inv_gd dF(f) -- dX with ds = 0, dz = inv_gd, dz_fac = 0 (for a mirror twin too:
+        // zm = inv_gd (f + f0') has the same slope)
+        dD0 = dDV = dG0 = dG = dY = 0.0;
+        ds     = {0.0, 0.0};
+        dz_fac = 0.0;
       } else {
         const int ts = jp.species[q];
         dD0 = lm.dmix_dvmr(AB200_VAR_D0, ts); dDV = lm.dmix_dvmr(AB200_VAR_DV, ts); dG0 = lm.dmix_dvmr(AB200_VAR_G0, ts);
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
         dz_fac = -(dD0 + dDV) / f0s;  // :1176
       }
       cplx dzq{igd * -(dD0 + dDV), igd * dG0};
+      if (jp.kind[q] >= AB200_TARGET_WIND_U) dzq = {igd, 0.0};
       if (sfl & SUB_MIRRORED) {
         // mirrored dT / dVMR (lbl_lineshape_voigt_lte_mirrored.cpp:305-325): s (dz + dz_fac z_) (dFp + dFm) with
         // z_ = zp - zm = -2 inv_gd f0', independent of the frequency: fold it into dz and drop the x-proportional part,
@@ -202,6 +209,14 @@ constexpr int JAC_F_TILE = JAC_NT * JAC_R;
 constexpr int JAC_Q  = 4;   // targets per pass
 constexpr int JAC_BASE_FIELDS = 10;  // f0', igd, y, s_re, s_im, E1, E1p, cut_re, cut_im | y2, y^2+1/2, y2^2+1/2, y y2-1/2, s_re/sqrt(pi), 2y, 2y2
 constexpr int JAC_Q_FIELDS    = 7;   // ds_re, ds_im, dz_re, dz_im, dz_fac, dcut_re, dcut_im | dz_im + dz_fac y
+
+// dscl(f) of df_core_calc, :1040-1049
+__device__ __forceinline__ double line_scale_df(double f, double T, double P) {
+  constexpr double c = cst::c * cst::c / (8 * cst::pi);
+  const double N = P / (cst::k * T);
+  const double r = (cst::h * f) / (cst::k * T);
+  return N * (r * exp(-r) - expm1(-r)) * c;
+}
 
 // dscl(f) of dt_core_calc, :990-1000
 __device__ __forceinline__ double line_scale_dT(double f, double T, double P) {
@@ -482,7 +497,16 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
 #pragma unroll
       for (int q = 0; q < NQ; q++) {
         cplx d = cscale(scl, acc[q][r]);
-        if (jp.kind[jp.q0 + q] == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
+        const int kind = jp.kind[jp.q0 + q];
+        if (kind == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
+        if (kind >= AB200_TARGET_WIND_U) {
+          // compute_derivative :1514-1523, then spectral_propmat_jacWindFix (m_frequency_grid.cc:106-182): x * f * df_du
+          d = cadd(d, cscale(line_scale_df(f[r], T, P), shape[r]));
+          if (jp.wind_jac) {  // null: AB200_FLAG_WIND_ROWS_DF, the caller's agenda applies the fix
+            const double wj = jp.wind_jac[3 * lev + (kind - AB200_TARGET_WIND_U)];
+            d = cscale(wj, cscale(f[r], d));
+          }
+        }
         double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
         o[0] += npm[0] * d.re; o[1] += npm[1] * d.re; o[2] += npm[2] * d.re; o[3] += npm[3] * d.re;
         o[4] += npm[4] * d.im; o[5] += npm[5] * d.im; o[6] += npm[6] * d.im;

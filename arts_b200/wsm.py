@@ -104,21 +104,24 @@ def _rte(option) -> int:
 # ---------------------------------------------------------------------------
 def spectral_propmatAddLines(spectral_propmat, spectral_propmat_jac, freq_grid, jac_targets, select_species,
                              abs_bands, atm_point: AtmPath, no_negative_absorption=1):
-    """``spectral_propmat[nf,7] += lines`` at one atmospheric point (src/m_lbl.cc:242-300)."""
+    """``spectral_propmat[nf,7] += lines`` at one atmospheric point (src/m_lbl.cc:242-300).  ``freq_grid`` is the point's
+    (already wind-shifted) grid and wind rows are left as the frequency derivative, like in the reference, whose agenda
+    runs ``spectral_propmat_jacWindFix`` afterwards."""
     if atm_point.np_ != 1:
         raise ValueError("spectral_propmatAddLines takes a single AtmPoint")
     K = spectral_propmat.reshape(1, *spectral_propmat.shape)
     dK = None if spectral_propmat_jac is None else spectral_propmat_jac.reshape(1, *spectral_propmat_jac.shape)
     spectral_propmat_pathFromPath(abs_bands, freq_grid, atm_point, jac_targets=jac_targets,
                                   select_species=select_species, no_negative_absorption=no_negative_absorption,
-                                  out=K, out_jac=dK, accumulate=True)
+                                  out=K, out_jac=dK, accumulate=True, wind_rows_df=True)
     return spectral_propmat
 
 
 def spectral_propmat_pathFromPath(abs_bands, freq_grid_path, atm_path: AtmPath, jac_targets=(),
                                   select_species=abi.SPECIES_BATH, no_negative_absorption=1, out=None, out_jac=None,
-                                  accumulate=False):
-    """All levels of ``spectral_propmat_path`` with the lines-only agenda (src/m_propmat.cc:5-65).
+                                  accumulate=False, wind_rows_df=False):
+    """All levels of ``spectral_propmat_path`` with the lines-only agenda (src/m_propmat.cc:5-65), its closing
+    ``spectral_propmat_jacWindFix`` included unless ``wind_rows_df``.
 
     Returns ``(K[np,nf,7], dK[np,nq,nf,7])``.
     """
@@ -131,6 +134,8 @@ def spectral_propmat_pathFromPath(abs_bands, freq_grid_path, atm_path: AtmPath, 
     if K.shape != (np_, nf, 7) or not K.flags.c_contiguous or K.dtype != np.float64:
         raise ValueError("spectral_propmat must be a C-contiguous float64 [np, nf, 7] array")
     flags = 0 if accumulate else abi.FLAG_K_ZERO_INIT
+    if wind_rows_df:
+        flags |= abi.FLAG_WIND_ROWS_DF
     a = atm_path.desc()
     check(lib().ab200_propmat_levels(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
                                      int(no_negative_absorption), nq, tg, flags, dptr(K), dptr(dK)))

@@ -68,8 +68,16 @@ enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1, AB200_LINESHAPE_VP
 enum { AB200_CUTOFF_NONE = 0, AB200_CUTOFF_BYLINE = 1 };
 /* TransmittanceOption (arts_options.cc:953-1030); linsrc is the default rte_option. */
 enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 /* unpolarised layers only, else AB200_ERR_UNSUPPORTED */ };
-/* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR). */
-enum { AB200_TARGET_T = 0, AB200_TARGET_VMR = 1 };
+/* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR, AtmKey::wind_u/v/w).  The wind rows are the
+ * frequency derivative of the line absorption (single_shape::df, lbl_lineshape_voigt_lte.cpp:275, :1036-1062, :1514-1523)
+ * times f * freq_wind_shift_jac (spectral_propmat_jacWindFix, src/m_frequency_grid.cc:106-182, wind_shift :56-82). */
+enum {
+  AB200_TARGET_T = 0,
+  AB200_TARGET_VMR = 1,
+  AB200_TARGET_WIND_U = 2,
+  AB200_TARGET_WIND_V = 3,
+  AB200_TARGET_WIND_W = 4
+};
 
 /* flags (bit mask) */
 #define AB200_FLAG_K_ZERO_INIT 1u /* caller's K/dK are known to be zero: skip their H2D (+= still holds) */
@@ -77,6 +85,9 @@ enum { AB200_TARGET_T = 0, AB200_TARGET_VMR = 1 };
                                      literal rtepack_transmission.cc:64-70 arithmetic */
 #define AB200_FLAG_RETURN_K 4u    /* clearsky_emission: also copy K back to the host */
 #define AB200_FLAG_NO_EMISSION 8u /* fused path: pure transmission, J = 0 at every level (spectral_radCumulativeTransmission) */
+#define AB200_FLAG_WIND_ROWS_DF 16u /* wind rows stay the frequency derivative d propmat / d f (what                   \
+                                      spectral_propmatAddLines leaves in spectral_propmat_jac): for a caller whose agenda   \
+                                      runs spectral_propmat_jacWindFix itself.  Without it the rows are d propmat / d wind */
 
 /* ---- catalog: AbsorptionBands flattened (lbl_data.h:31-68,196-300) ----- */
 typedef struct ab200_catalog_desc {

@@ -200,10 +200,10 @@ AtmPt atm_at(const ab200_catalog_desc& d, const ab200_atm_path& a, int ip) {
   return p;
 }
 
-// wind_shift, src/m_frequency_grid.cc:4-55 (the frequency scaling factor only; the wind Jacobian
-// is outside the path) with path::mirror, src/core/path/path_point.cpp:33-39.
+// wind_shift, src/m_frequency_grid.cc:4-84: the frequency scaling factor and freq_wind_shift_jac
+// (= d fac / d(u, v, w) / fac), with path::mirror, src/core/path/path_point.cpp:33-39.
 // Returns false for a non-positive factor (the reference throws).
-bool wind_factor(const AtmPt& atm, Numeric& fac) {
+bool wind_factor(const AtmPt& atm, Numeric& fac, Numeric* jac = nullptr) {
   constexpr Numeric c = Constant::c;
   const Numeric u = atm.wind[0], v = atm.wind[1], w = atm.wind[2];
   Numeric za = 180 - atm.los[0], aa = atm.los[1] + 180;
@@ -216,15 +216,47 @@ bool wind_factor(const AtmPt& atm, Numeric& fac) {
   const Numeric aa_f = std::atan2(u, v);
   const Numeric za_p = deg2rad(za);
   const Numeric aa_p = deg2rad(aa);
+  const Numeric scl  = f2 * std::sqrt(f2 - w2);
   const Numeric czaf = std::cos(za_f);
   const Numeric szaf = std::sin(za_f);
   const Numeric czap = std::cos(za_p);
   const Numeric szap = std::sin(za_p);
   const Numeric caa  = std::cos(aa_f - aa_p);
+  const Numeric saa  = std::sin(aa_p - aa_f);
   const Numeric dp   = czaf * czap + szaf * szap * caa;
   fac                = 1.0 - (f * dp) / c;
   if (fac <= 0) return false;
-  if (std::isnan(fac)) fac = 1.0;  // "Zero shift if nan" :40-44
+  if (std::isnan(fac)) {  // "Zero shift if nan" :40-44
+    fac = 1.0;
+    if (jac) jac[0] = jac[1] = jac[2] = 0.0;
+    return true;
+  }
+  if (jac) {
+    {  // :56-63
+      const Numeric df_du    = (f == 0) ? 1.0 : u / f;
+      const Numeric dczaf_du = (f2 == 0) ? 0.0 : (-w * df_du / f2);
+      const Numeric dszaf_du = (f2 == w2) ? 0.0 : (w2 * df_du / scl);
+      const Numeric dcaa_du  = (u2v2 == 0) ? 0.0 : (v * saa / u2v2);
+      const Numeric ddp_du   = czap * dczaf_du + szap * caa * dszaf_du + szap * szaf * dcaa_du;
+      jac[0]                 = -(dp * df_du + f * ddp_du) / c;
+    }
+    {  // :65-72
+      const Numeric df_dv    = (f == 0) ? 1.0 : v / f;
+      const Numeric dczaf_dv = (f2 == 0) ? 0.0 : (-w * df_dv / f2);
+      const Numeric dszaf_dv = (f2 == w2) ? 0.0 : (w2 * df_dv / scl);
+      const Numeric dcaa_dv  = (u2v2 == 0) ? 0.0 : (-u * saa / u2v2);
+      const Numeric ddp_dv   = czap * dczaf_dv + szap * caa * dszaf_dv + szap * szaf * dcaa_dv;
+      jac[1]                 = -(dp * df_dv + f * ddp_dv) / c;
+    }
+    {  // :74-80
+      const Numeric df_dw    = (f == 0) ? 1.0 : w / f;
+      const Numeric dczaf_dw = (f2 == 0) ? 0.0 : (-w * df_dw / f2 + 1.0 / f);
+      const Numeric dszaf_dw = (scl == 0) ? 0.0 : ((w2 * df_dw - f * w) / scl);
+      const Numeric ddp_dw   = czap * dczaf_dw + szap * caa * dszaf_dw;
+      jac[2]                 = -(dp * df_dw + f * ddp_dw) / c;
+    }
+    for (int i = 0; i < 3; i++) jac[i] /= fac;  // :82
+  }
   return true;
 }
 
@@ -405,6 +437,15 @@ struct single_shape {
     const Complex dz{std::max(1e-4 * std::abs(z_.real()), 1e-4), std::max(1e-4 * std::abs(z_.imag()), 1e-4)};
     const Complex F_2 = Faddeeva::w(z_ + dz, 0);
     return (F_2 - F_) / dz;
+  }
+  // single_shape::df, lbl_lineshape_voigt_lte.cpp:275 (dF(f) :245-248); mirrored: ..._mirrored.cpp:244-248, :262
+  Complex df(Numeric f) const {
+    const Complex z_ = z(f);
+    if (mirror) {
+      const Complex zm_ = zm(f);
+      return s * inv_gd * (dF(z_, F(z_)) + dF(zm_, F(zm_)));
+    }
+    return s * inv_gd * dF(z_, F(z_));
   }
   // single_shape::dT / dVMR, lbl_lineshape_voigt_lte.cpp:310-323; mirrored: lbl_lineshape_voigt_lte_mirrored.cpp:305-325
   // (z_ = zp - zm, F_ = Fp + Fm, dF_ = dFp + dFm - literal, including the frequency-independent z_)
@@ -648,6 +689,34 @@ void calculate_band(double* pm, double* dpm, Index nf_total, const double* f_gri
     double* dp = dpm + (static_cast<Index>(iq) * nf_total + f_lo) * 7;
     const Numeric T = atm.T;
     bool is_T = targets[iq].kind == AB200_TARGET_T;
+    const bool is_wind = targets[iq].kind >= AB200_TARGET_WIND_U and targets[iq].kind <= AB200_TARGET_WIND_W;
+    if (is_wind) {
+      // df_core_calc :1036-1062 (band_shape::df :438-443, :610-627; single_shape::df :275), compute_derivative
+      // :1514-1523; the three wind components share it, spectral_propmat_jacWindFix tells them apart
+      const Numeric N = number_density(atm.P, T);
+      for (Index i = 0; i < f_n; i++) {
+        constexpr Numeric c = Constant::c * Constant::c / (8 * Constant::pi);
+        const Numeric r     = (Constant::h * fg[i]) / (Constant::k * T);
+        dscl[i]             = N * (r * std::exp(-r) - std::expm1(-r)) * c;
+      }
+      if (has_cut) {
+        for (size_t i = 0; i < nl; i++) dcut[i] = lines[i].df(lines[i].f0 + cutoff);
+        for (Index i = 0; i < f_n; i++) {
+          const auto [start, count] = freq_range(lines, fg[i], cutoff);
+          Complex out{};
+          for (Index j = start; j < start + count; j++) out += lines[j].df(fg[i]) - dcut[j];
+          dshape[i] = out;
+        }
+      } else {
+        for (Index i = 0; i < f_n; i++) {
+          Complex out{};
+          for (size_t j = 0; j < nl; j++) out += lines[j].df(fg[i]);
+          dshape[i] = out;
+        }
+      }
+      for (Index i = 0; i < f_n; i++) add_scaled(dp + i * 7, npm, dscl[i] * shape[i] + scl[i] * dshape[i]);
+      continue;
+    }
     if (is_T) {
       // dt_core_calc :984-1033
       const Numeric N = number_density(atm.P, T), dN = dnumber_density_dt(atm.P, T);
@@ -1318,14 +1387,10 @@ int orc_norm_view(int pol, const double* mag, const double* los, double* npm) {
 // there are at least as many levels as threads, else over contiguous frequency
 // chunks per level (m_lbl.cc:273-295 with omp_offset_count,
 // matpack_mdspan_algorithm.cc:4-18).  The result does not depend on the choice.
-int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f_in, int64_t f_level_stride_in,
-                       const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
-                       int32_t nq, const ab200_target* targets, double* K, double* dK) {
-  if (!d || !atm || !f_in || !K) return fail(AB200_ERR_INVALID, "null argument");
-  PathGrid pg;
-  if (int rc = path_grid(*d, *atm, nf, f_in, f_level_stride_in, pg)) return rc;
-  const double* f              = pg.f;
-  const int64_t f_level_stride = pg.stride;
+// f, f_level_stride: the levels' grids after freq_grid_pathFromPath (path_grid above); atm still carries the winds
+static int propmat_levels_on_path_grids(const ab200_catalog_desc* d, int64_t nf, const double* f, int64_t f_level_stride,
+                                        const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
+                                        int32_t nq, const ab200_target* targets, double* K, double* dK) {
   for (int ib = 0; ib < d->n_bands; ib++)
     if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE && d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE_MIRROR)
       return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE and VP_LTE_MIRROR bands");
@@ -1356,6 +1421,43 @@ int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f_
       }
     }
   }
+  // spectral_propmat_jacWindFix, src/m_frequency_grid.cc:106-182, on the level's (shifted) grid with the level's
+  // freq_wind_shift_jac (freq_grid_pathFromPath runs wind_shift at every point, calm ones included)
+  for (int q = 0; q < nq; q++) {
+    const int kind = targets[q].kind;
+    if (kind < AB200_TARGET_WIND_U or kind > AB200_TARGET_WIND_W) continue;
+    for (int ip = 0; ip < np; ip++) {
+      Numeric fac, jac[3];
+      if (not wind_factor(atm_at(*d, *atm, ip), fac, jac)) return fail(AB200_ERR_INVALID, "Negative frequency scaling factor");
+      const Numeric df_dx = jac[kind - AB200_TARGET_WIND_U];
+      double* row         = dK + (static_cast<Index>(ip) * nq + q) * nf * 7;
+      const double* fl    = f + ip * f_level_stride;
+      for (int64_t i = 0; i < nf; i++)
+        for (int c = 0; c < 7; c++) row[i * 7 + c] = row[i * 7 + c] * fl[i] * df_dx;
+    }
+  }
+  return 0;
+}
+
+int orc_propmat_levels(const ab200_catalog_desc* d, int64_t nf, const double* f_in, int64_t f_level_stride_in,
+                       const ab200_atm_path* atm, int32_t select_species, int32_t no_negative_absorption,
+                       int32_t nq, const ab200_target* targets, double* K, double* dK) {
+  if (!d || !atm || !f_in || !K) return fail(AB200_ERR_INVALID, "null argument");
+  PathGrid pg;
+  if (int rc = path_grid(*d, *atm, nf, f_in, f_level_stride_in, pg)) return rc;
+  return propmat_levels_on_path_grids(d, nf, pg.f, pg.stride, atm, select_species, no_negative_absorption, nq, targets, K,
+                                      dK);
+}
+
+// wind_shift alone (tests): fac and freq_wind_shift_jac of one path point
+int orc_wind_shift(const double* wind, const double* los, double* fac, double* jac) {
+  AtmPt a{};
+  for (int i = 0; i < 3; i++) a.wind[i] = wind[i];
+  a.los[0] = los[0];
+  a.los[1] = los[1];
+  Numeric fc;
+  if (not wind_factor(a, fc, jac)) return fail(AB200_ERR_INVALID, "Negative frequency scaling factor");
+  *fac = fc;
   return 0;
 }
 
@@ -1566,12 +1668,10 @@ int orc_clearsky_emission(const ab200_catalog_desc* d, int64_t nf, const double*
   std::vector<double> K(static_cast<size_t>(np) * nf * 7, 0.0), dK(static_cast<size_t>(np) * nq * nf * 7, 0.0);
   PathGrid pg;
   if (int rcg = path_grid(*d, *atm, nf, f, f_level_stride, pg)) return rcg;
-  ab200_atm_path atm_nw = *atm;  // the grids below are already shifted
-  atm_nw.wind           = nullptr;
-  f                     = pg.f;
-  f_level_stride        = pg.stride;
-  int rc = orc_propmat_levels(d, nf, f, f_level_stride, &atm_nw, select_species, no_negative_absorption, nq, targets,
-                              K.data(), dK.data());
+  f              = pg.f;  // the grids below are already shifted
+  f_level_stride = pg.stride;
+  int rc = propmat_levels_on_path_grids(d, nf, f, f_level_stride, atm, select_species, no_negative_absorption, nq,
+                                        targets, K.data(), dK.data());
   if (rc) return rc;
   // m_tramat.cc:14-24
   int it = -1;
@@ -2019,6 +2119,8 @@ int orc_lookup_levels(const ab200_lookup_table* tables, int32_t n_tables, int64_
     for (int q = 0; q < nq; q++) {
       const Numeric d = target_d[q];
       if (not std::isnormal(d)) return fail(AB200_ERR_INVALID, "The target is not good, it lacks a perturbation value.");
+      if (targets[q].kind != AB200_TARGET_T and targets[q].kind != AB200_TARGET_VMR)
+        return fail(AB200_ERR_UNSUPPORTED, "only temperature and VMR targets");  // the library's scope, m_lookup.cc:88-108 not restated
       std::copy(vmr, vmr + n_species, vm.begin());
       Numeric T = atm->T[ip];
       if (targets[q].kind == AB200_TARGET_T) T += d; else vm[targets[q].species] += d;

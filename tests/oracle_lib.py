@@ -49,6 +49,7 @@ def lib():
         L.orc_planck.argtypes = [C.c_int64, dp, C.c_double, dp]
         L.orc_tran.argtypes = [dp, dp, C.c_double, C.c_uint32, dp, dp]
         L.orc_wigner3j.argtypes = [C.c_int] * 6 + [dp]
+        L.orc_wind_shift.argtypes = [dp, dp, dp, dp]
         L.orc_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp]
         L.orc_norm_view.argtypes = [C.c_int, dp, dp, dp]
         L.orc_cia_levels.argtypes = [C.POINTER(abi.CiaRecordDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
@@ -102,6 +103,15 @@ def propmat_levels(cat: HostCatalog, f, atm: AtmPath, select_species=abi.SPECIES
     _check(lib().orc_propmat_levels(C.byref(d), nf, dptr(f), stride, C.byref(a), select_species,
                                     no_negative_absorption, nq, tg, dptr(K), dptr(dK)))
     return K, dK
+
+
+def wind_shift(wind, los):
+    """(fac, freq_wind_shift_jac[3]) of one path point."""
+    wind = np.ascontiguousarray(wind, dtype=np.float64)
+    los = np.ascontiguousarray(los, dtype=np.float64)
+    fac, jac = np.zeros(1), np.zeros(3)
+    _check(lib().orc_wind_shift(dptr(wind), dptr(los), dptr(fac), dptr(jac)))
+    return float(fac[0]), jac
 
 
 def tramat(K, dK, r, dr, rte_option, flags=0):

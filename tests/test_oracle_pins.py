@@ -273,6 +273,77 @@ def test_oracle_wind_shift_factor(orc):
     np.testing.assert_allclose(K2, K0, rtol=1e-9)
 
 
+def test_oracle_wind_shift_jacobian(orc):
+    """freq_wind_shift_jac (src/m_frequency_grid.cc:56-82) = d fac / d(u, v, w) / fac: against centred differences of
+    fac itself and against the direct form -n / (c fac) (n = propagation direction); at zero wind the reference's
+    special cases make all three components -cos(za_p) / c (df = 1, every angle derivative 0)."""
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        wind = rng.normal(0, 40, 3)
+        los = np.array([rng.uniform(5, 175), rng.uniform(-175, 175)])
+        fac, jac = orc.wind_shift(wind, los)
+        za, aa = np.deg2rad(180 - los[0]), np.deg2rad(los[1] + 180)
+        n = np.array([np.sin(za) * np.sin(aa), np.sin(za) * np.cos(aa), np.cos(za)])
+        assert fac == pytest.approx(1 - wind @ n / synth.C0, rel=1e-15)
+        np.testing.assert_allclose(jac, -n / synth.C0 / fac, rtol=1e-9, atol=1e-18)
+        for i in range(3):
+            h = 1.0
+            wp, wm = wind.copy(), wind.copy()
+            wp[i] += h; wm[i] -= h
+            fd = (orc.wind_shift(wp, los)[0] - orc.wind_shift(wm, los)[0]) / (2 * h) / fac
+            assert jac[i] == pytest.approx(fd, rel=1e-6, abs=1e-14)
+    fac, jac = orc.wind_shift(np.zeros(3), np.array([40.0, 20.0]))
+    assert fac == 1.0
+    np.testing.assert_allclose(jac, -np.cos(np.deg2rad(140.0)) / synth.C0 * np.ones(3), rtol=1e-15)
+    # purely vertical wind: the horizontal rows vanish with sin(za_f) = 0
+    fac, jac = orc.wind_shift(np.array([0.0, 0.0, 12.0]), np.array([140.0, 30.0]))
+    assert jac[2] == pytest.approx(-np.cos(np.deg2rad(40.0)) / synth.C0 / fac, rel=1e-12)
+
+
+@pytest.mark.parametrize("cutoff", [None, 40e6])
+def test_oracle_wind_propmat_jacobian_like_reference_test(orc, cutoff):
+    """The reference's tests/core/wind/propmat_jac.py on a synthetic line: wind (10, 10, 10) m/s, los (40, 20), a grid
+    of +-50 MHz around the line without the central +-1 MHz, analytic d propmat / d wind (df of the lines, then
+    spectral_propmat_jacWindFix) against (propmat(wind + 0.1 e_i) - propmat(wind)) / 0.1 at rtol 1e-3."""
+    import copy
+
+    c = synth.case_c1(nl=1, nf=1000, cutoff=cutoff)
+    f0 = c.cat.f0[0]
+    f = np.linspace(-50e6, 50e6, 1000) + f0
+    f = f[np.abs(f - f0) > 1000e3]
+    if cutoff:
+        f = f[np.abs(f - f0) < cutoff - 200e3]  # inside the window; the perturbed run must not move a point across its edge
+    atm = copy.deepcopy(c.atm)
+    atm.P[:] = 1.2e3  # ~30 km like the reference's point
+    atm.los = np.array([[40.0, 20.0]])
+    atm.wind = np.array([[10.0, 10.0, 10.0]])
+    for i, key in enumerate(("wind_u", "wind_v", "wind_w")):
+        K0, dK = orc.propmat_levels(c.cat, f, atm, targets=((key,),))
+        a1 = copy.deepcopy(atm)
+        a1.wind[0, i] += 0.1
+        K1, _ = orc.propmat_levels(c.cat, f, a1)
+        fd = (K1[0, :, 0] - K0[0, :, 0]) / 0.1
+        if cutoff is None:
+            np.testing.assert_allclose(fd / dK[0, 0, :, 0], 1.0, rtol=1e-3)
+        else:
+            # band_shape::df(cut, f) (lbl_lineshape_voigt_lte.cpp:610-627) subtracts the frequency derivative AT the window
+            # edge, although the subtracted cutoff value does not move with f: the analytic row is short of the
+            # perturbation by scl(f) * f * jac_i * Re(dcut), one constant for the whole window (sic, restated as is)
+            fac, jac = orc.wind_shift(atm.wind[0], atm.los[0])
+            fs = fac * f
+            h, k = 6.62607015e-34, 1.380649e-23
+            T, P = atm.T[0], atm.P[0]
+            scl = -(P / (k * T)) * fs * np.expm1(-h * fs / (k * T)) * synth.C0**2 / (8 * np.pi)
+            q = (fd - dK[0, 0, :, 0]) / (scl * fs * jac[i])
+            assert np.abs(q).min() > 0
+            np.testing.assert_allclose(q, np.median(q), rtol=2e-2)
+    # all three rows are one frequency derivative times f * freq_wind_shift_jac[i]
+    _, dK3 = orc.propmat_levels(c.cat, f, atm, targets=(("wind_u",), ("wind_v",), ("wind_w",)))
+    _, jac = orc.wind_shift(atm.wind[0], atm.los[0])
+    np.testing.assert_allclose(dK3[0, 1, :, 0] * jac[0], dK3[0, 0, :, 0] * jac[1], rtol=1e-13)
+    np.testing.assert_allclose(dK3[0, 2, :, 0] * jac[0], dK3[0, 0, :, 0] * jac[2], rtol=1e-13)
+
+
 def test_unit_conversion_functions_against_their_definitions(orc):
     """invplanck / dinvplanckdI / invrayjean / dplanck_dt of the transform operators and the surface-blackbody
     Jacobian (physics_funcs.cc:76-83,153-158,172-176,254-263), pinned to closed forms evaluated with mpmath-free

@@ -22,6 +22,7 @@ CUTOFF_NONE, CUTOFF_BYLINE = 0, 1
 RTE_CONSTANT, RTE_LINSRC, RTE_LINPROP = 0, 1, 2
 TARGET_T, TARGET_VMR = 0, 1
 TARGET_WIND_U, TARGET_WIND_V, TARGET_WIND_W = 2, 3, 4
+TARGET_MAG_U, TARGET_MAG_V, TARGET_MAG_W = 5, 6, 7
 FLAG_K_ZERO_INIT, FLAG_TRAN_EXACT, FLAG_RETURN_K, FLAG_NO_EMISSION, FLAG_WIND_ROWS_DF = 1, 2, 4, 8, 16
 
 RTE_OPTIONS = {"constant": RTE_CONSTANT, "linsrc": RTE_LINSRC, "lintau": RTE_LINSRC, "linprop": RTE_LINPROP}
@@ -471,7 +472,7 @@ class Observer:
 
 
 def make_targets(targets) -> tuple[C.Array | None, int]:
-    """targets: iterable of ("T",) / ("VMR", species_id) / ("wind_u",) .. ("wind_w",) or (kind, species) ints."""
+    """targets: iterable of ("T",) / ("VMR", species_id) / ("wind_u",) .. ("wind_w",) / ("mag_u",) .. ("mag_w",) or (kind, species) ints."""
     lst = []
     for t in targets or ():
         if isinstance(t, str):
@@ -483,6 +484,8 @@ def make_targets(targets) -> tuple[C.Array | None, int]:
             lst.append((TARGET_VMR, int(t[1])))
         elif kind in ("wind_u", "wind_v", "wind_w"):  # AtmKey::wind_*
             lst.append((TARGET_WIND_U + "uvw".index(kind[-1]), 0))
+        elif kind in ("mag_u", "mag_v", "mag_w"):  # AtmKey::mag_*
+            lst.append((TARGET_MAG_U + "uvw".index(kind[-1]), 0))
         else:
             lst.append((int(kind), int(t[1]) if len(t) > 1 else 0))
     if not lst:

@@ -81,7 +81,7 @@ struct ab200_path {
   double* d_Ilev = nullptr;  // [np][nf][4] radiance arriving at each level
   double* d_jac = nullptr;   // [levels_per_batch][ntiles][nq][2][TL][4]
   double* d_jcom = nullptr;  // [levels_per_batch][ntiles][TL]
-  double *d_dQdT = nullptr, *d_dr = nullptr, *d_invT = nullptr, *d_ffac = nullptr, *d_wjac = nullptr;
+  double *d_dQdT = nullptr, *d_dr = nullptr, *d_invT = nullptr, *d_ffac = nullptr, *d_wjac = nullptr, *d_dnpm = nullptr, *d_magr = nullptr;
   int32_t tg_kind[AB200_MAX_TARGETS] = {0}, tg_species[AB200_MAX_TARGETS] = {0};
   int32_t it = -1;  // position of the temperature target
   bool dk_preloaded = false;
@@ -180,7 +180,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   AB_TRY(dev_alloc(&p->d_f, snp * nf));
   // packed small arrays: T, P, H [np] | vmr [np][ns] | isorat, Q [np][ni] | npm [np][4][7] | frange [np][2] | r [np]
   //                      | dQdT [np][ni] | dr [2][np][nq] | 1/T [np] | wind factor [np] | freq_wind_shift_jac [np][3]
-  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq) + 2 + 3);
+  //                      | dnorm_view [np][3][4][7] | mag / |mag| [np][3]
+  p->small_doubles = snp * (3 + cat->n_species + 2 * cat->n_isot + 28 + 2 + 1 + cat->n_isot + 2 * static_cast<size_t>(nq) + 2 + 3 + 84 + 3);
   AB_TRY(dev_alloc(&p->d_small, p->small_doubles));
   if (p->small_doubles) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_small), p->small_doubles * sizeof(double)));
   double* q = p->d_small;
@@ -197,7 +198,9 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->d_dr = q; q += 2 * snp * nq;
   p->d_invT = q; q += snp;
   p->d_ffac = q; q += snp;
-  p->d_wjac = q;
+  p->d_wjac = q; q += 3 * snp;
+  p->d_dnpm = q; q += 84 * snp;
+  p->d_magr = q;
   AB_TRY(dev_alloc(&p->d_Ibkg, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_I, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_K, snp * p->k_pitch * 7));
@@ -287,9 +290,12 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
       } else if (targets[q].kind == AB200_TARGET_WIND_U || targets[q].kind == AB200_TARGET_WIND_V ||
                  targets[q].kind == AB200_TARGET_WIND_W) {
         // frequency derivative of the lines times f * freq_wind_shift_jac; nothing to check
+      } else if (targets[q].kind == AB200_TARGET_MAG_U || targets[q].kind == AB200_TARGET_MAG_V ||
+                 targets[q].kind == AB200_TARGET_MAG_W) {
+        // Zeeman splitting derivative and the derivative of the polarisation matrix; nothing to check
       } else {
         return set_error(AB200_ERR_UNSUPPORTED, "Jacobian target " + std::to_string(q) +
-                                                    ": only temperature, species VMR and wind targets are on the GPU path");
+                                                    ": only temperature, species VMR, wind and magnetic-field targets are on the GPU path");
       }
     }
   }
@@ -299,7 +305,8 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   double* h = p->h_small;
   double *hT = h, *hP = hT + scap, *hH = hP + scap, *hv = hH + scap, *hi = hv + scap * cat->n_species,
          *hQ = hi + scap * cat->n_isot, *hn = hQ + scap * cat->n_isot, *hfr = hn + scap * 28, *hr = hfr + scap * 2,
-         *hdQ = hr + scap, *hdr = hdQ + scap * cat->n_isot, *hiT = hdr + 2 * scap * p->nq, *hff = hiT + scap, *hwj = hff + scap;
+         *hdQ = hr + scap, *hdr = hdQ + scap * cat->n_isot, *hiT = hdr + 2 * scap * p->nq, *hff = hiT + scap, *hwj = hff + scap, *hdn = hwj + 3 * scap,
+         *hmr = hdn + 84 * scap;
   std::fill(hdr, hdr + 2 * scap * p->nq, 0.0);
   for (int ip = 0; ip < np; ip++) {
     if (!(atm->T[ip] > 0) || !(atm->P[ip] >= 0))
@@ -318,6 +325,10 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
     if (!atm->wind) fac = 1.0;
     hff[ip] = fac;
     for (int pol = 0; pol < 4; pol++) norm_view(pol, mag, los, hn + (static_cast<size_t>(ip) * 4 + pol) * 7);
+    for (int c = 0; c < 3; c++) {
+      for (int pol = 0; pol < 4; pol++) dnorm_view(pol, c, mag, los, hdn + ((static_cast<size_t>(ip) * 3 + c) * 4 + pol) * 7);
+      hmr[3 * ip + c] = mag[c] / hH[ip];  // dH/dmag_c, lbl_lineshape_voigt_lte.cpp:1071-1072 (NaN without a field, like there)
+    }
     const double* fl = f + ip * f_level_stride;
     if (!p->grid_bounds.empty()) {
       hfr[2 * ip]     = fac * p->grid_bounds[2 * ip];
@@ -478,6 +489,8 @@ int ab200_path_run_propmat(ab200_path* p) {
       js.jac = p->d_jac;
       js.jcom = p->d_jcom;
       js.dK = p->d_dK + static_cast<size_t>(lev0) * p->nq * p->k_pitch * 7;
+      jp.mag_ratio = p->d_magr + 3 * static_cast<size_t>(lev0);
+      js.dnpm = p->d_dnpm + 84 * static_cast<size_t>(lev0);
       js.wind_jac = (p->flags & AB200_FLAG_WIND_ROWS_DF) ? nullptr : p->d_wjac + 3 * static_cast<size_t>(lev0);
       AB_TRY(launch_prepare_jac(pp, jp, nlev, p->stream));
       for (int mode = 0; mode < 2; mode++) {

@@ -86,6 +86,38 @@ void norm_view(int pol, const double mag[3], const double los[2], double npm[7])
   }
 }
 
+// dnorm_view_du / dv / dw, lbl_zeeman.cpp:457-536 with magnetic_angles::dtheta_d*, deta_d* (:361-411)
+void dnorm_view(int pol, int comp, const double mag[3], const double los[2], double dnpm[7]) {
+  const double deg = cst::pi / 180;
+  const double u = mag[0], v = mag[1], w = mag[2];
+  const double sa = std::sin(los[1] * deg), ca = std::cos(los[1] * deg);
+  const double sz = std::sin(los[0] * deg), cz = std::cos(los[0] * deg);
+  const double H    = std::hypot(u, v, w);
+  const double uct  = sz * sa * u + sz * ca * v + cz * w;
+  const double duct = u * sa * cz + v * ca * cz - w * sz;
+  const double theta = H == 0 ? 0 : std::acos(uct / H);
+  const double eta   = -std::atan2(ca * u - sa * v, -duct);
+  const double rat   = (uct / H) * (uct / H);
+  const double H2 = H * H, H3 = H * H * H;
+  const double nom   = comp == 0 ? u * uct - sa * sz * H2 : comp == 1 ? v * uct - ca * sz * H2 : w * uct - cz * H2;
+  const double dtheta = (H == 0.0 || rat == 1.0) ? 0 : nom / (std::sqrt(1.0 - rat) * H3);
+  const double b2 = ca * u - sa * v;
+  const double den = b2 * b2 + duct * duct;
+  const double deta = H == 0 ? 0 : (comp == 0 ? (cz * v - ca * sz * w) : comp == 1 ? (sa * sz * w - cz * u) : sz * b2) / den;
+  const double CT = std::cos(theta), ST = std::sin(theta), CE = std::cos(2 * eta), SE = std::sin(2 * eta);
+  const double ST2  = ST * ST;
+  const double dST2 = 2 * dtheta * ST * CT;
+  const double dQ   = 2 * dtheta * ST * CE * CT - 2 * deta * SE * ST2;
+  const double dU   = 2 * deta * ST2 * CE + 2 * dtheta * SE * ST * CT;
+  const double dCT  = -dtheta * ST;
+  switch (pol) {
+    case POL_PI: { const double t[7] = {dST2, -dQ, dU, 0, 0, dU, dQ}; std::copy(t, t + 7, dnpm); } break;
+    case POL_SM: { const double t[7] = {-dST2, dQ, -dU, 2 * dCT, -2 * dCT, -dU, -dQ}; std::copy(t, t + 7, dnpm); } break;
+    case POL_SP: { const double t[7] = {-dST2, dQ, -dU, -2 * dCT, 2 * dCT, -dU, -dQ}; std::copy(t, t + 7, dnpm); } break;
+    default: std::fill(dnpm, dnpm + 7, 0.0); break;
+  }
+}
+
 bool wind_factor(const double wind[3], const double los[2], double* fac_out, double* jac_out) {
   const double deg = cst::pi / 180;
   const double u = wind[0], v = wind[1], w = wind[2];

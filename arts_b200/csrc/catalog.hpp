@@ -85,5 +85,6 @@ double zeeman_splitting(double gu, double gl, int two_Ju, int two_Jl, int pol, i
 // zeeman::norm_view, lbl_zeeman.cpp:413-455
 void norm_view(int pol, const double mag[3], const double los[2], double npm[7]);
 // wind_shift frequency factor, src/m_frequency_grid.cc:4-55 with path::mirror (path_point.cpp:33-39); false if <= 0
+void dnorm_view(int pol, int comp, const double mag[3], const double los[2], double dnpm[7]);
 bool wind_factor(const double wind[3], const double los[2], double* fac, double* jac = nullptr);
 }  // namespace ab200

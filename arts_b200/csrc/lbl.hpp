@@ -60,6 +60,7 @@ struct JacPrepParams {
   const double* dQdT;                  // [nlev][n_isot], offset to the batch
   double* jac;                         // [nlev][ntiles][nq][2][TL][4]
   double* jcom;                        // [nlev][ntiles][TL]
+  const double* mag_ratio;             // [nlev][3] mag_c / |mag| of the batch's levels (magnetic-field targets)
 };
 struct JacSumParams {
   int32_t nq, q0;
@@ -69,6 +70,7 @@ struct JacSumParams {
   const double* jac;
   const double* jcom;
   double* dK;  // [nlev][nq][k_pitch][7], offset to the batch
+  const double* dnpm;      // [nlev][3][4][7] dnorm_view_d{u,v,w} per polarisation (magnetic-field targets)
   const double* wind_jac;  // [nlev][3] freq_wind_shift_jac of the batch's levels (wind targets); null = leave d/df
 };
 

@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
                               cscale(f0s * sl, lmc));
         ds     = cscale(Sz * (cst::inv_sqrt_pi * igd * r * x) / (2 * T * f0s), num);
         dz_fac = (-2 * T * dD0 - 2 * T * dDV - f0s) / (2 * T * f0s);  // :1013-1015
+      } else if (jp.kind[q] >= AB200_TARGET_MAG_U) {
+        // single_shape::dH, :305-307: s dz dF, dz = -inv_gd dH/dmag_c Splitting (:1071-1078); lines without Zeeman
+        // splitting have dz = 0 and pol = no segments are skipped in the sum kernel's epilogue (:1484-1486)
+        dD0 = dDV = dG0 = dG = dY = 0.0;
+        ds     = {0.0, 0.0};
+        dz_fac = 0.0;
       } else if (jp.kind[q] >= AB200_TARGET_WIND_U) {
         // single_shape::df, :275: s inv_gd dF(f) -- dX with ds = 0, dz = inv_gd, dz_fac = 0 (for a mirror twin too:
         // zm = inv_gd (f + f0') has the same slope)
@@ -176,7 +182,12 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
         dz_fac = -(dD0 + dDV) / f0s;  // :1176
       }
       cplx dzq{igd * -(dD0 + dDV), igd * dG0};
-      if (jp.kind[q] >= AB200_TARGET_WIND_U) dzq = {igd, 0.0};
+      if (jp.kind[q] >= AB200_TARGET_MAG_U) {
+        const double dzc = p.sub_dzc[slot];
+        dzq = {dzc == 0.0 ? 0.0 : -igd * jp.mag_ratio[3 * lev + (jp.kind[q] - AB200_TARGET_MAG_U)] * dzc, 0.0};
+      } else if (jp.kind[q] >= AB200_TARGET_WIND_U) {
+        dzq = {igd, 0.0};
+      }
       if (sfl & SUB_MIRRORED) {
         // mirrored dT / dVMR (lbl_lineshape_voigt_lte_mirrored.cpp:305-325): s (dz + dz_fac z_) (dFp + dFm) with
         // z_ = zp - zm = -2 inv_gd f0', independent of the frequency: fold it into dz and drop the x-proportional part,
@@ -499,6 +510,18 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
         cplx d = cscale(scl, acc[q][r]);
         const int kind = jp.kind[jp.q0 + q];
         if (kind == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
+        if (kind >= AB200_TARGET_MAG_U) {
+          // compute_derivative :1484-1513 with zeeman::scale(npm, dnpm, scl shape, scl dshape), lbl_zeeman.h:442-453
+          if (seg.pol == POL_NO) continue;
+          const double* __restrict__ dn = jp.dnpm + ((int64_t(lev) * 3 + (kind - AB200_TARGET_MAG_U)) * 4 + seg.pol) * 7;
+          const cplx F = cscale(scl, shape[r]);
+          double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
+          o[0] += dn[0] * F.re + npm[0] * d.re; o[1] += dn[1] * F.re + npm[1] * d.re;
+          o[2] += dn[2] * F.re + npm[2] * d.re; o[3] += dn[3] * F.re + npm[3] * d.re;
+          o[4] += dn[4] * F.im + npm[4] * d.im; o[5] += dn[5] * F.im + npm[5] * d.im;
+          o[6] += dn[6] * F.im + npm[6] * d.im;
+          continue;
+        }
         if (kind >= AB200_TARGET_WIND_U) {
           // compute_derivative :1514-1523, then spectral_propmat_jacWindFix (m_frequency_grid.cc:106-182): x * f * df_du
           d = cadd(d, cscale(line_scale_df(f[r], T, P), shape[r]));

@@ -68,7 +68,7 @@ enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1, AB200_LINESHAPE_VP
 enum { AB200_CUTOFF_NONE = 0, AB200_CUTOFF_BYLINE = 1 };
 /* TransmittanceOption (arts_options.cc:953-1030); linsrc is the default rte_option. */
 enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 /* unpolarised layers only, else AB200_ERR_UNSUPPORTED */ };
-/* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR, AtmKey::wind_u/v/w).  The wind rows are the
+/* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR, AtmKey::wind_u/v/w, AtmKey::mag_u/v/w).  The wind rows are the
  * frequency derivative of the line absorption (single_shape::df, lbl_lineshape_voigt_lte.cpp:275, :1036-1062, :1514-1523)
  * times f * freq_wind_shift_jac (spectral_propmat_jacWindFix, src/m_frequency_grid.cc:106-182, wind_shift :56-82). */
 enum {
@@ -76,7 +76,13 @@ enum {
   AB200_TARGET_VMR = 1,
   AB200_TARGET_WIND_U = 2,
   AB200_TARGET_WIND_V = 3,
-  AB200_TARGET_WIND_W = 4
+  AB200_TARGET_WIND_W = 4,
+  /* AtmKey::mag_u/v/w: Zeeman polarisations only (lbl_lineshape_voigt_lte.cpp:1484-1513): the splitting derivative
+   * s dz dF with dz = -inv_gd (mag_c / H) Splitting (:1066-1162, single_shape::dH :305-307) through the polarisation
+   * matrix and the matrix's own derivative dnorm_view_d{u,v,w} (lbl_zeeman.cpp:361-411, 457-536; scale lbl_zeeman.h:442-453) */
+  AB200_TARGET_MAG_U = 5,
+  AB200_TARGET_MAG_V = 6,
+  AB200_TARGET_MAG_W = 7
 };
 
 /* flags (bit mask) */

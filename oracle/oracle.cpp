@@ -418,6 +418,48 @@ void norm_view(Pol p, const Numeric mag[3], const Numeric los[2], Numeric npm[7]
   for (int i = 0; i < 7; i++) npm[i] = src[i];
 }
 
+// zeeman::dnorm_view_du / dv / dw, lbl_zeeman.cpp:457-536, with magnetic_angles::dtheta_d* and deta_d* (:361-411);
+// comp = 0, 1, 2 for u, v, w
+void dnorm_view(Pol p, int comp, const Numeric mag[3], const Numeric los[2], Numeric dnpm[7]) {
+  const Numeric u = mag[0], v = mag[1], w = mag[2];
+  const Numeric sa = std::sin(deg2rad(los[1])), ca = std::cos(deg2rad(los[1]));
+  const Numeric sz = std::sin(deg2rad(los[0])), cz = std::cos(deg2rad(los[0]));
+  const Numeric H    = std::hypot(u, v, w);
+  const Numeric uct  = sz * sa * u + sz * ca * v + cz * w;
+  const Numeric duct = u * sa * cz + v * ca * cz - w * sz;
+  const Numeric theta = H == 0 ? 0 : std::acos(uct / H);
+  const Numeric eta   = -std::atan2(ca * u - sa * v, -duct);
+  Numeric dtheta, deta;
+  {
+    const Numeric rat = pow2(uct / H);
+    const Numeric nom = comp == 0   ? u * uct - sa * sz * pow2(H)
+                        : comp == 1 ? v * uct - ca * sz * pow2(H)
+                                    : w * uct - cz * pow2(H);
+    dtheta = (H == 0.0 or rat == 1.0) ? 0 : nom / (std::sqrt(1.0 - rat) * (H * H * H));
+    const Numeric den = pow2(ca * u - sa * v) + pow2(duct);
+    deta = H == 0 ? 0
+                  : (comp == 0   ? (cz * v - ca * sz * w)
+                     : comp == 1 ? (sa * sz * w - cz * u)
+                                 : sz * (ca * u - sa * v)) /
+                        den;
+  }
+  const Numeric CT   = std::cos(theta);
+  const Numeric ST   = std::sin(theta);
+  const Numeric CE   = std::cos(2 * eta);
+  const Numeric SE   = std::sin(2 * eta);
+  const Numeric ST2  = pow2(ST);
+  const Numeric dST2 = 2 * dtheta * ST * CT;
+  const Numeric dQ   = 2 * dtheta * ST * CE * CT - 2 * deta * SE * ST2;
+  const Numeric dU   = 2 * deta * ST2 * CE + 2 * dtheta * SE * ST * CT;
+  const Numeric dCT  = -dtheta * ST;
+  const Numeric pi_[7] = {dST2, -dQ, dU, 0, 0, dU, dQ};
+  const Numeric sm_[7] = {-dST2, dQ, -dU, 2 * dCT, -2 * dCT, -dU, -dQ};
+  const Numeric sp_[7] = {-dST2, dQ, -dU, -2 * dCT, 2 * dCT, -dU, -dQ};
+  const Numeric no_[7] = {0, 0, 0, 0, 0, 0, 0};
+  const Numeric* src = p == POL_PI ? pi_ : p == POL_SM ? sm_ : p == POL_SP ? sp_ : no_;
+  for (int i = 0; i < 7; i++) dnpm[i] = src[i];
+}
+
 // ---------------------------------------------------------------------------
 // single_shape: src/core/lbl/lbl_lineshape_voigt_lte.h:20-56 and
 // lbl_lineshape_voigt_lte.cpp:22-36,145-204,239-268
@@ -437,6 +479,15 @@ struct single_shape {
     const Complex dz{std::max(1e-4 * std::abs(z_.real()), 1e-4), std::max(1e-4 * std::abs(z_.imag()), 1e-4)};
     const Complex F_2 = Faddeeva::w(z_ + dz, 0);
     return (F_2 - F_) / dz;
+  }
+  // single_shape::dH, lbl_lineshape_voigt_lte.cpp:305-307; mirrored: s dz_dH (dFp + dFm), ..._mirrored.cpp
+  Complex dH(Complex dz_dH, Numeric f) const {
+    const Complex z_ = z(f);
+    if (mirror) {
+      const Complex zm_ = zm(f);
+      return s * dz_dH * (dF(z_, F(z_)) + dF(zm_, F(zm_)));
+    }
+    return s * dz_dH * dF(z_, F(z_));
   }
   // single_shape::df, lbl_lineshape_voigt_lte.cpp:275 (dF(f) :245-248); mirrored: ..._mirrored.cpp:244-248, :262
   Complex df(Numeric f) const {
@@ -715,6 +766,42 @@ void calculate_band(double* pm, double* dpm, Index nf_total, const double* f_gri
         }
       }
       for (Index i = 0; i < f_n; i++) add_scaled(dp + i * 7, npm, dscl[i] * shape[i] + scl[i] * dshape[i]);
+      continue;
+    }
+    if (targets[iq].kind >= AB200_TARGET_MAG_U and targets[iq].kind <= AB200_TARGET_MAG_W) {
+      // compute_derivative :1484-1513 with dmag_{u,v,w}_core_calc :1066-1162 (band_shape::dH :445-455, :629-655)
+      if (pol == POL_NO) continue;
+      const int comp      = targets[iq].kind - AB200_TARGET_MAG_U;
+      const Numeric H     = std::hypot(atm.mag[0], atm.mag[1], atm.mag[2]);
+      const Numeric dH_dm = atm.mag[comp] / H;
+      for (size_t i = 0; i < nl; i++) {
+        const LineView ln{d, pos[i].line};
+        const ZeemanView z{d.z_on[ln.l] != 0, d.z_gu[ln.l], d.z_gl[ln.l], d.two_Ju[ln.l], d.two_Jl[ln.l]};
+        dz[i] = -lines[i].inv_gd * dH_dm * z.Splitting(pol, pos[i].iz);
+      }
+      if (has_cut) {
+        for (size_t i = 0; i < nl; i++) dcut[i] = lines[i].dH(dz[i], lines[i].f0 + cutoff);
+        for (Index i = 0; i < f_n; i++) {
+          const auto [start, count] = freq_range(lines, fg[i], cutoff);
+          Complex out{};
+          for (Index j = start; j < start + count; j++) out += lines[j].dH(dz[j], fg[i]) - dcut[j];
+          dshape[i] = out;
+        }
+      } else {
+        for (Index i = 0; i < f_n; i++) {
+          Complex out{};
+          for (size_t j = 0; j < nl; j++) out += lines[j].dH(dz[j], fg[i]);
+          dshape[i] = out;
+        }
+      }
+      Numeric dnpm[7];
+      dnorm_view(pol, comp, atm.mag, atm.los, dnpm);
+      for (Index i = 0; i < f_n; i++) {  // zeeman::scale(a, da, F, dF), lbl_zeeman.h:442-453
+        const Complex F = scl[i] * shape[i], dF = scl[i] * dshape[i];
+        double* o = dp + i * 7;
+        for (int c = 0; c < 4; c++) o[c] += dnpm[c] * F.real() + npm[c] * dF.real();
+        for (int c = 4; c < 7; c++) o[c] += dnpm[c] * F.imag() + npm[c] * dF.imag();
+      }
       continue;
     }
     if (is_T) {
@@ -1379,6 +1466,11 @@ int orc_zeeman_components(int on, double gu, double gl, int tJu, int tJl, int po
 
 int orc_norm_view(int pol, const double* mag, const double* los, double* npm) {
   norm_view(static_cast<Pol>(pol), mag, los, npm);
+  return 0;
+}
+
+int orc_dnorm_view(int pol, int comp, const double* mag, const double* los, double* dnpm) {
+  dnorm_view(static_cast<Pol>(pol), comp, mag, los, dnpm);
   return 0;
 }
 

@@ -52,6 +52,7 @@ def lib():
         L.orc_wind_shift.argtypes = [dp, dp, dp, dp]
         L.orc_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp]
         L.orc_norm_view.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_dnorm_view.argtypes = [C.c_int, C.c_int, dp, dp, dp]
         L.orc_cia_levels.argtypes = [C.POINTER(abi.CiaRecordDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
                                      C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), C.c_double, C.c_double, C.c_int32, dp, dp]
         L.orc_lookup_levels.argtypes = [C.POINTER(abi.LookupTableDesc), C.c_int32, C.c_int64, dp, C.c_int64, C.POINTER(abi.AtmPathDesc),
@@ -223,6 +224,14 @@ def norm_view(pol, mag, los):
     los = np.ascontiguousarray(los, dtype=np.float64)
     out = np.empty(7)
     lib().orc_norm_view(pol, dptr(mag), dptr(los), dptr(out))
+    return out
+
+
+def dnorm_view(pol, comp, mag, los):
+    mag = np.ascontiguousarray(mag, dtype=np.float64)
+    los = np.ascontiguousarray(los, dtype=np.float64)
+    out = np.empty(7)
+    lib().orc_dnorm_view(pol, comp, dptr(mag), dptr(los), dptr(out))
     return out
 
 

@@ -177,7 +177,7 @@ def test_jacobian_errors_are_loud(wsm):
         wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=(("T",),), flags=abi.FLAG_TRAN_EXACT)
     assert e.value.code == abi.ERR_UNSUPPORTED
     with pytest.raises(Ab200Error) as e:
-        wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=((5, 0),))
+        wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=((99, 0),))
     assert e.value.code == abi.ERR_UNSUPPORTED
 
 

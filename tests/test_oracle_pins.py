@@ -344,6 +344,55 @@ def test_oracle_wind_propmat_jacobian_like_reference_test(orc, cutoff):
     np.testing.assert_allclose(dK3[0, 2, :, 0] * jac[0], dK3[0, 0, :, 0] * jac[2], rtol=1e-13)
 
 
+def test_oracle_dnorm_view_against_differences(orc):
+    """dnorm_view_d{u,v,w} (lbl_zeeman.cpp:457-536) = d norm_view / d mag_c, by centred differences, every
+    polarisation; without a field the reference returns zeros."""
+    rng = np.random.default_rng(12)
+    for _ in range(10):
+        mag = rng.normal(0, 3e-5, 3)
+        los = np.array([rng.uniform(5, 175), rng.uniform(-175, 175)])
+        for pol in range(4):
+            for c in range(3):
+                h = 1e-9
+                mp, mm = mag.copy(), mag.copy()
+                mp[c] += h; mm[c] -= h
+                fd = (orc.norm_view(pol, mp, los) - orc.norm_view(pol, mm, los)) / (2 * h)
+                d = orc.dnorm_view(pol, c, mag, los)
+                np.testing.assert_allclose(d, fd, rtol=1e-6, atol=1e-6 * max(np.abs(fd).max(), 1.0))
+    assert not orc.dnorm_view(1, 0, np.zeros(3), np.array([40.0, 0.0])).any()
+    assert not orc.dnorm_view(0, 2, np.array([1e-5, 2e-5, 3e-5]), np.array([40.0, 0.0])).any()  # pol = no
+
+
+@pytest.mark.parametrize("comp", [0, 1, 2])
+def test_oracle_magnetic_propmat_jacobian_like_reference_test(orc, comp):
+    """The reference's tests/core/zeeman/propmat_jac.py on the synthetic O2 Zeeman catalog: 250 K, 1 Pa, the same field
+    and los (40, 0), three frequencies 5-6 MHz above the 118.75 GHz line, analytic d propmat / d mag against a
+    perturbation at rtol 1e-3 for all seven components.  The reference tests mag_w with a forward step of 1e-11 T; here a
+    centred step of 1e-10 T (less rounding noise) and all three components - mag_u, a tenth of |B| in this fixture, at
+    2e-2: its two terms nearly cancel in D and U, which shows the ~1e-4 relative error of the reference's
+    forward-difference dF (lbl_lineshape_voigt_lte.cpp:250-268) at the per-cent level."""
+    import copy
+
+    from arts_b200._abi import AtmPath
+
+    cat = synth.o2_zeeman_catalog()
+    f = np.linspace(5e6, 6e6, 3) + 118.750348e9
+    B = np.array([[-3.132846e-06, 2.62680294e-05, 1.39844339e-05]])
+    atm = AtmPath(T=np.array([250.0]), P=np.array([1.0]), vmr=np.array([[0.2]]), isorat=np.array([[0.995]]),
+                  Q=np.array([[215.0 * 250 / 296]]), dQdT=np.array([[215.0 / 296]]), mag=B, los=np.array([[40.0, 0.0]]))
+    key = ("mag_u", "mag_v", "mag_w")[comp]
+    K0, dK = orc.propmat_levels(cat, f, atm, targets=((key,),))
+    dx = 1e-10
+    a1, a2 = copy.deepcopy(atm), copy.deepcopy(atm)
+    a1.mag[0, comp] += dx
+    a2.mag[0, comp] -= dx
+    K1, _ = orc.propmat_levels(cat, f, a1)
+    K2, _ = orc.propmat_levels(cat, f, a2)
+    d = (K1[0] - K2[0]) / (2 * dx)
+    assert np.abs(dK[0, 0]).min() > 0
+    np.testing.assert_allclose(d, dK[0, 0], rtol=2e-2 if comp == 0 else 1e-3, atol=1e-6 * np.abs(dK[0, 0]).max())
+
+
 def test_unit_conversion_functions_against_their_definitions(orc):
     """invplanck / dinvplanckdI / invrayjean / dplanck_dt of the transform operators and the surface-blackbody
     Jacobian (physics_funcs.cc:76-83,153-158,172-176,254-263), pinned to closed forms evaluated with mpmath-free

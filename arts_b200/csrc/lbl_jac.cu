@@ -299,7 +299,9 @@ __device__ __forceinline__ void far_pair(const FarLine& c, double x, double x2, 
 }
 
 // CTAs per SM the shared-memory footprint allows: (10 + 7 NQ) x 2 KB -> 34 / 48 / 62 / 76 KB
-template <int NQ>
+// EXT: the pass holds a wind or magnetic-field target (their epilogue costs the temperature / VMR passes 6 % in
+// registers and spills when it is compiled in, so those keep an instantiation without it)
+template <int NQ, bool EXT>
 __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_sum_jac_kernel(SumParams p, JacSumParams jp) {
   extern __shared__ __align__(16) double sm[];  // [JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS][TL]
   double* const sb = sm;
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
         cplx d = cscale(scl, acc[q][r]);
         const int kind = jp.kind[jp.q0 + q];
         if (kind == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
-        if (kind >= AB200_TARGET_MAG_U) {
+        if (EXT && kind >= AB200_TARGET_MAG_U) {
           // compute_derivative :1484-1513 with zeeman::scale(npm, dnpm, scl shape, scl dshape), lbl_zeeman.h:442-453
           if (seg.pol == POL_NO) continue;
           const double* __restrict__ dn = jp.dnpm + ((int64_t(lev) * 3 + (kind - AB200_TARGET_MAG_U)) * 4 + seg.pol) * 7;
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
           o[6] += dn[6] * F.im + npm[6] * d.im;
           continue;
         }
-        if (kind >= AB200_TARGET_WIND_U) {
+        if (EXT && kind >= AB200_TARGET_WIND_U) {
           // compute_derivative :1514-1523, then spectral_propmat_jacWindFix (m_frequency_grid.cc:106-182): x * f * df_du
           d = cadd(d, cscale(line_scale_df(f[r], T, P), shape[r]));
           if (jp.wind_jac) {  // null: AB200_FLAG_WIND_ROWS_DF, the caller's agenda applies the fix
@@ -547,18 +549,24 @@ int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev
   return 0;
 }
 
-template <int NQ>
-static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
+template <int NQ, bool EXT>
+static int launch_sum_jac_ne(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
   const size_t smem = size_t(JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS) * TL * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_kernel<NQ, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr = true;
   }
-  lbl_sum_jac_kernel<NQ><<<grid, JAC_NT, smem, stream>>>(p, jp);
+  lbl_sum_jac_kernel<NQ, EXT><<<grid, JAC_NT, smem, stream>>>(p, jp);
   count_launch();
   AB_CUDA(cudaGetLastError());
   return 0;
+}
+template <int NQ>
+static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
+  bool ext = false;
+  for (int q = 0; q < NQ; q++) ext |= jp.kind[jp.q0 + q] >= AB200_TARGET_WIND_U;
+  return ext ? launch_sum_jac_ne<NQ, true>(p, jp, grid, stream) : launch_sum_jac_ne<NQ, false>(p, jp, grid, stream);
 }
 
 int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream) {

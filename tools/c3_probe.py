@@ -39,3 +39,18 @@ rep = {"workload": f"C3: {n_sub} Zeeman sub-lines x {c.nf} frequencies x {c.np_}
        "propmat_ms": 1e3 * float(np.median(ts)), "evals_per_s": evals / float(np.median(ts)),
        "kernel_ms": {k: v[0] / max(v[1], 1) for k, v in tm.items()}, "regions": p.region_histogram().tolist()}
 print(json.dumps(rep))
+# Jacobian rows of the Zeeman configuration: temperature + the three magnetic-field components, and the three wind rows
+p.close() if hasattr(p, "close") else None
+for name, tg in (("T+mag_uvw", (("T",), ("mag_u",), ("mag_v",), ("mag_w",))), ("wind_uvw", (("wind_u",), ("wind_v",), ("wind_w",)))):
+    pj = wsm.Path(cat, c.nf, c.np_, len(tg))
+    pj.upload(c.f, c.atm, c.r, c.I_bkg, rte_option=c.rte_option, targets=tg, hse_derivative=1)
+    pj.run_propmat(); pj.run_stokes(); pj.sync()
+    tp, tsk = [], []
+    for _ in range(args.reps):
+        t0 = time.perf_counter()
+        pj.run_propmat(); pj.sync()
+        t1 = time.perf_counter()
+        pj.run_stokes(); pj.sync()
+        tp.append(t1 - t0); tsk.append(time.perf_counter() - t1)
+    print(json.dumps({"targets": name, "propmat_ms": 1e3 * float(np.median(tp)), "stokes_jac_ms": 1e3 * float(np.median(tsk))}))
+    pj.close() if hasattr(pj, "close") else None

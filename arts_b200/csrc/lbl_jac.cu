@@ -346,6 +346,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
       // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|); CTA uniform
       const bool far = !tile_has_cut && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9);
       const bool far_closed = far && jp.real_lines;
+      const bool far_cplx   = far && !jp.real_lines && jp.pair_far;  // complex lines (Zeeman, line mixing): see far_cplx_loop
       __syncthreads();  // previous tile fully consumed
       // stage the tile: the records of K1 + the derivative records of this pass, SoA in shared memory
       const double* g = prep + t * tile_doubles();
@@ -374,6 +375,33 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
             o[2 * TL + l] = sp * u1.x;                                 // B_q
             o[4 * TL + l] = sp * dz_fac;                               // C_q
             o[3 * TL + l] = sp * (u1.y + dz_fac * y);                  // D_q: Im(dz + dz_fac z) does not depend on f
+          }
+        }
+      } else if (far_cplx) {
+        // complex strengths: shape and dX need both parts.  With sp = s / sqrt(pi), tq = dz + dz_fac z = (dz + i dz_fac y)
+        // + dz_fac x:  dX = ds F + (a + b x) dF,  a = s (dz + i dz_fac y),  b = s dz_fac  (all / sqrt(pi)), so a target
+        // costs 12 FMAs on the shared numerators G1..G6 of the pair
+        for (int l = tid; l < count; l += JAC_NT) {
+          const double f0s = g[(0 * TL + l) * REC_GROUP];
+          const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
+          const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
+          const double s_im = g[(2 * TL + l) * REC_GROUP + 1];
+          const double y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
+          const cplx sp{n.y * cst::inv_sqrt_pi, s_im * cst::inv_sqrt_pi};
+          // 0 f0', 1 igd, 2 y | 3 y2, 4 y^2+1/2, 5 y2^2+1/2, 6 y y2-1/2, 7 Re sp, 8 Im sp
+          sb[0 * TL + l] = f0s; sb[1 * TL + l] = m.y; sb[2 * TL + l] = y; sb[3 * TL + l] = y2;
+          sb[4 * TL + l] = y * y + 0.5; sb[5 * TL + l] = y2 * y2 + 0.5; sb[6 * TL + l] = y * y2 - 0.5;
+          sb[7 * TL + l] = sp.re; sb[8 * TL + l] = sp.im;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+            const double2 u0 = j0[0], u1 = j0[1];                      // ds_re, ds_im | dz_re, dz_im
+            const double dz_fac = jt[q * (2 * TL * 4) + (1 * TL + l) * 4];
+            const cplx a = cmul(sp, {u1.x, u1.y + dz_fac * y});
+            double* o = sq + q * JAC_Q_FIELDS * TL;
+            o[0 * TL + l] = u0.x * cst::inv_sqrt_pi; o[1 * TL + l] = u0.y * cst::inv_sqrt_pi;
+            o[2 * TL + l] = a.re; o[3 * TL + l] = a.im;
+            o[4 * TL + l] = sp.re * dz_fac; o[5 * TL + l] = sp.im * dz_fac;
           }
         }
       } else {
@@ -435,6 +463,38 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
         };
         if (tile_im) far_loop(std::true_type{});
         else far_loop(std::false_type{});
+        continue;
+      }
+      if (far_cplx) {
+#pragma unroll 1
+        for (int l = 0; l < count; l++) {
+          const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
+          if (__double2hiint(igd) == 0) continue;
+          const double y = sb[2 * TL + l], y2 = sb[3 * TL + l];
+          const FarLine c{y, y2, 2.0 * y, 2.0 * y2, sb[4 * TL + l], sb[5 * TL + l], sb[6 * TL + l]};
+          const double spr = sb[7 * TL + l], spi = sb[8 * TL + l];
+#pragma unroll
+          for (int r = 0; r < JAC_R; r++) {
+            const double x  = __dmul_rn(igd, __dsub_rn(f[r], f0s));
+            const double x2 = __dadd_rn(x, fmax(__dmul_rn(1e-4, fabs(x)), 1e-4));
+            double G1, G2, G3, G4, G5;
+            far_pair<true>(c, x, x2, G1, G2, G3, G4, G5);
+            const double G6 = __dmul_rn(x, G3);
+            shape[r].re = __fma_rn(spr, G1, __fma_rn(-spi, G5, shape[r].re));
+            shape[r].im = __fma_rn(spr, G5, __fma_rn(spi, G1, shape[r].im));
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              const double* o = sq + q * JAC_Q_FIELDS * TL;
+              const double dr = o[0 * TL + l], di = o[1 * TL + l], ar = o[2 * TL + l], ai = o[3 * TL + l],
+                           br = o[4 * TL + l], bi = o[5 * TL + l];
+              // dF = (G2 - i G3) / sqrt(pi), F = (G1 + i G5) / sqrt(pi)
+              acc[q][r].re = __fma_rn(dr, G1, __fma_rn(-di, G5, __fma_rn(ar, G2, __fma_rn(ai, G3,
+                             __fma_rn(br, G4, __fma_rn(bi, G6, acc[q][r].re))))));
+              acc[q][r].im = __fma_rn(dr, G5, __fma_rn(di, G1, __fma_rn(-ar, G3, __fma_rn(ai, G2,
+                             __fma_rn(-br, G6, __fma_rn(bi, G4, acc[q][r].im))))));
+            }
+          }
+        }
         continue;
       }
       for (int l = 0; l < count; l++) {

@@ -23,6 +23,7 @@ RTE_CONSTANT, RTE_LINSRC, RTE_LINPROP = 0, 1, 2
 TARGET_T, TARGET_VMR = 0, 1
 TARGET_WIND_U, TARGET_WIND_V, TARGET_WIND_W = 2, 3, 4
 TARGET_MAG_U, TARGET_MAG_V, TARGET_MAG_W = 5, 6, 7
+TARGET_LINE_F0, TARGET_LINE_E0, TARGET_LINE_A, TARGET_LINE_LS = 8, 9, 10, 11
 FLAG_K_ZERO_INIT, FLAG_TRAN_EXACT, FLAG_RETURN_K, FLAG_NO_EMISSION, FLAG_WIND_ROWS_DF = 1, 2, 4, 8, 16
 
 RTE_OPTIONS = {"constant": RTE_CONSTANT, "linsrc": RTE_LINSRC, "lintau": RTE_LINSRC, "linprop": RTE_LINPROP}
@@ -81,7 +82,7 @@ class AtmPathDesc(C.Structure):
 
 
 class Target(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("species", C.c_int32)]
+    _fields_ = [("kind", C.c_int32), ("species", C.c_int32), ("line", C.c_int64), ("ls_var", C.c_int32), ("coeff", C.c_int32)]
 
 
 class HitranIsotopologue(C.Structure):
@@ -472,28 +473,36 @@ class Observer:
 
 
 def make_targets(targets) -> tuple[C.Array | None, int]:
-    """targets: iterable of ("T",) / ("VMR", species_id) / ("wind_u",) .. ("wind_w",) / ("mag_u",) .. ("mag_w",) or (kind, species) ints."""
+    """targets: iterable of ("T",) / ("VMR", species_id) / ("wind_u",) .. ("wind_w",) / ("mag_u",) .. ("mag_w",) /
+    ("line_f0", line) / ("line_e0", line) / ("line_a", line) / ("line_ls", line, var, species, coeff) or (kind, species) ints."""
     lst = []
     for t in targets or ():
         if isinstance(t, str):
             t = (t,)
         kind = t[0]
         if kind in ("T", "t"):
-            lst.append((TARGET_T, 0))
+            lst.append((TARGET_T, 0, 0, 0, 0))
         elif kind in ("VMR", "vmr"):
-            lst.append((TARGET_VMR, int(t[1])))
+            lst.append((TARGET_VMR, int(t[1]), 0, 0, 0))
         elif kind in ("wind_u", "wind_v", "wind_w"):  # AtmKey::wind_*
-            lst.append((TARGET_WIND_U + "uvw".index(kind[-1]), 0))
+            lst.append((TARGET_WIND_U + "uvw".index(kind[-1]), 0, 0, 0, 0))
         elif kind in ("mag_u", "mag_v", "mag_w"):  # AtmKey::mag_*
-            lst.append((TARGET_MAG_U + "uvw".index(kind[-1]), 0))
+            lst.append((TARGET_MAG_U + "uvw".index(kind[-1]), 0, 0, 0, 0))
+        elif kind in ("line_f0", "line_e0", "line_a"):  # lbl::line_key with LineByLineVariable
+            lst.append(({"line_f0": TARGET_LINE_F0, "line_e0": TARGET_LINE_E0, "line_a": TARGET_LINE_A}[kind], 0, int(t[1]), 0, 0))
+        elif kind == "line_ls":  # lbl::line_key with LineShapeModelVariable, broadener and coefficient
+            lst.append((TARGET_LINE_LS, int(t[3]), int(t[1]), int(t[2]), int(t[4])))
         else:
-            lst.append((int(kind), int(t[1]) if len(t) > 1 else 0))
+            lst.append((int(kind), int(t[1]) if len(t) > 1 else 0, 0, 0, 0))
     if not lst:
         return None, 0
     arr = (Target * len(lst))()
-    for i, (k, s) in enumerate(lst):
+    for i, (k, s, ln, var, co) in enumerate(lst):
         arr[i].kind = k
         arr[i].species = s
+        arr[i].line = ln
+        arr[i].ls_var = var
+        arr[i].coeff = co
     return arr, len(lst)
 
 

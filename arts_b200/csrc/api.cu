@@ -83,6 +83,8 @@ struct ab200_path {
   double* d_jcom = nullptr;  // [levels_per_batch][ntiles][TL]
   double *d_dQdT = nullptr, *d_dr = nullptr, *d_invT = nullptr, *d_ffac = nullptr, *d_wjac = nullptr, *d_dnpm = nullptr, *d_magr = nullptr;
   int32_t tg_kind[AB200_MAX_TARGETS] = {0}, tg_species[AB200_MAX_TARGETS] = {0};
+  int64_t tg_line[AB200_MAX_TARGETS] = {0};
+  int32_t tg_ls_var[AB200_MAX_TARGETS] = {0}, tg_coeff[AB200_MAX_TARGETS] = {0};
   int32_t it = -1;  // position of the temperature target
   bool dk_preloaded = false;
 
@@ -293,9 +295,23 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
       } else if (targets[q].kind == AB200_TARGET_MAG_U || targets[q].kind == AB200_TARGET_MAG_V ||
                  targets[q].kind == AB200_TARGET_MAG_W) {
         // Zeeman splitting derivative and the derivative of the polarisation matrix; nothing to check
+      } else if (targets[q].kind >= AB200_TARGET_LINE_F0 && targets[q].kind <= AB200_TARGET_LINE_LS) {
+        const ab200_target& t = targets[q];
+        if (t.line < 0 || t.line >= cat->n_lines)
+          return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": line out of range");
+        if (!cat->line_target_ok[static_cast<size_t>(t.line)])
+          return set_error(AB200_ERR_UNSUPPORTED, "Jacobian target " + std::to_string(q) +
+                                                      ": line targets need a VP_LTE band without cutoff");
+        if (t.kind == AB200_TARGET_LINE_LS) {
+          if (t.ls_var < 0 || t.ls_var >= AB200_NVAR || t.coeff < 0 || t.coeff > 3)
+            return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": line-shape variable or coefficient out of range");
+          if (t.species != AB200_SPECIES_BATH && (t.species < 0 || t.species >= cat->n_species))
+            return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": broadener species out of range");
+        }
+        p->tg_line[q] = t.line; p->tg_ls_var[q] = t.ls_var; p->tg_coeff[q] = t.coeff;
       } else {
         return set_error(AB200_ERR_UNSUPPORTED, "Jacobian target " + std::to_string(q) +
-                                                    ": only temperature, species VMR, wind and magnetic-field targets are on the GPU path");
+                                                    ": unknown target kind");
       }
     }
   }
@@ -482,6 +498,7 @@ int ab200_path_run_propmat(ab200_path* p) {
       for (int q = 0; q < p->nq; q++) {
         jp.kind[q] = js.kind[q] = p->tg_kind[q];
         jp.species[q] = p->tg_species[q];
+        jp.line[q] = p->tg_line[q]; jp.ls_var[q] = p->tg_ls_var[q]; jp.coeff[q] = p->tg_coeff[q];
       }
       jp.dQdT = p->d_dQdT + static_cast<size_t>(lev0) * cat->n_isot;
       jp.jac = p->d_jac;

@@ -283,6 +283,10 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   // VP_LTE_MIRROR (lbl_lineshape_voigt_lte_mirrored.cpp:220): F(f) = w(z(f)) + w(zm(f)), zm = inv_gd (f + f0') + i z_imag.
   // The mirror image is the same sub-line centred at -f0': every slot of a mirrored band gets a twin slot whose centre
   // the prepare kernel negates (SUB_TWIN); it sorts to the negative end of a merged segment and is always far.
+  cat->line_target_ok.assign(static_cast<size_t>(d->n_lines), 0);
+  for (int32_t b = 0; b < d->n_bands; b++)
+    if (d->band_lineshape[b] == AB200_LINESHAPE_VP_LTE && d->band_cutoff_type[b] == AB200_CUTOFF_NONE)
+      std::fill(cat->line_target_ok.begin() + d->band_offset[b], cat->line_target_ok.begin() + d->band_offset[b + 1], uint8_t{1});
   auto band_of = [&](int64_t l) {
     return std::upper_bound(d->band_offset, d->band_offset + d->n_bands + 1, l) - d->band_offset - 1;
   };

@@ -56,7 +56,9 @@ struct SumParams {
 struct JacPrepParams {
   int32_t nq;
   int32_t kind[AB200_MAX_TARGETS];     // AB200_TARGET_*
-  int32_t species[AB200_MAX_TARGETS];  // for VMR targets
+  int32_t species[AB200_MAX_TARGETS];  // for VMR targets; line-shape targets: the broadener
+  int64_t line[AB200_MAX_TARGETS];     // line targets: the catalog line
+  int32_t ls_var[AB200_MAX_TARGETS], coeff[AB200_MAX_TARGETS];  // line-shape targets: AB200_VAR_*, X0..X3
   const double* dQdT;                  // [nlev][n_isot], offset to the batch
   double* jac;                         // [nlev][ntiles][nq][2][TL][4]
   double* jcom;                        // [nlev][ntiles][TL]

@@ -154,6 +154,40 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
                               cscale(f0s * sl, lmc));
         ds     = cscale(Sz * (cst::inv_sqrt_pi * igd * r * x) / (2 * T * f0s), num);
         dz_fac = (-2 * T * dD0 - 2 * T * dDV - f0s) / (2 * T * f0s);  // :1013-1015
+      } else if (jp.kind[q] >= AB200_TARGET_LINE_F0) {
+        // line targets (line_key): only the sub-lines of jp.line[q] have a record, set_filter :1192-1201
+        dD0 = dDV = dG0 = dG = dY = 0.0;
+        ds     = {0.0, 0.0};
+        dz_fac = 0.0;
+        if (par == jp.line[q]) {
+          const cplx s{s_re, s_im};
+          const double pre = cst::inv_sqrt_pi * igd * r * x;
+          if (jp.kind[q] == AB200_TARGET_LINE_F0) {
+            // df0_core_calc :1204-1238, dline_strength_calc_df0 :66-84 with line::ds_df0_s_ratio = -3 / f0 (lbl_data.h:118)
+            const double dsl = (-3.0 / f0c) * sl;
+            ds     = cscale(Sz * pre * (f0s * dsl - sl) / f0s, lmc);
+            dz_fac = -1.0 / f0s;
+            dD0    = 1.0;  // dz = -inv_gd below
+          } else if (jp.kind[q] == AB200_TARGET_LINE_E0) {
+            ds = cscale(-1.0 / (cst::k * T), s);  // de0_core_calc :1241-1265, ds_de0_s_ratio lbl_data.h:101-103
+          } else if (jp.kind[q] == AB200_TARGET_LINE_A) {
+            ds = cscale(1.0 / p.a[par], s);  // da_core_calc :1268-1290
+          } else {
+            const double d = lm.dmix_dX(jp.ls_var[q], jp.species[q], jp.coeff[q]);
+            switch (jp.ls_var[q]) {
+              case AB200_VAR_G0: dG0 = d; break;  // dG0_core_calc :1293-1317: dz = i inv_gd dG0_dX
+              case AB200_VAR_D0:                  // dD0_core_calc :1320-1349
+              case AB200_VAR_DV:                  // dDV_core_calc :1419-1450
+                dz_fac = -d / f0s;
+                ds     = cscale(-d / f0s, s);
+                dD0    = d;
+                break;
+              case AB200_VAR_Y: ds = cmul({0.0, -d * Sz * pre}, {sl, 0.0}); break;  // dline_strength_calc_dY :38-50
+              case AB200_VAR_G: ds = {Sz * pre * d * sl, 0.0}; break;               // dline_strength_calc_dG :52-64
+              default: break;
+            }
+          }
+        }
       } else if (jp.kind[q] >= AB200_TARGET_MAG_U) {
         // single_shape::dH, :305-307: s dz dF, dz = -inv_gd dH/dmag_c Splitting (:1071-1078); lines without Zeeman
         // splitting have dz = 0 and pol = no segments are skipped in the sum kernel's epilogue (:1484-1486)
@@ -182,7 +216,9 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
         dz_fac = -(dD0 + dDV) / f0s;  // :1176
       }
       cplx dzq{igd * -(dD0 + dDV), igd * dG0};
-      if (jp.kind[q] >= AB200_TARGET_MAG_U) {
+      if (jp.kind[q] >= AB200_TARGET_LINE_F0) {
+        // dzq above is the whole of it
+      } else if (jp.kind[q] >= AB200_TARGET_MAG_U) {
         const double dzc = p.sub_dzc[slot];
         dzq = {dzc == 0.0 ? 0.0 : -igd * jp.mag_ratio[3 * lev + (jp.kind[q] - AB200_TARGET_MAG_U)] * dzc, 0.0};
       } else if (jp.kind[q] >= AB200_TARGET_WIND_U) {
@@ -572,7 +608,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
         cplx d = cscale(scl, acc[q][r]);
         const int kind = jp.kind[jp.q0 + q];
         if (kind == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
-        if (EXT && kind >= AB200_TARGET_MAG_U) {
+        if (EXT && kind >= AB200_TARGET_MAG_U && kind <= AB200_TARGET_MAG_W) {
           // compute_derivative :1484-1513 with zeeman::scale(npm, dnpm, scl shape, scl dshape), lbl_zeeman.h:442-453
           if (seg.pol == POL_NO) continue;
           const double* __restrict__ dn = jp.dnpm + ((int64_t(lev) * 3 + (kind - AB200_TARGET_MAG_U)) * 4 + seg.pol) * 7;
@@ -584,7 +620,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
           o[6] += dn[6] * F.im + npm[6] * d.im;
           continue;
         }
-        if (EXT && kind >= AB200_TARGET_WIND_U) {
+        if (EXT && kind >= AB200_TARGET_WIND_U && kind <= AB200_TARGET_WIND_W) {
           // compute_derivative :1514-1523, then spectral_propmat_jacWindFix (m_frequency_grid.cc:106-182): x * f * df_du
           d = cadd(d, cscale(line_scale_df(f[r], T, P), shape[r]));
           if (jp.wind_jac) {  // null: AB200_FLAG_WIND_ROWS_DF, the caller's agenda applies the fix
@@ -625,7 +661,7 @@ static int launch_sum_jac_ne(const SumParams& p, const JacSumParams& jp, dim3 gr
 template <int NQ>
 static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
   bool ext = false;
-  for (int q = 0; q < NQ; q++) ext |= jp.kind[jp.q0 + q] >= AB200_TARGET_WIND_U;
+  for (int q = 0; q < NQ; q++) ext |= jp.kind[jp.q0 + q] >= AB200_TARGET_WIND_U && jp.kind[jp.q0 + q] <= AB200_TARGET_MAG_W;
   return ext ? launch_sum_jac_ne<NQ, true>(p, jp, grid, stream) : launch_sum_jac_ne<NQ, false>(p, jp, grid, stream);
 }
 

@@ -48,6 +48,40 @@ __device__ __forceinline__ double tm_dT(int type, const double* __restrict__ x, 
   }
 }
 
+// d/dX_k of the above, k = 0..3 (lbl_temperature_model.h, the d*_dX0..dX3 members; 0 where a model has no such coefficient)
+__device__ __forceinline__ double tm_dX(int type, int k, const double* __restrict__ x, double T0, double T) {
+  const double q = T0 / T;
+  switch (type) {
+    case AB200_TM_T0: return k == 0 ? 1.0 : 0.0;
+    case AB200_TM_T1: return k == 0 ? pow(q, x[1]) : k == 1 ? x[0] * pow(q, x[1]) * log(q) : 0.0;
+    case AB200_TM_T2:
+      return k == 0   ? pow(q, x[1]) * (1 + x[2] * log(T / T0))
+             : k == 1 ? x[0] * pow(q, x[1]) * (x[2] * log(T / T0) + 1.) * log(q)
+             : k == 2 ? x[0] * pow(q, x[1]) * log(T / T0)
+                      : 0.0;
+    case AB200_TM_T3: return k == 0 ? 1.0 : k == 1 ? T - T0 : 0.0;
+    case AB200_TM_T4:
+      return k == 0   ? pow(q, x[2])
+             : k == 1 ? pow(q, x[2]) * (q - 1.)
+             : k == 2 ? pow(q, x[2]) * (x[0] + x[1] * (q - 1)) * log(q)
+                      : 0.0;
+    case AB200_TM_T5:
+      return k == 0 ? pow(q, 1.5 * x[1] + 0.25) : k == 1 ? 1.5 * x[0] * pow(q, 1.5 * x[1] + 0.25) * log(q) : 0.0;
+    case AB200_TM_AER:
+      if (k == 0) return T < 250.0 ? 1 - (T - 200.0) / (250.0 - 200.0) : 0.0;
+      if (k == 1) return T < 250.0 ? (T - 200.0) / (250.0 - 200.0) : T > 296.0 ? 0.0 : 1 - (T - 250.0) / (296.0 - 250.0);
+      if (k == 2) return T < 250.0 ? 0.0 : T > 296.0 ? 1 - (T - 296.0) / (340.0 - 296.0) : (T - 250.0) / (296.0 - 250.0);
+      return T > 296.0 ? (T - 296.0) / (340.0 - 296.0) : 0.0;
+    case AB200_TM_DPL:
+      return k == 0   ? pow(q, x[1])
+             : k == 1 ? x[0] * pow(q, x[1]) * log(q)
+             : k == 2 ? pow(q, x[3])
+                      : x[2] * pow(q, x[3]) * log(q);
+    case AB200_TM_POLY: return k == 0 ? 1.0 : k == 1 ? T : k == 2 ? T * T : T * T * T;
+    default: return 0.0;
+  }
+}
+
 // view of one catalog line's broadening table on the device
 struct LineModel {
   const int64_t* ls_offset;
@@ -99,6 +133,26 @@ struct LineModel {
     double t = 0.0;
     for (int64_t i = ls_offset[line]; i < ls_offset[line + 1]; i++) t += vmr[ls_species[i]];
     return (t - x) / t * t;  // sic, lbl_lineshape_model.cpp:112
+  }
+  // model::dVAR_dX(atm, species, coeff), lbl_lineshape_model.cpp:150-246 (species_model::dVAR_dXk :38-63)
+  __device__ __forceinline__ double dmix_dX(int var, int species, int coeff) const {
+    int64_t ptr = -1, bth = -1;
+    double vsum = 0.0, vall = 0.0;
+    for (int64_t i = ls_offset[line]; i < ls_offset[line + 1]; i++) {
+      const int sp = ls_species[i];
+      if (sp == species) ptr = i;
+      if (sp == AB200_SPECIES_BATH) bth = i;
+      else vsum += vmr[sp];
+    }
+    if (ptr < 0) return 0.0;
+    const int type = ls_type[ptr * AB200_NVAR + var];
+    const double x = type == AB200_TM_ABSENT
+                         ? 0.0
+                         : pscale(var, P) * tm_dX(type, coeff, ls_X + (ptr * AB200_NVAR + var) * 4, T0, T);
+    if (species == AB200_SPECIES_BATH) return (1 - vsum) * x;
+    if (bth >= 0) return vmr[species] * x;
+    vall = vsum;  // no bath entry: every broadener is a species
+    return x * vmr[species] / vall;
   }
 };
 

@@ -82,7 +82,15 @@ enum {
    * matrix and the matrix's own derivative dnorm_view_d{u,v,w} (lbl_zeeman.cpp:361-411, 457-536; scale lbl_zeeman.h:442-453) */
   AB200_TARGET_MAG_U = 5,
   AB200_TARGET_MAG_V = 6,
-  AB200_TARGET_MAG_W = 7
+  AB200_TARGET_MAG_W = 7,
+  /* JacobianTargets::line (lbl::line_key, lbl_lineshape_voigt_lte.cpp:1562-1637): one catalog line's f0, e0, Einstein
+   * coefficient, or one coefficient X0..X3 of one broadener's G0 / D0 / DV / Y / G model (G2, D2, FVC, ETA give zero
+   * rows, :1616-1619).  Only sub-lines of that line contribute (set_filter :1192-1201).  Bands with a ByLine cutoff are
+   * AB200_ERR_UNSUPPORTED: the reference indexes the cutoff window's sub-span with whole-band indices there (:723-739) */
+  AB200_TARGET_LINE_F0 = 8,
+  AB200_TARGET_LINE_E0 = 9,
+  AB200_TARGET_LINE_A = 10,
+  AB200_TARGET_LINE_LS = 11
 };
 
 /* flags (bit mask) */
@@ -146,7 +154,10 @@ typedef struct ab200_atm_path {
 
 typedef struct ab200_target {
   int32_t kind;    /* AB200_TARGET_* */
-  int32_t species; /* for AB200_TARGET_VMR */
+  int32_t species; /* AB200_TARGET_VMR: the species; AB200_TARGET_LINE_LS: the broadener (or AB200_SPECIES_BATH) */
+  int64_t line;    /* AB200_TARGET_LINE_*: index of the line in the flattened catalog (band_offset order) */
+  int32_t ls_var;  /* AB200_TARGET_LINE_LS: AB200_VAR_* */
+  int32_t coeff;   /* AB200_TARGET_LINE_LS: 0..3 for X0..X3 (LineShapeModelCoefficient) */
 } ab200_target;
 
 typedef struct ab200_catalog ab200_catalog; /* opaque, immutable after create, shareable across threads */

@@ -260,6 +260,47 @@ bool wind_factor(const AtmPt& atm, Numeric& fac, Numeric* jac = nullptr) {
   return true;
 }
 
+// d/dX0 .. d/dX3 of the temperature models: lbl_temperature_model.h:65-275 (the d*_dX* members; coefficients a model
+// does not have give 0, the EMPTY overloads :37-60)
+Numeric tm_dX(int type, int k, const double* x, Numeric T0, Numeric T) {
+  using std::log;
+  using std::pow;
+  switch (type) {
+    case AB200_TM_T0: return k == 0 ? 1 : 0;
+    case AB200_TM_T1:
+      if (k == 0) return pow(T0 / T, x[1]);
+      if (k == 1) return x[0] * pow(T0 / T, x[1]) * log(T0 / T);
+      return 0;
+    case AB200_TM_T2:
+      if (k == 0) return pow(T0 / T, x[1]) * (1 + x[2] * log(T / T0));
+      if (k == 1) return x[0] * pow(T0 / T, x[1]) * (x[2] * log(T / T0) + 1.) * log(T0 / T);
+      if (k == 2) return x[0] * pow(T0 / T, x[1]) * log(T / T0);
+      return 0;
+    case AB200_TM_T3: return k == 0 ? 1 : k == 1 ? T - T0 : 0;
+    case AB200_TM_T4:
+      if (k == 0) return pow(T0 / T, x[2]);
+      if (k == 1) return pow(T0 / T, x[2]) * (T0 / T - 1.);
+      if (k == 2) return pow(T0 / T, x[2]) * (x[0] + x[1] * (T0 / T - 1)) * log(T0 / T);
+      return 0;
+    case AB200_TM_T5:
+      if (k == 0) return pow(T0 / T, 1.5 * x[1] + 0.25);
+      if (k == 1) return 1.5 * x[0] * pow(T0 / T, 1.5 * x[1] + 0.25) * log(T0 / T);
+      return 0;
+    case AB200_TM_AER:
+      if (k == 0) return T < 250.0 ? 1 - (T - 200.0) / (250.0 - 200.0) : 0;
+      if (k == 1) return T < 250.0 ? (T - 200.0) / (250.0 - 200.0) : T > 296.0 ? 0 : 1 - (T - 250.0) / (296.0 - 250.0);
+      if (k == 2) return T < 250.0 ? 0 : T > 296.0 ? 1 - (T - 296.0) / (340.0 - 296.0) : (T - 250.0) / (296.0 - 250.0);
+      return T > 296.0 ? (T - 296.0) / (340.0 - 296.0) : 0;
+    case AB200_TM_DPL:
+      if (k == 0) return pow(T0 / T, x[1]);
+      if (k == 1) return x[0] * pow(T0 / T, x[1]) * log(T0 / T);
+      if (k == 2) return pow(T0 / T, x[3]);
+      return x[2] * pow(T0 / T, x[3]) * log(T0 / T);
+    case AB200_TM_POLY: return k == 0 ? 1.0 : k == 1 ? T : k == 2 ? T * T : T * T * T;
+  }
+  return std::numeric_limits<Numeric>::quiet_NaN();
+}
+
 // ---------------------------------------------------------------------------
 // Line-shape model: src/core/lbl/lbl_lineshape_model.cpp:14-35 (pressure
 // scaling), :70-113 (mixing + dVMR), :127-148 (dT).
@@ -316,6 +357,30 @@ struct LineView {
     Numeric t = 0.0;
     for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++) t += atm.vmr_of(d.ls_species[i]);
     return (t - x) / t * t;  // sic, lbl_lineshape_model.cpp:112
+  }
+
+  // model::dVAR_dX(atm, species, coeff): lbl_lineshape_model.cpp:150-246 with species_model::dVAR_dXk :38-63
+  Numeric dmix_dX(int var, const AtmPt& atm, int species, int coeff) const {
+    Index ptr = -1, bth = -1;
+    for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++) {
+      if (d.ls_species[i] == species) ptr = i;
+      if (d.ls_species[i] == AB200_SPECIES_BATH) bth = i;
+    }
+    if (ptr < 0) return 0.0;
+    const int type  = d.ls_type[ptr * AB200_NVAR + var];
+    const Numeric x = type == AB200_TM_ABSENT
+                          ? 0.0
+                          : pscale(var, atm.P) * tm_dX(type, coeff, d.ls_X + (ptr * AB200_NVAR + var) * 4, T0(), atm.T);
+    if (species == AB200_SPECIES_BATH) {
+      Numeric vmr = 0.0;
+      for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++)
+        vmr += d.ls_species[i] == AB200_SPECIES_BATH ? 0.0 : atm.vmr_of(d.ls_species[i]);
+      return (1 - vmr) * x;
+    }
+    if (bth >= 0) return atm.vmr_of(species) * x;
+    Numeric vmr = 0.0;
+    for (Index i = d.ls_offset[l]; i < d.ls_offset[l + 1]; i++) vmr += atm.vmr_of(d.ls_species[i]);
+    return x * atm.vmr_of(species) / vmr;
   }
 
   // line::s(T,Q): lbl_data.h:66-68
@@ -529,6 +594,30 @@ Complex line_strength_calc(Numeric inv_gd, int isot, int spec, const LineView& l
   const Numeric r = atm.isorat[isot];
   const Numeric x = atm.vmr_of(spec);
   return Constant::inv_sqrt_pi * inv_gd * r * x * lm * s;
+}
+
+// dline_strength_calc_dY / dG / df0, lbl_lineshape_voigt_lte.cpp:38-84 (line::ds_df0_s_ratio = -3 / f0, lbl_data.h:118)
+Complex dline_strength_calc_dY(Numeric dY, Numeric inv_gd, int isot, int spec, const LineView& ln, const AtmPt& atm) {
+  const auto s    = ln.s(atm.T, atm.Q[isot]);
+  const Numeric r = atm.isorat[isot];
+  const Numeric x = atm.vmr_of(spec);
+  return Constant::inv_sqrt_pi * inv_gd * r * x * Complex(0, -dY) * s;
+}
+Complex dline_strength_calc_dG(Numeric dG, Numeric inv_gd, int isot, int spec, const LineView& ln, const AtmPt& atm) {
+  const auto s    = ln.s(atm.T, atm.Q[isot]);
+  const Numeric r = atm.isorat[isot];
+  const Numeric x = atm.vmr_of(spec);
+  return Constant::inv_sqrt_pi * inv_gd * r * x * dG * s;
+}
+Complex dline_strength_calc_df0(Numeric f0, Numeric inv_gd, int isot, int spec, const LineView& ln, const AtmPt& atm) {
+  const auto s    = ln.s(atm.T, atm.Q[isot]);
+  const auto ds   = (-3 / ln.f0()) * s;
+  const Numeric G = ln.mix(AB200_VAR_G, atm);
+  const Numeric Y = ln.mix(AB200_VAR_Y, atm);
+  const Complex lm{1 + G, -Y};
+  const Numeric r = atm.isorat[isot];
+  const Numeric x = atm.vmr_of(spec);
+  return Constant::inv_sqrt_pi * inv_gd * r * x * (f0 * ds - s) * lm / f0;
 }
 
 // dline_strength_calc_dVMR, lbl_lineshape_voigt_lte.cpp:86-114
@@ -766,6 +855,76 @@ void calculate_band(double* pm, double* dpm, Index nf_total, const double* f_gri
         }
       }
       for (Index i = 0; i < f_n; i++) add_scaled(dp + i * 7, npm, dscl[i] * shape[i] + scl[i] * dshape[i]);
+      continue;
+    }
+    if (targets[iq].kind >= AB200_TARGET_LINE_F0 and targets[iq].kind <= AB200_TARGET_LINE_LS) {
+      // compute_derivative(line_key) :1562-1637 without cutoff: only the band that holds the line (lbl_lineshape.cpp
+      // hands line targets to their own band), only its (Zeeman sub-)lines (set_filter :1192-1201)
+      const ab200_target& key = targets[iq];
+      if (key.line < d.band_offset[ib] or key.line >= d.band_offset[ib + 1]) continue;
+      if (has_cut) continue;  // rejected by orc_propmat_levels before it gets here
+      std::fill(dshape.begin(), dshape.end(), Complex{});
+      for (size_t i = 0; i < nl; i++) {
+        if (pos[i].line != key.line) continue;
+        const LineView ln{d, pos[i].line};
+        const ZeemanView z{d.z_on[ln.l] != 0, d.z_gu[ln.l], d.z_gl[ln.l], d.two_Ju[ln.l], d.two_Jl[ln.l]};
+        const single_shape& lshp = lines[i];
+        const Numeric inv_gd = lshp.inv_gd, f0 = lshp.f0;
+        Complex dsi{}, dzi{};
+        Numeric dzf  = 0;
+        bool only_ds = false, only_dz = false;
+        switch (key.kind) {
+          case AB200_TARGET_LINE_F0:  // df0_core_calc :1204-1238, single_shape::df0 :277-283
+            dzf = -1.0 / f0;
+            dsi = z.Strength(pol, pos[i].iz) * dline_strength_calc_df0(f0, inv_gd, isot, spec, ln, atm);
+            dzi = -inv_gd;
+            break;
+          case AB200_TARGET_LINE_E0:  // de0_core_calc :1241-1265, ds_de0_s_ratio lbl_data.h:101-103, de0 :329-331
+            dsi     = (-1 / (Constant::k * atm.T)) * lshp.s;
+            only_ds = true;
+            break;
+          case AB200_TARGET_LINE_A:  // da_core_calc :1268-1290, da :325-327
+            dsi     = (1.0 / ln.a()) * lshp.s;
+            only_ds = true;
+            break;
+          default: {
+            const Numeric dv = ln.dmix_dX(key.ls_var, atm, key.species, key.coeff);
+            switch (key.ls_var) {
+              case AB200_VAR_G0:  // dG0_core_calc :1293-1317, dG0 :301-303
+                dzi     = Complex(0, inv_gd * dv);
+                only_dz = true;
+                break;
+              case AB200_VAR_D0:  // dD0_core_calc :1320-1349, dD0 :293-299
+              case AB200_VAR_DV:  // dDV_core_calc :1419-1450, dDV :285-291
+                dzf = -dv / f0;
+                dsi = key.ls_var == AB200_VAR_D0 ? -dv * lshp.s / f0 : lshp.s * dzf;
+                dzi = -dv * inv_gd;
+                break;
+              case AB200_VAR_Y:  // dY_core_calc :1352-1383, dY :337-339
+                dsi     = z.Strength(pol, pos[i].iz) * dline_strength_calc_dY(dv, inv_gd, isot, spec, ln, atm);
+                only_ds = true;
+                break;
+              case AB200_VAR_G:  // dG_core_calc :1386-1416, dG :333-335
+                dsi     = z.Strength(pol, pos[i].iz) * dline_strength_calc_dG(dv, inv_gd, isot, spec, ln, atm);
+                only_ds = true;
+                break;
+              default: break;
+            }
+          }
+        }
+        for (Index j = 0; j < f_n; j++) {
+          const Complex z_ = lshp.z(fg[j]);
+          const Complex F_ = single_shape::F(z_);
+          if (only_ds) {
+            dshape[j] += dsi * F_;
+          } else if (only_dz) {
+            dshape[j] += lshp.s * dzi * single_shape::dF(z_, F_);
+          } else {
+            dshape[j] += dsi * F_ + lshp.s * (dzi + dzf * z_) * single_shape::dF(z_, F_);
+          }
+        }
+      }
+      for (Index i = 0; i < f_n; i++) add_scaled(dp + i * 7, npm, scl[i] * dshape[i]);
       continue;
     }
     if (targets[iq].kind >= AB200_TARGET_MAG_U and targets[iq].kind <= AB200_TARGET_MAG_W) {
@@ -1487,6 +1646,14 @@ static int propmat_levels_on_path_grids(const ab200_catalog_desc* d, int64_t nf,
     if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE && d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE_MIRROR)
       return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE and VP_LTE_MIRROR bands");
   if (nq > 0 && !dK) return fail(AB200_ERR_INVALID, "dK is null with nq > 0");
+  for (int q = 0; q < nq; q++) {
+    if (targets[q].kind < AB200_TARGET_LINE_F0 or targets[q].kind > AB200_TARGET_LINE_LS) continue;
+    if (targets[q].line < 0 or targets[q].line >= d->n_lines) return fail(AB200_ERR_INVALID, "line target out of range");
+    const int64_t b = std::upper_bound(d->band_offset, d->band_offset + d->n_bands + 1, targets[q].line) - d->band_offset - 1;
+    // with a cutoff the reference indexes the window's sub-span with whole-band indices (:723-739): nothing to restate
+    if (d->band_cutoff_type[b] != AB200_CUTOFF_NONE or d->band_lineshape[b] != AB200_LINESHAPE_VP_LTE)
+      return fail(AB200_ERR_UNSUPPORTED, "line targets need a VP_LTE band without cutoff");
+  }
   const int np       = atm->np;
   const int nthreads = omp_get_max_threads();
   if (np >= nthreads || nf < nthreads) {

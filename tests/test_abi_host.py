@@ -151,7 +151,7 @@ def test_host_catalog_desc_keeps_arrays_alive_and_typed():
     assert d.f0[0] == c.cat.f0[0] and d.band_offset[d.n_bands] == d.n_lines
     a = c.atm.desc()
     assert a.np == 2 and a.T[1] == c.atm.T[1]
-    assert C.sizeof(abi.Target) == 8
+    assert C.sizeof(abi.Target) == 24  # kind, species, line (int64), ls_var, coeff
 
 
 def test_header_compiles_as_c99_and_host_entry_points_work_from_c(tmp_path):

@@ -792,3 +792,64 @@ def test_standard_continua_against_their_published_forms(orc):
     _, dK2 = orc.predef_levels(list(expect), {"H2O": 0, "O2": 1}, f[:5], abi.AtmPath(T=T, P=P, vmr=vmr, isorat=np.ones((2, 1)), Q=np.ones((2, 1))),
                                targets=(("VMR", 2),), target_d=(1e-4,), select_species=0)
     assert not dK2.any()
+
+
+def _line_target_fixture():
+    """Two bands, several broadeners incl. Bath, line mixing on: one level, a grid around the target line."""
+    c = synth.tiny_case(nl=12, nf=64, np_=1)
+    line = 5
+    c.f = c.cat.f0[line] + np.linspace(-3e8, 3e8, 61)
+    c.atm.P[:] = 3e3
+    c.atm.vmr[:, 0] = 0.3  # the self broadener must matter
+    rng = np.random.default_rng(4)
+    lo, hi = c.cat.ls_offset[line], c.cat.ls_offset[line + 1]
+    c.cat.ls_type[lo:hi, abi.VAR_Y] = abi.TM_T1
+    c.cat.ls_X[lo:hi, abi.VAR_Y, 0] = rng.uniform(1e-7, 3e-7, hi - lo)
+    c.cat.ls_X[lo:hi, abi.VAR_Y, 1] = 0.8
+    c.cat.ls_type[lo:hi, abi.VAR_G] = abi.TM_T1
+    c.cat.ls_X[lo:hi, abi.VAR_G, 0] = rng.uniform(1e-12, 3e-12, hi - lo)
+    c.cat.ls_X[lo:hi, abi.VAR_G, 1] = 1.1
+    c.cat.ls_type[lo:hi, abi.VAR_DV] = abi.TM_T1
+    c.cat.ls_X[lo:hi, abi.VAR_DV, 0] = rng.uniform(1e-3, 3e-3, hi - lo)
+    c.cat.ls_X[lo:hi, abi.VAR_DV, 1] = 0.5
+    return c, line
+
+
+def test_oracle_line_parameter_jacobians_against_perturbed_catalogs(orc):
+    """compute_derivative(line_key) (lbl_lineshape_voigt_lte.cpp:1562-1637): f0, e0, a and every line-shape coefficient
+    of one line against centred differences of the forward model with that one catalog number moved.  The analytic rows
+    carry the reference's forward-difference dF (~1e-4 relative), hence rtol 2e-3 on the rows that use it."""
+    import copy
+
+    c, line = _line_target_fixture()
+    lo = c.cat.ls_offset[line]
+    sp0 = int(c.cat.ls_species[lo])  # first broadener of the line
+    cases = [(("line_f0", line), "f0", None, 1e6), (("line_e0", line), "e0", None, 1e-24), (("line_a", line), "a", None, None)]
+    for var in (abi.VAR_G0, abi.VAR_D0, abi.VAR_DV, abi.VAR_Y, abi.VAR_G):
+        for k in (0, 1):
+            cases.append((("line_ls", line, var, sp0, k), "ls", (var, k, 0), None))  # the self broadener
+            cases.append((("line_ls", line, var, abi.SPECIES_BATH, k), "ls", (var, k, 1), None))  # Bath
+    assert c.cat.ls_species[lo + 1] == abi.SPECIES_BATH
+    dK = np.concatenate([orc.propmat_levels(c.cat, c.f, c.atm, targets=[t for t, *_ in cases[i:i + 8]])[1] for i in range(0, len(cases), 8)], axis=1)
+    for q, (tg, what, vk, h) in enumerate(cases):
+        cp, cm = copy.deepcopy(c.cat), copy.deepcopy(c.cat)
+        if what == "ls":
+            x = c.cat.ls_X[lo + vk[2], vk[0], vk[1]]
+            h = 1e-4 * abs(x)
+            cp.ls_X[lo + vk[2], vk[0], vk[1]] += h
+            cm.ls_X[lo + vk[2], vk[0], vk[1]] -= h
+        else:
+            arr = getattr(c.cat, what)
+            h = h or 0.1 * abs(arr[line])  # the Einstein coefficient enters linearly: any step is exact
+            getattr(cp, what)[line] += h
+            getattr(cm, what)[line] -= h
+        Kp, _ = orc.propmat_levels(cp, c.f, c.atm)
+        Km, _ = orc.propmat_levels(cm, c.f, c.atm)
+        fd = (Kp[0] - Km[0]) / (2 * h)
+        sc = np.abs(fd[:, 0]).max()
+        assert sc > 0, tg
+        np.testing.assert_allclose(dK[0, q, :, 0], fd[:, 0], rtol=2e-3, atol=2e-4 * sc, err_msg=str(tg))
+    # a broadener the line does not have, and a line of another band: zero rows
+    _, dz = orc.propmat_levels(c.cat, c.f, c.atm, targets=[("line_ls", line, abi.VAR_G0, 3, 0)])
+    present = set(int(s) for s in c.cat.ls_species[lo:c.cat.ls_offset[line + 1]])
+    assert (3 in present) or not dz.any()

@@ -499,6 +499,8 @@ int ab200_path_run_propmat(ab200_path* p) {
         jp.kind[q] = js.kind[q] = p->tg_kind[q];
         jp.species[q] = p->tg_species[q];
         jp.line[q] = p->tg_line[q]; jp.ls_var[q] = p->tg_ls_var[q]; jp.coeff[q] = p->tg_coeff[q];
+        if (p->tg_kind[q] >= AB200_TARGET_LINE_F0)
+          std::copy_n(cat->line_tiles.data() + p->tg_line[q] * 8, 8, &js.line_tiles[q][0][0]);
       }
       jp.dQdT = p->d_dQdT + static_cast<size_t>(lev0) * cat->n_isot;
       jp.jac = p->d_jac;

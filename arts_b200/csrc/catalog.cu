@@ -283,6 +283,7 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   // VP_LTE_MIRROR (lbl_lineshape_voigt_lte_mirrored.cpp:220): F(f) = w(z(f)) + w(zm(f)), zm = inv_gd (f + f0') + i z_imag.
   // The mirror image is the same sub-line centred at -f0': every slot of a mirrored band gets a twin slot whose centre
   // the prepare kernel negates (SUB_TWIN); it sorts to the negative end of a merged segment and is always far.
+  cat->line_tiles.assign(static_cast<size_t>(d->n_lines) * 8, -1);
   cat->line_target_ok.assign(static_cast<size_t>(d->n_lines), 0);
   for (int32_t b = 0; b < d->n_bands; b++)
     if (d->band_lineshape[b] == AB200_LINESHAPE_VP_LTE && d->band_cutoff_type[b] == AB200_CUTOFF_NONE)
@@ -319,6 +320,11 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
       tile_mode.push_back(static_cast<uint8_t>(seg.mode));
       for (int64_t i = lo; i < lo + TL; i++) {
         if (i < hi) {
+          if (!(fl[order[i]] & SUB_TWIN)) {
+            int64_t* lt = cat->line_tiles.data() + (par[order[i]] * 4 + seg.pol) * 2;
+            if (lt[0] < 0) lt[0] = cat->ntiles + t;
+            lt[1] = cat->ntiles + t + 1;
+          }
           sub_parent.push_back(par[order[i]]);
           sub_Sz.push_back(sz[order[i]]);
           sub_dzc.push_back(dz[order[i]]);

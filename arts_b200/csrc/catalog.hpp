@@ -51,6 +51,7 @@ struct ab200_catalog {
   std::vector<int32_t> isot_species;
   std::vector<double> isot_mass;
   std::vector<ab200::Segment> segments;
+  std::vector<int64_t> line_tiles;      // [n_lines][4 pol][2]: first and last + 1 tile holding sub-lines of the line (-1, -1: none)
   std::vector<uint8_t> line_target_ok;  // per line: its band is plain VP_LTE without cutoff (line-parameter Jacobians)
   std::vector<int32_t> tile_count;  // real (sub-)lines per tile
   int64_t ntiles = 0;

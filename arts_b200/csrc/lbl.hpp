@@ -72,6 +72,7 @@ struct JacSumParams {
   const double* jac;
   const double* jcom;
   double* dK;  // [nlev][nq][k_pitch][7], offset to the batch
+  int64_t line_tiles[AB200_MAX_TARGETS][4][2];  // line targets: the tiles that hold the line's sub-lines, per polarisation
   const double* dnpm;      // [nlev][3][4][7] dnorm_view_d{u,v,w} per polarisation (magnetic-field targets)
   const double* wind_jac;  // [nlev][3] freq_wind_shift_jac of the batch's levels (wind targets); null = leave d/df
 };

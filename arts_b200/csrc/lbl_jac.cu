@@ -360,9 +360,27 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
   const double* __restrict__ jcom = jp.jcom + int64_t(lev) * p.ntiles * TL;
   const double T = p.T[lev], P = p.P[lev];
 
+  // a pass of line targets only visits the tiles that hold those lines: everything else has all-zero records and the
+  // forward shape is not needed (no dscl term)
+  bool line_only = true;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) line_only &= jp.kind[jp.q0 + q] >= AB200_TARGET_LINE_F0;
+
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
     const double cutoff  = seg.has_cutoff ? seg.cutoff : DBL_MAX;
+    int64_t t_lo = seg.tile_begin, t_hi = seg.tile_end;
+    if (line_only) {
+      int64_t lo = INT64_MAX, hi = -1;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int64_t a = jp.line_tiles[jp.q0 + q][seg.pol][0], b = jp.line_tiles[jp.q0 + q][seg.pol][1];
+        if (a >= 0) { lo = a < lo ? a : lo; hi = b > hi ? b : hi; }
+      }
+      t_lo = lo > t_lo ? lo : t_lo;
+      t_hi = hi < t_hi ? hi : t_hi;
+      if (t_lo >= t_hi) continue;  // none of the pass's lines in this segment
+    }
     cplx shape[JAC_R], acc[NQ][JAC_R];
 #pragma unroll
     for (int r = 0; r < JAC_R; r++) {
@@ -370,7 +388,14 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
 #pragma unroll
       for (int q = 0; q < NQ; q++) acc[q][r] = {0.0, 0.0};
     }
-    for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
+    for (int64_t t = t_lo; t < t_hi; t++) {
+      if (line_only) {  // [t_lo, t_hi) is only the hull of the lines' tile ranges
+        bool hit = false;
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+          hit |= t >= jp.line_tiles[jp.q0 + q][seg.pol][0] && t < jp.line_tiles[jp.q0 + q][seg.pol][1];
+        if (!hit) continue;
+      }
       const double* __restrict__ s4 = summ + t * SUMMARY_DOUBLES;
       if (s4[0] > s4[1]) continue;  // no contributing line (CTA uniform)
       const double dist = fmax(0.0, fmax(fblk_min - s4[1], s4[0] - fblk_max));

@@ -85,6 +85,18 @@ class Target(C.Structure):
     _fields_ = [("kind", C.c_int32), ("species", C.c_int32), ("line", C.c_int64), ("ls_var", C.c_int32), ("coeff", C.c_int32)]
 
 
+class XmlIsotopologue(C.Structure):
+    """ab200_xml_isotopologue: SpeciesIsotope tag -> species index and mass."""
+
+    _fields_ = [("name", C.c_char_p), ("species", C.c_int32), ("mass", C.c_double)]
+
+
+class XmlSpecies(C.Structure):
+    """ab200_xml_species: broadener name as written in the file -> species index (or SPECIES_BATH)."""
+
+    _fields_ = [("name", C.c_char_p), ("species", C.c_int32)]
+
+
 class HitranIsotopologue(C.Structure):
     """ab200_hitran_isotopologue: (HITRAN molecule number, isotopologue character) -> species index and mass."""
 

@@ -92,6 +92,14 @@ def lib():
                                         C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]
     L.ab200_hitran_read_par_file.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.HitranIsotopologue),
                                              C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]
+    L.ab200_xml_read_bands.argtypes = [C.c_char_p, C.c_int64, C.POINTER(abi.XmlIsotopologue), C.c_int32, C.POINTER(abi.XmlSpecies),
+                                       C.c_int32, C.c_int32, C.POINTER(_vp)]
+    L.ab200_xml_read_bands_file.argtypes = [C.c_char_p, C.POINTER(abi.XmlIsotopologue), C.c_int32, C.POINTER(abi.XmlSpecies),
+                                            C.c_int32, C.c_int32, C.POINTER(_vp)]
+    L.ab200_xml_desc.argtypes = [_vp]
+    L.ab200_xml_desc.restype = C.POINTER(abi.CatalogDesc)
+    L.ab200_xml_destroy.argtypes = [_vp]
+    L.ab200_xml_destroy.restype = None
     L.ab200_hitran_desc.argtypes = [_vp]
     L.ab200_hitran_desc.restype = C.POINTER(abi.CatalogDesc)
     L.ab200_hitran_destroy.argtypes = [_vp]

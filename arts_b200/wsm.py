@@ -461,6 +461,55 @@ def measurement_vecFromSensor(abs_bands, freq_grid, simulations, jac_targets=(),
     return y, J
 
 
+def _host_catalog_from_desc(d) -> HostCatalog:
+    """Copy of a loader's ``ab200_catalog_desc`` into numpy arrays (the loader's handle can be destroyed afterwards)."""
+    nl, nls, nb, ni = d.n_lines, d.n_ls, d.n_bands, d.n_isot
+
+    def arr(p, n, dtype):
+        return np.ctypeslib.as_array(p, shape=(n,)).astype(dtype, copy=True) if n else np.zeros(0, dtype)
+
+    return HostCatalog(
+        n_species=d.n_species, isot_species=arr(d.isot_species, ni, np.int32), isot_mass=arr(d.isot_mass, ni, np.float64),
+        band_isot=arr(d.band_isot, nb, np.int32), band_offset=arr(d.band_offset, nb + 1, np.int64),
+        f0=arr(d.f0, nl, np.float64), a=arr(d.a, nl, np.float64), e0=arr(d.e0, nl, np.float64),
+        gu=arr(d.gu, nl, np.float64), gl=arr(d.gl, nl, np.float64), T0=arr(d.T0, nl, np.float64),
+        ls_offset=arr(d.ls_offset, nl + 1, np.int64), ls_species=arr(d.ls_species, nls, np.int32),
+        ls_type=arr(d.ls_type, nls * abi.NVAR, np.int32).reshape(nls, abi.NVAR),
+        ls_X=arr(d.ls_X, nls * abi.NVAR * 4, np.float64).reshape(nls, abi.NVAR, 4),
+        band_lineshape=arr(d.band_lineshape, nb, np.int32), band_cutoff_type=arr(d.band_cutoff_type, nb, np.int32),
+        band_cutoff_value=arr(d.band_cutoff_value, nb, np.float64),
+        z_on=arr(d.z_on, nl, np.uint8), z_gu=arr(d.z_gu, nl, np.float64), z_gl=arr(d.z_gl, nl, np.float64),
+        two_Ju=arr(d.two_Ju, nl, np.int32), two_Jl=arr(d.two_Jl, nl, np.int32))
+
+
+def abs_bandsReadXML(file=None, isotopologues=(), species_names=None, n_species=None, text=None) -> HostCatalog:
+    """The reference's ``abs_bands`` XML (``xml_io_stream<AbsorptionBand>``, src/core/lbl/lbl_data.cpp:412-470) straight
+    into the SoA catalog.  ``isotopologues``: ``(tag, species index, mass [g/mol])`` per SpeciesIsotope the file may
+    name; ``species_names``: ``{name as written in the file: species index or SPECIES_BATH}`` for the broadeners.
+    One band per ``<AbsorptionBand>`` in file order."""
+    iso = (abi.XmlIsotopologue * len(isotopologues))()
+    keep = []
+    for k, (tag, sp, mass) in enumerate(isotopologues):
+        keep.append(str(tag).encode())
+        iso[k].name, iso[k].species, iso[k].mass = keep[-1], int(sp), float(mass)
+    species_names = dict(species_names or {})
+    nm = (abi.XmlSpecies * max(len(species_names), 1))()
+    for k, (name, sp) in enumerate(species_names.items()):
+        keep.append(str(name).encode())
+        nm[k].name, nm[k].species = keep[-1], int(sp)
+    ns = int(n_species) if n_species is not None else 1 + max([int(i[1]) for i in isotopologues] + [int(v) for v in species_names.values()])
+    h = C.c_void_p()
+    if text is not None:
+        raw = text.encode() if isinstance(text, str) else bytes(text)
+        check(lib().ab200_xml_read_bands(raw, len(raw), iso, len(isotopologues), nm, len(species_names), ns, C.byref(h)))
+    else:
+        check(lib().ab200_xml_read_bands_file(str(file).encode(), iso, len(isotopologues), nm, len(species_names), ns, C.byref(h)))
+    try:
+        return _host_catalog_from_desc(lib().ab200_xml_desc(h).contents)
+    finally:
+        lib().ab200_xml_destroy(h)
+
+
 def abs_bandsReadHITRAN(file=None, frequency_range=(-np.inf, np.inf), isotopologues=(), n_species=None, text=None,
                         file_formatter=("par",), line_strength_option="A", compute_zeeman_parameters=0, n_threads=0):
     """``abs_bandsReadHITRAN`` (src/m_lbl.cc:302-338) for the plain 160-column ``.par`` format, straight into the SoA
@@ -489,22 +538,7 @@ def abs_bandsReadHITRAN(file=None, frequency_range=(-np.inf, np.inf), isotopolog
         check(lib().ab200_hitran_read_par_file(str(file).encode(), float(frequency_range[0]), float(frequency_range[1]), tab,
                                                len(isotopologues), ns, int(n_threads), C.byref(h)))
     try:
-        d = lib().ab200_hitran_desc(h).contents
-        nl, nls, nb, ni = d.n_lines, d.n_ls, d.n_bands, d.n_isot
-
-        def arr(p, n, dtype):
-            return np.ctypeslib.as_array(p, shape=(n,)).astype(dtype, copy=True) if n else np.zeros(0, dtype)
-
-        return HostCatalog(
-            n_species=d.n_species, isot_species=arr(d.isot_species, ni, np.int32), isot_mass=arr(d.isot_mass, ni, np.float64),
-            band_isot=arr(d.band_isot, nb, np.int32), band_offset=arr(d.band_offset, nb + 1, np.int64),
-            f0=arr(d.f0, nl, np.float64), a=arr(d.a, nl, np.float64), e0=arr(d.e0, nl, np.float64),
-            gu=arr(d.gu, nl, np.float64), gl=arr(d.gl, nl, np.float64), T0=arr(d.T0, nl, np.float64),
-            ls_offset=arr(d.ls_offset, nl + 1, np.int64), ls_species=arr(d.ls_species, nls, np.int32),
-            ls_type=arr(d.ls_type, nls * abi.NVAR, np.int32).reshape(nls, abi.NVAR),
-            ls_X=arr(d.ls_X, nls * abi.NVAR * 4, np.float64).reshape(nls, abi.NVAR, 4),
-            band_lineshape=arr(d.band_lineshape, nb, np.int32), band_cutoff_type=arr(d.band_cutoff_type, nb, np.int32),
-            band_cutoff_value=arr(d.band_cutoff_value, nb, np.float64))
+        return _host_catalog_from_desc(lib().ab200_hitran_desc(h).contents)
     finally:
         lib().ab200_hitran_destroy(h)
 

@@ -391,6 +391,32 @@ int ab200_hitran_read_par_file(const char *filename, double fmin, double fmax,
 const ab200_catalog_desc *ab200_hitran_desc(const ab200_hitran_catalog *cat);
 void ab200_hitran_destroy(ab200_hitran_catalog *cat);
 
+/* ---- catalog ingest: the reference's own AbsorptionBands XML straight into the SoA ----------------
+ * xml_io_stream<AbsorptionBand>::read (src/core/lbl/lbl_data.cpp:435-470) inside the
+ * <Map type="AbsorptionBand" key="QuantumIdentifier"> of an abs_bands file, every line with operator>>(line)
+ * (lbl_data.cpp:52-58: f0 a e0 gu gl, zeeman::model lbl_zeeman.cpp:311-319, line_shape::model
+ * lbl_lineshape_model.cpp:260-296 with temperature::data lbl_temperature_model.cpp:28-43, local quantum numbers
+ * quantum.cc:150-163).  One band per <AbsorptionBand> in file order.  Names are resolved through the caller's tables:
+ * isotopologue tags ("H2O-161") and broadener names in whatever spelling the files use ("Nitrogen", "N2", "Bath").
+ * G2 / D2 / FVC / ETA entries must be all-zero (dropped, like model::clear_zeroes), POLY takes at most four coefficients,
+ * a line with Zeeman on needs its local J; anything else the GPU path cannot hold is AB200_ERR_UNSUPPORTED. */
+typedef struct ab200_xml_isotopologue {
+  const char *name; /* SpeciesIsotope tag, e.g. "O2-66" */
+  int32_t species;  /* the caller's species index */
+  double mass;      /* g/mol */
+} ab200_xml_isotopologue;
+typedef struct ab200_xml_species {
+  const char *name; /* SpeciesEnum name as written in the file */
+  int32_t species;  /* species index or AB200_SPECIES_BATH */
+} ab200_xml_species;
+typedef struct ab200_xml_catalog ab200_xml_catalog; /* owns the arrays the description points to */
+int ab200_xml_read_bands(const char *text, int64_t len, const ab200_xml_isotopologue *isotopologues, int32_t n_isot,
+                         const ab200_xml_species *names, int32_t n_names, int32_t n_species, ab200_xml_catalog **out);
+int ab200_xml_read_bands_file(const char *filename, const ab200_xml_isotopologue *isotopologues, int32_t n_isot,
+                              const ab200_xml_species *names, int32_t n_names, int32_t n_species, ab200_xml_catalog **out);
+const ab200_catalog_desc *ab200_xml_desc(const ab200_xml_catalog *cat);
+void ab200_xml_destroy(ab200_xml_catalog *cat);
+
 /* ---- partition functions: Q(T) and dQ/dT of every isotopologue at every level ---------------------
  * PartitionFunctions::Q / dQdT (src/partfun/partfun.h) are generated at build time from data tables by
  * src/partfun/make_auto_partfuns.cc; the four table kinds and their literal formulas:

@@ -325,7 +325,7 @@ def run_b200(args):
                                   "peak_with_rcp_mix_tflops": dfma_mix_tflops,
                                   "note": "frac > 1 because the reference's closed form costs 28 algorithmic FLOP per far-wing "
                                           "evaluation and the kernel needs 7 FP64-pipe instructions (14 FLOP slots) + 1 MUFU; "
-                                          "dfma_equiv / peak is the FP64-pipe utilisation (ncu: profiles/r1f_lbl_sum_real.ncu.txt)"},
+                                          "dfma_equiv / peak is the FP64-pipe utilisation (ncu: profiles/r1h_lbl_sum_real.ncu.txt)"},
                      "kernel_share_of_step": k_ms / ms if ms else None},
         "roofline_stokes": {"bound": "hbm", "kernel": "stokes_chain_kernel", "achieved": st_gbs, "peak": hbm_peak,
                             "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": traffic.get("stokes_chain_kernel"),

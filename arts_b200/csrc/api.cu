@@ -309,6 +309,8 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
             return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": broadener species out of range");
         }
         p->tg_line[q] = t.line; p->tg_ls_var[q] = t.ls_var; p->tg_coeff[q] = t.coeff;
+      } else if (targets[q].kind == AB200_TARGET_P) {
+        return set_error(AB200_ERR_UNSUPPORTED, "Not implemented, pressure derivative");  // lbl_lineshape_voigt_lte.cpp:1482
       } else {
         return set_error(AB200_ERR_UNSUPPORTED, "Jacobian target " + std::to_string(q) +
                                                     ": unknown target kind");

@@ -90,7 +90,9 @@ enum {
   AB200_TARGET_LINE_F0 = 8,
   AB200_TARGET_LINE_E0 = 9,
   AB200_TARGET_LINE_A = 10,
-  AB200_TARGET_LINE_LS = 11
+  AB200_TARGET_LINE_LS = 11,
+  /* AtmKey::p: "Not implemented, pressure derivative" in the reference (:1482); AB200_ERR_UNSUPPORTED with that text */
+  AB200_TARGET_P = 12
 };
 
 /* flags (bit mask) */

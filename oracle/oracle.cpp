@@ -1646,6 +1646,8 @@ static int propmat_levels_on_path_grids(const ab200_catalog_desc* d, int64_t nf,
     if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE && d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE_MIRROR)
       return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE and VP_LTE_MIRROR bands");
   if (nq > 0 && !dK) return fail(AB200_ERR_INVALID, "dK is null with nq > 0");
+  for (int q = 0; q < nq; q++)
+    if (targets[q].kind == AB200_TARGET_P) return fail(AB200_ERR_UNSUPPORTED, "Not implemented, pressure derivative");  // :1482
   for (int q = 0; q < nq; q++) {
     if (targets[q].kind < AB200_TARGET_LINE_F0 or targets[q].kind > AB200_TARGET_LINE_LS) continue;
     if (targets[q].line < 0 or targets[q].line >= d->n_lines) return fail(AB200_ERR_INVALID, "line target out of range");

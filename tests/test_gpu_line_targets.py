@@ -84,6 +84,11 @@ def test_line_target_errors(wsm, orc):
     with pytest.raises(RuntimeError):
         orc.propmat_levels(c.cat, c.f, c.atm, targets=[("line_f0", 3)])
     c = synth.tiny_case(nl=16, nf=32, np_=2)
+    with pytest.raises(wsm.Ab200Error) as e:  # AtmKey::p, lbl_lineshape_voigt_lte.cpp:1482
+        wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=[("p",)])
+    assert e.value.code == abi.ERR_UNSUPPORTED and "pressure derivative" in str(e.value)
+    with pytest.raises(RuntimeError, match="pressure derivative"):
+        orc.propmat_levels(c.cat, c.f, c.atm, targets=[("p",)])
     for bad in (("line_a", 16), ("line_a", -1), ("line_ls", 2, 9, 0, 0), ("line_ls", 2, abi.VAR_G0, 0, 4), ("line_ls", 2, abi.VAR_G0, 77, 0)):
         with pytest.raises(wsm.Ab200Error) as e:
             wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=[bad])

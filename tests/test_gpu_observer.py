@@ -178,3 +178,22 @@ def test_measurement_vec_from_sensor_ragged_batch(wsm, orc):
     # one workspace, same numbers bit for bit (the order of accumulation is the order of the simulations)
     y1, J1 = wsm.measurement_vecFromSensor(base.cat, base.f, sims, jac_targets=TARGETS, n_workspaces=1)
     assert np.array_equal(y, y1) and np.array_equal(J, J1)
+
+
+def test_observer_with_wind_magnetic_and_line_targets(wsm, orc):
+    """The state-space accumulation and the sensor sum-up are target-agnostic: wind, magnetic-field and line-parameter rows
+    (scalar dK rows, polarised dK rows, rows of one line) go through the same epilogue as T / VMR."""
+    c = synth.tiny_case(nf=38 * 6, np_=5, zeeman=True, targets=TARGETS)
+    rng = np.random.default_rng(7)  # a calm path: its wind rows are not zero (DESIGN.md quirk 12)
+    line = int(np.flatnonzero(c.cat.z_on)[0])
+    tg = (("T",), ("wind_w",), ("mag_v",), ("line_a", line), ("VMR", 0), ("line_ls", line, abi.VAR_G0, abi.SPECIES_BATH, 0))
+    # RJBT: the Planck brightness-temperature transform scales a Q / U / V row by dinvplanckdI((I + V) / 2) -
+    # dinvplanckdI((I - V) / 2) (spectral_radiance_transform_operator.cc:46-87), a difference of nearly equal numbers
+    # where |V| / I ~ 1e-8 as around this fixture's 118 GHz line: there a 1e-12 difference in I shows up at 1e-5 in the row
+    obs = _observer(c, len(tg), "RJBT", rng, bkg_T=260.0)
+    ref = _oracle(orc, c, tg, obs)
+    got = _gpu(wsm, c, tg, obs)
+    _compare(got, ref, jac_rtol=5e-7)
+    n_grid = 4
+    for t in range(len(tg)):
+        assert np.abs(ref[1][t * n_grid:(t + 1) * n_grid]).max() > 0, tg[t]

@@ -25,6 +25,7 @@ TARGET_WIND_U, TARGET_WIND_V, TARGET_WIND_W = 2, 3, 4
 TARGET_MAG_U, TARGET_MAG_V, TARGET_MAG_W = 5, 6, 7
 TARGET_LINE_F0, TARGET_LINE_E0, TARGET_LINE_A, TARGET_LINE_LS = 8, 9, 10, 11
 TARGET_P = 12
+TARGET_ISORAT = 13
 FLAG_K_ZERO_INIT, FLAG_TRAN_EXACT, FLAG_RETURN_K, FLAG_NO_EMISSION, FLAG_WIND_ROWS_DF = 1, 2, 4, 8, 16
 
 RTE_OPTIONS = {"constant": RTE_CONSTANT, "linsrc": RTE_LINSRC, "lintau": RTE_LINSRC, "linprop": RTE_LINPROP}
@@ -503,6 +504,8 @@ def make_targets(targets) -> tuple[C.Array | None, int]:
             lst.append((TARGET_MAG_U + "uvw".index(kind[-1]), 0, 0, 0, 0))
         elif kind in ("line_f0", "line_e0", "line_a"):  # lbl::line_key with LineByLineVariable
             lst.append(({"line_f0": TARGET_LINE_F0, "line_e0": TARGET_LINE_E0, "line_a": TARGET_LINE_A}[kind], 0, int(t[1]), 0, 0))
+        elif kind in ("isorat", "ISORAT"):  # SpeciesIsotope ratio: ("isorat", isotopologue index)
+            lst.append((TARGET_ISORAT, int(t[1]), 0, 0, 0))
         elif kind in ("p", "P"):  # AtmKey::p: the reference's "Not implemented, pressure derivative"
             lst.append((TARGET_P, 0, 0, 0, 0))
         elif kind == "line_ls":  # lbl::line_key with LineShapeModelVariable, broadener and coefficient

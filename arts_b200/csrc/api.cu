@@ -309,6 +309,12 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
             return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": broadener species out of range");
         }
         p->tg_line[q] = t.line; p->tg_ls_var[q] = t.ls_var; p->tg_coeff[q] = t.coeff;
+      } else if (targets[q].kind == AB200_TARGET_ISORAT) {
+        if (targets[q].species < 0 || targets[q].species >= cat->n_isot)
+          return set_error(AB200_ERR_INVALID, "Jacobian target " + std::to_string(q) + ": isotopologue out of range");
+        for (int ip = 0; ip < np; ip++)
+          if (atm->isorat[static_cast<size_t>(ip) * cat->n_isot + targets[q].species] == 0)
+            return set_error(AB200_ERR_INVALID, "Does not support 0 for isotopologue ratios");  // :1539
       } else if (targets[q].kind == AB200_TARGET_P) {
         return set_error(AB200_ERR_UNSUPPORTED, "Not implemented, pressure derivative");  // lbl_lineshape_voigt_lte.cpp:1482
       } else {
@@ -501,7 +507,7 @@ int ab200_path_run_propmat(ab200_path* p) {
         jp.kind[q] = js.kind[q] = p->tg_kind[q];
         jp.species[q] = p->tg_species[q];
         jp.line[q] = p->tg_line[q]; jp.ls_var[q] = p->tg_ls_var[q]; jp.coeff[q] = p->tg_coeff[q];
-        if (p->tg_kind[q] >= AB200_TARGET_LINE_F0)
+        if (p->tg_kind[q] >= AB200_TARGET_LINE_F0 && p->tg_kind[q] <= AB200_TARGET_LINE_LS)
           std::copy_n(cat->line_tiles.data() + p->tg_line[q] * 8, 8, &js.line_tiles[q][0][0]);
       }
       jp.dQdT = p->d_dQdT + static_cast<size_t>(lev0) * cat->n_isot;

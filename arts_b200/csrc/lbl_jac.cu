@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
                               cscale(f0s * sl, lmc));
         ds     = cscale(Sz * (cst::inv_sqrt_pi * igd * r * x) / (2 * T * f0s), num);
         dz_fac = (-2 * T * dD0 - 2 * T * dDV - f0s) / (2 * T * f0s);  // :1013-1015
+      } else if (jp.kind[q] == AB200_TARGET_ISORAT) {
+        // compute_derivative(SpeciesIsotope) :1526-1544: scl shape / isorat for the bands of that isotopologue; as a
+        // record (ds = s / isorat, nothing else) it also works inside species-merged segments and with cutoffs
+        dD0 = dDV = dG0 = dG = dY = 0.0;
+        ds     = isot == jp.species[q] ? cscale(1.0 / r, {s_re, s_im}) : cplx{0.0, 0.0};
+        dz_fac = 0.0;
       } else if (jp.kind[q] >= AB200_TARGET_LINE_F0) {
         // line targets (line_key): only the sub-lines of jp.line[q] have a record, set_filter :1192-1201
         dD0 = dDV = dG0 = dG = dY = 0.0;
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
       }
       cplx dzq{igd * -(dD0 + dDV), igd * dG0};
       if (jp.kind[q] >= AB200_TARGET_LINE_F0) {
-        // dzq above is the whole of it
+        // dzq above is the whole of it (line targets, isotopologue ratio)
       } else if (jp.kind[q] >= AB200_TARGET_MAG_U) {
         const double dzc = p.sub_dzc[slot];
         dzq = {dzc == 0.0 ? 0.0 : -igd * jp.mag_ratio[3 * lev + (jp.kind[q] - AB200_TARGET_MAG_U)] * dzc, 0.0};
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
   // forward shape is not needed (no dscl term)
   bool line_only = true;
 #pragma unroll
-  for (int q = 0; q < NQ; q++) line_only &= jp.kind[jp.q0 + q] >= AB200_TARGET_LINE_F0;
+  for (int q = 0; q < NQ; q++) line_only &= jp.kind[jp.q0 + q] >= AB200_TARGET_LINE_F0 && jp.kind[jp.q0 + q] <= AB200_TARGET_LINE_LS;
 
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];

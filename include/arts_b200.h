@@ -92,7 +92,10 @@ enum {
   AB200_TARGET_LINE_A = 10,
   AB200_TARGET_LINE_LS = 11,
   /* AtmKey::p: "Not implemented, pressure derivative" in the reference (:1482); AB200_ERR_UNSUPPORTED with that text */
-  AB200_TARGET_P = 12
+  AB200_TARGET_P = 12,
+  /* SpeciesIsotope (isotopologue ratio): scl shape / ratio of the bands of that isotopologue (:1526-1544);
+   * .species holds the ISOTOPOLOGUE index; a zero ratio is the reference's error */
+  AB200_TARGET_ISORAT = 13
 };
 
 /* flags (bit mask) */
@@ -156,7 +159,8 @@ typedef struct ab200_atm_path {
 
 typedef struct ab200_target {
   int32_t kind;    /* AB200_TARGET_* */
-  int32_t species; /* AB200_TARGET_VMR: the species; AB200_TARGET_LINE_LS: the broadener (or AB200_SPECIES_BATH) */
+  int32_t species; /* AB200_TARGET_VMR: the species; AB200_TARGET_LINE_LS: the broadener (or AB200_SPECIES_BATH);
+                      AB200_TARGET_ISORAT: the isotopologue */
   int64_t line;    /* AB200_TARGET_LINE_*: index of the line in the flattened catalog (band_offset order) */
   int32_t ls_var;  /* AB200_TARGET_LINE_LS: AB200_VAR_* */
   int32_t coeff;   /* AB200_TARGET_LINE_LS: 0..3 for X0..X3 (LineShapeModelCoefficient) */

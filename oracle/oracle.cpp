@@ -857,6 +857,13 @@ void calculate_band(double* pm, double* dpm, Index nf_total, const double* f_gri
       for (Index i = 0; i < f_n; i++) add_scaled(dp + i * 7, npm, dscl[i] * shape[i] + scl[i] * dshape[i]);
       continue;
     }
+    if (targets[iq].kind == AB200_TARGET_ISORAT) {
+      // compute_derivative(SpeciesIsotope) :1526-1544 (a zero ratio is rejected by orc_propmat_levels, :1539)
+      if (targets[iq].species != isot) continue;
+      const Numeric isorat = atm.isorat[isot];
+      for (Index i = 0; i < f_n; i++) add_scaled(dp + i * 7, npm, scl[i] * shape[i] / isorat);
+      continue;
+    }
     if (targets[iq].kind >= AB200_TARGET_LINE_F0 and targets[iq].kind <= AB200_TARGET_LINE_LS) {
       // compute_derivative(line_key) :1562-1637 without cutoff: only the band that holds the line (lbl_lineshape.cpp
       // hands line targets to their own band), only its (Zeeman sub-)lines (set_filter :1192-1201)
@@ -1646,8 +1653,15 @@ static int propmat_levels_on_path_grids(const ab200_catalog_desc* d, int64_t nf,
     if (d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE && d->band_lineshape[ib] != AB200_LINESHAPE_VP_LTE_MIRROR)
       return fail(AB200_ERR_UNSUPPORTED, "only VP_LTE and VP_LTE_MIRROR bands");
   if (nq > 0 && !dK) return fail(AB200_ERR_INVALID, "dK is null with nq > 0");
-  for (int q = 0; q < nq; q++)
+  for (int q = 0; q < nq; q++) {
     if (targets[q].kind == AB200_TARGET_P) return fail(AB200_ERR_UNSUPPORTED, "Not implemented, pressure derivative");  // :1482
+    if (targets[q].kind == AB200_TARGET_ISORAT) {
+      if (targets[q].species < 0 or targets[q].species >= d->n_isot) return fail(AB200_ERR_INVALID, "isotopologue out of range");
+      for (int ip = 0; ip < atm->np; ip++)
+        if (atm->isorat[static_cast<Index>(ip) * d->n_isot + targets[q].species] == 0)
+          return fail(AB200_ERR_INVALID, "Does not support 0 for isotopologue ratios");  // :1539
+    }
+  }
   for (int q = 0; q < nq; q++) {
     if (targets[q].kind < AB200_TARGET_LINE_F0 or targets[q].kind > AB200_TARGET_LINE_LS) continue;
     if (targets[q].line < 0 or targets[q].line >= d->n_lines) return fail(AB200_ERR_INVALID, "line target out of range");

@@ -11,6 +11,7 @@ import pytest
 
 from arts_b200 import _abi as abi
 from arts_b200 import synth
+from tests.conftest import assert_propmat_close
 
 pytestmark = pytest.mark.gpu
 
@@ -226,3 +227,27 @@ def test_propmat_jacobian_far_tiles_without_bath_broadener(wsm, orc):
         for lev in range(c.np_):
             assert_jac_close(dK[lev, q], dKr[lev, q], what=f"dK target {q} level {lev}")
     assert np.abs(dKr[:, 0]).max() > 0
+
+
+@pytest.mark.parametrize("cutoff", [None, 2e9])
+def test_isotopologue_ratio_rows(wsm, orc, cutoff):
+    """compute_derivative(SpeciesIsotope), lbl_lineshape_voigt_lte.cpp:1526-1544: as a derivative record (ds = s / ratio)
+    inside species-merged segments, with cutoffs, next to other targets, and for Zeeman bands."""
+    c = synth.tiny_case(nl=300, nf=700, np_=4, cutoff=cutoff)
+    ni = len(c.cat.isot_species)
+    tg = [("isorat", 0), ("T",), ("isorat", ni - 1), ("VMR", 0), ("isorat", 1 % ni)]
+    Kr, dKr = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    K, dK = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=tg)
+    assert_propmat_close(K, Kr, atol_scale=1e-11 if cutoff else 1e-12)
+    for q in range(len(tg)):
+        assert np.abs(dKr[:, q]).max() > 0
+        assert_jac_close(dK[:, q], dKr[:, q], what=f"dK target {tg[q]}")
+    z = synth.tiny_case(nf=38 * 8, np_=3, zeeman=True)
+    Kr, dKr = orc.propmat_levels(z.cat, z.f, z.atm, targets=[("isorat", 0)])
+    K, dK = wsm.spectral_propmat_pathFromPath(z.cat, z.f, z.atm, jac_targets=[("isorat", 0)])
+    assert_jac_close(dK[:, 0], dKr[:, 0], rtol=1e-9, what="Zeeman isotopologue-ratio row")
+    np.testing.assert_allclose(dK[:, 0] * z.atm.isorat[:, 0][:, None, None], K, rtol=1e-9, atol=1e-12 * np.abs(K).max())
+    z.atm.isorat[1, 0] = 0.0
+    with pytest.raises(wsm.Ab200Error) as e:
+        wsm.spectral_propmat_pathFromPath(z.cat, z.f, z.atm, jac_targets=[("isorat", 0)])
+    assert e.value.code == abi.ERR_INVALID and "isotopologue ratios" in str(e.value)

@@ -853,3 +853,25 @@ def test_oracle_line_parameter_jacobians_against_perturbed_catalogs(orc):
     _, dz = orc.propmat_levels(c.cat, c.f, c.atm, targets=[("line_ls", line, abi.VAR_G0, 3, 0)])
     present = set(int(s) for s in c.cat.ls_species[lo:c.cat.ls_offset[line + 1]])
     assert (3 in present) or not dz.any()
+
+
+def test_oracle_isotopologue_ratio_jacobian(orc):
+    """compute_derivative(SpeciesIsotope) (lbl_lineshape_voigt_lte.cpp:1526-1544): the bands of the target isotopologue,
+    divided by its ratio - the absorption is linear in the ratio, so a finite difference of any size reproduces it, and the
+    rows of all isotopologues times their ratios add up to the absorption itself."""
+    import copy
+
+    c = synth.tiny_case(nl=40, nf=120, np_=3)
+    ni = len(c.cat.isot_species)
+    tg = [("isorat", i) for i in range(ni)]
+    K, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    total = sum(dK[:, i] * c.atm.isorat[:, i][:, None, None] for i in range(ni))
+    np.testing.assert_allclose(total, K, rtol=1e-12, atol=1e-300)
+    a2 = copy.deepcopy(c.atm)
+    a2.isorat[:, 0] *= 1.5
+    K2, _ = orc.propmat_levels(c.cat, c.f, a2)
+    fd = (K2 - K) / (0.5 * c.atm.isorat[:, 0])[:, None, None]
+    np.testing.assert_allclose(dK[:, 0], fd, rtol=1e-10, atol=1e-13 * np.abs(fd).max())
+    a2.isorat[1, 0] = 0.0
+    with pytest.raises(RuntimeError, match="Does not support 0 for isotopologue ratios"):
+        orc.propmat_levels(c.cat, c.f, a2, targets=tg[:1])

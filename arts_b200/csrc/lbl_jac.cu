@@ -703,9 +703,12 @@ int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t s
     const char* e = getenv("AB200_JAC_PAIR_FAR");
     jp.pair_far = e ? atoi(e) : 1;
   }
-  for (int q0 = 0; q0 < jp.nq; q0 += JAC_Q) {
+  // targets per pass: JAC_Q, or AB200_JAC_PASS (1..4) for experiments
+  int per_pass = JAC_Q;
+  if (const char* e = getenv(jp.real_lines ? "AB200_JAC_PASS_REAL" : "AB200_JAC_PASS_CPLX")) per_pass = std::max(1, std::min(JAC_Q, atoi(e)));
+  for (int q0 = 0; q0 < jp.nq; q0 += per_pass) {
     jp.q0 = q0;
-    switch (std::min(JAC_Q, jp.nq - q0)) {
+    switch (std::min(per_pass, jp.nq - q0)) {
       case 1: AB_TRY(launch_sum_jac_n<1>(p, jp, grid, stream)); break;
       case 2: AB_TRY(launch_sum_jac_n<2>(p, jp, grid, stream)); break;
       case 3: AB_TRY(launch_sum_jac_n<3>(p, jp, grid, stream)); break;

@@ -8,6 +8,9 @@
                             (arts_b200.synth) from oracle/_ref/liboracle.so, which links the reference's
                             own Faddeeva.cc object.  The GPU parity tests compare with these on the box
                             in addition to the live oracle.
+* jacobian_goldens.npz      propagation-matrix and radiance Jacobians of a small Zeeman path, one target of every
+                            kind (temperature, VMR, wind, magnetic field, isotopologue ratio, line centre, line-shape
+                            coefficient)
 """
 import json
 import os
@@ -34,6 +37,17 @@ def golden_cases():
     }
 
 
+def jacobian_case():
+    """Small Zeeman path and one target of every kind the library takes; shared with tests/test_gpu_goldens.py."""
+    from arts_b200 import _abi as abi
+
+    c = synth.case_c3(nf=38 * 4, np_=4, los=(130.0, 25.0))
+    line = 5
+    tg = (("T",), ("VMR", 0), ("wind_w",), ("mag_u",), ("isorat", 0), ("line_f0", line),
+          ("line_ls", line, abi.VAR_G0, abi.SPECIES_BATH, 0))
+    return c, tg
+
+
 def main():
     out = {"constant_k": _linsrc_fixture(orc, False), "varying": _linsrc_fixture(orc, True),
            "source": "tests/core/linsrc/test_linsrc_convergence.py:24-92,110-178 through oracle/oracle.cpp"}
@@ -48,6 +62,10 @@ def main():
                 arrays[f"{name}_I_{opt}"] = I
                 arrays[f"{name}_Tb_{opt}"] = orc.planck_tb(c.f, I)
     np.savez_compressed(os.path.join(HERE, "path_goldens.npz"), **arrays)
+    c, tg = jacobian_case()
+    K, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    I, dI = orc.clearsky_emission(c.cat, c.f, c.atm, c.r, c.I_bkg, targets=tg, hse_derivative=1)
+    np.savez_compressed(os.path.join(HERE, "jacobian_goldens.npz"), K=K, dK=dK, I=I, dI=dI)
     print("wrote", sorted(arrays), "threads", orc.num_threads())
 
 

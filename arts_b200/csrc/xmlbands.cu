@@ -164,6 +164,13 @@ int build(const char* text, int64_t len, const ab200_xml_isotopologue* isots, in
   if (n_bands < 0) return set_error(AB200_ERR_INVALID, "ab200_xml_read_bands: no <Map type=\"AbsorptionBand\"> found");
 
   c->band_offset.push_back(0);
+  {  // size hints (untouched reserve costs nothing; the vectors still grow past them): one allocation per array instead
+     // of doubling copies.  In the reference's files a line takes ~150 characters and up, a broadener entry ~45
+    const size_t nl_max = static_cast<size_t>(len) / 120 + 16, ns_max = static_cast<size_t>(len) / 45 + 16;
+    for (auto* v : {&c->f0, &c->a, &c->e0, &c->gu, &c->gl, &c->T0, &c->z_gu, &c->z_gl}) v->reserve(nl_max);
+    c->z_on.reserve(nl_max); c->two_Ju.reserve(nl_max); c->two_Jl.reserve(nl_max); c->ls_offset.reserve(nl_max + 1);
+    c->ls_species.reserve(ns_max); c->ls_type.reserve(ns_max * AB200_NVAR); c->ls_X.reserve(ns_max * AB200_NVAR * 4);
+  }
   for (int64_t ib = 0; ib < n_bands; ib++) {
     if (!cur.tag(name, attrs) || name != "QuantumIdentifier") return fail_at("expected <QuantumIdentifier>", ib, -1);
     if (!cur.token(v)) return fail_at("empty QuantumIdentifier", ib, -1);

@@ -102,7 +102,8 @@ class XmlSpecies(C.Structure):
 class HitranIsotopologue(C.Structure):
     """ab200_hitran_isotopologue: (HITRAN molecule number, isotopologue character) -> species index and mass."""
 
-    _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double)]
+    _fields_ = [("M", C.c_int32), ("I", C.c_char), ("species", C.c_int32), ("mass", C.c_double), ("hitran_ratio", C.c_double),
+                ("Q296", C.c_double)]
 
 
 class PredefSpecies(C.Structure):

@@ -88,9 +88,9 @@ def lib():
     L.ab200_path_add_cia.argtypes = [_vp, _vp, C.c_double, C.c_int32, C.c_double]
     L.ab200_cia_levels.argtypes = [_vp, C.c_int64, _dp, C.c_int64, C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(abi.Target), C.c_double, C.c_double, C.c_int32, _dp, _dp]
-    L.ab200_hitran_read_par.argtypes = [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.POINTER(abi.HitranIsotopologue),
+    L.ab200_hitran_read_par.argtypes = [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.POINTER(abi.HitranIsotopologue),
                                         C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]
-    L.ab200_hitran_read_par_file.argtypes = [C.c_char_p, C.c_double, C.c_double, C.POINTER(abi.HitranIsotopologue),
+    L.ab200_hitran_read_par_file.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_int32, C.POINTER(abi.HitranIsotopologue),
                                              C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]
     L.ab200_xml_read_bands.argtypes = [C.c_char_p, C.c_int64, C.POINTER(abi.XmlIsotopologue), C.c_int32, C.POINTER(abi.XmlSpecies),
                                        C.c_int32, C.c_int32, C.POINTER(_vp)]

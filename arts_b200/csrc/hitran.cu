@@ -73,7 +73,7 @@ inline bool parse(const char* p, int n, T& x) {  // :28-49: the whole trimmed co
 std::string quoted(const char* p, size_t n) { return "\"" + std::string(p, n) + "\""; }
 
 // One record [p, p + n) (without the newline).  Returns the status and fills rec / err.
-Status parse_record(const char* p, size_t n, double fmin, const ab200_hitran_isotopologue* tab, int32_t ntab, Record& rec,
+Status parse_record(const char* p, size_t n, double fmin, int32_t strength, const ab200_hitran_isotopologue* tab, int32_t ntab, Record& rec,
                     std::string& err) {
   auto fail = [&](const std::string& m) {
     err = m + "\n\nFailed to read HITRAN line record:\n\n" + std::string(p, n);
@@ -108,12 +108,20 @@ Status parse_record(const char* p, size_t n, double fmin, const ab200_hitran_iso
   for (const Col& c : cols)
     if (!parse(p + c.off, c.len, *c.out)) return fail("Failed to parse value from string " + quoted(p + c.off, c.len));
   if (n > 160) return fail("Part of the line was not parsed: '" + std::string(p + 160, n - 160) + "'");
-  (void)S;  // HitranLineStrengthOption::A: the Einstein coefficient of the file is used (:197-209)
-  (void)kS_FACTOR;
   rec.gamma_air  = rec.gamma_air * kGAMMA_FACTOR;
   rec.gamma_self = rec.gamma_self * kGAMMA_FACTOR;
   rec.E          = rec.E * kE_FACTOR;
   rec.delta      = rec.delta * kGAMMA_FACTOR;
+  if (strength == AB200_HITRAN_STRENGTH_S) {
+    // hitran_record::from :193-200: line::hitran_a (lbl_data.cpp:164-169) = compute_a(S / Ia) = einstein_a(s, gu, e0, f0,
+    // 296 K, Q(296)) (:34-40, :155-162); HitranLineStrengthOption::A keeps the file's coefficient
+    if (rec.g_upp == 0.0) rec.g_upp = rec.g_low = -1.0;
+    constexpr double kK = 1.380649e-23, kPI = 3.14159265358979323846, T0 = 296.0;
+    const double s  = (S * kS_FACTOR) / tab[rec.isot].hitran_ratio;
+    const double cf = kC / rec.f0;
+    rec.A = -8.0 * kPI * tab[rec.isot].Q296 * s /
+            (rec.g_upp * std::exp(-rec.E / (kK * T0)) * std::expm1(-(kH * rec.f0) / (kK * T0)) * (cf * cf));
+  }
   // hitran_record::from :211-216
   if (!std::isnormal(rec.A) || !std::isnormal(rec.g_upp))
     return fail("Invalid Einstein coefficient " + std::to_string(rec.A) + " or gu " + std::to_string(rec.g_upp) +
@@ -121,7 +129,7 @@ Status parse_record(const char* p, size_t n, double fmin, const ab200_hitran_iso
   return ST_OK;
 }
 
-int build(const char* text, int64_t len, double fmin, double fmax, const ab200_hitran_isotopologue* tab, int32_t ntab,
+int build(const char* text, int64_t len, double fmin, double fmax, int32_t strength, const ab200_hitran_isotopologue* tab, int32_t ntab,
           int32_t n_species, int32_t n_threads, ab200_hitran_catalog** out) {
   if (!out) return set_error(AB200_ERR_INVALID, "ab200_hitran_read_par: null output");
   *out = nullptr;
@@ -130,6 +138,13 @@ int build(const char* text, int64_t len, double fmin, double fmax, const ab200_h
   for (int32_t i = 0; i < ntab; i++)
     if (tab[i].species < 0 || tab[i].species >= n_species || !(tab[i].mass > 0))
       return set_error(AB200_ERR_INVALID, "ab200_hitran_read_par: isotopologue " + std::to_string(i) + " has a bad species or mass");
+  if (strength != AB200_HITRAN_STRENGTH_S && strength != AB200_HITRAN_STRENGTH_A)
+    return set_error(AB200_ERR_INVALID, "ab200_hitran_read_par: unknown line_strength_option");
+  if (strength == AB200_HITRAN_STRENGTH_S)
+    for (int32_t i = 0; i < ntab; i++)
+      if (!(tab[i].hitran_ratio > 0) || !(tab[i].Q296 > 0))
+        return set_error(AB200_ERR_INVALID, "ab200_hitran_read_par: line_strength_option S needs hitran_ratio and Q296 of isotopologue " +
+                                                std::to_string(i));
 
   // record boundaries (std::getline: '\n' separated, a trailing newline does not make an empty record)
   std::vector<int64_t> start;
@@ -155,7 +170,7 @@ int build(const char* text, int64_t len, double fmin, double fmax, const ab200_h
     const int64_t lo = nrec * t / nt, hi = nrec * (t + 1) / nt;
     std::string err;
     for (int64_t i = lo; i < hi; i++) {
-      status[i] = parse_record(text + start[i], rec_len(i), fmin, tab, ntab, recs[i], err);
+      status[i] = parse_record(text + start[i], rec_len(i), fmin, strength, tab, ntab, recs[i], err);
       if (status[i] == ST_ERROR && first_err_at[t] < 0) {
         first_err_at[t] = i;
         first_err[t]    = err;
@@ -351,12 +366,14 @@ int ab200_partfun_eval(const ab200_partfun_table* tables, int32_t n_isot, int32_
   return AB200_OK;
 }
 
-int ab200_hitran_read_par(const char* text, int64_t len, double fmin, double fmax, const ab200_hitran_isotopologue* isotopologues,
+int ab200_hitran_read_par(const char* text, int64_t len, double fmin, double fmax, int32_t line_strength_option,
+                          const ab200_hitran_isotopologue* isotopologues,
                           int32_t n_isot, int32_t n_species, int32_t n_threads, ab200_hitran_catalog** out) {
-  return ab200::build(text, len, fmin, fmax, isotopologues, n_isot, n_species, n_threads, out);
+  return ab200::build(text, len, fmin, fmax, line_strength_option, isotopologues, n_isot, n_species, n_threads, out);
 }
 
-int ab200_hitran_read_par_file(const char* filename, double fmin, double fmax, const ab200_hitran_isotopologue* isotopologues,
+int ab200_hitran_read_par_file(const char* filename, double fmin, double fmax, int32_t line_strength_option,
+                               const ab200_hitran_isotopologue* isotopologues,
                                int32_t n_isot, int32_t n_species, int32_t n_threads, ab200_hitran_catalog** out) {
   if (!filename) return ab200::set_error(AB200_ERR_INVALID, "ab200_hitran_read_par_file: null file name");
   std::FILE* f = std::fopen(filename, "rb");
@@ -368,7 +385,8 @@ int ab200_hitran_read_par_file(const char* filename, double fmin, double fmax, c
   const size_t got = buf.empty() ? 0 : std::fread(buf.data(), 1, buf.size(), f);
   std::fclose(f);
   if (got != buf.size()) return ab200::set_error(AB200_ERR_INVALID, std::string("Cannot read file: ") + filename);
-  return ab200::build(buf.data(), static_cast<int64_t>(buf.size()), fmin, fmax, isotopologues, n_isot, n_species, n_threads, out);
+  return ab200::build(buf.data(), static_cast<int64_t>(buf.size()), fmin, fmax, line_strength_option, isotopologues, n_isot, n_species, n_threads,
+                      out);
 }
 
 const ab200_catalog_desc* ab200_hitran_desc(const ab200_hitran_catalog* cat) { return cat ? &cat->desc : nullptr; }

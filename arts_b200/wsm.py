@@ -511,31 +511,36 @@ def abs_bandsReadXML(file=None, isotopologues=(), species_names=None, n_species=
 
 
 def abs_bandsReadHITRAN(file=None, frequency_range=(-np.inf, np.inf), isotopologues=(), n_species=None, text=None,
-                        file_formatter=("par",), line_strength_option="A", compute_zeeman_parameters=0, n_threads=0):
+                        file_formatter=("par",), line_strength_option="S", compute_zeeman_parameters=0, n_threads=0):
     """``abs_bandsReadHITRAN`` (src/m_lbl.cc:302-338) for the plain 160-column ``.par`` format, straight into the SoA
     catalog: ``isotopologues`` is a list of ``(M, I, species index, mass [g/mol])`` (what ``Hitran::id_from_lookup`` and
-    the isotopologue table give the shim).  Returns a ``HostCatalog`` (one band per isotopologue).
+    the isotopologue table give the shim), with two more entries ``(..., Hitran isotopologue ratio, Q(296 K))`` for
+    ``line_strength_option="S"`` (the reference's default: the Einstein coefficient from the line strength, ``line::hitran_a``).
+    Returns a ``HostCatalog`` (one band per isotopologue).
 
     Records below ``frequency_range[0]`` are skipped and reading stops at the first one above ``frequency_range[1]``
-    (src/core/lbl/lbl_hitran.cpp:146-172).  Quantum-number columns, the ``S`` line-strength option and Zeeman
-    parameters are outside this loader.
+    (src/core/lbl/lbl_hitran.cpp:146-172).  Quantum-number columns and Zeeman parameters are outside this loader.
     """
     if tuple(file_formatter) != ("par",):
         raise Ab200Error(abi.ERR_UNSUPPORTED if hasattr(abi, "ERR_UNSUPPORTED") else 2,
                          "only file_formatter = ['par'] is on this path (no quantum-number columns)")
-    if line_strength_option != "A" or compute_zeeman_parameters:
-        raise Ab200Error(2, "only line_strength_option = 'A' without Zeeman parameters is on this path")
+    if line_strength_option not in ("A", "S") or compute_zeeman_parameters:
+        raise Ab200Error(2, "line_strength_option must be 'S' or 'A', and Zeeman parameters are outside this loader")
+    opt = 0 if line_strength_option == "S" else 1  # AB200_HITRAN_STRENGTH_S / _A
     tab = (abi.HitranIsotopologue * len(isotopologues))()
-    for k, (M, I, sp, mass) in enumerate(isotopologues):
+    for k, row in enumerate(isotopologues):
+        M, I, sp, mass = row[:4]
         tab[k].M, tab[k].I, tab[k].species, tab[k].mass = int(M), str(I).encode()[:1], int(sp), float(mass)
+        if len(row) > 4:  # (..., hitran isotopologue ratio, Q(296 K)) for line_strength_option = "S"
+            tab[k].hitran_ratio, tab[k].Q296 = float(row[4]), float(row[5])
     ns = int(n_species) if n_species is not None else 1 + max(int(i[2]) for i in isotopologues)
     h = C.c_void_p()
     if text is not None:
         raw = text.encode() if isinstance(text, str) else bytes(text)
-        check(lib().ab200_hitran_read_par(raw, len(raw), float(frequency_range[0]), float(frequency_range[1]), tab,
+        check(lib().ab200_hitran_read_par(raw, len(raw), float(frequency_range[0]), float(frequency_range[1]), opt, tab,
                                           len(isotopologues), ns, int(n_threads), C.byref(h)))
     else:
-        check(lib().ab200_hitran_read_par_file(str(file).encode(), float(frequency_range[0]), float(frequency_range[1]), tab,
+        check(lib().ab200_hitran_read_par_file(str(file).encode(), float(frequency_range[0]), float(frequency_range[1]), opt, tab,
                                                len(isotopologues), ns, int(n_threads), C.byref(h)))
     try:
         return _host_catalog_from_desc(lib().ab200_hitran_desc(h).contents)

@@ -373,7 +373,7 @@ int ab200_path_add_predefined(ab200_path *p, const int32_t *models, int32_t n_mo
                               const double *target_d);
 
 /* ---- catalog ingest: HITRAN .par records straight into the SoA of ab200_catalog_desc -------------
- * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], line_strength_option = "A",
+ * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], either line_strength_option,
  * compute_zeeman_parameters = 0: read_par_line (src/core/lbl/lbl_hitran.cpp:66-89, the 160-column record and its unit
  * conversions), read_hitran_par (:146-172: records below frequency_range[0] are skipped, reading stops at the first
  * one above frequency_range[1]) and hitran_record::from (:180-237: T0 = 296 K, G0 = T1(gamma, n) for the line's own
@@ -385,12 +385,18 @@ typedef struct ab200_hitran_isotopologue {
   char I;          /* HITRAN isotopologue character (column 3) */
   int32_t species; /* the caller's species index of this isotopologue (Hitran::id_from_lookup + SpeciesEnum) */
   double mass;     /* g/mol */
+  double hitran_ratio; /* Hitran::isotopologue_ratios()[isot]; used by AB200_HITRAN_STRENGTH_S only */
+  double Q296;         /* PartitionFunctions::Q(296, isot);    used by AB200_HITRAN_STRENGTH_S only */
 } ab200_hitran_isotopologue;
+/* HitranLineStrengthOption: S (the reference's default) turns the record's line strength into the Einstein coefficient,
+ * a = einstein_a(S / ratio, gu, e0, f0, 296 K, Q(296)) (line::hitran_a lbl_data.cpp:155-169, einstein_a :34-40;
+ * g_upp == 0 becomes gu = gl = -1, lbl_hitran.cpp:193-200); A takes the file's own coefficient */
+enum { AB200_HITRAN_STRENGTH_S = 0, AB200_HITRAN_STRENGTH_A = 1 };
 typedef struct ab200_hitran_catalog ab200_hitran_catalog; /* owns the arrays the description points to */
-int ab200_hitran_read_par(const char *text, int64_t len, double fmin, double fmax,
+int ab200_hitran_read_par(const char *text, int64_t len, double fmin, double fmax, int32_t line_strength_option,
                           const ab200_hitran_isotopologue *isotopologues, int32_t n_isot, int32_t n_species,
                           int32_t n_threads, ab200_hitran_catalog **out);
-int ab200_hitran_read_par_file(const char *filename, double fmin, double fmax,
+int ab200_hitran_read_par_file(const char *filename, double fmin, double fmax, int32_t line_strength_option,
                                const ab200_hitran_isotopologue *isotopologues, int32_t n_isot, int32_t n_species,
                                int32_t n_threads, ab200_hitran_catalog **out);
 /* the description to hand to ab200_catalog_create (valid until ab200_hitran_destroy) */

@@ -11,15 +11,21 @@ int main(void) {
   const char *rec =
       " 11    0.072049 1.875E-30 4.668E-12.09460.391 1922.82890.730.002760          0 1 0          0 1 0  4  2  2        5  "
       "1  5      534253807294713152     9.0   11.0\n";
-  ab200_hitran_isotopologue tab[1] = {{1, '1', 0, 18.010565}};
+  ab200_hitran_isotopologue tab[1] = {{1, '1', 0, 18.010565, 0.997317, 174.58}};
   ab200_hitran_catalog *h = NULL;
-  int rc = ab200_hitran_read_par(rec, (int64_t)strlen(rec), -INFINITY, INFINITY, tab, 1, 1, 1, &h);
+  int rc = ab200_hitran_read_par(rec, (int64_t)strlen(rec), -INFINITY, INFINITY, AB200_HITRAN_STRENGTH_A, tab, 1, 1, 1, &h);
   if (rc != AB200_OK) { printf("read_par failed: %s\n", ab200_last_error()); return 1; }
   const ab200_catalog_desc *d = ab200_hitran_desc(h);
   if (d->n_lines != 1 || d->n_bands != 1 || fabs(d->f0[0] - 2.15997e9) > 1e5 || d->gu[0] != 9.0) { printf("bad record\n"); return 2; }
   ab200_hitran_destroy(h);
+  /* the reference's default option: the Einstein coefficient from the line strength column, within 2e-4 of the file's own */
+  rc = ab200_hitran_read_par(rec, (int64_t)strlen(rec), -INFINITY, INFINITY, AB200_HITRAN_STRENGTH_S, tab, 1, 1, 1, &h);
+  if (rc != AB200_OK) { printf("read_par S failed: %s\n", ab200_last_error()); return 1; }
+  d = ab200_hitran_desc(h);
+  if (fabs(d->a[0] / 4.668e-12 - 1.0) > 1e-3) { printf("bad Einstein coefficient from S: %g\n", d->a[0]); return 2; }
+  ab200_hitran_destroy(h);
 
-  rc = ab200_hitran_read_par("xx\n", 3, -INFINITY, INFINITY, tab, 1, 1, 1, &h);
+  rc = ab200_hitran_read_par("xx\n", 3, -INFINITY, INFINITY, AB200_HITRAN_STRENGTH_A, tab, 1, 1, 1, &h);
   if (rc != AB200_ERR_INVALID || !strstr(ab200_last_error(), "Unexpected end of string")) { printf("error path: %d %s\n", rc, ab200_last_error()); return 3; }
 
   const double grid[3] = {100.0, 200.0, 300.0}, q[3] = {10.0, 30.0, 60.0}, T[2] = {150.0, 250.0};

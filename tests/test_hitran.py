@@ -12,7 +12,15 @@ from arts_b200 import wsm
 from tests import hitran_ref
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TABLE = [(1, "1", 0, 18.010565), (1, "2", 0, 20.014811), (2, "1", 1, 43.98983), (7, "1", 2, 31.98983), (7, "A", 2, 35.0)]
+# (M, I, species, mass, HITRAN isotopologue ratio, Q(296 K)); the last two only matter for line_strength_option = "S"
+TABLE = [(1, "1", 0, 18.010565, 0.997317, 174.58), (1, "2", 0, 20.014811, 1.99983e-3, 176.05), (2, "1", 1, 43.98983, 0.984204, 286.09),
+         (7, "1", 2, 31.98983, 0.995262, 215.73), (7, "A", 2, 35.0, 1e-3, 500.0)]
+
+
+def _read(*a, **k):
+    """The loader with line_strength_option = "A" (the file's own Einstein coefficient) unless a test says otherwise."""
+    k.setdefault("line_strength_option", "A")
+    return wsm.abs_bandsReadHITRAN(*a, **k)
 
 
 def _record(M, I, nu, S, A, ga, gs, E, n, d, gu, gl, filler=None):
@@ -71,7 +79,7 @@ def test_reference_fixture_single_line():
     """The reference's fixture: the 2.16 GHz H2O line, read column by column."""
     g = json.load(open(os.path.join(HERE, "golden", "hitran_single_line.json")))
     col = g["columns"]
-    cat = wsm.abs_bandsReadHITRAN(text=g["record"] + "\n", isotopologues=TABLE)
+    cat = _read(text=g["record"] + "\n", isotopologues=TABLE)
     c100 = 100 * 299792458.0
     assert len(cat.f0) == 1 and cat.band_isot[0] == 0 and cat.isot_species[0] == 0
     assert cat.f0[0] == col["nu_cm-1"] * c100
@@ -85,7 +93,7 @@ def test_reference_fixture_single_line():
     _compare(cat, ref)
     # with the quantum-number tail the record is longer than the `par` format: the reference's error
     with pytest.raises(wsm.Ab200Error, match="Part of the line was not parsed"):
-        wsm.abs_bandsReadHITRAN(text=g["record"] + ",ElecStateLabel=X\n", isotopologues=TABLE)
+        _read(text=g["record"] + ",ElecStateLabel=X\n", isotopologues=TABLE)
 
 
 @pytest.mark.parametrize("threads", [1, 3, 0])
@@ -93,14 +101,14 @@ def test_synthetic_file_matches_restatement(threads, tmp_path):
     text = _synthetic_file()
     for (fmin, fmax) in ((-np.inf, np.inf), (3e12, 6e13), (5e13, 5.0001e13), (2e14, 3e14)):
         ref = hitran_ref.read_par(text, fmin, fmax, TABLE)
-        cat = wsm.abs_bandsReadHITRAN(text=text, frequency_range=(fmin, fmax), isotopologues=TABLE, n_threads=threads)
+        cat = _read(text=text, frequency_range=(fmin, fmax), isotopologues=TABLE, n_threads=threads)
         _compare(cat, ref)
     path = tmp_path / "lines.par"
     path.write_text(text)
-    cat_f = wsm.abs_bandsReadHITRAN(file=str(path), isotopologues=TABLE, n_threads=threads)
+    cat_f = _read(file=str(path), isotopologues=TABLE, n_threads=threads)
     _compare(cat_f, hitran_ref.read_par(text, -np.inf, np.inf, TABLE))
     # no trailing newline
-    _compare(wsm.abs_bandsReadHITRAN(text=text[:-1], isotopologues=TABLE), hitran_ref.read_par(text[:-1], -np.inf, np.inf, TABLE))
+    _compare(_read(text=text[:-1], isotopologues=TABLE), hitran_ref.read_par(text[:-1], -np.inf, np.inf, TABLE))
 
 
 def test_error_behaviour_follows_the_reference():
@@ -117,22 +125,22 @@ def test_error_behaviour_follows_the_reference():
     for name, (bad, msg) in cases.items():
         text = good + "\n" + bad + "\n" + good + "\n"
         with pytest.raises(wsm.Ab200Error, match=msg):
-            wsm.abs_bandsReadHITRAN(text=text, isotopologues=TABLE)
+            _read(text=text, isotopologues=TABLE)
         with pytest.raises(hitran_ref.HitranError):
             hitran_ref.read_par(text, -np.inf, np.inf, TABLE)
         # the same record below the window is never looked at beyond its frequency (:72-73) ...
         if name not in ("short record", "blank line", "carriage return"):
-            cat = wsm.abs_bandsReadHITRAN(text=text, frequency_range=(kay(100.5), np.inf), isotopologues=TABLE)
+            cat = _read(text=text, frequency_range=(kay(100.5), np.inf), isotopologues=TABLE)
             assert len(cat.f0) == 0
         # ... and one after the first record above the window is never read (:163-166)
         text2 = good + "\n" + above + "\n" + bad + "\n"
-        cat = wsm.abs_bandsReadHITRAN(text=text2, frequency_range=(-np.inf, kay(2000.0)), isotopologues=TABLE)
+        cat = _read(text=text2, frequency_range=(-np.inf, kay(2000.0)), isotopologues=TABLE)
         assert len(cat.f0) == 1
         assert len(hitran_ref.read_par(text2, -np.inf, kay(2000.0), TABLE)) == 1
     with pytest.raises(wsm.Ab200Error, match="Cannot open file"):
-        wsm.abs_bandsReadHITRAN(file="/nonexistent/lines.par", isotopologues=TABLE)
+        _read(file="/nonexistent/lines.par", isotopologues=TABLE)
     with pytest.raises(wsm.Ab200Error):
-        wsm.abs_bandsReadHITRAN(text=good + "\n", isotopologues=TABLE, file_formatter=("par", "statep", "statepp"))
+        _read(text=good + "\n", isotopologues=TABLE, file_formatter=("par", "statep", "statepp"))
 
 
 def kay(x):
@@ -143,7 +151,7 @@ def kay(x):
 def test_hitran_catalog_through_the_gpu_path(orc):
     """The loaded SoA is what ab200_catalog_create consumes: propagation matrix against the oracle on the same arrays."""
     text = _synthetic_file(n=800, seed=9)
-    cat = wsm.abs_bandsReadHITRAN(text=text, frequency_range=(kay(500.0), kay(900.0)), isotopologues=TABLE)
+    cat = _read(text=text, frequency_range=(kay(500.0), kay(900.0)), isotopologues=TABLE)
     assert 50 < len(cat.f0) < 400
     cat.a *= 1e-3
     nlev = 3
@@ -217,3 +225,31 @@ def test_partition_function_tables():
     assert (Q[:, 2] == 42.0).all() and not dQ[:, 2].any()
     with pytest.raises(wsm.Ab200Error, match="Temperature grid must be increasing"):
         wsm.partition_functions([("interp", grid[::-1], qv)], T)
+
+
+def test_line_strength_option_S_is_the_default_and_matches_the_file(tmp_path):
+    """HitranLineStrengthOption::S (the reference's default, src/workspace_methods.cpp:3278): the Einstein coefficient
+    comes from the line-strength column, a = einstein_a(S / ratio, gu, e0, f0, 296 K, Q(296)) (line::hitran_a,
+    lbl_data.cpp:34-40,155-169).  Bit for bit against the Python restatement; on the reference's fixture record the
+    result reproduces the file's own A column (HITRAN computes one from the other) within 2e-4; g_upp = 0 -> gu = gl = -1."""
+    g = json.load(open(os.path.join(HERE, "golden", "hitran_single_line.json")))
+    text = g["record"] + "\n"
+    cat = wsm.abs_bandsReadHITRAN(text=text, isotopologues=TABLE)  # default option
+    ref = hitran_ref.read_par(text, -np.inf, np.inf, TABLE, option="S")
+    assert cat.a[0] == ref[0]["a"]
+    assert cat.a[0] == pytest.approx(g["columns"]["A_s-1"], rel=2e-4)
+    cat_a = _read(text=text, isotopologues=TABLE)
+    assert cat_a.a[0] == g["columns"]["A_s-1"] and cat_a.f0[0] == cat.f0[0] and cat_a.e0[0] == cat.e0[0]
+    rng = np.random.default_rng(9)
+    lines = []
+    for i in range(200):
+        M, I = [(1, "1"), (1, "2"), (2, "1"), (7, "1")][i % 4]
+        lines.append(_record(M, I, 10.0 + 5.0 * i, float(10 ** rng.uniform(-28, -20)), float(10 ** rng.uniform(-8, 0)), 0.07, 0.3,
+                             float(rng.uniform(0, 3000)), 0.7, -0.002, 0.0 if i % 50 == 7 else float(2 * (i % 9) + 1), 3.0))
+    text = "\n".join(lines) + "\n"
+    cat = wsm.abs_bandsReadHITRAN(text=text, isotopologues=TABLE, n_threads=3)
+    ref = hitran_ref.read_par(text, -np.inf, np.inf, TABLE, option="S")
+    _compare(cat, ref)
+    assert (cat.gu == -1.0).sum() == 4 and (cat.gl[cat.gu == -1.0] == -1.0).all()
+    with pytest.raises(wsm.Ab200Error):  # option S without the two extra table entries
+        wsm.abs_bandsReadHITRAN(text=text, isotopologues=[t[:4] for t in TABLE])

@@ -860,12 +860,14 @@ void* ab200_path_device_ptr(ab200_path* p, int which) {
 // host-buffer entry points (what the WSM shims call)
 // ---------------------------------------------------------------------------
 namespace {
-std::atomic<uint64_t> g_serial{0};
 struct PathCache {
   ab200_path* path = nullptr;
   const ab200_catalog* cat = nullptr;
+  uint64_t serial = 0;  // of the catalog the workspace was sized for: an address can be reused by a later catalog
   int64_t nf = -1, ntiles = -1;
   int32_t np = -1, nq = -1;
+  int32_t n_species = -1, n_isot = -1;
+  size_t nseg = 0;
 };
 thread_local PathCache t_cache;
 thread_local bool t_stream_set = false;
@@ -875,7 +877,8 @@ thread_local void* t_stream = nullptr;
 // shapes (once per (pos, los) under measurement_vecFromSensor, src/m_rad.cc:321-343)
 int cached_path(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab200_path** out) {
   PathCache& c = t_cache;
-  if (c.path && c.cat == cat && c.nf == nf && c.np == np && c.nq == nq && c.ntiles == cat->ntiles) {
+  if (c.path && c.cat == cat && c.serial == cat->serial && c.nf == nf && c.np == np && c.nq == nq && c.ntiles == cat->ntiles &&
+      c.n_species == cat->n_species && c.n_isot == cat->n_isot && c.nseg == cat->segments.size()) {
     *out = c.path;
     if (t_stream_set && c.path->stream != static_cast<cudaStream_t>(t_stream)) AB_TRY(ab200_path_set_stream(c.path, t_stream));
     return AB200_OK;
@@ -885,7 +888,7 @@ int cached_path(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab
     c.path = nullptr;
   }
   AB_TRY(ab200_path_create(cat, nf, np, nq, out));
-  c = PathCache{*out, cat, nf, cat->ntiles, np, nq};
+  c = PathCache{*out, cat, cat->serial, nf, cat->ntiles, np, nq, cat->n_species, cat->n_isot, cat->segments.size()};
   if (t_stream_set) AB_TRY(ab200_path_set_stream(*out, t_stream));
   return AB200_OK;
 }

@@ -7,6 +7,7 @@
 // coefficients) is done once here; what depends on the atmosphere is left to the prepare
 // kernel (lbl.cu).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <numeric>
 
@@ -245,6 +246,8 @@ extern "C" int ab200_catalog_create(const ab200_catalog_desc* d, ab200_catalog**
   }
 
   auto cat = new ab200_catalog();
+  static std::atomic<uint64_t> next_serial{1};
+  cat->serial = next_serial.fetch_add(1);
   cudaError_t e = cudaGetDevice(&cat->device);
   if (e != cudaSuccess) {
     delete cat;

@@ -44,6 +44,7 @@ struct SegmentDev {
 
 struct ab200_catalog {
   int device = 0;
+  uint64_t serial = 0;  // unique per ab200_catalog_create: cached workspaces are keyed on it, not on the address
   int32_t n_species = 0, n_isot = 0, n_bands = 0;
   int64_t n_lines = 0, n_ls = 0;
   int64_t counts[4] = {0, 0, 0, 0};  // sub-lines per polarisation

@@ -107,7 +107,10 @@ Status parse_record(const char* p, size_t n, double fmin, int32_t strength, cons
                       {153, 7, &rec.g_low}};
   for (const Col& c : cols)
     if (!parse(p + c.off, c.len, *c.out)) return fail("Failed to parse value from string " + quoted(p + c.off, c.len));
-  if (n > 160) return fail("Part of the line was not parsed: '" + std::string(p + 160, n - 160) + "'");
+  // read_hitran_par_record skips ONE separator character after the par block (`if (not data.end_of_string()) data.skip(1)`,
+  // lbl_hitran.cpp:126) and only then reports a remainder (:133-135): a 161-byte record (CRLF files, one trailing
+  // separator) loads, from 162 bytes on the text after the separator is the error
+  if (n > 161) return fail("Part of the line was not parsed: '" + std::string(p + 161, n - 161) + "'");
   rec.gamma_air  = rec.gamma_air * kGAMMA_FACTOR;
   rec.gamma_self = rec.gamma_self * kGAMMA_FACTOR;
   rec.E          = rec.E * kE_FACTOR;

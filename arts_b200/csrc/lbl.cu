@@ -676,17 +676,13 @@ int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
   SumParams p = p_in;
   static const int skip_near = [] { const char* e = getenv("AB200_DEBUG_SKIP_NEAR"); return e ? atoi(e) : 0; }();
   p.debug_skip_near = skip_near;
-  static bool attr_set[2] = {false, false};
   if (mode == 0) {
     const size_t smem = lbl_real_smem_bytes();
     // geometry variants (R frequencies per thread, threads per CTA, line unroll); 0 is the tuned default
     static const int variant = [] { const char* e = getenv("AB200_SUM_VARIANT"); return e ? atoi(e) : 0; }();
     auto go = [&](auto kernel, int nt, int r) -> int {
-      static bool attr = false;
-      if (!attr) {
-        AB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        attr = true;
-      }
+      // per device and cheap: set before every launch (a second GPU of the same process needs its own opt-in)
+      AB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       dim3 grid(static_cast<unsigned>((p.nf + nt * r - 1) / (nt * r)), static_cast<unsigned>(nlev));
       kernel<<<grid, nt, smem, stream>>>(p);
       return 0;
@@ -712,11 +708,8 @@ int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
     static const int variant = [] { const char* e = getenv("AB200_CPLX_VARIANT"); return e ? atoi(e) : 0; }();
     dim3 grid(static_cast<unsigned>((p.nf + CPLX_F_TILE - 1) / CPLX_F_TILE), static_cast<unsigned>(nlev));
     auto go = [&](auto kernel) -> int {
-      static bool attr = false;
-      if (!attr) {
-        AB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        attr = true;
-      }
+      // per device and cheap: set before every launch (a second GPU of the same process needs its own opt-in)
+      AB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
       kernel<<<grid, CPLX_NT, smem, stream>>>(p);
       return 0;
     };

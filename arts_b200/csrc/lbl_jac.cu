@@ -679,11 +679,7 @@ int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev
 template <int NQ, bool EXT>
 static int launch_sum_jac_ne(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
   const size_t smem = size_t(JAC_BASE_FIELDS + NQ * JAC_Q_FIELDS) * TL * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_kernel<NQ, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr = true;
-  }
+  AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_kernel<NQ, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));  // per device
   lbl_sum_jac_kernel<NQ, EXT><<<grid, JAC_NT, smem, stream>>>(p, jp);
   count_launch();
   AB_CUDA(cudaGetLastError());

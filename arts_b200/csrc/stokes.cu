@@ -127,7 +127,8 @@ __device__ __forceinline__ double planck_fast(double f, double af3, double invT)
 template <int OPT, bool SCALAR>
 __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
   __shared__ __align__(128) double sK[ST_NT / 32][ST_STAGES][32 * 7];
-  __shared__ uint64_t full[ST_NT / 32][ST_STAGES];
+  __shared__ uint64_t full[ST_NT / 32][ST_STAGES];   // TMA -> the warp's lanes
+  __shared__ uint64_t empty[ST_NT / 32][ST_STAGES];  // the warp's 32 lanes -> lane 0 (consumer release)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t iv0 = int64_t(blockIdx.x) * ST_NT + warp * 32;
   if (iv0 >= p.nf) return;  // whole warp idle
@@ -137,7 +138,10 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
   constexpr uint32_t ROW_BYTES = 32 * 7 * sizeof(double);
 
   if (lane == 0) {
-    for (int s = 0; s < ST_STAGES; s++) mbar_init(&full[warp][s], 1);
+    for (int s = 0; s < ST_STAGES; s++) {
+      mbar_init(&full[warp][s], 1);
+      mbar_init(&empty[warp][s], 32);
+    }
     mbar_fence_init();
   }
   __syncwarp();
@@ -173,15 +177,14 @@ __global__ void __launch_bounds__(ST_NT) stokes_chain_kernel(StokesParams p) {
     Propmat k{};
     if (SCALAR) k.A = sK[warp][st][lane * 7];
     else k = load_propmat(&sK[warp][st][lane * 7]);
-    // Stage st may only be refilled once every lane's shared-memory loads have RETURNED: a warp barrier orders
-    // instruction issue, not the completion of LDS, and a TMA write overtaking a queued LDS was observed on B200
-    // (a few wrong lanes per 1e7 steps).  The ballot consumes the loaded registers of all lanes (scoreboard wait),
-    // and the proxy fence orders those generic-proxy reads before the async-proxy write.
-    int bits = __double2hiint(k.A);
-    if (!SCALAR) bits |= __double2hiint(k.B) | __double2hiint(k.C) | __double2hiint(k.D) | __double2hiint(k.U) |
-                         __double2hiint(k.V) | __double2hiint(k.W);
-    const unsigned landed = __ballot_sync(0xffffffffu, bits != 0x7ff00001);
-    if (lane == 0 && landed != 0u && n + ST_STAGES < np) {
+    // Stage st may only be refilled once every lane's shared-memory loads have RETURNED (a warp barrier orders
+    // instruction issue, not the completion of LDS; a TMA write overtaking a queued LDS was observed on B200).
+    // Consumer release, as in lbl_sum_real_kernel: every lane arrives on the stage's `empty` mbarrier after its loads
+    // (mbarrier.arrive has release semantics: the lane's prior reads are performed before the arrival is visible);
+    // lane 0 waits for all 32 arrivals, orders the generic-proxy reads before the async-proxy write, and refills.
+    mbar_arrive(&empty[warp][st]);
+    if (lane == 0 && n + ST_STAGES < np) {
+      mbar_wait(&empty[warp][st], (n / ST_STAGES) & 1);
       fence_proxy_async_smem();
       issue(n + ST_STAGES);
     }

@@ -4,21 +4,24 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload: BASELINE.json configs[1] ("C2"): 5 species, 1e5 synthetic Voigt lines, 100-level nadir
-path, 1e5 frequencies PER GPU (weak scaling: the N-GPU run uses an N x 1e5-point grid over the
-same 1-1000 GHz span, cut into contiguous shards like the reference's OpenMP frequency chunks),
-linsrc Stokes chain, spectral_rad gathered over NCCL.  One "step" = one pass of the hot path over
-that input: line prepare (K1) + line sum (K2/K3) + fused Stokes chain (K4-K6) + gather.
+Workload (default, `--workload c4`): BASELINE.json configs[3], the case north_star states its targets on —
+10^6 synthetic lines x 10^6 frequencies (1-100 THz) x 100 levels, no cutoff, linsrc Stokes chain — taken one
+frequency shard per GPU: every GPU owns 125 000 frequencies.  The N-GPU run covers every (8/N)-th point of the
+10^6-point grid, cut into contiguous blocks like the reference's OpenMP frequency chunks (src/m_lbl.cc:273-295),
+so N = 8 IS the 10^6 x 10^6 x 100 case and N = 1 is a uniformly strided eighth of it ("weak" scaling: the work per
+GPU is fixed).  `--workload c2` keeps round 1's configs[1] line.  One "step" = one pass of the hot path over that
+input: line prepare (K1) + line sum (K2/K3) + fused Stokes chain (K4-K6) + the NCCL gather of spectral_rad.
 
-Printed (rank 0, one JSON line): `value` = line*freq*level evaluations per second of the whole job
-with inputs resident in HBM, timed with CUDA events, max over ranks; `e2e` = the same metric
-through the reference-facing C-ABI call with HOST buffers (H2D and D2H inside the timed region);
-`roofline` for the dominant kernel (FP64-pipe bound line sum: algorithmic FLOPs of SURVEY.md 8(d)
-over the event-timed kernel duration, against the DFMA peak measured in this run);
-`roofline_stokes` (HBM bound); `cpu_baseline` = the CPU oracle (a port of the reference's path
-linked with the reference's own Faddeeva.cc) on this box's host cores on a bounded sample.
+Printed (rank 0, one JSON line): `value` = line*freq*level evaluations per second of the whole job with inputs
+resident in HBM, timed with CUDA events, max over ranks; `e2e` = the same metric through the reference-facing
+C-ABI call with HOST buffers (H2D and D2H inside the timed region); `roofline` for the dominant kernel (FP64-pipe
+bound line sum: algorithmic FLOPs of SURVEY.md 8(d) over the event-timed kernel duration, against the DFMA peak
+measured in this run); `roofline_stokes` (HBM bound); `cpu_baseline` = the CPU oracle (a port of the reference's
+path linked with the reference's own Faddeeva.cc) on this box's host cores on a bounded sample; `extra` = the
+configs[3]-ii variant (750 GHz ByLine cutoff) on the same shard.
 
-`--impl reference` times that CPU implementation alone, on the same config and metric.
+`--impl reference` times that CPU implementation alone, on the same config and metric, with ALL host cores
+(the OpenMP team is set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers).
 """
 from __future__ import annotations
 
@@ -48,30 +51,52 @@ def parse_args():
     ap.add_argument("--rte", default="linsrc", choices=["linsrc", "constant"])
     # workload size knobs (defaults = BASELINE configs[1]); smaller values are for quick checks only
     ap.add_argument("--lines-per-species", type=int, default=20_000)
-    ap.add_argument("--nf-per-gpu", type=int, default=100_000)
+    ap.add_argument("--nf-per-gpu", type=int, default=0, help="frequencies per GPU (default: 125000 for c4, 100000 for c2)")
     ap.add_argument("--levels", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of one baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"],
-                    help="c2 = BASELINE configs[1] (default, weak scaling); c4 = configs[3]: 1e6 lines x 1e6 frequencies x 100 "
-                         "levels, the frequency grid of FIXED total size sharded over the GPUs (strong scaling)")
+    ap.add_argument("--workload", default="c4", choices=["c2", "c4", "c4strong"],
+                    help="c4 (default) = BASELINE configs[3] one 125000-frequency shard per GPU (N = 8 is the full 1e6 x 1e6 x 100 "
+                         "case); c4strong = the same grid of FIXED total size --c4-nf sharded over the GPUs; c2 = configs[1]")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="OpenMP threads of the CPU arm (0 = all cores of the box)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3]-ii (750 GHz cutoff) extra measurement")
     ap.add_argument("--c4-lines", type=int, default=1_000_000)
     ap.add_argument("--c4-nf", type=int, default=1_000_000)
     ap.add_argument("--c4-cutoff-ghz", type=float, default=0.0,
                     help="configs[3] variant (ii) of SURVEY 8(d): ByLine cutoff in GHz (0 = none); the metric then counts NOMINAL pairs")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.nf_per_gpu <= 0:
+        a.nf_per_gpu = 100_000 if a.workload == "c2" else 125_000
+    return a
 
 
-def workload(args, world):
+def workload(args, world, cutoff_ghz=None):
     from arts_b200 import synth
 
-    if args.workload == "c4":
-        cut = args.c4_cutoff_ghz * 1e9 if args.c4_cutoff_ghz > 0 else None
+    cutoff_ghz = args.c4_cutoff_ghz if cutoff_ghz is None else cutoff_ghz
+    if args.workload in ("c4", "c4strong"):
+        cut = cutoff_ghz * 1e9 if cutoff_ghz > 0 else None
         case = synth.case_c4(n_lines=args.c4_lines, nf=args.c4_nf, np_=args.levels, cutoff=cut)
         case.rte_option = args.rte
-        cut_txt = "no cutoff" if cut is None else f"ByLine cutoff {args.c4_cutoff_ghz:g} GHz (value counts nominal line x frequency pairs)"
-        return case, (f"C4 (BASELINE configs[3]): {args.c4_lines} lines x {args.c4_nf} frequencies (1-100 THz, total, sharded over "
-                      f"the GPUs) x {args.levels} levels, {cut_txt}, {args.rte} Stokes chain")
+        cut_txt = "no cutoff" if cut is None else f"ByLine cutoff {cutoff_ghz:g} GHz (value counts nominal line x frequency pairs)"
+        if args.workload == "c4strong":
+            return case, (f"C4 (BASELINE configs[3]): {args.c4_lines} lines x {args.c4_nf} frequencies (1-100 THz, total, sharded over "
+                          f"the GPUs) x {args.levels} levels, {cut_txt}, {args.rte} Stokes chain")
+        # one shard of nf_per_gpu frequencies per GPU: the N-GPU run covers every (c4_nf / (N nf_per_gpu))-th grid point
+        nf_run = args.nf_per_gpu * world
+        if nf_run <= args.c4_nf and args.c4_nf % nf_run == 0:
+            stride = args.c4_nf // nf_run
+            case.f = np.ascontiguousarray(case.f[::stride])
+            case.I_bkg = np.ascontiguousarray(case.I_bkg[::stride])
+            grid_txt = (f"every {stride}-th point of the {args.c4_nf}-point 1-100 THz grid" if stride > 1
+                        else f"the whole {args.c4_nf}-point 1-100 THz grid")
+        else:
+            case.f = np.linspace(case.f[0], case.f[-1], nf_run)
+            case.I_bkg = np.zeros((nf_run, 4))
+            case.I_bkg[:, 0] = synth.planck(case.f, 288.0)
+            grid_txt = f"{nf_run} points over 1-100 THz"
+        return case, (f"C4 shard (BASELINE configs[3]: 1e6 lines x 1e6 frequencies x 100 levels over 8 GPUs): {args.c4_lines} lines x "
+                      f"{args.nf_per_gpu} frequencies per GPU ({grid_txt}) x {args.levels} levels, {cut_txt}, {args.rte} Stokes chain")
     nf = args.nf_per_gpu * world
     case = synth.case_c2(lines_per_species=args.lines_per_species, nf=nf, np_=args.levels, rte_option=args.rte)
     name = (f"C2 (BASELINE configs[1]): 5 species x {args.lines_per_species} Voigt lines, {args.levels}-level nadir path, "
@@ -141,17 +166,30 @@ def oracle_sample(case, idx, rte):
     return time.perf_counter() - t0
 
 
-def calibrate_sample(case, rte, target_s):
-    """Strided (grid-representative) frequency sample sized so that one oracle pass takes ~target_s."""
+CPU_FLAGS = ("oracle/oracle.cpp: g++ -O3 -fopenmp -ffp-contract=off, no -march=native (built in the CPU container, run on the "
+             "box); the reference's Faddeeva.cc object: -O2 -ffp-contract=off")
+
+
+def cpu_threads(args):
+    """All cores this process may use — set explicitly, whatever OMP_NUM_THREADS the launcher exported
+    (torch.distributed.run sets it to 1 for its workers)."""
     from tests import oracle_lib as orc
 
-    nthreads = orc.num_threads()
+    want = args.cpu_threads if args.cpu_threads > 0 else len(os.sched_getaffinity(0))
+    got = orc.set_num_threads(want)
+    if got != want:
+        print(f"bench.py: warning: asked the CPU arm for {want} threads, OpenMP gives {got}", file=sys.stderr)
+    return got
+
+
+def calibrate_sample(case, rte, target_s, nthreads):
+    """Strided (grid-representative) frequency sample sized so that one oracle pass takes ~target_s."""
     n0 = max(nthreads, 16)
     idx = np.linspace(0, case.nf - 1, n0).astype(np.int64)
     oracle_sample(case, idx[: max(nthreads // 2, 2)], rte)  # page in
     t = oracle_sample(case, idx, rte)
     n = int(min(case.nf, max(n0, n0 * target_s / max(t, 1e-6))))
-    return np.unique(np.linspace(0, case.nf - 1, n).astype(np.int64)), nthreads
+    return np.unique(np.linspace(0, case.nf - 1, n).astype(np.int64))
 
 
 def run_reference(args):
@@ -159,8 +197,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    case, name = workload(args, 1)
-    idx, cores = calibrate_sample(case, args.rte, args.cpu_seconds)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = cpu_threads(args)
+    case, name = workload(args, world)  # the same grid (and workload string) as the GPU arm at this N
+    idx = calibrate_sample(case, args.rte, args.cpu_seconds, cores)
     for _ in range(args.warmup):
         oracle_sample(case, idx[: max(len(idx) // 8, 1)], args.rte)
     ts = [oracle_sample(case, idx, args.rte) for _ in range(args.steps)]
@@ -172,7 +212,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count(),
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "kind": "port", "sample": sample,
+                         "build_flags": CPU_FLAGS,
                          "note": "oracle/oracle.cpp (restatement of the reference's lbl + rtepack path) linked with the "
                                  "reference's own 3rdparty/Faddeeva/Faddeeva.cc object; the reference itself needs "
                                  "GCC >= 14 and external data and cannot be built here (DESIGN.md)"},
@@ -273,12 +315,14 @@ def run_b200(args):
     except OSError:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = {}
-    try:  # per-launch DRAM bytes from the committed ncu capture of this shape (profiles/traffic.json), else null
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if tj["shape"] == {"lines": nl, "nf_per_gpu": cnt, "levels": np_}:
-            traffic = tj
-    except (OSError, KeyError, ValueError):
+    # DRAM bytes per launch cannot be counted inside an un-profiled run: they come from the committed `ncu --set full`
+    # capture of THIS shape (profiles/traffic.json lists one entry per shape, with the .ncu.txt it was read from), else null
+    traffic, traffic_src = {}, None
+    try:
+        for tj in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
+            if tj["shape"] == {"lines": nl, "nf_per_gpu": cnt, "levels": np_}:
+                traffic, traffic_src = tj, tj.get("source")
+    except (OSError, KeyError, ValueError, TypeError):
         pass
     st_bytes = roofline.stokes_bytes_per_step(np_) * cnt * np_
     st_gbs = st_bytes / (s_ms_per * 1e-3) / 1e9 if s_ms_per > 0 else 0.0
@@ -305,7 +349,7 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c4strong" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "lines": nl, "levels": np_, "nf_total": nf_total, "nf_per_gpu": cnt,
                    "sharding": "contiguous frequency blocks (matpack::omp_offset_count), catalog replicated, "
@@ -318,6 +362,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "kernel": "lbl_sum_real_kernel", "achieved": achieved_tf, "peak": dfma_tflops,
                      "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None, "traffic": traffic.get("lbl_sum_real_kernel"),
+                     "traffic_source": traffic_src, "launches_per_step": k_n / args.steps,
                      "peak_source": "DFMA loop measured in this run (ab200_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 figure",
                      "algorithmic_flop_per_eval": fl_eval, "regions": region_frac, "kernel_ms": k_ms_per,
                      "executed": {"fp64_instr_per_far_eval": 7,
@@ -337,11 +382,39 @@ def run_b200(args):
         "checksum_I": checksum,
     }
 
+    if args.workload == "c4" and args.c4_cutoff_ghz == 0 and not args.no_extra:
+        # configs[3]-ii of SURVEY 8(d): the same shard with a 750 GHz ByLine cutoff (HITRAN practice); nominal pairs counted
+        path.close()
+        cat.close()
+        case2, name2 = workload(args, world, cutoff_ghz=750.0)
+        mine2, _, cnt2 = shard.shard_case(case2, rank, world)
+        cat = wsm.Catalog(case2.cat)
+        path = wsm.Path(cat, cnt2, np_, 0, stream=stream.cuda_stream)
+        path.set_grid_bounds(np.tile([case2.f[0], case2.f[-1]], (np_, 1)))
+        path.upload(mine2.f, mine2.atm, mine2.r, mine2.I_bkg, rte_option=args.rte)
+        for _ in range(2):
+            path.run_propmat(); path.run_stokes()
+        barrier()
+        n2 = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n2):
+            path.run_propmat(); path.run_stokes()
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        ms2 = float(ms2.item())
+        line["extra"] = {"c4_cutoff750": {"workload": name2, "ms_per_step": ms2 / n2, "steps": n2,
+                                          "value": evals_per_step * n2 / (ms2 * 1e-3), "unit": UNIT + " (nominal pairs)"}}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        idx, cores = calibrate_sample(case, args.rte, args.cpu_seconds)
+        cores = cpu_threads(args)
+        idx = calibrate_sample(case, args.rte, args.cpu_seconds, cores)
         t = oracle_sample(case, idx, args.rte)
         line["cpu_baseline"] = {
-            "value": float(nl) * len(idx) * np_ / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "value": float(nl) * len(idx) * np_ / t, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
+            "build_flags": CPU_FLAGS,
             "sample": f"{len(idx)} of {nf_total} frequencies (uniform stride) x all {nl} lines x {np_} levels, {t:.1f} s"}
     if rank == 0:
         emit(line)

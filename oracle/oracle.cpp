@@ -1601,6 +1601,11 @@ extern "C" {
 
 const char* orc_last_error(void) { return g_err.c_str(); }
 int orc_num_threads(void) { return omp_get_max_threads(); }
+// bench.py's CPU arm sets the team size explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers
+int orc_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
 
 // Faddeeva::w of the reference, vectorised (lbl_lineshape_voigt_lte.cpp:239)
 int orc_faddeeva_w(int64_t n, const double* zr, const double* zi, double* wr, double* wi) {

@@ -57,7 +57,7 @@ def read_par(text, fmin, fmax, table, option="A"):
         rec = dict(isot=isot, f0=f0, a=_num(ln[25:35], float), gamma_air=_num(ln[35:40], float) * GAMMA,
                    gamma_self=_num(ln[40:45], float) * GAMMA, e0=_num(ln[45:55], float) * ENERGY, n=_num(ln[55:59], float),
                    delta=_num(ln[59:67], float) * GAMMA, gu=_num(ln[146:153], float), gl=_num(ln[153:160], float))
-        if len(ln) > 160:
+        if len(ln) > 161:  # one separator character after the par block is skipped (lbl_hitran.cpp:126), then :133-135
             raise HitranError("Part of the line was not parsed")
         import math
         if option == "S":

@@ -78,6 +78,11 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP team size of the oracle (bench.py's CPU arm: all host cores, whatever OMP_NUM_THREADS the launcher exported)."""
+    return int(lib().orc_set_num_threads(int(n)))
+
+
 def faddeeva_w(z):
     z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
     zr, zi = np.ascontiguousarray(z.real), np.ascontiguousarray(z.imag)

@@ -111,13 +111,26 @@ def test_synthetic_file_matches_restatement(threads, tmp_path):
     _compare(_read(text=text[:-1], isotopologues=TABLE), hitran_ref.read_par(text[:-1], -np.inf, np.inf, TABLE))
 
 
+def test_crlf_and_one_trailing_separator_load_like_the_reference():
+    """`if (not data.end_of_string()) data.skip(1)` (lbl_hitran.cpp:126): a 161-byte record — a CRLF file, or one trailing
+    separator — loads; only from 162 bytes on is the remainder an error (:133-135)."""
+    recs = [_record(1, "1", 100.0 + 7 * i, 1e-25, 1e-3, 0.07, 0.4, 300.0, 0.7, -0.004, 9, 11) for i in range(5)]
+    unix = "\n".join(recs) + "\n"
+    ref = hitran_ref.read_par(unix, -np.inf, np.inf, TABLE)
+    for text in ("\r\n".join(recs) + "\r\n", ",\n".join(recs) + ",\n", "\r\n".join(recs)):
+        _compare(_read(text=text, isotopologues=TABLE), ref)
+        _compare(_read(text=text, isotopologues=TABLE), hitran_ref.read_par(text, -np.inf, np.inf, TABLE))
+    with pytest.raises(wsm.Ab200Error, match="Part of the line was not parsed: 'x'"):
+        _read(text=recs[0] + ",x\n", isotopologues=TABLE)
+
+
 def test_error_behaviour_follows_the_reference():
     good = _record(1, "1", 100.0, 1e-25, 1e-3, 0.07, 0.4, 300.0, 0.7, -0.004, 9, 11)
     above = _record(1, "1", 3000.0, 1e-25, 1e-3, 0.07, 0.4, 300.0, 0.7, -0.004, 9, 11)
     cases = {
         "unknown isotopologue": (_record(9, "1", 100.0, 1e-25, 1e-3, 0.07, 0.4, 300.0, 0.7, 0.0, 9, 11), "isotopologue table"),
         "short record": (good[:120], "Unexpected end of string"),
-        "carriage return": (good + "\r", "Part of the line was not parsed"),
+        "two trailing characters": (good + " \r", "Part of the line was not parsed"),
         "garbage in a column": (good[:25] + "  1.0E-0x " + good[35:], "Failed to parse value"),
         "zero upper degeneracy": (_record(1, "1", 100.0, 1e-25, 1e-3, 0.07, 0.4, 300.0, 0.7, 0.0, 0, 11), "Invalid Einstein coefficient"),
         "blank line": ("", "Unexpected end of string"),
@@ -129,7 +142,7 @@ def test_error_behaviour_follows_the_reference():
         with pytest.raises(hitran_ref.HitranError):
             hitran_ref.read_par(text, -np.inf, np.inf, TABLE)
         # the same record below the window is never looked at beyond its frequency (:72-73) ...
-        if name not in ("short record", "blank line", "carriage return"):
+        if name not in ("short record", "blank line", "two trailing characters"):
             cat = _read(text=text, frequency_range=(kay(100.5), np.inf), isotopologues=TABLE)
             assert len(cat.f0) == 0
         # ... and one after the first record above the window is never read (:163-166)

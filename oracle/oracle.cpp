@@ -115,19 +115,25 @@ constexpr Numeric dnumber_density_dt(Numeric p, Numeric t) { return -p / (Consta
 // ---------------------------------------------------------------------------
 // Temperature models: src/core/lbl/lbl_temperature_model.h:62-314
 // ---------------------------------------------------------------------------
+// nonstd::pow, src/core/util/nonstd.h:29-33: the reference's temperature models do NOT call std::pow but
+// exp(v log x) ("factor 4 faster"); the two differ in the last bits (pinned by tests/test_refslice_pins.py)
+inline Numeric ns_pow(Numeric x, Numeric v) {
+  return std::signbit(x) ? -std::exp(v * std::log(x < 0 ? -x : x)) : std::exp(v * std::log(x));
+}
+
 Numeric tm_value(int type, const double* x, Numeric T0, Numeric T) {
   switch (type) {
     case AB200_TM_T0: return x[0];
-    case AB200_TM_T1: return x[0] * std::pow(T0 / T, x[1]);
-    case AB200_TM_T2: return x[0] * std::pow(T0 / T, x[1]) * (1 + x[2] * std::log(T / T0));
+    case AB200_TM_T1: return x[0] * ns_pow(T0 / T, x[1]);
+    case AB200_TM_T2: return x[0] * ns_pow(T0 / T, x[1]) * (1 + x[2] * std::log(T / T0));
     case AB200_TM_T3: return x[0] + x[1] * (T - T0);
-    case AB200_TM_T4: return (x[0] + x[1] * (T0 / T - 1)) * std::pow(T0 / T, x[2]);
-    case AB200_TM_T5: return x[0] * std::pow(T0 / T, 0.25 + 1.5 * x[1]);
+    case AB200_TM_T4: return (x[0] + x[1] * (T0 / T - 1)) * ns_pow(T0 / T, x[2]);
+    case AB200_TM_T5: return x[0] * ns_pow(T0 / T, 0.25 + 1.5 * x[1]);
     case AB200_TM_AER:
       if (T < 250.0) return x[0] + (T - 200.0) * (x[1] - x[0]) / (250.0 - 200.0);
       if (T > 296.0) return x[2] + (T - 296.0) * (x[3] - x[2]) / (340.0 - 296.0);
       return x[1] + (T - 250.0) * (x[2] - x[1]) / (296.0 - 250.0);
-    case AB200_TM_DPL: return x[0] * std::pow(T0 / T, x[1]) + x[2] * std::pow(T0 / T, x[3]);
+    case AB200_TM_DPL: return x[0] * ns_pow(T0 / T, x[1]) + x[2] * ns_pow(T0 / T, x[3]);
     case AB200_TM_POLY: {
       Numeric poly_fac = 1.0, poly_sum = 0.0;
       for (int i = 0; i < 4; i++) {
@@ -144,21 +150,21 @@ Numeric tm_value(int type, const double* x, Numeric T0, Numeric T) {
 Numeric tm_dT(int type, const double* x, Numeric T0, Numeric T) {
   switch (type) {
     case AB200_TM_T0: return 0;
-    case AB200_TM_T1: return -x[0] * x[1] * std::pow(T0 / T, x[1]) / T;
+    case AB200_TM_T1: return -x[0] * x[1] * ns_pow(T0 / T, x[1]) / T;
     case AB200_TM_T2:
-      return -x[0] * x[1] * std::pow(T0 / T, x[1]) * (x[2] * std::log(T / T0) + 1.) / T +
-             x[0] * x[2] * std::pow(T0 / T, x[1]) / T;
+      return -x[0] * x[1] * ns_pow(T0 / T, x[1]) * (x[2] * std::log(T / T0) + 1.) / T +
+             x[0] * x[2] * ns_pow(T0 / T, x[1]) / T;
     case AB200_TM_T3: return x[1];
     case AB200_TM_T4:
-      return -x[2] * std::pow(T0 / T, x[2]) * (x[0] + x[1] * (T0 / T - 1.)) / T -
-             T0 * x[1] * std::pow(T0 / T, x[2]) / (T * T);
-    case AB200_TM_T5: return -x[0] * std::pow(T0 / T, 1.5 * x[1] + 0.25) * (1.5 * x[1] + 0.25) / T;
+      return -x[2] * ns_pow(T0 / T, x[2]) * (x[0] + x[1] * (T0 / T - 1.)) / T -
+             T0 * x[1] * ns_pow(T0 / T, x[2]) / (T * T);
+    case AB200_TM_T5: return -x[0] * ns_pow(T0 / T, 1.5 * x[1] + 0.25) * (1.5 * x[1] + 0.25) / T;
     case AB200_TM_AER:
       if (T < 250.0) return (x[1] - x[0]) / (250.0 - 200.0);
       if (T > 296.0) return (x[3] - x[2]) / (340.0 - 296.0);
       return (x[2] - x[1]) / (296.0 - 250.0);
     case AB200_TM_DPL:
-      return -x[0] * x[1] * std::pow(T0 / T, x[1]) / T + -x[2] * x[3] * std::pow(T0 / T, x[3]) / T;
+      return -x[0] * x[1] * ns_pow(T0 / T, x[1]) / T + -x[2] * x[3] * ns_pow(T0 / T, x[3]) / T;
     case AB200_TM_POLY: {
       Numeric poly_fac = 1.0, poly_sum = 0.0;
       for (int i = 1; i < 4; ++i) {
@@ -264,7 +270,7 @@ bool wind_factor(const AtmPt& atm, Numeric& fac, Numeric* jac = nullptr) {
 // does not have give 0, the EMPTY overloads :37-60)
 Numeric tm_dX(int type, int k, const double* x, Numeric T0, Numeric T) {
   using std::log;
-  using std::pow;
+  const auto pow = [](Numeric x, Numeric v) { return ns_pow(x, v); };  // nonstd::pow, as the reference
   switch (type) {
     case AB200_TM_T0: return k == 0 ? 1 : 0;
     case AB200_TM_T1:
@@ -1111,10 +1117,12 @@ inline muelmat operator*(const muelmat& a, const muelmat& b) {  // rtepack_muell
                        a.m[4 * i + 3] * b.m[12 + j];
   return o;
 }
-inline muelmat operator*(muelmat a, Numeric s) {
-  for (auto& x : a.m) x *= s;
-  return a;
-}
+// muelmat * Numeric, rtepack_mueller_matrix.h:190-193 -> `a *= b`.  muelmat declares operator*=(const muelmat&)
+// (:101), which HIDES the element-wise operator*= of its cdata_t base, so the scalar is converted to b*I by the
+// diagonal constructor (:13-14) and the full 4x4 product runs.  Same value for finite input; the sign of a zero
+// entry (x*b + y*0 + z*0 + w*0 is +0 where x*b is -0) and NaN/Inf propagation differ from an element-wise scaling.
+// Found by the bitwise pin against the sliced reference code (tests/test_refslice_pins.py).
+inline muelmat operator*(muelmat a, Numeric s) { return a * muelmat(s); }
 inline muelmat operator*(Numeric s, muelmat a) { return a * s; }
 inline muelmat operator+(muelmat a, const muelmat& b) {
   for (int i = 0; i < 16; i++) a.m[i] += b.m[i];
@@ -2506,6 +2514,82 @@ int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, doubl
   const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};
   store(T, ts());
   if (L) store(L, ts.linsrc());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Unit-level views of stage 1 for tests/test_refslice_pins.py: the same numbers the pipeline above uses,
+// exposed so that they can be compared BITWISE with the reference's own function bodies compiled from
+// /root/reference (oracle/slice_ref.py -> oracle/_ref/librefslice.so).
+// ---------------------------------------------------------------------------
+int orc_tmodel(int type, const double* x, double T0, double T, double* val, double* dT) {
+  *val = tm_value(type, x, T0, T);
+  *dT  = tm_dT(type, x, T0, T);
+  return 0;
+}
+
+// One catalog line at one path level: mix[15] = G0, D0, DV, G, Y, then their d/dT, then their d/dVMR(target_species);
+// zee[2] = Splitting, Strength of component (pol, iz) (0, 1 for pol = POL_NO); shape[5] = f0, inv_gd, z_imag, Re s, Im s
+// built as band_shape_helper does (mode 0 / 1: single_shape_builder, inv_gd from the unsplit centre) or as the
+// single_shape constructor does (mode 2: inv_gd from the split centre, lbl_lineshape_voigt_lte.cpp:226-237);
+// ds[4] = dline_strength_calc_dT, dline_strength_calc_dVMR(target_species) at that shape's inv_gd and f0.
+int orc_line_level(const ab200_catalog_desc* d, const ab200_atm_path* atm_path, int32_t ip, int64_t il, int32_t pol, int32_t iz,
+                   int32_t target_species, int32_t mode, double* mix, double* zee, double* shape, double* ds) {
+  const AtmPt atm = atm_at(*d, *atm_path, ip);
+  const LineView ln{*d, il};
+  int ib = 0;
+  while (ib + 1 < d->n_bands and d->band_offset[ib + 1] <= il) ib++;
+  const int isot = d->band_isot[ib];
+  const int spec = d->isot_species[isot];
+  static const int vars[5] = {AB200_VAR_G0, AB200_VAR_D0, AB200_VAR_DV, AB200_VAR_G, AB200_VAR_Y};
+  for (int k = 0; k < 5; k++) {
+    mix[k]      = ln.mix(vars[k], atm);
+    mix[5 + k]  = ln.mix(vars[k], atm, true);
+    mix[10 + k] = ln.dmix_dVMR(vars[k], atm, target_species);
+  }
+  const ZeemanView z{d->z_on[il] != 0, d->z_gu[il], d->z_gl[il], d->two_Ju[il], d->two_Jl[il]};
+  const Pol p = static_cast<Pol>(pol);
+  zee[0]      = z.Splitting(p, iz);
+  zee[1]      = z.Strength(p, iz);
+  const Numeric H              = std::hypot(atm.mag[0], atm.mag[1], atm.mag[2]);
+  const Numeric f0             = line_center_calc(ln, atm);
+  const Numeric scaled_gd_part = std::sqrt(Constant::doppler_broadening_const_squared * atm.T / d->isot_mass[isot]);
+  const Numeric G0             = ln.mix(AB200_VAR_G0, atm);
+  single_shape s;
+  if (mode == 0) {
+    s.f0     = f0;
+    s.inv_gd = 1.0 / (scaled_gd_part * f0);
+    s.z_imag = G0 * s.inv_gd;
+    s.s      = line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+  } else if (mode == 1) {
+    s.f0     = f0 + H * zee[0];
+    s.inv_gd = 1.0 / (scaled_gd_part * f0);
+    s.z_imag = G0 * s.inv_gd;
+    s.s      = zee[1] * line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+  } else {
+    s.f0     = f0 + H * zee[0];
+    s.inv_gd = 1.0 / (std::sqrt(Constant::doppler_broadening_const_squared * atm.T / d->isot_mass[isot]) * s.f0);
+    s.z_imag = G0 * s.inv_gd;
+    s.s      = zee[1] * line_strength_calc(s.inv_gd, isot, spec, ln, atm);
+  }
+  shape[0] = s.f0, shape[1] = s.inv_gd, shape[2] = s.z_imag, shape[3] = s.s.real(), shape[4] = s.s.imag();
+  const Complex dT = dline_strength_calc_dT(s.inv_gd, s.f0, isot, spec, ln, atm);
+  const Complex dV = dline_strength_calc_dVMR(s.inv_gd, s.f0, isot, spec, target_species, ln, atm);
+  ds[0] = dT.real(), ds[1] = dT.imag(), ds[2] = dV.real(), ds[3] = dV.imag();
+  return 0;
+}
+
+// single_shape at n frequencies: out[i] = {Re, Im of s F(f); Re, Im of dF(f); Re, Im of dX(ds, dz, dz_fac, f)}
+int orc_shape_eval(const double* shape, const double* dsdz, int64_t n, const double* f, double* out) {
+  single_shape s;
+  s.f0 = shape[0], s.inv_gd = shape[1], s.z_imag = shape[2], s.s = Complex{shape[3], shape[4]};
+  const Complex ds{dsdz[0], dsdz[1]}, dz{dsdz[2], dsdz[3]};
+  for (int64_t i = 0; i < n; i++) {
+    const Complex z_ = s.z(f[i]);
+    const Complex v = s(f[i]), dd = single_shape::dF(z_, single_shape::F(z_)), t = s.dX(ds, dz, dsdz[4], f[i]);
+    out[6 * i + 0] = v.real(), out[6 * i + 1] = v.imag(), out[6 * i + 2] = dd.real(), out[6 * i + 3] = dd.imag();
+    out[6 * i + 4] = t.real(), out[6 * i + 5] = t.imag();
+  }
   return 0;
 }
 

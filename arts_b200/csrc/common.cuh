@@ -49,7 +49,7 @@ constexpr int REC_DOUBLES = REC_GROUP * N_GROUPS;
 constexpr size_t tile_doubles() { return size_t(TL) * REC_DOUBLES; }
 
 // tile summary written by the prepare kernel: f0'min, f0'max, min igd, min y | min cutoff, max cutoff,
-// sum of the cutoff values ls(f0' + cutoff) (real part), unused — over the contributing lines of the tile
+// sum of the cutoff values ls(f0' + cutoff) (real part), max igd — over the contributing lines of the tile
 constexpr int SUMMARY_DOUBLES = 8;
 
 // far-wing boundary of the reference's Faddeeva: x + |y| > 4000 -> nu <= 2 closed form

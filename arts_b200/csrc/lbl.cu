@@ -153,37 +153,38 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
   // tile summary over contributing lines: min/max f0', min igd, min y; min/max cutoff, sum of the cutoff values
   // (summed in line order, like the per-pair loop of the real kernel does: bit-identical when every line is in window)
   double v_min = real_line ? f0s : DBL_MAX, v_max = real_line ? f0s : -DBL_MAX;
-  double v_igd = real_line ? igd : DBL_MAX, v_y = real_line ? y : DBL_MAX;
+  double v_igd = real_line ? igd : DBL_MAX, v_y = real_line ? y : DBL_MAX, v_igx = real_line ? igd : 0.0;
   double v_cmin = real_line ? fmin(v_cut, DBL_MAX) : DBL_MAX, v_cmax = real_line ? fmin(v_cut, DBL_MAX) : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     v_min  = fmin(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
     v_max  = fmax(v_max, __shfl_xor_sync(0xffffffffu, v_max, o));
     v_igd  = fmin(v_igd, __shfl_xor_sync(0xffffffffu, v_igd, o));
+    v_igx  = fmax(v_igx, __shfl_xor_sync(0xffffffffu, v_igx, o));
     v_y    = fmin(v_y, __shfl_xor_sync(0xffffffffu, v_y, o));
     v_cmin = fmin(v_cmin, __shfl_xor_sync(0xffffffffu, v_cmin, o));
     v_cmax = fmax(v_cmax, __shfl_xor_sync(0xffffffffu, v_cmax, o));
   }
-  __shared__ double red[TL / 32][6];
+  __shared__ double red[TL / 32][7];
   __shared__ double cutvals[TL];
   cutvals[lane] = v_cutval;
   if ((lane & 31) == 0) {
     double* r = red[lane >> 5];
-    r[0] = v_min; r[1] = v_max; r[2] = v_igd; r[3] = v_y; r[4] = v_cmin; r[5] = v_cmax;
+    r[0] = v_min; r[1] = v_max; r[2] = v_igd; r[3] = v_y; r[4] = v_cmin; r[5] = v_cmax; r[6] = v_igx;
   }
   __syncthreads();
   if (lane == 0) {
     for (int w = 1; w < TL / 32; w++) {
       v_min = fmin(v_min, red[w][0]); v_max = fmax(v_max, red[w][1]);
       v_igd = fmin(v_igd, red[w][2]); v_y = fmin(v_y, red[w][3]);
-      v_cmin = fmin(v_cmin, red[w][4]); v_cmax = fmax(v_cmax, red[w][5]);
+      v_cmin = fmin(v_cmin, red[w][4]); v_cmax = fmax(v_cmax, red[w][5]); v_igx = fmax(v_igx, red[w][6]);
     }
     v_cutval = 0.0;
     if (v_cmin < DBL_MAX)
       for (int l = 0; l < TL; l++) v_cutval += cutvals[l];
     double* s = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
     s[0] = v_min; s[1] = v_max; s[2] = v_igd; s[3] = v_y;
-    s[4] = v_cmin; s[5] = v_cmax; s[6] = v_cutval; s[7] = 0.0;
+    s[4] = v_cmin; s[5] = v_cmax; s[6] = v_cutval; s[7] = v_igx;
   }
 }
 

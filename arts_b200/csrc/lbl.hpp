@@ -67,6 +67,7 @@ struct JacPrepParams {
 struct JacSumParams {
   int32_t nq, q0;
   int32_t real_lines;  // the segments of this launch are mode 0: real strengths, pol = no (closed-form far path)
+  int32_t skip_vfar;   // real lines: pairs with |x| > VFAR_LIMIT of cutoff-free tiles are summed by lbl_sum_jac_vfar_kernel
   int32_t pair_far;    // near tiles of real lines: far pairs take the closed form (AB200_JAC_PAIR_FAR=0 turns it off, debugging)
   int32_t kind[AB200_MAX_TARGETS];
   const double* jac;

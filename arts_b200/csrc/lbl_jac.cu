@@ -14,6 +14,7 @@
 // region map as the reference (far closed forms, continued fraction, series).
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 
 #include "catalog.hpp"
 #include "faddeeva.cuh"
@@ -340,6 +341,216 @@ __device__ __forceinline__ void far_pair(const FarLine& c, double x, double x2, 
   G5 = IM ? __dmul_rn(__fma_rn(Wr, Pr, __dmul_rn(Wi, Pi)), n) : 0.0;
 }
 
+// ---------------------------------------------------------------------------
+// Very far pairs of REAL lines: one rational function per pair, shared by every target.
+//
+// In line space, zeta = u + i g (u = f - f0', g = G0), zeta2 = k u + i g2 the displaced point of the reference's
+// forward difference (:250-268: dz = 1e-4 (|x|, y) component-wise, so k = 1 + 1e-4 for u > 0 and 1 - 1e-4 for u < 0;
+// g2 = GD y2), h = GD^2 / 2:
+//   F  = c z / (z^2 - 1/2)                          = c GD zeta2 / (zeta zeta2 - h (1 + dz/z))
+//   dF = -c (z z2 + 1/2) / ((z^2 - 1/2)(z2^2 - 1/2)) = -c GD^2 / (zeta zeta2 - 3 h) (1 + O(h^2 / |zeta|^4))
+// Both are written over the ONE denominator Pi = zeta zeta2 - 2 h = (k U - a0) + i c1 u (U = u^2, a0 = g g2 + 2 h,
+// c1 = g2 + k g): each then carries a relative error h / |Pi| = 1 / (2 |z|^2) <= 3.5e-9 for |x| > VFAR_LIMIT, of opposite
+// sign for F and dF.  With n = 1 / |Pi|^2 = 1 / (k^2 U^2 + b1 U + a0^2):
+//   sqrt(pi) Re F  = GD (k^2 g U + g2 a0) n,       sqrt(pi) Im F = GD u (k^2 U - k a0 + g2 c1) n
+//   sqrt(pi) Re dF = -GD^2 c1 u n,                 sqrt(pi) Im dF = -GD^2 (k U - a0) n
+// so Re(ds F + s (dz + dz_fac z) dF) of a target is (alpha_q + gamma_q u + beta_q U (+ delta_q u U)) n with per-line
+// coefficients, and the pair costs DADD u, DMUL U, 2 DFMA |Pi|^2, MUFU + 2 DFMA n, 2 DFMA for the forward shape and
+// 3 DFMA per target: 8 + 3 NQ FP64-pipe instructions (14 for T + VMR) against 35 + 4 NQ of far_pair and 7 of the
+// forward kernel.
+//
+// WHICH pairs take this form is a property of the pair alone: |x| > VFAR_LIMIT with x = fl(igd fl(f - f0')), in tiles
+// without cutoffs of real-line segments.  lbl_sum_jac_vfar_kernel sums exactly those pairs, lbl_sum_jac_kernel exactly the
+// others, so a Jacobian row at a frequency does not depend on block boundaries or on the shard the frequency fell in.
+// The tile summaries only decide how much testing a (tile, block) needs: every pair in (dist igd_min > VFAR_LIMIT: no
+// test, one sign), no pair possible (skipped), or mixed (one predicated pass per sign of u).
+// ---------------------------------------------------------------------------
+constexpr double VFAR_LIMIT = 1.2e4;
+constexpr int VF_NT = 128;
+__device__ __forceinline__ bool vfar_all(const double* __restrict__ s4, double dist) {
+  return dist > 0.0 && s4[2] * dist * (1.0 - 2e-4) > VFAR_LIMIT;
+}
+// the epilogue's frequency factors, out of line: inlined per frequency and target kind they are most of the kernel's code
+__device__ __noinline__ void vf_scales(double f, double T, double P, bool need_T, bool need_df, double& scl, double& scl_dT,
+                                       double& scl_df) {
+  scl    = line_scale_v(f, T, P);
+  scl_dT = need_T ? line_scale_dT(f, T, P) : 0.0;
+  scl_df = need_df ? line_scale_df(f, T, P) : 0.0;
+}
+constexpr int vf_stride(int nq) { return (6 + 4 * nq + 1) & ~1; }  // doubles per staged line: f0', b1, a0^2, alpha0, beta0 | 4 per target | +-igd
+
+#ifndef VF_MB4
+#define VF_MB4 4
+#endif
+#ifndef VF_MB2
+#define VF_MB2 5
+#endif
+#ifndef VF_UNROLL
+#define VF_UNROLL 1
+#endif
+template <int NQ, int R>
+__global__ void __launch_bounds__(VF_NT, (R == 4 ? VF_MB4 : VF_MB2)) lbl_sum_jac_vfar_kernel(SumParams p, JacSumParams jp) {
+  constexpr int S = vf_stride(NQ);
+  constexpr int F_TILE = VF_NT * R;
+  extern __shared__ __align__(16) double sm[];  // [TL][S]
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t fblk = int64_t(blockIdx.x) * F_TILE;
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double ffac = p.ffac[lev];
+  double f[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int64_t i = fblk + r * VF_NT + tid;
+    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
+  }
+  const double fblk_min = ffac * fg[fblk];
+  const double fblk_max = ffac * fg[(fblk + F_TILE - 1 < p.nf) ? fblk + F_TILE - 1 : p.nf - 1];
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
+  const double T = p.T[lev], P = p.P[lev];
+
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    double shape[R], acc[NQ][R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      shape[r] = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) acc[q][r] = 0.0;
+    }
+    bool any_tile = false;
+    for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
+      const double* __restrict__ s4 = summ + t * SUMMARY_DOUBLES;
+      if (s4[0] > s4[1] || s4[4] < DBL_MAX) continue;  // no contributing line | lines with cutoffs: the other kernel
+      const double dist = fmax(fblk_min - s4[1], s4[0] - fblk_max);
+      const bool all = vfar_all(s4, dist);
+      // u > 0 needs a line below a frequency of the block, u < 0 one above; |x| <= max igd * that distance
+      const bool side_pos = all ? s4[1] < fblk_min : s4[7] * (fblk_max - s4[0]) * (1.0 + 1e-9) > VFAR_LIMIT;
+      const bool side_neg = all ? s4[0] > fblk_max : s4[7] * (s4[1] - fblk_min) * (1.0 + 1e-9) > VFAR_LIMIT;
+      const int count = p.tile_count[t];
+      const double* g = prep + t * tile_doubles();
+      const double* jt = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
+#pragma unroll 1
+      for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? side_pos : side_neg)) continue;
+        any_tile = true;
+        const double sg = side == 0 ? 1.0 : -1.0;
+        const double k  = 1.0 + sg * 1e-4;
+        const double k2 = k * k;
+        __syncthreads();  // previous stage consumed
+        bool any_im = false;
+#pragma unroll 1
+        for (int l = tid; l < count; l += VF_NT) {
+          const double f0s = g[(0 * TL + l) * REC_GROUP];
+          const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
+          const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
+          double* o = sm + l * S;
+          if (m.y == 0.0) {  // inactive cutoff line / padding: contributes exactly 0, never passes the pair test
+            o[0] = 0.0; o[1] = 0.0; o[2] = 1.0;
+#pragma unroll
+            for (int j = 3; j < S; j++) o[j] = 0.0;
+            continue;
+          }
+          const double igd = m.y, GD = 1.0 / igd, y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
+          const double gg = y * GD, g2 = y2 * GD, h = 0.5 * GD * GD;
+          const double a0 = gg * g2 + 2.0 * h, c1 = g2 + k * gg;
+          const double sp = n.y * cst::inv_sqrt_pi;
+          o[0] = f0s;
+          o[1] = g2 * g2 + k2 * gg * gg - 4.0 * k * h;  // b1 = c1^2 - 2 k a0
+          o[2] = a0 * a0;
+          o[3] = sp * GD * g2 * a0;                     // alpha0
+          o[4] = sp * GD * k2 * gg;                     // beta0
+          o[5 + 4 * NQ] = sg * igd;
+          const double spG2 = sp * GD * GD;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+            const double2 u0 = j0[0], u1 = j0[1];  // ds_re, ds_im | dz_re, dz_im
+            const double dz_fac = jt[q * (2 * TL * 4) + (1 * TL + l) * 4];
+            const double dsr = u0.x * cst::inv_sqrt_pi * GD, dsi = u0.y * cst::inv_sqrt_pi * GD;
+            const double t_im = u1.y + dz_fac * y;
+            any_im |= u0.y != 0.0;
+            o[5 + 4 * q + 0] = dsr * g2 * a0 - spG2 * t_im * a0;                       // alpha
+            o[5 + 4 * q + 1] = -spG2 * u1.x * c1 - dsi * (g2 * c1 - k * a0);           // gamma
+            o[5 + 4 * q + 2] = dsr * k2 * gg + spG2 * (k * t_im - dz_fac * igd * c1);  // beta
+            o[5 + 4 * q + 3] = -dsi * k2;                                               // delta (only where Im ds != 0)
+          }
+        }
+        const bool tile_im = __syncthreads_or(any_im) != 0;
+        auto loop = [&](auto im_tag, auto test_tag) {
+          constexpr bool IM = decltype(im_tag)::value;
+          constexpr bool TEST = decltype(test_tag)::value;
+#pragma unroll VF_UNROLL
+          for (int l = 0; l < count; l++) {
+            const double* __restrict__ o = sm + l * S;
+            const double2 c01 = *reinterpret_cast<const double2*>(o), c23 = *reinterpret_cast<const double2*>(o + 2);
+            const double b0 = o[4];
+            const double sigd = TEST ? o[5 + 4 * NQ] : 0.0;
+            double cq[NQ][4];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              cq[q][0] = o[5 + 4 * q]; cq[q][1] = o[6 + 4 * q]; cq[q][2] = o[7 + 4 * q];
+              cq[q][3] = IM ? o[8 + 4 * q] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              const double u = __dsub_rn(f[r], c01.x);
+              const double U = __dmul_rn(u, u);
+              double n = far_rcp(__fma_rn(__fma_rn(k2, U, c01.y), U, c23.x));
+              if (TEST) n = __dmul_rn(sigd, u) > VFAR_LIMIT ? n : 0.0;  // the pair test: |fl(igd fl(f - f0'))| > VFAR_LIMIT
+              shape[r] = __fma_rn(__fma_rn(b0, U, c23.y), n, shape[r]);
+#pragma unroll
+              for (int q = 0; q < NQ; q++) {
+                double v = __fma_rn(cq[q][2], U, cq[q][0]);
+                if (IM) v = __fma_rn(__dmul_rn(cq[q][3], u), U, v);
+                acc[q][r] = __fma_rn(__fma_rn(cq[q][1], u, v), n, acc[q][r]);
+              }
+            }
+          }
+        };
+        if (all) {
+          if (tile_im) loop(std::true_type{}, std::false_type{});
+          else loop(std::false_type{}, std::false_type{});
+        } else {
+          if (tile_im) loop(std::true_type{}, std::true_type{});
+          else loop(std::false_type{}, std::true_type{});
+        }
+      }
+    }
+    if (!any_tile) continue;
+    // compute_derivative :1474-1481, :1553-1560 (see lbl_sum_jac_kernel's epilogue): real strengths, only Re is used
+    const double* __restrict__ npm = p.npm + (int64_t(lev) * 4 + seg.pol) * 7;
+    if (npm[0] == 0 && npm[1] == 0 && npm[2] == 0 && npm[3] == 0) continue;
+    bool need_T = false, need_df = false;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      need_T |= jp.kind[jp.q0 + q] == AB200_TARGET_T;
+      need_df |= jp.kind[jp.q0 + q] >= AB200_TARGET_WIND_U && jp.kind[jp.q0 + q] <= AB200_TARGET_WIND_W;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int64_t i = fblk + r * VF_NT + tid;
+      if (i >= p.nf) continue;
+      double scl, scl_dT, scl_df;
+      vf_scales(f[r], T, P, need_T, need_df, scl, scl_dT, scl_df);
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        double d = scl * acc[q][r];
+        const int kind = jp.kind[jp.q0 + q];
+        if (kind == AB200_TARGET_T) d += scl_dT * shape[r];
+        if (kind >= AB200_TARGET_MAG_U && kind <= AB200_TARGET_MAG_W) continue;  // pol = no: :1484-1486
+        if (kind >= AB200_TARGET_WIND_U && kind <= AB200_TARGET_WIND_W) {
+          d += scl_df * shape[r];
+          if (jp.wind_jac) d = jp.wind_jac[3 * lev + (kind - AB200_TARGET_WIND_U)] * (f[r] * d);
+        }
+        double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
+        o[0] += npm[0] * d; o[1] += npm[1] * d; o[2] += npm[2] * d; o[3] += npm[3] * d;
+      }
+    }
+  }
+}
+
 // CTAs per SM the shared-memory footprint allows: (10 + 7 NQ) x 2 KB -> 34 / 48 / 62 / 76 KB
 // EXT: the pass holds a wind or magnetic-field target (their epilogue costs the temperature / VMR passes 6 % in
 // registers and spills when it is compiled in, so those keep an instantiation without it)
@@ -409,6 +620,9 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
       const double tile_cut    = jp.real_lines ? s4[5] : cutoff;
       const bool tile_has_cut  = jp.real_lines ? s4[4] < DBL_MAX : seg.has_cutoff != 0;
       if (dist > tile_cut * (1.0 + 1e-9)) continue;
+      // pairs with |x| > VFAR_LIMIT of cutoff-free real-line tiles belong to lbl_sum_jac_vfar_kernel
+      const bool vf_pairs = jp.skip_vfar && !tile_has_cut;
+      if (vf_pairs && vfar_all(s4, fmax(fblk_min - s4[1], s4[0] - fblk_max))) continue;
       const int count = p.tile_count[t];
       // far for every pair of the tile and its displaced point (x shrinks by at most 1e-4 |x|); CTA uniform
       const bool far = !tile_has_cut && s4[2] * dist * (1.0 - 2e-4) + s4[3] > FAR_LIMIT * (1.0 + 1e-9);
@@ -515,6 +729,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
 #pragma unroll
             for (int r = 0; r < JAC_R; r++) {
               const double x  = __dmul_rn(igd, __dsub_rn(f[r], f0s));
+              if (vf_pairs && fabs(x) > VFAR_LIMIT) continue;
               const double x2 = __dadd_rn(x, fmax(__dmul_rn(1e-4, fabs(x)), 1e-4));
               double G1, G2, G3, G4, G5;
               far_pair<IM>(c, x, x2, G1, G2, G3, G4, G5);
@@ -588,6 +803,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
 #pragma unroll
         for (int r = 0; r < JAC_R; r++) {
           if (lhas && !(f0s >= f[r] - lcut && f0s <= f[r] + lcut)) continue;
+          if (vf_pairs && fabs(__dmul_rn(igd, __dsub_rn(f[r], f0s))) > VFAR_LIMIT) continue;
           if (jp.real_lines && jp.pair_far) {
             const double x  = __dmul_rn(igd, __dsub_rn(f[r], f0s));
             const double x2 = __dadd_rn(x, fmax(__dmul_rn(1e-4, fabs(x)), 1e-4));
@@ -685,6 +901,31 @@ static int launch_sum_jac_ne(const SumParams& p, const JacSumParams& jp, dim3 gr
   AB_CUDA(cudaGetLastError());
   return 0;
 }
+template <int NQ, int R>
+static int launch_sum_jac_vfar_r(const SumParams& p, const JacSumParams& jp, int nlev, cudaStream_t stream) {
+  const size_t smem = size_t(vf_stride(NQ)) * TL * sizeof(double);
+  AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_vfar_kernel<NQ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const dim3 grid(static_cast<unsigned>((p.nf + VF_NT * R - 1) / (VF_NT * R)), static_cast<unsigned>(nlev));
+  lbl_sum_jac_vfar_kernel<NQ, R><<<grid, VF_NT, smem, stream>>>(p, jp);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+// frequencies per thread: 4 (512-frequency blocks) unless the grid is so small that whole-wave quantisation costs more
+// than the shorter blocks' extra staging (one path of configs[4]: 20 x 100 blocks on 148 SMs)
+template <int NQ>
+static int launch_sum_jac_vfar(const SumParams& p, const JacSumParams& jp, int nlev, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  auto eff = [&](int r, int per_sm) {
+    const double items = double((p.nf + VF_NT * r - 1) / (VF_NT * r)) * nlev, slots = double(sms) * per_sm;
+    return items / (std::ceil(items / slots) * slots);
+  };
+  int R = eff(2, VF_MB2) > eff(4, VF_MB4) + 0.05 ? 2 : 4;
+  if (const char* e = getenv("AB200_JAC_VFAR_R")) R = atoi(e) == 2 ? 2 : 4;
+  return R == 2 ? launch_sum_jac_vfar_r<NQ, 2>(p, jp, nlev, stream) : launch_sum_jac_vfar_r<NQ, 4>(p, jp, nlev, stream);
+}
 template <int NQ>
 static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
   bool ext = false;
@@ -702,9 +943,24 @@ int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t s
   // targets per pass: JAC_Q, or AB200_JAC_PASS (1..4) for experiments
   int per_pass = JAC_Q;
   if (const char* e = getenv(jp.real_lines ? "AB200_JAC_PASS_REAL" : "AB200_JAC_PASS_CPLX")) per_pass = std::max(1, std::min(JAC_Q, atoi(e)));
+  const bool vfar_on = [] { const char* e = getenv("AB200_JAC_VFAR"); return e ? atoi(e) != 0 : true; }();
   for (int q0 = 0; q0 < jp.nq; q0 += per_pass) {
     jp.q0 = q0;
-    switch (std::min(per_pass, jp.nq - q0)) {
+    const int nq_pass = std::min(per_pass, jp.nq - q0);
+    // real lines: the very far pairs go to the one-rational-function kernel, unless the pass holds line
+    // targets only (those visit a handful of tiles and need no forward shape)
+    bool line_only = true;
+    for (int q = 0; q < nq_pass; q++) line_only &= jp.kind[q0 + q] >= AB200_TARGET_LINE_F0 && jp.kind[q0 + q] <= AB200_TARGET_LINE_LS;
+    jp.skip_vfar = (jp.real_lines && vfar_on && !line_only) ? 1 : 0;
+    if (jp.skip_vfar) {
+      switch (nq_pass) {
+        case 1: AB_TRY(launch_sum_jac_vfar<1>(p, jp, nlev, stream)); break;
+        case 2: AB_TRY(launch_sum_jac_vfar<2>(p, jp, nlev, stream)); break;
+        case 3: AB_TRY(launch_sum_jac_vfar<3>(p, jp, nlev, stream)); break;
+        default: AB_TRY(launch_sum_jac_vfar<4>(p, jp, nlev, stream)); break;
+      }
+    }
+    switch (nq_pass) {
       case 1: AB_TRY(launch_sum_jac_n<1>(p, jp, grid, stream)); break;
       case 2: AB_TRY(launch_sum_jac_n<2>(p, jp, grid, stream)); break;
       case 3: AB_TRY(launch_sum_jac_n<3>(p, jp, grid, stream)); break;

@@ -251,3 +251,39 @@ def test_isotopologue_ratio_rows(wsm, orc, cutoff):
     with pytest.raises(wsm.Ab200Error) as e:
         wsm.spectral_propmat_pathFromPath(z.cat, z.f, z.atm, jac_targets=[("isorat", 0)])
     assert e.value.code == abi.ERR_INVALID and "isotopologue ratios" in str(e.value)
+
+
+def _many_lines_case(np_=3, nf=2600):
+    """Enough lines and grid that every tile class occurs for a 512-frequency block: wholly very far (|x| > 1.2e4 for every
+    pair), mixed (the pair test decides, both signs of f - f0') and near."""
+    c = synth.case_c2(lines_per_species=900, nf=nf, np_=np_, bands_per_species=3)
+    return c
+
+
+def test_very_far_pairs_closed_form(wsm, orc):
+    """Pairs with |x| > 1.2e4 of real lines take ONE rational function shared by all targets (lbl_sum_jac_vfar_kernel):
+    truncation 1 / (2 |z|^2) <= 3.5e-9 per pair.  Against the oracle's literal forward difference, per level (the far
+    wings of the upper levels must not hide behind the line cores of the lowest one), T + own + foreign VMR + a wind row."""
+    c = _many_lines_case()
+    tg = (("T",), ("VMR", 0), ("VMR", 3), ("wind_u",))
+    c.atm.wind = np.tile(np.array([12.0, -7.0, 0.4]), (c.np_, 1))
+    c.atm.los = np.tile(np.array([137.0, 21.0]), (c.np_, 1))
+    Kr, dKr = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    K, dK = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=tg)
+    assert_propmat_close(K, Kr)
+    for q in range(len(tg)):
+        for lev in range(c.np_):
+            assert np.abs(dKr[lev, q]).max() > 0
+            assert_jac_close(dK[lev, q], dKr[lev, q], rtol=2e-8, what=f"dK target {tg[q]} level {lev}")
+
+
+def test_jacobian_rows_do_not_depend_on_the_frequency_partition(wsm):
+    """Which closed form a (line, frequency) pair takes is a property of the pair alone, so a Jacobian row at a frequency
+    has the same bits on the whole grid and on any sub-grid (shard), whatever the block boundaries."""
+    c = _many_lines_case(np_=2, nf=3000)
+    tg = (("T",), ("VMR", 1))
+    K, dK = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=tg)
+    for lo, hi in ((0, 700), (333, 1900), (1777, 3000)):
+        Ks, dKs = wsm.spectral_propmat_pathFromPath(c.cat, c.f[lo:hi], c.atm, jac_targets=tg)
+        assert np.array_equal(Ks, K[:, lo:hi]), (lo, hi)
+        assert np.array_equal(dKs, dK[:, :, lo:hi]), (lo, hi)

@@ -502,21 +502,38 @@ int ab200_path_run_propmat(ab200_path* p) {
     if (p->nq > 0) {
       JacPrepParams jp{};
       JacSumParams js{};
-      jp.nq = js.nq = p->nq;
+      // computed targets: the three magnetic-field components share one derivative record, the three wind components another
+      int nc = 0, c_mag = -1, c_wind = -1;
       for (int q = 0; q < p->nq; q++) {
-        jp.kind[q] = js.kind[q] = p->tg_kind[q];
-        jp.species[q] = p->tg_species[q];
-        jp.line[q] = p->tg_line[q]; jp.ls_var[q] = p->tg_ls_var[q]; jp.coeff[q] = p->tg_coeff[q];
-        if (p->tg_kind[q] >= AB200_TARGET_LINE_F0 && p->tg_kind[q] <= AB200_TARGET_LINE_LS)
-          std::copy_n(cat->line_tiles.data() + p->tg_line[q] * 8, 8, &js.line_tiles[q][0][0]);
+        const int kind = p->tg_kind[q];
+        const bool mag = kind >= AB200_TARGET_MAG_U && kind <= AB200_TARGET_MAG_W;
+        const bool wind = kind >= AB200_TARGET_WIND_U && kind <= AB200_TARGET_WIND_W;
+        const int comp = mag ? kind - AB200_TARGET_MAG_U : wind ? kind - AB200_TARGET_WIND_U : 0;
+        int c;
+        if (mag && c_mag >= 0 && js.out_row[c_mag][comp] < 0) c = c_mag;  // (a component asked for twice gets its own entry)
+        else if (wind && c_wind >= 0 && js.out_row[c_wind][comp] < 0) c = c_wind;
+        else {
+          c = nc++;
+          js.out_row[c][0] = js.out_row[c][1] = js.out_row[c][2] = -1;
+          jp.kind[c] = js.kind[c] = mag ? AB200_TARGET_MAG_U : wind ? AB200_TARGET_WIND_U : kind;
+          jp.species[c] = p->tg_species[q];
+          jp.line[c] = p->tg_line[q]; jp.ls_var[c] = p->tg_ls_var[q]; jp.coeff[c] = p->tg_coeff[q];
+          if (kind >= AB200_TARGET_LINE_F0 && kind <= AB200_TARGET_LINE_LS)
+            std::copy_n(cat->line_tiles.data() + p->tg_line[q] * 8, 8, &js.line_tiles[c][0][0]);
+          if (mag) c_mag = c;
+          if (wind) c_wind = c;
+        }
+        js.out_row[c][comp] = q;
       }
+      jp.nq = js.nq = nc;
+      js.nrows = p->nq;
       jp.dQdT = p->d_dQdT + static_cast<size_t>(lev0) * cat->n_isot;
       jp.jac = p->d_jac;
       jp.jcom = p->d_jcom;
       js.jac = p->d_jac;
       js.jcom = p->d_jcom;
       js.dK = p->d_dK + static_cast<size_t>(lev0) * p->nq * p->k_pitch * 7;
-      jp.mag_ratio = p->d_magr + 3 * static_cast<size_t>(lev0);
+      js.mag_ratio = p->d_magr + 3 * static_cast<size_t>(lev0);
       js.dnpm = p->d_dnpm + 84 * static_cast<size_t>(lev0);
       js.wind_jac = (p->flags & AB200_FLAG_WIND_ROWS_DF) ? nullptr : p->d_wjac + 3 * static_cast<size_t>(lev0);
       AB_TRY(launch_prepare_jac(pp, jp, nlev, p->stream));

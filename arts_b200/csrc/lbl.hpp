@@ -53,6 +53,9 @@ struct SumParams {
 };
 
 // Jacobian targets (lbl_jac.cu)
+// Jacobian targets as COMPUTED: one entry per distinct derivative record.  The three magnetic-field components are one
+// entry (kind AB200_TARGET_MAG_U) and so are the three wind components (AB200_TARGET_WIND_U); JacSumParams::out_row maps
+// an entry to the rows of the caller's dK it feeds.
 struct JacPrepParams {
   int32_t nq;
   int32_t kind[AB200_MAX_TARGETS];     // AB200_TARGET_*
@@ -62,10 +65,12 @@ struct JacPrepParams {
   const double* dQdT;                  // [nlev][n_isot], offset to the batch
   double* jac;                         // [nlev][ntiles][nq][2][TL][4]
   double* jcom;                        // [nlev][ntiles][TL]
-  const double* mag_ratio;             // [nlev][3] mag_c / |mag| of the batch's levels (magnetic-field targets)
 };
 struct JacSumParams {
-  int32_t nq, q0;
+  int32_t nq, q0;      // computed targets (stride of the derivative records), first one of this pass
+  int32_t nrows;       // rows of dK per level (the caller's targets)
+  int32_t out_row[AB200_MAX_TARGETS][3];  // computed target -> dK row; magnetic / wind entries: rows of u, v, w (-1: not requested)
+  const double* mag_ratio;  // [nlev][3] mag_c / |mag| of the batch's levels (magnetic-field targets)
   int32_t real_lines;  // the segments of this launch are mode 0: real strengths, pol = no (closed-form far path)
   int32_t skip_vfar;   // real lines: pairs with |x| > VFAR_LIMIT of cutoff-free tiles are summed by lbl_sum_jac_vfar_kernel
   int32_t pair_far;    // near tiles of real lines: far pairs take the closed form (AB200_JAC_PAIR_FAR=0 turns it off, debugging)

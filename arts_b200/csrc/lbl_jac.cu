@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_jac_kernel(PrepareParams p, Ja
         // dzq above is the whole of it (line targets, isotopologue ratio)
       } else if (jp.kind[q] >= AB200_TARGET_MAG_U) {
         const double dzc = p.sub_dzc[slot];
-        dzq = {dzc == 0.0 ? 0.0 : -igd * jp.mag_ratio[3 * lev + (jp.kind[q] - AB200_TARGET_MAG_U)] * dzc, 0.0};
+        dzq = {dzc == 0.0 ? 0.0 : -igd * dzc, 0.0};  // times mag_c / |mag| in the sum kernels' epilogue (one row for u, v, w)
       } else if (jp.kind[q] >= AB200_TARGET_WIND_U) {
         dzq = {igd, 0.0};
       }
@@ -341,6 +341,49 @@ __device__ __forceinline__ void far_pair(const FarLine& c, double x, double x2, 
   G5 = IM ? __dmul_rn(__fma_rn(Wr, Pr, __dmul_rn(Wi, Pi)), n) : 0.0;
 }
 
+// compute_derivative's last step (:1474-1561) for one computed target at one frequency: dpm += npm (.) d.  The three
+// magnetic-field components share ONE computed row (single_shape::dH with dz = -inv_gd Splitting, :305-307, :1071-1078:
+// the component only scales it by mag_c / |mag|, a per-level number) and so do the three wind components (single_shape::df,
+// :275; the component enters through freq_wind_shift_jac in spectral_propmat_jacWindFix): out_row lists the requested ones.
+__device__ __forceinline__ void jac_store_rows(const JacSumParams& jp, int cq, int kind, int lev, int pol, int64_t i, int64_t k_pitch,
+                                               const double* __restrict__ npm, double f, double scl, double scl_df, cplx shape, cplx d) {
+  const int32_t* rows = jp.out_row[cq];
+  if (kind == AB200_TARGET_MAG_U) {
+    // compute_derivative :1484-1513 with zeeman::scale(npm, dnpm, scl shape, scl dshape), lbl_zeeman.h:442-453
+    if (pol == POL_NO) return;
+    const cplx F = cscale(scl, shape);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (rows[c] < 0) continue;
+      const double* __restrict__ dn = jp.dnpm + ((int64_t(lev) * 3 + c) * 4 + pol) * 7;
+      const cplx dc = cscale(jp.mag_ratio[3 * lev + c], d);
+      double* o = jp.dK + ((int64_t(lev) * jp.nrows + rows[c]) * k_pitch + i) * 7;
+      o[0] += dn[0] * F.re + npm[0] * dc.re; o[1] += dn[1] * F.re + npm[1] * dc.re;
+      o[2] += dn[2] * F.re + npm[2] * dc.re; o[3] += dn[3] * F.re + npm[3] * dc.re;
+      o[4] += dn[4] * F.im + npm[4] * dc.im; o[5] += dn[5] * F.im + npm[5] * dc.im;
+      o[6] += dn[6] * F.im + npm[6] * dc.im;
+    }
+    return;
+  }
+  if (kind == AB200_TARGET_WIND_U) {
+    // compute_derivative :1514-1523, then spectral_propmat_jacWindFix (m_frequency_grid.cc:106-182): x * f * df_du
+    d = cadd(d, cscale(scl_df, shape));
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (rows[c] < 0) continue;
+      // wind_jac null: AB200_FLAG_WIND_ROWS_DF, the caller's agenda applies the fix
+      const cplx dc = jp.wind_jac ? cscale(jp.wind_jac[3 * lev + c], cscale(f, d)) : d;
+      double* o = jp.dK + ((int64_t(lev) * jp.nrows + rows[c]) * k_pitch + i) * 7;
+      o[0] += npm[0] * dc.re; o[1] += npm[1] * dc.re; o[2] += npm[2] * dc.re; o[3] += npm[3] * dc.re;
+      o[4] += npm[4] * dc.im; o[5] += npm[5] * dc.im; o[6] += npm[6] * dc.im;
+    }
+    return;
+  }
+  double* o = jp.dK + ((int64_t(lev) * jp.nrows + rows[0]) * k_pitch + i) * 7;
+  o[0] += npm[0] * d.re; o[1] += npm[1] * d.re; o[2] += npm[2] * d.re; o[3] += npm[3] * d.re;
+  o[4] += npm[4] * d.im; o[5] += npm[5] * d.im; o[6] += npm[6] * d.im;
+}
+
 // ---------------------------------------------------------------------------
 // Very far pairs of REAL lines: one rational function per pair, shared by every target.
 //
@@ -349,9 +392,11 @@ __device__ __forceinline__ void far_pair(const FarLine& c, double x, double x2, 
 // g2 = GD y2), h = GD^2 / 2:
 //   F  = c z / (z^2 - 1/2)                          = c GD zeta2 / (zeta zeta2 - h (1 + dz/z))
 //   dF = -c (z z2 + 1/2) / ((z^2 - 1/2)(z2^2 - 1/2)) = -c GD^2 / (zeta zeta2 - 3 h) (1 + O(h^2 / |zeta|^4))
-// Both are written over the ONE denominator Pi = zeta zeta2 - 2 h = (k U - a0) + i c1 u (U = u^2, a0 = g g2 + 2 h,
-// c1 = g2 + k g): each then carries a relative error h / |Pi| = 1 / (2 |z|^2) <= 3.5e-9 for |x| > VFAR_LIMIT, of opposite
-// sign for F and dF.  With n = 1 / |Pi|^2 = 1 / (k^2 U^2 + b1 U + a0^2):
+// Both are written over the ONE denominator Pi = zeta zeta2 - h = (k U - a0) + i c1 u (U = u^2, a0 = g g2 + h,
+// c1 = g2 + k g).  That is F itself (relative error 1e-4 h / |Pi| < 1e-12: rows that hold F only - isotopologue ratio,
+// line strength - keep the forward model's accuracy), and the forward difference dF with a relative error
+// 2 h / |Pi| = 1 / |z|^2 <= 6.9e-9 for |x| > VFAR_LIMIT - of a quantity that is itself a 1e-4 finite-difference
+// approximation of w'(z).  With n = 1 / |Pi|^2 = 1 / (k^2 U^2 + b1 U + a0^2):
 //   sqrt(pi) Re F  = GD (k^2 g U + g2 a0) n,       sqrt(pi) Im F = GD u (k^2 U - k a0 + g2 c1) n
 //   sqrt(pi) Re dF = -GD^2 c1 u n,                 sqrt(pi) Im dF = -GD^2 (k U - a0) n
 // so Re(ds F + s (dz + dz_fac z) dF) of a target is (alpha_q + gamma_q u + beta_q U (+ delta_q u U)) n with per-line
@@ -377,6 +422,11 @@ __device__ __noinline__ void vf_scales(double f, double T, double P, bool need_T
   scl_dT = need_T ? line_scale_dT(f, T, P) : 0.0;
   scl_df = need_df ? line_scale_df(f, T, P) : 0.0;
 }
+// every pair of a line with the frequencies of [fblk_min, fblk_max] passes the pair test (block-uniform shortcut)
+__device__ __forceinline__ bool line_all_vfar(double f0s, double igd, double fblk_min, double fblk_max) {
+  const double dl = fmax(fblk_min - f0s, f0s - fblk_max);
+  return dl > 0.0 && igd * dl * (1.0 - 2e-4) > VFAR_LIMIT;
+}
 constexpr int vf_stride(int nq) { return (6 + 4 * nq + 1) & ~1; }  // doubles per staged line: f0', b1, a0^2, alpha0, beta0 | 4 per target | +-igd
 
 #ifndef VF_MB4
@@ -388,11 +438,13 @@ constexpr int vf_stride(int nq) { return (6 + 4 * nq + 1) & ~1; }  // doubles pe
 #ifndef VF_UNROLL
 #define VF_UNROLL 1
 #endif
+constexpr int VF_UNROLL_N = VF_UNROLL;
 template <int NQ, int R>
 __global__ void __launch_bounds__(VF_NT, (R == 4 ? VF_MB4 : VF_MB2)) lbl_sum_jac_vfar_kernel(SumParams p, JacSumParams jp) {
   constexpr int S = vf_stride(NQ);
   constexpr int F_TILE = VF_NT * R;
   extern __shared__ __align__(16) double sm[];  // [TL][S]
+  __shared__ int wcnt[VF_NT / 32];
   const int tid = threadIdx.x;
   const int lev = blockIdx.y;
   const int64_t fblk = int64_t(blockIdx.x) * F_TILE;
@@ -438,51 +490,68 @@ __global__ void __launch_bounds__(VF_NT, (R == 4 ? VF_MB4 : VF_MB2)) lbl_sum_jac
         const double sg = side == 0 ? 1.0 : -1.0;
         const double k  = 1.0 + sg * 1e-4;
         const double k2 = k * k;
-        __syncthreads();  // previous stage consumed
+        // stage the lines of this side that can hold a very far pair in this block, in line order (in tiles that are
+        // wholly very far: every contributing line)
+        const double edge = side == 0 ? fblk_max : fblk_min;
+        int nkeep = 0;
         bool any_im = false;
+        __syncthreads();  // previous stage consumed
 #pragma unroll 1
-        for (int l = tid; l < count; l += VF_NT) {
-          const double f0s = g[(0 * TL + l) * REC_GROUP];
-          const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
-          const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
-          double* o = sm + l * S;
-          if (m.y == 0.0) {  // inactive cutoff line / padding: contributes exactly 0, never passes the pair test
-            o[0] = 0.0; o[1] = 0.0; o[2] = 1.0;
-#pragma unroll
-            for (int j = 3; j < S; j++) o[j] = 0.0;
-            continue;
+        for (int c0 = 0; c0 < count; c0 += VF_NT) {
+          const int l = c0 + tid;
+          double f0s = 0.0, igd = 0.0, y = 0.0, s_re = 0.0;
+          if (l < count) {
+            f0s = g[(0 * TL + l) * REC_GROUP];
+            const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
+            const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
+            igd = m.y; y = n.x; s_re = n.y;
           }
-          const double igd = m.y, GD = 1.0 / igd, y = n.x, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
-          const double gg = y * GD, g2 = y2 * GD, h = 0.5 * GD * GD;
-          const double a0 = gg * g2 + 2.0 * h, c1 = g2 + k * gg;
-          const double sp = n.y * cst::inv_sqrt_pi;
-          o[0] = f0s;
-          o[1] = g2 * g2 + k2 * gg * gg - 4.0 * k * h;  // b1 = c1^2 - 2 k a0
-          o[2] = a0 * a0;
-          o[3] = sp * GD * g2 * a0;                     // alpha0
-          o[4] = sp * GD * k2 * gg;                     // beta0
-          o[5 + 4 * NQ] = sg * igd;
-          const double spG2 = sp * GD * GD;
+          const bool keep = igd != 0.0 && (all || sg * igd * (edge - f0s) * (1.0 + 1e-9) > VFAR_LIMIT);
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
+          __syncthreads();
+          int pos = nkeep + __popc(bal & ((1u << (tid & 31)) - 1u)), tot = 0;
 #pragma unroll
-          for (int q = 0; q < NQ; q++) {
-            const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
-            const double2 u0 = j0[0], u1 = j0[1];  // ds_re, ds_im | dz_re, dz_im
-            const double dz_fac = jt[q * (2 * TL * 4) + (1 * TL + l) * 4];
-            const double dsr = u0.x * cst::inv_sqrt_pi * GD, dsi = u0.y * cst::inv_sqrt_pi * GD;
-            const double t_im = u1.y + dz_fac * y;
-            any_im |= u0.y != 0.0;
-            o[5 + 4 * q + 0] = dsr * g2 * a0 - spG2 * t_im * a0;                       // alpha
-            o[5 + 4 * q + 1] = -spG2 * u1.x * c1 - dsi * (g2 * c1 - k * a0);           // gamma
-            o[5 + 4 * q + 2] = dsr * k2 * gg + spG2 * (k * t_im - dz_fac * igd * c1);  // beta
-            o[5 + 4 * q + 3] = -dsi * k2;                                               // delta (only where Im ds != 0)
+          for (int w = 0; w < VF_NT / 32; w++) {
+            pos += w < (tid >> 5) ? wcnt[w] : 0;
+            tot += wcnt[w];
           }
+          if (keep) {
+            double* o = sm + pos * S;
+            const double GD = 1.0 / igd, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
+            const double gg = y * GD, g2 = y2 * GD, h = 0.5 * GD * GD;
+            const double a0 = gg * g2 + h, c1 = g2 + k * gg;
+            const double sp = s_re * cst::inv_sqrt_pi;
+            o[0] = f0s;
+            o[1] = g2 * g2 + k2 * gg * gg - 2.0 * k * h;  // b1 = c1^2 - 2 k a0
+            o[2] = a0 * a0;
+            o[3] = sp * GD * g2 * a0;                     // alpha0
+            o[4] = sp * GD * k2 * gg;                     // beta0
+            o[5 + 4 * NQ] = sg * igd;
+            const double spG2 = sp * GD * GD;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+              const double2 u0 = j0[0], u1 = j0[1];  // ds_re, ds_im | dz_re, dz_im
+              const double dz_fac = jt[q * (2 * TL * 4) + (1 * TL + l) * 4];
+              const double dsr = u0.x * cst::inv_sqrt_pi * GD, dsi = u0.y * cst::inv_sqrt_pi * GD;
+              const double t_im = u1.y + dz_fac * y;
+              any_im |= u0.y != 0.0;
+              o[5 + 4 * q + 0] = dsr * g2 * a0 - spG2 * t_im * a0;                       // alpha
+              o[5 + 4 * q + 1] = -spG2 * u1.x * c1 - dsi * (g2 * c1 - k * a0);           // gamma
+              o[5 + 4 * q + 2] = dsr * k2 * gg + spG2 * (k * t_im - dz_fac * igd * c1);  // beta
+              o[5 + 4 * q + 3] = -dsi * k2;                                               // delta (only where Im ds != 0)
+            }
+          }
+          nkeep += tot;
+          __syncthreads();  // wcnt may be rewritten
         }
         const bool tile_im = __syncthreads_or(any_im) != 0;
         auto loop = [&](auto im_tag, auto test_tag) {
           constexpr bool IM = decltype(im_tag)::value;
           constexpr bool TEST = decltype(test_tag)::value;
-#pragma unroll VF_UNROLL
-          for (int l = 0; l < count; l++) {
+#pragma unroll VF_UNROLL_N
+          for (int l = 0; l < nkeep; l++) {
             const double* __restrict__ o = sm + l * S;
             const double2 c01 = *reinterpret_cast<const double2*>(o), c23 = *reinterpret_cast<const double2*>(o + 2);
             const double b0 = o[4];
@@ -526,7 +595,7 @@ __global__ void __launch_bounds__(VF_NT, (R == 4 ? VF_MB4 : VF_MB2)) lbl_sum_jac
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
       need_T |= jp.kind[jp.q0 + q] == AB200_TARGET_T;
-      need_df |= jp.kind[jp.q0 + q] >= AB200_TARGET_WIND_U && jp.kind[jp.q0 + q] <= AB200_TARGET_WIND_W;
+      need_df |= jp.kind[jp.q0 + q] == AB200_TARGET_WIND_U;
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -538,14 +607,202 @@ __global__ void __launch_bounds__(VF_NT, (R == 4 ? VF_MB4 : VF_MB2)) lbl_sum_jac
       for (int q = 0; q < NQ; q++) {
         double d = scl * acc[q][r];
         const int kind = jp.kind[jp.q0 + q];
+        const int32_t* rows = jp.out_row[jp.q0 + q];
         if (kind == AB200_TARGET_T) d += scl_dT * shape[r];
-        if (kind >= AB200_TARGET_MAG_U && kind <= AB200_TARGET_MAG_W) continue;  // pol = no: :1484-1486
-        if (kind >= AB200_TARGET_WIND_U && kind <= AB200_TARGET_WIND_W) {
+        if (kind == AB200_TARGET_MAG_U) continue;  // pol = no: :1484-1486
+        if (kind == AB200_TARGET_WIND_U) {         // one computed row d/df for the requested components
           d += scl_df * shape[r];
-          if (jp.wind_jac) d = jp.wind_jac[3 * lev + (kind - AB200_TARGET_WIND_U)] * (f[r] * d);
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            if (rows[c] < 0) continue;
+            const double dc = jp.wind_jac ? jp.wind_jac[3 * lev + c] * (f[r] * d) : d;
+            double* o = jp.dK + ((int64_t(lev) * jp.nrows + rows[c]) * p.k_pitch + i) * 7;
+            o[0] += npm[0] * dc; o[1] += npm[1] * dc; o[2] += npm[2] * dc; o[3] += npm[3] * dc;
+          }
+          continue;
         }
-        double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
+        double* o = jp.dK + ((int64_t(lev) * jp.nrows + rows[0]) * p.k_pitch + i) * 7;
         o[0] += npm[0] * d; o[1] += npm[1] * d; o[2] += npm[2] * d; o[3] += npm[3] * d;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The same for COMPLEX lines (Zeeman components, line mixing): strength, strength derivative and both parts of F and dF
+// enter, so each of Re and Im of s F and of every target's dX is a cubic (alpha + gamma u + beta U + delta u U) n:
+//   sqrt(pi) F  = [(A0 + A1 U) + i u (B0 + B1 U)] n,   A0 = GD g2 a0, A1 = GD k^2 g, B0 = GD (g2 c1 - k a0), B1 = GD k^2
+//   sqrt(pi) dF = [C1 u + i (D0 + D1 U)] n,            C1 = -GD^2 c1, D0 = GD^2 a0, D1 = -GD^2 k
+//   dX = ds F + s (dz + dz_fac z) dF,   s (dz + dz_fac z) = (w0 + w1 u),  w0 = s (dz + i dz_fac y), w1 = s dz_fac igd
+// 7 shared FP64 instructions per pair + 8 for the shape + 8 per target (far_cplx path: ~45 + 12 per target).  The pair rule
+// and the split with lbl_sum_jac_kernel are those of the real kernel above; a tile is staged in chunks of VC_CH lines.
+// ---------------------------------------------------------------------------
+constexpr int VC_CH = 128;
+constexpr int vc_stride(int nq) { return 12 + 8 * nq; }
+
+template <int NQ, int R>
+__global__ void __launch_bounds__(VF_NT, (NQ <= 2 ? 4 : 3)) lbl_sum_jac_vfar_cplx_kernel(SumParams p, JacSumParams jp) {
+  constexpr int S = vc_stride(NQ);
+  constexpr int F_TILE = VF_NT * R;
+  extern __shared__ __align__(16) double sm[];  // [VC_CH][S]
+  __shared__ int wcnt[VF_NT / 32];
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t fblk = int64_t(blockIdx.x) * F_TILE;
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double ffac = p.ffac[lev];
+  double f[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int64_t i = fblk + r * VF_NT + tid;
+    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
+  }
+  const double fblk_min = ffac * fg[fblk];
+  const double fblk_max = ffac * fg[(fblk + F_TILE - 1 < p.nf) ? fblk + F_TILE - 1 : p.nf - 1];
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
+  const double T = p.T[lev], P = p.P[lev];
+
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    if (seg.has_cutoff) continue;  // segments with a cutoff: the other kernel
+    cplx shape[R], acc[NQ][R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      shape[r] = {0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < NQ; q++) acc[q][r] = {0.0, 0.0};
+    }
+    bool any_tile = false;
+    for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
+      const double* __restrict__ s4 = summ + t * SUMMARY_DOUBLES;
+      if (s4[0] > s4[1]) continue;
+      const double dist = fmax(fblk_min - s4[1], s4[0] - fblk_max);
+      const bool all = vfar_all(s4, dist);
+      const bool side_pos = all ? s4[1] < fblk_min : s4[7] * (fblk_max - s4[0]) * (1.0 + 1e-9) > VFAR_LIMIT;
+      const bool side_neg = all ? s4[0] > fblk_max : s4[7] * (s4[1] - fblk_min) * (1.0 + 1e-9) > VFAR_LIMIT;
+      const int count = p.tile_count[t];
+      const double* g = prep + t * tile_doubles();
+      const double* jt = jp.jac + ((int64_t(lev) * p.ntiles + t) * jp.nq + jp.q0) * (2 * TL * 4);
+#pragma unroll 1
+      for (int side = 0; side < 2; side++) {
+        if (!(side == 0 ? side_pos : side_neg)) continue;
+        any_tile = true;
+        const double sg = side == 0 ? 1.0 : -1.0;
+        const double k  = 1.0 + sg * 1e-4;
+        const double k2 = k * k;
+        const double edge = side == 0 ? fblk_max : fblk_min;
+#pragma unroll 1
+        for (int c0 = 0; c0 < count; c0 += VC_CH) {
+          static_assert(VC_CH == VF_NT, "one line per thread and chunk");
+          const int l = c0 + tid;
+          double f0s = 0.0, igd = 0.0, y = 0.0, s_re = 0.0, s_im = 0.0;
+          if (l < count) {
+            f0s = g[(0 * TL + l) * REC_GROUP];
+            const double2 m = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP);      // B1, igd
+            const double2 n = *reinterpret_cast<const double2*>(g + (1 * TL + l) * REC_GROUP + 2);  // y, s_re
+            igd = m.y; y = n.x; s_re = n.y;
+            s_im = g[(2 * TL + l) * REC_GROUP + 1];
+          }
+          // the lines of this side that can hold a very far pair in this block, compacted in line order
+          const bool keep = igd != 0.0 && (all || sg * igd * (edge - f0s) * (1.0 + 1e-9) > VFAR_LIMIT);
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          __syncthreads();  // previous chunk consumed, wcnt free
+          if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
+          __syncthreads();
+          int pos = __popc(bal & ((1u << (tid & 31)) - 1u)), nc = 0;
+#pragma unroll
+          for (int w = 0; w < VF_NT / 32; w++) {
+            pos += w < (tid >> 5) ? wcnt[w] : 0;
+            nc += wcnt[w];
+          }
+          if (keep) {
+            double* o = sm + pos * S;
+            const double GD = 1.0 / igd, y2 = y + fmax(1e-4 * fabs(y), 1e-4);
+            const double gg = y * GD, g2 = y2 * GD, h = 0.5 * GD * GD;
+            const double a0 = gg * g2 + h, c1 = g2 + k * gg;
+            const double A0 = GD * g2 * a0, A1 = GD * k2 * gg, B0 = GD * (g2 * c1 - k * a0), B1 = GD * k2;
+            const double C1 = -GD * GD * c1, D0 = GD * GD * a0, D1 = -GD * GD * k;
+            const double spr = s_re * cst::inv_sqrt_pi, spi = s_im * cst::inv_sqrt_pi;
+            o[0] = f0s;
+            o[1] = g2 * g2 + k2 * gg * gg - 2.0 * k * h;
+            o[2] = a0 * a0;
+            o[3] = sg * igd;
+            o[4] = spr * A0; o[5] = -spi * B0; o[6] = spr * A1; o[7] = -spi * B1;   // Re s F: alpha, gamma, beta, delta
+            o[8] = spi * A0; o[9] = spr * B0;  o[10] = spi * A1; o[11] = spr * B1;   // Im s F
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+              const double2* j0 = reinterpret_cast<const double2*>(jt + q * (2 * TL * 4) + (0 * TL + l) * 4);
+              const double2 u0 = j0[0], u1 = j0[1];  // ds_re, ds_im | dz_re, dz_im
+              const double dz_fac = jt[q * (2 * TL * 4) + (1 * TL + l) * 4];
+              const double dr = u0.x * cst::inv_sqrt_pi, di = u0.y * cst::inv_sqrt_pi;
+              const double t0 = u1.x, t1 = dz_fac * igd, ti = u1.y + dz_fac * y;
+              const double w0r = spr * t0 - spi * ti, w1r = spr * t1, w0i = spi * t0 + spr * ti, w1i = spi * t1;
+              double* oq = o + 12 + 8 * q;
+              oq[0] = dr * A0 - w0i * D0;
+              oq[1] = -di * B0 + w0r * C1 - w1i * D0;
+              oq[2] = dr * A1 + w1r * C1 - w0i * D1;
+              oq[3] = -di * B1 - w1i * D1;
+              oq[4] = di * A0 + w0r * D0;
+              oq[5] = dr * B0 + w1r * D0 + w0i * C1;
+              oq[6] = di * A1 + w0r * D1 + w1i * C1;
+              oq[7] = dr * B1 + w1r * D1;
+            }
+          }
+          __syncthreads();
+          auto loop = [&](auto test_tag) {
+            constexpr bool TEST = decltype(test_tag)::value;
+#pragma unroll 1
+            for (int lc = 0; lc < nc; lc++) {
+              const double* __restrict__ o = sm + lc * S;
+              const double2 c01 = *reinterpret_cast<const double2*>(o), c23 = *reinterpret_cast<const double2*>(o + 2);
+#pragma unroll
+              for (int r = 0; r < R; r++) {
+                const double u = __dsub_rn(f[r], c01.x);
+                const double U = __dmul_rn(u, u);
+                const double W = __dmul_rn(u, U);
+                double n = far_rcp(__fma_rn(__fma_rn(k2, U, c01.y), U, c23.x));
+                if (TEST) n = __dmul_rn(c23.y, u) > VFAR_LIMIT ? n : 0.0;
+                auto cubic = [&](const double* c) { return __fma_rn(c[3], W, __fma_rn(c[2], U, __fma_rn(c[1], u, c[0]))); };
+                shape[r].re = __fma_rn(cubic(o + 4), n, shape[r].re);
+                shape[r].im = __fma_rn(cubic(o + 8), n, shape[r].im);
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                  acc[q][r].re = __fma_rn(cubic(o + 12 + 8 * q), n, acc[q][r].re);
+                  acc[q][r].im = __fma_rn(cubic(o + 16 + 8 * q), n, acc[q][r].im);
+                }
+              }
+            }
+          };
+          if (all) loop(std::false_type{});
+          else loop(std::true_type{});
+        }
+      }
+    }
+    if (!any_tile) continue;
+    // epilogue of lbl_sum_jac_kernel (compute_derivative :1474-1561) on this kernel's partial sums: it is linear in them
+    const double* __restrict__ npm = p.npm + (int64_t(lev) * 4 + seg.pol) * 7;
+    const bool all_zero = npm[0] == 0 && npm[1] == 0 && npm[2] == 0 && npm[3] == 0 && npm[4] == 0 && npm[5] == 0 &&
+                          npm[6] == 0;
+    if (all_zero) continue;
+    bool need_T = false, need_df = false;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      need_T |= jp.kind[jp.q0 + q] == AB200_TARGET_T;
+      need_df |= jp.kind[jp.q0 + q] == AB200_TARGET_WIND_U;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int64_t i = fblk + r * VF_NT + tid;
+      if (i >= p.nf) continue;
+      double scl, scl_dT, scl_df;
+      vf_scales(f[r], T, P, need_T, need_df, scl, scl_dT, scl_df);
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        cplx d = cscale(scl, acc[q][r]);
+        const int kind = jp.kind[jp.q0 + q];
+        if (kind == AB200_TARGET_T) d = cadd(d, cscale(scl_dT, shape[r]));
+        jac_store_rows(jp, jp.q0 + q, kind, lev, seg.pol, i, p.k_pitch, npm, f[r], scl, scl_df, shape[r], d);
       }
     }
   }
@@ -716,6 +973,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
           for (int l = 0; l < count; l++) {
             const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
             if (__double2hiint(igd) == 0) continue;  // igd == 0: inactive cutoff line (integer test, off the FP64 pipe)
+            if (vf_pairs && line_all_vfar(f0s, igd, fblk_min, fblk_max)) continue;
             const FarLine c{sb[2 * TL + l], sb[3 * TL + l], sb[8 * TL + l], sb[9 * TL + l], sb[4 * TL + l], sb[5 * TL + l],
                             sb[6 * TL + l]};
             const double sp = sb[7 * TL + l];
@@ -752,12 +1010,14 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
         for (int l = 0; l < count; l++) {
           const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l];
           if (__double2hiint(igd) == 0) continue;
+          if (vf_pairs && line_all_vfar(f0s, igd, fblk_min, fblk_max)) continue;
           const double y = sb[2 * TL + l], y2 = sb[3 * TL + l];
           const FarLine c{y, y2, 2.0 * y, 2.0 * y2, sb[4 * TL + l], sb[5 * TL + l], sb[6 * TL + l]};
           const double spr = sb[7 * TL + l], spi = sb[8 * TL + l];
 #pragma unroll
           for (int r = 0; r < JAC_R; r++) {
             const double x  = __dmul_rn(igd, __dsub_rn(f[r], f0s));
+            if (vf_pairs && fabs(x) > VFAR_LIMIT) continue;
             const double x2 = __dadd_rn(x, fmax(__dmul_rn(1e-4, fabs(x)), 1e-4));
             double G1, G2, G3, G4, G5;
             far_pair<true>(c, x, x2, G1, G2, G3, G4, G5);
@@ -782,6 +1042,7 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
       for (int l = 0; l < count; l++) {
         const double f0s = sb[0 * TL + l], igd = sb[1 * TL + l], y = sb[2 * TL + l];
         if (igd == 0.0) continue;  // inactive cutoff line
+        if (vf_pairs && line_all_vfar(f0s, igd, fblk_min, fblk_max)) continue;  // every pair of the line belongs to the other kernel
         const cplx s{sb[3 * TL + l], sb[4 * TL + l]};
         const double lcut = jp.real_lines ? sb[8 * TL + l] : cutoff;
         const bool lhas   = lcut < DBL_MAX;
@@ -855,29 +1116,9 @@ __global__ void __launch_bounds__(JAC_NT, (NQ <= 2 ? 4 : NQ == 3 ? 3 : 2)) lbl_s
         cplx d = cscale(scl, acc[q][r]);
         const int kind = jp.kind[jp.q0 + q];
         if (kind == AB200_TARGET_T) d = cadd(d, cscale(line_scale_dT(f[r], T, P), shape[r]));
-        if (EXT && kind >= AB200_TARGET_MAG_U && kind <= AB200_TARGET_MAG_W) {
-          // compute_derivative :1484-1513 with zeeman::scale(npm, dnpm, scl shape, scl dshape), lbl_zeeman.h:442-453
-          if (seg.pol == POL_NO) continue;
-          const double* __restrict__ dn = jp.dnpm + ((int64_t(lev) * 3 + (kind - AB200_TARGET_MAG_U)) * 4 + seg.pol) * 7;
-          const cplx F = cscale(scl, shape[r]);
-          double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
-          o[0] += dn[0] * F.re + npm[0] * d.re; o[1] += dn[1] * F.re + npm[1] * d.re;
-          o[2] += dn[2] * F.re + npm[2] * d.re; o[3] += dn[3] * F.re + npm[3] * d.re;
-          o[4] += dn[4] * F.im + npm[4] * d.im; o[5] += dn[5] * F.im + npm[5] * d.im;
-          o[6] += dn[6] * F.im + npm[6] * d.im;
-          continue;
-        }
-        if (EXT && kind >= AB200_TARGET_WIND_U && kind <= AB200_TARGET_WIND_W) {
-          // compute_derivative :1514-1523, then spectral_propmat_jacWindFix (m_frequency_grid.cc:106-182): x * f * df_du
-          d = cadd(d, cscale(line_scale_df(f[r], T, P), shape[r]));
-          if (jp.wind_jac) {  // null: AB200_FLAG_WIND_ROWS_DF, the caller's agenda applies the fix
-            const double wj = jp.wind_jac[3 * lev + (kind - AB200_TARGET_WIND_U)];
-            d = cscale(wj, cscale(f[r], d));
-          }
-        }
-        double* o = jp.dK + ((int64_t(lev) * jp.nq + jp.q0 + q) * p.k_pitch + i) * 7;
-        o[0] += npm[0] * d.re; o[1] += npm[1] * d.re; o[2] += npm[2] * d.re; o[3] += npm[3] * d.re;
-        o[4] += npm[4] * d.im; o[5] += npm[5] * d.im; o[6] += npm[6] * d.im;
+        if (!EXT && (kind == AB200_TARGET_MAG_U || kind == AB200_TARGET_WIND_U)) continue;  // unreachable: EXT is set for these passes
+        const double scl_df = (EXT && kind == AB200_TARGET_WIND_U) ? line_scale_df(f[r], T, P) : 0.0;
+        jac_store_rows(jp, jp.q0 + q, kind, lev, seg.pol, i, p.k_pitch, npm, f[r], scl, scl_df, shape[r], d);
       }
     }
   }
@@ -927,9 +1168,20 @@ static int launch_sum_jac_vfar(const SumParams& p, const JacSumParams& jp, int n
   return R == 2 ? launch_sum_jac_vfar_r<NQ, 2>(p, jp, nlev, stream) : launch_sum_jac_vfar_r<NQ, 4>(p, jp, nlev, stream);
 }
 template <int NQ>
+static int launch_sum_jac_vfar_cplx(const SumParams& p, const JacSumParams& jp, int nlev, cudaStream_t stream) {
+  constexpr int R = 2;
+  const size_t smem = size_t(vc_stride(NQ)) * VC_CH * sizeof(double);
+  AB_CUDA(cudaFuncSetAttribute(lbl_sum_jac_vfar_cplx_kernel<NQ, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  const dim3 grid(static_cast<unsigned>((p.nf + VF_NT * R - 1) / (VF_NT * R)), static_cast<unsigned>(nlev));
+  lbl_sum_jac_vfar_cplx_kernel<NQ, R><<<grid, VF_NT, smem, stream>>>(p, jp);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int NQ>
 static int launch_sum_jac_n(const SumParams& p, const JacSumParams& jp, dim3 grid, cudaStream_t stream) {
   bool ext = false;
-  for (int q = 0; q < NQ; q++) ext |= jp.kind[jp.q0 + q] >= AB200_TARGET_WIND_U && jp.kind[jp.q0 + q] <= AB200_TARGET_MAG_W;
+  for (int q = 0; q < NQ; q++) ext |= jp.kind[jp.q0 + q] == AB200_TARGET_WIND_U || jp.kind[jp.q0 + q] == AB200_TARGET_MAG_U;
   return ext ? launch_sum_jac_ne<NQ, true>(p, jp, grid, stream) : launch_sum_jac_ne<NQ, false>(p, jp, grid, stream);
 }
 
@@ -951,8 +1203,16 @@ int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t s
     // targets only (those visit a handful of tiles and need no forward shape)
     bool line_only = true;
     for (int q = 0; q < nq_pass; q++) line_only &= jp.kind[q0 + q] >= AB200_TARGET_LINE_F0 && jp.kind[q0 + q] <= AB200_TARGET_LINE_LS;
-    jp.skip_vfar = (jp.real_lines && vfar_on && !line_only) ? 1 : 0;
-    if (jp.skip_vfar) {
+    jp.skip_vfar = (vfar_on && !line_only) ? 1 : 0;
+    if (jp.skip_vfar && !jp.real_lines) {
+      switch (nq_pass) {
+        case 1: AB_TRY((launch_sum_jac_vfar_cplx<1>(p, jp, nlev, stream))); break;
+        case 2: AB_TRY((launch_sum_jac_vfar_cplx<2>(p, jp, nlev, stream))); break;
+        case 3: AB_TRY((launch_sum_jac_vfar_cplx<3>(p, jp, nlev, stream))); break;
+        default: AB_TRY((launch_sum_jac_vfar_cplx<4>(p, jp, nlev, stream))); break;
+      }
+    }
+    if (jp.skip_vfar && jp.real_lines) {
       switch (nq_pass) {
         case 1: AB_TRY(launch_sum_jac_vfar<1>(p, jp, nlev, stream)); break;
         case 2: AB_TRY(launch_sum_jac_vfar<2>(p, jp, nlev, stream)); break;

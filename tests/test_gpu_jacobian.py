@@ -262,7 +262,7 @@ def _many_lines_case(np_=3, nf=2600):
 
 def test_very_far_pairs_closed_form(wsm, orc):
     """Pairs with |x| > 1.2e4 of real lines take ONE rational function shared by all targets (lbl_sum_jac_vfar_kernel):
-    truncation 1 / (2 |z|^2) <= 3.5e-9 per pair.  Against the oracle's literal forward difference, per level (the far
+    F to 1e-12, the forward difference dF to 1 / |z|^2 <= 6.9e-9 per pair.  Against the oracle's literal forward difference, per level (the far
     wings of the upper levels must not hide behind the line cores of the lowest one), T + own + foreign VMR + a wind row."""
     c = _many_lines_case()
     tg = (("T",), ("VMR", 0), ("VMR", 3), ("wind_u",))
@@ -287,3 +287,24 @@ def test_jacobian_rows_do_not_depend_on_the_frequency_partition(wsm):
         Ks, dKs = wsm.spectral_propmat_pathFromPath(c.cat, c.f[lo:hi], c.atm, jac_targets=tg)
         assert np.array_equal(Ks, K[:, lo:hi]), (lo, hi)
         assert np.array_equal(dKs, dK[:, :, lo:hi]), (lo, hi)
+
+
+def test_very_far_pairs_complex_lines(wsm, orc):
+    """Zeeman components and line mixing (complex strengths): the very far pairs of the configs[2] band — every other line of
+    the band is 0.5 GHz or more away in units of a 70 kHz Doppler width — take the complex one-denominator form
+    (lbl_sum_jac_vfar_cplx_kernel).  T, VMR, the three magnetic-field components and a wind row, per level."""
+    c = synth.case_c3(nf=38 * 24, np_=4, los=(120.0, 30.0))
+    tg = (("T",), ("VMR", 0), ("mag_u",), ("mag_v",), ("mag_w",), ("wind_v",))
+    c.atm.wind = np.tile(np.array([5.0, -3.0, 0.2]), (c.np_, 1))
+    Kr, dKr = orc.propmat_levels(c.cat, c.f, c.atm, targets=tg)
+    K, dK = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, jac_targets=tg)
+    assert_propmat_close(K, Kr)
+    for q in range(len(tg)):
+        for lev in range(c.np_):
+            assert np.abs(dKr[lev, q]).max() > 0
+            assert_jac_close(dK[lev, q], dKr[lev, q], rtol=5e-8, what=f"dK target {tg[q]} level {lev}")
+    # sub-grid: the pair rule is the same; the other (near) classes of complex lines are block-dependent in the last bits
+    lo, hi = 100, 700
+    Ks, dKs = wsm.spectral_propmat_pathFromPath(c.cat, c.f[lo:hi], c.atm, jac_targets=tg)
+    for q in range(len(tg)):
+        assert_jac_close(dKs[:, q], dK[:, q, lo:hi], rtol=1e-12, what=f"sub-grid row {tg[q]}")

@@ -57,6 +57,14 @@ def lib():
     L.ab200_rte_transmission.argtypes = abi.SIG_TRANSMISSION
     L.ab200_clearsky_emission.argtypes = [_vp] + abi.SIG_CLEARSKY_CORE
     L.ab200_planck_tb.argtypes = [C.c_int64, _dp, _dp]
+    L.ab200_set_thread_grid_bounds.argtypes = [C.c_int32, _dp]
+    L.ab200_multi_create.argtypes = [C.POINTER(abi.CatalogDesc), C.c_int32, C.POINTER(C.c_int32), C.POINTER(_vp)]
+    L.ab200_multi_destroy.argtypes = [_vp]
+    L.ab200_multi_destroy.restype = None
+    L.ab200_multi_device_count.argtypes = [_vp]
+    L.ab200_multi_device_count.restype = C.c_int32
+    L.ab200_multi_clearsky_emission.argtypes = [_vp] + abi.SIG_CLEARSKY_CORE
+    L.ab200_multi_propmat_levels.argtypes = [_vp] + abi.SIG_PROPMAT_LEVELS_CORE + [C.c_uint32, _dp, _dp]
     L.ab200_path_create.argtypes = [_vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(_vp)]
     L.ab200_path_destroy.argtypes = [_vp]
     L.ab200_path_destroy.restype = None

@@ -889,6 +889,7 @@ struct PathCache {
 thread_local PathCache t_cache;
 thread_local bool t_stream_set = false;
 thread_local void* t_stream = nullptr;
+thread_local std::vector<double> t_bounds;  // [np][2] bounds of the whole grid the thread's next calls are a shard of (empty: none)
 
 // one cached workspace per host thread: the shims are called repeatedly with the same
 // shapes (once per (pos, los) under measurement_vecFromSensor, src/m_rad.cc:321-343)
@@ -910,6 +911,30 @@ int cached_path(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab
   return AB200_OK;
 }
 }  // namespace
+
+// the host-buffer entry points of this thread take a SHARD of a frequency grid: ByLine cutoffs select their lines with the
+// bounds of the whole grid (band_data::active_lines, lbl_data.cpp:61-68), whatever part of it a call carries
+int ab200_set_thread_grid_bounds(int32_t np, const double* bounds) {
+  if (np <= 0 || !bounds) {
+    t_bounds.clear();
+    return AB200_OK;
+  }
+  for (int ip = 0; ip < np; ip++)
+    if (!(bounds[2 * ip] <= bounds[2 * ip + 1])) return set_error(AB200_ERR_INVALID, "ab200_set_thread_grid_bounds: bounds must be ascending and finite");
+  t_bounds.assign(bounds, bounds + 2 * static_cast<size_t>(np));
+  return AB200_OK;
+}
+static int apply_thread_bounds(ab200_path* p, int np) {
+  if (t_bounds.empty()) {
+    p->grid_bounds.clear();
+    return AB200_OK;
+  }
+  if (t_bounds.size() != 2 * static_cast<size_t>(np))
+    return set_error(AB200_ERR_INVALID, "ab200_set_thread_grid_bounds was given " + std::to_string(t_bounds.size() / 2) +
+                                            " levels, the call has " + std::to_string(np));
+  p->grid_bounds = t_bounds;
+  return AB200_OK;
+}
 
 int ab200_set_thread_stream(void* stream) {
   t_stream_set = stream != nullptr;
@@ -935,6 +960,7 @@ int ab200_propmat_levels(const ab200_catalog* cat, int64_t nf, const double* f, 
   if (nq > 0 && !dK) return set_error(AB200_ERR_INVALID, "ab200_propmat_levels: dK is null with nq > 0");
   ab200_path* p = nullptr;
   AB_TRY(cached_path(cat, nf, atm->np, nq, &p));
+  AB_TRY(apply_thread_bounds(p, atm->np));
   AB_TRY(ab200_path_upload(p, f, f_level_stride, atm, select_species, no_negative_absorption, targets, nullptr, 0,
                            AB200_RTE_LINSRC, nullptr, flags));
   if (!(flags & AB200_FLAG_K_ZERO_INIT) && nf && atm->np) {  // += into the caller's values
@@ -1013,6 +1039,7 @@ int ab200_clearsky_emission(const ab200_catalog* cat, int64_t nf, const double* 
   if (nq > 0 && !dI) return set_error(AB200_ERR_INVALID, "ab200_clearsky_emission: dI is null with nq > 0");
   ab200_path* p = nullptr;
   AB_TRY(cached_path(cat, nf, atm->np, nq, &p));
+  AB_TRY(apply_thread_bounds(p, atm->np));
   AB_TRY(ab200_path_upload(p, f, f_level_stride, atm, select_species, no_negative_absorption, targets, r,
                            hse_derivative, rte_option, I_bkg, flags));
   AB_TRY(ab200_path_run_propmat(p));

@@ -1,0 +1,276 @@
+// multi.cu — ONE host process driving several GPUs behind the C ABI.
+//
+// The reference is a single process whose frequency loop is an OpenMP team (src/m_lbl.cc:273-295: chunks of ONE
+// freq_grid per thread; src/m_rad.cc:321-343 for the batch of paths).  A shim inside that process therefore sees one
+// call per path with the whole grid; ab200_multi_* splits that call's frequencies over the visible devices — one
+// catalog replica, one worker thread (with its own stream, pinned staging and cached workspace) per device — and every
+// device copies its results straight into the caller's arrays.  No collective: the path is independent per frequency.
+//
+// Split: 512-frequency blocks dealt round-robin (block b -> device b mod N).  The cost of a frequency is not uniform
+// (the number of near pairs grows with frequency where Doppler widths do, and with a ByLine cutoff so does the number of
+// lines in window), so contiguous chunks like the reference's omp_offset_count are unbalanced: round 1 measured 1.71x
+// on 2 GPUs for configs[3] with a 750 GHz cutoff.  512 is the block width of the line-sum kernels, so a device's CTAs see
+// exactly the blocks of the single-device run, and because the value at a frequency does not depend on the block or
+// shard it is computed in, the result is bit-identical to the one-device result.  Line selection of
+// ByLine cutoffs uses the bounds of the WHOLE grid (band_data::active_lines, lbl_data.cpp:61-68), handed to each worker
+// through ab200_set_thread_grid_bounds.
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+constexpr int64_t MB = 512;  // frequencies per dealt block (= F_TILE of the line-sum kernels)
+
+struct Worker {
+  int device = 0;
+  ab200_catalog* cat = nullptr;
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = false, quit = false;
+  int rc = 0;
+  std::string err;
+  // gather / scatter buffers of this worker (host)
+  std::vector<double> f, bkg, I, dI, K, dK;
+
+  void loop() {
+    ab200_set_device(device);
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return has_job || quit; });
+      if (quit) break;
+      lk.unlock();
+      const int r = job();
+      const std::string e = r ? ab200_last_error() : "";
+      lk.lock();
+      rc = r;
+      err = e;
+      has_job = false;
+      done = true;
+      cv.notify_all();
+    }
+    ab200_release_thread_cache();
+  }
+};
+}  // namespace
+
+struct ab200_multi {
+  std::vector<Worker*> w;
+  std::mutex call_mu;  // one multi-device call at a time per set (the workers' workspaces are per set)
+};
+
+namespace {
+// the frequencies of device d: blocks d, d + n, d + 2n, ... of MB frequencies
+int64_t local_count(int64_t nf, int n, int d) {
+  const int64_t nb = (nf + MB - 1) / MB;
+  int64_t c = 0;
+  for (int64_t b = d; b < nb; b += n) c += std::min(MB, nf - b * MB);
+  return c;
+}
+template <class Fn>  // fn(global offset, local offset, count) for every block of device d
+void for_blocks(int64_t nf, int n, int d, Fn fn) {
+  const int64_t nb = (nf + MB - 1) / MB;
+  int64_t lo = 0;
+  for (int64_t b = d; b < nb; b += n) {
+    const int64_t cnt = std::min(MB, nf - b * MB);
+    fn(b * MB, lo, cnt);
+    lo += cnt;
+  }
+}
+
+int run_all(ab200_multi* m, const std::function<int(Worker&, int)>& body) {
+  std::lock_guard<std::mutex> call(m->call_mu);
+  const int n = static_cast<int>(m->w.size());
+  for (int d = 0; d < n; d++) {
+    Worker& w = *m->w[d];
+    std::lock_guard<std::mutex> lk(w.mu);
+    w.job = [&body, &w, d] { return body(w, d); };
+    w.done = false;
+    w.has_job = true;
+    w.cv.notify_all();
+  }
+  int rc = 0;
+  std::string err;
+  for (int d = 0; d < n; d++) {
+    Worker& w = *m->w[d];
+    std::unique_lock<std::mutex> lk(w.mu);
+    w.cv.wait(lk, [&] { return w.done; });
+    if (w.rc && !rc) {
+      rc = w.rc;
+      err = "device " + std::to_string(w.device) + ": " + w.err;
+    }
+  }
+  return rc ? ab200::set_error(rc, err) : AB200_OK;
+}
+
+// bounds of the whole grid per level, as ab200_path_upload derives them from a grid it is given in full
+void grid_bounds(int64_t nf, const double* f, int64_t stride, int np, std::vector<double>& b) {
+  b.resize(2 * static_cast<size_t>(np));
+  for (int ip = 0; ip < np; ip++) {
+    const double* g = f + static_cast<size_t>(ip) * stride;
+    b[2 * ip] = g[0];
+    b[2 * ip + 1] = g[nf - 1];
+  }
+}
+}  // namespace
+
+int ab200_multi_create(const ab200_catalog_desc* desc, int32_t n_devices, const int32_t* devices, ab200_multi** out) {
+  if (!desc || !out) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_create: null argument");
+  *out = nullptr;
+  const int avail = ab200_device_count();
+  if (n_devices <= 0) n_devices = avail;
+  if (avail < 1 || (!devices && n_devices > avail))
+    return ab200::set_error(AB200_ERR_CUDA, "ab200_multi_create: " + std::to_string(n_devices) + " devices requested, " +
+                                                std::to_string(avail) + " visible (arts_b200 has no CPU fallback)");
+  for (int i = 0; devices && i < n_devices; i++)  // an explicit list may name a device more than once (two workers on it)
+    if (devices[i] < 0 || devices[i] >= avail)
+      return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_create: device " + std::to_string(devices[i]) + " is not one of the " +
+                                                     std::to_string(avail) + " visible devices");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  ab200_multi* m = new ab200_multi;
+  for (int i = 0; i < n_devices; i++) {
+    Worker* w = new Worker;
+    w->device = devices ? devices[i] : i;
+    int rc = ab200_set_device(w->device);
+    if (!rc) rc = ab200_catalog_create(desc, &w->cat);  // one replica per device
+    if (rc) {
+      delete w;
+      cudaSetDevice(prev);
+      ab200_multi_destroy(m);
+      return rc;
+    }
+    m->w.push_back(w);
+  }
+  cudaSetDevice(prev);
+  for (Worker* w : m->w) w->th = std::thread([w] { w->loop(); });
+  *out = m;
+  return AB200_OK;
+}
+
+void ab200_multi_destroy(ab200_multi* m) {
+  if (!m) return;
+  for (Worker* w : m->w) {
+    if (w->th.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->quit = true;
+        w->cv.notify_all();
+      }
+      w->th.join();
+    }
+    if (w->cat) ab200_catalog_destroy(w->cat);
+    delete w;
+  }
+  delete m;
+}
+
+int32_t ab200_multi_device_count(const ab200_multi* m) { return m ? static_cast<int32_t>(m->w.size()) : 0; }
+
+int ab200_multi_clearsky_emission(ab200_multi* m, int64_t nf, const double* f, int64_t f_level_stride, const ab200_atm_path* atm,
+                                  int32_t select_species, int32_t no_negative_absorption, int32_t nq, const ab200_target* targets,
+                                  const double* r, int32_t hse_derivative, int32_t rte_option, const double* I_bkg, uint32_t flags,
+                                  double* I, double* dI, double* K_out) {
+  if (!m || !atm || !f || !I || !I_bkg) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_clearsky_emission: null argument");
+  if (f_level_stride != 0 && f_level_stride != nf)
+    return ab200::set_error(AB200_ERR_INVALID, "f_level_stride must be 0 (shared grid) or nf (one grid per level)");
+  if (nq > 0 && !dI) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_clearsky_emission: dI is null with nq > 0");
+  if (nf == 0) return AB200_OK;
+  const int n = static_cast<int>(m->w.size()), np = atm->np;
+  const int nlev_f = f_level_stride ? np : 1;
+  const bool want_K = (flags & AB200_FLAG_RETURN_K) && K_out;
+  std::vector<double> bounds;
+  grid_bounds(nf, f, f_level_stride, f_level_stride ? np : 1, bounds);
+  if (!f_level_stride) {
+    bounds.resize(2 * static_cast<size_t>(std::max(np, 1)));
+    for (int ip = 1; ip < np; ip++) bounds[2 * ip] = bounds[0], bounds[2 * ip + 1] = bounds[1];
+  }
+  const size_t row = static_cast<size_t>(np) * nq * 4;  // doubles of dI per frequency
+  return run_all(m, [&](Worker& w, int d) -> int {
+    const int64_t cnt = local_count(nf, n, d);
+    if (cnt == 0) return AB200_OK;
+    w.f.resize(static_cast<size_t>(cnt) * nlev_f);
+    w.bkg.resize(static_cast<size_t>(cnt) * 4);
+    w.I.resize(static_cast<size_t>(cnt) * 4);
+    if (nq > 0) w.dI.resize(static_cast<size_t>(cnt) * row);
+    if (want_K) w.K.resize(static_cast<size_t>(np) * cnt * 7);
+    for_blocks(nf, n, d, [&](int64_t g, int64_t l, int64_t c) {
+      for (int ip = 0; ip < nlev_f; ip++)
+        std::memcpy(&w.f[static_cast<size_t>(ip) * cnt + l], f + static_cast<size_t>(ip) * f_level_stride + g, c * sizeof(double));
+      std::memcpy(&w.bkg[4 * l], I_bkg + 4 * g, 4 * c * sizeof(double));
+    });
+    AB_TRY(ab200_set_thread_grid_bounds(np, bounds.data()));
+    const int rc = ab200_clearsky_emission(w.cat, cnt, w.f.data(), f_level_stride ? cnt : 0, atm, select_species, no_negative_absorption,
+                                           nq, targets, r, hse_derivative, rte_option, w.bkg.data(), flags, w.I.data(),
+                                           nq > 0 ? w.dI.data() : nullptr, want_K ? w.K.data() : nullptr);
+    ab200_set_thread_grid_bounds(0, nullptr);
+    if (rc) return rc;
+    for_blocks(nf, n, d, [&](int64_t g, int64_t l, int64_t c) {
+      std::memcpy(I + 4 * g, &w.I[4 * l], 4 * c * sizeof(double));
+      if (nq > 0) std::memcpy(dI + g * row, &w.dI[l * row], c * row * sizeof(double));
+      if (want_K)
+        for (int ip = 0; ip < np; ip++)
+          std::memcpy(K_out + (static_cast<size_t>(ip) * nf + g) * 7, &w.K[(static_cast<size_t>(ip) * cnt + l) * 7], 7 * c * sizeof(double));
+    });
+    return AB200_OK;
+  });
+}
+
+int ab200_multi_propmat_levels(ab200_multi* m, int64_t nf, const double* f, int64_t f_level_stride, const ab200_atm_path* atm,
+                               int32_t select_species, int32_t no_negative_absorption, int32_t nq, const ab200_target* targets,
+                               uint32_t flags, double* K, double* dK) {
+  if (!m || !atm || !f || !K) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_propmat_levels: null argument");
+  if (f_level_stride != 0 && f_level_stride != nf)
+    return ab200::set_error(AB200_ERR_INVALID, "f_level_stride must be 0 (shared grid) or nf (one grid per level)");
+  if (nq > 0 && !dK) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_propmat_levels: dK is null with nq > 0");
+  if (nf == 0) return AB200_OK;
+  const int n = static_cast<int>(m->w.size()), np = atm->np;
+  const int nlev_f = f_level_stride ? np : 1;
+  std::vector<double> bounds;
+  grid_bounds(nf, f, f_level_stride, f_level_stride ? np : 1, bounds);
+  if (!f_level_stride) {
+    bounds.resize(2 * static_cast<size_t>(std::max(np, 1)));
+    for (int ip = 1; ip < np; ip++) bounds[2 * ip] = bounds[0], bounds[2 * ip + 1] = bounds[1];
+  }
+  return run_all(m, [&](Worker& w, int d) -> int {
+    const int64_t cnt = local_count(nf, n, d);
+    if (cnt == 0) return AB200_OK;
+    w.f.resize(static_cast<size_t>(cnt) * nlev_f);
+    w.K.resize(static_cast<size_t>(np) * cnt * 7);
+    if (nq > 0) w.dK.resize(static_cast<size_t>(np) * nq * cnt * 7);
+    const bool in = !(flags & AB200_FLAG_K_ZERO_INIT);  // += into the caller's values
+    for_blocks(nf, n, d, [&](int64_t g, int64_t l, int64_t c) {
+      for (int ip = 0; ip < nlev_f; ip++)
+        std::memcpy(&w.f[static_cast<size_t>(ip) * cnt + l], f + static_cast<size_t>(ip) * f_level_stride + g, c * sizeof(double));
+      if (in) {
+        for (int ip = 0; ip < np; ip++) {
+          std::memcpy(&w.K[(static_cast<size_t>(ip) * cnt + l) * 7], K + (static_cast<size_t>(ip) * nf + g) * 7, 7 * c * sizeof(double));
+          for (int q = 0; q < nq; q++)
+            std::memcpy(&w.dK[((static_cast<size_t>(ip) * nq + q) * cnt + l) * 7], dK + ((static_cast<size_t>(ip) * nq + q) * nf + g) * 7,
+                        7 * c * sizeof(double));
+        }
+      }
+    });
+    AB_TRY(ab200_set_thread_grid_bounds(np, bounds.data()));
+    const int rc = ab200_propmat_levels(w.cat, cnt, w.f.data(), f_level_stride ? cnt : 0, atm, select_species, no_negative_absorption, nq,
+                                        targets, flags, w.K.data(), nq > 0 ? w.dK.data() : nullptr);
+    ab200_set_thread_grid_bounds(0, nullptr);
+    if (rc) return rc;
+    for_blocks(nf, n, d, [&](int64_t g, int64_t l, int64_t c) {
+      for (int ip = 0; ip < np; ip++) {
+        std::memcpy(K + (static_cast<size_t>(ip) * nf + g) * 7, &w.K[(static_cast<size_t>(ip) * cnt + l) * 7], 7 * c * sizeof(double));
+        for (int q = 0; q < nq; q++)
+          std::memcpy(dK + ((static_cast<size_t>(ip) * nq + q) * nf + g) * 7, &w.dK[((static_cast<size_t>(ip) * nq + q) * cnt + l) * 7],
+                      7 * c * sizeof(double));
+      }
+    });
+    return AB200_OK;
+  });
+}

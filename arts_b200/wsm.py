@@ -80,8 +80,10 @@ class Catalog:
             pass
 
 
-def _as_catalog(abs_bands) -> Catalog:
-    return abs_bands if isinstance(abs_bands, Catalog) else Catalog(abs_bands)
+def _as_catalog(abs_bands):
+    if isinstance(abs_bands, Catalog) or type(abs_bands).__name__ == "MultiDevice":
+        return abs_bands
+    return Catalog(abs_bands)
 
 
 def _f_arg(f, np_):
@@ -117,6 +119,42 @@ def spectral_propmatAddLines(spectral_propmat, spectral_propmat_jac, freq_grid, 
     return spectral_propmat
 
 
+class MultiDevice:
+    """One host process, several GPUs (ab200_multi): a catalog replica and a worker thread per device.  Pass it where a
+    catalog goes in ``spectral_radClearskyEmission`` / ``spectral_propmat_pathFromPath``: the call's frequency grid is
+    dealt over the devices in 512-frequency blocks and every device writes its blocks into the caller's arrays — the
+    reference's OpenMP frequency loop (src/m_lbl.cc:273-295) with devices for threads."""
+
+    def __init__(self, host: HostCatalog, n_devices: int = 0, devices=None):
+        self.host = host
+        self._h = C.c_void_p()
+        d = host.desc()
+        dev = None
+        if devices is not None:
+            n_devices = len(devices)
+            dev = (C.c_int32 * n_devices)(*[int(x) for x in devices])
+        check(lib().ab200_multi_create(C.byref(d), int(n_devices), dev, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def n_devices(self):
+        return int(lib().ab200_multi_device_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().ab200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def spectral_propmat_pathFromPath(abs_bands, freq_grid_path, atm_path: AtmPath, jac_targets=(),
                                   select_species=abi.SPECIES_BATH, no_negative_absorption=1, out=None, out_jac=None,
                                   accumulate=False, wind_rows_df=False):
@@ -137,8 +175,9 @@ def spectral_propmat_pathFromPath(abs_bands, freq_grid_path, atm_path: AtmPath, 
     if wind_rows_df:
         flags |= abi.FLAG_WIND_ROWS_DF
     a = atm_path.desc()
-    check(lib().ab200_propmat_levels(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
-                                     int(no_negative_absorption), nq, tg, flags, dptr(K), dptr(dK)))
+    fn = lib().ab200_multi_propmat_levels if isinstance(cat, MultiDevice) else lib().ab200_propmat_levels
+    check(fn(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
+             int(no_negative_absorption), nq, tg, flags, dptr(K), dptr(dK)))
     return K, dK
 
 
@@ -258,9 +297,10 @@ def spectral_radClearskyEmission(abs_bands, freq_grid_path, atm_path: AtmPath, r
     if return_propmat:
         flags |= abi.FLAG_RETURN_K
     a = atm_path.desc()
-    check(lib().ab200_clearsky_emission(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
-                                        int(no_negative_absorption), nq, tg, dptr(r), int(hse_derivative),
-                                        _rte(rte_option), dptr(bkg), flags, dptr(I), dptr(dI), dptr(K)))
+    fn = lib().ab200_multi_clearsky_emission if isinstance(cat, MultiDevice) else lib().ab200_clearsky_emission
+    check(fn(cat.handle, nf, dptr(f), stride, C.byref(a), int(select_species),
+             int(no_negative_absorption), nq, tg, dptr(r), int(hse_derivative),
+             _rte(rte_option), dptr(bkg), flags, dptr(I), dptr(dI), dptr(K)))
     return (I, dI, K) if return_propmat else (I, dI)
 
 

@@ -507,6 +507,33 @@ int ab200_set_thread_stream(void *stream);
  * called repeatedly with identical shapes, src/m_rad.cc:321-343).  Drops the calling thread's. */
 int ab200_release_thread_cache(void);
 
+/* The host-buffer calls that follow on this thread carry a SHARD of a frequency grid whose first / last frequency per
+ * level are bounds [np][2]: ByLine cutoffs select their lines with the bounds of the whole grid
+ * (band_data::active_lines, src/core/lbl/lbl_data.cpp:61-68).  np <= 0 or NULL clears it.  For callers that shard the
+ * grid themselves; ab200_multi_* uses it for its workers. */
+int ab200_set_thread_grid_bounds(int32_t np, const double *bounds);
+
+/* ---- one process, several GPUs ------------------------------------------------------------------------------
+ * The reference is ONE process whose frequency loop is an OpenMP team (src/m_lbl.cc:273-295), so a shim inside it makes
+ * one call per path with the whole grid.  An ab200_multi holds one catalog replica and one worker thread (own stream,
+ * pinned staging, cached workspace) per device; ab200_multi_clearsky_emission / _propmat_levels take exactly the
+ * arguments of the single-device calls, deal the grid's 512-frequency blocks round-robin over the devices and let every
+ * device write its blocks into the caller's arrays.  No collective; the results are bit-identical to the one-device
+ * calls (the value at a frequency does not depend on the shard it is computed in).
+ *   n_devices <= 0: every visible device; devices NULL: 0 .. n_devices-1. */
+typedef struct ab200_multi ab200_multi;
+int ab200_multi_create(const ab200_catalog_desc *desc, int32_t n_devices, const int32_t *devices, ab200_multi **out);
+void ab200_multi_destroy(ab200_multi *m);
+int32_t ab200_multi_device_count(const ab200_multi *m);
+int ab200_multi_clearsky_emission(ab200_multi *m, int64_t nf, const double *f, int64_t f_level_stride,
+                                  const ab200_atm_path *atm, int32_t select_species, int32_t no_negative_absorption,
+                                  int32_t nq, const ab200_target *targets, const double *r, int32_t hse_derivative,
+                                  int32_t rte_option, const double *I_bkg, uint32_t flags, double *I, double *dI,
+                                  double *K_out);
+int ab200_multi_propmat_levels(ab200_multi *m, int64_t nf, const double *f, int64_t f_level_stride,
+                               const ab200_atm_path *atm, int32_t select_species, int32_t no_negative_absorption,
+                               int32_t nq, const ab200_target *targets, uint32_t flags, double *K, double *dK);
+
 /* Host-only helpers of the Zeeman pre-expansion (no GPU needed; used by tests and shims):
  * sub-line strengths / splitting coefficients [Hz/T] of one line and polarisation
  * (pol: 0 no, 1 pi, 2 sigma-, 3 sigma+; lbl_zeeman.cpp:261-309, lbl_zeeman.h:342-352); returns the

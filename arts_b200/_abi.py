@@ -169,6 +169,14 @@ class PartfunTable(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("grid", _dp), ("coef", _dp)]
 
 
+class AtmProfileDesc(C.Structure):
+    """ab200_atm_profile: the AtmField of a 1-D atmosphere, flattened."""
+
+    _fields_ = [("nalt", C.c_int32), ("alt", _dp), ("T", _dp), ("P", _dp), ("vmr", _dp), ("isorat", _dp), ("mag", _dp), ("wind", _dp),
+                ("alt_low", C.c_int32), ("alt_upp", C.c_int32), ("top_of_atmosphere", C.c_double), ("partfun", C.POINTER(PartfunTable))]
+
+
+EXTRAP = {"None": 0, "Zero": 1, "Nearest": 2, "Linear": 3}
 PARTFUN_KINDS = {"interp": 0, "coeff": 1, "const": 2, "static_interp": 3}
 
 

@@ -58,6 +58,7 @@ def lib():
     L.ab200_clearsky_emission.argtypes = [_vp] + abi.SIG_CLEARSKY_CORE
     L.ab200_planck_tb.argtypes = [C.c_int64, _dp, _dp]
     L.ab200_set_thread_grid_bounds.argtypes = [C.c_int32, _dp]
+    L.ab200_atm_path_from_profile.argtypes = [C.POINTER(abi.AtmProfileDesc), C.c_int32, C.c_int32, C.c_int32, _dp, C.POINTER(C.c_uint8)] + [_dp] * 8
     L.ab200_multi_create.argtypes = [C.POINTER(abi.CatalogDesc), C.c_int32, C.POINTER(C.c_int32), C.POINTER(_vp)]
     L.ab200_multi_destroy.argtypes = [_vp]
     L.ab200_multi_destroy.restype = None

@@ -649,6 +649,56 @@ def partition_functions(tables, T):
     return Q, dQ
 
 
+class AtmProfile:
+    """The ``AtmField`` of a 1-D atmosphere flattened once (ab200_atm_profile): altitude grid, T, P, VMRs [nalt, ns], constant
+    isotopologue ratios, optional magnetic field and wind [nalt, 3], the extrapolation rule below / above the grid
+    (``"None" | "Zero" | "Nearest" | "Linear"``), ``top_of_atmosphere`` and the partition-function tables of the
+    isotopologues (as for ``partition_functions``)."""
+
+    def __init__(self, alt, T, P, vmr, isorat, mag=None, wind=None, alt_low="None", alt_upp="None", top_of_atmosphere=None,
+                 partfun_tables=None):
+        a = lambda x: None if x is None else np.ascontiguousarray(x, dtype=np.float64)  # noqa: E731
+        self.alt, self.T, self.P, self.vmr, self.isorat, self.mag, self.wind = a(alt), a(T), a(P), a(vmr), a(isorat), a(mag), a(wind)
+        self.vmr = self.vmr.reshape(len(self.alt), -1)
+        self.alt_low, self.alt_upp = alt_low, alt_upp
+        self.toa = float(self.alt[-1] if top_of_atmosphere is None else top_of_atmosphere)
+        self._pf_keep, self._pf = [], None
+        if partfun_tables is not None:
+            self._pf = (abi.PartfunTable * len(partfun_tables))()
+            for k, (kind, grid, coef) in enumerate(partfun_tables):
+                g = None if grid is None else np.ascontiguousarray(grid, dtype=np.float64)
+                c = np.ascontiguousarray(np.atleast_1d(coef), dtype=np.float64)
+                self._pf_keep.append((g, c))
+                self._pf[k].kind, self._pf[k].n, self._pf[k].grid, self._pf[k].coef = abi.PARTFUN_KINDS[kind], len(c), dptr(g), dptr(c)
+
+    def desc(self):
+        d = abi.AtmProfileDesc()
+        d.nalt, d.alt, d.T, d.P, d.vmr, d.isorat = len(self.alt), dptr(self.alt), dptr(self.T), dptr(self.P), dptr(self.vmr), dptr(self.isorat)
+        d.mag, d.wind = dptr(self.mag), dptr(self.wind)
+        d.alt_low, d.alt_upp, d.top_of_atmosphere = abi.EXTRAP[self.alt_low], abi.EXTRAP[self.alt_upp], self.toa
+        d.partfun = self._pf
+        return d
+
+
+def atm_pathFromPath(ray_path_alt, atm_field: AtmProfile, los=None, in_atm=None) -> AtmPath:
+    """``atm_pathFromPath`` (src/m_ppvar.cc:38-45) for a 1-D atmosphere: ``AtmField::at`` at every path point (the top of the
+    atmosphere for points outside it), as flat arrays ready for the path entry points.  ``ray_path_alt`` = pos[0] of the
+    points; ``los`` [np, 2] is carried along."""
+    alt = np.ascontiguousarray(ray_path_alt, dtype=np.float64)
+    n, ns, ni = len(alt), atm_field.vmr.shape[1], len(atm_field.isorat)
+    T, P, vmr, iso = np.empty(n), np.empty(n), np.empty((n, ns)), np.empty((n, ni))
+    has_pf = atm_field._pf is not None  # without tables Q stays NaN: the caller fills it (PartitionFunctions::Q)
+    Q, dQ = (np.empty((n, ni)), np.empty((n, ni))) if has_pf else (np.full((n, ni), np.nan), None)
+    mag = np.empty((n, 3)) if atm_field.mag is not None else None
+    wind = np.empty((n, 3)) if atm_field.wind is not None else None
+    ia = None if in_atm is None else np.ascontiguousarray(in_atm, dtype=np.uint8)
+    d = atm_field.desc()
+    check(lib().ab200_atm_path_from_profile(C.byref(d), ns, ni, n, dptr(alt), None if ia is None else ia.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                            dptr(T), dptr(P), dptr(vmr), dptr(iso), dptr(Q if has_pf else None), dptr(dQ), dptr(mag), dptr(wind)))
+    return AtmPath(T=T, P=P, vmr=vmr, isorat=iso, Q=Q, dQdT=dQ, mag=mag, los=None if los is None else np.asarray(los, dtype=np.float64),
+                   wind=wind)
+
+
 class Lookup:
     """``abs_lookup_data`` on the device (ab200_lookup): a list of ``_abi.LookupTable``."""
 

@@ -450,6 +450,37 @@ typedef struct ab200_partfun_table {
 /* Q, dQdT: [np][n_isot] like in ab200_atm_path; dQdT may be NULL. */
 int ab200_partfun_eval(const ab200_partfun_table *tables, int32_t n_isot, int32_t np, const double *T, double *Q, double *dQdT);
 
+/* ---- atm_pathFromPath for a 1-D atmosphere (src/m_ppvar.cc:38-45) ------------------------------------
+ * forward_atm_path (src/core/path/atm_path.cpp:19-28): AtmField::at at every path point, with the top of the atmosphere for
+ * points outside it.  The AtmField of a 1-D atmosphere - every key a GeodeticField3 on one altitude grid with 1 x 1
+ * latitude / longitude, isotopologue ratios plain numbers - is flattened ONCE into this struct; a path then costs np linear
+ * (Lagrange order 1, functional_atm_field_interp.cpp:6-10) interpolations on flat arrays instead of a walk over the
+ * AtmPoint maps per path.  Out-of-grid altitudes follow the field's InterpolationExtrapolation (atm_field.cpp:536-566,
+ * :890-924): None is an error, Zero gives 0, Nearest the boundary value, Linear the end stencil; an altitude above
+ * top_of_atmosphere is an error (:928-935), as are NaN temperature / pressure and NaN or negative VMRs (:601-640).
+ * Host function (no GPU needed): a path is O(np) numbers and ab200_path_upload consumes host arrays. */
+#define AB200_EXTRAP_NONE 0
+#define AB200_EXTRAP_ZERO 1
+#define AB200_EXTRAP_NEAREST 2
+#define AB200_EXTRAP_LINEAR 3
+typedef struct ab200_atm_profile {
+  int32_t nalt;             /* altitude grid points (>= 1; 1: constant, extrapolation Nearest) */
+  const double *alt;        /* [nalt] ascending [m] */
+  const double *T, *P;      /* [nalt] */
+  const double *vmr;        /* [nalt][n_species] */
+  const double *isorat;     /* [n_isot] */
+  const double *mag, *wind; /* [nalt][3], or NULL (absent from the field: 0) */
+  int32_t alt_low, alt_upp; /* AB200_EXTRAP_* below alt[0] / above alt[nalt-1] */
+  double top_of_atmosphere; /* AtmField::top_of_atmosphere [m] */
+  const struct ab200_partfun_table *partfun; /* [n_isot] Q(T) tables, or NULL (Q, dQdT are then not written) */
+} ab200_atm_profile;
+/* alt [np] = pos[0] of the path points, in_atm [np] = PropagationPathPoint::has(PathPositionType::atm) (NULL: all inside).
+ * Outputs are the arrays of ab200_atm_path: T, P [np], vmr [np][n_species], isorat, Q, dQdT [np][n_isot], mag, wind [np][3];
+ * dQdT, mag, wind may be NULL. */
+int ab200_atm_path_from_profile(const ab200_atm_profile *prof, int32_t n_species, int32_t n_isot, int32_t np, const double *alt,
+                                const uint8_t *in_atm, double *T, double *P, double *vmr, double *isorat, double *Q,
+                                double *dQdT, double *mag, double *wind);
+
 /* ---- observer epilogue on the device (the callers' glue around the path) --------------------
  * What spectral_rad_observer_agenda / measurement_vecFromSensor do on the host after the RTE, applied to the
  * resident results of one path so that only the state-space Jacobian or the sensor channels cross PCIe:

@@ -2593,4 +2593,58 @@ int orc_shape_eval(const double* shape, const double* dsdz, int64_t n, const dou
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// atm_pathFromPath for a 1-D AtmField: forward_atm_path (src/core/path/atm_path.cpp:19-28) ->
+// Atm::Field::at (src/core/atm/atm_field.cpp:928-947) -> Data::at (:890-924) with find_limit / select (:536-566) ->
+// lagrange_interp::interp with the order-1 altitude lag (functional_atm_field_interp.cpp:6-10,53-65).  The lag is the
+// same code the CIA restatement uses (cia::start_index / cia::weights above).
+// ---------------------------------------------------------------------------
+int orc_atm_path_from_profile(const ab200_atm_profile* f, int32_t n_species, int32_t n_isot, int32_t np, const double* alt,
+                              const uint8_t* in_atm, double* T, double* P, double* vmr, double* isorat, double* mag, double* wind) {
+  const Index n = f->nalt;
+  for (int ip = 0; ip < np; ip++) {
+    Numeric a = (in_atm and not in_atm[ip]) ? f->top_of_atmosphere : alt[ip];
+    if (a > f->top_of_atmosphere) return fail(AB200_ERR_INVALID, "Cannot get values above the top of the atmosphere");
+    // select(), :536-550
+    int type = AB200_EXTRAP_LINEAR;
+    const int lowt = n == 1 ? AB200_EXTRAP_NEAREST : f->alt_low, uppt = n == 1 ? AB200_EXTRAP_NEAREST : f->alt_upp;
+    if (a < f->alt[0]) {
+      type = lowt;
+      if (type == AB200_EXTRAP_NEAREST) a = f->alt[0];
+    } else if (f->alt[n - 1] < a) {
+      type = uppt;
+      if (type == AB200_EXTRAP_NEAREST) a = f->alt[n - 1];
+    }
+    if (type == AB200_EXTRAP_NONE) return fail(AB200_ERR_INVALID, "Limit breached");
+    double w[2] = {1.0, 0.0};
+    Index i0 = 0;
+    const Index order = n == 1 ? 0 : 1;
+    if (type != AB200_EXTRAP_ZERO and order == 1) {
+      i0 = cia::start_index(f->alt, n, 1, a);
+      cia::weights(w, f->alt, i0, 1, a);
+    }
+    auto at = [&](const double* v, Index stride) -> Numeric {
+      if (type == AB200_EXTRAP_ZERO) return 0.0;
+      if (order == 0) return v[0];
+      Numeric out = 0.0;  // lagrange_interp::interp: sum over the stencil in index order
+      for (Index j = 0; j < 2; j++) out += w[j] * v[(i0 + j) * stride];
+      return out;
+    };
+    T[ip] = at(f->T, 1);
+    P[ip] = at(f->P, 1);
+    if (std::isnan(P[ip]) or std::isnan(T[ip])) return fail(AB200_ERR_INVALID, "Pressure or temperature is NaN");
+    for (int s = 0; s < n_species; s++) {
+      const Numeric v = at(f->vmr + s, n_species);
+      if (std::isnan(v) or v < 0.0) return fail(AB200_ERR_INVALID, "bad VMR");
+      vmr[static_cast<Index>(ip) * n_species + s] = v;
+    }
+    for (int i = 0; i < n_isot; i++) isorat[static_cast<Index>(ip) * n_isot + i] = f->isorat[i];
+    for (int c = 0; c < 3; c++) {
+      if (mag) mag[3 * ip + c] = f->mag ? at(f->mag + c, 3) : 0.0;
+      if (wind) wind[3 * ip + c] = f->wind ? at(f->wind + c, 3) : 0.0;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -93,3 +93,29 @@ def test_repeated_steps_are_bit_identical(wsm):
         p.close()
     cat.close()
     cat3.close()
+
+
+def test_config5_path_with_jacobians_full_size(wsm, orc):
+    """BASELINE configs[4], one path of the batch at its full size: 1e4 lines x 1e4 frequencies x 100 levels with
+    temperature and VMR Jacobian rows (hse_derivative on), fused chain.  The spectrum and the rows of a strided frequency
+    sample must equal a separate GPU run on just those frequencies bit for bit (the very-far / near split of the Jacobian
+    line sum is decided per pair), and that run is compared with the oracle: K <= 1e-9, Tb <= 1e-6 K, rows <= 2e-7 of the
+    column maximum."""
+    c = synth.case_c5_single()
+    assert c.cat.n_lines == 10_000 and c.nf == 10_000 and c.np_ == 100
+    tg = (("T",), ("VMR", 0))
+    cat = wsm.Catalog(c.cat)
+    I, dI = wsm.spectral_radClearskyEmission(cat, c.f, c.atm, c.r, c.I_bkg, jac_targets=tg, hse_derivative=1)
+    idx = np.unique(np.linspace(0, c.nf - 1, 40).astype(np.int64))
+    fs, bs = np.ascontiguousarray(c.f[idx]), np.ascontiguousarray(c.I_bkg[idx])
+    Is, dIs, Ks = wsm.spectral_radClearskyEmission(cat, fs, c.atm, c.r, bs, jac_targets=tg, hse_derivative=1, return_propmat=True)
+    assert np.array_equal(Is, I[idx]) and np.array_equal(dIs, dI[idx])
+    Ir, dIr, Kr = orc.clearsky_emission(c.cat, fs, c.atm, c.r, bs, targets=tg, hse_derivative=1, return_K=True)
+    assert_propmat_close(Ks, Kr)
+    tb, tbr = wsm.spectral_radApplyPlanckTb(Is, fs), orc.planck_tb(fs, Ir)
+    assert np.abs(tb - tbr).max() <= 1e-6
+    for q in range(len(tg)):
+        a, b = dIs[:, :, q, 0], dIr[:, :, q, 0]
+        assert np.abs(b).max() > 0
+        assert np.abs(a - b).max() <= 2e-7 * np.abs(b).max(), (q, np.abs(a - b).max() / np.abs(b).max())
+    cat.close()

@@ -70,6 +70,8 @@ struct ab200_path {
   // workspace
   double* d_prep = nullptr;
   double* d_summary = nullptr;
+  double* d_mom = nullptr;  // [levels_per_batch][ntiles][MOM_DOUBLES] far-field moments of the tiles
+  double* d_mp_acc = nullptr;  // [real segments][levels_per_batch][k_pitch] far-field part of the line sums
   int32_t levels_per_batch = 0;
   int* d_flags = nullptr;
   // outputs
@@ -122,7 +124,7 @@ struct ab200_path {
   bool o_ran = false, o_has_jx = false;
 
   ~ab200_path() {
-    cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary);
+    cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary); cudaFree(d_mom); cudaFree(d_mp_acc);
     cudaFree(d_flags); cudaFree(d_K); cudaFree(d_I);
     cudaFree(d_dK); cudaFree(d_dI); cudaFree(d_Ilev); cudaFree(d_jac); cudaFree(d_jcom);
     if (h_small) cudaFreeHost(h_small);
@@ -218,6 +220,12 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->levels_per_batch = std::max(lpb, 1);
   AB_TRY(dev_alloc(&p->d_prep, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * tile_doubles()));
   AB_TRY(dev_alloc(&p->d_summary, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * SUMMARY_DOUBLES));
+  AB_TRY(dev_alloc(&p->d_mom, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * MOM_DOUBLES));
+  {
+    size_t nseg0 = 0;  // real merged segments: each keeps the far-field part of its line sum per (level, frequency)
+    for (const auto& sg : cat->segments) nseg0 += sg.mode == 0 ? 1 : 0;
+    AB_TRY(dev_alloc(&p->d_mp_acc, nseg0 * p->levels_per_batch * static_cast<size_t>(p->k_pitch)));
+  }
   if (nq > 0) {
     AB_TRY(dev_alloc(&p->d_jac, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * nq * 2 * TL * 4));
     AB_TRY(dev_alloc(&p->d_jcom, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * TL));
@@ -462,6 +470,9 @@ void fill_params(const ab200_path* p, int lev0, PrepareParams& pp, SumParams& sp
   sp.T = p->d_T + lev0; sp.P = p->d_P + lev0;
   sp.npm = p->d_npm + static_cast<size_t>(lev0) * 28;
   sp.prep = p->d_prep; sp.summary = p->d_summary; sp.tile_count = cat->d_tile_count; sp.tile_mode = cat->d_tile_mode; sp.ntiles = cat->ntiles;
+  static const bool multipole = [] { const char* e = getenv("AB200_MULTIPOLE"); return e ? atoi(e) != 0 : true; }();
+  sp.mom = multipole ? p->d_mom : nullptr;
+  sp.mp_acc = p->d_mp_acc;
   sp.no_negative_absorption = p->no_neg;
   sp.K = p->d_K + static_cast<size_t>(lev0) * p->k_pitch * 7;
 }
@@ -488,6 +499,7 @@ int ab200_path_run_propmat(ab200_path* p) {
     {
       LaunchTimer t(p, 0);
       AB_TRY(launch_prepare(pp, nlev, p->stream));
+      if (sp.mom && p->nsegs[0] > 0) AB_TRY(launch_moments(pp, p->d_mom, nlev, p->stream));
       t.stop();
     }
     sp.k_store_full = store_full ? 1 : 0;

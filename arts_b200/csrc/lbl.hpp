@@ -48,6 +48,8 @@ struct SumParams {
   int32_t no_negative_absorption;
   double* K;  // [nlev][k_pitch][7], offset to the batch
   int64_t k_pitch;
+  double* mp_acc;     // [nsegs][nlev][k_pitch] far-field part of each real segment's line sum (scratch, written by lbl_farfield_kernel)
+  const double* mom;  // [nlev][ntiles][MOM_DOUBLES] far-field moments of the tiles (real kernel), or null: every far tile line by line
   int32_t debug_skip_near;  // measurement only (AB200_DEBUG_SKIP_NEAR=1): near tiles contribute nothing
   int32_t k_store_full;  // real kernel: K is not initialised; write whole records {A,0,0,0,0,0,0} with vector stores
 };
@@ -84,6 +86,7 @@ struct JacSumParams {
 };
 
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream);
+int launch_moments(const PrepareParams& p, double* mom, int nlev, cudaStream_t stream);
 int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev, cudaStream_t stream);
 int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream);
 int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream);

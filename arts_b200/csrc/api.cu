@@ -64,14 +64,14 @@ struct ab200_path {
   double* h_small = nullptr;  // pinned staging of the same
   size_t small_doubles = 0;
   double* d_Ibkg = nullptr;
-  SegmentDev* d_segs = nullptr;  // [2][nsegments] capacity; mode-0 list then mode-1 list
+  SegmentDev* d_segs = nullptr;  // [3][nsegments] capacity: mode-0 list (line-by-line kernel), mode-1 list, mode-0 far-field list
   SegmentDev* h_segs = nullptr;
-  int32_t nsegs[2] = {0, 0};
+  int32_t nsegs[3] = {0, 0, 0};  // [2]: real segments without cutoffs, summed by lbl_fmm.cu
+  FmmBuffers fmm{};              // one allocation (fmm.L0), sized for levels_per_batch levels
+  int32_t* d_tile_seg = nullptr; // [ntiles] index of the tile's far-field segment in the catalog, -1 for the others
   // workspace
   double* d_prep = nullptr;
   double* d_summary = nullptr;
-  double* d_mom = nullptr;  // [levels_per_batch][ntiles][MOM_DOUBLES] far-field moments of the tiles
-  double* d_mp_acc = nullptr;  // [real segments][levels_per_batch][k_pitch] far-field part of the line sums
   int32_t levels_per_batch = 0;
   int* d_flags = nullptr;
   // outputs
@@ -124,7 +124,7 @@ struct ab200_path {
   bool o_ran = false, o_has_jx = false;
 
   ~ab200_path() {
-    cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary); cudaFree(d_mom); cudaFree(d_mp_acc);
+    cudaFree(d_f); cudaFree(d_small); cudaFree(d_Ibkg); cudaFree(d_segs); cudaFree(d_prep); cudaFree(d_summary); cudaFree(fmm.L0); cudaFree(d_tile_seg);
     cudaFree(d_flags); cudaFree(d_K); cudaFree(d_I);
     cudaFree(d_dK); cudaFree(d_dI); cudaFree(d_Ilev); cudaFree(d_jac); cudaFree(d_jcom);
     if (h_small) cudaFreeHost(h_small);
@@ -209,8 +209,8 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   AB_TRY(dev_alloc(&p->d_I, static_cast<size_t>(nf) * 4));
   AB_TRY(dev_alloc(&p->d_K, snp * p->k_pitch * 7));
   const size_t nseg = cat->segments.size();
-  AB_TRY(dev_alloc(&p->d_segs, 2 * nseg));
-  if (nseg) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_segs), 2 * nseg * sizeof(SegmentDev)));
+  AB_TRY(dev_alloc(&p->d_segs, 3 * nseg));
+  if (nseg) AB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p->h_segs), 3 * nseg * sizeof(SegmentDev)));
   AB_TRY(dev_alloc(&p->d_flags, 1));
   AB_CUDA(cudaMemset(p->d_flags, 0, sizeof(int)));
 
@@ -220,11 +220,31 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   p->levels_per_batch = std::max(lpb, 1);
   AB_TRY(dev_alloc(&p->d_prep, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * tile_doubles()));
   AB_TRY(dev_alloc(&p->d_summary, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * SUMMARY_DOUBLES));
-  AB_TRY(dev_alloc(&p->d_mom, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * MOM_DOUBLES));
   {
-    size_t nseg0 = 0;  // real merged segments: each keeps the far-field part of its line sum per (level, frequency)
-    for (const auto& sg : cat->segments) nseg0 += sg.mode == 0 ? 1 : 0;
-    AB_TRY(dev_alloc(&p->d_mp_acc, nseg0 * p->levels_per_batch * static_cast<size_t>(p->k_pitch)));
+    // far-field sums of the real, cutoff-free segments (lbl_fmm.cu): moment records of four cluster levels + scratch
+    size_t nff = 0;
+    std::vector<int32_t> tseg(static_cast<size_t>(cat->ntiles), -1);
+    for (size_t i = 0; i < cat->segments.size(); i++) {
+      const Segment& sg = cat->segments[i];
+      if (sg.mode != 0 || sg.has_cutoff) continue;
+      nff++;
+      for (int64_t t = sg.tile_begin; t < sg.tile_end; t++) tseg[t] = static_cast<int32_t>(i);
+    }
+    if (nff > 0 && cat->ntiles > 0) {
+      const size_t L = static_cast<size_t>(p->levels_per_batch), nt = static_cast<size_t>(cat->ntiles);
+      p->fmm.ngroups = (cat->ntiles + FMM_GROUP - 1) / FMM_GROUP;
+      const size_t n0 = L * nt * 16 * MOM_DOUBLES, n1 = L * nt * 4 * MOM_DOUBLES, n2 = L * nt * MOM_DOUBLES,
+                   n3 = L * static_cast<size_t>(p->fmm.ngroups) * MOM_DOUBLES, nsc = L * nt * 2,
+                   nacc = nff * L * static_cast<size_t>(p->k_pitch);
+      AB_TRY(dev_alloc(&p->fmm.L0, n0 + n1 + n2 + n3 + nsc + nacc));
+      p->fmm.L1 = p->fmm.L0 + n0;
+      p->fmm.L2 = p->fmm.L1 + n1;
+      p->fmm.L3 = p->fmm.L2 + n2;
+      p->fmm.scan = p->fmm.L3 + n3;
+      p->fmm.far_acc = p->fmm.scan + nsc;
+      AB_TRY(dev_alloc(&p->d_tile_seg, nt));
+      AB_CUDA(cudaMemcpy(p->d_tile_seg, tseg.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
   }
   if (nq > 0) {
     AB_TRY(dev_alloc(&p->d_jac, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * nq * 2 * TL * 4));
@@ -400,13 +420,16 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
 
   // segments selected by species (lbl_lineshape.cpp:191), split by kernel
   const size_t nseg = cat->segments.size();
-  p->nsegs[0] = p->nsegs[1] = 0;
+  // AB200_FARFIELD=0 routes every real segment through the line-by-line kernel (A/B measurements, tests); read per upload
+  const bool farfield = [] { const char* e = getenv("AB200_FARFIELD"); return e ? atoi(e) != 0 : true; }();
+  p->nsegs[0] = p->nsegs[1] = p->nsegs[2] = 0;
   for (const Segment& s : cat->segments) {
     if (!(select_species == AB200_SPECIES_BATH || select_species == s.species)) continue;
     SegmentDev d{s.tile_begin, s.tile_end, s.cutoff, s.pol, s.has_cutoff};
-    p->h_segs[s.mode * nseg + p->nsegs[s.mode]++] = d;
+    const int list = s.mode == 1 ? 1 : (farfield && p->fmm.L0 && !s.has_cutoff) ? 2 : 0;
+    p->h_segs[list * nseg + p->nsegs[list]++] = d;
   }
-  if (nseg) AB_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, 2 * nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice, p->stream));
+  if (nseg) AB_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, 3 * nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice, p->stream));
 
   AB_CUDA(cudaEventRecord(p->ev_staged, p->stream));
   p->f_stride   = f_level_stride;
@@ -470,9 +493,6 @@ void fill_params(const ab200_path* p, int lev0, PrepareParams& pp, SumParams& sp
   sp.T = p->d_T + lev0; sp.P = p->d_P + lev0;
   sp.npm = p->d_npm + static_cast<size_t>(lev0) * 28;
   sp.prep = p->d_prep; sp.summary = p->d_summary; sp.tile_count = cat->d_tile_count; sp.tile_mode = cat->d_tile_mode; sp.ntiles = cat->ntiles;
-  static const bool multipole = [] { const char* e = getenv("AB200_MULTIPOLE"); return e ? atoi(e) != 0 : true; }();
-  sp.mom = multipole ? p->d_mom : nullptr;
-  sp.mp_acc = p->d_mp_acc;
   sp.no_negative_absorption = p->no_neg;
   sp.K = p->d_K + static_cast<size_t>(lev0) * p->k_pitch * 7;
 }
@@ -486,7 +506,7 @@ int ab200_path_run_propmat(ab200_path* p) {
   const size_t kbytes = static_cast<size_t>(p->np) * p->k_pitch * 7 * sizeof(double);
   // With mode-0 (real) segments selected the real line sum writes whole K records itself (vector stores);
   // only without them, or when the caller's K is accumulated into, K is zeroed / kept and updated in place.
-  const bool store_full = !p->k_preloaded && p->nsegs[0] > 0 && cat->ntiles > 0 && p->nf > 0;
+  const bool store_full = !p->k_preloaded && p->nsegs[0] + p->nsegs[2] > 0 && cat->ntiles > 0 && p->nf > 0;
   if (!p->k_preloaded && !store_full && kbytes) AB_CUDA(cudaMemsetAsync(p->d_K, 0, kbytes, p->stream));
   if (p->nq > 0 && !p->dk_preloaded && kbytes) AB_CUDA(cudaMemsetAsync(p->d_dK, 0, kbytes * p->nq, p->stream));
   if (cat->ntiles == 0 || p->nf == 0) return AB200_OK;
@@ -499,11 +519,20 @@ int ab200_path_run_propmat(ab200_path* p) {
     {
       LaunchTimer t(p, 0);
       AB_TRY(launch_prepare(pp, nlev, p->stream));
-      if (sp.mom && p->nsegs[0] > 0) AB_TRY(launch_moments(pp, p->d_mom, nlev, p->stream));
       t.stop();
     }
-    sp.k_store_full = store_full ? 1 : 0;
+    // real segments: the line-by-line kernel (segments with ByLine cutoffs) writes whole K records when it runs; the
+    // far-field sums then add to them, or write the records themselves when they are alone
+    sp.k_store_full = (store_full && p->nsegs[0] > 0) ? 1 : 0;
     for (int mode = 0; mode < 2; mode++) {
+      if (mode == 1 && p->nsegs[2] > 0) {
+        SumParams sf = sp;
+        sf.segs = p->d_segs + 2 * nseg;
+        sf.nsegs = p->nsegs[2];
+        LaunchTimer t(p, 1);
+        AB_TRY(launch_fmm(pp, sf, p->fmm, p->d_tile_seg, nlev, (store_full && p->nsegs[0] == 0) ? 1 : 0, p->stream));
+        t.stop();
+      }
       sp.segs = p->d_segs + mode * nseg;
       sp.nsegs = p->nsegs[mode];
       if (sp.nsegs == 0) continue;
@@ -549,11 +578,11 @@ int ab200_path_run_propmat(ab200_path* p) {
       js.dnpm = p->d_dnpm + 84 * static_cast<size_t>(lev0);
       js.wind_jac = (p->flags & AB200_FLAG_WIND_ROWS_DF) ? nullptr : p->d_wjac + 3 * static_cast<size_t>(lev0);
       AB_TRY(launch_prepare_jac(pp, jp, nlev, p->stream));
-      for (int mode = 0; mode < 2; mode++) {
-        sp.segs = p->d_segs + mode * nseg;
-        sp.nsegs = p->nsegs[mode];
+      for (int list = 0; list < 3; list++) {  // 0 and 2: real segments (with / without cutoffs), 1: complex
+        sp.segs = p->d_segs + list * nseg;
+        sp.nsegs = p->nsegs[list];
         if (sp.nsegs == 0) continue;
-        js.real_lines = mode == 0 ? 1 : 0;
+        js.real_lines = list != 1 ? 1 : 0;
         AB_TRY(launch_sum_jac(sp, js, nlev, p->stream));
       }
     }

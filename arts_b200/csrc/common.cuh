@@ -66,11 +66,12 @@ constexpr double FAR_LIMIT_REAL_SUM = 1000.0;
 // nu(z)-term recurrence.  The Jacobian kernels do not use it: their forward difference amplifies w's error by 1e4.
 constexpr double MID_LIMIT = 48.0;
 
-// Far-field (multipole) moments of a line tile, see lbl_moments_kernel (lbl.cu): centre, acceptance distance, radius and
-// MP_P scaled real moments per (level, tile)
+// Far-field (multipole) sums of the real, cutoff-free segments (lbl_fmm.cu): per cluster and level a record of
+// MOM_DOUBLES doubles {centre c, acceptance distance rho, radius R, m_1 .. m_MP_P, pad}
 constexpr int MP_P = 16;
 constexpr double MP_THETA = 6.0;
-constexpr int MOM_DOUBLES = 20;  // c, rho, R, m_1 .. m_16, pad
+constexpr int MOM_DOUBLES = 20;
+constexpr int FMM_GROUP = 16;  // tiles per coarsest cluster
 
 constexpr int AB200_MAX_TARGETS = 8;  // Jacobian targets per call (temperature + species VMRs)
 

@@ -189,94 +189,6 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
 }
 
 // ---------------------------------------------------------------------------
-// Far-field moments of a tile (real merged segments without cutoffs).
-//
-// Beyond |x| + y = 1000 the real kernel evaluates every line with the closed form s w(z) = S zeta / (zeta^2 - h),
-// zeta = u + i g, S = i Si (faddeeva.cuh).  Its partial fractions are two simple poles,
-//     S zeta / (zeta^2 - h) = (S / 2) [1 / (zeta - a) + 1 / (zeta + a)],   a = sqrt(h) = GD / sqrt(2),
-// and with the tile centre c, v = f - c, delta_l = f0'_l - c every pole is 1 / (v - p), p = delta_l +- a_l - i g_l:
-//     sum_l Re(S_l zeta_l / (zeta_l^2 - h_l)) = (1 / v) sum_{k >= 1} m_k (R / v)^k,
-//     m_k = sum_l -(Si_l / 2) Im[(p_l+ / R)^k + (p_l- / R)^k]          (k = 0 vanishes: S is imaginary)
-// for |v| > max |p| - the multipole expansion of 256 lines about their centre.  Past |v| >= MP_THETA R the first MP_P
-// moments reproduce the line-by-line sum of the SAME closed form to 3e-13 (measured against 40-digit arithmetic, widths from
-// 1e2 to 3e9 Hz), so a far tile costs MP_P + 8 FP64 instructions per frequency instead of 7 x 256.  Im(p^k) is carried by
-// the recurrence (A, B) <- (d A + g B, d B - g A), whose two terms have the same sign: it keeps its relative accuracy
-// however small g / |delta| is (Doppler regime).  rho, the acceptance distance, also covers the kernel's own far criterion
-// for every line of the tile: |f - c| > rho  =>  |x_l| + y_l > 1000 (1 + 1e-9) for all l.
-// WHICH (tile, frequency) pairs take the expansion depends on that frequency alone, so spectra stay bit-identical under any
-// frequency partition; block-level shortcuts only skip work whose result is already decided.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL) lbl_moments_kernel(PrepareParams p, double* __restrict__ mom) {
-  const int64_t tile = blockIdx.x;
-  const int lev      = blockIdx.y;
-  const int lane     = threadIdx.x;
-  const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
-  const double* __restrict__ s4  = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
-  double* __restrict__ out       = mom + (int64_t(lev) * p.ntiles + tile) * MOM_DOUBLES;
-  if (p.tile_mode[tile] != 0 || s4[0] > s4[1] || s4[4] < DBL_MAX) {  // complex tile, no contributing line, or cutoffs: never
-    if (lane < MOM_DOUBLES) out[lane] = lane == 1 ? DBL_MAX : 0.0;
-    return;
-  }
-  const double f0s = rec[(0 * TL + lane) * REC_GROUP + 0];
-  const double igd = rec[(1 * TL + lane) * REC_GROUP + 1];
-  const double y   = rec[(1 * TL + lane) * REC_GROUP + 2];
-  const double sre = rec[(1 * TL + lane) * REC_GROUP + 3];
-  const bool live  = igd != 0.0;
-  const double c   = 0.5 * (s4[0] + s4[1]);
-  const double GD  = live ? 1.0 / igd : 0.0;
-  const double g   = y * GD, a = GD * 0.70710678118654752440, Si = sre * GD * cst::inv_sqrt_pi;
-  const double d   = live ? f0s - c : 0.0;
-  double Rl = live ? fabs(d) + a + g : 0.0;
-  double Dl = live ? fabs(d) + fmax(0.0, FAR_LIMIT_REAL_SUM * (1.0 + 1e-9) - y) * GD : 0.0;
-  __shared__ double red[TL / 32][MP_P];
-  __shared__ double sR, sD;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Rl = fmax(Rl, __shfl_xor_sync(0xffffffffu, Rl, o));
-    Dl = fmax(Dl, __shfl_xor_sync(0xffffffffu, Dl, o));
-  }
-  if ((lane & 31) == 0) { red[lane >> 5][0] = Rl; red[lane >> 5][1] = Dl; }
-  __syncthreads();
-  if (lane == 0) {
-    double R = 0.0, D = 0.0;
-    for (int w = 0; w < TL / 32; w++) { R = fmax(R, red[w][0]); D = fmax(D, red[w][1]); }
-    sR = R; sD = D;
-  }
-  __syncthreads();
-  const double R  = sR;
-  const double iR = R > 0.0 ? 1.0 / R : 0.0;
-  const double dp = (d + a) * iR, dm = (d - a) * iR, gh = g * iR;
-  double Ap = 1.0, Bp = 0.0, Am = 1.0, Bm = 0.0, term[MP_P];
-#pragma unroll
-  for (int k = 0; k < MP_P; k++) {
-    const double Ap1 = __fma_rn(dp, Ap, gh * Bp), Bp1 = __fma_rn(dp, Bp, -(gh * Ap));
-    const double Am1 = __fma_rn(dm, Am, gh * Bm), Bm1 = __fma_rn(dm, Bm, -(gh * Am));
-    Ap = Ap1; Bp = Bp1; Am = Am1; Bm = Bm1;
-    term[k] = live ? -0.5 * Si * (Bp + Bm) : 0.0;
-  }
-  __syncthreads();  // red is reused
-#pragma unroll
-  for (int k = 0; k < MP_P; k++) {
-    double v = term[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 31) == 0) red[lane >> 5][k] = v;
-  }
-  __syncthreads();
-  if (lane < MP_P) {
-    double v = 0.0;
-    for (int w = 0; w < TL / 32; w++) v += red[w][lane];
-    out[3 + lane] = v;
-  }
-  if (lane == 0) {
-    out[0] = c;
-    out[1] = R > 0.0 ? fmax(MP_THETA * R, sD) * (1.0 + 1e-12) : DBL_MAX;
-    out[2] = R;
-    out[3 + MP_P] = 0.0;
-  }
-}
-
-// ---------------------------------------------------------------------------
 // K2 / K3
 // ---------------------------------------------------------------------------
 // default geometry of the real line sum: 128 threads x 4 frequencies per thread = 512-frequency blocks
@@ -305,8 +217,6 @@ __device__ __forceinline__ uint8_t classify_tile(const double* __restrict__ s, d
 //           subtracted once per frequency as the tile's sum)
 //   PART    windows cut through the pair set: per-pair predicate
 constexpr uint8_t CLS_PART = 3;
-constexpr uint8_t CLS_MP = 4;     // real kernel: the far-field expansion serves every frequency of the block
-constexpr uint8_t CLS_MIXED = 8;  // flag: it serves some of them
 __device__ __forceinline__ uint8_t classify_tile_real(const double* __restrict__ s, double fblk_min, double fblk_max,
                                                       double far_limit) {
   const double f0min = s[0], f0max = s[1];
@@ -339,71 +249,6 @@ __device__ __forceinline__ void flag_lines(uint8_t* __restrict__ flag, const dou
   }
 }
 
-// --------------------------- far-field pass of the real segments --------------------------------------------------
-// For every frequency the tiles whose expansion it accepts (|f - c| > rho, lbl_moments_kernel), summed in tile order into
-// mp_acc [segment][level][k_pitch]; lbl_sum_real_kernel starts each segment's sum from it and adds the other tiles line by
-// line.  No shared memory, no barriers: moments are warp-uniform loads, each thread runs FF_R Horner chains.
-constexpr int FF_NT = 128;
-template <int FF_R>
-__global__ void __launch_bounds__(FF_NT) lbl_farfield_kernel(SumParams p) {
-  const int tid = threadIdx.x;
-  const int lev = blockIdx.y;
-  const int64_t fblk = int64_t(blockIdx.x) * (FF_NT * FF_R);
-  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
-  const double ffac = p.ffac[lev];
-  double f[FF_R];
-#pragma unroll
-  for (int r = 0; r < FF_R; r++) {
-    const int64_t i = fblk + r * FF_NT + tid;
-    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
-  }
-  const double fblk_min = ffac * fg[fblk];
-  const double fblk_max = ffac * fg[(fblk + FF_NT * FF_R - 1 < p.nf) ? fblk + FF_NT * FF_R - 1 : p.nf - 1];
-  const double* __restrict__ mom = p.mom + int64_t(lev) * p.ntiles * MOM_DOUBLES;
-  for (int is = 0; is < p.nsegs; is++) {
-    const SegmentDev seg = p.segs[is];
-    double acc[FF_R];
-#pragma unroll
-    for (int r = 0; r < FF_R; r++) acc[r] = 0.0;
-#pragma unroll 1
-    for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
-      const double* __restrict__ mo = mom + t * MOM_DOUBLES;
-      const double2 cr = __ldg(reinterpret_cast<const double2*>(mo));  // c, rho
-      if (!(fmax(fabs(fblk_min - cr.x), fabs(fblk_max - cr.x)) > cr.y)) continue;  // no frequency of the block accepts it
-      const double2 m01 = __ldg(reinterpret_cast<const double2*>(mo) + 1);           // R, m_1
-      double tau[FF_R], tt[FF_R], s[FF_R];
-#pragma unroll
-      for (int r = 0; r < FF_R; r++) {
-        const double v = __dsub_rn(f[r], cr.x);
-        tt[r]  = (fabs(v) > cr.y) ? fast_rcp(v) : 0.0;  // the frequency's own test; 0 switches the tile off exactly
-        tau[r] = __dmul_rn(m01.x, tt[r]);
-      }
-      const double2* __restrict__ mk = reinterpret_cast<const double2*>(mo) + 2;  // m_2 .. m_17 (m_17 = 0 pad) as pairs
-      {
-        const double2 top = __ldg(mk + (MP_P - 2) / 2);  // m_16, pad
-#pragma unroll
-        for (int r = 0; r < FF_R; r++) s[r] = top.x;
-      }
-#pragma unroll
-      for (int j = (MP_P - 2) / 2 - 1; j >= 0; j--) {
-        const double2 pr = __ldg(mk + j);  // m_{2j+2}, m_{2j+3}
-#pragma unroll
-        for (int r = 0; r < FF_R; r++) s[r] = __fma_rn(__fma_rn(s[r], tau[r], pr.y), tau[r], pr.x);
-      }
-#pragma unroll
-      for (int r = 0; r < FF_R; r++) {
-        s[r]   = __fma_rn(s[r], tau[r], m01.y);
-        acc[r] = __fma_rn(__dmul_rn(s[r], tau[r]), tt[r], acc[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < FF_R; r++) {
-      const int64_t i = fblk + r * FF_NT + tid;
-      if (i < p.k_pitch) p.mp_acc[(int64_t(is) * gridDim.y + lev) * p.k_pitch + i] = acc[r];
-    }
-  }
-}
-
 // --------------------------- real-only kernel (mode 0) ----------------------
 // Segments: merged bands without line mixing / Zeeman (ByLine cutoffs allowed, per line); output: Propmat.A only.
 // 6 CTAs (24 warps) per SM: 80 registers, 36 KB of shared memory.  Measured on B200 (profiles/r1_ab_decoupled.txt):
@@ -416,7 +261,6 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
   constexpr int F_TILE = SUM_NT * SUM_R;
   constexpr int STAGES = REAL_STAGES;
   constexpr int STAGE_DOUBLES = 2 * TL * REC_GROUP;  // groups 0 and 1; E1 (group 2) of the rare series pairs comes from L2
-  static_assert(REAL_CHUNK <= 2048, "the tile list keeps 11 bits of tile index");
   static_assert(F_TILE * 7 <= REAL_RING_DOUBLES, "the K store staging reuses the line-record ring");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* sbuf      = reinterpret_cast<double*>(smem_raw);
@@ -452,7 +296,6 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
 
   const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
-  const double* __restrict__ mom  = p.mom ? p.mom + int64_t(lev) * p.ntiles * MOM_DOUBLES : nullptr;
   uint32_t it = 0;  // tiles consumed so far by this CTA (ring position)
   double kacc[SUM_R];  // sum over the segments of the clamped, scaled line sums: one K update per frequency
 #pragma unroll
@@ -463,40 +306,23 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
     // far-wing closed form beyond x + y = 1000: relative error 2.5 / x^4 of a term (2.5e-12).  With cutoffs the
     // cutoff value of a far window edge comes from the same form (prepare kernel), so the difference is as accurate
     constexpr double far_limit = FAR_LIMIT_REAL_SUM;
-    // the far-field part of the segment's sum (lbl_farfield_kernel), then the remaining tiles line by line in tile order
     double accS[SUM_R];
 #pragma unroll
-    for (int r = 0; r < SUM_R; r++) {
-      const int64_t i = fblk + r * SUM_NT + tid;
-      accS[r] = (mom && i < p.k_pitch) ? p.mp_acc[(int64_t(is) * gridDim.y + lev) * p.k_pitch + i] : 0.0;
-    }
+    for (int r = 0; r < SUM_R; r++) accS[r] = 0.0;
 
     for (int64_t c0 = seg.tile_begin; c0 < seg.tile_end; c0 += REAL_CHUNK) {
       const int nall = int(min(int64_t(REAL_CHUNK), seg.tile_end - c0));
       __syncthreads();  // every warp is done with the previous chunk's list
-      for (int t = tid; t < nall; t += SUM_NT) {
-        uint8_t cls = classify_tile_real(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, far_limit);
-        if (mom && (cls == CLS_FAR || cls == CLS_NEAR)) {
-          // far-field expansion of the tile: for every frequency of the block (the tile leaves the line-by-line list),
-          // for none, or for some (both passes run; each frequency keeps the value its own test selects)
-          const double2 cr = *reinterpret_cast<const double2*>(mom + (c0 + t) * MOM_DOUBLES);  // c, rho
-          const double vmin = fmax(0.0, fmax(cr.x - fblk_max, fblk_min - cr.x));
-          const double vmax = fmax(fabs(fblk_min - cr.x), fabs(fblk_max - cr.x));
-          if (vmin > cr.y) cls = CLS_MP;
-          else if (vmax > cr.y) cls |= CLS_MIXED;
-        }
-        act[t] = cls;
-      }
+      for (int t = tid; t < nall; t += SUM_NT)
+        act[t] = classify_tile_real(summ + (c0 + t) * SUMMARY_DOUBLES, fblk_min, fblk_max, far_limit);
       __syncthreads();
       if (tid < 32) {  // warp 0 compacts the non-skipped tiles in place (j <= t), keeping catalog order
         int n = 0;
         for (int t0 = 0; t0 < nall; t0 += 32) {
           const int t = t0 + tid;
           const uint16_t c = t < nall ? act[t] : uint16_t(CLS_SKIP);
-          const bool keep  = c != CLS_SKIP && c != CLS_MP;
-          const unsigned m = __ballot_sync(0xffffffffu, keep);
-          // entry: tile index in the chunk (11 bits) | mixed (bit 13) | class (bits 14-15)
-          if (keep) act[n + __popc(m & ((1u << tid) - 1u))] = uint16_t(t | ((c & CLS_MIXED) ? 0x2000 : 0) | ((c & 3) << 14));
+          const unsigned m = __ballot_sync(0xffffffffu, c != CLS_SKIP);
+          if (c != CLS_SKIP) act[n + __popc(m & ((1u << tid) - 1u))] = uint16_t(t | (c << 14));
           n += __popc(m);
           __syncwarp();
         }
@@ -513,7 +339,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
         if (DECOUPLED && g >= STAGES) mbar_wait(&empty[st], ((g / STAGES) - 1) & 1);
         constexpr uint32_t bytes = 2 * TL * REC_GROUP * sizeof(double);
         mbar_expect_tx(&full[st], bytes);
-        tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + (act[t] & 0x7ff)) * tile_doubles(), bytes, &full[st]);
+        tma_load_1d(sbuf + size_t(st) * STAGE_DOUBLES, prep + (c0 + (act[t] & 0x3fff)) * tile_doubles(), bytes, &full[st]);
       };
       // prefetch distance: with the CTA barrier a stage is free as soon as the previous tile is done
       // (STAGES - 1 tiles in flight); decoupled warps keep one stage of slack so that the producer
@@ -529,8 +355,7 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
         const double2* __restrict__ rec  = reinterpret_cast<const double2*>(sbuf + size_t(st) * STAGE_DOUBLES);
         const double2* __restrict__ rec1 = rec + 2 * TL;
         const int tile_cls = act[t] >> 14;
-        const bool tile_mixed = (act[t] & 0x2000) != 0;
-        const int64_t tile = c0 + (act[t] & 0x7ff);
+        const int64_t tile = c0 + (act[t] & 0x3fff);
         const int count = p.tile_count[tile];
         double acc[SUM_R];
 #pragma unroll
@@ -589,11 +414,6 @@ __global__ void __launch_bounds__(SUM_NT, AB200_SUM_MINB) lbl_sum_real_kernel(Su
             for (int r = 0; r < SUM_R; r++) acc[r] -= cutp[r];
             cut_sum = 0.0;
           }
-        }
-        if (tile_mixed) {  // frequencies whose own test chose the far-field expansion already have the tile
-          const double2 cr = *reinterpret_cast<const double2*>(mom + tile * MOM_DOUBLES);
-#pragma unroll
-          for (int r = 0; r < SUM_R; r++) acc[r] = (fabs(__dsub_rn(f[r], cr.x)) > cr.y) ? 0.0 : acc[r];
         }
         // every pair of a FAR / NEAR tile is inside its window: the cutoff values of all its lines at once
 #pragma unroll
@@ -852,28 +672,12 @@ int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream) {
   return 0;
 }
 
-int launch_moments(const PrepareParams& p, double* mom, int nlev, cudaStream_t stream) {
-  if (p.ntiles == 0 || nlev == 0 || !mom) return 0;
-  dim3 grid(static_cast<unsigned>(p.ntiles), static_cast<unsigned>(nlev));
-  lbl_moments_kernel<<<grid, TL, 0, stream>>>(p, mom);
-  count_launch();
-  AB_CUDA(cudaGetLastError());
-  return 0;
-}
-
 int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
   if (p_in.nsegs == 0 || nlev == 0 || p_in.nf == 0) return 0;
   SumParams p = p_in;
   static const int skip_near = [] { const char* e = getenv("AB200_DEBUG_SKIP_NEAR"); return e ? atoi(e) : 0; }();
   p.debug_skip_near = skip_near;
   if (mode == 0) {
-    if (p.mom) {  // the far-field part of every real segment first (its sums seed the line-by-line kernel)
-      constexpr int FR = 4;
-      dim3 grid(static_cast<unsigned>((p.nf + FF_NT * FR - 1) / (FF_NT * FR)), static_cast<unsigned>(nlev));
-      lbl_farfield_kernel<FR><<<grid, FF_NT, 0, stream>>>(p);
-      count_launch();
-      AB_CUDA(cudaGetLastError());
-    }
     const size_t smem = lbl_real_smem_bytes();
     // geometry variants (R frequencies per thread, threads per CTA, line unroll); 0 is the tuned default
     static const int variant = [] { const char* e = getenv("AB200_SUM_VARIANT"); return e ? atoi(e) : 0; }();
@@ -890,10 +694,6 @@ int launch_sum(const SumParams& p_in, int nlev, int mode, cudaStream_t stream) {
     const int64_t blocks512 = (p.nf + 511) / 512 * nlev;
     int v = variant;
     if (v == 0 && blocks512 < 2 * 148) v = ((p.nf + 127) / 128 * nlev < 2 * 148) ? 11 : 10;
-    // With the far-field pass only the tiles within reach of a block are summed line by line; their number grows with the
-    // block's frequency span, so narrow blocks win (AB200_SUM_MP_VARIANT overrides; measured in profiles/)
-    static const int mp_variant = [] { const char* e = getenv("AB200_SUM_MP_VARIANT"); return e ? atoi(e) : 10; }();
-    if (variant == 0 && p.mom && v == 0) v = mp_variant;
     switch (v) {
       case 10: AB_TRY(go(lbl_sum_real_kernel<false, 1, 128, 8>, 128, 1)); break;
       case 11: AB_TRY(go(lbl_sum_real_kernel<false, 1, 64, 8>, 64, 1)); break;

@@ -48,13 +48,24 @@ struct SumParams {
   int32_t no_negative_absorption;
   double* K;  // [nlev][k_pitch][7], offset to the batch
   int64_t k_pitch;
-  double* mp_acc;     // [nsegs][nlev][k_pitch] far-field part of each real segment's line sum (scratch, written by lbl_farfield_kernel)
-  const double* mom;  // [nlev][ntiles][MOM_DOUBLES] far-field moments of the tiles (real kernel), or null: every far tile line by line
   int32_t debug_skip_near;  // measurement only (AB200_DEBUG_SKIP_NEAR=1): near tiles contribute nothing
   int32_t k_store_full;  // real kernel: K is not initialised; write whole records {A,0,0,0,0,0,0} with vector stores
 };
 
 // Jacobian targets (lbl_jac.cu)
+// far-field sums (lbl_fmm.cu): moment records of the four cluster levels for one batch of levels, and scratch
+struct FmmBuffers {
+  double* L0;       // [nlev][ntiles][16][MOM_DOUBLES] 16-line clusters
+  double* L1;       // [nlev][ntiles][4][MOM_DOUBLES]  64-line clusters
+  double* L2;       // [nlev][ntiles][MOM_DOUBLES]     tiles
+  double* L3;       // [nlev][ngroups][MOM_DOUBLES]    groups of FMM_GROUP tiles
+  double* scan;     // [nlev][ntiles][2] running bounds of the tiles' acceptance intervals
+  double* far_acc;  // [segments][nlev][k_pitch] far-field part of each segment's sum
+  int64_t ngroups;
+};
+int launch_fmm(const PrepareParams& pp, const SumParams& sp, const FmmBuffers& fb, const int32_t* tile_seg, int nlev, int store_full,
+               cudaStream_t stream);
+
 // Jacobian targets as COMPUTED: one entry per distinct derivative record.  The three magnetic-field components are one
 // entry (kind AB200_TARGET_MAG_U) and so are the three wind components (AB200_TARGET_WIND_U); JacSumParams::out_row maps
 // an entry to the rows of the caller's dK it feeds.
@@ -86,7 +97,6 @@ struct JacSumParams {
 };
 
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream);
-int launch_moments(const PrepareParams& p, double* mom, int nlev, cudaStream_t stream);
 int launch_prepare_jac(const PrepareParams& p, const JacPrepParams& jp, int nlev, cudaStream_t stream);
 int launch_sum_jac(const SumParams& p, JacSumParams jp, int nlev, cudaStream_t stream);
 int launch_sum(const SumParams& p, int nlev, int mode, cudaStream_t stream);

@@ -1,0 +1,539 @@
+// lbl_fmm.cu — the line sum of real, cutoff-free segments as a hierarchical far-field (multipole) sum.
+//
+// Replaces, for merged real segments without ByLine cutoffs, the line-by-line K2 loop of lbl_sum_real_kernel
+// (reference band_shape::operator(), src/core/lbl/lbl_lineshape_voigt_lte.cpp:431-436, per pair s Faddeeva::w(z) :239).
+//
+// Beyond |x| + y = 48 the forward kernels already evaluate w(z) with four terms of its continued fraction collapsed to
+// one rational function (faddeeva.cuh w_mid: w = (i/sqrt(pi)) z (t - 5/2) / (t^2 - 3 t + 3/4), t = z^2, 1.3e-12).  Its
+// partial fractions are four simple poles on the real z axis - the 4-point Gauss-Hermite rule,
+//     w(z) ~ (i/sqrt(pi)) sum_j w_j [1 / (z - r_j) + 1 / (z + r_j)],  r = 0.52465, 1.65068,  w = 0.454124, 0.045876,
+// so in line space (zeta = u + i g, u = f - f0', z = zeta / GD) a line is S sum_j w_j [1/(zeta - a_j) + 1/(zeta + a_j)],
+// S = i s GD / sqrt(pi), a_j = GD r_j.  About a centre c (v = f - c, delta = f0' - c) every pole is 1 / (v - p),
+// p = delta +- a_j - i g, and a CLUSTER of lines collapses to
+//     sum_l Re(s_l w(z_l)) = (1 / v) sum_{k>=1} m_k (R / v)^k,   m_k = -sum_l Si_l sum_j w_j Im[(p_lj+ / R)^k + (p_lj- / R)^k],
+// valid for |v| > R = max |p|.  MP_P = 16 moments and |v| >= MP_THETA R = 6 R reproduce the pair-by-pair sum of the same
+// rational function to 3e-13 (measured against 40-digit arithmetic for widths from 1e2 to 3e9 Hz); a cluster then costs
+// MP_P + 8 FP64 instructions per frequency whatever its size.  Im(p^k) is carried by (A, B) <- (d A + g B, d B - g A),
+// whose terms have equal signs: relative accuracy does not depend on g / |delta| (Doppler regime).
+//
+// Clusters: 16 lines, 64 lines, a tile (256), 16 tiles.  A cluster X is ACCEPTED by a frequency when |f - c_X| > rho_X,
+//     rho_X = max(6 R_X, every line of X has |x| + y > 48 (1 + 1e-9) beyond it, rho_child + |c_child - c_X| for its children),
+// so acceptance is nested (a frequency that accepts X accepts every cluster inside X) and depends on the frequency
+// alone.  A line contributes through its coarsest accepted cluster (lbl_fmm_far_kernel); pairs whose 16-line cluster is
+// not accepted are evaluated one by one with the per-pair arithmetic of lbl_sum_real_kernel (lbl_fmm_near_kernel).
+// The split never depends on block, shard or GPU boundaries: spectra stay bit-identical under any frequency partition.
+//
+// configs[3] (1e6 lines): per (frequency, level) ~700 cluster visits + ~100-400 pairs instead of 1e6 pairs.
+#include <cfloat>
+
+#include "catalog.hpp"
+#include "faddeeva.cuh"
+#include "lbl.hpp"
+
+namespace ab200 {
+
+namespace {
+constexpr double GH_R0 = 0.52464762327529031788, GH_R1 = 1.65068012388578455588;   // sqrt((3 -+ sqrt 6) / 2)
+constexpr double GH_W0 = 0.45412414523193150818, GH_W1 = 0.04587585476806849182;   // (t_j - 5/2) / (2 (t_j - t_other))
+
+__device__ __forceinline__ double warp_max(double v, int width) {
+  for (int o = width / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v, int width) {
+  for (int o = width / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// moments of one line about centre c with scale 1 / R: term[k] = -Si sum_j w_j (B_{j+} + B_{j-}) at power k + 1
+__device__ __forceinline__ void line_terms(bool live, double d, double GD, double g, double Si, double iR, double* term) {
+  const double gh = g * iR;
+  const double dd[4] = {(d + GH_R0 * GD) * iR, (d - GH_R0 * GD) * iR, (d + GH_R1 * GD) * iR, (d - GH_R1 * GD) * iR};
+  double A[4] = {1.0, 1.0, 1.0, 1.0}, B[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < MP_P; k++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const double A1 = __fma_rn(dd[j], A[j], gh * B[j]), B1 = __fma_rn(dd[j], B[j], -(gh * A[j]));
+      A[j] = A1; B[j] = B1;
+    }
+    term[k] = live ? -Si * (GH_W0 * (B[0] + B[1]) + GH_W1 * (B[2] + B[3])) : 0.0;
+  }
+}
+__device__ __forceinline__ double line_radius(double d, double GD, double g) { return fabs(d) + GH_R1 * GD + g; }
+// |f - c| beyond which the line's |x| + y exceeds the mid limit with the margin of the per-pair test
+__device__ __forceinline__ double line_reach(double d, double GD, double y) {
+  return fabs(d) + fmax(0.0, MID_LIMIT * (1.0 + 1e-9) - y) * GD;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// moments of the 16-line, 64-line and tile clusters: one CTA per (tile, level), one thread per line
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams p, FmmBuffers fb) {
+  static_assert(TL == 256, "cluster sizes 16 / 64 / 256");
+  const int64_t tile = blockIdx.x;
+  const int lev      = blockIdx.y;
+  const int lane     = threadIdx.x;
+  const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
+  const double* __restrict__ s4  = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
+  double* __restrict__ o2 = fb.L2 + (int64_t(lev) * p.ntiles + tile) * MOM_DOUBLES;
+  double* __restrict__ o1 = fb.L1 + (int64_t(lev) * p.ntiles + tile) * 4 * MOM_DOUBLES;
+  double* __restrict__ o0 = fb.L0 + (int64_t(lev) * p.ntiles + tile) * 16 * MOM_DOUBLES;
+  if (p.tile_mode[tile] != 0 || s4[4] < DBL_MAX) {  // complex tile or ByLine cutoffs: never accepted
+    for (int i = lane; i < 21 * MOM_DOUBLES; i += TL) {
+      double* o = i < MOM_DOUBLES ? o2 + i : i < 5 * MOM_DOUBLES ? o1 + (i - MOM_DOUBLES) : o0 + (i - 5 * MOM_DOUBLES);
+      *o = (i % MOM_DOUBLES) == 1 ? DBL_MAX : 0.0;
+    }
+    return;
+  }
+  const double f0s = rec[(0 * TL + lane) * REC_GROUP + 0];
+  const double igd = rec[(1 * TL + lane) * REC_GROUP + 1];
+  const double y   = rec[(1 * TL + lane) * REC_GROUP + 2];
+  const double sre = rec[(1 * TL + lane) * REC_GROUP + 3];
+  const bool live  = igd != 0.0;
+  const double GD  = live ? 1.0 / igd : 0.0;
+  const double g   = y * GD, Si = sre * GD * cst::inv_sqrt_pi;
+
+  __shared__ double sh[TL / 32][MP_P + 4];
+  __shared__ double c1s[4], rho1s[4], c0s[16], rho0s[16];
+  __shared__ double c2s;
+  const int warp = lane >> 5;
+
+  // --- centres: midpoint of the live lines' centres per cluster
+  const double lo = live ? f0s : DBL_MAX, hi = live ? f0s : -DBL_MAX;
+  const double lo0 = warp_min(lo, 16), hi0 = warp_max(hi, 16);
+  const double lo32 = warp_min(lo0, 32), hi32 = warp_max(hi0, 32);
+  if ((lane & 31) == 0) { sh[warp][0] = lo32; sh[warp][1] = hi32; }
+  __syncthreads();
+  const int w1 = warp & ~1;
+  const double lo1 = fmin(sh[w1][0], sh[w1 + 1][0]), hi1 = fmax(sh[w1][1], sh[w1 + 1][1]);
+  double lo2 = DBL_MAX, hi2 = -DBL_MAX;
+  for (int w = 0; w < TL / 32; w++) { lo2 = fmin(lo2, sh[w][0]); hi2 = fmax(hi2, sh[w][1]); }
+  __syncthreads();
+  const bool e0 = lo0 > hi0, e1 = lo1 > hi1, e2 = lo2 > hi2;  // empty clusters
+  const double c2 = e2 ? 0.0 : 0.5 * (lo2 + hi2);
+  const double c1 = e1 ? c2 : 0.5 * (lo1 + hi1);
+  const double c0 = e0 ? c1 : 0.5 * (lo0 + hi0);
+  const double d0 = live ? f0s - c0 : 0.0, d1 = live ? f0s - c1 : 0.0, d2 = live ? f0s - c2 : 0.0;
+
+  // --- radii and reaches
+  const double R0 = warp_max(live ? line_radius(d0, GD, g) : 0.0, 16), D0 = warp_max(live ? line_reach(d0, GD, y) : 0.0, 16);
+  double R1 = warp_max(live ? line_radius(d1, GD, g) : 0.0, 32), D1 = warp_max(live ? line_reach(d1, GD, y) : 0.0, 32);
+  double R2 = warp_max(live ? line_radius(d2, GD, g) : 0.0, 32), D2 = warp_max(live ? line_reach(d2, GD, y) : 0.0, 32);
+  if ((lane & 31) == 0) { sh[warp][0] = R1; sh[warp][1] = D1; sh[warp][2] = R2; sh[warp][3] = D2; }
+  __syncthreads();
+  R1 = fmax(sh[w1][0], sh[w1 + 1][0]); D1 = fmax(sh[w1][1], sh[w1 + 1][1]);
+  R2 = 0.0; D2 = 0.0;
+  for (int w = 0; w < TL / 32; w++) { R2 = fmax(R2, sh[w][2]); D2 = fmax(D2, sh[w][3]); }
+  __syncthreads();
+
+  // --- nested acceptance distances, finest first
+  const double rho0 = e0 ? 0.0 : fmax(MP_THETA * R0, D0) * (1.0 + 1e-12);
+  if ((lane & 15) == 0) { c0s[lane >> 4] = c0; rho0s[lane >> 4] = e0 ? -1.0 : rho0; }
+  __syncthreads();
+  double rho1 = e1 ? 0.0 : fmax(MP_THETA * R1, D1);
+  for (int q = 0; q < 4; q++) {
+    const int qq = (lane >> 6) * 4 + q;
+    if (rho0s[qq] >= 0.0) rho1 = fmax(rho1, rho0s[qq] + fabs(c0s[qq] - c1));
+  }
+  rho1 = e1 ? 0.0 : rho1 * (1.0 + 1e-12);
+  if ((lane & 63) == 0) { c1s[lane >> 6] = c1; rho1s[lane >> 6] = e1 ? -1.0 : rho1; }
+  if (lane == 0) c2s = c2;
+  __syncthreads();
+  double rho2 = e2 ? 0.0 : fmax(MP_THETA * R2, D2);
+  for (int s = 0; s < 4; s++)
+    if (rho1s[s] >= 0.0) rho2 = fmax(rho2, rho1s[s] + fabs(c1s[s] - c2));
+  rho2 = e2 ? 0.0 : rho2 * (1.0 + 1e-12);
+
+  // --- moments
+  double term[MP_P];
+  // 16-line clusters
+  line_terms(live, d0, GD, g, Si, R0 > 0.0 ? 1.0 / R0 : 0.0, term);
+#pragma unroll
+  for (int k = 0; k < MP_P; k++) {
+    double v = term[k];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    term[k] = v;
+  }
+  if ((lane & 15) == 0) {
+    double* o = o0 + (lane >> 4) * MOM_DOUBLES;
+    o[0] = c0; o[1] = rho0; o[2] = R0;
+#pragma unroll
+    for (int k = 0; k < MP_P; k++) o[3 + k] = term[k];
+    o[3 + MP_P] = 0.0;
+  }
+  // 64-line clusters
+  line_terms(live, d1, GD, g, Si, R1 > 0.0 ? 1.0 / R1 : 0.0, term);
+#pragma unroll
+  for (int k = 0; k < MP_P; k++) {
+    double v = term[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 31) == 0) sh[warp][k] = v;
+  }
+  __syncthreads();
+  if (lane < 4 * MP_P) {
+    const int s = lane / MP_P, k = lane % MP_P;
+    o1[s * MOM_DOUBLES + 3 + k] = sh[2 * s][k] + sh[2 * s + 1][k];
+  }
+  if ((lane & 63) == 0) {
+    double* o = o1 + (lane >> 6) * MOM_DOUBLES;
+    o[0] = c1; o[1] = rho1; o[2] = R1; o[3 + MP_P] = 0.0;
+  }
+  __syncthreads();
+  // the tile
+  line_terms(live, d2, GD, g, Si, R2 > 0.0 ? 1.0 / R2 : 0.0, term);
+#pragma unroll
+  for (int k = 0; k < MP_P; k++) {
+    double v = term[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 31) == 0) sh[warp][k] = v;
+  }
+  __syncthreads();
+  if (lane < MP_P) {
+    double v = 0.0;
+    for (int w = 0; w < TL / 32; w++) v += sh[w][lane];
+    o2[3 + lane] = v;
+  }
+  if (lane == 0) { o2[0] = c2s; o2[1] = rho2; o2[2] = R2; o2[3 + MP_P] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------
+// moments of the 16-tile groups: one CTA per (group, level), 16 lines per thread
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TL) lbl_fmm_moments_group_kernel(PrepareParams p, FmmBuffers fb, const int32_t* __restrict__ tile_seg) {
+  const int64_t grp  = blockIdx.x;
+  const int lev      = blockIdx.y;
+  const int lane     = threadIdx.x;
+  const int64_t t0   = grp * FMM_GROUP, t1 = min(t0 + FMM_GROUP, p.ntiles);
+  double* __restrict__ out = fb.L3 + (int64_t(lev) * fb.ngroups + grp) * MOM_DOUBLES;
+  const double* __restrict__ m2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
+  const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
+  __shared__ double sh[TL / 32][MP_P];
+  __shared__ double sc, sR, sD;
+  __shared__ int ok;
+  if (lane == 0) {
+    // a group is usable when it is complete, inside one real segment, and every tile can be accepted
+    bool good = t1 - t0 == FMM_GROUP;
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int64_t t = t0; t < t1; t++) {
+      good = good && tile_seg[t] == tile_seg[t0] && tile_seg[t] >= 0 && m2[t * MOM_DOUBLES + 1] < DBL_MAX;
+      const double* s4 = summ + t * SUMMARY_DOUBLES;
+      if (s4[0] <= s4[1]) { lo = fmin(lo, s4[0]); hi = fmax(hi, s4[1]); }
+    }
+    ok = good && lo <= hi;
+    sc = ok ? 0.5 * (lo + hi) : 0.0;
+  }
+  __syncthreads();
+  if (!ok) {
+    if (lane < MOM_DOUBLES) out[lane] = lane == 1 ? DBL_MAX : 0.0;
+    return;
+  }
+  const double c = sc;
+  // pass 1: radius and reach
+  double R = 0.0, D = 0.0;
+  for (int64_t t = t0; t < t1; t++) {
+    const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + t) * tile_doubles();
+    const double igd = rec[(1 * TL + lane) * REC_GROUP + 1];
+    if (igd == 0.0) continue;
+    const double GD = 1.0 / igd, y = rec[(1 * TL + lane) * REC_GROUP + 2], d = rec[(0 * TL + lane) * REC_GROUP] - c;
+    R = fmax(R, line_radius(d, GD, y * GD));
+    D = fmax(D, line_reach(d, GD, y));
+  }
+  R = warp_max(R, 32); D = warp_max(D, 32);
+  if ((lane & 31) == 0) { sh[lane >> 5][0] = R; sh[lane >> 5][1] = D; }
+  __syncthreads();
+  if (lane == 0) {
+    double r = 0.0, dd = 0.0;
+    for (int w = 0; w < TL / 32; w++) { r = fmax(r, sh[w][0]); dd = fmax(dd, sh[w][1]); }
+    sR = r; sD = dd;
+  }
+  __syncthreads();
+  R = sR;
+  const double iR = R > 0.0 ? 1.0 / R : 0.0;
+  double sum[MP_P];
+#pragma unroll
+  for (int k = 0; k < MP_P; k++) sum[k] = 0.0;
+  for (int64_t t = t0; t < t1; t++) {  // fixed order: tiles ascending per thread, then the reduction tree
+    const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + t) * tile_doubles();
+    const double igd = rec[(1 * TL + lane) * REC_GROUP + 1];
+    if (igd == 0.0) continue;
+    const double GD = 1.0 / igd, y = rec[(1 * TL + lane) * REC_GROUP + 2], d = rec[(0 * TL + lane) * REC_GROUP] - c;
+    const double Si = rec[(1 * TL + lane) * REC_GROUP + 3] * GD * cst::inv_sqrt_pi;
+    double term[MP_P];
+    line_terms(true, d, GD, y * GD, Si, iR, term);
+#pragma unroll
+    for (int k = 0; k < MP_P; k++) sum[k] += term[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < MP_P; k++) {
+    double v = sum[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((lane & 31) == 0) sh[lane >> 5][k] = v;
+  }
+  __syncthreads();
+  if (lane < MP_P) {
+    double v = 0.0;
+    for (int w = 0; w < TL / 32; w++) v += sh[w][lane];
+    out[3 + lane] = v;
+  }
+  if (lane == 0) {
+    double rho = fmax(MP_THETA * R, sD);
+    for (int64_t t = t0; t < t1; t++) {
+      const double* s4 = summ + t * SUMMARY_DOUBLES;
+      if (s4[0] <= s4[1]) rho = fmax(rho, m2[t * MOM_DOUBLES + 1] + fabs(m2[t * MOM_DOUBLES] - c));
+    }
+    out[0] = c; out[1] = rho * (1.0 + 1e-12); out[2] = R; out[3 + MP_P] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// far-field pass: every frequency sums the expansions of its coarsest accepted clusters, in catalog order
+// ---------------------------------------------------------------------------
+constexpr int FF_NT = 128, FF_R = 4;
+
+struct Mask4 {
+  bool m[FF_R];
+};
+
+// adds the expansion of cluster `mo` for the frequencies with on[r] (tt = 0 switches a frequency off exactly)
+__device__ __forceinline__ void ff_add(const double* __restrict__ mo, double c, const double* f, const bool* on, double* acc) {
+  const double2 m01 = __ldg(reinterpret_cast<const double2*>(mo) + 1);  // R, m_1
+  double tau[FF_R], tt[FF_R], s[FF_R];
+#pragma unroll
+  for (int r = 0; r < FF_R; r++) {
+    tt[r]  = on[r] ? fast_rcp(__dsub_rn(f[r], c)) : 0.0;
+    tau[r] = __dmul_rn(m01.x, tt[r]);
+  }
+  const double2* __restrict__ mk = reinterpret_cast<const double2*>(mo) + 2;  // (m_2, m_3) ... (m_16, pad)
+  {
+    const double2 top = __ldg(mk + (MP_P - 2) / 2);
+#pragma unroll
+    for (int r = 0; r < FF_R; r++) s[r] = top.x;
+  }
+#pragma unroll
+  for (int j = (MP_P - 2) / 2 - 1; j >= 0; j--) {
+    const double2 pr = __ldg(mk + j);
+#pragma unroll
+    for (int r = 0; r < FF_R; r++) s[r] = __fma_rn(__fma_rn(s[r], tau[r], pr.y), tau[r], pr.x);
+  }
+#pragma unroll
+  for (int r = 0; r < FF_R; r++) {
+    s[r]   = __fma_rn(s[r], tau[r], m01.y);
+    acc[r] = __fma_rn(__dmul_rn(s[r], tau[r]), tt[r], acc[r]);
+  }
+}
+
+// One level of the descent.  `parent_on[r]`: frequency r accepts an ancestor (its contribution is already in).  Returns
+// whether every frequency of the warp is served by this cluster or an ancestor, and updates on_out.
+__device__ __forceinline__ bool ff_visit(const double* __restrict__ mo, const double* f, double fmin_b, double fmax_b, const bool* parent_on,
+                                         bool* on_out, double* acc) {
+  const double2 cr = __ldg(reinterpret_cast<const double2*>(mo));  // c, rho
+  const double vmax = fmax(fabs(fmin_b - cr.x), fabs(fmax_b - cr.x));
+  bool add[FF_R];
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < FF_R; r++) {
+    const bool acc_r = fabs(__dsub_rn(f[r], cr.x)) > cr.y;  // the frequency's own test
+    on_out[r] = parent_on[r] || acc_r;
+    add[r]    = acc_r && !parent_on[r];
+    any |= add[r];
+  }
+  if (vmax > cr.y && __any_sync(0xffffffffu, any)) ff_add(mo, cr.x, f, add, acc);
+  bool all = true;
+#pragma unroll
+  for (int r = 0; r < FF_R; r++) all = all && on_out[r];
+  return __all_sync(0xffffffffu, all);  // every frequency of the warp is served: nothing below this cluster is needed
+}
+
+__global__ void __launch_bounds__(FF_NT) lbl_fmm_far_kernel(SumParams p, FmmBuffers fb) {
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t fblk = int64_t(blockIdx.x) * (FF_NT * FF_R);
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double ffac = p.ffac[lev];
+  // a warp owns 32 * FF_R consecutive frequencies: its descent follows a narrow band of the spectrum
+  const int64_t wbase = fblk + (tid >> 5) * (32 * FF_R) + (tid & 31);
+  double f[FF_R];
+#pragma unroll
+  for (int r = 0; r < FF_R; r++) {
+    const int64_t i = wbase + r * 32;
+    f[r] = ffac * fg[i < p.nf ? i : p.nf - 1];
+  }
+  // bounds of the WARP's frequencies decide which clusters the warp descends into (uniform per warp; the values added
+  // never depend on them)
+  double fmin_b = fmin(fmin(f[0], f[1]), fmin(f[2], f[3])), fmax_b = fmax(fmax(f[0], f[1]), fmax(f[2], f[3]));
+  fmin_b = warp_min(fmin_b, 32);
+  fmax_b = warp_max(fmax_b, 32);
+  const double* __restrict__ L3 = fb.L3 + int64_t(lev) * fb.ngroups * MOM_DOUBLES;
+  const double* __restrict__ L2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
+  const double* __restrict__ L1 = fb.L1 + int64_t(lev) * p.ntiles * 4 * MOM_DOUBLES;
+  const double* __restrict__ L0 = fb.L0 + int64_t(lev) * p.ntiles * 16 * MOM_DOUBLES;
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    double acc[FF_R];
+    bool none[FF_R];
+#pragma unroll
+    for (int r = 0; r < FF_R; r++) { acc[r] = 0.0; none[r] = false; }
+    for (int64_t g = seg.tile_begin / FMM_GROUP; g * FMM_GROUP < seg.tile_end; g++) {
+      bool onG[FF_R];
+      if (ff_visit(L3 + g * MOM_DOUBLES, f, fmin_b, fmax_b, none, onG, acc)) continue;
+      const int64_t ta = max(g * FMM_GROUP, seg.tile_begin), tb = min((g + 1) * FMM_GROUP, seg.tile_end);
+      for (int64_t t = ta; t < tb; t++) {
+        bool onT[FF_R];
+        if (ff_visit(L2 + t * MOM_DOUBLES, f, fmin_b, fmax_b, onG, onT, acc)) continue;
+#pragma unroll 1
+        for (int s = 0; s < 4; s++) {
+          bool onS[FF_R];
+          if (ff_visit(L1 + (t * 4 + s) * MOM_DOUBLES, f, fmin_b, fmax_b, onT, onS, acc)) continue;
+#pragma unroll 1
+          for (int q = 0; q < 4; q++) {
+            bool onQ[FF_R];
+            ff_visit(L0 + (t * 16 + s * 4 + q) * MOM_DOUBLES, f, fmin_b, fmax_b, onS, onQ, acc);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < FF_R; r++) {
+      const int64_t i = wbase + r * 32;
+      if (i < p.k_pitch) fb.far_acc[(int64_t(is) * gridDim.y + lev) * p.k_pitch + i] = acc[r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// near pass: one thread per frequency sums, pair by pair, the lines of the 16-line clusters it does not accept, adds the
+// far-field part, scales, clamps per segment and writes K (K3: ComputeData ctor scale :944-953, clamp :1688-1692)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fmm_line_scale(double f, double T, double P) {
+  constexpr double c = cst::c * cst::c / (8 * cst::pi);
+  const double N     = P / (cst::k * T);
+  const double r     = (cst::h * f) / (cst::k * T);
+  return -N * f * expm1(-r) * c;
+}
+
+__global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffers fb, int store_full) {
+  const int tid = threadIdx.x;
+  const int lev = blockIdx.y;
+  const int64_t i = int64_t(blockIdx.x) * 128 + tid;
+  const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
+  const double f = p.ffac[lev] * fg[i < p.nf ? i : p.nf - 1];
+  const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
+  const double* __restrict__ L2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
+  const double* __restrict__ L1 = fb.L1 + int64_t(lev) * p.ntiles * 4 * MOM_DOUBLES;
+  const double* __restrict__ L0 = fb.L0 + int64_t(lev) * p.ntiles * 16 * MOM_DOUBLES;
+  const double* __restrict__ scan = fb.scan + int64_t(lev) * p.ntiles * 2;
+  const double T = p.T[lev], P = p.P[lev];
+  double kacc = 0.0;
+  for (int is = 0; is < p.nsegs; is++) {
+    const SegmentDev seg = p.segs[is];
+    // Tiles that may be needed: c_t - rho_t <= f <= c_t + rho_t.  scan holds the running maximum of c + rho from the
+    // segment's first tile and the running minimum of c - rho from its last (lbl_fmm_scan_kernel), both monotone whatever
+    // the order of the shifted line centres, so two bisections bracket the candidates.
+    int64_t a = seg.tile_begin, b = seg.tile_end;
+    while (a < b) {  // first tile with max_{t' <= t}(c + rho) >= f
+      const int64_t m = (a + b) >> 1;
+      if (__ldg(scan + 2 * m) < f) a = m + 1;
+      else b = m;
+    }
+    int64_t lo = a, hi = seg.tile_end;
+    while (lo < hi) {  // first tile with min_{t' >= t}(c - rho) > f
+      const int64_t m = (lo + hi) >> 1;
+      if (__ldg(scan + 2 * m + 1) <= f) lo = m + 1;
+      else hi = m;
+    }
+    double acc = 0.0;
+    for (int64_t t = a; t < lo; t++) {
+      const double2 c2 = __ldg(reinterpret_cast<const double2*>(L2 + t * MOM_DOUBLES));
+      if (fabs(__dsub_rn(f, c2.x)) > c2.y) continue;  // the tile (or a group above it) is in the far-field sum
+      const double* __restrict__ g0 = prep + t * tile_doubles();
+      const int count = p.tile_count[t];
+      for (int s = 0; s < 4; s++) {
+        const double2 c1 = __ldg(reinterpret_cast<const double2*>(L1 + (t * 4 + s) * MOM_DOUBLES));
+        if (fabs(__dsub_rn(f, c1.x)) > c1.y) continue;
+        for (int q = 0; q < 4; q++) {
+          const double2 c0 = __ldg(reinterpret_cast<const double2*>(L0 + (t * 16 + s * 4 + q) * MOM_DOUBLES));
+          if (fabs(__dsub_rn(f, c0.x)) > c0.y) continue;
+          const int l0 = (s * 4 + q) * 16, l1 = min(l0 + 16, count);
+          for (int l = l0; l < l1; l++) {  // the per-pair arithmetic of lbl_sum_real_kernel's near loop
+            const double2 ra = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP));      // f0', c3
+            const double2 rb = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP) + 1);  // kappa, A1
+            const double2 rc = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP));      // B1, igd
+            if (rc.y == 0.0) continue;
+            const double2 rd = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP) + 1);  // y, s_re
+            const double u  = __dsub_rn(f, ra.x);
+            const double ax = __dmul_rn(fabs(u), rc.y);
+            if (__dadd_rn(ax, rd.x) > FAR_LIMIT_REAL_SUM) {
+              acc = far_accumulate_re(acc, u, ra.y, rb.x, rb.y, rc.x);
+            } else {
+              double wr, wi;
+              w_near_fast(rc.y * u, rd.x, __ldg(g0 + (2 * TL + l) * REC_GROUP), wr, wi);
+              acc = __fma_rn(rd.y, wr, acc);
+            }
+          }
+        }
+      }
+    }
+    const double tot = i < p.k_pitch ? fb.far_acc[(int64_t(is) * gridDim.y + lev) * p.k_pitch + i] + acc : 0.0;
+    const double F = fmm_line_scale(f, T, P) * tot;
+    if (!(p.no_negative_absorption && F < 0.0)) kacc += F;
+  }
+  if (i >= p.nf) {
+    if (store_full && i < p.k_pitch) {
+      double* o = p.K + (int64_t(lev) * p.k_pitch + i) * 7;
+#pragma unroll
+      for (int c = 0; c < 7; c++) o[c] = 0.0;
+    }
+    return;
+  }
+  double* o = p.K + (int64_t(lev) * p.k_pitch + i) * 7;
+  if (store_full) {
+    o[0] = kacc;
+#pragma unroll
+    for (int c = 1; c < 7; c++) o[c] = 0.0;
+  } else {
+    o[0] += kacc;
+  }
+}
+
+// running bounds of the tiles' acceptance intervals per (segment, level): scan[t] = {max_{t' <= t}(c + rho), min_{t' >= t}(c - rho)}
+__global__ void lbl_fmm_scan_kernel(SumParams p, FmmBuffers fb) {
+  if (threadIdx.x != 0) return;
+  const SegmentDev seg = p.segs[blockIdx.x];
+  const int lev = blockIdx.y;
+  const double* __restrict__ L2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
+  double* __restrict__ scan = fb.scan + int64_t(lev) * p.ntiles * 2;
+  double m = -DBL_MAX;
+  for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
+    m = fmax(m, L2[t * MOM_DOUBLES] + L2[t * MOM_DOUBLES + 1]);
+    scan[2 * t] = m;
+  }
+  m = DBL_MAX;
+  for (int64_t t = seg.tile_end - 1; t >= seg.tile_begin; t--) {
+    m = fmin(m, L2[t * MOM_DOUBLES] - L2[t * MOM_DOUBLES + 1]);
+    scan[2 * t + 1] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------
+int launch_fmm(const PrepareParams& pp, const SumParams& sp, const FmmBuffers& fb, const int32_t* tile_seg, int nlev, int store_full,
+               cudaStream_t stream) {
+  if (pp.ntiles == 0 || nlev == 0 || sp.nf == 0 || sp.nsegs == 0) return 0;
+  lbl_fmm_moments_tile_kernel<<<dim3(static_cast<unsigned>(pp.ntiles), static_cast<unsigned>(nlev)), TL, 0, stream>>>(pp, fb);
+  lbl_fmm_moments_group_kernel<<<dim3(static_cast<unsigned>(fb.ngroups), static_cast<unsigned>(nlev)), TL, 0, stream>>>(pp, fb, tile_seg);
+  lbl_fmm_scan_kernel<<<dim3(static_cast<unsigned>(sp.nsegs), static_cast<unsigned>(nlev)), 32, 0, stream>>>(sp, fb);
+  lbl_fmm_far_kernel<<<dim3(static_cast<unsigned>((sp.nf + FF_NT * FF_R - 1) / (FF_NT * FF_R)), static_cast<unsigned>(nlev)), FF_NT, 0,
+                       stream>>>(sp, fb);
+  lbl_fmm_near_kernel<<<dim3(static_cast<unsigned>((sp.k_pitch + 127) / 128), static_cast<unsigned>(nlev)), 128, 0, stream>>>(sp, fb, store_full);
+  count_launch(5);
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ab200

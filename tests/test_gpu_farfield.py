@@ -1,0 +1,92 @@
+"""The far-field (multipole) line sum of real, cutoff-free segments (arts_b200/csrc/lbl_fmm.cu): every cluster level in use
+(16 lines, 64 lines, tiles, groups of 16 tiles), against the oracle (<= 1e-9 on the propagation matrix) and against the
+line-by-line kernel on the same inputs (AB200_FARFIELD=0), in the pressure-broadened and in the Doppler regime; bitwise
+invariance under frequency partitions; segments with cutoffs next to segments without."""
+import os
+
+import numpy as np
+import pytest
+
+from arts_b200 import _abi as abi
+from arts_b200 import synth
+from tests.conftest import assert_propmat_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense_case(n_lines=40_000, nf=3000, np_=6, f_lo=2e12, f_hi=3e12):
+    """One species, n_lines over [f_lo, f_hi] (157 tiles = 10 groups of 16): a frequency sees near lines, 16- and 64-line
+    clusters, tiles and whole groups; levels from 1000 hPa (y ~ 10..100) to 0.1 hPa (y << 1)."""
+    c = synth.case_c4(n_lines=n_lines, nf=16, np_=np_)
+    rng = np.random.default_rng(42)
+    c.cat.f0[:] = np.sort(rng.uniform(f_lo, f_hi, n_lines))
+    c.f = np.sort(np.concatenate([np.linspace(f_lo - 2e11, f_hi + 2e11, nf - 600), rng.uniform(f_lo, f_hi, 600)]))
+    c.I_bkg = np.zeros((len(c.f), 4))
+    c.I_bkg[:, 0] = synth.planck(c.f, 288.0)
+    c.atm.P[:] = np.geomspace(1.0e5, 10.0, np_)
+    return c
+
+
+def _linebyline(fn):
+    os.environ["AB200_FARFIELD"] = "0"
+    try:
+        return fn()
+    finally:
+        del os.environ["AB200_FARFIELD"]
+
+
+def test_farfield_matches_oracle_and_line_by_line(wsm, orc):
+    c = _dense_case()
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    K0, _ = _linebyline(lambda: wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm))
+    assert not np.array_equal(K, K0)  # two different evaluations ...
+    rel = np.abs(K[..., 0] - K0[..., 0]) / K0[..., 0]
+    assert rel.max() <= 1e-11, rel.max()  # ... of the same sums
+    idx = np.unique(np.linspace(0, c.nf - 1, 120).astype(int))
+    Kr, _ = orc.propmat_levels(c.cat, c.f[idx], c.atm)
+    assert_propmat_close(K[:, idx], Kr)
+    assert np.all(K[..., 1:] == 0.0)
+
+
+def test_farfield_is_bitwise_invariant_under_partitions(wsm):
+    c = _dense_case(n_lines=12_000, nf=2200, np_=3)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    for lo, hi in ((0, 300), (129, 1500), (1000, 2200), (2100, 2200)):
+        Ks, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f[lo:hi], c.atm)
+        assert np.array_equal(Ks, K[:, lo:hi]), (lo, hi)
+    sel = np.arange(0, c.nf, 7)  # a strided sub-grid: other blocks, other warps, same bits
+    Ks, _ = wsm.spectral_propmat_pathFromPath(c.cat, np.ascontiguousarray(c.f[sel]), c.atm)
+    assert np.array_equal(Ks, K[:, sel])
+
+
+def test_farfield_next_to_cutoff_segments_and_accumulation(wsm, orc):
+    """Two species: one with ByLine cutoffs (line-by-line kernel, writes the K records) and one without (far-field sums,
+    added on top); `+=` into a caller's K; the fused chain on top."""
+    c = synth.case_c2(lines_per_species=1500, nf=1800, np_=5, bands_per_species=3)
+    nb = len(c.cat.band_cutoff_type)
+    c.cat.band_cutoff_type[: nb // 5] = abi.CUTOFF_BYLINE  # the first species' bands
+    c.cat.band_cutoff_value[: nb // 5] = 40e9
+    Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    assert_propmat_close(K, Kr, atol_scale=1e-11)
+    K2 = np.full_like(K, 0.125)
+    wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, out=K2, accumulate=True)
+    np.testing.assert_allclose(K2[..., 0] - 0.125, K[..., 0], rtol=1e-9, atol=1e-12 * K[..., 0].max())
+    assert np.all(K2[..., 1:] == 0.125)
+    I, _ = wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg)
+    Ir, _ = orc.clearsky_emission(c.cat, c.f, c.atm, c.r, c.I_bkg)
+    assert np.abs(wsm.spectral_radApplyPlanckTb(I, c.f) - orc.planck_tb(c.f, Ir)).max() <= 1e-6
+
+
+def test_farfield_with_shifted_level_grids_and_species_selection(wsm, orc):
+    """Per-level frequency grids (wind shift) and select_species: the far-field segments follow both."""
+    c = synth.case_c2(lines_per_species=800, nf=900, np_=4, bands_per_species=2)
+    c.atm.wind = np.tile(np.array([30.0, -12.0, 1.5]), (c.np_, 1)) * np.arange(1, c.np_ + 1)[:, None]
+    c.atm.los = np.tile(np.array([151.0, 40.0]), (c.np_, 1))
+    Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm)
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    assert_propmat_close(K, Kr)
+    for sp in (0, 3):
+        Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm, select_species=sp)
+        K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, select_species=sp)
+        assert_propmat_close(K, Kr)

@@ -419,11 +419,12 @@ __device__ __forceinline__ double fmm_line_scale(double f, double T, double P) {
 }
 
 __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffers fb, int store_full) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int lev = blockIdx.y;
-  const int64_t i = int64_t(blockIdx.x) * 128 + tid;
+  const int64_t i = int64_t(blockIdx.x) * 128 + tid;  // this lane's frequency (epilogue); the pair sums are formed warp-wide
   const double* __restrict__ fg = p.f + int64_t(lev) * p.f_stride;
-  const double f = p.ffac[lev] * fg[i < p.nf ? i : p.nf - 1];
+  const double ffac = p.ffac[lev];
+  const double f_own = ffac * fg[i < p.nf ? i : p.nf - 1];
   const double* __restrict__ prep = p.prep + int64_t(lev) * p.ntiles * tile_doubles();
   const double* __restrict__ L2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
   const double* __restrict__ L1 = fb.L1 + int64_t(lev) * p.ntiles * 4 * MOM_DOUBLES;
@@ -433,39 +434,50 @@ __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffe
   double kacc = 0.0;
   for (int is = 0; is < p.nsegs; is++) {
     const SegmentDev seg = p.segs[is];
-    // Tiles that may be needed: c_t - rho_t <= f <= c_t + rho_t.  scan holds the running maximum of c + rho from the
-    // segment's first tile and the running minimum of c - rho from its last (lbl_fmm_scan_kernel), both monotone whatever
-    // the order of the shifted line centres, so two bisections bracket the candidates.
-    int64_t a = seg.tile_begin, b = seg.tile_end;
-    while (a < b) {  // first tile with max_{t' <= t}(c + rho) >= f
-      const int64_t m = (a + b) >> 1;
-      if (__ldg(scan + 2 * m) < f) a = m + 1;
-      else b = m;
-    }
-    int64_t lo = a, hi = seg.tile_end;
-    while (lo < hi) {  // first tile with min_{t' >= t}(c - rho) > f
-      const int64_t m = (lo + hi) >> 1;
-      if (__ldg(scan + 2 * m + 1) <= f) lo = m + 1;
-      else hi = m;
-    }
-    double acc = 0.0;
-    for (int64_t t = a; t < lo; t++) {
-      const double2 c2 = __ldg(reinterpret_cast<const double2*>(L2 + t * MOM_DOUBLES));
-      if (fabs(__dsub_rn(f, c2.x)) > c2.y) continue;  // the tile (or a group above it) is in the far-field sum
-      const double* __restrict__ g0 = prep + t * tile_doubles();
-      const int count = p.tile_count[t];
-      for (int s = 0; s < 4; s++) {
-        const double2 c1 = __ldg(reinterpret_cast<const double2*>(L1 + (t * 4 + s) * MOM_DOUBLES));
-        if (fabs(__dsub_rn(f, c1.x)) > c1.y) continue;
-        for (int q = 0; q < 4; q++) {
-          const double2 c0 = __ldg(reinterpret_cast<const double2*>(L0 + (t * 16 + s * 4 + q) * MOM_DOUBLES));
-          if (fabs(__dsub_rn(f, c0.x)) > c0.y) continue;
-          const int l0 = (s * 4 + q) * 16, l1 = min(l0 + 16, count);
-          for (int l = l0; l < l1; l++) {  // the per-pair arithmetic of lbl_sum_real_kernel's near loop
-            const double2 ra = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP));      // f0', c3
-            const double2 rb = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP) + 1);  // kappa, A1
+    double direct = 0.0;  // this lane's frequency
+    // One frequency at a time, the 32 lanes share its pairs: lines that are near one frequency sit in the same regime of
+    // w(z), so the lanes run the same branch; 32 neighbouring frequencies of a coarse grid do not.  Lane k sums the lines
+    // k mod 16 of every second needed cluster in catalog order and a fixed shuffle tree adds the 32 partial sums: the value
+    // depends on the frequency and the catalog only.
+#pragma unroll 1
+    for (int j = 0; j < 32; j++) {
+      const double f = __shfl_sync(0xffffffffu, f_own, j);
+      // Tiles that may be needed: c_t - rho_t <= f <= c_t + rho_t.  scan holds the running maximum of c + rho from the
+      // segment's first tile and the running minimum of c - rho from its last (lbl_fmm_scan_kernel), both monotone whatever
+      // the order of the shifted line centres, so two bisections bracket the candidates.
+      int64_t a = seg.tile_begin, b = seg.tile_end;
+      while (a < b) {  // first tile with max_{t' <= t}(c + rho) >= f
+        const int64_t m = (a + b) >> 1;
+        if (__ldg(scan + 2 * m) < f) a = m + 1;
+        else b = m;
+      }
+      int64_t lo = a, hi = seg.tile_end;
+      while (lo < hi) {  // first tile with min_{t' >= t}(c - rho) > f
+        const int64_t m = (lo + hi) >> 1;
+        if (__ldg(scan + 2 * m + 1) <= f) lo = m + 1;
+        else hi = m;
+      }
+      double acc = 0.0;
+      for (int64_t t = a; t < lo; t++) {
+        const double2 c2 = __ldg(reinterpret_cast<const double2*>(L2 + t * MOM_DOUBLES));
+        if (fabs(__dsub_rn(f, c2.x)) > c2.y) continue;  // the tile (or a group above it) is in the far-field sum
+        const double* __restrict__ g0 = prep + t * tile_doubles();
+        const int count = p.tile_count[t];
+#pragma unroll 1
+        for (int s = 0; s < 4; s++) {
+          const double2 c1 = __ldg(reinterpret_cast<const double2*>(L1 + (t * 4 + s) * MOM_DOUBLES));
+          if (fabs(__dsub_rn(f, c1.x)) > c1.y) continue;
+#pragma unroll
+          for (int qp = 0; qp < 2; qp++) {  // two 16-line clusters per step, one per half warp
+            const int q = s * 4 + qp * 2 + (lane >> 4);
+            const double2 c0 = __ldg(reinterpret_cast<const double2*>(L0 + (t * 16 + q) * MOM_DOUBLES));
+            const int l = q * 16 + (lane & 15);
+            if (fabs(__dsub_rn(f, c0.x)) > c0.y || l >= count) continue;
+            // the per-pair arithmetic of lbl_sum_real_kernel's near loop
             const double2 rc = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP));      // B1, igd
             if (rc.y == 0.0) continue;
+            const double2 ra = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP));      // f0', c3
+            const double2 rb = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP) + 1);  // kappa, A1
             const double2 rd = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP) + 1);  // y, s_re
             const double u  = __dsub_rn(f, ra.x);
             const double ax = __dmul_rn(fabs(u), rc.y);
@@ -479,9 +491,12 @@ __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffe
           }
         }
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == j) direct = acc;
     }
-    const double tot = i < p.k_pitch ? fb.far_acc[(int64_t(is) * gridDim.y + lev) * p.k_pitch + i] + acc : 0.0;
-    const double F = fmm_line_scale(f, T, P) * tot;
+    const double tot = i < p.k_pitch ? fb.far_acc[(int64_t(is) * gridDim.y + lev) * p.k_pitch + i] + direct : 0.0;
+    const double F = fmm_line_scale(f_own, T, P) * tot;
     if (!(p.no_negative_absorption && F < 0.0)) kacc += F;
   }
   if (i >= p.nf) {

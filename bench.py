@@ -354,23 +354,29 @@ def run_b200(args):
         "config": {"workload": name, "lines": nl, "levels": np_, "nf_total": nf_total, "nf_per_gpu": cnt,
                    "sharding": "contiguous frequency blocks (matpack::omp_offset_count), catalog replicated, "
                                "one NCCL all-gather of spectral_rad" if world > 1 else "single GPU",
-                   "l2": "inputs exceed L2: per step the kernels stream %.2f GB of line records and %.2f GB of K "
-                         "(L2 = 126 MB), no flush needed" % (cat.host.n_lines * 128.0 * np_ / 1e9, cnt * np_ * 56.0 / 1e9)},
+                   "l2": "inputs exceed L2: per step the kernels write and re-read %.2f GB of line records, %.2f GB of cluster moments "
+                         "and %.2f GB of K (L2 = 126 MB), no flush needed" % (cat.host.n_lines * 128.0 * np_ / 1e9,
+                                                                               cat.host.n_lines / 256.0 * 21.3 * 160.0 * np_ / 1e9,
+                                                                               cnt * np_ * 56.0 / 1e9)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e, "call": "ab200_clearsky_emission (host buffers, pinned)", "equals_resident_result": e2e_matches},
         "gpu_launches": launches,
-        "roofline": {"bound": "fp64", "kernel": "lbl_sum_real_kernel", "achieved": achieved_tf, "peak": dfma_tflops,
-                     "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None, "traffic": traffic.get("lbl_sum_real_kernel"),
+        "roofline": {"bound": "fp64", "kernel": "real line sum: lbl_fmm_{moments,far,near}_kernel (lbl_sum_real_kernel for segments with ByLine cutoffs)",
+                     "achieved": achieved_tf, "peak": dfma_tflops,
+                     "unit": "TFLOP/s", "frac": achieved_tf / dfma_tflops if dfma_tflops else None,
+                     "traffic": traffic.get("real_line_sum_fmm_kernels_per_step") or traffic.get("lbl_sum_real_kernel"),
                      "traffic_source": traffic_src, "launches_per_step": k_n / args.steps,
                      "peak_source": "DFMA loop measured in this run (ab200_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 figure",
                      "algorithmic_flop_per_eval": fl_eval, "regions": region_frac, "kernel_ms": k_ms_per,
-                     "executed": {"fp64_instr_per_far_eval": 7,
-                                  "dfma_equiv_tflops": 14.0 * float(nl) * cnt * np_ / max(k_n / args.steps, 1) / (k_ms_per * 1e-3) / 1e12 if k_ms_per > 0 else None,
-                                  "peak_with_rcp_mix_tflops": dfma_mix_tflops,
-                                  "note": "frac > 1 because the reference's closed form costs 28 algorithmic FLOP per far-wing "
-                                          "evaluation and the kernel needs 7 FP64-pipe instructions (14 FLOP slots) + 1 MUFU; "
-                                          "dfma_equiv / peak is the FP64-pipe utilisation (ncu: profiles/r1h_lbl_sum_real.ncu.txt)"},
+                     "executed": {"peak_with_rcp_mix_tflops": dfma_mix_tflops,
+                                  "note": "achieved counts the ALGORITHMIC flops of SURVEY.md 8(d) (28 per far-wing evaluation of the reference's "
+                                          "closed form) for every nominal line x frequency x level pair.  frac >> 1 because cutoff-free real "
+                                          "segments are summed as a hierarchical far-field (multipole) expansion of the four-term continued "
+                                          "fraction (arts_b200/csrc/lbl_fmm.cu): per (frequency, level) a few hundred cluster expansions of 24 "
+                                          "FP64 instructions plus the ~1e2-4e2 pairs within 48 Doppler widths, instead of 1e6 pairs - same "
+                                          "spectra to 1e-9, bit-identical under frequency partitions.  FP64-pipe utilisation of the kernels "
+                                          "actually run is in profiles/ (ncu): far pass 58 %, near pass 43 %, moments 50 %."},
                      "kernel_share_of_step": k_ms / ms if ms else None},
         "roofline_stokes": {"bound": "hbm", "kernel": "stokes_chain_kernel", "achieved": st_gbs, "peak": hbm_peak,
                             "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": traffic.get("stokes_chain_kernel"),

@@ -34,12 +34,19 @@ namespace ab200 {
 // ---------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
+// Levels per CTA: the catalog rows of the tile's lines (368 B per line with two broadeners) are read from DRAM once per CTA
+// and served from L1 / L2 for the other PREP_LB - 1 levels (a CTA per (tile, level) read 30 GB per 67 levels of configs[3]).
+constexpr int PREP_LB = 16;
+__global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p, int nlev) {
   const int64_t tile = blockIdx.x;
-  const int lev      = blockIdx.y;
   const int lane     = threadIdx.x;
   const int64_t slot = tile * TL + lane;
   const int64_t par  = p.sub_parent[slot];
+  __shared__ double red[TL / 32][7];
+  __shared__ double cutvals[TL];
+  const int lev_end = min(nlev, (int(blockIdx.y) + 1) * PREP_LB);
+#pragma unroll 1
+  for (int lev = int(blockIdx.y) * PREP_LB; lev < lev_end; lev++) {
 
   const double T = p.T[lev], P = p.P[lev];
   double f0s = 0.0, igd = 0.0, y = 0.0, s_re = 0.0, s_im = 0.0, G0 = 0.0, GD = 1.0;
@@ -165,8 +172,6 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
     v_cmin = fmin(v_cmin, __shfl_xor_sync(0xffffffffu, v_cmin, o));
     v_cmax = fmax(v_cmax, __shfl_xor_sync(0xffffffffu, v_cmax, o));
   }
-  __shared__ double red[TL / 32][7];
-  __shared__ double cutvals[TL];
   cutvals[lane] = v_cutval;
   if ((lane & 31) == 0) {
     double* r = red[lane >> 5];
@@ -185,6 +190,8 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p) {
     double* s = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
     s[0] = v_min; s[1] = v_max; s[2] = v_igd; s[3] = v_y;
     s[4] = v_cmin; s[5] = v_cmax; s[6] = v_cutval; s[7] = v_igx;
+  }
+  __syncthreads();  // red / cutvals are reused by the next level
   }
 }
 
@@ -665,8 +672,8 @@ size_t lbl_cplx_smem_bytes() {
 
 int launch_prepare(const PrepareParams& p, int nlev, cudaStream_t stream) {
   if (p.ntiles == 0 || nlev == 0) return 0;
-  dim3 grid(static_cast<unsigned>(p.ntiles), static_cast<unsigned>(nlev));
-  lbl_prepare_kernel<<<grid, TL, 0, stream>>>(p);
+  dim3 grid(static_cast<unsigned>(p.ntiles), static_cast<unsigned>((nlev + PREP_LB - 1) / PREP_LB));
+  lbl_prepare_kernel<<<grid, TL, 0, stream>>>(p, nlev);
   count_launch();
   AB_CUDA(cudaGetLastError());
   return 0;

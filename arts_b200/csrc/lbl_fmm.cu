@@ -65,6 +65,26 @@ __device__ __forceinline__ double line_radius(double d, double GD, double g) { r
 __device__ __forceinline__ double line_reach(double d, double GD, double y) {
   return fabs(d) + fmax(0.0, MID_LIMIT * (1.0 + 1e-9) - y) * GD;
 }
+
+// Moments of a parent cluster from those of a child (multipole-to-multipole shift).  With a_j = m_j R_c^j the coefficients
+// of 1 / v^(j+1) about the child's centre, the same poles seen from the parent's centre sit at p + dc (dc = c_child -
+// c_parent, real), so a'_k = sum_{j<=k} C(k, j) dc^(k-j) a_j: exact, no truncation (a'_k needs only a_1 .. a_k; a_0 = 0
+// because the strengths are imaginary).  In scaled form every factor is <= 1:
+//     m'_k = sum_{j=1..k} C(k, j) (dc / R_p)^(k-j) (R_c / R_p)^j m_j,     |dc| + R_c <= R_p.
+__constant__ double BINOM[MP_P + 1][MP_P + 1];
+__device__ __forceinline__ double m2m_term(int k, double x, double r, const double* __restrict__ m /* m[j-1] = m_j */) {
+  double xp[MP_P + 1];
+  xp[0] = 1.0;
+#pragma unroll
+  for (int e = 1; e <= MP_P; e++) xp[e] = xp[e - 1] * x;
+  double sum = 0.0, rp = 1.0;
+#pragma unroll
+  for (int j = 1; j <= MP_P; j++) {
+    rp *= r;
+    if (j <= k) sum = __fma_rn(BINOM[k][j] * xp[k - j] * rp, m[j - 1], sum);
+  }
+  return sum;
+}
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -164,132 +184,90 @@ __global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams 
     for (int k = 0; k < MP_P; k++) o[3 + k] = term[k];
     o[3 + MP_P] = 0.0;
   }
-  // 64-line clusters
-  line_terms(live, d1, GD, g, Si, R1 > 0.0 ? 1.0 / R1 : 0.0, term);
+  // 64-line clusters and the tile: shifted sums of their children's moments (no second pass over the lines)
+  __shared__ double m0s[16][MP_P], m1s[4][MP_P], R0s[16], R1s[4];
+  if ((lane & 15) == 0) {
 #pragma unroll
-  for (int k = 0; k < MP_P; k++) {
-    double v = term[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 31) == 0) sh[warp][k] = v;
+    for (int k = 0; k < MP_P; k++) m0s[lane >> 4][k] = term[k];
+    R0s[lane >> 4] = R0;
   }
+  if ((lane & 63) == 0) R1s[lane >> 6] = R1;
   __syncthreads();
   if (lane < 4 * MP_P) {
-    const int s = lane / MP_P, k = lane % MP_P;
-    o1[s * MOM_DOUBLES + 3 + k] = sh[2 * s][k] + sh[2 * s + 1][k];
+    const int sidx = lane / MP_P, k = lane % MP_P + 1;
+    const double iR = R1s[sidx] > 0.0 ? 1.0 / R1s[sidx] : 0.0;
+    double v = 0.0;
+    for (int q = 0; q < 4; q++) {  // children in catalog order
+      const int qq = sidx * 4 + q;
+      if (rho0s[qq] < 0.0) continue;  // empty
+      v += m2m_term(k, (c0s[qq] - c1s[sidx]) * iR, R0s[qq] * iR, m0s[qq]);
+    }
+    m1s[sidx][k - 1] = v;
+    o1[sidx * MOM_DOUBLES + 3 + k - 1] = v;
   }
   if ((lane & 63) == 0) {
     double* o = o1 + (lane >> 6) * MOM_DOUBLES;
     o[0] = c1; o[1] = rho1; o[2] = R1; o[3 + MP_P] = 0.0;
   }
   __syncthreads();
-  // the tile
-  line_terms(live, d2, GD, g, Si, R2 > 0.0 ? 1.0 / R2 : 0.0, term);
-#pragma unroll
-  for (int k = 0; k < MP_P; k++) {
-    double v = term[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 31) == 0) sh[warp][k] = v;
-  }
-  __syncthreads();
   if (lane < MP_P) {
+    const int k = lane + 1;
+    const double iR = R2 > 0.0 ? 1.0 / R2 : 0.0;
     double v = 0.0;
-    for (int w = 0; w < TL / 32; w++) v += sh[w][lane];
+    for (int sidx = 0; sidx < 4; sidx++) {
+      if (rho1s[sidx] < 0.0) continue;
+      v += m2m_term(k, (c1s[sidx] - c2s) * iR, R1s[sidx] * iR, m1s[sidx]);
+    }
     o2[3 + lane] = v;
   }
   if (lane == 0) { o2[0] = c2s; o2[1] = rho2; o2[2] = R2; o2[3 + MP_P] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------
-// moments of the 16-tile groups: one CTA per (group, level), 16 lines per thread
+// moments of the 16-tile groups: one warp per (group, level), from the 16 tile records
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL) lbl_fmm_moments_group_kernel(PrepareParams p, FmmBuffers fb, const int32_t* __restrict__ tile_seg) {
-  const int64_t grp  = blockIdx.x;
-  const int lev      = blockIdx.y;
-  const int lane     = threadIdx.x;
-  const int64_t t0   = grp * FMM_GROUP, t1 = min(t0 + FMM_GROUP, p.ntiles);
+__global__ void __launch_bounds__(32) lbl_fmm_moments_group_kernel(PrepareParams p, FmmBuffers fb, const int32_t* __restrict__ tile_seg) {
+  const int64_t grp = blockIdx.x;
+  const int lev     = blockIdx.y;
+  const int lane    = threadIdx.x;
+  const int64_t t0  = grp * FMM_GROUP, t1 = min(t0 + FMM_GROUP, p.ntiles);
   double* __restrict__ out = fb.L3 + (int64_t(lev) * fb.ngroups + grp) * MOM_DOUBLES;
   const double* __restrict__ m2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
-  __shared__ double sh[TL / 32][MP_P];
-  __shared__ double sc, sR, sD;
-  __shared__ int ok;
-  if (lane == 0) {
-    // a group is usable when it is complete, inside one real segment, and every tile can be accepted
-    bool good = t1 - t0 == FMM_GROUP;
-    double lo = DBL_MAX, hi = -DBL_MAX;
-    for (int64_t t = t0; t < t1; t++) {
-      good = good && tile_seg[t] == tile_seg[t0] && tile_seg[t] >= 0 && m2[t * MOM_DOUBLES + 1] < DBL_MAX;
-      const double* s4 = summ + t * SUMMARY_DOUBLES;
-      if (s4[0] <= s4[1]) { lo = fmin(lo, s4[0]); hi = fmax(hi, s4[1]); }
-    }
-    ok = good && lo <= hi;
-    sc = ok ? 0.5 * (lo + hi) : 0.0;
+  // a group is usable when it is complete, inside one real segment, and every tile can be accepted; its centre is the
+  // midpoint of its lines' centres, its radius the largest reach of a child seen from there (every lane computes the same)
+  bool good = t1 - t0 == FMM_GROUP;
+  double lo = DBL_MAX, hi = -DBL_MAX;
+  for (int64_t t = t0; t < t1; t++) {
+    good = good && tile_seg[t] == tile_seg[t0] && tile_seg[t] >= 0 && m2[t * MOM_DOUBLES + 1] < DBL_MAX;
+    const double* s4 = summ + t * SUMMARY_DOUBLES;
+    if (s4[0] <= s4[1]) { lo = fmin(lo, s4[0]); hi = fmax(hi, s4[1]); }
   }
-  __syncthreads();
-  if (!ok) {
+  if (!(good && lo <= hi)) {
     if (lane < MOM_DOUBLES) out[lane] = lane == 1 ? DBL_MAX : 0.0;
     return;
   }
-  const double c = sc;
-  // pass 1: radius and reach
-  double R = 0.0, D = 0.0;
+  const double c = 0.5 * (lo + hi);
+  double R = 0.0, rho = 0.0;
   for (int64_t t = t0; t < t1; t++) {
-    const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + t) * tile_doubles();
-    const double igd = rec[(1 * TL + lane) * REC_GROUP + 1];
-    if (igd == 0.0) continue;
-    const double GD = 1.0 / igd, y = rec[(1 * TL + lane) * REC_GROUP + 2], d = rec[(0 * TL + lane) * REC_GROUP] - c;
-    R = fmax(R, line_radius(d, GD, y * GD));
-    D = fmax(D, line_reach(d, GD, y));
+    const double* s4 = summ + t * SUMMARY_DOUBLES;
+    if (s4[0] > s4[1]) continue;  // empty tile
+    const double dist = fabs(m2[t * MOM_DOUBLES] - c);
+    R   = fmax(R, m2[t * MOM_DOUBLES + 2] + dist);
+    rho = fmax(rho, m2[t * MOM_DOUBLES + 1] + dist);
   }
-  R = warp_max(R, 32); D = warp_max(D, 32);
-  if ((lane & 31) == 0) { sh[lane >> 5][0] = R; sh[lane >> 5][1] = D; }
-  __syncthreads();
-  if (lane == 0) {
-    double r = 0.0, dd = 0.0;
-    for (int w = 0; w < TL / 32; w++) { r = fmax(r, sh[w][0]); dd = fmax(dd, sh[w][1]); }
-    sR = r; sD = dd;
-  }
-  __syncthreads();
-  R = sR;
+  rho = fmax(rho, MP_THETA * R) * (1.0 + 1e-12);
   const double iR = R > 0.0 ? 1.0 / R : 0.0;
-  double sum[MP_P];
-#pragma unroll
-  for (int k = 0; k < MP_P; k++) sum[k] = 0.0;
-  for (int64_t t = t0; t < t1; t++) {  // fixed order: tiles ascending per thread, then the reduction tree
-    const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + t) * tile_doubles();
-    const double igd = rec[(1 * TL + lane) * REC_GROUP + 1];
-    if (igd == 0.0) continue;
-    const double GD = 1.0 / igd, y = rec[(1 * TL + lane) * REC_GROUP + 2], d = rec[(0 * TL + lane) * REC_GROUP] - c;
-    const double Si = rec[(1 * TL + lane) * REC_GROUP + 3] * GD * cst::inv_sqrt_pi;
-    double term[MP_P];
-    line_terms(true, d, GD, y * GD, Si, iR, term);
-#pragma unroll
-    for (int k = 0; k < MP_P; k++) sum[k] += term[k];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < MP_P; k++) {
-    double v = sum[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 31) == 0) sh[lane >> 5][k] = v;
-  }
-  __syncthreads();
   if (lane < MP_P) {
     double v = 0.0;
-    for (int w = 0; w < TL / 32; w++) v += sh[w][lane];
+    for (int64_t t = t0; t < t1; t++) {  // tiles in catalog order
+      const double* s4 = summ + t * SUMMARY_DOUBLES;
+      if (s4[0] > s4[1]) continue;
+      v += m2m_term(lane + 1, (m2[t * MOM_DOUBLES] - c) * iR, m2[t * MOM_DOUBLES + 2] * iR, m2 + t * MOM_DOUBLES + 3);
+    }
     out[3 + lane] = v;
   }
-  if (lane == 0) {
-    double rho = fmax(MP_THETA * R, sD);
-    for (int64_t t = t0; t < t1; t++) {
-      const double* s4 = summ + t * SUMMARY_DOUBLES;
-      if (s4[0] <= s4[1]) rho = fmax(rho, m2[t * MOM_DOUBLES + 1] + fabs(m2[t * MOM_DOUBLES] - c));
-    }
-    out[0] = c; out[1] = rho * (1.0 + 1e-12); out[2] = R; out[3 + MP_P] = 0.0;
-  }
+  if (lane == 0) { out[0] = c; out[1] = rho; out[2] = R; out[3 + MP_P] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------
@@ -540,8 +518,23 @@ __global__ void lbl_fmm_scan_kernel(SumParams p, FmmBuffers fb) {
 int launch_fmm(const PrepareParams& pp, const SumParams& sp, const FmmBuffers& fb, const int32_t* tile_seg, int nlev, int store_full,
                cudaStream_t stream) {
   if (pp.ntiles == 0 || nlev == 0 || sp.nf == 0 || sp.nsegs == 0) return 0;
+  {
+    // binomial coefficients of the moment shift: per device, before the first launch on it
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+      double h[MP_P + 1][MP_P + 1] = {};
+      for (int n = 0; n <= MP_P; n++) {
+        h[n][0] = 1.0;
+        for (int k = 1; k <= n; k++) h[n][k] = h[n - 1][k - 1] + (k <= n - 1 ? h[n - 1][k] : 0.0);
+      }
+      AB_CUDA(cudaMemcpyToSymbol(BINOM, h, sizeof(h)));
+      done[dev] = true;
+    }
+  }
   lbl_fmm_moments_tile_kernel<<<dim3(static_cast<unsigned>(pp.ntiles), static_cast<unsigned>(nlev)), TL, 0, stream>>>(pp, fb);
-  lbl_fmm_moments_group_kernel<<<dim3(static_cast<unsigned>(fb.ngroups), static_cast<unsigned>(nlev)), TL, 0, stream>>>(pp, fb, tile_seg);
+  lbl_fmm_moments_group_kernel<<<dim3(static_cast<unsigned>(fb.ngroups), static_cast<unsigned>(nlev)), 32, 0, stream>>>(pp, fb, tile_seg);
   lbl_fmm_scan_kernel<<<dim3(static_cast<unsigned>(sp.nsegs), static_cast<unsigned>(nlev)), 32, 0, stream>>>(sp, fb);
   lbl_fmm_far_kernel<<<dim3(static_cast<unsigned>((sp.nf + FF_NT * FF_R - 1) / (FF_NT * FF_R)), static_cast<unsigned>(nlev)), FF_NT, 0,
                        stream>>>(sp, fb);

@@ -66,7 +66,7 @@ struct ab200_path {
   double* d_Ibkg = nullptr;
   SegmentDev* d_segs = nullptr;  // [3][nsegments] capacity: mode-0 list (line-by-line kernel), mode-1 list, mode-0 far-field list
   SegmentDev* h_segs = nullptr;
-  int32_t nsegs[3] = {0, 0, 0};  // [2]: real segments without cutoffs, summed by lbl_fmm.cu
+  int32_t nsegs[3] = {0, 0, 0};  // [2]: real segments summed by lbl_fmm.cu ([0]: by the line-by-line kernel, AB200_FARFIELD=0)
   FmmBuffers fmm{};              // one allocation (fmm.L0), sized for levels_per_batch levels
   int32_t* d_tile_seg = nullptr; // [ntiles] index of the tile's far-field segment in the catalog, -1 for the others
   // workspace
@@ -221,12 +221,12 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   AB_TRY(dev_alloc(&p->d_prep, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * tile_doubles()));
   AB_TRY(dev_alloc(&p->d_summary, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * SUMMARY_DOUBLES));
   {
-    // far-field sums of the real, cutoff-free segments (lbl_fmm.cu): moment records of four cluster levels + scratch
+    // far-field sums of the real segments (lbl_fmm.cu): moment records of four cluster levels + scratch
     size_t nff = 0;
     std::vector<int32_t> tseg(static_cast<size_t>(cat->ntiles), -1);
     for (size_t i = 0; i < cat->segments.size(); i++) {
       const Segment& sg = cat->segments[i];
-      if (sg.mode != 0 || sg.has_cutoff) continue;
+      if (sg.mode != 0) continue;
       nff++;
       for (int64_t t = sg.tile_begin; t < sg.tile_end; t++) tseg[t] = static_cast<int32_t>(i);
     }
@@ -426,7 +426,7 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   for (const Segment& s : cat->segments) {
     if (!(select_species == AB200_SPECIES_BATH || select_species == s.species)) continue;
     SegmentDev d{s.tile_begin, s.tile_end, s.cutoff, s.pol, s.has_cutoff};
-    const int list = s.mode == 1 ? 1 : (farfield && p->fmm.L0 && !s.has_cutoff) ? 2 : 0;
+    const int list = s.mode == 1 ? 1 : (farfield && p->fmm.L0) ? 2 : 0;
     p->h_segs[list * nseg + p->nsegs[list]++] = d;
   }
   if (nseg) AB_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, 3 * nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice, p->stream));
@@ -521,8 +521,8 @@ int ab200_path_run_propmat(ab200_path* p) {
       AB_TRY(launch_prepare(pp, nlev, p->stream));
       t.stop();
     }
-    // real segments: the line-by-line kernel (segments with ByLine cutoffs) writes whole K records when it runs; the
-    // far-field sums then add to them, or write the records themselves when they are alone
+    // real segments: the line-by-line kernel (AB200_FARFIELD=0) writes whole K records when it runs; the far-field sums
+    // add to them, or write the records themselves when they are alone
     sp.k_store_full = (store_full && p->nsegs[0] > 0) ? 1 : 0;
     for (int mode = 0; mode < 2; mode++) {
       if (mode == 1 && p->nsegs[2] > 0) {

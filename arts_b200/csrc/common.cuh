@@ -67,10 +67,14 @@ constexpr double FAR_LIMIT_REAL_SUM = 1000.0;
 constexpr double MID_LIMIT = 48.0;
 
 // Far-field (multipole) sums of the real, cutoff-free segments (lbl_fmm.cu): per cluster and level a record of
-// MOM_DOUBLES doubles {centre c, acceptance distance rho, radius R, m_1 .. m_MP_P, pad}
+// MOM_DOUBLES doubles
 constexpr int MP_P = 16;
 constexpr double MP_THETA = 6.0;
-constexpr int MOM_DOUBLES = 20;
+constexpr int MOM_DOUBLES = 24;
+// record slots: centre, acceptance distance, radius, m_1 .. m_16, then for lines with ByLine cutoffs the distance up to
+// which every line of the cluster is inside its window, the distance beyond which every line is outside, and the sum of
+// the lines' cutoff values ls(f0' + cutoff)
+constexpr int MOM_C = 0, MOM_RHO = 1, MOM_R = 2, MOM_M1 = 3, MOM_IN = 19, MOM_OUT = 20, MOM_CUT = 21;
 constexpr int FMM_GROUP = 16;  // tiles per coarsest cluster
 
 constexpr int AB200_MAX_TARGETS = 8;  // Jacobian targets per call (temperature + species VMRs)

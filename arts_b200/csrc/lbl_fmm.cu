@@ -1,7 +1,7 @@
-// lbl_fmm.cu — the line sum of real, cutoff-free segments as a hierarchical far-field (multipole) sum.
+// lbl_fmm.cu — the line sum of real segments (with or without ByLine cutoffs) as a hierarchical far-field (multipole) sum.
 //
-// Replaces, for merged real segments without ByLine cutoffs, the line-by-line K2 loop of lbl_sum_real_kernel
-// (reference band_shape::operator(), src/core/lbl/lbl_lineshape_voigt_lte.cpp:431-436, per pair s Faddeeva::w(z) :239).
+// Replaces, for merged real segments, the line-by-line K2 loop of lbl_sum_real_kernel (reference band_shape::operator(),
+// src/core/lbl/lbl_lineshape_voigt_lte.cpp:431-436 and with cutoff :591-608, per pair s Faddeeva::w(z) :239).
 //
 // Beyond |x| + y = 48 the forward kernels already evaluate w(z) with four terms of its continued fraction collapsed to
 // one rational function (faddeeva.cuh w_mid: w = (i/sqrt(pi)) z (t - 5/2) / (t^2 - 3 t + 3/4), t = z^2, 1.3e-12).  Its
@@ -22,6 +22,11 @@
 // alone.  A line contributes through its coarsest accepted cluster (lbl_fmm_far_kernel); pairs whose 16-line cluster is
 // not accepted are evaluated one by one with the per-pair arithmetic of lbl_sum_real_kernel (lbl_fmm_near_kernel).
 // The split never depends on block, shard or GPU boundaries: spectra stay bit-identical under any frequency partition.
+// ByLine cutoffs: a line contributes ls(f) - ls(f0' + cutoff) inside its window and nothing outside.  A cluster's
+// expansion (minus the sum of its cutoff values) then serves the frequencies between rho and the distance IN up to which
+// every line is inside its window; beyond OUT every line is outside and the cluster contributes 0; in between the
+// window edges cut through the cluster and its lines are taken pair by pair with the per-pair window test.  IN and OUT are
+// nested like rho.
 //
 // configs[3] (1e6 lines): per (frequency, level) ~700 cluster visits + ~100-400 pairs instead of 1e6 pairs.
 #include <cfloat>
@@ -66,6 +71,14 @@ __device__ __forceinline__ double line_reach(double d, double GD, double y) {
   return fabs(d) + fmax(0.0, MID_LIMIT * (1.0 + 1e-9) - y) * GD;
 }
 
+// A frequency at distance v from a cluster's centre is SERVED by the cluster's record when the expansion applies (beyond rho
+// and, with ByLine cutoffs, while every line is still inside its window) or when every line is outside its window
+// (contribution 0).  `ann` tells the first case.
+__device__ __forceinline__ bool fmm_served(double v, double rho, double in, double out, bool& ann) {
+  ann = v > rho && v <= in;
+  return ann || v > out;
+}
+
 // Moments of a parent cluster from those of a child (multipole-to-multipole shift).  With a_j = m_j R_c^j the coefficients
 // of 1 / v^(j+1) about the child's centre, the same poles seen from the parent's centre sit at p + dc (dc = c_child -
 // c_parent, real), so a'_k = sum_{j<=k} C(k, j) dc^(k-j) a_j: exact, no truncation (a'_k needs only a_1 .. a_k; a_0 = 0
@@ -96,14 +109,14 @@ __global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams 
   const int lev      = blockIdx.y;
   const int lane     = threadIdx.x;
   const double* __restrict__ rec = p.prep + (int64_t(lev) * p.ntiles + tile) * tile_doubles();
-  const double* __restrict__ s4  = p.summary + (int64_t(lev) * p.ntiles + tile) * SUMMARY_DOUBLES;
   double* __restrict__ o2 = fb.L2 + (int64_t(lev) * p.ntiles + tile) * MOM_DOUBLES;
   double* __restrict__ o1 = fb.L1 + (int64_t(lev) * p.ntiles + tile) * 4 * MOM_DOUBLES;
   double* __restrict__ o0 = fb.L0 + (int64_t(lev) * p.ntiles + tile) * 16 * MOM_DOUBLES;
-  if (p.tile_mode[tile] != 0 || s4[4] < DBL_MAX) {  // complex tile or ByLine cutoffs: never accepted
+  if (p.tile_mode[tile] != 0) {  // complex tile: never served
     for (int i = lane; i < 21 * MOM_DOUBLES; i += TL) {
       double* o = i < MOM_DOUBLES ? o2 + i : i < 5 * MOM_DOUBLES ? o1 + (i - MOM_DOUBLES) : o0 + (i - 5 * MOM_DOUBLES);
-      *o = (i % MOM_DOUBLES) == 1 ? DBL_MAX : 0.0;
+      const int k = i % MOM_DOUBLES;
+      *o = (k == MOM_RHO || k == MOM_OUT) ? DBL_MAX : k == MOM_IN ? -1.0 : 0.0;
     }
     return;
   }
@@ -114,11 +127,17 @@ __global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams 
   const bool live  = igd != 0.0;
   const double GD  = live ? 1.0 / igd : 0.0;
   const double g   = y * GD, Si = sre * GD * cst::inv_sqrt_pi;
+  // ByLine cutoff of the line (real merged segments keep it in the s_im slot) and its cutoff value ls(f0' + cutoff)
+  const double cutl = live ? rec[(2 * TL + lane) * REC_GROUP + 1] : DBL_MAX;
+  const bool has_cut = live && cutl < DBL_MAX;
+  const double cval = has_cut ? rec[(2 * TL + lane) * REC_GROUP + 2] : 0.0;
 
-  __shared__ double sh[TL / 32][MP_P + 4];
-  __shared__ double c1s[4], rho1s[4], c0s[16], rho0s[16];
+  __shared__ double sh[TL / 32][8];
+  __shared__ double c1s[4], rho1s[4], in1s[4], out1s[4], cs1s[4], c0s[16], rho0s[16], in0s[16], out0s[16], cs0s[16];
   __shared__ double c2s;
+  __shared__ double m0s[16][MP_P], m1s[4][MP_P], R0s[16], R1s[4];
   const int warp = lane >> 5;
+  const int w1 = warp & ~1;
 
   // --- centres: midpoint of the live lines' centres per cluster
   const double lo = live ? f0s : DBL_MAX, hi = live ? f0s : -DBL_MAX;
@@ -126,7 +145,6 @@ __global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams 
   const double lo32 = warp_min(lo0, 32), hi32 = warp_max(hi0, 32);
   if ((lane & 31) == 0) { sh[warp][0] = lo32; sh[warp][1] = hi32; }
   __syncthreads();
-  const int w1 = warp & ~1;
   const double lo1 = fmin(sh[w1][0], sh[w1 + 1][0]), hi1 = fmax(sh[w1][1], sh[w1 + 1][1]);
   double lo2 = DBL_MAX, hi2 = -DBL_MAX;
   for (int w = 0; w < TL / 32; w++) { lo2 = fmin(lo2, sh[w][0]); hi2 = fmax(hi2, sh[w][1]); }
@@ -137,38 +155,73 @@ __global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams 
   const double c0 = e0 ? c1 : 0.5 * (lo0 + hi0);
   const double d0 = live ? f0s - c0 : 0.0, d1 = live ? f0s - c1 : 0.0, d2 = live ? f0s - c2 : 0.0;
 
-  // --- radii and reaches
+  // --- per cluster: radius R, reach D of the mid form, window bounds (every line inside its window up to IN, every line
+  // outside beyond OUT) and the sum of the cutoff values
   const double R0 = warp_max(live ? line_radius(d0, GD, g) : 0.0, 16), D0 = warp_max(live ? line_reach(d0, GD, y) : 0.0, 16);
+  const double I0 = warp_min(has_cut ? cutl - fabs(d0) : DBL_MAX, 16), O0 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d0) : DBL_MAX, 16);
+  double CS0 = cval;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) CS0 += __shfl_xor_sync(0xffffffffu, CS0, o);
   double R1 = warp_max(live ? line_radius(d1, GD, g) : 0.0, 32), D1 = warp_max(live ? line_reach(d1, GD, y) : 0.0, 32);
+  double I1 = warp_min(has_cut ? cutl - fabs(d1) : DBL_MAX, 32), O1 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d1) : DBL_MAX, 32);
   double R2 = warp_max(live ? line_radius(d2, GD, g) : 0.0, 32), D2 = warp_max(live ? line_reach(d2, GD, y) : 0.0, 32);
-  if ((lane & 31) == 0) { sh[warp][0] = R1; sh[warp][1] = D1; sh[warp][2] = R2; sh[warp][3] = D2; }
+  double I2 = warp_min(has_cut ? cutl - fabs(d2) : DBL_MAX, 32), O2 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d2) : DBL_MAX, 32);
+  if ((lane & 31) == 0) {
+    double* r = sh[warp];
+    r[0] = R1; r[1] = D1; r[2] = I1; r[3] = O1; r[4] = R2; r[5] = D2; r[6] = I2; r[7] = O2;
+  }
   __syncthreads();
   R1 = fmax(sh[w1][0], sh[w1 + 1][0]); D1 = fmax(sh[w1][1], sh[w1 + 1][1]);
-  R2 = 0.0; D2 = 0.0;
-  for (int w = 0; w < TL / 32; w++) { R2 = fmax(R2, sh[w][2]); D2 = fmax(D2, sh[w][3]); }
+  I1 = fmin(sh[w1][2], sh[w1 + 1][2]); O1 = fmax(sh[w1][3], sh[w1 + 1][3]);
+  R2 = 0.0; D2 = 0.0; I2 = DBL_MAX; O2 = 0.0;
+  for (int w = 0; w < TL / 32; w++) {
+    R2 = fmax(R2, sh[w][4]); D2 = fmax(D2, sh[w][5]); I2 = fmin(I2, sh[w][6]); O2 = fmax(O2, sh[w][7]);
+  }
   __syncthreads();
 
-  // --- nested acceptance distances, finest first
+  // --- nested service bounds, finest first: a frequency served by a cluster is served by every cluster inside it
   const double rho0 = e0 ? 0.0 : fmax(MP_THETA * R0, D0) * (1.0 + 1e-12);
-  if ((lane & 15) == 0) { c0s[lane >> 4] = c0; rho0s[lane >> 4] = e0 ? -1.0 : rho0; }
+  const double in0  = e0 ? DBL_MAX : (I0 < DBL_MAX ? I0 * (1.0 - 1e-12) : DBL_MAX);
+  const double out0 = e0 ? DBL_MAX : (O0 < DBL_MAX ? O0 * (1.0 + 1e-12) : DBL_MAX);
+  if ((lane & 15) == 0) {
+    const int q = lane >> 4;
+    c0s[q] = c0; rho0s[q] = e0 ? -1.0 : rho0; in0s[q] = in0; out0s[q] = out0; cs0s[q] = CS0; R0s[q] = R0;
+  }
   __syncthreads();
-  double rho1 = e1 ? 0.0 : fmax(MP_THETA * R1, D1);
+  double rho1 = e1 ? 0.0 : fmax(MP_THETA * R1, D1), in1 = I1 < DBL_MAX ? I1 * (1.0 - 1e-12) : DBL_MAX,
+         out1 = O1 < DBL_MAX ? O1 * (1.0 + 1e-12) : DBL_MAX, cs1 = 0.0;
   for (int q = 0; q < 4; q++) {
     const int qq = (lane >> 6) * 4 + q;
-    if (rho0s[qq] >= 0.0) rho1 = fmax(rho1, rho0s[qq] + fabs(c0s[qq] - c1));
+    if (rho0s[qq] < 0.0) continue;
+    const double dist = fabs(c0s[qq] - c1);
+    rho1 = fmax(rho1, rho0s[qq] + dist);
+    in1  = fmin(in1, in0s[qq] < DBL_MAX ? in0s[qq] - dist : DBL_MAX);
+    out1 = fmax(out1, out0s[qq] < DBL_MAX ? out0s[qq] + dist : DBL_MAX);
+    cs1 += cs0s[qq];
   }
   rho1 = e1 ? 0.0 : rho1 * (1.0 + 1e-12);
-  if ((lane & 63) == 0) { c1s[lane >> 6] = c1; rho1s[lane >> 6] = e1 ? -1.0 : rho1; }
+  if (e1) { in1 = DBL_MAX; out1 = DBL_MAX; }
+  if ((lane & 63) == 0) {
+    const int sidx = lane >> 6;
+    c1s[sidx] = c1; rho1s[sidx] = e1 ? -1.0 : rho1; in1s[sidx] = in1; out1s[sidx] = out1; cs1s[sidx] = cs1; R1s[sidx] = R1;
+  }
   if (lane == 0) c2s = c2;
   __syncthreads();
-  double rho2 = e2 ? 0.0 : fmax(MP_THETA * R2, D2);
-  for (int s = 0; s < 4; s++)
-    if (rho1s[s] >= 0.0) rho2 = fmax(rho2, rho1s[s] + fabs(c1s[s] - c2));
+  double rho2 = e2 ? 0.0 : fmax(MP_THETA * R2, D2), in2 = I2 < DBL_MAX ? I2 * (1.0 - 1e-12) : DBL_MAX,
+         out2 = O2 < DBL_MAX ? O2 * (1.0 + 1e-12) : DBL_MAX, cs2 = 0.0;
+  for (int sidx = 0; sidx < 4; sidx++) {
+    if (rho1s[sidx] < 0.0) continue;
+    const double dist = fabs(c1s[sidx] - c2);
+    rho2 = fmax(rho2, rho1s[sidx] + dist);
+    in2  = fmin(in2, in1s[sidx] < DBL_MAX ? in1s[sidx] - dist : DBL_MAX);
+    out2 = fmax(out2, out1s[sidx] < DBL_MAX ? out1s[sidx] + dist : DBL_MAX);
+    cs2 += cs1s[sidx];
+  }
   rho2 = e2 ? 0.0 : rho2 * (1.0 + 1e-12);
+  if (e2) { in2 = DBL_MAX; out2 = DBL_MAX; }
 
-  // --- moments
+  // --- moments of the 16-line clusters from the lines
   double term[MP_P];
-  // 16-line clusters
   line_terms(live, d0, GD, g, Si, R0 > 0.0 ? 1.0 / R0 : 0.0, term);
 #pragma unroll
   for (int k = 0; k < MP_P; k++) {
@@ -179,48 +232,41 @@ __global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams 
   }
   if ((lane & 15) == 0) {
     double* o = o0 + (lane >> 4) * MOM_DOUBLES;
-    o[0] = c0; o[1] = rho0; o[2] = R0;
+    o[MOM_C] = c0; o[MOM_RHO] = rho0; o[MOM_R] = R0; o[MOM_IN] = in0; o[MOM_OUT] = out0; o[MOM_CUT] = CS0;
 #pragma unroll
-    for (int k = 0; k < MP_P; k++) o[3 + k] = term[k];
-    o[3 + MP_P] = 0.0;
+    for (int k = 0; k < MP_P; k++) { o[MOM_M1 + k] = term[k]; m0s[lane >> 4][k] = term[k]; }
+    o[22] = 0.0; o[23] = 0.0;
   }
-  // 64-line clusters and the tile: shifted sums of their children's moments (no second pass over the lines)
-  __shared__ double m0s[16][MP_P], m1s[4][MP_P], R0s[16], R1s[4];
-  if ((lane & 15) == 0) {
-#pragma unroll
-    for (int k = 0; k < MP_P; k++) m0s[lane >> 4][k] = term[k];
-    R0s[lane >> 4] = R0;
-  }
-  if ((lane & 63) == 0) R1s[lane >> 6] = R1;
   __syncthreads();
-  if (lane < 4 * MP_P) {
-    const int sidx = lane / MP_P, k = lane % MP_P + 1;
+  // --- 64-line clusters and the tile: shifted sums of their children's moments (no second pass over the lines); one
+  // (parent, k, child) per thread, children added in catalog order ((0 + 1) + (2 + 3))
+  {
+    const int q = lane & 3, k = ((lane >> 2) & 15) + 1, sidx = lane >> 6, qq = sidx * 4 + q;
     const double iR = R1s[sidx] > 0.0 ? 1.0 / R1s[sidx] : 0.0;
-    double v = 0.0;
-    for (int q = 0; q < 4; q++) {  // children in catalog order
-      const int qq = sidx * 4 + q;
-      if (rho0s[qq] < 0.0) continue;  // empty
-      v += m2m_term(k, (c0s[qq] - c1s[sidx]) * iR, R0s[qq] * iR, m0s[qq]);
+    double v = rho0s[qq] < 0.0 ? 0.0 : m2m_term(k, (c0s[qq] - c1s[sidx]) * iR, R0s[qq] * iR, m0s[qq]);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (q == 0) {
+      m1s[sidx][k - 1] = v;
+      o1[sidx * MOM_DOUBLES + MOM_M1 + k - 1] = v;
     }
-    m1s[sidx][k - 1] = v;
-    o1[sidx * MOM_DOUBLES + 3 + k - 1] = v;
   }
   if ((lane & 63) == 0) {
     double* o = o1 + (lane >> 6) * MOM_DOUBLES;
-    o[0] = c1; o[1] = rho1; o[2] = R1; o[3 + MP_P] = 0.0;
+    o[MOM_C] = c1; o[MOM_RHO] = rho1; o[MOM_R] = R1; o[MOM_IN] = in1; o[MOM_OUT] = out1; o[MOM_CUT] = cs1; o[22] = 0.0; o[23] = 0.0;
   }
   __syncthreads();
-  if (lane < MP_P) {
-    const int k = lane + 1;
+  if (lane < 4 * MP_P) {
+    const int sidx = lane & 3, k = (lane >> 2) + 1;
     const double iR = R2 > 0.0 ? 1.0 / R2 : 0.0;
-    double v = 0.0;
-    for (int sidx = 0; sidx < 4; sidx++) {
-      if (rho1s[sidx] < 0.0) continue;
-      v += m2m_term(k, (c1s[sidx] - c2s) * iR, R1s[sidx] * iR, m1s[sidx]);
-    }
-    o2[3 + lane] = v;
+    double v = rho1s[sidx] < 0.0 ? 0.0 : m2m_term(k, (c1s[sidx] - c2s) * iR, R1s[sidx] * iR, m1s[sidx]);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (sidx == 0) o2[MOM_M1 + k - 1] = v;
   }
-  if (lane == 0) { o2[0] = c2s; o2[1] = rho2; o2[2] = R2; o2[3 + MP_P] = 0.0; }
+  if (lane == 0) {
+    o2[MOM_C] = c2s; o2[MOM_RHO] = rho2; o2[MOM_R] = R2; o2[MOM_IN] = in2; o2[MOM_OUT] = out2; o2[MOM_CUT] = cs2; o2[22] = 0.0; o2[23] = 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -234,27 +280,31 @@ __global__ void __launch_bounds__(32) lbl_fmm_moments_group_kernel(PrepareParams
   double* __restrict__ out = fb.L3 + (int64_t(lev) * fb.ngroups + grp) * MOM_DOUBLES;
   const double* __restrict__ m2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
   const double* __restrict__ summ = p.summary + int64_t(lev) * p.ntiles * SUMMARY_DOUBLES;
-  // a group is usable when it is complete, inside one real segment, and every tile can be accepted; its centre is the
-  // midpoint of its lines' centres, its radius the largest reach of a child seen from there (every lane computes the same)
+  // a group is usable when it is complete and inside one real segment; its centre is the midpoint of its lines' centres,
+  // its radius the largest reach of a child seen from there (every lane computes the same)
   bool good = t1 - t0 == FMM_GROUP;
   double lo = DBL_MAX, hi = -DBL_MAX;
   for (int64_t t = t0; t < t1; t++) {
-    good = good && tile_seg[t] == tile_seg[t0] && tile_seg[t] >= 0 && m2[t * MOM_DOUBLES + 1] < DBL_MAX;
+    good = good && tile_seg[t] == tile_seg[t0] && tile_seg[t] >= 0;
     const double* s4 = summ + t * SUMMARY_DOUBLES;
     if (s4[0] <= s4[1]) { lo = fmin(lo, s4[0]); hi = fmax(hi, s4[1]); }
   }
   if (!(good && lo <= hi)) {
-    if (lane < MOM_DOUBLES) out[lane] = lane == 1 ? DBL_MAX : 0.0;
+    if (lane < MOM_DOUBLES) out[lane] = (lane == MOM_RHO || lane == MOM_OUT) ? DBL_MAX : lane == MOM_IN ? -1.0 : 0.0;
     return;
   }
   const double c = 0.5 * (lo + hi);
-  double R = 0.0, rho = 0.0;
+  double R = 0.0, rho = 0.0, in = DBL_MAX, outb = 0.0, cs = 0.0;
   for (int64_t t = t0; t < t1; t++) {
     const double* s4 = summ + t * SUMMARY_DOUBLES;
     if (s4[0] > s4[1]) continue;  // empty tile
-    const double dist = fabs(m2[t * MOM_DOUBLES] - c);
-    R   = fmax(R, m2[t * MOM_DOUBLES + 2] + dist);
-    rho = fmax(rho, m2[t * MOM_DOUBLES + 1] + dist);
+    const double* r = m2 + t * MOM_DOUBLES;
+    const double dist = fabs(r[MOM_C] - c);
+    R    = fmax(R, r[MOM_R] + dist);
+    rho  = fmax(rho, r[MOM_RHO] + dist);
+    in   = fmin(in, r[MOM_IN] < DBL_MAX ? r[MOM_IN] - dist : DBL_MAX);
+    outb = fmax(outb, r[MOM_OUT] < DBL_MAX ? r[MOM_OUT] + dist : DBL_MAX);
+    cs += r[MOM_CUT];
   }
   rho = fmax(rho, MP_THETA * R) * (1.0 + 1e-12);
   const double iR = R > 0.0 ? 1.0 / R : 0.0;
@@ -263,11 +313,14 @@ __global__ void __launch_bounds__(32) lbl_fmm_moments_group_kernel(PrepareParams
     for (int64_t t = t0; t < t1; t++) {  // tiles in catalog order
       const double* s4 = summ + t * SUMMARY_DOUBLES;
       if (s4[0] > s4[1]) continue;
-      v += m2m_term(lane + 1, (m2[t * MOM_DOUBLES] - c) * iR, m2[t * MOM_DOUBLES + 2] * iR, m2 + t * MOM_DOUBLES + 3);
+      const double* r = m2 + t * MOM_DOUBLES;
+      v += m2m_term(lane + 1, (r[MOM_C] - c) * iR, r[MOM_R] * iR, r + MOM_M1);
     }
-    out[3 + lane] = v;
+    out[MOM_M1 + lane] = v;
   }
-  if (lane == 0) { out[0] = c; out[1] = rho; out[2] = R; out[3 + MP_P] = 0.0; }
+  if (lane == 0) {
+    out[MOM_C] = c; out[MOM_RHO] = rho; out[MOM_R] = R; out[MOM_IN] = in; out[MOM_OUT] = outb; out[MOM_CUT] = cs; out[22] = 0.0; out[23] = 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -300,10 +353,12 @@ __device__ __forceinline__ void ff_add(const double* __restrict__ mo, double c, 
 #pragma unroll
     for (int r = 0; r < FF_R; r++) s[r] = __fma_rn(__fma_rn(s[r], tau[r], pr.y), tau[r], pr.x);
   }
+  const double cutsum = __ldg(mo + MOM_CUT);  // ls(f) - ls(f0' + cutoff), :591-608: the cluster's cutoff values at once
 #pragma unroll
   for (int r = 0; r < FF_R; r++) {
     s[r]   = __fma_rn(s[r], tau[r], m01.y);
     acc[r] = __fma_rn(__dmul_rn(s[r], tau[r]), tt[r], acc[r]);
+    acc[r] = __dsub_rn(acc[r], on[r] ? cutsum : 0.0);
   }
 }
 
@@ -312,17 +367,18 @@ __device__ __forceinline__ void ff_add(const double* __restrict__ mo, double c, 
 __device__ __forceinline__ bool ff_visit(const double* __restrict__ mo, const double* f, double fmin_b, double fmax_b, const bool* parent_on,
                                          bool* on_out, double* acc) {
   const double2 cr = __ldg(reinterpret_cast<const double2*>(mo));  // c, rho
-  const double vmax = fmax(fabs(fmin_b - cr.x), fabs(fmax_b - cr.x));
+  const double in = __ldg(mo + MOM_IN), out = __ldg(mo + MOM_OUT);
   bool add[FF_R];
   bool any = false;
 #pragma unroll
   for (int r = 0; r < FF_R; r++) {
-    const bool acc_r = fabs(__dsub_rn(f[r], cr.x)) > cr.y;  // the frequency's own test
-    on_out[r] = parent_on[r] || acc_r;
-    add[r]    = acc_r && !parent_on[r];
+    bool ann;
+    const bool served = fmm_served(fabs(__dsub_rn(f[r], cr.x)), cr.y, in, out, ann);  // the frequency's own test
+    on_out[r] = parent_on[r] || served;
+    add[r]    = ann && !parent_on[r];
     any |= add[r];
   }
-  if (vmax > cr.y && __any_sync(0xffffffffu, any)) ff_add(mo, cr.x, f, add, acc);
+  if (__any_sync(0xffffffffu, any)) ff_add(mo, cr.x, f, add, acc);
   bool all = true;
 #pragma unroll
   for (int r = 0; r < FF_R; r++) all = all && on_out[r];
@@ -420,9 +476,9 @@ __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffe
 #pragma unroll 1
     for (int j = 0; j < 32; j++) {
       const double f = __shfl_sync(0xffffffffu, f_own, j);
-      // Tiles that may be needed: c_t - rho_t <= f <= c_t + rho_t.  scan holds the running maximum of c + rho from the
-      // segment's first tile and the running minimum of c - rho from its last (lbl_fmm_scan_kernel), both monotone whatever
-      // the order of the shifted line centres, so two bisections bracket the candidates.
+      // Tiles that may be needed: |f - c_t| <= U_t, the last distance at which the tile does not serve a frequency.  scan
+      // holds the running maximum of c + U from the segment's first tile and the running minimum of c - U from its last
+      // (lbl_fmm_scan_kernel), both monotone whatever the order of the shifted line centres: two bisections bracket them.
       int64_t a = seg.tile_begin, b = seg.tile_end;
       while (a < b) {  // first tile with max_{t' <= t}(c + rho) >= f
         const int64_t m = (a + b) >> 1;
@@ -437,26 +493,38 @@ __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffe
       }
       double acc = 0.0;
       for (int64_t t = a; t < lo; t++) {
-        const double2 c2 = __ldg(reinterpret_cast<const double2*>(L2 + t * MOM_DOUBLES));
-        if (fabs(__dsub_rn(f, c2.x)) > c2.y) continue;  // the tile (or a group above it) is in the far-field sum
+        bool ann;
+        const double* __restrict__ r2 = L2 + t * MOM_DOUBLES;
+        const double2 c2 = __ldg(reinterpret_cast<const double2*>(r2));
+        if (fmm_served(fabs(__dsub_rn(f, c2.x)), c2.y, __ldg(r2 + MOM_IN), __ldg(r2 + MOM_OUT), ann)) continue;  // in the far-field sum
         const double* __restrict__ g0 = prep + t * tile_doubles();
         const int count = p.tile_count[t];
 #pragma unroll 1
         for (int s = 0; s < 4; s++) {
-          const double2 c1 = __ldg(reinterpret_cast<const double2*>(L1 + (t * 4 + s) * MOM_DOUBLES));
-          if (fabs(__dsub_rn(f, c1.x)) > c1.y) continue;
+          const double* __restrict__ r1 = L1 + (t * 4 + s) * MOM_DOUBLES;
+          const double2 c1 = __ldg(reinterpret_cast<const double2*>(r1));
+          if (fmm_served(fabs(__dsub_rn(f, c1.x)), c1.y, __ldg(r1 + MOM_IN), __ldg(r1 + MOM_OUT), ann)) continue;
 #pragma unroll
           for (int qp = 0; qp < 2; qp++) {  // two 16-line clusters per step, one per half warp
             const int q = s * 4 + qp * 2 + (lane >> 4);
-            const double2 c0 = __ldg(reinterpret_cast<const double2*>(L0 + (t * 16 + q) * MOM_DOUBLES));
+            const double* __restrict__ r0 = L0 + (t * 16 + q) * MOM_DOUBLES;
+            const double2 c0 = __ldg(reinterpret_cast<const double2*>(r0));
             const int l = q * 16 + (lane & 15);
-            if (fabs(__dsub_rn(f, c0.x)) > c0.y || l >= count) continue;
+            if (fmm_served(fabs(__dsub_rn(f, c0.x)), c0.y, __ldg(r0 + MOM_IN), __ldg(r0 + MOM_OUT), ann) || l >= count) continue;
             // the per-pair arithmetic of lbl_sum_real_kernel's near loop
             const double2 rc = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP));      // B1, igd
             if (rc.y == 0.0) continue;
             const double2 ra = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP));      // f0', c3
             const double2 rb = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP) + 1);  // kappa, A1
             const double2 rd = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP) + 1);  // y, s_re
+            if (seg.has_cutoff) {
+              // frequency_spans (lbl_lineshape_voigt_lte.h:123-133) and ls(f) - ls(f0' + cutoff) (:591-608)
+              const double lcut = __ldg(g0 + (2 * TL + l) * REC_GROUP + 1);
+              if (lcut < DBL_MAX) {
+                if (!(ra.x >= f - lcut && ra.x <= f + lcut)) continue;
+                acc = __dsub_rn(acc, __ldg(g0 + (2 * TL + l) * REC_GROUP + 2));
+              }
+            }
             const double u  = __dsub_rn(f, ra.x);
             const double ax = __dmul_rn(fabs(u), rc.y);
             if (__dadd_rn(ax, rd.x) > FAR_LIMIT_REAL_SUM) {
@@ -502,14 +570,19 @@ __global__ void lbl_fmm_scan_kernel(SumParams p, FmmBuffers fb) {
   const int lev = blockIdx.y;
   const double* __restrict__ L2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
   double* __restrict__ scan = fb.scan + int64_t(lev) * p.ntiles * 2;
+  // U: beyond it the tile serves every frequency (past its acceptance distance, or past every window if it has cutoffs)
+  auto U = [&](int64_t t) {
+    const double* r = L2 + t * MOM_DOUBLES;
+    return r[MOM_IN] < DBL_MAX ? fmax(r[MOM_RHO], r[MOM_OUT]) : r[MOM_RHO];
+  };
   double m = -DBL_MAX;
   for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
-    m = fmax(m, L2[t * MOM_DOUBLES] + L2[t * MOM_DOUBLES + 1]);
+    m = fmax(m, L2[t * MOM_DOUBLES] + U(t));
     scan[2 * t] = m;
   }
   m = DBL_MAX;
   for (int64_t t = seg.tile_end - 1; t >= seg.tile_begin; t--) {
-    m = fmin(m, L2[t * MOM_DOUBLES] - L2[t * MOM_DOUBLES + 1]);
+    m = fmin(m, L2[t * MOM_DOUBLES] - U(t));
     scan[2 * t + 1] = m;
   }
 }

@@ -1,4 +1,4 @@
-"""The far-field (multipole) line sum of real, cutoff-free segments (arts_b200/csrc/lbl_fmm.cu): every cluster level in use
+"""The far-field (multipole) line sum of real segments (arts_b200/csrc/lbl_fmm.cu): every cluster level in use
 (16 lines, 64 lines, tiles, groups of 16 tiles), against the oracle (<= 1e-9 on the propagation matrix) and against the
 line-by-line kernel on the same inputs (AB200_FARFIELD=0), in the pressure-broadened and in the Doppler regime; bitwise
 invariance under frequency partitions; segments with cutoffs next to segments without."""
@@ -90,3 +90,34 @@ def test_farfield_with_shifted_level_grids_and_species_selection(wsm, orc):
         Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm, select_species=sp)
         K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm, select_species=sp)
         assert_propmat_close(K, Kr)
+
+
+@pytest.mark.parametrize("cutoff", [750e9, 60e9, 3e9])
+def test_farfield_with_byline_cutoffs(wsm, orc, cutoff):
+    """ByLine cutoffs inside the far-field sums: clusters wholly inside their windows (expansion minus the cutoff values),
+    wholly outside (nothing) and cut by a window edge (pair by pair with the window test), for a window much wider than a
+    tile, comparable to one, and narrower than a 64-line cluster; against the oracle, against the line-by-line kernel, and
+    bitwise on sub-grids."""
+    c = _dense_case(n_lines=24_000, nf=2600, np_=4)
+    c.cat.band_cutoff_type[:] = abi.CUTOFF_BYLINE
+    c.cat.band_cutoff_value[:] = cutoff
+    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    K0, _ = _linebyline(lambda: wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm))
+    scale = np.abs(K0[..., 0]).max(axis=1, keepdims=True)
+    assert (np.abs(K[..., 0] - K0[..., 0]) <= 1e-11 * np.abs(K0[..., 0]) + 1e-13 * scale).all()
+    idx = np.unique(np.linspace(0, c.nf - 1, 90).astype(int))
+    Kr, _ = orc.propmat_levels(c.cat, c.f[idx], c.atm)
+    # (the oracle on the sample alone selects its active lines with the sample's own first / last frequency - the same
+    # ones, the sample starts and ends with the grid)
+    assert_propmat_close(K[:, idx], Kr, atol_scale=1e-11)
+    lo, hi = 400, 1700
+    cat = wsm.Catalog(c.cat)
+    path = wsm.Path(cat, hi - lo, c.np_)
+    path.set_grid_bounds(np.tile([c.f[0], c.f[-1]], (c.np_, 1)))  # a shard of the whole grid: same active lines
+    path.upload(c.f[lo:hi], c.atm, c.r, c.I_bkg[lo:hi])
+    path.run_propmat()
+    Kshard = np.empty((c.np_, hi - lo, 7))
+    path.download(K=Kshard)
+    assert np.array_equal(Kshard, K[:, lo:hi])
+    path.close()
+    cat.close()

@@ -188,8 +188,8 @@ def test_errors_are_loud(wsm):
 
 def test_mid_wing_closed_form_accuracy(wsm, orc):
     """Where the reference still runs its continued fraction (1000 < |x| + y < 4000) the real line sum uses closed forms:
-    the two-term far form from 1000 in the line-by-line kernel (segments with ByLine cutoffs; 2.5/x^4 <= 2.5e-12 relative),
-    and the far-field sums of cutoff-free segments (lbl_fmm.cu) the four-term form from 48 (<= 1.3e-12).  Both far inside
+    the two-term far form from 1000 in the line-by-line kernel (2.5/x^4 <= 2.5e-12 relative), and the far-field sums
+    (lbl_fmm.cu) the four-term form from 48 (<= 1.3e-12).  Both far inside
     the 1e-9 bound."""
     c = synth.case_c1(nl=1, nf=4000)
     c.atm.P[:] = 5.0  # nearly pure Doppler line: y << 1, x = (f - f0') / G_D
@@ -201,11 +201,14 @@ def test_mid_wing_closed_form_accuracy(wsm, orc):
     K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
     rel = np.abs(K[0, :, 0] - Kr[0, :, 0]) / Kr[0, :, 0]
     assert rel.max() <= 4e-12, (rel.max(), x[np.argmax(rel)])
-    # the line-by-line kernel (a ByLine cutoff wide enough to hold every frequency routes the line through it)
-    c.cat.band_cutoff_type[:] = abi.CUTOFF_BYLINE
-    c.cat.band_cutoff_value[:] = 1e13
-    Kr, _ = orc.propmat_levels(c.cat, c.f, c.atm)
-    K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    # the line-by-line kernel (AB200_FARFIELD=0)
+    import os
+
+    os.environ["AB200_FARFIELD"] = "0"
+    try:
+        K, _ = wsm.spectral_propmat_pathFromPath(c.cat, c.f, c.atm)
+    finally:
+        del os.environ["AB200_FARFIELD"]
     rel = np.abs(K[0, :, 0] - Kr[0, :, 0]) / Kr[0, :, 0]
     assert rel.max() <= 4e-12, (rel.max(), x[np.argmax(rel)])
     assert rel[(x > 1000) & (x < 4000)].max() > 1e-15  # the two-term closed form is really in use there

@@ -421,12 +421,17 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   // segments selected by species (lbl_lineshape.cpp:191), split by kernel
   const size_t nseg = cat->segments.size();
   // AB200_FARFIELD=0 routes every real segment through the line-by-line kernel (A/B measurements, tests); read per upload
-  const bool farfield = [] { const char* e = getenv("AB200_FARFIELD"); return e ? atoi(e) != 0 : true; }();
+  const int farfield_mode = [] { const char* e = getenv("AB200_FARFIELD"); return e ? atoi(e) : 1; }();
+  const bool farfield = farfield_mode != 0;
   p->nsegs[0] = p->nsegs[1] = p->nsegs[2] = 0;
   for (const Segment& s : cat->segments) {
     if (!(select_species == AB200_SPECIES_BATH || select_species == s.species)) continue;
     SegmentDev d{s.tile_begin, s.tile_end, s.cutoff, s.pol, s.has_cutoff};
-    const int list = s.mode == 1 ? 1 : (farfield && p->fmm.L0) ? 2 : 0;
+    // Far-field sums pay a fixed ~3e3 warp instructions per (frequency, level) (tree descent, bracket search, the pairs inside
+    // 48 Doppler widths) where the line-by-line kernel pays 7 / 32 per line: they win from ~1.5e4 lines per segment
+    // (measured: 1e4 lines 5.9 -> 8.9 ms, 1e5 lines 472 -> 45 ms, 1e6 lines 6067 -> 94 ms per step).  AB200_FARFIELD=2 forces them.
+    const bool big = s.nsub >= FMM_MIN_LINES || farfield_mode == 2;
+    const int list = s.mode == 1 ? 1 : (farfield && big && p->fmm.L0) ? 2 : 0;
     p->h_segs[list * nseg + p->nsegs[list]++] = d;
   }
   if (nseg) AB_CUDA(cudaMemcpyAsync(p->d_segs, p->h_segs, 3 * nseg * sizeof(SegmentDev), cudaMemcpyHostToDevice, p->stream));

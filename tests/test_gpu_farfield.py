@@ -27,12 +27,21 @@ def _dense_case(n_lines=40_000, nf=3000, np_=6, f_lo=2e12, f_hi=3e12):
     return c
 
 
+@pytest.fixture(autouse=True)
+def _force_farfield():
+    """Segments below FMM_MIN_LINES (24 576 lines) keep the line-by-line kernel by default; these tests want the far-field
+    sums on small catalogs too (AB200_FARFIELD=2, read at every upload)."""
+    os.environ["AB200_FARFIELD"] = "2"
+    yield
+    del os.environ["AB200_FARFIELD"]
+
+
 def _linebyline(fn):
     os.environ["AB200_FARFIELD"] = "0"
     try:
         return fn()
     finally:
-        del os.environ["AB200_FARFIELD"]
+        os.environ["AB200_FARFIELD"] = "2"
 
 
 def test_farfield_matches_oracle_and_line_by_line(wsm, orc):

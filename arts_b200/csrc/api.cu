@@ -103,6 +103,8 @@ struct ab200_path {
   uint32_t flags = 0;
   cudaEvent_t ev_staged = nullptr;  // the pinned staging blocks may be refilled once this has completed
   bool uploaded = false, k_preloaded = false;
+  bool stage2_only = false;  // no line-sum workspace: K comes from other workspaces (ab200::path_adopt_K)
+  bool k_adopted = false;    // K was copied in from workspaces that ran the line sum for this catalog and species selection
   bool k_only_A = false;  // K / dK were cleared and filled by a term that only touches A (lookup tables): scalar Stokes path
 
   // observer epilogue (ab200_path_run_observer)
@@ -164,6 +166,12 @@ int64_t ab200_launch_count(int reset) {
 // path workspace
 // ---------------------------------------------------------------------------
 int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, ab200_path** out) {
+  return ab200::path_create_ex(cat, nf, np, nq, false, out);
+}
+
+// stage2_only: a workspace that only ever runs the Stokes chain on a K handed over by other workspaces (multi.cu's
+// level-sharded split): no line records, cluster moments or Jacobian scratch are allocated.
+extern "C++" int ab200::path_create_ex(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, bool stage2_only, ab200_path** out) {
   if (!cat || !out) return set_error(AB200_ERR_INVALID, "ab200_path_create: null argument");
   *out = nullptr;
   if (nf < 0 || np < 0 || nq < 0) return set_error(AB200_ERR_INVALID, "ab200_path_create: negative size");
@@ -218,6 +226,11 @@ int ab200_path_create(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t 
   int lpb = np;
   if (per_level > 0) lpb = static_cast<int>(std::max<size_t>(1, std::min<size_t>(snp, PREP_BUDGET_BYTES / per_level)));
   p->levels_per_batch = std::max(lpb, 1);
+  p->stage2_only = stage2_only;
+  if (stage2_only) {
+    *out = p.release();
+    return AB200_OK;
+  }
   AB_TRY(dev_alloc(&p->d_prep, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * tile_doubles()));
   AB_TRY(dev_alloc(&p->d_summary, static_cast<size_t>(p->levels_per_batch) * cat->ntiles * SUMMARY_DOUBLES));
   {
@@ -446,6 +459,22 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   p->k_preloaded = false;
   p->dk_preloaded = false;
   p->k_only_A = false;
+  p->k_adopted = false;
+  return AB200_OK;
+}
+
+// ---- internal hooks for multi.cu (level-sharded line sum, frequency-sharded Stokes chain) ----
+extern "C++" cudaStream_t ab200::path_stream(ab200_path* p) { return p->stream; }
+extern "C++" double* ab200::path_K(ab200_path* p, int64_t* k_pitch) {
+  *k_pitch = p->k_pitch;
+  return p->d_K;
+}
+// K [np][k_pitch][7] of an uploaded workspace has been filled with rows that other workspaces of the same catalog, species
+// selection and flags summed (copies queued on this workspace's stream): the Stokes chain runs as if it had summed them.
+extern "C++" int ab200::path_adopt_K(ab200_path* p) {
+  if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "path_adopt_K: path not uploaded");
+  p->k_preloaded = false;
+  p->k_adopted = true;
   return AB200_OK;
 }
 
@@ -505,6 +534,7 @@ void fill_params(const ab200_path* p, int lev0, PrepareParams& pp, SumParams& sp
 
 int ab200_path_run_propmat(ab200_path* p) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_run_propmat: path not uploaded");
+  if (p->stage2_only) return set_error(AB200_ERR_INVALID, "ab200_path_run_propmat: this workspace has no line-sum buffers");
   const ab200_catalog* cat = p->cat;
   AB_CUDA(cudaSetDevice(cat->device));
   p->k_only_A = false;

@@ -84,6 +84,11 @@ enum Pol : int { POL_NO = 0, POL_PI = 1, POL_SM = 2, POL_SP = 3 };
 
 // ---- error plumbing ---------------------------------------------------------
 int set_error(int code, const std::string& msg);
+// internal hooks between api.cu and multi.cu
+int path_create_ex(const ab200_catalog* cat, int64_t nf, int32_t np, int32_t nq, bool stage2_only, ab200_path** out);
+cudaStream_t path_stream(ab200_path* p);
+double* path_K(ab200_path* p, int64_t* k_pitch);
+int path_adopt_K(ab200_path* p);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(int n = 1);
 

@@ -14,6 +14,15 @@
 // shard it is computed in, the result is bit-identical to the one-device result.  Line selection of
 // ByLine cutoffs uses the bounds of the WHOLE grid (band_data::active_lines, lbl_data.cpp:61-68), handed to each worker
 // through ab200_set_thread_grid_bounds.
+//
+// Second split (default for forward calls on a shared grid, AB200_MULTI_SPLIT=freq switches it off): LEVELS for the line
+// sum, frequencies for the Stokes chain.  The line records and the cluster moments of the far-field sums are work per
+// (line, level) that every frequency shard would repeat (30 of 93 ms per configs[3] shard: 8 devices gave 5.3x).  Device d
+// therefore sums levels d, d + N, d + 2N, ... for ALL frequencies (nothing is replicated), and the one exchange the path
+// then has is a transpose of K: device d pulls its contiguous frequency slice of every peer's levels straight out of the
+// peer's HBM over NVLink (one strided cudaMemcpy2DAsync per peer, ordered by events, no host staging, 0.6 GB per device at
+// 1e6 x 100) and runs the fused Stokes chain on it.  The value of K at a (frequency, level) does not depend on the
+// partition, so the radiances stay bit-identical to the one-device call.
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -39,6 +48,13 @@ struct Worker {
   std::string err;
   // gather / scatter buffers of this worker (host)
   std::vector<double> f, bkg, I, dI, K, dK;
+  // level-sharded split: p1 sums this device's levels over the whole grid, p2 runs the Stokes chain on this device's
+  // frequency slice of all levels
+  ab200_path *p1 = nullptr, *p2 = nullptr;
+  int64_t p1_nf = -1, p2_nf = -1;
+  int32_t p1_np = -1, p2_np = -1;
+  cudaEvent_t ev_k = nullptr;  // K of p1 is complete
+  std::vector<double> aT, aP, avmr, aiso, aQ, amag, alos, awind, ar;  // this device's levels of the caller's atm path
 
   void loop() {
     ab200_set_device(device);
@@ -56,6 +72,9 @@ struct Worker {
       done = true;
       cv.notify_all();
     }
+    if (p1) ab200_path_destroy(p1);
+    if (p2) ab200_path_destroy(p2);
+    if (ev_k) cudaEventDestroy(ev_k);
     ab200_release_thread_cache();
   }
 };
@@ -64,6 +83,7 @@ struct Worker {
 struct ab200_multi {
   std::vector<Worker*> w;
   std::mutex call_mu;  // one multi-device call at a time per set (the workers' workspaces are per set)
+  int32_t n_species = 0, n_isot = 0;
 };
 
 namespace {
@@ -136,6 +156,8 @@ int ab200_multi_create(const ab200_catalog_desc* desc, int32_t n_devices, const 
   int prev = 0;
   cudaGetDevice(&prev);
   ab200_multi* m = new ab200_multi;
+  m->n_species = desc->n_species;
+  m->n_isot = desc->n_isot;
   for (int i = 0; i < n_devices; i++) {
     Worker* w = new Worker;
     w->device = devices ? devices[i] : i;
@@ -149,6 +171,17 @@ int ab200_multi_create(const ab200_catalog_desc* desc, int32_t n_devices, const 
     }
     m->w.push_back(w);
   }
+  // peers read each other's K directly (NVLink); without peer access the same copies are staged by the driver
+  for (Worker* a : m->w)
+    for (Worker* b : m->w) {
+      if (a->device == b->device) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a->device, b->device) == cudaSuccess && can) {
+        cudaSetDevice(a->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+        if (e != cudaSuccess) cudaGetLastError();  // already enabled: fine
+      }
+    }
   cudaSetDevice(prev);
   for (Worker* w : m->w) w->th = std::thread([w] { w->loop(); });
   *out = m;
@@ -174,6 +207,109 @@ void ab200_multi_destroy(ab200_multi* m) {
 
 int32_t ab200_multi_device_count(const ab200_multi* m) { return m ? static_cast<int32_t>(m->w.size()) : 0; }
 
+namespace {
+bool level_split_wanted() {
+  const char* e = getenv("AB200_MULTI_SPLIT");
+  return !(e && std::string(e) == "freq");
+}
+
+// Forward clear-sky call, levels dealt over the devices for the line sum, contiguous frequency slices for the Stokes chain.
+int clearsky_level_split(ab200_multi* m, int64_t nf, const double* f, const ab200_atm_path* atm, int32_t select_species,
+                         int32_t no_neg, const double* r, int32_t rte_option, const double* I_bkg, uint32_t flags, double* I,
+                         double* K_out) {
+  const int n = static_cast<int>(m->w.size()), np = atm->np;
+  // frequency slice of device d for stage 2: whole 128-frequency rows (the TMA boxes of the Stokes kernel)
+  const int64_t chunk = ((nf + n - 1) / n + 127) / 128 * 128;
+  auto slice = [&](int d, int64_t& off, int64_t& cnt) {
+    off = std::min<int64_t>(nf, static_cast<int64_t>(d) * chunk);
+    cnt = std::min<int64_t>(chunk, nf - off);
+  };
+  const bool want_K = (flags & AB200_FLAG_RETURN_K) && K_out;
+  // phase A: every device uploads, sums its levels over the whole grid and records an event
+  int rc = run_all(m, [&](Worker& w, int d) -> int {
+    const int npd = (np - d + n - 1) / n;  // levels d, d + n, ...
+    const int npd_cap = (np + n - 1) / n;
+    if (!w.p1 || w.p1_nf != nf || w.p1_np != npd_cap) {
+      if (w.p1) ab200_path_destroy(w.p1);
+      w.p1 = nullptr;
+      AB_TRY(ab200_path_create(w.cat, nf, npd_cap, 0, &w.p1));
+      w.p1_nf = nf; w.p1_np = npd_cap;
+    }
+    int64_t off, cnt;
+    slice(d, off, cnt);
+    if (!w.p2 || w.p2_nf != cnt || w.p2_np != np) {
+      if (w.p2) ab200_path_destroy(w.p2);
+      w.p2 = nullptr;
+      AB_TRY(ab200::path_create_ex(w.cat, cnt, np, 0, true, &w.p2));
+      w.p2_nf = cnt; w.p2_np = np;
+    }
+    if (!w.ev_k) AB_CUDA(cudaEventCreateWithFlags(&w.ev_k, cudaEventDisableTiming));
+    // this device's levels of the atmosphere
+    const int nsp = m->n_species, nis = m->n_isot;
+    w.aT.resize(npd); w.aP.resize(npd); w.avmr.resize(static_cast<size_t>(npd) * nsp); w.aiso.resize(static_cast<size_t>(npd) * nis);
+    w.aQ.resize(static_cast<size_t>(npd) * nis); w.amag.resize(3 * static_cast<size_t>(npd)); w.alos.resize(2 * static_cast<size_t>(npd));
+    w.awind.resize(3 * static_cast<size_t>(npd)); w.ar.assign(static_cast<size_t>(std::max(npd, 1)), 0.0);
+    for (int j = 0; j < npd; j++) {
+      const size_t ip = static_cast<size_t>(d) + static_cast<size_t>(j) * n;
+      w.aT[j] = atm->T[ip]; w.aP[j] = atm->P[ip];
+      std::copy(atm->vmr + ip * nsp, atm->vmr + (ip + 1) * nsp, w.avmr.begin() + static_cast<size_t>(j) * nsp);
+      std::copy(atm->isorat + ip * nis, atm->isorat + (ip + 1) * nis, w.aiso.begin() + static_cast<size_t>(j) * nis);
+      std::copy(atm->Q + ip * nis, atm->Q + (ip + 1) * nis, w.aQ.begin() + static_cast<size_t>(j) * nis);
+      if (atm->mag) std::copy(atm->mag + 3 * ip, atm->mag + 3 * ip + 3, w.amag.begin() + 3 * static_cast<size_t>(j));
+      if (atm->los) std::copy(atm->los + 2 * ip, atm->los + 2 * ip + 2, w.alos.begin() + 2 * static_cast<size_t>(j));
+      if (atm->wind) std::copy(atm->wind + 3 * ip, atm->wind + 3 * ip + 3, w.awind.begin() + 3 * static_cast<size_t>(j));
+    }
+    ab200_atm_path sub{};
+    sub.np = npd; sub.T = w.aT.data(); sub.P = w.aP.data(); sub.vmr = w.avmr.data(); sub.isorat = w.aiso.data(); sub.Q = w.aQ.data();
+    sub.dQdT = nullptr; sub.mag = atm->mag ? w.amag.data() : nullptr; sub.los = atm->los ? w.alos.data() : nullptr;
+    sub.wind = atm->wind ? w.awind.data() : nullptr;
+    AB_TRY(ab200_path_set_grid_bounds(w.p1, nullptr));
+    AB_TRY(ab200_path_upload(w.p1, f, 0, &sub, select_species, no_neg, nullptr, w.ar.data(), 0, rte_option, nullptr, flags));
+    if (npd > 0) AB_TRY(ab200_path_run_propmat(w.p1));
+    AB_CUDA(cudaEventRecord(w.ev_k, ab200::path_stream(w.p1)));
+    // stage-2 workspace: this device's frequency slice, all levels
+    if (cnt > 0) {
+      AB_TRY(ab200_path_set_grid_bounds(w.p2, nullptr));
+      AB_TRY(ab200_path_upload(w.p2, f + off, 0, atm, select_species, no_neg, nullptr, r, 0, rte_option, I_bkg + 4 * off, flags));
+    }
+    return AB200_OK;
+  });
+  if (rc) return rc;
+  // phase B: pull the slice of every device's levels, run the Stokes chain, return the radiances
+  return run_all(m, [&](Worker& w, int d) -> int {
+    int64_t off, cnt;
+    slice(d, off, cnt);
+    AB_TRY(ab200_path_sync(w.p1));  // device error flags of the line sum (also keeps p1 alive until its K is complete)
+    if (cnt == 0) return AB200_OK;
+    int64_t pitch2 = 0;
+    double* K2 = ab200::path_K(w.p2, &pitch2);
+    cudaStream_t s2 = ab200::path_stream(w.p2);
+    for (int e = 0; e < n; e++) {
+      Worker& src = *m->w[(d + e) % n];  // start with the own rows, then round the ring: no two devices pull from one peer at once
+      const int de = (d + e) % n;
+      const int npe = (np - de + n - 1) / n;
+      if (npe <= 0) continue;
+      int64_t pitch1 = 0;
+      const double* K1 = ab200::path_K(src.p1, &pitch1);
+      AB_CUDA(cudaStreamWaitEvent(s2, src.ev_k, 0));
+      // rows j = 0..npe-1 of the peer are levels de + j n of the path
+      AB_CUDA(cudaMemcpy2DAsync(K2 + static_cast<size_t>(de) * pitch2 * 7, static_cast<size_t>(n) * pitch2 * 56, K1 + static_cast<size_t>(off) * 7,
+                                static_cast<size_t>(pitch1) * 56, static_cast<size_t>(cnt) * 56, static_cast<size_t>(npe), cudaMemcpyDefault, s2));
+    }
+    AB_TRY(ab200::path_adopt_K(w.p2));
+    AB_TRY(ab200_path_run_stokes(w.p2));
+    if (want_K) {
+      w.K.resize(static_cast<size_t>(np) * cnt * 7);
+      AB_TRY(ab200_path_download(w.p2, I + 4 * off, nullptr, w.K.data(), nullptr));
+      for (int ip = 0; ip < np; ip++)
+        std::memcpy(K_out + (static_cast<size_t>(ip) * nf + off) * 7, &w.K[static_cast<size_t>(ip) * cnt * 7], 7 * cnt * sizeof(double));
+      return AB200_OK;
+    }
+    return ab200_path_download(w.p2, I + 4 * off, nullptr, nullptr, nullptr);
+  });
+}
+}  // namespace
+
 int ab200_multi_clearsky_emission(ab200_multi* m, int64_t nf, const double* f, int64_t f_level_stride, const ab200_atm_path* atm,
                                   int32_t select_species, int32_t no_negative_absorption, int32_t nq, const ab200_target* targets,
                                   const double* r, int32_t hse_derivative, int32_t rte_option, const double* I_bkg, uint32_t flags,
@@ -184,6 +320,8 @@ int ab200_multi_clearsky_emission(ab200_multi* m, int64_t nf, const double* f, i
   if (nq > 0 && !dI) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_clearsky_emission: dI is null with nq > 0");
   if (nf == 0) return AB200_OK;
   const int n = static_cast<int>(m->w.size()), np = atm->np;
+  if (n > 1 && nq == 0 && f_level_stride == 0 && np >= n && nf >= 128 * static_cast<int64_t>(n) && level_split_wanted() && (np < 2 || r))
+    return clearsky_level_split(m, nf, f, atm, select_species, no_negative_absorption, r, rte_option, I_bkg, flags, I, K_out);
   const int nlev_f = f_level_stride ? np : 1;
   const bool want_K = (flags & AB200_FLAG_RETURN_K) && K_out;
   std::vector<double> bounds;

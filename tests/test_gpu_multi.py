@@ -63,3 +63,40 @@ def test_multi_device_zeeman_and_errors(wsm):
     m.close()
     with pytest.raises(wsm.Ab200Error):
         wsm.MultiDevice(c.cat, n_devices=wsm.device_count() + 1)
+
+
+@pytest.mark.parametrize("ndev", [2, 3])
+@pytest.mark.parametrize("cutoff", [None, 3e9])
+def test_level_split_forward_is_bitwise_the_single_device_result(wsm, ndev, cutoff, monkeypatch):
+    """Forward calls on a shared grid split the LEVELS of the line sum over the devices and the frequencies of the Stokes
+    chain, with one transpose of K between them (device-to-device copies); 10 levels over 3 devices and a grid that is not
+    a multiple of 128 exercise the ragged ends.  Same bits as one device and as the frequency split."""
+    c = synth.case_c2(lines_per_species=300, nf=5 * 512 + 137, np_=10, bands_per_species=3)
+    if cutoff:
+        c.cat.band_cutoff_type[:] = 1
+        c.cat.band_cutoff_value[:] = cutoff
+    I1, _, K1 = wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, return_propmat=True)
+    m = wsm.MultiDevice(c.cat, devices=_devices(wsm, ndev))
+    for _ in range(2):
+        I, _, K = wsm.spectral_radClearskyEmission(m, c.f, c.atm, c.r, c.I_bkg, return_propmat=True)
+        assert np.array_equal(K, K1)
+        assert np.array_equal(I, I1)
+    I, _ = wsm.spectral_radClearskyEmission(m, c.f, c.atm, c.r, c.I_bkg, rte_option="constant")
+    Ic, _ = wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, rte_option="constant")
+    assert np.array_equal(I, Ic)
+    monkeypatch.setenv("AB200_MULTI_SPLIT", "freq")
+    I, _ = wsm.spectral_radClearskyEmission(m, c.f, c.atm, c.r, c.I_bkg)
+    assert np.array_equal(I, I1)
+    m.close()
+
+
+def test_level_split_with_far_field_sums_and_wind(wsm, monkeypatch):
+    monkeypatch.setenv("AB200_FARFIELD", "2")  # far-field sums for every real segment, whatever its size
+    c = synth.case_c2(lines_per_species=400, nf=3000, np_=7, bands_per_species=2)
+    c.atm.wind = np.tile([10.0, -5.0, 0.5], (c.np_, 1)) * np.linspace(0.5, 1.5, c.np_)[:, None]
+    c.atm.los = np.tile([140.0, 20.0], (c.np_, 1))
+    I1, _ = wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg)
+    m = wsm.MultiDevice(c.cat, devices=_devices(wsm, 2))
+    I, _ = wsm.spectral_radClearskyEmission(m, c.f, c.atm, c.r, c.I_bkg)
+    assert np.array_equal(I, I1)
+    m.close()

@@ -121,6 +121,7 @@ def lib():
     L.ab200_measure_dfma_peak.argtypes = [C.c_int, _dp, _dp]
     L.ab200_measure_dfma_mix.argtypes = [C.c_int, _dp, _dp]
     L.ab200_faddeeva_w.argtypes = [C.c_int64, _dp, _dp, _dp, _dp]
+    L.ab200_dawson.argtypes = [C.c_int64, _dp, _dp, _dp, _dp]
     L.ab200_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, _dp, _dp]
     L.ab200_norm_view.argtypes = [C.c_int, _dp, _dp, _dp]
     _lib = L

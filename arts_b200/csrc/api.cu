@@ -906,10 +906,6 @@ static int check_flags(ab200_path* p) {
       return set_error(AB200_ERR_INVALID,
                        "Problem with CIA species: the temperature of a level is outside the extrapolation range of a data set "
                        "(check_limit for Temperature, lagrange_interp.h:572-650; pass ignore_errors to get NaN instead)");
-    if (h & 4)
-      return set_error(AB200_ERR_UNSUPPORTED,
-                       "rte_option linprop with a polarised propagation matrix and a positive absorption gradient is outside "
-                       "the GPU path (rtepack_transmission.cc:467-474; no CPU fallback)");
     return set_error(AB200_ERR_UNSUPPORTED, "negative pressure broadening (G0 < 0) is outside the GPU path");
   }
   return AB200_OK;
@@ -1160,10 +1156,6 @@ int ab200_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const doub
                        d_flag, 0));
   int h_flag = 0;
   AB_CUDA(cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (h_flag & 4)
-    return set_error(AB200_ERR_UNSUPPORTED,
-                     "rte_option linprop with a polarised propagation matrix and a positive absorption gradient is outside the "
-                     "GPU path (rtepack_transmission.cc:467-474; no CPU fallback)");
   AB_CUDA(cudaMemcpy(T, dT_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
   AB_CUDA(cudaMemcpy(P, dP_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
   if (linsrc) AB_CUDA(cudaMemcpy(L, dL_.p, nm * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1333,6 +1325,21 @@ int ab200_faddeeva_w(int64_t n, const double* zr, const double* zi, double* wr, 
   AB_TRY(launch_faddeeva(n, a.p, b.p, c.p, d.p, 0));
   AB_CUDA(cudaMemcpy(wr, c.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   AB_CUDA(cudaMemcpy(wi, d.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return AB200_OK;
+}
+
+// Faddeeva::Dawson(complex) on the device (the element-wise function of rtepack::dawson(specmat)), for tests
+int ab200_dawson(int64_t n, const double* zr, const double* zi, double* dr, double* di) {
+  if (n < 0) return set_error(AB200_ERR_INVALID, "ab200_dawson: negative size");
+  if (n == 0) return AB200_OK;
+  if (!zr || !zi || !dr || !di) return set_error(AB200_ERR_INVALID, "ab200_dawson: null argument");
+  DevBuf a, b, c, d;
+  AB_TRY(a.alloc(n)); AB_TRY(b.alloc(n)); AB_TRY(c.alloc(n)); AB_TRY(d.alloc(n));
+  AB_CUDA(cudaMemcpy(a.p, zr, n * sizeof(double), cudaMemcpyHostToDevice));
+  AB_CUDA(cudaMemcpy(b.p, zi, n * sizeof(double), cudaMemcpyHostToDevice));
+  AB_TRY(launch_dawson(n, a.p, b.p, c.p, d.p, 0));
+  AB_CUDA(cudaMemcpy(dr, c.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  AB_CUDA(cudaMemcpy(di, d.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   return AB200_OK;
 }
 

@@ -526,5 +526,274 @@ struct Tran {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// rte_option = linprop for POLARISED layers (tran::linsrc_linprop :467-474): Lambda = Re[alpha^-1 (D(u1) - T D(u0))] / r with
+// alpha = sqrt((k2 - k1) / 2r) the complex square root of the absorption gradient (specmat sqrt(const propmat&), :872-1002),
+// u = alpha^-1 k / 2 and D the ELEMENT-WISE Dawson function of a complex 4x4 matrix (rtepack_spectral_matrix.cc:6-26, sic).
+// Rare and heavy (up to 32 complex Dawson evaluations through the register-resident w(z)); the functions are __noinline__ and
+// keep their matrices in local memory so that the kernels' common paths keep their register budget.
+// ---------------------------------------------------------------------------------------------------------------------
+struct cx {
+  double r, i;
+};
+__device__ __forceinline__ cx cmk(double r, double i = 0.0) { return cx{r, i}; }
+__device__ __forceinline__ cx operator+(cx a, cx b) { return cx{a.r + b.r, a.i + b.i}; }
+__device__ __forceinline__ cx operator-(cx a, cx b) { return cx{a.r - b.r, a.i - b.i}; }
+__device__ __forceinline__ cx operator-(cx a) { return cx{-a.r, -a.i}; }
+__device__ __forceinline__ cx operator*(cx a, cx b) { return cx{a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
+__device__ __forceinline__ cx operator*(cx a, double b) { return cx{a.r * b, a.i * b}; }
+__device__ __forceinline__ cx operator*(double b, cx a) { return cx{a.r * b, a.i * b}; }
+__device__ __forceinline__ cx operator/(cx a, double b) { return cx{a.r / b, a.i / b}; }
+__device__ __forceinline__ cx operator/(cx a, cx b) {  // Smith's algorithm (what the compiler's complex division does)
+  if (fabs(b.r) >= fabs(b.i)) {
+    const double q = b.i / b.r, d = b.r + b.i * q;
+    return cx{(a.r + a.i * q) / d, (a.i - a.r * q) / d};
+  }
+  const double q = b.r / b.i, d = b.r * q + b.i;
+  return cx{(a.r * q + a.i) / d, (a.i * q - a.r) / d};
+}
+// principal square root; the sign of a zero imaginary part picks the side of the cut like csqrt
+__device__ __forceinline__ cx csqrt_(cx z) {
+  if (z.r == 0.0 && z.i == 0.0) return cx{0.0, z.i};
+  const double t = sqrt(0.5 * (fabs(z.r) + hypot(z.r, z.i)));
+  if (z.r >= 0.0) return cx{t, z.i / (2.0 * t)};
+  return cx{fabs(z.i) / (2.0 * t), copysign(t, z.i)};
+}
+
+// Faddeeva::Dawson(complex) (3rdparty/Faddeeva/Faddeeva.cc:461-570): D(z) = i sqrt(pi)/2 (exp(-z^2) - w(z)) with the package's
+// series where that difference cancels (|z| small; small |y| and |xy| next to the real axis)
+__device__ inline cx dawson_c(cx z) {
+  constexpr double spi2 = 0.886226925452758013649083741671;
+  const double x = z.r, y = z.i;
+  if (y == 0.0) return cx{dawson(x), 0.0};
+  if (x == 0.0) {
+    const double y2 = y * y;
+    if (y2 < 2.5e-5) return cx{x, y * (1. + y2 * (0.6666666666666666666666666666666666666667 + y2 * 0.26666666666666666666666666666666666667))};
+    return cx{x, spi2 * (y >= 0 ? exp(y2) - erfcx(y) : erfcx(-y) - exp(y2))};
+  }
+  const double mRe = (y - x) * (x + y), mIm = -2 * x * y;  // -z^2
+  if (fabs(y) < 5e-3) {
+    if (fabs(x) < 5e-3) {  // dawson(z) = z - 2/3 z^3 + 4/15 z^5
+      const cx mz2{mRe, mIm};
+      const cx p = cmk(1.0) + mz2 * (cmk(0.6666666666666666666666666666666666666667) + mz2 * 0.2666666666666666666666666666666666666667);
+      return z * p;
+    }
+    if (fabs(mIm) < 5e-3) {  // expansion in y about the real axis, :541-569
+      const double x2 = x * x, y2 = y * y;
+      if (x2 > 1600) {
+        if (x2 > 25e14) {
+          const double xy2 = (x * y) * (x * y);
+          return cx{(0.5 + y2 * (0.5 + 0.25 * y2 - 0.16666666666666666667 * xy2)) / x,
+                    y * (-1 + y2 * (-0.66666666666666666667 + 0.13333333333333333333 * xy2 - 0.26666666666666666667 * y2)) / (2 * x2 - 1)};
+        }
+        const double q = 1. / (-15 + x2 * (90 + x2 * (-60 + 8 * x2)));
+        return cx{q * (x * (33 + x2 * (-28 + 4 * x2) + y2 * (18 - 4 * x2 + 4 * y2))),
+                  q * (y * (-15 + x2 * (24 - 4 * x2) + y2 * (4 * x2 - 10 - 4 * y2)))};
+      }
+      const double D = dawson(x);
+      return cx{D + y2 * (D + x - 2 * D * x2) +
+                    y2 * y2 * (D * (0.5 - x2 * (2 - 0.66666666666666666667 * x2)) + x * (0.83333333333333333333 - 0.33333333333333333333 * x2)),
+                y * (1 - 2 * D * x + y2 * 0.66666666666666666667 * (1 - x2 - D * x * (3 - 2 * x2)) +
+                     y2 * y2 * (0.26666666666666666667 - x2 * (0.6 - 0.13333333333333333333 * x2) -
+                                D * x * (1 - x2 * (1.3333333333333333333 - 0.26666666666666666667 * x2))))};
+    }
+  }
+  double s, c, wr, wi;
+  sincos(mIm, &s, &c);
+  const double e = exp(mRe);
+  cx res;
+  if (y >= 0) {
+    faddeeva_w(x, y, wr, wi);
+    res = cx{e * c - wr, e * s - wi};
+  } else {
+    faddeeva_w(-x, -y, wr, wi);
+    res = cx{wr - e * c, wi - e * s};
+  }
+  return cx{-spi2 * res.i, spi2 * res.r};
+}
+
+// specmat sqrt(const propmat&), :872-1002: Cayley-Hamilton coefficients d0..d3 of the principal square root, then the matrix
+__device__ inline void sqrt_propmat(const Propmat& pm, cx* __restrict__ K) {
+  constexpr double eps = 2.220446049250313e-16;
+  const double a  = pm.A;
+  const cx sqrt_a = csqrt_(cmk(a));
+  for (int i = 0; i < 16; i++) K[i] = cmk(0.0);
+  if (!pm.is_polarized()) {
+    K[0] = K[5] = K[10] = K[15] = sqrt_a;
+    return;
+  }
+  const double b = pm.B, c = pm.C, d = pm.D, u = pm.U, v = pm.V, w = pm.W;
+  const double b2 = b * b, c2 = c * c, d2 = d * d, u2 = u * u, v2 = v * v, w2 = w * w;
+  cx d0c = cmk(0.0), d1c = cmk(0.0), d2c = cmk(0.0), d3c = cmk(0.0);
+  if (pm.is_rotational()) {
+    const double rho = norm3d(u, v, w);
+    if (rho <= eps) return;  // {0.0}
+    const double r = sqrt(2.0 * rho);
+    d1c = cmk(1.0 / r);
+    d2c = cmk(-1.0 / (rho * r));
+  } else {
+    const double B = u2 + v2 + w2 - b2 - c2 - d2;
+    const double t = d * u - c * v + b * w;
+    const double C = -(t * t);
+    const double S = sqrt(B * B - 4 * C);
+    const double x2 = fmax(0.0, 0.5 * (S - B)), abs_y2 = fmax(0.0, 0.5 * (S + B));
+    const double x = sqrt(x2), ys = sqrt(abs_y2);
+    const cx sx = csqrt_(cmk(a + x)), dx = csqrt_(cmk(a - x));
+    const cx sy = csqrt_(cx{a, ys}), dy = csqrt_(cx{a, 0.0 - ys});
+    const cx Sx = sx + dx, Dx = sx - dx, Sy = sy + dy, Dy = sy - dy;
+    if (x2 + abs_y2 <= eps) {
+      d0c = sqrt_a;
+      if (a <= eps) {  // sic, :934
+        d1c = cmk(0.5) / sqrt_a;
+        d2c = cmk(0.125) / (sqrt_a * a);
+        d3c = cmk(0.0625) / (sqrt_a * (a * a));
+      }
+    } else {
+      const double inv_sum_sq = 1.0 / (x2 + abs_y2);
+      d0c = (abs_y2 * Sx + x2 * Sy) * (0.5 * inv_sum_sq);
+      d2c = (Sx - Sy) * (0.5 * inv_sum_sq);
+      const cx term1 = (x <= eps && a <= eps) ? cmk(0.0) : (x <= eps) ? cmk(0.5) / sqrt_a : (0.5 * Dx) / x;
+      const cx term2 = (abs_y2 <= eps && a <= eps) ? cmk(0.0) : (abs_y2 <= eps) ? cmk(0.5) / sqrt_a : (0.5 * Dy) / cx{0.0, ys};
+      d1c = (abs_y2 * term1 + x2 * term2) * inv_sum_sq;
+      d3c = (term1 - term2) * inv_sum_sq;
+    }
+  }
+  const double k2_00 = b2 + c2 + d2, k2_11 = b2 - u2 - v2, k2_22 = c2 - u2 - w2, k2_33 = d2 - v2 - w2;
+  const double k2_01 = -(c * u + d * v), k2_02 = b * u - d * w, k2_03 = b * v + c * w;
+  const double k2_12 = b * c - v * w, k2_13 = b * d + u * w, k2_23 = c * d - u * v;
+  const double k3_01 = b * k2_00 - u * k2_02 - v * k2_03;
+  const double k3_02 = c * k2_00 + u * k2_01 - w * k2_03;
+  const double k3_03 = d * k2_00 + v * k2_01 + w * k2_02;
+  const double k3_12 = -c * k2_01 + u * k2_11 - w * k2_13;
+  const double k3_13 = -d * k2_01 + v * k2_11 + w * k2_12;
+  const double k3_23 = -d * k2_02 + v * k2_12 + w * k2_22;
+  K[0]  = d0c + d2c * k2_00;
+  K[5]  = d0c + d2c * k2_11;
+  K[10] = d0c + d2c * k2_22;
+  K[15] = d0c + d2c * k2_33;
+  K[1]  = d1c * b + d2c * k2_01 + d3c * k3_01;
+  K[4]  = d1c * b - d2c * k2_01 + d3c * k3_01;
+  K[2]  = d1c * c + d2c * k2_02 + d3c * k3_02;
+  K[8]  = d1c * c - d2c * k2_02 + d3c * k3_02;
+  K[3]  = d1c * d + d2c * k2_03 + d3c * k3_03;
+  K[12] = d1c * d - d2c * k2_03 + d3c * k3_03;
+  K[6]  = d1c * u + d2c * k2_12 + d3c * k3_12;
+  K[9]  = d2c * k2_12 - d1c * u - d3c * k3_12;
+  K[7]  = d1c * v + d2c * k2_13 + d3c * k3_13;
+  K[13] = d2c * k2_13 - d1c * v - d3c * k3_13;
+  K[11] = d1c * w + d2c * k2_23 + d3c * k3_23;
+  K[14] = d2c * k2_23 - d1c * w - d3c * k3_23;
+}
+
+// inverse of a complex 4x4 matrix, adj(A) / det(A) (rtepack_spectral_matrix.h:203-242), through the twelve 2x2 minors of
+// the Laplace expansion
+__device__ inline void spec_inv(const cx* __restrict__ a, cx* __restrict__ o) {
+  const cx s0 = a[0] * a[5] - a[4] * a[1], s1 = a[0] * a[6] - a[4] * a[2], s2 = a[0] * a[7] - a[4] * a[3];
+  const cx s3 = a[1] * a[6] - a[5] * a[2], s4 = a[1] * a[7] - a[5] * a[3], s5 = a[2] * a[7] - a[6] * a[3];
+  const cx c5 = a[10] * a[15] - a[14] * a[11], c4 = a[9] * a[15] - a[13] * a[11], c3 = a[9] * a[14] - a[13] * a[10];
+  const cx c2 = a[8] * a[15] - a[12] * a[11], c1 = a[8] * a[14] - a[12] * a[10], c0 = a[8] * a[13] - a[12] * a[9];
+  const cx det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+  const cx id  = cmk(1.0) / det;
+  o[0]  = (a[5] * c5 - a[6] * c4 + a[7] * c3) * id;
+  o[1]  = (a[2] * c4 - a[1] * c5 - a[3] * c3) * id;
+  o[2]  = (a[13] * s5 - a[14] * s4 + a[15] * s3) * id;
+  o[3]  = (a[10] * s4 - a[9] * s5 - a[11] * s3) * id;
+  o[4]  = (a[6] * c2 - a[4] * c5 - a[7] * c1) * id;
+  o[5]  = (a[0] * c5 - a[2] * c2 + a[3] * c1) * id;
+  o[6]  = (a[14] * s2 - a[12] * s5 - a[15] * s1) * id;
+  o[7]  = (a[8] * s5 - a[10] * s2 + a[11] * s1) * id;
+  o[8]  = (a[4] * c4 - a[5] * c2 + a[7] * c0) * id;
+  o[9]  = (a[1] * c2 - a[0] * c4 - a[3] * c0) * id;
+  o[10] = (a[12] * s4 - a[13] * s2 + a[15] * s0) * id;
+  o[11] = (a[9] * s2 - a[8] * s4 - a[11] * s0) * id;
+  o[12] = (a[5] * c1 - a[4] * c3 - a[6] * c0) * id;
+  o[13] = (a[0] * c3 - a[1] * c1 + a[2] * c0) * id;
+  o[14] = (a[13] * s1 - a[12] * s3 - a[14] * s0) * id;
+  o[15] = (a[8] * s3 - a[9] * s1 + a[10] * s0) * id;
+}
+
+// Lambda of a polarised layer with an absorption gradient >= 1e-8 (:467-474).  Tm = T of the layer; ncol = 4: the whole matrix
+// L [16]; ncol = 1: only its first column L[0], L[4], L[8], L[12] (all the LTE recursion uses), which needs the first columns
+// of u0, u1 and of the Dawson matrices only: 8 instead of 32 complex Dawson evaluations.
+static __device__ __noinline__ void linprop_lambda_pol(const double* __restrict__ Tm, const Propmat& k1, const Propmat& k2, double r, int ncol,
+                                                double* __restrict__ L) {
+  const double dn = 2.0 * r;
+  const Propmat a2{(k2.A - k1.A) / dn, (k2.B - k1.B) / dn, (k2.C - k1.C) / dn, (k2.D - k1.D) / dn,
+                   (k2.U - k1.U) / dn, (k2.V - k1.V) / dn, (k2.W - k1.W) / dn};
+  cx al[16], ai[16];
+  sqrt_propmat(a2, al);
+  spec_inv(al, ai);
+  // M = dawson(u1) - T dawson(u0), u = alpha^-1 (k / 2) (specmat x propmat, rtepack_multitype.h:145-168)
+  cx M[16];
+  for (int pass = 0; pass < 2; pass++) {
+    const Propmat& k = pass ? k2 : k1;
+    const double a = k.A / 2.0, b = k.B / 2.0, c = k.C / 2.0, d = k.D / 2.0, u = k.U / 2.0, v = k.V / 2.0, w = k.W / 2.0;
+    cx D[16];
+    for (int i = 0; i < 4; i++) {
+      const cx m1 = ai[4 * i], m2 = ai[4 * i + 1], m3 = ai[4 * i + 2], m4 = ai[4 * i + 3];
+      D[4 * i] = dawson_c(a * m1 + b * m2 + c * m3 + d * m4);
+      if (ncol > 1) {
+        D[4 * i + 1] = dawson_c(a * m2 + b * m1 - m3 * u - m4 * v);
+        D[4 * i + 2] = dawson_c(a * m3 + c * m1 + m2 * u - m4 * w);
+        D[4 * i + 3] = dawson_c(a * m4 + d * m1 + m2 * v + m3 * w);
+      }
+    }
+    if (pass == 0) {
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < ncol; j++)
+          M[4 * i + j] = -(Tm[4 * i + 0] * D[j] + Tm[4 * i + 1] * D[4 + j] + Tm[4 * i + 2] * D[8 + j] + Tm[4 * i + 3] * D[12 + j]);
+    } else {
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < ncol; j++) M[4 * i + j] = D[4 * i + j] + M[4 * i + j];
+    }
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < ncol; j++) {
+      double acc = 0.0;
+      for (int k = 0; k < 4; k++) acc += ai[4 * i + k].r * M[4 * k + j].r - ai[4 * i + k].i * M[4 * k + j].i;
+      L[4 * i + j] = acc / r;
+    }
+}
+
+// tran::linsrc_linprop (:449-475), whichever branch the layer takes; t is the layer's tran state, Tm its T
+static __device__ __noinline__ void linprop_lambda_any(const Tran& t, const double* __restrict__ Tm, const Propmat& k1, const Propmat& k2, double r,
+                                                double* __restrict__ L) {
+  const double alpha2 = (k2.A - k1.A) / (2.0 * r);
+  if (alpha2 < 1e-8 || !t.polarized) {
+    if (!t.polarized) {
+      const double l = alpha2 < 1e-8 ? func_F(t.a) : linprop_lambda(k1.A, k2.A, r, Tm[0]);
+      for (int i = 0; i < 16; i++) L[i] = 0.0;
+      L[0] = L[5] = L[10] = L[15] = l;
+    } else {
+      t.L(L);
+    }
+    return;
+  }
+  linprop_lambda_pol(Tm, k1, k2, r, 4, L);
+}
+
+// tran::linsrc_linprop_deriv for a polarised layer with a gradient (:543-555): forward perturbation of 1e-6 (dk, dr) of the
+// level the target belongs to ("These derivaties don't work so we use perturbations..."); lambda = the layer's Lambda
+static __device__ __noinline__ void linprop_lambda_pol_deriv(const double* __restrict__ lambda, const Propmat& k1, const Propmat& k2, const Propmat& dk,
+                                                      double r, double dr, bool k1_deriv, double* __restrict__ dL) {
+  constexpr double eps = 1e-6;
+  Propmat kp = k1_deriv ? k1 : k2;
+  kp.A += dk.A * eps; kp.B += dk.B * eps; kp.C += dk.C * eps; kp.D += dk.D * eps; kp.U += dk.U * eps; kp.V += dk.V * eps; kp.W += dk.W * eps;
+  const Propmat& q1 = k1_deriv ? kp : k1;
+  const Propmat& q2 = k1_deriv ? k2 : kp;
+  const double rp = r + dr * eps;
+  Tran tp;
+  tp.init(q1, q2, rp, false);
+  double Tp[16], Lp[16];
+  if (tp.polarized) {
+    tp.T(Tp);
+  } else {
+    for (int i = 0; i < 16; i++) Tp[i] = 0.0;
+    Tp[0] = Tp[5] = Tp[10] = Tp[15] = tp.exp_a;
+  }
+  linprop_lambda_any(tp, Tp, q1, q2, rp, Lp);
+  for (int i = 0; i < 16; i++) dL[i] = (Lp[i] - lambda[i]) / eps;
+}
+
 }  // namespace rte
 }  // namespace ab200

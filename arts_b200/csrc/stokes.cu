@@ -66,12 +66,18 @@ __device__ __forceinline__ void rte_step(double* __restrict__ I, const Propmat& 
   }
   double Tm[16];
   t.T(Tm);
-  if (LINSRC && linprop && linprop_case(k0.A, k1.A, r, true) == 2) atomicOr(flags, 4);  // polarised linprop
   if (LINSRC) {
     const double v[4] = {I[0] - j1, I[1], I[2], I[3]};  // I - J_{i+1}
     double o[4], l[4];
     mat_vec(Tm, v, o);
-    t.L_col0(j1 - j0, l);
+    if (linprop && linprop_case(k0.A, k1.A, r, true) == 2) {  // polarised layer with an absorption gradient, :467-474
+      double Lc[16];
+      linprop_lambda_pol(Tm, k0, k1, r, 1, Lc);
+      const double dj = j1 - j0;
+      l[0] = Lc[0] * dj; l[1] = Lc[4] * dj; l[2] = Lc[8] * dj; l[3] = Lc[12] * dj;
+    } else {
+      t.L_col0(j1 - j0, l);
+    }
     I[0] = o[0] + l[0] + j0;
     I[1] = o[1] + l[1];
     I[2] = o[2] + l[2];
@@ -308,8 +314,12 @@ __global__ void tramat_kernel(int np, int64_t nf, const double* __restrict__ K, 
   store16(T + idx * 16, m);
   if (linsrc) {
     const int lc = linprop ? linprop_case(k1.A, k2.A, r[i - 1], t.polarized) : 0;
-    if (lc == 2) atomicOr(flags, 4);
-    if (lc == 1) diag16(m, linprop_lambda(k1.A, k2.A, r[i - 1], t.exp_a));
+    if (lc == 2) {
+      double Tm[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++) Tm[e] = m[e];
+      linprop_lambda_pol(Tm, k1, k2, r[i - 1], 4, m);
+    } else if (lc == 1) diag16(m, linprop_lambda(k1.A, k2.A, r[i - 1], t.exp_a));
     else if (t.polarized) t.L(m);
     else diag16(m, func_F(t.a));
     store16(L + idx * 16, m);
@@ -419,6 +429,22 @@ int launch_rte_emission(int linsrc, int np, int64_t nf, const double* T, const d
                         const double* I_bkg, double* I, cudaStream_t stream) {
   if (nf == 0) return 0;
   rte_emission_kernel<<<static_cast<unsigned>((nf + 127) / 128), 128, 0, stream>>>(linsrc, np, nf, T, L, J, I_bkg, I);
+  count_launch();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// stand-alone complex Dawson function (tests, ab200_dawson): the evaluator of the polarised linprop layers
+__global__ void dawson_kernel(int64_t n, const double* zr, const double* zi, double* dr, double* di) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const rte::cx d = rte::dawson_c(rte::cx{zr[i], zi[i]});
+  dr[i] = d.r;
+  di[i] = d.i;
+}
+int launch_dawson(int64_t n, const double* zr, const double* zi, double* dr, double* di, cudaStream_t stream) {
+  if (n == 0) return 0;
+  dawson_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(n, zr, zi, dr, di);
   count_launch();
   AB_CUDA(cudaGetLastError());
   return 0;

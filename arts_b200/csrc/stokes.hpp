@@ -21,7 +21,7 @@ struct StokesParams {
   double* I_lev;       // optional [np][nf][4]: radiance arriving at every level (for the Jacobian pass), or nullptr
   int32_t rte_option;
   int32_t tran_exact;
-  int* flags;          // device error flags (bit 2: polarised layer with rte_option linprop)
+  int* flags;          // device error flags
   int32_t scalar;      // K is known to have only A != 0 (no polarised segment was summed): scalar fast path
   int32_t no_emission; // J = 0 at every level: pure transmission (AB200_FLAG_NO_EMISSION)
 };
@@ -82,4 +82,5 @@ int launch_srcvec(int np, int64_t nf, int nq, const double* K, const double* f, 
 int launch_rte_emission(int linsrc, int np, int64_t nf, const double* T, const double* L, const double* J,
                         const double* I_bkg, double* I, cudaStream_t stream);
 
+int launch_dawson(int64_t n, const double* zr, const double* zi, double* dr, double* di, cudaStream_t stream);
 }  // namespace ab200

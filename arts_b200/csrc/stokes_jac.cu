@@ -105,11 +105,15 @@ __global__ void tramat_jac_kernel(int np, int64_t nf, int nq, const double* __re
       double* l1 = dL + half + ((iv * np + i) * nq + j) * 16;
       // linprop (TransmittanceMatrix::linprop :1225-1247) passes dr1 to BOTH derivative calls (:1238, sic)
       const int lc = linprop ? linprop_case(k1.A, k2.A, ri, t.polarized) : 0;
-      if (lc == 1) diag_of(m, linprop_lambda_deriv(k1.A, k2.A, dk0.A, Tm[0], dt00_0, ri, dr1, true));
+      double Lm[16];
+      if (lc == 2) linprop_lambda_pol(Tm, k1, k2, ri, 4, Lm);  // the perturbed Lambda is compared with the layer's own, :545-555
+      if (lc == 2) linprop_lambda_pol_deriv(Lm, k1, k2, dk0, ri, dr1, true, m);
+      else if (lc == 1) diag_of(m, linprop_lambda_deriv(k1.A, k2.A, dk0.A, Tm[0], dt00_0, ri, dr1, true));
       else t.linsrc_deriv(dk0, ri, linprop ? dr1 : dr0, m);
 #pragma unroll
       for (int e = 0; e < 16; e++) l0[e] = m[e];
-      if (lc == 1) diag_of(m, linprop_lambda_deriv(k1.A, k2.A, dk1.A, Tm[0], dt00_1, ri, dr1, false));
+      if (lc == 2) linprop_lambda_pol_deriv(Lm, k1, k2, dk1, ri, dr1, false, m);
+      else if (lc == 1) diag_of(m, linprop_lambda_deriv(k1.A, k2.A, dk1.A, Tm[0], dt00_1, ri, dr1, false));
       else t.linsrc_deriv(dk1, ri, dr1, m);
 #pragma unroll
       for (int e = 0; e < 16; e++) l1[e] = m[e];
@@ -258,9 +262,9 @@ __global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
     double Tm[16], Lm[16];
     if (t.polarized) t.T(Tm); else diag_of(Tm, t.exp_a);
     const int lc = (LINSRC && p.rte_option == AB200_RTE_LINPROP) ? linprop_case(k0.A, k1.A, ri, t.polarized) : 0;
-    if (lc == 2) atomicOr(p.flags, 4);
     if (LINSRC) {
-      if (lc == 1) diag_of(Lm, linprop_lambda(k0.A, k1.A, ri, t.exp_a));
+      if (lc == 2) linprop_lambda_pol(Tm, k0, k1, ri, 4, Lm);
+      else if (lc == 1) diag_of(Lm, linprop_lambda(k0.A, k1.A, ri, t.exp_a));
       else if (t.polarized) t.L(Lm);
       else diag_of(Lm, func_F(t.a));
     }
@@ -288,7 +292,10 @@ __global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
       t.deriv(Tm, k0, k1, dk1, ri, dr1, dT1);
       if (LINSRC) {
         const bool lp = p.rte_option == AB200_RTE_LINPROP;  // dr1 in both calls for linprop (:1238, sic)
-        if (lc == 1) {
+        if (lc == 2) {
+          linprop_lambda_pol_deriv(Lm, k0, k1, dk0, ri, dr1, true, dL0);
+          linprop_lambda_pol_deriv(Lm, k0, k1, dk1, ri, dr1, false, dL1);
+        } else if (lc == 1) {
           diag_of(dL0, linprop_lambda_deriv(k0.A, k1.A, dk0.A, Tm[0], dT0[0], ri, dr1, true));
           diag_of(dL1, linprop_lambda_deriv(k0.A, k1.A, dk1.A, Tm[0], dT1[0], ri, dr1, false));
         } else {

@@ -321,6 +321,15 @@ def faddeeva_w(z):
     return wr + 1j * wi
 
 
+def dawson(z):
+    """Device Faddeeva::Dawson(z), complex z (tests)."""
+    z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
+    zr, zi = np.ascontiguousarray(z.real), np.ascontiguousarray(z.imag)
+    dr, di = np.empty_like(zr), np.empty_like(zr)
+    check(lib().ab200_dawson(len(zr), dptr(zr), dptr(zi), dptr(dr), dptr(di)))
+    return dr + 1j * di
+
+
 def measure_dfma_peak(iters=20000):
     t, ms = C.c_double(), C.c_double()
     check(lib().ab200_measure_dfma_peak(int(iters), C.byref(t), C.byref(ms)))

@@ -33,7 +33,7 @@ extern "C" {
 /* ---- error codes ------------------------------------------------------ */
 #define AB200_OK 0
 #define AB200_ERR_INVALID 1     /* bad argument or shape (the shim's ARTS_USER_ERROR) */
-#define AB200_ERR_UNSUPPORTED 2 /* input outside the path (non VP_LTE band, linprop, ...) */
+#define AB200_ERR_UNSUPPORTED 2 /* input outside the path (non VP_LTE band, pressure target, ...) */
 #define AB200_ERR_CUDA 3        /* CUDA runtime failure / no device */
 #define AB200_ERR_NOMEM 4
 
@@ -67,7 +67,7 @@ enum { AB200_LINESHAPE_VP_LTE = 0, AB200_LINESHAPE_OTHER = 1, AB200_LINESHAPE_VP
 /* LineByLineCutoffType (lbl_data.h:178-194). */
 enum { AB200_CUTOFF_NONE = 0, AB200_CUTOFF_BYLINE = 1 };
 /* TransmittanceOption (arts_options.cc:953-1030); linsrc is the default rte_option. */
-enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 /* unpolarised layers only, else AB200_ERR_UNSUPPORTED */ };
+enum { AB200_RTE_CONSTANT = 0, AB200_RTE_LINSRC = 1, AB200_RTE_LINPROP = 2 };
 /* Jacobian target kinds that reach the kernels (AtmKey::t, SpeciesEnum VMR, AtmKey::wind_u/v/w, AtmKey::mag_u/v/w).  The wind rows are the
  * frequency derivative of the line absorption (single_shape::df, lbl_lineshape_voigt_lte.cpp:275, :1036-1062, :1514-1523)
  * times f * freq_wind_shift_jac (spectral_propmat_jacWindFix, src/m_frequency_grid.cc:106-182, wind_shift :56-82). */
@@ -596,6 +596,9 @@ int ab200_measure_dfma_peak(int iters, double *tflops, double *ms);
 int ab200_measure_dfma_mix(int iters, double *tflops, double *ms);
 /* Register-resident w(z) for tests: evaluates the device Faddeeva at n points (host arrays). */
 int ab200_faddeeva_w(int64_t n, const double *zr, const double *zi, double *wr, double *wi);
+/* Device Faddeeva::Dawson(z) for complex z (3rdparty/Faddeeva/Faddeeva.cc:461-570), the element-wise function of
+ * rtepack::dawson(specmat) in polarised linprop layers (rtepack_transmission.cc:467-474): for tests. */
+int ab200_dawson(int64_t n, const double *zr, const double *zi, double *dr, double *di);
 
 #ifdef __cplusplus
 }

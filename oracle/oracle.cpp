@@ -48,6 +48,8 @@ namespace Faddeeva {
 extern std::complex<double> w(std::complex<double> z, double relerr);
 // reference 3rdparty/Faddeeva/Faddeeva.hh:56 (used by tran::linsrc_linprop, rtepack_transmission.cc:453)
 extern double Dawson(double x);
+// reference 3rdparty/Faddeeva/Faddeeva.hh:55 (element-wise in rtepack::dawson(specmat), rtepack_spectral_matrix.cc:6-26)
+extern std::complex<double> Dawson(std::complex<double> z, double relerr);
 }  // namespace Faddeeva
 
 namespace {
@@ -1140,6 +1142,192 @@ inline stokvec operator*(const muelmat& a, const stokvec& b) {
   return o;
 }
 
+
+// ---------------------------------------------------------------------------
+// rtepack::specmat — src/core/rtepack/rtepack_spectral_matrix.h:12-242: a 4x4 complex matrix, row major.  Only what the
+// polarised branch of tran::linsrc_linprop (rtepack_transmission.cc:467-474) touches.  Scaling by a Complex goes
+// through the diagonal constructor and the FULL matrix product (`a *= b` finds specmat::operator*=(const specmat&),
+// :56-107, like muelmat above), so `inv(A) = adj(A) / det(A)` (:242, :185-188) is adj(A) x ((1/det) I).
+// ---------------------------------------------------------------------------
+struct specmat {
+  Complex m[16];
+  specmat(Complex tau = 1.0) {
+    for (auto& x : m) x = 0;
+    m[0] = m[5] = m[10] = m[15] = tau;
+  }
+};
+inline specmat operator*(const specmat& a, const specmat& b) {  // :56-107
+  specmat o(0.0);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      o.m[4 * i + j] = a.m[4 * i + 0] * b.m[0 + j] + a.m[4 * i + 1] * b.m[4 + j] + a.m[4 * i + 2] * b.m[8 + j] +
+                       a.m[4 * i + 3] * b.m[12 + j];
+  return o;
+}
+inline specmat operator/(const specmat& a, const Complex& b) { return a * specmat(1.0 / b); }  // :185-188
+inline specmat operator-(specmat a, const specmat& b) {
+  for (int i = 0; i < 16; i++) a.m[i] -= b.m[i];
+  return a;
+}
+inline Complex det(const specmat& A) {  // :203-210
+  const Complex *q = A.m, a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5], g = q[6], h = q[7], i = q[8], j = q[9],
+                k = q[10], l = q[11], m = q[12], n = q[13], o = q[14], p = q[15];
+  return a * (f * (k * p - l * o) + g * (l * n - j * p) + h * (j * o - k * n)) +
+         b * (e * (l * o - k * p) + g * (i * p - l * m) + h * (k * m - i * o)) +
+         c * (e * (j * p - l * n) + f * (l * m - i * p) + h * (i * n - j * m)) +
+         d * (e * (k * n - j * o) + f * (i * o - k * m) + g * (j * m - i * n));
+}
+inline specmat adj(const specmat& A) {  // :223-240
+  const Complex *q = A.m, a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5], g = q[6], h = q[7], i = q[8], j = q[9],
+                k = q[10], l = q[11], m = q[12], n = q[13], o = q[14], p = q[15];
+  specmat r(0.0);
+  r.m[0]  = f * (k * p - l * o) + g * (l * n - j * p) + h * (j * o - k * n);
+  r.m[1]  = b * (l * o - k * p) + c * (j * p - l * n) + d * (k * n - j * o);
+  r.m[2]  = b * (g * p - h * o) + c * (h * n - f * p) + d * (f * o - g * n);
+  r.m[3]  = b * (h * k - g * l) + c * (f * l - h * j) + d * (g * j - f * k);
+  r.m[4]  = e * (l * o - k * p) + g * (i * p - l * m) + h * (k * m - i * o);
+  r.m[5]  = a * (k * p - l * o) + c * (l * m - i * p) + d * (i * o - k * m);
+  r.m[6]  = a * (h * o - g * p) + c * (e * p - h * m) + d * (g * m - e * o);
+  r.m[7]  = a * (g * l - h * k) + c * (h * i - e * l) + d * (e * k - g * i);
+  r.m[8]  = e * (j * p - l * n) + f * (l * m - i * p) + h * (i * n - j * m);
+  r.m[9]  = a * (l * n - j * p) + b * (i * p - l * m) + d * (j * m - i * n);
+  r.m[10] = a * (f * p - h * n) + b * (h * m - e * p) + d * (e * n - f * m);
+  r.m[11] = a * (h * j - f * l) + b * (e * l - h * i) + d * (f * i - e * j);
+  r.m[12] = e * (k * n - j * o) + f * (i * o - k * m) + g * (j * m - i * n);
+  r.m[13] = a * (j * o - k * n) + b * (k * m - i * o) + c * (i * n - j * m);
+  r.m[14] = a * (g * n - f * o) + b * (e * o - g * m) + c * (f * m - e * n);
+  r.m[15] = a * (f * k - g * j) + b * (g * i - e * k) + c * (e * j - f * i);
+  return r;
+}
+inline specmat inv(const specmat& A) { return adj(A) / det(A); }  // :242
+// specmat * propmat, rtepack_multitype.h:145-168 (the order of the four terms is the reference's)
+inline specmat operator*(const specmat& s, const propmat& k) {
+  const Numeric a = k.v[0], b = k.v[1], c = k.v[2], d = k.v[3], u = k.v[4], v = k.v[5], w = k.v[6];
+  specmat o(0.0);
+  for (int i = 0; i < 4; i++) {
+    const Complex m1 = s.m[4 * i], m2 = s.m[4 * i + 1], m3 = s.m[4 * i + 2], m4 = s.m[4 * i + 3];
+    o.m[4 * i + 0] = a * m1 + b * m2 + c * m3 + d * m4;
+    o.m[4 * i + 1] = a * m2 + b * m1 - m3 * u - m4 * v;
+    o.m[4 * i + 2] = a * m3 + c * m1 + m2 * u - m4 * w;
+    o.m[4 * i + 3] = a * m4 + d * m1 + m2 * v + m3 * w;
+  }
+  return o;
+}
+// muelmat * specmat, rtepack_multitype.h:200-250
+inline specmat operator*(const muelmat& a, const specmat& b) {
+  specmat o(0.0);
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++)
+      o.m[4 * i + j] = a.m[4 * i + 0] * b.m[0 + j] + a.m[4 * i + 1] * b.m[4 + j] + a.m[4 * i + 2] * b.m[8 + j] +
+                       a.m[4 * i + 3] * b.m[12 + j];
+  return o;
+}
+// element-wise Dawson function, rtepack_spectral_matrix.cc:6-26
+inline specmat dawson(const specmat& A) {
+  specmat o(0.0);
+  for (int i = 0; i < 16; i++) o.m[i] = Faddeeva::Dawson(A.m[i], 0);
+  return o;
+}
+inline muelmat real(const specmat& A) {  // rtepack_multitype.cc:116-133
+  muelmat o;
+  for (int i = 0; i < 16; i++) o.m[i] = std::real(A.m[i]);
+  return o;
+}
+// propmat / Numeric: element-wise (matpack_mdspan_cdata_t.h:316-319); propmat - propmat
+inline propmat operator/(propmat a, Numeric b) {
+  for (auto& x : a.v) x /= b;
+  return a;
+}
+inline propmat operator-(propmat a, const propmat& b) {
+  for (int i = 0; i < 7; i++) a.v[i] -= b.v[i];
+  return a;
+}
+inline propmat operator+(propmat a, const propmat& b) {
+  for (int i = 0; i < 7; i++) a.v[i] += b.v[i];
+  return a;
+}
+inline propmat operator*(propmat a, Numeric b) {
+  for (auto& x : a.v) x *= b;
+  return a;
+}
+
+// specmat sqrt(const propmat&), rtepack_transmission.cc:872-1002: the principal square root of the propagation matrix
+// through its Cayley-Hamilton coefficients d0..d3 (complex: a - x and a +- i y may lie left of the branch cut).
+inline specmat sqrt_pm(const propmat& pm) {
+  const Numeric a      = pm.A();
+  const Complex sqrt_a = std::sqrt(Complex(a));
+  if (not pm.is_polarized()) return specmat(sqrt_a);
+  const Numeric b = pm.B(), c = pm.C(), d = pm.D(), u = pm.U(), v = pm.V(), w = pm.W();
+  const Numeric b2 = b * b, c2 = c * c, d2 = d * d, u2 = u * u, v2 = v * v, w2 = w * w;
+  Complex d0c{}, d1c{}, d2c{}, d3c{};
+  constexpr Numeric eps = std::numeric_limits<Numeric>::epsilon();
+  if (pm.is_rotational()) {
+    const Numeric rho = std::hypot(u, v, w);
+    if (rho <= eps) return specmat(0.0);
+    const Numeric r = std::sqrt(2.0 * rho);
+    d0c             = 0.0;
+    d1c             = 1.0 / r;
+    d2c             = -1.0 / (rho * r);
+    d3c             = 0.0;
+  } else {
+    const Numeric B      = u2 + v2 + w2 - b2 - c2 - d2;
+    const Numeric C      = -pow2(d * u - c * v + b * w);
+    const Numeric S      = std::sqrt(B * B - 4 * C);
+    const Numeric x2     = std::max(0.0, 0.5 * (S - B));
+    const Numeric abs_y2 = std::max(0.0, 0.5 * (S + B));
+    const Numeric x      = std::sqrt(x2);
+    const Complex y      = Complex(0, std::sqrt(abs_y2));
+    const Complex sx     = std::sqrt(Complex(a + x));
+    const Complex dx     = std::sqrt(Complex(a - x));
+    const Complex sy     = std::sqrt(a + y);
+    const Complex dy     = std::sqrt(a - y);
+    const Complex Sx = sx + dx, Dx = sx - dx, Sy = sy + dy, Dy = sy - dy;
+    if (x2 + abs_y2 <= eps) {
+      d0c = sqrt_a;
+      if (a <= eps) {  // sic (:934): the series coefficients are set for a SMALL a
+        d1c = 0.5 / sqrt_a;
+        d2c = 0.125 / (a * sqrt_a);
+        d3c = 0.0625 / (a * a * sqrt_a);
+      }
+    } else {
+      const Numeric inv_sum_sq = 1.0 / (x2 + abs_y2);
+      d0c                      = (abs_y2 * Sx + x2 * Sy) * (0.5 * inv_sum_sq);
+      d2c                      = (Sx - Sy) * (0.5 * inv_sum_sq);
+      const Complex term1 = (x <= eps and a <= eps) ? Complex(0.0) : (x <= eps) ? 0.5 / sqrt_a : 0.5 * Dx / x;
+      const Complex term2 = (abs_y2 <= eps and a <= eps) ? Complex(0.0) : (abs_y2 <= eps) ? 0.5 / sqrt_a : 0.5 * Dy / y;
+      d1c                 = (abs_y2 * term1 + x2 * term2) * inv_sum_sq;
+      d3c                 = (term1 - term2) * inv_sum_sq;
+    }
+  }
+  const Numeric k2_00 = b2 + c2 + d2, k2_11 = b2 - u2 - v2, k2_22 = c2 - u2 - w2, k2_33 = d2 - v2 - w2;
+  const Numeric k2_01 = -(c * u + d * v), k2_02 = b * u - d * w, k2_03 = b * v + c * w;
+  const Numeric k2_12 = b * c - v * w, k2_13 = b * d + u * w, k2_23 = c * d - u * v;
+  const Numeric k3_01 = b * k2_00 - u * k2_02 - v * k2_03;
+  const Numeric k3_02 = c * k2_00 + u * k2_01 - w * k2_03;
+  const Numeric k3_03 = d * k2_00 + v * k2_01 + w * k2_02;
+  const Numeric k3_12 = -c * k2_01 + u * k2_11 - w * k2_13;
+  const Numeric k3_13 = -d * k2_01 + v * k2_11 + w * k2_12;
+  const Numeric k3_23 = -d * k2_02 + v * k2_12 + w * k2_22;
+  specmat K;  // the default constructor is the identity (:14-16); every element is assigned below
+  K.m[0]  = d0c + d2c * k2_00;
+  K.m[5]  = d0c + d2c * k2_11;
+  K.m[10] = d0c + d2c * k2_22;
+  K.m[15] = d0c + d2c * k2_33;
+  K.m[1]  = d1c * b + d2c * k2_01 + d3c * k3_01;
+  K.m[4]  = d1c * b - d2c * k2_01 + d3c * k3_01;
+  K.m[2]  = d1c * c + d2c * k2_02 + d3c * k3_02;
+  K.m[8]  = d1c * c - d2c * k2_02 + d3c * k3_02;
+  K.m[3]  = d1c * d + d2c * k2_03 + d3c * k3_03;
+  K.m[12] = d1c * d - d2c * k2_03 + d3c * k3_03;
+  K.m[6]  = d1c * u + d2c * k2_12 + d3c * k3_12;
+  K.m[9]  = -d1c * u + d2c * k2_12 - d3c * k3_12;
+  K.m[7]  = d1c * v + d2c * k2_13 + d3c * k3_13;
+  K.m[13] = -d1c * v + d2c * k2_13 - d3c * k3_13;
+  K.m[11] = d1c * w + d2c * k2_23 + d3c * k3_23;
+  K.m[14] = -d1c * w + d2c * k2_23 - d3c * k3_23;
+  return K;
+}
+
 // ---------------------------------------------------------------------------
 // rtepack::tran — src/core/rtepack/rtepack_transmission.cc:20-150 (ctor and
 // operator()), :207-275 (linsrc), :277-447 (linsrc_deriv), :558-674 (deriv).
@@ -1506,32 +1694,44 @@ struct tran {
     return muelmat(dl0) + Sm * dl1 + dSm * l1 + S2m * dl2 + dS2m * l2 + S3m * dl3 + dS3m * l3;
   }
 
-  // tran::linsrc_linprop, :449-475.  Only the unpolarised branch is restated (the polarised one needs the
-  // complex matrix sqrt / inverse / dawson of :872-1002, outside the path: DESIGN.md section 7); `ok` reports it.
-  muelmat linsrc_linprop(const muelmat& t, const propmat& k1, const propmat& k2, const Numeric r, bool& ok) const {
-    ok = true;
-    const Numeric alpha2A = (k2.A() - k1.A()) / (2.0 * r);
-    if (alpha2A < 1e-8) return linsrc();  // "Ignore when the gradient is negative"
-    if (polarized) {
-      ok = false;
-      return muelmat::zero();
+  // tran::linsrc_linprop, :449-475: the unpolarised Dawson form and the polarised one through the complex matrix
+  // square root of the absorption gradient, its inverse and the ELEMENT-WISE Dawson function of :467-474.
+  muelmat linsrc_linprop(const muelmat& t, const propmat& k1, const propmat& k2, const Numeric r) const {
+    const propmat alpha2 = (k2 - k1) / (2.0 * r);
+    if (alpha2.A() < 1e-8) return linsrc();  // "Ignore when the gradient is negative"
+    if (not polarized) {
+      const Numeric alpha = std::sqrt(alpha2.A());
+      const Numeric u0    = k1.A() / (2.0 * alpha);
+      const Numeric u1    = k2.A() / (2.0 * alpha);
+      return muelmat((Faddeeva::Dawson(u1) - t.m[0] * Faddeeva::Dawson(u0)) / (r * alpha));
     }
-    const Numeric alpha = std::sqrt(alpha2A);
-    const Numeric u0    = k1.A() / (2.0 * alpha);
-    const Numeric u1    = k2.A() / (2.0 * alpha);
-    return muelmat((Faddeeva::Dawson(u1) - t.m[0] * Faddeeva::Dawson(u0)) / (r * alpha));
+    const specmat alpha     = sqrt_pm(alpha2);
+    const specmat alpha_inv = inv(alpha);
+    const specmat u0        = alpha_inv * (k1 / 2.0);
+    const specmat u1        = alpha_inv * (k2 / 2.0);
+    muelmat o               = real(alpha_inv * (dawson(u1) - t * dawson(u0)));
+    for (auto& x : o.m) x /= r;  // muelmat / Numeric is element-wise (rtepack_mueller_matrix.h:197-200)
+    return o;
   }
 
-  // tran::linsrc_linprop_deriv, :477-556 (unpolarised closed form; the polarised branch is a perturbation
-  // of the unsupported polarised linsrc_linprop)
-  muelmat linsrc_linprop_deriv(const muelmat& t, const propmat& k1, const propmat& k2, const propmat& dk_in,
-                               const muelmat& dt, const Numeric r, const Numeric dr, bool k1_deriv, bool& ok) const {
-    ok = true;
-    const Numeric alpha2A = (k2.A() - k1.A()) / (2.0 * r);
+  // tran::linsrc_linprop_deriv, :477-556: closed form for unpolarised layers, a forward perturbation of 1e-6 times
+  // (dk, dr) for polarised ones ("These derivaties don't work so we use perturbations...", :543).  `exact` is the
+  // oracle's own switch and is handed on to the perturbed tran.
+  muelmat linsrc_linprop_deriv(const muelmat& lambda, const muelmat& t, const propmat& k1, const propmat& k2, const propmat& dk_in,
+                               const muelmat& dt, const Numeric r, const Numeric dr, bool k1_deriv, bool exact) const {
+    const Numeric alpha2A = ((k2 - k1) / (2.0 * r)).A();
     if (alpha2A < 1e-8) return linsrc_deriv(dk_in, r, dr);
     if (polarized) {
-      ok = false;
-      return muelmat::zero();
+      constexpr Numeric eps = 1e-6;
+      const propmat k1p = k1_deriv ? k1 + dk_in * eps : k1;
+      const propmat k2p = k1_deriv ? k2 : k2 + dk_in * eps;
+      const Numeric rp  = r + dr * eps;
+      const tran tran_p{k1p, k2p, rp, exact};
+      const muelmat tp      = tran_p();
+      const muelmat lambdap = tran_p.linsrc_linprop(tp, k1p, k2p, rp);
+      muelmat o;
+      for (int i = 0; i < 16; i++) o.m[i] = (lambdap.m[i] - lambda.m[i]) / eps;
+      return o;
     }
     const Numeric k1a = k1.A(), k2a = k2.A(), dk = dk_in.A();
     const Numeric delta_k = k2a - k1a;
@@ -1759,7 +1959,6 @@ int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double
   const bool exact   = flags & AB200_FLAG_TRAN_EXACT;
   const bool linprop = rte_option == AB200_RTE_LINPROP;
   const bool linsrc  = rte_option == AB200_RTE_LINSRC || linprop;  // L, dL exist for both (:1300-1306)
-  bool all_ok        = true;
   const muelmat id;
   const muelmat zero = muelmat::zero();
   // :1300-1314 identity / zero init
@@ -1787,13 +1986,10 @@ int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double
       const tran ts{k1, k2, r[i - 1], exact};
       const muelmat Tm = ts();
       store(T + (iv * np + i) * 16, Tm);
-      bool ok = true;
-      if (linprop) store(L + (iv * np + i) * 16, ts.linsrc_linprop(Tm, k1, k2, r[i - 1], ok));
-      else if (linsrc) store(L + (iv * np + i) * 16, ts.linsrc());
-      if (not ok) {
-#pragma omp atomic write
-        all_ok = false;
-      }
+      muelmat Lm;
+      if (linprop) Lm = ts.linsrc_linprop(Tm, k1, k2, r[i - 1]);
+      else if (linsrc) Lm = ts.linsrc();
+      if (linsrc) store(L + (iv * np + i) * 16, Lm);
       for (int j = 0; j < nq; j++) {
         const Numeric dr0 = dr[(0 * (np - 1) + (i - 1)) * nq + j];
         const Numeric dr1 = dr[(1 * (np - 1) + (i - 1)) * nq + j];
@@ -1802,10 +1998,9 @@ int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double
         store(dXi(dT, 0, iv, i - 1, j), dT0m);
         store(dXi(dT, 1, iv, i, j), dT1m);
         if (linprop) {  // TransmittanceMatrix::linprop :1225-1247; note dr1 in BOTH calls (:1238)
-          bool ok2 = true;
           store(dXi(dL, 0, iv, i - 1, j),
-                ts.linsrc_linprop_deriv(Tm, k1, k2, dK_at(i - 1, j, iv), dT0m, r[i - 1], dr1, true, ok2));
-          store(dXi(dL, 1, iv, i, j), ts.linsrc_linprop_deriv(Tm, k1, k2, dK_at(i, j, iv), dT1m, r[i - 1], dr1, false, ok2));
+                ts.linsrc_linprop_deriv(Lm, Tm, k1, k2, dK_at(i - 1, j, iv), dT0m, r[i - 1], dr1, true, exact));
+          store(dXi(dL, 1, iv, i, j), ts.linsrc_linprop_deriv(Lm, Tm, k1, k2, dK_at(i, j, iv), dT1m, r[i - 1], dr1, false, exact));
         } else if (linsrc) {
           store(dXi(dL, 0, iv, i - 1, j), ts.linsrc_deriv(dK_at(i - 1, j, iv), r[i - 1], dr0));
           store(dXi(dL, 1, iv, i, j), ts.linsrc_deriv(dK_at(i, j, iv), r[i - 1], dr1));
@@ -1823,8 +2018,6 @@ int orc_tramat(int32_t np, int64_t nf, int32_t nq, const double* K, const double
       store(P + (i * np + j) * 16, acc);
     }
   }
-  if (not all_ok)
-    return fail(AB200_ERR_UNSUPPORTED, "linprop with a polarised propagation matrix is outside the restated path");
   return 0;
 }
 
@@ -2510,6 +2703,23 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
 }
 
 // rtepack::tran for single inputs (tests: exp(-K r) against scipy expm, src/tests/test_rtepack.cc:12-33)
+// Faddeeva::Dawson(complex) of the reference's object, n points
+int orc_dawson(int64_t n, const double* zr, const double* zi, double* dr, double* di) {
+  for (int64_t i = 0; i < n; i++) {
+    const Complex d = Faddeeva::Dawson(Complex(zr[i], zi[i]), 0);
+    dr[i] = d.real();
+    di[i] = d.imag();
+  }
+  return 0;
+}
+
+// specmat sqrt(const propmat&): out [16][2] (re, im)
+int orc_sqrt_propmat(const double* k, double* out) {
+  const specmat s = sqrt_pm(load_pm(k));
+  for (int i = 0; i < 16; i++) out[2 * i] = s.m[i].real(), out[2 * i + 1] = s.m[i].imag();
+  return 0;
+}
+
 int orc_tran(const double* k1, const double* k2, double r, uint32_t flags, double* T, double* L) {
   const tran ts{load_pm(k1), load_pm(k2), r, (flags & AB200_FLAG_TRAN_EXACT) != 0};
   store(T, ts());

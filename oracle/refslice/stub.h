@@ -92,6 +92,24 @@ struct cdata_t {
 template <class T>
 concept any_cdata = requires { typename std::remove_cvref_t<T>::refslice_cdata_tag; };
 
+// scaling by a value of the element type: matpack_mdspan_cdata_t.h:301-319 (these templates, not an implicit conversion
+// of the scalar to the class, are what `propmat / Numeric` resolves to: element-wise)
+template <any_cdata T>
+constexpr T operator*(T x, const std::convertible_to<typename T::value_type> auto& y) {
+  x *= static_cast<typename T::value_type>(y);
+  return x;
+}
+template <any_cdata T>
+constexpr T operator*(const std::convertible_to<typename T::value_type> auto& y, T x) {
+  x *= static_cast<typename T::value_type>(y);
+  return x;
+}
+template <any_cdata T>
+constexpr T operator/(T x, const std::convertible_to<typename T::value_type> auto& y) {
+  x /= static_cast<typename T::value_type>(y);
+  return x;
+}
+
 // row-major dense view: what the sliced loops of rtepack_rtestep.cc index with [i], [i, j] and npages()/nrows()/ncols()
 template <class T, Size N>
 struct view_t {
@@ -145,6 +163,7 @@ struct tuple_element<I, T> {
 using Vector4  = matpack::cdata_t<Numeric, 4>;
 using Vector7  = matpack::cdata_t<Numeric, 7>;
 using Matrix44 = matpack::cdata_t<Numeric, 4, 4>;
+using ComplexMatrix44 = matpack::cdata_t<Complex, 4, 4>;
 using ConstVectorView = matpack::view_t<const Numeric, 1>;
 
 // rtepack_common.h forward-declares these; rtepack_stokes_vector.h names the two enums only in functions that are not sliced
@@ -152,4 +171,5 @@ namespace rtepack {
 struct propmat;
 struct muelmat;
 struct stokvec;
+struct specmat;
 }  // namespace rtepack

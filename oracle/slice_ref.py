@@ -40,10 +40,18 @@ SLICES = {
     "propmat_struct_ops": ("src/core/rtepack/rtepack_propagation_matrix.h", r"struct propmat final : Vector7 \{", r"constexpr propmat avg\(const propmat &a, const propmat &b\) \{", (12, 109), "block"),
     "muelmat_struct_ops": ("src/core/rtepack/rtepack_mueller_matrix.h", r"struct muelmat final : Matrix44 \{", r"constexpr muelmat inv\(const muelmat &A\) \{", (12, 252), "block"),
     "multitype": ("src/core/rtepack/rtepack_multitype.h", r"constexpr muelmat to_muelmat\(const propmat &k\) \{", r"constexpr stokvec operator\*\(const muelmat &a, const stokvec &b\) \{", (11, 68), "block_skip_decls"),
+    # the complex 4x4 matrix of the polarised linprop branch and its mixed products (specmat x propmat, muelmat x specmat, ...)
+    "specmat_struct_ops": ("src/core/rtepack/rtepack_spectral_matrix.h", r"struct specmat final : ComplexMatrix44 \{", r"constexpr specmat inv\(const specmat &A\) \{", (12, 242), "block"),
+    "multitype_specmat": ("src/core/rtepack/rtepack_multitype.h", r"//! Mutliply a specmat with a muelmat matrix", r"constexpr specmat operator-\(const propmat &pm, const specmat &s\) \{", (120, 353), "block"),
+    "real_specmat": ("src/core/rtepack/rtepack_multitype.cc", r"muelmat real\(const specmat &A\) \{", None, (116, 133), "block"),
+    "specmat_dawson": ("src/core/rtepack/rtepack_spectral_matrix.cc", r"specmat dawson\(const specmat &A\) \{", None, (6, 25), "block"),
     # tran: declaration, then ctor + operator() :20-150, linsrc + linsrc_deriv :207-447, deriv :558-674
     "tran_struct": ("src/core/rtepack/rtepack_transmission.h", r"struct tran \{", None, (69, 109), "block"),
     "tran_ctor_call": ("src/core/rtepack/rtepack_transmission.cc", r"static constexpr Numeric too_small = 1e-4;", r"muelmat tran::operator\(\)\(\) const noexcept \{", (20, 150), "block"),
     "tran_linsrc": ("src/core/rtepack/rtepack_transmission.cc", r"muelmat tran::linsrc\(\) const noexcept \{", r"muelmat tran::linsrc_deriv\(const propmat &dk,", (207, 447), "block"),
+    # rte_option linprop: sqrt of a propagation matrix :872-1002, linsrc_linprop + its derivative :449-556
+    "propmat_sqrt": ("src/core/rtepack/rtepack_transmission.cc", r"specmat sqrt\(const propmat &pm\) \{", None, (872, 1002), "block"),
+    "tran_linprop": ("src/core/rtepack/rtepack_transmission.cc", r"muelmat tran::linsrc_linprop\(const muelmat &t,", r"muelmat tran::linsrc_linprop_deriv\(const muelmat &lambda,", (449, 556), "block"),
     "tran_deriv": ("src/core/rtepack/rtepack_transmission.cc", r"muelmat tran::deriv\(const muelmat &t,", None, (558, 674), "block"),
     # rte_emission's two recursions (anonymous namespace), rtepack_rtestep.cc:265-372
     "rte_constant_linevo": ("src/core/rtepack/rtepack_rtestep.cc", r"void constant\(stokvec_vector_view &Is,", r"void linevo\(stokvec_vector_view &Is,", (265, 371), "block"),

@@ -48,6 +48,8 @@ def lib():
         L.orc_planck_tb.argtypes = [C.c_int64, dp, dp]
         L.orc_planck.argtypes = [C.c_int64, dp, C.c_double, dp]
         L.orc_tran.argtypes = [dp, dp, C.c_double, C.c_uint32, dp, dp]
+        L.orc_sqrt_propmat.argtypes = [dp, dp]
+        L.orc_dawson.argtypes = [C.c_int64, dp, dp, dp, dp]
         L.orc_wigner3j.argtypes = [C.c_int] * 6 + [dp]
         L.orc_wind_shift.argtypes = [dp, dp, dp, dp]
         L.orc_zeeman_components.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp]
@@ -89,6 +91,15 @@ def faddeeva_w(z):
     wr, wi = np.empty_like(zr), np.empty_like(zr)
     _check(lib().orc_faddeeva_w(len(zr), dptr(zr), dptr(zi), dptr(wr), dptr(wi)))
     return wr + 1j * wi
+
+
+def dawson(z):
+    """the reference's own Faddeeva::Dawson(complex) object code"""
+    z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
+    zr, zi = np.ascontiguousarray(z.real), np.ascontiguousarray(z.imag)
+    dr, di = np.empty_like(zr), np.empty_like(zr)
+    _check(lib().orc_dawson(len(zr), dptr(zr), dptr(zi), dptr(dr), dptr(di)))
+    return dr + 1j * di
 
 
 def _f_arg(f, np_):

@@ -51,3 +51,20 @@ def test_dense_sweep_vs_reference(wsm, orc, seed):
     # symmetry w(-x + iy) = conj(w(x + iy)) must hold bit for bit
     gm = wsm.faddeeva_w(-z.real + 1j * z.imag)
     assert np.array_equal(gm.real, got.real) and np.array_equal(gm.imag, -got.imag)
+
+
+def test_complex_dawson_against_the_reference_object(wsm, orc):
+    """Faddeeva::Dawson(z) for complex z (Faddeeva.cc:461-570), the element-wise function of rtepack::dawson(specmat) in
+    polarised linprop layers: every branch of the package (both axes, the |z| < 5e-3 Taylor series, the expansion about the
+    real axis for small |y| and |xy| incl. |x| > 40 and |x| > 5e7, both half planes of the general formula)."""
+    rng = np.random.default_rng(5)
+    z = [0.0, 1e-3, -2.5, 30.0, 1e-3j, -1e-3j, 0.3j, -2j, 4j, 1e-3 + 1e-3j, -4e-3 + 2e-3j, 2.0 + 1e-3j, 0.7 - 4e-3j,
+         60.0 + 5e-5j, -45.0 - 1e-5j, 6e7 + 1e-11j, 1.5 + 0.5j, -1.5 - 0.5j, 8.0 + 0.2j, 3.0 - 1.0j, 0.01 + 0.01j]
+    mag = 10 ** rng.uniform(-3, 1.2, 4000)
+    ang = rng.uniform(-np.pi, np.pi, 4000)
+    z = np.concatenate([np.array(z, dtype=np.complex128), mag * np.exp(1j * ang), rng.uniform(-6, 6, 2000) + 1j * 10 ** rng.uniform(-6, -2, 2000)])
+    z = z[np.abs(z.imag) < np.abs(z.real) + 3.0]  # exp(y^2 - x^2) stays in range
+    got, ref = wsm.dawson(z), orc.dawson(z)
+    assert np.all(np.isfinite(ref)) and np.all(np.isfinite(got))
+    err = np.abs(got - ref) / np.abs(np.where(ref == 0, 1.0, ref))
+    assert err.max() <= 2e-12, (err.max(), z[np.argmax(err)])

@@ -1,6 +1,7 @@
-"""rte_option = linprop for unpolarised layers: tran::linsrc_linprop / linsrc_linprop_deriv
-(rtepack_transmission.cc:449-541) with Faddeeva::Dawson, TransmittanceMatrix::linprop (:1195-1252); polarised
-layers with a positive absorption gradient need the complex matrix functions of :872-1002 and are rejected."""
+"""rte_option = linprop: tran::linsrc_linprop / linsrc_linprop_deriv (rtepack_transmission.cc:449-556)
+with Faddeeva::Dawson, TransmittanceMatrix::linprop (:1195-1252).  Unpolarised layers take the scalar Dawson form and
+its closed derivative; polarised layers with an absorption gradient take the complex matrix square root (:872-1002), its
+inverse and the element-wise complex Dawson function, with a 1e-6 perturbation for the derivative (:543-555)."""
 import json
 import os
 
@@ -95,17 +96,77 @@ def test_fused_linprop_scalar(wsm, orc, targets):
         assert np.abs(dI[:, :, q, 0] - dIr[:, :, q, 0]).max() <= 5e-7 * sc
 
 
-def test_polarised_linprop_is_rejected(wsm):
-    rng = np.random.default_rng(3)
-    np_, nf = 5, 40
-    K = np.zeros((np_, nf, 7))
-    K[..., 0] = np.linspace(1e-4, 5e-4, np_)[:, None]
-    K[..., 1:] = rng.uniform(-1e-5, 1e-5, (np_, nf, 6))
-    r = np.full(np_ - 1, 100.0)
-    with pytest.raises(wsm.Ab200Error) as e:
-        wsm.spectral_tramat_pathFromPath(K, None, r, np.full(np_, 250.0), "linprop")
-    assert e.value.code == abi.ERR_UNSUPPORTED
-    # decreasing absorption: every layer falls back to the (polarised) linsrc operator -> fine
-    tm = wsm.spectral_tramat_pathFromPath(K[::-1].copy(), None, r, np.full(np_, 250.0), "linprop")
-    ts = wsm.spectral_tramat_pathFromPath(K[::-1].copy(), None, r, np.full(np_, 250.0), "linsrc")
-    assert np.array_equal(tm.L, ts.L)
+def _polarised_K(rng, np_, nf, pol=0.2):
+    """absorption rising along the path (positive gradient in most layers) with a polarised part of relative size pol"""
+    a = 10 ** rng.uniform(-5.5, -3.7, (1, nf, 1)) * (1.0 + np.arange(np_)[:, None, None] * rng.uniform(0.3, 2.0, (1, nf, 1)))
+    K = a * np.concatenate([np.ones((np_, nf, 1)), rng.uniform(-pol, pol, (np_, nf, 6))], axis=2)
+    return np.ascontiguousarray(K)
+
+
+def test_unfused_polarised_linprop_with_jacobians(wsm, orc):
+    rng = np.random.default_rng(31)
+    np_, nf, nq = 7, 150, 2
+    K = _polarised_K(rng, np_, nf)
+    K[:, ::7, 1:] = 0.0    # unpolarised columns in between
+    K[3:, 5::11, 0] *= 0.2  # and layers with a falling absorption: the linsrc fall-back (:456)
+    dK = K[:, None] * rng.uniform(-1e-2, 1e-2, (np_, nq, nf, 7))
+    r = 10 ** rng.uniform(1.0, 2.5, np_ - 1)
+    grad = (K[1:, :, 0] - K[:-1, :, 0]) / (2 * r[:, None]) >= 1e-8
+    assert 0.3 < grad.mean() < 0.99
+    Tlev = np.linspace(210.0, 290.0, np_)
+    f = np.linspace(50e9, 70e9, nf)
+    dr = np.zeros((2, np_ - 1, nq))
+    dr[0, :, 0] = r / (2 * Tlev[:-1])
+    dr[1, :, 0] = r / (2 * Tlev[1:])
+    Tr, Lr, Pr, dTr, dLr = orc.tramat(K, dK, r, dr, "linprop")
+    tm = wsm.spectral_tramat_pathFromPath(K, dK, r, Tlev, "linprop", hse_derivative=1, it=0)
+    L = tm.L.reshape(Lr.shape)
+    sc = np.abs(Lr).max(axis=2, keepdims=True)  # per (frequency, level): the matrix is ~ Lambda * identity + small terms
+    assert np.abs(L - Lr).max() <= 1e-11 * sc.max()
+    np.testing.assert_allclose(L, Lr, rtol=0, atol=1e-11 * float(sc.max()))
+    _, Ls, _, _, _ = orc.tramat(K, dK, r, dr, "linsrc")
+    assert np.abs(Lr - Ls).max() > 1e-6  # the Dawson form is not the linsrc operator
+    # the polarised derivative is a forward difference with eps = 1e-6 of Lambda itself: errors of Lambda (1e-13) show at 1e-7
+    dL = tm.dL.reshape(dLr.shape)
+    assert np.abs(dL - dLr).max() <= 3e-6 * np.abs(dLr).max() + 1e-6 * 1e-11 / 1e-6
+    bkg = np.zeros((nf, 4))
+    bkg[:, 0] = synth.planck(f, 2.735)
+    Jr, dJr = orc.srcvec(K, f, Tlev, it=0, nq=nq)
+    J, dJ = wsm.spectral_rad_srcvec_pathFromPropmat(K, f, Tlev, it=0, nq=nq)
+    Ir, dIr = orc.rte_emission("linprop", Tr, Lr, Pr, dTr, dLr, Jr, dJr, bkg)
+    I, dI = wsm.spectral_radStepByStepEmission(tm, J, dJ, bkg)
+    np.testing.assert_allclose(I, Ir, rtol=0, atol=1e-11 * np.abs(Ir).max())
+    assert np.abs(dI - dIr).max() <= 3e-6 * np.abs(dIr).max()
+    # decreasing absorption everywhere: every layer falls back to the (polarised) linsrc operator
+    Kd = np.ascontiguousarray(_polarised_K(rng, np_, 40)[::-1])
+    tl = wsm.spectral_tramat_pathFromPath(Kd, None, r, Tlev, "linprop")
+    ts = wsm.spectral_tramat_pathFromPath(Kd, None, r, Tlev, "linsrc")
+    assert np.array_equal(tl.L, ts.L)
+
+
+@pytest.mark.parametrize("targets", [(), (("T",), ("mag_u",))])
+def test_fused_polarised_linprop_zeeman(wsm, orc, targets):
+    """Zeeman-split O2 lines (full 4x4 propagation matrix), looking down so that the absorption rises along the path towards
+    the surface: the fused chain (first column of Lambda only: 8 complex Dawson evaluations per layer) and the fused
+    Jacobian pass against the oracle's un-fused restatement."""
+    c = synth.case_c3(nf=38 * 12, np_=9, los=(140.0, 30.0))
+    a = c.atm
+
+    def rev(x):
+        return None if x is None else np.ascontiguousarray(x[::-1])
+
+    # sensor above the path (level 0 = 80 km): the absorption rises away from the sensor; thin layers keep the gradient
+    # (K_{i+1} - K_i) / 2r above the reference's 1e-8 threshold in 45 % of the (frequency, layer) pairs
+    atm = abi.AtmPath(T=rev(a.T), P=rev(a.P), vmr=rev(a.vmr), isorat=rev(a.isorat), Q=rev(a.Q), dQdT=rev(a.dQdT), mag=rev(a.mag),
+                      los=rev(a.los))
+    r = np.ascontiguousarray(c.r[::-1]) * 0.02
+    Ir, dIr = orc.clearsky_emission(c.cat, c.f, atm, r, c.I_bkg, rte_option="linprop", targets=targets, hse_derivative=0)
+    I, dI = wsm.spectral_radClearskyEmission(c.cat, c.f, atm, r, c.I_bkg, rte_option="linprop", jac_targets=targets)
+    Is, _ = wsm.spectral_radClearskyEmission(c.cat, c.f, atm, r, c.I_bkg, rte_option="linsrc")
+    assert np.abs(I - Is).max() > 1e-2 * np.abs(I).max(), "fixture must reach the polarised Dawson branch"
+    np.testing.assert_allclose(I, Ir, rtol=0, atol=1e-10 * np.abs(Ir).max())
+    tb, tbr = wsm.spectral_radApplyPlanckTb(I, c.f), orc.planck_tb(c.f, Ir)
+    assert np.abs(tb[:, 0] - tbr[:, 0]).max() <= 1e-6
+    for q in range(len(targets)):
+        sc = np.abs(dIr[:, :, q, :]).max()
+        assert np.abs(dI[:, :, q, :] - dIr[:, :, q, :]).max() <= 1e-5 * sc

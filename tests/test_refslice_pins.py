@@ -40,6 +40,7 @@ def ref():
         getattr(L, n).argtypes = [C.c_double, C.c_double]
         getattr(L, n).restype = C.c_double
     L.refslice_tran.argtypes = [dp, dp, C.c_double, dp, dp]
+    L.refslice_sqrt_propmat.argtypes = [dp, dp]
     L.refslice_tramat.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, dp, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
     L.refslice_rte_emission.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [dp] * 9
     L.refslice_tmodel.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, dp, dp]
@@ -178,6 +179,60 @@ def test_tramat_with_derivatives_bitwise(ref, scale, option):
     if option == "linsrc":
         assert_same_bits(L, Lr, "L")
         assert_same_bits(dL, dLr, "dL")
+
+
+def test_sqrt_of_a_propagation_matrix_bitwise(ref):
+    """`specmat sqrt(const propmat&)` (rtepack_transmission.cc:872-1002), every branch: unpolarised, rotational (with and
+    without a rotation), the x2 + |y2| <= eps series, a <= eps, and the general case; and S*S gives the matrix back."""
+    L = orc.lib()
+    rng = np.random.default_rng(21)
+    ks = [np.array([0.3, 0, 0, 0, 0, 0, 0.]), np.array([0., 0, 0, 0, 1e-3, -2e-3, 5e-4]), np.array([0., 0, 0, 0, 0, 0, 1e-17]),
+          np.array([2e-17, 1e-9, 0, 0, 0, 0, 0.]), np.array([1e-3, 1e-9, -1e-9, 0, 1e-9, 0, 0.]), np.array([-0.2, 0.01, 0.02, -0.03, 0.004, 0.005, -0.006])]
+    for _ in range(300):
+        a = 10 ** rng.uniform(-9, 0)
+        ks.append(a * np.concatenate([[1.0], rng.uniform(-.3, .3, 6)]))
+        ks.append(a * np.concatenate([[1.0], rng.uniform(-.3, .3, 3), [0, 0, 0]]))
+        ks.append(a * np.concatenate([[rng.uniform(-1, 1)], rng.uniform(-1e-3, 1e-3, 6)]))
+    for k in ks:
+        k = np.ascontiguousarray(k)
+        a, b = np.empty(32), np.empty(32)
+        orc._check(L.orc_sqrt_propmat(dptr(k), dptr(a)))
+        ref.refslice_sqrt_propmat(dptr(k), dptr(b))
+        assert_same_bits(a, b, f"sqrt(propmat) for {k!r}")
+    k = np.array([0.5, 0.05, -0.02, 0.03, 0.01, -0.04, 0.02])
+    out = np.empty(32)
+    ref.refslice_sqrt_propmat(dptr(k), dptr(out))
+    S = (out[0::2] + 1j * out[1::2]).reshape(4, 4)
+    A, B, Cc, D, U, V, W = k
+    Km = np.array([[A, B, Cc, D], [B, A, U, V], [Cc, -U, A, W], [D, -V, -W, A]])
+    np.testing.assert_allclose(S @ S, Km, rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("scale", ["perf", "physical", "scalar", "gradient"])
+def test_tramat_linprop_bitwise(ref, scale):
+    """rte_option linprop (TransmittanceMatrix::linprop, rtepack_transmission.cc:1195-1252): tran::linsrc_linprop with its
+    polarised branch (complex matrix sqrt, inverse, element-wise Dawson, :467-474), the fall-back to linsrc below an
+    absorption gradient of 1e-8, and linsrc_linprop_deriv (closed form unpolarised, 1e-6 perturbation polarised)."""
+    rng = np.random.default_rng(23)
+    if scale == "gradient":  # physically scaled, absorption rising along the path so that most layers take the Dawson form
+        np_, nf, nq = 7, 129, 2
+        a = 10 ** rng.uniform(-6, -3.5, (1, nf, 1)) * (1.0 + np.arange(np_)[:, None, None] * rng.uniform(0.2, 3.0, (1, nf, 1)))
+        K = a * np.concatenate([np.ones((np_, nf, 1)), rng.uniform(-.2, .2, (np_, nf, 6))], axis=2)
+        K[:, ::5, 1:] = 0.0  # some unpolarised columns
+        dK = K[:, None] * rng.uniform(-1e-2, 1e-2, (np_, nq, nf, 7))
+        r = 10 ** rng.uniform(0.5, 2.5, np_ - 1)
+        dr = rng.uniform(0, 1, (2, np_ - 1, nq)) * r[None, :, None] / 500.0
+        K, dK, dr = np.ascontiguousarray(K), np.ascontiguousarray(dK), np.ascontiguousarray(dr)
+    else:
+        K, dK, r, dr = _random_path(rng, 9, 257, 3, scale)
+    T, L, P, dT, dL = orc.tramat(K, dK, r, dr, "linprop")
+    Tr, Lr, Pr, dTr, dLr = _ref_tramat(ref, K, dK, r, dr, 2)
+    if scale == "gradient":
+        assert np.mean((K[1:, :, 0] - K[:-1, :, 0]) / (2 * r[:, None]) >= 1e-8) > 0.5
+    assert_same_bits(T, Tr, "T")
+    assert_same_bits(dT, dTr, "dT")
+    assert_same_bits(L, Lr, "L")
+    assert_same_bits(dL, dLr, "dL")
 
 
 @pytest.mark.parametrize("scale", ["perf", "physical", "scalar"])

@@ -113,7 +113,7 @@ class PredefSpecies(C.Structure):
 
 
 PREDEF_MODELS = {"O2-SelfContStandardType": 0, "N2-SelfContStandardType": 1, "H2O-ForeignContStandardType": 2,
-                 "H2O-SelfContStandardType": 3}
+                 "H2O-SelfContStandardType": 3, "H2O-PWR98": 4, "O2-PWR98": 5, "H2O-MPM89": 6, "O2-MPM89": 7, "N2-SelfContMPM93": 8}
 
 
 def predef_args(models, species):

@@ -762,7 +762,7 @@ int ab200_path_add_predefined(ab200_path* p, const int32_t* models, int32_t n_mo
   AB_CUDA(cudaSetDevice(p->cat->device));
   return predef_on_path(models, n_models, species, target_d, p->nf, p->d_f, p->f_stride, p->d_ffac, p->d_T, p->d_P, p->d_vmr,
                         p->cat->n_species, p->select_species, p->d_K, p->d_dK, p->k_pitch, p->nq, p->tg_kind, p->tg_species, p->np,
-                        p->stream);
+                        p->d_flags, p->stream);
 }
 
 int ab200_path_add_cia(ab200_path* p, const ab200_cia* cia, double T_extrapolfac, int32_t ignore_errors, double dT) {
@@ -898,6 +898,9 @@ static int check_flags(ab200_path* p) {
   if (h) {
     cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->stream);
     if (h & 2) return set_error(AB200_ERR_INVALID, "non-finite line-shape parameter (f0', 1/GD, G0 or strength) at some level");
+    if (h & 32)  // PWR98.cc:363-370, MPM89.cc:345-352
+      return set_error(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold "
+                                          "of 1e-25.  Therefore no calculation is performed.");
     if (h & 16)
       return set_error(AB200_ERR_INVALID,
                        "Error in check_limit: a frequency, pressure, temperature offset or water ratio is outside the "

@@ -6,16 +6,26 @@
 //                   (O2 :51-84, N2 :118-138, H2O foreign :166-184, H2O self :212-226), the temperature row and the
 //                   CO2 / O2 / N2 / H2O / liquidcloud VMR rows by the reference's perturbation (model(x + d) - model(x)) / d.
 //
-// One thread per (frequency, level); HBM bound on K (16 B per element, + 16 B per affected Jacobian row).
+//                   The full microwave models — PWR98::water / oxygen (src/core/predefined/PWR98.cc:40-242, :297-434),
+//                   MPM89::water / oxygen (MPM89.cc:95-180, :270-411) — are resonant line lists (15 to 44 lines) plus a
+//                   continuum.  Their per-line strength, width and mixing terms depend on the level only (two `pow` and one
+//                   `exp` per line): the CTA evaluates them ONCE per (level, perturbed state) into shared memory and every
+//                   frequency then pays two divisions per line.  MPM93::nitrogen (MPM93.cc:33-73) is a closed form.
+//
+// One thread per (frequency, level); HBM bound on K (16 B per element, + 16 B per affected Jacobian row) for the closed-form
+// continua, arithmetic bound (2 x lines divisions per frequency and state) for the line lists.
 #include <cmath>
 
 #include "predef.hpp"
+
+#define AB200_TABLE_Q static __device__ const
+#include "predef_tables.h"
 
 namespace ab200 {
 
 struct PredefParams {
   int32_t n_models;
-  int32_t models[8];
+  int32_t models[16];
   ab200_predef_species sp;
   int64_t nf;
   const double* f;
@@ -29,13 +39,15 @@ struct PredefParams {
   int32_t nq, it;
   int32_t tg_kind[AB200_MAX_TARGETS], tg_species[AB200_MAX_TARGETS];
   double tg_d[AB200_MAX_TARGETS];
+  int* flags;  // device error flags (bit 5: an O2 mixing ratio below the full models' threshold)
 };
 
 struct PredefPoint {
   double T, P, o2, n2, h2o;
 };
 
-__device__ __forceinline__ double predef_model(int m, double f, const PredefPoint& a) {
+// ONE body (no inlining), like predef_line_model below: base and perturbed evaluations must round alike
+__device__ __noinline__ double predef_model(int m, double f, const PredefPoint& a) {
   switch (m) {
     case AB200_PREDEF_O2_SELFCONT_STANDARD: {  // Standard::oxygen
       constexpr double C = (1.108e-14 / (3.0e2 * 3.0e2));
@@ -56,6 +68,15 @@ __device__ __forceinline__ double predef_model(int m, double f, const PredefPoin
       const double dummy = C * pow(300. / a.T, x + 3) * a.P * pdry;
       return a.h2o * dummy * (f * f);
     }
+    case AB200_PREDEF_N2_SELFCONT_MPM93: {  // MPM93::nitrogen
+      constexpr double xT = 3.500, xf = 1.500, S = 2.296e-31;
+      const double G         = 1.930e-5 * pow(10.000, -9.000 * xf);
+      constexpr double fac   = 4.0 * 3.141592653589793238462643383279502884 / 299792458.0;
+      const double th        = 300.0 / a.T;
+      const double pd        = a.P * (1.0000 - a.h2o);
+      const double strength  = S * (pd * pd) * pow(th, xT);
+      return a.n2 * fac * strength * (f * f) / (1.000 + G * pow(f, xf)) * a.n2;
+    }
     default: {  // Standard::water_self
       constexpr double C = 1.796e-33, x = 4.5;
       const double dummy = C * pow(300. / a.T, x + 3) * (a.P * a.P) * a.h2o;
@@ -65,45 +86,220 @@ __device__ __forceinline__ double predef_model(int m, double f, const PredefPoin
 }
 
 __host__ __device__ inline int predef_species_of(int m, const ab200_predef_species& s) {
-  return m == AB200_PREDEF_O2_SELFCONT_STANDARD ? s.o2 : m == AB200_PREDEF_N2_SELFCONT_STANDARD ? s.n2 : s.h2o;
+  switch (m) {
+    case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: return s.o2;
+    case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: return s.n2;
+    default: return s.h2o;
+  }
+}
+__host__ __device__ inline bool predef_is_line_list(int m) { return m >= AB200_PREDEF_H2O_PWR98 && m <= AB200_PREDEF_O2_MPM89; }
+
+// ---- line-list models: per (level, state) tables in shared memory ----------------------------------------------------
+constexpr int PD_MAX_LINES  = 44;
+constexpr int PD_MAX_STATES = 1 + AB200_MAX_TARGETS;
+struct PredefTables {
+  double line[PD_MAX_STATES][PD_MAX_LINES][4];  // centre [GHz], strength, width, mixing term
+  double scal[PD_MAX_STATES][6];                // continuum and scale factors of the state
+};
+__device__ __forceinline__ int predef_nlines(int m) {
+  return m == AB200_PREDEF_H2O_PWR98 ? AB200_PWR98_H2O_LINES : m == AB200_PREDEF_O2_PWR98 ? AB200_PWR98_O2_LINES
+       : m == AB200_PREDEF_H2O_MPM89 ? AB200_MPM89_H2O_LINES : AB200_MPM89_O2_LINES;
+}
+// line l of model m at the point a: what depends on the level only
+__device__ __forceinline__ void predef_line_record(int m, int l, const PredefPoint& a, double* __restrict__ r) {
+  if (m == AB200_PREDEF_H2O_PWR98) {  // PWR98.cc:206-216
+    const double* c  = ab200_pwr98_h2o + 7 * l;
+    const double ti  = 300.0 / a.T;
+    const double pvap = 1e-2 * a.P * a.h2o, pda = (1e-2 * a.P) - pvap;
+    r[0] = c[0];
+    r[1] = c[1] * pow(ti, 2.5) * exp(c[2] * (1.0 - ti));
+    r[2] = (c[3] * pda * pow(ti, c[4])) + (c[5] * pvap * pow(ti, c[6]));
+    r[3] = 0.0;
+  } else if (m == AB200_PREDEF_O2_PWR98) {  // PWR98.cc:372-398
+    const double* c = ab200_pwr98_o2 + 6 * l;
+    const double TH = 3.0000e2 / a.T, TH1 = TH - 1.000e0, B = pow(TH, 0.80);
+    const double PRESWV = 1e-2 * (a.P * a.h2o), PRESDA = 1e-2 * (a.P * (1.000e0 - a.h2o));
+    const double DEN  = 0.001 * (PRESDA * B + 1.1 * PRESWV * TH);
+    const double DENS = 0.001 * (PRESDA + 1.1 * PRESWV) * TH;
+    r[0] = c[0];
+    r[1] = c[1] * exp(-c[4] * TH1);
+    r[2] = c[3] * ((fabs(c[0] - 118.75) < 0.10) ? DENS : DEN);
+    r[3] = 0.001 * 0.01 * a.P * B * (c[2] + c[5] * TH1);
+  } else if (m == AB200_PREDEF_H2O_MPM89) {  // MPM89.cc:160-170
+    const double* c    = ab200_mpm89_h2o + 7 * l;
+    const double theta = 300.0 / a.T, pwv_dummy = 1e-3 * a.P, pwv = pwv_dummy * a.h2o, pda = pwv_dummy - pwv;
+    r[0] = c[0];
+    r[1] = pwv_dummy * c[1] * pow(theta, 3.5) * exp(c[2] * (1.000 - theta));
+    r[2] = c[3] * 0.001 * (c[5] * pwv * pow(theta, c[6]) + pda * pow(theta, c[4]));
+    r[3] = 0.0;
+  } else {  // MPM89::oxygen, MPM89.cc:372-400
+    const double* c    = ab200_mpm89_o2 + 7 * l;
+    const double theta = 300.0 / a.T, pwv = 1e-3 * a.P * a.h2o, pda = (1e-3 * a.P) - pwv;
+    r[0] = c[0];
+    r[1] = c[1] * 1.000e-6 * pda * (theta * theta * theta) * exp(c[2] * (1.000 - theta)) / c[0];
+    r[2] = c[3] * 1.000e-3 * ((pda * pow(theta, 0.80 - c[4])) + (1.10 * pwv * theta));
+    r[3] = (c[5] + c[6] * theta) * 1.000e-3 * pda * pow(theta, 0.8);
+  }
+}
+__device__ __forceinline__ void predef_state_scalars(int m, const PredefPoint& a, double* __restrict__ s) {
+  if (m == AB200_PREDEF_H2O_PWR98) {
+    const double ti = 300.0 / a.T, pvap_dummy = 1e-2 * a.P, pvap = 1e-2 * a.P * a.h2o, pda = (1e-2 * a.P) - pvap;
+    s[0] = a.h2o;
+    s[1] = 3.335e16 * (2.1667 * a.P / a.T);                                                                  // den_dummy
+    s[2] = pvap_dummy * (ti * ti * ti) * 1.000e-9 * ((0.543 * pda) + (17.96 * pvap * pow(ti, 4.5)));         // con
+  } else if (m == AB200_PREDEF_O2_PWR98) {
+    const double TH = 3.0000e2 / a.T, B = pow(TH, 0.80);
+    const double PRESWV = 1e-2 * (a.P * a.h2o), PRESDA = 1e-2 * (a.P * (1.000e0 - a.h2o));
+    s[0] = a.o2;
+    s[1] = 1.23e-10 * (TH * TH) * a.P;                               // CCONT
+    s[2] = 0.56 * (0.001 * (PRESDA * B + 1.1 * PRESWV * TH));         // DFNR
+    s[3] = a.P;
+    s[4] = TH * TH * TH;
+  } else if (m == AB200_PREDEF_H2O_MPM89) {
+    const double theta = 300.0 / a.T, pwv_dummy = 1e-3 * a.P, pwv = pwv_dummy * a.h2o, pda = pwv_dummy - pwv;
+    s[0] = a.h2o;
+    s[1] = pwv_dummy * (theta * theta * theta) * 1.000e-5 * ((0.113 * pda) + (3.57 * pwv * pow(theta, 7.5)));  // Nppc
+  } else {
+    const double theta = 300.0 / a.T, pwv = 1e-3 * a.P * a.h2o, pda = (1e-3 * a.P) - pwv;
+    s[0] = a.o2;
+    s[1] = 6.140e-4 * pda * (theta * theta);           // strength_cont
+    s[2] = 5.60e-3 * (pwv + pda) * pow(theta, 0.800);  // gam_cont
+  }
+}
+// the model at frequency f [Hz] from the tables of one state.  ONE body (no inlining): the base and the perturbed evaluation of a
+// difference quotient must round alike, so that a target the model does not depend on gives an exact zero.
+__device__ __noinline__ double predef_line_model(int m, double f, const double (*__restrict__ L)[4], const double* __restrict__ s) {
+  const double ff = f * 1e-9;
+  if (m == AB200_PREDEF_H2O_PWR98) {
+    double sum = 0.0;
+    for (int l = 0; l < AB200_PWR98_H2O_LINES; l++) {
+      const double fl = L[l][0], width = L[l][2], wsq = width * width;
+      const double df0 = ff - fl, df1 = ff + fl;
+      const double base = width / (wsq + 562500.000);
+      double res = 0.0;
+      if (fabs(df0) < 750.0) res += width / (df0 * df0 + wsq) - base;
+      if (fabs(df1) < 750.0) res += width / (df1 * df1 + wsq) - base;
+      const double q = ff / fl;
+      sum += L[l][1] * res * (q * q);
+    }
+    const double absl = 0.3183e-4 * s[1] * sum;
+    return s[0] * 1.000e-3 * (absl + (s[2] * ff * ff));
+  }
+  if (m == AB200_PREDEF_O2_PWR98) {
+    if (s[0] == 0.) return 0.0;
+    const double DFNR = s[2];
+    const double CONT = s[1] * (ff * ff * DFNR / (ff * ff + DFNR * DFNR));
+    double SUM = 0.0;
+    for (int l = 0; l < AB200_PWR98_O2_LINES; l++) {
+      const double F = L[l][0], DF = L[l][2], Y = L[l][3];
+      const double SF1 = (DF + (ff - F) * Y) / ((ff - F) * (ff - F) + DF * DF);
+      const double SF2 = (DF - (ff + F) * Y) / ((ff + F) * (ff + F) + DF * DF);
+      SUM += L[l][1] * (SF1 + SF2) * (ff / F) * (ff / F);
+    }
+    return s[0] * (CONT + (2.414322e7 * SUM * s[3] * s[4] / 3.141592653589793238462643383279502884));
+  }
+  constexpr double dB_km_to_1_m = 1e-3 / (10.0 * 0.434294481903251827651128918916605082);
+  if (m == AB200_PREDEF_H2O_MPM89) {
+    auto term = [&](int l) {
+      const double fl = L[l][0], gam = L[l][2];
+      const double f_minus = 1.000 / ((ff - fl) * (ff - fl) + gam * gam);
+      const double f_plus  = 1.000 / ((ff + fl) * (ff + fl) + gam * gam);
+      return L[l][1] * (fabs(ff / fl) * gam * (f_minus + f_plus));
+    };
+    double acc = 0.0;  // the reference's std::transform_reduce adds in groups of four (libstdc++ <numeric>)
+    int l = 0;
+    for (; l + 4 <= AB200_MPM89_H2O_LINES; l += 4) acc += (term(l) + term(l + 1)) + (term(l + 2) + term(l + 3));
+    for (; l < AB200_MPM89_H2O_LINES; l++) acc += term(l);
+    return s[0] * dB_km_to_1_m * 0.1820 * ff * (acc + (s[1] * ff));
+  }
+  if (s[0] == 0.) return 0.0;
+  auto term = [&](int l) {
+    const double fl = L[l][0], gam = L[l][2], delta = L[l][3];
+    const double f_minus = (gam - delta * (fl - ff)) / ((fl - ff) * (fl - ff) + gam * gam);
+    const double f_plus  = (gam - delta * (fl + ff)) / ((fl + ff) * (fl + ff) + gam * gam);
+    return L[l][1] * (ff * (f_minus + f_plus));
+  };
+  double acc = 0.0;
+  for (int l = 0; l + 4 <= AB200_MPM89_O2_LINES; l += 4) acc += (term(l) + term(l + 1)) + (term(l + 2) + term(l + 3));
+  const double Nppc = s[1] * ff * s[2] / ((ff * ff) + (s[2] * s[2]));
+  return s[0] * dB_km_to_1_m * 0.1820 * ff * (((acc < 0.000) ? 0.0 : acc) + Nppc) / 0.2085;
 }
 
 __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
+  __shared__ PredefTables tab;
+  __shared__ PredefPoint pts[PD_MAX_STATES];
+  __shared__ int state_of[AB200_MAX_TARGETS];  // state of target q's perturbed point, 0 when the target does not move the point
+  __shared__ int nstates;
   const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (iv >= p.nf) return;
   const int lev = blockIdx.y;
-  const double f = (p.ffac ? p.ffac[lev] : 1.0) * p.f[int64_t(lev) * p.f_stride + iv];
   const double* __restrict__ vmr = p.vmr + int64_t(lev) * p.n_species;
   auto v = [&](int idx) { return idx >= 0 ? vmr[idx] : 0.0; };
   const PredefPoint a{p.T[lev], p.P[lev], v(p.sp.o2), v(p.sp.n2), v(p.sp.h2o)};
+  if (threadIdx.x == 0) {
+    // perturbed points: temperature target (:267-279), then the VMR targets of CO2, O2, N2, H2O, liquidcloud (:237-241, :300-314)
+    int n = 1;
+    pts[0] = a;
+    const int vmr_idx[5] = {p.sp.co2, p.sp.o2, p.sp.n2, p.sp.h2o, p.sp.liquidcloud};
+    for (int q = 0; q < p.nq; q++) {
+      state_of[q] = 0;
+      PredefPoint b = a;
+      bool moved = false, counted = false;
+      if (q == p.it) {
+        b.T += p.tg_d[q];
+        moved = counted = true;
+      } else if (p.tg_kind[q] == AB200_TARGET_VMR) {
+        bool first = true;  // jac_targets.find: the first target of that species
+        for (int q2 = 0; q2 < q; q2++) first = first && !(p.tg_kind[q2] == AB200_TARGET_VMR && p.tg_species[q2] == p.tg_species[q]);
+        for (int j = 0; j < 5 && first; j++)
+          if (vmr_idx[j] >= 0 && vmr_idx[j] == p.tg_species[q]) counted = true;
+        if (counted) {
+          const int idx = p.tg_species[q];
+          if (idx == p.sp.o2) b.o2 += p.tg_d[q], moved = true;
+          if (idx == p.sp.n2) b.n2 += p.tg_d[q], moved = true;
+          if (idx == p.sp.h2o) b.h2o += p.tg_d[q], moved = true;
+        }
+      }
+      if (moved) {
+        pts[n] = b;
+        state_of[q] = n++;
+      } else if (counted) {
+        state_of[q] = -1;  // a counted target that leaves the point alone: (model - model) / d = 0, nothing to add
+      } else {
+        state_of[q] = -2;  // not a target of this method
+      }
+    }
+    nstates = n;
+  }
+  __syncthreads();
+  const double f = iv < p.nf ? (p.ffac ? p.ffac[lev] : 1.0) * p.f[int64_t(lev) * p.f_stride + iv] : 1.0;
   double kacc = 0.0, dacc[AB200_MAX_TARGETS];
 #pragma unroll
   for (int q = 0; q < AB200_MAX_TARGETS; q++) dacc[q] = 0.0;
-  const int vmr_idx[5] = {p.sp.co2, p.sp.o2, p.sp.n2, p.sp.h2o, p.sp.liquidcloud};  // vmrs_jac order, :237-241
   for (int k = 0; k < p.n_models; k++) {
     const int m = p.models[k];
-    if (p.select_species != AB200_SPECIES_BATH && predef_species_of(m, p.sp) != p.select_species) continue;
-    const double pm = predef_model(m, f, a);
-    kacc += pm;
-    if (p.it >= 0) {
-      PredefPoint b = a;
-      b.T += p.tg_d[p.it];
-      dacc[p.it] += (predef_model(m, f, b) - pm) / p.tg_d[p.it];
+    if (p.select_species != AB200_SPECIES_BATH && predef_species_of(m, p.sp) != p.select_species) continue;  // CTA-uniform
+    const bool lines = predef_is_line_list(m);
+    if (lines) {
+      if ((m == AB200_PREDEF_O2_PWR98 || m == AB200_PREDEF_O2_MPM89) && threadIdx.x == 0)
+        for (int st = 0; st < nstates; st++)
+          if (pts[st].o2 != 0. && pts[st].o2 < 1.000e-25) atomicOr(p.flags, 32);
+      __syncthreads();  // the previous model's tables have been read
+      const int nl = predef_nlines(m);
+      for (int e = threadIdx.x; e < nstates * nl; e += blockDim.x) predef_line_record(m, e % nl, pts[e / nl], tab.line[e / nl][e % nl]);
+      if (threadIdx.x < nstates) predef_state_scalars(m, pts[threadIdx.x], tab.scal[threadIdx.x]);
+      __syncthreads();
     }
-    for (int j = 0; j < 5; j++) {
-      const int idx = vmr_idx[j];
-      if (idx < 0) continue;
-      for (int q = 0; q < p.nq; q++)
-        if (p.tg_kind[q] == AB200_TARGET_VMR && p.tg_species[q] == idx) {
-          PredefPoint b = a;
-          if (idx == p.sp.o2) b.o2 += p.tg_d[q];
-          if (idx == p.sp.n2) b.n2 += p.tg_d[q];
-          if (idx == p.sp.h2o) b.h2o += p.tg_d[q];
-          dacc[q] += (predef_model(m, f, b) - pm) / p.tg_d[q];
-          break;
-        }
+    if (iv >= p.nf) continue;
+    const double pm = lines ? predef_line_model(m, f, tab.line[0], tab.scal[0]) : predef_model(m, f, a);
+    kacc += pm;
+    for (int q = 0; q < p.nq; q++) {
+      const int st = state_of[q];
+      if (st <= 0) continue;
+      const double pq = lines ? predef_line_model(m, f, tab.line[st], tab.scal[st]) : predef_model(m, f, pts[st]);
+      dacc[q] += (pq - pm) / p.tg_d[q];
     }
   }
+  if (iv >= p.nf) return;
   p.K[(int64_t(lev) * p.k_pitch + iv) * 7] += kacc;
   for (int q = 0; q < p.nq; q++)
     if (dacc[q] != 0.0) p.dK[((int64_t(lev) * p.nq + q) * p.k_pitch + iv) * 7] += dacc[q];
@@ -112,20 +308,20 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
 // fills the model / species / target part of the parameters and validates it; 0 or an error code with the message set
 int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, const ab200_predef_species* sp, int32_t n_species, int32_t nq,
                  const int32_t* tg_kind, const int32_t* tg_species, const double* target_d) {
-  if (n_models < 0 || n_models > 8 || (n_models > 0 && !models) || !sp)
-    return set_error(AB200_ERR_INVALID, "predefined models: null argument or more than 8 models");
+  if (n_models < 0 || n_models > 16 || (n_models > 0 && !models) || !sp)
+    return set_error(AB200_ERR_INVALID, "predefined models: null argument or more than 16 models");
   pp.n_models = n_models;
   pp.sp = *sp;
   for (int idx : {sp->o2, sp->n2, sp->h2o, sp->co2, sp->liquidcloud})
     if (idx >= n_species) return set_error(AB200_ERR_INVALID, "predefined models: species index beyond the VMR vector");
   for (int k = 0; k < n_models; k++) {
     const int m = models[k];
-    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_H2O_SELFCONT_STANDARD)
+    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_N2_SELFCONT_MPM93)
       return set_error(AB200_ERR_UNSUPPORTED, "predefined model " + std::to_string(m) +
-                                                  " is outside the GPU path (only the four StandardType continua are; no CPU fallback)");
+                                                  " is outside the GPU path (the StandardType continua, PWR98, MPM89 and the MPM93 N2 "
+                                                  "continuum are; no CPU fallback)");
     const bool need_h2o = m != AB200_PREDEF_N2_SELFCONT_STANDARD;
-    if ((m == AB200_PREDEF_O2_SELFCONT_STANDARD && sp->o2 < 0) || (m == AB200_PREDEF_N2_SELFCONT_STANDARD && sp->n2 < 0) ||
-        (need_h2o && sp->h2o < 0))
+    if (predef_species_of(m, *sp) < 0 || (need_h2o && sp->h2o < 0))
       return set_error(AB200_ERR_INVALID, "predefined model " + std::to_string(m) + " needs a species the atmosphere does not carry");
     pp.models[k] = m;
   }
@@ -153,8 +349,9 @@ int launch_predef(const PredefParams& p, int nlev, cudaStream_t stream) {
 int predef_on_path(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, const double* target_d, int64_t nf,
                    const double* d_f, int64_t f_stride, const double* d_ffac, const double* d_T, const double* d_P, const double* d_vmr,
                    int32_t n_species, int32_t select_species, double* d_K, double* d_dK, int64_t k_pitch, int32_t nq,
-                   const int32_t* tg_kind, const int32_t* tg_species, int np, cudaStream_t stream) {
+                   const int32_t* tg_kind, const int32_t* tg_species, int np, int* d_flags, cudaStream_t stream) {
   PredefParams pp{};
+  pp.flags = d_flags;
   AB_TRY(predef_setup(pp, models, n_models, sp, n_species, nq, tg_kind, tg_species, target_d));
   pp.nf = nf; pp.f = d_f; pp.f_stride = f_stride; pp.ffac = d_ffac; pp.T = d_T; pp.P = d_P; pp.vmr = d_vmr;
   pp.n_species = n_species; pp.select_species = select_species; pp.K = d_K; pp.dK = d_dK; pp.k_pitch = k_pitch;
@@ -186,7 +383,10 @@ extern "C" int ab200_predef_levels(const int32_t* models, int32_t n_models, cons
       if (src && bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return 1; }
       return 0;
     }
-  } bf, bT, bP, bv, bK, bdK;
+  } bf, bT, bP, bv, bK, bdK, bflag;
+  const int zero = 0;
+  if (bflag.put(&zero, sizeof(int))) return set_error(AB200_ERR_NOMEM, "ab200_predef_levels: device allocation failed");
+  pp.flags = static_cast<int*>(bflag.p);
   const size_t nfl = static_cast<size_t>(nf) * (f_level_stride ? np : 1), nk = static_cast<size_t>(np) * nf * 7;
   if (bf.put(f, nfl * 8) || bT.put(atm->T, np * 8) || bP.put(atm->P, np * 8) || bv.put(atm->vmr, static_cast<size_t>(np) * n_species * 8) ||
       bK.put(K, nk * 8) || bdK.put(dK, nk * nq * 8))
@@ -196,6 +396,11 @@ extern "C" int ab200_predef_levels(const int32_t* models, int32_t n_models, cons
   pp.n_species = n_species; pp.select_species = select_species;
   pp.K = static_cast<double*>(bK.p); pp.dK = static_cast<double*>(bdK.p); pp.k_pitch = nf;
   AB_TRY(launch_predef(pp, np, nullptr));
+  int h_flag = 0;
+  AB_CUDA(cudaMemcpy(&h_flag, bflag.p, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h_flag & 32)
+    return set_error(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of "
+                                        "1e-25.  Therefore no calculation is performed.");
   AB_CUDA(cudaMemcpy(K, bK.p, nk * 8, cudaMemcpyDeviceToHost));
   if (nq > 0) AB_CUDA(cudaMemcpy(dK, bdK.p, nk * nq * 8, cudaMemcpyDeviceToHost));
   return AB200_OK;

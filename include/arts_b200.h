@@ -356,11 +356,17 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
  * (src/core/absorption/predefined_absorption_models.cc:219-317): the model's closed form added to K.A, the temperature row
  * by perturbation (model(T + d) - model(T)) / d and VMR rows by perturbation for targets of CO2, O2, N2, H2O and
  * liquidcloud only (:237-241, compute_vmr_deriv :202-216).  Models on the path: the four "StandardType" continua of
- * src/core/predefined/standard.cc (Rosenkranz 1993 / 1998); every other model name is AB200_ERR_UNSUPPORTED. */
+ * src/core/predefined/standard.cc (Rosenkranz 1993 / 1998) and the full microwave models PWR98 (H2O, O2), MPM89 (H2O, O2) and
+ * the MPM93 N2 continuum; every other model name is AB200_ERR_UNSUPPORTED. */
 #define AB200_PREDEF_O2_SELFCONT_STANDARD 0     /* "O2-SelfContStandardType",     Standard::oxygen        standard.cc:51-84 */
 #define AB200_PREDEF_N2_SELFCONT_STANDARD 1     /* "N2-SelfContStandardType",     Standard::nitrogen      :118-138 */
 #define AB200_PREDEF_H2O_FOREIGNCONT_STANDARD 2 /* "H2O-ForeignContStandardType", Standard::water_foreign :166-184 */
 #define AB200_PREDEF_H2O_SELFCONT_STANDARD 3    /* "H2O-SelfContStandardType",    Standard::water_self    :212-226 */
+#define AB200_PREDEF_H2O_PWR98 4          /* "H2O-PWR98",        PWR98::water    src/core/predefined/PWR98.cc:40-242  (15 lines + continuum) */
+#define AB200_PREDEF_O2_PWR98 5           /* "O2-PWR98",         PWR98::oxygen   PWR98.cc:297-434 (40 lines with mixing + dry continuum) */
+#define AB200_PREDEF_H2O_MPM89 6          /* "H2O-MPM89",        MPM89::water    MPM89.cc:95-180  (30 lines + continuum) */
+#define AB200_PREDEF_O2_MPM89 7           /* "O2-MPM89",         MPM89::oxygen   MPM89.cc:270-411 (44 lines with mixing + Debye term) */
+#define AB200_PREDEF_N2_SELFCONT_MPM93 8  /* "N2-SelfContMPM93", MPM93::nitrogen MPM93.cc:33-73 */
 typedef struct ab200_predef_species { /* indices into the vmr vector, -1 when the atmosphere does not carry the species */
   int32_t o2, n2, h2o, co2, liquidcloud;
 } ab200_predef_species;

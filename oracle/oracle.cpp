@@ -42,6 +42,7 @@
 #include <vector>
 
 #include "../include/arts_b200.h"
+#include "../arts_b200/csrc/predef_tables.h"  // published line lists of PWR98 / MPM89 (data only; pinned through the sliced reference)
 
 namespace Faddeeva {
 // reference 3rdparty/Faddeeva/Faddeeva.hh:36
@@ -2644,15 +2645,128 @@ Numeric model(int m, Numeric f, const Pt& a) {
       const Numeric dummy = C * pow(300. / a.T, x + 3) * a.P * pdry;
       return a.h2o * dummy * pow2(f);
     }
-    default: {  // Standard::water_self :212-226
+    case AB200_PREDEF_H2O_SELFCONT_STANDARD: {  // Standard::water_self :212-226
       constexpr Numeric C = 1.796e-33, x = 4.5;
       const Numeric dummy = C * pow(300. / a.T, x + 3) * pow2(a.P) * a.h2o;
       return a.h2o * dummy * pow2(f);
     }
+    case AB200_PREDEF_H2O_PWR98: {  // PWR98::water, src/core/predefined/PWR98.cc:40-242
+      const Numeric t = a.T, p_pa = a.P, vmr = a.h2o;
+      const Numeric pvap_dummy = 1e-2 * p_pa;
+      const Numeric pvap       = 1e-2 * p_pa * vmr;
+      const Numeric pda        = (1e-2 * p_pa) - pvap;
+      const Numeric den_dummy  = 3.335e16 * (2.1667 * p_pa / t);
+      const Numeric ti         = (300.0 / t);
+      const Numeric ti2        = pow(ti, 2.5);
+      const Numeric con        = pvap_dummy * pow3(ti) * 1.000e-9 * ((0.543 * pda) + (17.96 * pvap * pow(ti, 4.5)));
+      const Numeric ff         = f * 1e-9;
+      Numeric sum              = 0.000;
+      for (int l = 0; l < AB200_PWR98_H2O_LINES; l++) {
+        const Numeric* c       = ab200_pwr98_h2o + 7 * l;  // fl, s1, b2, w3, x, ws, xs
+        const Numeric width    = (c[3] * pda * pow(ti, c[4])) + (c[5] * pvap * pow(ti, c[6]));
+        const Numeric wsq      = width * width;
+        const Numeric strength = c[1] * ti2 * std::exp(c[2] * (1.0 - ti));
+        const Numeric df0 = ff - c[0], df1 = ff + c[0];
+        const Numeric base = width / (wsq + 562500.000);  // Clough's local line definition: 750 GHz cutoff
+        Numeric res        = 0.000;
+        if (std::fabs(df0) < 750.0) res += width / (df0 * df0 + wsq) - base;
+        if (std::fabs(df1) < 750.0) res += width / (df1 * df1 + wsq) - base;
+        sum += strength * res * pow2(ff / c[0]);
+      }
+      const Numeric absl = 0.3183e-4 * den_dummy * sum;
+      return vmr * 1.000e-3 * (absl + (con * ff * ff));
+    }
+    case AB200_PREDEF_O2_PWR98: {  // PWR98::oxygen, PWR98.cc:297-434
+      const Numeric t = a.T, p_pa = a.P, vmr = a.o2, h2o = a.h2o;
+      constexpr Numeric WB300 = 0.56, X = 0.80;
+      if (vmr == 0.) return 0.0;
+      const Numeric TH = 3.0000e2 / t, TH1 = (TH - 1.000e0), B = pow(TH, X);
+      const Numeric PRESWV = 1e-2 * (p_pa * h2o);
+      const Numeric PRESDA = 1e-2 * (p_pa * (1.000e0 - h2o));
+      const Numeric DEN    = 0.001 * (PRESDA * B + 1.1 * PRESWV * TH);
+      const Numeric DENS   = 0.001 * (PRESDA + 1.1 * PRESWV) * TH;
+      const Numeric DFNR   = WB300 * DEN;
+      const Numeric CCONT  = 1.23e-10 * pow2(TH) * p_pa;
+      const Numeric ff     = 1e-9 * f;
+      const Numeric CONT   = CCONT * (ff * ff * DFNR / (ff * ff + DFNR * DFNR));
+      Numeric SUM          = 0.000e0;
+      for (int l = 0; l < AB200_PWR98_O2_LINES; ++l) {
+        const Numeric* c = ab200_pwr98_o2 + 6 * l;  // F, S300, Y300, W300, BE, V
+        const Numeric DF  = c[3] * ((std::fabs((c[0] - 118.75)) < 0.10) ? DENS : DEN);
+        const Numeric Y   = 0.001 * 0.01 * p_pa * B * (c[2] + c[5] * TH1);
+        const Numeric STR = c[1] * std::exp(-c[4] * TH1);
+        const Numeric SF1 = (DF + (ff - c[0]) * Y) / ((ff - c[0]) * (ff - c[0]) + DF * DF);
+        const Numeric SF2 = (DF - (ff + c[0]) * Y) / ((ff + c[0]) * (ff + c[0]) + DF * DF);
+        SUM += STR * (SF1 + SF2) * (ff / c[0]) * (ff / c[0]);
+      }
+      return vmr * (CONT + (2.414322e7 * SUM * p_pa * pow3(TH) / Constant::pi));
+    }
+    case AB200_PREDEF_H2O_MPM89: {  // MPM89::water, MPM89.cc:95-180, line shape :36-65
+      constexpr Numeric dB_km_to_1_m = (1e-3 / (10.0 * std::numbers::log10e));  // Constant::log10_euler
+      const Numeric t = a.T, p_pa = a.P, vmr = a.h2o;
+      const Numeric pwv_dummy = 1e-3 * p_pa;
+      const Numeric theta     = (300.0 / t);
+      const Numeric pwv       = pwv_dummy * vmr;
+      const Numeric pda       = pwv_dummy - pwv;
+      const Numeric Nppc      = pwv_dummy * pow3(theta) * 1.000e-5 * ((0.113 * pda) + (3.57 * pwv * pow(theta, 7.5)));
+      const Numeric ff        = f * 1e-9;
+      struct Row { Numeric v[7]; };
+      const Row* rows = reinterpret_cast<const Row*>(ab200_mpm89_h2o);
+      const Numeric Nppl = std::transform_reduce(rows, rows + AB200_MPM89_H2O_LINES, 0.0, std::plus{}, [&](const Row& r) {
+        const Numeric* l       = r.v;
+        const Numeric strength = pwv_dummy * l[1] * pow(theta, 3.5) * std::exp(l[2] * (1.000 - theta));
+        const Numeric gam      = l[3] * 0.001 * (l[5] * pwv * pow(theta, l[6]) + pda * pow(theta, l[4]));
+        const Numeric f_minus  = 1.000 / ((ff - l[0]) * (ff - l[0]) + gam * gam);
+        const Numeric f_plus   = 1.000 / ((ff + l[0]) * (ff + l[0]) + gam * gam);
+        return strength * (std::fabs(ff / l[0]) * gam * (f_minus + f_plus));
+      });
+      return vmr * dB_km_to_1_m * 0.1820 * ff * (Nppl + (Nppc * ff));
+    }
+    case AB200_PREDEF_O2_MPM89: {  // MPM89::oxygen, MPM89.cc:270-411, line shape :207-235
+      constexpr Numeric dB_km_to_1_m = (1e-3 / (10.0 * std::numbers::log10e));
+      const Numeric t = a.T, p_pa = a.P, vmr = a.o2, h2o = a.h2o;
+      const Numeric S0 = 6.140e-4, G0 = 5.60e-3, X0 = 0.800, VMRISO = 0.2085;
+      if (vmr == 0.) return 0.0;
+      const Numeric theta = (300.0 / t);
+      const Numeric pwv   = 1e-3 * p_pa * h2o;
+      const Numeric pda   = (1e-3 * p_pa) - pwv;
+      const Numeric strength_cont = S0 * pda * pow2(theta);
+      const Numeric gam_cont      = G0 * (pwv + pda) * pow(theta, X0);
+      const Numeric ff            = f * 1e-9;
+      const Numeric Nppc          = strength_cont * ff * gam_cont / (pow2(ff) + pow2(gam_cont));
+      struct Row { Numeric v[7]; };
+      const Row* rows = reinterpret_cast<const Row*>(ab200_mpm89_o2);
+      const Numeric Nppl = std::transform_reduce(rows, rows + AB200_MPM89_O2_LINES, 0.0, std::plus{}, [&](const Row& r) {
+        const Numeric* l       = r.v;
+        const Numeric strength = l[1] * 1.000e-6 * pda * pow3(theta) * std::exp(l[2] * (1.000 - theta)) / l[0];
+        const Numeric gam      = (l[3] * 1.000e-3 * ((pda * pow(theta, (0.80 - l[4]))) + (1.10 * pwv * theta)));
+        const Numeric delta    = ((l[5] + l[6] * theta) * 1.000e-3 * pda * pow(theta, 0.8));
+        const Numeric f_minus  = (gam - delta * (l[0] - ff)) / ((l[0] - ff) * (l[0] - ff) + gam * gam);
+        const Numeric f_plus   = (gam - delta * (l[0] + ff)) / ((l[0] + ff) * (l[0] + ff) + gam * gam);
+        return strength * (ff * (f_minus + f_plus));
+      });
+      return vmr * dB_km_to_1_m * 0.1820 * ff * (((Nppl < 0.000) ? 0.0 : Nppl) + Nppc) / VMRISO;
+    }
+    default: {  // MPM93::nitrogen, MPM93.cc:33-73
+      constexpr Numeric xT = 3.500, xf = 1.500, gxf = 9.000 * xf, S = 2.296e-31;
+      static const Numeric G = 1.930e-5 * pow(10.000, -gxf);
+      constexpr Numeric fac  = 4.0 * Constant::pi / Constant::c;
+      const Numeric th       = 300.0 / a.T;
+      const Numeric strength = S * pow((a.P * (1.0000 - a.h2o)), 2.0) * pow(th, xT);
+      return a.n2 * fac * strength * pow(f, 2.0) / (1.000 + G * pow(f, xf)) * a.n2;
+    }
   }
 }
 int species_of(int m, const ab200_predef_species& s) {  // isot.spec of the model tag
-  return m == AB200_PREDEF_O2_SELFCONT_STANDARD ? s.o2 : m == AB200_PREDEF_N2_SELFCONT_STANDARD ? s.n2 : s.h2o;
+  switch (m) {
+    case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: return s.o2;
+    case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: return s.n2;
+    default: return s.h2o;
+  }
+}
+// the full O2 models refuse a non-zero O2 mixing ratio below 1e-25 (PWR98.cc:363-370, MPM89.cc:345-352)
+bool o2_vmr_refused(int m, const Pt& a) {
+  return (m == AB200_PREDEF_O2_PWR98 or m == AB200_PREDEF_O2_MPM89) and a.o2 != 0. and a.o2 < 1.000e-25;
 }
 }  // namespace predef
 
@@ -2672,7 +2786,9 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
     const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o)};
     for (int k = 0; k < n_models; k++) {
       const int m = models[k];
-      if (m < 0 or m > AB200_PREDEF_H2O_SELFCONT_STANDARD) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (m < 0 or m > AB200_PREDEF_N2_SELFCONT_MPM93) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (predef::o2_vmr_refused(m, a))
+        return fail(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of 1e-25");
       if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;
       for (Index i = 0; i < nf; i++) {
         const Numeric pm = predef::model(m, f[i], a);

@@ -68,6 +68,18 @@ SLICES = {
     "single_shape_derivs": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"single_shape::zFdF::zFdF\(const Complex z_\)", r"Complex single_shape::dY\(const Complex ds_dY, const Numeric f\) const \{", (270, 339), "block"),
 }
 
+# the full microwave absorption models (second translation unit, refslice/template_predef.cpp.in)
+SLICES_PREDEF = {
+    "pwr98_water": ("src/core/predefined/PWR98.cc", r"void water\(PropmatVector& propmat_clearsky,", None, (40, 242), "block"),
+    "pwr98_oxygen": ("src/core/predefined/PWR98.cc", r"void oxygen\(PropmatVector& propmat_clearsky,", None, (297, 434), "block"),
+    "mpm89_lineshape_h2o": ("src/core/predefined/MPM89.cc", r"constexpr Numeric MPMLineShapeFunction\(const Numeric gamma,", None, (34, 65), "block"),
+    "mpm89_water": ("src/core/predefined/MPM89.cc", r"void water\(PropmatVector& propmat_clearsky,", None, (95, 180), "block"),
+    "mpm89_lineshape_o2": ("src/core/predefined/MPM89.cc", r"constexpr Numeric MPMLineShapeO2Function\(const Numeric gamma,", None, (203, 236), "block"),
+    "mpm89_oxygen": ("src/core/predefined/MPM89.cc", r"void oxygen\(PropmatVector& propmat_clearsky,", None, (270, 411), "block"),
+    "mpm93_nitrogen": ("src/core/predefined/MPM93.cc", r"void nitrogen\(PropmatVector& propmat_clearsky,", None, (33, 73), "block"),
+}
+SLICES.update(SLICES_PREDEF)
+
 
 def _strip_for_braces(line: str) -> str:
     """Drop // comments, string and character literals before counting braces."""
@@ -130,11 +142,8 @@ def cut(ref, name):
     return rel, found, text
 
 
-def main():
-    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
-    out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(HERE, "_ref")
-    os.makedirs(out_dir, exist_ok=True)
-    with open(os.path.join(HERE, "refslice", "template.cpp.in")) as fh:
+def generate(ref, out_dir, template, out_name, names):
+    with open(os.path.join(HERE, "refslice", template)) as fh:
         tpl = fh.read().split("\n")
     manifest, out, used = {}, [], set()
     for ln in tpl:
@@ -149,14 +158,23 @@ def main():
         out.append(f"//>>> SLICE {name}: {rel}:{found[0]}-{found[1]}")
         out.extend(text)
         out.append(f"//<<< SLICE {name}")
-    unused = set(SLICES) - used
+    unused = set(names) - used
     if unused:
-        raise SystemExit(f"slice_ref: slices never placed by the template: {sorted(unused)}")
-    with open(os.path.join(out_dir, "refslice_gen.cpp"), "w") as fh:
+        raise SystemExit(f"slice_ref: slices never placed by {template}: {sorted(unused)}")
+    with open(os.path.join(out_dir, out_name), "w") as fh:
         fh.write("\n".join(out))
+    return manifest
+
+
+def main():
+    ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(HERE, "_ref")
+    os.makedirs(out_dir, exist_ok=True)
+    manifest = generate(ref, out_dir, "template.cpp.in", "refslice_gen.cpp", set(SLICES) - set(SLICES_PREDEF))
+    manifest.update(generate(ref, out_dir, "template_predef.cpp.in", "refslice_predef_gen.cpp", set(SLICES_PREDEF)))
     with open(os.path.join(out_dir, "refslice_manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
-    print(f"slice_ref: {len(manifest)} slices, {sum(v['lines'] for v in manifest.values())} reference lines -> {out_dir}/refslice_gen.cpp")
+    print(f"slice_ref: {len(manifest)} slices, {sum(v['lines'] for v in manifest.values())} reference lines -> {out_dir}/refslice_gen.cpp, refslice_predef_gen.cpp")
 
 
 if __name__ == "__main__":

@@ -68,3 +68,74 @@ def test_lines_plus_continua_on_the_resident_path(wsm, orc):
     for q in range(2):
         assert_jac_close(dI[:, :, q], dIr[:, :, q], rtol=5e-7, what=f"lines + continua dI target {q}")
     path.close(); cat.close()
+
+
+FULL_MODELS = ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93"]
+
+
+@pytest.mark.parametrize("models", [["H2O-PWR98", "O2-PWR98", "N2-SelfContMPM93"], ["H2O-MPM89", "O2-MPM89"], FULL_MODELS + MODELS])
+def test_full_microwave_models_host_buffers(wsm, orc, models):
+    """PWR98 (H2O, O2), MPM89 (H2O, O2), MPM93 N2: the per-level line tables the CTA builds in shared memory against the
+    oracle's per-frequency restatement (itself pinned bit for bit to the reference's object code, tests/test_refslice_pins.py),
+    every level of a 9-level profile, 1-1000 GHz with the 60 GHz band resolved, temperature + three VMR rows."""
+    f = np.sort(np.concatenate([np.linspace(1e9, 1e12, 1500), np.linspace(50e9, 70e9, 700), np.linspace(118.2e9, 119.3e9, 60)]))
+    atm = _atm(9)
+    tg, d = (("T",), ("VMR", 0), ("VMR", 1), ("VMR", 2)), (0.1, 1e-6, 1e-4, 1e-4)
+    for sel in (abi.SPECIES_BATH, 0, 1):
+        Kr, dKr = orc.predef_levels(models, SPECIES, f, atm, select_species=sel, targets=tg, target_d=d)
+        K = np.zeros((atm.np_, len(f), 7)); dK = np.zeros((atm.np_, 4, len(f), 7))
+        wsm.spectral_propmatAddPredefined(K, dK, models, sel, tg, f, atm, SPECIES, target_d=d)
+        sc = np.abs(Kr[..., 0]).max(axis=1, keepdims=True)
+        # 1e-9 of the element where the absorption is not a near-cancelling sum of positive and negative mixing terms
+        assert (np.abs(K[..., 0] - Kr[..., 0]) <= 1e-11 * np.abs(Kr[..., 0]) + 1e-14 * sc).all()
+        for q in range(4):
+            err, dsc = np.abs(dK[:, q, :, 0] - dKr[:, q, :, 0]).max(), np.abs(dKr[:, q, :, 0]).max()
+            assert err <= 2e-6 * dsc, (models, sel, q, err, dsc)
+        assert not K[..., 1:].any() and not dK[..., 1:].any()
+    assert Kr[..., 0].max() > 0
+
+
+def test_full_o2_models_refuse_a_tiny_o2_mixing_ratio(wsm):
+    f = np.linspace(50e9, 70e9, 300)
+    atm = _atm(3)
+    atm.vmr[1, 1] = 1e-26
+    K = np.zeros((3, len(f), 7))
+    for m in ("O2-PWR98", "O2-MPM89"):
+        with pytest.raises(wsm.Ab200Error, match="below the threshold"):
+            wsm.spectral_propmatAddPredefined(K, None, [m], abi.SPECIES_BATH, (), f, atm, SPECIES)
+    atm.vmr[1, 1] = 0.0  # exactly zero: the models add nothing at that level (PWR98.cc:359-361)
+    wsm.spectral_propmatAddPredefined(K, None, ["O2-PWR98", "O2-MPM89"], abi.SPECIES_BATH, (), f, atm, SPECIES)
+    assert not K[1].any() and K[0, :, 0].min() > 0
+
+
+def test_microwave_window_tb_with_full_models(wsm, orc):
+    """A clear-sky microwave spectrum made of the full models alone (no catalog lines): K from PWR98 + MPM93 on the resident
+    path, fused Stokes chain, brightness temperatures within 1e-6 K of the oracle's un-fused chain."""
+    c = synth.tiny_case(nl=8, nf=900, np_=12, targets=())
+    f = np.linspace(10e9, 200e9, 900)
+    species = {"H2O": 0, "O2": 1}
+    models = ["H2O-PWR98", "O2-PWR98"]
+    K = np.zeros((c.np_, 900, 7))
+    orc.predef_levels(models, species, f, c.atm, K=K)
+    T, L, P, dT, dL = orc.tramat(K, None, c.r, None, "linsrc")
+    J, dJ = orc.srcvec(K, f, c.atm.T, -1, 0)
+    bkg = np.zeros((900, 4)); bkg[:, 0] = synth.planck(f, 2.725)
+    Ir, _ = orc.rte_emission("linsrc", T, L, P, dT, dL, J, dJ, bkg)
+    cat = wsm.Catalog(c.cat)
+    path = wsm.Path(cat, 900, c.np_, 0)
+    path.upload(f, c.atm, c.r, bkg)
+    path.run_propmat()
+    path.add_predefined(models, species)
+    path.run_stokes()
+    I = np.empty((900, 4)); Kg = np.empty((c.np_, 900, 7))
+    path.download(I=I, K=Kg)
+    Kl, _ = orc.propmat_levels(c.cat, f, c.atm)
+    np.testing.assert_allclose(Kg[..., 0], K[..., 0] + Kl[..., 0], rtol=1e-9)
+    K2 = K + Kl
+    T, L, P, dT, dL = orc.tramat(K2, None, c.r, None, "linsrc")
+    J, dJ = orc.srcvec(K2, f, c.atm.T, -1, 0)
+    Ir, _ = orc.rte_emission("linsrc", T, L, P, dT, dL, J, dJ, bkg)
+    tb, tbr = wsm.spectral_radApplyPlanckTb(I, f), orc.planck_tb(f, Ir)
+    assert np.abs(tb - tbr).max() <= 1e-6
+    assert tb[:, 0].max() - tb[:, 0].min() > 20.0  # the 22, 60, 118 and 183 GHz features are there
+    path.close(); cat.close()

@@ -41,6 +41,7 @@ def ref():
         getattr(L, n).restype = C.c_double
     L.refslice_tran.argtypes = [dp, dp, C.c_double, dp, dp]
     L.refslice_sqrt_propmat.argtypes = [dp, dp]
+    L.refslice_predef.argtypes = [C.c_int32, C.c_int64, dp] + [C.c_double] * 5 + [dp]
     L.refslice_tramat.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, dp, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
     L.refslice_rte_emission.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [dp] * 9
     L.refslice_tmodel.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, dp, dp]
@@ -373,3 +374,37 @@ def test_shape_evaluation_and_fd_derivative_bitwise(ref):
         assert_same_bits(out[:, 0:2], outr[:, 0:2], "s * F(f)")
         assert_same_bits(out[:, 2:4], outr[:, 2:4], "dF(f)")
         assert_same_bits(out[:, 4:6], outr[:, 4:6], "single_shape::dT(ds, dz, dz_fac, f)")
+
+
+@pytest.mark.parametrize("model", ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93"])
+def test_full_microwave_absorption_models_bitwise(ref, model):
+    """f2: the oracle's restatement of PWR98::water / oxygen (src/core/predefined/PWR98.cc:40-242, :297-434), MPM89::water /
+    oxygen (MPM89.cc:95-180, :270-411) and MPM93::nitrogen (MPM93.cc:33-73), with the line lists of
+    arts_b200/csrc/predef_tables.h, against the reference's own object code over 1-1000 GHz and surface-to-mesosphere points,
+    every bit: a wrong digit in a coefficient table cannot pass."""
+    from arts_b200 import _abi as abi
+    rng = np.random.default_rng(29)
+    f = np.ascontiguousarray(np.concatenate([np.linspace(1e9, 1000e9, 700), rng.uniform(50e9, 70e9, 200), rng.uniform(0.1e9, 1.2e12, 100)]))
+    mid = abi.PREDEF_MODELS[model]
+    for k in range(40):
+        T = rng.uniform(180, 320)
+        P = 10 ** rng.uniform(0.5, 5.05)
+        o2, n2, h2o = 0.21 * rng.uniform(0.5, 1.1), 0.78 * rng.uniform(0.5, 1.1), 10 ** rng.uniform(-6, -1.4)
+        if k == 7:
+            h2o = 0.0
+        if k == 9:
+            o2 = 0.0  # the full O2 models return without adding anything
+        atm = abi.AtmPath(T=np.array([T]), P=np.array([P]), vmr=np.array([[o2, n2, h2o]]), isorat=np.ones((1, 1)), Q=np.ones((1, 1)))
+        K, _ = orc.predef_levels([model], {"O2": 0, "N2": 1, "H2O": 2}, f, atm)
+        A = np.zeros(len(f))
+        assert ref.refslice_predef(mid, len(f), dptr(f), T, P, o2, n2, h2o, dptr(A)) == 0
+        assert_same_bits(K[0, :, 0], A, f"{model} at T={T} P={P} vmr=({o2}, {n2}, {h2o})")
+        assert np.all(K[0, :, 1:] == 0)
+        if k not in (7, 9):
+            assert A.max() > 0
+    if model.startswith("O2-") and "Cont" not in model:  # vmr below 1e-25: the reference's user error, and the oracle's
+        A = np.zeros(len(f))
+        assert ref.refslice_predef(mid, len(f), dptr(f), 250.0, 1e4, 1e-26, 0.78, 1e-3, dptr(A)) == 1
+        atm = abi.AtmPath(T=np.array([250.0]), P=np.array([1e4]), vmr=np.array([[1e-26, 0.78, 1e-3]]), isorat=np.ones((1, 1)), Q=np.ones((1, 1)))
+        with pytest.raises(Exception):
+            orc.predef_levels([model], {"O2": 0, "N2": 1, "H2O": 2}, f, atm)

@@ -473,67 +473,100 @@ __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffe
     // w(z), so the lanes run the same branch; 32 neighbouring frequencies of a coarse grid do not.  Lane k sums the lines
     // k mod 16 of every second needed cluster in catalog order and a fixed shuffle tree adds the 32 partial sums: the value
     // depends on the frequency and the catalog only.
+    int64_t a = seg.tile_begin, lo = seg.tile_begin;
+    const int half = lane >> 4, k16 = lane & 15;
 #pragma unroll 1
     for (int j = 0; j < 32; j++) {
       const double f = __shfl_sync(0xffffffffu, f_own, j);
       // Tiles that may be needed: |f - c_t| <= U_t, the last distance at which the tile does not serve a frequency.  scan
       // holds the running maximum of c + U from the segment's first tile and the running minimum of c - U from its last
-      // (lbl_fmm_scan_kernel), both monotone whatever the order of the shifted line centres: two bisections bracket them.
-      int64_t a = seg.tile_begin, b = seg.tile_end;
-      while (a < b) {  // first tile with max_{t' <= t}(c + rho) >= f
-        const int64_t m = (a + b) >> 1;
-        if (__ldg(scan + 2 * m) < f) a = m + 1;
-        else b = m;
+      // (lbl_fmm_scan_kernel), both monotone whatever the order of the shifted line centres, so the bracket is
+      //   a = first tile with max_{t' <= t}(c + U) >= f,      end = max(a, first tile with min_{t' >= t}(c - U) > f).
+      // The warp's first frequency finds it by two bisections; the next ones walk from their neighbour's bracket (a grid is
+      // ascending: usually zero or one step instead of two dozen dependent loads).
+      if (j == 0) {
+        int64_t b = seg.tile_end;
+        while (a < b) {
+          const int64_t m = (a + b) >> 1;
+          if (__ldg(scan + 2 * m) < f) a = m + 1;
+          else b = m;
+        }
+        int64_t hi = seg.tile_end;
+        while (lo < hi) {
+          const int64_t m = (lo + hi) >> 1;
+          if (__ldg(scan + 2 * m + 1) <= f) lo = m + 1;
+          else hi = m;
+        }
+      } else {
+        while (a < seg.tile_end && __ldg(scan + 2 * a) < f) a++;
+        while (a > seg.tile_begin && !(__ldg(scan + 2 * (a - 1)) < f)) a--;
+        while (lo < seg.tile_end && __ldg(scan + 2 * lo + 1) <= f) lo++;
+        while (lo > seg.tile_begin && !(__ldg(scan + 2 * (lo - 1) + 1) <= f)) lo--;
       }
-      int64_t lo = a, hi = seg.tile_end;
-      while (lo < hi) {  // first tile with min_{t' >= t}(c - rho) > f
-        const int64_t m = (lo + hi) >> 1;
-        if (__ldg(scan + 2 * m + 1) <= f) lo = m + 1;
-        else hi = m;
-      }
+      const int64_t t_end = lo > a ? lo : a;
       double acc = 0.0;
-      for (int64_t t = a; t < lo; t++) {
-        bool ann;
-        const double* __restrict__ r2 = L2 + t * MOM_DOUBLES;
-        const double2 c2 = __ldg(reinterpret_cast<const double2*>(r2));
-        if (fmm_served(fabs(__dsub_rn(f, c2.x)), c2.y, __ldg(r2 + MOM_IN), __ldg(r2 + MOM_OUT), ann)) continue;  // in the far-field sum
-        const double* __restrict__ g0 = prep + t * tile_doubles();
-        const int count = p.tile_count[t];
+      // Two tiles = 32 clusters of 16 lines per step: lane (h, q) tests cluster q of tile t0 + h against the frequency - its
+      // own acceptance data and that of its 64-line and 256-line parents, three independent loads - and a ballot collects the
+      // clusters whose lines must be summed pair by pair.  (The tests used to run one after the other down the tree: some
+      // forty dependent round trips to L2 per frequency, which is what the pass was waiting on.)
 #pragma unroll 1
-        for (int s = 0; s < 4; s++) {
-          const double* __restrict__ r1 = L1 + (t * 4 + s) * MOM_DOUBLES;
+      for (int64_t t0 = a; t0 < t_end; t0 += 2) {
+        const int64_t tt = t0 + half;
+        bool need = tt < t_end;
+        int count = 0;
+        if (need) {
+          bool ann;
+          const double* __restrict__ r2 = L2 + tt * MOM_DOUBLES;
+          const double* __restrict__ r1 = L1 + (tt * 4 + (k16 >> 2)) * MOM_DOUBLES;
+          const double* __restrict__ r0 = L0 + (tt * 16 + k16) * MOM_DOUBLES;
+          const double2 c2 = __ldg(reinterpret_cast<const double2*>(r2));
           const double2 c1 = __ldg(reinterpret_cast<const double2*>(r1));
-          if (fmm_served(fabs(__dsub_rn(f, c1.x)), c1.y, __ldg(r1 + MOM_IN), __ldg(r1 + MOM_OUT), ann)) continue;
-#pragma unroll
-          for (int qp = 0; qp < 2; qp++) {  // two 16-line clusters per step, one per half warp
-            const int q = s * 4 + qp * 2 + (lane >> 4);
-            const double* __restrict__ r0 = L0 + (t * 16 + q) * MOM_DOUBLES;
-            const double2 c0 = __ldg(reinterpret_cast<const double2*>(r0));
-            const int l = q * 16 + (lane & 15);
-            if (fmm_served(fabs(__dsub_rn(f, c0.x)), c0.y, __ldg(r0 + MOM_IN), __ldg(r0 + MOM_OUT), ann) || l >= count) continue;
-            // the per-pair arithmetic of lbl_sum_real_kernel's near loop
-            const double2 rc = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP));      // B1, igd
-            if (rc.y == 0.0) continue;
-            const double2 ra = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP));      // f0', c3
-            const double2 rb = __ldg(reinterpret_cast<const double2*>(g0 + (0 * TL + l) * REC_GROUP) + 1);  // kappa, A1
-            const double2 rd = __ldg(reinterpret_cast<const double2*>(g0 + (1 * TL + l) * REC_GROUP) + 1);  // y, s_re
-            if (seg.has_cutoff) {
-              // frequency_spans (lbl_lineshape_voigt_lte.h:123-133) and ls(f) - ls(f0' + cutoff) (:591-608)
-              const double lcut = __ldg(g0 + (2 * TL + l) * REC_GROUP + 1);
-              if (lcut < DBL_MAX) {
-                if (!(ra.x >= f - lcut && ra.x <= f + lcut)) continue;
-                acc = __dsub_rn(acc, __ldg(g0 + (2 * TL + l) * REC_GROUP + 2));
-              }
+          const double2 c0 = __ldg(reinterpret_cast<const double2*>(r0));
+          const double in2 = __ldg(r2 + MOM_IN), out2 = __ldg(r2 + MOM_OUT);
+          const double in1 = __ldg(r1 + MOM_IN), out1 = __ldg(r1 + MOM_OUT);
+          const double in0 = __ldg(r0 + MOM_IN), out0 = __ldg(r0 + MOM_OUT);
+          count = p.tile_count[tt];
+          need = !fmm_served(fabs(__dsub_rn(f, c2.x)), c2.y, in2, out2, ann) && !fmm_served(fabs(__dsub_rn(f, c1.x)), c1.y, in1, out1, ann) &&
+                 !fmm_served(fabs(__dsub_rn(f, c0.x)), c0.y, in0, out0, ann) && k16 * 16 < count;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        // Half warp h sums the clusters with q mod 2 == h, in catalog order, lane k its line k: the same assignment whatever
+        // the set of needed clusters, so a lane's partial sum depends on the frequency and the catalog only.
+        unsigned mine = mask & (half ? 0xAAAAAAAAu : 0x55555555u);
+        while (__any_sync(0xffffffffu, mine != 0u)) {
+          const int bit = mine ? __ffs(mine) - 1 : 0;
+          const bool on = mine != 0u;
+          mine &= mine - 1u;
+          const int cnt = __shfl_sync(0xffffffffu, count, bit & 16);  // lanes 0 and 16 hold the counts of the two tiles
+          const int l = (bit & 15) * 16 + k16;
+          if (!on || l >= cnt) continue;
+          const double* __restrict__ g0 = prep + (t0 + (bit >> 4)) * tile_doubles();
+          // the per-pair arithmetic of lbl_sum_real_kernel's near loop; the line's record in one batch of loads
+          const double* __restrict__ ga = g0 + (0 * TL + l) * REC_GROUP;
+          const double* __restrict__ gb = g0 + (1 * TL + l) * REC_GROUP;
+          const double* __restrict__ gc = g0 + (2 * TL + l) * REC_GROUP;
+          const double2 rc = __ldg(reinterpret_cast<const double2*>(gb));      // B1, igd
+          const double2 ra = __ldg(reinterpret_cast<const double2*>(ga));      // f0', c3
+          const double2 rb = __ldg(reinterpret_cast<const double2*>(ga) + 1);  // kappa, A1
+          const double2 rd = __ldg(reinterpret_cast<const double2*>(gb) + 1);  // y, s_re
+          const double2 re = __ldg(reinterpret_cast<const double2*>(gc));      // E1(y), the line's cutoff
+          if (rc.y == 0.0) continue;
+          if (seg.has_cutoff) {
+            // frequency_spans (lbl_lineshape_voigt_lte.h:123-133) and ls(f) - ls(f0' + cutoff) (:591-608)
+            const double lcut = re.y;
+            if (lcut < DBL_MAX) {
+              if (!(ra.x >= f - lcut && ra.x <= f + lcut)) continue;
+              acc = __dsub_rn(acc, __ldg(gc + 2));
             }
-            const double u  = __dsub_rn(f, ra.x);
-            const double ax = __dmul_rn(fabs(u), rc.y);
-            if (__dadd_rn(ax, rd.x) > FAR_LIMIT_REAL_SUM) {
-              acc = far_accumulate_re(acc, u, ra.y, rb.x, rb.y, rc.x);
-            } else {
-              double wr, wi;
-              w_near_fast(rc.y * u, rd.x, __ldg(g0 + (2 * TL + l) * REC_GROUP), wr, wi);
-              acc = __fma_rn(rd.y, wr, acc);
-            }
+          }
+          const double u  = __dsub_rn(f, ra.x);
+          const double ax = __dmul_rn(fabs(u), rc.y);
+          if (__dadd_rn(ax, rd.x) > FAR_LIMIT_REAL_SUM) {
+            acc = far_accumulate_re(acc, u, ra.y, rb.x, rb.y, rc.x);
+          } else {
+            double wr, wi;
+            w_near_fast(rc.y * u, rd.x, re.x, wr, wi);
+            acc = __fma_rn(rd.y, wr, acc);
           }
         }
       }

@@ -605,7 +605,9 @@ __global__ void __launch_bounds__(128) lbl_fmm_near_kernel(SumParams p, FmmBuffe
 
 // running bounds of the tiles' acceptance intervals per (segment, level): scan[t] = {max_{t' <= t}(c + rho), min_{t' >= t}(c - rho)}
 __global__ void lbl_fmm_scan_kernel(SumParams p, FmmBuffers fb) {
-  if (threadIdx.x != 0) return;
+  // one warp per (segment, level): 32 tiles per step, inclusive max / min scan by shuffles plus the carry of the steps before
+  // (max and min are exact and associative: the same numbers as a serial sweep)
+  const int lane = threadIdx.x;
   const SegmentDev seg = p.segs[blockIdx.x];
   const int lev = blockIdx.y;
   const double* __restrict__ L2 = fb.L2 + int64_t(lev) * p.ntiles * MOM_DOUBLES;
@@ -615,15 +617,31 @@ __global__ void lbl_fmm_scan_kernel(SumParams p, FmmBuffers fb) {
     const double* r = L2 + t * MOM_DOUBLES;
     return r[MOM_IN] < DBL_MAX ? fmax(r[MOM_RHO], r[MOM_OUT]) : r[MOM_RHO];
   };
-  double m = -DBL_MAX;
-  for (int64_t t = seg.tile_begin; t < seg.tile_end; t++) {
-    m = fmax(m, L2[t * MOM_DOUBLES] + U(t));
-    scan[2 * t] = m;
+  double carry = -DBL_MAX;
+  for (int64_t t0 = seg.tile_begin; t0 < seg.tile_end; t0 += 32) {
+    const int64_t t = t0 + lane;
+    double v = t < seg.tile_end ? L2[t * MOM_DOUBLES] + U(t) : -DBL_MAX;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double w = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v = fmax(v, w);
+    }
+    v = fmax(v, carry);
+    if (t < seg.tile_end) scan[2 * t] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
-  m = DBL_MAX;
-  for (int64_t t = seg.tile_end - 1; t >= seg.tile_begin; t--) {
-    m = fmin(m, L2[t * MOM_DOUBLES] - U(t));
-    scan[2 * t + 1] = m;
+  carry = DBL_MAX;
+  for (int64_t t1 = seg.tile_end; t1 > seg.tile_begin; t1 -= 32) {  // tiles t1 - 1 - lane, from the segment's last tile down
+    const int64_t t = t1 - 1 - lane;
+    double v = t >= seg.tile_begin ? L2[t * MOM_DOUBLES] - U(t) : DBL_MAX;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double w = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v = fmin(v, w);
+    }
+    v = fmin(v, carry);
+    if (t >= seg.tile_begin) scan[2 * t + 1] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
 }
 

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p, int nl
     const int isot = p.line_isot[par];
     const int spec = p.isot_species[isot];
     const double T0 = p.T0[par];
+    const double q_T = T0 / T, lq_T = log(q_T);  // shared by every variable and broadener of the line
     // model::{G0,D0,DV,Y,G}(atm): VMR-weighted mixture, Bath = remainder
     double res[AB200_NVAR], bth[AB200_NVAR];
     double vmr_sum = 0.0;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p, int nl
         double val = 0.0;
         if (type != AB200_TM_ABSENT) {
           const double ps = (v == AB200_VAR_G || v == AB200_VAR_DV) ? P * P : P;  // lbl_lineshape_model.cpp:27-35
-          val = ps * tm_value(type, p.ls_X + (i * AB200_NVAR + v) * 4, T0, T);
+          val = ps * tm_value_lq(type, p.ls_X + (i * AB200_NVAR + v) * 4, T0, T, q_T, lq_T);
         }
         if (sp == AB200_SPECIES_BATH) bth[v] = val; else res[v] += vm * val;
       }

@@ -27,6 +27,28 @@ __device__ __forceinline__ double tm_value(int type, const double* __restrict__ 
   }
 }
 
+// The same values with the power written as the reference writes it, nonstd::pow(x, v) = exp(v log x)
+// (lbl_temperature_model.h:36-60 through src/core/util/nonstd.h:25-31), and log(T0 / T) handed in: all the variables and
+// broadeners of a line share T0 / T, so a line pays one log and one exp per power instead of a full pow() each.
+__device__ __forceinline__ double tm_value_lq(int type, const double* __restrict__ x, double T0, double T, double q /* T0 / T */,
+                                              double lq /* log(T0 / T) */) {
+  switch (type) {
+    case AB200_TM_T0: return x[0];
+    case AB200_TM_T1: return x[0] * exp(x[1] * lq);
+    case AB200_TM_T2: return x[0] * exp(x[1] * lq) * (1 + x[2] * log(T / T0));
+    case AB200_TM_T3: return x[0] + x[1] * (T - T0);
+    case AB200_TM_T4: return (x[0] + x[1] * (q - 1)) * exp(x[2] * lq);
+    case AB200_TM_T5: return x[0] * exp((0.25 + 1.5 * x[1]) * lq);
+    case AB200_TM_AER:
+      if (T < 250.0) return x[0] + (T - 200.0) * (x[1] - x[0]) / (250.0 - 200.0);
+      if (T > 296.0) return x[2] + (T - 296.0) * (x[3] - x[2]) / (340.0 - 296.0);
+      return x[1] + (T - 250.0) * (x[2] - x[1]) / (296.0 - 250.0);
+    case AB200_TM_DPL: return x[0] * exp(x[1] * lq) + x[2] * exp(x[3] * lq);
+    case AB200_TM_POLY: return x[0] + T * (x[1] + T * (x[2] + T * x[3]));
+    default: return 0.0;
+  }
+}
+
 // d/dT of the above (lbl_temperature_model.h, the d*_dT members)
 __device__ __forceinline__ double tm_dT(int type, const double* __restrict__ x, double T0, double T) {
   switch (type) {

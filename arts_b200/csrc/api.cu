@@ -440,9 +440,12 @@ int ab200_path_upload(ab200_path* p, const double* f, int64_t f_level_stride, co
   for (const Segment& s : cat->segments) {
     if (!(select_species == AB200_SPECIES_BATH || select_species == s.species)) continue;
     SegmentDev d{s.tile_begin, s.tile_end, s.cutoff, s.pol, s.has_cutoff};
-    // Far-field sums pay a fixed ~3e3 warp instructions per (frequency, level) (tree descent, bracket search, the pairs inside
-    // 48 Doppler widths) where the line-by-line kernel pays 7 / 32 per line: they win from ~1.5e4 lines per segment
-    // (measured: 1e4 lines 5.9 -> 8.9 ms, 1e5 lines 472 -> 45 ms, 1e6 lines 6067 -> 94 ms per step).  AB200_FARFIELD=2 forces them.
+    // Far-field sums cost ~5e-10 s per (frequency, level, segment) almost whatever the segment's size, plus 2.8e-10 s per
+    // (line, level) for the records and moments; the line-by-line kernel costs 6e-13 s per pair: they win from ~800 lines per
+    // segment (measured on configs[1] shapes, 1e5 frequencies x 100 levels, line by line -> far field per step: 1000 lines per
+    // species 25.3 -> 21.3 ms, 2000: 48.8 -> 24.5, 2e4 (configs[1]): 472.9 -> 49.4; one configs[4] path, 1e4 frequencies,
+    // 2000 lines per species: 5.9 -> 3.0 ms; 500 lines per species: 13.7 -> 18.2 ms, stays line by line).  AB200_FARFIELD=2
+    // forces them, = 0 switches them off.
     const bool big = s.nsub >= FMM_MIN_LINES || farfield_mode == 2;
     const int list = s.mode == 1 ? 1 : (farfield && big && p->fmm.L0) ? 2 : 0;
     p->h_segs[list * nseg + p->nsegs[list]++] = d;

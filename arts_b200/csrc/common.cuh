@@ -76,7 +76,7 @@ constexpr int MOM_DOUBLES = 24;
 // the lines' cutoff values ls(f0' + cutoff)
 constexpr int MOM_C = 0, MOM_RHO = 1, MOM_R = 2, MOM_M1 = 3, MOM_IN = 19, MOM_OUT = 20, MOM_CUT = 21;
 constexpr int FMM_GROUP = 16;  // tiles per coarsest cluster
-constexpr int64_t FMM_MIN_LINES = 24576;  // real segments with fewer (sub-)lines keep the line-by-line kernel
+constexpr int64_t FMM_MIN_LINES = 1024;  // real segments with fewer (sub-)lines keep the line-by-line kernel (break-even ~800)
 
 constexpr int AB200_MAX_TARGETS = 8;  // Jacobian targets per call (temperature + species VMRs)
 

@@ -29,7 +29,7 @@ def _dense_case(n_lines=40_000, nf=3000, np_=6, f_lo=2e12, f_hi=3e12):
 
 @pytest.fixture(autouse=True)
 def _force_farfield():
-    """Segments below FMM_MIN_LINES (24 576 lines) keep the line-by-line kernel by default; these tests want the far-field
+    """Segments below FMM_MIN_LINES (1024 lines) keep the line-by-line kernel by default; these tests want the far-field
     sums on small catalogs too (AB200_FARFIELD=2, read at every upload)."""
     os.environ["AB200_FARFIELD"] = "2"
     yield

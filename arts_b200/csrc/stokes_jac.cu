@@ -235,7 +235,9 @@ __device__ __forceinline__ void emit(const StokesJacParams& p, int64_t iv, int i
   }
 }
 
-template <bool LINSRC>
+// LINPROP: the Dawson-function code (unpolarised closed form, polarised complex matrix form and its perturbation derivative)
+// only exists in its own instantiation, so that the linsrc chain keeps its registers
+template <bool LINSRC, bool LINPROP = false>
 __global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
   const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (iv >= p.nf) return;
@@ -261,10 +263,10 @@ __global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
     t.init(k0, k1, ri, false);
     double Tm[16], Lm[16];
     if (t.polarized) t.T(Tm); else diag_of(Tm, t.exp_a);
-    const int lc = (LINSRC && p.rte_option == AB200_RTE_LINPROP) ? linprop_case(k0.A, k1.A, ri, t.polarized) : 0;
+    const int lc = (LINSRC && LINPROP) ? linprop_case(k0.A, k1.A, ri, t.polarized) : 0;
     if (LINSRC) {
-      if (lc == 2) linprop_lambda_pol(Tm, k0, k1, ri, 4, Lm);
-      else if (lc == 1) diag_of(Lm, linprop_lambda(k0.A, k1.A, ri, t.exp_a));
+      if (LINPROP && lc == 2) linprop_lambda_pol(Tm, k0, k1, ri, 4, Lm);
+      else if (LINPROP && lc == 1) diag_of(Lm, linprop_lambda(k0.A, k1.A, ri, t.exp_a));
       else if (t.polarized) t.L(Lm);
       else diag_of(Lm, func_F(t.a));
     }
@@ -291,11 +293,11 @@ __global__ void __launch_bounds__(64, 1) stokes_jac_kernel(StokesJacParams p) {
       t.deriv(Tm, k0, k1, dk0, ri, dr0, dT0);
       t.deriv(Tm, k0, k1, dk1, ri, dr1, dT1);
       if (LINSRC) {
-        const bool lp = p.rte_option == AB200_RTE_LINPROP;  // dr1 in both calls for linprop (:1238, sic)
-        if (lc == 2) {
+        const bool lp = LINPROP;  // dr1 in both calls for linprop (:1238, sic)
+        if (LINPROP && lc == 2) {
           linprop_lambda_pol_deriv(Lm, k0, k1, dk0, ri, dr1, true, dL0);
           linprop_lambda_pol_deriv(Lm, k0, k1, dk1, ri, dr1, false, dL1);
-        } else if (lc == 1) {
+        } else if (LINPROP && lc == 1) {
           diag_of(dL0, linprop_lambda_deriv(k0.A, k1.A, dk0.A, Tm[0], dT0[0], ri, dr1, true));
           diag_of(dL1, linprop_lambda_deriv(k0.A, k1.A, dk1.A, Tm[0], dT1[0], ri, dr1, false));
         } else {
@@ -432,7 +434,8 @@ int launch_stokes_jac(const StokesJacParams& p, cudaStream_t stream) {
   }
   const unsigned grid = static_cast<unsigned>((p.nf + 63) / 64);
   if (p.rte_option != AB200_RTE_CONSTANT)
-    stokes_jac_kernel<true><<<grid, 64, 0, stream>>>(p);
+    if (p.rte_option == AB200_RTE_LINPROP) stokes_jac_kernel<true, true><<<grid, 64, 0, stream>>>(p);
+    else stokes_jac_kernel<true><<<grid, 64, 0, stream>>>(p);
   else
     stokes_jac_kernel<false><<<grid, 64, 0, stream>>>(p);
   count_launch();

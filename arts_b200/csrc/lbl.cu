@@ -37,7 +37,7 @@ namespace ab200 {
 // Levels per CTA: the catalog rows of the tile's lines (368 B per line with two broadeners) are read from DRAM once per CTA
 // and served from L1 / L2 for the other PREP_LB - 1 levels (a CTA per (tile, level) read 30 GB per 67 levels of configs[3]).
 constexpr int PREP_LB = 16;
-__global__ void __launch_bounds__(TL) lbl_prepare_kernel(PrepareParams p, int nlev) {
+__global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int nlev) {
   const int64_t tile = blockIdx.x;
   const int lane     = threadIdx.x;
   const int64_t slot = tile * TL + lane;

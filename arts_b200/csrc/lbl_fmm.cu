@@ -103,7 +103,7 @@ __device__ __forceinline__ double m2m_term(int k, double x, double r, const doub
 // ---------------------------------------------------------------------------
 // moments of the 16-line, 64-line and tile clusters: one CTA per (tile, level), one thread per line
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TL) lbl_fmm_moments_tile_kernel(PrepareParams p, FmmBuffers fb) {
+__global__ void __launch_bounds__(TL, 4) lbl_fmm_moments_tile_kernel(PrepareParams p, FmmBuffers fb) {
   static_assert(TL == 256, "cluster sizes 16 / 64 / 256");
   const int64_t tile = blockIdx.x;
   const int lev      = blockIdx.y;

@@ -86,65 +86,95 @@ __device__ __forceinline__ double interp1(const double* __restrict__ field, cons
   return out;
 }
 
-// table::absorption for one frequency; vmr of species `sp_pert` is raised by `dv` (a perturbed Jacobian point)
-__device__ double table_absorption(const LutParams& p, int k, double f, double T, double P, const double* __restrict__ vmr,
-                                   int sp_pert, double dv, bool& ok) {
+// What table::absorption needs of one (table, atmospheric state): the Lagrange stencils and weights in log-pressure, temperature
+// offset and water ratio, and the number density of the species.  They depend on the level (and on the perturbed Jacobian
+// point) only, so one thread of the CTA builds them in shared memory and every frequency reuses them; a thread's own work is
+// the frequency stencil, once per table, and the (to+1)(wo+1)(po+1)(fo+1) products.
+struct LutState {
+  Lag pl, tl, wl;
+  double scale;  // vmr(species) * P / (k T)
+  int ok;
+};
+constexpr int LUT_MAX_STATES = 1 + AB200_MAX_TARGETS;
+
+__device__ void lut_state(const LutParams& p, int k, double T, double P, const double* __restrict__ vmr, int sp_pert, double dv,
+                          LutState& st) {
   const int32_t* m = p.t.meta + 8 * k;
-  const int species = m[0], nf = m[1], np = m[2], nt = m[3], nw = m[4], do_t = m[5], do_w = m[6];
-  if (int64_t(nf) * np * nt * nw == 0) return 0.0;  // xsec.empty(), lookup_map.cpp:201
+  const int species = m[0], np = m[2], nt = m[3], nw = m[4], do_t = m[5], do_w = m[6];
   const int64_t* o = p.t.off + 7 * k;
   const double* pool = p.t.pool;
   auto v_of = [&](int s) { return vmr[s] + (s == sp_pert ? dv : 0.0); };
-  Lag fl, pl, tl, wl;
-  tl.i0 = wl.i0 = 0; tl.order = wl.order = 0; tl.w[0] = wl.w[0] = 1.0;
-  ok &= make_lag(fl, pool + o[0], nf, p.fo, f, p.extpol);
-  ok &= make_lag(pl, pool + o[1], np, p.po, log(P), p.extpol);
-  if (do_w) ok &= make_lag(wl, pool + o[3], nw, p.wo, v_of(p.h2o_species) / interp1(pool + o[5], pl), p.extpol);
-  if (do_t) ok &= make_lag(tl, pool + o[2], nt, p.to, T - interp1(pool + o[4], pl), p.extpol);
-  const double* __restrict__ xs = pool + o[6];
+  bool ok = true;
+  st.tl.i0 = st.wl.i0 = 0; st.tl.order = st.wl.order = 0; st.tl.w[0] = st.wl.w[0] = 1.0;
+  ok &= make_lag(st.pl, pool + o[1], np, p.po, log(P), p.extpol);
+  if (do_w) ok &= make_lag(st.wl, pool + o[3], nw, p.wo, v_of(p.h2o_species) / interp1(pool + o[5], st.pl), p.extpol);
+  if (do_t) ok &= make_lag(st.tl, pool + o[2], nt, p.to, T - interp1(pool + o[4], st.pl), p.extpol);
+  st.scale = v_of(species) * (P / (cst::k * T));
+  st.ok = ok ? 1 : 0;
+}
+
+// table::absorption (lookup_map.cpp:190-238) for one frequency stencil and one prepared state
+__device__ __forceinline__ double table_absorption(const LutParams& p, int k, const Lag& fl, const LutState& st) {
+  const int32_t* m = p.t.meta + 8 * k;
+  const int nf = m[1], np = m[2], nw = m[4], do_t = m[5], do_w = m[6];
+  const double* __restrict__ xs = p.t.pool + p.t.off[7 * k + 6];
   double out = 0.0;
-  for (int a = 0; a <= tl.order; a++)
-    for (int b = 0; b <= wl.order; b++)
-      for (int c = 0; c <= pl.order; c++) {
-        const double* __restrict__ row = xs + ((int64_t(tl.i0 + a) * nw + wl.i0 + b) * np + pl.i0 + c) * nf + fl.i0;
+  for (int a = 0; a <= st.tl.order; a++)
+    for (int b = 0; b <= st.wl.order; b++)
+      for (int c = 0; c <= st.pl.order; c++) {
+        const double* __restrict__ row = xs + ((int64_t(st.tl.i0 + a) * nw + st.wl.i0 + b) * np + st.pl.i0 + c) * nf + fl.i0;
         for (int d = 0; d <= fl.order; d++) {
           double v = row[d];
-          if (do_t) v *= tl.w[a];
-          if (do_w) v *= wl.w[b];
-          v *= pl.w[c];
+          if (do_t) v *= st.tl.w[a];
+          if (do_w) v *= st.wl.w[b];
+          v *= st.pl.w[c];
           v *= fl.w[d];
           out += v;
         }
       }
-  return out * (v_of(species) * (P / (cst::k * T)));
-}
-
-__device__ double total_absorption(const LutParams& p, double f, double T, double P, const double* __restrict__ vmr, int sp_pert,
-                                   double dv, bool& ok) {
-  double sum = 0.0;
-  for (int k = 0; k < p.t.n_tables; k++) {
-    if (p.select_species != AB200_SPECIES_BATH && p.t.meta[8 * k] != p.select_species) continue;
-    sum += table_absorption(p, k, f, T, P, vmr, sp_pert, dv, ok);
-  }
-  return sum;
+  return out * st.scale;
 }
 
 __global__ void __launch_bounds__(128) lookup_kernel(LutParams p) {
+  __shared__ LutState sst[LUT_MAX_STATES];
   const int64_t iv = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (iv >= p.nf) return;
   const int lev = blockIdx.y;
-  const double f = (p.ffac ? p.ffac[lev] : 1.0) * p.f[int64_t(lev) * p.f_stride + iv];
+  const bool live = iv < p.nf;
+  const double f = live ? (p.ffac ? p.ffac[lev] : 1.0) * p.f[int64_t(lev) * p.f_stride + iv] : 0.0;
   const double T = p.T[lev], P = p.P[lev];
   const double* __restrict__ vmr = p.vmr + int64_t(lev) * p.n_species;
   bool ok = true;
-  const double ab = total_absorption(p, f, T, P, vmr, -1, 0.0, ok);
+  double ab = 0.0, dab[AB200_MAX_TARGETS];
+#pragma unroll
+  for (int q = 0; q < AB200_MAX_TARGETS; q++) dab[q] = 0.0;
+  for (int k = 0; k < p.t.n_tables; k++) {
+    const int32_t* m = p.t.meta + 8 * k;
+    if (p.select_species != AB200_SPECIES_BATH && m[0] != p.select_species) continue;  // CTA-uniform
+    if (int64_t(m[1]) * m[2] * m[3] * m[4] == 0) continue;                              // xsec.empty(), lookup_map.cpp:201
+    __syncthreads();  // the previous table's states have been read
+    if (threadIdx.x <= p.nq) {  // state 0: the level itself; state 1 + q: the perturbed point of target q
+      const int q = int(threadIdx.x) - 1;
+      const bool is_T = q >= 0 && p.tg_kind[q] == AB200_TARGET_T;
+      lut_state(p, k, (q >= 0 && is_T) ? T + p.tg_d[q] : T, P, vmr, (q >= 0 && !is_T) ? p.tg_species[q] : -1,
+                (q >= 0 && !is_T) ? p.tg_d[q] : 0.0, sst[threadIdx.x]);
+    }
+    __syncthreads();
+    if (!live) continue;
+    Lag fl;
+    ok &= make_lag(fl, p.t.pool + p.t.off[7 * k], m[1], p.fo, f, p.extpol);
+    ok &= sst[0].ok != 0;
+    ab += table_absorption(p, k, fl, sst[0]);
+    for (int q = 0; q < p.nq; q++) {
+      ok &= sst[1 + q].ok != 0;
+      dab[q] += table_absorption(p, k, fl, sst[1 + q]);
+    }
+  }
+  if (!live) return;
   if (p.no_neg == 0 || ab > 0.0) p.K[(int64_t(lev) * p.k_pitch + iv) * 7] += ab;  // m_lookup.cc:73-77
   for (int q = 0; q < p.nq; q++) {
     const double d = p.tg_d[q];
-    const bool is_T = p.tg_kind[q] == AB200_TARGET_T;
-    const double dab = total_absorption(p, f, is_T ? T + d : T, P, vmr, is_T ? -1 : p.tg_species[q], is_T ? 0.0 : d, ok);
-    if (p.no_neg == 0 || dab > 0.0)  // the row is ASSIGNED (sic, :130-135)
-      p.dK[((int64_t(lev) * p.nq + q) * p.k_pitch + iv) * 7] = (dab - ab) * (1.0 / d);
+    if (p.no_neg == 0 || dab[q] > 0.0)  // the row is ASSIGNED (sic, :130-135)
+      p.dK[((int64_t(lev) * p.nq + q) * p.k_pitch + iv) * 7] = (dab[q] - ab) * (1.0 / d);
   }
   if (!ok) atomicOr(p.flags, 16);
 }

@@ -67,6 +67,8 @@ def lib():
     L.ab200_multi_clearsky_emission.argtypes = [_vp] + abi.SIG_CLEARSKY_CORE
     L.ab200_multi_propmat_levels.argtypes = [_vp] + abi.SIG_PROPMAT_LEVELS_CORE + [C.c_uint32, _dp, _dp]
     L.ab200_path_create.argtypes = [_vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(_vp)]
+    L.ab200_path_create_stage2.argtypes = [_vp, C.c_int64, C.c_int32, C.POINTER(_vp)]
+    L.ab200_path_adopt_K.argtypes = [_vp]
     L.ab200_path_destroy.argtypes = [_vp]
     L.ab200_path_destroy.restype = None
     L.ab200_path_set_stream.argtypes = [_vp, _vp]

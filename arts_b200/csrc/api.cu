@@ -270,6 +270,11 @@ extern "C++" int ab200::path_create_ex(const ab200_catalog* cat, int64_t nf, int
   return AB200_OK;
 }
 
+int ab200_path_create_stage2(const ab200_catalog* cat, int64_t nf, int32_t np, ab200_path** out) {
+  return ab200::path_create_ex(cat, nf, np, 0, true, out);
+}
+int ab200_path_adopt_K(ab200_path* p) { return ab200::path_adopt_K(p); }
+
 void ab200_path_destroy(ab200_path* p) { delete p; }
 
 int ab200_path_set_stream(ab200_path* p, void* stream) {

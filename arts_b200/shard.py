@@ -95,6 +95,55 @@ def shard_case(case, rank: int, world: int):
 
 
 # ---------------------------------------------------------------------------
+# levels for the line sum, frequencies for the Stokes chain: one transpose of K between them
+# ---------------------------------------------------------------------------
+def level_sets(np_: int, n: int) -> list[list[int]]:
+    """Levels dealt round-robin: rank r sums levels r, r + n, r + 2n, ... (the split of ab200_multi_*, multi.cu)."""
+    return [list(range(r, np_, n)) for r in range(n)]
+
+
+class LevelExchange:
+    """The one exchange of the level split: rank r holds ``K1`` [levels of r][k_pitch_all][7] for ALL frequencies and needs
+    ``K2`` [np][k_pitch_local][7] for ITS frequency block — an all-to-all of K (NCCL over NVLink / NVSwitch on the GPU box,
+    gloo in the CPU tests).  Rows are copied, never reduced, and K at a (frequency, level) does not depend on the partition,
+    so the radiances are bit-identical to the frequency split and to one GPU.
+
+    Why: the line records and the cluster moments of the far-field sums are work per (line, level); a frequency shard
+    repeats them for every rank (25 of 60 ms per configs[3] shard), a level shard does not.
+    """
+
+    def __init__(self, np_: int, nf_total: int, rank: int, world: int, group=None):
+        import torch
+
+        self.np_, self.nf, self.rank, self.world, self.group = int(np_), int(nf_total), rank, world, group
+        self.ranges = frequency_ranges(self.nf, world)
+        if len({c for _, c in self.ranges}) != 1:
+            raise ValueError("the level exchange needs equal frequency blocks (nf divisible by the number of ranks)")
+        self.cnt = self.ranges[0][1]
+        self.levels = level_sets(self.np_, world)
+        self.mine = self.levels[rank]
+        self.out_split = [len(l) for l in self.levels]            # rows received from every rank
+        self.in_split = [len(self.mine)] * world                  # rows sent to every rank
+        self.level_of_row = torch.tensor([l for ls in self.levels for l in ls], dtype=torch.long)
+
+    def exchange(self, K1, K2):
+        """K1 [len(mine), >= nf, 7] -> K2 [np, >= cnt, 7] (views of the library's device buffers; extra columns are padding)."""
+        import torch
+        import torch.distributed as dist
+
+        n_mine, cnt, w = len(self.mine), self.cnt, self.world
+        if self.level_of_row.device != K1.device:
+            self.level_of_row = self.level_of_row.to(K1.device)
+        # [levels][rank blocks][cnt][7] -> [rank blocks][levels][cnt][7]: the rows for rank e are contiguous
+        send = K1[:, : w * cnt, :].reshape(n_mine, w, cnt, 7).permute(1, 0, 2, 3).contiguous().view(w * n_mine, cnt * 7)
+        recv = torch.empty((self.np_, cnt * 7), dtype=K1.dtype, device=K1.device)
+        if n_mine == 0 and all(s == 0 for s in self.out_split):
+            return
+        dist.all_to_all_single(recv, send, output_split_sizes=self.out_split, input_split_sizes=self.in_split, group=self.group)
+        K2[:, :cnt, :].index_copy_(0, self.level_of_row, recv.view(self.np_, cnt, 7))
+
+
+# ---------------------------------------------------------------------------
 # second axis: a batch of propagation paths (BASELINE configs[4]) sharded over the ranks
 # ---------------------------------------------------------------------------
 def path_ranges(n_paths: int, n: int) -> list[tuple[int, int]]:

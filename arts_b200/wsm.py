@@ -345,11 +345,16 @@ def measure_dfma_mix(iters=20000):
 class Path:
     """Device-resident workspace of one propagation path (ab200_path): upload once, run, download."""
 
-    def __init__(self, cat: Catalog, nf: int, np_: int, nq: int = 0, stream=None):
+    def __init__(self, cat: Catalog, nf: int, np_: int, nq: int = 0, stream=None, stage2_only: bool = False):
         self.cat, self.nf, self.np_, self.nq = cat, int(nf), int(np_), int(nq)
         self.np_cap = int(np_)
+        self.k_pitch = (self.nf + 127) // 128 * 128  # frequencies per level row of the resident K [np][k_pitch][7]
         self._h = C.c_void_p()
-        check(lib().ab200_path_create(cat.handle, self.nf, self.np_, self.nq, C.byref(self._h)))
+        if stage2_only:  # Stokes chain only; K comes from other workspaces (adopt_K)
+            assert self.nq == 0
+            check(lib().ab200_path_create_stage2(cat.handle, self.nf, self.np_, C.byref(self._h)))
+        else:
+            check(lib().ab200_path_create(cat.handle, self.nf, self.np_, self.nq, C.byref(self._h)))
         if stream is not None:
             check(lib().ab200_path_set_stream(self._h, C.c_void_p(int(stream))))
 
@@ -389,6 +394,10 @@ class Path:
 
     def run_propmat(self):
         check(lib().ab200_path_run_propmat(self._h))
+
+    def adopt_K(self):
+        """The resident K was filled by the caller with rows summed by other workspaces of the same catalog / selection."""
+        check(lib().ab200_path_adopt_K(self._h))
 
     def run_stokes(self):
         check(lib().ab200_path_run_stokes(self._h))

@@ -252,18 +252,42 @@ def run_b200(args):
 
     stream = torch.cuda.current_stream()
     cat = wsm.Catalog(case.cat)
-    path = wsm.Path(cat, cnt, np_, 0, stream=stream.cuda_stream)
-    path.set_grid_bounds(np.tile([case.f[0], case.f[-1]], (np_, 1)))
-    path.upload(mine.f, mine.atm, mine.r, mine.I_bkg, rte_option=args.rte)
+    # N > 1: the LEVELS of the line sum are dealt over the ranks (rank r: levels r, r + N, ... for ALL frequencies, so the
+    # per-(line, level) work - line records, cluster moments - is not repeated by every frequency shard), one NCCL all-to-all
+    # transposes K, and every rank runs the Stokes chain on its contiguous frequency block; AB200_BENCH_SPLIT=freq keeps the
+    # plain frequency split.  Same bits either way (tests/test_shard_gloo.py, tests/test_gpu_multi.py).
+    level_split = (world > 1 and np_ >= world and cnt * world == nf_total and os.environ.get("AB200_BENCH_SPLIT", "level") != "freq")
+    if level_split:
+        from arts_b200 import _abi as abi
+
+        ex = shard.LevelExchange(np_, nf_total, rank, world)
+        a = case.atm
+        pick = lambda x: None if x is None else np.ascontiguousarray(x[ex.mine])  # noqa: E731
+        sub = abi.AtmPath(T=pick(a.T), P=pick(a.P), vmr=pick(a.vmr), isorat=pick(a.isorat), Q=pick(a.Q), dQdT=pick(a.dQdT),
+                          mag=pick(a.mag), los=pick(a.los), wind=pick(a.wind))
+        lpath = wsm.Path(cat, nf_total, len(ex.mine), 0, stream=stream.cuda_stream)
+        lpath.upload(case.f, sub, np.zeros(max(len(ex.mine) - 1, 1)), None, rte_option=args.rte)
+        path = wsm.Path(cat, cnt, np_, 0, stream=stream.cuda_stream, stage2_only=True)
+        path.upload(mine.f, mine.atm, mine.r, mine.I_bkg, rte_option=args.rte)
+        K1 = shard.as_torch(lpath.device_ptr(1), (len(ex.mine), lpath.k_pitch, 7), dev)
+        K2 = shard.as_torch(path.device_ptr(1), (np_, path.k_pitch, 7), dev)
+    else:
+        path = wsm.Path(cat, cnt, np_, 0, stream=stream.cuda_stream)
+        path.set_grid_bounds(np.tile([case.f[0], case.f[-1]], (np_, 1)))
+        path.upload(mine.f, mine.atm, mine.r, mine.I_bkg, rte_option=args.rte)
+        lpath = path
     I_local = shard.as_torch(path.device_ptr(0), (cnt, 4), dev)
 
     dfma_tflops, _ = wsm.measure_dfma_peak(20000)
     dfma_mix_tflops, _ = wsm.measure_dfma_mix(20000)
-    hist = path.region_histogram(200_000, seed=1)
+    hist = lpath.region_histogram(200_000, seed=1)
     fl_eval, region_frac = roofline.flops_per_eval(hist)
 
     def step():
-        path.run_propmat()
+        lpath.run_propmat()
+        if level_split:
+            ex.exchange(K1, K2)
+            path.adopt_K()
         path.run_stokes()
         if world > 1:
             return shard.gather_spectral_rad(I_local, nf_total)
@@ -279,7 +303,9 @@ def run_b200(args):
         step()
     barrier()
     path.timings()  # drop warm-up records
+    lpath.timings()
     path.set_timing(True)
+    lpath.set_timing(True)
     wsm.lib().ab200_launch_count(1)
     sampler = ClockSampler(local)
     sampler.start()
@@ -295,8 +321,11 @@ def run_b200(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = int(wsm.lib().ab200_launch_count(0))
-    kt = path.timings()
+    kt = dict(lpath.timings())
+    if lpath is not path:
+        kt["stokes"] = path.timings()["stokes"]
     path.set_timing(False)
+    lpath.set_timing(False)
     checksum = float(out[:, 0].sum().item())
 
     evals_per_step = float(nl) * nf_total * np_
@@ -327,40 +356,65 @@ def run_b200(args):
     st_bytes = roofline.stokes_bytes_per_step(np_) * cnt * np_
     st_gbs = st_bytes / (s_ms_per * 1e-3) / 1e9 if s_ms_per > 0 else 0.0
 
-    # e2e: the reference-facing C-ABI call with host (pinned) buffers, H2D + D2H inside the timed region
-    f_h = torch.from_numpy(mine.f).pin_memory().numpy()
-    b_h = torch.from_numpy(mine.I_bkg).pin_memory().numpy()
-    wsm.set_thread_stream(stream.cuda_stream)
-    wsm.spectral_radClearskyEmission(cat, f_h, mine.atm, mine.r, b_h, rte_option=args.rte)  # builds the thread workspace
-    barrier()
+    # e2e: the reference-facing C-ABI call with host (pinned) buffers, H2D + D2H inside the timed region.  N = 1:
+    # ab200_clearsky_emission.  N > 1: the call a shim inside the reference's ONE process makes, ab200_multi_clearsky_emission
+    # over the N devices for the whole grid (rank 0 drives it; the other ranks wait on a CPU barrier and leave their GPUs idle).
     n_e2e = max(2, min(args.steps, 3))
-    e0.record()
-    for _ in range(n_e2e):
-        I_host, _ = wsm.spectral_radClearskyEmission(cat, f_h, mine.atm, mine.r, b_h, rte_option=args.rte)
-    e1.record()
-    barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = evals_per_step * n_e2e / (float(ms_e2e.item()) * 1e-3)
+    if world == 1:
+        f_h = torch.from_numpy(mine.f).pin_memory().numpy()
+        b_h = torch.from_numpy(mine.I_bkg).pin_memory().numpy()
+        wsm.set_thread_stream(stream.cuda_stream)
+        wsm.spectral_radClearskyEmission(cat, f_h, mine.atm, mine.r, b_h, rte_option=args.rte)  # builds the thread workspace
+        barrier()
+        e0.record()
+        for _ in range(n_e2e):
+            I_host, _ = wsm.spectral_radClearskyEmission(cat, f_h, mine.atm, mine.r, b_h, rte_option=args.rte)
+        e1.record()
+        barrier()
+        ms_e2e = float(e0.elapsed_time(e1))
+        e2e_call = "ab200_clearsky_emission (host buffers, pinned)"
+        e2e_matches = bool(np.array_equal(I_host, I_local.cpu().numpy()))
+    else:
+        cpu_group = dist.new_group(backend="gloo")
+        ms_e2e, e2e_matches, f_h, b_h, I_host = 0.0, None, case.f, case.I_bkg, np.empty((nf_total, 4))
+        barrier()
+        if rank == 0:
+            f_h = torch.from_numpy(case.f).pin_memory().numpy()
+            b_h = torch.from_numpy(case.I_bkg).pin_memory().numpy()
+            multi = wsm.MultiDevice(case.cat, n_devices=world)
+            wsm.spectral_radClearskyEmission(multi, f_h, case.atm, case.r, b_h, rte_option=args.rte)  # builds the workspaces
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n_e2e):
+                I_host, _ = wsm.spectral_radClearskyEmission(multi, f_h, case.atm, case.r, b_h, rte_option=args.rte)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_e2e = float(e0.elapsed_time(e1))
+            multi.close()
+            e2e_matches = bool(np.array_equal(I_host, out.cpu().numpy()))
+        dist.barrier(group=cpu_group)
+        e2e_call = f"ab200_multi_clearsky_emission (one host process, {world} devices, host buffers, pinned)"
+    e2e_value = evals_per_step * n_e2e / (ms_e2e * 1e-3) if ms_e2e > 0 else None
     h2d = int(f_h.nbytes + b_h.nbytes + 8 * np_ * (3 + 3 * case.cat.n_species + 28 + 3))
     d2h = int(I_host.nbytes)
-    e2e_matches = bool(np.array_equal(I_host, I_local.cpu().numpy()))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c4strong" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "lines": nl, "levels": np_, "nf_total": nf_total, "nf_per_gpu": cnt,
-                   "sharding": "contiguous frequency blocks (matpack::omp_offset_count), catalog replicated, "
-                               "one NCCL all-gather of spectral_rad" if world > 1 else "single GPU",
+                   "sharding": ("levels of the line sum dealt over the ranks (rank r: levels r, r + N, ... for all frequencies), one NCCL "
+                                "all-to-all of K, Stokes chain on contiguous frequency blocks, one NCCL all-gather of spectral_rad"
+                                if level_split else
+                                "contiguous frequency blocks (matpack::omp_offset_count), catalog replicated, one NCCL all-gather of "
+                                "spectral_rad") if world > 1 else "single GPU",
                    "l2": "inputs exceed L2: per step the kernels write and re-read %.2f GB of line records, %.2f GB of cluster moments "
                          "and %.2f GB of K (L2 = 126 MB), no flush needed" % (cat.host.n_lines * 128.0 * np_ / 1e9,
                                                                                cat.host.n_lines / 256.0 * 21.3 * 160.0 * np_ / 1e9,
                                                                                cnt * np_ * 56.0 / 1e9)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "call": "ab200_clearsky_emission (host buffers, pinned)", "equals_resident_result": e2e_matches},
+                "steps": n_e2e, "call": e2e_call, "equals_resident_result": e2e_matches},
         "gpu_launches": launches,
         "roofline": {"bound": "fp64", "kernel": "real line sum: lbl_fmm_{moments,far,near}_kernel (lbl_sum_real_kernel for segments with ByLine cutoffs)",
                      "achieved": achieved_tf, "peak": dfma_tflops,
@@ -390,6 +444,9 @@ def run_b200(args):
 
     if args.workload == "c4" and args.c4_cutoff_ghz == 0 and not args.no_extra:
         # configs[3]-ii of SURVEY 8(d): the same shard with a 750 GHz ByLine cutoff (HITRAN practice); nominal pairs counted
+        # (plain frequency split at N > 1)
+        if lpath is not path:
+            lpath.close()
         path.close()
         cat.close()
         case2, name2 = workload(args, world, cutoff_ghz=750.0)
@@ -398,6 +455,7 @@ def run_b200(args):
         path = wsm.Path(cat, cnt2, np_, 0, stream=stream.cuda_stream)
         path.set_grid_bounds(np.tile([case2.f[0], case2.f[-1]], (np_, 1)))
         path.upload(mine2.f, mine2.atm, mine2.r, mine2.I_bkg, rte_option=args.rte)
+        lpath = path
         for _ in range(2):
             path.run_propmat(); path.run_stokes()
         barrier()
@@ -424,6 +482,8 @@ def run_b200(args):
             "sample": f"{len(idx)} of {nf_total} frequencies (uniform stride) x all {nl} lines x {np_} levels, {t:.1f} s"}
     if rank == 0:
         emit(line)
+    if lpath is not path:
+        lpath.close()
     path.close()
     cat.close()
     if world > 1:

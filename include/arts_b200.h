@@ -242,6 +242,12 @@ int ab200_planck_tb(int64_t nf, const double *f, double *I);
 /* ---- device-resident path workspace (what clearsky_emission is built on) --- */
 /* stream: a cudaStream_t (as void*) the caller wants the kernels on, or NULL for the library's own. */
 int ab200_path_create(const ab200_catalog *cat, int64_t nf, int32_t np, int32_t nq, ab200_path **out);
+/* A workspace that only runs the Stokes chain (and downloads): no line records, cluster moments or Jacobian scratch.  Its K
+ * [np][k_pitch][7], k_pitch = nf rounded up to 128 (ab200_path_device_ptr(p, 1)), is filled by the caller with rows that other
+ * workspaces of the SAME catalog, species selection and flags summed - e.g. after an exchange between devices that deal the
+ * levels of the line sum - and handed over with ab200_path_adopt_K after ab200_path_upload. */
+int ab200_path_create_stage2(const ab200_catalog *cat, int64_t nf, int32_t np, ab200_path **out);
+int ab200_path_adopt_K(ab200_path *p);
 void ab200_path_destroy(ab200_path *p);
 int ab200_path_set_stream(ab200_path *p, void *stream);
 /* H2D of one path's inputs (asynchronous on the path's stream; small arrays go through pinned staging owned by the

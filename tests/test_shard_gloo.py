@@ -117,3 +117,50 @@ def test_path_sharded_measurement_reduction(tmp_path, world, n_paths):
         np.testing.assert_allclose(ys, seq[:, -1], rtol=1e-9, atol=1e-9 * np.abs(contrib).max())
         np.testing.assert_allclose(Js, seq[:, :-1], rtol=1e-9, atol=1e-9 * np.abs(contrib).max())
     assert shard.path_ranges(10, 3) == [(0, 3), (3, 3), (6, 4)]
+
+
+def _level_worker(rank, world, port, nf, np_, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from arts_b200 import _abi as abi
+        from tests import oracle_lib as orc
+
+        case = synth.tiny_case(nl=48, nf=nf, np_=np_)
+        ex = shard.LevelExchange(np_, nf, rank, world)
+        assert ex.mine == list(range(rank, np_, world))
+        a = case.atm
+        sub = abi.AtmPath(T=a.T[ex.mine], P=a.P[ex.mine], vmr=a.vmr[ex.mine], isorat=a.isorat[ex.mine], Q=a.Q[ex.mine])
+        K1, _ = orc.propmat_levels(case.cat, case.f, sub)  # this rank's levels, ALL frequencies (stands in for the GPU line sum)
+        pitch1, pitch2 = nf + 5, ex.cnt + 3                # the library pads its level rows; the exchange must not care
+        K1p = torch.full((len(ex.mine), pitch1, 7), float("nan"), dtype=torch.float64)
+        K1p[:, :nf] = torch.from_numpy(K1)
+        K2p = torch.full((np_, pitch2, 7), float("nan"), dtype=torch.float64)
+        ex.exchange(K1p, K2p)
+        off, cnt = shard.frequency_ranges(nf, world)[rank]
+        K2 = np.ascontiguousarray(K2p[:, :cnt].numpy())
+        assert torch.isnan(K2p[:, cnt:]).all()
+        T, L, P, dT, dL = orc.tramat(K2, None, case.r, None, "linsrc")
+        J, dJ = orc.srcvec(K2, case.f[off:off + cnt], a.T, -1, 0)
+        I, _ = orc.rte_emission("linsrc", T, L, P, dT, dL, J, dJ, np.ascontiguousarray(case.I_bkg[off:off + cnt]))
+        full = shard.gather_spectral_rad(torch.from_numpy(np.ascontiguousarray(I)), nf)
+        np.save(os.path.join(tmp, f"lvl_{rank}.npy"), full.numpy())
+        np.save(os.path.join(tmp, f"K2_{rank}.npy"), K2)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nf,np_", [(2, 300, 7), (3, 66, 5), (2, 64, 2)])
+def test_level_split_exchange_is_bit_identical(tmp_path, orc, world, nf, np_):
+    """Levels dealt over the ranks for the line sum, frequency blocks for the Stokes chain, one all-to-all of K between them
+    (shard.LevelExchange, the torchrun twin of ab200_multi_*'s level split): K and the radiances equal the unsharded run bit
+    for bit, with ragged level counts (7 over 2, 5 over 3) and padded level rows."""
+    port = _free_port()
+    mp.spawn(_level_worker, args=(world, port, nf, np_, str(tmp_path)), nprocs=world, join=True)
+    case = synth.tiny_case(nl=48, nf=nf, np_=np_)
+    Kref, _ = orc.propmat_levels(case.cat, case.f, case.atm)
+    ref, _ = orc.clearsky_emission(case.cat, case.f, case.atm, case.r, case.I_bkg)
+    for r in range(world):
+        off, cnt = shard.frequency_ranges(nf, world)[r]
+        assert np.array_equal(np.load(tmp_path / f"K2_{r}.npy"), Kref[:, off:off + cnt]), f"K of rank {r}"
+        assert np.array_equal(np.load(tmp_path / f"lvl_{r}.npy"), ref), f"rank {r}"

@@ -100,3 +100,44 @@ def test_level_split_with_far_field_sums_and_wind(wsm, monkeypatch):
     I, _ = wsm.spectral_radClearskyEmission(m, c.f, c.atm, c.r, c.I_bkg)
     assert np.array_equal(I, I1)
     m.close()
+
+
+def test_stage2_workspace_adopts_K_from_level_workspaces(wsm):
+    """The C-ABI pieces of the level split (ab200_path_create_stage2, ab200_path_adopt_K), as bench.py uses them under torchrun:
+    two workspaces sum the even and the odd levels for all frequencies, their K rows are copied (torch, device to device) into
+    a Stokes-only workspace of a frequency block, and the radiances equal the ordinary one-workspace run bit for bit - for a
+    scalar case (the scalar Stokes instantiation must be chosen from the catalog, not from who wrote K) and a Zeeman case."""
+    torch = pytest.importorskip("torch")
+    from arts_b200 import _abi as abi
+    from arts_b200 import shard
+
+    dev = torch.device("cuda", 0)
+    for c in (synth.case_c2(lines_per_species=300, nf=777, np_=7, bands_per_species=3), synth.case_c3(nf=38 * 9, np_=5, los=(120.0, 30.0))):
+        I1, _, K1 = wsm.spectral_radClearskyEmission(c.cat, c.f, c.atm, c.r, c.I_bkg, return_propmat=True)
+        cat = wsm.Catalog(c.cat)
+        off, cnt = 128, c.nf - 128 - 7  # a frequency block in the middle of the grid
+        p2 = wsm.Path(cat, cnt, c.np_, 0, stage2_only=True)
+        p2.upload(c.f[off:off + cnt], c.atm, c.r, c.I_bkg[off:off + cnt])
+        K2 = shard.as_torch(p2.device_ptr(1), (c.np_, p2.k_pitch, 7), dev)
+        a = c.atm
+        for part in (0, 1):
+            lv = list(range(part, c.np_, 2))
+            pick = lambda x: None if x is None else np.ascontiguousarray(x[lv])  # noqa: E731
+            sub = abi.AtmPath(T=pick(a.T), P=pick(a.P), vmr=pick(a.vmr), isorat=pick(a.isorat), Q=pick(a.Q), mag=pick(a.mag), los=pick(a.los))
+            p1 = wsm.Path(cat, c.nf, len(lv), 0)
+            p1.upload(c.f, sub, np.zeros(max(len(lv) - 1, 1)), None)
+            p1.run_propmat()
+            p1.sync()
+            Kp = shard.as_torch(p1.device_ptr(1), (len(lv), p1.k_pitch, 7), dev)
+            K2[lv, :cnt, :] = Kp[:, off:off + cnt, :]
+            torch.cuda.synchronize()
+            p1.close()
+        with pytest.raises(wsm.Ab200Error, match="no line-sum buffers"):
+            p2.run_propmat()
+        p2.adopt_K()
+        p2.run_stokes()
+        I = np.empty((cnt, 4)); K = np.empty((c.np_, cnt, 7))
+        p2.download(I=I, K=K)
+        assert np.array_equal(K, K1[:, off:off + cnt])
+        assert np.array_equal(I, I1[off:off + cnt])
+        p2.close(); cat.close()

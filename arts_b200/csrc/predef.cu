@@ -11,12 +11,17 @@
 //                   continuum.  Their per-line strength, width and mixing terms depend on the level only (two `pow` and one
 //                   `exp` per line): the CTA evaluates them ONCE per (level, perturbed state) into shared memory and every
 //                   frequency then pays two divisions per line.  MPM93::nitrogen (MPM93.cc:33-73) is a closed form.
+//                   Rosenkranz's 2021 / 2022 revisions (src/core/predefined/PWR20xx.cc) go the same way: compute_h2o (:21-166,
+//                   16 / 20 lines, pressure shifts, the speed-dependent shape through the complex erfcx = w(i z) within ten
+//                   half-widths of a line that has a quadratic width), compute_o2 (:494-573, 49 lines with first- and
+//                   second-order mixing), compute_n2 (:792-833, closed form).
 //
 // One thread per (frequency, level); HBM bound on K (16 B per element, + 16 B per affected Jacobian row) for the closed-form
 // continua, arithmetic bound (2 x lines divisions per frequency and state) for the line lists.
 #include <cmath>
 
 #include "predef.hpp"
+#include "faddeeva.cuh"  // w(z): the complex erfcx of the speed-dependent PWR2021 / PWR2022 water lines
 
 #define AB200_TABLE_Q static __device__ const
 #include "predef_tables.h"
@@ -68,6 +73,13 @@ __device__ __noinline__ double predef_model(int m, double f, const PredefPoint& 
       const double dummy = C * pow(300. / a.T, x + 3) * a.P * pdry;
       return a.h2o * dummy * (f * f);
     }
+    case AB200_PREDEF_N2_SELFCONT_PWR2021: {  // PWR20xx::compute_n2
+      const double theta = 300.0 / a.T;
+      const double pdry_hpa = (a.P * (1.0 - a.h2o)) * 1e-2;
+      const double cont = (a.n2 / 0.781) * 9.95e-14 * (pdry_hpa * pdry_hpa) * pow(theta, 3.22);
+      const double f_ghz = f * 1e-9, q = f_ghz / 450.0;
+      return cont * (0.5 + 0.5 / (1.0 + q * q)) * (f_ghz * f_ghz) / 1000.0;
+    }
     case AB200_PREDEF_N2_SELFCONT_MPM93: {  // MPM93::nitrogen
       constexpr double xT = 3.500, xf = 1.500, S = 2.296e-31;
       const double G         = 1.930e-5 * pow(10.000, -9.000 * xf);
@@ -87,23 +99,36 @@ __device__ __noinline__ double predef_model(int m, double f, const PredefPoint& 
 
 __host__ __device__ inline int predef_species_of(int m, const ab200_predef_species& s) {
   switch (m) {
-    case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: return s.o2;
-    case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: return s.n2;
+    case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
+    case AB200_PREDEF_O2_PWR2022: return s.o2;
+    case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
     default: return s.h2o;
   }
 }
-__host__ __device__ inline bool predef_is_line_list(int m) { return m >= AB200_PREDEF_H2O_PWR98 && m <= AB200_PREDEF_O2_MPM89; }
+__host__ __device__ inline bool predef_is_line_list(int m) {
+  return (m >= AB200_PREDEF_H2O_PWR98 && m <= AB200_PREDEF_O2_MPM89) || (m >= AB200_PREDEF_H2O_PWR2021 && m <= AB200_PREDEF_O2_PWR2022);
+}
 
 // ---- line-list models: per (level, state) tables in shared memory ----------------------------------------------------
-constexpr int PD_MAX_LINES  = 44;
+constexpr int PD_MAX_LINES  = 49;
 constexpr int PD_MAX_STATES = 1 + AB200_MAX_TARGETS;
+constexpr int PD_REC = 8;
+static_assert(AB200_PWR2021_O2_LINES == AB200_PWR2022_O2_LINES && AB200_PWR2022_O2_LINES <= PD_MAX_LINES, "O2 line lists of PWR2021 / PWR2022");
 struct PredefTables {
-  double line[PD_MAX_STATES][PD_MAX_LINES][4];  // centre [GHz], strength, width, mixing term
-  double scal[PD_MAX_STATES][6];                // continuum and scale factors of the state
+  double line[PD_MAX_STATES][PD_MAX_LINES][PD_REC];  // centre [GHz], strength, width, mixing / shift / quadratic terms
+  double scal[PD_MAX_STATES][6];                     // continuum and scale factors of the state
 };
 __device__ __forceinline__ int predef_nlines(int m) {
-  return m == AB200_PREDEF_H2O_PWR98 ? AB200_PWR98_H2O_LINES : m == AB200_PREDEF_O2_PWR98 ? AB200_PWR98_O2_LINES
-       : m == AB200_PREDEF_H2O_MPM89 ? AB200_MPM89_H2O_LINES : AB200_MPM89_O2_LINES;
+  switch (m) {
+    case AB200_PREDEF_H2O_PWR98: return AB200_PWR98_H2O_LINES;
+    case AB200_PREDEF_O2_PWR98: return AB200_PWR98_O2_LINES;
+    case AB200_PREDEF_H2O_MPM89: return AB200_MPM89_H2O_LINES;
+    case AB200_PREDEF_O2_MPM89: return AB200_MPM89_O2_LINES;
+    case AB200_PREDEF_H2O_PWR2021: return AB200_PWR2021_H2O_LINES;
+    case AB200_PREDEF_H2O_PWR2022: return AB200_PWR2022_H2O_LINES;
+    case AB200_PREDEF_O2_PWR2021: return AB200_PWR2021_O2_LINES;
+    default: return AB200_PWR2022_O2_LINES;
+  }
 }
 // line l of model m at the point a: what depends on the level only
 __device__ __forceinline__ void predef_line_record(int m, int l, const PredefPoint& a, double* __restrict__ r) {
@@ -132,6 +157,34 @@ __device__ __forceinline__ void predef_line_record(int m, int l, const PredefPoi
     r[1] = pwv_dummy * c[1] * pow(theta, 3.5) * exp(c[2] * (1.000 - theta));
     r[2] = c[3] * 0.001 * (c[5] * pwv * pow(theta, c[6]) + pda * pow(theta, c[4]));
     r[3] = 0.0;
+  } else if (m == AB200_PREDEF_H2O_PWR2021 || m == AB200_PREDEF_H2O_PWR2022) {  // PWR20xx::compute_h2o, PWR20xx.cc:63-120
+    const bool y21   = m == AB200_PREDEF_H2O_PWR2021;
+    const double* c  = (y21 ? ab200_pwr2021_h2o : ab200_pwr2022_h2o) + 19 * l;
+    const double* sc = y21 ? ab200_pwr2021_h2o_scalars : ab200_pwr2022_h2o_scalars;
+    const double p_hpa = a.P * 1e-2, pvap_hpa = a.h2o * p_hpa, pdry_hpa = p_hpa - pvap_hpa;
+    const double pvap_bar = pvap_hpa * 1e-3, pdry_bar = pdry_hpa * 1e-3;
+    const double th = sc[0] / a.T, lth = log(th);
+    const double xd_air = c[8] <= 0 ? c[4] : c[8], xd_self = c[10] <= 0 ? c[6] : c[10];  // missing exponents: the width's
+    const double x2_air = c[14] <= 0 ? c[4] : c[14], x2_self = c[16] <= 0 ? c[6] : c[16];
+    const double w0 = c[3] * pdry_bar * pow(th, c[4]) + c[5] * pvap_bar * pow(th, c[6]);
+    r[0] = c[0];
+    r[1] = c[1] * pow(th, 2.5) * exp(c[2] * (1.0 - th));
+    r[2] = w0;
+    r[3] = c[13] * pdry_bar * pow(th, x2_air) + c[15] * pvap_bar * pow(th, x2_self);                                      // w2
+    r[4] = c[17] * pdry_bar + c[18] * pvap_bar;                                                                          // d2
+    r[5] = c[7] * pdry_bar * (1.0 - c[11] * lth) * pow(th, xd_air) + c[9] * pvap_bar * (1.0 - c[12] * lth) * pow(th, xd_self);  // shift
+    r[6] = w0 / (750.0 * 750.0 + w0 * w0);                                                                               // base
+  } else if (m == AB200_PREDEF_O2_PWR2021 || m == AB200_PREDEF_O2_PWR2022) {  // PWR20xx::compute_o2, PWR20xx.cc:516-545
+    const double* c = (m == AB200_PREDEF_O2_PWR2021 ? ab200_pwr2021_o2 : ab200_pwr2022_o2) + 10 * l;
+    const double theta = 300.0 / a.T, tm1 = theta - 1.0, b = pow(theta, 0.754);
+    const double pvap_pa = a.h2o * a.P, pdry_pa = a.P - pvap_pa;
+    const double den = (pdry_pa * 1e-5) * b + 1.2 * (pvap_pa * 1e-5) * theta, pe2 = den * den;
+    r[0] = c[0];
+    r[1] = c[1] * exp(-c[2] * tm1);
+    r[2] = c[3] * den;                   // width
+    r[3] = 1.0 + pe2 * (c[6] + c[7] * tm1);  // g
+    r[4] = den * (c[4] + c[5] * tm1);    // y
+    r[5] = pe2 * (c[8] + c[9] * tm1);    // delta_nu
   } else {  // MPM89::oxygen, MPM89.cc:372-400
     const double* c    = ab200_mpm89_o2 + 7 * l;
     const double theta = 300.0 / a.T, pwv = 1e-3 * a.P * a.h2o, pda = (1e-3 * a.P) - pwv;
@@ -159,6 +212,20 @@ __device__ __forceinline__ void predef_state_scalars(int m, const PredefPoint& a
     const double theta = 300.0 / a.T, pwv_dummy = 1e-3 * a.P, pwv = pwv_dummy * a.h2o, pda = pwv_dummy - pwv;
     s[0] = a.h2o;
     s[1] = pwv_dummy * (theta * theta * theta) * 1.000e-5 * ((0.113 * pda) + (3.57 * pwv * pow(theta, 7.5)));  // Nppc
+  } else if (m == AB200_PREDEF_H2O_PWR2021 || m == AB200_PREDEF_H2O_PWR2022) {
+    const double* sc = m == AB200_PREDEF_H2O_PWR2021 ? ab200_pwr2021_h2o_scalars : ab200_pwr2022_h2o_scalars;
+    const double p_hpa = a.P * 1e-2, pvap_hpa = a.h2o * p_hpa, pdry_hpa = p_hpa - pvap_hpa, thc = sc[1] / a.T;
+    s[0] = a.h2o;
+    s[1] = (sc[2] * pdry_hpa * pow(thc, sc[3]) + sc[4] * pvap_hpa * pow(thc, sc[5])) * pvap_hpa;  // continuum / (f^2 conv)
+    s[2] = a.P;
+    s[3] = a.T;
+  } else if (m == AB200_PREDEF_O2_PWR2021 || m == AB200_PREDEF_O2_PWR2022) {
+    const double theta = 300.0 / a.T, b = pow(theta, 0.754);
+    const double pvap_pa = a.h2o * a.P, pdry_pa = a.P - pvap_pa;
+    s[0] = a.o2;
+    s[1] = 0.56 * ((pdry_pa * 1e-5) * b + 1.2 * (pvap_pa * 1e-5) * theta);  // df_cont
+    s[2] = theta;
+    s[3] = pdry_pa;
   } else {
     const double theta = 300.0 / a.T, pwv = 1e-3 * a.P * a.h2o, pda = (1e-3 * a.P) - pwv;
     s[0] = a.o2;
@@ -168,7 +235,7 @@ __device__ __forceinline__ void predef_state_scalars(int m, const PredefPoint& a
 }
 // the model at frequency f [Hz] from the tables of one state.  ONE body (no inlining): the base and the perturbed evaluation of a
 // difference quotient must round alike, so that a target the model does not depend on gives an exact zero.
-__device__ __noinline__ double predef_line_model(int m, double f, const double (*__restrict__ L)[4], const double* __restrict__ s) {
+__device__ __noinline__ double predef_line_model(int m, double f, const double (*__restrict__ L)[PD_REC], const double* __restrict__ s) {
   const double ff = f * 1e-9;
   if (m == AB200_PREDEF_H2O_PWR98) {
     double sum = 0.0;
@@ -197,6 +264,54 @@ __device__ __noinline__ double predef_line_model(int m, double f, const double (
       SUM += L[l][1] * (SF1 + SF2) * (ff / F) * (ff / F);
     }
     return s[0] * (CONT + (2.414322e7 * SUM * s[3] * s[4] / 3.141592653589793238462643383279502884));
+  }
+  if (m == AB200_PREDEF_H2O_PWR2021 || m == AB200_PREDEF_H2O_PWR2022) {  // PWR20xx.cc:124-165
+    const int nl = m == AB200_PREDEF_H2O_PWR2021 ? AB200_PWR2021_H2O_LINES : AB200_PWR2022_H2O_LINES;
+    double line_sum = 0.0;
+    for (int l = 0; l < nl; l++) {
+      const double fl = L[l][0], w0 = L[l][2], w2 = L[l][3], d2 = L[l][4], shift = L[l][5], base = L[l][6];
+      const double df_1 = ff - fl - shift, df_2 = ff + fl + shift;
+      double resonant = 0.0;
+      if ((w2 > 0) && (fabs(df_1) < (10.0 * w0))) {
+        // speed-dependent Voigt core: sd = 2 (1 - sqrt(pi) xrt erfcx(xrt)) / (w2 - i d2), xrt = sqrt((w0 - 1.5 w2 + i (df + 1.5 d2)) / (w2 - i d2))
+        const double nr = w0 - 1.5 * w2, ni = df_1 + 1.5 * d2, dn = w2 * w2 + d2 * d2;
+        const double xr = (nr * w2 - ni * d2) / dn, xi = (ni * w2 + nr * d2) / dn;  // (nr + i ni) / (w2 - i d2)
+        const double mod = hypot(xr, xi);
+        double rr, ri;  // principal square root
+        if (mod == 0.0) { rr = 0.0; ri = 0.0; }
+        else if (xr >= 0.0) { rr = sqrt(0.5 * (mod + xr)); ri = xi / (2.0 * rr); }
+        else { ri = copysign(sqrt(0.5 * (mod - xr)), xi); rr = xi / (2.0 * ri); }
+        double er, ei;
+        faddeeva_w(-ri, rr, er, ei);  // erfcx(z) = w(i z)
+        constexpr double spi = 1.77245385090551603;
+        const double pr = spi * (rr * er - ri * ei), pi_ = spi * (rr * ei + ri * er);
+        const double qr = 2.0 * (1.0 - pr), qi = -2.0 * pi_;
+        resonant += (qr * w2 - qi * d2) / dn - base;  // Re[(qr + i qi) / (w2 - i d2)]
+      } else if (fabs(df_1) < 750.0) {
+        resonant += w0 / (df_1 * df_1 + w0 * w0) - base;
+      }
+      if (fabs(df_2) < 750.0) resonant += w0 / (df_2 * df_2 + w0 * w0) - base;
+      const double q = ff / fl;
+      line_sum += L[l][1] * resonant * (q * q);
+    }
+    line_sum = 1e-13 * 0.318309886183790671537767526745028724 * line_sum * s[2] * s[0] / (cst::k * s[3]);
+    return line_sum + s[1] * (ff * ff) * 1e-3;
+  }
+  if (m == AB200_PREDEF_O2_PWR2021 || m == AB200_PREDEF_O2_PWR2022) {  // PWR20xx.cc:547-570
+    const double f2 = ff * ff, dfc = s[1], theta = s[2];
+    const double cont = 1.584e-17 * f2 * dfc / (theta * (f2 + dfc * dfc));
+    double sum = 0.0;
+    for (int l = 0; l < AB200_PWR2021_O2_LINES; l++) {
+      const double fl = L[l][0], width = L[l][2], g = L[l][3], y = L[l][4], dnu = L[l][5];
+      const double df_1 = ff - fl - dnu, df_2 = ff + fl + dnu;
+      const double sfac_1 = (width * g + df_1 * y) / (df_1 * df_1 + width * width);
+      const double sfac_2 = (width * g - df_2 * y) / (df_2 * df_2 + width * width);
+      const double q = ff / fl;
+      sum += L[l][1] * (sfac_1 + sfac_2) * (q * q);
+    }
+    sum += cont;
+    const double absorption = 1.004 * 1e-13 * s[0] * 0.318309886183790671537767526745028724 / (cst::k * 300.0) * sum * s[3] * (theta * theta * theta);
+    return absorption > 0 ? absorption : 0.0;
   }
   constexpr double dB_km_to_1_m = 1e-3 / (10.0 * 0.434294481903251827651128918916605082);
   if (m == AB200_PREDEF_H2O_MPM89) {
@@ -316,10 +431,10 @@ int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, cons
     if (idx >= n_species) return set_error(AB200_ERR_INVALID, "predefined models: species index beyond the VMR vector");
   for (int k = 0; k < n_models; k++) {
     const int m = models[k];
-    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_N2_SELFCONT_MPM93)
+    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_N2_SELFCONT_PWR2021)
       return set_error(AB200_ERR_UNSUPPORTED, "predefined model " + std::to_string(m) +
-                                                  " is outside the GPU path (the StandardType continua, PWR98, MPM89 and the MPM93 N2 "
-                                                  "continuum are; no CPU fallback)");
+                                                  " is outside the GPU path (the StandardType continua, PWR98, MPM89, MPM93 N2 and "
+                                                  "PWR2021 / PWR2022 are; no CPU fallback)");
     const bool need_h2o = m != AB200_PREDEF_N2_SELFCONT_STANDARD;
     if (predef_species_of(m, *sp) < 0 || (need_h2o && sp->h2o < 0))
       return set_error(AB200_ERR_INVALID, "predefined model " + std::to_string(m) + " needs a species the atmosphere does not carry");

@@ -362,8 +362,8 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
  * (src/core/absorption/predefined_absorption_models.cc:219-317): the model's closed form added to K.A, the temperature row
  * by perturbation (model(T + d) - model(T)) / d and VMR rows by perturbation for targets of CO2, O2, N2, H2O and
  * liquidcloud only (:237-241, compute_vmr_deriv :202-216).  Models on the path: the four "StandardType" continua of
- * src/core/predefined/standard.cc (Rosenkranz 1993 / 1998) and the full microwave models PWR98 (H2O, O2), MPM89 (H2O, O2) and
- * the MPM93 N2 continuum; every other model name is AB200_ERR_UNSUPPORTED. */
+ * src/core/predefined/standard.cc (Rosenkranz 1993 / 1998) and the full microwave models PWR98 (H2O, O2), MPM89 (H2O, O2),
+ * the MPM93 N2 continuum and Rosenkranz's 2021 / 2022 revisions (H2O, O2, N2); every other model name is AB200_ERR_UNSUPPORTED. */
 #define AB200_PREDEF_O2_SELFCONT_STANDARD 0     /* "O2-SelfContStandardType",     Standard::oxygen        standard.cc:51-84 */
 #define AB200_PREDEF_N2_SELFCONT_STANDARD 1     /* "N2-SelfContStandardType",     Standard::nitrogen      :118-138 */
 #define AB200_PREDEF_H2O_FOREIGNCONT_STANDARD 2 /* "H2O-ForeignContStandardType", Standard::water_foreign :166-184 */
@@ -373,6 +373,11 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
 #define AB200_PREDEF_H2O_MPM89 6          /* "H2O-MPM89",        MPM89::water    MPM89.cc:95-180  (30 lines + continuum) */
 #define AB200_PREDEF_O2_MPM89 7           /* "O2-MPM89",         MPM89::oxygen   MPM89.cc:270-411 (44 lines with mixing + Debye term) */
 #define AB200_PREDEF_N2_SELFCONT_MPM93 8  /* "N2-SelfContMPM93", MPM93::nitrogen MPM93.cc:33-73 */
+#define AB200_PREDEF_H2O_PWR2021 9           /* "H2O-PWR2021",        PWR20xx::compute_h2o_2021 src/core/predefined/PWR20xx.cc:169-381 (16 lines) */
+#define AB200_PREDEF_H2O_PWR2022 10          /* "H2O-PWR2022",        PWR20xx::compute_h2o_2022 :383-491 (20 lines; shape :21-166) */
+#define AB200_PREDEF_O2_PWR2021 11           /* "O2-PWR2021",         PWR20xx::compute_o2_2021  :576-682 (49 lines; shape :494-573) */
+#define AB200_PREDEF_O2_PWR2022 12           /* "O2-PWR2022",         PWR20xx::compute_o2_2022  :684-790 */
+#define AB200_PREDEF_N2_SELFCONT_PWR2021 13  /* "N2-SelfContPWR2021", PWR20xx::compute_n2       :792-833 */
 typedef struct ab200_predef_species { /* indices into the vmr vector, -1 when the atmosphere does not carry the species */
   int32_t o2, n2, h2o, co2, liquidcloud;
 } ab200_predef_species;

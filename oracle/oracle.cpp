@@ -51,6 +51,8 @@ extern std::complex<double> w(std::complex<double> z, double relerr);
 extern double Dawson(double x);
 // reference 3rdparty/Faddeeva/Faddeeva.hh:55 (element-wise in rtepack::dawson(specmat), rtepack_spectral_matrix.cc:6-26)
 extern std::complex<double> Dawson(std::complex<double> z, double relerr);
+// reference 3rdparty/Faddeeva/Faddeeva.hh:46 (the speed-dependent line shape of PWR20xx::compute_h2o, PWR20xx.cc:145)
+extern std::complex<double> erfcx(std::complex<double> z, double relerr);
 }  // namespace Faddeeva
 
 namespace {
@@ -2623,9 +2625,106 @@ namespace predef {
 struct Pt {
   Numeric T, P, o2, n2, h2o;
 };
+
+// PWR20xx::compute_h2o, src/core/predefined/PWR20xx.cc:21-166: 16 / 20 H2O lines with pressure shifts, the speed-dependent
+// shape 2 (1 - sqrt(pi) xrt erfcx(xrt)) / (w2 - i d2) within 10 half-widths of a line that has a w2, Van Vleck-Weisskopf
+// wings with Clough's 750 GHz local-line definition elsewhere, and the foreign + self continuum.  tab: one row of 19 numbers
+// per line (arts_b200/csrc/predef_tables.h), sc: tref_lines, tref_cont, c_f, xc_f, c_s, xc_s.
+Numeric pwr20xx_h2o(const double* tab, int nl, const double* sc, Numeric f_hz, const Pt& a) {
+  using std::pow;
+  const Numeric t = a.T, p_pa = a.P, h2o_vmr = a.h2o;
+  const Numeric tref_lines = sc[0], tref_cont = sc[1], c_f = sc[2], xc_f = sc[3], c_s = sc[4], xc_s = sc[5];
+  const Numeric p_hpa = p_pa * 1e-2, pvap_hpa = h2o_vmr * p_hpa, pdry_hpa = p_hpa - pvap_hpa;
+  const Numeric pvap_bar = pvap_hpa * 1e-3, pdry_bar = pdry_hpa * 1e-3;
+  const Numeric theta_cont = tref_cont / t, theta_line = tref_lines / t;
+  const Numeric log_theta_line = std::log(theta_line);
+  constexpr Numeric line_cutoff = 750.0;
+  const Numeric f = f_hz * 1e-9;
+  constexpr Numeric conv_cont = 1e-3;
+  const Numeric cont = ((c_f * pdry_hpa * pow(theta_cont, xc_f) + c_s * pvap_hpa * pow(theta_cont, xc_s)) * pvap_hpa * pow2(f) * conv_cont);
+  Numeric line_sum = 0.0;
+  for (int i = 0; i < nl; i++) {
+    const double* c = tab + 19 * i;
+    const Numeric frequency_ghz = c[0], strength_296 = c[1], B = c[2], w0_air = c[3], xw_air = c[4], w0_self = c[5], xw_self = c[6],
+                  d_air = c[7], d_self = c[9], a_air = c[11], a_self = c[12], w2_air = c[13], w2_self = c[15], d2_air = c[17],
+                  d2_self = c[18];
+    // exponents that are not given fall back to the width's (:63-76)
+    const Numeric xd_air = c[8] <= 0 ? xw_air : c[8], xd_self = c[10] <= 0 ? xw_self : c[10];
+    const Numeric x2_air = c[14] <= 0 ? xw_air : c[14], x2_self = c[16] <= 0 ? xw_self : c[16];
+    const Numeric w0 = w0_air * pdry_bar * pow(theta_line, xw_air) + w0_self * pvap_bar * pow(theta_line, xw_self);
+    const Numeric w2 = w2_air * pdry_bar * pow(theta_line, x2_air) + w2_self * pvap_bar * pow(theta_line, x2_self);
+    const Numeric d2 = d2_air * pdry_bar + d2_self * pvap_bar;
+    const Numeric shift_f = d_air * pdry_bar * (1.0 - a_air * log_theta_line) * pow(theta_line, xd_air);
+    const Numeric shift_s = d_self * pvap_bar * (1.0 - a_self * log_theta_line) * pow(theta_line, xd_self);
+    const Numeric shift = shift_f + shift_s;
+    const Numeric strength = strength_296 * pow(theta_line, 2.5) * std::exp(B * (1.0 - theta_line));
+    const Numeric base = w0 / (pow2(line_cutoff) + pow2(w0));
+    const Numeric df_1 = f - frequency_ghz - shift, df_2 = f + frequency_ghz + shift;
+    Numeric resonant = 0.0;
+    if ((w2 > 0) && (std::abs(df_1) < (10.0 * w0))) {
+      const Complex denom = Complex(w2, -d2);
+      const Complex xc    = Complex(w0 - 1.5 * w2, df_1 + 1.5 * d2) / denom;
+      const Complex xrt   = std::sqrt(xc);
+      constexpr Numeric magic_number = 1.77245385090551603;
+      const Complex pxw = magic_number * xrt * Faddeeva::erfcx(xrt, 0);
+      const Complex sd  = 2.0 * (1.0 - pxw) / denom;
+      resonant += sd.real() - base;
+    } else if (std::abs(df_1) < line_cutoff) {
+      resonant += w0 / (pow2(df_1) + pow2(w0)) - base;
+    }
+    if (std::abs(df_2) < line_cutoff) resonant += w0 / (pow2(df_2) + pow2(w0)) - base;
+    line_sum += strength * resonant * pow2(f / frequency_ghz);
+  }
+  constexpr Numeric conv = 1e-13;
+  line_sum = conv * Constant::inv_pi * line_sum * p_pa * h2o_vmr / (Constant::k * t);
+  return line_sum + cont;
+}
+// PWR20xx::compute_o2, PWR20xx.cc:494-573: 49 O2 lines with first- and second-order mixing (y, g, delta_nu) and the dry
+// continuum; a non-positive total adds nothing (:567-569).  tab: one row of 10 numbers per line.
+Numeric pwr20xx_o2(const double* tab, int nl, Numeric f_hz, const Pt& a) {
+  const Numeric t = a.T, p_pa = a.P, o2_vmr = a.o2, h2o_vmr = a.h2o;
+  constexpr Numeric cont_width_300 = 0.56, x = 0.754, t_ref = 300.0;
+  const Numeric theta = t_ref / t, theta_minus_1 = theta - 1.0;
+  const Numeric b = std::pow(theta, x);
+  const Numeric pvap_pa = h2o_vmr * p_pa, pdry_pa = p_pa - pvap_pa;
+  const Numeric pvap_bar = pvap_pa * 1e-5, pdry_bar = pdry_pa * 1e-5;
+  const Numeric den = pdry_bar * b + 1.2 * pvap_bar * theta;
+  const Numeric df_cont = cont_width_300 * den, pe2 = pow2(den);
+  const Numeric f_ghz = f_hz * 1e-9, f2_ghz = pow2(f_ghz);
+  const Numeric cont = 1.584e-17 * f2_ghz * df_cont / (theta * (f2_ghz + pow2(df_cont)));
+  Numeric lines_sum = 0.0;  // std::valarray::sum(): the first element, then += in order
+  for (int i = 0; i < nl; i++) {
+    const double* c = tab + 10 * i;  // frequency_ghz, strength_300, be, width_300, y0, y1, g0, g1, dnu0, dnu1
+    const Numeric y = den * (c[4] + c[5] * theta_minus_1), delta_nu = pe2 * (c[8] + c[9] * theta_minus_1);
+    const Numeric g = 1.0 + pe2 * (c[6] + c[7] * theta_minus_1), width = c[3] * den;
+    const Numeric strength = c[1] * std::exp(-c[2] * theta_minus_1);
+    const Numeric df_1 = f_ghz - c[0] - delta_nu, df_2 = f_ghz + c[0] + delta_nu;
+    const Numeric den_1 = pow2(df_1) + pow2(width), den_2 = pow2(df_2) + pow2(width);
+    const Numeric sfac_1 = (width * g + df_1 * y) / den_1, sfac_2 = (width * g - df_2 * y) / den_2;
+    const Numeric line = strength * (sfac_1 + sfac_2) * pow2((f_ghz / c[0]));
+    lines_sum = i == 0 ? line : lines_sum + line;
+  }
+  const Numeric sum = lines_sum + cont;
+  constexpr Numeric conv = 1e-13;
+  const Numeric absorption = 1.004 * conv * o2_vmr * Constant::inv_pi / (Constant::k * t_ref) * sum * pdry_pa * pow3(theta);
+  return absorption > 0 ? absorption : 0.0;
+}
 Numeric model(int m, Numeric f, const Pt& a) {
   using std::pow;
   switch (m) {
+    case AB200_PREDEF_H2O_PWR2021: return pwr20xx_h2o(ab200_pwr2021_h2o, AB200_PWR2021_H2O_LINES, ab200_pwr2021_h2o_scalars, f, a);
+    case AB200_PREDEF_H2O_PWR2022: return pwr20xx_h2o(ab200_pwr2022_h2o, AB200_PWR2022_H2O_LINES, ab200_pwr2022_h2o_scalars, f, a);
+    case AB200_PREDEF_O2_PWR2021: return pwr20xx_o2(ab200_pwr2021_o2, AB200_PWR2021_O2_LINES, f, a);
+    case AB200_PREDEF_O2_PWR2022: return pwr20xx_o2(ab200_pwr2022_o2, AB200_PWR2022_O2_LINES, f, a);
+    case AB200_PREDEF_N2_SELFCONT_PWR2021: {  // PWR20xx::compute_n2, PWR20xx.cc:792-833
+      const Numeric theta = 300.0 / a.T;
+      const Numeric pdry_pa = a.P * (1.0 - a.h2o), pdry_hpa = pdry_pa * 1e-2;
+      constexpr Numeric assumed_n2_vmr = 0.781, continuum_coefficient = 9.95e-14;
+      const Numeric cont = (a.n2 / assumed_n2_vmr) * continuum_coefficient * pow2(pdry_hpa) * pow(theta, 3.22);
+      const Numeric f_ghz = f * 1e-9;
+      const Numeric frequency_dependence = 0.5 + 0.5 / (1.0 + pow2(f_ghz / 450.0));
+      return cont * frequency_dependence * pow2(f_ghz) / 1000.0;
+    }
     case AB200_PREDEF_O2_SELFCONT_STANDARD: {  // Standard::oxygen :51-84
       constexpr Numeric C = (1.108e-14 / pow2(3.0e2));
       const Numeric G0 = 5600.000, G0A = 1.000, G0B = 1.100, XG0d = 0.800, XG0w = 1.000;
@@ -2759,8 +2858,9 @@ Numeric model(int m, Numeric f, const Pt& a) {
 }
 int species_of(int m, const ab200_predef_species& s) {  // isot.spec of the model tag
   switch (m) {
-    case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: return s.o2;
-    case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: return s.n2;
+    case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
+    case AB200_PREDEF_O2_PWR2022: return s.o2;
+    case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
     default: return s.h2o;
   }
 }
@@ -2786,7 +2886,7 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
     const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o)};
     for (int k = 0; k < n_models; k++) {
       const int m = models[k];
-      if (m < 0 or m > AB200_PREDEF_N2_SELFCONT_MPM93) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (m < 0 or m > AB200_PREDEF_N2_SELFCONT_PWR2021) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
       if (predef::o2_vmr_refused(m, a))
         return fail(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of 1e-25");
       if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;

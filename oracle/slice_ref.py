@@ -76,6 +76,14 @@ SLICES_PREDEF = {
     "mpm89_water": ("src/core/predefined/MPM89.cc", r"void water\(PropmatVector& propmat_clearsky,", None, (95, 180), "block"),
     "mpm89_lineshape_o2": ("src/core/predefined/MPM89.cc", r"constexpr Numeric MPMLineShapeO2Function\(const Numeric gamma,", None, (203, 236), "block"),
     "mpm89_oxygen": ("src/core/predefined/MPM89.cc", r"void oxygen\(PropmatVector& propmat_clearsky,", None, (270, 411), "block"),
+    # Rosenkranz 2021 / 2022: the shared H2O and O2 line-shape functions, the four table-carrying wrappers, the N2 continuum
+    "pwr20xx_h2o_shape": ("src/core/predefined/PWR20xx.cc", r"void compute_h2o\(PropmatVector& propmat_clearsky,", None, (21, 166), "block"),
+    "pwr20xx_h2o_2021": ("src/core/predefined/PWR20xx.cc", r"void compute_h2o_2021\(PropmatVector& propmat_clearsky,", None, (169, 381), "block"),
+    "pwr20xx_h2o_2022": ("src/core/predefined/PWR20xx.cc", r"void compute_h2o_2022\(PropmatVector& propmat_clearsky,", None, (383, 491), "block"),
+    "pwr20xx_o2_shape": ("src/core/predefined/PWR20xx.cc", r"void compute_o2\(PropmatVector& propmat_clearsky,", None, (494, 573), "block"),
+    "pwr20xx_o2_2021": ("src/core/predefined/PWR20xx.cc", r"void compute_o2_2021\(PropmatVector& propmat_clearsky,", None, (576, 682), "block"),
+    "pwr20xx_o2_2022": ("src/core/predefined/PWR20xx.cc", r"void compute_o2_2022\(PropmatVector& propmat_clearsky,", None, (684, 790), "block"),
+    "pwr20xx_n2": ("src/core/predefined/PWR20xx.cc", r"void compute_n2\(PropmatVector& propmat_clearsky,", None, (792, 833), "block"),
     "mpm93_nitrogen": ("src/core/predefined/MPM93.cc", r"void nitrogen\(PropmatVector& propmat_clearsky,", None, (33, 73), "block"),
 }
 SLICES.update(SLICES_PREDEF)

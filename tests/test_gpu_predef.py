@@ -71,11 +71,14 @@ def test_lines_plus_continua_on_the_resident_path(wsm, orc):
 
 
 FULL_MODELS = ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93"]
+PWR20XX = ["H2O-PWR2021", "O2-PWR2021", "N2-SelfContPWR2021", "H2O-PWR2022", "O2-PWR2022"]
 
 
-@pytest.mark.parametrize("models", [["H2O-PWR98", "O2-PWR98", "N2-SelfContMPM93"], ["H2O-MPM89", "O2-MPM89"], FULL_MODELS + MODELS])
+@pytest.mark.parametrize("models", [["H2O-PWR98", "O2-PWR98", "N2-SelfContMPM93"], ["H2O-MPM89", "O2-MPM89"], FULL_MODELS + MODELS,
+                                    ["H2O-PWR2021", "O2-PWR2021", "N2-SelfContPWR2021"], ["H2O-PWR2022", "O2-PWR2022"], PWR20XX + MODELS])
 def test_full_microwave_models_host_buffers(wsm, orc, models):
-    """PWR98 (H2O, O2), MPM89 (H2O, O2), MPM93 N2: the per-level line tables the CTA builds in shared memory against the
+    """PWR98 (H2O, O2), MPM89 (H2O, O2), MPM93 N2, PWR2021 / PWR2022 (H2O with its speed-dependent cores through the device's
+    w(i z), O2 with second-order mixing, N2): the per-level line tables the CTA builds in shared memory against the
     oracle's per-frequency restatement (itself pinned bit for bit to the reference's object code, tests/test_refslice_pins.py),
     every level of a 9-level profile, 1-1000 GHz with the 60 GHz band resolved, temperature + three VMR rows."""
     f = np.sort(np.concatenate([np.linspace(1e9, 1e12, 1500), np.linspace(50e9, 70e9, 700), np.linspace(118.2e9, 119.3e9, 60)]))

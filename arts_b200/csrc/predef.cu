@@ -100,13 +100,14 @@ __device__ __noinline__ double predef_model(int m, double f, const PredefPoint& 
 __host__ __device__ inline int predef_species_of(int m, const ab200_predef_species& s) {
   switch (m) {
     case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
-    case AB200_PREDEF_O2_PWR2022: return s.o2;
+    case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: return s.o2;
     case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
     default: return s.h2o;
   }
 }
 __host__ __device__ inline bool predef_is_line_list(int m) {
-  return (m >= AB200_PREDEF_H2O_PWR98 && m <= AB200_PREDEF_O2_MPM89) || (m >= AB200_PREDEF_H2O_PWR2021 && m <= AB200_PREDEF_O2_PWR2022);
+  return (m >= AB200_PREDEF_H2O_PWR98 && m <= AB200_PREDEF_O2_MPM89) || (m >= AB200_PREDEF_H2O_PWR2021 && m <= AB200_PREDEF_O2_PWR2022) ||
+         m == AB200_PREDEF_O2_TRE05;
 }
 
 // ---- line-list models: per (level, state) tables in shared memory ----------------------------------------------------
@@ -127,6 +128,7 @@ __device__ __forceinline__ int predef_nlines(int m) {
     case AB200_PREDEF_H2O_PWR2021: return AB200_PWR2021_H2O_LINES;
     case AB200_PREDEF_H2O_PWR2022: return AB200_PWR2022_H2O_LINES;
     case AB200_PREDEF_O2_PWR2021: return AB200_PWR2021_O2_LINES;
+    case AB200_PREDEF_O2_TRE05: return AB200_TRE05_O2_LINES;
     default: return AB200_PWR2022_O2_LINES;
   }
 }
@@ -185,6 +187,13 @@ __device__ __forceinline__ void predef_line_record(int m, int l, const PredefPoi
     r[3] = 1.0 + pe2 * (c[6] + c[7] * tm1);  // g
     r[4] = den * (c[4] + c[5] * tm1);    // y
     r[5] = pe2 * (c[8] + c[9] * tm1);    // delta_nu
+  } else if (m == AB200_PREDEF_O2_TRE05) {  // TRE05::oxygen, TRE05.cc:274-284 (note: the mixing term scales with the TOTAL pressure)
+    const double* c    = ab200_tre05_o2 + 7 * l;
+    const double theta = 300.0 / a.T, pwv = 1.000000e-2 * a.P * a.h2o, pda = (1.000000e-2 * a.P) - pwv;
+    r[0] = c[0];
+    r[1] = 1.000e-6 * pda * c[1] / c[0] * (theta * theta * theta) * exp(c[2] * (1.0 - theta));
+    r[2] = c[3] * 0.001 * ((pda * pow(theta, 0.8 - c[4])) + (1.10 * pwv * theta));
+    r[3] = (c[5] + c[6] * theta) * (pda + pwv) * pow(theta, 0.8) * 0.001;
   } else {  // MPM89::oxygen, MPM89.cc:372-400
     const double* c    = ab200_mpm89_o2 + 7 * l;
     const double theta = 300.0 / a.T, pwv = 1e-3 * a.P * a.h2o, pda = (1e-3 * a.P) - pwv;
@@ -219,6 +228,11 @@ __device__ __forceinline__ void predef_state_scalars(int m, const PredefPoint& a
     s[1] = (sc[2] * pdry_hpa * pow(thc, sc[3]) + sc[4] * pvap_hpa * pow(thc, sc[5])) * pvap_hpa;  // continuum / (f^2 conv)
     s[2] = a.P;
     s[3] = a.T;
+  } else if (m == AB200_PREDEF_O2_TRE05) {
+    const double theta = 300.0 / a.T, pwv = 1.000000e-2 * a.P * a.h2o, pda = (1.000000e-2 * a.P) - pwv;
+    s[0] = a.o2;
+    s[1] = 6.140e-5 * pda * (theta * theta);           // strength_cont
+    s[2] = 0.560e-3 * (pwv + pda) * pow(theta, 0.800);  // gam_cont
   } else if (m == AB200_PREDEF_O2_PWR2021 || m == AB200_PREDEF_O2_PWR2022) {
     const double theta = 300.0 / a.T, b = pow(theta, 0.754);
     const double pvap_pa = a.h2o * a.P, pdry_pa = a.P - pvap_pa;
@@ -327,6 +341,19 @@ __device__ __noinline__ double predef_line_model(int m, double f, const double (
     for (; l < AB200_MPM89_H2O_LINES; l++) acc += term(l);
     return s[0] * dB_km_to_1_m * 0.1820 * ff * (acc + (s[1] * ff));
   }
+  if (m == AB200_PREDEF_O2_TRE05) {  // TRE05.cc:268-294: the MPM93 O2 form, lines added one after the other
+    if (s[0] == 0.) return 0.0;
+    double acc = 0.0;
+    for (int l = 0; l < AB200_TRE05_O2_LINES; l++) {
+      const double fl = L[l][0], gam = L[l][2], delta = L[l][3];
+      const double f_minus = (gam - delta * (fl - ff)) / ((fl - ff) * (fl - ff) + gam * gam);
+      const double f_plus  = (gam - delta * (fl + ff)) / ((fl + ff) * (fl + ff) + gam * gam);
+      acc += L[l][1] * (ff * (f_minus + f_plus));
+    }
+    if (acc < 0.000) acc = 0.0;
+    const double Nppc = s[1] * ff * s[2] / ((ff * ff) + (s[2] * s[2]));
+    return s[0] * dB_km_to_1_m * 0.1820 * ff * (acc + Nppc) / 0.2085;
+  }
   if (s[0] == 0.) return 0.0;
   auto term = [&](int l) {
     const double fl = L[l][0], gam = L[l][2], delta = L[l][3];
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
     if (p.select_species != AB200_SPECIES_BATH && predef_species_of(m, p.sp) != p.select_species) continue;  // CTA-uniform
     const bool lines = predef_is_line_list(m);
     if (lines) {
-      if ((m == AB200_PREDEF_O2_PWR98 || m == AB200_PREDEF_O2_MPM89) && threadIdx.x == 0)
+      if ((m == AB200_PREDEF_O2_PWR98 || m == AB200_PREDEF_O2_MPM89 || m == AB200_PREDEF_O2_TRE05) && threadIdx.x == 0)
         for (int st = 0; st < nstates; st++)
           if (pts[st].o2 != 0. && pts[st].o2 < 1.000e-25) atomicOr(p.flags, 32);
       __syncthreads();  // the previous model's tables have been read
@@ -431,7 +458,7 @@ int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, cons
     if (idx >= n_species) return set_error(AB200_ERR_INVALID, "predefined models: species index beyond the VMR vector");
   for (int k = 0; k < n_models; k++) {
     const int m = models[k];
-    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_N2_SELFCONT_PWR2021)
+    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_O2_TRE05)
       return set_error(AB200_ERR_UNSUPPORTED, "predefined model " + std::to_string(m) +
                                                   " is outside the GPU path (the StandardType continua, PWR98, MPM89, MPM93 N2 and "
                                                   "PWR2021 / PWR2022 are; no CPU fallback)");

@@ -2716,6 +2716,30 @@ Numeric model(int m, Numeric f, const Pt& a) {
     case AB200_PREDEF_H2O_PWR2022: return pwr20xx_h2o(ab200_pwr2022_h2o, AB200_PWR2022_H2O_LINES, ab200_pwr2022_h2o_scalars, f, a);
     case AB200_PREDEF_O2_PWR2021: return pwr20xx_o2(ab200_pwr2021_o2, AB200_PWR2021_O2_LINES, f, a);
     case AB200_PREDEF_O2_PWR2022: return pwr20xx_o2(ab200_pwr2022_o2, AB200_PWR2022_O2_LINES, f, a);
+    case AB200_PREDEF_O2_TRE05: {  // TRE05::oxygen, src/core/predefined/TRE05.cc:115-296 (line shape :37-70)
+      constexpr Numeric dB_km_to_1_m = (1.00000e-3 / (10.0 * std::numbers::log10e));
+      constexpr Numeric VMRISO = 0.2085, S0 = 6.140e-5, G0 = 0.560e-3, X0 = 0.800, Hz_to_GHz = 1.000000e-9, Pa_to_hPa = 1.000000e-2;
+      const Numeric t = a.T, p_pa = a.P, oxygen_vmr = a.o2, water_vmr = a.h2o;
+      if (oxygen_vmr == 0.) return 0.0;
+      const Numeric theta = (300.0 / t);
+      const Numeric pwv = Pa_to_hPa * p_pa * water_vmr, pda = (Pa_to_hPa * p_pa) - pwv;
+      const Numeric strength_cont = S0 * pda * pow(theta, 2.);
+      const Numeric gam_cont      = G0 * (pwv + pda) * pow(theta, X0);
+      const Numeric ff            = f * Hz_to_GHz;
+      const Numeric Nppc          = strength_cont * ff * gam_cont / (pow(ff, 2.) + pow(gam_cont, 2.));
+      Numeric Nppl = 0.0;
+      for (int i = 0; i < AB200_TRE05_O2_LINES; i++) {
+        const double* l = ab200_tre05_o2 + 7 * i;
+        const Numeric strength = 1.000e-6 * pda * l[1] / l[0] * pow(theta, 3.) * std::exp(l[2] * (1.0 - theta));
+        const Numeric gam      = (l[3] * 0.001 * ((pda * pow(theta, (0.8 - l[4]))) + (1.10 * pwv * theta)));
+        const Numeric delta    = ((l[5] + l[6] * theta) * (pda + pwv) * pow(theta, 0.8) * 0.001);
+        const Numeric f_minus  = (gam - delta * (l[0] - ff)) / ((l[0] - ff) * (l[0] - ff) + gam * gam);
+        const Numeric f_plus   = (gam - delta * (l[0] + ff)) / ((l[0] + ff) * (l[0] + ff) + gam * gam);
+        Nppl += strength * (ff * (f_minus + f_plus));
+      }
+      if (Nppl < 0.000) Nppl = 0.0000;
+      return oxygen_vmr * dB_km_to_1_m * 0.1820 * ff * (Nppl + Nppc) / VMRISO;
+    }
     case AB200_PREDEF_N2_SELFCONT_PWR2021: {  // PWR20xx::compute_n2, PWR20xx.cc:792-833
       const Numeric theta = 300.0 / a.T;
       const Numeric pdry_pa = a.P * (1.0 - a.h2o), pdry_hpa = pdry_pa * 1e-2;
@@ -2859,14 +2883,14 @@ Numeric model(int m, Numeric f, const Pt& a) {
 int species_of(int m, const ab200_predef_species& s) {  // isot.spec of the model tag
   switch (m) {
     case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
-    case AB200_PREDEF_O2_PWR2022: return s.o2;
+    case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: return s.o2;
     case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
     default: return s.h2o;
   }
 }
 // the full O2 models refuse a non-zero O2 mixing ratio below 1e-25 (PWR98.cc:363-370, MPM89.cc:345-352)
 bool o2_vmr_refused(int m, const Pt& a) {
-  return (m == AB200_PREDEF_O2_PWR98 or m == AB200_PREDEF_O2_MPM89) and a.o2 != 0. and a.o2 < 1.000e-25;
+  return (m == AB200_PREDEF_O2_PWR98 or m == AB200_PREDEF_O2_MPM89 or m == AB200_PREDEF_O2_TRE05) and a.o2 != 0. and a.o2 < 1.000e-25;
 }
 }  // namespace predef
 
@@ -2886,7 +2910,7 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
     const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o)};
     for (int k = 0; k < n_models; k++) {
       const int m = models[k];
-      if (m < 0 or m > AB200_PREDEF_N2_SELFCONT_PWR2021) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (m < 0 or m > AB200_PREDEF_O2_TRE05) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
       if (predef::o2_vmr_refused(m, a))
         return fail(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of 1e-25");
       if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;

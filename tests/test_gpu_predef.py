@@ -71,7 +71,7 @@ def test_lines_plus_continua_on_the_resident_path(wsm, orc):
 
 
 FULL_MODELS = ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93"]
-PWR20XX = ["H2O-PWR2021", "O2-PWR2021", "N2-SelfContPWR2021", "H2O-PWR2022", "O2-PWR2022"]
+PWR20XX = ["H2O-PWR2021", "O2-PWR2021", "N2-SelfContPWR2021", "H2O-PWR2022", "O2-PWR2022", "O2-TRE05"]
 
 
 @pytest.mark.parametrize("models", [["H2O-PWR98", "O2-PWR98", "N2-SelfContMPM93"], ["H2O-MPM89", "O2-MPM89"], FULL_MODELS + MODELS,
@@ -103,7 +103,7 @@ def test_full_o2_models_refuse_a_tiny_o2_mixing_ratio(wsm):
     atm = _atm(3)
     atm.vmr[1, 1] = 1e-26
     K = np.zeros((3, len(f), 7))
-    for m in ("O2-PWR98", "O2-MPM89"):
+    for m in ("O2-PWR98", "O2-MPM89", "O2-TRE05"):
         with pytest.raises(wsm.Ab200Error, match="below the threshold"):
             wsm.spectral_propmatAddPredefined(K, None, [m], abi.SPECIES_BATH, (), f, atm, SPECIES)
     atm.vmr[1, 1] = 0.0  # exactly zero: the models add nothing at that level (PWR98.cc:359-361)

@@ -377,7 +377,7 @@ def test_shape_evaluation_and_fd_derivative_bitwise(ref):
 
 
 @pytest.mark.parametrize("model", ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93", "H2O-PWR2021", "H2O-PWR2022",
-                                   "O2-PWR2021", "O2-PWR2022", "N2-SelfContPWR2021"])
+                                   "O2-PWR2021", "O2-PWR2022", "N2-SelfContPWR2021", "O2-TRE05"])
 def test_full_microwave_absorption_models_bitwise(ref, model):
     """f2: the oracle's restatement of PWR98::water / oxygen (src/core/predefined/PWR98.cc:40-242, :297-434), MPM89::water /
     oxygen (MPM89.cc:95-180, :270-411), MPM93::nitrogen (MPM93.cc:33-73) and Rosenkranz's 2021 / 2022 revisions
@@ -404,7 +404,7 @@ def test_full_microwave_absorption_models_bitwise(ref, model):
         assert np.all(K[0, :, 1:] == 0)
         if k not in (7, 9):
             assert A.max() > 0
-    if model in ("O2-PWR98", "O2-MPM89"):  # vmr below 1e-25: the reference's user error, and the oracle's
+    if model in ("O2-PWR98", "O2-MPM89", "O2-TRE05"):  # vmr below 1e-25: the reference's user error, and the oracle's
         A = np.zeros(len(f))
         assert ref.refslice_predef(mid, len(f), dptr(f), 250.0, 1e4, 1e-26, 0.78, 1e-3, dptr(A)) == 1
         atm = abi.AtmPath(T=np.array([250.0]), P=np.array([1e4]), vmr=np.array([[1e-26, 0.78, 1e-3]]), isorat=np.ones((1, 1)), Q=np.ones((1, 1)))

@@ -100,14 +100,14 @@ __device__ __noinline__ double predef_model(int m, double f, const PredefPoint& 
 __host__ __device__ inline int predef_species_of(int m, const ab200_predef_species& s) {
   switch (m) {
     case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
-    case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: return s.o2;
+    case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: case AB200_PREDEF_O2_MPM2020: return s.o2;
     case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
     default: return s.h2o;
   }
 }
 __host__ __device__ inline bool predef_is_line_list(int m) {
   return (m >= AB200_PREDEF_H2O_PWR98 && m <= AB200_PREDEF_O2_MPM89) || (m >= AB200_PREDEF_H2O_PWR2021 && m <= AB200_PREDEF_O2_PWR2022) ||
-         m == AB200_PREDEF_O2_TRE05;
+         m == AB200_PREDEF_O2_TRE05 || m == AB200_PREDEF_O2_MPM2020;
 }
 
 // ---- line-list models: per (level, state) tables in shared memory ----------------------------------------------------
@@ -129,6 +129,7 @@ __device__ __forceinline__ int predef_nlines(int m) {
     case AB200_PREDEF_H2O_PWR2022: return AB200_PWR2022_H2O_LINES;
     case AB200_PREDEF_O2_PWR2021: return AB200_PWR2021_O2_LINES;
     case AB200_PREDEF_O2_TRE05: return AB200_TRE05_O2_LINES;
+    case AB200_PREDEF_O2_MPM2020: return AB200_MPM2020_O2_LINES;
     default: return AB200_PWR2022_O2_LINES;
   }
 }
@@ -187,6 +188,15 @@ __device__ __forceinline__ void predef_line_record(int m, int l, const PredefPoi
     r[3] = 1.0 + pe2 * (c[6] + c[7] * tm1);  // g
     r[4] = den * (c[4] + c[5] * tm1);    // y
     r[5] = pe2 * (c[8] + c[9] * tm1);    // delta_nu
+  } else if (m == AB200_PREDEF_O2_MPM2020) {  // MPM2020::compute, MPM2020.cc:113-139: the std::transform block
+    const double* c = ab200_mpm2020_o2 + 10 * l;  // f0, c, a2, ga, y0, y1, g0, g1, dv0, dv1
+    const double p = a.P * 1e-5, theta = 300. / a.T, dt = theta - 1, ta1 = pow(theta, 0.754) * p, ta2 = ta1 * ta1;
+    r[0] = c[0];
+    r[1] = (c[1] / c[0]) * ((theta * theta * theta) * p) * exp(-c[2] * dt);
+    r[2] = c[3] * ta1;               // ga
+    r[3] = (c[6] + c[7] * dt) * ta2;  // g
+    r[4] = (c[4] + c[5] * dt) * ta1;  // y
+    r[5] = (c[8] + c[9] * dt) * ta2;  // dv
   } else if (m == AB200_PREDEF_O2_TRE05) {  // TRE05::oxygen, TRE05.cc:274-284 (note: the mixing term scales with the TOTAL pressure)
     const double* c    = ab200_tre05_o2 + 7 * l;
     const double theta = 300.0 / a.T, pwv = 1.000000e-2 * a.P * a.h2o, pda = (1.000000e-2 * a.P) - pwv;
@@ -228,6 +238,8 @@ __device__ __forceinline__ void predef_state_scalars(int m, const PredefPoint& a
     s[1] = (sc[2] * pdry_hpa * pow(thc, sc[3]) + sc[4] * pvap_hpa * pow(thc, sc[5])) * pvap_hpa;  // continuum / (f^2 conv)
     s[2] = a.P;
     s[3] = a.T;
+  } else if (m == AB200_PREDEF_O2_MPM2020) {
+    s[0] = a.o2;
   } else if (m == AB200_PREDEF_O2_TRE05) {
     const double theta = 300.0 / a.T, pwv = 1.000000e-2 * a.P * a.h2o, pda = (1.000000e-2 * a.P) - pwv;
     s[0] = a.o2;
@@ -340,6 +352,16 @@ __device__ __noinline__ double predef_line_model(int m, double f, const double (
     for (; l + 4 <= AB200_MPM89_H2O_LINES; l += 4) acc += (term(l) + term(l + 1)) + (term(l + 2) + term(l + 3));
     for (; l < AB200_MPM89_H2O_LINES; l++) acc += term(l);
     return s[0] * dB_km_to_1_m * 0.1820 * ff * (acc + (s[1] * ff));
+  }
+  if (m == AB200_PREDEF_O2_MPM2020) {  // sum_lines, MPM2020.cc:18-36, and :142-147
+    double acc = 0.0;
+    for (int l = 0; l < AB200_MPM2020_O2_LINES; l++) {
+      const double f0 = L[l][0], ga = L[l][2], g = L[l][3], y = L[l][4], dv = L[l][5];
+      const double d1 = ff - f0 - dv, d2 = ff + f0 + dv;
+      acc += L[l][1] * ((ga * (1 + g) + y * d1) / (ga * ga + d1 * d1) + (ga * (1 + g) - y * d2) / (ga * ga + d2 * d2));
+    }
+    constexpr double conv = 0.1820 * 1e-7 / (2.0946 * 0.434294481903251827651128918916605082);
+    return acc > 0 ? conv * s[0] * (ff * ff) * acc : 0.0;
   }
   if (m == AB200_PREDEF_O2_TRE05) {  // TRE05.cc:268-294: the MPM93 O2 form, lines added one after the other
     if (s[0] == 0.) return 0.0;
@@ -458,7 +480,7 @@ int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, cons
     if (idx >= n_species) return set_error(AB200_ERR_INVALID, "predefined models: species index beyond the VMR vector");
   for (int k = 0; k < n_models; k++) {
     const int m = models[k];
-    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_O2_TRE05)
+    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_O2_MPM2020)
       return set_error(AB200_ERR_UNSUPPORTED, "predefined model " + std::to_string(m) +
                                                   " is outside the GPU path (the StandardType continua, PWR98, MPM89, MPM93 N2 and "
                                                   "PWR2021 / PWR2022 are; no CPU fallback)");

@@ -379,6 +379,7 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
 #define AB200_PREDEF_O2_PWR2022 12           /* "O2-PWR2022",         PWR20xx::compute_o2_2022  :684-790 */
 #define AB200_PREDEF_N2_SELFCONT_PWR2021 13  /* "N2-SelfContPWR2021", PWR20xx::compute_n2       :792-833 */
 #define AB200_PREDEF_O2_TRE05 14             /* "O2-TRE05",           TRE05::oxygen src/core/predefined/TRE05.cc:115-296 (44 lines, MPM93 form) */
+#define AB200_PREDEF_O2_MPM2020 15           /* "O2-MPM2020",         MPM2020::compute src/core/predefined/MPM2020.cc:38-149 (38 lines, second-order mixing) */
 typedef struct ab200_predef_species { /* indices into the vmr vector, -1 when the atmosphere does not carry the species */
   int32_t o2, n2, h2o, co2, liquidcloud;
 } ab200_predef_species;

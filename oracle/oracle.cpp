@@ -2716,6 +2716,22 @@ Numeric model(int m, Numeric f, const Pt& a) {
     case AB200_PREDEF_H2O_PWR2022: return pwr20xx_h2o(ab200_pwr2022_h2o, AB200_PWR2022_H2O_LINES, ab200_pwr2022_h2o_scalars, f, a);
     case AB200_PREDEF_O2_PWR2021: return pwr20xx_o2(ab200_pwr2021_o2, AB200_PWR2021_O2_LINES, f, a);
     case AB200_PREDEF_O2_PWR2022: return pwr20xx_o2(ab200_pwr2022_o2, AB200_PWR2022_O2_LINES, f, a);
+    case AB200_PREDEF_O2_MPM2020: {  // MPM2020::compute + sum_lines, src/core/predefined/MPM2020.cc:18-36, :38-149
+      constexpr Numeric conv = 0.1820 * 1e-7 / (2.0946 * std::numbers::log10e), x = 0.754;
+      const Numeric p = a.P * 1e-5, theta = 300. / a.T, dt = theta - 1, tadapt = std::pow(theta, x);
+      const Numeric ta1 = tadapt * p, ta2 = pow2(tadapt * p), tp = pow3(theta) * p;
+      const Numeric f_ghz = f * 1e-9;
+      Numeric acc = 0;
+      for (int i = 0; i < AB200_MPM2020_O2_LINES; i++) {
+        const double* l = ab200_mpm2020_o2 + 10 * i;  // f0, c, a2, ga, y0, y1, g0, g1, dv0, dv1
+        const Numeric y = (l[4] + l[5] * dt) * ta1, g = (l[6] + l[7] * dt) * ta2, dv = (l[8] + l[9] * dt) * ta2;
+        const Numeric ga = l[3] * ta1;
+        const Numeric c  = (l[1] / l[0]) * tp * std::exp(-l[2] * dt);
+        acc += c * ((ga * (1 + g) + y * (f_ghz - l[0] - dv)) / (pow2(ga) + pow2(f_ghz - l[0] - dv)) +
+                    (ga * (1 + g) - y * (f_ghz + l[0] + dv)) / (pow2(ga) + pow2(f_ghz + l[0] + dv)));
+      }
+      return acc > 0 ? conv * a.o2 * pow2(f_ghz) * acc : 0.0;
+    }
     case AB200_PREDEF_O2_TRE05: {  // TRE05::oxygen, src/core/predefined/TRE05.cc:115-296 (line shape :37-70)
       constexpr Numeric dB_km_to_1_m = (1.00000e-3 / (10.0 * std::numbers::log10e));
       constexpr Numeric VMRISO = 0.2085, S0 = 6.140e-5, G0 = 0.560e-3, X0 = 0.800, Hz_to_GHz = 1.000000e-9, Pa_to_hPa = 1.000000e-2;
@@ -2883,7 +2899,7 @@ Numeric model(int m, Numeric f, const Pt& a) {
 int species_of(int m, const ab200_predef_species& s) {  // isot.spec of the model tag
   switch (m) {
     case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
-    case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: return s.o2;
+    case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: case AB200_PREDEF_O2_MPM2020: return s.o2;
     case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
     default: return s.h2o;
   }
@@ -2910,7 +2926,7 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
     const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o)};
     for (int k = 0; k < n_models; k++) {
       const int m = models[k];
-      if (m < 0 or m > AB200_PREDEF_O2_TRE05) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (m < 0 or m > AB200_PREDEF_O2_MPM2020) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
       if (predef::o2_vmr_refused(m, a))
         return fail(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of 1e-25");
       if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;

@@ -86,6 +86,7 @@ SLICES_PREDEF = {
     "pwr20xx_n2": ("src/core/predefined/PWR20xx.cc", r"void compute_n2\(PropmatVector& propmat_clearsky,", None, (792, 833), "block"),
     "tre05_lineshape_o2": ("src/core/predefined/TRE05.cc", r"constexpr Numeric MPMLineShapeO2Function\(const Numeric gamma,", None, (37, 70), "block"),
     "tre05_oxygen": ("src/core/predefined/TRE05.cc", r"void oxygen\(PropmatVector& propmat_clearsky,", None, (115, 296), "block"),
+    "mpm2020_all": ("src/core/predefined/MPM2020.cc", r"constexpr Index num = 38;", r"void compute\(PropmatVector& propmat_clearsky,", (16, 149), "block"),
     "mpm93_nitrogen": ("src/core/predefined/MPM93.cc", r"void nitrogen\(PropmatVector& propmat_clearsky,", None, (33, 73), "block"),
 }
 SLICES.update(SLICES_PREDEF)

@@ -71,7 +71,7 @@ def test_lines_plus_continua_on_the_resident_path(wsm, orc):
 
 
 FULL_MODELS = ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93"]
-PWR20XX = ["H2O-PWR2021", "O2-PWR2021", "N2-SelfContPWR2021", "H2O-PWR2022", "O2-PWR2022", "O2-TRE05"]
+PWR20XX = ["H2O-PWR2021", "O2-PWR2021", "N2-SelfContPWR2021", "H2O-PWR2022", "O2-PWR2022", "O2-TRE05", "O2-MPM2020"]
 
 
 @pytest.mark.parametrize("models", [["H2O-PWR98", "O2-PWR98", "N2-SelfContMPM93"], ["H2O-MPM89", "O2-MPM89"], FULL_MODELS + MODELS,

@@ -377,7 +377,7 @@ def test_shape_evaluation_and_fd_derivative_bitwise(ref):
 
 
 @pytest.mark.parametrize("model", ["H2O-PWR98", "O2-PWR98", "H2O-MPM89", "O2-MPM89", "N2-SelfContMPM93", "H2O-PWR2021", "H2O-PWR2022",
-                                   "O2-PWR2021", "O2-PWR2022", "N2-SelfContPWR2021", "O2-TRE05"])
+                                   "O2-PWR2021", "O2-PWR2022", "N2-SelfContPWR2021", "O2-TRE05", "O2-MPM2020"])
 def test_full_microwave_absorption_models_bitwise(ref, model):
     """f2: the oracle's restatement of PWR98::water / oxygen (src/core/predefined/PWR98.cc:40-242, :297-434), MPM89::water /
     oxygen (MPM89.cc:95-180, :270-411), MPM93::nitrogen (MPM93.cc:33-73) and Rosenkranz's 2021 / 2022 revisions

@@ -11,10 +11,15 @@ frequency shard per GPU: every GPU owns 125 000 frequencies.  The N-GPU run cove
 so N = 8 IS the 10^6 x 10^6 x 100 case and N = 1 is a uniformly strided eighth of it ("weak" scaling: the work per
 GPU is fixed).  `--workload c2` keeps round 1's configs[1] line.  One "step" = one pass of the hot path over that
 input: line prepare (K1) + line sum (K2/K3) + fused Stokes chain (K4-K6) + the NCCL gather of spectral_rad.
+At N > 1 the LEVELS of the line sum are dealt over the ranks (rank r: levels r, r + N, ... for all N x 125 000
+frequencies, so the per-(line, level) work is not repeated by every frequency shard), one NCCL all-to-all transposes
+K, and every rank runs the Stokes chain on its contiguous frequency block (arts_b200/shard.py LevelExchange, DESIGN.md
+section 6; AB200_BENCH_SPLIT=freq keeps the plain frequency split; same bits either way).
 
 Printed (rank 0, one JSON line): `value` = line*freq*level evaluations per second of the whole job with inputs
 resident in HBM, timed with CUDA events, max over ranks; `e2e` = the same metric through the reference-facing
-C-ABI call with HOST buffers (H2D and D2H inside the timed region); `roofline` for the dominant kernel (FP64-pipe
+C-ABI call with HOST buffers (H2D and D2H inside the timed region; at N > 1 the one-process multi-device call
+ab200_multi_clearsky_emission over the N devices, driven by rank 0); `roofline` for the dominant kernel (FP64-pipe
 bound line sum: algorithmic FLOPs of SURVEY.md 8(d) over the event-timed kernel duration, against the DFMA peak
 measured in this run); `roofline_stokes` (HBM bound); `cpu_baseline` = the CPU oracle (a port of the reference's
 path linked with the reference's own Faddeeva.cc) on this box's host cores on a bounded sample; `extra` = the

@@ -45,6 +45,8 @@ struct PredefParams {
   int32_t tg_kind[AB200_MAX_TARGETS], tg_species[AB200_MAX_TARGETS];
   double tg_d[AB200_MAX_TARGETS];
   int* flags;  // device error flags (bit 5: an O2 mixing ratio below the full models' threshold)
+  const double* wjac;  // [np][3] freq_wind_shift_jac per level: wind rows are d/df times f times this (spectral_propmat_jacWindFix,
+                       // what the line kernels leave in dK); null: the rows stay d/df (spectral_propmatAddPredefined alone)
 };
 
 struct PredefPoint {
@@ -423,9 +425,14 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
           if (idx == p.sp.h2o) b.h2o += p.tg_d[q], moved = true;
         }
       }
+      const bool wind = p.tg_kind[q] >= AB200_TARGET_WIND_U && p.tg_kind[q] <= AB200_TARGET_WIND_W;
+      bool first_wind = wind;  // jac_targets.find: the first target of that component
+      for (int q2 = 0; q2 < q && wind; q2++) first_wind = first_wind && p.tg_kind[q2] != p.tg_kind[q];
       if (moved) {
         pts[n] = b;
         state_of[q] = n++;
+      } else if (first_wind) {
+        state_of[q] = -3;  // frequency derivative by the target's perturbation (freq_jac, :280-296)
       } else if (counted) {
         state_of[q] = -1;  // a counted target that leaves the point alone: (model - model) / d = 0, nothing to add
       } else {
@@ -458,6 +465,13 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
     kacc += pm;
     for (int q = 0; q < p.nq; q++) {
       const int st = state_of[q];
+      if (st == -3) {  // wind target: (model(f + d) - model(f)) / d, then the wind fix of the resident rows
+        const double fd = f + p.tg_d[q];
+        const double pq = lines ? predef_line_model(m, fd, tab.line[0], tab.scal[0]) : predef_model(m, fd, a);
+        const double row = (pq - pm) / p.tg_d[q];
+        dacc[q] += p.wjac ? row * f * p.wjac[3 * lev + (p.tg_kind[q] - AB200_TARGET_WIND_U)] : row;
+        continue;
+      }
       if (st <= 0) continue;
       const double pq = lines ? predef_line_model(m, f, tab.line[st], tab.scal[st]) : predef_model(m, f, pts[st]);
       dacc[q] += (pq - pm) / p.tg_d[q];
@@ -513,9 +527,10 @@ int launch_predef(const PredefParams& p, int nlev, cudaStream_t stream) {
 int predef_on_path(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, const double* target_d, int64_t nf,
                    const double* d_f, int64_t f_stride, const double* d_ffac, const double* d_T, const double* d_P, const double* d_vmr,
                    int32_t n_species, int32_t select_species, double* d_K, double* d_dK, int64_t k_pitch, int32_t nq,
-                   const int32_t* tg_kind, const int32_t* tg_species, int np, int* d_flags, cudaStream_t stream) {
+                   const int32_t* tg_kind, const int32_t* tg_species, int np, int* d_flags, const double* d_wjac, cudaStream_t stream) {
   PredefParams pp{};
   pp.flags = d_flags;
+  pp.wjac = d_wjac;
   AB_TRY(predef_setup(pp, models, n_models, sp, n_species, nq, tg_kind, tg_species, target_d));
   pp.nf = nf; pp.f = d_f; pp.f_stride = f_stride; pp.ffac = d_ffac; pp.T = d_T; pp.P = d_P; pp.vmr = d_vmr;
   pp.n_species = n_species; pp.select_species = select_species; pp.K = d_K; pp.dK = d_dK; pp.k_pitch = k_pitch;

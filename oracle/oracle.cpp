@@ -2939,6 +2939,14 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
           b.T += target_d[it];
           dk(it) += (predef::model(m, f[i], b) - pm) / target_d[it];
         }
+        // freq_jac :280-296: every wind target present gets (model(f + d) - model(f)) / d, the frequency derivative that
+        // spectral_propmat_jacWindFix later turns into a wind row (the first target of each component, jac_targets.find)
+        for (int kind : {AB200_TARGET_WIND_U, AB200_TARGET_WIND_V, AB200_TARGET_WIND_W})
+          for (int q = 0; q < nq; q++)
+            if (targets[q].kind == kind) {
+              dk(q) += (predef::model(m, f[i] + target_d[q], a) - pm) / target_d[q];
+              break;
+            }
         // vmrs_jac :237-241: the first target of CO2, O2, N2, H2O, liquidcloud, in that order
         for (int idx : {sp->co2, sp->o2, sp->n2, sp->h2o, sp->liquidcloud}) {
           if (idx < 0) continue;

@@ -142,3 +142,56 @@ def test_microwave_window_tb_with_full_models(wsm, orc):
     assert np.abs(tb - tbr).max() <= 1e-6
     assert tb[:, 0].max() - tb[:, 0].min() > 20.0  # the 22, 60, 118 and 183 GHz features are there
     path.close(); cat.close()
+
+
+def test_wind_rows_of_the_continua(wsm, orc):
+    """freq_jac of PredefinedModel::compute (predefined_absorption_models.cc:280-296): a wind target's row is the frequency
+    derivative (model(f + d) - model(f)) / d.  Alone (spectral_propmatAddPredefined) it stays d/df; on the resident path it gets
+    the wind fix of the line rows, times f times freq_wind_shift_jac (spectral_propmat_jacWindFix), unless the caller asked for
+    d/df rows."""
+    f = np.linspace(20e9, 200e9, 901)
+    atm = _atm(5)
+    models = ["H2O-PWR98", "O2-PWR98", "O2-SelfContStandardType", "H2O-PWR2022"]
+    tg, d = (("wind_v",), ("T",), ("wind_u",)), (1e3, 0.1, 2e3)
+    Kr, dKr = orc.predef_levels(models, SPECIES, f, atm, targets=tg, target_d=d)
+    K = np.zeros((atm.np_, len(f), 7)); dK = np.zeros((atm.np_, 3, len(f), 7))
+    wsm.spectral_propmatAddPredefined(K, dK, models, abi.SPECIES_BATH, tg, f, atm, SPECIES, target_d=d)
+    np.testing.assert_allclose(K[..., 0], Kr[..., 0], rtol=1e-11)
+    for q in range(3):
+        sc = np.abs(dKr[:, q, :, 0]).max()
+        assert sc > 0 and np.abs(dK[:, q, :, 0] - dKr[:, q, :, 0]).max() <= 1e-5 * sc, q  # a 1e3 Hz difference quotient of 1e-15 noise
+    # independent check of the oracle row: centred difference of the model in frequency
+    Kp, _ = orc.predef_levels(models, SPECIES, f + 5e5, atm)
+    Km, _ = orc.predef_levels(models, SPECIES, f - 5e5, atm)
+    cd = (Kp[..., 0] - Km[..., 0]) / 1e6
+    assert np.abs(dKr[:, 0, :, 0] - cd).max() <= 2e-3 * np.abs(cd).max()  # narrow O2 lines at 20 hPa against a 1 MHz stencil
+
+    # resident path: lines + continua with a wind target, against lines alone + the oracle's d/df row times f * freq_wind_shift_jac
+    c = synth.tiny_case(nl=64, nf=400, np_=6, targets=(("wind_u",),))
+    c.atm.wind = np.tile([12.0, -7.0, 1.0], (c.np_, 1))
+    c.atm.los = np.tile([130.0, 25.0], (c.np_, 1))
+    species = {"H2O": 0, "O2": 1}
+    mdl = ["H2O-PWR98", "O2-PWR98"]
+    cat = wsm.Catalog(c.cat)
+
+    def run(with_continua, flags=0):
+        path = wsm.Path(cat, c.nf, c.np_, 1)
+        path.upload(c.f, c.atm, c.r, c.I_bkg, targets=(("wind_u",),), flags=flags)
+        path.run_propmat()
+        if with_continua:
+            path.add_predefined(mdl, species, target_d=(1e3,))
+        Kg = np.empty((c.np_, c.nf, 7)); dKg = np.empty((c.np_, 1, c.nf, 7))
+        path.download(K=Kg, dK=dKg)
+        path.close()
+        return Kg, dKg
+
+    (K0, dK0), (K1, dK1) = run(False), run(True)
+    fac_jac = [orc.wind_shift(c.atm.wind[i], c.atm.los[i]) for i in range(c.np_)]
+    f_lev = np.stack([fj[0] * c.f for fj in fac_jac])  # the shifted grid of every level
+    _, dref = orc.predef_levels(mdl, species, f_lev, c.atm, targets=(("wind_u",),), target_d=(1e3,))
+    want = dref[:, 0, :, 0] * f_lev * np.array([fj[1][0] for fj in fac_jac])[:, None]
+    got = dK1[:, 0, :, 0] - dK0[:, 0, :, 0]
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    (_, dK0f), (_, dK1f) = run(False, abi.FLAG_WIND_ROWS_DF), run(True, abi.FLAG_WIND_ROWS_DF)
+    assert np.abs((dK1f - dK0f)[:, 0, :, 0] - dref[:, 0, :, 0]).max() <= 1e-5 * np.abs(dref[:, 0, :, 0]).max()
+    cat.close()

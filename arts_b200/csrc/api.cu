@@ -777,6 +777,10 @@ int ab200_path_add_cia(ab200_path* p, const ab200_cia* cia, double T_extrapolfac
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: path not uploaded");
   if (!cia) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: null CIA data");
   if (cia_device(cia) != p->cat->device) return set_error(AB200_ERR_INVALID, "ab200_path_add_cia: CIA data and path live on different devices");
+  for (int q = 0; q < p->nq; q++)
+    if (p->tg_kind[q] >= AB200_TARGET_WIND_U && p->tg_kind[q] <= AB200_TARGET_WIND_W)
+      return set_error(AB200_ERR_UNSUPPORTED, "collision-induced absorption with a wind target (the re-extraction at f + df of "
+                                              "src/m_cia.cc:78-81, :123-129) is outside the GPU path; no CPU fallback");
   if (p->it >= 0 && !std::isnormal(dT))  // m_cia.cc:89-91
     return set_error(AB200_ERR_INVALID, "dt must be >0 and not NaN or Inf: " + std::to_string(dT));
   AB_CUDA(cudaSetDevice(p->cat->device));

@@ -247,6 +247,10 @@ extern "C" int ab200_cia_levels(const ab200_cia* cia, int64_t nf, const double* 
   if (nq > 0 && (!targets || !dK)) return set_error(AB200_ERR_INVALID, "ab200_cia_levels: null Jacobian argument with nq > 0");
   if (f_level_stride != 0 && f_level_stride != nf) return set_error(AB200_ERR_INVALID, "f_level_stride must be 0 or nf");
   if (cia_max_species(cia) >= n_species) return set_error(AB200_ERR_INVALID, "ab200_cia_levels: a CIA record names a species beyond n_species");
+  for (int q = 0; q < nq; q++)
+    if (targets[q].kind >= AB200_TARGET_WIND_U && targets[q].kind <= AB200_TARGET_WIND_W)
+      return set_error(AB200_ERR_UNSUPPORTED, "collision-induced absorption with a wind target (the re-extraction at f + df of "
+                                              "src/m_cia.cc:78-81, :123-129) is outside the GPU path; no CPU fallback");
   const int np = atm->np;
   if (np == 0 || nf == 0) return AB200_OK;
   CiaParams cp{};

@@ -43,6 +43,10 @@ def test_cia_levels_host_buffers(wsm, orc):
     K = np.zeros((atm.np_, len(f), 7))
     wsm.spectral_propmatAddCIA(K, None, f2, (), abi.SPECIES_BATH, cia, atm)
     np.testing.assert_allclose(K[..., 0], Kr[..., 0], rtol=1e-11, atol=1e-13 * Kr.max())
+    # a wind target would need the re-extraction at f + df (m_cia.cc:78-81): refused, not ignored
+    with pytest.raises(wsm.Ab200Error, match="wind target") as e:
+        wsm.spectral_propmatAddCIA(np.zeros((atm.np_, len(f), 7)), np.zeros((atm.np_, 1, len(f), 7)), f, (("wind_u",),), abi.SPECIES_BATH, cia, atm)
+    assert e.value.code == abi.ERR_UNSUPPORTED
     cia.close()
 
 

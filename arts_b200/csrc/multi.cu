@@ -6,7 +6,9 @@
 // catalog replica, one worker thread (with its own stream, pinned staging and cached workspace) per device — and every
 // device copies its results straight into the caller's arrays.  No collective: the path is independent per frequency.
 //
-// Split: 512-frequency blocks dealt round-robin (block b -> device b mod N).  The cost of a frequency is not uniform
+// ab200_multi_propmat_levels deals contiguous blocks of LEVELS (its outputs are level-major: no replication, no exchange).
+// ab200_multi_clearsky_emission with Jacobian targets or per-level grids splits the frequencies:
+// 512-frequency blocks dealt round-robin (block b -> device b mod N).  The cost of a frequency is not uniform
 // (the number of near pairs grows with frequency where Doppler widths do, and with a ByLine cutoff so does the number of
 // lines in window), so contiguous chunks like the reference's omp_offset_count are unbalanced: round 1 measured 1.71x
 // on 2 GPUs for configs[3] with a 750 GHz cutoff.  512 is the block width of the line-sum kernels, so a device's CTAs see
@@ -368,47 +370,28 @@ int ab200_multi_propmat_levels(ab200_multi* m, int64_t nf, const double* f, int6
   if (f_level_stride != 0 && f_level_stride != nf)
     return ab200::set_error(AB200_ERR_INVALID, "f_level_stride must be 0 (shared grid) or nf (one grid per level)");
   if (nq > 0 && !dK) return ab200::set_error(AB200_ERR_INVALID, "ab200_multi_propmat_levels: dK is null with nq > 0");
-  if (nf == 0) return AB200_OK;
+  if (nf == 0 || atm->np == 0) return AB200_OK;
+  // K [np][nf][7] and dK [np][nq][nf][7] are level-major: device d takes a contiguous block of LEVELS for all frequencies and
+  // writes its rows straight into the caller's arrays (`+=` included) - nothing is replicated (the line records and cluster
+  // moments are work per level), nothing is exchanged, nothing is gathered on the host.  Levels do not interact in this call,
+  // so every row is the row of the one-device call bit for bit.
   const int n = static_cast<int>(m->w.size()), np = atm->np;
-  const int nlev_f = f_level_stride ? np : 1;
-  std::vector<double> bounds;
-  grid_bounds(nf, f, f_level_stride, f_level_stride ? np : 1, bounds);
-  if (!f_level_stride) {
-    bounds.resize(2 * static_cast<size_t>(std::max(np, 1)));
-    for (int ip = 1; ip < np; ip++) bounds[2 * ip] = bounds[0], bounds[2 * ip + 1] = bounds[1];
-  }
+  const int per = (np + n - 1) / n;
   return run_all(m, [&](Worker& w, int d) -> int {
-    const int64_t cnt = local_count(nf, n, d);
-    if (cnt == 0) return AB200_OK;
-    w.f.resize(static_cast<size_t>(cnt) * nlev_f);
-    w.K.resize(static_cast<size_t>(np) * cnt * 7);
-    if (nq > 0) w.dK.resize(static_cast<size_t>(np) * nq * cnt * 7);
-    const bool in = !(flags & AB200_FLAG_K_ZERO_INIT);  // += into the caller's values
-    for_blocks(nf, n, d, [&](int64_t g, int64_t l, int64_t c) {
-      for (int ip = 0; ip < nlev_f; ip++)
-        std::memcpy(&w.f[static_cast<size_t>(ip) * cnt + l], f + static_cast<size_t>(ip) * f_level_stride + g, c * sizeof(double));
-      if (in) {
-        for (int ip = 0; ip < np; ip++) {
-          std::memcpy(&w.K[(static_cast<size_t>(ip) * cnt + l) * 7], K + (static_cast<size_t>(ip) * nf + g) * 7, 7 * c * sizeof(double));
-          for (int q = 0; q < nq; q++)
-            std::memcpy(&w.dK[((static_cast<size_t>(ip) * nq + q) * cnt + l) * 7], dK + ((static_cast<size_t>(ip) * nq + q) * nf + g) * 7,
-                        7 * c * sizeof(double));
-        }
-      }
-    });
-    AB_TRY(ab200_set_thread_grid_bounds(np, bounds.data()));
-    const int rc = ab200_propmat_levels(w.cat, cnt, w.f.data(), f_level_stride ? cnt : 0, atm, select_species, no_negative_absorption, nq,
-                                        targets, flags, w.K.data(), nq > 0 ? w.dK.data() : nullptr);
-    ab200_set_thread_grid_bounds(0, nullptr);
-    if (rc) return rc;
-    for_blocks(nf, n, d, [&](int64_t g, int64_t l, int64_t c) {
-      for (int ip = 0; ip < np; ip++) {
-        std::memcpy(K + (static_cast<size_t>(ip) * nf + g) * 7, &w.K[(static_cast<size_t>(ip) * cnt + l) * 7], 7 * c * sizeof(double));
-        for (int q = 0; q < nq; q++)
-          std::memcpy(dK + ((static_cast<size_t>(ip) * nq + q) * nf + g) * 7, &w.dK[((static_cast<size_t>(ip) * nq + q) * cnt + l) * 7],
-                      7 * c * sizeof(double));
-      }
-    });
-    return AB200_OK;
+    const int l0 = std::min(np, d * per), l1 = std::min(np, l0 + per);
+    if (l1 <= l0) return AB200_OK;
+    ab200_atm_path sub = *atm;
+    sub.np = l1 - l0;
+    sub.T = atm->T + l0; sub.P = atm->P + l0;
+    sub.vmr = atm->vmr + static_cast<size_t>(l0) * m->n_species;
+    sub.isorat = atm->isorat + static_cast<size_t>(l0) * m->n_isot;
+    sub.Q = atm->Q + static_cast<size_t>(l0) * m->n_isot;
+    sub.dQdT = atm->dQdT ? atm->dQdT + static_cast<size_t>(l0) * m->n_isot : nullptr;
+    sub.mag = atm->mag ? atm->mag + 3 * static_cast<size_t>(l0) : nullptr;
+    sub.los = atm->los ? atm->los + 2 * static_cast<size_t>(l0) : nullptr;
+    sub.wind = atm->wind ? atm->wind + 3 * static_cast<size_t>(l0) : nullptr;
+    return ab200_propmat_levels(w.cat, nf, f + static_cast<size_t>(l0) * f_level_stride, f_level_stride, &sub, select_species,
+                                no_negative_absorption, nq, targets, flags, K + static_cast<size_t>(l0) * nf * 7,
+                                nq > 0 ? dK + static_cast<size_t>(l0) * nq * nf * 7 : nullptr);
   });
 }

@@ -157,6 +157,29 @@ int main(void) {
   for (j = 0; j < NF; j++)
     if (fabs((K2[7 * j] - 0.25) - K[7 * j]) > 1e-9 * fabs(K[7 * j]) + 1e-25 || K2[7 * j + 1] != 0.25) { printf("+= semantics\n"); return 12; }
 
+  /* one host process, several devices: two workers (on device 0 twice when the box has one GPU), levels
+   * dealt over them for the line sum, K transposed between them, the Stokes chain per frequency slice - the bits of one device */
+  {
+    const int32_t devs[2] = {0, ab200_device_count() > 1 ? 1 : 0};
+    ab200_multi *mu = NULL;
+    if (ab200_clearsky_emission(cat, NF, f, 0, &atm, AB200_SPECIES_BATH, 1, 0, NULL, r, 0, AB200_RTE_LINSRC, I_bkg, 0, Io, NULL, NULL) != AB200_OK) {
+      printf("clearsky: %s\n", ab200_last_error()); return 13;
+    }
+    if (ab200_multi_create(&d, 2, devs, &mu) != AB200_OK || ab200_multi_device_count(mu) != 2) { printf("multi_create: %s\n", ab200_last_error()); return 14; }
+    if (ab200_multi_clearsky_emission(mu, NF, f, 0, &atm, AB200_SPECIES_BATH, 1, 0, NULL, r, 0, AB200_RTE_LINSRC, I_bkg, 0, I, NULL, NULL) != AB200_OK) {
+      printf("multi clearsky: %s\n", ab200_last_error()); return 15;
+    }
+    for (i = 0; i < NF * 4; i++)
+      if (I[i] != Io[i]) { printf("multi-device radiance differs from the one-device radiance at %ld\n", (long)i); return 16; }
+    for (i = 0; i < NF * 7; i++) K2[i] = 0.0;
+    if (ab200_multi_propmat_levels(mu, NF, f, 0, &one, AB200_SPECIES_BATH, 1, 0, NULL, AB200_FLAG_K_ZERO_INIT, K2, NULL) != AB200_OK) {
+      printf("multi propmat: %s\n", ab200_last_error()); return 17;
+    }
+    for (j = 0; j < NF; j++)
+      if (K2[7 * j] != K[7 * j]) { printf("multi-device propmat differs at %ld\n", (long)j); return 18; }
+    ab200_multi_destroy(mu);
+  }
+
   ab200_catalog_destroy(cat);
   printf("abi gpu ok: propmat %.2e, Tb %.2e K\n", worst, tb_err);
   return 0;

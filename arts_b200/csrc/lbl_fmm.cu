@@ -158,24 +158,39 @@ __global__ void __launch_bounds__(TL, 4) lbl_fmm_moments_tile_kernel(PreparePara
   // --- per cluster: radius R, reach D of the mid form, window bounds (every line inside its window up to IN, every line
   // outside beyond OUT) and the sum of the cutoff values
   const double R0 = warp_max(live ? line_radius(d0, GD, g) : 0.0, 16), D0 = warp_max(live ? line_reach(d0, GD, y) : 0.0, 16);
-  const double I0 = warp_min(has_cut ? cutl - fabs(d0) : DBL_MAX, 16), O0 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d0) : DBL_MAX, 16);
-  double CS0 = cval;
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) CS0 += __shfl_xor_sync(0xffffffffu, CS0, o);
   double R1 = warp_max(live ? line_radius(d1, GD, g) : 0.0, 32), D1 = warp_max(live ? line_reach(d1, GD, y) : 0.0, 32);
-  double I1 = warp_min(has_cut ? cutl - fabs(d1) : DBL_MAX, 32), O1 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d1) : DBL_MAX, 32);
   double R2 = warp_max(live ? line_radius(d2, GD, g) : 0.0, 32), D2 = warp_max(live ? line_reach(d2, GD, y) : 0.0, 32);
-  double I2 = warp_min(has_cut ? cutl - fabs(d2) : DBL_MAX, 32), O2 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d2) : DBL_MAX, 32);
+  // Window bounds and cutoff sums: a tile without a ByLine cutoff (the common case) has IN = +inf, OUT = +inf where a cluster has
+  // a line (0 where it is empty) and no cutoff values - the seven reductions below would only confirm that.  The vote is on the
+  // cutoff itself (+inf for a dead lane), not on has_cut: with `__syncthreads_or(has_cut)` nvcc 12.9 folds the OUT operands below
+  // to `live ? +inf : 0` (the cutoff case is dropped from the PTX), and every cutoff cluster falls back to the pair-by-pair pass
+  // (tests/test_gpu_farfield.py::test_cutoff_case_is_served_by_the_far_field times exactly that)
+  const bool tile_has_cut = __syncthreads_or(cutl < DBL_MAX) != 0;
+  double I0 = DBL_MAX, O0 = e0 ? 0.0 : DBL_MAX, CS0 = 0.0, I1 = DBL_MAX, O1 = DBL_MAX, I2 = DBL_MAX, O2 = DBL_MAX;
+  if (tile_has_cut) {
+    I0 = warp_min(has_cut ? cutl - fabs(d0) : DBL_MAX, 16);
+    O0 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d0) : DBL_MAX, 16);
+    CS0 = cval;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) CS0 += __shfl_xor_sync(0xffffffffu, CS0, o);
+    I1 = warp_min(has_cut ? cutl - fabs(d1) : DBL_MAX, 32); O1 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d1) : DBL_MAX, 32);
+    I2 = warp_min(has_cut ? cutl - fabs(d2) : DBL_MAX, 32); O2 = warp_max(!live ? 0.0 : has_cut ? cutl + fabs(d2) : DBL_MAX, 32);
+  }
   if ((lane & 31) == 0) {
     double* r = sh[warp];
     r[0] = R1; r[1] = D1; r[2] = I1; r[3] = O1; r[4] = R2; r[5] = D2; r[6] = I2; r[7] = O2;
   }
   __syncthreads();
   R1 = fmax(sh[w1][0], sh[w1 + 1][0]); D1 = fmax(sh[w1][1], sh[w1 + 1][1]);
-  I1 = fmin(sh[w1][2], sh[w1 + 1][2]); O1 = fmax(sh[w1][3], sh[w1 + 1][3]);
-  R2 = 0.0; D2 = 0.0; I2 = DBL_MAX; O2 = 0.0;
-  for (int w = 0; w < TL / 32; w++) {
-    R2 = fmax(R2, sh[w][4]); D2 = fmax(D2, sh[w][5]); I2 = fmin(I2, sh[w][6]); O2 = fmax(O2, sh[w][7]);
+  R2 = 0.0; D2 = 0.0;
+  for (int w = 0; w < TL / 32; w++) { R2 = fmax(R2, sh[w][4]); D2 = fmax(D2, sh[w][5]); }
+  if (tile_has_cut) {
+    I1 = fmin(sh[w1][2], sh[w1 + 1][2]); O1 = fmax(sh[w1][3], sh[w1 + 1][3]);
+    I2 = DBL_MAX; O2 = 0.0;
+    for (int w = 0; w < TL / 32; w++) { I2 = fmin(I2, sh[w][6]); O2 = fmax(O2, sh[w][7]); }
+  } else {
+    O1 = e1 ? 0.0 : DBL_MAX;
+    O2 = e2 ? 0.0 : DBL_MAX;
   }
   __syncthreads();
 

@@ -114,7 +114,8 @@ class PredefSpecies(C.Structure):
 
 PREDEF_MODELS = {"O2-SelfContStandardType": 0, "N2-SelfContStandardType": 1, "H2O-ForeignContStandardType": 2,
                  "H2O-SelfContStandardType": 3, "H2O-PWR98": 4, "O2-PWR98": 5, "H2O-MPM89": 6, "O2-MPM89": 7, "N2-SelfContMPM93": 8,
-                 "H2O-PWR2021": 9, "H2O-PWR2022": 10, "O2-PWR2021": 11, "O2-PWR2022": 12, "N2-SelfContPWR2021": 13, "O2-TRE05": 14, "O2-MPM2020": 15}
+                 "H2O-PWR2021": 9, "H2O-PWR2022": 10, "O2-PWR2021": 11, "O2-PWR2022": 12, "N2-SelfContPWR2021": 13, "O2-TRE05": 14, "O2-MPM2020": 15,
+                 "liquidcloud-ELL07": 16}
 
 
 def predef_args(models, species):

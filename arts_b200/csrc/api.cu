@@ -913,6 +913,9 @@ static int check_flags(ab200_path* p) {
     if (h & 32)  // PWR98.cc:363-370, MPM89.cc:345-352
       return set_error(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold "
                                           "of 1e-25.  Therefore no calculation is performed.");
+    if (h & 64)  // ELL07.cc:99-117
+      return set_error(AB200_ERR_INVALID, "Liquid cloud absorption model ELL07: liquid water content above 5e-3 kg/m3, temperature outside "
+                                          "210-373 K or frequencies above 25 THz (only valid inside these ranges)");
     if (h & 16)
       return set_error(AB200_ERR_INVALID,
                        "Error in check_limit: a frequency, pressure, temperature offset or water ratio is outside the "

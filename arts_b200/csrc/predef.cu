@@ -49,8 +49,13 @@ struct PredefParams {
                        // what the line kernels leave in dK); null: the rows stay d/df (spectral_propmatAddPredefined alone)
 };
 
+// ELL07.cc:99-117
+#define PREDEF_ELL07_RANGE_MSG                                                                                                       \
+  "Liquid cloud absorption model ELL07: liquid water content above 5e-3 kg/m3, temperature outside 210-373 K or frequencies above " \
+  "25 THz (only valid inside these ranges)"
+
 struct PredefPoint {
-  double T, P, o2, n2, h2o;
+  double T, P, o2, n2, h2o, lwc;
 };
 
 // ONE body (no inlining), like predef_line_model below: base and perturbed evaluations must round alike
@@ -91,6 +96,41 @@ __device__ __noinline__ double predef_model(int m, double f, const PredefPoint& 
       const double strength  = S * (pd * pd) * pow(th, xT);
       return a.n2 * fac * strength * (f * f) / (1.000 + G * pow(f, xf)) * a.n2;
     }
+    case AB200_PREDEF_LIQUIDCLOUD_ELL07: {  // ELL07::compute, ELL07.cc:39-188 (range errors: predef_kernel)
+      if (a.lwc < 1e-10) return 0.0;
+      constexpr double two_pi = 6.283185307179586476925286766559005768, pi = 3.141592653589793238462643383279502884;
+      constexpr double dB_km_to_1_m = 1e-3 / (10.0 * 0.434294481903251827651128918916605082);
+      const double tc = a.T - 273.15, tc2 = tc * tc, tc3 = tc2 * tc;
+      const double eps_s = 87.9144 - 0.404399 * tc - 9.58726e-4 * tc2 - 1.32802e-6 * tc3;
+      // three Debye relaxations (Ellison 2007, table 2) ...
+      const double del[3] = {79.23882 * exp(-0.004300598 * tc), 3.815866 * exp(-0.01117295 * tc), 1.634967 * exp(-0.006841548 * tc)};
+      const double tau[3] = {1.382264e-13 * exp(652.7648 / (tc + 133.1383)), 3.510354e-16 * exp(1249.533 / (tc + 133.1383)),
+                             6.30035e-15 * exp(405.5169 / (tc + 133.1383))};
+      // ... and two resonances: amplitude, centre, relaxation time
+      const double dr[2] = {0.8379692 + -0.006118594 * tc + -0.000012936798 * tc2, 0.6165532 + 0.007238532 * tc + -0.00009523366 * tc2};
+      const double fr[2] = {4235901000000.0 + -14260880000.0 * tc + 273815700.0 * tc2 + -1246943.0 * tc3,
+                            15983170000000.0 + -74413570000.0 * tc + 497448000.0 * tc2};
+      const double tr[2] = {9.618642e-14 + 1.795786e-16 * tc + -9.310017E-18 * tc2 + 1.655473e-19 * tc3,
+                            2.882476e-14 + -3.142118e-16 * tc + 3.528051e-18 * tc2};
+      const double w = two_pi * f;
+      double re_d = 0.0, im_d = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const double q = 1. + (w * tau[i]) * (w * tau[i]);
+        re_d += (tau[i] * tau[i]) * del[i] / q;
+        im_d += tau[i] * del[i] / q;
+      }
+      double re = eps_s - (w * w) * re_d, im = w * im_d;
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const double wp = two_pi * tr[i] * (fr[i] + f), wm = two_pi * tr[i] * (fr[i] - f);
+        const double qp = 1. + wp * wp, qm = 1. + wm * wm;
+        re -= (two_pi * tr[i]) * (two_pi * tr[i]) * dr[i] / 2. * (f * (fr[i] + f) / qp - f * (fr[i] - f) / qm);
+        im += pi * f * tr[i] * dr[i] * (1. / qp + 1. / qm);
+      }
+      const double ImNw = 1.500 / 1.00e3 * (3.000 * im / ((re + 2.000) * (re + 2.000) + im * im));
+      return a.lwc * 1.000e6 * dB_km_to_1_m * 0.1820 * (f * 1e-9) * ImNw;
+    }
     default: {  // Standard::water_self
       constexpr double C = 1.796e-33, x = 4.5;
       const double dummy = C * pow(300. / a.T, x + 3) * (a.P * a.P) * a.h2o;
@@ -104,6 +144,7 @@ __host__ __device__ inline int predef_species_of(int m, const ab200_predef_speci
     case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
     case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: case AB200_PREDEF_O2_MPM2020: return s.o2;
     case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
+    case AB200_PREDEF_LIQUIDCLOUD_ELL07: return s.liquidcloud;
     default: return s.h2o;
   }
 }
@@ -400,7 +441,7 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
   const int lev = blockIdx.y;
   const double* __restrict__ vmr = p.vmr + int64_t(lev) * p.n_species;
   auto v = [&](int idx) { return idx >= 0 ? vmr[idx] : 0.0; };
-  const PredefPoint a{p.T[lev], p.P[lev], v(p.sp.o2), v(p.sp.n2), v(p.sp.h2o)};
+  const PredefPoint a{p.T[lev], p.P[lev], v(p.sp.o2), v(p.sp.n2), v(p.sp.h2o), v(p.sp.liquidcloud)};
   if (threadIdx.x == 0) {
     // perturbed points: temperature target (:267-279), then the VMR targets of CO2, O2, N2, H2O, liquidcloud (:237-241, :300-314)
     int n = 1;
@@ -423,6 +464,7 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
           if (idx == p.sp.o2) b.o2 += p.tg_d[q], moved = true;
           if (idx == p.sp.n2) b.n2 += p.tg_d[q], moved = true;
           if (idx == p.sp.h2o) b.h2o += p.tg_d[q], moved = true;
+          if (idx == p.sp.liquidcloud) b.lwc += p.tg_d[q], moved = true;
         }
       }
       const bool wind = p.tg_kind[q] >= AB200_TARGET_WIND_U && p.tg_kind[q] <= AB200_TARGET_WIND_W;
@@ -460,6 +502,17 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
       if (threadIdx.x < nstates) predef_state_scalars(m, pts[threadIdx.x], tab.scal[threadIdx.x]);
       __syncthreads();
     }
+    if (m == AB200_PREDEF_LIQUIDCLOUD_ELL07) {  // the reference's user errors, ELL07.cc:99-117 (only where there is liquid water)
+      bool bad = false;
+      for (int st = 0; st < nstates; st++) {
+        const PredefPoint& b = pts[st];
+        if (b.lwc < 1e-10) continue;
+        bad = bad || b.lwc > 5.00e-3 || b.T < 210 || b.T > 373 || (iv < p.nf && f > 25e12);
+        for (int q = 0; q < p.nq && st == 0; q++)
+          if (state_of[q] == -3) bad = bad || (iv < p.nf && f + p.tg_d[q] > 25e12);
+      }
+      if (bad) atomicOr(p.flags, 64);
+    }
     if (iv >= p.nf) continue;
     const double pm = lines ? predef_line_model(m, f, tab.line[0], tab.scal[0]) : predef_model(m, f, a);
     kacc += pm;
@@ -494,11 +547,11 @@ int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, cons
     if (idx >= n_species) return set_error(AB200_ERR_INVALID, "predefined models: species index beyond the VMR vector");
   for (int k = 0; k < n_models; k++) {
     const int m = models[k];
-    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_O2_MPM2020)
+    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_LIQUIDCLOUD_ELL07)
       return set_error(AB200_ERR_UNSUPPORTED, "predefined model " + std::to_string(m) +
                                                   " is outside the GPU path (the StandardType continua, PWR98, MPM89, MPM93 N2 and "
-                                                  "PWR2021 / PWR2022 are; no CPU fallback)");
-    const bool need_h2o = m != AB200_PREDEF_N2_SELFCONT_STANDARD;
+                                                  "PWR2021 / PWR2022, TRE05, MPM2020 and ELL07 are; no CPU fallback)");
+    const bool need_h2o = m != AB200_PREDEF_N2_SELFCONT_STANDARD && m != AB200_PREDEF_LIQUIDCLOUD_ELL07;
     if (predef_species_of(m, *sp) < 0 || (need_h2o && sp->h2o < 0))
       return set_error(AB200_ERR_INVALID, "predefined model " + std::to_string(m) + " needs a species the atmosphere does not carry");
     pp.models[k] = m;
@@ -580,6 +633,7 @@ extern "C" int ab200_predef_levels(const int32_t* models, int32_t n_models, cons
   if (h_flag & 32)
     return set_error(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of "
                                         "1e-25.  Therefore no calculation is performed.");
+  if (h_flag & 64) return set_error(AB200_ERR_INVALID, PREDEF_ELL07_RANGE_MSG);
   AB_CUDA(cudaMemcpy(K, bK.p, nk * 8, cudaMemcpyDeviceToHost));
   if (nq > 0) AB_CUDA(cudaMemcpy(dK, bdK.p, nk * nq * 8, cudaMemcpyDeviceToHost));
   return AB200_OK;

@@ -380,6 +380,10 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
 #define AB200_PREDEF_N2_SELFCONT_PWR2021 13  /* "N2-SelfContPWR2021", PWR20xx::compute_n2       :792-833 */
 #define AB200_PREDEF_O2_TRE05 14             /* "O2-TRE05",           TRE05::oxygen src/core/predefined/TRE05.cc:115-296 (44 lines, MPM93 form) */
 #define AB200_PREDEF_O2_MPM2020 15           /* "O2-MPM2020",         MPM2020::compute src/core/predefined/MPM2020.cc:38-149 (38 lines, second-order mixing) */
+#define AB200_PREDEF_LIQUIDCLOUD_ELL07 16    /* "liquidcloud-ELL07",  ELL07::compute src/core/predefined/ELL07.cc:39-188: Ellison (2007) permittivity of liquid
+                                                water (three Debye terms + two resonances), Rayleigh droplets; the "mixing ratio" of the species
+                                                `liquidcloud` is the liquid water content [kg/m3].  Nothing below 1e-10 kg/m3; above 5e-3 kg/m3, outside
+                                                210-373 K or above 25 THz the reference's user error (AB200_ERR_INVALID) */
 typedef struct ab200_predef_species { /* indices into the vmr vector, -1 when the atmosphere does not carry the species */
   int32_t o2, n2, h2o, co2, liquidcloud;
 } ab200_predef_species;

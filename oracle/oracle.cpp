@@ -2623,7 +2623,7 @@ int orc_lookup_levels(const ab200_lookup_table* tables, int32_t n_tables, int64_
 // ---------------------------------------------------------------------------
 namespace predef {
 struct Pt {
-  Numeric T, P, o2, n2, h2o;
+  Numeric T, P, o2, n2, h2o, lwc = 0.0;
 };
 
 // PWR20xx::compute_h2o, src/core/predefined/PWR20xx.cc:21-166: 16 / 20 H2O lines with pressure shifts, the speed-dependent
@@ -2765,6 +2765,43 @@ Numeric model(int m, Numeric f, const Pt& a) {
       const Numeric frequency_dependence = 0.5 + 0.5 / (1.0 + pow2(f_ghz / 450.0));
       return cont * frequency_dependence * pow2(f_ghz) / 1000.0;
     }
+    case AB200_PREDEF_LIQUIDCLOUD_ELL07: {  // ELL07::compute, src/core/predefined/ELL07.cc:39-188 (user errors: ell07_refused below)
+      using Constant::pi;
+      using Constant::two_pi;
+      constexpr Numeric dB_km_to_1_m = (1e-3 / (10.0 * std::numbers::log10e));  // Constant::log10_euler, arts_constants.h
+      const Numeric lwc = a.lwc;
+      if (lwc < 1e-10) return 0.0;
+      constexpr Numeric m = 1.00e3;
+      // table 2 of Ellison (2007): Debye amplitudes a_i exp(-b_i t), relaxation times c_i exp(d_i / (t + tc)), two resonances p_i
+      constexpr Numeric a1 = 79.23882, a2 = 3.815866, a3 = 1.634967, tc = 133.1383, b1 = 0.004300598, b2 = 0.01117295, b3 = 0.006841548;
+      constexpr Numeric c1 = 1.382264e-13, c2 = 3.510354e-16, c3 = 6.30035e-15, d1 = 652.7648, d2 = 1249.533, d3 = 405.5169;
+      constexpr Numeric p0 = 0.8379692, p1 = -0.006118594, p2 = -0.000012936798, p3 = 4235901000000.0, p4 = -14260880000.0,
+                        p5 = 273815700.0, p6 = -1246943.0, p7 = 9.618642e-14, p8 = 1.795786e-16, p9 = -9.310017E-18, p10 = 1.655473e-19,
+                        p11 = 0.6165532, p12 = 0.007238532, p13 = -0.00009523366, p14 = 15983170000000.0, p15 = -74413570000.0,
+                        p16 = 497448000.0, p17 = 2.882476e-14, p18 = -3.142118e-16, p19 = 3.528051e-18;
+      const Numeric t_cels    = a.T - 273.15;
+      const Numeric epsilon_s = 87.9144 - 0.404399 * t_cels - 9.58726e-4 * pow2(t_cels) - 1.32802e-6 * pow3(t_cels);
+      const Numeric delta1 = a1 * std::exp(-b1 * t_cels), delta2 = a2 * std::exp(-b2 * t_cels), delta3 = a3 * std::exp(-b3 * t_cels);
+      const Numeric tau1 = c1 * std::exp(d1 / (t_cels + tc)), tau2 = c2 * std::exp(d2 / (t_cels + tc)), tau3 = c3 * std::exp(d3 / (t_cels + tc));
+      const Numeric delta4 = p0 + p1 * t_cels + p2 * pow2(t_cels);
+      const Numeric f0     = p3 + p4 * t_cels + p5 * pow2(t_cels) + p6 * pow3(t_cels);
+      const Numeric tau4   = p7 + p8 * t_cels + p9 * pow2(t_cels) + p10 * pow3(t_cels);
+      const Numeric delta5 = p11 + p12 * t_cels + p13 * pow2(t_cels);
+      const Numeric f1     = p14 + p15 * t_cels + p16 * pow2(t_cels);
+      const Numeric tau5   = p17 + p18 * t_cels + p19 * pow2(t_cels);
+      auto debye_re = [&](Numeric tau, Numeric delta) { return pow2(tau) * delta / (1. + pow2(two_pi * f * tau)); };
+      auto debye_im = [&](Numeric tau, Numeric delta) { return tau * delta / (1. + pow2(two_pi * f * tau)); };
+      auto lor      = [&](Numeric tau, Numeric fc) { return 1. + pow2(two_pi * tau * fc); };
+      const Numeric Reepsilon =
+          epsilon_s - pow2((two_pi * f)) * (debye_re(tau1, delta1) + debye_re(tau2, delta2) + debye_re(tau3, delta3)) -
+          pow2(two_pi * tau4) * delta4 / 2. * (f * (f0 + f) / lor(tau4, f0 + f) - f * (f0 - f) / lor(tau4, f0 - f)) -
+          pow2(two_pi * tau5) * delta5 / 2. * (f * (f1 + f) / lor(tau5, f1 + f) - f * (f1 - f) / lor(tau5, f1 - f));
+      const Numeric Imepsilon = two_pi * f * (debye_im(tau1, delta1) + debye_im(tau2, delta2) + debye_im(tau3, delta3)) +
+                                pi * f * tau4 * delta4 * (1. / lor(tau4, f0 + f) + 1. / lor(tau4, f0 - f)) +
+                                pi * f * tau5 * delta5 * (1. / lor(tau5, f1 + f) + 1. / lor(tau5, f1 - f));
+      const Numeric ImNw = 1.500 / m * (3.000 * Imepsilon / (pow2((Reepsilon + 2.000)) + pow2(Imepsilon)));
+      return lwc * 1.000e6 * dB_km_to_1_m * 0.1820 * (f * 1e-9) * ImNw;
+    }
     case AB200_PREDEF_O2_SELFCONT_STANDARD: {  // Standard::oxygen :51-84
       constexpr Numeric C = (1.108e-14 / pow2(3.0e2));
       const Numeric G0 = 5600.000, G0A = 1.000, G0B = 1.100, XG0d = 0.800, XG0w = 1.000;
@@ -2901,8 +2938,15 @@ int species_of(int m, const ab200_predef_species& s) {  // isot.spec of the mode
     case AB200_PREDEF_O2_SELFCONT_STANDARD: case AB200_PREDEF_O2_PWR98: case AB200_PREDEF_O2_MPM89: case AB200_PREDEF_O2_PWR2021:
     case AB200_PREDEF_O2_PWR2022: case AB200_PREDEF_O2_TRE05: case AB200_PREDEF_O2_MPM2020: return s.o2;
     case AB200_PREDEF_N2_SELFCONT_STANDARD: case AB200_PREDEF_N2_SELFCONT_MPM93: case AB200_PREDEF_N2_SELFCONT_PWR2021: return s.n2;
+    case AB200_PREDEF_LIQUIDCLOUD_ELL07: return s.liquidcloud;
     default: return s.h2o;
   }
+}
+// ELL07.cc:52-54, :99-117: where there is liquid water, only up to 5e-3 kg/m3, inside 210-373 K and up to 25 THz
+bool ell07_refused(int m, const Pt& a, const double* f, Index nf, Numeric df = 0.0) {
+  if (m != AB200_PREDEF_LIQUIDCLOUD_ELL07 or a.lwc < 1e-10) return false;
+  if (a.lwc > 5.00e-3 or a.T < 210 or a.T > 373) return true;
+  return std::any_of(f, f + nf, [df](Numeric x) { return x + df > 25e12; });
 }
 // the full O2 models refuse a non-zero O2 mixing ratio below 1e-25 (PWR98.cc:363-370, MPM89.cc:345-352)
 bool o2_vmr_refused(int m, const Pt& a) {
@@ -2923,10 +2967,27 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
   for (int ip = 0; ip < np; ip++) {
     const double* f   = f_in + ip * f_level_stride;
     const double* vmr = atm->vmr + static_cast<Index>(ip) * n_species;
-    const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o)};
+    const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o), v(vmr, sp->liquidcloud)};
     for (int k = 0; k < n_models; k++) {
       const int m = models[k];
-      if (m < 0 or m > AB200_PREDEF_O2_MPM2020) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (m < 0 or m > AB200_PREDEF_LIQUIDCLOUD_ELL07) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      {  // every point the reference evaluates the model at raises its own range error
+        bool bad = predef::ell07_refused(m, a, f, nf);
+        if (it >= 0) {
+          predef::Pt b = a;
+          b.T += target_d[it];
+          bad = bad or predef::ell07_refused(m, b, f, nf);
+        }
+        for (int q = 0; q < nq; q++) {
+          if (targets[q].kind >= AB200_TARGET_WIND_U and targets[q].kind <= AB200_TARGET_WIND_W) bad = bad or predef::ell07_refused(m, a, f, nf, target_d[q]);
+          if (targets[q].kind == AB200_TARGET_VMR and targets[q].species == sp->liquidcloud and sp->liquidcloud >= 0) {
+            predef::Pt b = a;
+            b.lwc += target_d[q];
+            bad = bad or predef::ell07_refused(m, b, f, nf);
+          }
+        }
+        if (bad) return fail(AB200_ERR_INVALID, "Liquid cloud absorption model ELL07 outside its range of validity");
+      }
       if (predef::o2_vmr_refused(m, a))
         return fail(AB200_ERR_INVALID, "O2 full absorption model has detected a O2 volume mixing ratio which is below the threshold of 1e-25");
       if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;
@@ -2956,6 +3017,7 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
               if (idx == sp->o2) b.o2 += target_d[q];
               if (idx == sp->n2) b.n2 += target_d[q];
               if (idx == sp->h2o) b.h2o += target_d[q];
+              if (idx == sp->liquidcloud) b.lwc += target_d[q];
               dk(q) += (predef::model(m, f[i], b) - pm) / target_d[q];
               break;
             }

@@ -87,6 +87,7 @@ SLICES_PREDEF = {
     "tre05_lineshape_o2": ("src/core/predefined/TRE05.cc", r"constexpr Numeric MPMLineShapeO2Function\(const Numeric gamma,", None, (37, 70), "block"),
     "tre05_oxygen": ("src/core/predefined/TRE05.cc", r"void oxygen\(PropmatVector& propmat_clearsky,", None, (115, 296), "block"),
     "mpm2020_all": ("src/core/predefined/MPM2020.cc", r"constexpr Index num = 38;", r"void compute\(PropmatVector& propmat_clearsky,", (16, 149), "block"),
+    "ell07_compute": ("src/core/predefined/ELL07.cc", r"void compute\(PropmatVector& propmat_clearsky,", None, (39, 188), "block"),
     "mpm93_nitrogen": ("src/core/predefined/MPM93.cc", r"void nitrogen\(PropmatVector& propmat_clearsky,", None, (33, 73), "block"),
 }
 SLICES.update(SLICES_PREDEF)

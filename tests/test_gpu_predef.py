@@ -195,3 +195,56 @@ def test_wind_rows_of_the_continua(wsm, orc):
     (_, dK0f), (_, dK1f) = run(False, abi.FLAG_WIND_ROWS_DF), run(True, abi.FLAG_WIND_ROWS_DF)
     assert np.abs((dK1f - dK0f)[:, 0, :, 0] - dref[:, 0, :, 0]).max() <= 1e-5 * np.abs(dref[:, 0, :, 0]).max()
     cat.close()
+
+
+def test_liquid_cloud_ell07(wsm, orc):
+    """"liquidcloud-ELL07" (src/core/predefined/ELL07.cc:39-188): liquid water absorption from Ellison's 2007 permittivity; the
+    species' "mixing ratio" is the liquid water content [kg/m3].  Forward and the T / liquidcloud / wind rows against the oracle
+    (which is pinned bit for bit to the reference's ELL07.cc slice), composed with the gas models, selection by species, levels
+    without cloud, and the reference's range errors."""
+    sp = {"H2O": 0, "O2": 1, "N2": 2, "liquidcloud": 3}
+    n = 6
+    atm = _atm(n)
+    lwc = np.array([0.0, 2e-4, 4.9e-3, 3e-5, 9.9e-11, 1e-10])  # (the perturbed points must stay inside the model's range too)
+    atm.vmr = np.ascontiguousarray(np.concatenate([atm.vmr, lwc[:, None]], 1))
+    f = np.concatenate([np.linspace(1e9, 1e12, 700), np.geomspace(1e12, 24.9e12, 200)])
+    tg, d = (("T",), ("VMR", 3), ("wind_u",), ("VMR", 0)), (0.1, 1e-7, 1e3, 1e-6)
+    for models, sel in ((["liquidcloud-ELL07"], abi.SPECIES_BATH), (["liquidcloud-ELL07", "H2O-PWR98", "O2-PWR98"], abi.SPECIES_BATH),
+                        (["liquidcloud-ELL07", "H2O-PWR98"], 3), (["liquidcloud-ELL07", "H2O-PWR98"], 0)):
+        ff = f if len(models) == 1 else f[:700]
+        Kr, dKr = orc.predef_levels(models, sp, ff, atm, select_species=sel, targets=tg, target_d=d)
+        K = np.zeros((n, len(ff), 7)); dK = np.zeros((n, 4, len(ff), 7))
+        wsm.spectral_propmatAddPredefined(K, dK, models, sel, tg, ff, atm, sp, target_d=d)
+        sc = np.abs(Kr[..., 0]).max(axis=1, keepdims=True)
+        assert (np.abs(K[..., 0] - Kr[..., 0]) <= 1e-12 * np.abs(Kr[..., 0]) + 1e-14 * sc).all()
+        for q in range(4):
+            dsc = np.abs(dKr[:, q, :, 0]).max()
+            # rows are difference quotients over d: the 1e-14 agreement of the model values themselves is divided by d
+            tol = 1e-5 * dsc + 1e-13 * np.abs(Kr[..., 0]).max() / abs(d[q])
+            assert np.abs(dK[:, q, :, 0] - dKr[:, q, :, 0]).max() <= max(tol, 1e-300), (models, sel, q)
+        assert not K[..., 1:].any() and not dK[..., 1:].any()
+        if models == ["liquidcloud-ELL07"]:
+            assert not K[0].any() and not K[4].any() and K[5, :, 0].max() > 0  # nothing below 1e-10 kg/m3
+            assert K[2, :, 0].max() > K[1, :, 0].max() > K[3, :, 0].max() > 0
+            # the liquidcloud row of a linear model is the model per unit content; level 4 crosses the 1e-10 threshold with the step
+            np.testing.assert_allclose(dK[1, 1, :, 0] * lwc[1], K[1, :, 0], rtol=1e-6)
+            assert dK[4, 1, :, 0].max() > 0 and not dK[0, 0].any()
+    K = np.zeros((n, len(f), 7))
+    for T0, w0, ff, tgb, db in ((295.0, 5.001e-3, f, (), ()), (209.0, 1e-4, f, (), ()), (374.0, 1e-4, f, (), ()),
+                                (295.0, 1e-4, np.append(f, 25.1e12), (), ()), (295.0, 5e-3, f, (("VMR", 3),), (1e-7,)),
+                                (372.95, 1e-4, f, (("T",),), (0.1,)), (295.0, 1e-4, np.append(f, 25e12), (("wind_w",),), (1e3,))):
+        bad = _atm(n)
+        bad.vmr = np.ascontiguousarray(np.concatenate([bad.vmr, lwc[:, None]], 1))
+        bad.T[1], bad.vmr[1, 3] = T0, w0
+        Kb = np.zeros((n, len(ff), 7)); dKb = np.zeros((n, len(tgb), len(ff), 7))
+        with pytest.raises(wsm.Ab200Error, match="ELL07"):  # at the point itself, or at a perturbed point of a Jacobian row
+            wsm.spectral_propmatAddPredefined(Kb, dKb if tgb else None, ["liquidcloud-ELL07"], abi.SPECIES_BATH, tgb, ff, bad, sp, target_d=db)
+        with pytest.raises(Exception, match="ELL07"):
+            orc.predef_levels(["liquidcloud-ELL07"], sp, ff, bad, targets=tgb, target_d=db)
+    cold = _atm(n)
+    cold.vmr = np.ascontiguousarray(np.concatenate([cold.vmr, np.zeros((n, 1))], 1))
+    cold.T[:] = 150.0  # no liquid water anywhere: the range checks are never reached
+    wsm.spectral_propmatAddPredefined(K, None, ["liquidcloud-ELL07"], abi.SPECIES_BATH, (), f, cold, sp)
+    assert not K.any()
+    with pytest.raises(wsm.Ab200Error, match="does not carry"):
+        wsm.spectral_propmatAddPredefined(K, None, ["liquidcloud-ELL07"], abi.SPECIES_BATH, (), f, _atm(n), SPECIES)

@@ -42,6 +42,7 @@ def ref():
     L.refslice_tran.argtypes = [dp, dp, C.c_double, dp, dp]
     L.refslice_sqrt_propmat.argtypes = [dp, dp]
     L.refslice_predef.argtypes = [C.c_int32, C.c_int64, dp] + [C.c_double] * 5 + [dp]
+    L.refslice_ell07.argtypes = [C.c_int64, dp, C.c_double, C.c_double, dp]
     L.refslice_tramat.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, dp, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
     L.refslice_rte_emission.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [dp] * 9
     L.refslice_tmodel.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, dp, dp]
@@ -410,3 +411,35 @@ def test_full_microwave_absorption_models_bitwise(ref, model):
         atm = abi.AtmPath(T=np.array([250.0]), P=np.array([1e4]), vmr=np.array([[1e-26, 0.78, 1e-3]]), isorat=np.ones((1, 1)), Q=np.ones((1, 1)))
         with pytest.raises(Exception):
             orc.predef_levels([model], {"O2": 0, "N2": 1, "H2O": 2}, f, atm)
+
+
+def test_ell07_liquid_cloud_bitwise(ref):
+    """f2: the oracle's restatement of ELL07::compute (src/core/predefined/ELL07.cc:39-188, Ellison's 2007 permittivity of liquid water:
+    three Debye relaxations and two resonances) against the reference's own object code, every bit, from 1 GHz to the model's 25 THz limit
+    over its whole temperature range; below 1e-10 kg/m3 nothing is added; beyond 5e-3 kg/m3, 210-373 K or 25 THz both raise the error."""
+    from arts_b200 import _abi as abi
+    rng = np.random.default_rng(31)
+    f = np.ascontiguousarray(np.concatenate([np.geomspace(1e9, 25e12, 600), rng.uniform(1e9, 1e12, 300), [25e12]]))
+    sp = {"liquidcloud": 0}
+
+    def atm_of(T, lwc):
+        return abi.AtmPath(T=np.array([T]), P=np.array([8e4]), vmr=np.array([[lwc]]), isorat=np.ones((1, 1)), Q=np.ones((1, 1)))
+
+    for k in range(40):
+        T = [210.0, 373.0, 273.15][k] if k < 3 else rng.uniform(210, 373)
+        lwc = [1e-10, 5e-3][k] if k < 2 else 10 ** rng.uniform(-9.9, -2.31)
+        K, _ = orc.predef_levels(["liquidcloud-ELL07"], sp, f, atm_of(T, lwc))
+        A = np.zeros(len(f))
+        assert ref.refslice_ell07(len(f), dptr(f), T, lwc, dptr(A)) == 0
+        assert_same_bits(K[0, :, 0], A, f"ELL07 at T={T} lwc={lwc}")
+        assert A.max() > 0 and np.all(K[0, :, 1:] == 0)  # (negative values occur below the fit range of 0-100 C, in the reference too)
+    A = np.full(len(f), 0.5)
+    assert ref.refslice_ell07(len(f), dptr(f), 100.0, 9.9e-11, dptr(A)) == 0 and np.all(A == 0.5)  # returns before any check
+    K, _ = orc.predef_levels(["liquidcloud-ELL07"], sp, f, atm_of(100.0, 9.9e-11))
+    assert not K.any()
+    f_hi = np.append(f, 25.000001e12)
+    for T, lwc, ff in ((250.0, 5.001e-3, f), (209.9, 1e-4, f), (373.1, 1e-4, f), (250.0, 1e-4, f_hi)):
+        A = np.zeros(len(ff))
+        assert ref.refslice_ell07(len(ff), dptr(np.ascontiguousarray(ff)), T, lwc, dptr(A)) == 1
+        with pytest.raises(Exception, match="ELL07"):
+            orc.predef_levels(["liquidcloud-ELL07"], sp, ff, atm_of(T, lwc))

@@ -115,7 +115,15 @@ class PredefSpecies(C.Structure):
 PREDEF_MODELS = {"O2-SelfContStandardType": 0, "N2-SelfContStandardType": 1, "H2O-ForeignContStandardType": 2,
                  "H2O-SelfContStandardType": 3, "H2O-PWR98": 4, "O2-PWR98": 5, "H2O-MPM89": 6, "O2-MPM89": 7, "N2-SelfContMPM93": 8,
                  "H2O-PWR2021": 9, "H2O-PWR2022": 10, "O2-PWR2021": 11, "O2-PWR2022": 12, "N2-SelfContPWR2021": 13, "O2-TRE05": 14, "O2-MPM2020": 15,
-                 "liquidcloud-ELL07": 16}
+                 "liquidcloud-ELL07": 16, "H2O-ForeignContCKDMT400": 17, "H2O-SelfContCKDMT400": 18, "H2O-ForeignContCKDMT430": 19,
+                 "H2O-SelfContCKDMT430": 20}
+
+
+class MtckdWater(C.Structure):
+    """ab200_mtckd_water: MT_CKD400::WaterData / MT_CKD430::WaterData (src/core/predefined/predef_data.h:14-42)."""
+
+    _fields_ = [("n", C.c_int32), ("ref_temp", C.c_double), ("ref_press", C.c_double), ("wavenumbers", _dp), ("self_absco_ref", _dp),
+                ("for_absco_ref", _dp), ("self_texp", _dp)]
 
 
 def predef_args(models, species):

@@ -84,6 +84,11 @@ def lib():
     L.ab200_predef_levels.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(abi.PredefSpecies), C.c_int64, _dp, C.c_int64,
                                       C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), _dp, _dp, _dp]
     L.ab200_path_add_predefined.argtypes = [_vp, C.POINTER(C.c_int32), C.c_int32, C.POINTER(abi.PredefSpecies), _dp]
+    L.ab200_predef_data_create.argtypes = [C.POINTER(abi.MtckdWater), C.POINTER(abi.MtckdWater), C.c_int32, C.POINTER(_vp)]
+    L.ab200_predef_data_destroy.argtypes = [_vp]
+    L.ab200_predef_data_destroy.restype = None
+    L.ab200_predef_levels_data.argtypes = L.ab200_predef_levels.argtypes + [_vp]
+    L.ab200_path_add_predefined_data.argtypes = L.ab200_path_add_predefined.argtypes + [_vp]
     L.ab200_lookup_create.argtypes = [C.POINTER(abi.LookupTableDesc), C.c_int32, C.POINTER(_vp)]
     L.ab200_lookup_destroy.argtypes = [_vp]
     L.ab200_lookup_destroy.restype = None

@@ -766,11 +766,16 @@ int ab200_path_add_lookup(ab200_path* p, const ab200_lookup* lut, int32_t h2o_sp
 
 int ab200_path_add_predefined(ab200_path* p, const int32_t* models, int32_t n_models, const ab200_predef_species* species,
                               const double* target_d) {
+  return ab200_path_add_predefined_data(p, models, n_models, species, target_d, nullptr);
+}
+
+int ab200_path_add_predefined_data(ab200_path* p, const int32_t* models, int32_t n_models, const ab200_predef_species* species,
+                                   const double* target_d, const ab200_predef_data* data) {
   if (!p || !p->uploaded) return set_error(AB200_ERR_INVALID, "ab200_path_add_predefined: path not uploaded");
   AB_CUDA(cudaSetDevice(p->cat->device));
   return predef_on_path(models, n_models, species, target_d, p->nf, p->d_f, p->f_stride, p->d_ffac, p->d_T, p->d_P, p->d_vmr,
                         p->cat->n_species, p->select_species, p->d_K, p->d_dK, p->k_pitch, p->nq, p->tg_kind, p->tg_species, p->np,
-                        p->d_flags, (p->flags & AB200_FLAG_WIND_ROWS_DF) ? nullptr : p->d_wjac, p->stream);
+                        p->d_flags, (p->flags & AB200_FLAG_WIND_ROWS_DF) ? nullptr : p->d_wjac, p->stream, data);
 }
 
 int ab200_path_add_cia(ab200_path* p, const ab200_cia* cia, double T_extrapolfac, int32_t ignore_errors, double dT) {

@@ -28,6 +28,13 @@
 
 namespace ab200 {
 
+// one MT_CKD 4.x water table on the device: wavenumbers, self, foreign, self exponent, each [n]
+struct MtckdDev {
+  int32_t n;
+  double ref_temp, ref_press;
+  const double *v, *self, *fore, *texp;
+};
+
 struct PredefParams {
   int32_t n_models;
   int32_t models[16];
@@ -45,6 +52,7 @@ struct PredefParams {
   int32_t tg_kind[AB200_MAX_TARGETS], tg_species[AB200_MAX_TARGETS];
   double tg_d[AB200_MAX_TARGETS];
   int* flags;  // device error flags (bit 5: an O2 mixing ratio below the full models' threshold)
+  MtckdDev ckd[2];     // MT_CKD 4.0 / 4.3 water tables on the device (n == 0: not loaded)
   const double* wjac;  // [np][3] freq_wind_shift_jac per level: wind rows are d/df times f times this (spectral_propmat_jacWindFix,
                        // what the line kernels leave in dK); null: the rows stay d/df (spectral_propmatAddPredefined alone)
 };
@@ -138,6 +146,64 @@ __device__ __noinline__ double predef_model(int m, double f, const PredefPoint& 
     }
   }
 }
+
+// ---- MT_CKD 4.x water continua: MT_CKD400.cc:37-92 (radiation term, four-point interpolation), :99-172 (foreign), :174-256 (self) ----
+__device__ __forceinline__ double mtckd_radfn(double XVI, double XKT) {
+  if (XKT > 0.0) {
+    const double XVIOKT = XVI / XKT;
+    if (XVIOKT <= 0.01) return 0.5 * XVIOKT * XVI;
+    if (XVIOKT <= 10) {
+      const double EXPVKT = expm1(-XVIOKT);
+      return -XVI * EXPVKT / (2 + EXPVKT);
+    }
+    return XVI;
+  }
+  return XVI;
+}
+__device__ __forceinline__ int mtckd_lower_bound(const double* __restrict__ v, int n, double x) {  // first i with v[i] >= x
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// f: the frequency; f_first: the first frequency of the level's grid (where the reference's cursor starts, :139-143).
+// ONE body for base and perturbed points (exact zeros for targets the model does not depend on).
+__device__ __noinline__ double predef_mtckd(bool self, const MtckdDev& d, double f, double f_first, const PredefPoint& a) {
+  // Conversion::freq2kaycm(x) = x / (100 c)
+  const int n = d.n;
+  if (f < 0) return 0.0;
+  const double x = f / (100 * 299792458.0), last = d.v[n - 1];
+  if (x > last || f_first / (100 * 299792458.0) > last) return 0.0;
+  const double dvc = d.v[1] - d.v[0], recdvc = 1 / dvc;
+  // the cursor of the reference: starts at lower_bound(x_first - 2 dvc) and advances while x > v[cur + 1]
+  const int cur0 = mtckd_lower_bound(d.v, n, f_first / (100 * 299792458.0) - 2 * dvc);
+  int cur = mtckd_lower_bound(d.v, n, x) - 1;
+  cur = cur > cur0 ? cur : cur0;
+  const double P0 = (1e-3 * d.ref_press) * 1e5, T0 = d.ref_temp, xkt = a.T / 1.4387752;
+  const double rho_rat = (a.P / P0) * (T0 / a.T);
+  const double num_den_cm2 = 1e-6 * a.h2o * a.P / (1.380649e-23 * a.T);
+  const double r = T0 / a.T;
+  double k[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    int i = cur - 1 + j;
+    if (i < 0) i += 2;  // the zero-frequency mirror (:147-152; only reachable with cur == 0)
+    if (i >= n) {
+      k[j] = 0.0;
+    } else if (self) {
+      k[j] = d.self[i] * a.h2o * rho_rat * pow(r, d.texp[i]) * mtckd_radfn(d.v[i], xkt);
+    } else {
+      k[j] = d.fore[i] * (1.0 - a.h2o) * rho_rat * mtckd_radfn(d.v[i], xkt);
+    }
+  }
+  const double P = recdvc * (x - d.v[cur]);
+  const double C = (3 - 2 * P) * P * P, B = 0.5 * P * (1 - P), B1 = B * (1 - P), B2 = B * P;
+  const double out = 1e2 * num_den_cm2 * (-k[0] * B1 + k[1] * (1 - C + B2) + k[2] * (C + B1) - k[3] * B2);
+  return out >= 0 ? out : 0.0;
+}
+__host__ __device__ inline bool predef_is_mtckd(int m) { return m >= AB200_PREDEF_H2O_FOREIGNCONT_CKDMT400 && m <= AB200_PREDEF_H2O_SELFCONT_CKDMT430; }
 
 __host__ __device__ inline int predef_species_of(int m, const ab200_predef_species& s) {
   switch (m) {
@@ -514,6 +580,23 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
       if (bad) atomicOr(p.flags, 64);
     }
     if (iv >= p.nf) continue;
+    if (predef_is_mtckd(m)) {  // table models: their own evaluator, same row rules
+      const MtckdDev& cd = p.ckd[m >= AB200_PREDEF_H2O_FOREIGNCONT_CKDMT430];
+      const bool self = m == AB200_PREDEF_H2O_SELFCONT_CKDMT400 || m == AB200_PREDEF_H2O_SELFCONT_CKDMT430;
+      const double f_first = (p.ffac ? p.ffac[lev] : 1.0) * p.f[int64_t(lev) * p.f_stride];
+      const double pm = predef_mtckd(self, cd, f, f_first, a);
+      kacc += pm;
+      for (int q = 0; q < p.nq; q++) {
+        const int st = state_of[q];
+        if (st == -3) {
+          const double row = (predef_mtckd(self, cd, f + p.tg_d[q], f_first + p.tg_d[q], a) - pm) / p.tg_d[q];
+          dacc[q] += p.wjac ? row * f * p.wjac[3 * lev + (p.tg_kind[q] - AB200_TARGET_WIND_U)] : row;
+        } else if (st > 0) {
+          dacc[q] += (predef_mtckd(self, cd, f, f_first, pts[st]) - pm) / p.tg_d[q];
+        }
+      }
+      continue;
+    }
     const double pm = lines ? predef_line_model(m, f, tab.line[0], tab.scal[0]) : predef_model(m, f, a);
     kacc += pm;
     for (int q = 0; q < p.nq; q++) {
@@ -537,8 +620,17 @@ __global__ void __launch_bounds__(128) predef_kernel(PredefParams p) {
 }
 
 // fills the model / species / target part of the parameters and validates it; 0 or an error code with the message set
+}  // namespace ab200
+// device-resident MT_CKD tables: one allocation, four arrays per table
+struct ab200_predef_data {
+  int device = 0;
+  double* d_buf = nullptr;
+  ab200::MtckdDev ckd[2]{};
+};
+namespace ab200 {
+
 int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, const ab200_predef_species* sp, int32_t n_species, int32_t nq,
-                 const int32_t* tg_kind, const int32_t* tg_species, const double* target_d) {
+                 const int32_t* tg_kind, const int32_t* tg_species, const double* target_d, const ab200_predef_data* data) {
   if (n_models < 0 || n_models > 16 || (n_models > 0 && !models) || !sp)
     return set_error(AB200_ERR_INVALID, "predefined models: null argument or more than 16 models");
   pp.n_models = n_models;
@@ -547,10 +639,18 @@ int predef_setup(PredefParams& pp, const int32_t* models, int32_t n_models, cons
     if (idx >= n_species) return set_error(AB200_ERR_INVALID, "predefined models: species index beyond the VMR vector");
   for (int k = 0; k < n_models; k++) {
     const int m = models[k];
-    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_LIQUIDCLOUD_ELL07)
+    if (m < AB200_PREDEF_O2_SELFCONT_STANDARD || m > AB200_PREDEF_H2O_SELFCONT_CKDMT430)
       return set_error(AB200_ERR_UNSUPPORTED, "predefined model " + std::to_string(m) +
                                                   " is outside the GPU path (the StandardType continua, PWR98, MPM89, MPM93 N2 and "
-                                                  "PWR2021 / PWR2022, TRE05, MPM2020 and ELL07 are; no CPU fallback)");
+                                                  "PWR2021 / PWR2022, TRE05, MPM2020, ELL07 and the MT_CKD 4.x water continua are; no CPU fallback)");
+    if (predef_is_mtckd(m)) {  // check(data), MT_CKD400.cc:94-98
+      const int which = m >= AB200_PREDEF_H2O_FOREIGNCONT_CKDMT430;
+      if (!data || data->ckd[which].n == 0) return set_error(AB200_ERR_INVALID, "No data (MT_CKD water continuum without its model data)");
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (data->device != dev) return set_error(AB200_ERR_INVALID, "predefined model data lives on another device");
+      pp.ckd[which] = data->ckd[which];
+    }
     const bool need_h2o = m != AB200_PREDEF_N2_SELFCONT_STANDARD && m != AB200_PREDEF_LIQUIDCLOUD_ELL07;
     if (predef_species_of(m, *sp) < 0 || (need_h2o && sp->h2o < 0))
       return set_error(AB200_ERR_INVALID, "predefined model " + std::to_string(m) + " needs a species the atmosphere does not carry");
@@ -580,11 +680,12 @@ int launch_predef(const PredefParams& p, int nlev, cudaStream_t stream) {
 int predef_on_path(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, const double* target_d, int64_t nf,
                    const double* d_f, int64_t f_stride, const double* d_ffac, const double* d_T, const double* d_P, const double* d_vmr,
                    int32_t n_species, int32_t select_species, double* d_K, double* d_dK, int64_t k_pitch, int32_t nq,
-                   const int32_t* tg_kind, const int32_t* tg_species, int np, int* d_flags, const double* d_wjac, cudaStream_t stream) {
+                   const int32_t* tg_kind, const int32_t* tg_species, int np, int* d_flags, const double* d_wjac, cudaStream_t stream,
+                   const ab200_predef_data* data) {
   PredefParams pp{};
   pp.flags = d_flags;
   pp.wjac = d_wjac;
-  AB_TRY(predef_setup(pp, models, n_models, sp, n_species, nq, tg_kind, tg_species, target_d));
+  AB_TRY(predef_setup(pp, models, n_models, sp, n_species, nq, tg_kind, tg_species, target_d, data));
   pp.nf = nf; pp.f = d_f; pp.f_stride = f_stride; pp.ffac = d_ffac; pp.T = d_T; pp.P = d_P; pp.vmr = d_vmr;
   pp.n_species = n_species; pp.select_species = select_species; pp.K = d_K; pp.dK = d_dK; pp.k_pitch = k_pitch;
   return launch_predef(pp, np, stream);
@@ -594,9 +695,75 @@ int predef_on_path(const int32_t* models, int32_t n_models, const ab200_predef_s
 
 using namespace ab200;
 
+extern "C" int ab200_predef_data_create(const ab200_mtckd_water* ckdmt400, const ab200_mtckd_water* ckdmt430, int32_t device,
+                                        ab200_predef_data** out) {
+  if (!out) return set_error(AB200_ERR_INVALID, "ab200_predef_data_create: null output");
+  *out = nullptr;
+  const ab200_mtckd_water* src[2] = {ckdmt400, ckdmt430};
+  size_t total = 0;
+  for (const ab200_mtckd_water* w : src) {
+    if (!w) continue;
+    // abs_predef_dataAddWaterMTCKD400, m_predefined_absorption_models.cc:78-86 (the lengths are one n here)
+    if (!w->wavenumbers || !w->self_absco_ref || !w->for_absco_ref || !w->self_texp)
+      return set_error(AB200_ERR_INVALID, "ab200_predef_data_create: null table");
+    if (w->n < 4) return set_error(AB200_ERR_INVALID, "It makes no sense to have input shorter than 4");
+    for (int i = 1; i < w->n; i++)
+      if (!(w->wavenumbers[i] >= w->wavenumbers[i - 1]))
+        return set_error(AB200_ERR_INVALID, "The wavenumbers must be increasing in a regular manner");
+    total += 4 * static_cast<size_t>(w->n);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return set_error(AB200_ERR_CUDA, "ab200_predef_data_create: no such CUDA device (this library has no CPU fallback)");
+  }
+  AB_CUDA(cudaSetDevice(device));
+  auto* d = new ab200_predef_data;
+  d->device = device;
+  if (cudaMalloc(&d->d_buf, (total ? total : 1) * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    delete d;
+    return set_error(AB200_ERR_NOMEM, "ab200_predef_data_create: device allocation failed");
+  }
+  double* at = d->d_buf;
+  for (int k = 0; k < 2; k++) {
+    const ab200_mtckd_water* w = src[k];
+    if (!w) continue;
+    const double* cols[4] = {w->wavenumbers, w->self_absco_ref, w->for_absco_ref, w->self_texp};
+    for (const double* c : cols) {
+      if (cudaMemcpy(at, c, static_cast<size_t>(w->n) * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d->d_buf);
+        delete d;
+        return set_error(AB200_ERR_CUDA, "ab200_predef_data_create: copy to the device failed");
+      }
+      at += w->n;
+    }
+    const double* base = at - 4 * static_cast<size_t>(w->n);
+    d->ckd[k] = MtckdDev{w->n, w->ref_temp, w->ref_press, base, base + w->n, base + 2 * static_cast<size_t>(w->n), base + 3 * static_cast<size_t>(w->n)};
+  }
+  *out = d;
+  return AB200_OK;
+}
+
+extern "C" void ab200_predef_data_destroy(ab200_predef_data* data) {
+  if (!data) return;
+  cudaSetDevice(data->device);
+  cudaFree(data->d_buf);
+  delete data;
+}
+
 extern "C" int ab200_predef_levels(const int32_t* models, int32_t n_models, const ab200_predef_species* species, int64_t nf, const double* f,
                                    int64_t f_level_stride, const ab200_atm_path* atm, int32_t n_species, int32_t select_species, int32_t nq,
                                    const ab200_target* targets, const double* target_d, double* K, double* dK) {
+  return ab200_predef_levels_data(models, n_models, species, nf, f, f_level_stride, atm, n_species, select_species, nq, targets, target_d, K, dK,
+                                  nullptr);
+}
+
+extern "C" int ab200_predef_levels_data(const int32_t* models, int32_t n_models, const ab200_predef_species* species, int64_t nf,
+                                        const double* f, int64_t f_level_stride, const ab200_atm_path* atm, int32_t n_species,
+                                        int32_t select_species, int32_t nq, const ab200_target* targets, const double* target_d, double* K,
+                                        double* dK, const ab200_predef_data* data) {
   if (!atm || !K || (nf > 0 && !f)) return set_error(AB200_ERR_INVALID, "ab200_predef_levels: null argument");
   if (nf < 0 || atm->np < 0 || nq < 0 || nq > AB200_MAX_TARGETS || n_species <= 0) return set_error(AB200_ERR_INVALID, "ab200_predef_levels: bad size");
   if (nq > 0 && (!targets || !dK)) return set_error(AB200_ERR_INVALID, "ab200_predef_levels: null Jacobian argument with nq > 0");
@@ -604,7 +771,8 @@ extern "C" int ab200_predef_levels(const int32_t* models, int32_t n_models, cons
   int32_t kind[AB200_MAX_TARGETS], spc[AB200_MAX_TARGETS];
   for (int q = 0; q < nq; q++) { kind[q] = targets[q].kind; spc[q] = targets[q].species; }
   PredefParams pp{};
-  AB_TRY(predef_setup(pp, models, n_models, species, n_species, nq, kind, spc, target_d));
+  if (data) AB_CUDA(cudaSetDevice(data->device));
+  AB_TRY(predef_setup(pp, models, n_models, species, n_species, nq, kind, spc, target_d, data));
   const int np = atm->np;
   if (np == 0 || nf == 0 || n_models == 0) return AB200_OK;
   struct Buf {

@@ -290,3 +290,13 @@ def tiny_case(nl=64, nf=257, np_=6, seed=11, zeeman=False, cutoff=None, rte_opti
     I_bkg = np.zeros((nf, 4))
     I_bkg[:, 0] = planck(f, 288.0)
     return Case("tiny", cat, f, atm, r, I_bkg, rte_option=rte_option, targets=tuple(targets))
+
+
+def mtckd_table(seed=5, n=2003, v0=-20.0, dv=10.0):
+    """A synthetic MT_CKD-4.x-like water table (the real coefficients are external catalog data): regular wavenumbers from -20 cm-1,
+    smooth band structure over six decades, temperature exponents between 0 and 9."""
+    rng = np.random.default_rng(seed)
+    wn = v0 + dv * np.arange(n)
+    bands = sum(np.exp(-0.5 * ((wn - c) / w) ** 2) for c, w in ((0, 150), (1600, 120), (3700, 200), (5300, 150), (7200, 200), (10600, 250)))
+    return dict(ref_temp=296.0, ref_press=1013.0, wavenumbers=wn, self_absco_ref=1e-20 * (1e-6 + bands) * rng.uniform(0.8, 1.2, n),
+                for_absco_ref=3e-23 * (1e-6 + bands) * rng.uniform(0.8, 1.2, n), self_texp=rng.uniform(0.0, 9.0, n))

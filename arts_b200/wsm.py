@@ -417,12 +417,14 @@ class Path:
                                           int(t_interp_order), int(water_interp_order), int(f_interp_order), float(extpolfac),
                                           int(bool(zero_init))))
 
-    def add_predefined(self, models, species, target_d=()):
+    def add_predefined(self, models, species, target_d=(), data: "PredefData" = None):
         """``spectral_propmatAddPredefined`` (src/m_predefined_absorption_models.cc:156-191) on the resident K / dK: ``models`` are
-        tag names ("O2-SelfContStandardType", ...), ``species`` maps "O2" / "N2" / "H2O" / "CO2" / "liquidcloud" to VMR indices."""
+        tag names ("O2-SelfContStandardType", ...), ``species`` maps "O2" / "N2" / "H2O" / "CO2" / "liquidcloud" to VMR indices,
+        ``data`` carries the tables of the MT_CKD 4.x water continua."""
         ids, sp = abi.predef_args(models, species)
         d = np.ascontiguousarray(target_d, dtype=np.float64)
-        check(lib().ab200_path_add_predefined(self._h, abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), dptr(d if len(d) else None)))
+        check(lib().ab200_path_add_predefined_data(self._h, abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), dptr(d if len(d) else None),
+                                                   data.handle if data is not None else None))
 
     def add_cia(self, cia: "Cia", T_extrapolfac=0.5, ignore_errors=0, dT=0.1):
         """``spectral_propmatAddCIA`` (src/m_cia.cc:27-178) on the resident K / dK, after ``run_propmat``."""
@@ -798,10 +800,49 @@ def spectral_propmatAddLookup(spectral_propmat, spectral_propmat_jac, freq_grid,
     return K, dK
 
 
+class PredefData:
+    """The data part of ``abs_predef_data`` on the device (ab200_predef_data): what ``abs_predef_dataAddWaterMTCKD400`` / ``...430``
+    (src/m_predefined_absorption_models.cc:69-148) load.  ``ckdmt400`` / ``ckdmt430``: dicts with ref_temp [K], ref_press [hPa],
+    wavenumbers, self_absco_ref, for_absco_ref, self_texp (equal lengths >= 4, ascending regular wavenumbers), or None."""
+
+    def __init__(self, ckdmt400=None, ckdmt430=None, device=0):
+        keep = []
+
+        def desc(w):
+            if w is None:
+                return None
+            cols = [np.ascontiguousarray(w[k], dtype=np.float64) for k in ("wavenumbers", "self_absco_ref", "for_absco_ref", "self_texp")]
+            if len({len(c) for c in cols}) != 1:
+                raise ValueError("Mismatching size, all vector inputs must be the same length")
+            keep.extend(cols)
+            return abi.MtckdWater(len(cols[0]), float(w["ref_temp"]), float(w["ref_press"]), *(dptr(c) for c in cols))
+
+        a, b = desc(ckdmt400), desc(ckdmt430)
+        self._h = C.c_void_p()
+        check(lib().ab200_predef_data_create(C.byref(a) if a is not None else None, C.byref(b) if b is not None else None, int(device),
+                                             C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            lib().ab200_predef_data_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def spectral_propmatAddPredefined(spectral_propmat, spectral_propmat_jac, abs_predef_data, select_species, jac_targets, freq_grid,
-                                  atm_path: AtmPath, species, target_d=()):
-    """src/m_predefined_absorption_models.cc:156-191 for every level: ``abs_predef_data`` is a list of model tag names,
-    ``species`` maps "O2" / "N2" / "H2O" / "CO2" / "liquidcloud" to VMR indices; K [np, nf, 7] and dK [np, nq, nf, 7] are +=."""
+                                  atm_path: AtmPath, species, target_d=(), data: PredefData = None):
+    """src/m_predefined_absorption_models.cc:156-191 for every level: ``abs_predef_data`` is a list of model tag names (``data``
+    their tables, MT_CKD 4.x only), ``species`` maps "O2" / "N2" / "H2O" / "CO2" / "liquidcloud" to VMR indices; K [np, nf, 7]
+    and dK [np, nq, nf, 7] are +=."""
     np_ = atm_path.np_
     f, stride, nf = _f_arg(freq_grid, np_)
     tg, nq = make_targets(jac_targets)
@@ -811,7 +852,7 @@ def spectral_propmatAddPredefined(spectral_propmat, spectral_propmat_jac, abs_pr
         raise ValueError("Mismatch dimensions on internal matrices of xsec and frequency")
     d = np.ascontiguousarray(target_d, dtype=np.float64)
     a = atm_path.desc()
-    check(lib().ab200_predef_levels(abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), nf, dptr(f), stride, C.byref(a),
-                                    atm_path.vmr.shape[1], int(select_species), nq, tg, dptr(d if nq else None), dptr(K),
-                                    dptr(dK if nq else None)))
+    check(lib().ab200_predef_levels_data(abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), nf, dptr(f), stride, C.byref(a),
+                                         atm_path.vmr.shape[1], int(select_species), nq, tg, dptr(d if nq else None), dptr(K),
+                                         dptr(dK if nq else None), data.handle if data is not None else None))
     return K, dK

@@ -384,6 +384,10 @@ int ab200_path_add_lookup(ab200_path *p, const ab200_lookup *lut, int32_t h2o_sp
                                                 water (three Debye terms + two resonances), Rayleigh droplets; the "mixing ratio" of the species
                                                 `liquidcloud` is the liquid water content [kg/m3].  Nothing below 1e-10 kg/m3; above 5e-3 kg/m3, outside
                                                 210-373 K or above 25 THz the reference's user error (AB200_ERR_INVALID) */
+#define AB200_PREDEF_H2O_FOREIGNCONT_CKDMT400 17 /* "H2O-ForeignContCKDMT400", MT_CKD400::compute_foreign_h2o src/core/predefined/MT_CKD400.cc:99-172 */
+#define AB200_PREDEF_H2O_SELFCONT_CKDMT400 18    /* "H2O-SelfContCKDMT400",    MT_CKD400::compute_self_h2o    :174-256 */
+#define AB200_PREDEF_H2O_FOREIGNCONT_CKDMT430 19 /* "H2O-ForeignContCKDMT430", MT_CKD430::compute_foreign_h2o src/core/predefined/MT_CKD430.cc (same arithmetic) */
+#define AB200_PREDEF_H2O_SELFCONT_CKDMT430 20    /* "H2O-SelfContCKDMT430",    MT_CKD430::compute_self_h2o */
 typedef struct ab200_predef_species { /* indices into the vmr vector, -1 when the atmosphere does not carry the species */
   int32_t o2, n2, h2o, co2, liquidcloud;
 } ab200_predef_species;
@@ -394,6 +398,36 @@ int ab200_predef_levels(const int32_t *models, int32_t n_models, const ab200_pre
                         double *K, double *dK);
 int ab200_path_add_predefined(ab200_path *p, const int32_t *models, int32_t n_models, const ab200_predef_species *species,
                               const double *target_d);
+
+/* Model data of the MT_CKD 4.x water continua (PredefinedModelData, src/core/predefined/predef_data.h:14-42): the coefficient
+ * tables the user loads with abs_predef_dataAddWaterMTCKD400 / ...430 (src/m_predefined_absorption_models.cc:69-148; same
+ * checks: equal lengths >= 4, ascending wavenumbers) on a regular wavenumber grid [cm-1].  The continuum of a frequency is the
+ * four-point interpolation XINT_FUN (MT_CKD400.cc:84-92) of the scaled coefficients around its wavenumber, times the radiation
+ * term RADFN_FUN (:37-77); the first table entry is mirrored below the grid and frequencies beyond the last wavenumber get
+ * nothing (:139-171).  The reference walks the table with a cursor along the ascending grid; here every frequency finds its
+ * own interval (same interval, same four coefficients). */
+typedef struct ab200_mtckd_water {
+  int32_t n;                     /* table length */
+  double ref_temp, ref_press;    /* [K], [hPa] */
+  const double *wavenumbers;     /* [n] cm-1, regular */
+  const double *self_absco_ref;  /* [n] */
+  const double *for_absco_ref;   /* [n] */
+  const double *self_texp;       /* [n] */
+} ab200_mtckd_water;
+typedef struct ab200_predef_data ab200_predef_data; /* device-resident copy of the tables */
+/* ckdmt400 / ckdmt430: the data of the "...CKDMT400" / "...CKDMT430" tags, NULL when not loaded (a model without its data is
+ * the reference's "No data" error).  MT_CKD430::WaterData also carries for_closure_absco_ref, which none of the dispatched
+ * functions reads (predefined_absorption_models.cc:62-77); it only has to be non-empty there, so it is not passed. */
+int ab200_predef_data_create(const ab200_mtckd_water *ckdmt400, const ab200_mtckd_water *ckdmt430, int32_t device,
+                             ab200_predef_data **out);
+void ab200_predef_data_destroy(ab200_predef_data *data);
+/* ab200_predef_levels / ab200_path_add_predefined with model data (data may be NULL: same as the calls above) */
+int ab200_predef_levels_data(const int32_t *models, int32_t n_models, const ab200_predef_species *species, int64_t nf,
+                             const double *f, int64_t f_level_stride, const ab200_atm_path *atm, int32_t n_species,
+                             int32_t select_species, int32_t nq, const ab200_target *targets, const double *target_d,
+                             double *K, double *dK, const ab200_predef_data *data);
+int ab200_path_add_predefined_data(ab200_path *p, const int32_t *models, int32_t n_models, const ab200_predef_species *species,
+                                   const double *target_d, const ab200_predef_data *data);
 
 /* ---- catalog ingest: HITRAN .par records straight into the SoA of ab200_catalog_desc -------------
  * abs_bandsReadHITRAN (src/m_lbl.cc:302-338) with file_formatter = ["par"], either line_strength_option,

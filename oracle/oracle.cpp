@@ -31,6 +31,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <complex>
 #include <cstdint>
@@ -2952,13 +2953,79 @@ bool ell07_refused(int m, const Pt& a, const double* f, Index nf, Numeric df = 0
 bool o2_vmr_refused(int m, const Pt& a) {
   return (m == AB200_PREDEF_O2_PWR98 or m == AB200_PREDEF_O2_MPM89 or m == AB200_PREDEF_O2_TRE05) and a.o2 != 0. and a.o2 < 1.000e-25;
 }
+// MT_CKD 4.x water continua, src/core/predefined/MT_CKD400.cc: RADFN_FUN :37-77, XINT_FUN :84-92, compute_foreign_h2o :99-172,
+// compute_self_h2o :174-256 (MT_CKD430.cc: the same two functions).  Sequential like the reference: a cursor walks the regular
+// wavenumber table along the ascending frequency grid and keeps the four scaled coefficients around it.  out [nf] +=.
+Numeric mtckd_radfn(const Numeric XVI, const Numeric XKT) {
+  if (XKT > 0.0) {
+    const Numeric XVIOKT = XVI / XKT;
+    if (XVIOKT <= 0.01) return 0.5 * XVIOKT * XVI;
+    if (XVIOKT <= 10) {
+      const Numeric EXPVKT = std::expm1(-XVIOKT);
+      return -XVI * EXPVKT / (2 + EXPVKT);
+    }
+    return XVI;
+  }
+  return XVI;
+}
+Numeric mtckd_xint(const Numeric P, const std::array<Numeric, 4>& A) {
+  const Numeric C = (3 - 2 * P) * P * P, B = 0.5 * P * (1 - P), B1 = B * (1 - P), B2 = B * P;
+  return -A[0] * B1 + A[1] * (1 - C + B2) + A[2] * (C + B1) - A[3] * B2;
+}
+void mtckd(bool self, const ab200_mtckd_water& w, Index n, const double* f_grid, Numeric df, const Pt& a, Numeric* out) {
+  auto kaycm = [](Numeric x) { return x / (100 * Constant::c); };  // Conversion::freq2kaycm
+  const Numeric P = a.P, T = a.T, vmrh2o = a.h2o;
+  if (n == 0) return;
+  const Numeric* wn = w.wavenumbers;
+  const Index data_size = w.n;
+  const Numeric last_wavenumber = wn[data_size - 1];
+  if (kaycm(f_grid[0] + df) > last_wavenumber) return;
+  constexpr Numeric RADCN2 = 1.4387752;
+  const Numeric dvc = wn[1] - wn[0], recdvc = 1 / dvc;
+  const Numeric P0 = (1e-3 * w.ref_press) * 1e5;  // Conversion::bar2pa
+  const Numeric T0 = w.ref_temp, xkt = T / RADCN2, rho_rat = (P / P0) * (T0 / T);
+  const Numeric num_den_cm2 = 1e-6 * vmrh2o * P / (Constant::k * T);
+  const Numeric r = T0 / T;
+  auto scl = [&](Index i) {
+    return self ? w.self_absco_ref[i] * vmrh2o * rho_rat * std::pow(r, w.self_texp[i]) * mtckd_radfn(wn[i], xkt)
+                : w.for_absco_ref[i] * (1.0 - vmrh2o) * rho_rat * mtckd_radfn(wn[i], xkt);
+  };
+  Index cur = std::distance(wn, std::lower_bound(wn, wn + data_size, kaycm(f_grid[0] + df) - 2 * dvc));
+  std::array<Numeric, 4> k{0, 0, 0, 0};
+  for (Index i = -1; i < 3 and cur + i < data_size; i++) k[i + 1] = (i < 0 and cur == 0) ? scl(cur + i + 2) : scl(cur + i);
+  for (Index s = 0; s < n; ++s) {
+    const Numeric fs = f_grid[s] + df;
+    if (fs < 0) continue;
+    const Numeric x = kaycm(fs);
+    if (x > last_wavenumber) return;
+    while (x > wn[cur + 1]) {
+      std::shift_left(k.begin(), k.end(), 1);
+      k.back() = data_size > cur + 3 ? scl(cur + 3) : 0;
+      cur++;
+    }
+    const Numeric o = 1e2 * num_den_cm2 * mtckd_xint(recdvc * (x - wn[cur]), k);
+    out[s] += o >= 0 ? o : 0;
+  }
+}
+bool is_mtckd(int m) { return m >= AB200_PREDEF_H2O_FOREIGNCONT_CKDMT400 and m <= AB200_PREDEF_H2O_SELFCONT_CKDMT430; }
 }  // namespace predef
 
 // spectral_propmatAddPredefined (m_predefined_absorption_models.cc:156-191) + PredefinedModel::compute
 // (predefined_absorption_models.cc:219-317) for every level
+int orc_predef_levels_data(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, int64_t nf, const double* f_in,
+                           int64_t f_level_stride, const ab200_atm_path* atm, int32_t n_species, int32_t select_species, int32_t nq,
+                           const ab200_target* targets, const double* target_d, double* K, double* dK, const ab200_mtckd_water* ckdmt400,
+                           const ab200_mtckd_water* ckdmt430);
 int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, int64_t nf, const double* f_in,
                       int64_t f_level_stride, const ab200_atm_path* atm, int32_t n_species, int32_t select_species, int32_t nq,
                       const ab200_target* targets, const double* target_d, double* K, double* dK) {
+  return orc_predef_levels_data(models, n_models, sp, nf, f_in, f_level_stride, atm, n_species, select_species, nq, targets, target_d, K, dK,
+                                nullptr, nullptr);
+}
+int orc_predef_levels_data(const int32_t* models, int32_t n_models, const ab200_predef_species* sp, int64_t nf, const double* f_in,
+                           int64_t f_level_stride, const ab200_atm_path* atm, int32_t n_species, int32_t select_species, int32_t nq,
+                           const ab200_target* targets, const double* target_d, double* K, double* dK, const ab200_mtckd_water* ckdmt400,
+                           const ab200_mtckd_water* ckdmt430) {
   const int np = atm->np;
   auto v = [&](const double* vmr, int idx) { return idx >= 0 ? vmr[idx] : 0.0; };
   int it = -1;
@@ -2970,7 +3037,43 @@ int orc_predef_levels(const int32_t* models, int32_t n_models, const ab200_prede
     const predef::Pt a{atm->T[ip], atm->P[ip], v(vmr, sp->o2), v(vmr, sp->n2), v(vmr, sp->h2o), v(vmr, sp->liquidcloud)};
     for (int k = 0; k < n_models; k++) {
       const int m = models[k];
-      if (m < 0 or m > AB200_PREDEF_LIQUIDCLOUD_ELL07) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (m < 0 or m > AB200_PREDEF_H2O_SELFCONT_CKDMT430) return fail(AB200_ERR_UNSUPPORTED, "predefined model outside the path");
+      if (predef::is_mtckd(m)) {
+        const ab200_mtckd_water* w = m >= AB200_PREDEF_H2O_FOREIGNCONT_CKDMT430 ? ckdmt430 : ckdmt400;
+        if (not w or w->n == 0) return fail(AB200_ERR_INVALID, "No data");  // check(data), MT_CKD400.cc:94-98
+        if (select_species != AB200_SPECIES_BATH and predef::species_of(m, *sp) != select_species) continue;
+        const bool self = m == AB200_PREDEF_H2O_SELFCONT_CKDMT400 or m == AB200_PREDEF_H2O_SELFCONT_CKDMT430;
+        std::vector<Numeric> pm(nf, 0.0), pq(nf);
+        predef::mtckd(self, *w, nf, f, 0.0, a, pm.data());
+        auto row = [&](int q, const predef::Pt& b, Numeric df) {  // (model' - model) / d, predefined_absorption_models.cc:256-314
+          std::fill(pq.begin(), pq.end(), 0.0);
+          predef::mtckd(self, *w, nf, f, df, b, pq.data());
+          for (Index i = 0; i < nf; i++) dK[((static_cast<Index>(ip) * nq + q) * nf + i) * 7] += (pq[i] - pm[i]) / target_d[q];
+        };
+        for (Index i = 0; i < nf; i++) K[(static_cast<Index>(ip) * nf + i) * 7] += pm[i];
+        if (it >= 0) {
+          predef::Pt b = a;
+          b.T += target_d[it];
+          row(it, b, 0.0);
+        }
+        for (int kind : {AB200_TARGET_WIND_U, AB200_TARGET_WIND_V, AB200_TARGET_WIND_W})
+          for (int q = 0; q < nq; q++)
+            if (targets[q].kind == kind) {
+              row(q, a, target_d[q]);
+              break;
+            }
+        for (int idx : {sp->co2, sp->o2, sp->n2, sp->h2o, sp->liquidcloud}) {
+          if (idx < 0) continue;
+          for (int q = 0; q < nq; q++)
+            if (targets[q].kind == AB200_TARGET_VMR and targets[q].species == idx) {
+              predef::Pt b = a;
+              if (idx == sp->h2o) b.h2o += target_d[q];
+              row(q, b, 0.0);
+              break;
+            }
+        }
+        continue;
+      }
       {  // every point the reference evaluates the model at raises its own range error
         bool bad = predef::ell07_refused(m, a, f, nf);
         if (it >= 0) {

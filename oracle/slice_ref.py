@@ -88,6 +88,16 @@ SLICES_PREDEF = {
     "tre05_oxygen": ("src/core/predefined/TRE05.cc", r"void oxygen\(PropmatVector& propmat_clearsky,", None, (115, 296), "block"),
     "mpm2020_all": ("src/core/predefined/MPM2020.cc", r"constexpr Index num = 38;", r"void compute\(PropmatVector& propmat_clearsky,", (16, 149), "block"),
     "ell07_compute": ("src/core/predefined/ELL07.cc", r"void compute\(PropmatVector& propmat_clearsky,", None, (39, 188), "block"),
+    "mtckd400_radfn": ("src/core/predefined/MT_CKD400.cc", r"Numeric RADFN_FUN\(const Numeric XVI, const Numeric XKT\) noexcept \{", None, (37, 78), "block"),
+    "mtckd400_xint": ("src/core/predefined/MT_CKD400.cc", r"constexpr Numeric XINT_FUN\(const Numeric P,", None, (85, 93), "block"),
+    "mtckd400_check": ("src/core/predefined/MT_CKD400.cc", r"void check\(const WaterData& data\) \{", None, (95, 99), "block"),
+    "mtckd400_foreign": ("src/core/predefined/MT_CKD400.cc", r"void compute_foreign_h2o\(PropmatVector& propmat_clearsky,", None, (102, 177), "block"),
+    "mtckd400_self": ("src/core/predefined/MT_CKD400.cc", r"void compute_self_h2o\(PropmatVector& propmat_clearsky,", None, (179, 256), "block"),
+    "mtckd430_radfn": ("src/core/predefined/MT_CKD430.cc", r"Numeric RADFN_FUN\(const Numeric XVI, const Numeric XKT\) noexcept \{", None, (37, 78), "block"),
+    "mtckd430_xint": ("src/core/predefined/MT_CKD430.cc", r"constexpr Numeric XINT_FUN\(const Numeric P,", None, (85, 93), "block"),
+    "mtckd430_check": ("src/core/predefined/MT_CKD430.cc", r"void check\(const WaterData& data\) \{", None, (95, 100), "block"),
+    "mtckd430_foreign": ("src/core/predefined/MT_CKD430.cc", r"void compute_foreign_h2o\(PropmatVector& propmat_clearsky,", None, (180, 255), "block"),
+    "mtckd430_self": ("src/core/predefined/MT_CKD430.cc", r"void compute_self_h2o\(PropmatVector& propmat_clearsky,", None, (257, 334), "block"),
     "mpm93_nitrogen": ("src/core/predefined/MPM93.cc", r"void nitrogen\(PropmatVector& propmat_clearsky,", None, (33, 73), "block"),
 }
 SLICES.update(SLICES_PREDEF)

@@ -62,6 +62,7 @@ def lib():
                                         C.c_int32, C.c_int32, C.c_int32, C.c_double, dp, dp]
         L.orc_predef_levels.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(abi.PredefSpecies), C.c_int64, dp, C.c_int64,
                                         C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int32, C.c_int32, C.POINTER(abi.Target), dp, dp, dp]
+        L.orc_predef_levels_data.argtypes = L.orc_predef_levels.argtypes + [C.POINTER(abi.MtckdWater), C.POINTER(abi.MtckdWater)]
         L.orc_background.argtypes = [C.c_int64, dp, C.c_double, dp, dp]
         L.orc_observer.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(abi.ObserverDesc), dp, dp, dp, dp, dp, dp]
         for name in ("orc_invplanck", "orc_dinvplanckdI", "orc_invrayjean", "orc_dplanck_dt"):
@@ -323,8 +324,18 @@ def lookup_levels(tables, f, atm: AtmPath, h2o_species=-1, select_species=abi.SP
     return K, dK
 
 
-def predef_levels(models, species, f, atm: AtmPath, select_species=abi.SPECIES_BATH, targets=(), target_d=(), K=None, dK=None):
-    """spectral_propmatAddPredefined per level (m_predefined_absorption_models.cc:156-191)."""
+def _mtckd(w, keep):
+    if w is None:
+        return None
+    cols = [np.ascontiguousarray(w[k], dtype=np.float64) for k in ("wavenumbers", "self_absco_ref", "for_absco_ref", "self_texp")]
+    keep.extend(cols)
+    return C.byref(abi.MtckdWater(len(cols[0]), float(w["ref_temp"]), float(w["ref_press"]), *(dptr(c) for c in cols)))
+
+
+def predef_levels(models, species, f, atm: AtmPath, select_species=abi.SPECIES_BATH, targets=(), target_d=(), K=None, dK=None,
+                  ckdmt400=None, ckdmt430=None):
+    """spectral_propmatAddPredefined per level (m_predefined_absorption_models.cc:156-191); ckdmt400 / ckdmt430: the MT_CKD 4.x
+    water tables as dicts (arts_b200.wsm.PredefData)."""
     f, stride, nf = _f_arg(f, atm.np_)
     tg, nq = make_targets(targets)
     ids, sp = abi.predef_args(models, species)
@@ -332,6 +343,7 @@ def predef_levels(models, species, f, atm: AtmPath, select_species=abi.SPECIES_B
     dK = np.zeros((atm.np_, nq, nf, 7)) if dK is None else dK
     d = np.ascontiguousarray(target_d, dtype=np.float64)
     a = atm.desc()
-    _check(lib().orc_predef_levels(abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1],
-                                   select_species, nq, tg, dptr(d), dptr(K), dptr(dK)))
+    keep = []
+    _check(lib().orc_predef_levels_data(abi.ptr(ids, C.c_int32), len(ids), C.byref(sp), nf, dptr(f), stride, C.byref(a), atm.vmr.shape[1],
+                                        select_species, nq, tg, dptr(d), dptr(K), dptr(dK), _mtckd(ckdmt400, keep), _mtckd(ckdmt430, keep)))
     return K, dK

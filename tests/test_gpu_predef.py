@@ -35,7 +35,7 @@ def test_predef_levels_host_buffers(wsm, orc):
     Kr, _ = orc.predef_levels(MODELS, SPECIES, f, atm)
     np.testing.assert_allclose(K2[..., 0], 0.25 + Kr[..., 0], rtol=1e-15)
     with pytest.raises(wsm.Ab200Error, match="outside the GPU path"):
-        wsm.spectral_propmatAddPredefined(K2, None, [17], abi.SPECIES_BATH, (), f, atm, SPECIES)
+        wsm.spectral_propmatAddPredefined(K2, None, [99], abi.SPECIES_BATH, (), f, atm, SPECIES)
     with pytest.raises(wsm.Ab200Error, match="does not carry"):
         wsm.spectral_propmatAddPredefined(K2, None, MODELS, abi.SPECIES_BATH, (), f, atm, {"O2": 1, "N2": 2})
 
@@ -248,3 +248,69 @@ def test_liquid_cloud_ell07(wsm, orc):
     assert not K.any()
     with pytest.raises(wsm.Ab200Error, match="does not carry"):
         wsm.spectral_propmatAddPredefined(K, None, ["liquidcloud-ELL07"], abi.SPECIES_BATH, (), f, _atm(n), SPECIES)
+
+
+def test_mt_ckd_water_continua(wsm, orc):
+    """"H2O-ForeignContCKDMT400" / "H2O-SelfContCKDMT400" and the 4.3 pair (src/core/predefined/MT_CKD400.cc:102-256, MT_CKD430.cc):
+    table-driven water continua.  The reference walks the coefficient table with a cursor along the grid; the device finds every
+    frequency's interval on its own - checked against the oracle's sequential restatement (pinned bit for bit to the reference's
+    object code) on grids that start below / inside / near the end of the table, per-level grids, with T / H2O / wind rows, composed
+    with other models on the resident path, and without data ("No data")."""
+    w = synth.mtckd_table()
+    w2 = synth.mtckd_table(seed=6, n=1500, v0=-20.0, dv=12.5)
+    data = wsm.PredefData(ckdmt400=w, ckdmt430=w2)
+    kay = 100 * 299792458.0
+    atm = _atm(5)
+    tags = ["H2O-ForeignContCKDMT400", "H2O-SelfContCKDMT400", "H2O-ForeignContCKDMT430", "H2O-SelfContCKDMT430"]
+    tg, d = (("T",), ("VMR", 0), ("wind_u",), ("VMR", 1)), (0.1, 1e-6, 1e4, 1e-4)
+    rng = np.random.default_rng(3)
+    wn = w["wavenumbers"]
+    grids = [np.linspace(1e9, 6.2e14, 4000), np.sort(rng.uniform(2e12, 1.2e14, 1500)), np.linspace(wn[-4] * kay, wn[-1] * kay * 1.0005, 300),
+             np.concatenate([[0.0, wn[2] * kay, wn[3] * kay], np.linspace(1e12, 2e12, 50)]),
+             np.stack([np.linspace(3e12, 9e13, 700) * (1 + 1e-5 * i) for i in range(5)])]  # the last one: a grid per level
+    for f in grids:
+        for models in (tags, tags[1:2]):
+            Kr, dKr = orc.predef_levels(models, SPECIES, f, atm, targets=tg, target_d=d, ckdmt400=w, ckdmt430=w2)
+            nf = f.shape[-1]
+            K = np.zeros((atm.np_, nf, 7)); dK = np.zeros((atm.np_, 4, nf, 7))
+            wsm.spectral_propmatAddPredefined(K, dK, models, abi.SPECIES_BATH, tg, f, atm, SPECIES, target_d=d, data=data)
+            sc = np.abs(Kr[..., 0]).max(axis=1, keepdims=True)
+            assert (np.abs(K[..., 0] - Kr[..., 0]) <= 1e-12 * np.abs(Kr[..., 0]) + 1e-15 * sc).all()
+            for q in range(4):
+                dsc = np.abs(dKr[:, q, :, 0]).max()
+                tol = 1e-5 * dsc + 1e-13 * np.abs(Kr[..., 0]).max() / abs(d[q])
+                assert np.abs(dK[:, q, :, 0] - dKr[:, q, :, 0]).max() <= max(tol, 1e-300), (models, q)
+            assert not dK[:, 3].any() and not K[..., 1:].any()  # O2 is not a variable of these models: exact zeros
+        assert Kr[..., 0].max() > 0
+    # on the resident path, after the lines, with a gas model next to them; species selection keeps or drops them
+    c = synth.tiny_case(nl=64, nf=400, np_=6, targets=(("T",), ("VMR", 0)))
+    species = {"H2O": 0, "O2": 1}
+    models = ["H2O-SelfContCKDMT400", "O2-PWR98", "H2O-ForeignContCKDMT430"]
+    for sel in (abi.SPECIES_BATH, 0, 1):
+        K, dK = orc.propmat_levels(c.cat, c.f, c.atm, targets=c.targets, select_species=sel)
+        orc.predef_levels(models, species, c.f, c.atm, select_species=sel, targets=c.targets, target_d=(0.1, 1e-6), K=K, dK=dK, ckdmt400=w, ckdmt430=w2)
+        cat = wsm.Catalog(c.cat)
+        path = wsm.Path(cat, c.nf, c.np_, 2)
+        path.upload(c.f, c.atm, c.r, c.I_bkg, targets=c.targets, select_species=sel)
+        path.run_propmat()
+        path.add_predefined(models, species, target_d=(0.1, 1e-6), data=data)
+        Kg = np.empty_like(K); dKg = np.empty_like(dK)
+        path.download(K=Kg, dK=dKg)
+        path.close()
+        cat.close()
+        np.testing.assert_allclose(Kg[..., 0], K[..., 0], rtol=1e-9)
+        for q in range(2):
+            assert np.abs(dKg[:, q, :, 0] - dK[:, q, :, 0]).max() <= 1e-5 * np.abs(dK[:, q, :, 0]).max()
+    K = np.zeros((atm.np_, 10, 7))
+    with pytest.raises(wsm.Ab200Error, match="No data"):
+        wsm.spectral_propmatAddPredefined(K, None, tags[:1], abi.SPECIES_BATH, (), np.linspace(1e12, 2e12, 10), atm, SPECIES)
+    only400 = wsm.PredefData(ckdmt400=w)
+    with pytest.raises(wsm.Ab200Error, match="No data"):
+        wsm.spectral_propmatAddPredefined(K, None, tags[2:3], abi.SPECIES_BATH, (), np.linspace(1e12, 2e12, 10), atm, SPECIES, data=only400)
+    only400.close()
+    bad = dict(w, wavenumbers=w["wavenumbers"][::-1].copy())
+    with pytest.raises(wsm.Ab200Error, match="increasing"):
+        wsm.PredefData(ckdmt400=bad)
+    with pytest.raises(wsm.Ab200Error, match="shorter than 4"):
+        wsm.PredefData(ckdmt400={k: (v[:3] if hasattr(v, "__len__") else v) for k, v in w.items()})
+    data.close()

@@ -43,6 +43,7 @@ def ref():
     L.refslice_sqrt_propmat.argtypes = [dp, dp]
     L.refslice_predef.argtypes = [C.c_int32, C.c_int64, dp] + [C.c_double] * 5 + [dp]
     L.refslice_ell07.argtypes = [C.c_int64, dp, C.c_double, C.c_double, dp]
+    L.refslice_mtckd.argtypes = [C.c_int32, C.c_int32, C.c_int32, dp, dp, dp, dp, C.c_double, C.c_double, C.c_int64, dp] + [C.c_double] * 3 + [dp]
     L.refslice_tramat.argtypes = [C.c_int32, C.c_int64, C.c_int32, dp, dp, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
     L.refslice_rte_emission.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [dp] * 9
     L.refslice_tmodel.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, dp, dp]
@@ -443,3 +444,38 @@ def test_ell07_liquid_cloud_bitwise(ref):
         assert ref.refslice_ell07(len(ff), dptr(np.ascontiguousarray(ff)), T, lwc, dptr(A)) == 1
         with pytest.raises(Exception, match="ELL07"):
             orc.predef_levels(["liquidcloud-ELL07"], sp, ff, atm_of(T, lwc))
+
+
+@pytest.mark.parametrize("tag", ["H2O-ForeignContCKDMT400", "H2O-SelfContCKDMT400", "H2O-ForeignContCKDMT430", "H2O-SelfContCKDMT430"])
+def test_mt_ckd_water_continua_bitwise(ref, tag):
+    """f2: the oracle's restatement of MT_CKD400::compute_foreign_h2o / compute_self_h2o (src/core/predefined/MT_CKD400.cc:102-177,
+    :179-256; RADFN_FUN :37-78, XINT_FUN :85-93) and of the MT_CKD430 pair (MT_CKD430.cc:180-255, :257-334) against the reference's
+    own object code, every bit: grids that start below, inside and above the table, the mirrored first entry, the end of the
+    table, a frequency exactly on a table point, negative frequencies, all three branches of the radiation term."""
+    from arts_b200 import _abi as abi
+    from arts_b200 import synth
+    w = synth.mtckd_table()
+    wn = w["wavenumbers"]
+    version, self_ = (400 if "400" in tag else 430), int("Self" in tag)
+    kay = 100 * 299792458.0
+    rng = np.random.default_rng(37)
+    grids = [np.linspace(1e9, 6.3e14, 2500), np.sort(rng.uniform(3e12, 9e13, 800)), np.linspace(wn[-3] * kay, wn[-1] * kay * 1.001, 50),
+             np.array([-1e9, 0.0, wn[2] * kay, wn[3] * kay, 5e12]), np.linspace(5.99e14, 5.9959e14, 7), np.linspace(6.1e14, 6.2e14, 5),
+             np.linspace(1e6, 4e9, 40)]
+    sp = {"H2O": 0}
+    for f in grids:
+        f = np.ascontiguousarray(f)
+        for k in range(6):
+            T, P, h2o = rng.uniform(180, 320), 10 ** rng.uniform(1.0, 5.05), [0.0, 1e-6, 0.04][k] if k < 3 else 10 ** rng.uniform(-6, -1.4)
+            atm = abi.AtmPath(T=np.array([T]), P=np.array([P]), vmr=np.array([[h2o]]), isorat=np.ones((1, 1)), Q=np.ones((1, 1)))
+            K, _ = orc.predef_levels([tag], sp, f, atm, **{"ckdmt400" if version == 400 else "ckdmt430": w})
+            A = np.zeros(len(f))
+            cols = [np.ascontiguousarray(w[c]) for c in ("wavenumbers", "self_absco_ref", "for_absco_ref", "self_texp")]
+            assert ref.refslice_mtckd(version, self_, len(wn), *(dptr(c) for c in cols), w["ref_temp"], w["ref_press"], len(f), dptr(f), T, P, h2o,
+                                      dptr(A)) == 0
+            assert_same_bits(K[0, :, 0], A, f"{tag} at T={T} P={P} h2o={h2o} f0={f[0]}")
+            assert np.all(A >= 0) and np.all(K[0, :, 1:] == 0)
+            if h2o > 0 and len(f) > 100:  # (near 0 cm-1 the interpolant of a noisy table may be negative and is clipped)
+                assert A.max() > 0
+    with pytest.raises(Exception, match="No data"):
+        orc.predef_levels([tag], sp, grids[0], atm)

@@ -163,16 +163,10 @@ __global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int
   double v_min = real_line ? f0s : DBL_MAX, v_max = real_line ? f0s : -DBL_MAX;
   double v_igd = real_line ? igd : DBL_MAX, v_y = real_line ? y : DBL_MAX, v_igx = real_line ? igd : 0.0;
   double v_cmin = real_line ? fmin(v_cut, DBL_MAX) : DBL_MAX, v_cmax = real_line ? fmin(v_cut, DBL_MAX) : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    v_min  = fmin(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
-    v_max  = fmax(v_max, __shfl_xor_sync(0xffffffffu, v_max, o));
-    v_igd  = fmin(v_igd, __shfl_xor_sync(0xffffffffu, v_igd, o));
-    v_igx  = fmax(v_igx, __shfl_xor_sync(0xffffffffu, v_igx, o));
-    v_y    = fmin(v_y, __shfl_xor_sync(0xffffffffu, v_y, o));
-    v_cmin = fmin(v_cmin, __shfl_xor_sync(0xffffffffu, v_cmin, o));
-    v_cmax = fmax(v_cmax, __shfl_xor_sync(0xffffffffu, v_cmax, o));
-  }
+  v_min = lanes_min(v_min); v_max = lanes_max(v_max);  // integer warp reductions on the ordered bits (common.cuh)
+  v_igd = lanes_min(v_igd); v_igx = lanes_max(v_igx);
+  v_y   = lanes_min(v_y);
+  v_cmin = lanes_min(v_cmin); v_cmax = lanes_max(v_cmax);
   cutvals[lane] = v_cutval;
   if ((lane & 31) == 0) {
     double* r = red[lane >> 5];

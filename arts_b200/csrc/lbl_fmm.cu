@@ -41,14 +41,12 @@ namespace {
 constexpr double GH_R0 = 0.52464762327529031788, GH_R1 = 1.65068012388578455588;   // sqrt((3 -+ sqrt 6) / 2)
 constexpr double GH_W0 = 0.45412414523193150818, GH_W1 = 0.04587585476806849182;   // (t_j - 5/2) / (2 (t_j - t_other))
 
-__device__ __forceinline__ double warp_max(double v, int width) {
-  for (int o = width / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+// maximum / minimum over the warp (width 32) or over the lane's half-warp (width 16): common.cuh lanes_max / lanes_min
+__device__ __forceinline__ unsigned width_mask(int width) {
+  return width == 32 ? 0xffffffffu : ((threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu);
 }
-__device__ __forceinline__ double warp_min(double v, int width) {
-  for (int o = width / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
+__device__ __forceinline__ double warp_max(double v, int width) { return lanes_max(v, width_mask(width)); }
+__device__ __forceinline__ double warp_min(double v, int width) { return lanes_min(v, width_mask(width)); }
 
 // moments of one line about centre c with scale 1 / R: term[k] = -Si sum_j w_j (B_{j+} + B_{j-}) at power k + 1
 __device__ __forceinline__ void line_terms(bool live, double d, double GD, double g, double Si, double iR, double* term) {

@@ -42,11 +42,15 @@ __global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int
   const int lane     = threadIdx.x;
   const int64_t slot = tile * TL + lane;
   const int64_t par  = p.sub_parent[slot];
-  __shared__ double red[TL / 32][7];
-  __shared__ double cutvals[TL];
+  // double-buffered by level parity: ONE barrier per level (thread 0 reads a level's buffers between that level's barrier and
+  // the next one; the other warps write the same buffers again only after the next barrier)
+  __shared__ double red_buf[2][TL / 32][7];
+  __shared__ double cutvals_buf[2][TL];
   const int lev_end = min(nlev, (int(blockIdx.y) + 1) * PREP_LB);
 #pragma unroll 1
   for (int lev = int(blockIdx.y) * PREP_LB; lev < lev_end; lev++) {
+  double (*red)[7] = red_buf[lev & 1];
+  double* cutvals  = cutvals_buf[lev & 1];
 
   const double T = p.T[lev], P = p.P[lev];
   double f0s = 0.0, igd = 0.0, y = 0.0, s_re = 0.0, s_im = 0.0, G0 = 0.0, GD = 1.0;
@@ -186,7 +190,6 @@ __global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int
     s[0] = v_min; s[1] = v_max; s[2] = v_igd; s[3] = v_y;
     s[4] = v_cmin; s[5] = v_cmax; s[6] = v_cutval; s[7] = v_igx;
   }
-  __syncthreads();  // red / cutvals are reused by the next level
   }
 }
 

@@ -137,7 +137,9 @@ __device__ __forceinline__ void w_cf(double x, double y, double& wr_out, double&
   //   w = N / D,  z - k / w = (z N - k D) / N   =>   (N, D) <- (z N - k D, N),
   // six FMA-class instructions per term, and a single reciprocal at the end for w(z) = (i / sqrt(pi)) D / N.
   // |N| grows like |z|^nu <= 4000^4 or 6^20: no scaling needed.  Same term count nu(z) as the reference (:729).
-  const int nu = int(3.9 + 11.398 / (0.08254 * x + 0.1421 * y + 0.2023));  // floor of a positive number
+  // (the quotient through the reciprocal: within 2 ulp of the division, so the floor differs only where 3.9 + q is that close to an
+  // integer - and there one term more or less of a converged fraction changes nothing above 1e-16)
+  const int nu = int(3.9 + 11.398 * fast_rcp(0.08254 * x + 0.1421 * y + 0.2023));  // floor of a positive number
   double Nr = x, Ni = y, Dr = 1.0, Di = 0.0;
   double k = 0.5 * double(nu - 1);
   for (int j = nu - 1; j > 0; j--) {

@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(TL, 4) lbl_fmm_moments_tile_kernel(PreparePara
   if ((lane & 31) == 0) { sh[warp][0] = lo32; sh[warp][1] = hi32; }
   __syncthreads();
   const double lo1 = fmin(sh[w1][0], sh[w1 + 1][0]), hi1 = fmax(sh[w1][1], sh[w1 + 1][1]);
-  double lo2 = DBL_MAX, hi2 = -DBL_MAX;
-  for (int w = 0; w < TL / 32; w++) { lo2 = fmin(lo2, sh[w][0]); hi2 = fmax(hi2, sh[w][1]); }
+  // over the tile's eight warps: lane l takes warp l & 7's value, one integer warp reduction (instead of eight loads and fmin each)
+  static_assert(TL / 32 == 8, "eight warps per tile");
+  const double lo2 = lanes_min(sh[lane & 7][0]), hi2 = lanes_max(sh[lane & 7][1]);
   __syncthreads();
   const bool e0 = lo0 > hi0, e1 = lo1 > hi1, e2 = lo2 > hi2;  // empty clusters
   const double c2 = e2 ? 0.0 : 0.5 * (lo2 + hi2);
@@ -180,12 +181,10 @@ __global__ void __launch_bounds__(TL, 4) lbl_fmm_moments_tile_kernel(PreparePara
   }
   __syncthreads();
   R1 = fmax(sh[w1][0], sh[w1 + 1][0]); D1 = fmax(sh[w1][1], sh[w1 + 1][1]);
-  R2 = 0.0; D2 = 0.0;
-  for (int w = 0; w < TL / 32; w++) { R2 = fmax(R2, sh[w][4]); D2 = fmax(D2, sh[w][5]); }
+  R2 = lanes_max(sh[lane & 7][4]); D2 = lanes_max(sh[lane & 7][5]);
   if (tile_has_cut) {
     I1 = fmin(sh[w1][2], sh[w1 + 1][2]); O1 = fmax(sh[w1][3], sh[w1 + 1][3]);
-    I2 = DBL_MAX; O2 = 0.0;
-    for (int w = 0; w < TL / 32; w++) { I2 = fmin(I2, sh[w][6]); O2 = fmax(O2, sh[w][7]); }
+    I2 = lanes_min(sh[lane & 7][6]); O2 = lanes_max(sh[lane & 7][7]);
   } else {
     O1 = e1 ? 0.0 : DBL_MAX;
     O2 = e2 ? 0.0 : DBL_MAX;
@@ -201,37 +200,44 @@ __global__ void __launch_bounds__(TL, 4) lbl_fmm_moments_tile_kernel(PreparePara
     c0s[q] = c0; rho0s[q] = e0 ? -1.0 : rho0; in0s[q] = in0; out0s[q] = out0; cs0s[q] = CS0; R0s[q] = R0;
   }
   __syncthreads();
-  double rho1 = e1 ? 0.0 : fmax(MP_THETA * R1, D1), in1 = I1 < DBL_MAX ? I1 * (1.0 - 1e-12) : DBL_MAX,
-         out1 = O1 < DBL_MAX ? O1 * (1.0 + 1e-12) : DBL_MAX, cs1 = 0.0;
-  for (int q = 0; q < 4; q++) {
-    const int qq = (lane >> 6) * 4 + q;
-    if (rho0s[qq] < 0.0) continue;
-    const double dist = fabs(c0s[qq] - c1);
-    rho1 = fmax(rho1, rho0s[qq] + dist);
-    in1  = fmin(in1, in0s[qq] < DBL_MAX ? in0s[qq] - dist : DBL_MAX);
-    out1 = fmax(out1, out0s[qq] < DBL_MAX ? out0s[qq] + dist : DBL_MAX);
-    cs1 += cs0s[qq];
-  }
-  rho1 = e1 ? 0.0 : rho1 * (1.0 + 1e-12);
-  if (e1) { in1 = DBL_MAX; out1 = DBL_MAX; }
+  // (the bounds of a 64-line cluster are needed by its first lane only, those of the tile by lane 0)
+  double rho1 = 0.0, in1 = DBL_MAX, out1 = DBL_MAX, cs1 = 0.0;
   if ((lane & 63) == 0) {
+    rho1 = e1 ? 0.0 : fmax(MP_THETA * R1, D1);
+    in1  = I1 < DBL_MAX ? I1 * (1.0 - 1e-12) : DBL_MAX;
+    out1 = O1 < DBL_MAX ? O1 * (1.0 + 1e-12) : DBL_MAX;
+    for (int q = 0; q < 4; q++) {
+      const int qq = (lane >> 6) * 4 + q;
+      if (rho0s[qq] < 0.0) continue;
+      const double dist = fabs(c0s[qq] - c1);
+      rho1 = fmax(rho1, rho0s[qq] + dist);
+      in1  = fmin(in1, in0s[qq] < DBL_MAX ? in0s[qq] - dist : DBL_MAX);
+      out1 = fmax(out1, out0s[qq] < DBL_MAX ? out0s[qq] + dist : DBL_MAX);
+      cs1 += cs0s[qq];
+    }
+    rho1 = e1 ? 0.0 : rho1 * (1.0 + 1e-12);
+    if (e1) { in1 = DBL_MAX; out1 = DBL_MAX; }
     const int sidx = lane >> 6;
     c1s[sidx] = c1; rho1s[sidx] = e1 ? -1.0 : rho1; in1s[sidx] = in1; out1s[sidx] = out1; cs1s[sidx] = cs1; R1s[sidx] = R1;
   }
   if (lane == 0) c2s = c2;
   __syncthreads();
-  double rho2 = e2 ? 0.0 : fmax(MP_THETA * R2, D2), in2 = I2 < DBL_MAX ? I2 * (1.0 - 1e-12) : DBL_MAX,
-         out2 = O2 < DBL_MAX ? O2 * (1.0 + 1e-12) : DBL_MAX, cs2 = 0.0;
-  for (int sidx = 0; sidx < 4; sidx++) {
-    if (rho1s[sidx] < 0.0) continue;
-    const double dist = fabs(c1s[sidx] - c2);
-    rho2 = fmax(rho2, rho1s[sidx] + dist);
-    in2  = fmin(in2, in1s[sidx] < DBL_MAX ? in1s[sidx] - dist : DBL_MAX);
-    out2 = fmax(out2, out1s[sidx] < DBL_MAX ? out1s[sidx] + dist : DBL_MAX);
-    cs2 += cs1s[sidx];
+  double rho2 = 0.0, in2 = DBL_MAX, out2 = DBL_MAX, cs2 = 0.0;
+  if (lane == 0) {
+    rho2 = e2 ? 0.0 : fmax(MP_THETA * R2, D2);
+    in2  = I2 < DBL_MAX ? I2 * (1.0 - 1e-12) : DBL_MAX;
+    out2 = O2 < DBL_MAX ? O2 * (1.0 + 1e-12) : DBL_MAX;
+    for (int sidx = 0; sidx < 4; sidx++) {
+      if (rho1s[sidx] < 0.0) continue;
+      const double dist = fabs(c1s[sidx] - c2);
+      rho2 = fmax(rho2, rho1s[sidx] + dist);
+      in2  = fmin(in2, in1s[sidx] < DBL_MAX ? in1s[sidx] - dist : DBL_MAX);
+      out2 = fmax(out2, out1s[sidx] < DBL_MAX ? out1s[sidx] + dist : DBL_MAX);
+      cs2 += cs1s[sidx];
+    }
+    rho2 = e2 ? 0.0 : rho2 * (1.0 + 1e-12);
+    if (e2) { in2 = DBL_MAX; out2 = DBL_MAX; }
   }
-  rho2 = e2 ? 0.0 : rho2 * (1.0 + 1e-12);
-  if (e2) { in2 = DBL_MAX; out2 = DBL_MAX; }
 
   // --- moments of the 16-line clusters from the lines
   double term[MP_P];

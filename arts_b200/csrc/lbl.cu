@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int
   // the next one; the other warps write the same buffers again only after the next barrier)
   __shared__ double red_buf[2][TL / 32][7];
   __shared__ double cutvals_buf[2][TL];
+  // log(T0 / T) of the tile's first line for the NEXT level, formed by thread 0 before the barrier: the catalogs give nearly every
+  // line the same reference temperature (296 K), so the other threads pick it up instead of evaluating the same logarithm
+  __shared__ double lq_next[2];
+  const double T0_tile = p.T0[max(p.sub_parent[tile * TL], int64_t(0))];
   const int lev_end = min(nlev, (int(blockIdx.y) + 1) * PREP_LB);
 #pragma unroll 1
   for (int lev = int(blockIdx.y) * PREP_LB; lev < lev_end; lev++) {
@@ -59,7 +63,8 @@ __global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int
     const int isot = p.line_isot[par];
     const int spec = p.isot_species[isot];
     const double T0 = p.T0[par];
-    const double q_T = T0 / T, lq_T = log(q_T);  // shared by every variable and broadener of the line
+    const double q_T = T0 / T;  // shared by every variable and broadener of the line
+    const double lq_T = (T0 == T0_tile && lev != int(blockIdx.y) * PREP_LB) ? lq_next[lev & 1] : log(q_T);
     // model::{G0,D0,DV,Y,G}(atm): VMR-weighted mixture, Bath = remainder
     double res[AB200_NVAR], bth[AB200_NVAR];
     double vmr_sum = 0.0;
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(TL, 3) lbl_prepare_kernel(PrepareParams p, int
     double* r = red[lane >> 5];
     r[0] = v_min; r[1] = v_max; r[2] = v_igd; r[3] = v_y; r[4] = v_cmin; r[5] = v_cmax; r[6] = v_igx;
   }
+  if (lane == 32 && lev + 1 < lev_end) lq_next[(lev + 1) & 1] = log(T0_tile / p.T[lev + 1]);  // (warp 1: warp 0 has the summary)
   __syncthreads();
   if (lane == 0) {
     for (int w = 1; w < TL / 32; w++) {

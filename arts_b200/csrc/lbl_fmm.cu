@@ -84,15 +84,13 @@ __device__ __forceinline__ bool fmm_served(double v, double rho, double in, doub
 //     m'_k = sum_{j=1..k} C(k, j) (dc / R_p)^(k-j) (R_c / R_p)^j m_j,     |dc| + R_c <= R_p.
 __constant__ double BINOM[MP_P + 1][MP_P + 1];
 __device__ __forceinline__ double m2m_term(int k, double x, double r, const double* __restrict__ m /* m[j-1] = m_j */) {
-  double xp[MP_P + 1];
-  xp[0] = 1.0;
-#pragma unroll
-  for (int e = 1; e <= MP_P; e++) xp[e] = xp[e - 1] * x;
+  // Horner in x over j = 1 .. k: sum_j [C(k, j) r^j m_j] x^(k-j) (no table of powers: k differs from thread to thread, and an
+  // array indexed by it would live in local memory)
   double sum = 0.0, rp = 1.0;
 #pragma unroll
   for (int j = 1; j <= MP_P; j++) {
     rp *= r;
-    if (j <= k) sum = __fma_rn(BINOM[k][j] * xp[k - j] * rp, m[j - 1], sum);
+    if (j <= k) sum = __fma_rn(sum, x, BINOM[k][j] * rp * m[j - 1]);
   }
   return sum;
 }

@@ -435,7 +435,7 @@ def run_b200(args):
                                           "fraction (arts_b200/csrc/lbl_fmm.cu): per (frequency, level) a few hundred cluster expansions of 24 "
                                           "FP64 instructions plus the ~1e2-4e2 pairs within 48 Doppler widths, instead of 1e6 pairs - same "
                                           "spectra to 1e-9, bit-identical under frequency partitions.  FP64-pipe utilisation of the kernels "
-                                          "actually run is in profiles/r2x_fmm_kernels.ncu.txt (ncu): far pass 67 %, near pass 57 %, moments 30 %, prepare 20 %."},
+                                          "actually run is in profiles/r3c_fmm_kernels.ncu.txt (ncu): far pass 67 %, near pass 61 %, moments 37 %, prepare 19 %."},
                      "kernel_share_of_step": k_ms / ms if ms else None},
         "roofline_stokes": {"bound": "hbm", "kernel": "stokes_chain_kernel", "achieved": st_gbs, "peak": hbm_peak,
                             "unit": "GB/s", "frac": st_gbs / hbm_peak, "traffic": traffic.get("stokes_chain_kernel"),

@@ -479,3 +479,55 @@ def test_mt_ckd_water_continua_bitwise(ref, tag):
                 assert A.max() > 0
     with pytest.raises(Exception, match="No data"):
         orc.predef_levels([tag], sp, grids[0], atm)
+
+
+def test_zeeman_strengths_against_the_reference_wigner_library(ref):
+    """The 3j symbols of the Zeeman strengths (lbl_zeeman.cpp:261-277: C * wigner3j(Jl, 1, Ju, Ml, dM, -Mu)^2) against the
+    reference's own vendored wigxjpf compiled where it lies (oracle/Makefile; called as wigner_functions.cc:41-71 calls it).
+    wigxjpf sums the Racah series in exact multi-word integer arithmetic and rounds once, so it is the correctly rounded value:
+    the oracle's long double Racah sum and the product's closed form for j2 = 1 (catalog.cu, host) must agree with it to a few
+    ulp for every component of every J up to 60 (half-integer J included) and must be EXACTLY zero wherever it is."""
+    from arts_b200 import _lib
+    ref.refwig_wigner3j.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_double)]
+    L = _lib.lib()
+    out = C.c_double()
+    worst_orc = worst_lib = 0.0
+    n_checked = 0
+    for tJl in range(0, 121):
+        for tJu in (tJl - 2, tJl, tJl + 2):
+            if tJu < 0:
+                continue
+            for pol, dm in ((1, 0), (2, -1), (3, 1)):
+                cap = tJl + 8
+                s, d = np.zeros(cap), np.zeros(cap)
+                n = L.ab200_zeeman_components(1, 1.0, 1.0, tJu, tJl, pol, cap, dptr(s), dptr(d))
+                assert n == tJl + 1
+                fac = 1.5 if pol == 1 else 0.75
+                for i in range(n):
+                    tml = -tJl + 2 * i
+                    tmu = tml + 2 * dm
+                    if abs(tmu) > tJu:
+                        assert s[i] == 0.0
+                        continue
+                    assert ref.refwig_wigner3j(tJl, 2, tJu, tml, 2 * dm, -tmu, C.byref(out)) == 0
+                    w = out.value
+                    o = orc.wigner3j(tJl, 2, tJu, tml, 2 * dm, -tmu)
+                    if w == 0.0:
+                        assert o == 0.0 and s[i] == 0.0, (tJl, tJu, tml, dm)
+                        continue
+                    worst_orc = max(worst_orc, abs(o - w) / abs(w))
+                    worst_lib = max(worst_lib, abs(s[i] - fac * w * w) / (fac * w * w))
+                    n_checked += 1
+    assert n_checked > 40000
+    assert worst_lib <= 8 * np.finfo(float).eps, worst_lib
+    assert worst_orc <= 64 * np.finfo(float).eps, worst_orc
+    # general arguments of the oracle's Racah sum (j2 != 1), including the selection-rule zeros
+    rng = np.random.default_rng(5)
+    for _ in range(3000):
+        tj = rng.integers(0, 40, 3)
+        tm = [int(rng.integers(-j, j + 1)) for j in tj[:2]]
+        tm = [t - ((t + j) % 2) for t, j in zip(tm, tj[:2])]  # m and j of the same parity
+        tm.append(-tm[0] - tm[1])
+        assert ref.refwig_wigner3j(*map(int, tj), *tm, C.byref(out)) == 0
+        o = orc.wigner3j(*map(int, tj), *tm)
+        assert abs(o - out.value) <= 1e-13 * max(abs(out.value), 1e-3), (tj, tm, o, out.value)

@@ -3218,6 +3218,20 @@ int orc_line_level(const ab200_catalog_desc* d, const ab200_atm_path* atm_path, 
   return 0;
 }
 
+// The line-shape model of one catalog line at one path level, one variable: out[7] = VAR(atm), dVAR_dT(atm),
+// dVAR_dVMR(atm, target_species), dVAR_dX0..3(atm, target_species) - the restatement of lbl_lineshape_model.cpp:70-246 above,
+// for the bitwise comparison with the reference's own text (oracle/refslice/template_mix.cpp.in).
+int orc_line_mix(const ab200_catalog_desc* d, const ab200_atm_path* atm_path, int32_t ip, int64_t il, int32_t var,
+                 int32_t target_species, double* out) {
+  const AtmPt atm = atm_at(*d, *atm_path, ip);
+  const LineView ln{*d, il};
+  out[0] = ln.mix(var, atm);
+  out[1] = ln.mix(var, atm, true);
+  out[2] = ln.dmix_dVMR(var, atm, target_species);
+  for (int c = 0; c < 4; c++) out[3 + c] = ln.dmix_dX(var, atm, target_species, c);
+  return 0;
+}
+
 // single_shape at n frequencies: out[i] = {Re, Im of s F(f); Re, Im of dF(f); Re, Im of dX(ds, dz, dz_fac, f)}
 int orc_shape_eval(const double* shape, const double* dsdz, int64_t n, const double* f, double* out) {
   single_shape s;

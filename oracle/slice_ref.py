@@ -102,6 +102,16 @@ SLICES_PREDEF = {
 }
 SLICES.update(SLICES_PREDEF)
 
+# the line-shape model of a line: per-broadener pressure scaling, the broadener mixing loop and its derivatives, the holder of a
+# temperature model (third translation unit, refslice/template_mix.cpp.in)
+SLICES_MIX = {
+    "tmodel_functions_mix": SLICES["tmodel_functions"],
+    "tmodel_data_class": ("src/core/lbl/lbl_temperature_model.h", r"class data \{", None, (284, 343), "block"),
+    "lsm_structs": ("src/core/lbl/lbl_lineshape_model.h", r"struct species_model \{", r"struct model \{", (17, 224), "block"),
+    "lsm_mixing": ("src/core/lbl/lbl_lineshape_model.cpp", r"#define VARIABLE\(name, PVAR, DPVAR\)", r"std::istream& operator>>\(std::istream& is, species_model& x\) \{", (14, 259), "lines_excl"),
+}
+SLICES.update(SLICES_MIX)
+
 
 def _strip_for_braces(line: str) -> str:
     """Drop // comments, string and character literals before counting braces."""
@@ -140,8 +150,8 @@ def cut(ref, name):
     with open(path) as fh:
         lines = fh.read().split("\n")
     first = _find_unique(lines, first_rx, 0, rel)
-    if mode == "lines":
-        last = _find_unique(lines, last_rx, first, rel)
+    if mode in ("lines", "lines_excl"):
+        last = _find_unique(lines, last_rx, first, rel) - (mode == "lines_excl")  # lines_excl: up to the line before the anchor
     else:
         last_start = first if last_rx is None else _find_unique(lines, last_rx, first, rel)
         last = _block_end(lines, last_start, rel)
@@ -192,11 +202,12 @@ def main():
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     out_dir = sys.argv[2] if len(sys.argv) > 2 else os.path.join(HERE, "_ref")
     os.makedirs(out_dir, exist_ok=True)
-    manifest = generate(ref, out_dir, "template.cpp.in", "refslice_gen.cpp", set(SLICES) - set(SLICES_PREDEF))
+    manifest = generate(ref, out_dir, "template.cpp.in", "refslice_gen.cpp", set(SLICES) - set(SLICES_PREDEF) - set(SLICES_MIX))
     manifest.update(generate(ref, out_dir, "template_predef.cpp.in", "refslice_predef_gen.cpp", set(SLICES_PREDEF)))
+    manifest.update(generate(ref, out_dir, "template_mix.cpp.in", "refslice_mix_gen.cpp", set(SLICES_MIX)))
     with open(os.path.join(out_dir, "refslice_manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
-    print(f"slice_ref: {len(manifest)} slices, {sum(v['lines'] for v in manifest.values())} reference lines -> {out_dir}/refslice_gen.cpp, refslice_predef_gen.cpp")
+    print(f"slice_ref: {len(manifest)} slices, {sum(v['lines'] for v in manifest.values())} reference lines -> {out_dir}/refslice_gen.cpp, refslice_predef_gen.cpp, refslice_mix_gen.cpp")
 
 
 if __name__ == "__main__":

@@ -531,3 +531,81 @@ def test_zeeman_strengths_against_the_reference_wigner_library(ref):
         assert ref.refwig_wigner3j(*map(int, tj), *tm, C.byref(out)) == 0
         o = orc.wigner3j(*map(int, tj), *tm)
         assert abs(o - out.value) <= 1e-13 * max(abs(out.value), 1e-3), (tj, tm, o, out.value)
+
+
+def test_broadener_mixing_loop_bitwise(ref):
+    """The line-shape model of a line against the reference's own text compiled from slices (oracle/refslice/template_mix.cpp.in):
+    species_model::VAR with its pressure scaling (lbl_lineshape_model.cpp:14-35), the broadener mixing loop model::VAR(atm)
+    (:70-90), dVAR_dVMR (:92-113, the `(t - x) / t * t` included), dVAR_dT (:127-148), dVAR_dX0..3 (:153-218) and the dispatch
+    of temperature::data over the nine model types (lbl_temperature_model.h:284-343) - every bit, for all five variables the
+    Voigt LTE engine reads, random model types (absent ones included), one to five broadeners with and without a Bath entry,
+    derivative targets that are a broadener, the Bath and a species outside the map.
+
+    The reference keeps the broadeners in a std::unordered_map, so its loop sums them in the map's iteration order; the slice
+    reports that order and the catalog of the oracle call lists the broadeners in it."""
+    L = orc.lib()
+    dp = C.POINTER(C.c_double)
+    ip32 = C.POINTER(C.c_int32)
+    L.orc_line_mix.argtypes = [C.POINTER(abi.CatalogDesc), C.POINTER(abi.AtmPathDesc), C.c_int32, C.c_int64, C.c_int32, C.c_int32, dp]
+    ref.refslice_lsm_mix.argtypes = [C.c_int, ip32, ip32, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, ip32]
+    ref_var = {abi.VAR_G0: 0, abi.VAR_D0: 1, abi.VAR_DV: 8, abi.VAR_Y: 6, abi.VAR_G: 7}  # order of the reference's enum in the slice glue
+    rng = np.random.default_rng(71)
+    nsp = 6
+    nl = 60
+    case = synth.tiny_case(nl=nl, nf=8, np_=4)
+    cat, atm = case.cat, case.atm
+    # a catalog with 1..5 broadeners per line and random temperature models
+    counts = rng.integers(1, 6, nl)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    n_ls = int(off[-1])
+    species = np.empty(n_ls, np.int32)
+    for il in range(nl):
+        with_bath = rng.random() < 0.6
+        ids = list(rng.permutation(nsp)[: counts[il] - int(with_bath)]) + ([abi.SPECIES_BATH] if with_bath else [])
+        species[off[il]:off[il + 1]] = rng.permutation(np.array(ids, np.int32))
+    ls_type = rng.integers(-1, 9, (n_ls, abi.NVAR)).astype(np.int32)
+    ls_X = np.stack([rng.uniform(1e3, 3e4, (n_ls, abi.NVAR)), rng.uniform(0.3, 1.2, (n_ls, abi.NVAR)), rng.uniform(-50, 50, (n_ls, abi.NVAR)),
+                     rng.uniform(0.1, 0.9, (n_ls, abi.NVAR))], axis=-1)
+    vmr = rng.uniform(1e-4, 0.3, (case.np_, nsp))
+    n_checked = 0
+    inserted = []  # per line: the broadeners in the order they are put into the reference's map
+    for il in range(nl):
+        a, b = int(off[il]), int(off[il + 1])
+        nb = b - a
+        sp0 = species[a:b].copy()
+        sp_ref = np.ascontiguousarray(sp0 + 1, dtype=np.int32)  # Bath (-1) -> 0, species k -> k + 1
+        ty9 = np.full((nb, 9), -1, np.int32)
+        X9 = np.zeros((nb, 9, 4))
+        for v, rv in ref_var.items():
+            ty9[:, rv] = ls_type[a:b, v]
+            X9[:, rv] = ls_X[a:b, v]
+        order = np.zeros(nb, np.int32)
+        out = np.empty(8)
+        v0 = np.ascontiguousarray(vmr[0, np.maximum(sp0, 0)])
+        assert ref.refslice_lsm_mix(nb, sp_ref.ctypes.data_as(ip32), ty9.ctypes.data_as(ip32), dptr(X9), dptr(v0), 296.0, 250.0, 1e4, 0, 0,
+                                    dptr(out), order.ctypes.data_as(ip32)) == 0
+        inserted.append((sp0, sp_ref, ty9, X9, order.copy()))
+        perm = [int(np.where(sp_ref == o)[0][0]) for o in order]  # the map's iteration order -> the catalog's order
+        species[a:b], ls_type[a:b], ls_X[a:b] = species[a:b][perm], ls_type[a:b][perm], ls_X[a:b][perm]
+    cat.ls_offset, cat.ls_species, cat.ls_type, cat.ls_X = off, species, ls_type, ls_X
+    cat.n_species = max(cat.n_species, nsp)
+    d = cat.desc()
+    patm = abi.AtmPath(T=atm.T, P=atm.P, vmr=vmr, isorat=np.ones((case.np_, cat.n_isot)), Q=np.ones((case.np_, cat.n_isot)))
+    pa = patm.desc()
+    for il in range(nl):
+        sp0, sp_ref, ty9, X9, order0 = inserted[il]
+        nb = len(sp0)
+        inside = [int(s) for s in sp0]
+        outside = [s for s in range(nsp) if s not in inside][:1]
+        for ipl in range(case.np_):
+            vl = np.ascontiguousarray(vmr[ipl, np.maximum(sp0, 0)])
+            for v, rv in ref_var.items():
+                for target in inside + outside:
+                    r_out, o_out, order = np.empty(8), np.empty(7), np.zeros(nb, np.int32)
+                    assert ref.refslice_lsm_mix(nb, sp_ref.ctypes.data_as(ip32), ty9.ctypes.data_as(ip32), dptr(X9), dptr(vl), float(cat.T0[il]),
+                                                float(atm.T[ipl]), float(atm.P[ipl]), rv, target + 1, dptr(r_out), order.ctypes.data_as(ip32)) == 0
+                    assert list(order) == list(order0)
+                    orc._check(L.orc_line_mix(C.byref(d), C.byref(pa), ipl, il, v, target, dptr(o_out)))
+                    assert_same_bits(o_out, r_out[:7], f"line {il} level {ipl} variable {v} target {target}: VAR, dT, dVMR, dX0..3")
+                    n_checked += 1
+    assert n_checked > 3000

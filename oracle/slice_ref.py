@@ -66,6 +66,16 @@ SLICES = {
     "single_shape_ctor": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"single_shape::single_shape\(const SpeciesIsotope& spec,", None, (226, 237), "block"),
     "single_shape_F_dF": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"Complex single_shape::F\(const Complex z_\) \{ return Faddeeva::w\(z_\); \}", r"Complex single_shape::dF\(const Complex z_, const Complex F_\) \{", (239, 268), "block"),
     "single_shape_derivs": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"single_shape::zFdF::zFdF\(const Complex z_\)", r"Complex single_shape::dY\(const Complex ds_dY, const Numeric f\) const \{", (270, 339), "block"),
+    # the band sum: window of a frequency under a ByLine cutoff, the sums with and without cutoff, scl(f), the clamp and the
+    # accumulation into the propagation matrix
+    "number_density": ("src/core/physics/physics_funcs.h", r"constexpr Numeric number_density\(Numeric p, Numeric t\) noexcept \{", None, (54, 56), "block"),
+    "band_offset_spans": ("src/core/lbl/lbl_lineshape_voigt_lte.h", r"constexpr std::pair<Index, Index> find_offset_and_count_of_frequency_range\(", r"constexpr auto frequency_spans\(const Numeric cutoff,", (123, 155), "block"),
+    "band_shape_struct": ("src/core/lbl/lbl_lineshape_voigt_lte.h", r"struct band_shape \{", None, (158, 365), "block"),
+    "band_shape_ctor_sum": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"band_shape::band_shape\(std::vector<single_shape>&& ls, const Numeric cut\)", r"Complex band_shape::operator\(\)\(const Numeric f\) const \{", (428, 436), "block"),
+    "band_shape_cut": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"Complex band_shape::operator\(\)\(const ConstComplexVectorView& cut,", r"void band_shape::operator\(\)\(ComplexVectorView cut\) const \{", (591, 608), "block"),
+    "computedata_ctor_scl": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"ComputeData::ComputeData\(const ConstVectorView& f_grid,", None, (936, 956), "block"),
+    "calculate_accumulate": ("src/core/lbl/lbl_lineshape_voigt_lte.cpp", r"const auto F = com_data.scl\[i\] \* com_data.shape\[i\];", r"pm\[i\] \+= zeeman::scale\(com_data.npm, F\);", (1689, 1691), "lines"),
+    "zeeman_scale": ("src/core/lbl/lbl_zeeman.h", r"constexpr Propmat scale\(const Propmat &a, const Complex F\) noexcept \{", None, (432, 440), "block"),
 }
 
 # the full microwave absorption models (second translation unit, refslice/template_predef.cpp.in)
